@@ -1,0 +1,136 @@
+"""CPU: pin the oracle (oracle/pcaudio_oracle.py) against the golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py), and cross-check the STFT restatement
+against two independent implementations."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pcaudio_oracle as orc
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def pcg():
+    return dict(np.load(os.path.join(G, "pointcloud_golden.npz")))
+
+
+@pytest.fixture(scope="module")
+def encg():
+    return dict(np.load(os.path.join(G, "encoder_golden.npz")))
+
+
+def sub(d, prefix):
+    return {k[len(prefix):]: torch.from_numpy(v) for k, v in d.items() if k.startswith(prefix)}
+
+
+def test_cloud_3d_matches_reference(pcg):
+    for i in range(pcg["x3"].shape[2]):
+        got = orc.cloud_3d(pcg["x3"], pcg["farr"], pcg["tarr"], i)
+        assert got.dtype == np.float32
+        np.testing.assert_array_equal(got, pcg["pc_temp"][i])
+
+
+@pytest.mark.parametrize("K", [1, 17, 64, 288])
+def test_cloud_3d_maxk_matches_reference(pcg, K):
+    for i in range(pcg["x3"].shape[2]):
+        got, order = orc.cloud_3d_maxk_f64(pcg["x3"], pcg["farr"], pcg["tarr"], i, K)
+        np.testing.assert_array_equal(got, pcg[f"pc_temp_maxk_{K}"][i])   # bit exact, float64
+        assert got.dtype == np.float64 and len(order) == K
+
+
+def test_cloud_2d_matches_reference(pcg):
+    for i in range(pcg["x2"].shape[1]):
+        np.testing.assert_array_equal(orc.cloud_2d(pcg["x2"], pcg["farr"], i), pcg["pc_2d"][i])
+
+
+@pytest.mark.parametrize("K", [1, 10, 48])
+def test_pc_maxk_matches_reference(pcg, K):
+    xs, fs_ = orc.pc_maxk(pcg["x2"], pcg["farr"], K)
+    np.testing.assert_array_equal(xs, pcg[f"pc_maxK_x_{K}"])
+    np.testing.assert_array_equal(fs_, pcg[f"pc_maxK_f_{K}"])
+    for i in range(pcg["x2"].shape[1]):
+        np.testing.assert_array_equal(orc.cloud_2d_ss(xs, fs_, i), pcg[f"pc_ss_{K}"][i])
+
+
+def test_topk_tie_rule():
+    keys = np.array([1.0, 3.0, 3.0, 2.0, 3.0, -1.0], dtype=np.float32)
+    assert orc.topk_order(keys, 4).tolist() == [1, 2, 4, 3]
+
+
+def test_mab_blocks_match_reference(encg):
+    tol = dict(rtol=1e-5, atol=1e-6)
+    Q, K = torch.from_numpy(encg["mab_Q"]), torch.from_numpy(encg["mab_K"])
+    np.testing.assert_allclose(orc.mab_forward(sub(encg, "mab."), "", Q, K, 4).numpy(), encg["mab_out"], **tol)
+    np.testing.assert_allclose(orc.mab_forward(sub(encg, "mabln."), "", Q, K, 4).numpy(), encg["mabln_out"], **tol)
+    X = torch.from_numpy(encg["isab_X"])
+    np.testing.assert_allclose(orc.isab_forward(sub(encg, "isab."), "", X, 4).numpy(), encg["isab_out"], **tol)
+    X = torch.from_numpy(encg["pma_X"])
+    np.testing.assert_allclose(orc.pma_forward(sub(encg, "pma."), "", X, 4).numpy(), encg["pma_out"], **tol)
+    X = torch.from_numpy(encg["sab_X"])
+    np.testing.assert_allclose(orc.sab_forward(sub(encg, "sab."), "", X, 2).numpy(), encg["sab_out"], **tol)
+
+
+@pytest.mark.parametrize("d_in", [2, 3])
+def test_st_matches_reference(encg, d_in):
+    p = sub(encg, f"st{d_in}.")
+    X = torch.from_numpy(encg[f"st{d_in}_X"])
+    out = orc.st_forward(p, X, 8).numpy()
+    assert out.shape == (3, 10)
+    np.testing.assert_allclose(out, encg[f"st{d_in}_out"], rtol=1e-4, atol=1e-5)
+    out1 = orc.st_forward(p, X[:1], 8).numpy()
+    assert out1.shape == (10,)                       # .squeeze() quirk, Code/models.py:44
+    np.testing.assert_allclose(out1, encg[f"st{d_in}_out_b1"], rtol=1e-4, atol=1e-5)
+
+
+def test_modelnet_and_deepset_match_reference(encg):
+    out = orc.modelnet_forward(sub(encg, "mn."), torch.from_numpy(encg["mn_X"]), 4).numpy()
+    np.testing.assert_allclose(out, encg["mn_out"], rtol=1e-4, atol=1e-5)
+    out = orc.deepset_forward(sub(encg, "ds."), torch.from_numpy(encg["ds_X"]), 2, 5).numpy()
+    np.testing.assert_allclose(out, encg["ds_out"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag,heads", [("fst", 8), ("3st", 8)])
+def test_shipped_checkpoints(tag, heads):
+    w = orc.strip_module_prefix({k: torch.from_numpy(v) for k, v in
+                                 np.load(os.path.join(G, f"{tag}_weights.npz")).items()})
+    ck = np.load(os.path.join(G, "checkpoint_golden.npz"))
+    out = orc.st_forward(w, torch.from_numpy(ck[f"{tag}_X"]), heads).numpy()
+    np.testing.assert_allclose(out, ck[f"{tag}_out"], rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------ STFT (unpinned vs librosa)
+@pytest.mark.parametrize("n_fft,win,L", [(1024, 1024, 16000), (2048, 2048, 16000), (2048, 1434, 9000),
+                                         (512, 512, 4000)])
+def test_stft_against_torch_and_scipy(n_fft, win, L):
+    import scipy.signal
+    x = orc.synth_audio(1, L, 16000, 5)[0]
+    hop = int(win * 0.5)
+    S = orc.stft_librosa080(x, n_fft, win, hop)
+    assert S.dtype == np.complex64 and S.shape == (n_fft // 2 + 1, 1 + L // hop)
+    wt = torch.from_numpy(orc.padded_window(n_fft, win))
+    St = torch.stft(torch.from_numpy(x).double(), n_fft, hop_length=hop, win_length=n_fft, window=wt,
+                    center=True, pad_mode="reflect", return_complex=True).numpy()
+    scale = np.abs(St).max()
+    assert np.abs(S - St).max() / scale < 1e-6
+    if win == n_fft:
+        # independent framing/padding implementation
+        _, _, Ss = scipy.signal.stft(np.pad(x.astype(np.float64), n_fft // 2, mode="reflect"), window=orc.hann_periodic(n_fft),
+                                     nperseg=n_fft, noverlap=n_fft - hop, boundary=None, padded=False,
+                                     scaling="spectrum")
+        Ss = Ss * orc.hann_periodic(n_fft).sum()
+        assert Ss.shape == S.shape
+        assert np.abs(S - Ss).max() / scale < 1e-6
+
+
+def test_logmag_recipe_shapes_and_chunking():
+    x = orc.synth_audio(1, 16000, 16000, 9)[0]
+    a = orc.logmag_recipe(x, 1024, 0.5, drop_nyquist=True)
+    assert a.dtype == np.float32 and a.shape == (512, 32)
+    c = orc.chunk_frames(a, 10)
+    assert c.shape == (512, 10, 3)
+    np.testing.assert_array_equal(c[:, :, 1], a[:, 10:20])
+    farr, tarr = orc.coord_tables(16000, 512, 1024, 0.5, 10)
+    assert farr[-1] == 0.5 and tarr.shape == (10,) and abs(tarr[-1] - 0.32) < 1e-12
