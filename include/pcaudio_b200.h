@@ -1,0 +1,202 @@
+/*
+ * pcaudio_b200 -- C ABI of the B200 (sm_100a) audio -> point-cloud -> set-encoder hot path.
+ *
+ * The reference (SubramaniKrishna/point-cloud-audio) is pure Python and has no FFI layer
+ * (SURVEY.md 8b); every entry point below therefore cites the reference *Python* interface
+ * whose arithmetic it replaces.  The host-side mirror of those interfaces (same class /
+ * function names and argument meaning) lives in point-cloud-audio_b200/ and binds these
+ * symbols with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with `host_`;
+ *   - all tensors are dense, row-major, float32 unless stated; sizes are element counts;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are
+ *     asynchronous on that stream and never call cudaDeviceSynchronize;
+ *   - the library allocates no device memory: scratch is caller-provided (`workspace`);
+ *   - return 0 on success, a positive cudaError_t, or a negative PCA_E* code; the message is
+ *     available from pca_last_error() (thread local).  No exceptions cross the boundary.
+ */
+#ifndef PCAUDIO_B200_H
+#define PCAUDIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCA_VERSION 100 /* 0.1.0 */
+
+enum {
+    PCA_OK = 0,
+    PCA_EINVAL = -1,      /* bad shape / null pointer / misaligned */
+    PCA_EUNSUPPORTED = -2, /* dims outside what the kernels implement */
+    PCA_EWORKSPACE = -3,  /* workspace too small */
+    PCA_EDEVICE = -4      /* not an sm_100 device */
+};
+
+/* precision of the set-encoder kernels */
+enum {
+    PCA_PREC_FP32 = 0, /* CUDA-core fp32 everywhere (1e-3 parity path) */
+    PCA_PREC_BF16 = 2  /* tcgen05 bf16 operands, fp32 accumulate (2e-2 parity path) */
+};
+
+int pca_version(void);
+const char* pca_last_error(void);
+
+/* ---------------------------------------------------------------- L2: spectral front end
+ * Replaces the inline recipe
+ *   x = librosa.stft(x, n_fft, win_length, hop_length=int(N*hf), window='hann') / N
+ *   [x = x[:-1,:]] ; a = np.log(1.0e-8 + np.abs(x))
+ * Code/settransformer.py:49-50, Code/settransformertemp.py:51-53, Code/pceval.py:76-77.
+ *
+ * audio   (n_clips, n_samples)
+ * window  (n_fft)   periodic Hann of win_length centred/zero-padded to n_fft (host-built in
+ *                   float64, rounded once)
+ * twiddle (n_fft/2, 2) = (cos, -sin)(2 pi k / n_fft), k < n_fft/2
+ * out     (n_clips, nt_out, nf_out), frequency fastest; nf_out = n_fft/2+1-drop_nyquist;
+ *         frame t is centred on sample t*hop (reflect padding by index mirroring);
+ *         nt_out <= 1 + n_samples/hop frames are produced (the 3ST chunking of
+ *         Code/settransformertemp.py:54-58 keeps only floor(Nt/Ntemp)*Ntemp of them).
+ * scale   multiplies |STFT| before the log (= 1/N). */
+int pca_stft_logmag_f32(const float* audio, int n_clips, int n_samples, int n_fft, int hop,
+                        const float* window, const float* twiddle, float scale, int drop_nyquist,
+                        int nt_out, float* out, void* stream);
+
+/* ---------------------------------------------------------------- L3: point clouds
+ * ESC_pc.__getitem__ (Code/dataset.py:50-54) when tarr == NULL: rows (farr[f], x[f]);
+ * ESC_pc_temp.__getitem__ (Code/dataset.py:160-166) otherwise: point p = t*nf + f has
+ * columns (farr[f], tarr[t], x[f,t]).  logmag is (n_clouds, nt, nf) f-fastest (nt = 1 for
+ * 2-D clouds); pts is (n_clouds, nt*nf, 2|3). */
+int pca_build_clouds_f32(const float* logmag, int n_clouds, int nf, int nt, const float* farr,
+                         const float* tarr, float* pts, void* stream);
+
+/* ESC_pc_temp_maxKSS.__getitem__ (Code/dataset.py:194-202) and utils.pc_maxK
+ * (Code/utils.py:25-52): per cloud, the K largest keys.  With sorted_desc != 0 rows are
+ * emitted in the order of (-key).argsort(kind='stable')[:K]; otherwise in ascending flat
+ * index (scan) order.  Ties at the K boundary keep the lowest flat indices.
+ * pts (n_clouds, K, 2|3) may be NULL (indices only); idx (n_clouds, K) int32 flat indices
+ * p = t*nf + f may be NULL.  K <= nf*nt; sorted output needs K <= 16384. */
+int pca_topk_compact_f32(const float* keys, int n_clouds, int nf, int nt, const float* farr,
+                         const float* tarr, int K, int sorted_desc, float* pts, int32_t* idx,
+                         void* stream);
+
+/* ---------------------------------------------------------------- L4: set encoder
+ * Weights are passed as ONE packed float32 blob per block, nn.Linear layout (out, in):
+ *   MAB  := Wq (D,dq) | bq (D) | Wk (D,dk) | Wv (D,dk) | bk (D) | bv (D) | Wo (D,D) | bo (D)
+ *           [| ln0.w (D) | ln0.b (D) | ln1.w (D) | ln1.b (D)   when ln != 0]
+ *   ISAB := I (M,D) | MAB(dq=D, dk=d_in)   /mab0/ | MAB(dq=d_in, dk=D) /mab1/
+ *   PMA  := S (S,D) | MAB(dq=D, dk=D)
+ *   ST   := ISAB(d_in) | ISAB(D) | PMA | Wl (C,D) | bl (C)
+ * pca_*_param_count return the blob length so both sides agree. */
+typedef struct {
+    int d_in;   /* input point width (2 or 3 for audio) */
+    int D;      /* dim_hidden */
+    int H;      /* num_heads */
+    int M;      /* num_inds */
+    int S;      /* num_outputs (PMA seeds) */
+    int C;      /* dim_output (classes) */
+    int ln;     /* LayerNorm branches of MAB (modules.py:14-16,30,32) */
+} pca_st_dims;
+
+long long pca_mab_param_count(int dq, int dk, int D, int ln);
+long long pca_isab_param_count(int d_in, int D, int M, int ln);
+long long pca_pma_param_count(int D, int S, int ln);
+long long pca_st_param_count(const pca_st_dims* dims);
+
+/* MAB.forward (set_transformer-master/modules.py:19-33).
+ * Q (Bq, nq, dq) with Bq == B, or Bq == 1 to broadcast one query set over the batch (the
+ * I.repeat / S.repeat of modules.py:52,63 is never materialised); K (B, nk, dk);
+ * out (B, nq, D). */
+size_t pca_mab_workspace_bytes(int B, int nq, int nk, int dq, int dk, int D, int H);
+int pca_mab_fwd_f32(const float* Q, int q_batch, const float* K, int B, int nq, int nk, int dq,
+                    int dk, int D, int H, int ln, const float* params, float* out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ISAB.forward (modules.py:51-53): X (B,N,d_in) -> out (B,N,D). */
+size_t pca_isab_workspace_bytes(int B, int N, int d_in, int D, int H, int M);
+int pca_isab_fwd_f32(const float* X, int B, int N, int d_in, int D, int H, int M, int ln,
+                     const float* params, float* out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* PMA.forward (modules.py:62-63): X (B,N,D) -> out (B,S,D). */
+size_t pca_pma_workspace_bytes(int B, int N, int D, int H, int S);
+int pca_pma_fwd_f32(const float* X, int B, int N, int D, int H, int S, int ln,
+                    const float* params, float* out, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ST.forward (Code/models.py:43-44) == main_pointcloud.SetTransformer.forward in eval mode
+ * (set_transformer-master/main_pointcloud.py:36-37): X (B,N,d_in) -> logits (B,S,C)
+ * (the caller applies the reference's .squeeze()).  The batch is processed in chunks that
+ * fit `workspace_bytes` (any size >= pca_st_workspace_bytes(dims, 1, N, precision) works;
+ * larger is faster).  precision: PCA_PREC_FP32 (all dims) or PCA_PREC_BF16 (tcgen05 path;
+ * D=64, H=8, M=64, S=1, ln=0 only -- anything else returns PCA_EUNSUPPORTED). */
+size_t pca_st_workspace_bytes(const pca_st_dims* dims, int B, int N, int precision);
+int pca_st_fwd(const float* X, int B, int N, const pca_st_dims* dims, const float* params,
+               float* logits, void* workspace, size_t workspace_bytes, int precision,
+               void* stream);
+
+/* DeepSet.forward (set_transformer-master/models.py:25-28) / SmallDeepSet
+ * (max_regression_demo.ipynb:41-48): 4 shared Linear (+ReLU) over points, pool over points
+ * (0 mean, 1 max, 2 sum), 4 Linear decoder.  params := for enc then dec, 4 x (W (out,in) | b).
+ * X (B,N,d_in) -> out (B, num_outputs*dim_output). */
+size_t pca_deepset_workspace_bytes(int B, int N, int d_in, int dim_hidden, int out_dim);
+int pca_deepset_fwd_f32(const float* X, int B, int N, int d_in, int dim_hidden, int out_dim,
+                        int pool, const float* params, float* out, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- whole path, one call
+ * audio -> STFT/log-magnitude -> [Ntemp chunking] -> [top-K] -> clouds -> ST -> logits.
+ * This is what the reference's eval loop does per batch (Code/pc_temp3d_eval.py:126-185,
+ * Code/pceval.py:73-99) minus file I/O.  mode 2: one (f,mag) cloud per frame (FST);
+ * mode 3: one (f,t,mag) cloud per ntemp-frame chunk (3ST; ntemp = frames per clip gives
+ * clip-as-cloud).  top_k == 0 keeps every point. */
+typedef struct {
+    int n_samples;
+    int n_fft;
+    int hop;
+    float scale;        /* 1/N applied to |STFT| */
+    int mode;           /* 2 = FST frame clouds, 3 = 3ST chunk clouds */
+    int ntemp;          /* mode 3: frames per cloud */
+    int top_k;          /* 0 = all points */
+    int precision;      /* PCA_PREC_* for the encoder */
+    pca_st_dims st;
+} pca_pipeline_cfg;
+
+/* number of clouds produced per clip and points per cloud for a config */
+int pca_pipeline_clouds_per_clip(const pca_pipeline_cfg* cfg);
+int pca_pipeline_points_per_cloud(const pca_pipeline_cfg* cfg);
+size_t pca_pipeline_workspace_bytes(const pca_pipeline_cfg* cfg, int n_clips);
+
+/* Device-resident variant: audio (n_clips, n_samples) and logits
+ * (n_clips*clouds_per_clip, S, C) are device buffers. */
+int pca_pipeline_run(const pca_pipeline_cfg* cfg, const float* audio, int n_clips,
+                     const float* window, const float* twiddle, const float* farr,
+                     const float* tarr, const float* st_params, float* logits, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* Host-buffer variant (the end-to-end call): host_audio / host_logits are HOST pointers
+ * (pinned for asynchronous copies); dev_audio / dev_logits are caller-owned device staging
+ * buffers.  Enqueues H2D copy, the kernels and the D2H copy on `stream`; the caller
+ * synchronises the stream before reading host_logits. */
+int pca_pipeline_run_host(const pca_pipeline_cfg* cfg, const float* host_audio, int n_clips,
+                          float* dev_audio, const float* window, const float* twiddle,
+                          const float* farr, const float* tarr, const float* st_params,
+                          float* dev_logits, float* host_logits, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* number of kernels the library has launched in this process (for bench.py gpu_launches) */
+unsigned long long pca_launch_count(void);
+
+/* Measurement aid: while enabled, every kernel launch is bracketed by CUDA events on its stream.
+ * pca_profile_report synchronises those events and writes a JSON object
+ *   {"<kernel>": {"launches": n, "ms": total device ms, "flops": algorithmic flops, "bytes": algorithmic bytes}, ...}
+ * into buf, then clears the records.  Enabling/disabling also clears them. */
+void pca_profile_enable(int on);
+int pca_profile_report(char* buf, size_t buf_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCAUDIO_B200_H */

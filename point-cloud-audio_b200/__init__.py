@@ -1,0 +1,16 @@
+"""pcaudio_b200 -- B200-native drop-in for the audio -> point-cloud -> set-encoder hot path of
+SubramaniKrishna/point-cloud-audio.  Host mirrors keep the reference's names and signatures; the
+arithmetic runs in hand-written sm_100a CUDA kernels behind a C ABI (include/pcaudio_b200.h)."""
+from . import _lib
+from .data_processing import load_esc, tt_split
+from .dataset import ESC_pc, ESC_pc_ss, ESC_pc_temp, ESC_pc_temp_maxKSS
+from .frontend import build_clouds, coord_tables, spectral_point_cloud, stft_logmag, topk_points
+from .models import ST, DeepSet, SetTransformer, strip_module_prefix
+from .modules import ISAB, MAB, PMA, SAB
+from .pipeline import AudioConfig, AudioSetPipeline
+from .utils import pc_maxK
+
+__all__ = ["load_esc", "tt_split", "ESC_pc", "ESC_pc_ss", "ESC_pc_temp", "ESC_pc_temp_maxKSS", "build_clouds",
+           "coord_tables", "spectral_point_cloud", "stft_logmag", "topk_points", "ST", "DeepSet",
+           "SetTransformer", "strip_module_prefix", "ISAB", "MAB", "PMA", "SAB", "AudioConfig",
+           "AudioSetPipeline", "pc_maxK"]

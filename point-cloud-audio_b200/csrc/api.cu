@@ -1,0 +1,500 @@
+// extern "C" surface of libpcaudio_b200.so (see include/pcaudio_b200.h) and the host-side
+// orchestration of the kernels.  No torch types, no device allocation, no global mutable state
+// beyond the launch counter and the thread-local error slot.
+#include "common.cuh"
+#include <string.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace pca {
+
+// ---- kernels / launchers defined in the other translation units
+int launch_stft_logmag(const float*, int, int, int, int, const float*, const float*, float, int, int, float*, cudaStream_t);
+int launch_build_clouds(const float*, int, int, int, const float*, const float*, float*, cudaStream_t);
+int launch_topk(const float*, int, int, int, const float*, const float*, int, int, float*, int32_t*, cudaStream_t);
+int launch_linear(const float*, const float*, const float*, float*, long long, int, int, int, cudaStream_t);
+int launch_attn(const float*, long long, const float*, int, int, int, int, int, float*, float*, cudaStream_t);
+size_t attn_part_floats(int B, int nq, int nk, int D, int H);
+int launch_layernorm(float*, long long, int, const float*, const float*, cudaStream_t);
+int launch_pool(const float*, int, int, int, int, float*, cudaStream_t);
+// tcgen05 path (encoder_tc.cu)
+size_t st_tc_workspace_bytes(const pca_st_dims* d, int B, int N);
+int st_tc_supported(const pca_st_dims* d, int N);
+int st_tc_forward(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
+                  void* ws, size_t ws_bytes, cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+char* err_buf() { return g_err; }
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return (int)e;
+}
+
+// ------------------------------------------------------------------------------------ profiling
+struct ProfRec { const char* name; cudaEvent_t a, b; double flops, bytes; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+
+LaunchTimer::LaunchTimer(const char* name, cudaStream_t s, double flops, double bytes) : slot(-1), st(s) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRec r{name, nullptr, nullptr, flops, bytes};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+LaunchTimer::~LaunchTimer() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].b, st);
+}
+
+// ------------------------------------------------------------------------------------ params
+struct MabParams {
+    const float *Wq, *bq, *Wkv, *bkv, *Wo, *bo, *ln0w, *ln0b, *ln1w, *ln1b;
+};
+static long long mab_count(int dq, int dk, int D, int ln) {
+    return (long long)D * dq + D + 2LL * D * dk + 2LL * D + (long long)D * D + D + (ln ? 4LL * D : 0);
+}
+static MabParams mab_slice(const float* p, int dq, int dk, int D, int ln) {
+    MabParams m;
+    m.Wq = p; p += (long long)D * dq;
+    m.bq = p; p += D;
+    m.Wkv = p; p += 2LL * D * dk;      // Wk then Wv: one (2D, dk) matrix
+    m.bkv = p; p += 2LL * D;           // bk then bv
+    m.Wo = p; p += (long long)D * D;
+    m.bo = p; p += D;
+    m.ln0w = m.ln0b = m.ln1w = m.ln1b = nullptr;
+    if (ln) { m.ln0w = p; m.ln0b = p + D; m.ln1w = p + 2 * D; m.ln1b = p + 3 * D; }
+    return m;
+}
+
+// ------------------------------------------------------------------------------------ MAB (fp32)
+// workspace: Qp (qb*nq*D) | KV (B*nk*2D) | O (B*nq*D) | part
+static size_t mab_ws_floats(int B, int qb, int nq, int nk, int D, int H) {
+    Arena a(nullptr, 0);
+    a.take<float>((size_t)qb * nq * D);
+    a.take<float>((size_t)B * nk * 2 * D);
+    a.take<float>((size_t)B * nq * D);
+    a.take<float>(attn_part_floats(B, nq, nk, D, H));
+    return a.off;
+}
+
+// Q (qb, nq, dq) with qb in {1, B}; K (B, nk, dk); out (B, nq, D)
+static int mab_forward(const float* Q, int qb, const float* K, int B, int nq, int nk, int dq, int dk, int D,
+                       int H, int ln, const float* params, float* out, void* ws, size_t ws_bytes,
+                       cudaStream_t st) {
+    if (qb != 1 && qb != B) return fail(PCA_EINVAL, "MAB: query batch must be 1 or B");
+    if (nq <= 0 || nk <= 0) return fail(PCA_EINVAL, "MAB: empty query or key set (nq=%d, nk=%d)", nq, nk);
+    const MabParams m = mab_slice(params, dq, dk, D, ln);
+    Arena a(ws, ws_bytes);
+    float* Qp = a.take<float>((size_t)qb * nq * D);
+    float* KV = a.take<float>((size_t)B * nk * 2 * D);
+    float* O = a.take<float>((size_t)B * nq * D);
+    float* part = a.take<float>(attn_part_floats(B, nq, nk, D, H));
+    if (!a.ok()) return fail(PCA_EWORKSPACE, "MAB: workspace too small (%zu bytes given)", ws_bytes);
+    PCA_TRY(launch_linear(Q, m.Wq, m.bq, Qp, (long long)qb * nq, dq, D, 0, st));
+    PCA_TRY(launch_linear(K, m.Wkv, m.bkv, KV, (long long)B * nk, dk, 2 * D, 0, st));
+    PCA_TRY(launch_attn(Qp, qb == 1 ? 0 : (long long)nq * D, KV, B, nq, nk, D, H, O, part, st));
+    if (ln) PCA_TRY(launch_layernorm(O, (long long)B * nq, D, m.ln0w, m.ln0b, st));
+    PCA_TRY(launch_linear(O, m.Wo, m.bo, out, (long long)B * nq, D, D, 2, st));
+    if (ln) PCA_TRY(launch_layernorm(out, (long long)B * nq, D, m.ln1w, m.ln1b, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ ISAB / PMA / ST (fp32)
+static size_t isab_ws_bytes(int B, int N, int d_in, int D, int H, int M) {
+    Arena a(nullptr, 0);
+    a.take<float>((size_t)B * M * D);   // H
+    size_t w0 = mab_ws_floats(B, 1, M, N, D, H), w1 = mab_ws_floats(B, B, N, M, D, H);
+    return a.off + (w0 > w1 ? w0 : w1);
+}
+static int isab_forward(const float* X, int B, int N, int d_in, int D, int H, int M, int ln,
+                        const float* params, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const float* I = params;
+    const float* p0 = I + (long long)M * D;
+    const float* p1 = p0 + mab_count(D, d_in, D, ln);
+    Arena a(ws, ws_bytes);
+    float* Hb = a.take<float>((size_t)B * M * D);
+    if (!a.ok()) return fail(PCA_EWORKSPACE, "ISAB: workspace too small");
+    void* sub = (char*)ws + a.off;
+    const size_t sub_bytes = ws_bytes - a.off;
+    PCA_TRY(mab_forward(I, 1, X, B, M, N, D, d_in, D, H, ln, p0, Hb, sub, sub_bytes, st));      // mab0(I, X)
+    PCA_TRY(mab_forward(X, B, Hb, B, N, M, d_in, D, D, H, ln, p1, out, sub, sub_bytes, st));    // mab1(X, H)
+    return 0;
+}
+static size_t pma_ws_bytes(int B, int N, int D, int H, int S) { return mab_ws_floats(B, 1, S, N, D, H); }
+static int pma_forward(const float* X, int B, int N, int D, int H, int S, int ln, const float* params,
+                       float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const float* Sd = params;
+    return mab_forward(Sd, 1, X, B, S, N, D, D, D, H, ln, Sd + (long long)S * D, out, ws, ws_bytes, st);
+}
+
+static long long st_count(const pca_st_dims* d) {
+    return (long long)d->M * d->D + mab_count(d->D, d->d_in, d->D, d->ln) + mab_count(d->d_in, d->D, d->D, d->ln) +
+           (long long)d->M * d->D + mab_count(d->D, d->D, d->D, d->ln) + mab_count(d->D, d->D, d->D, d->ln) +
+           (long long)d->S * d->D + mab_count(d->D, d->D, d->D, d->ln) + (long long)d->C * d->D + d->C;
+}
+
+static size_t st_f32_ws_bytes(const pca_st_dims* d, int B, int N) {
+    Arena a(nullptr, 0);
+    a.take<float>((size_t)B * N * d->D);   // Y1
+    a.take<float>((size_t)B * N * d->D);   // Y2
+    a.take<float>((size_t)B * d->S * d->D);
+    size_t w0 = isab_ws_bytes(B, N, d->d_in, d->D, d->H, d->M);
+    size_t w1 = isab_ws_bytes(B, N, d->D, d->D, d->H, d->M);
+    size_t w2 = pma_ws_bytes(B, N, d->D, d->H, d->S);
+    size_t w = w0 > w1 ? w0 : w1;
+    w = w > w2 ? w : w2;
+    return a.off + w;
+}
+
+static int st_f32_forward_chunk(const float* X, int B, int N, const pca_st_dims* d, const float* params,
+                                float* logits, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int D = d->D, H = d->H, M = d->M, S = d->S, C = d->C, ln = d->ln;
+    const float* p_isab0 = params;
+    const float* p_isab1 = p_isab0 + (long long)M * D + mab_count(D, d->d_in, D, ln) + mab_count(d->d_in, D, D, ln);
+    const float* p_pma = p_isab1 + (long long)M * D + 2 * mab_count(D, D, D, ln);
+    const float* p_lin = p_pma + (long long)S * D + mab_count(D, D, D, ln);
+    Arena a(ws, ws_bytes);
+    float* Y1 = a.take<float>((size_t)B * N * D);
+    float* Y2 = a.take<float>((size_t)B * N * D);
+    float* P = a.take<float>((size_t)B * S * D);
+    if (!a.ok()) return fail(PCA_EWORKSPACE, "ST: workspace too small");
+    void* sub = (char*)ws + a.off;
+    const size_t sub_bytes = ws_bytes - a.off;
+    PCA_TRY(isab_forward(X, B, N, d->d_in, D, H, M, ln, p_isab0, Y1, sub, sub_bytes, st));
+    PCA_TRY(isab_forward(Y1, B, N, D, D, H, M, ln, p_isab1, Y2, sub, sub_bytes, st));
+    PCA_TRY(pma_forward(Y2, B, N, D, H, S, ln, p_pma, P, sub, sub_bytes, st));
+    PCA_TRY(launch_linear(P, p_lin, p_lin + (long long)C * D, logits, (long long)B * S, D, C, 0, st));
+    return 0;
+}
+
+static int check_dims(const pca_st_dims* d) {
+    if (!d) return fail(PCA_EINVAL, "ST: null dims");
+    if (d->d_in <= 0 || d->D <= 0 || d->H <= 0 || d->M <= 0 || d->S <= 0 || d->C <= 0)
+        return fail(PCA_EINVAL, "ST: non-positive dimension");
+    if (d->D % d->H) return fail(PCA_EINVAL, "ST: dim_hidden %d not divisible by num_heads %d", d->D, d->H);
+    if (d->D % 4) return fail(PCA_EUNSUPPORTED, "ST: dim_hidden must be a multiple of 4");
+    return 0;
+}
+
+static int st_forward(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
+                      void* ws, size_t ws_bytes, int precision, cudaStream_t st) {
+    PCA_TRY(check_dims(d));
+    if (!X || !params || !logits) return fail(PCA_EINVAL, "ST: null pointer");
+    if (B < 0 || N <= 0) return fail(PCA_EINVAL, "ST: bad batch/points (B=%d, N=%d)", B, N);
+    if (B == 0) return 0;
+    if (precision == PCA_PREC_BF16) {
+        if (!st_tc_supported(d, N))
+            return fail(PCA_EUNSUPPORTED, "ST: tcgen05 path needs D=64,H=8,M=64,S=1,ln=0,d_in<=3 (got D=%d,H=%d,M=%d,S=%d,ln=%d,d_in=%d)",
+                        d->D, d->H, d->M, d->S, d->ln, d->d_in);
+        return st_tc_forward(X, B, N, d, params, logits, ws, ws_bytes, st);
+    }
+    if (precision != PCA_PREC_FP32) return fail(PCA_EINVAL, "ST: unknown precision %d", precision);
+    // largest chunk of clouds whose scratch fits the caller's workspace
+    const size_t one = st_f32_ws_bytes(d, 1, N);
+    if (ws_bytes < one || !ws) return fail(PCA_EWORKSPACE, "ST: workspace %zu B < minimum %zu B", ws_bytes, one);
+    int chunk = B;
+    while (chunk > 1 && st_f32_ws_bytes(d, chunk, N) > ws_bytes) chunk = (chunk + 1) / 2;
+    if (chunk > 32768) chunk = 32768;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int bc = (B - b0) < chunk ? (B - b0) : chunk;
+        PCA_TRY(st_f32_forward_chunk(X + (long long)b0 * N * d->d_in, bc, N, d, params,
+                                     logits + (long long)b0 * d->S * d->C, ws, ws_bytes, st));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ DeepSet
+static size_t deepset_ws_bytes(int B, int N, int dh) {
+    Arena a(nullptr, 0);
+    a.take<float>((size_t)B * N * dh);
+    a.take<float>((size_t)B * N * dh);
+    a.take<float>((size_t)B * dh);
+    a.take<float>((size_t)B * dh);
+    return a.off;
+}
+static int deepset_forward(const float* X, int B, int N, int d_in, int dh, int out_dim, int pool,
+                           const float* p, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    Arena a(ws, ws_bytes);
+    float* t0 = a.take<float>((size_t)B * N * dh);
+    float* t1 = a.take<float>((size_t)B * N * dh);
+    float* u0 = a.take<float>((size_t)B * dh);
+    float* u1 = a.take<float>((size_t)B * dh);
+    if (!a.ok() || !ws) return fail(PCA_EWORKSPACE, "DeepSet: workspace too small");
+    const long long rows = (long long)B * N;
+    const float* W[8]; const float* bb[8];
+    int din = d_in;
+    for (int i = 0; i < 8; ++i) {
+        const int dout = (i == 7) ? out_dim : dh;
+        const int di = (i == 0) ? d_in : dh;
+        W[i] = p; p += (long long)dout * di;
+        bb[i] = p; p += dout;
+        (void)din;
+    }
+    PCA_TRY(launch_linear(X, W[0], bb[0], t0, rows, d_in, dh, 1, st));
+    PCA_TRY(launch_linear(t0, W[1], bb[1], t1, rows, dh, dh, 1, st));
+    PCA_TRY(launch_linear(t1, W[2], bb[2], t0, rows, dh, dh, 1, st));
+    PCA_TRY(launch_linear(t0, W[3], bb[3], t1, rows, dh, dh, 0, st));
+    PCA_TRY(launch_pool(t1, B, N, dh, pool, u0, st));
+    PCA_TRY(launch_linear(u0, W[4], bb[4], u1, B, dh, dh, 1, st));
+    PCA_TRY(launch_linear(u1, W[5], bb[5], u0, B, dh, dh, 1, st));
+    PCA_TRY(launch_linear(u0, W[6], bb[6], u1, B, dh, dh, 1, st));
+    PCA_TRY(launch_linear(u1, W[7], bb[7], out, B, dh, out_dim, 0, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ pipeline
+struct PipeShape { int nt_all, nt_out, nf, clouds_per_clip, pts_full, pts; int width; };
+static int pipe_shape(const pca_pipeline_cfg* c, PipeShape* s) {
+    if (!c) return fail(PCA_EINVAL, "pipeline: null cfg");
+    if (c->hop <= 0 || c->n_fft <= 0 || c->n_samples <= 0) return fail(PCA_EINVAL, "pipeline: bad STFT config");
+    s->nt_all = 1 + c->n_samples / c->hop;
+    if (c->mode == 2) {
+        s->nf = c->n_fft / 2 + 1;            // FST keeps the Nyquist bin (Code/settransformer.py:40)
+        s->nt_out = s->nt_all;
+        s->clouds_per_clip = s->nt_all;
+        s->pts_full = s->nf;
+        s->width = 2;
+    } else if (c->mode == 3) {
+        if (c->ntemp <= 0) return fail(PCA_EINVAL, "pipeline: mode 3 needs ntemp > 0");
+        s->nf = c->n_fft / 2;                // 3ST drops it (Code/settransformertemp.py:52)
+        s->clouds_per_clip = s->nt_all / c->ntemp;
+        s->nt_out = s->clouds_per_clip * c->ntemp;
+        s->pts_full = s->nf * c->ntemp;
+        s->width = 3;
+    } else {
+        return fail(PCA_EINVAL, "pipeline: mode must be 2 (FST) or 3 (3ST)");
+    }
+    if (c->top_k < 0 || c->top_k > s->pts_full) return fail(PCA_EINVAL, "pipeline: top_k outside [0, %d]", s->pts_full);
+    s->pts = c->top_k ? c->top_k : s->pts_full;
+    if (c->st.d_in != s->width) return fail(PCA_EINVAL, "pipeline: mode %d clouds are %d-wide but st.d_in=%d", c->mode, s->width, c->st.d_in);
+    return 0;
+}
+
+static size_t st_any_ws_bytes(const pca_st_dims* d, int B, int N, int precision) {
+    if (precision == PCA_PREC_BF16) return st_tc_workspace_bytes(d, B, N);
+    return st_f32_ws_bytes(d, B, N);
+}
+
+static size_t pipe_ws_bytes(const pca_pipeline_cfg* c, const PipeShape& s, int n_clips, size_t* st_off) {
+    Arena a(nullptr, 0);
+    const size_t n_clouds = (size_t)n_clips * s.clouds_per_clip;
+    a.take<float>((size_t)n_clips * s.nt_out * s.nf);        // log-magnitudes
+    a.take<float>(n_clouds * s.pts * s.width);               // clouds
+    if (st_off) *st_off = a.off;
+    // encoder scratch: enough for chunks of <= 256 clouds (more only helps launch overhead)
+    int chunk = (int)(n_clouds < 256 ? n_clouds : 256);
+    if (chunk < 1) chunk = 1;
+    return a.off + st_any_ws_bytes(&c->st, chunk, s.pts, c->precision);
+}
+
+static int pipeline_run(const pca_pipeline_cfg* c, const float* audio, int n_clips, const float* window,
+                        const float* twiddle, const float* farr, const float* tarr, const float* st_params,
+                        float* logits, void* ws, size_t ws_bytes, cudaStream_t st) {
+    PipeShape s;
+    PCA_TRY(pipe_shape(c, &s));
+    if (n_clips < 0) return fail(PCA_EINVAL, "pipeline: negative clip count");
+    if (n_clips == 0 || s.clouds_per_clip == 0) return 0;
+    if (s.width == 3 && !tarr) return fail(PCA_EINVAL, "pipeline: mode 3 needs tarr");
+    size_t st_off = 0;
+    const size_t need = pipe_ws_bytes(c, s, n_clips, &st_off);
+    if (!ws || ws_bytes < need) return fail(PCA_EWORKSPACE, "pipeline: workspace %zu B < %zu B", ws_bytes, need);
+    Arena a(ws, ws_bytes);
+    const int n_clouds = n_clips * s.clouds_per_clip;
+    float* logmag = a.take<float>((size_t)n_clips * s.nt_out * s.nf);
+    float* pts = a.take<float>((size_t)n_clouds * s.pts * s.width);
+    PCA_TRY(launch_stft_logmag(audio, n_clips, c->n_samples, c->n_fft, c->hop, window, twiddle, c->scale,
+                               c->mode == 3, s.nt_out, logmag, st));
+    const int nt_cloud = c->mode == 3 ? c->ntemp : 1;
+    const float* tarr_use = c->mode == 3 ? tarr : nullptr;
+    if (c->top_k)
+        PCA_TRY(launch_topk(logmag, n_clouds, s.nf, nt_cloud, farr, tarr_use, c->top_k, 1, pts, nullptr, st));
+    else
+        PCA_TRY(launch_build_clouds(logmag, n_clouds, s.nf, nt_cloud, farr, tarr_use, pts, st));
+    return st_forward(pts, n_clouds, s.pts, &c->st, st_params, logits, (char*)ws + st_off, ws_bytes - st_off,
+                      c->precision, st);
+}
+
+}  // namespace pca
+
+// ====================================================================================== C ABI
+using namespace pca;
+
+extern "C" {
+
+int pca_version(void) { return PCA_VERSION; }
+const char* pca_last_error(void) { return err_buf(); }
+unsigned long long pca_launch_count(void) { return g_launches.load(); }
+
+void pca_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on.store(on ? 1 : 0);
+}
+
+int pca_profile_report(char* buf, size_t buf_len) {
+    if (!buf || buf_len < 3) return fail(PCA_EINVAL, "profile_report: buffer too small");
+    struct Agg { long long n = 0; double ms = 0, flops = 0, bytes = 0; };
+    std::map<std::string, Agg> agg;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        for (auto& r : g_prof) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+                Agg& a = agg[r.name];
+                a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+            }
+            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        }
+        g_prof.clear();
+    }
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+                 first ? "" : ", ", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops, kv.second.bytes);
+        out += line;
+        first = false;
+    }
+    out += "}";
+    if (out.size() + 1 > buf_len) return fail(PCA_EINVAL, "profile_report: need %zu bytes", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
+
+int pca_stft_logmag_f32(const float* audio, int n_clips, int n_samples, int n_fft, int hop,
+                        const float* window, const float* twiddle, float scale, int drop_nyquist,
+                        int nt_out, float* out, void* stream) {
+    return launch_stft_logmag(audio, n_clips, n_samples, n_fft, hop, window, twiddle, scale, drop_nyquist,
+                              nt_out, out, (cudaStream_t)stream);
+}
+
+int pca_build_clouds_f32(const float* logmag, int n_clouds, int nf, int nt, const float* farr,
+                         const float* tarr, float* pts, void* stream) {
+    return launch_build_clouds(logmag, n_clouds, nf, nt, farr, tarr, pts, (cudaStream_t)stream);
+}
+
+int pca_topk_compact_f32(const float* keys, int n_clouds, int nf, int nt, const float* farr,
+                         const float* tarr, int K, int sorted_desc, float* pts, int32_t* idx, void* stream) {
+    return launch_topk(keys, n_clouds, nf, nt, farr, tarr, K, sorted_desc, pts, idx, (cudaStream_t)stream);
+}
+
+long long pca_mab_param_count(int dq, int dk, int D, int ln) { return mab_count(dq, dk, D, ln); }
+long long pca_isab_param_count(int d_in, int D, int M, int ln) {
+    return (long long)M * D + mab_count(D, d_in, D, ln) + mab_count(d_in, D, D, ln);
+}
+long long pca_pma_param_count(int D, int S, int ln) { return (long long)S * D + mab_count(D, D, D, ln); }
+long long pca_st_param_count(const pca_st_dims* dims) { return dims ? st_count(dims) : -1; }
+
+size_t pca_mab_workspace_bytes(int B, int nq, int nk, int dq, int dk, int D, int H) {
+    (void)dq; (void)dk;
+    return mab_ws_floats(B, B, nq, nk, D, H);
+}
+int pca_mab_fwd_f32(const float* Q, int q_batch, const float* K, int B, int nq, int nk, int dq, int dk,
+                    int D, int H, int ln, const float* params, float* out, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    if (!Q || !K || !params || !out) return fail(PCA_EINVAL, "MAB: null pointer");
+    if (B == 0) return 0;
+    if (D % 4 || D % H) return fail(PCA_EUNSUPPORTED, "MAB: need D %% 4 == 0 and D %% H == 0");
+    return mab_forward(Q, q_batch, K, B, nq, nk, dq, dk, D, H, ln, params, out, workspace, workspace_bytes,
+                       (cudaStream_t)stream);
+}
+
+size_t pca_isab_workspace_bytes(int B, int N, int d_in, int D, int H, int M) { return isab_ws_bytes(B, N, d_in, D, H, M); }
+int pca_isab_fwd_f32(const float* X, int B, int N, int d_in, int D, int H, int M, int ln, const float* params,
+                     float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!X || !params || !out) return fail(PCA_EINVAL, "ISAB: null pointer");
+    if (B == 0) return 0;
+    if (N <= 0) return fail(PCA_EINVAL, "ISAB: empty set");
+    if (D % 4 || D % H) return fail(PCA_EUNSUPPORTED, "ISAB: need D %% 4 == 0 and D %% H == 0");
+    return isab_forward(X, B, N, d_in, D, H, M, ln, params, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t pca_pma_workspace_bytes(int B, int N, int D, int H, int S) { return pma_ws_bytes(B, N, D, H, S); }
+int pca_pma_fwd_f32(const float* X, int B, int N, int D, int H, int S, int ln, const float* params, float* out,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    if (!X || !params || !out) return fail(PCA_EINVAL, "PMA: null pointer");
+    if (B == 0) return 0;
+    if (N <= 0) return fail(PCA_EINVAL, "PMA: empty set");
+    if (D % 4 || D % H) return fail(PCA_EUNSUPPORTED, "PMA: need D %% 4 == 0 and D %% H == 0");
+    return pma_forward(X, B, N, D, H, S, ln, params, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t pca_st_workspace_bytes(const pca_st_dims* dims, int B, int N, int precision) {
+    if (!dims || B <= 0 || N <= 0) return 0;
+    return st_any_ws_bytes(dims, B, N, precision);
+}
+int pca_st_fwd(const float* X, int B, int N, const pca_st_dims* dims, const float* params, float* logits,
+               void* workspace, size_t workspace_bytes, int precision, void* stream) {
+    return st_forward(X, B, N, dims, params, logits, workspace, workspace_bytes, precision, (cudaStream_t)stream);
+}
+
+size_t pca_deepset_workspace_bytes(int B, int N, int d_in, int dim_hidden, int out_dim) {
+    (void)d_in; (void)out_dim;
+    return deepset_ws_bytes(B, N, dim_hidden);
+}
+int pca_deepset_fwd_f32(const float* X, int B, int N, int d_in, int dim_hidden, int out_dim, int pool,
+                        const float* params, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!X || !params || !out) return fail(PCA_EINVAL, "DeepSet: null pointer");
+    if (B == 0) return 0;
+    if (N <= 0) return fail(PCA_EINVAL, "DeepSet: empty set");
+    return deepset_forward(X, B, N, d_in, dim_hidden, out_dim, pool, params, out, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
+}
+
+int pca_pipeline_clouds_per_clip(const pca_pipeline_cfg* cfg) {
+    PipeShape s;
+    return pipe_shape(cfg, &s) ? -1 : s.clouds_per_clip;
+}
+int pca_pipeline_points_per_cloud(const pca_pipeline_cfg* cfg) {
+    PipeShape s;
+    return pipe_shape(cfg, &s) ? -1 : s.pts;
+}
+size_t pca_pipeline_workspace_bytes(const pca_pipeline_cfg* cfg, int n_clips) {
+    PipeShape s;
+    if (pipe_shape(cfg, &s) || n_clips <= 0) return 0;
+    return pipe_ws_bytes(cfg, s, n_clips, nullptr);
+}
+int pca_pipeline_run(const pca_pipeline_cfg* cfg, const float* audio, int n_clips, const float* window,
+                     const float* twiddle, const float* farr, const float* tarr, const float* st_params,
+                     float* logits, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!audio || !window || !twiddle || !farr || !st_params || !logits) return fail(PCA_EINVAL, "pipeline: null pointer");
+    return pipeline_run(cfg, audio, n_clips, window, twiddle, farr, tarr, st_params, logits, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
+}
+int pca_pipeline_run_host(const pca_pipeline_cfg* cfg, const float* host_audio, int n_clips, float* dev_audio,
+                          const float* window, const float* twiddle, const float* farr, const float* tarr,
+                          const float* st_params, float* dev_logits, float* host_logits, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    if (!host_audio || !dev_audio || !dev_logits || !host_logits) return fail(PCA_EINVAL, "pipeline: null pointer");
+    PipeShape s;
+    PCA_TRY(pipe_shape(cfg, &s));
+    cudaStream_t st = (cudaStream_t)stream;
+    PCA_CHECK_CUDA(cudaMemcpyAsync(dev_audio, host_audio, (size_t)n_clips * cfg->n_samples * sizeof(float),
+                                   cudaMemcpyHostToDevice, st));
+    PCA_TRY(pca_pipeline_run(cfg, dev_audio, n_clips, window, twiddle, farr, tarr, st_params, dev_logits,
+                             workspace, workspace_bytes, stream));
+    const size_t out_bytes = (size_t)n_clips * s.clouds_per_clip * cfg->st.S * cfg->st.C * sizeof(float);
+    PCA_CHECK_CUDA(cudaMemcpyAsync(host_logits, dev_logits, out_bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// Shared helpers for the pcaudio_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/pcaudio_b200.h"
+
+namespace pca {
+
+// thread-local error slot (re-entrant, one caller thread per GPU)
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+
+// Optional per-kernel device timing (pca_profile_enable): brackets a launch with CUDA events on the
+// launching stream and records the algorithmic flops / bytes the launcher states for it.
+struct LaunchTimer {
+    LaunchTimer(const char* name, cudaStream_t st, double flops, double bytes);
+    ~LaunchTimer();
+    int slot;
+    cudaStream_t st;
+};
+
+#define PCA_CHECK_CUDA(expr)                                                  \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) return ::pca::cuda_fail(_e, #expr);            \
+    } while (0)
+
+#define PCA_CHECK_LAUNCH(name)                                                \
+    do {                                                                      \
+        ::pca::count_launch();                                                \
+        cudaError_t _e = cudaPeekAtLastError();                               \
+        if (_e != cudaSuccess) return ::pca::cuda_fail(_e, name);             \
+    } while (0)
+
+#define PCA_TRY(expr)                                                         \
+    do {                                                                      \
+        int _r = (expr);                                                      \
+        if (_r != 0) return _r;                                               \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// bump allocator over the caller's workspace
+struct Arena {
+    char* base;
+    size_t cap;
+    size_t off;
+    Arena(void* p, size_t n) : base((char*)p), cap(n), off(0) {}
+    template <typename T>
+    T* take(size_t count) {
+        size_t bytes = align_up(count * sizeof(T), 256);
+        if (base == nullptr) { off += bytes; return nullptr; }   // sizing pass
+        if (off + bytes > cap) { off = (size_t)-1 / 2; return nullptr; }
+        T* r = (T*)(base + off);
+        off += bytes;
+        return r;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace pca

@@ -1,0 +1,384 @@
+// fp32 CUDA-core set-encoder kernels (generic over every MAB shape of the reference):
+//   linear_f32_kernel : Y = act(X W^T + b) / Y = X + relu(X W^T + b)   (modules.py:20-21,31)
+//   attn_f32_kernel   : O = Qp + softmax(Qp_h Kp_h^T / sqrt(D)) Vp_h    (modules.py:23-29)
+//                       flash-style online softmax, split over keys when the query set is small
+//                       (ISAB mab0 / PMA), one warp per head with broadcast K/V reads from smem.
+//   attn_merge_kernel : merges the key splits.
+//   layernorm_kernel  : ln0 / ln1 branches (modules.py:30,32).
+//   pool_kernel       : DeepSet mean / max / sum over points (set_transformer-master/models.py:26).
+// This is the 1e-3 (fp32) parity path and the only path for dims the tcgen05 kernels do not cover.
+#include "common.cuh"
+#include <float.h>
+#include <math.h>
+
+namespace pca {
+
+// ------------------------------------------------------------------------------------ linear
+constexpr int LBM = 128, LBN = 64, LBK = 16, LTHREADS = 256;
+
+template <int MODE>   // 0 plain, 1 relu, 2 residual: Y = X + relu(XW^T + b) (din == dout)
+__global__ void __launch_bounds__(LTHREADS)
+linear_f32_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
+                  float* __restrict__ Y, long long rows, int din, int dout) {
+    __shared__ __align__(16) float Xs[LBK][LBM + 4];
+    __shared__ __align__(16) float Ws[LBK][LBN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long long row0 = (long long)blockIdx.x * LBM;
+    const int col0 = blockIdx.y * LBN;
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < din; k0 += LBK) {
+        // X tile: 128 rows x 16 k  (8 elements / thread), W tile: 64 rows x 16 k (4 / thread)
+        const int lk = tid & 15, lr = tid >> 4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int m = lr + 16 * j;
+            const long long r = row0 + m;
+            const int k = k0 + lk;
+            Xs[lk][m] = (r < rows && k < din) ? __ldg(X + r * din + k) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = lr + 16 * j;
+            const int c = col0 + n;
+            const int k = k0 + lk;
+            Ws[lk][n] = (c < dout && k < din) ? __ldg(W + (long long)c * din + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < LBK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&Xs[k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&Xs[k][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long r = row0 + ty * 8 + i;
+        if (r >= rows) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = col0 + tx * 4 + j;
+            if (c >= dout) continue;
+            float v = acc[i][j] + __ldg(bias + c);
+            if (MODE == 1) v = fmaxf(v, 0.f);
+            if (MODE == 2) v = __ldg(X + r * din + c) + fmaxf(v, 0.f);
+            Y[r * dout + c] = v;
+        }
+    }
+}
+
+int launch_linear(const float* X, const float* W, const float* b, float* Y, long long rows, int din,
+                  int dout, int mode, cudaStream_t st) {
+    if (rows == 0) return 0;
+    if (mode == 2 && din != dout) return fail(PCA_EINVAL, "linear: residual mode needs din == dout");
+    dim3 grid((unsigned)((rows + LBM - 1) / LBM), (dout + LBN - 1) / LBN);
+    {
+        LaunchTimer lt("linear_f32_kernel", st, 2.0 * rows * din * dout, 4.0 * rows * (din + dout));
+        if (mode == 0) linear_f32_kernel<0><<<grid, LTHREADS, 0, st>>>(X, W, b, Y, rows, din, dout);
+        else if (mode == 1) linear_f32_kernel<1><<<grid, LTHREADS, 0, st>>>(X, W, b, Y, rows, din, dout);
+        else linear_f32_kernel<2><<<grid, LTHREADS, 0, st>>>(X, W, b, Y, rows, din, dout);
+    }
+    PCA_CHECK_LAUNCH("linear_f32_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ attention
+// Block = H warps (warp w <-> head w).  Lane <-> (query ql, key slice ks): TQ queries per block,
+// KS = 32/TQ key slices.  K|V rows ([Kp (D) | Vp (D)] per key) are staged in smem tiles; all lanes
+// of a warp with the same key slice read the same address (broadcast).
+template <int DH>
+__global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstride,
+                                const float* __restrict__ KV, int nq, int nk, int D, int tq_log,
+                                int tk, int nsplit, int chunk, float scale_log2e,
+                                float* __restrict__ O, float* __restrict__ part) {
+    extern __shared__ __align__(16) float kv_s[];     // tk rows x (2D + 4)
+    const int H = blockDim.x >> 5;
+    const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int TQ = 1 << tq_log, KS = 32 >> tq_log;
+    const int ql = lane & (TQ - 1), ks = lane >> tq_log;
+    const int b = blockIdx.z, split = blockIdx.y;
+    const int q = blockIdx.x * TQ + ql;
+    const bool qvalid = q < nq;
+    const int rs = 2 * D + 4;                          // padded smem row stride (floats)
+
+    float qv[DH], acc[DH];
+    const float* qptr = Qp + (long long)b * q_bstride + (long long)(qvalid ? q : 0) * D + h * DH;
+#pragma unroll
+    for (int j = 0; j < DH; ++j) { qv[j] = __ldg(qptr + j) * scale_log2e; acc[j] = 0.f; }
+    float m = -INFINITY, l = 0.f;
+
+    const int k_begin = split * chunk;
+    const int k_end = min(nk, k_begin + chunk);
+    const float* kvb = KV + (long long)b * nk * 2 * D;
+
+    for (int kt = k_begin; kt < k_end; kt += tk) {
+        const int tn = min(tk, k_end - kt);
+        // cooperative, coalesced float4 load of tn rows x 2D floats
+        const int vec_per_row = (2 * D) >> 2;
+        for (int i = threadIdx.x; i < tn * vec_per_row; i += blockDim.x) {
+            const int r = i / vec_per_row, c = i - r * vec_per_row;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(kvb + (long long)(kt + r) * 2 * D) + c);
+            *reinterpret_cast<float4*>(kv_s + r * rs + c * 4) = v;
+        }
+        __syncthreads();
+        if (qvalid) {
+            for (int kk = ks; kk < tn; kk += 4 * KS) {
+                // up to 4 keys of this lane's slice per softmax update
+                float s[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int key = kk + u * KS;
+                    if (key < tn) {
+                        const float* kr = kv_s + key * rs + h * DH;
+                        float d = 0.f;
+#pragma unroll
+                        for (int j = 0; j < DH; j += 4) {
+                            const float4 kq = *reinterpret_cast<const float4*>(kr + j);
+                            d = fmaf(qv[j], kq.x, d); d = fmaf(qv[j + 1], kq.y, d);
+                            d = fmaf(qv[j + 2], kq.z, d); d = fmaf(qv[j + 3], kq.w, d);
+                        }
+                        s[u] = d;
+                    } else {
+                        s[u] = -INFINITY;
+                    }
+                }
+                const float mn = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
+                const float alpha = exp2f(m - mn);      // m = -inf on the first update -> 0
+                m = mn;
+                l *= alpha;
+#pragma unroll
+                for (int j = 0; j < DH; ++j) acc[j] *= alpha;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int key = kk + u * KS;
+                    if (key < tn) {
+                        const float p = exp2f(s[u] - mn);
+                        l += p;
+                        const float* vr = kv_s + key * rs + D + h * DH;
+#pragma unroll
+                        for (int j = 0; j < DH; j += 4) {
+                            const float4 vv = *reinterpret_cast<const float4*>(vr + j);
+                            acc[j] = fmaf(p, vv.x, acc[j]); acc[j + 1] = fmaf(p, vv.y, acc[j + 1]);
+                            acc[j + 2] = fmaf(p, vv.z, acc[j + 2]); acc[j + 3] = fmaf(p, vv.w, acc[j + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // merge the key slices of one query across lanes (xor over the slice bits)
+    for (int off = TQ; off < 32; off <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m, off);
+        const float lo = __shfl_xor_sync(0xffffffffu, l, off);
+        const float mn = fmaxf(m, mo);
+        const float a0 = (m == -INFINITY) ? 0.f : exp2f(m - mn);
+        const float a1 = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
+        l = l * a0 + lo * a1;
+#pragma unroll
+        for (int j = 0; j < DH; ++j) {
+            const float ao = __shfl_xor_sync(0xffffffffu, acc[j], off);
+            acc[j] = acc[j] * a0 + ao * a1;
+        }
+        m = mn;
+    }
+    if (!qvalid || ks != 0) return;
+    if (nsplit == 1) {
+        const float inv = 1.f / l;
+        float* o = O + ((long long)b * nq + q) * D + h * DH;
+#pragma unroll
+        for (int j = 0; j < DH; ++j) o[j] = __ldg(qptr + j) + acc[j] * inv;
+    } else {
+        float* pp = part + ((((long long)b * nsplit + split) * nq + q) * H + h) * (DH + 2);
+        pp[0] = m; pp[1] = l;
+#pragma unroll
+        for (int j = 0; j < DH; ++j) pp[2 + j] = acc[j];
+    }
+}
+
+template <int DH>
+__global__ void attn_merge_kernel(const float* __restrict__ part, const float* __restrict__ Qp,
+                                  long long q_bstride, int B, int nq, int H, int nsplit,
+                                  float* __restrict__ O) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * nq * H;
+    if (i >= total) return;
+    const int h = (int)(i % H);
+    const int q = (int)((i / H) % nq);
+    const int b = (int)(i / ((long long)H * nq));
+    float m = -INFINITY;
+    for (int s = 0; s < nsplit; ++s)
+        m = fmaxf(m, part[((((long long)b * nsplit + s) * nq + q) * H + h) * (DH + 2)]);
+    float l = 0.f, acc[DH];
+#pragma unroll
+    for (int j = 0; j < DH; ++j) acc[j] = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+        const float* pp = part + ((((long long)b * nsplit + s) * nq + q) * H + h) * (DH + 2);
+        const float a = (pp[0] == -INFINITY) ? 0.f : exp2f(pp[0] - m);
+        l += pp[1] * a;
+#pragma unroll
+        for (int j = 0; j < DH; ++j) acc[j] = fmaf(pp[2 + j], a, acc[j]);
+    }
+    const float inv = 1.f / l;
+    const int D = H * DH;
+    const float* qptr = Qp + (long long)b * q_bstride + (long long)q * D + h * DH;
+    float* o = O + ((long long)b * nq + q) * D + h * DH;
+#pragma unroll
+    for (int j = 0; j < DH; ++j) o[j] = __ldg(qptr + j) + acc[j] * inv;
+}
+
+struct AttnPlan { int tq_log, tk, nsplit, chunk; size_t smem; size_t part_floats; };
+
+static AttnPlan plan_attn(int B, int nq, int nk, int D, int H) {
+    AttnPlan p;
+    int tq = 32;
+    while (tq > 1 && (tq >> 1) >= nq) tq >>= 1;
+    p.tq_log = 0;
+    while ((1 << p.tq_log) < tq) ++p.tq_log;
+    const int rs = 2 * D + 4;
+    int tk = (40 * 1024) / (rs * 4);
+    tk = tk > 128 ? 128 : tk;
+    tk &= ~3;
+    if (tk < 4) tk = 4;
+    if (tk > nk) tk = (nk + 3) & ~3;
+    p.tk = tk;
+    p.smem = (size_t)tk * rs * 4;
+    const long long qtiles = (nq + tq - 1) / tq;
+    const long long base_blocks = (long long)B * qtiles;
+    int nsplit = 1;
+    const long long target = 148LL * 4;
+    if (base_blocks < target) {
+        nsplit = (int)((target + base_blocks - 1) / base_blocks);
+        const int max_split = (nk + 4 * tk - 1) / (4 * tk);      // keep >= 4 tiles per split
+        if (nsplit > max_split) nsplit = max_split;
+        if (nsplit < 1) nsplit = 1;
+    }
+    int chunk = (nk + nsplit - 1) / nsplit;
+    chunk = (chunk + tk - 1) / tk * tk;
+    nsplit = (nk + chunk - 1) / chunk;
+    p.nsplit = nsplit;
+    p.chunk = chunk;
+    const int dh = D / H;
+    p.part_floats = nsplit > 1 ? (size_t)B * nsplit * nq * H * (dh + 2) : 0;
+    return p;
+}
+
+size_t attn_part_floats(int B, int nq, int nk, int D, int H) { return plan_attn(B, nq, nk, D, H).part_floats; }
+
+template <int DH>
+static int launch_attn_t(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk,
+                         int D, int H, float* O, float* part, cudaStream_t st) {
+    const AttnPlan p = plan_attn(B, nq, nk, D, H);
+    const int tq = 1 << p.tq_log;
+    dim3 grid((nq + tq - 1) / tq, p.nsplit, B);
+    const float scale_log2e = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
+    if (p.smem > 48 * 1024)
+        PCA_CHECK_CUDA(cudaFuncSetAttribute(attn_f32_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    {
+        LaunchTimer lt("attn_f32_kernel", st, 4.0 * B * nq * (double)nk * D,
+                       4.0 * ((double)B * nk * 2 * D + 2.0 * B * nq * D));
+        attn_f32_kernel<DH><<<grid, 32 * H, p.smem, st>>>(Qp, q_bstride, KV, nq, nk, D, p.tq_log, p.tk,
+                                                          p.nsplit, p.chunk, scale_log2e, O, part);
+    }
+    PCA_CHECK_LAUNCH("attn_f32_kernel");
+    if (p.nsplit > 1) {
+        const long long total = (long long)B * nq * H;
+        {
+            LaunchTimer lt("attn_merge_kernel", st, 0.0, 4.0 * (double)p.part_floats);
+            attn_merge_kernel<DH><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(part, Qp, q_bstride, B, nq, H, p.nsplit, O);
+        }
+        PCA_CHECK_LAUNCH("attn_merge_kernel");
+    }
+    return 0;
+}
+
+int launch_attn(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D,
+                int H, float* O, float* part, cudaStream_t st) {
+    if (B == 0 || nq == 0) return 0;
+    if (H < 1 || H > 32 || D % H) return fail(PCA_EUNSUPPORTED, "attention: need 1 <= H <= 32 and D %% H == 0 (D=%d, H=%d)", D, H);
+    if (B > 65535) return fail(PCA_EUNSUPPORTED, "attention: batch chunk %d exceeds the grid limit", B);
+    switch (D / H) {
+        case 4: return launch_attn_t<4>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st);
+        case 8: return launch_attn_t<8>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st);
+        case 16: return launch_attn_t<16>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st);
+        case 32: return launch_attn_t<32>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st);
+        case 64: return launch_attn_t<64>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st);
+        default: return fail(PCA_EUNSUPPORTED, "attention: head dim %d not in {4,8,16,32,64}", D / H);
+    }
+}
+
+// ------------------------------------------------------------------------------------ layernorm
+__global__ void layernorm_kernel(float* __restrict__ X, long long rows, int D, const float* __restrict__ g,
+                                 const float* __restrict__ bta) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float* x = X + r * D;
+    float s = 0.f;
+    for (int j = lane; j < D; j += 32) s += x[j];
+    const float mean = warp_sum(s) / D;
+    float v = 0.f;
+    for (int j = lane; j < D; j += 32) { const float d = x[j] - mean; v += d * d; }
+    const float rstd = rsqrtf(warp_sum(v) / D + 1e-5f);
+    for (int j = lane; j < D; j += 32) x[j] = (x[j] - mean) * rstd * __ldg(g + j) + __ldg(bta + j);
+}
+
+int launch_layernorm(float* X, long long rows, int D, const float* g, const float* b, cudaStream_t st) {
+    if (rows == 0) return 0;
+    LaunchTimer lt("layernorm_kernel", st, 0.0, 8.0 * rows * D);
+    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(X, rows, D, g, b);
+    PCA_CHECK_LAUNCH("layernorm_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ pooling
+// X (B, N, D) -> out (B, D); pool 0 mean, 1 max, 2 sum
+__global__ void pool_kernel(const float* __restrict__ X, int N, int D, int pool, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int b = blockIdx.y;
+    const int d = blockIdx.x * 32 + threadIdx.x;
+    const int ty = threadIdx.y;
+    float v = pool == 1 ? -INFINITY : 0.f;
+    if (d < D) {
+        const float* x = X + (long long)b * N * D + d;
+        for (int p = ty; p < N; p += 8) {
+            const float t = __ldg(x + (long long)p * D);
+            v = pool == 1 ? fmaxf(v, t) : v + t;
+        }
+    }
+    red[ty][threadIdx.x] = v;
+    __syncthreads();
+    if (ty == 0 && d < D) {
+        for (int i = 1; i < 8; ++i) v = pool == 1 ? fmaxf(v, red[i][threadIdx.x]) : v + red[i][threadIdx.x];
+        if (pool == 0) v /= (float)N;
+        out[(long long)b * D + d] = v;
+    }
+}
+
+int launch_pool(const float* X, int B, int N, int D, int pool, float* out, cudaStream_t st) {
+    if (B == 0) return 0;
+    if (pool < 0 || pool > 2) return fail(PCA_EINVAL, "pool: mode %d not in {0 mean, 1 max, 2 sum}", pool);
+    if (B > 65535) return fail(PCA_EUNSUPPORTED, "pool: batch too large");
+    dim3 grid((D + 31) / 32, B), block(32, 8);
+    LaunchTimer lt("pool_kernel", st, 0.0, 4.0 * (double)B * N * D);
+    pool_kernel<<<grid, block, 0, st>>>(X, N, D, pool, out);
+    PCA_CHECK_LAUNCH("pool_kernel");
+    return 0;
+}
+
+}  // namespace pca

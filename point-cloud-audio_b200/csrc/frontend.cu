@@ -1,0 +1,374 @@
+// Spectral front end and point selection for sm_100a.
+//
+//   stft_logmag_kernel : reflect-padded framing (index mirroring, no padded copy) -> periodic
+//                        Hann -> real FFT (packed as a half-length complex Stockham radix-4
+//                        FFT in shared memory) -> |.|*scale -> log(1e-8 + .)
+//                        replaces librosa.stft + np.log recipe (Code/settransformer.py:49-50,
+//                        Code/settransformertemp.py:51-53).
+//   build_clouds_kernel: ESC_pc / ESC_pc_temp __getitem__ (Code/dataset.py:50-54,160-166).
+//   topk_kernel        : ESC_pc_temp_maxKSS / pc_maxK selection (Code/dataset.py:194-202,
+//                        Code/utils.py:42-45): 4-pass 8-bit radix select on order-preserving
+//                        keys, warp-ballot/prefix-sum compaction in flat-index order (ties keep
+//                        the lowest indices), bitonic sort of the K survivors for the
+//                        descending-magnitude emission order.
+#include "common.cuh"
+#include <math.h>
+
+namespace pca {
+
+// ------------------------------------------------------------------------------------ STFT
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+__global__ void stft_logmag_kernel(const float* __restrict__ audio, int L, int n_fft, int hop,
+                                   const float* __restrict__ window,
+                                   const float2* __restrict__ twiddle, float scale, int nf_out,
+                                   int nt_out, int frames_per_block, float* __restrict__ out) {
+    extern __shared__ float2 smem_f2[];
+    const int nc = n_fft >> 1;             // complex FFT length
+    float2* tw = smem_f2;                  // nc entries: exp(-2 pi i k / n_fft)
+    float2* bufa = tw + nc;
+    float2* bufb = bufa + nc;
+    float* win = reinterpret_cast<float*>(bufb + nc);   // n_fft entries
+
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int clip = blockIdx.y;
+    const float* x = audio + (size_t)clip * L;
+
+    for (int i = tid; i < nc; i += nthr) tw[i] = twiddle[i];
+    for (int i = tid; i < n_fft; i += nthr) win[i] = window[i];
+    __syncthreads();
+
+    const int t0 = blockIdx.x * frames_per_block;
+    const int t1 = min(nt_out, t0 + frames_per_block);
+    const int tw_shift_base = 31 - __clz(n_fft);   // log2(n_fft)
+
+    for (int t = t0; t < t1; ++t) {
+        // ---- load + window, pack even/odd samples into one complex sequence
+        const int start = t * hop - nc;            // centre=True: frame t starts at t*hop - n_fft/2
+        for (int i = tid; i < nc; i += nthr) {
+            int j0 = start + 2 * i, j1 = j0 + 1;
+            j0 = j0 < 0 ? -j0 : (j0 >= L ? 2 * (L - 1) - j0 : j0);
+            j1 = j1 < 0 ? -j1 : (j1 >= L ? 2 * (L - 1) - j1 : j1);
+            bufa[i] = make_float2(win[2 * i] * __ldg(x + j0), win[2 * i + 1] * __ldg(x + j1));
+        }
+        __syncthreads();
+
+        // ---- Stockham autosort, radix 4 (+ one radix-2 stage when log2(nc) is odd)
+        float2* src = bufa;
+        float2* dst = bufb;
+        int n = nc, s_log = 0;
+        while (n >= 4) {
+            const int n1 = n >> 2;
+            const int tsh = tw_shift_base - (31 - __clz(n));     // log2(n_fft / n)
+            for (int i = tid; i < (nc >> 2); i += nthr) {
+                const int p = i >> s_log, q = i & ((1 << s_log) - 1);
+                const float2 w1 = tw[p << tsh];
+                const float2 w2 = tw[(2 * p) << tsh];
+                const float2 w3 = cmul(w1, w2);
+                const float2 a = src[q + ((p) << s_log)];
+                const float2 b = src[q + ((p + n1) << s_log)];
+                const float2 c = src[q + ((p + 2 * n1) << s_log)];
+                const float2 d = src[q + ((p + 3 * n1) << s_log)];
+                const float2 apc = make_float2(a.x + c.x, a.y + c.y);
+                const float2 amc = make_float2(a.x - c.x, a.y - c.y);
+                const float2 bpd = make_float2(b.x + d.x, b.y + d.y);
+                const float2 jbmd = make_float2(-(b.y - d.y), b.x - d.x);   // i*(b-d)
+                const int o = q + ((4 * p) << s_log);
+                dst[o] = make_float2(apc.x + bpd.x, apc.y + bpd.y);
+                dst[o + (1 << s_log)] = cmul(w1, make_float2(amc.x - jbmd.x, amc.y - jbmd.y));
+                dst[o + (2 << s_log)] = cmul(w2, make_float2(apc.x - bpd.x, apc.y - bpd.y));
+                dst[o + (3 << s_log)] = cmul(w3, make_float2(amc.x + jbmd.x, amc.y + jbmd.y));
+            }
+            __syncthreads();
+            float2* tmp = src; src = dst; dst = tmp;
+            n >>= 2;
+            s_log += 2;
+        }
+        if (n == 2) {   // p = 0 only, twiddle = 1
+            for (int q = tid; q < (nc >> 1); q += nthr) {
+                const float2 a = src[q];
+                const float2 b = src[q + (nc >> 1)];
+                dst[q] = make_float2(a.x + b.x, a.y + b.y);
+                dst[q + (nc >> 1)] = make_float2(a.x - b.x, a.y - b.y);
+            }
+            __syncthreads();
+            float2* tmp = src; src = dst; dst = tmp;
+        }
+
+        // ---- split the packed spectrum, magnitude, log
+        float* o = out + ((size_t)clip * nt_out + t) * nf_out;
+        for (int k = tid; k < nf_out; k += nthr) {
+            float re, im;
+            if (k == 0) {
+                re = src[0].x + src[0].y; im = 0.f;
+            } else if (k == nc) {
+                re = src[0].x - src[0].y; im = 0.f;
+            } else {
+                const float2 zk = src[k];
+                const float2 zc = src[nc - k];
+                const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+                // odd part = -i/2 * (zk - conj(zc))
+                const float2 od = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+                const float2 r = cmul(tw[k], od);
+                re = e.x + r.x; im = e.y + r.y;
+            }
+            const float mag = sqrtf(re * re + im * im) * scale;
+            o[k] = logf(1.0e-8f + mag);
+        }
+        __syncthreads();   // bufa/bufb reused by the next frame
+    }
+}
+
+// ------------------------------------------------------------------------------------ clouds
+__global__ void build_clouds_kernel(const float* __restrict__ logmag, long long total, int nf, int nt,
+                                    const float* __restrict__ farr, const float* __restrict__ tarr,
+                                    float* __restrict__ pts) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int npts = nf * nt;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int p = (int)(i % npts);
+        const int f = p % nf, t = p / nf;
+        const float v = logmag[i];
+        if (tarr != nullptr) {
+            float* o = pts + i * 3;
+            o[0] = __ldg(farr + f); o[1] = __ldg(tarr + t); o[2] = v;
+        } else {
+            *reinterpret_cast<float2*>(pts + i * 2) = make_float2(__ldg(farr + f), v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ top-K
+__device__ __forceinline__ uint32_t ordered_key(float x) {
+    uint32_t u = __float_as_uint(x);
+    if (u == 0x80000000u) u = 0u;                       // -0.0 ties with +0.0, as in (-x).argsort()
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // larger float -> larger uint
+}
+
+constexpr int TOPK_THREADS = 512;
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __restrict__ farr,
+            const float* __restrict__ tarr, int K, int kpad, int sorted, float* __restrict__ pts_all,
+            int32_t* __restrict__ idx_all) {
+    extern __shared__ unsigned long long sortbuf[];      // kpad entries when sorted
+    __shared__ int hist[256];
+    __shared__ int warp_gt[TOPK_THREADS / 32], warp_eq[TOPK_THREADS / 32];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_remaining;
+    __shared__ int s_gt_base, s_eq_base;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int cloud = blockIdx.x;
+    const float* keys = keys_all + (size_t)cloud * N;
+    const int width = tarr != nullptr ? 3 : 2;
+    float* pts = pts_all ? pts_all + (size_t)cloud * K * width : nullptr;
+    int32_t* idx_out = idx_all ? idx_all + (size_t)cloud * K : nullptr;
+
+    // ---- K-th largest key by radix select (skipped when every point is kept)
+    uint32_t kth = 0;
+    int n_ties_take = 0;
+    const bool all = (K >= N);
+    if (!all) {
+        if (tid == 0) { s_prefix = 0; s_remaining = K; }
+        uint32_t mask = 0;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int i = tid; i < 256; i += TOPK_THREADS) hist[i] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            for (int base = 0; base < N; base += TOPK_THREADS) {
+                const int i = base + tid;
+                const bool act = i < N;
+                uint32_t o = act ? ordered_key(__ldg(keys + i)) : 0u;
+                const bool cand = act && ((o & mask) == prefix);
+                const uint32_t digit = (o >> shift) & 255u;
+                // warp-aggregated shared atomics: log-magnitudes share their top bytes
+                const uint32_t cmask = __ballot_sync(0xffffffffu, cand);
+                if (cand) {
+                    const uint32_t peers = __match_any_sync(cmask, digit);
+                    if ((peers & ((1u << lane) - 1)) == 0) atomicAdd(&hist[digit], __popc(peers));
+                }
+            }
+            __syncthreads();
+            if (wid == 0) {
+                // lane l owns digits [8l, 8l+8); find the digit holding the `remaining`-th largest
+                const int remaining = s_remaining;
+                int c[8], tot = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; tot += c[j]; }
+                int suf = tot;        // inclusive suffix sum over lanes >= lane
+#pragma unroll
+                for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                    const int v = __shfl_down_sync(0xffffffffu, suf, o2);
+                    if (lane + o2 < 32) suf += v;
+                }
+                const int above = suf - tot;   // candidates with a larger digit than this lane's
+                if (above < remaining && remaining <= above + tot) {
+                    int cum = above;
+#pragma unroll
+                    for (int j = 7; j >= 0; --j) {
+                        if (cum < remaining && remaining <= cum + c[j]) {
+                            s_prefix = prefix | ((uint32_t)(lane * 8 + j) << shift);
+                            s_remaining = remaining - cum;
+                        }
+                        cum += c[j];
+                    }
+                }
+            }
+            mask |= 255u << shift;
+            __syncthreads();
+        }
+        kth = s_prefix;
+        n_ties_take = s_remaining;
+    }
+    if (tid == 0) { s_gt_base = 0; s_eq_base = 0; }
+    if (sorted) {
+        for (int i = tid; i < kpad; i += TOPK_THREADS) sortbuf[i] = ~0ull;
+    }
+    __syncthreads();
+
+    // ---- ordered compaction: position = (#selected before me) in flat-index order
+    for (int base = 0; base < N; base += TOPK_THREADS) {
+        const int i = base + tid;
+        const bool act = i < N;
+        float kv = 0.f;
+        uint32_t o = 0;
+        if (act) { kv = __ldg(keys + i); o = ordered_key(kv); }
+        const bool gt = act && (all || o > kth);
+        const bool eq = act && !all && (o == kth);
+        const uint32_t bg = __ballot_sync(0xffffffffu, gt);
+        const uint32_t be = __ballot_sync(0xffffffffu, eq);
+        const uint32_t lt = (1u << lane) - 1;
+        if (lane == 0) { warp_gt[wid] = __popc(bg); warp_eq[wid] = __popc(be); }
+        __syncthreads();
+        int gt_before = s_gt_base, eq_before = s_eq_base;
+        for (int w = 0; w < wid; ++w) { gt_before += warp_gt[w]; eq_before += warp_eq[w]; }
+        gt_before += __popc(bg & lt);
+        eq_before += __popc(be & lt);
+        const bool sel = gt || (eq && eq_before < n_ties_take);
+        if (sel) {
+            const int pos = gt_before + min(eq_before, n_ties_take);
+            if (sorted) {
+                sortbuf[pos] = ((unsigned long long)(~o) << 32) | (uint32_t)i;
+            } else {
+                const int f = i % nf, t = i / nf;
+                if (pts) {
+                    if (width == 3) { pts[pos * 3] = __ldg(farr + f); pts[pos * 3 + 1] = __ldg(tarr + t); pts[pos * 3 + 2] = kv; }
+                    else { pts[pos * 2] = __ldg(farr + f); pts[pos * 2 + 1] = kv; }
+                }
+                if (idx_out) idx_out[pos] = i;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int g = 0, e = 0;
+            for (int w = 0; w < TOPK_THREADS / 32; ++w) { g += warp_gt[w]; e += warp_eq[w]; }
+            s_gt_base += g; s_eq_base += e;
+        }
+        __syncthreads();
+    }
+    if (!sorted) return;
+
+    // ---- bitonic sort of the survivors: ascending (~key, index) == descending key, stable
+    for (int k2 = 2; k2 <= kpad; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (kpad >> 1); t += TOPK_THREADS) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int ixj = i | j;
+                const unsigned long long a = sortbuf[i], b = sortbuf[ixj];
+                const bool asc = (i & k2) == 0;
+                if ((a > b) == asc) { sortbuf[i] = b; sortbuf[ixj] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int r = tid; r < K; r += TOPK_THREADS) {
+        const int i = (int)(uint32_t)sortbuf[r];
+        const float kv = __ldg(keys + i);
+        const int f = i % nf, t = i / nf;
+        if (pts) {
+            if (width == 3) { pts[r * 3] = __ldg(farr + f); pts[r * 3 + 1] = __ldg(tarr + t); pts[r * 3 + 2] = kv; }
+            else { pts[r * 2] = __ldg(farr + f); pts[r * 2 + 1] = kv; }
+        }
+        if (idx_out) idx_out[r] = i;
+    }
+}
+
+// ------------------------------------------------------------------------------------ host
+int launch_stft_logmag(const float* audio, int n_clips, int n_samples, int n_fft, int hop,
+                       const float* window, const float* twiddle, float scale, int drop_nyquist,
+                       int nt_out, float* out, cudaStream_t st) {
+    if (!audio || !window || !twiddle || !out) return fail(PCA_EINVAL, "stft: null pointer");
+    if (n_fft < 16 || n_fft > 8192 || (n_fft & (n_fft - 1))) return fail(PCA_EUNSUPPORTED, "stft: n_fft=%d must be a power of two in [16, 8192]", n_fft);
+    if (hop <= 0 || n_clips < 0 || n_samples <= n_fft / 2) return fail(PCA_EINVAL, "stft: need hop > 0 and n_samples > n_fft/2 (reflect padding)");
+    const int nt_max = 1 + n_samples / hop;
+    if (nt_out < 0 || nt_out > nt_max) return fail(PCA_EINVAL, "stft: nt_out=%d exceeds 1 + n_samples/hop = %d", nt_out, nt_max);
+    if (n_clips == 0 || nt_out == 0) return 0;
+    const int nc = n_fft / 2;
+    const int nf_out = nc + 1 - (drop_nyquist ? 1 : 0);
+    int threads = nc / 4;
+    threads = threads < 64 ? 64 : (threads > 512 ? 512 : threads);
+    // enough blocks to fill 148 SMs several times over, while amortising the table loads
+    int fpb = 1;
+    while ((long long)n_clips * ((nt_out + fpb - 1) / fpb) > 148LL * 32 && fpb < nt_out) fpb *= 2;
+    dim3 grid((nt_out + fpb - 1) / fpb, n_clips);
+    const size_t smem = (size_t)3 * nc * sizeof(float2) + (size_t)n_fft * sizeof(float);
+    if (smem > 48 * 1024) PCA_CHECK_CUDA(cudaFuncSetAttribute(stft_logmag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        const double frames = (double)n_clips * nt_out;
+        LaunchTimer lt("stft_logmag_kernel", st, frames * (2.5 * n_fft * log2((double)n_fft) + n_fft + 6.0 * nf_out),
+                       4.0 * n_clips * n_samples + 4.0 * frames * nf_out);
+        stft_logmag_kernel<<<grid, threads, smem, st>>>(audio, n_samples, n_fft, hop, window,
+                                                        reinterpret_cast<const float2*>(twiddle), scale,
+                                                        nf_out, nt_out, fpb, out);
+    }
+    PCA_CHECK_LAUNCH("stft_logmag_kernel");
+    return 0;
+}
+
+int launch_build_clouds(const float* logmag, int n_clouds, int nf, int nt, const float* farr,
+                        const float* tarr, float* pts, cudaStream_t st) {
+    if (!logmag || !farr || !pts) return fail(PCA_EINVAL, "build_clouds: null pointer");
+    if (n_clouds < 0 || nf <= 0 || nt <= 0) return fail(PCA_EINVAL, "build_clouds: bad shape");
+    const long long total = (long long)n_clouds * nf * nt;
+    if (total == 0) return 0;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    {
+        LaunchTimer lt("build_clouds_kernel", st, 0.0, 4.0 * total * (1 + (tarr ? 3 : 2)));
+        build_clouds_kernel<<<(int)blocks, 256, 0, st>>>(logmag, total, nf, nt, farr, tarr, pts);
+    }
+    PCA_CHECK_LAUNCH("build_clouds_kernel");
+    return 0;
+}
+
+int launch_topk(const float* keys, int n_clouds, int nf, int nt, const float* farr, const float* tarr,
+                int K, int sorted_desc, float* pts, int32_t* idx, cudaStream_t st) {
+    if (!keys || (!pts && !idx)) return fail(PCA_EINVAL, "topk: null pointer");
+    if (pts && !farr) return fail(PCA_EINVAL, "topk: farr required when pts is requested");
+    if (n_clouds < 0 || nf <= 0 || nt <= 0) return fail(PCA_EINVAL, "topk: bad shape");
+    const long long N = (long long)nf * nt;
+    if (N > (1LL << 30)) return fail(PCA_EUNSUPPORTED, "topk: cloud too large");
+    if (K < 0 || K > N) return fail(PCA_EINVAL, "topk: K=%d outside [0, %lld]", K, N);
+    if (n_clouds == 0 || K == 0) return 0;
+    int kpad = 0;
+    size_t smem = 0;
+    if (sorted_desc) {
+        if (K > 16384) return fail(PCA_EUNSUPPORTED, "topk: sorted output supports K <= 16384 (got %d)", K);
+        kpad = 2;
+        while (kpad < K) kpad <<= 1;
+        smem = (size_t)kpad * sizeof(unsigned long long);
+        if (smem > 48 * 1024) PCA_CHECK_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    {
+        // algorithmic traffic: keys read once, 16 B per selected point written
+        LaunchTimer lt("topk_kernel", st, 0.0, (double)n_clouds * (4.0 * N + 16.0 * K));
+        topk_kernel<<<n_clouds, TOPK_THREADS, smem, st>>>(keys, (int)N, nf, farr, tarr, K, kpad, sorted_desc, pts, idx);
+    }
+    PCA_CHECK_LAUNCH("topk_kernel");
+    return 0;
+}
+
+}  // namespace pca

@@ -1,0 +1,155 @@
+"""Host mirror of the point-cloud Dataset classes of Code/dataset.py with identical constructor and
+``__getitem__`` contracts.  Clouds are built (and, for maxKSS, selected and ordered) on the GPU in one
+batched launch over the whole spectrogram stack; ``__getitem__`` hands back slices of that result as
+CPU tensors so the reference's ``DataLoader(pin_memory=True)`` loops keep working, and
+``cuda_batch`` exposes the device-resident batch for the fast path."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from . import _runtime as rt
+from .frontend import build_clouds, topk_points
+
+
+def _dev(device):
+    return torch.device("cuda" if device is None else device)
+
+
+class ESC_pc(Dataset):
+    """FST dataset (Code/dataset.py:30-54): x (N, T) spectral frames, y (T,) labels, farr (N,).
+    Item idx is the (N, 2) float32 cloud with rows (farr[f], x[f, idx])."""
+
+    def __init__(self, x, y, farr, device=None):
+        self.x = x
+        self.labels = y
+        self.farr = farr
+        self._device = _dev(device)
+        self._pts = None
+
+    def __len__(self):
+        return self.x.shape[1]
+
+    def _clouds(self) -> torch.Tensor:
+        if self._pts is None:
+            frames = torch.from_numpy(np.ascontiguousarray(np.asarray(self.x).T, dtype=np.float32)).to(self._device)
+            self._pts = build_clouds(frames, self.farr, None)          # (T, N, 2) on the GPU
+            self._host = None
+        return self._pts
+
+    def cuda_batch(self, indices) -> torch.Tensor:
+        """(len(indices), N, 2) float32 CUDA tensor -- the collated batch without the host round trip."""
+        return self._clouds()[torch.as_tensor(indices, device=self._device, dtype=torch.long)]
+
+    def __getitem__(self, idx):
+        pts = self._clouds()
+        if getattr(self, "_host", None) is None:
+            self._host = pts.cpu()
+        return self._host[idx].clone(), torch.tensor(self.labels[idx])
+
+
+class ESC_pc_ss(Dataset):
+    """FST dataset for the subsampling experiments (Code/dataset.py:58-79): x, farr are the (K, T)
+    outputs of pc_maxK / pc_randK; item idx is the (K, 2) float32 cloud (farr[k, idx], x[k, idx]).
+    Pure re-zipping of already-selected values: a strided copy, done once on the device."""
+
+    def __init__(self, x, y, farr, device=None):
+        self.x = x
+        self.labels = y
+        self.farr = farr
+        self._device = _dev(device)
+        self._pts = None
+        self._host = None
+
+    def __len__(self):
+        return self.x.shape[1]
+
+    def _clouds(self):
+        if self._pts is None:
+            # float64 -> float32 exactly once, like torch.from_numpy(pc).float() (Code/dataset.py:79)
+            f = torch.from_numpy(np.ascontiguousarray(np.asarray(self.farr, dtype=np.float64).T)).to(self._device)
+            v = torch.from_numpy(np.ascontiguousarray(np.asarray(self.x, dtype=np.float64).T)).to(self._device)
+            self._pts = torch.stack([f, v], dim=2).float()               # (T, K, 2)
+        return self._pts
+
+    def cuda_batch(self, indices):
+        return self._clouds()[torch.as_tensor(indices, device=self._device, dtype=torch.long)]
+
+    def __getitem__(self, idx):
+        if self._host is None:
+            self._host = self._clouds().cpu()
+        return self._host[idx].clone(), torch.tensor(self.labels[idx])
+
+
+class ESC_pc_temp(Dataset):
+    """3ST dataset (Code/dataset.py:138-166): x (N, Nt, T); item idx is the (N*Nt, 3) float32 cloud whose
+    point p = t*N + f has columns (farr[f], tarr[t], x[f, t, idx])."""
+
+    def __init__(self, x, y, farr, tarr, device=None):
+        self.x = x
+        self.labels = y
+        self.farr = farr
+        self.tarr = tarr
+        self._device = _dev(device)
+        self._pts = None
+        self._host = None
+
+    def __len__(self):
+        return self.labels.shape[0]
+
+    def _logmag(self) -> torch.Tensor:
+        # (N, Nt, T) -> (T, Nt, N): cloud-major, frequency fastest
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(self.x).transpose(2, 1, 0), dtype=np.float32)).to(self._device)
+
+    def _clouds(self):
+        if self._pts is None:
+            self._pts = build_clouds(self._logmag(), self.farr, self.tarr)
+        return self._pts
+
+    def cuda_batch(self, indices):
+        return self._clouds()[torch.as_tensor(indices, device=self._device, dtype=torch.long)]
+
+    def __getitem__(self, idx):
+        if self._host is None:
+            self._host = self._clouds().cpu()
+        return self._host[idx].clone(), torch.tensor(self.labels[idx])
+
+
+class ESC_pc_temp_maxKSS(ESC_pc_temp):
+    """3ST dataset with max-K subsampling (Code/dataset.py:169-202): the K largest-magnitude points of
+    the cloud, rows in descending-magnitude order.  Like the reference, items are float64 (K, 3)
+    tensors (``torch.tensor(pc)`` of a float64 array); the caller casts with ``.float()``
+    (Code/pc_temp3d_eval.py:181).  Selection and ordering run in the CUDA radix-select kernel; the
+    float64 rows are gathered from the caller's coordinate vectors by the returned indices, so they are
+    bit-identical to the reference."""
+
+    def __init__(self, x, y, farr, tarr, K, device=None):
+        super().__init__(x, y, farr, tarr, device)
+        self.K = K
+        self._idx = None
+
+    def _select(self):
+        if self._idx is None:
+            n_pts = np.asarray(self.x).shape[0] * np.asarray(self.x).shape[1]
+            k = min(int(self.K), n_pts)
+            self._pts, idx = topk_points(self._logmag(), self.farr, self.tarr, k, sorted_desc=True)
+            self._idx = idx
+            self._idx_host = idx.cpu().numpy().astype(np.int64)
+        return self._pts, self._idx
+
+    def cuda_batch(self, indices):
+        """(B, K, 3) float32 -- equals torch.stack(items).float() of the reference."""
+        return self._select()[0][torch.as_tensor(indices, device=self._device, dtype=torch.long)]
+
+    def indices(self, idx) -> np.ndarray:
+        self._select()
+        return self._idx_host[idx]
+
+    def __getitem__(self, idx):
+        order = self.indices(idx)
+        nf = np.asarray(self.farr).shape[0]
+        f, t = order % nf, order // nf
+        pc = np.stack([np.asarray(self.farr, dtype=np.float64)[f], np.asarray(self.tarr, dtype=np.float64)[t],
+                       np.asarray(self.x)[f, t, idx].astype(np.float64)], axis=1)
+        return torch.tensor(pc), torch.tensor(self.labels[idx])

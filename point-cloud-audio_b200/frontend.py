@@ -1,0 +1,121 @@
+"""Batched spectral front end and point selection (host mirror over the C ABI).
+
+The reference has no function for "audio -> points": the recipe is inline script code
+(Code/settransformer.py:45-54, Code/settransformertemp.py:49-61, Code/pc_temp3d_eval.py:126-143).
+``stft_logmag`` / ``spectral_point_cloud`` are the batched equivalents; their results equal that
+recipe followed by the Dataset ``__getitem__`` of Code/dataset.py applied per clip.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib, _runtime as rt
+
+
+def coord_tables(fs: float, nf: int, n_fft: int, hop_factor: float, ntemp: int | None = None):
+    """farr = linspace(0, fs/2, Nf)/fs ; tarr = linspace(0, (hf*Nfft/fs)*Ntemp, Ntemp), float64,
+    exactly the expressions of Code/settransformer.py:40 and Code/settransformertemp.py:40-41."""
+    farr = np.linspace(0, fs / 2, nf) / fs
+    tarr = None if ntemp is None else np.linspace(0, ((hop_factor * n_fft) / fs) * ntemp, ntemp)
+    return farr, tarr
+
+
+def stft_logmag(audio: torch.Tensor, n_fft: int, win_length: int | None = None, hop_factor: float = 0.5,
+                drop_nyquist: bool = False, divisor: float | None = None, n_frames: int | None = None) -> torch.Tensor:
+    """log(1e-8 + |librosa.stft(x, n_fft, win_length, hop=int(win_length*hf), 'hann')| / divisor).
+
+    audio (B, L) float32 CUDA -> (B, Nt, Nf) float32 CUDA, frequency fastest (the transpose of the
+    reference's (Nf, Nt) matrix, i.e. already in point order p = t*Nf + f).  ``divisor`` defaults to
+    win_length (the scripts divide by N: Code/settransformer.py:49, Code/pceval.py:76)."""
+    rt.require_cuda(audio, "stft_logmag")
+    if audio.dim() != 2:
+        raise ValueError("audio must be (n_clips, n_samples)")
+    audio = rt.f32c(audio)
+    win_length = n_fft if win_length is None else int(win_length)
+    hop = int(win_length * hop_factor)
+    divisor = float(win_length if divisor is None else divisor)
+    B, L = audio.shape
+    nt_all = 1 + L // hop
+    nt = nt_all if n_frames is None else int(n_frames)
+    nf = n_fft // 2 + 1 - (1 if drop_nyquist else 0)
+    win, tw = rt.stft_tables(n_fft, win_length, audio.device)
+    out = torch.empty((B, nt, nf), dtype=torch.float32, device=audio.device)
+    with torch.cuda.device(audio.device):
+        _lib.check(_lib.lib().pca_stft_logmag_f32(
+            _lib.ptr(audio), B, L, n_fft, hop, _lib.ptr(win), _lib.ptr(tw), 1.0 / divisor,
+            int(drop_nyquist), nt, _lib.ptr(out), rt.stream_ptr(audio.device)), "stft_logmag")
+    return out
+
+
+def build_clouds(logmag: torch.Tensor, farr, tarr=None) -> torch.Tensor:
+    """(n_clouds, nt, nf) log-magnitudes -> (n_clouds, nt*nf, 3) clouds (f, t, mag), or
+    (n_clouds, nf, 2) clouds (f, mag) when tarr is None.  ESC_pc_temp / ESC_pc __getitem__ batched
+    (Code/dataset.py:160-166, 50-54)."""
+    rt.require_cuda(logmag, "build_clouds")
+    logmag = rt.f32c(logmag)
+    if logmag.dim() == 2:
+        logmag = logmag.unsqueeze(1)
+    n, nt, nf = logmag.shape
+    dev = logmag.device
+    f_t = farr if isinstance(farr, torch.Tensor) else rt.coord_table(farr, dev)
+    t_t = None if tarr is None else (tarr if isinstance(tarr, torch.Tensor) else rt.coord_table(tarr, dev))
+    if tarr is None and nt != 1:
+        raise ValueError("2-D clouds take one frame per cloud")
+    width = 2 if t_t is None else 3
+    pts = torch.empty((n, nt * nf, width), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pca_build_clouds_f32(_lib.ptr(logmag), n, nf, nt, _lib.ptr(f_t), _lib.ptr(t_t),
+                                                   _lib.ptr(pts), rt.stream_ptr(dev)), "build_clouds")
+    return pts
+
+
+def topk_points(logmag: torch.Tensor, farr, tarr, k: int, sorted_desc: bool = True, want_points: bool = True):
+    """Per cloud, the k largest log-magnitudes as (f[, t], mag) rows plus their flat indices
+    p = t*nf + f.  Emission order (-mag).argsort(kind='stable')[:k] when sorted_desc
+    (ESC_pc_temp_maxKSS, Code/dataset.py:199-200; pc_maxK, Code/utils.py:43-45), else scan order.
+    Returns (pts (n,k,2|3) float32 or None, idx (n,k) int32)."""
+    rt.require_cuda(logmag, "topk_points")
+    logmag = rt.f32c(logmag)
+    if logmag.dim() == 2:
+        logmag = logmag.unsqueeze(1)
+    n, nt, nf = logmag.shape
+    dev = logmag.device
+    f_t = None if farr is None else (farr if isinstance(farr, torch.Tensor) else rt.coord_table(farr, dev))
+    t_t = None if tarr is None else (tarr if isinstance(tarr, torch.Tensor) else rt.coord_table(tarr, dev))
+    width = 2 if t_t is None else 3
+    pts = torch.empty((n, k, width), dtype=torch.float32, device=dev) if want_points else None
+    idx = torch.empty((n, k), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pca_topk_compact_f32(_lib.ptr(logmag), n, nf, nt, _lib.ptr(f_t), _lib.ptr(t_t), int(k),
+                                                   int(sorted_desc), _lib.ptr(pts), _lib.ptr(idx),
+                                                   rt.stream_ptr(dev)), "topk_points")
+    return pts, idx
+
+
+def spectral_point_cloud(audio: torch.Tensor, *, n_fft: int, sr: float, win_length: int | None = None,
+                         hop_factor: float = 0.5, drop_nyquist: bool = True, ntemp: int | None = None,
+                         top_k: int | None = None, sorted_desc: bool = True):
+    """NEW batched front end: audio (B, L) -> (points (B', K, 3), counts (B',), indices).
+
+    Per clip: STFT recipe -> log-magnitude -> [drop Nyquist] -> non-overlapping ``ntemp``-frame chunks
+    (remainder dropped; ntemp=None keeps the whole clip as one cloud) -> (f, t, mag) clouds -> optional
+    top-K.  B' = B * chunks_per_clip, clouds of one clip are consecutive."""
+    win_length = n_fft if win_length is None else int(win_length)
+    hop = int(win_length * hop_factor)
+    B, L = audio.shape
+    nt_all = 1 + L // hop
+    ntemp_eff = nt_all if ntemp is None else int(ntemp)
+    chunks = nt_all // ntemp_eff
+    nf = n_fft // 2 + 1 - (1 if drop_nyquist else 0)
+    logmag = stft_logmag(audio, n_fft, win_length, hop_factor, drop_nyquist, n_frames=chunks * ntemp_eff)
+    logmag = logmag.view(B * chunks, ntemp_eff, nf)
+    farr, tarr = coord_tables(sr, nf, n_fft, hop_factor, ntemp_eff)
+    n_pts = ntemp_eff * nf
+    if top_k is None or top_k >= n_pts and not sorted_desc:
+        pts = build_clouds(logmag, farr, tarr)
+        idx = torch.arange(n_pts, dtype=torch.int32, device=audio.device).expand(B * chunks, -1)
+    else:
+        pts, idx = topk_points(logmag, farr, tarr, min(int(top_k), n_pts), sorted_desc)
+    counts = torch.full((B * chunks,), pts.shape[1], dtype=torch.int32, device=audio.device)
+    return pts, counts, idx

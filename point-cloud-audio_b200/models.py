@@ -1,0 +1,165 @@
+"""Drop-in set models: ``ST`` (Code/models.py:13-44), the ModelNet ``SetTransformer``
+(set_transformer-master/main_pointcloud.py:13-37) and ``DeepSet``
+(set_transformer-master/models.py:3-28).  Same constructor signatures, module trees and state-dict
+keys as the reference (shipped checkpoints load directly, with or without the DataParallel
+``module.`` prefix); ``forward`` is ONE call into the fused CUDA path."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib, _runtime as rt
+from .modules import ISAB, PMA, SAB, _PackedParams, _guard, _mab_tensors
+
+# scratch budget for the encoder: the batch is processed in chunks that fit (bigger = fewer launches)
+ST_WORKSPACE_BYTES = 1 << 30
+
+
+def strip_module_prefix(state_dict):
+    """Checkpoints saved from nn.DataParallel carry a 'module.' prefix (Code/settransformer.py:94,160)."""
+    return {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+
+
+class _SetEncoderBase(nn.Module):
+    """ISAB, ISAB -> PMA -> Linear, run through pca_st_fwd."""
+
+    precision = _lib.PREC_FP32
+
+    def _parts(self):
+        raise NotImplementedError
+
+    def set_precision(self, precision: str):
+        """'fp32' (CUDA-core, 1e-3 parity) or 'bf16' (tcgen05 tensor-core tiles, 2e-2 parity)."""
+        self.precision = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision]
+        return self
+
+    def _dims(self):
+        isab0, isab1, pma, lin = self._parts()
+        return _lib.StDims(d_in=isab0.mab0.fc_k.in_features, D=isab0.mab0.dim_V, H=isab0.mab0.num_heads,
+                           M=isab0.I.shape[1], S=pma.S.shape[1], C=lin.out_features, ln=isab0.mab0._ln)
+
+    def _blob(self):
+        isab0, isab1, pma, lin = self._parts()
+        ts = isab0._tensors() + isab1._tensors() + pma._tensors() + [lin.weight, lin.bias]
+        if not hasattr(self, "_packed"):
+            object.__setattr__(self, "_packed", _PackedParams())
+        return self._packed.get(ts)
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        return super().load_state_dict(strip_module_prefix(state_dict), *args, **kwargs)
+
+    def encode(self, X: torch.Tensor) -> torch.Tensor:
+        """(B, N, d_in) CUDA -> logits (B, S, C) (before the reference's .squeeze())."""
+        rt.require_cuda(X, type(self).__name__ + ".forward")
+        X = rt.f32c(X)
+        B, N, d_in = X.shape
+        dims = self._dims()
+        if d_in != dims.d_in:
+            raise ValueError(f"expected clouds of width {dims.d_in}, got {d_in}")
+        blob = self._blob()
+        L = _lib.lib()
+        assert blob.numel() == L.pca_st_param_count(C.byref(dims))
+        out = torch.empty((B, dims.S, dims.C), dtype=torch.float32, device=X.device)
+        if B == 0:
+            return out
+        need1 = L.pca_st_workspace_bytes(C.byref(dims), 1, N, self.precision)
+        needB = L.pca_st_workspace_bytes(C.byref(dims), B, N, self.precision)
+        ws = rt.workspace(X.device, max(need1, min(needB, ST_WORKSPACE_BYTES)))
+        with torch.cuda.device(X.device):
+            _lib.check(L.pca_st_fwd(_lib.ptr(X), B, N, C.byref(dims), _lib.ptr(blob), _lib.ptr(out), _lib.ptr(ws),
+                                    ws.numel(), self.precision, rt.stream_ptr(X.device)),
+                       type(self).__name__ + ".forward")
+        return _guard(out, self)
+
+
+class ST(_SetEncoderBase):
+    """Set Transformer for 2-D / 3-D spectral point clouds (Code/models.py:13-44)."""
+
+    def __init__(self, dim_input=2, num_outputs=1, dim_output=10, num_inds=4, dim_hidden=4, num_heads=2, ln=False):
+        super().__init__()
+        self.enc = nn.Sequential(
+            ISAB(dim_input, dim_hidden, num_heads, num_inds, ln=ln),
+            ISAB(dim_hidden, dim_hidden, num_heads, num_inds, ln=ln),
+        )
+        self.dec = nn.Sequential(
+            PMA(dim_hidden, num_heads, num_outputs, ln=ln),
+            nn.Linear(dim_hidden, dim_output),
+        )
+
+    def _parts(self):
+        return self.enc[0], self.enc[1], self.dec[0], self.dec[1]
+
+    def forward(self, X):
+        return self.encode(X).squeeze()       # (B,1,C)->(B,C); (C,) when B == 1 (Code/models.py:44)
+
+
+class SetTransformer(_SetEncoderBase):
+    """ModelNet40 classifier of set_transformer-master/main_pointcloud.py:13-37: ST with Dropout
+    around the PMA.  Eval-mode forward runs the fused path; train-mode dropout belongs to the
+    training scope row and raises."""
+
+    def __init__(self, dim_input=3, num_outputs=1, dim_output=40, num_inds=32, dim_hidden=128, num_heads=4, ln=False):
+        super().__init__()
+        self.enc = nn.Sequential(
+            ISAB(dim_input, dim_hidden, num_heads, num_inds, ln=ln),
+            ISAB(dim_hidden, dim_hidden, num_heads, num_inds, ln=ln),
+        )
+        self.dec = nn.Sequential(
+            nn.Dropout(),
+            PMA(dim_hidden, num_heads, num_outputs, ln=ln),
+            nn.Dropout(),
+            nn.Linear(dim_hidden, dim_output),
+        )
+
+    def _parts(self):
+        return self.enc[0], self.enc[1], self.dec[1], self.dec[3]
+
+    def forward(self, X):
+        if self.training:
+            raise NotImplementedError("SetTransformer: train-mode (Dropout) forward is not implemented; call .eval()")
+        return self.encode(X).squeeze()
+
+
+class DeepSet(nn.Module):
+    """Shared 4-layer MLP over points -> pool -> 4-layer decoder (set_transformer-master/models.py:3-28).
+    ``pool`` extends the reference's mean with SmallDeepSet's max / sum (max_regression_demo.ipynb:41-48)."""
+
+    def __init__(self, dim_input, num_outputs, dim_output, dim_hidden=128, pool="mean"):
+        super().__init__()
+        self.num_outputs = num_outputs
+        self.dim_output = dim_output
+        self.pool = pool
+        self.enc = nn.Sequential(
+            nn.Linear(dim_input, dim_hidden), nn.ReLU(),
+            nn.Linear(dim_hidden, dim_hidden), nn.ReLU(),
+            nn.Linear(dim_hidden, dim_hidden), nn.ReLU(),
+            nn.Linear(dim_hidden, dim_hidden))
+        self.dec = nn.Sequential(
+            nn.Linear(dim_hidden, dim_hidden), nn.ReLU(),
+            nn.Linear(dim_hidden, dim_hidden), nn.ReLU(),
+            nn.Linear(dim_hidden, dim_hidden), nn.ReLU(),
+            nn.Linear(dim_hidden, num_outputs * dim_output))
+        self._packed = _PackedParams()
+
+    def forward(self, X):
+        rt.require_cuda(X, "DeepSet.forward")
+        X = rt.f32c(X)
+        B, N, d_in = X.shape
+        dh = self.enc[0].out_features
+        out_dim = self.num_outputs * self.dim_output
+        ts = []
+        for seq in (self.enc, self.dec):
+            for i in (0, 2, 4, 6):
+                ts += [seq[i].weight, seq[i].bias]
+        blob = self._packed.get(ts)
+        out = torch.empty((B, out_dim), dtype=torch.float32, device=X.device)
+        L = _lib.lib()
+        ws = rt.workspace(X.device, L.pca_deepset_workspace_bytes(B, N, d_in, dh, out_dim))
+        pool = {"mean": 0, "max": 1, "sum": 2}[self.pool]
+        with torch.cuda.device(X.device):
+            _lib.check(L.pca_deepset_fwd_f32(_lib.ptr(X), B, N, d_in, dh, out_dim, pool, _lib.ptr(blob),
+                                             _lib.ptr(out), _lib.ptr(ws), ws.numel(), rt.stream_ptr(X.device)),
+                       "DeepSet.forward")
+        return _guard(out.reshape(-1, self.num_outputs, self.dim_output), self)

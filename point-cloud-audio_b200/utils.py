@@ -1,0 +1,26 @@
+"""Host mirror of Code/utils.py for the hot path: ``pc_maxK`` with the selection done on the GPU."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .frontend import topk_points
+
+
+def pc_maxK(x, farr, Kmax, device="cuda"):
+    """Per-frame top-K of the spectrum (Code/utils.py:25-52).
+
+    x: array (N, T) spectral frames; farr: (N,) frequency coordinates; returns
+    (subsampled_x (K, T), subsampled_x_fs (K, T)) with each column in descending-magnitude order,
+    same dtypes as the inputs.  The K largest bins per frame and their order come from the CUDA
+    radix-select/compaction kernel; values are gathered from the caller's arrays by index, so they
+    are bit-identical to the reference's fancy indexing."""
+    x = np.asarray(x)
+    farr = np.asarray(farr)
+    n, t = x.shape
+    k = min(int(Kmax), n)
+    keys = torch.from_numpy(np.ascontiguousarray(x.T, dtype=np.float32)).to(device)     # (T, N)
+    _, idx = topk_points(keys, None, None, k, sorted_desc=True, want_points=False)
+    idx = idx.cpu().numpy().astype(np.int64)                                              # (T, K)
+    cols = np.arange(t)[:, None]
+    return x[idx, cols].T.copy(), farr[idx].T.copy()

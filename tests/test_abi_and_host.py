@@ -1,0 +1,166 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/pcaudio_b200.h declares, the
+ctypes prototypes cover them, and the host-side logic (param packing, sharding, tables) is right.
+No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    import pcaudio_b200 as pca
+    return pca
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "pcaudio_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pca_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    from pcaudio_b200 import _lib
+    names = header_symbols()
+    assert len(names) >= 20
+    handle = C.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in the header but not exported"
+    assert sorted(_lib.PROTOTYPES) == names, "ctypes prototypes out of sync with the header"
+    assert _lib.lib().pca_version() == 100
+
+
+def test_no_oracle_import_in_product():
+    pkg = os.path.join(ROOT, "point-cloud-audio_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower(), f"{f} mentions the oracle"
+
+
+def test_param_counts_match_reference_models(built):
+    pca = built
+    from pcaudio_b200 import _lib
+    for d_in, expect in ((2, 80202), (3, 80394)):          # model_params of the shipped configs
+        m = pca.ST(dim_input=d_in, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8)
+        n = sum(p.numel() for p in m.parameters())
+        assert n == expect
+        dims = m._dims()
+        assert _lib.lib().pca_st_param_count(C.byref(dims)) == n
+        assert m._blob().numel() == n
+    mn = pca.SetTransformer(dim_hidden=256, num_heads=4, num_inds=16)
+    assert sum(p.numel() for p in mn.parameters()) == 1140264
+
+
+def test_state_dict_keys_and_module_prefix(built, golden_dir):
+    pca = built
+    w = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, "3st_weights.npz")).items()}
+    assert all(k.startswith("module.") for k in w)
+    m = pca.ST(dim_input=3, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8)
+    m.load_state_dict(w)                                            # DataParallel prefix accepted
+    assert set(m.state_dict()) == {k[7:] for k in w}
+    blob = m._blob()
+    # canonical order starts with enc.0.I then mab0.fc_q.weight
+    np.testing.assert_array_equal(blob[:64 * 64].numpy(), w["module.enc.0.I"].reshape(-1).numpy())
+    np.testing.assert_array_equal(blob[64 * 64:2 * 64 * 64].numpy(), w["module.enc.0.mab0.fc_q.weight"].reshape(-1).numpy())
+    # cache invalidation on in-place update
+    with torch.no_grad():
+        m.enc[0].I.add_(1.0)
+    assert torch.equal(m._blob()[:4096], (w["module.enc.0.I"].reshape(-1) + 1.0))
+
+
+def test_cpu_tensors_fail_loudly(built):
+    pca = built
+    m = pca.ST(dim_input=2, num_outputs=1, dim_output=10, num_inds=4, dim_hidden=8, num_heads=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(2, 5, 2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pca.stft_logmag(torch.zeros(1, 4000), 256)
+
+
+def test_missing_library_fails_loudly(built, monkeypatch):
+    from pcaudio_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libpcaudio_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_coord_tables_match_oracle(built):
+    from oracle import pcaudio_oracle as orc
+    f1, t1 = built.coord_tables(16000, 512, 1024, 0.5, 10)
+    f2, t2 = orc.coord_tables(16000, 512, 1024, 0.5, 10)
+    np.testing.assert_array_equal(f1, f2)
+    np.testing.assert_array_equal(t1, t2)
+
+
+def test_pipeline_shape_queries(built):
+    from pcaudio_b200 import _lib
+    L = _lib.lib()
+    dims = _lib.StDims(d_in=2, D=64, H=8, M=64, S=1, C=10, ln=0)
+    cfg = _lib.PipelineCfg(n_samples=16000, n_fft=2048, hop=1024, scale=1 / 2048, mode=2, ntemp=0, top_k=0,
+                           precision=0, st=dims)
+    assert L.pca_pipeline_clouds_per_clip(C.byref(cfg)) == 16
+    assert L.pca_pipeline_points_per_cloud(C.byref(cfg)) == 1025
+    dims3 = _lib.StDims(d_in=3, D=64, H=8, M=64, S=1, C=10, ln=0)
+    cfg3 = _lib.PipelineCfg(n_samples=64000, n_fft=1024, hop=512, scale=1 / 1024, mode=3, ntemp=10, top_k=0,
+                            precision=0, st=dims3)
+    assert L.pca_pipeline_clouds_per_clip(C.byref(cfg3)) == 12       # 126 frames -> 12 chunks of 10
+    assert L.pca_pipeline_points_per_cloud(C.byref(cfg3)) == 5120
+    cfg3.top_k = 256
+    assert L.pca_pipeline_points_per_cloud(C.byref(cfg3)) == 256
+    cfg3.st.d_in = 2                                                  # width mismatch is an error, not UB
+    assert L.pca_pipeline_clouds_per_clip(C.byref(cfg3)) == -1
+    assert b"wide" in L.pca_last_error()
+
+
+def test_shard_range_partitions():
+    from pcaudio_b200.parallel import shard_range
+    for n in (0, 1, 7, 256, 1000):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from pcaudio_b200.parallel import allreduce_mean_, gather_rows, init_distributed, shard_range
+    r, w, _ = init_distributed("gloo")
+    full = torch.arange(7 * 3, dtype=torch.float32).reshape(7, 3)
+    lo, hi = shard_range(7, r, w)
+    got = gather_rows(full[lo:hi].clone(), 7, r, w)
+    g = torch.full((5,), float(r + 1))
+    allreduce_mean_(g, w)
+    q.put((r, torch.equal(got, full), g.tolist()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shard_gather_and_grad_allreduce():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29611
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for r, ok, g in res:
+        assert ok, f"rank {r}: gathered rows differ from the unsharded tensor"
+        assert g == [1.5] * 5
