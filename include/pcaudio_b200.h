@@ -196,6 +196,13 @@ unsigned long long pca_launch_count(void);
 void pca_profile_enable(int on);
 int pca_profile_report(char* buf, size_t buf_len);
 
+/* Unit probe of the tcgen05 building blocks used by the bf16 encoder path: one CTA computes
+ * D (128, N) = A (128, K) * B (K, N), bf16 operands, fp32 accumulation in TMEM.
+ * a_mode: 0 A (128,K) via shared memory K-major, 1 A via TMEM, 2 A given as (K,128) via shared memory MN-major;
+ * b_mode: 0 B given as (N,K) K-major, 1 B given as (K,N) MN-major.  N, K multiples of 16 in [16,128]. */
+int pca_debug_umma_probe(const float* A, const float* B, float* D, int N, int K, int a_mode, int b_mode,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

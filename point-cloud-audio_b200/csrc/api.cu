@@ -19,6 +19,7 @@ int launch_attn(const float*, long long, const float*, int, int, int, int, int, 
 size_t attn_part_floats(int B, int nq, int nk, int D, int H);
 int launch_layernorm(float*, long long, int, const float*, const float*, cudaStream_t);
 int launch_pool(const float*, int, int, int, int, float*, cudaStream_t);
+int launch_umma_probe(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 // tcgen05 path (encoder_tc.cu)
 size_t st_tc_workspace_bytes(const pca_st_dims* d, int B, int N);
 int st_tc_supported(const pca_st_dims* d, int N);
@@ -495,6 +496,10 @@ int pca_pipeline_run_host(const pca_pipeline_cfg* cfg, const float* host_audio, 
     const size_t out_bytes = (size_t)n_clips * s.clouds_per_clip * cfg->st.S * cfg->st.C * sizeof(float);
     PCA_CHECK_CUDA(cudaMemcpyAsync(host_logits, dev_logits, out_bytes, cudaMemcpyDeviceToHost, st));
     return 0;
+}
+
+int pca_debug_umma_probe(const float* A, const float* B, float* D, int N, int K, int a_mode, int b_mode, void* stream) {
+    return launch_umma_probe(A, B, D, N, K, a_mode, b_mode, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -41,6 +41,8 @@ def stft_logmag(audio: torch.Tensor, n_fft: int, win_length: int | None = None, 
     nf = n_fft // 2 + 1 - (1 if drop_nyquist else 0)
     win, tw = rt.stft_tables(n_fft, win_length, audio.device)
     out = torch.empty((B, nt, nf), dtype=torch.float32, device=audio.device)
+    if out.numel() == 0:
+        return out
     with torch.cuda.device(audio.device):
         _lib.check(_lib.lib().pca_stft_logmag_f32(
             _lib.ptr(audio), B, L, n_fft, hop, _lib.ptr(win), _lib.ptr(tw), 1.0 / divisor,
