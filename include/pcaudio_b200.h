@@ -196,6 +196,13 @@ unsigned long long pca_launch_count(void);
 void pca_profile_enable(int on);
 int pca_profile_report(char* buf, size_t buf_len);
 
+/* Debug variant of pca_st_fwd(precision = PCA_PREC_BF16) that also returns the intermediate stages as fp32:
+ * H1, H2 (B, M, D) inducing-point summaries of the two ISABs, Y1, Y2 (B, N, D) ISAB outputs, pooled (B, D) PMA
+ * output before the final Linear.  Any stage pointer may be NULL.  The workspace must hold the whole batch. */
+int pca_debug_st_stages(const float* X, int B, int N, const pca_st_dims* dims, const float* params,
+                        float* logits, float* H1, float* Y1, float* H2, float* Y2, float* pooled,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* Unit probe of the tcgen05 building blocks used by the bf16 encoder path: one CTA computes
  * D (128, N) = A (128, K) * B (K, N), bf16 operands, fp32 accumulation in TMEM.
  * a_mode: 0 A (128,K) via shared memory K-major, 1 A via TMEM, 2 A given as (K,128) via shared memory MN-major;

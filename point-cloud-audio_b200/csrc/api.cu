@@ -25,6 +25,9 @@ size_t st_tc_workspace_bytes(const pca_st_dims* d, int B, int N);
 int st_tc_supported(const pca_st_dims* d, int N);
 int st_tc_forward(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
                   void* ws, size_t ws_bytes, cudaStream_t st);
+int st_tc_forward_stages(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
+                         float* H1, float* Y1, float* H2, float* Y2, float* pooled, void* ws, size_t ws_bytes,
+                         cudaStream_t st);
 
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
@@ -65,25 +68,6 @@ LaunchTimer::~LaunchTimer() {
 }
 
 // ------------------------------------------------------------------------------------ params
-struct MabParams {
-    const float *Wq, *bq, *Wkv, *bkv, *Wo, *bo, *ln0w, *ln0b, *ln1w, *ln1b;
-};
-static long long mab_count(int dq, int dk, int D, int ln) {
-    return (long long)D * dq + D + 2LL * D * dk + 2LL * D + (long long)D * D + D + (ln ? 4LL * D : 0);
-}
-static MabParams mab_slice(const float* p, int dq, int dk, int D, int ln) {
-    MabParams m;
-    m.Wq = p; p += (long long)D * dq;
-    m.bq = p; p += D;
-    m.Wkv = p; p += 2LL * D * dk;      // Wk then Wv: one (2D, dk) matrix
-    m.bkv = p; p += 2LL * D;           // bk then bv
-    m.Wo = p; p += (long long)D * D;
-    m.bo = p; p += D;
-    m.ln0w = m.ln0b = m.ln1w = m.ln1b = nullptr;
-    if (ln) { m.ln0w = p; m.ln0b = p + D; m.ln1w = p + 2 * D; m.ln1b = p + 3 * D; }
-    return m;
-}
-
 // ------------------------------------------------------------------------------------ MAB (fp32)
 // workspace: Qp (qb*nq*D) | KV (B*nk*2D) | O (B*nq*D) | part
 static size_t mab_ws_floats(int B, int qb, int nq, int nk, int D, int H) {
@@ -299,8 +283,10 @@ static size_t pipe_ws_bytes(const pca_pipeline_cfg* c, const PipeShape& s, int n
     a.take<float>((size_t)n_clips * s.nt_out * s.nf);        // log-magnitudes
     a.take<float>(n_clouds * s.pts * s.width);               // clouds
     if (st_off) *st_off = a.off;
-    // encoder scratch: enough for chunks of <= 256 clouds (more only helps launch overhead)
-    int chunk = (int)(n_clouds < 256 ? n_clouds : 256);
+    // encoder scratch: chunks of <= 256 clouds for the fp32 path (more only helps launch overhead); the
+    // tcgen05 path runs one CTA per cloud, so it gets up to 4096 clouds per launch to fill many waves
+    const size_t cap = c->precision == PCA_PREC_BF16 ? 4096 : 256;
+    int chunk = (int)(n_clouds < cap ? n_clouds : cap);
     if (chunk < 1) chunk = 1;
     return a.off + st_any_ws_bytes(&c->st, chunk, s.pts, c->precision);
 }
@@ -496,6 +482,17 @@ int pca_pipeline_run_host(const pca_pipeline_cfg* cfg, const float* host_audio, 
     const size_t out_bytes = (size_t)n_clips * s.clouds_per_clip * cfg->st.S * cfg->st.C * sizeof(float);
     PCA_CHECK_CUDA(cudaMemcpyAsync(host_logits, dev_logits, out_bytes, cudaMemcpyDeviceToHost, st));
     return 0;
+}
+
+int pca_debug_st_stages(const float* X, int B, int N, const pca_st_dims* dims, const float* params, float* logits,
+                        float* H1, float* Y1, float* H2, float* Y2, float* pooled, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    PCA_TRY(check_dims(dims));
+    if (!X || !params || !logits) return fail(PCA_EINVAL, "ST stages: null pointer");
+    if (B <= 0 || N <= 0) return fail(PCA_EINVAL, "ST stages: bad shape");
+    if (!st_tc_supported(dims, N)) return fail(PCA_EUNSUPPORTED, "ST stages: dims not supported by the tcgen05 path");
+    return st_tc_forward_stages(X, B, N, dims, params, logits, H1, Y1, H2, Y2, pooled, workspace, workspace_bytes,
+                                (cudaStream_t)stream);
 }
 
 int pca_debug_umma_probe(const float* A, const float* B, float* D, int N, int K, int a_mode, int b_mode, void* stream) {

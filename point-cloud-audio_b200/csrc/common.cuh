@@ -64,6 +64,26 @@ struct Arena {
     bool ok() const { return off <= cap; }
 };
 
+// packed MAB parameter blob (layout documented in include/pcaudio_b200.h)
+struct MabParams {
+    const float *Wq, *bq, *Wkv, *bkv, *Wo, *bo, *ln0w, *ln0b, *ln1w, *ln1b;
+};
+__host__ __device__ static inline long long mab_count(int dq, int dk, int D, int ln) {
+    return (long long)D * dq + D + 2LL * D * dk + 2LL * D + (long long)D * D + D + (ln ? 4LL * D : 0);
+}
+__host__ __device__ static inline MabParams mab_slice(const float* p, int dq, int dk, int D, int ln) {
+    MabParams m;
+    m.Wq = p; p += (long long)D * dq;
+    m.bq = p; p += D;
+    m.Wkv = p; p += 2LL * D * dk;      // Wk then Wv: one (2D, dk) matrix
+    m.bkv = p; p += 2LL * D;           // bk then bv
+    m.Wo = p; p += (long long)D * D;
+    m.bo = p; p += D;
+    m.ln0w = m.ln0b = m.ln1w = m.ln1b = nullptr;
+    if (ln) { m.ln0w = p; m.ln0b = p + D; m.ln1w = p + 2 * D; m.ln1b = p + 3 * D; }
+    return m;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

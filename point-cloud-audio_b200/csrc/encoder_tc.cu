@@ -1,10 +1,1047 @@
-// tcgen05 / TMEM set-encoder kernels for the audio dims (D=64, H=8, M=64) -- placeholder until the
-// kernels land; reports "unsupported" so callers fail loudly instead of silently falling back.
+// tcgen05 / TMEM set-encoder path for the audio Set Transformer dims (D=64, H=8 -> head dim 8, M=64
+// inducing points, one PMA seed, no LayerNorm; ST of Code/models.py:13-44 with the hyper-parameters of
+// Code/settransformer.py:81-85).  bf16 operands, fp32 accumulation in TMEM, fp32 softmax statistics.
+//
+//   prep_kernel            : batch-independent work hoisted out of the per-cloud path: fc_q(I), fc_q(S)
+//                            (the I.repeat / S.repeat of modules.py:52,63 is never materialised) and the
+//                            bf16 UMMA operand images of the weights.
+//   mab_reduce_tc_kernel   : MAB(Q = inducing points | seed, K = points)  (ISAB mab0, PMA).  Rows of the
+//                            128-row MMA tile are (head-of-pair, query); two heads are stacked per MMA so the
+//                            K=16 bf16 instruction depth is fully used by 2 x head-dim 8.  Online softmax over
+//                            the points with the running statistics in registers (thread = row).
+//   finalize_isab_kernel   : merges the point splits, O = Qp + A V, H = O + relu(fc_o(O)), then the K/V
+//                            projections of H for mab1, emitted as block-diagonal bf16 operand images.
+//   mab_apply_tc_kernel    : MAB(Q = points, K = H) (ISAB mab1): per 128-point tile, Q projection,
+//                            QK^T (2 heads per MMA via the block-diagonal K image), softmax over the 64 keys in
+//                            registers, P V with P fed from TMEM, +Qp residual, fc_o + ReLU residual.
+//   finalize_pma_kernel    : merge, residuals, final Linear -> logits.
 #include "common.cuh"
+#include "tc_prims.cuh"
+
 namespace pca {
-size_t st_tc_workspace_bytes(const pca_st_dims*, int, int) { return 0; }
-int st_tc_supported(const pca_st_dims*, int) { return 0; }
-int st_tc_forward(const float*, int, int, const pca_st_dims*, const float*, float*, void*, size_t, cudaStream_t) {
-    return fail(PCA_EUNSUPPORTED, "tcgen05 encoder path not built");
+using namespace tc;
+
+constexpr int TD = 64, TH = 8, TM = 64;                   // dims this path is specialised for
+constexpr float kScaleLog2e = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(dim_V)
+constexpr int TC_THREADS = 13 * 32;                        // 8 softmax warps, 1 MMA warp, 4 producer warps
+
+struct TcConsts {
+    float Qp0[TM * TD];        // isab0.mab0 fc_q(I)
+    float Qp1[TM * TD];        // isab1.mab0 fc_q(I)
+    float QpS[TD];             // pma fc_q(S)
+    float pad[64];
+    uint8_t Aq0[16384], Aq1[16384], AqP[16384];   // stacked-pair query operands [4 pairs][2 chunks][128 rows][16 B]
+    uint8_t Wkv1[16384], WkvP[16384];             // [Wk;Wv] as B operand (N=128, K=64): [8 chunks][128 rows][16 B]
+    uint8_t Wq1[8192], Wo0[8192], Wo1[8192];      // (N=64, K=64) B operands: [8 chunks][64 rows][16 B]
+};
+
+// ------------------------------------------------------------------------------------ prep
+__device__ void pack_b_operand(const float* __restrict__ W, int n_rows, uint8_t* __restrict__ out) {
+    // W (n_rows, 64) row-major fp32 -> bf16 [k/8][n][k%8]
+    for (int i = threadIdx.x; i < n_rows * 64; i += blockDim.x) {
+        const int n = i / 64, k = i % 64;
+        *reinterpret_cast<__nv_bfloat16*>(out + (k / 8) * (n_rows * 16) + n * 16 + (k % 8) * 2) = __float2bfloat16(W[i]);
+    }
 }
+
+// Qp = fc_q(Qin) for nq (64 or 1) queries, and the stacked-pair A operand image
+__device__ void prep_queries(const float* __restrict__ Qin, int nq, const float* __restrict__ Wq,
+                             const float* __restrict__ bq, float* __restrict__ Qp_out, uint8_t* __restrict__ Aq,
+                             float* sq /* smem 64*64 */) {
+    for (int i = threadIdx.x; i < nq * TD; i += blockDim.x) {
+        const int m = i / TD, f = i % TD;
+        float a = bq[f];
+        for (int k = 0; k < TD; ++k) a = fmaf(Qin[m * TD + k], Wq[f * TD + k], a);
+        sq[i] = a;
+        Qp_out[i] = a;
+    }
+    __syncthreads();
+    // Aq[p][c][r][d]: rows 0-63 carry head 2p in chunk 0, rows 64-127 carry head 2p+1 in chunk 1
+    for (int i = threadIdx.x; i < 4 * 2 * 128 * 8; i += blockDim.x) {
+        const int d = i & 7, r = (i >> 3) & 127, c = (i >> 10) & 1, p = i >> 11;
+        float v = 0.f;
+        if ((r >> 6) == c) {
+            const int m = (nq == 1) ? 0 : (r & 63);
+            v = sq[m * TD + (2 * p + c) * 8 + d] * kScaleLog2e;
+        }
+        *reinterpret_cast<__nv_bfloat16*>(Aq + p * 4096 + c * 2048 + r * 16 + d * 2) = __float2bfloat16(v);
+    }
+}
+
+__global__ void prep_kernel(const float* __restrict__ params, int d_in, TcConsts* __restrict__ c) {
+    __shared__ float sq[TM * TD];
+    const long long n_isab0 = (long long)TM * TD + mab_count(TD, d_in, TD, 0) + mab_count(d_in, TD, TD, 0);
+    const float* p_isab0 = params;
+    const float* p_isab1 = p_isab0 + n_isab0;
+    const float* p_pma = p_isab1 + (long long)TM * TD + 2 * mab_count(TD, TD, TD, 0);
+    const MabParams m00 = mab_slice(p_isab0 + TM * TD, TD, d_in, TD, 0);
+    const MabParams m01 = mab_slice(p_isab0 + TM * TD + mab_count(TD, d_in, TD, 0), d_in, TD, TD, 0);
+    const MabParams m10 = mab_slice(p_isab1 + TM * TD, TD, TD, TD, 0);
+    const MabParams m11 = mab_slice(p_isab1 + TM * TD + mab_count(TD, TD, TD, 0), TD, TD, TD, 0);
+    const MabParams mp = mab_slice(p_pma + TD, TD, TD, TD, 0);
+    switch (blockIdx.x) {
+        case 0: prep_queries(p_isab0, TM, m00.Wq, m00.bq, c->Qp0, c->Aq0, sq); break;
+        case 1: prep_queries(p_isab1, TM, m10.Wq, m10.bq, c->Qp1, c->Aq1, sq); break;
+        case 2: prep_queries(p_pma, 1, mp.Wq, mp.bq, c->QpS, c->AqP, sq); break;
+        case 3: pack_b_operand(m10.Wkv, 128, c->Wkv1); break;
+        case 4: pack_b_operand(mp.Wkv, 128, c->WkvP); break;
+        case 5: pack_b_operand(m11.Wq, 64, c->Wq1); break;
+        case 6: pack_b_operand(m01.Wo, 64, c->Wo0); break;
+        case 7: pack_b_operand(m11.Wo, 64, c->Wo1); break;
+        default: break;
+    }
+}
+
+// ------------------------------------------------------------------------------------ shared helpers
+__device__ __forceinline__ void copy_to_smem(uint8_t* dst, const uint8_t* __restrict__ src, int bytes) {
+    for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16)
+        *reinterpret_cast<uint4*>(dst + i) = __ldg(reinterpret_cast<const uint4*>(src + i));
+}
+__device__ __forceinline__ void st_shared_8bf16(uint8_t* dst, const float* v) {
+    uint4 u;
+    u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
+    u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst) = u;
+}
+
+// ------------------------------------------------------------------------------------ reduce kernel
+struct RParams {
+    const float* X32;             // (B, N, d_in) fp32      [DIN64 == false]
+    const __nv_bfloat16* Y16;     // (B, N, 64) bf16        [DIN64 == true]
+    int N, d_in, tiles_total, tiles_per_split, nsplit;
+    const uint8_t* Aq;            // 16 KB stacked-pair query operand
+    const float* Wkv32;           // (128, d_in) fp32       [DIN64 == false]
+    const float* bkv;             // (128)
+    const uint8_t* Wkv16;         // 16 KB B operand        [DIN64 == true]
+    float* part;                  // (B, nsplit, 8, 64, 10): m (log2 domain), l, acc[8]
+};
+
+// TMEM columns of the reduce kernel
+constexpr uint32_t RC_S = 0;        // 2 score / probability buffers of 128 columns
+constexpr uint32_t RC_O = 256;      // 4 pair outputs of 16 columns
+constexpr uint32_t RC_PROJ = 320;   // 128 columns: K|V projection accumulator (DIN64)
+
+struct RSmem {
+    static constexpr int AQ = 0;
+    static constexpr int KV = 16384;              // 2 stages x (K 16384 | V 16384)
+    static constexpr int W = KV + 65536;          // Wkv16 operand (DIN64)
+    static constexpr int Y = W + 16384;           // Y tile operand (DIN64)
+    static constexpr int SMALL = Y + 16384;       // fp32: Wkv32 padded (128 x 4) + bkv (128)
+    static constexpr int BARS = SMALL + (128 * 4 + 128) * 4;
+    static constexpr int TOTAL = BARS + 16 * 8 + 16;
+};
+
+template <bool DIN64>
+__global__ void __launch_bounds__(TC_THREADS, 1) mab_reduce_tc_kernel(const RParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sAq = smem + RSmem::AQ;
+    uint8_t* sKV = smem + RSmem::KV;
+    uint8_t* sW = smem + RSmem::W;
+    uint8_t* sY = smem + RSmem::Y;
+    float* sWsm = reinterpret_cast<float*>(smem + RSmem::SMALL);
+    float* sBias = sWsm + 128 * 4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RSmem::BARS);
+    uint64_t* kv_full = bars;          // [2] count 128
+    uint64_t* kv_empty = bars + 2;     // [2] count 1 (tcgen05.commit)
+    uint64_t* s_full = bars + 4;       // [2] count 1
+    uint64_t* p_ready = bars + 6;      // [2] count 128
+    uint64_t* o_full = bars + 8;       // [4] count 1
+    uint64_t* y_full = bars + 12;      // count 128
+    uint64_t* proj_done = bars + 13;   // count 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cloud = blockIdx.y, split = blockIdx.x;
+    const int tile0 = split * P.tiles_per_split;
+    const int ntiles = min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+
+    // ---- one-time setup
+    copy_to_smem(sAq, P.Aq, 16384);
+    if (DIN64) copy_to_smem(sW, P.Wkv16, 16384);
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+        sBias[i] = P.bkv[i];
+        if (!DIN64) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sWsm[i * 4 + k] = (k < P.d_in) ? P.Wkv32[i * P.d_in + k] : 0.f;
+        }
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 128); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); }
+        for (int i = 0; i < 4; ++i) mbar_init(&o_full[i], 1);
+        mbar_init(y_full, 128);
+        mbar_init(proj_done, 1);
+        fence_barrier_init();
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp >= 9) {
+        // =================================================================== producer: K|V tiles
+        const int quad = warp & 3;
+        const int row = 32 * quad + lane;
+        for (int it = 0; it < ntiles; ++it) {
+            const int stage = it & 1;
+            const int n = (tile0 + it) * 128 + row;
+            const bool valid = n < P.N;
+            uint8_t* sK = sKV + stage * 32768;
+            uint8_t* sV = sK + 16384;
+            if (!DIN64) {
+                float x[4] = {0.f, 0.f, 0.f, 0.f};
+                if (valid) {
+                    const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                    for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
+                }
+                if (it >= 2) mbar_wait(&kv_empty[stage], ((it >> 1) - 1) & 1);
+#pragma unroll 4
+                for (int c = 0; c < 16; ++c) {
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 w = *reinterpret_cast<const float4*>(sWsm + (c * 8 + j) * 4);
+                        o[j] = valid ? fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], sBias[c * 8 + j])))) : 0.f;
+                    }
+                    st_shared_8bf16((c < 8 ? sK + c * 2048 : sV + (c - 8) * 2048) + row * 16, o);
+                }
+            } else {
+                const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
+                uint4 yv[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+                // the previous tile's projection MMA (the only reader of sY) has completed: proj_done was waited
+#pragma unroll
+                for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sY + c * 2048 + row * 16) = yv[c];
+                fence_async_smem();
+                fence_before_sync();
+                mbar_arrive(y_full);
+                mbar_wait(proj_done, it & 1);
+                fence_after_sync();
+                if (it >= 2) mbar_wait(&kv_empty[stage], ((it >> 1) - 1) & 1);
+#pragma unroll
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_addr(tb, 32 * quad, RC_PROJ + c0), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = valid ? __uint_as_float(v[8 * q + j]) + sBias[c0 + 8 * q + j] : 0.f;
+                        const int chunk = c0 / 8 + q;
+                        st_shared_8bf16((chunk < 8 ? sK + chunk * 2048 : sV + (chunk - 8) * 2048) + row * 16, o);
+                    }
+                }
+            }
+            fence_async_smem();
+            fence_before_sync();
+            mbar_arrive(&kv_full[stage]);
+        }
+    } else if (warp == 8) {
+        // =================================================================== MMA issuer
+        const bool leader = lane == 0;
+        const uint32_t idesc_s = idesc_bf16(128, 128, 0, 0);
+        const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
+        const uint32_t aq = smem_u32(sAq), kvb = smem_u32(sKV), wb = smem_u32(sW), yb = smem_u32(sY);
+        uint32_t ph_p[2] = {0, 0};
+        auto issue_proj = [&]() {
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_ss(tmem_addr(tb, 0, RC_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
+                           idesc_s, ks > 0);
+                mma_commit(proj_done);
+            }
+            __syncwarp();
+        };
+        auto issue_s = [&](int p, uint32_t kbase) {
+            if (leader) {
+                mma_ss(tmem_addr(tb, 0, RC_S + 128 * (p & 1)), smem_desc(aq + p * 4096, 2048, 128),
+                       smem_desc(kbase + 2 * p * 2048, 2048, 128), idesc_s, 0);
+                mma_commit(&s_full[p & 1]);
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int p, uint32_t vbase) {
+            const int g = p & 1;
+            mbar_wait(&p_ready[g], ph_p[g]);
+            ph_p[g] ^= 1;
+            fence_after_sync();
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    mma_ts(tmem_addr(tb, 0, RC_O + 16 * p), tmem_addr(tb, 0, RC_S + 128 * g + ks * 8),
+                           smem_desc(vbase + 2 * p * 2048 + ks * 256, 128, 2048), idesc_pv, ks > 0);
+                mma_commit(&o_full[p]);
+            }
+            __syncwarp();
+        };
+        if (DIN64) {
+            mbar_wait(y_full, 0);
+            fence_after_sync();
+            issue_proj();
+        }
+        for (int it = 0; it < ntiles; ++it) {
+            const int stage = it & 1;
+            const uint32_t kbase = kvb + stage * 32768, vbase = kbase + 16384;
+            mbar_wait(&kv_full[stage], (it >> 1) & 1);
+            fence_after_sync();
+            issue_s(0, kbase);
+            issue_s(1, kbase);
+            if (DIN64 && it + 1 < ntiles) {
+                mbar_wait(y_full, (it + 1) & 1);
+                fence_after_sync();
+                issue_proj();
+            }
+            issue_pv(0, vbase);
+            issue_s(2, kbase);
+            issue_pv(1, vbase);
+            issue_s(3, kbase);
+            issue_pv(2, vbase);
+            issue_pv(3, vbase);
+            if (leader) mma_commit(&kv_empty[stage]);
+            __syncwarp();
+        }
+    } else {
+        // =================================================================== softmax warpgroups
+        const int g = warp >> 2, quad = warp & 3;
+        const int row = 32 * quad + lane;
+        const uint32_t lane_base = 32 * quad;
+        const uint32_t ocol_off = (row >= 64) ? 8u : 0u;      // second head of the pair lives in columns 8..15
+        float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+        float acc[2][8];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+        float alpha[2] = {0.f, 0.f};
+        uint32_t ph_s = 0;
+
+        auto softmax_item = [&](const int pp, const int n_valid) {
+            mbar_wait(&s_full[g], ph_s);
+            ph_s ^= 1;
+            fence_after_sync();
+            const uint32_t sbase = tmem_addr(tb, lane_base, RC_S + 128 * g);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(sbase + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < n_valid) mx = fmaxf(mx, __uint_as_float(v[j]));
+            }
+            const float m_new = fmaxf(m_run[pp], mx);
+            alpha[pp] = ex2(m_run[pp] - m_new);
+            float sum = 0.f;
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t v[32], pk[16];
+                tmem_ld32(sbase + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = (c0 + j < n_valid) ? ex2(__uint_as_float(v[j]) - m_new) : 0.f;
+                    const float p1 = (c0 + j + 1 < n_valid) ? ex2(__uint_as_float(v[j + 1]) - m_new) : 0.f;
+                    sum += p0 + p1;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                }
+                tmem_st16(sbase + (c0 >> 1), pk);      // P (bf16) overwrites score columns already consumed
+            }
+            l_run[pp] = l_run[pp] * alpha[pp] + sum;
+            m_run[pp] = m_new;
+            tmem_st_wait();
+            fence_before_sync();
+            mbar_arrive(&p_ready[g]);
+        };
+        auto consume_item = [&](const int pp, const int it) {
+            const int p = g + 2 * pp;
+            mbar_wait(&o_full[p], it & 1);
+            fence_after_sync();
+            uint32_t o[8];
+            tmem_ld8(tmem_addr(tb, lane_base, RC_O + 16 * p + ocol_off), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[pp][j] = fmaf(acc[pp][j], alpha[pp], __uint_as_float(o[j]));
+        };
+        for (int it = 0; it < ntiles; ++it) {
+            const int n_valid = min(128, P.N - (tile0 + it) * 128);
+            // alpha[1] of the previous tile must be consumed before softmax_item(1) overwrites it
+            softmax_item(0, n_valid);
+            if (it > 0) consume_item(1, it - 1);
+            softmax_item(1, n_valid);
+            consume_item(0, it);
+        }
+        consume_item(1, ntiles - 1);
+        fence_before_sync();
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+            const int h = 2 * (g + 2 * pp) + (row >> 6);
+            float* dst = P.part + ((((size_t)cloud * P.nsplit + split) * TH + h) * TM + (row & 63)) * 10;
+            dst[0] = m_run[pp];
+            dst[1] = l_run[pp];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[2 + j] = acc[pp][j];
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tb, 512);
+}
+
+// ------------------------------------------------------------------------------------ finalize (ISAB)
+// One block per cloud.  part -> O -> H = O + relu(fc_o(O)) -> [Kp | Vp] = H [Wk;Wv]^T + b  ->  block-diagonal
+// bf16 operand images:  Kblk/Vblk [4 pairs][2 chunks][128 rows][16 B], chunk = h % 2, row = (h % 2) * 64 + m.
+struct FParams {
+    const float* part; int nsplit;
+    const float* Qp;              // (64, 64) hoisted fc_q(I)
+    const float* Wo; const float* bo;        // mab0.fc_o
+    const float* Wkv; const float* bkv;      // mab1 [Wk;Wv] (128, 64), (128)
+    uint8_t* KVblk;               // per cloud 32768 B
+    float* H_debug;               // nullable (B, 64, 64)
+};
+
+__global__ void __launch_bounds__(256) finalize_isab_kernel(const FParams P) {
+    extern __shared__ __align__(16) float fs[];
+    float* sO = fs;                    // 64 x 65
+    float* sH = sO + 64 * 65;          // 64 x 65
+    float* sWT = sH + 64 * 65;         // 64 x 128 (k-major transposed weights; fc_o uses the first 64 columns)
+    const int cloud = blockIdx.x, tid = threadIdx.x;
+
+    for (int i = tid; i < 64 * 64; i += 256) { const int f = i / 64, k = i % 64; sWT[k * 128 + f] = P.Wo[i]; }
+    // merge the splits: 512 (h, m) rows, 2 per thread
+    for (int r = tid; r < TH * TM; r += 256) {
+        const int h = r / TM, m = r % TM;
+        float mmax = -INFINITY;
+        for (int s = 0; s < P.nsplit; ++s)
+            mmax = fmaxf(mmax, P.part[((((size_t)cloud * P.nsplit + s) * TH + h) * TM + m) * 10]);
+        float l = 0.f, a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int s = 0; s < P.nsplit; ++s) {
+            const float* pp = P.part + ((((size_t)cloud * P.nsplit + s) * TH + h) * TM + m) * 10;
+            const float w = exp2f(pp[0] - mmax);
+            l = fmaf(pp[1], w, l);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = fmaf(pp[2 + j], w, a[j]);
+        }
+        const float inv = 1.f / l;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sO[m * 65 + h * 8 + j] = P.Qp[m * TD + h * 8 + j] + a[j] * inv;
+    }
+    __syncthreads();
+    {   // H = O + relu(O Wo^T + bo): thread -> column f, rows m = tid/64 + 4 i
+        const int f = tid & 63, m0 = tid >> 6;
+        float a[16];
+        const float b = P.bo[f];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = b;
+        for (int k = 0; k < 64; ++k) {
+            const float w = sWT[k * 128 + f];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = fmaf(sO[(m0 + 4 * i) * 65 + k], w, a[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int m = m0 + 4 * i;
+            const float hv = sO[m * 65 + f] + fmaxf(a[i], 0.f);
+            sH[m * 65 + f] = hv;
+            if (P.H_debug) P.H_debug[((size_t)cloud * TM + m) * TD + f] = hv;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 128 * 64; i += 256) { const int j = i / 64, k = i % 64; sWT[k * 128 + j] = P.Wkv[i]; }
+    __syncthreads();
+    {   // KV = H Wkv^T + bkv: thread -> column j (128), rows m = tid/128 + 2 i
+        const int j = tid & 127, m0 = tid >> 7;
+        float a[32];
+        const float b = P.bkv[j];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] = b;
+        for (int k = 0; k < 64; ++k) {
+            const float w = sWT[k * 128 + j];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = fmaf(sH[(m0 + 2 * i) * 65 + k], w, a[i]);
+        }
+        // scatter into the block-diagonal images (bf16); j < 64 -> K image, else V image
+        uint8_t* img = P.KVblk + (size_t)cloud * 32768 + (j >= 64 ? 16384 : 0);
+        const int f = j & 63, h = f >> 3, d = f & 7;
+        const int pr = h >> 1, c = h & 1;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int m = m0 + 2 * i;
+            *reinterpret_cast<__nv_bfloat16*>(img + pr * 4096 + c * 2048 + (c * 64 + m) * 16 + d * 2) = __float2bfloat16(a[i]);
+            // the off-diagonal block of this chunk is zero
+            *reinterpret_cast<__nv_bfloat16*>(img + pr * 4096 + c * 2048 + ((1 - c) * 64 + m) * 16 + d * 2) = __float2bfloat16(0.f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ apply kernel
+struct AParams {
+    const float* X32;             // (B, N, d_in)           [DIN64 == false]
+    const __nv_bfloat16* Y16in;   // (B, N, 64)             [DIN64 == true]
+    int N, d_in, tiles_total, tiles_per_split;
+    const uint8_t* KVblk;         // per cloud: K image 16384 B | V image 16384 B
+    const float* Wq32;            // (64, d_in)             [DIN64 == false]
+    const float* bq;              // (64)
+    const uint8_t* Wq16;          // 8 KB B operand         [DIN64 == true]
+    const uint8_t* Wo16;          // 8 KB B operand
+    const float* bo;              // (64)
+    __nv_bfloat16* Yout;          // (B, N, 64)
+};
+
+constexpr uint32_t AC_S = 0;        // 2 x 128
+constexpr uint32_t AC_O = 256;      // 64
+constexpr uint32_t AC_F = 320;      // 64
+constexpr uint32_t AC_QP = 384;     // 2 x 64 (DIN64)
+
+struct ASmem {
+    static constexpr int KB = 0;                  // K image 16384
+    static constexpr int VB = 16384;              // V image 16384
+    static constexpr int WO = 32768;              // 8192
+    static constexpr int WQ = WO + 8192;          // 8192
+    static constexpr int AQ = WQ + 8192;          // 2 stages x 16384
+    static constexpr int YA = AQ + 32768;         // 16384
+    static constexpr int O1 = YA + 16384;         // 16384
+    static constexpr int SMALL = O1 + 16384;      // fp32: Wq32 padded (64 x 4) | bq (64) | bo (64)
+    static constexpr int BARS = SMALL + (64 * 4 + 128) * 4;
+    static constexpr int TOTAL = BARS + 24 * 8 + 16;
+};
+
+template <bool DIN64>
+__global__ void __launch_bounds__(TC_THREADS, 1) mab_apply_tc_kernel(const AParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sKb = smem + ASmem::KB;
+    uint8_t* sVb = smem + ASmem::VB;
+    uint8_t* sWo = smem + ASmem::WO;
+    uint8_t* sWq = smem + ASmem::WQ;
+    uint8_t* sAQ = smem + ASmem::AQ;
+    uint8_t* sYA = smem + ASmem::YA;
+    uint8_t* sO1 = smem + ASmem::O1;
+    float* sWq32 = reinterpret_cast<float*>(smem + ASmem::SMALL);
+    float* sBq = sWq32 + 64 * 4;
+    float* sBo = sBq + 64;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ASmem::BARS);
+    uint64_t* aq_full = bars;          // [2] count 128
+    uint64_t* aq_empty = bars + 2;     // [2] count 1
+    uint64_t* s_full = bars + 4;       // [2] count 1
+    uint64_t* p_ready = bars + 6;      // [2] count 128
+    uint64_t* o_full = bars + 8;       // [4] count 1
+    uint64_t* o1_ready = bars + 12;    // count 256
+    uint64_t* f_full = bars + 13;      // count 1
+    uint64_t* ya_full = bars + 14;     // count 128
+    uint64_t* qp_done = bars + 15;     // count 1
+    uint64_t* qp_free = bars + 16;     // [2] count 256
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cloud = blockIdx.y, split = blockIdx.x;
+    const int tile0 = split * P.tiles_per_split;
+    const int ntiles = min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+
+    copy_to_smem(sKb, P.KVblk + (size_t)cloud * 32768, 32768);
+    copy_to_smem(sWo, P.Wo16, 8192);
+    if (DIN64) copy_to_smem(sWq, P.Wq16, 8192);
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+        sBq[i] = P.bq[i];
+        sBo[i] = P.bo[i];
+        if (!DIN64) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sWq32[i * 4 + k] = (k < P.d_in) ? P.Wq32[i * P.d_in + k] : 0.f;
+        }
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&aq_full[i], 128); mbar_init(&aq_empty[i], 1); mbar_init(&s_full[i], 1);
+            mbar_init(&p_ready[i], 128); mbar_init(&qp_free[i], 256);
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(&o_full[i], 1);
+        mbar_init(o1_ready, 256);
+        mbar_init(f_full, 1);
+        mbar_init(ya_full, 128);
+        mbar_init(qp_done, 1);
+        fence_barrier_init();
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp >= 9) {
+        // =================================================================== producer: scaled query operand
+        const int quad = warp & 3;
+        const int row = 32 * quad + lane;
+        for (int it = 0; it < ntiles; ++it) {
+            const int stage = it & 1;
+            const int n = (tile0 + it) * 128 + row;
+            const bool valid = n < P.N;
+            uint8_t* dst = sAQ + stage * 16384;
+            if (!DIN64) {
+                float x[4] = {0.f, 0.f, 0.f, 0.f};
+                if (valid) {
+                    const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                    for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
+                }
+                if (it >= 2) mbar_wait(&aq_empty[stage], ((it >> 1) - 1) & 1);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 w = *reinterpret_cast<const float4*>(sWq32 + (c * 8 + j) * 4);
+                        const float q = fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], sBq[c * 8 + j]))));
+                        o[j] = valid ? q * kScaleLog2e : 0.f;
+                    }
+                    st_shared_8bf16(dst + c * 2048 + row * 16, o);
+                }
+            } else {
+                const uint4* src = reinterpret_cast<const uint4*>(P.Y16in + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
+                uint4 yv[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sYA + c * 2048 + row * 16) = yv[c];
+                fence_async_smem();
+                fence_before_sync();
+                mbar_arrive(ya_full);
+                mbar_wait(qp_done, it & 1);
+                fence_after_sync();
+                if (it >= 2) mbar_wait(&aq_empty[stage], ((it >> 1) - 1) & 1);
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_addr(tb, 32 * quad, AC_QP + 64 * (it & 1) + c0), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            o[j] = valid ? (__uint_as_float(v[8 * q + j]) + sBq[c0 + 8 * q + j]) * kScaleLog2e : 0.f;
+                        st_shared_8bf16(dst + (c0 / 8 + q) * 2048 + row * 16, o);
+                    }
+                }
+            }
+            fence_async_smem();
+            fence_before_sync();
+            mbar_arrive(&aq_full[stage]);
+        }
+    } else if (warp == 8) {
+        // =================================================================== MMA issuer
+        const bool leader = lane == 0;
+        const uint32_t idesc_s = idesc_bf16(128, 128, 0, 0);
+        const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
+        const uint32_t idesc_64 = idesc_bf16(128, 64, 0, 0);
+        const uint32_t kb = smem_u32(sKb), vb = smem_u32(sVb), wo = smem_u32(sWo), wq = smem_u32(sWq);
+        const uint32_t aqb = smem_u32(sAQ), yab = smem_u32(sYA), o1b = smem_u32(sO1);
+        uint32_t ph_p[2] = {0, 0};
+        auto issue_qproj = [&](int t) {
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_ss(tmem_addr(tb, 0, AC_QP + 64 * (t & 1)), smem_desc(yab + ks * 4096, 2048, 128),
+                           smem_desc(wq + ks * 2048, 1024, 128), idesc_64, ks > 0);
+                mma_commit(qp_done);
+            }
+            __syncwarp();
+        };
+        auto issue_s = [&](int p, uint32_t abase) {
+            if (leader) {
+                mma_ss(tmem_addr(tb, 0, AC_S + 128 * (p & 1)), smem_desc(abase + 2 * p * 2048, 2048, 128),
+                       smem_desc(kb + p * 4096, 2048, 128), idesc_s, 0);
+                mma_commit(&s_full[p & 1]);
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int p) {
+            const int g = p & 1;
+            mbar_wait(&p_ready[g], ph_p[g]);
+            ph_p[g] ^= 1;
+            fence_after_sync();
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    mma_ts(tmem_addr(tb, 0, AC_O + 16 * p), tmem_addr(tb, 0, AC_S + 128 * g + ks * 8),
+                           smem_desc(vb + p * 4096 + ks * 256, 128, 2048), idesc_pv, ks > 0);
+                mma_commit(&o_full[p]);
+            }
+            __syncwarp();
+        };
+        if (DIN64) {
+            mbar_wait(ya_full, 0);
+            fence_after_sync();
+            issue_qproj(0);
+        }
+        for (int it = 0; it < ntiles; ++it) {
+            const int stage = it & 1;
+            const uint32_t abase = aqb + stage * 16384;
+            mbar_wait(&aq_full[stage], (it >> 1) & 1);
+            fence_after_sync();
+            issue_s(0, abase);
+            issue_s(1, abase);
+            if (DIN64 && it + 1 < ntiles) {
+                mbar_wait(ya_full, (it + 1) & 1);
+                if (it + 1 >= 2) mbar_wait(&qp_free[(it + 1) & 1], (((it + 1) >> 1) - 1) & 1);
+                fence_after_sync();
+                issue_qproj(it + 1);
+            }
+            issue_pv(0);
+            issue_s(2, abase);
+            issue_pv(1);
+            issue_s(3, abase);
+            issue_pv(2);
+            issue_pv(3);
+            if (leader) mma_commit(&aq_empty[stage]);
+            __syncwarp();
+            mbar_wait(o1_ready, it & 1);
+            fence_after_sync();
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_ss(tmem_addr(tb, 0, AC_F), smem_desc(o1b + ks * 4096, 2048, 128), smem_desc(wo + ks * 2048, 1024, 128),
+                           idesc_64, ks > 0);
+                mma_commit(f_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // =================================================================== softmax + epilogue warpgroups
+        const int g = warp >> 2, quad = warp & 3;
+        const int row = 32 * quad + lane;
+        const uint32_t lane_base = 32 * quad;
+        uint32_t ph_s = 0;
+        for (int it = 0; it < ntiles; ++it) {
+            const int n = (tile0 + it) * 128 + row;
+            const bool valid = n < P.N;
+            float inv_l[2][2];
+            // ---- softmax over the 64 keys of each head, two heads per pair
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+                mbar_wait(&s_full[g], ph_s);
+                ph_s ^= 1;
+                fence_after_sync();
+                const uint32_t sbase = tmem_addr(tb, lane_base, AC_S + 128 * g);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(sbase + 64 * hh, v0);
+                    tmem_ld32(sbase + 64 * hh + 32, v1);
+                    tmem_ld_wait();
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
+                    float sum = 0.f;
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const float p0 = ex2(__uint_as_float(v0[j]) - mx), p1 = ex2(__uint_as_float(v0[j + 1]) - mx);
+                        sum += p0 + p1;
+                        pk[j >> 1] = pack_bf16(p0, p1);
+                    }
+                    tmem_st16(sbase + 32 * hh, pk);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const float p0 = ex2(__uint_as_float(v1[j]) - mx), p1 = ex2(__uint_as_float(v1[j + 1]) - mx);
+                        sum += p0 + p1;
+                        pk[j >> 1] = pack_bf16(p0, p1);
+                    }
+                    tmem_st16(sbase + 32 * hh + 16, pk);
+                    inv_l[pp][hh] = 1.f / sum;
+                }
+                tmem_st_wait();
+                fence_before_sync();
+                mbar_arrive(&p_ready[g]);
+            }
+            // ---- O1 = Qp + (P V) / l, features 16p .. 16p+15 for this warpgroup's two pairs
+            float x[4] = {0.f, 0.f, 0.f, 0.f};
+            if (!DIN64 && valid) {
+                const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
+            }
+            float o1[2][16];
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+                const int p = g + 2 * pp;
+                mbar_wait(&o_full[p], it & 1);
+                fence_after_sync();
+                uint32_t o[16], qv[16];
+                tmem_ld16(tmem_addr(tb, lane_base, AC_O + 16 * p), o);
+                if (DIN64) tmem_ld16(tmem_addr(tb, lane_base, AC_QP + 64 * (it & 1) + 16 * p), qv);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int f = 16 * p + j;
+                    float q;
+                    if (DIN64) {
+                        q = __uint_as_float(qv[j]) + sBq[f];
+                    } else {
+                        const float4 w = *reinterpret_cast<const float4*>(sWq32 + f * 4);
+                        q = fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], sBq[f]))));
+                    }
+                    o1[pp][j] = q + __uint_as_float(o[j]) * inv_l[pp][j >> 3];
+                }
+                st_shared_8bf16(sO1 + (2 * p) * 2048 + row * 16, &o1[pp][0]);
+                st_shared_8bf16(sO1 + (2 * p + 1) * 2048 + row * 16, &o1[pp][8]);
+            }
+            if (DIN64) {
+                fence_before_sync();
+                mbar_arrive(&qp_free[it & 1]);
+            }
+            fence_async_smem();
+            fence_before_sync();
+            mbar_arrive(o1_ready);
+            // ---- Y = O1 + relu(fc_o(O1))
+            mbar_wait(f_full, it & 1);
+            fence_after_sync();
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+                const int p = g + 2 * pp;
+                uint32_t fv[16];
+                tmem_ld16(tmem_addr(tb, lane_base, AC_F + 16 * p), fv);
+                tmem_ld_wait();
+                uint4 out[2];
+                uint32_t* ow = reinterpret_cast<uint32_t*>(out);
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    const float y0 = o1[pp][j] + fmaxf(__uint_as_float(fv[j]) + sBo[16 * p + j], 0.f);
+                    const float y1 = o1[pp][j + 1] + fmaxf(__uint_as_float(fv[j + 1]) + sBo[16 * p + j + 1], 0.f);
+                    ow[j >> 1] = pack_bf16(y0, y1);
+                }
+                if (valid) {
+                    uint4* dst = reinterpret_cast<uint4*>(P.Yout + ((size_t)cloud * P.N + n) * 64 + 16 * p);
+                    dst[0] = out[0];
+                    dst[1] = out[1];
+                }
+            }
+            fence_before_sync();
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tb, 512);
+}
+
+// ------------------------------------------------------------------------------------ finalize (PMA + Linear)
+struct PParams {
+    const float* part; int nsplit;
+    const float* QpS;             // (64)
+    const float* Wo; const float* bo;        // pma.mab.fc_o
+    const float* Wl; const float* bl; int C; // final Linear (C, 64)
+    float* logits;                // (B, C)
+    float* pooled_debug;          // nullable (B, 64)
+};
+
+__global__ void __launch_bounds__(64) finalize_pma_kernel(const PParams P) {
+    __shared__ float sO[64], sO1[64];
+    const int cloud = blockIdx.x, f = threadIdx.x;
+    const int h = f >> 3, d = f & 7;
+    // every row of a head carries the same query (the seed); row 0 of each head is used
+    float mmax = -INFINITY;
+    for (int s = 0; s < P.nsplit; ++s)
+        mmax = fmaxf(mmax, P.part[((((size_t)cloud * P.nsplit + s) * TH + h) * TM) * 10]);
+    float l = 0.f, a = 0.f;
+    for (int s = 0; s < P.nsplit; ++s) {
+        const float* pp = P.part + ((((size_t)cloud * P.nsplit + s) * TH + h) * TM) * 10;
+        const float w = exp2f(pp[0] - mmax);
+        l = fmaf(pp[1], w, l);
+        a = fmaf(pp[2 + d], w, a);
+    }
+    sO[f] = P.QpS[f] + a / l;
+    __syncthreads();
+    float acc = P.bo[f];
+    for (int k = 0; k < 64; ++k) acc = fmaf(sO[k], P.Wo[f * 64 + k], acc);
+    const float o1 = sO[f] + fmaxf(acc, 0.f);
+    sO1[f] = o1;
+    if (P.pooled_debug) P.pooled_debug[(size_t)cloud * 64 + f] = o1;
+    __syncthreads();
+    for (int c = f; c < P.C; c += 64) {
+        float z = P.bl[c];
+        for (int k = 0; k < 64; ++k) z = fmaf(sO1[k], P.Wl[c * 64 + k], z);
+        P.logits[(size_t)cloud * P.C + c] = z;
+    }
+}
+
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __bfloat162float(in[i]);
+}
+
+// ------------------------------------------------------------------------------------ host orchestration
+struct TcSplit { int tiles_total, tiles_per_split, nsplit; };
+static TcSplit plan_split(int B, int N) {
+    TcSplit s;
+    s.tiles_total = (N + 127) / 128;
+    int want = (2 * 148 + B - 1) / B;              // enough CTAs for two waves when the batch is small
+    if (want < 1) want = 1;
+    if (want > s.tiles_total) want = s.tiles_total;
+    s.tiles_per_split = (s.tiles_total + want - 1) / want;
+    s.nsplit = (s.tiles_total + s.tiles_per_split - 1) / s.tiles_per_split;
+    return s;
+}
+
+struct TcLayout { size_t consts, part, kvblk, y1, y2, total; };
+static TcLayout tc_layout(int B, int N) {
+    const TcSplit s = plan_split(B, N);
+    Arena a(nullptr, 0);
+    TcLayout L;
+    L.consts = a.off; a.take<uint8_t>(sizeof(TcConsts));
+    L.part = a.off; a.take<float>((size_t)B * s.nsplit * TH * TM * 10);
+    L.kvblk = a.off; a.take<uint8_t>((size_t)B * 32768);
+    L.y1 = a.off; a.take<__nv_bfloat16>((size_t)B * N * 64);
+    L.y2 = a.off; a.take<__nv_bfloat16>((size_t)B * N * 64);
+    L.total = a.off;
+    return L;
+}
+
+size_t st_tc_workspace_bytes(const pca_st_dims* d, int B, int N) {
+    (void)d;
+    return tc_layout(B, N).total;
+}
+
+int st_tc_supported(const pca_st_dims* d, int N) {
+    return d->D == TD && d->H == TH && d->M == TM && d->S == 1 && d->ln == 0 && d->d_in >= 1 && d->d_in <= 4 && N >= 1;
+}
+
+struct TcDebug { float *H1, *Y1, *H2, *Y2, *pooled; };
+
+static double st_flops_per_point(int d_in) { return 2.0 * (3.0 * d_in * TD + 8.0 * TM * TD + 7.0 * TD * TD + 2.0 * TD); }
+
+static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
+                       uint8_t* ws, const TcConsts* c, const TcDebug* dbg, cudaStream_t st) {
+    const TcLayout L = tc_layout(B, N);
+    const TcSplit sp = plan_split(B, N);
+    float* part = reinterpret_cast<float*>(ws + L.part);
+    uint8_t* kvblk = ws + L.kvblk;
+    __nv_bfloat16* Y1 = reinterpret_cast<__nv_bfloat16*>(ws + L.y1);
+    __nv_bfloat16* Y2 = reinterpret_cast<__nv_bfloat16*>(ws + L.y2);
+    const int d_in = d->d_in;
+    const float* p_isab0 = params;
+    const long long n_isab0 = (long long)TM * TD + mab_count(TD, d_in, TD, 0) + mab_count(d_in, TD, TD, 0);
+    const float* p_isab1 = p_isab0 + n_isab0;
+    const float* p_pma = p_isab1 + (long long)TM * TD + 2 * mab_count(TD, TD, TD, 0);
+    const float* p_lin = p_pma + TD + mab_count(TD, TD, TD, 0);
+    const MabParams m00 = mab_slice(p_isab0 + TM * TD, TD, d_in, TD, 0);
+    const MabParams m01 = mab_slice(p_isab0 + TM * TD + mab_count(TD, d_in, TD, 0), d_in, TD, TD, 0);
+    const MabParams m10 = mab_slice(p_isab1 + TM * TD, TD, TD, TD, 0);
+    const MabParams m11 = mab_slice(p_isab1 + TM * TD + mab_count(TD, TD, TD, 0), TD, TD, TD, 0);
+    const MabParams mp = mab_slice(p_pma + TD, TD, TD, TD, 0);
+
+    const dim3 grid(sp.nsplit, B);
+    const double pts = (double)B * N;
+    const size_t fsmem = (size_t)(2 * 64 * 65 + 64 * 128) * sizeof(float);
+
+    // ---- ISAB 0
+    {
+        RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, c->Aq0, m00.Wkv, m00.bkv, nullptr, part};
+        LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * d_in * TD + 2.0 * TM * TD), pts * 4.0 * d_in);
+        mab_reduce_tc_kernel<false><<<grid, TC_THREADS, RSmem::TOTAL, st>>>(r);
+    }
+    PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<small>");
+    {
+        FParams f{part, sp.nsplit, c->Qp0, m00.Wo, m00.bo, m01.Wkv, m01.bkv, kvblk, dbg ? dbg->H1 : nullptr};
+        LaunchTimer lt("finalize_isab_kernel", st, (double)B * 2.0 * (TM * TD * TD + TM * TD * 2 * TD), (double)B * 32768.0);
+        finalize_isab_kernel<<<B, 256, fsmem, st>>>(f);
+    }
+    PCA_CHECK_LAUNCH("finalize_isab_kernel");
+    {
+        AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, kvblk, m01.Wq, m01.bq, nullptr, c->Wo0, m01.bo, Y1};
+        LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * d_in * TD + 2.0 * TM * TD + TD * TD), pts * (4.0 * d_in + 128.0));
+        mab_apply_tc_kernel<false><<<grid, TC_THREADS, ASmem::TOTAL, st>>>(a);
+    }
+    PCA_CHECK_LAUNCH("mab_apply_tc_kernel<small>");
+    // ---- ISAB 1
+    {
+        RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, c->Aq1, nullptr, m10.bkv, c->Wkv1, part};
+        LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TM * TD), pts * 128.0);
+        mab_reduce_tc_kernel<true><<<grid, TC_THREADS, RSmem::TOTAL, st>>>(r);
+    }
+    PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<64>");
+    {
+        FParams f{part, sp.nsplit, c->Qp1, m10.Wo, m10.bo, m11.Wkv, m11.bkv, kvblk, dbg ? dbg->H2 : nullptr};
+        LaunchTimer lt("finalize_isab_kernel", st, (double)B * 2.0 * (TM * TD * TD + TM * TD * 2 * TD), (double)B * 32768.0);
+        finalize_isab_kernel<<<B, 256, fsmem, st>>>(f);
+    }
+    PCA_CHECK_LAUNCH("finalize_isab_kernel");
+    {
+        AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, kvblk, nullptr, m11.bq, c->Wq1, c->Wo1, m11.bo, Y2};
+        LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * TD * TD + 2.0 * TM * TD + TD * TD), pts * 256.0);
+        mab_apply_tc_kernel<true><<<grid, TC_THREADS, ASmem::TOTAL, st>>>(a);
+    }
+    PCA_CHECK_LAUNCH("mab_apply_tc_kernel<64>");
+    // ---- PMA + Linear
+    {
+        RParams r{nullptr, Y2, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, c->AqP, nullptr, mp.bkv, c->WkvP, part};
+        LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TD), pts * 128.0);
+        mab_reduce_tc_kernel<true><<<grid, TC_THREADS, RSmem::TOTAL, st>>>(r);
+    }
+    PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<pma>");
+    {
+        PParams p{part, sp.nsplit, c->QpS, mp.Wo, mp.bo, p_lin, p_lin + (long long)d->C * TD, d->C, logits, dbg ? dbg->pooled : nullptr};
+        LaunchTimer lt("finalize_pma_kernel", st, (double)B * 2.0 * (TD * TD + TD * d->C), (double)B * 4.0 * d->C);
+        finalize_pma_kernel<<<B, 64, 0, st>>>(p);
+    }
+    PCA_CHECK_LAUNCH("finalize_pma_kernel");
+    if (dbg) {
+        const long long n = (long long)B * N * 64;
+        if (dbg->Y1) { bf16_to_f32_kernel<<<1024, 256, 0, st>>>(Y1, dbg->Y1, n); PCA_CHECK_LAUNCH("bf16_to_f32_kernel"); }
+        if (dbg->Y2) { bf16_to_f32_kernel<<<1024, 256, 0, st>>>(Y2, dbg->Y2, n); PCA_CHECK_LAUNCH("bf16_to_f32_kernel"); }
+    }
+    (void)st_flops_per_point;
+    return 0;
+}
+
+static int tc_configure() {
+    static bool done = false;       // attributes are per-function, idempotent; races are benign
+    if (done) return 0;
+    int dev = 0, major = 0;
+    PCA_CHECK_CUDA(cudaGetDevice(&dev));
+    PCA_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return fail(PCA_EDEVICE, "tcgen05 path needs an sm_100 device (found compute capability %d.x)", major);
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSmem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSmem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASmem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASmem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((2 * 64 * 65 + 64 * 128) * sizeof(float))));
+    done = true;
+    return 0;
+}
+
+int st_tc_forward_dbg(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits, void* ws,
+                      size_t ws_bytes, const TcDebug* dbg, cudaStream_t st) {
+    PCA_TRY(tc_configure());
+    const size_t one = tc_layout(1, N).total;
+    if (!ws || ws_bytes < one) return fail(PCA_EWORKSPACE, "ST(bf16): workspace %zu B < minimum %zu B", ws_bytes, one);
+    int chunk = B;
+    while (chunk > 1 && tc_layout(chunk, N).total > ws_bytes) chunk = (chunk + 1) / 2;
+    if (chunk > 65535) chunk = 65535;
+    if (dbg && chunk < B) return fail(PCA_EWORKSPACE, "ST(bf16) debug: workspace must hold the whole batch");
+    uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+    TcConsts* c = reinterpret_cast<TcConsts*>(w8 + tc_layout(chunk, N).consts);
+    prep_kernel<<<8, 256, 0, st>>>(params, d->d_in, c);
+    PCA_CHECK_LAUNCH("prep_kernel");
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int bc = (B - b0) < chunk ? (B - b0) : chunk;
+        // the layout of a smaller last chunk fits inside the layout of `chunk` (same consts offset 0)
+        PCA_TRY(st_tc_chunk(X + (size_t)b0 * N * d->d_in, bc, N, d, params, logits + (size_t)b0 * d->C, w8, c, dbg, st));
+    }
+    return 0;
+}
+
+int st_tc_forward(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits, void* ws,
+                  size_t ws_bytes, cudaStream_t st) {
+    return st_tc_forward_dbg(X, B, N, d, params, logits, ws, ws_bytes, nullptr, st);
+}
+
+int st_tc_forward_stages(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
+                         float* H1, float* Y1, float* H2, float* Y2, float* pooled, void* ws, size_t ws_bytes,
+                         cudaStream_t st) {
+    TcDebug dbg{H1, Y1, H2, Y2, pooled};
+    return st_tc_forward_dbg(X, B, N, d, params, logits, ws, ws_bytes, &dbg, st);
+}
+
 }  // namespace pca

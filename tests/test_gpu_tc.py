@@ -37,3 +37,53 @@ def test_umma_probe(pca, a_mode, b_mode, N, K):
     torch.cuda.synchronize()
     err = (D.cpu() - ref).abs().max().item()
     assert err < 1e-3 * K ** 0.5, f"a_mode={a_mode} b_mode={b_mode} N={N} K={K}: max abs err {err}"
+
+
+# ------------------------------------------------------------------------------------ bf16 encoder path
+@pytest.mark.parametrize("d_in,B,N", [(2, 3, 300), (3, 2, 128), (2, 5, 1025), (3, 2, 5120), (2, 1, 1), (3, 1, 16384)])
+def test_tc_stages_vs_oracle(pca, d_in, B, N):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import debug_tc_stages
+    errs = debug_tc_stages.run(d_in, B, N)
+    for k, v in errs.items():
+        assert v < BF16_REL_TOL, f"stage {k}: rel err {v:.3e} (all: {errs})"
+
+
+@pytest.mark.parametrize("tag,d_in", [("fst", 2), ("3st", 3)])
+def test_tc_shipped_checkpoints_match_reference(pca, tag, d_in):
+    dev = torch.device("cuda:0")
+    w = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, f"{tag}_weights.npz")).items()}
+    ck = np.load(os.path.join(G, "checkpoint_golden.npz"))
+    st = pca.ST(dim_input=d_in, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev)
+    st.load_state_dict(w)
+    st.set_precision("bf16")
+    with torch.no_grad():
+        out = st(torch.from_numpy(ck[f"{tag}_X"]).to(dev)).cpu().numpy()
+    ref = ck[f"{tag}_out"]
+    assert np.abs(out - ref).max() / np.abs(ref).max() < BF16_REL_TOL
+    assert (out.argmax(1) == ref.argmax(1)).all()
+
+
+def test_tc_pipeline_matches_fp32_pipeline(pca):
+    """Whole path (audio -> logits) at the BASELINE config-2 shape, bf16 encoder vs fp32 encoder."""
+    from oracle import pcaudio_oracle as orc
+    dev = torch.device("cuda:0")
+    w = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, "fst_weights.npz")).items()}
+    st = pca.ST(dim_input=2, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev)
+    st.load_state_dict(w)
+    audio = torch.from_numpy(orc.synth_audio(8, 16000, 16000, seed=202)).to(dev)
+    p32 = pca.AudioSetPipeline(st, pca.AudioConfig(window_size=2048, n_samples=16000, mode=2, precision="fp32"), dev)
+    p16 = pca.AudioSetPipeline(st, pca.AudioConfig(window_size=2048, n_samples=16000, mode=2, precision="bf16"), dev)
+    a, b = p32(audio).cpu().numpy(), p16(audio).cpu().numpy()
+    assert a.shape == b.shape == (128, 10)
+    assert np.abs(a - b).max() / np.abs(a).max() < BF16_REL_TOL
+    halves = torch.cat([p16(audio[:4]), p16(audio[4:])]).cpu().numpy()
+    np.testing.assert_array_equal(halves, b)           # batch sharding is bit-identical
+
+
+def test_tc_unsupported_dims_fail_loudly(pca):
+    dev = torch.device("cuda:0")
+    st = pca.ST(dim_input=2, num_outputs=1, dim_output=10, num_inds=16, dim_hidden=32, num_heads=4).to(dev).set_precision("bf16")
+    with pytest.raises(RuntimeError, match="tcgen05 path needs"):
+        st(torch.zeros(2, 10, 2, device=dev))
