@@ -872,13 +872,13 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 
 // ------------------------------------------------------------------------------------ host orchestration
 struct TcSplit { int tiles_total, tiles_per_split, nsplit; };
+// The point range of a cloud is cut into fixed spans of 16 tiles (2048 points).  The cut depends on N only, never
+// on the batch size, so a cloud's logits are bit-identical however the batch is sharded across calls / GPUs.
 static TcSplit plan_split(int B, int N) {
+    (void)B;
     TcSplit s;
     s.tiles_total = (N + 127) / 128;
-    int want = (2 * 148 + B - 1) / B;              // enough CTAs for two waves when the batch is small
-    if (want < 1) want = 1;
-    if (want > s.tiles_total) want = s.tiles_total;
-    s.tiles_per_split = (s.tiles_total + want - 1) / want;
+    s.tiles_per_split = 16;
     s.nsplit = (s.tiles_total + s.tiles_per_split - 1) / s.tiles_per_split;
     return s;
 }
