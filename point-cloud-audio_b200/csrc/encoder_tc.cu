@@ -23,7 +23,6 @@ using namespace tc;
 
 constexpr int TD = 64, TH = 8, TM = 64;                   // dims this path is specialised for
 constexpr float kScaleLog2e = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(dim_V)
-constexpr int TC_THREADS = 13 * 32;                        // 8 softmax warps, 1 MMA warp, 4 producer warps
 
 struct TcConsts {
     float Qp0[TM * TD];        // isab0.mab0 fc_q(I)
@@ -33,7 +32,18 @@ struct TcConsts {
     uint8_t Aq0[16384], Aq1[16384], AqP[16384];   // stacked-pair query operands [4 pairs][2 chunks][128 rows][16 B]
     uint8_t Wkv1[16384], WkvP[16384];             // [Wk;Wv] as B operand (N=128, K=64): [8 chunks][128 rows][16 B]
     uint8_t Wq1[8192], Wo0[8192], Wo1[8192];      // (N=64, K=64) B operands: [8 chunks][64 rows][16 B]
+    // k-major fp32 copies for finalize_isab: mab0.fc_o^T (64 x 64) and mab1 [Wk;Wv]^T (64 x 128), per ISAB
+    float WoT[2][64 * 64];
+    float WkvT[2][64 * 128];
 };
+
+__device__ void transpose_weight(const float* __restrict__ W, int n_rows, float* __restrict__ out) {
+    // W (n_rows, 64) -> out (64, n_rows)
+    for (int i = threadIdx.x; i < n_rows * 64; i += blockDim.x) {
+        const int n = i / 64, k = i % 64;
+        out[k * n_rows + n] = W[i];
+    }
+}
 
 // ------------------------------------------------------------------------------------ prep
 __device__ void pack_b_operand(const float* __restrict__ W, int n_rows, uint8_t* __restrict__ out) {
@@ -56,14 +66,19 @@ __device__ void prep_queries(const float* __restrict__ Qin, int nq, const float*
         Qp_out[i] = a;
     }
     __syncthreads();
+    if (nq == 1) {
+        // PMA all-heads image (128 x 64, [8 chunks][128 rows][16 B]): row r carries head r / 16 in chunk r / 16
+        for (int i = threadIdx.x; i < 8 * 128 * 8; i += blockDim.x) {
+            const int d = i & 7, r = (i >> 3) & 127, c = i >> 10;
+            const float v = ((r >> 4) == c) ? sq[c * 8 + d] * kScaleLog2e : 0.f;
+            *reinterpret_cast<__nv_bfloat16*>(Aq + c * 2048 + r * 16 + d * 2) = __float2bfloat16(v);
+        }
+        return;
+    }
     // Aq[p][c][r][d]: rows 0-63 carry head 2p in chunk 0, rows 64-127 carry head 2p+1 in chunk 1
     for (int i = threadIdx.x; i < 4 * 2 * 128 * 8; i += blockDim.x) {
         const int d = i & 7, r = (i >> 3) & 127, c = (i >> 10) & 1, p = i >> 11;
-        float v = 0.f;
-        if ((r >> 6) == c) {
-            const int m = (nq == 1) ? 0 : (r & 63);
-            v = sq[m * TD + (2 * p + c) * 8 + d] * kScaleLog2e;
-        }
+        const float v = ((r >> 6) == c) ? sq[(r & 63) * TD + (2 * p + c) * 8 + d] * kScaleLog2e : 0.f;
         *reinterpret_cast<__nv_bfloat16*>(Aq + p * 4096 + c * 2048 + r * 16 + d * 2) = __float2bfloat16(v);
     }
 }
@@ -88,6 +103,10 @@ __global__ void prep_kernel(const float* __restrict__ params, int d_in, TcConsts
         case 5: pack_b_operand(m11.Wq, 64, c->Wq1); break;
         case 6: pack_b_operand(m01.Wo, 64, c->Wo0); break;
         case 7: pack_b_operand(m11.Wo, 64, c->Wo1); break;
+        case 8: transpose_weight(m00.Wo, 64, c->WoT[0]); break;
+        case 9: transpose_weight(m01.Wkv, 128, c->WkvT[0]); break;
+        case 10: transpose_weight(m10.Wo, 64, c->WoT[1]); break;
+        case 11: transpose_weight(m11.Wkv, 128, c->WkvT[1]); break;
         default: break;
     }
 }
@@ -109,7 +128,7 @@ struct RParams {
     const float* X32;             // (B, N, d_in) fp32      [DIN64 == false]
     const __nv_bfloat16* Y16;     // (B, N, 64) bf16        [DIN64 == true]
     int N, d_in, tiles_total, tiles_per_split, nsplit;
-    const uint8_t* Aq;            // 16 KB stacked-pair query operand
+    const uint8_t* Aq;            // 16 KB query operand (stacked pairs, or all-heads image in PMA mode)
     const float* Wkv32;           // (128, d_in) fp32       [DIN64 == false]
     const float* bkv;             // (128)
     const uint8_t* Wkv16;         // 16 KB B operand        [DIN64 == true]
@@ -118,8 +137,8 @@ struct RParams {
 
 // TMEM columns of the reduce kernel
 constexpr uint32_t RC_S = 0;        // 2 score / probability buffers of 128 columns
-constexpr uint32_t RC_O = 256;      // 4 pair outputs of 16 columns
-constexpr uint32_t RC_PROJ = 320;   // 128 columns: K|V projection accumulator (DIN64)
+constexpr uint32_t RC_O = 256;      // pair mode: 4 pair outputs of 16 columns; PMA mode: 2 outputs of 64 columns
+constexpr uint32_t RC_PROJ = 384;   // 128 columns: K|V projection accumulator (DIN64)
 
 struct RSmem {
     static constexpr int AQ = 0;
@@ -131,8 +150,31 @@ struct RSmem {
     static constexpr int TOTAL = BARS + 16 * 8 + 16;
 };
 
-template <bool DIN64>
-__global__ void __launch_bounds__(TC_THREADS, 1) mab_reduce_tc_kernel(const RParams P) {
+// One 32-column chunk of the online softmax: p = 2^(s - m) as bf16 pairs, partial row sum (packed fp32x2 math).
+__device__ __forceinline__ void exp_chunk32(const uint32_t* v, const float2 neg_m2, float2& sum2, uint32_t* pk) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        const float2 x = add2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), neg_m2);
+        const float2 pr = make_float2(ex2(x.x), ex2(x.y));
+        sum2 = add2(sum2, pr);
+        pk[j >> 1] = pack_bf16(pr.x, pr.y);
+    }
+}
+__device__ __forceinline__ float max_chunk32(const uint32_t* v, float mx) {
+    float m0 = mx, m1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        m0 = max3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+        m1 = max3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+    return fmaxf(m0, m1);
+}
+
+// Warp roles (16 warps): 0-7 softmax (two warpgroups), 8-11 producer, 12 MMA issuer, 13-15 idle.
+constexpr int TC_THREADS16 = 16 * 32;
+
+template <bool DIN64, bool PMA>
+__global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce_tc_kernel(const RParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sAq = smem + RSmem::AQ;
     uint8_t* sKV = smem + RSmem::KV;
@@ -165,7 +207,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mab_reduce_tc_kernel(const RPar
             for (int k = 0; k < 4; ++k) sWsm[i * 4 + k] = (k < P.d_in) ? P.Wkv32[i * P.d_in + k] : 0.f;
         }
     }
-    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    if (warp == 12) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 128); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); }
         for (int i = 0; i < 4; ++i) mbar_init(&o_full[i], 1);
@@ -179,7 +221,104 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mab_reduce_tc_kernel(const RPar
     fence_after_sync();
     const uint32_t tb = *tmem_slot;
 
-    if (warp >= 9) {
+    if (warp >= 12) {
+        reg_dec<40>();
+        if (warp == 12) {
+            // =================================================================== MMA issuer
+            const bool leader = lane == 0;
+            const uint32_t idesc_s = idesc_bf16(128, 128, 0, 0);
+            const uint32_t idesc_pv = idesc_bf16(128, PMA ? 64 : 16, 0, 1);
+            const uint32_t aq = smem_u32(sAq), kvb = smem_u32(sKV), wb = smem_u32(sW), yb = smem_u32(sY);
+            uint32_t ph_p[2] = {0, 0};
+            auto issue_proj = [&]() {
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_ss(tmem_addr(tb, 0, RC_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
+                               idesc_s, ks > 0);
+                    mma_commit(proj_done);
+                }
+                __syncwarp();
+            };
+            auto issue_s = [&](int p, uint32_t kbase) {          // pair mode: 2 heads, K = 16
+                if (leader) {
+                    mma_ss(tmem_addr(tb, 0, RC_S + 128 * (p & 1)), smem_desc(aq + p * 4096, 2048, 128),
+                           smem_desc(kbase + 2 * p * 2048, 2048, 128), idesc_s, 0);
+                    mma_commit(&s_full[p & 1]);
+                }
+                __syncwarp();
+            };
+            auto issue_pv = [&](int p, uint32_t vbase) {
+                const int g = p & 1;
+                mbar_wait(&p_ready[g], ph_p[g]);
+                ph_p[g] ^= 1;
+                fence_after_sync();
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_ts(tmem_addr(tb, 0, RC_O + 16 * p), tmem_addr(tb, 0, RC_S + 128 * g + ks * 8),
+                               smem_desc(vbase + 2 * p * 2048 + ks * 256, 128, 2048), idesc_pv, ks > 0);
+                    mma_commit(&o_full[p]);
+                }
+                __syncwarp();
+            };
+            if (DIN64) {
+                mbar_wait(y_full, 0);
+                fence_after_sync();
+                issue_proj();
+            }
+            for (int it = 0; it < ntiles; ++it) {
+                const int stage = it & 1;
+                const uint32_t kbase = kvb + stage * 32768, vbase = kbase + 16384;
+                mbar_wait(&kv_full[stage], (it >> 1) & 1);
+                fence_after_sync();
+                if (!PMA) {
+                    issue_s(0, kbase);
+                    issue_s(1, kbase);
+                } else {
+                    // all 8 heads in one accumulate chain: A = all-heads query image (128 x 64), B = K tile
+                    const int g = it & 1;
+                    if (leader) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ss(tmem_addr(tb, 0, RC_S + 128 * g), smem_desc(aq + ks * 4096, 2048, 128),
+                                   smem_desc(kbase + ks * 4096, 2048, 128), idesc_s, ks > 0);
+                        mma_commit(&s_full[g]);
+                    }
+                    __syncwarp();
+                }
+                if (DIN64 && it + 1 < ntiles) {
+                    mbar_wait(y_full, (it + 1) & 1);
+                    fence_after_sync();
+                    issue_proj();
+                }
+                if (!PMA) {
+                    issue_pv(0, vbase);
+                    issue_s(2, kbase);
+                    issue_pv(1, vbase);
+                    issue_s(3, kbase);
+                    issue_pv(2, vbase);
+                    issue_pv(3, vbase);
+                } else {
+                    const int g = it & 1;
+                    mbar_wait(&p_ready[g], ph_p[g]);
+                    ph_p[g] ^= 1;
+                    fence_after_sync();
+                    if (leader) {
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_ts(tmem_addr(tb, 0, RC_O + 64 * g), tmem_addr(tb, 0, RC_S + 128 * g + ks * 8),
+                                   smem_desc(vbase + ks * 256, 128, 2048), idesc_pv, ks > 0);
+                        mma_commit(&o_full[g]);
+                    }
+                    __syncwarp();
+                }
+                if (leader) mma_commit(&kv_empty[stage]);
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 8) {
+        reg_dec<88>();
         // =================================================================== producer: K|V tiles
         const int quad = warp & 3;
         const int row = 32 * quad + lane;
@@ -224,7 +363,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mab_reduce_tc_kernel(const RPar
                 for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(tmem_addr(tb, 32 * quad, RC_PROJ + c0), v);
-                    tmem_ld_wait();
+                    tmem_ld_wait32(v);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         float o[8];
@@ -239,77 +378,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mab_reduce_tc_kernel(const RPar
             fence_before_sync();
             mbar_arrive(&kv_full[stage]);
         }
-    } else if (warp == 8) {
-        // =================================================================== MMA issuer
-        const bool leader = lane == 0;
-        const uint32_t idesc_s = idesc_bf16(128, 128, 0, 0);
-        const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
-        const uint32_t aq = smem_u32(sAq), kvb = smem_u32(sKV), wb = smem_u32(sW), yb = smem_u32(sY);
-        uint32_t ph_p[2] = {0, 0};
-        auto issue_proj = [&]() {
-            if (leader) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma_ss(tmem_addr(tb, 0, RC_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
-                           idesc_s, ks > 0);
-                mma_commit(proj_done);
-            }
-            __syncwarp();
-        };
-        auto issue_s = [&](int p, uint32_t kbase) {
-            if (leader) {
-                mma_ss(tmem_addr(tb, 0, RC_S + 128 * (p & 1)), smem_desc(aq + p * 4096, 2048, 128),
-                       smem_desc(kbase + 2 * p * 2048, 2048, 128), idesc_s, 0);
-                mma_commit(&s_full[p & 1]);
-            }
-            __syncwarp();
-        };
-        auto issue_pv = [&](int p, uint32_t vbase) {
-            const int g = p & 1;
-            mbar_wait(&p_ready[g], ph_p[g]);
-            ph_p[g] ^= 1;
-            fence_after_sync();
-            if (leader) {
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    mma_ts(tmem_addr(tb, 0, RC_O + 16 * p), tmem_addr(tb, 0, RC_S + 128 * g + ks * 8),
-                           smem_desc(vbase + 2 * p * 2048 + ks * 256, 128, 2048), idesc_pv, ks > 0);
-                mma_commit(&o_full[p]);
-            }
-            __syncwarp();
-        };
-        if (DIN64) {
-            mbar_wait(y_full, 0);
-            fence_after_sync();
-            issue_proj();
-        }
-        for (int it = 0; it < ntiles; ++it) {
-            const int stage = it & 1;
-            const uint32_t kbase = kvb + stage * 32768, vbase = kbase + 16384;
-            mbar_wait(&kv_full[stage], (it >> 1) & 1);
-            fence_after_sync();
-            issue_s(0, kbase);
-            issue_s(1, kbase);
-            if (DIN64 && it + 1 < ntiles) {
-                mbar_wait(y_full, (it + 1) & 1);
-                fence_after_sync();
-                issue_proj();
-            }
-            issue_pv(0, vbase);
-            issue_s(2, kbase);
-            issue_pv(1, vbase);
-            issue_s(3, kbase);
-            issue_pv(2, vbase);
-            issue_pv(3, vbase);
-            if (leader) mma_commit(&kv_empty[stage]);
-            __syncwarp();
-        }
     } else {
+        reg_inc<184>();
         // =================================================================== softmax warpgroups
         const int g = warp >> 2, quad = warp & 3;
         const int row = 32 * quad + lane;
         const uint32_t lane_base = 32 * quad;
-        const uint32_t ocol_off = (row >= 64) ? 8u : 0u;      // second head of the pair lives in columns 8..15
         float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
         float acc[2][8];
 #pragma unroll
@@ -318,78 +392,152 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mab_reduce_tc_kernel(const RPar
             for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
         float alpha[2] = {0.f, 0.f};
         uint32_t ph_s = 0;
+        const uint32_t sbase = tmem_addr(tb, lane_base, RC_S + 128 * g);
 
         auto softmax_item = [&](const int pp, const int n_valid) {
             mbar_wait(&s_full[g], ph_s);
             ph_s ^= 1;
             fence_after_sync();
-            const uint32_t sbase = tmem_addr(tb, lane_base, RC_S + 128 * g);
-            float mx = -INFINITY;
+            uint32_t va[32], vb[32];
+            if (n_valid == 128) {
+                // ---- pass 1: row max, TMEM loads software-pipelined against the max chain
+                tmem_ld32(sbase, va);
+                tmem_ld_wait32(va);
+                tmem_ld32(sbase + 32, vb);
+                float mx = max_chunk32(va, -INFINITY);
+                tmem_ld_wait32(vb);
+                tmem_ld32(sbase + 64, va);
+                mx = max_chunk32(vb, mx);
+                tmem_ld_wait32(va);
+                tmem_ld32(sbase + 96, vb);
+                mx = max_chunk32(va, mx);
+                tmem_ld_wait32(vb);
+                tmem_ld32(sbase, va);                       // first chunk of pass 2 already in flight
+                mx = max_chunk32(vb, mx);
+                const float m_new = fmaxf(m_run[pp], mx);
+                alpha[pp] = ex2(m_run[pp] - m_new);
+                const float2 neg_m2 = make_float2(-m_new, -m_new);
+                float2 sum2 = make_float2(0.f, 0.f);
+                uint32_t pk[16];
+                // ---- pass 2: probabilities; P (bf16) overwrites score columns that were already consumed
+                tmem_ld_wait32(va);
+                tmem_ld32(sbase + 32, vb);
+                exp_chunk32(va, neg_m2, sum2, pk);
+                tmem_st16(sbase, pk);
+                tmem_ld_wait32(vb);
+                tmem_ld32(sbase + 64, va);
+                exp_chunk32(vb, neg_m2, sum2, pk);
+                tmem_st16(sbase + 16, pk);
+                tmem_ld_wait32(va);
+                tmem_ld32(sbase + 96, vb);
+                exp_chunk32(va, neg_m2, sum2, pk);
+                tmem_st16(sbase + 32, pk);
+                tmem_ld_wait32(vb);
+                exp_chunk32(vb, neg_m2, sum2, pk);
+                tmem_st16(sbase + 48, pk);
+                l_run[pp] = l_run[pp] * alpha[pp] + (sum2.x + sum2.y);
+                m_run[pp] = m_new;
+            } else {
+                // ---- ragged last tile: only columns < n_valid take part; the rest of P is zero
+                float mx = -INFINITY;
+                for (int c0 = 0; c0 < n_valid; c0 += 32) {
+                    tmem_ld32(sbase + c0, va);
+                    tmem_ld_wait32(va);
 #pragma unroll
-            for (int c0 = 0; c0 < 128; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(sbase + c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c0 + j < n_valid) mx = fmaxf(mx, __uint_as_float(v[j]));
-            }
-            const float m_new = fmaxf(m_run[pp], mx);
-            alpha[pp] = ex2(m_run[pp] - m_new);
-            float sum = 0.f;
-#pragma unroll
-            for (int c0 = 0; c0 < 128; c0 += 32) {
-                uint32_t v[32], pk[16];
-                tmem_ld32(sbase + c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float p0 = (c0 + j < n_valid) ? ex2(__uint_as_float(v[j]) - m_new) : 0.f;
-                    const float p1 = (c0 + j + 1 < n_valid) ? ex2(__uint_as_float(v[j + 1]) - m_new) : 0.f;
-                    sum += p0 + p1;
-                    pk[j >> 1] = pack_bf16(p0, p1);
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < n_valid) mx = fmaxf(mx, __uint_as_float(va[j]));
                 }
-                tmem_st16(sbase + (c0 >> 1), pk);      // P (bf16) overwrites score columns already consumed
+                const float m_new = fmaxf(m_run[pp], mx);
+                alpha[pp] = ex2(m_run[pp] - m_new);
+                float sum = 0.f;
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t pk[16];
+                    if (c0 < n_valid) {
+                        tmem_ld32(sbase + c0, va);
+                        tmem_ld_wait32(va);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float p0 = (c0 + j < n_valid) ? ex2(__uint_as_float(va[j]) - m_new) : 0.f;
+                            const float p1 = (c0 + j + 1 < n_valid) ? ex2(__uint_as_float(va[j + 1]) - m_new) : 0.f;
+                            sum += p0 + p1;
+                            pk[j >> 1] = pack_bf16(p0, p1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[j] = 0u;
+                    }
+                    tmem_st16(sbase + (c0 >> 1), pk);
+                }
+                l_run[pp] = l_run[pp] * alpha[pp] + sum;
+                m_run[pp] = m_new;
             }
-            l_run[pp] = l_run[pp] * alpha[pp] + sum;
-            m_run[pp] = m_new;
             tmem_st_wait();
             fence_before_sync();
             mbar_arrive(&p_ready[g]);
         };
-        auto consume_item = [&](const int pp, const int it) {
-            const int p = g + 2 * pp;
-            mbar_wait(&o_full[p], it & 1);
-            fence_after_sync();
-            uint32_t o[8];
-            tmem_ld8(tmem_addr(tb, lane_base, RC_O + 16 * p + ocol_off), o);
-            tmem_ld_wait();
+        if (!PMA) {
+            const uint32_t ocol_off = (row >= 64) ? 8u : 0u;      // second head of the pair lives in columns 8..15
+            auto consume_item = [&](const int pp, const int it) {
+                const int p = g + 2 * pp;
+                mbar_wait(&o_full[p], it & 1);
+                fence_after_sync();
+                uint32_t o[8];
+                tmem_ld8(tmem_addr(tb, lane_base, RC_O + 16 * p + ocol_off), o);
+                tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[pp][j] = fmaf(acc[pp][j], alpha[pp], __uint_as_float(o[j]));
-        };
-        for (int it = 0; it < ntiles; ++it) {
-            const int n_valid = min(128, P.N - (tile0 + it) * 128);
-            // alpha[1] of the previous tile must be consumed before softmax_item(1) overwrites it
-            softmax_item(0, n_valid);
-            if (it > 0) consume_item(1, it - 1);
-            softmax_item(1, n_valid);
-            consume_item(0, it);
-        }
-        consume_item(1, ntiles - 1);
-        fence_before_sync();
+                for (int j = 0; j < 8; ++j) acc[pp][j] = fmaf(acc[pp][j], alpha[pp], __uint_as_float(o[j]));
+            };
+            for (int it = 0; it < ntiles; ++it) {
+                const int n_valid = min(128, P.N - (tile0 + it) * 128);
+                softmax_item(0, n_valid);
+                if (it > 0) consume_item(1, it - 1);
+                softmax_item(1, n_valid);
+                consume_item(0, it);
+            }
+            consume_item(1, ntiles - 1);
 #pragma unroll
-        for (int pp = 0; pp < 2; ++pp) {
-            const int h = 2 * (g + 2 * pp) + (row >> 6);
-            float* dst = P.part + ((((size_t)cloud * P.nsplit + split) * TH + h) * TM + (row & 63)) * 10;
-            dst[0] = m_run[pp];
-            dst[1] = l_run[pp];
+            for (int pp = 0; pp < 2; ++pp) {
+                const int h = 2 * (g + 2 * pp) + (row >> 6);
+                float* dst = P.part + ((((size_t)cloud * P.nsplit + split) * TH + h) * TM + (row & 63)) * 10;
+                dst[0] = m_run[pp];
+                dst[1] = l_run[pp];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[2 + j] = acc[pp][j];
+                for (int j = 0; j < 8; ++j) dst[2 + j] = acc[pp][j];
+            }
+        } else {
+            // PMA: rows are (head = row / 16, 16 redundant copies); warpgroup g owns the tiles with it % 2 == g
+            const bool hi = (lane >> 4) != 0;
+            auto consume_pma = [&](const int it) {
+                mbar_wait(&o_full[g], (it >> 1) & 1);
+                fence_after_sync();
+                uint32_t o[16];
+                tmem_ld16(tmem_addr(tb, lane_base, RC_O + 64 * g + 16 * quad), o);
+                tmem_ld_wait16(o);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    acc[0][j] = fmaf(acc[0][j], alpha[0], __uint_as_float(hi ? o[8 + j] : o[j]));
+            };
+            int last = -1;
+            for (int it = g; it < ntiles; it += 2) {
+                const int n_valid = min(128, P.N - (tile0 + it) * 128);
+                softmax_item(0, n_valid);
+                consume_pma(it);
+                last = it;
+            }
+            (void)last;
+            if ((row & 15) == 0) {
+                const int h = row >> 4;
+                float* dst = P.part + ((((size_t)cloud * P.nsplit + split) * TH + h) * TM + g) * 10;
+                dst[0] = m_run[0];
+                dst[1] = l_run[0];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[2 + j] = acc[0][j];
+            }
         }
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tb, 512);
+    if (warp == 12) tmem_dealloc(tb, 512);
 }
 
 // ------------------------------------------------------------------------------------ finalize (ISAB)
@@ -398,20 +546,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mab_reduce_tc_kernel(const RPar
 struct FParams {
     const float* part; int nsplit;
     const float* Qp;              // (64, 64) hoisted fc_q(I)
-    const float* Wo; const float* bo;        // mab0.fc_o
-    const float* Wkv; const float* bkv;      // mab1 [Wk;Wv] (128, 64), (128)
+    const float* WoT; const float* bo;       // mab0.fc_o transposed (k, f), bias
+    const float* WkvT; const float* bkv;     // mab1 [Wk;Wv] transposed (k, 128), bias (128)
     uint8_t* KVblk;               // per cloud 32768 B
     float* H_debug;               // nullable (B, 64, 64)
 };
 
+constexpr int FT_LD = 68;        // padded leading dimension of the transposed O / H tiles
+constexpr size_t FT_SMEM = (size_t)(2 * 64 * FT_LD + 64 * 128) * sizeof(float);
+
 __global__ void __launch_bounds__(256) finalize_isab_kernel(const FParams P) {
     extern __shared__ __align__(16) float fs[];
-    float* sO = fs;                    // 64 x 65
-    float* sH = sO + 64 * 65;          // 64 x 65
-    float* sWT = sH + 64 * 65;         // 64 x 128 (k-major transposed weights; fc_o uses the first 64 columns)
+    float* sOT = fs;                       // O^T  [k][m]
+    float* sHT = sOT + 64 * FT_LD;         // H^T  [k][m]
+    float* sWT = sHT + 64 * FT_LD;         // weights, k-major [k][128]
     const int cloud = blockIdx.x, tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
 
-    for (int i = tid; i < 64 * 64; i += 256) { const int f = i / 64, k = i % 64; sWT[k * 128 + f] = P.Wo[i]; }
+    for (int i = tid; i < 64 * 16; i += 256) {       // fc_o^T: 64 x 64 floats as float4
+        const int k = i >> 4, f4 = i & 15;
+        *reinterpret_cast<float4*>(sWT + k * 128 + f4 * 4) = __ldg(reinterpret_cast<const float4*>(P.WoT + k * 64) + f4);
+    }
     // merge the splits: 512 (h, m) rows, 2 per thread
     for (int r = tid; r < TH * TM; r += 256) {
         const int h = r / TM, m = r % TM;
@@ -428,52 +583,74 @@ __global__ void __launch_bounds__(256) finalize_isab_kernel(const FParams P) {
         }
         const float inv = 1.f / l;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sO[m * 65 + h * 8 + j] = P.Qp[m * TD + h * 8 + j] + a[j] * inv;
+        for (int j = 0; j < 8; ++j) sOT[(h * 8 + j) * FT_LD + m] = P.Qp[m * TD + h * 8 + j] + a[j] * inv;
     }
     __syncthreads();
-    {   // H = O + relu(O Wo^T + bo): thread -> column f, rows m = tid/64 + 4 i
-        const int f = tid & 63, m0 = tid >> 6;
-        float a[16];
-        const float b = P.bo[f];
+    {   // H = O + relu(O Wo^T + bo): 4 x 4 register tile per thread (rows 4ty.., columns 4tx..)
+        float acc[4][4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = b;
+        for (int j = 0; j < 4; ++j) {
+            const float b = P.bo[4 * tx + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][j] = b;
+        }
+#pragma unroll 8
         for (int k = 0; k < 64; ++k) {
-            const float w = sWT[k * 128 + f];
+            const float4 a = *reinterpret_cast<const float4*>(sOT + k * FT_LD + 4 * ty);
+            const float4 w = *reinterpret_cast<const float4*>(sWT + k * 128 + 4 * tx);
+            const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-            for (int i = 0; i < 16; ++i) a[i] = fmaf(sO[(m0 + 4 * i) * 65 + k], w, a[i]);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int m = m0 + 4 * i;
-            const float hv = sO[m * 65 + f] + fmaxf(a[i], 0.f);
-            sH[m * 65 + f] = hv;
-            if (P.H_debug) P.H_debug[((size_t)cloud * TM + m) * TD + f] = hv;
-        }
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = 4 * ty + i, f = 4 * tx + j;
+                const float hv = sOT[f * FT_LD + m] + fmaxf(acc[i][j], 0.f);
+                sHT[f * FT_LD + m] = hv;
+                if (P.H_debug) P.H_debug[((size_t)cloud * TM + m) * TD + f] = hv;
+            }
     }
     __syncthreads();
-    for (int i = tid; i < 128 * 64; i += 256) { const int j = i / 64, k = i % 64; sWT[k * 128 + j] = P.Wkv[i]; }
+    for (int i = tid; i < 64 * 32; i += 256) {       // [Wk;Wv]^T: 64 x 128 floats as float4
+        const int k = i >> 5, j4 = i & 31;
+        *reinterpret_cast<float4*>(sWT + k * 128 + j4 * 4) = __ldg(reinterpret_cast<const float4*>(P.WkvT + k * 128) + j4);
+    }
     __syncthreads();
-    {   // KV = H Wkv^T + bkv: thread -> column j (128), rows m = tid/128 + 2 i
-        const int j = tid & 127, m0 = tid >> 7;
-        float a[32];
-        const float b = P.bkv[j];
+    {   // [Kp | Vp] = H Wkv^T + b: 4 x 8 register tile (rows 4ty.., columns 8tx.. = one head chunk)
+        float acc[4][8];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) a[i] = b;
-        for (int k = 0; k < 64; ++k) {
-            const float w = sWT[k * 128 + j];
+        for (int j = 0; j < 8; ++j) {
+            const float b = P.bkv[8 * tx + j];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) a[i] = fmaf(sH[(m0 + 2 * i) * 65 + k], w, a[i]);
+            for (int i = 0; i < 4; ++i) acc[i][j] = b;
         }
-        // scatter into the block-diagonal images (bf16); j < 64 -> K image, else V image
-        uint8_t* img = P.KVblk + (size_t)cloud * 32768 + (j >= 64 ? 16384 : 0);
-        const int f = j & 63, h = f >> 3, d = f & 7;
-        const int pr = h >> 1, c = h & 1;
+#pragma unroll 4
+        for (int k = 0; k < 64; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(sHT + k * FT_LD + 4 * ty);
+            const float4 w0 = *reinterpret_cast<const float4*>(sWT + k * 128 + 8 * tx);
+            const float4 w1 = *reinterpret_cast<const float4*>(sWT + k * 128 + 8 * tx + 4);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int m = m0 + 2 * i;
-            *reinterpret_cast<__nv_bfloat16*>(img + pr * 4096 + c * 2048 + (c * 64 + m) * 16 + d * 2) = __float2bfloat16(a[i]);
-            // the off-diagonal block of this chunk is zero
-            *reinterpret_cast<__nv_bfloat16*>(img + pr * 4096 + c * 2048 + ((1 - c) * 64 + m) * 16 + d * 2) = __float2bfloat16(0.f);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        }
+        // block-diagonal operand images: chunk c = h % 2 holds head h in rows c*64 + m and zeros in the other half
+        uint8_t* img = P.KVblk + (size_t)cloud * 32768 + (tx >= 8 ? 16384 : 0);
+        const int h = tx & 7, pr = h >> 1, c = h & 1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = 4 * ty + i;
+            uint4 u;
+            u.x = pack_bf16(acc[i][0], acc[i][1]); u.y = pack_bf16(acc[i][2], acc[i][3]);
+            u.z = pack_bf16(acc[i][4], acc[i][5]); u.w = pack_bf16(acc[i][6], acc[i][7]);
+            *reinterpret_cast<uint4*>(img + pr * 4096 + c * 2048 + (c * 64 + m) * 16) = u;
+            *reinterpret_cast<uint4*>(img + pr * 4096 + c * 2048 + ((1 - c) * 64 + m) * 16) = make_uint4(0, 0, 0, 0);
         }
     }
 }
@@ -511,7 +688,7 @@ struct ASmem {
 };
 
 template <bool DIN64>
-__global__ void __launch_bounds__(TC_THREADS, 1) mab_apply_tc_kernel(const AParams P) {
+__global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply_tc_kernel(const AParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sKb = smem + ASmem::KB;
     uint8_t* sVb = smem + ASmem::VB;
@@ -552,7 +729,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mab_apply_tc_kernel(const APara
             for (int k = 0; k < 4; ++k) sWq32[i * 4 + k] = (k < P.d_in) ? P.Wq32[i * P.d_in + k] : 0.f;
         }
     }
-    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    if (warp == 12) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&aq_full[i], 128); mbar_init(&aq_empty[i], 1); mbar_init(&s_full[i], 1);
@@ -571,7 +748,89 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mab_apply_tc_kernel(const APara
     fence_after_sync();
     const uint32_t tb = *tmem_slot;
 
-    if (warp >= 9) {
+    if (warp >= 12) {
+        reg_dec<40>();
+        if (warp == 12) {
+            // =================================================================== MMA issuer
+            const bool leader = lane == 0;
+            const uint32_t idesc_s = idesc_bf16(128, 128, 0, 0);
+            const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
+            const uint32_t idesc_64 = idesc_bf16(128, 64, 0, 0);
+            const uint32_t kb = smem_u32(sKb), vb = smem_u32(sVb), wo = smem_u32(sWo), wq = smem_u32(sWq);
+            const uint32_t aqb = smem_u32(sAQ), yab = smem_u32(sYA), o1b = smem_u32(sO1);
+            uint32_t ph_p[2] = {0, 0};
+            auto issue_qproj = [&](int t) {
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_ss(tmem_addr(tb, 0, AC_QP + 64 * (t & 1)), smem_desc(yab + ks * 4096, 2048, 128),
+                               smem_desc(wq + ks * 2048, 1024, 128), idesc_64, ks > 0);
+                    mma_commit(qp_done);
+                }
+                __syncwarp();
+            };
+            auto issue_s = [&](int p, uint32_t abase) {
+                if (leader) {
+                    mma_ss(tmem_addr(tb, 0, AC_S + 128 * (p & 1)), smem_desc(abase + 2 * p * 2048, 2048, 128),
+                           smem_desc(kb + p * 4096, 2048, 128), idesc_s, 0);
+                    mma_commit(&s_full[p & 1]);
+                }
+                __syncwarp();
+            };
+            auto issue_pv = [&](int p) {
+                const int g = p & 1;
+                mbar_wait(&p_ready[g], ph_p[g]);
+                ph_p[g] ^= 1;
+                fence_after_sync();
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_ts(tmem_addr(tb, 0, AC_O + 16 * p), tmem_addr(tb, 0, AC_S + 128 * g + ks * 8),
+                               smem_desc(vb + p * 4096 + ks * 256, 128, 2048), idesc_pv, ks > 0);
+                    mma_commit(&o_full[p]);
+                }
+                __syncwarp();
+            };
+            if (DIN64) {
+                mbar_wait(ya_full, 0);
+                fence_after_sync();
+                issue_qproj(0);
+            }
+            for (int it = 0; it < ntiles; ++it) {
+                const int stage = it & 1;
+                const uint32_t abase = aqb + stage * 16384;
+                mbar_wait(&aq_full[stage], (it >> 1) & 1);
+                fence_after_sync();
+                issue_s(0, abase);
+                issue_s(1, abase);
+                if (DIN64 && it + 1 < ntiles) {
+                    mbar_wait(ya_full, (it + 1) & 1);
+                    if (it + 1 >= 2) mbar_wait(&qp_free[(it + 1) & 1], (((it + 1) >> 1) - 1) & 1);
+                    fence_after_sync();
+                    issue_qproj(it + 1);
+                }
+                issue_pv(0);
+                issue_s(2, abase);
+                issue_pv(1);
+                issue_s(3, abase);
+                issue_pv(2);
+                issue_pv(3);
+                if (leader) mma_commit(&aq_empty[stage]);
+                __syncwarp();
+                mbar_wait(o1_ready, it & 1);
+                fence_after_sync();
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_ss(tmem_addr(tb, 0, AC_F), smem_desc(o1b + ks * 4096, 2048, 128), smem_desc(wo + ks * 2048, 1024, 128),
+                               idesc_64, ks > 0);
+                    mma_commit(f_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 8) {
+        reg_dec<88>();
         // =================================================================== producer: scaled query operand
         const int quad = warp & 3;
         const int row = 32 * quad + lane;
@@ -615,7 +874,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mab_apply_tc_kernel(const APara
                 for (int c0 = 0; c0 < 64; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(tmem_addr(tb, 32 * quad, AC_QP + 64 * (it & 1) + c0), v);
-                    tmem_ld_wait();
+                    tmem_ld_wait32(v);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         float o[8];
@@ -630,129 +889,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mab_apply_tc_kernel(const APara
             fence_before_sync();
             mbar_arrive(&aq_full[stage]);
         }
-    } else if (warp == 8) {
-        // =================================================================== MMA issuer
-        const bool leader = lane == 0;
-        const uint32_t idesc_s = idesc_bf16(128, 128, 0, 0);
-        const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
-        const uint32_t idesc_64 = idesc_bf16(128, 64, 0, 0);
-        const uint32_t kb = smem_u32(sKb), vb = smem_u32(sVb), wo = smem_u32(sWo), wq = smem_u32(sWq);
-        const uint32_t aqb = smem_u32(sAQ), yab = smem_u32(sYA), o1b = smem_u32(sO1);
-        uint32_t ph_p[2] = {0, 0};
-        auto issue_qproj = [&](int t) {
-            if (leader) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma_ss(tmem_addr(tb, 0, AC_QP + 64 * (t & 1)), smem_desc(yab + ks * 4096, 2048, 128),
-                           smem_desc(wq + ks * 2048, 1024, 128), idesc_64, ks > 0);
-                mma_commit(qp_done);
-            }
-            __syncwarp();
-        };
-        auto issue_s = [&](int p, uint32_t abase) {
-            if (leader) {
-                mma_ss(tmem_addr(tb, 0, AC_S + 128 * (p & 1)), smem_desc(abase + 2 * p * 2048, 2048, 128),
-                       smem_desc(kb + p * 4096, 2048, 128), idesc_s, 0);
-                mma_commit(&s_full[p & 1]);
-            }
-            __syncwarp();
-        };
-        auto issue_pv = [&](int p) {
-            const int g = p & 1;
-            mbar_wait(&p_ready[g], ph_p[g]);
-            ph_p[g] ^= 1;
-            fence_after_sync();
-            if (leader) {
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    mma_ts(tmem_addr(tb, 0, AC_O + 16 * p), tmem_addr(tb, 0, AC_S + 128 * g + ks * 8),
-                           smem_desc(vb + p * 4096 + ks * 256, 128, 2048), idesc_pv, ks > 0);
-                mma_commit(&o_full[p]);
-            }
-            __syncwarp();
-        };
-        if (DIN64) {
-            mbar_wait(ya_full, 0);
-            fence_after_sync();
-            issue_qproj(0);
-        }
-        for (int it = 0; it < ntiles; ++it) {
-            const int stage = it & 1;
-            const uint32_t abase = aqb + stage * 16384;
-            mbar_wait(&aq_full[stage], (it >> 1) & 1);
-            fence_after_sync();
-            issue_s(0, abase);
-            issue_s(1, abase);
-            if (DIN64 && it + 1 < ntiles) {
-                mbar_wait(ya_full, (it + 1) & 1);
-                if (it + 1 >= 2) mbar_wait(&qp_free[(it + 1) & 1], (((it + 1) >> 1) - 1) & 1);
-                fence_after_sync();
-                issue_qproj(it + 1);
-            }
-            issue_pv(0);
-            issue_s(2, abase);
-            issue_pv(1);
-            issue_s(3, abase);
-            issue_pv(2);
-            issue_pv(3);
-            if (leader) mma_commit(&aq_empty[stage]);
-            __syncwarp();
-            mbar_wait(o1_ready, it & 1);
-            fence_after_sync();
-            if (leader) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma_ss(tmem_addr(tb, 0, AC_F), smem_desc(o1b + ks * 4096, 2048, 128), smem_desc(wo + ks * 2048, 1024, 128),
-                           idesc_64, ks > 0);
-                mma_commit(f_full);
-            }
-            __syncwarp();
-        }
     } else {
+        reg_inc<184>();
         // =================================================================== softmax + epilogue warpgroups
         const int g = warp >> 2, quad = warp & 3;
         const int row = 32 * quad + lane;
         const uint32_t lane_base = 32 * quad;
+        const uint32_t sbase = tmem_addr(tb, lane_base, AC_S + 128 * g);
         uint32_t ph_s = 0;
         for (int it = 0; it < ntiles; ++it) {
             const int n = (tile0 + it) * 128 + row;
             const bool valid = n < P.N;
-            float inv_l[2][2];
+            const bool warp_live = (tile0 + it) * 128 + 32 * quad < P.N;    // warps whose 32 rows are all padding idle
+            float inv_l[2][2] = {{1.f, 1.f}, {1.f, 1.f}};
             // ---- softmax over the 64 keys of each head, two heads per pair
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
                 mbar_wait(&s_full[g], ph_s);
                 ph_s ^= 1;
                 fence_after_sync();
-                const uint32_t sbase = tmem_addr(tb, lane_base, AC_S + 128 * g);
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint32_t v0[32], v1[32];
-                    tmem_ld32(sbase + 64 * hh, v0);
-                    tmem_ld32(sbase + 64 * hh + 32, v1);
-                    tmem_ld_wait();
-                    float mx = -INFINITY;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
-                    float sum = 0.f;
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const float p0 = ex2(__uint_as_float(v0[j]) - mx), p1 = ex2(__uint_as_float(v0[j + 1]) - mx);
-                        sum += p0 + p1;
-                        pk[j >> 1] = pack_bf16(p0, p1);
-                    }
-                    tmem_st16(sbase + 32 * hh, pk);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const float p0 = ex2(__uint_as_float(v1[j]) - mx), p1 = ex2(__uint_as_float(v1[j + 1]) - mx);
-                        sum += p0 + p1;
-                        pk[j >> 1] = pack_bf16(p0, p1);
-                    }
-                    tmem_st16(sbase + 32 * hh + 16, pk);
-                    inv_l[pp][hh] = 1.f / sum;
+                if (warp_live) {
+                    uint32_t va[32], vb[32], pk[16];
+                    tmem_ld32(sbase, va);
+                    tmem_ld32(sbase + 32, vb);
+                    tmem_ld_wait32(va);
+                    tmem_ld_wait32(vb);
+                    // head 0 of the pair: columns 0..63
+                    float mx = max_chunk32(vb, max_chunk32(va, -INFINITY));
+                    float2 neg2 = make_float2(-mx, -mx), sum2 = make_float2(0.f, 0.f);
+                    exp_chunk32(va, neg2, sum2, pk);
+                    tmem_ld32(sbase + 64, va);                       // head 1, first half, in flight
+                    tmem_st16(sbase, pk);
+                    exp_chunk32(vb, neg2, sum2, pk);
+                    tmem_ld32(sbase + 96, vb);
+                    tmem_st16(sbase + 16, pk);
+                    inv_l[pp][0] = __fdividef(1.f, sum2.x + sum2.y);
+                    tmem_ld_wait32(va);
+                    tmem_ld_wait32(vb);
+                    // head 1: columns 64..127; its P goes to columns 32..63 (scores of head 0, consumed)
+                    mx = max_chunk32(vb, max_chunk32(va, -INFINITY));
+                    neg2 = make_float2(-mx, -mx);
+                    sum2 = make_float2(0.f, 0.f);
+                    exp_chunk32(va, neg2, sum2, pk);
+                    tmem_st16(sbase + 32, pk);
+                    exp_chunk32(vb, neg2, sum2, pk);
+                    tmem_st16(sbase + 48, pk);
+                    inv_l[pp][1] = __fdividef(1.f, sum2.x + sum2.y);
+                    tmem_st_wait();
                 }
-                tmem_st_wait();
                 fence_before_sync();
                 mbar_arrive(&p_ready[g]);
             }
@@ -768,24 +952,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mab_apply_tc_kernel(const APara
                 const int p = g + 2 * pp;
                 mbar_wait(&o_full[p], it & 1);
                 fence_after_sync();
-                uint32_t o[16], qv[16];
-                tmem_ld16(tmem_addr(tb, lane_base, AC_O + 16 * p), o);
-                if (DIN64) tmem_ld16(tmem_addr(tb, lane_base, AC_QP + 64 * (it & 1) + 16 * p), qv);
-                tmem_ld_wait();
+                if (warp_live) {
+                    uint32_t o[16], qv[16];
+                    tmem_ld16(tmem_addr(tb, lane_base, AC_O + 16 * p), o);
+                    if (DIN64) tmem_ld16(tmem_addr(tb, lane_base, AC_QP + 64 * (it & 1) + 16 * p), qv);
+                    tmem_ld_wait16(o);
+                    if (DIN64) tmem_ld_wait16(qv);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int f = 16 * p + j;
-                    float q;
-                    if (DIN64) {
-                        q = __uint_as_float(qv[j]) + sBq[f];
-                    } else {
-                        const float4 w = *reinterpret_cast<const float4*>(sWq32 + f * 4);
-                        q = fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], sBq[f]))));
+                    for (int j = 0; j < 16; ++j) {
+                        const int f = 16 * p + j;
+                        float q;
+                        if (DIN64) {
+                            q = __uint_as_float(qv[j]) + sBq[f];
+                        } else {
+                            const float4 w = *reinterpret_cast<const float4*>(sWq32 + f * 4);
+                            q = fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], sBq[f]))));
+                        }
+                        o1[pp][j] = q + __uint_as_float(o[j]) * inv_l[pp][j >> 3];
                     }
-                    o1[pp][j] = q + __uint_as_float(o[j]) * inv_l[pp][j >> 3];
+                    st_shared_8bf16(sO1 + (2 * p) * 2048 + row * 16, &o1[pp][0]);
+                    st_shared_8bf16(sO1 + (2 * p + 1) * 2048 + row * 16, &o1[pp][8]);
                 }
-                st_shared_8bf16(sO1 + (2 * p) * 2048 + row * 16, &o1[pp][0]);
-                st_shared_8bf16(sO1 + (2 * p + 1) * 2048 + row * 16, &o1[pp][8]);
             }
             if (DIN64) {
                 fence_before_sync();
@@ -797,24 +984,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mab_apply_tc_kernel(const APara
             // ---- Y = O1 + relu(fc_o(O1))
             mbar_wait(f_full, it & 1);
             fence_after_sync();
+            if (warp_live) {
 #pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-                const int p = g + 2 * pp;
-                uint32_t fv[16];
-                tmem_ld16(tmem_addr(tb, lane_base, AC_F + 16 * p), fv);
-                tmem_ld_wait();
-                uint4 out[2];
-                uint32_t* ow = reinterpret_cast<uint32_t*>(out);
+                for (int pp = 0; pp < 2; ++pp) {
+                    const int p = g + 2 * pp;
+                    uint32_t fv[16];
+                    tmem_ld16(tmem_addr(tb, lane_base, AC_F + 16 * p), fv);
+                    tmem_ld_wait16(fv);
+                    uint4 out[2];
+                    uint32_t* ow = reinterpret_cast<uint32_t*>(out);
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    const float y0 = o1[pp][j] + fmaxf(__uint_as_float(fv[j]) + sBo[16 * p + j], 0.f);
-                    const float y1 = o1[pp][j + 1] + fmaxf(__uint_as_float(fv[j + 1]) + sBo[16 * p + j + 1], 0.f);
-                    ow[j >> 1] = pack_bf16(y0, y1);
-                }
-                if (valid) {
-                    uint4* dst = reinterpret_cast<uint4*>(P.Yout + ((size_t)cloud * P.N + n) * 64 + 16 * p);
-                    dst[0] = out[0];
-                    dst[1] = out[1];
+                    for (int j = 0; j < 16; j += 2) {
+                        const float y0 = o1[pp][j] + fmaxf(__uint_as_float(fv[j]) + sBo[16 * p + j], 0.f);
+                        const float y1 = o1[pp][j + 1] + fmaxf(__uint_as_float(fv[j + 1]) + sBo[16 * p + j + 1], 0.f);
+                        ow[j >> 1] = pack_bf16(y0, y1);
+                    }
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(P.Yout + ((size_t)cloud * P.N + n) * 64 + 16 * p);
+                        dst[0] = out[0];
+                        dst[1] = out[1];
+                    }
                 }
             }
             fence_before_sync();
@@ -822,7 +1011,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mab_apply_tc_kernel(const APara
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tb, 512);
+    if (warp == 12) tmem_dealloc(tb, 512);
 }
 
 // ------------------------------------------------------------------------------------ finalize (PMA + Linear)
@@ -839,17 +1028,19 @@ __global__ void __launch_bounds__(64) finalize_pma_kernel(const PParams P) {
     __shared__ float sO[64], sO1[64];
     const int cloud = blockIdx.x, f = threadIdx.x;
     const int h = f >> 3, d = f & 7;
-    // every row of a head carries the same query (the seed); row 0 of each head is used
+    // partial slots: (split, warpgroup 0/1) -- each softmax warpgroup of the reduce kernel owns alternate tiles
     float mmax = -INFINITY;
     for (int s = 0; s < P.nsplit; ++s)
-        mmax = fmaxf(mmax, P.part[((((size_t)cloud * P.nsplit + s) * TH + h) * TM) * 10]);
+        for (int w2 = 0; w2 < 2; ++w2)
+            mmax = fmaxf(mmax, P.part[((((size_t)cloud * P.nsplit + s) * TH + h) * TM + w2) * 10]);
     float l = 0.f, a = 0.f;
-    for (int s = 0; s < P.nsplit; ++s) {
-        const float* pp = P.part + ((((size_t)cloud * P.nsplit + s) * TH + h) * TM) * 10;
-        const float w = exp2f(pp[0] - mmax);
-        l = fmaf(pp[1], w, l);
-        a = fmaf(pp[2 + d], w, a);
-    }
+    for (int s = 0; s < P.nsplit; ++s)
+        for (int w2 = 0; w2 < 2; ++w2) {
+            const float* pp = P.part + ((((size_t)cloud * P.nsplit + s) * TH + h) * TM + w2) * 10;
+            const float w = exp2f(pp[0] - mmax);
+            l = fmaf(pp[1], w, l);
+            a = fmaf(pp[2 + d], w, a);
+        }
     sO[f] = P.QpS[f] + a / l;
     __syncthreads();
     float acc = P.bo[f];
@@ -932,17 +1123,17 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
 
     const dim3 grid(sp.nsplit, B);
     const double pts = (double)B * N;
-    const size_t fsmem = (size_t)(2 * 64 * 65 + 64 * 128) * sizeof(float);
+    const size_t fsmem = FT_SMEM;
 
     // ---- ISAB 0
     {
         RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, c->Aq0, m00.Wkv, m00.bkv, nullptr, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * d_in * TD + 2.0 * TM * TD), pts * 4.0 * d_in);
-        mab_reduce_tc_kernel<false><<<grid, TC_THREADS, RSmem::TOTAL, st>>>(r);
+        mab_reduce_tc_kernel<false, false><<<grid, TC_THREADS16, RSmem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<small>");
     {
-        FParams f{part, sp.nsplit, c->Qp0, m00.Wo, m00.bo, m01.Wkv, m01.bkv, kvblk, dbg ? dbg->H1 : nullptr};
+        FParams f{part, sp.nsplit, c->Qp0, c->WoT[0], m00.bo, c->WkvT[0], m01.bkv, kvblk, dbg ? dbg->H1 : nullptr};
         LaunchTimer lt("finalize_isab_kernel", st, (double)B * 2.0 * (TM * TD * TD + TM * TD * 2 * TD), (double)B * 32768.0);
         finalize_isab_kernel<<<B, 256, fsmem, st>>>(f);
     }
@@ -950,18 +1141,18 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     {
         AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, kvblk, m01.Wq, m01.bq, nullptr, c->Wo0, m01.bo, Y1};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * d_in * TD + 2.0 * TM * TD + TD * TD), pts * (4.0 * d_in + 128.0));
-        mab_apply_tc_kernel<false><<<grid, TC_THREADS, ASmem::TOTAL, st>>>(a);
+        mab_apply_tc_kernel<false><<<grid, TC_THREADS16, ASmem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<small>");
     // ---- ISAB 1
     {
         RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, c->Aq1, nullptr, m10.bkv, c->Wkv1, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TM * TD), pts * 128.0);
-        mab_reduce_tc_kernel<true><<<grid, TC_THREADS, RSmem::TOTAL, st>>>(r);
+        mab_reduce_tc_kernel<true, false><<<grid, TC_THREADS16, RSmem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<64>");
     {
-        FParams f{part, sp.nsplit, c->Qp1, m10.Wo, m10.bo, m11.Wkv, m11.bkv, kvblk, dbg ? dbg->H2 : nullptr};
+        FParams f{part, sp.nsplit, c->Qp1, c->WoT[1], m10.bo, c->WkvT[1], m11.bkv, kvblk, dbg ? dbg->H2 : nullptr};
         LaunchTimer lt("finalize_isab_kernel", st, (double)B * 2.0 * (TM * TD * TD + TM * TD * 2 * TD), (double)B * 32768.0);
         finalize_isab_kernel<<<B, 256, fsmem, st>>>(f);
     }
@@ -969,14 +1160,14 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     {
         AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, kvblk, nullptr, m11.bq, c->Wq1, c->Wo1, m11.bo, Y2};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * TD * TD + 2.0 * TM * TD + TD * TD), pts * 256.0);
-        mab_apply_tc_kernel<true><<<grid, TC_THREADS, ASmem::TOTAL, st>>>(a);
+        mab_apply_tc_kernel<true><<<grid, TC_THREADS16, ASmem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<64>");
     // ---- PMA + Linear
     {
         RParams r{nullptr, Y2, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, c->AqP, nullptr, mp.bkv, c->WkvP, part};
-        LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TD), pts * 128.0);
-        mab_reduce_tc_kernel<true><<<grid, TC_THREADS, RSmem::TOTAL, st>>>(r);
+        LaunchTimer lt("pma_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TD), pts * 128.0);
+        mab_reduce_tc_kernel<true, true><<<grid, TC_THREADS16, RSmem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<pma>");
     {
@@ -1001,12 +1192,12 @@ static int tc_configure() {
     PCA_CHECK_CUDA(cudaGetDevice(&dev));
     PCA_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major != 10) return fail(PCA_EDEVICE, "tcgen05 path needs an sm_100 device (found compute capability %d.x)", major);
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSmem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSmem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSmem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSmem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSmem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASmem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASmem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)((2 * 64 * 65 + 64 * 128) * sizeof(float))));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
     done = true;
     return 0;
 }
@@ -1022,7 +1213,7 @@ int st_tc_forward_dbg(const float* X, int B, int N, const pca_st_dims* d, const 
     if (dbg && chunk < B) return fail(PCA_EWORKSPACE, "ST(bf16) debug: workspace must hold the whole batch");
     uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
     TcConsts* c = reinterpret_cast<TcConsts*>(w8 + tc_layout(chunk, N).consts);
-    prep_kernel<<<8, 256, 0, st>>>(params, d->d_in, c);
+    prep_kernel<<<12, 256, 0, st>>>(params, d->d_in, c);
     PCA_CHECK_LAUNCH("prep_kernel");
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int bc = (B - b0) < chunk ? (B - b0) : chunk;
