@@ -132,7 +132,8 @@ struct RParams {
     const float* Wkv32;           // (128, d_in) fp32       [DIN64 == false]
     const float* bkv;             // (128)
     const uint8_t* Wkv16;         // 16 KB B operand        [DIN64 == true]
-    float* part;                  // (B, nsplit, 8, 64, 10): m (log2 domain), l, acc[8]
+    float* part;                  // (B, slots, 8, 10, 64): per (head, query) row: m (log2 domain), l, acc[8];
+                                  // query index fastest so that a warp's 32 rows store/load 128 contiguous bytes
 };
 
 // TMEM columns of the reduce kernel
@@ -498,11 +499,11 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce_tc_kernel(const RP
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
                 const int h = 2 * (g + 2 * pp) + (row >> 6);
-                float* dst = P.part + ((((size_t)cloud * P.nsplit + split) * TH + h) * TM + (row & 63)) * 10;
+                float* dst = P.part + (((size_t)cloud * P.nsplit + split) * TH + h) * 10 * TM + (row & 63);
                 dst[0] = m_run[pp];
-                dst[1] = l_run[pp];
+                dst[TM] = l_run[pp];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dst[2 + j] = acc[pp][j];
+                for (int j = 0; j < 8; ++j) dst[(2 + j) * TM] = acc[pp][j];
             }
         } else {
             // PMA: rows are (head = row / 16, 16 redundant copies); warpgroup g owns the tiles with it % 2 == g
@@ -527,11 +528,11 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce_tc_kernel(const RP
             (void)last;
             if ((row & 15) == 0) {
                 const int h = row >> 4;
-                float* dst = P.part + ((((size_t)cloud * P.nsplit + split) * TH + h) * TM + g) * 10;
+                float* dst = P.part + (((size_t)cloud * P.nsplit + split) * TH + h) * 10 * TM + g;
                 dst[0] = m_run[0];
-                dst[1] = l_run[0];
+                dst[TM] = l_run[0];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dst[2 + j] = acc[0][j];
+                for (int j = 0; j < 8; ++j) dst[(2 + j) * TM] = acc[0][j];
             }
         }
     }
@@ -572,14 +573,14 @@ __global__ void __launch_bounds__(256) finalize_isab_kernel(const FParams P) {
         const int h = r / TM, m = r % TM;
         float mmax = -INFINITY;
         for (int s = 0; s < P.nsplit; ++s)
-            mmax = fmaxf(mmax, P.part[((((size_t)cloud * P.nsplit + s) * TH + h) * TM + m) * 10]);
+            mmax = fmaxf(mmax, P.part[(((size_t)cloud * P.nsplit + s) * TH + h) * 10 * TM + m]);
         float l = 0.f, a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int s = 0; s < P.nsplit; ++s) {
-            const float* pp = P.part + ((((size_t)cloud * P.nsplit + s) * TH + h) * TM + m) * 10;
+            const float* pp = P.part + (((size_t)cloud * P.nsplit + s) * TH + h) * 10 * TM + m;
             const float w = exp2f(pp[0] - mmax);
-            l = fmaf(pp[1], w, l);
+            l = fmaf(pp[TM], w, l);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = fmaf(pp[2 + j], w, a[j]);
+            for (int j = 0; j < 8; ++j) a[j] = fmaf(pp[(2 + j) * TM], w, a[j]);
         }
         const float inv = 1.f / l;
 #pragma unroll
@@ -669,49 +670,360 @@ struct AParams {
     __nv_bfloat16* Yout;          // (B, N, 64)
 };
 
-constexpr uint32_t AC_S = 0;        // 2 x 128
-constexpr uint32_t AC_O = 256;      // 64
-constexpr uint32_t AC_F = 320;      // 64
-constexpr uint32_t AC_QP = 384;     // 2 x 64 (DIN64)
+// ====================================================================================== chain-scheduled kernels
+// Second generation of the two hot kernels.  The 128 score columns of a head pair are produced and consumed as
+// two independent 64-column "chains" per softmax warpgroup (4 chains per CTA, each with its own TMEM half-buffer
+// and barriers).  A single MMA-issuing thread POLLS the chains instead of following a fixed order, so the
+// P V -> next Q K^T round trip of one chain is hidden behind the softmax of the warpgroup's other chain and the
+// two warpgroups never wait on each other.
 
-struct ASmem {
-    static constexpr int KB = 0;                  // K image 16384
-    static constexpr int VB = 16384;              // V image 16384
-    static constexpr int WO = 32768;              // 8192
-    static constexpr int WQ = WO + 8192;          // 8192
+// one mbarrier arrival per warp (barrier counts are in warps): every lane has fenced its own writes, the
+// __syncwarp orders them before the elected lane's releasing arrive
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+
+// TMEM columns (reduce): 4 x 64 score/probability half-buffers | 8 x 16 outputs (pair, half) | projection
+constexpr uint32_t R2_S = 0, R2_O = 256, R2_PROJ = 384;
+
+struct R2Smem {
+    static constexpr int AQ = 0;
+    static constexpr int KV = 16384;
+    static constexpr int W = KV + 65536;
+    static constexpr int Y = W + 16384;
+    static constexpr int SMALL = Y + 16384;
+    static constexpr int BARS = SMALL + (128 * 4 + 128) * 4;
+    static constexpr int TOTAL = BARS + 32 * 8 + 16;
+};
+
+// 64-column softmax step on registers: returns the chunk max
+__device__ __forceinline__ float max64(const uint32_t* va, const uint32_t* vb) { return max_chunk32(vb, max_chunk32(va, -INFINITY)); }
+
+template <bool DIN64>
+__global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const RParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sAq = smem + R2Smem::AQ;
+    uint8_t* sKV = smem + R2Smem::KV;
+    uint8_t* sW = smem + R2Smem::W;
+    uint8_t* sY = smem + R2Smem::Y;
+    float* sWsm = reinterpret_cast<float*>(smem + R2Smem::SMALL);
+    float* sBias = sWsm + 128 * 4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + R2Smem::BARS);
+    uint64_t* kv_full = bars;          // [2] count 128
+    uint64_t* kv_empty = bars + 2;     // [2] count 1
+    uint64_t* s_full = bars + 4;       // [4] count 1
+    uint64_t* p_ready = bars + 8;      // [4] count 128
+    uint64_t* o_full = bars + 12;      // [8] count 1   (region = 2 * pair + half)
+    uint64_t* y_full = bars + 20;      // count 128
+    uint64_t* proj_done = bars + 21;   // count 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cloud = blockIdx.y, split = blockIdx.x;
+    const int tile0 = split * P.tiles_per_split;
+    const int ntiles = min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+
+    copy_to_smem(sAq, P.Aq, 16384);
+    if (DIN64) copy_to_smem(sW, P.Wkv16, 16384);
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+        sBias[i] = P.bkv[i];
+        if (!DIN64) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sWsm[i * 4 + k] = (k < P.d_in) ? P.Wkv32[i * P.d_in + k] : 0.f;
+        }
+    }
+    if (warp == 12) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 4); mbar_init(&kv_empty[i], 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
+        for (int i = 0; i < 8; ++i) mbar_init(&o_full[i], 1);
+        mbar_init(y_full, 4);
+        mbar_init(proj_done, 1);
+        fence_barrier_init();
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp >= 12) {
+        reg_dec<40>();
+        if (lane == 0) {
+            // =================================================================== one MMA-issuing thread per chain
+            // chain c = warp - 12: strictly serial  Q K^T -> (warpgroup softmax) -> P V -> next Q K^T  on its own
+            // half-buffer; the four chains never wait on each other.
+            const int c = warp - 12, half = c & 1;
+            const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
+            const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
+            const uint32_t aq = smem_u32(sAq), kvb = smem_u32(sKV);
+            const int nitems = 2 * ntiles;
+            for (int j = 0; j < nitems; ++j) {
+                const int t = j >> 1, p = (c >> 1) + 2 * (j & 1);
+                const uint32_t kbase = kvb + (t & 1) * 32768, vbase = kbase + 16384;
+                if ((j & 1) == 0) {
+                    mbar_wait(&kv_full[t & 1], (t >> 1) & 1);
+                    fence_after_sync();
+                }
+                mma_ss(tmem_addr(tb, 0, R2_S + 64 * c), smem_desc(aq + p * 4096, 2048, 128),
+                       smem_desc(kbase + 2 * p * 2048 + half * 1024, 2048, 128), idesc_s, 0);
+                mma_commit(&s_full[c]);
+                mbar_wait(&p_ready[c], j & 1);
+                fence_after_sync();
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_ts(tmem_addr(tb, 0, R2_O + 16 * (2 * p + half)), tmem_addr(tb, 0, R2_S + 64 * c + ks * 8),
+                           smem_desc(vbase + 2 * p * 2048 + half * 1024 + ks * 256, 128, 2048), idesc_pv, ks > 0);
+                mma_commit(&o_full[2 * p + half]);
+                if (j & 1) mma_commit(&kv_empty[t & 1]);        // 4 chains x 1 arrival free the K|V stage
+            }
+        }
+    } else if (warp >= 8) {
+        reg_dec<88>();
+        // =================================================================== producer: K|V tiles
+        const int quad = warp & 3;
+        const int row = 32 * quad + lane;
+        for (int it = 0; it < ntiles; ++it) {
+            const int stage = it & 1;
+            const int n = (tile0 + it) * 128 + row;
+            const bool valid = n < P.N;
+            uint8_t* sK = sKV + stage * 32768;
+            uint8_t* sV = sK + 16384;
+            if (!DIN64) {
+                float x[4] = {0.f, 0.f, 0.f, 0.f};
+                if (valid) {
+                    const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                    for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
+                }
+                if (it >= 2) mbar_wait(&kv_empty[stage], ((it >> 1) - 1) & 1);
+#pragma unroll 4
+                for (int c = 0; c < 16; ++c) {
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 w = *reinterpret_cast<const float4*>(sWsm + (c * 8 + j) * 4);
+                        o[j] = valid ? fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], sBias[c * 8 + j])))) : 0.f;
+                    }
+                    st_shared_8bf16((c < 8 ? sK + c * 2048 : sV + (c - 8) * 2048) + row * 16, o);
+                }
+            } else {
+                const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
+                uint4 yv[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sY + c * 2048 + row * 16) = yv[c];
+                fence_async_smem();
+                fence_before_sync();
+                warp_arrive(y_full);
+                if (warp == 8 && lane == 0) {
+                    // one producer thread issues the K|V projection MMA once all 128 rows of Y are staged
+                    mbar_wait(y_full, it & 1);
+                    fence_after_sync();
+                    const uint32_t yb = smem_u32(sY), wb = smem_u32(sW);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_ss(tmem_addr(tb, 0, R2_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
+                               idesc_bf16(128, 128, 0, 0), ks > 0);
+                    mma_commit(proj_done);
+                }
+                mbar_wait(proj_done, it & 1);
+                fence_after_sync();
+                if (it >= 2) mbar_wait(&kv_empty[stage], ((it >> 1) - 1) & 1);
+#pragma unroll
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_addr(tb, 32 * quad, R2_PROJ + c0), v);
+                    tmem_ld_wait32(v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = valid ? __uint_as_float(v[8 * q + j]) + sBias[c0 + 8 * q + j] : 0.f;
+                        const int chunk = c0 / 8 + q;
+                        st_shared_8bf16((chunk < 8 ? sK + chunk * 2048 : sV + (chunk - 8) * 2048) + row * 16, o);
+                    }
+                }
+            }
+            fence_async_smem();
+            fence_before_sync();
+            warp_arrive(&kv_full[stage]);
+        }
+    } else {
+        reg_inc<184>();
+        // =================================================================== softmax warpgroups (2 chains each)
+        const int g = warp >> 2, quad = warp & 3;
+        const int row = 32 * quad + lane;
+        const uint32_t lane_base = 32 * quad;
+        const uint32_t ocol_off = (row >= 64) ? 8u : 0u;
+        // running statistics per (half, pp)
+        float m_run[2][2], l_run[2][2], alpha[2][2], acc[2][2][8];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                m_run[a][b] = -INFINITY; l_run[a][b] = 0.f; alpha[a][b] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[a][b][j] = 0.f;
+            }
+        uint32_t ph_s[2] = {0, 0};
+
+        uint32_t va[32], vb[32];        // scores of the item being processed / prefetched for the next item
+        auto issue_loads = [&](const int half) {
+            const int c = 2 * g + half;
+            mbar_wait(&s_full[c], ph_s[half]);
+            ph_s[half] ^= 1;
+            fence_after_sync();
+            const uint32_t sb = tmem_addr(tb, lane_base, R2_S + 64 * c);
+            tmem_ld32(sb, va);
+            tmem_ld32(sb + 32, vb);
+        };
+        // One 64-column item.  va/vb already hold (in-flight) loads of this item; while its exponentials run, the
+        // loads of the warpgroup's NEXT item (other chain) are issued so TMEM latency never sits on the MUFU path.
+        auto softmax_item = [&](const int half, const int pp, const int nv, const bool has_next) {
+            const int c = 2 * g + half, cn = 2 * g + (half ^ 1);
+            const uint32_t sbase = tmem_addr(tb, lane_base, R2_S + 64 * c);
+            const uint32_t snext = tmem_addr(tb, lane_base, R2_S + 64 * cn);
+            uint32_t pk[16];
+            tmem_ld_wait64(va, vb);
+            if (nv == 64) {
+                const float m_new = fmaxf(m_run[half][pp], max64(va, vb));
+                alpha[half][pp] = ex2(m_run[half][pp] - m_new);
+                const float2 neg2 = make_float2(-m_new, -m_new);
+                float2 sum2 = make_float2(0.f, 0.f);
+                exp_chunk32(va, neg2, sum2, pk);
+                tmem_st16(sbase, pk);
+                if (has_next) {
+                    mbar_wait(&s_full[cn], ph_s[half ^ 1]);
+                    ph_s[half ^ 1] ^= 1;
+                    fence_after_sync();
+                    tmem_ld32(snext, va);
+                }
+                exp_chunk32(vb, neg2, sum2, pk);
+                tmem_st16(sbase + 16, pk);
+                if (has_next) tmem_ld32(snext + 32, vb);
+                l_run[half][pp] = l_run[half][pp] * alpha[half][pp] + (sum2.x + sum2.y);
+                m_run[half][pp] = m_new;
+            } else {
+                // ragged tail: columns >= nv are padding (nv may be 0: the half contributes nothing)
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (j < nv) mx = fmaxf(mx, __uint_as_float(va[j]));
+                    if (32 + j < nv) mx = fmaxf(mx, __uint_as_float(vb[j]));
+                }
+                const float m_new = fmaxf(m_run[half][pp], mx);
+                alpha[half][pp] = (m_new == -INFINITY) ? 1.f : ex2(m_run[half][pp] - m_new);
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = (j < nv) ? ex2(__uint_as_float(va[j]) - m_new) : 0.f;
+                    const float p1 = (j + 1 < nv) ? ex2(__uint_as_float(va[j + 1]) - m_new) : 0.f;
+                    sum += p0 + p1;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                }
+                tmem_st16(sbase, pk);
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = (32 + j < nv) ? ex2(__uint_as_float(vb[j]) - m_new) : 0.f;
+                    const float p1 = (33 + j < nv) ? ex2(__uint_as_float(vb[j + 1]) - m_new) : 0.f;
+                    sum += p0 + p1;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                }
+                tmem_st16(sbase + 16, pk);
+                l_run[half][pp] = l_run[half][pp] * alpha[half][pp] + sum;
+                m_run[half][pp] = m_new;
+                if (has_next) issue_loads(half ^ 1);
+            }
+            tmem_st_wait();
+            fence_before_sync();
+            warp_arrive(&p_ready[c]);
+        };
+        auto consume_item = [&](const int half, const int pp, const int it) {
+            const int p = g + 2 * pp;
+            mbar_wait(&o_full[2 * p + half], it & 1);
+            fence_after_sync();
+            uint32_t o[8];
+            tmem_ld8(tmem_addr(tb, lane_base, R2_O + 16 * (2 * p + half) + ocol_off), o);
+            // wait::ld would also drain the prefetched score loads, which is harmless (they are needed next anyway)
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[half][pp][j] = fmaf(acc[half][pp][j], alpha[half][pp], __uint_as_float(o[j]));
+        };
+        issue_loads(0);
+        for (int it = 0; it < ntiles; ++it) {
+            const int n_valid = min(128, P.N - (tile0 + it) * 128);
+            const int nv0 = min(64, n_valid), nv1 = max(0, n_valid - 64);
+            softmax_item(0, 0, nv0, true);
+            if (it > 0) consume_item(1, 1, it - 1);
+            softmax_item(1, 0, nv1, true);
+            consume_item(0, 0, it);
+            softmax_item(0, 1, nv0, true);
+            consume_item(1, 0, it);
+            softmax_item(1, 1, nv1, it + 1 < ntiles);
+            consume_item(0, 1, it);
+        }
+        consume_item(1, 1, ntiles - 1);
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+                const int h = 2 * (g + 2 * pp) + (row >> 6);
+                float* dst = P.part + (((size_t)cloud * (2 * P.nsplit) + 2 * split + half) * TH + h) * 10 * TM + (row & 63);
+                dst[0] = m_run[half][pp];
+                dst[TM] = l_run[half][pp];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[(2 + j) * TM] = acc[half][pp][j];
+            }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tb, 512);
+}
+
+// TMEM columns (apply): 4 x 64 half-buffers | 4 x 16 pair outputs | 64 fc_o | 2 x 64 Q projection
+constexpr uint32_t A2_S = 0, A2_O = 256, A2_F = 320, A2_QP = 384;
+
+struct A2Smem {
+    static constexpr int KB = 0;
+    static constexpr int VB = 16384;
+    static constexpr int WO = 32768;
+    static constexpr int WQ = WO + 8192;
     static constexpr int AQ = WQ + 8192;          // 2 stages x 16384
-    static constexpr int YA = AQ + 32768;         // 16384
-    static constexpr int O1 = YA + 16384;         // 16384
+    static constexpr int YA = AQ + 32768;
+    static constexpr int O1 = YA + 16384;
     static constexpr int SMALL = O1 + 16384;      // fp32: Wq32 padded (64 x 4) | bq (64) | bo (64)
     static constexpr int BARS = SMALL + (64 * 4 + 128) * 4;
-    static constexpr int TOTAL = BARS + 24 * 8 + 16;
+    static constexpr int TOTAL = BARS + 32 * 8 + 16;
 };
 
 template <bool DIN64>
-__global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply_tc_kernel(const AParams P) {
+__global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sKb = smem + ASmem::KB;
-    uint8_t* sVb = smem + ASmem::VB;
-    uint8_t* sWo = smem + ASmem::WO;
-    uint8_t* sWq = smem + ASmem::WQ;
-    uint8_t* sAQ = smem + ASmem::AQ;
-    uint8_t* sYA = smem + ASmem::YA;
-    uint8_t* sO1 = smem + ASmem::O1;
-    float* sWq32 = reinterpret_cast<float*>(smem + ASmem::SMALL);
+    uint8_t* sKb = smem + A2Smem::KB;
+    uint8_t* sVb = smem + A2Smem::VB;
+    uint8_t* sWo = smem + A2Smem::WO;
+    uint8_t* sWq = smem + A2Smem::WQ;
+    uint8_t* sAQ = smem + A2Smem::AQ;
+    uint8_t* sYA = smem + A2Smem::YA;
+    uint8_t* sO1 = smem + A2Smem::O1;
+    float* sWq32 = reinterpret_cast<float*>(smem + A2Smem::SMALL);
     float* sBq = sWq32 + 64 * 4;
     float* sBo = sBq + 64;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ASmem::BARS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A2Smem::BARS);
     uint64_t* aq_full = bars;          // [2] count 128
     uint64_t* aq_empty = bars + 2;     // [2] count 1
-    uint64_t* s_full = bars + 4;       // [2] count 1
-    uint64_t* p_ready = bars + 6;      // [2] count 128
-    uint64_t* o_full = bars + 8;       // [4] count 1
-    uint64_t* o1_ready = bars + 12;    // count 256
-    uint64_t* f_full = bars + 13;      // count 1
-    uint64_t* ya_full = bars + 14;     // count 128
-    uint64_t* qp_done = bars + 15;     // count 1
-    uint64_t* qp_free = bars + 16;     // [2] count 256
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    uint64_t* s_full = bars + 4;       // [4] count 1
+    uint64_t* p_ready = bars + 8;      // [4] count 128
+    uint64_t* o_full = bars + 12;      // [4] count 1
+    uint64_t* o1_ready = bars + 16;    // count 256
+    uint64_t* f_full = bars + 17;      // count 1
+    uint64_t* ya_full = bars + 18;     // count 128
+    uint64_t* qp_done = bars + 19;     // count 1
+    uint64_t* qp_free = bars + 20;     // [2] count 256
+    uint64_t* pv0_done = bars + 22;    // [4] count 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cloud = blockIdx.y, split = blockIdx.x;
@@ -731,14 +1043,12 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply_tc_kernel(const APa
     }
     if (warp == 12) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&aq_full[i], 128); mbar_init(&aq_empty[i], 1); mbar_init(&s_full[i], 1);
-            mbar_init(&p_ready[i], 128); mbar_init(&qp_free[i], 256);
-        }
-        for (int i = 0; i < 4; ++i) mbar_init(&o_full[i], 1);
-        mbar_init(o1_ready, 256);
+        for (int i = 0; i < 2; ++i) { mbar_init(&aq_full[i], 4); mbar_init(&aq_empty[i], 4); mbar_init(&qp_free[i], 8); }
+        for (int i = 0; i < 4; ++i) mbar_init(&pv0_done[i], 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); }
+        mbar_init(o1_ready, 8);
         mbar_init(f_full, 1);
-        mbar_init(ya_full, 128);
+        mbar_init(ya_full, 4);
         mbar_init(qp_done, 1);
         fence_barrier_init();
     }
@@ -750,84 +1060,51 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply_tc_kernel(const APa
 
     if (warp >= 12) {
         reg_dec<40>();
-        if (warp == 12) {
-            // =================================================================== MMA issuer
-            const bool leader = lane == 0;
-            const uint32_t idesc_s = idesc_bf16(128, 128, 0, 0);
+        if (lane == 0) {
+            // =================================================================== one MMA-issuing thread per chain
+            // chain c = warp - 12 <-> head hh = c & 1 of the pairs (c >> 1) + 2 pp.  The two heads of a pair share the
+            // pair's 16 output columns: hh = 0 writes (accumulate off), hh = 1 accumulates after pv0_done.
+            const int c = warp - 12, hh = c & 1;
+            const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
             const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
             const uint32_t idesc_64 = idesc_bf16(128, 64, 0, 0);
-            const uint32_t kb = smem_u32(sKb), vb = smem_u32(sVb), wo = smem_u32(sWo), wq = smem_u32(sWq);
-            const uint32_t aqb = smem_u32(sAQ), yab = smem_u32(sYA), o1b = smem_u32(sO1);
-            uint32_t ph_p[2] = {0, 0};
-            auto issue_qproj = [&](int t) {
-                if (leader) {
+            const uint32_t kb = smem_u32(sKb), vb = smem_u32(sVb), wo = smem_u32(sWo);
+            const uint32_t aqb = smem_u32(sAQ), o1b = smem_u32(sO1);
+            const int nitems = 2 * ntiles;
+            auto issue_f = [&](int t) {          // fc_o of tile t once both warpgroups have staged O1
+                mbar_wait(o1_ready, t & 1);
+                fence_after_sync();
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_ss(tmem_addr(tb, 0, AC_QP + 64 * (t & 1)), smem_desc(yab + ks * 4096, 2048, 128),
-                               smem_desc(wq + ks * 2048, 1024, 128), idesc_64, ks > 0);
-                    mma_commit(qp_done);
-                }
-                __syncwarp();
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_ss(tmem_addr(tb, 0, A2_F), smem_desc(o1b + ks * 4096, 2048, 128), smem_desc(wo + ks * 2048, 1024, 128),
+                           idesc_64, ks > 0);
+                mma_commit(f_full);
             };
-            auto issue_s = [&](int p, uint32_t abase) {
-                if (leader) {
-                    mma_ss(tmem_addr(tb, 0, AC_S + 128 * (p & 1)), smem_desc(abase + 2 * p * 2048, 2048, 128),
-                           smem_desc(kb + p * 4096, 2048, 128), idesc_s, 0);
-                    mma_commit(&s_full[p & 1]);
-                }
-                __syncwarp();
-            };
-            auto issue_pv = [&](int p) {
-                const int g = p & 1;
-                mbar_wait(&p_ready[g], ph_p[g]);
-                ph_p[g] ^= 1;
-                fence_after_sync();
-                if (leader) {
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        mma_ts(tmem_addr(tb, 0, AC_O + 16 * p), tmem_addr(tb, 0, AC_S + 128 * g + ks * 8),
-                               smem_desc(vb + p * 4096 + ks * 256, 128, 2048), idesc_pv, ks > 0);
-                    mma_commit(&o_full[p]);
-                }
-                __syncwarp();
-            };
-            if (DIN64) {
-                mbar_wait(ya_full, 0);
-                fence_after_sync();
-                issue_qproj(0);
-            }
-            for (int it = 0; it < ntiles; ++it) {
-                const int stage = it & 1;
-                const uint32_t abase = aqb + stage * 16384;
-                mbar_wait(&aq_full[stage], (it >> 1) & 1);
-                fence_after_sync();
-                issue_s(0, abase);
-                issue_s(1, abase);
-                if (DIN64 && it + 1 < ntiles) {
-                    mbar_wait(ya_full, (it + 1) & 1);
-                    if (it + 1 >= 2) mbar_wait(&qp_free[(it + 1) & 1], (((it + 1) >> 1) - 1) & 1);
+            for (int j = 0; j < nitems; ++j) {
+                const int t = j >> 1, pp = j & 1, p = (c >> 1) + 2 * pp;
+                if (pp == 0) {
+                    mbar_wait(&aq_full[t & 1], (t >> 1) & 1);
                     fence_after_sync();
-                    issue_qproj(it + 1);
                 }
-                issue_pv(0);
-                issue_s(2, abase);
-                issue_pv(1);
-                issue_s(3, abase);
-                issue_pv(2);
-                issue_pv(3);
-                if (leader) mma_commit(&aq_empty[stage]);
-                __syncwarp();
-                mbar_wait(o1_ready, it & 1);
+                mma_ss(tmem_addr(tb, 0, A2_S + 64 * c), smem_desc(aqb + (t & 1) * 16384 + 2 * p * 2048, 2048, 128),
+                       smem_desc(kb + p * 4096 + hh * 1024, 2048, 128), idesc_s, 0);
+                mma_commit(&s_full[c]);
+                if (pp == 0 && t > 0) {
+                    // the pair outputs of tile t-1 are consumed once its O1 is staged; chain 0 also launches its fc_o
+                    if (c == 0) issue_f(t - 1);
+                    else { mbar_wait(o1_ready, (t - 1) & 1); fence_after_sync(); }
+                }
+                mbar_wait(&p_ready[c], j & 1);
                 fence_after_sync();
-                if (leader) {
+                if (hh == 1) { mbar_wait(&pv0_done[p], t & 1); fence_after_sync(); }
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_ss(tmem_addr(tb, 0, AC_F), smem_desc(o1b + ks * 4096, 2048, 128), smem_desc(wo + ks * 2048, 1024, 128),
-                               idesc_64, ks > 0);
-                    mma_commit(f_full);
-                }
-                __syncwarp();
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_ts(tmem_addr(tb, 0, A2_O + 16 * p), tmem_addr(tb, 0, A2_S + 64 * c + ks * 8),
+                           smem_desc(vb + p * 4096 + hh * 1024 + ks * 256, 128, 2048), idesc_pv, (hh == 1 || ks > 0) ? 1u : 0u);
+                mma_commit(hh == 0 ? &pv0_done[p] : &o_full[p]);
+                if (pp == 1) mma_commit(&aq_empty[t & 1]);      // 4 chains x 1 arrival free the query stage
             }
+            if (c == 0) issue_f(ntiles - 1);
         }
     } else if (warp >= 8) {
         reg_dec<88>();
@@ -866,14 +1143,27 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply_tc_kernel(const APa
                 for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sYA + c * 2048 + row * 16) = yv[c];
                 fence_async_smem();
                 fence_before_sync();
-                mbar_arrive(ya_full);
+                warp_arrive(ya_full);
+                if (warp == 8 && lane == 0) {
+                    // one producer thread issues the Q projection MMA (its TMEM buffer must have been read by the
+                    // epilogue of two tiles ago)
+                    mbar_wait(ya_full, it & 1);
+                    if (it >= 2) mbar_wait(&qp_free[it & 1], ((it >> 1) - 1) & 1);
+                    fence_after_sync();
+                    const uint32_t yab = smem_u32(sYA), wq = smem_u32(sWq);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_ss(tmem_addr(tb, 0, A2_QP + 64 * (it & 1)), smem_desc(yab + ks * 4096, 2048, 128),
+                               smem_desc(wq + ks * 2048, 1024, 128), idesc_bf16(128, 64, 0, 0), ks > 0);
+                    mma_commit(qp_done);
+                }
                 mbar_wait(qp_done, it & 1);
                 fence_after_sync();
                 if (it >= 2) mbar_wait(&aq_empty[stage], ((it >> 1) - 1) & 1);
 #pragma unroll
                 for (int c0 = 0; c0 < 64; c0 += 32) {
                     uint32_t v[32];
-                    tmem_ld32(tmem_addr(tb, 32 * quad, AC_QP + 64 * (it & 1) + c0), v);
+                    tmem_ld32(tmem_addr(tb, 32 * quad, A2_QP + 64 * (it & 1) + c0), v);
                     tmem_ld_wait32(v);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -887,7 +1177,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply_tc_kernel(const APa
             }
             fence_async_smem();
             fence_before_sync();
-            mbar_arrive(&aq_full[stage]);
+            warp_arrive(&aq_full[stage]);
         }
     } else {
         reg_inc<184>();
@@ -895,67 +1185,110 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply_tc_kernel(const APa
         const int g = warp >> 2, quad = warp & 3;
         const int row = 32 * quad + lane;
         const uint32_t lane_base = 32 * quad;
-        const uint32_t sbase = tmem_addr(tb, lane_base, AC_S + 128 * g);
-        uint32_t ph_s = 0;
+        uint32_t ph_s[2] = {0, 0};
+        float o1[2][16];                 // O1 of the tile whose fc_o is in flight (features 16p.. of the two pairs)
+        float inv_l[2][2] = {{1.f, 1.f}, {1.f, 1.f}};
+
+        uint32_t va[32], vb[32];
+        auto issue_loads = [&](const int hh, const bool live) {
+            const int c = 2 * g + hh;
+            mbar_wait(&s_full[c], ph_s[hh]);
+            ph_s[hh] ^= 1;
+            fence_after_sync();
+            if (live) {
+                const uint32_t sb = tmem_addr(tb, lane_base, A2_S + 64 * c);
+                tmem_ld32(sb, va);
+                tmem_ld32(sb + 32, vb);
+            }
+        };
+        // softmax over the 64 keys of one head; the next item's scores (other chain) are prefetched meanwhile
+        auto softmax_item = [&](const int hh, const int pp, const bool live, const bool has_next) {
+            const int c = 2 * g + hh, cn = 2 * g + (hh ^ 1);
+            const uint32_t sbase = tmem_addr(tb, lane_base, A2_S + 64 * c);
+            const uint32_t snext = tmem_addr(tb, lane_base, A2_S + 64 * cn);
+            if (live) {
+                uint32_t pk[16];
+                tmem_ld_wait64(va, vb);
+                const float mx = max64(va, vb);
+                const float2 neg2 = make_float2(-mx, -mx);
+                float2 sum2 = make_float2(0.f, 0.f);
+                exp_chunk32(va, neg2, sum2, pk);
+                tmem_st16(sbase, pk);
+                if (has_next) {
+                    mbar_wait(&s_full[cn], ph_s[hh ^ 1]);
+                    ph_s[hh ^ 1] ^= 1;
+                    fence_after_sync();
+                    tmem_ld32(snext, va);
+                }
+                exp_chunk32(vb, neg2, sum2, pk);
+                tmem_st16(sbase + 16, pk);
+                if (has_next) tmem_ld32(snext + 32, vb);
+                inv_l[pp][hh] = __fdividef(1.f, sum2.x + sum2.y);
+                tmem_st_wait();
+            } else if (has_next) {
+                mbar_wait(&s_full[cn], ph_s[hh ^ 1]);
+                ph_s[hh ^ 1] ^= 1;
+                fence_after_sync();
+            }
+            fence_before_sync();
+            warp_arrive(&p_ready[c]);
+        };
+        // Y = O1 + relu(fc_o(O1) + bo) for the tile whose O1 is held in o1[][]
+        auto f_epilogue = [&](const int t) {
+            const int n = (tile0 + t) * 128 + row;
+            const bool valid = n < P.N;
+            const bool live = (tile0 + t) * 128 + 32 * quad < P.N;
+            mbar_wait(f_full, t & 1);
+            fence_after_sync();
+            if (live) {
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp) {
+                    const int p = g + 2 * pp;
+                    uint32_t fv[16];
+                    tmem_ld16(tmem_addr(tb, lane_base, A2_F + 16 * p), fv);
+                    tmem_ld_wait16(fv);
+                    uint4 out[2];
+                    uint32_t* ow = reinterpret_cast<uint32_t*>(out);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        const float y0 = o1[pp][j] + fmaxf(__uint_as_float(fv[j]) + sBo[16 * p + j], 0.f);
+                        const float y1 = o1[pp][j + 1] + fmaxf(__uint_as_float(fv[j + 1]) + sBo[16 * p + j + 1], 0.f);
+                        ow[j >> 1] = pack_bf16(y0, y1);
+                    }
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(P.Yout + ((size_t)cloud * P.N + n) * 64 + 16 * p);
+                        dst[0] = out[0];
+                        dst[1] = out[1];
+                    }
+                }
+            }
+            fence_before_sync();
+        };
         for (int it = 0; it < ntiles; ++it) {
             const int n = (tile0 + it) * 128 + row;
             const bool valid = n < P.N;
-            const bool warp_live = (tile0 + it) * 128 + 32 * quad < P.N;    // warps whose 32 rows are all padding idle
-            float inv_l[2][2] = {{1.f, 1.f}, {1.f, 1.f}};
-            // ---- softmax over the 64 keys of each head, two heads per pair
-#pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-                mbar_wait(&s_full[g], ph_s);
-                ph_s ^= 1;
-                fence_after_sync();
-                if (warp_live) {
-                    uint32_t va[32], vb[32], pk[16];
-                    tmem_ld32(sbase, va);
-                    tmem_ld32(sbase + 32, vb);
-                    tmem_ld_wait32(va);
-                    tmem_ld_wait32(vb);
-                    // head 0 of the pair: columns 0..63
-                    float mx = max_chunk32(vb, max_chunk32(va, -INFINITY));
-                    float2 neg2 = make_float2(-mx, -mx), sum2 = make_float2(0.f, 0.f);
-                    exp_chunk32(va, neg2, sum2, pk);
-                    tmem_ld32(sbase + 64, va);                       // head 1, first half, in flight
-                    tmem_st16(sbase, pk);
-                    exp_chunk32(vb, neg2, sum2, pk);
-                    tmem_ld32(sbase + 96, vb);
-                    tmem_st16(sbase + 16, pk);
-                    inv_l[pp][0] = __fdividef(1.f, sum2.x + sum2.y);
-                    tmem_ld_wait32(va);
-                    tmem_ld_wait32(vb);
-                    // head 1: columns 64..127; its P goes to columns 32..63 (scores of head 0, consumed)
-                    mx = max_chunk32(vb, max_chunk32(va, -INFINITY));
-                    neg2 = make_float2(-mx, -mx);
-                    sum2 = make_float2(0.f, 0.f);
-                    exp_chunk32(va, neg2, sum2, pk);
-                    tmem_st16(sbase + 32, pk);
-                    exp_chunk32(vb, neg2, sum2, pk);
-                    tmem_st16(sbase + 48, pk);
-                    inv_l[pp][1] = __fdividef(1.f, sum2.x + sum2.y);
-                    tmem_st_wait();
-                }
-                fence_before_sync();
-                mbar_arrive(&p_ready[g]);
-            }
+            const bool live = (tile0 + it) * 128 + 32 * quad < P.N;     // warps whose 32 rows are all padding idle
+            issue_loads(0, live);
+            softmax_item(0, 0, live, true);
+            if (it > 0) f_epilogue(it - 1);          // deferred: the fc_o round trip hides behind the first softmax
+            softmax_item(1, 0, live, true);
+            softmax_item(0, 1, live, true);
+            softmax_item(1, 1, live, false);
             // ---- O1 = Qp + (P V) / l, features 16p .. 16p+15 for this warpgroup's two pairs
             float x[4] = {0.f, 0.f, 0.f, 0.f};
             if (!DIN64 && valid) {
                 const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
                 for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
             }
-            float o1[2][16];
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
                 const int p = g + 2 * pp;
                 mbar_wait(&o_full[p], it & 1);
                 fence_after_sync();
-                if (warp_live) {
+                if (live) {
                     uint32_t o[16], qv[16];
-                    tmem_ld16(tmem_addr(tb, lane_base, AC_O + 16 * p), o);
-                    if (DIN64) tmem_ld16(tmem_addr(tb, lane_base, AC_QP + 64 * (it & 1) + 16 * p), qv);
+                    tmem_ld16(tmem_addr(tb, lane_base, A2_O + 16 * p), o);
+                    if (DIN64) tmem_ld16(tmem_addr(tb, lane_base, A2_QP + 64 * (it & 1) + 16 * p), qv);
                     tmem_ld_wait16(o);
                     if (DIN64) tmem_ld_wait16(qv);
 #pragma unroll
@@ -976,38 +1309,13 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply_tc_kernel(const APa
             }
             if (DIN64) {
                 fence_before_sync();
-                mbar_arrive(&qp_free[it & 1]);
+                warp_arrive(&qp_free[it & 1]);
             }
             fence_async_smem();
             fence_before_sync();
-            mbar_arrive(o1_ready);
-            // ---- Y = O1 + relu(fc_o(O1))
-            mbar_wait(f_full, it & 1);
-            fence_after_sync();
-            if (warp_live) {
-#pragma unroll
-                for (int pp = 0; pp < 2; ++pp) {
-                    const int p = g + 2 * pp;
-                    uint32_t fv[16];
-                    tmem_ld16(tmem_addr(tb, lane_base, AC_F + 16 * p), fv);
-                    tmem_ld_wait16(fv);
-                    uint4 out[2];
-                    uint32_t* ow = reinterpret_cast<uint32_t*>(out);
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        const float y0 = o1[pp][j] + fmaxf(__uint_as_float(fv[j]) + sBo[16 * p + j], 0.f);
-                        const float y1 = o1[pp][j + 1] + fmaxf(__uint_as_float(fv[j + 1]) + sBo[16 * p + j + 1], 0.f);
-                        ow[j >> 1] = pack_bf16(y0, y1);
-                    }
-                    if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>(P.Yout + ((size_t)cloud * P.N + n) * 64 + 16 * p);
-                        dst[0] = out[0];
-                        dst[1] = out[1];
-                    }
-                }
-            }
-            fence_before_sync();
+            warp_arrive(o1_ready);
         }
+        f_epilogue(ntiles - 1);
     }
     fence_before_sync();
     __syncthreads();
@@ -1032,14 +1340,14 @@ __global__ void __launch_bounds__(64) finalize_pma_kernel(const PParams P) {
     float mmax = -INFINITY;
     for (int s = 0; s < P.nsplit; ++s)
         for (int w2 = 0; w2 < 2; ++w2)
-            mmax = fmaxf(mmax, P.part[((((size_t)cloud * P.nsplit + s) * TH + h) * TM + w2) * 10]);
+            mmax = fmaxf(mmax, P.part[(((size_t)cloud * P.nsplit + s) * TH + h) * 10 * TM + w2]);
     float l = 0.f, a = 0.f;
     for (int s = 0; s < P.nsplit; ++s)
         for (int w2 = 0; w2 < 2; ++w2) {
-            const float* pp = P.part + ((((size_t)cloud * P.nsplit + s) * TH + h) * TM + w2) * 10;
+            const float* pp = P.part + (((size_t)cloud * P.nsplit + s) * TH + h) * 10 * TM + w2;
             const float w = exp2f(pp[0] - mmax);
-            l = fmaf(pp[1], w, l);
-            a = fmaf(pp[2 + d], w, a);
+            l = fmaf(pp[TM], w, l);
+            a = fmaf(pp[(2 + d) * TM], w, a);
         }
     sO[f] = P.QpS[f] + a / l;
     __syncthreads();
@@ -1080,7 +1388,7 @@ static TcLayout tc_layout(int B, int N) {
     Arena a(nullptr, 0);
     TcLayout L;
     L.consts = a.off; a.take<uint8_t>(sizeof(TcConsts));
-    L.part = a.off; a.take<float>((size_t)B * s.nsplit * TH * TM * 10);
+    L.part = a.off; a.take<float>((size_t)B * 2 * s.nsplit * TH * TM * 10);
     L.kvblk = a.off; a.take<uint8_t>((size_t)B * 32768);
     L.y1 = a.off; a.take<__nv_bfloat16>((size_t)B * N * 64);
     L.y2 = a.off; a.take<__nv_bfloat16>((size_t)B * N * 64);
@@ -1129,11 +1437,11 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     {
         RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, c->Aq0, m00.Wkv, m00.bkv, nullptr, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * d_in * TD + 2.0 * TM * TD), pts * 4.0 * d_in);
-        mab_reduce_tc_kernel<false, false><<<grid, TC_THREADS16, RSmem::TOTAL, st>>>(r);
+        mab_reduce2_tc_kernel<false><<<grid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<small>");
     {
-        FParams f{part, sp.nsplit, c->Qp0, c->WoT[0], m00.bo, c->WkvT[0], m01.bkv, kvblk, dbg ? dbg->H1 : nullptr};
+        FParams f{part, 2 * sp.nsplit, c->Qp0, c->WoT[0], m00.bo, c->WkvT[0], m01.bkv, kvblk, dbg ? dbg->H1 : nullptr};
         LaunchTimer lt("finalize_isab_kernel", st, (double)B * 2.0 * (TM * TD * TD + TM * TD * 2 * TD), (double)B * 32768.0);
         finalize_isab_kernel<<<B, 256, fsmem, st>>>(f);
     }
@@ -1141,18 +1449,18 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     {
         AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, kvblk, m01.Wq, m01.bq, nullptr, c->Wo0, m01.bo, Y1};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * d_in * TD + 2.0 * TM * TD + TD * TD), pts * (4.0 * d_in + 128.0));
-        mab_apply_tc_kernel<false><<<grid, TC_THREADS16, ASmem::TOTAL, st>>>(a);
+        mab_apply2_tc_kernel<false><<<grid, TC_THREADS16, A2Smem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<small>");
     // ---- ISAB 1
     {
         RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, c->Aq1, nullptr, m10.bkv, c->Wkv1, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TM * TD), pts * 128.0);
-        mab_reduce_tc_kernel<true, false><<<grid, TC_THREADS16, RSmem::TOTAL, st>>>(r);
+        mab_reduce2_tc_kernel<true><<<grid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<64>");
     {
-        FParams f{part, sp.nsplit, c->Qp1, c->WoT[1], m10.bo, c->WkvT[1], m11.bkv, kvblk, dbg ? dbg->H2 : nullptr};
+        FParams f{part, 2 * sp.nsplit, c->Qp1, c->WoT[1], m10.bo, c->WkvT[1], m11.bkv, kvblk, dbg ? dbg->H2 : nullptr};
         LaunchTimer lt("finalize_isab_kernel", st, (double)B * 2.0 * (TM * TD * TD + TM * TD * 2 * TD), (double)B * 32768.0);
         finalize_isab_kernel<<<B, 256, fsmem, st>>>(f);
     }
@@ -1160,7 +1468,7 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     {
         AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, kvblk, nullptr, m11.bq, c->Wq1, c->Wo1, m11.bo, Y2};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * TD * TD + 2.0 * TM * TD + TD * TD), pts * 256.0);
-        mab_apply_tc_kernel<true><<<grid, TC_THREADS16, ASmem::TOTAL, st>>>(a);
+        mab_apply2_tc_kernel<true><<<grid, TC_THREADS16, A2Smem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<64>");
     // ---- PMA + Linear
@@ -1192,11 +1500,11 @@ static int tc_configure() {
     PCA_CHECK_CUDA(cudaGetDevice(&dev));
     PCA_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major != 10) return fail(PCA_EDEVICE, "tcgen05 path needs an sm_100 device (found compute capability %d.x)", major);
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSmem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSmem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSmem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASmem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASmem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
     done = true;
     return 0;
