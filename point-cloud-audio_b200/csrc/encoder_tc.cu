@@ -128,6 +128,7 @@ struct RParams {
     const float* X32;             // (B, N, d_in) fp32      [DIN64 == false]
     const __nv_bfloat16* Y16;     // (B, N, 64) bf16        [DIN64 == true]
     int N, d_in, tiles_total, tiles_per_split, nsplit;
+    int n_work;                   // work items (cloud, split) for the persistent kernels
     const uint8_t* Aq;            // 16 KB query operand (stacked pairs, or all-heads image in PMA mode)
     const float* Wkv32;           // (128, d_in) fp32       [DIN64 == false]
     const float* bkv;             // (128)
@@ -660,7 +661,7 @@ __global__ void __launch_bounds__(256) finalize_isab_kernel(const FParams P) {
 struct AParams {
     const float* X32;             // (B, N, d_in)           [DIN64 == false]
     const __nv_bfloat16* Y16in;   // (B, N, 64)             [DIN64 == true]
-    int N, d_in, tiles_total, tiles_per_split;
+    int N, d_in, tiles_total, tiles_per_split, nsplit, n_work;
     const uint8_t* KVblk;         // per cloud: K image 16384 B | V image 16384 B
     const float* Wq32;            // (64, d_in)             [DIN64 == false]
     const float* bq;              // (64)
@@ -700,6 +701,9 @@ struct R2Smem {
 // 64-column softmax step on registers: returns the chunk max
 __device__ __forceinline__ float max64(const uint32_t* va, const uint32_t* vb) { return max_chunk32(vb, max_chunk32(va, -INFINITY)); }
 
+// Persistent: grid = min(#work items, #SMs); CTA k walks the work items (cloud, point-split) k, k + grid, ...
+// Barriers, TMEM and the resident operands are set up once; all pipelines (producer -> MMA -> softmax) run
+// straight across work-item boundaries, so there is no per-cloud fill/drain bubble.
 template <bool DIN64>
 __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const RParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -710,19 +714,23 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const R
     float* sWsm = reinterpret_cast<float*>(smem + R2Smem::SMALL);
     float* sBias = sWsm + 128 * 4;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + R2Smem::BARS);
-    uint64_t* kv_full = bars;          // [2] count 128
-    uint64_t* kv_empty = bars + 2;     // [2] count 1
+    uint64_t* kv_full = bars;          // [2] count 4 (producer warps)
+    uint64_t* kv_empty = bars + 2;     // [2] count 4 (chains)
     uint64_t* s_full = bars + 4;       // [4] count 1
-    uint64_t* p_ready = bars + 8;      // [4] count 128
+    uint64_t* p_ready = bars + 8;      // [4] count 4 (warps of the owning warpgroup)
     uint64_t* o_full = bars + 12;      // [8] count 1   (region = 2 * pair + half)
-    uint64_t* y_full = bars + 20;      // count 128
+    uint64_t* y_full = bars + 20;      // count 4
     uint64_t* proj_done = bars + 21;   // count 1
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cloud = blockIdx.y, split = blockIdx.x;
-    const int tile0 = split * P.tiles_per_split;
-    const int ntiles = min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+    const int n_work = P.n_work, wstep = gridDim.x;
+    auto work_tiles = [&](int w, int& cloud, int& split, int& tile0) {
+        cloud = w / P.nsplit;
+        split = w - cloud * P.nsplit;
+        tile0 = split * P.tiles_per_split;
+        return min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+    };
 
     copy_to_smem(sAq, P.Aq, 16384);
     if (DIN64) copy_to_smem(sW, P.Wkv16, 16384);
@@ -758,25 +766,30 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const R
             const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
             const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
             const uint32_t aq = smem_u32(sAq), kvb = smem_u32(sKV);
-            const int nitems = 2 * ntiles;
-            for (int j = 0; j < nitems; ++j) {
-                const int t = j >> 1, p = (c >> 1) + 2 * (j & 1);
-                const uint32_t kbase = kvb + (t & 1) * 32768, vbase = kbase + 16384;
-                if ((j & 1) == 0) {
-                    mbar_wait(&kv_full[t & 1], (t >> 1) & 1);
+            int gt = 0;                                    // tiles processed by this CTA so far
+            for (int w = blockIdx.x; w < n_work; w += wstep) {
+                int cloud, split, tile0;
+                const int ntiles = work_tiles(w, cloud, split, tile0);
+                for (int it = 0; it < ntiles; ++it, ++gt) {
+                    const uint32_t kbase = kvb + (gt & 1) * 32768, vbase = kbase + 16384;
+                    mbar_wait(&kv_full[gt & 1], (gt >> 1) & 1);
                     fence_after_sync();
-                }
-                mma_ss(tmem_addr(tb, 0, R2_S + 64 * c), smem_desc(aq + p * 4096, 2048, 128),
-                       smem_desc(kbase + 2 * p * 2048 + half * 1024, 2048, 128), idesc_s, 0);
-                mma_commit(&s_full[c]);
-                mbar_wait(&p_ready[c], j & 1);
-                fence_after_sync();
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma_ts(tmem_addr(tb, 0, R2_O + 16 * (2 * p + half)), tmem_addr(tb, 0, R2_S + 64 * c + ks * 8),
-                           smem_desc(vbase + 2 * p * 2048 + half * 1024 + ks * 256, 128, 2048), idesc_pv, ks > 0);
-                mma_commit(&o_full[2 * p + half]);
-                if (j & 1) mma_commit(&kv_empty[t & 1]);        // 4 chains x 1 arrival free the K|V stage
+                    for (int pp = 0; pp < 2; ++pp) {
+                        const int p = (c >> 1) + 2 * pp;
+                        mma_ss(tmem_addr(tb, 0, R2_S + 64 * c), smem_desc(aq + p * 4096, 2048, 128),
+                               smem_desc(kbase + 2 * p * 2048 + half * 1024, 2048, 128), idesc_s, 0);
+                        mma_commit(&s_full[c]);
+                        mbar_wait(&p_ready[c], pp);          // two items per tile: parities 0, 1
+                        fence_after_sync();
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ts(tmem_addr(tb, 0, R2_O + 16 * (2 * p + half)), tmem_addr(tb, 0, R2_S + 64 * c + ks * 8),
+                                   smem_desc(vbase + 2 * p * 2048 + half * 1024 + ks * 256, 128, 2048), idesc_pv, ks > 0);
+                        mma_commit(&o_full[2 * p + half]);
+                    }
+                    mma_commit(&kv_empty[gt & 1]);            // 4 chains x 1 arrival free the K|V stage
+                }
             }
         }
     } else if (warp >= 8) {
@@ -784,71 +797,76 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const R
         // =================================================================== producer: K|V tiles
         const int quad = warp & 3;
         const int row = 32 * quad + lane;
-        for (int it = 0; it < ntiles; ++it) {
-            const int stage = it & 1;
-            const int n = (tile0 + it) * 128 + row;
-            const bool valid = n < P.N;
-            uint8_t* sK = sKV + stage * 32768;
-            uint8_t* sV = sK + 16384;
-            if (!DIN64) {
-                float x[4] = {0.f, 0.f, 0.f, 0.f};
-                if (valid) {
-                    const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
-                    for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
-                }
-                if (it >= 2) mbar_wait(&kv_empty[stage], ((it >> 1) - 1) & 1);
-#pragma unroll 4
-                for (int c = 0; c < 16; ++c) {
-                    float o[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 w = *reinterpret_cast<const float4*>(sWsm + (c * 8 + j) * 4);
-                        o[j] = valid ? fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], sBias[c * 8 + j])))) : 0.f;
+        int gt = 0;
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, split, tile0;
+            const int ntiles = work_tiles(w, cloud, split, tile0);
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int stage = gt & 1;
+                const int n = (tile0 + it) * 128 + row;
+                const bool valid = n < P.N;
+                uint8_t* sK = sKV + stage * 32768;
+                uint8_t* sV = sK + 16384;
+                if (!DIN64) {
+                    float x[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (valid) {
+                        const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                        for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
                     }
-                    st_shared_8bf16((c < 8 ? sK + c * 2048 : sV + (c - 8) * 2048) + row * 16, o);
-                }
-            } else {
-                const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
-                uint4 yv[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sY + c * 2048 + row * 16) = yv[c];
-                fence_async_smem();
-                fence_before_sync();
-                warp_arrive(y_full);
-                if (warp == 8 && lane == 0) {
-                    // one producer thread issues the K|V projection MMA once all 128 rows of Y are staged
-                    mbar_wait(y_full, it & 1);
-                    fence_after_sync();
-                    const uint32_t yb = smem_u32(sY), wb = smem_u32(sW);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_ss(tmem_addr(tb, 0, R2_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
-                               idesc_bf16(128, 128, 0, 0), ks > 0);
-                    mma_commit(proj_done);
-                }
-                mbar_wait(proj_done, it & 1);
-                fence_after_sync();
-                if (it >= 2) mbar_wait(&kv_empty[stage], ((it >> 1) - 1) & 1);
-#pragma unroll
-                for (int c0 = 0; c0 < 128; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_addr(tb, 32 * quad, R2_PROJ + c0), v);
-                    tmem_ld_wait32(v);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
+#pragma unroll 4
+                    for (int c = 0; c < 16; ++c) {
                         float o[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] = valid ? __uint_as_float(v[8 * q + j]) + sBias[c0 + 8 * q + j] : 0.f;
-                        const int chunk = c0 / 8 + q;
-                        st_shared_8bf16((chunk < 8 ? sK + chunk * 2048 : sV + (chunk - 8) * 2048) + row * 16, o);
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 wv = *reinterpret_cast<const float4*>(sWsm + (c * 8 + j) * 4);
+                            o[j] = valid ? fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBias[c * 8 + j])))) : 0.f;
+                        }
+                        st_shared_8bf16((c < 8 ? sK + c * 2048 : sV + (c - 8) * 2048) + row * 16, o);
+                    }
+                } else {
+                    const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
+                    uint4 yv[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sY + c * 2048 + row * 16) = yv[c];
+                    fence_async_smem();
+                    fence_before_sync();
+                    warp_arrive(y_full);
+                    if (warp == 8 && lane == 0) {
+                        // one producer thread issues the K|V projection MMA once all 128 rows of Y are staged
+                        mbar_wait(y_full, gt & 1);
+                        fence_after_sync();
+                        const uint32_t yb = smem_u32(sY), wb = smem_u32(sW);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ss(tmem_addr(tb, 0, R2_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
+                                   idesc_bf16(128, 128, 0, 0), ks > 0);
+                        mma_commit(proj_done);
+                    }
+                    mbar_wait(proj_done, gt & 1);
+                    fence_after_sync();
+                    if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
+#pragma unroll
+                    for (int c0 = 0; c0 < 128; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_addr(tb, 32 * quad, R2_PROJ + c0), v);
+                        tmem_ld_wait32(v);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float o[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = valid ? __uint_as_float(v[8 * q + j]) + sBias[c0 + 8 * q + j] : 0.f;
+                            const int chunk = c0 / 8 + q;
+                            st_shared_8bf16((chunk < 8 ? sK + chunk * 2048 : sV + (chunk - 8) * 2048) + row * 16, o);
+                        }
                     }
                 }
+                fence_async_smem();
+                fence_before_sync();
+                warp_arrive(&kv_full[stage]);
             }
-            fence_async_smem();
-            fence_before_sync();
-            warp_arrive(&kv_full[stage]);
         }
     } else {
         reg_inc<184>();
@@ -859,17 +877,10 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const R
         const uint32_t ocol_off = (row >= 64) ? 8u : 0u;
         // running statistics per (half, pp)
         float m_run[2][2], l_run[2][2], alpha[2][2], acc[2][2][8];
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                m_run[a][b] = -INFINITY; l_run[a][b] = 0.f; alpha[a][b] = 0.f;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[a][b][j] = 0.f;
-            }
         uint32_t ph_s[2] = {0, 0};
-
         uint32_t va[32], vb[32];        // scores of the item being processed / prefetched for the next item
+        int gt = 0;
+
         auto issue_loads = [&](const int half) {
             const int c = 2 * g + half;
             mbar_wait(&s_full[c], ph_s[half]);
@@ -940,42 +951,55 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const R
             fence_before_sync();
             warp_arrive(&p_ready[c]);
         };
-        auto consume_item = [&](const int half, const int pp, const int it) {
+        auto consume_item = [&](const int half, const int pp, const int tile_parity) {
             const int p = g + 2 * pp;
-            mbar_wait(&o_full[2 * p + half], it & 1);
+            mbar_wait(&o_full[2 * p + half], tile_parity);
             fence_after_sync();
             uint32_t o[8];
             tmem_ld8(tmem_addr(tb, lane_base, R2_O + 16 * (2 * p + half) + ocol_off), o);
-            // wait::ld would also drain the prefetched score loads, which is harmless (they are needed next anyway)
+            // wait::ld also drains the prefetched score loads, which is harmless (they are needed next anyway)
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[half][pp][j] = fmaf(acc[half][pp][j], alpha[half][pp], __uint_as_float(o[j]));
         };
-        issue_loads(0);
-        for (int it = 0; it < ntiles; ++it) {
-            const int n_valid = min(128, P.N - (tile0 + it) * 128);
-            const int nv0 = min(64, n_valid), nv1 = max(0, n_valid - 64);
-            softmax_item(0, 0, nv0, true);
-            if (it > 0) consume_item(1, 1, it - 1);
-            softmax_item(1, 0, nv1, true);
-            consume_item(0, 0, it);
-            softmax_item(0, 1, nv0, true);
-            consume_item(1, 0, it);
-            softmax_item(1, 1, nv1, it + 1 < ntiles);
-            consume_item(0, 1, it);
-        }
-        consume_item(1, 1, ntiles - 1);
+        if (blockIdx.x < n_work) issue_loads(0);
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, split, tile0;
+            const int ntiles = work_tiles(w, cloud, split, tile0);
+            const bool more_work = w + wstep < n_work;
 #pragma unroll
-        for (int half = 0; half < 2; ++half)
+            for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-                const int h = 2 * (g + 2 * pp) + (row >> 6);
-                float* dst = P.part + (((size_t)cloud * (2 * P.nsplit) + 2 * split + half) * TH + h) * 10 * TM + (row & 63);
-                dst[0] = m_run[half][pp];
-                dst[TM] = l_run[half][pp];
+                for (int b = 0; b < 2; ++b) {
+                    m_run[a][b] = -INFINITY; l_run[a][b] = 0.f; alpha[a][b] = 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dst[(2 + j) * TM] = acc[half][pp][j];
+                    for (int j = 0; j < 8; ++j) acc[a][b][j] = 0.f;
+                }
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int n_valid = min(128, P.N - (tile0 + it) * 128);
+                const int nv0 = min(64, n_valid), nv1 = max(0, n_valid - 64);
+                softmax_item(0, 0, nv0, true);
+                if (it > 0) consume_item(1, 1, (gt - 1) & 1);
+                softmax_item(1, 0, nv1, true);
+                consume_item(0, 0, gt & 1);
+                softmax_item(0, 1, nv0, true);
+                consume_item(1, 0, gt & 1);
+                softmax_item(1, 1, nv1, it + 1 < ntiles || more_work);
+                consume_item(0, 1, gt & 1);
             }
+            consume_item(1, 1, (gt - 1) & 1);
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp) {
+                    const int h = 2 * (g + 2 * pp) + (row >> 6);
+                    float* dst = P.part + (((size_t)cloud * (2 * P.nsplit) + 2 * split + half) * TH + h) * 10 * TM + (row & 63);
+                    dst[0] = m_run[half][pp];
+                    dst[TM] = l_run[half][pp];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[(2 + j) * TM] = acc[half][pp][j];
+                }
+        }
     }
     fence_before_sync();
     __syncthreads();
@@ -986,23 +1010,23 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const R
 constexpr uint32_t A2_S = 0, A2_O = 256, A2_F = 320, A2_QP = 384;
 
 struct A2Smem {
-    static constexpr int KB = 0;
-    static constexpr int VB = 16384;
-    static constexpr int WO = 32768;
+    static constexpr int IMG = 0;                 // 2 x (K image 16384 | V image 16384), one per work item in flight
+    static constexpr int WO = 65536;
     static constexpr int WQ = WO + 8192;
     static constexpr int AQ = WQ + 8192;          // 2 stages x 16384
     static constexpr int YA = AQ + 32768;
     static constexpr int O1 = YA + 16384;
     static constexpr int SMALL = O1 + 16384;      // fp32: Wq32 padded (64 x 4) | bq (64) | bo (64)
     static constexpr int BARS = SMALL + (64 * 4 + 128) * 4;
-    static constexpr int TOTAL = BARS + 32 * 8 + 16;
+    static constexpr int TOTAL = BARS + 40 * 8 + 16;
 };
 
+// Persistent like the reduce kernel: one CTA per SM walks the work items (cloud, point-split); the per-cloud
+// K / V operand images of the next work item are staged while the current one is still being processed.
 template <bool DIN64>
 __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sKb = smem + A2Smem::KB;
-    uint8_t* sVb = smem + A2Smem::VB;
+    uint8_t* sImg = smem + A2Smem::IMG;
     uint8_t* sWo = smem + A2Smem::WO;
     uint8_t* sWq = smem + A2Smem::WQ;
     uint8_t* sAQ = smem + A2Smem::AQ;
@@ -1012,25 +1036,30 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
     float* sBq = sWq32 + 64 * 4;
     float* sBo = sBq + 64;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A2Smem::BARS);
-    uint64_t* aq_full = bars;          // [2] count 128
-    uint64_t* aq_empty = bars + 2;     // [2] count 1
+    uint64_t* aq_full = bars;          // [2] count 4
+    uint64_t* aq_empty = bars + 2;     // [2] count 4
     uint64_t* s_full = bars + 4;       // [4] count 1
-    uint64_t* p_ready = bars + 8;      // [4] count 128
+    uint64_t* p_ready = bars + 8;      // [4] count 4
     uint64_t* o_full = bars + 12;      // [4] count 1
-    uint64_t* o1_ready = bars + 16;    // count 256
+    uint64_t* o1_ready = bars + 16;    // count 8
     uint64_t* f_full = bars + 17;      // count 1
-    uint64_t* ya_full = bars + 18;     // count 128
+    uint64_t* ya_full = bars + 18;     // count 4
     uint64_t* qp_done = bars + 19;     // count 1
-    uint64_t* qp_free = bars + 20;     // [2] count 256
+    uint64_t* qp_free = bars + 20;     // [2] count 8
     uint64_t* pv0_done = bars + 22;    // [4] count 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+    uint64_t* img_full = bars + 26;    // [2] count 4 (producer warps)
+    uint64_t* img_empty = bars + 28;   // [2] count 4 (chains)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cloud = blockIdx.y, split = blockIdx.x;
-    const int tile0 = split * P.tiles_per_split;
-    const int ntiles = min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+    const int n_work = P.n_work, wstep = gridDim.x;
+    auto work_tiles = [&](int w, int& cloud, int& tile0) {
+        cloud = w / P.nsplit;
+        const int split = w - cloud * P.nsplit;
+        tile0 = split * P.tiles_per_split;
+        return min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+    };
 
-    copy_to_smem(sKb, P.KVblk + (size_t)cloud * 32768, 32768);
     copy_to_smem(sWo, P.Wo16, 8192);
     if (DIN64) copy_to_smem(sWq, P.Wq16, 8192);
     for (int i = threadIdx.x; i < 64; i += blockDim.x) {
@@ -1043,9 +1072,11 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
     }
     if (warp == 12) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&aq_full[i], 4); mbar_init(&aq_empty[i], 4); mbar_init(&qp_free[i], 8); }
-        for (int i = 0; i < 4; ++i) mbar_init(&pv0_done[i], 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&aq_full[i], 4); mbar_init(&aq_empty[i], 4); mbar_init(&qp_free[i], 8);
+            mbar_init(&img_full[i], 4); mbar_init(&img_empty[i], 4);
+        }
+        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); mbar_init(&pv0_done[i], 1); }
         mbar_init(o1_ready, 8);
         mbar_init(f_full, 1);
         mbar_init(ya_full, 4);
@@ -1068,11 +1099,10 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
             const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
             const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
             const uint32_t idesc_64 = idesc_bf16(128, 64, 0, 0);
-            const uint32_t kb = smem_u32(sKb), vb = smem_u32(sVb), wo = smem_u32(sWo);
+            const uint32_t img = smem_u32(sImg), wo = smem_u32(sWo);
             const uint32_t aqb = smem_u32(sAQ), o1b = smem_u32(sO1);
-            const int nitems = 2 * ntiles;
-            auto issue_f = [&](int t) {          // fc_o of tile t once both warpgroups have staged O1
-                mbar_wait(o1_ready, t & 1);
+            auto issue_f = [&](int tile_parity) {          // fc_o of a tile once both warpgroups have staged O1
+                mbar_wait(o1_ready, tile_parity);
                 fence_after_sync();
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
@@ -1080,104 +1110,131 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
                            idesc_64, ks > 0);
                 mma_commit(f_full);
             };
-            for (int j = 0; j < nitems; ++j) {
-                const int t = j >> 1, pp = j & 1, p = (c >> 1) + 2 * pp;
-                if (pp == 0) {
-                    mbar_wait(&aq_full[t & 1], (t >> 1) & 1);
-                    fence_after_sync();
-                }
-                mma_ss(tmem_addr(tb, 0, A2_S + 64 * c), smem_desc(aqb + (t & 1) * 16384 + 2 * p * 2048, 2048, 128),
-                       smem_desc(kb + p * 4096 + hh * 1024, 2048, 128), idesc_s, 0);
-                mma_commit(&s_full[c]);
-                if (pp == 0 && t > 0) {
-                    // the pair outputs of tile t-1 are consumed once its O1 is staged; chain 0 also launches its fc_o
-                    if (c == 0) issue_f(t - 1);
-                    else { mbar_wait(o1_ready, (t - 1) & 1); fence_after_sync(); }
-                }
-                mbar_wait(&p_ready[c], j & 1);
+            int gt = 0, wl = 0;
+            for (int w = blockIdx.x; w < n_work; w += wstep, ++wl) {
+                int cloud, tile0;
+                const int ntiles = work_tiles(w, cloud, tile0);
+                const uint32_t kb = img + (wl & 1) * 32768, vb = kb + 16384;
+                mbar_wait(&img_full[wl & 1], (wl >> 1) & 1);
                 fence_after_sync();
-                if (hh == 1) { mbar_wait(&pv0_done[p], t & 1); fence_after_sync(); }
+                for (int it = 0; it < ntiles; ++it, ++gt) {
+                    mbar_wait(&aq_full[gt & 1], (gt >> 1) & 1);
+                    fence_after_sync();
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma_ts(tmem_addr(tb, 0, A2_O + 16 * p), tmem_addr(tb, 0, A2_S + 64 * c + ks * 8),
-                           smem_desc(vb + p * 4096 + hh * 1024 + ks * 256, 128, 2048), idesc_pv, (hh == 1 || ks > 0) ? 1u : 0u);
-                mma_commit(hh == 0 ? &pv0_done[p] : &o_full[p]);
-                if (pp == 1) mma_commit(&aq_empty[t & 1]);      // 4 chains x 1 arrival free the query stage
+                    for (int pp = 0; pp < 2; ++pp) {
+                        const int p = (c >> 1) + 2 * pp;
+                        mma_ss(tmem_addr(tb, 0, A2_S + 64 * c), smem_desc(aqb + (gt & 1) * 16384 + 2 * p * 2048, 2048, 128),
+                               smem_desc(kb + p * 4096 + hh * 1024, 2048, 128), idesc_s, 0);
+                        mma_commit(&s_full[c]);
+                        if (pp == 0 && gt > 0) {
+                            // the pair outputs of the previous tile are consumed once its O1 is staged; chain 0 also
+                            // launches that tile's fc_o
+                            if (c == 0) issue_f((gt - 1) & 1);
+                            else { mbar_wait(o1_ready, (gt - 1) & 1); fence_after_sync(); }
+                        }
+                        mbar_wait(&p_ready[c], pp);
+                        fence_after_sync();
+                        if (hh == 1) { mbar_wait(&pv0_done[p], gt & 1); fence_after_sync(); }
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ts(tmem_addr(tb, 0, A2_O + 16 * p), tmem_addr(tb, 0, A2_S + 64 * c + ks * 8),
+                                   smem_desc(vb + p * 4096 + hh * 1024 + ks * 256, 128, 2048), idesc_pv, (hh == 1 || ks > 0) ? 1u : 0u);
+                        mma_commit(hh == 0 ? &pv0_done[p] : &o_full[p]);
+                    }
+                    mma_commit(&aq_empty[gt & 1]);          // 4 chains x 1 arrival free the query stage
+                }
+                mma_commit(&img_empty[wl & 1]);             // ... and the K / V images of this work item
             }
-            if (c == 0) issue_f(ntiles - 1);
+            if (c == 0 && gt > 0) issue_f((gt - 1) & 1);
         }
     } else if (warp >= 8) {
         reg_dec<88>();
-        // =================================================================== producer: scaled query operand
+        // =================================================================== producer: images + scaled query operand
         const int quad = warp & 3;
         const int row = 32 * quad + lane;
-        for (int it = 0; it < ntiles; ++it) {
-            const int stage = it & 1;
-            const int n = (tile0 + it) * 128 + row;
-            const bool valid = n < P.N;
-            uint8_t* dst = sAQ + stage * 16384;
-            if (!DIN64) {
-                float x[4] = {0.f, 0.f, 0.f, 0.f};
-                if (valid) {
-                    const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
-                    for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
-                }
-                if (it >= 2) mbar_wait(&aq_empty[stage], ((it >> 1) - 1) & 1);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float o[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 w = *reinterpret_cast<const float4*>(sWq32 + (c * 8 + j) * 4);
-                        const float q = fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], sBq[c * 8 + j]))));
-                        o[j] = valid ? q * kScaleLog2e : 0.f;
-                    }
-                    st_shared_8bf16(dst + c * 2048 + row * 16, o);
-                }
-            } else {
-                const uint4* src = reinterpret_cast<const uint4*>(P.Y16in + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
-                uint4 yv[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sYA + c * 2048 + row * 16) = yv[c];
+        const int ptid = threadIdx.x - 256;          // 0..127
+        int gt = 0, wl = 0;
+        for (int w = blockIdx.x; w < n_work; w += wstep, ++wl) {
+            int cloud, tile0;
+            const int ntiles = work_tiles(w, cloud, tile0);
+            {   // stage this cloud's block-diagonal K / V images (32 KB)
+                if (wl >= 2) mbar_wait(&img_empty[wl & 1], ((wl >> 1) - 1) & 1);
+                const uint4* src = reinterpret_cast<const uint4*>(P.KVblk + (size_t)cloud * 32768);
+                uint4* dst = reinterpret_cast<uint4*>(sImg + (wl & 1) * 32768);
+#pragma unroll 4
+                for (int i = ptid; i < 2048; i += 128) dst[i] = __ldg(src + i);
                 fence_async_smem();
                 fence_before_sync();
-                warp_arrive(ya_full);
-                if (warp == 8 && lane == 0) {
-                    // one producer thread issues the Q projection MMA (its TMEM buffer must have been read by the
-                    // epilogue of two tiles ago)
-                    mbar_wait(ya_full, it & 1);
-                    if (it >= 2) mbar_wait(&qp_free[it & 1], ((it >> 1) - 1) & 1);
-                    fence_after_sync();
-                    const uint32_t yab = smem_u32(sYA), wq = smem_u32(sWq);
+                warp_arrive(&img_full[wl & 1]);
+            }
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int stage = gt & 1;
+                const int n = (tile0 + it) * 128 + row;
+                const bool valid = n < P.N;
+                uint8_t* dst = sAQ + stage * 16384;
+                if (!DIN64) {
+                    float x[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (valid) {
+                        const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                        for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
+                    }
+                    if (gt >= 2) mbar_wait(&aq_empty[stage], ((gt >> 1) - 1) & 1);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_ss(tmem_addr(tb, 0, A2_QP + 64 * (it & 1)), smem_desc(yab + ks * 4096, 2048, 128),
-                               smem_desc(wq + ks * 2048, 1024, 128), idesc_bf16(128, 64, 0, 0), ks > 0);
-                    mma_commit(qp_done);
-                }
-                mbar_wait(qp_done, it & 1);
-                fence_after_sync();
-                if (it >= 2) mbar_wait(&aq_empty[stage], ((it >> 1) - 1) & 1);
-#pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_addr(tb, 32 * quad, A2_QP + 64 * (it & 1) + c0), v);
-                    tmem_ld_wait32(v);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int c = 0; c < 8; ++c) {
                         float o[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            o[j] = valid ? (__uint_as_float(v[8 * q + j]) + sBq[c0 + 8 * q + j]) * kScaleLog2e : 0.f;
-                        st_shared_8bf16(dst + (c0 / 8 + q) * 2048 + row * 16, o);
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 wv = *reinterpret_cast<const float4*>(sWq32 + (c * 8 + j) * 4);
+                            const float q = fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBq[c * 8 + j]))));
+                            o[j] = valid ? q * kScaleLog2e : 0.f;
+                        }
+                        st_shared_8bf16(dst + c * 2048 + row * 16, o);
+                    }
+                } else {
+                    const uint4* src = reinterpret_cast<const uint4*>(P.Y16in + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
+                    uint4 yv[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sYA + c * 2048 + row * 16) = yv[c];
+                    fence_async_smem();
+                    fence_before_sync();
+                    warp_arrive(ya_full);
+                    if (warp == 8 && lane == 0) {
+                        // one producer thread issues the Q projection MMA (its TMEM buffer must have been read by the
+                        // epilogue of two tiles ago)
+                        mbar_wait(ya_full, gt & 1);
+                        if (gt >= 2) mbar_wait(&qp_free[gt & 1], ((gt >> 1) - 1) & 1);
+                        fence_after_sync();
+                        const uint32_t yab = smem_u32(sYA), wq = smem_u32(sWq);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ss(tmem_addr(tb, 0, A2_QP + 64 * (gt & 1)), smem_desc(yab + ks * 4096, 2048, 128),
+                                   smem_desc(wq + ks * 2048, 1024, 128), idesc_bf16(128, 64, 0, 0), ks > 0);
+                        mma_commit(qp_done);
+                    }
+                    mbar_wait(qp_done, gt & 1);
+                    fence_after_sync();
+                    if (gt >= 2) mbar_wait(&aq_empty[stage], ((gt >> 1) - 1) & 1);
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_addr(tb, 32 * quad, A2_QP + 64 * (gt & 1) + c0), v);
+                        tmem_ld_wait32(v);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float o[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                o[j] = valid ? (__uint_as_float(v[8 * q + j]) + sBq[c0 + 8 * q + j]) * kScaleLog2e : 0.f;
+                            st_shared_8bf16(dst + (c0 / 8 + q) * 2048 + row * 16, o);
+                        }
                     }
                 }
+                fence_async_smem();
+                fence_before_sync();
+                warp_arrive(&aq_full[stage]);
             }
-            fence_async_smem();
-            fence_before_sync();
-            warp_arrive(&aq_full[stage]);
         }
     } else {
         reg_inc<184>();
@@ -1188,8 +1245,13 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
         uint32_t ph_s[2] = {0, 0};
         float o1[2][16];                 // O1 of the tile whose fc_o is in flight (features 16p.. of the two pairs)
         float inv_l[2][2] = {{1.f, 1.f}, {1.f, 1.f}};
-
         uint32_t va[32], vb[32];
+        // the tile whose fc_o epilogue is still pending (deferred behind the next tile's first softmax item)
+        __nv_bfloat16* pend_dst = nullptr;   // output row of this thread, nullptr = padding row
+        bool pend_live = false, pend_any = false;
+        int pend_parity = 0;
+        int gt = 0;
+
         auto issue_loads = [&](const int hh, const bool live) {
             const int c = 2 * g + hh;
             mbar_wait(&s_full[c], ph_s[hh]);
@@ -1233,14 +1295,11 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
             fence_before_sync();
             warp_arrive(&p_ready[c]);
         };
-        // Y = O1 + relu(fc_o(O1) + bo) for the tile whose O1 is held in o1[][]
-        auto f_epilogue = [&](const int t) {
-            const int n = (tile0 + t) * 128 + row;
-            const bool valid = n < P.N;
-            const bool live = (tile0 + t) * 128 + 32 * quad < P.N;
-            mbar_wait(f_full, t & 1);
+        // Y = O1 + relu(fc_o(O1) + bo) for the pending tile (its O1 is held in o1[][])
+        auto f_epilogue = [&]() {
+            mbar_wait(f_full, pend_parity);
             fence_after_sync();
-            if (live) {
+            if (pend_live) {
 #pragma unroll
                 for (int pp = 0; pp < 2; ++pp) {
                     const int p = g + 2 * pp;
@@ -1255,67 +1314,76 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
                         const float y1 = o1[pp][j + 1] + fmaxf(__uint_as_float(fv[j + 1]) + sBo[16 * p + j + 1], 0.f);
                         ow[j >> 1] = pack_bf16(y0, y1);
                     }
-                    if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>(P.Yout + ((size_t)cloud * P.N + n) * 64 + 16 * p);
+                    if (pend_dst != nullptr) {
+                        uint4* dst = reinterpret_cast<uint4*>(pend_dst + 16 * p);
                         dst[0] = out[0];
                         dst[1] = out[1];
                     }
                 }
             }
             fence_before_sync();
+            pend_any = false;
         };
-        for (int it = 0; it < ntiles; ++it) {
-            const int n = (tile0 + it) * 128 + row;
-            const bool valid = n < P.N;
-            const bool live = (tile0 + it) * 128 + 32 * quad < P.N;     // warps whose 32 rows are all padding idle
-            issue_loads(0, live);
-            softmax_item(0, 0, live, true);
-            if (it > 0) f_epilogue(it - 1);          // deferred: the fc_o round trip hides behind the first softmax
-            softmax_item(1, 0, live, true);
-            softmax_item(0, 1, live, true);
-            softmax_item(1, 1, live, false);
-            // ---- O1 = Qp + (P V) / l, features 16p .. 16p+15 for this warpgroup's two pairs
-            float x[4] = {0.f, 0.f, 0.f, 0.f};
-            if (!DIN64 && valid) {
-                const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
-                for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
-            }
-#pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-                const int p = g + 2 * pp;
-                mbar_wait(&o_full[p], it & 1);
-                fence_after_sync();
-                if (live) {
-                    uint32_t o[16], qv[16];
-                    tmem_ld16(tmem_addr(tb, lane_base, A2_O + 16 * p), o);
-                    if (DIN64) tmem_ld16(tmem_addr(tb, lane_base, A2_QP + 64 * (it & 1) + 16 * p), qv);
-                    tmem_ld_wait16(o);
-                    if (DIN64) tmem_ld_wait16(qv);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int f = 16 * p + j;
-                        float q;
-                        if (DIN64) {
-                            q = __uint_as_float(qv[j]) + sBq[f];
-                        } else {
-                            const float4 w = *reinterpret_cast<const float4*>(sWq32 + f * 4);
-                            q = fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], sBq[f]))));
-                        }
-                        o1[pp][j] = q + __uint_as_float(o[j]) * inv_l[pp][j >> 3];
-                    }
-                    st_shared_8bf16(sO1 + (2 * p) * 2048 + row * 16, &o1[pp][0]);
-                    st_shared_8bf16(sO1 + (2 * p + 1) * 2048 + row * 16, &o1[pp][8]);
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, tile0;
+            const int ntiles = work_tiles(w, cloud, tile0);
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int n = (tile0 + it) * 128 + row;
+                const bool valid = n < P.N;
+                const bool live = (tile0 + it) * 128 + 32 * quad < P.N;     // warps whose 32 rows are all padding idle
+                issue_loads(0, live);
+                softmax_item(0, 0, live, true);
+                if (pend_any) f_epilogue();              // deferred: the fc_o round trip hides behind the first softmax
+                softmax_item(1, 0, live, true);
+                softmax_item(0, 1, live, true);
+                softmax_item(1, 1, live, false);
+                // ---- O1 = Qp + (P V) / l, features 16p .. 16p+15 for this warpgroup's two pairs
+                float x[4] = {0.f, 0.f, 0.f, 0.f};
+                if (!DIN64 && valid) {
+                    const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                    for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
                 }
-            }
-            if (DIN64) {
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp) {
+                    const int p = g + 2 * pp;
+                    mbar_wait(&o_full[p], gt & 1);
+                    fence_after_sync();
+                    if (live) {
+                        uint32_t o[16], qv[16];
+                        tmem_ld16(tmem_addr(tb, lane_base, A2_O + 16 * p), o);
+                        if (DIN64) tmem_ld16(tmem_addr(tb, lane_base, A2_QP + 64 * (gt & 1) + 16 * p), qv);
+                        tmem_ld_wait16(o);
+                        if (DIN64) tmem_ld_wait16(qv);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int f = 16 * p + j;
+                            float q;
+                            if (DIN64) {
+                                q = __uint_as_float(qv[j]) + sBq[f];
+                            } else {
+                                const float4 wv = *reinterpret_cast<const float4*>(sWq32 + f * 4);
+                                q = fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBq[f]))));
+                            }
+                            o1[pp][j] = q + __uint_as_float(o[j]) * inv_l[pp][j >> 3];
+                        }
+                        st_shared_8bf16(sO1 + (2 * p) * 2048 + row * 16, &o1[pp][0]);
+                        st_shared_8bf16(sO1 + (2 * p + 1) * 2048 + row * 16, &o1[pp][8]);
+                    }
+                }
+                if (DIN64) {
+                    fence_before_sync();
+                    warp_arrive(&qp_free[gt & 1]);
+                }
+                fence_async_smem();
                 fence_before_sync();
-                warp_arrive(&qp_free[it & 1]);
+                warp_arrive(o1_ready);
+                pend_any = true;
+                pend_live = live;
+                pend_parity = gt & 1;
+                pend_dst = valid ? P.Yout + ((size_t)cloud * P.N + n) * 64 : nullptr;
             }
-            fence_async_smem();
-            fence_before_sync();
-            warp_arrive(o1_ready);
         }
-        f_epilogue(ntiles - 1);
+        if (pend_any) f_epilogue();
     }
     fence_before_sync();
     __syncthreads();
@@ -1370,6 +1438,7 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 }
 
 // ------------------------------------------------------------------------------------ host orchestration
+static int g_num_sms = 148;
 struct TcSplit { int tiles_total, tiles_per_split, nsplit; };
 // The point range of a cloud is cut into fixed spans of 16 tiles (2048 points).  The cut depends on N only, never
 // on the batch size, so a cloud's logits are bit-identical however the batch is sharded across calls / GPUs.
@@ -1430,14 +1499,16 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     const MabParams mp = mab_slice(p_pma + TD, TD, TD, TD, 0);
 
     const dim3 grid(sp.nsplit, B);
+    const int n_work = sp.nsplit * B;                          // persistent kernels: one CTA per SM walks the work items
+    const int pgrid = n_work < g_num_sms ? n_work : g_num_sms;
     const double pts = (double)B * N;
     const size_t fsmem = FT_SMEM;
 
     // ---- ISAB 0
     {
-        RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, c->Aq0, m00.Wkv, m00.bkv, nullptr, part};
+        RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->Aq0, m00.Wkv, m00.bkv, nullptr, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * d_in * TD + 2.0 * TM * TD), pts * 4.0 * d_in);
-        mab_reduce2_tc_kernel<false><<<grid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
+        mab_reduce2_tc_kernel<false><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<small>");
     {
@@ -1447,16 +1518,16 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     }
     PCA_CHECK_LAUNCH("finalize_isab_kernel");
     {
-        AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, kvblk, m01.Wq, m01.bq, nullptr, c->Wo0, m01.bo, Y1};
+        AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, kvblk, m01.Wq, m01.bq, nullptr, c->Wo0, m01.bo, Y1};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * d_in * TD + 2.0 * TM * TD + TD * TD), pts * (4.0 * d_in + 128.0));
-        mab_apply2_tc_kernel<false><<<grid, TC_THREADS16, A2Smem::TOTAL, st>>>(a);
+        mab_apply2_tc_kernel<false><<<pgrid, TC_THREADS16, A2Smem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<small>");
     // ---- ISAB 1
     {
-        RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, c->Aq1, nullptr, m10.bkv, c->Wkv1, part};
+        RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->Aq1, nullptr, m10.bkv, c->Wkv1, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TM * TD), pts * 128.0);
-        mab_reduce2_tc_kernel<true><<<grid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
+        mab_reduce2_tc_kernel<true><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<64>");
     {
@@ -1466,14 +1537,14 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     }
     PCA_CHECK_LAUNCH("finalize_isab_kernel");
     {
-        AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, kvblk, nullptr, m11.bq, c->Wq1, c->Wo1, m11.bo, Y2};
+        AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, kvblk, nullptr, m11.bq, c->Wq1, c->Wo1, m11.bo, Y2};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * TD * TD + 2.0 * TM * TD + TD * TD), pts * 256.0);
-        mab_apply2_tc_kernel<true><<<grid, TC_THREADS16, A2Smem::TOTAL, st>>>(a);
+        mab_apply2_tc_kernel<true><<<pgrid, TC_THREADS16, A2Smem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<64>");
     // ---- PMA + Linear
     {
-        RParams r{nullptr, Y2, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, c->AqP, nullptr, mp.bkv, c->WkvP, part};
+        RParams r{nullptr, Y2, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->AqP, nullptr, mp.bkv, c->WkvP, part};
         LaunchTimer lt("pma_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TD), pts * 128.0);
         mab_reduce_tc_kernel<true, true><<<grid, TC_THREADS16, RSmem::TOTAL, st>>>(r);
     }
@@ -1499,6 +1570,7 @@ static int tc_configure() {
     int dev = 0, major = 0;
     PCA_CHECK_CUDA(cudaGetDevice(&dev));
     PCA_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    PCA_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     if (major != 10) return fail(PCA_EDEVICE, "tcgen05 path needs an sm_100 device (found compute capability %d.x)", major);
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
