@@ -220,13 +220,11 @@ def run_ours(args):
 
     # ---- device-resident timing (value)
     sampler = ClockSampler(local)
-    launches0 = _lib.launch_count()
+    sampler.start()                       # spans warm-up, the timed region and the e2e region (all under load)
     for i in range(args.warmup):
         step_dev(i)
     launches_warm = _lib.launch_count()
-    sampler.start()
     ms = timed(step_dev, args.steps, 0)
-    clocks = sampler.stop()
     launches = _lib.launch_count() - launches_warm
     assert torch.isfinite(last["logits"]).all()
     value = world * CLIPS_PER_STEP * args.steps / (ms / 1e3)
@@ -234,6 +232,7 @@ def run_ours(args):
     # ---- end-to-end timing through the host-buffer entry point (e2e)
     ms_e2e = timed(step_host, args.steps, min(3, args.warmup))
     e2e_value = world * CLIPS_PER_STEP * args.steps / (ms_e2e / 1e3)
+    clocks = sampler.stop()
 
     # ---- per-kernel device times inside a (separately) timed region -> roofline of the dominant kernel
     _lib.profile_enable(True)
@@ -251,20 +250,25 @@ def run_ours(args):
             kernels[k] = {"launches_per_step": v["launches"] / prof_steps, "ms_per_step": v["ms"] / prof_steps,
                           "share": v["ms"] / tot}
         name, top = max(rep.items(), key=lambda kv: kv[1]["ms"])
+        # DRAM traffic per launch of that kernel from the committed ncu --set full capture (profiles/), if any
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(name)
         avg_s = top["ms"] / 1e3 / top["launches"]
         compute = top["flops"] > 0
         if compute:
             ach = top["flops"] / top["launches"] / avg_s / 1e12
             peak = peaks["tf_sustained"]
             roofline = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": None,
+                        "frac": ach / peak, "traffic": traffic,
                         "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
                         "avg_launch_ms": avg_s * 1e3, "share_of_step": top["ms"] / tot}
         else:
             ach = top["bytes"] / top["launches"] / avg_s / 1e9
             peak = peaks["hbm_gbs"]
             roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": None, "peak_source": f"{peaks['source']} copy bandwidth",
+                        "frac": ach / peak, "traffic": traffic, "peak_source": f"{peaks['source']} copy bandwidth",
                         "avg_launch_ms": avg_s * 1e3, "share_of_step": top["ms"] / tot}
     enc_flops = clouds_per_step * st_flops_per_cloud(pipe.points_per_cloud)
     whole = {"algorithmic_tflop_per_step": enc_flops / 1e12,
