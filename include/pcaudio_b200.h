@@ -203,6 +203,10 @@ int pca_debug_st_stages(const float* X, int B, int N, const pca_st_dims* dims, c
                         float* logits, float* H1, float* Y1, float* H2, float* Y2, float* pooled,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* Debug: when set to a device buffer of >= 8000 int64, CTA 0 / warp 0 of the first reduce kernel of every bf16 ST forward
+ * records (phase tag, clock64) pairs of its softmax loop there.  NULL switches it off. */
+void pca_debug_set_timeline(long long* device_buffer);
+
 /* Unit probe of the tcgen05 building blocks used by the bf16 encoder path: one CTA computes
  * D (128, N) = A (128, K) * B (K, N), bf16 operands, fp32 accumulation in TMEM.
  * a_mode: 0 A (128,K) via shared memory K-major, 1 A via TMEM, 2 A given as (K,128) via shared memory MN-major;

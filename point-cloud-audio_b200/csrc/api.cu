@@ -19,6 +19,7 @@ int launch_attn(const float*, long long, const float*, int, int, int, int, int, 
 size_t attn_part_floats(int B, int nq, int nk, int D, int H);
 int launch_layernorm(float*, long long, int, const float*, const float*, cudaStream_t);
 int launch_pool(const float*, int, int, int, int, float*, cudaStream_t);
+void set_timeline(long long* p);
 int launch_umma_probe(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 // tcgen05 path (encoder_tc.cu)
 size_t st_tc_workspace_bytes(const pca_st_dims* d, int B, int N);
@@ -494,6 +495,8 @@ int pca_debug_st_stages(const float* X, int B, int N, const pca_st_dims* dims, c
     return st_tc_forward_stages(X, B, N, dims, params, logits, H1, Y1, H2, Y2, pooled, workspace, workspace_bytes,
                                 (cudaStream_t)stream);
 }
+
+void pca_debug_set_timeline(long long* device_buffer) { set_timeline(device_buffer); }
 
 int pca_debug_umma_probe(const float* A, const float* B, float* D, int N, int K, int a_mode, int b_mode, void* stream) {
     return launch_umma_probe(A, B, D, N, K, a_mode, b_mode, (cudaStream_t)stream);

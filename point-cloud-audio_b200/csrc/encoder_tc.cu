@@ -133,6 +133,7 @@ struct RParams {
     const float* Wkv32;           // (128, d_in) fp32       [DIN64 == false]
     const float* bkv;             // (128)
     const uint8_t* Wkv16;         // 16 KB B operand        [DIN64 == true]
+    long long* timeline;          // debug: per-phase clock64 stamps of CTA 0 / softmax warp 0 (nullptr = off)
     float* part;                  // (B, slots, 8, 10, 64): per (head, query) row: m (log2 domain), l, acc[8];
                                   // query index fastest so that a warp's 32 rows store/load 128 contiguous bytes
 };
@@ -153,11 +154,13 @@ struct RSmem {
 };
 
 // One 32-column chunk of the online softmax: p = 2^(s - m) as bf16 pairs, partial row sum (packed fp32x2 math).
+// pairs of each 32-column chunk whose exponentials run on the FMA pipe (polynomial) instead of MUFU: 6 of 16
+constexpr uint32_t kPolyPairs = 0x0u;      // measured: no gain while the kernels are latency- rather than MUFU-bound
 __device__ __forceinline__ void exp_chunk32(const uint32_t* v, const float2 neg_m2, float2& sum2, uint32_t* pk) {
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
         const float2 x = add2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), neg_m2);
-        const float2 pr = make_float2(ex2(x.x), ex2(x.y));
+        const float2 pr = ((kPolyPairs >> (j >> 1)) & 1u) ? ex2_poly2(x) : make_float2(ex2(x.x), ex2(x.y));
         sum2 = add2(sum2, pr);
         pk[j >> 1] = pack_bf16(pr.x, pr.y);
     }
@@ -880,6 +883,11 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const R
         uint32_t ph_s[2] = {0, 0};
         uint32_t va[32], vb[32];        // scores of the item being processed / prefetched for the next item
         int gt = 0;
+        long long* tl = (P.timeline != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0) ? P.timeline : nullptr;
+        int tl_n = 0;
+        auto stamp = [&](int tag) {
+            if (tl != nullptr && tl_n < 4000) { tl[2 * tl_n] = tag; tl[2 * tl_n + 1] = clock64(); ++tl_n; }
+        };
 
         auto issue_loads = [&](const int half) {
             const int c = 2 * g + half;
@@ -897,7 +905,9 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const R
             const uint32_t sbase = tmem_addr(tb, lane_base, R2_S + 64 * c);
             const uint32_t snext = tmem_addr(tb, lane_base, R2_S + 64 * cn);
             uint32_t pk[16];
+            stamp(0);
             tmem_ld_wait64(va, vb);
+            stamp(1);
             if (nv == 64) {
                 const float m_new = fmaxf(m_run[half][pp], max64(va, vb));
                 alpha[half][pp] = ex2(m_run[half][pp] - m_new);
@@ -905,17 +915,20 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const R
                 float2 sum2 = make_float2(0.f, 0.f);
                 exp_chunk32(va, neg2, sum2, pk);
                 tmem_st16(sbase, pk);
+                stamp(2);
                 if (has_next) {
                     mbar_wait(&s_full[cn], ph_s[half ^ 1]);
                     ph_s[half ^ 1] ^= 1;
                     fence_after_sync();
                     tmem_ld32(snext, va);
                 }
+                stamp(3);
                 exp_chunk32(vb, neg2, sum2, pk);
                 tmem_st16(sbase + 16, pk);
                 if (has_next) tmem_ld32(snext + 32, vb);
                 l_run[half][pp] = l_run[half][pp] * alpha[half][pp] + (sum2.x + sum2.y);
                 m_run[half][pp] = m_new;
+                stamp(4);
             } else {
                 // ragged tail: columns >= nv are padding (nv may be 0: the half contributes nothing)
                 float mx = -INFINITY;
@@ -948,12 +961,15 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const R
                 if (has_next) issue_loads(half ^ 1);
             }
             tmem_st_wait();
+            stamp(5);
             fence_before_sync();
             warp_arrive(&p_ready[c]);
+            stamp(6);
         };
         auto consume_item = [&](const int half, const int pp, const int tile_parity) {
             const int p = g + 2 * pp;
             mbar_wait(&o_full[2 * p + half], tile_parity);
+            stamp(7);
             fence_after_sync();
             uint32_t o[8];
             tmem_ld8(tmem_addr(tb, lane_base, R2_O + 16 * (2 * p + half) + ocol_off), o);
@@ -961,6 +977,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const R
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[half][pp][j] = fmaf(acc[half][pp][j], alpha[half][pp], __uint_as_float(o[j]));
+            stamp(8);
         };
         if (blockIdx.x < n_work) issue_loads(0);
         for (int w = blockIdx.x; w < n_work; w += wstep) {
@@ -1439,6 +1456,8 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 
 // ------------------------------------------------------------------------------------ host orchestration
 static int g_num_sms = 148;
+static long long* g_timeline = nullptr;      // set through pca_debug_set_timeline
+void set_timeline(long long* p) { g_timeline = p; }
 struct TcSplit { int tiles_total, tiles_per_split, nsplit; };
 // The point range of a cloud is cut into fixed spans of 16 tiles (2048 points).  The cut depends on N only, never
 // on the batch size, so a cloud's logits are bit-identical however the batch is sharded across calls / GPUs.
@@ -1506,7 +1525,7 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
 
     // ---- ISAB 0
     {
-        RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->Aq0, m00.Wkv, m00.bkv, nullptr, part};
+        RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->Aq0, m00.Wkv, m00.bkv, nullptr, g_timeline, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * d_in * TD + 2.0 * TM * TD), pts * 4.0 * d_in);
         mab_reduce2_tc_kernel<false><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
@@ -1525,7 +1544,7 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<small>");
     // ---- ISAB 1
     {
-        RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->Aq1, nullptr, m10.bkv, c->Wkv1, part};
+        RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->Aq1, nullptr, m10.bkv, c->Wkv1, nullptr, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TM * TD), pts * 128.0);
         mab_reduce2_tc_kernel<true><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
@@ -1544,7 +1563,7 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<64>");
     // ---- PMA + Linear
     {
-        RParams r{nullptr, Y2, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->AqP, nullptr, mp.bkv, c->WkvP, part};
+        RParams r{nullptr, Y2, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->AqP, nullptr, mp.bkv, c->WkvP, nullptr, part};
         LaunchTimer lt("pma_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TD), pts * 128.0);
         mab_reduce_tc_kernel<true, true><<<grid, TC_THREADS16, RSmem::TOTAL, st>>>(r);
     }

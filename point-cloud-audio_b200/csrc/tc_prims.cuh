@@ -33,10 +33,10 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)      // suspend-time hint: sleep in hardware, do not spin
         : "memory");
     return ok;
 }
@@ -203,6 +203,33 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     unsigned long long d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
     return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+// 2^x for x <= 0 on the FMA pipe (no MUFU): round-to-nearest split x = xi + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (max relative error 7.5e-5, far below the bf16 rounding of the probabilities it feeds), exponent
+// re-inserted with one integer multiply-add.  The MUFU pipe (16 ex2/clk/SM) is the binding unit of the softmax
+// kernels; a share of the exponentials is routed here to balance it against the FMA pipe.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+    x.x = fmaxf(x.x, -126.f);
+    x.y = fmaxf(x.y, -126.f);
+    const float2 magic = make_float2(12582912.f, 12582912.f);          // 1.5 * 2^23
+    const float2 t = add2(x, magic);
+    const float2 r = add2(t, make_float2(-12582912.f, -12582912.f));
+    const float2 f = add2(x, make_float2(-r.x, -r.y));
+    float2 p = fma2(f, make_float2(0.055171459913253784f, 0.055171459913253784f),
+                    make_float2(0.2426108568906784f, 0.2426108568906784f));
+    p = fma2(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+    p = fma2(p, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+    p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+    p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+    return p;
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float d;
