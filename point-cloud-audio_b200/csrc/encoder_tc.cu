@@ -17,6 +17,7 @@
 //   finalize_pma_kernel    : merge, residuals, final Linear -> logits.
 #include "common.cuh"
 #include "tc_prims.cuh"
+#include <stdlib.h>
 
 namespace pca {
 using namespace tc;
@@ -885,9 +886,14 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const R
         int gt = 0;
         long long* tl = (P.timeline != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0) ? P.timeline : nullptr;
         int tl_n = 0;
+#ifdef PCA_TIMELINE
         auto stamp = [&](int tag) {
             if (tl != nullptr && tl_n < 4000) { tl[2 * tl_n] = tag; tl[2 * tl_n + 1] = clock64(); ++tl_n; }
         };
+#else
+        auto stamp = [&](int) {};
+        (void)tl; (void)tl_n;
+#endif
 
         auto issue_loads = [&](const int half) {
             const int c = 2 * g + half;
@@ -1407,6 +1413,644 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
     if (warp == 12) tmem_dealloc(tb, 512);
 }
 
+// ====================================================================================== 24-warp variants
+constexpr int TC_THREADS24 = 24 * 32;
+
+// 24-warp variant (16 softmax warps = 4 warpgroups, one chain each; 4 producer warps; 4 MMA threads): twice the
+// softmax warps per SM sub-partition hide the fixed latency of the per-item barrier / TMEM round trips.
+// Persistent: grid = min(#work items, #SMs); CTA k walks the work items (cloud, point-split) k, k + grid, ...
+// Barriers, TMEM and the resident operands are set up once; all pipelines (producer -> MMA -> softmax) run
+// straight across work-item boundaries, so there is no per-cloud fill/drain bubble.
+template <bool DIN64>
+__global__ void __launch_bounds__(TC_THREADS24, 1) mab_reduce4_tc_kernel(const RParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sAq = smem + R2Smem::AQ;
+    uint8_t* sKV = smem + R2Smem::KV;
+    uint8_t* sW = smem + R2Smem::W;
+    uint8_t* sY = smem + R2Smem::Y;
+    float* sWsm = reinterpret_cast<float*>(smem + R2Smem::SMALL);
+    float* sBias = sWsm + 128 * 4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + R2Smem::BARS);
+    uint64_t* kv_full = bars;          // [2] count 4 (producer warps)
+    uint64_t* kv_empty = bars + 2;     // [2] count 4 (chains)
+    uint64_t* s_full = bars + 4;       // [4] count 1
+    uint64_t* p_ready = bars + 8;      // [4] count 4 (warps of the owning warpgroup)
+    uint64_t* o_full = bars + 12;      // [8] count 1   (region = 2 * pair + half)
+    uint64_t* y_full = bars + 20;      // count 4
+    uint64_t* proj_done = bars + 21;   // count 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_work = P.n_work, wstep = gridDim.x;
+    auto work_tiles = [&](int w, int& cloud, int& split, int& tile0) {
+        cloud = w / P.nsplit;
+        split = w - cloud * P.nsplit;
+        tile0 = split * P.tiles_per_split;
+        return min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+    };
+
+    copy_to_smem(sAq, P.Aq, 16384);
+    if (DIN64) copy_to_smem(sW, P.Wkv16, 16384);
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+        sBias[i] = P.bkv[i];
+        if (!DIN64) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sWsm[i * 4 + k] = (k < P.d_in) ? P.Wkv32[i * P.d_in + k] : 0.f;
+        }
+    }
+    if (warp == 20) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 4); mbar_init(&kv_empty[i], 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
+        for (int i = 0; i < 8; ++i) mbar_init(&o_full[i], 1);
+        mbar_init(y_full, 4);
+        mbar_init(proj_done, 1);
+        fence_barrier_init();
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp >= 20) {
+        reg_dec<24>();
+        if (lane == 0) {
+            // =================================================================== one MMA-issuing thread per chain
+            // chain c = warp - 12: strictly serial  Q K^T -> (warpgroup softmax) -> P V -> next Q K^T  on its own
+            // half-buffer; the four chains never wait on each other.
+            const int c = warp - 20, half = c & 1;
+            const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
+            const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
+            const uint32_t aq = smem_u32(sAq), kvb = smem_u32(sKV);
+            int gt = 0;                                    // tiles processed by this CTA so far
+            for (int w = blockIdx.x; w < n_work; w += wstep) {
+                int cloud, split, tile0;
+                const int ntiles = work_tiles(w, cloud, split, tile0);
+                for (int it = 0; it < ntiles; ++it, ++gt) {
+                    const uint32_t kbase = kvb + (gt & 1) * 32768, vbase = kbase + 16384;
+                    mbar_wait(&kv_full[gt & 1], (gt >> 1) & 1);
+                    fence_after_sync();
+#pragma unroll
+                    for (int pp = 0; pp < 2; ++pp) {
+                        const int p = (c >> 1) + 2 * pp;
+                        mma_ss(tmem_addr(tb, 0, R2_S + 64 * c), smem_desc(aq + p * 4096, 2048, 128),
+                               smem_desc(kbase + 2 * p * 2048 + half * 1024, 2048, 128), idesc_s, 0);
+                        mma_commit(&s_full[c]);
+                        mbar_wait(&p_ready[c], pp);          // two items per tile: parities 0, 1
+                        fence_after_sync();
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)       // P columns 32..63: keys 32..63 first, then keys 0..31
+                            mma_ts(tmem_addr(tb, 0, R2_O + 16 * (2 * p + half)), tmem_addr(tb, 0, R2_S + 64 * c + 32 + ks * 8),
+                                   smem_desc(vbase + 2 * p * 2048 + half * 1024 + ((ks + 2) & 3) * 256, 128, 2048), idesc_pv, ks > 0);
+                        mma_commit(&o_full[2 * p + half]);
+                    }
+                    mma_commit(&kv_empty[gt & 1]);            // 4 chains x 1 arrival free the K|V stage
+                }
+            }
+        }
+    } else if (warp >= 16) {
+        reg_dec<56>();
+        // =================================================================== producer: K|V tiles
+        const int quad = warp & 3;
+        const int row = 32 * quad + lane;
+        int gt = 0;
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, split, tile0;
+            const int ntiles = work_tiles(w, cloud, split, tile0);
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int stage = gt & 1;
+                const int n = (tile0 + it) * 128 + row;
+                const bool valid = n < P.N;
+                uint8_t* sK = sKV + stage * 32768;
+                uint8_t* sV = sK + 16384;
+                if (!DIN64) {
+                    float x[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (valid) {
+                        const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                        for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
+                    }
+                    if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
+#pragma unroll 4
+                    for (int c = 0; c < 16; ++c) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 wv = *reinterpret_cast<const float4*>(sWsm + (c * 8 + j) * 4);
+                            o[j] = valid ? fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBias[c * 8 + j])))) : 0.f;
+                        }
+                        st_shared_8bf16((c < 8 ? sK + c * 2048 : sV + (c - 8) * 2048) + row * 16, o);
+                    }
+                } else {
+                    const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
+                    uint4 yv[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sY + c * 2048 + row * 16) = yv[c];
+                    fence_async_smem();
+                    fence_before_sync();
+                    warp_arrive(y_full);
+                    if (warp == 16 && lane == 0) {
+                        // one producer thread issues the K|V projection MMA once all 128 rows of Y are staged
+                        mbar_wait(y_full, gt & 1);
+                        fence_after_sync();
+                        const uint32_t yb = smem_u32(sY), wb = smem_u32(sW);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ss(tmem_addr(tb, 0, R2_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
+                                   idesc_bf16(128, 128, 0, 0), ks > 0);
+                        mma_commit(proj_done);
+                    }
+                    mbar_wait(proj_done, gt & 1);
+                    fence_after_sync();
+                    if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
+#pragma unroll
+                    for (int c0 = 0; c0 < 128; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_addr(tb, 32 * quad, R2_PROJ + c0), v);
+                        tmem_ld_wait32(v);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float o[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = valid ? __uint_as_float(v[8 * q + j]) + sBias[c0 + 8 * q + j] : 0.f;
+                            const int chunk = c0 / 8 + q;
+                            st_shared_8bf16((chunk < 8 ? sK + chunk * 2048 : sV + (chunk - 8) * 2048) + row * 16, o);
+                        }
+                    }
+                }
+                fence_async_smem();
+                fence_before_sync();
+                warp_arrive(&kv_full[stage]);
+            }
+        }
+    } else {
+        reg_inc<96>();
+        // =================================================================== softmax warpgroups (one chain each)
+        const int c = warp >> 2, quad = warp & 3;          // chain c: half = c & 1 of the pairs (c >> 1) + 2 pp
+        const int half = c & 1, g = c >> 1;
+        const int row = 32 * quad + lane;
+        const uint32_t lane_base = 32 * quad;
+        const uint32_t ocol_off = (row >= 64) ? 8u : 0u;
+        const uint32_t sbase = tmem_addr(tb, lane_base, R2_S + 64 * c);
+        float m_run[2], l_run[2], alpha[2], acc[2][8];
+        uint32_t ph_s = 0;
+        int gt = 0;
+
+        // One 64-key item with 32 live score registers: pass over keys 0..31 (max), keys 32..63 (max, kept), then
+        // probabilities of keys 32..63, reload keys 0..31, their probabilities.  P occupies columns 32..63 of the
+        // half-buffer in that order (the MMA thread feeds V rows in the matching order).
+        auto softmax_item = [&](const int pp, const int nv) {
+            mbar_wait(&s_full[c], ph_s);
+            ph_s ^= 1;
+            fence_after_sync();
+            uint32_t v[32], pk[16];
+            tmem_ld32(sbase, v);
+            tmem_ld_wait32(v);
+            if (nv == 64) {
+                const float mA = max_chunk32(v, -INFINITY);
+                tmem_ld32(sbase + 32, v);
+                tmem_ld_wait32(v);
+                const float m_new = fmaxf(m_run[pp], max_chunk32(v, mA));
+                alpha[pp] = ex2(m_run[pp] - m_new);
+                const float2 neg2 = make_float2(-m_new, -m_new);
+                float2 sum2 = make_float2(0.f, 0.f);
+                exp_chunk32(v, neg2, sum2, pk);
+                tmem_st16(sbase + 32, pk);
+                tmem_ld32(sbase, v);
+                tmem_ld_wait32(v);
+                exp_chunk32(v, neg2, sum2, pk);
+                tmem_st16(sbase + 48, pk);
+                l_run[pp] = l_run[pp] * alpha[pp] + (sum2.x + sum2.y);
+                m_run[pp] = m_new;
+            } else {
+                // ragged tail: keys >= nv are padding (nv may be 0: the half contributes nothing)
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < nv) mx = fmaxf(mx, __uint_as_float(v[j]));
+                tmem_ld32(sbase + 32, v);
+                tmem_ld_wait32(v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (32 + j < nv) mx = fmaxf(mx, __uint_as_float(v[j]));
+                const float m_new = fmaxf(m_run[pp], mx);
+                alpha[pp] = (m_new == -INFINITY) ? 1.f : ex2(m_run[pp] - m_new);
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = (32 + j < nv) ? ex2(__uint_as_float(v[j]) - m_new) : 0.f;
+                    const float p1 = (33 + j < nv) ? ex2(__uint_as_float(v[j + 1]) - m_new) : 0.f;
+                    sum += p0 + p1;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                }
+                tmem_st16(sbase + 32, pk);
+                tmem_ld32(sbase, v);
+                tmem_ld_wait32(v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = (j < nv) ? ex2(__uint_as_float(v[j]) - m_new) : 0.f;
+                    const float p1 = (j + 1 < nv) ? ex2(__uint_as_float(v[j + 1]) - m_new) : 0.f;
+                    sum += p0 + p1;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                }
+                tmem_st16(sbase + 48, pk);
+                l_run[pp] = l_run[pp] * alpha[pp] + sum;
+                m_run[pp] = m_new;
+            }
+            tmem_st_wait();
+            fence_before_sync();
+            warp_arrive(&p_ready[c]);
+        };
+        auto consume_item = [&](const int pp, const int tile_parity) {
+            const int p = g + 2 * pp;
+            mbar_wait(&o_full[2 * p + half], tile_parity);
+            fence_after_sync();
+            uint32_t o[8];
+            tmem_ld8(tmem_addr(tb, lane_base, R2_O + 16 * (2 * p + half) + ocol_off), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[pp][j] = fmaf(acc[pp][j], alpha[pp], __uint_as_float(o[j]));
+        };
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, split, tile0;
+            const int ntiles = work_tiles(w, cloud, split, tile0);
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                m_run[a] = -INFINITY; l_run[a] = 0.f; alpha[a] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+            }
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int n_valid = min(128, P.N - (tile0 + it) * 128);
+                const int nv = half == 0 ? min(64, n_valid) : max(0, n_valid - 64);
+                softmax_item(0, nv);
+                if (it > 0) consume_item(1, (gt - 1) & 1);
+                softmax_item(1, nv);
+                consume_item(0, gt & 1);
+            }
+            consume_item(1, (gt - 1) & 1);
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+                const int h = 2 * (g + 2 * pp) + (row >> 6);
+                float* dst = P.part + (((size_t)cloud * (2 * P.nsplit) + 2 * split + half) * TH + h) * 10 * TM + (row & 63);
+                dst[0] = m_run[pp];
+                dst[TM] = l_run[pp];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[(2 + j) * TM] = acc[pp][j];
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 20) tmem_dealloc(tb, 512);
+}
+
+// 24-warp variant of the apply kernel (see mab_reduce4_tc_kernel).
+// Persistent like the reduce kernel: one CTA per SM walks the work items (cloud, point-split); the per-cloud
+// K / V operand images of the next work item are staged while the current one is still being processed.
+template <bool DIN64>
+__global__ void __launch_bounds__(TC_THREADS24, 1) mab_apply4_tc_kernel(const AParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sImg = smem + A2Smem::IMG;
+    uint8_t* sWo = smem + A2Smem::WO;
+    uint8_t* sWq = smem + A2Smem::WQ;
+    uint8_t* sAQ = smem + A2Smem::AQ;
+    uint8_t* sYA = smem + A2Smem::YA;
+    uint8_t* sO1 = smem + A2Smem::O1;
+    float* sWq32 = reinterpret_cast<float*>(smem + A2Smem::SMALL);
+    float* sBq = sWq32 + 64 * 4;
+    float* sBo = sBq + 64;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A2Smem::BARS);
+    uint64_t* aq_full = bars;          // [2] count 4
+    uint64_t* aq_empty = bars + 2;     // [2] count 4
+    uint64_t* s_full = bars + 4;       // [4] count 1
+    uint64_t* p_ready = bars + 8;      // [4] count 4
+    uint64_t* o_full = bars + 12;      // [4] count 1
+    uint64_t* o1_ready = bars + 16;    // count 8
+    uint64_t* f_full = bars + 17;      // count 1
+    uint64_t* ya_full = bars + 18;     // count 4
+    uint64_t* qp_done = bars + 19;     // count 1
+    uint64_t* qp_free = bars + 20;     // [2] count 8
+    uint64_t* pv0_done = bars + 22;    // [4] count 1
+    uint64_t* img_full = bars + 26;    // [2] count 4 (producer warps)
+    uint64_t* img_empty = bars + 28;   // [2] count 4 (chains)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_work = P.n_work, wstep = gridDim.x;
+    auto work_tiles = [&](int w, int& cloud, int& tile0) {
+        cloud = w / P.nsplit;
+        const int split = w - cloud * P.nsplit;
+        tile0 = split * P.tiles_per_split;
+        return min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+    };
+
+    copy_to_smem(sWo, P.Wo16, 8192);
+    if (DIN64) copy_to_smem(sWq, P.Wq16, 8192);
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+        sBq[i] = P.bq[i];
+        sBo[i] = P.bo[i];
+        if (!DIN64) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sWq32[i * 4 + k] = (k < P.d_in) ? P.Wq32[i * P.d_in + k] : 0.f;
+        }
+    }
+    if (warp == 20) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&aq_full[i], 4); mbar_init(&aq_empty[i], 4); mbar_init(&qp_free[i], 16);
+            mbar_init(&img_full[i], 4); mbar_init(&img_empty[i], 4);
+        }
+        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); mbar_init(&pv0_done[i], 1); }
+        mbar_init(o1_ready, 16);
+        mbar_init(f_full, 1);
+        mbar_init(ya_full, 4);
+        mbar_init(qp_done, 1);
+        fence_barrier_init();
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp >= 20) {
+        reg_dec<24>();
+        if (lane == 0) {
+            // =================================================================== one MMA-issuing thread per chain
+            // chain c = warp - 12 <-> head hh = c & 1 of the pairs (c >> 1) + 2 pp.  The two heads of a pair share the
+            // pair's 16 output columns: hh = 0 writes (accumulate off), hh = 1 accumulates after pv0_done.
+            const int c = warp - 20, hh = c & 1;
+            const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
+            const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
+            const uint32_t idesc_64 = idesc_bf16(128, 64, 0, 0);
+            const uint32_t img = smem_u32(sImg), wo = smem_u32(sWo);
+            const uint32_t aqb = smem_u32(sAQ), o1b = smem_u32(sO1);
+            auto issue_f = [&](int tile_parity) {          // fc_o of a tile once both warpgroups have staged O1
+                mbar_wait(o1_ready, tile_parity);
+                fence_after_sync();
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_ss(tmem_addr(tb, 0, A2_F), smem_desc(o1b + ks * 4096, 2048, 128), smem_desc(wo + ks * 2048, 1024, 128),
+                           idesc_64, ks > 0);
+                mma_commit(f_full);
+            };
+            int gt = 0, wl = 0;
+            for (int w = blockIdx.x; w < n_work; w += wstep, ++wl) {
+                int cloud, tile0;
+                const int ntiles = work_tiles(w, cloud, tile0);
+                const uint32_t kb = img + (wl & 1) * 32768, vb = kb + 16384;
+                mbar_wait(&img_full[wl & 1], (wl >> 1) & 1);
+                fence_after_sync();
+                for (int it = 0; it < ntiles; ++it, ++gt) {
+                    mbar_wait(&aq_full[gt & 1], (gt >> 1) & 1);
+                    fence_after_sync();
+#pragma unroll
+                    for (int pp = 0; pp < 2; ++pp) {
+                        const int p = (c >> 1) + 2 * pp;
+                        mma_ss(tmem_addr(tb, 0, A2_S + 64 * c), smem_desc(aqb + (gt & 1) * 16384 + 2 * p * 2048, 2048, 128),
+                               smem_desc(kb + p * 4096 + hh * 1024, 2048, 128), idesc_s, 0);
+                        mma_commit(&s_full[c]);
+                        if (pp == 0 && gt > 0) {
+                            // the pair outputs of the previous tile are consumed once its O1 is staged; chain 0 also
+                            // launches that tile's fc_o
+                            if (c == 0) issue_f((gt - 1) & 1);
+                            else { mbar_wait(o1_ready, (gt - 1) & 1); fence_after_sync(); }
+                        }
+                        mbar_wait(&p_ready[c], pp);
+                        fence_after_sync();
+                        if (hh == 1) { mbar_wait(&pv0_done[p], gt & 1); fence_after_sync(); }
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)       // P columns 32..63: keys 32..63 first, then keys 0..31
+                            mma_ts(tmem_addr(tb, 0, A2_O + 16 * p), tmem_addr(tb, 0, A2_S + 64 * c + 32 + ks * 8),
+                                   smem_desc(vb + p * 4096 + hh * 1024 + ((ks + 2) & 3) * 256, 128, 2048), idesc_pv,
+                                   (hh == 1 || ks > 0) ? 1u : 0u);
+                        mma_commit(hh == 0 ? &pv0_done[p] : &o_full[p]);
+                    }
+                    mma_commit(&aq_empty[gt & 1]);          // 4 chains x 1 arrival free the query stage
+                }
+                mma_commit(&img_empty[wl & 1]);             // ... and the K / V images of this work item
+            }
+            if (c == 0 && gt > 0) issue_f((gt - 1) & 1);
+        }
+    } else if (warp >= 16) {
+        reg_dec<56>();
+        // =================================================================== producer: images + scaled query operand
+        const int quad = warp & 3;
+        const int row = 32 * quad + lane;
+        const int ptid = threadIdx.x - 512;          // 0..127
+        int gt = 0, wl = 0;
+        for (int w = blockIdx.x; w < n_work; w += wstep, ++wl) {
+            int cloud, tile0;
+            const int ntiles = work_tiles(w, cloud, tile0);
+            {   // stage this cloud's block-diagonal K / V images (32 KB)
+                if (wl >= 2) mbar_wait(&img_empty[wl & 1], ((wl >> 1) - 1) & 1);
+                const uint4* src = reinterpret_cast<const uint4*>(P.KVblk + (size_t)cloud * 32768);
+                uint4* dst = reinterpret_cast<uint4*>(sImg + (wl & 1) * 32768);
+#pragma unroll 4
+                for (int i = ptid; i < 2048; i += 128) dst[i] = __ldg(src + i);
+                fence_async_smem();
+                fence_before_sync();
+                warp_arrive(&img_full[wl & 1]);
+            }
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int stage = gt & 1;
+                const int n = (tile0 + it) * 128 + row;
+                const bool valid = n < P.N;
+                uint8_t* dst = sAQ + stage * 16384;
+                if (!DIN64) {
+                    float x[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (valid) {
+                        const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                        for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
+                    }
+                    if (gt >= 2) mbar_wait(&aq_empty[stage], ((gt >> 1) - 1) & 1);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 wv = *reinterpret_cast<const float4*>(sWq32 + (c * 8 + j) * 4);
+                            const float q = fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBq[c * 8 + j]))));
+                            o[j] = valid ? q * kScaleLog2e : 0.f;
+                        }
+                        st_shared_8bf16(dst + c * 2048 + row * 16, o);
+                    }
+                } else {
+                    const uint4* src = reinterpret_cast<const uint4*>(P.Y16in + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
+                    uint4 yv[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sYA + c * 2048 + row * 16) = yv[c];
+                    fence_async_smem();
+                    fence_before_sync();
+                    warp_arrive(ya_full);
+                    if (warp == 16 && lane == 0) {
+                        // one producer thread issues the Q projection MMA (its TMEM buffer must have been read by the
+                        // epilogue of two tiles ago)
+                        mbar_wait(ya_full, gt & 1);
+                        if (gt >= 2) mbar_wait(&qp_free[gt & 1], ((gt >> 1) - 1) & 1);
+                        fence_after_sync();
+                        const uint32_t yab = smem_u32(sYA), wq = smem_u32(sWq);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ss(tmem_addr(tb, 0, A2_QP + 64 * (gt & 1)), smem_desc(yab + ks * 4096, 2048, 128),
+                                   smem_desc(wq + ks * 2048, 1024, 128), idesc_bf16(128, 64, 0, 0), ks > 0);
+                        mma_commit(qp_done);
+                    }
+                    mbar_wait(qp_done, gt & 1);
+                    fence_after_sync();
+                    if (gt >= 2) mbar_wait(&aq_empty[stage], ((gt >> 1) - 1) & 1);
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_addr(tb, 32 * quad, A2_QP + 64 * (gt & 1) + c0), v);
+                        tmem_ld_wait32(v);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float o[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                o[j] = valid ? (__uint_as_float(v[8 * q + j]) + sBq[c0 + 8 * q + j]) * kScaleLog2e : 0.f;
+                            st_shared_8bf16(dst + (c0 / 8 + q) * 2048 + row * 16, o);
+                        }
+                    }
+                }
+                fence_async_smem();
+                fence_before_sync();
+                warp_arrive(&aq_full[stage]);
+            }
+        }
+    } else {
+        reg_inc<96>();
+        // =================================================================== softmax + epilogue warpgroups (one chain each)
+        const int c = warp >> 2, quad = warp & 3;          // chain c: head hh = c & 1 of the pairs (c >> 1) + 2 pp
+        const int hh = c & 1, g = c >> 1;
+        const int row = 32 * quad + lane;
+        const uint32_t lane_base = 32 * quad;
+        const uint32_t sbase = tmem_addr(tb, lane_base, A2_S + 64 * c);
+        uint32_t ph_s = 0;
+        float o1[2][8];                  // O1 of the tile whose fc_o is in flight: the 8 features of head 2p+hh, p = g, g+2
+        float inv_l[2] = {1.f, 1.f};
+        __nv_bfloat16* pend_dst = nullptr;
+        bool pend_live = false, pend_any = false;
+        int pend_parity = 0;
+        int gt = 0;
+
+        auto softmax_item = [&](const int pp, const bool live) {
+            mbar_wait(&s_full[c], ph_s);
+            ph_s ^= 1;
+            fence_after_sync();
+            if (live) {
+                uint32_t v[32], pk[16];
+                tmem_ld32(sbase, v);
+                tmem_ld_wait32(v);
+                const float mA = max_chunk32(v, -INFINITY);
+                tmem_ld32(sbase + 32, v);
+                tmem_ld_wait32(v);
+                const float mx = max_chunk32(v, mA);
+                const float2 neg2 = make_float2(-mx, -mx);
+                float2 sum2 = make_float2(0.f, 0.f);
+                exp_chunk32(v, neg2, sum2, pk);
+                tmem_st16(sbase + 32, pk);
+                tmem_ld32(sbase, v);
+                tmem_ld_wait32(v);
+                exp_chunk32(v, neg2, sum2, pk);
+                tmem_st16(sbase + 48, pk);
+                inv_l[pp] = __fdividef(1.f, sum2.x + sum2.y);
+                tmem_st_wait();
+            }
+            fence_before_sync();
+            warp_arrive(&p_ready[c]);
+        };
+        auto f_epilogue = [&]() {
+            mbar_wait(f_full, pend_parity);
+            fence_after_sync();
+            if (pend_live) {
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp) {
+                    const int p = g + 2 * pp, f0 = 16 * p + 8 * hh;
+                    uint32_t fv[8];
+                    tmem_ld8(tmem_addr(tb, lane_base, A2_F + f0), fv);
+                    tmem_ld_wait();
+                    uint4 out;
+                    uint32_t* ow = reinterpret_cast<uint32_t*>(&out);
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const float y0 = o1[pp][j] + fmaxf(__uint_as_float(fv[j]) + sBo[f0 + j], 0.f);
+                        const float y1 = o1[pp][j + 1] + fmaxf(__uint_as_float(fv[j + 1]) + sBo[f0 + j + 1], 0.f);
+                        ow[j >> 1] = pack_bf16(y0, y1);
+                    }
+                    if (pend_dst != nullptr) *reinterpret_cast<uint4*>(pend_dst + f0) = out;
+                }
+            }
+            fence_before_sync();
+            pend_any = false;
+        };
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, tile0;
+            const int ntiles = work_tiles(w, cloud, tile0);
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int n = (tile0 + it) * 128 + row;
+                const bool valid = n < P.N;
+                const bool live = (tile0 + it) * 128 + 32 * quad < P.N;     // warps whose 32 rows are all padding idle
+                softmax_item(0, live);
+                if (pend_any) f_epilogue();              // deferred: the fc_o round trip hides behind the first softmax
+                softmax_item(1, live);
+                // ---- O1 = Qp + (P V) / l for the 8 features of this chain's head in each of its two pairs
+                float x[4] = {0.f, 0.f, 0.f, 0.f};
+                if (!DIN64 && valid) {
+                    const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                    for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
+                }
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp) {
+                    const int p = g + 2 * pp, f0 = 16 * p + 8 * hh;
+                    mbar_wait(&o_full[p], gt & 1);
+                    fence_after_sync();
+                    if (live) {
+                        uint32_t o[8], qv[8];
+                        tmem_ld8(tmem_addr(tb, lane_base, A2_O + f0), o);
+                        if (DIN64) tmem_ld8(tmem_addr(tb, lane_base, A2_QP + 64 * (gt & 1) + f0), qv);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int f = f0 + j;
+                            float q;
+                            if (DIN64) {
+                                q = __uint_as_float(qv[j]) + sBq[f];
+                            } else {
+                                const float4 wv = *reinterpret_cast<const float4*>(sWq32 + f * 4);
+                                q = fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBq[f]))));
+                            }
+                            o1[pp][j] = q + __uint_as_float(o[j]) * inv_l[pp];
+                        }
+                        st_shared_8bf16(sO1 + (2 * p + hh) * 2048 + row * 16, &o1[pp][0]);
+                    }
+                }
+                if (DIN64) {
+                    fence_before_sync();
+                    warp_arrive(&qp_free[gt & 1]);
+                }
+                fence_async_smem();
+                fence_before_sync();
+                warp_arrive(o1_ready);
+                pend_any = true;
+                pend_live = live;
+                pend_parity = gt & 1;
+                pend_dst = valid ? P.Yout + ((size_t)cloud * P.N + n) * 64 : nullptr;
+            }
+        }
+        if (pend_any) f_epilogue();
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 20) tmem_dealloc(tb, 512);
+}
+
 // ------------------------------------------------------------------------------------ finalize (PMA + Linear)
 struct PParams {
     const float* part; int nsplit;
@@ -1456,6 +2100,9 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 
 // ------------------------------------------------------------------------------------ host orchestration
 static int g_num_sms = 148;
+// softmax warpgroups per CTA (2 = 16 warps with TMEM prefetch, 4 = 24 warps): measured best is 4 for the reduce kernel
+// and 2 for the apply kernel (profiles/); PCA_TC_REDUCE_WG / PCA_TC_APPLY_WG override for experiments
+static int g_reduce_wg = 4, g_apply_wg = 2;
 static long long* g_timeline = nullptr;      // set through pca_debug_set_timeline
 void set_timeline(long long* p) { g_timeline = p; }
 struct TcSplit { int tiles_total, tiles_per_split, nsplit; };
@@ -1527,7 +2174,8 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     {
         RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->Aq0, m00.Wkv, m00.bkv, nullptr, g_timeline, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * d_in * TD + 2.0 * TM * TD), pts * 4.0 * d_in);
-        mab_reduce2_tc_kernel<false><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
+        if (g_reduce_wg == 4) mab_reduce4_tc_kernel<false><<<pgrid, TC_THREADS24, R2Smem::TOTAL, st>>>(r);
+        else mab_reduce2_tc_kernel<false><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<small>");
     {
@@ -1539,14 +2187,16 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     {
         AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, kvblk, m01.Wq, m01.bq, nullptr, c->Wo0, m01.bo, Y1};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * d_in * TD + 2.0 * TM * TD + TD * TD), pts * (4.0 * d_in + 128.0));
-        mab_apply2_tc_kernel<false><<<pgrid, TC_THREADS16, A2Smem::TOTAL, st>>>(a);
+        if (g_apply_wg == 4) mab_apply4_tc_kernel<false><<<pgrid, TC_THREADS24, A2Smem::TOTAL, st>>>(a);
+        else mab_apply2_tc_kernel<false><<<pgrid, TC_THREADS16, A2Smem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<small>");
     // ---- ISAB 1
     {
         RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->Aq1, nullptr, m10.bkv, c->Wkv1, nullptr, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TM * TD), pts * 128.0);
-        mab_reduce2_tc_kernel<true><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
+        if (g_reduce_wg == 4) mab_reduce4_tc_kernel<true><<<pgrid, TC_THREADS24, R2Smem::TOTAL, st>>>(r);
+        else mab_reduce2_tc_kernel<true><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<64>");
     {
@@ -1558,7 +2208,8 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     {
         AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, kvblk, nullptr, m11.bq, c->Wq1, c->Wo1, m11.bo, Y2};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * TD * TD + 2.0 * TM * TD + TD * TD), pts * 256.0);
-        mab_apply2_tc_kernel<true><<<pgrid, TC_THREADS16, A2Smem::TOTAL, st>>>(a);
+        if (g_apply_wg == 4) mab_apply4_tc_kernel<true><<<pgrid, TC_THREADS24, A2Smem::TOTAL, st>>>(a);
+        else mab_apply2_tc_kernel<true><<<pgrid, TC_THREADS16, A2Smem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<64>");
     // ---- PMA + Linear
@@ -1594,6 +2245,12 @@ static int tc_configure() {
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSmem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce4_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce4_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply4_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply4_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
+    if (const char* v = getenv("PCA_TC_REDUCE_WG")) g_reduce_wg = (v[0] == '2') ? 2 : 4;
+    if (const char* v = getenv("PCA_TC_APPLY_WG")) g_apply_wg = (v[0] == '4') ? 4 : 2;
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
