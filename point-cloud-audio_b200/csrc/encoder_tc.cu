@@ -574,6 +574,30 @@ __global__ void __launch_bounds__(256) finalize_isab_kernel(const FParams P) {
         *reinterpret_cast<float4*>(sWT + k * 128 + f4 * 4) = __ldg(reinterpret_cast<const float4*>(P.WoT + k * 64) + f4);
     }
     // merge the splits: 512 (h, m) rows, 2 per thread
+    if (P.nsplit == 2) {
+        // common case (one point-split, two column halves): all 40 loads of the thread's two rows are issued up front
+        float v[2][2][10];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = tid + 256 * rr, h = r / TM, m = r % TM;
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                const float* pp = P.part + (((size_t)cloud * 2 + sl) * TH + h) * 10 * TM + m;
+#pragma unroll
+                for (int j = 0; j < 10; ++j) v[rr][sl][j] = __ldg(pp + j * TM);
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = tid + 256 * rr, h = r / TM, m = r % TM;
+            const float mmax = fmaxf(v[rr][0][0], v[rr][1][0]);
+            const float w0 = exp2f(v[rr][0][0] - mmax), w1 = exp2f(v[rr][1][0] - mmax);
+            const float inv = 1.f / fmaf(v[rr][0][1], w0, v[rr][1][1] * w1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                sOT[(h * 8 + j) * FT_LD + m] = __ldg(P.Qp + m * TD + h * 8 + j) + fmaf(v[rr][0][2 + j], w0, v[rr][1][2 + j] * w1) * inv;
+        }
+    } else
     for (int r = tid; r < TH * TM; r += 256) {
         const int h = r / TM, m = r % TM;
         float mmax = -INFINITY;
