@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpcaudio_b200.so")
+# PCAUDIO_B200_LIB points experiments at an alternative build of the same library (never at a fallback)
+LIB_PATH = os.environ.get("PCAUDIO_B200_LIB") or os.path.join(_HERE, "csrc", "libpcaudio_b200.so")
 
 PREC_FP32 = 0
 PREC_BF16 = 2

@@ -33,6 +33,8 @@ struct TcConsts {
     uint8_t Aq0[16384], Aq1[16384], AqP[16384];   // stacked-pair query operands [4 pairs][2 chunks][128 rows][16 B]
     uint8_t Wkv1[16384], WkvP[16384];             // [Wk;Wv] as B operand (N=128, K=64): [8 chunks][128 rows][16 B]
     uint8_t Wq1[8192], Wo0[8192], Wo1[8192];      // (N=64, K=64) B operands: [8 chunks][64 rows][16 B]
+    uint8_t AqPool[16384];                        // PMA: row r = scale * Wk_h^T fc_q(S)_h, h = r / 16 (A operand, 128 x 64)
+    uint8_t WqS0[2048];                           // isab0.mab1.fc_q (64, d_in <= 4) as a split-bf16 K=16 B operand
     // k-major fp32 copies for finalize_isab: mab0.fc_o^T (64 x 64) and mab1 [Wk;Wv]^T (64 x 128), per ISAB
     float WoT[2][64 * 64];
     float WkvT[2][64 * 128];
@@ -55,10 +57,38 @@ __device__ void pack_b_operand(const float* __restrict__ W, int n_rows, uint8_t*
     }
 }
 
+// Split-bf16 image of a narrow weight W (n_rows, d <= 4) as a K = 16 B operand [2 chunks][n_rows][16 B].  With the
+// matching A-side columns (split_x16) one K=16 MMA yields x.w to ~2^-17 relative (j = k % 4 is the input column):
+//   k in 0..3 : x_hi * w_hi     k in 4..7 : x_lo * w_hi     k in 8..11 : x_hi * w_lo     k in 12..15 : 0
+__device__ void pack_split_b_operand(const float* __restrict__ W, int n_rows, int d, uint8_t* __restrict__ out) {
+    for (int i = threadIdx.x; i < n_rows * 16; i += blockDim.x) {
+        const int n = i / 16, k = i % 16, j = k & 3;
+        float v = 0.f;
+        if (k < 12 && j < d) {
+            const float w = W[n * d + j];
+            const float hi = __bfloat162float(__float2bfloat16(w));
+            v = (k < 8) ? hi : (w - hi);
+        }
+        *reinterpret_cast<__nv_bfloat16*>(out + (k / 8) * (n_rows * 16) + n * 16 + (k % 8) * 2) = __float2bfloat16(v);
+    }
+}
+// A-side columns of the split product for one row x[0..4) (entries past d_in are zero)
+__device__ __forceinline__ void split_x16(const float* x, float* cols) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float hi = __bfloat162float(__float2bfloat16(x[j]));
+        cols[j] = hi;
+        cols[4 + j] = x[j] - hi;
+        cols[8 + j] = hi;
+        cols[12 + j] = 0.f;
+    }
+}
+
 // Qp = fc_q(Qin) for nq (64 or 1) queries, and the stacked-pair A operand image
 __device__ void prep_queries(const float* __restrict__ Qin, int nq, const float* __restrict__ Wq,
                              const float* __restrict__ bq, float* __restrict__ Qp_out, uint8_t* __restrict__ Aq,
-                             float* sq /* smem 64*64 */) {
+                             float* sq /* smem 64*64 */, const float* __restrict__ Wk = nullptr,
+                             uint8_t* __restrict__ AqPool = nullptr) {
     for (int i = threadIdx.x; i < nq * TD; i += blockDim.x) {
         const int m = i / TD, f = i % TD;
         float a = bq[f];
@@ -67,6 +97,23 @@ __device__ void prep_queries(const float* __restrict__ Qin, int nq, const float*
         Qp_out[i] = a;
     }
     __syncthreads();
+    if (nq == 1 && AqPool != nullptr) {
+        // Pooling by one seed (modules.py:62-63) folded through fc_k: the score of head h against point n is
+        //   q_h . (Wk_h y_n + bk_h) = (Wk_h^T q_h) . y_n + const(h)   and the constant cancels in the softmax over n,
+        // so the scores are a plain product of the un-projected points with one 64-vector per head.
+        // sq[64..64+512) = wqk[h][f] = scale * sum_d q[h*8+d] Wk[h*8+d][f]
+        for (int i = threadIdx.x; i < TH * TD; i += blockDim.x) {
+            const int h = i / TD, f = i % TD;
+            float a = 0.f;
+            for (int d = 0; d < 8; ++d) a = fmaf(sq[h * 8 + d], Wk[(h * 8 + d) * TD + f], a);
+            sq[64 + i] = a * kScaleLog2e;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 8 * 128 * 8; i += blockDim.x) {
+            const int d = i & 7, r = (i >> 3) & 127, c = i >> 10;
+            *reinterpret_cast<__nv_bfloat16*>(AqPool + c * 2048 + r * 16 + d * 2) = __float2bfloat16(sq[64 + (r >> 4) * TD + c * 8 + d]);
+        }
+    }
     if (nq == 1) {
         // PMA all-heads image (128 x 64, [8 chunks][128 rows][16 B]): row r carries head r / 16 in chunk r / 16
         for (int i = threadIdx.x; i < 8 * 128 * 8; i += blockDim.x) {
@@ -98,7 +145,7 @@ __global__ void prep_kernel(const float* __restrict__ params, int d_in, TcConsts
     switch (blockIdx.x) {
         case 0: prep_queries(p_isab0, TM, m00.Wq, m00.bq, c->Qp0, c->Aq0, sq); break;
         case 1: prep_queries(p_isab1, TM, m10.Wq, m10.bq, c->Qp1, c->Aq1, sq); break;
-        case 2: prep_queries(p_pma, 1, mp.Wq, mp.bq, c->QpS, c->AqP, sq); break;
+        case 2: prep_queries(p_pma, 1, mp.Wq, mp.bq, c->QpS, c->AqP, sq, mp.Wkv, c->AqPool); break;
         case 3: pack_b_operand(m10.Wkv, 128, c->Wkv1); break;
         case 4: pack_b_operand(mp.Wkv, 128, c->WkvP); break;
         case 5: pack_b_operand(m11.Wq, 64, c->Wq1); break;
@@ -108,6 +155,7 @@ __global__ void prep_kernel(const float* __restrict__ params, int d_in, TcConsts
         case 9: transpose_weight(m01.Wkv, 128, c->WkvT[0]); break;
         case 10: transpose_weight(m10.Wo, 64, c->WoT[1]); break;
         case 11: transpose_weight(m11.Wkv, 128, c->WkvT[1]); break;
+        case 12: pack_split_b_operand(m01.Wq, 64, d_in, c->WqS0); break;
         default: break;
     }
 }
@@ -697,6 +745,7 @@ struct AParams {
     const uint8_t* Wo16;          // 8 KB B operand
     const float* bo;              // (64)
     __nv_bfloat16* Yout;          // (B, N, 64)
+    long long* timeline;          // debug (PCA_TIMELINE builds): clock64 stamps of CTA 0 / softmax warp 0
 };
 
 // ====================================================================================== chain-scheduled kernels
@@ -1298,6 +1347,15 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
         bool pend_live = false, pend_any = false;
         int pend_parity = 0;
         int gt = 0;
+#ifdef PCA_TIMELINE
+        long long* tl = (P.timeline != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0) ? P.timeline : nullptr;
+        int tl_n = 0;
+        auto stamp = [&](int tag) {
+            if (tl != nullptr && tl_n < 4000) { tl[2 * tl_n] = tag; tl[2 * tl_n + 1] = clock64(); ++tl_n; }
+        };
+#else
+        auto stamp = [&](int) {};
+#endif
 
         auto issue_loads = [&](const int hh, const bool live) {
             const int c = 2 * g + hh;
@@ -1317,23 +1375,29 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
             const uint32_t snext = tmem_addr(tb, lane_base, A2_S + 64 * cn);
             if (live) {
                 uint32_t pk[16];
+                stamp(0);
                 tmem_ld_wait64(va, vb);
+                stamp(1);
                 const float mx = max64(va, vb);
                 const float2 neg2 = make_float2(-mx, -mx);
                 float2 sum2 = make_float2(0.f, 0.f);
                 exp_chunk32(va, neg2, sum2, pk);
                 tmem_st16(sbase, pk);
+                stamp(2);
                 if (has_next) {
                     mbar_wait(&s_full[cn], ph_s[hh ^ 1]);
                     ph_s[hh ^ 1] ^= 1;
                     fence_after_sync();
                     tmem_ld32(snext, va);
                 }
+                stamp(3);
                 exp_chunk32(vb, neg2, sum2, pk);
                 tmem_st16(sbase + 16, pk);
                 if (has_next) tmem_ld32(snext + 32, vb);
                 inv_l[pp][hh] = __fdividef(1.f, sum2.x + sum2.y);
+                stamp(4);
                 tmem_st_wait();
+                stamp(5);
             } else if (has_next) {
                 mbar_wait(&s_full[cn], ph_s[hh ^ 1]);
                 ph_s[hh ^ 1] ^= 1;
@@ -1341,10 +1405,13 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
             }
             fence_before_sync();
             warp_arrive(&p_ready[c]);
+            stamp(6);
         };
         // Y = O1 + relu(fc_o(O1) + bo) for the pending tile (its O1 is held in o1[][])
         auto f_epilogue = [&]() {
+            stamp(12);
             mbar_wait(f_full, pend_parity);
+            stamp(13);
             fence_after_sync();
             if (pend_live) {
 #pragma unroll
@@ -1370,6 +1437,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
             }
             fence_before_sync();
             pend_any = false;
+            stamp(14);
         };
         for (int w = blockIdx.x; w < n_work; w += wstep) {
             int cloud, tile0;
@@ -1378,7 +1446,9 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
                 const int n = (tile0 + it) * 128 + row;
                 const bool valid = n < P.N;
                 const bool live = (tile0 + it) * 128 + 32 * quad < P.N;     // warps whose 32 rows are all padding idle
+                stamp(15);
                 issue_loads(0, live);
+                stamp(16);
                 softmax_item(0, 0, live, true);
                 if (pend_any) f_epilogue();              // deferred: the fc_o round trip hides behind the first softmax
                 softmax_item(1, 0, live, true);
@@ -1394,6 +1464,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
                 for (int pp = 0; pp < 2; ++pp) {
                     const int p = g + 2 * pp;
                     mbar_wait(&o_full[p], gt & 1);
+                    stamp(7 + 2 * pp);
                     fence_after_sync();
                     if (live) {
                         uint32_t o[16], qv[16];
@@ -1416,6 +1487,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
                         st_shared_8bf16(sO1 + (2 * p) * 2048 + row * 16, &o1[pp][0]);
                         st_shared_8bf16(sO1 + (2 * p + 1) * 2048 + row * 16, &o1[pp][8]);
                     }
+                    stamp(8 + 2 * pp);
                 }
                 if (DIN64) {
                     fence_before_sync();
@@ -1424,6 +1496,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AP
                 fence_async_smem();
                 fence_before_sync();
                 warp_arrive(o1_ready);
+                stamp(11);
                 pend_any = true;
                 pend_live = live;
                 pend_parity = gt & 1;
@@ -2075,6 +2148,713 @@ __global__ void __launch_bounds__(TC_THREADS24, 1) mab_apply4_tc_kernel(const AP
     if (warp == 20) tmem_dealloc(tb, 512);
 }
 
+// ====================================================================================== apply kernel, third generation
+// 20 warps: 0-7 softmax (two warpgroups), 8-11 producer, 12-15 MMA (one issuing thread per chain), 16-19 epilogue.
+// Differences to mab_apply2_tc_kernel (motivated by the per-phase timeline in profiles/: a third of the tile time was
+// epilogue work on the softmax warps with the MUFU pipe idle):
+//   * the Q projection ALWAYS runs as an MMA into the tile's TMEM accumulator OQ (d_in <= 4: one K=16 split-bf16 step),
+//     and the P V products of all heads accumulate ON TOP of it, so O1 = Qp + A V materialises in TMEM without any
+//     register work (bias bq is added where OQ is read);
+//   * probabilities are normalised before they are written (P = e / sum), so no per-row rescale of the outputs;
+//   * the softmax warps do nothing but  wait -> tcgen05.ld -> max -> 2^x -> sum -> scale -> pack -> tcgen05.st -> arrive;
+//   * dedicated epilogue warps turn OQ into the bf16 A operand of fc_o (written back to TMEM, not shared memory), and
+//     after the fc_o MMA emit Y = O1 + relu(fc_o(O1) + bo).
+// A chain is a head PAIR (its two heads run back to back on the chain's score buffer and accumulate into the pair's 16
+// output columns from one issuing thread, so no cross-thread accumulate hazard exists).
+constexpr int TC_THREADS20 = 20 * 32;
+constexpr uint32_t A3_S = 0, A3_OQ = 256, A3_O1B = 384, A3_F = 416;      // 4 x 64 | 2 x 64 | 32 | 64  (of 512 columns)
+
+struct A3Smem {
+    static constexpr int IMG = 0;                 // 2 x (K image 16384 | V image 16384), one per work item in flight
+    static constexpr int WO = 65536;              // fc_o B operand (N=64, K=64)
+    static constexpr int WQ = WO + 8192;          // fc_q B operand: (N=64, K=64) or the split-bf16 K=16 image
+    static constexpr int AQ = WQ + 8192;          // 2 stages x 16384: scaled bf16 queries (A operand of Q K^T)
+    static constexpr int YA = AQ + 32768;         // input tile: Y (128 x 64 bf16) or the split-bf16 X columns (128 x 16)
+    static constexpr int SMALL = YA + 16384;      // bq (64) | bo (64)
+    static constexpr int BARS = SMALL + 128 * 4;
+    static constexpr int TOTAL = BARS + 40 * 8 + 16;
+};
+
+// pairs of each 32-column chunk whose exponentials run on the FMA pipe (degree-3 polynomial) instead of MUFU
+#ifndef PCA_POLY3
+#define PCA_POLY3 0x0u
+#endif
+#ifndef PCA_A3_PREFETCH
+#define PCA_A3_PREFETCH 0
+#endif
+#ifndef PCA_A3_STAGGER
+#define PCA_A3_STAGGER 0
+#endif
+constexpr uint32_t kPolyPairs3 = PCA_POLY3;
+// e = 2^(s - m) kept in place as fp32, partial row sum
+__device__ __forceinline__ void exp_keep32(uint32_t* v, const float2 neg_m2, float2& sum2) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        const float2 x = add2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), neg_m2);
+        const float2 e = ((kPolyPairs3 >> (j >> 1)) & 1u) ? ex2_poly2(x) : make_float2(ex2(x.x), ex2(x.y));
+        sum2 = add2(sum2, e);
+        v[j] = __float_as_uint(e.x);
+        v[j + 1] = __float_as_uint(e.y);
+    }
+}
+__device__ __forceinline__ void scale_pack32(const uint32_t* v, const float2 inv2, uint32_t* pk) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        const float2 p = mul2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), inv2);
+        pk[j >> 1] = pack_bf16(p.x, p.y);
+    }
+}
+
+template <bool DIN64>
+__global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sImg = smem + A3Smem::IMG;
+    uint8_t* sWo = smem + A3Smem::WO;
+    uint8_t* sWq = smem + A3Smem::WQ;
+    uint8_t* sAQ = smem + A3Smem::AQ;
+    uint8_t* sYA = smem + A3Smem::YA;
+    float* sBq = reinterpret_cast<float*>(smem + A3Smem::SMALL);
+    float* sBo = sBq + 64;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A3Smem::BARS);
+    uint64_t* aq_full = bars;          // [2] count 4 (producer warps)
+    uint64_t* aq_empty = bars + 2;     // [2] count 4 (chain commits)
+    uint64_t* s_full = bars + 4;       // [4] count 1
+    uint64_t* p_ready = bars + 8;      // [4] count 4 (warps of the owning warpgroup)
+    uint64_t* o_full = bars + 12;      // [2] count 4 (chain commits)          -- per OQ buffer
+    uint64_t* oq_free = bars + 14;     // [2] count 4 (epilogue warps)         -- per OQ buffer
+    uint64_t* ya_full = bars + 16;     // count 4
+    uint64_t* qp_done = bars + 17;     // count 1
+    uint64_t* o1_ready = bars + 18;    // count 4 (epilogue warps)
+    uint64_t* f_full = bars + 19;      // count 1
+    uint64_t* img_full = bars + 20;    // [2] count 4 (producer warps)
+    uint64_t* img_empty = bars + 22;   // [2] count 4 (chain commits)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_work = P.n_work, wstep = gridDim.x;
+    auto work_tiles = [&](int w, int& cloud, int& tile0) {
+        cloud = w / P.nsplit;
+        const int split = w - cloud * P.nsplit;
+        tile0 = split * P.tiles_per_split;
+        return min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+    };
+
+    copy_to_smem(sWo, P.Wo16, 8192);
+    copy_to_smem(sWq, P.Wq16, DIN64 ? 8192 : 2048);
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+        sBq[i] = P.bq[i];
+        sBo[i] = P.bo[i];
+    }
+    if (warp == 12) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&aq_full[i], 4); mbar_init(&aq_empty[i], 4); mbar_init(&o_full[i], 4); mbar_init(&oq_free[i], 4);
+            mbar_init(&img_full[i], 4); mbar_init(&img_empty[i], 4);
+        }
+        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
+        mbar_init(ya_full, 4);
+        mbar_init(qp_done, 1);
+        mbar_init(o1_ready, 4);
+        mbar_init(f_full, 1);
+        fence_barrier_init();
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp >= 16) {
+        // register budget: the CTA's pool is 20 warps x 96; softmax 8 x 152 + producer 4 x 56 + MMA 4 x 24 + epilogue 4 x 96 = 1920
+        // =================================================================== epilogue warps (thread = point row)
+        const int quad = warp & 3;
+        const int row = 32 * quad + lane;
+        const uint32_t lane_base = 32 * quad;
+        int gt = 0;
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, tile0;
+            const int ntiles = work_tiles(w, cloud, tile0);
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int buf = gt & 1;
+                const int n = (tile0 + it) * 128 + row;
+                const bool valid = n < P.N;
+                const bool live = (tile0 + it) * 128 + 32 * quad < P.N;
+                const uint32_t oq = tmem_addr(tb, lane_base, A3_OQ + 64 * buf);
+                // ---- O1 = OQ + bq  ->  bf16 A operand of fc_o, written back to TMEM
+                mbar_wait(&o_full[buf], (gt >> 1) & 1);
+                fence_after_sync();
+                if (live) {
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t v[32], pk[16];
+                        tmem_ld32(oq + 32 * hf, v);
+                        tmem_ld_wait32(v);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2)
+                            pk[j >> 1] = pack_bf16(__uint_as_float(v[j]) + sBq[32 * hf + j], __uint_as_float(v[j + 1]) + sBq[32 * hf + j + 1]);
+                        tmem_st16(tmem_addr(tb, lane_base, A3_O1B + 16 * hf), pk);
+                    }
+                    tmem_st_wait();
+                }
+                fence_before_sync();
+                warp_arrive(o1_ready);
+                if (warp == 16 && lane == 0) {
+                    // one epilogue thread issues fc_o: F = O1 Wo^T, A operand from TMEM
+                    mbar_wait(o1_ready, gt & 1);
+                    fence_after_sync();
+                    const uint32_t wo = smem_u32(sWo);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_ts(tmem_addr(tb, 0, A3_F), tmem_addr(tb, 0, A3_O1B + 8 * ks), smem_desc(wo + ks * 2048, 1024, 128),
+                               idesc_bf16(128, 64, 0, 0), ks > 0);
+                    mma_commit(f_full);
+                }
+                __syncwarp();
+                // ---- Y = O1 + relu(F + bo)
+                mbar_wait(f_full, gt & 1);
+                fence_after_sync();
+                if (live) {
+                    __nv_bfloat16* dst = P.Yout + ((size_t)cloud * P.N + (valid ? n : 0)) * 64;
+#pragma unroll
+                    for (int qf = 0; qf < 4; ++qf) {
+                        uint32_t o[16], f[16];
+                        tmem_ld16(oq + 16 * qf, o);
+                        tmem_ld16(tmem_addr(tb, lane_base, A3_F + 16 * qf), f);
+                        tmem_ld_wait16(o);
+                        tmem_ld_wait16(f);
+                        uint4 out[2];
+                        uint32_t* ow = reinterpret_cast<uint32_t*>(out);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            const int c0 = 16 * qf + j;
+                            const float y0 = (__uint_as_float(o[j]) + sBq[c0]) + fmaxf(__uint_as_float(f[j]) + sBo[c0], 0.f);
+                            const float y1 = (__uint_as_float(o[j + 1]) + sBq[c0 + 1]) + fmaxf(__uint_as_float(f[j + 1]) + sBo[c0 + 1], 0.f);
+                            ow[j >> 1] = pack_bf16(y0, y1);
+                        }
+                        if (valid) {
+                            uint4* d4 = reinterpret_cast<uint4*>(dst + 16 * qf);
+                            d4[0] = out[0];
+                            d4[1] = out[1];
+                        }
+                    }
+                }
+                fence_before_sync();
+                warp_arrive(&oq_free[buf]);
+            }
+        }
+    } else if (warp >= 12) {
+        reg_dec<24>();
+        if (lane == 0) {
+            // =================================================================== one MMA-issuing thread per chain (= head pair)
+            const int c = warp - 12;                      // pair c, score buffer c, output columns 16c..16c+15
+            const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
+            const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
+            const uint32_t img = smem_u32(sImg), aqb = smem_u32(sAQ);
+            int gt = 0, wl = 0;
+            for (int w = blockIdx.x; w < n_work; w += wstep, ++wl) {
+                int cloud, tile0;
+                const int ntiles = work_tiles(w, cloud, tile0);
+                const uint32_t kb = img + (wl & 1) * 32768 + c * 4096, vb = kb + 16384;
+                mbar_wait(&img_full[wl & 1], (wl >> 1) & 1);
+                fence_after_sync();
+                for (int it = 0; it < ntiles; ++it, ++gt) {
+                    const uint32_t a_desc_base = aqb + (gt & 1) * 16384 + 2 * c * 2048;
+                    const uint32_t d_o = tmem_addr(tb, 0, A3_OQ + 64 * (gt & 1) + 16 * c);
+                    mbar_wait(&aq_full[gt & 1], (gt >> 1) & 1);
+                    fence_after_sync();
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        mma_ss(tmem_addr(tb, 0, A3_S + 64 * c), smem_desc(a_desc_base, 2048, 128),
+                               smem_desc(kb + hh * 1024, 2048, 128), idesc_s, 0);
+                        mma_commit(&s_full[c]);
+                        mbar_wait(&p_ready[c], hh);          // two items per tile: parities 0, 1
+                        fence_after_sync();
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ts(d_o, tmem_addr(tb, 0, A3_S + 64 * c + ks * 8), smem_desc(vb + hh * 1024 + ks * 256, 128, 2048),
+                                   idesc_pv, 1u);
+                    }
+                    mma_commit(&o_full[gt & 1]);            // 4 chains: the tile's O1 is complete
+                    mma_commit(&aq_empty[gt & 1]);          // ... and its query stage is free
+                }
+                mma_commit(&img_empty[wl & 1]);
+            }
+        }
+    } else if (warp >= 8) {
+        reg_dec<56>();
+        // =================================================================== producer: images, Q projection, scaled query operand
+        const int quad = warp & 3;
+        const int row = 32 * quad + lane;
+        const int ptid = threadIdx.x - 256;          // 0..127
+        int gt = 0, wl = 0;
+        for (int w = blockIdx.x; w < n_work; w += wstep, ++wl) {
+            int cloud, tile0;
+            const int ntiles = work_tiles(w, cloud, tile0);
+            {   // stage this cloud's block-diagonal K / V images (32 KB)
+                if (wl >= 2) mbar_wait(&img_empty[wl & 1], ((wl >> 1) - 1) & 1);
+                const uint4* src = reinterpret_cast<const uint4*>(P.KVblk + (size_t)cloud * 32768);
+                uint4* dst = reinterpret_cast<uint4*>(sImg + (wl & 1) * 32768);
+#pragma unroll 4
+                for (int i = ptid; i < 2048; i += 128) dst[i] = __ldg(src + i);
+                fence_async_smem();
+                fence_before_sync();
+                warp_arrive(&img_full[wl & 1]);
+            }
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int stage = gt & 1;
+                const int n = (tile0 + it) * 128 + row;
+                const bool valid = n < P.N;
+                uint8_t* dst = sAQ + stage * 16384;
+                // ---- stage the input tile (sYA is free: the previous tile's projection MMA was waited for below)
+                if (!DIN64) {
+                    float x[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (valid) {
+                        const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                        for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
+                    }
+                    float cols[16];
+                    split_x16(x, cols);
+                    st_shared_8bf16(sYA + row * 16, cols);
+                    st_shared_8bf16(sYA + 2048 + row * 16, cols + 8);
+                } else {
+                    const uint4* src = reinterpret_cast<const uint4*>(P.Y16in + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
+                    uint4 yv[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sYA + c * 2048 + row * 16) = yv[c];
+                }
+                fence_async_smem();
+                fence_before_sync();
+                warp_arrive(ya_full);
+                if (warp == 8 && lane == 0) {
+                    // one producer thread issues the Q projection into the tile's accumulator (free once the epilogue of
+                    // two tiles ago has read it)
+                    mbar_wait(ya_full, gt & 1);
+                    if (gt >= 2) mbar_wait(&oq_free[stage], ((gt >> 1) - 1) & 1);
+                    fence_after_sync();
+                    const uint32_t yab = smem_u32(sYA), wq = smem_u32(sWq);
+#pragma unroll
+                    for (int ks = 0; ks < (DIN64 ? 4 : 1); ++ks)
+                        mma_ss(tmem_addr(tb, 0, A3_OQ + 64 * stage), smem_desc(yab + ks * 4096, 2048, 128),
+                               smem_desc(wq + ks * 2048, 1024, 128), idesc_bf16(128, 64, 0, 0), ks > 0);
+                    mma_commit(qp_done);
+                }
+                mbar_wait(qp_done, gt & 1);
+                fence_after_sync();
+                if (gt >= 2) mbar_wait(&aq_empty[stage], ((gt >> 1) - 1) & 1);
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_addr(tb, 32 * quad, A3_OQ + 64 * stage + c0), v);
+                    tmem_ld_wait32(v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = (__uint_as_float(v[8 * q + j]) + sBq[c0 + 8 * q + j]) * kScaleLog2e;
+                        st_shared_8bf16(dst + (c0 / 8 + q) * 2048 + row * 16, o);
+                    }
+                }
+                fence_async_smem();
+                fence_before_sync();
+                warp_arrive(&aq_full[stage]);
+            }
+        }
+    } else {
+        reg_inc<152>();
+        // =================================================================== softmax warpgroups (chains 2g, 2g+1)
+        const int g = warp >> 2, quad = warp & 3;
+        const uint32_t lane_base = 32 * quad;
+        uint32_t ph_s[2] = {0, 0};
+#ifdef PCA_TIMELINE
+        long long* tl = (P.timeline != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0) ? P.timeline : nullptr;
+        int tl_n = 0;
+        auto stamp = [&](int tag) {
+            if (tl != nullptr && tl_n < 4000) { tl[2 * tl_n] = tag; tl[2 * tl_n + 1] = clock64(); ++tl_n; }
+        };
+#else
+        auto stamp = [&](int) {};
+#endif
+        uint32_t va[32], vb[32];          // scores of the current item; refilled with the next item's while it finishes
+        // one 64-key item of chain 2g+j.  Its scores are already in flight into va / vb.  The next item (other chain of this
+        // warpgroup) was issued by its MMA thread a whole item ago, so its scores are prefetched as soon as va / vb free up.
+        auto softmax_item = [&](const int j, const bool live, const bool has_next) {
+            const int c = 2 * g + j, cn = 2 * g + (j ^ 1);
+            const uint32_t sbase = tmem_addr(tb, lane_base, A3_S + 64 * c);
+            const uint32_t snext = tmem_addr(tb, lane_base, A3_S + 64 * cn);
+            uint32_t pk[16];
+            stamp(20);
+            tmem_ld_wait64(va, vb);
+            stamp(25);
+            if (live) {
+                const float mx = max64(va, vb);
+                const float2 neg2 = make_float2(-mx, -mx);
+                float2 sum2 = make_float2(0.f, 0.f);
+                exp_keep32(va, neg2, sum2);
+                exp_keep32(vb, neg2, sum2);
+                const float inv = __fdividef(1.f, sum2.x + sum2.y);
+                const float2 inv2 = make_float2(inv, inv);
+                scale_pack32(va, inv2, pk);
+                tmem_st16(sbase, pk);
+                stamp(26);
+                if (has_next) {
+                    mbar_wait(&s_full[cn], ph_s[j ^ 1]);
+                    ph_s[j ^ 1] ^= 1;
+                    fence_after_sync();
+                    tmem_ld32(snext, va);
+                }
+                stamp(24);
+                scale_pack32(vb, inv2, pk);
+                tmem_st16(sbase + 16, pk);
+                if (has_next) tmem_ld32(snext + 32, vb);
+                tmem_st_wait();
+                stamp(27);
+            } else if (has_next) {
+                mbar_wait(&s_full[cn], ph_s[j ^ 1]);
+                ph_s[j ^ 1] ^= 1;
+                fence_after_sync();
+                tmem_ld32(snext, va);
+                tmem_ld32(snext + 32, vb);
+            }
+            fence_before_sync();
+            warp_arrive(&p_ready[c]);
+        };
+#if PCA_A3_PREFETCH
+        if (blockIdx.x < n_work) {
+            mbar_wait(&s_full[2 * g], ph_s[0]);
+            ph_s[0] ^= 1;
+            fence_after_sync();
+            tmem_ld32(tmem_addr(tb, lane_base, A3_S + 64 * (2 * g)), va);
+            tmem_ld32(tmem_addr(tb, lane_base, A3_S + 64 * (2 * g) + 32), vb);
+        }
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, tile0;
+            const int ntiles = work_tiles(w, cloud, tile0);
+            const bool more_work = w + wstep < n_work;
+            for (int it = 0; it < ntiles; ++it) {
+                const bool live = (tile0 + it) * 128 + 32 * quad < P.N;     // warps whose 32 rows are all padding idle
+                softmax_item(0, live, true);
+                softmax_item(1, live, true);
+                softmax_item(0, live, true);
+                softmax_item(1, live, it + 1 < ntiles || more_work);
+            }
+        }
+#else
+        (void)softmax_item;
+#if PCA_A3_STAGGER
+        if (g == 1) __nanosleep(PCA_A3_STAGGER);      // start the two warpgroups in anti-phase (they share the MUFU pipe)
+#endif
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, tile0;
+            const int ntiles = work_tiles(w, cloud, tile0);
+            for (int it = 0; it < ntiles; ++it) {
+                const bool live = (tile0 + it) * 128 + 32 * quad < P.N;     // warps whose 32 rows are all padding idle
+#pragma unroll
+                for (int step = 0; step < 4; ++step) {
+                    const int j = step & 1;
+                    const int c = 2 * g + j;
+                    const uint32_t sbase = tmem_addr(tb, lane_base, A3_S + 64 * c);
+                    stamp(20);
+                    mbar_wait(&s_full[c], ph_s[j]);
+                    ph_s[j] ^= 1;
+                    fence_after_sync();
+                    stamp(24);
+                    if (live) {
+                        uint32_t pk[16];
+                        tmem_ld32(sbase, va);
+                        tmem_ld32(sbase + 32, vb);
+                        tmem_ld_wait64(va, vb);
+                        stamp(25);
+                        const float mx = max64(va, vb);
+                        const float2 neg2 = make_float2(-mx, -mx);
+                        float2 sum2 = make_float2(0.f, 0.f);
+                        exp_keep32(va, neg2, sum2);
+                        exp_keep32(vb, neg2, sum2);
+                        const float inv = __fdividef(1.f, sum2.x + sum2.y);
+                        const float2 inv2 = make_float2(inv, inv);
+                        scale_pack32(va, inv2, pk);
+                        tmem_st16(sbase, pk);
+                        scale_pack32(vb, inv2, pk);
+                        tmem_st16(sbase + 16, pk);
+                        stamp(26);
+                        tmem_st_wait();
+                        stamp(27);
+                    }
+                    fence_before_sync();
+                    warp_arrive(&p_ready[c]);
+                }
+            }
+        }
+#endif
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tb, 512);
+}
+
+// ====================================================================================== pooled attention (PMA)
+// PMA with one seed, computed on the UN-projected points (see prep_queries): per 128-point tile
+//   S (128 rows = head x 16 copies, 128 points) = AqPool (128 x 64) . Ytile^T      [4 MMAs, K = 64]
+//   online softmax over the points per row, P (bf16) written over the consumed score columns
+//   Z (128 rows, 64 features) = P . Ytile                                            [8 MMAs, N = 64, MN-major B]
+// so neither fc_k nor fc_v is ever applied per point; fc_v is applied to the 8 pooled 64-vectors in finalize_pool_kernel
+// (sum_n p_n (Wv y_n + bv) = Wv (sum_n p_n y_n) + bv).  The kernel is a pure stream over Y (128 B per point):
+// persistent CTAs, 3-stage tile ring filled by 4 producer warps, two softmax warpgroups taking alternate tiles.
+struct PoolParams {
+    const __nv_bfloat16* Y16;     // (B, N, 64)
+    int N, tiles_total, tiles_per_split, nsplit, n_work;
+    const uint8_t* Aq;            // AqPool image
+    float* part;                  // (B, 2 nsplit, 8 heads, 66): m (log2 domain), l, Z[64]
+};
+constexpr int POOL_STAGES = 3;
+struct PoolSmem {
+    static constexpr int AQ = 0;
+    static constexpr int Y = 16384;                               // POOL_STAGES x 16384
+    static constexpr int BARS = Y + POOL_STAGES * 16384;
+    static constexpr int TOTAL = BARS + 16 * 8 + 16;
+};
+constexpr uint32_t PC_S = 0, PC_O = 256;      // 2 x 128 score columns | 2 x 64 output columns
+
+__global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const PoolParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sAq = smem + PoolSmem::AQ;
+    uint8_t* sY = smem + PoolSmem::Y;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PoolSmem::BARS);
+    uint64_t* y_full = bars;           // [3] count 4 (producer warps)
+    uint64_t* y_empty = bars + 3;      // [3] count 1 (commit)
+    uint64_t* s_full = bars + 6;       // [2] count 1
+    uint64_t* p_ready = bars + 8;      // [2] count 4
+    uint64_t* o_full = bars + 10;      // [2] count 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_work = P.n_work, wstep = gridDim.x;
+    auto work_tiles = [&](int w, int& cloud, int& split, int& tile0) {
+        cloud = w / P.nsplit;
+        split = w - cloud * P.nsplit;
+        tile0 = split * P.tiles_per_split;
+        return min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+    };
+    copy_to_smem(sAq, P.Aq, 16384);
+    if (warp == 12) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < POOL_STAGES; ++i) { mbar_init(&y_full[i], 4); mbar_init(&y_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); }
+        fence_barrier_init();
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp >= 12) {
+        reg_dec<40>();
+        if (warp == 12 && lane == 0) {
+            // =================================================================== MMA issuer (tiles in order; S runs one tile ahead)
+            const uint32_t idesc_s = idesc_bf16(128, 128, 0, 0);
+            const uint32_t idesc_pv = idesc_bf16(128, 64, 0, 1);
+            const uint32_t aq = smem_u32(sAq), yb = smem_u32(sY);
+            int total = 0;
+            for (int w = blockIdx.x; w < n_work; w += wstep) { int a, b, c; total += work_tiles(w, a, b, c); }
+            auto issue_s = [&](int t) {
+                const int stage = t % POOL_STAGES;
+                mbar_wait(&y_full[stage], (t / POOL_STAGES) & 1);
+                fence_after_sync();
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_ss(tmem_addr(tb, 0, PC_S + 128 * (t & 1)), smem_desc(aq + ks * 4096, 2048, 128),
+                           smem_desc(yb + stage * 16384 + ks * 4096, 2048, 128), idesc_s, ks > 0);
+                mma_commit(&s_full[t & 1]);
+            };
+            if (total > 0) issue_s(0);
+            for (int t = 0; t < total; ++t) {
+                // S(t+1) overwrites the buffer whose P was consumed by PV(t-1): issued earlier by this thread, in order
+                if (t + 1 < total) issue_s(t + 1);
+                const int b = t & 1, stage = t % POOL_STAGES;
+                mbar_wait(&p_ready[b], (t >> 1) & 1);
+                fence_after_sync();
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    mma_ts(tmem_addr(tb, 0, PC_O + 64 * b), tmem_addr(tb, 0, PC_S + 128 * b + ks * 8),
+                           smem_desc(yb + stage * 16384 + ks * 256, 128, 2048), idesc_pv, ks > 0);
+                mma_commit(&o_full[b]);
+                mma_commit(&y_empty[stage]);
+            }
+        }
+    } else if (warp >= 8) {
+        reg_dec<88>();
+        // =================================================================== producer: Y tiles -> [chunk][row][16 B]
+        const int row = 32 * (warp & 3) + lane;
+        int t = 0;
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, split, tile0;
+            const int ntiles = work_tiles(w, cloud, split, tile0);
+            for (int it = 0; it < ntiles; ++it, ++t) {
+                const int stage = t % POOL_STAGES;
+                const int n = (tile0 + it) * 128 + row;
+                const bool valid = n < P.N;
+                const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
+                uint4 yv[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+                if (t >= POOL_STAGES) mbar_wait(&y_empty[stage], ((t / POOL_STAGES) - 1) & 1);
+                uint8_t* dst = sY + stage * 16384;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + c * 2048 + row * 16) = yv[c];
+                fence_async_smem();
+                fence_before_sync();
+                warp_arrive(&y_full[stage]);
+            }
+        }
+    } else {
+        reg_inc<184>();
+        // =================================================================== softmax warpgroups: g takes the tiles with t % 2 == g
+        const int g = warp >> 2, quad = warp & 3;
+        const int row = 32 * quad + lane;
+        const uint32_t lane_base = 32 * quad;
+        const uint32_t sbase = tmem_addr(tb, lane_base, PC_S + 128 * g);
+        float m_run = -INFINITY, l_run = 0.f, alpha = 0.f;
+        float acc[64];
+        uint32_t ph_s = 0, ph_o = 0;
+        int t = 0;
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, split, tile0;
+            const int ntiles = work_tiles(w, cloud, split, tile0);
+            m_run = -INFINITY; l_run = 0.f; alpha = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+            for (int it = 0; it < ntiles; ++it, ++t) {
+                if ((t & 1) != g) continue;
+                const int n_valid = min(128, P.N - (tile0 + it) * 128);
+                mbar_wait(&s_full[g], ph_s);
+                ph_s ^= 1;
+                fence_after_sync();
+                // ---- pass 1: row max over the valid columns
+                float mx = -INFINITY;
+                {
+                    uint32_t v[32];
+#pragma unroll 1
+                    for (int c0 = 0; c0 < n_valid; c0 += 32) {
+                        tmem_ld32(sbase + c0, v);
+                        tmem_ld_wait32(v);
+                        if (c0 + 32 <= n_valid) mx = max_chunk32(v, mx);
+                        else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c0 + j < n_valid) mx = fmaxf(mx, __uint_as_float(v[j]));
+                        }
+                    }
+                }
+                const float m_new = fmaxf(m_run, mx);
+                alpha = ex2(m_run - m_new);
+                const float2 neg2 = make_float2(-m_new, -m_new);
+                float2 sum2 = make_float2(0.f, 0.f);
+                // ---- pass 2: probabilities; P (bf16) overwrites score columns that were already consumed
+#pragma unroll
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t v[32], pk[16];
+                    if (c0 < n_valid) {
+                        tmem_ld32(sbase + c0, v);
+                        tmem_ld_wait32(v);
+                        if (c0 + 32 <= n_valid) exp_chunk32(v, neg2, sum2, pk);
+                        else {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                const float p0 = (c0 + j < n_valid) ? ex2(__uint_as_float(v[j]) - m_new) : 0.f;
+                                const float p1 = (c0 + j + 1 < n_valid) ? ex2(__uint_as_float(v[j + 1]) - m_new) : 0.f;
+                                sum2.x += p0 + p1;
+                                pk[j >> 1] = pack_bf16(p0, p1);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[j] = 0u;
+                    }
+                    tmem_st16(sbase + (c0 >> 1), pk);
+                }
+                l_run = l_run * alpha + (sum2.x + sum2.y);
+                m_run = m_new;
+                tmem_st_wait();
+                fence_before_sync();
+                warp_arrive(&p_ready[g]);
+                // ---- Z += P Y (rescaled running sum in registers)
+                mbar_wait(&o_full[g], ph_o);
+                ph_o ^= 1;
+                fence_after_sync();
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t o[32];
+                    tmem_ld32(tmem_addr(tb, lane_base, PC_O + 64 * g + c0), o);
+                    tmem_ld_wait32(o);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] = fmaf(acc[c0 + j], alpha, __uint_as_float(o[j]));
+                }
+                fence_before_sync();
+            }
+            if ((row & 15) == 0) {
+                const int h = row >> 4;
+                float* dst = P.part + ((((size_t)cloud * P.nsplit + split) * 2 + g) * TH + h) * 66;
+                dst[0] = m_run;
+                dst[1] = l_run;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) dst[2 + j] = acc[j];
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tb, 512);
+}
+
+// merge the pooled partials, apply fc_v to the 8 pooled vectors, then the MAB tail and the final Linear
+struct PoolFinParams {
+    const float* part; int nslots;           // (B, nslots, 8, 66)
+    const float* QpS;                         // (64) fc_q(S)
+    const float* Wv; const float* bv;         // pma.mab.fc_v (64, 64), (64)
+    const float* Wo; const float* bo;         // pma.mab.fc_o
+    const float* Wl; const float* bl; int C;  // final Linear (C, 64)
+    float* logits;                            // (B, C)
+    float* pooled_debug;                      // nullable (B, 64)
+};
+__global__ void __launch_bounds__(64) finalize_pool_kernel(const PoolFinParams P) {
+    __shared__ float sZ[TH][TD + 1], sO[64], sO1[64];
+    const int cloud = blockIdx.x, f = threadIdx.x;
+    // thread f merges feature f of every head
+    for (int h = 0; h < TH; ++h) {
+        float mmax = -INFINITY;
+        for (int s = 0; s < P.nslots; ++s) mmax = fmaxf(mmax, P.part[(((size_t)cloud * P.nslots + s) * TH + h) * 66]);
+        float l = 0.f, z = 0.f;
+        for (int s = 0; s < P.nslots; ++s) {
+            const float* pp = P.part + (((size_t)cloud * P.nslots + s) * TH + h) * 66;
+            const float wgt = (pp[0] == -INFINITY) ? 0.f : exp2f(pp[0] - mmax);      // a warpgroup that saw no tile
+            l = fmaf(pp[1], wgt, l);
+            z = fmaf(pp[2 + f], wgt, z);
+        }
+        sZ[h][f] = z / l;
+    }
+    __syncthreads();
+    {
+        const int h = f >> 3;
+        float a = P.bv[f];
+        for (int k = 0; k < 64; ++k) a = fmaf(sZ[h][k], P.Wv[f * 64 + k], a);
+        sO[f] = P.QpS[f] + a;
+    }
+    __syncthreads();
+    float acc = P.bo[f];
+    for (int k = 0; k < 64; ++k) acc = fmaf(sO[k], P.Wo[f * 64 + k], acc);
+    const float o1 = sO[f] + fmaxf(acc, 0.f);
+    sO1[f] = o1;
+    if (P.pooled_debug) P.pooled_debug[(size_t)cloud * 64 + f] = o1;
+    __syncthreads();
+    for (int c = f; c < P.C; c += 64) {
+        float z = P.bl[c];
+        for (int k = 0; k < 64; ++k) z = fmaf(sO1[k], P.Wl[c * 64 + k], z);
+        P.logits[(size_t)cloud * P.C + c] = z;
+    }
+}
+
 // ------------------------------------------------------------------------------------ finalize (PMA + Linear)
 struct PParams {
     const float* part; int nsplit;
@@ -2126,7 +2906,7 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 static int g_num_sms = 148;
 // softmax warpgroups per CTA (2 = 16 warps with TMEM prefetch, 4 = 24 warps): measured best is 4 for the reduce kernel
 // and 2 for the apply kernel (profiles/); PCA_TC_REDUCE_WG / PCA_TC_APPLY_WG override for experiments
-static int g_reduce_wg = 4, g_apply_wg = 2;
+static int g_reduce_wg = 4, g_apply_wg = 3;      // apply: 3 = third-generation kernel (20 warps, epilogue warps)
 static long long* g_timeline = nullptr;      // set through pca_debug_set_timeline
 void set_timeline(long long* p) { g_timeline = p; }
 struct TcSplit { int tiles_total, tiles_per_split, nsplit; };
@@ -2209,9 +2989,10 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     }
     PCA_CHECK_LAUNCH("finalize_isab_kernel");
     {
-        AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, kvblk, m01.Wq, m01.bq, nullptr, c->Wo0, m01.bo, Y1};
+        AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, kvblk, m01.Wq, m01.bq, nullptr, c->Wo0, m01.bo, Y1, g_timeline};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * d_in * TD + 2.0 * TM * TD + TD * TD), pts * (4.0 * d_in + 128.0));
-        if (g_apply_wg == 4) mab_apply4_tc_kernel<false><<<pgrid, TC_THREADS24, A2Smem::TOTAL, st>>>(a);
+        if (g_apply_wg == 3) { a.Wq16 = c->WqS0; mab_apply3_tc_kernel<false><<<pgrid, TC_THREADS20, A3Smem::TOTAL, st>>>(a); }
+        else if (g_apply_wg == 4) mab_apply4_tc_kernel<false><<<pgrid, TC_THREADS24, A2Smem::TOTAL, st>>>(a);
         else mab_apply2_tc_kernel<false><<<pgrid, TC_THREADS16, A2Smem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<small>");
@@ -2230,25 +3011,27 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     }
     PCA_CHECK_LAUNCH("finalize_isab_kernel");
     {
-        AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, kvblk, nullptr, m11.bq, c->Wq1, c->Wo1, m11.bo, Y2};
+        AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, kvblk, nullptr, m11.bq, c->Wq1, c->Wo1, m11.bo, Y2, nullptr};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * TD * TD + 2.0 * TM * TD + TD * TD), pts * 256.0);
-        if (g_apply_wg == 4) mab_apply4_tc_kernel<true><<<pgrid, TC_THREADS24, A2Smem::TOTAL, st>>>(a);
+        if (g_apply_wg == 3) mab_apply3_tc_kernel<true><<<pgrid, TC_THREADS20, A3Smem::TOTAL, st>>>(a);
+        else if (g_apply_wg == 4) mab_apply4_tc_kernel<true><<<pgrid, TC_THREADS24, A2Smem::TOTAL, st>>>(a);
         else mab_apply2_tc_kernel<true><<<pgrid, TC_THREADS16, A2Smem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<64>");
     // ---- PMA + Linear
     {
-        RParams r{nullptr, Y2, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->AqP, nullptr, mp.bkv, c->WkvP, nullptr, part};
-        LaunchTimer lt("pma_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TD), pts * 128.0);
-        mab_reduce_tc_kernel<true, true><<<grid, TC_THREADS16, RSmem::TOTAL, st>>>(r);
+        PoolParams r{Y2, N, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->AqPool, part};
+        LaunchTimer lt("pma_pool_tc_kernel", st, pts * 2.0 * (2.0 * TH * TD), pts * 128.0);
+        pma_pool_tc_kernel<<<pgrid, TC_THREADS16, PoolSmem::TOTAL, st>>>(r);
     }
-    PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<pma>");
+    PCA_CHECK_LAUNCH("pma_pool_tc_kernel");
     {
-        PParams p{part, sp.nsplit, c->QpS, mp.Wo, mp.bo, p_lin, p_lin + (long long)d->C * TD, d->C, logits, dbg ? dbg->pooled : nullptr};
-        LaunchTimer lt("finalize_pma_kernel", st, (double)B * 2.0 * (TD * TD + TD * d->C), (double)B * 4.0 * d->C);
-        finalize_pma_kernel<<<B, 64, 0, st>>>(p);
+        PoolFinParams p{part, 2 * sp.nsplit, c->QpS, mp.Wkv + TD * TD, mp.bkv + TD, mp.Wo, mp.bo, p_lin, p_lin + (long long)d->C * TD,
+                        d->C, logits, dbg ? dbg->pooled : nullptr};
+        LaunchTimer lt("finalize_pool_kernel", st, (double)B * 2.0 * (2.0 * TD * TD + TD * d->C), (double)B * 4.0 * d->C);
+        finalize_pool_kernel<<<B, 64, 0, st>>>(p);
     }
-    PCA_CHECK_LAUNCH("finalize_pma_kernel");
+    PCA_CHECK_LAUNCH("finalize_pool_kernel");
     if (dbg) {
         const long long n = (long long)B * N * 64;
         if (dbg->Y1) { bf16_to_f32_kernel<<<1024, 256, 0, st>>>(Y1, dbg->Y1, n); PCA_CHECK_LAUNCH("bf16_to_f32_kernel"); }
@@ -2274,10 +3057,13 @@ static int tc_configure() {
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply4_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply4_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
     if (const char* v = getenv("PCA_TC_REDUCE_WG")) g_reduce_wg = (v[0] == '2') ? 2 : 4;
-    if (const char* v = getenv("PCA_TC_APPLY_WG")) g_apply_wg = (v[0] == '4') ? 4 : 2;
+    if (const char* v = getenv("PCA_TC_APPLY_WG")) g_apply_wg = (v[0] == '4') ? 4 : (v[0] == '2') ? 2 : 3;
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(pma_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PoolSmem::TOTAL));
     done = true;
     return 0;
 }
@@ -2293,7 +3079,7 @@ int st_tc_forward_dbg(const float* X, int B, int N, const pca_st_dims* d, const 
     if (dbg && chunk < B) return fail(PCA_EWORKSPACE, "ST(bf16) debug: workspace must hold the whole batch");
     uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
     TcConsts* c = reinterpret_cast<TcConsts*>(w8 + tc_layout(chunk, N).consts);
-    prep_kernel<<<12, 256, 0, st>>>(params, d->d_in, c);
+    prep_kernel<<<13, 256, 0, st>>>(params, d->d_in, c);
     PCA_CHECK_LAUNCH("prep_kernel");
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int bc = (B - b0) < chunk ? (B - b0) : chunk;

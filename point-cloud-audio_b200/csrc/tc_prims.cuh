@@ -204,6 +204,11 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
     return *reinterpret_cast<float2*>(&d);
 }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
     unsigned long long d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;"
