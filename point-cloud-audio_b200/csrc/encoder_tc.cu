@@ -33,6 +33,9 @@ struct TcConsts {
     uint8_t Aq0[16384], Aq1[16384], AqP[16384];   // stacked-pair query operands [4 pairs][2 chunks][128 rows][16 B]
     uint8_t Wkv1[16384], WkvP[16384];             // [Wk;Wv] as B operand (N=128, K=64): [8 chunks][128 rows][16 B]
     uint8_t Wq1[8192], Wo0[8192], Wo1[8192];      // (N=64, K=64) B operands: [8 chunks][64 rows][16 B]
+    // split-bf16 (hi | lo) B operands of the finalize GEMMs, per ISAB: mab0.fc_o (N=64, K=64) and mab1 [Wk;Wv] (N=128, K=64)
+    uint8_t WoS[2][2][8192];
+    uint8_t WkvS[2][2][16384];
     uint8_t AqPool[16384];                        // PMA: row r = scale * Wk_h^T fc_q(S)_h, h = r / 16 (A operand, 128 x 64)
     uint8_t WqS0[2048];                           // isab0.mab1.fc_q (64, d_in <= 4) as a split-bf16 K=16 B operand
     // k-major fp32 copies for finalize_isab: mab0.fc_o^T (64 x 64) and mab1 [Wk;Wv]^T (64 x 128), per ISAB
@@ -81,6 +84,17 @@ __device__ __forceinline__ void split_x16(const float* x, float* cols) {
         cols[4 + j] = x[j] - hi;
         cols[8 + j] = hi;
         cols[12 + j] = 0.f;
+    }
+}
+
+// W (n_rows, 64) -> two bf16 B-operand images: hi = bf16(W), lo = bf16(W - hi)
+__device__ void pack_b_operand_split(const float* __restrict__ W, int n_rows, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo) {
+    for (int i = threadIdx.x; i < n_rows * 64; i += blockDim.x) {
+        const int n = i / 64, k = i % 64;
+        const size_t off = (size_t)(k / 8) * (n_rows * 16) + n * 16 + (k % 8) * 2;
+        const __nv_bfloat16 h = __float2bfloat16(W[i]);
+        *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
+        *reinterpret_cast<__nv_bfloat16*>(lo + off) = __float2bfloat16(W[i] - __bfloat162float(h));
     }
 }
 
@@ -156,6 +170,10 @@ __global__ void prep_kernel(const float* __restrict__ params, int d_in, TcConsts
         case 10: transpose_weight(m10.Wo, 64, c->WoT[1]); break;
         case 11: transpose_weight(m11.Wkv, 128, c->WkvT[1]); break;
         case 12: pack_split_b_operand(m01.Wq, 64, d_in, c->WqS0); break;
+        case 13: pack_b_operand_split(m00.Wo, 64, c->WoS[0][0], c->WoS[0][1]); break;
+        case 14: pack_b_operand_split(m01.Wkv, 128, c->WkvS[0][0], c->WkvS[0][1]); break;
+        case 15: pack_b_operand_split(m10.Wo, 64, c->WoS[1][0], c->WoS[1][1]); break;
+        case 16: pack_b_operand_split(m11.Wkv, 128, c->WkvS[1][0], c->WkvS[1][1]); break;
         default: break;
     }
 }
@@ -731,6 +749,192 @@ __global__ void __launch_bounds__(256) finalize_isab_kernel(const FParams P) {
             *reinterpret_cast<uint4*>(img + pr * 4096 + c * 2048 + ((1 - c) * 64 + m) * 16) = make_uint4(0, 0, 0, 0);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------ finalize (ISAB) on tensor cores
+// Same arithmetic as finalize_isab_kernel, two clouds per CTA iteration (MMA rows = (cloud of the pair, inducing point)).
+// Both GEMMs run as 3-term split-bf16 products (a_hi w_hi + a_lo w_hi + a_hi w_lo, fp32 accumulate), i.e. to ~2^-17
+// relative -- the inducing-point summaries stay fp32-grade and only the K / V images are rounded to bf16, as before.
+struct F2Params {
+    const float* part; int nslots; int B;
+    const float* Qp;              // (64, 64) hoisted fc_q(I)
+    const uint8_t* WoS;           // hi 8192 | lo 8192
+    const float* bo;
+    const uint8_t* WkvS;          // hi 16384 | lo 16384
+    const float* bkv;
+    uint8_t* KVblk;               // per cloud 32768 B
+    float* H_debug;               // nullable (B, 64, 64)
+};
+constexpr uint32_t F2_A = 0, F2_F = 64, F2_KV = 128;       // hi 32 | lo 32 | F 64 | KV 128  (256 columns)
+struct F2Smem {
+    static constexpr int WO = 0;
+    static constexpr int WKV = 16384;
+    static constexpr int BIAS = WKV + 32768;      // bo (64) | bkv (128)
+    static constexpr int BARS = BIAS + 192 * 4;
+    static constexpr int TOTAL = BARS + 32;
+};
+
+__device__ __forceinline__ void st_split_a(uint32_t tb, uint32_t lane_base, const float* o) {
+    // A operand (this thread's row, K = 64) as bf16 pairs: hi in columns [0, 32), lo in [32, 64)
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(o[c0 + j], o[c0 + j + 1]);
+            hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[j >> 1] = pack_bf16(o[c0 + j] - __bfloat162float(h.x), o[c0 + j + 1] - __bfloat162float(h.y));
+        }
+        tmem_st16(tmem_addr(tb, lane_base, F2_A + (c0 >> 1)), hi);
+        tmem_st16(tmem_addr(tb, lane_base, F2_A + 32 + (c0 >> 1)), lo);
+    }
+}
+
+__global__ void __launch_bounds__(128) finalize_isab_tc_kernel(const F2Params P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sWo = smem + F2Smem::WO;
+    uint8_t* sWkv = smem + F2Smem::WKV;
+    float* sBo = reinterpret_cast<float*>(smem + F2Smem::BIAS);
+    float* sBkv = sBo + 64;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + F2Smem::BARS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    copy_to_smem(sWo, P.WoS, 16384);
+    copy_to_smem(sWkv, P.WkvS, 32768);
+    if (tid < 64) sBo[tid] = P.bo[tid];
+    sBkv[tid] = P.bkv[tid];
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+    const uint32_t lane_base = 32 * warp;
+    const int cc = tid >> 6, m = tid & 63;
+    const uint32_t wo = smem_u32(sWo), wkv = smem_u32(sWkv);
+    uint32_t ph = 0;
+    for (int pair = blockIdx.x; 2 * pair < P.B; pair += gridDim.x) {
+        const int cloud = 2 * pair + cc;
+        const bool valid = cloud < P.B;
+        float o[64];
+        // ---- merge the point splits / column halves: O = Qp + A V
+        if (valid) {
+#pragma unroll
+            for (int h = 0; h < TH; ++h) {
+                const float* pp = P.part + (((size_t)cloud * P.nslots) * TH + h) * 10 * TM + m;
+                const size_t sstride = (size_t)TH * 10 * TM;
+                float a[8], l, mmax;
+                if (P.nslots == 2) {
+                    float v0[10], v1[10];
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) { v0[j] = __ldg(pp + j * TM); v1[j] = __ldg(pp + sstride + j * TM); }
+                    mmax = fmaxf(v0[0], v1[0]);
+                    const float w0 = exp2f(v0[0] - mmax), w1 = exp2f(v1[0] - mmax);
+                    l = fmaf(v0[1], w0, v1[1] * w1);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = fmaf(v0[2 + j], w0, v1[2 + j] * w1);
+                } else {
+                    mmax = -INFINITY;
+                    for (int sl = 0; sl < P.nslots; ++sl) mmax = fmaxf(mmax, __ldg(pp + sl * sstride));
+                    l = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+                    for (int sl = 0; sl < P.nslots; ++sl) {
+                        const float* ps = pp + sl * sstride;
+                        const float wgt = exp2f(__ldg(ps) - mmax);
+                        l = fmaf(__ldg(ps + TM), wgt, l);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) a[j] = fmaf(__ldg(ps + (2 + j) * TM), wgt, a[j]);
+                    }
+                }
+                const float inv = 1.f / l;
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(P.Qp + m * TD + h * 8));
+                const float4 q1 = __ldg(reinterpret_cast<const float4*>(P.Qp + m * TD + h * 8) + 1);
+                const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[h * 8 + j] = fmaf(a[j], inv, qv[j]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) o[j] = 0.f;
+        }
+        // ---- F = O Wo^T (split product), H = O + relu(F + bo)
+        st_split_a(tb, lane_base, o);
+        tmem_st_wait();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            const uint32_t idesc = idesc_bf16(128, 64, 0, 0);
+#pragma unroll
+            for (int term = 0; term < 3; ++term)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_ts(tmem_addr(tb, 0, F2_F), tmem_addr(tb, 0, F2_A + (term == 1 ? 32 : 0) + 8 * ks),
+                           smem_desc(wo + (term == 2 ? 8192 : 0) + ks * 2048, 1024, 128), idesc, (term | ks) != 0);
+            mma_commit(bar);
+        }
+        mbar_wait(bar, ph);
+        ph ^= 1;
+        fence_after_sync();
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t f[32];
+            tmem_ld32(tmem_addr(tb, lane_base, F2_F + c0), f);
+            tmem_ld_wait32(f);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[c0 + j] += fmaxf(__uint_as_float(f[j]) + sBo[c0 + j], 0.f);
+        }
+        if (P.H_debug && valid) {
+            float4* hd = reinterpret_cast<float4*>(P.H_debug + ((size_t)cloud * TM + m) * TD);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hd[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+        // ---- [Kp | Vp] = H [Wk;Wv]^T + b (split product) -> block-diagonal bf16 operand images
+        st_split_a(tb, lane_base, o);
+        tmem_st_wait();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            const uint32_t idesc = idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+            for (int term = 0; term < 3; ++term)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_ts(tmem_addr(tb, 0, F2_KV), tmem_addr(tb, 0, F2_A + (term == 1 ? 32 : 0) + 8 * ks),
+                           smem_desc(wkv + (term == 2 ? 16384 : 0) + ks * 4096, 2048, 128), idesc, (term | ks) != 0);
+            mma_commit(bar);
+        }
+        mbar_wait(bar, ph);
+        ph ^= 1;
+        fence_after_sync();
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_addr(tb, lane_base, F2_KV + c0), v);
+            tmem_ld_wait32(v);
+            if (valid) {
+                uint8_t* img = P.KVblk + (size_t)cloud * 32768 + (c0 >= 64 ? 16384 : 0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int h = ((c0 & 63) >> 3) + q, pr = h >> 1, ch = h & 1;
+                    uint4 u;
+                    u.x = pack_bf16(__uint_as_float(v[8 * q + 0]) + sBkv[c0 + 8 * q + 0], __uint_as_float(v[8 * q + 1]) + sBkv[c0 + 8 * q + 1]);
+                    u.y = pack_bf16(__uint_as_float(v[8 * q + 2]) + sBkv[c0 + 8 * q + 2], __uint_as_float(v[8 * q + 3]) + sBkv[c0 + 8 * q + 3]);
+                    u.z = pack_bf16(__uint_as_float(v[8 * q + 4]) + sBkv[c0 + 8 * q + 4], __uint_as_float(v[8 * q + 5]) + sBkv[c0 + 8 * q + 5]);
+                    u.w = pack_bf16(__uint_as_float(v[8 * q + 6]) + sBkv[c0 + 8 * q + 6], __uint_as_float(v[8 * q + 7]) + sBkv[c0 + 8 * q + 7]);
+                    *reinterpret_cast<uint4*>(img + pr * 4096 + ch * 2048 + (ch * 64 + m) * 16) = u;
+                    *reinterpret_cast<uint4*>(img + pr * 4096 + ch * 2048 + ((1 - ch) * 64 + m) * 16) = make_uint4(0, 0, 0, 0);
+                }
+            }
+        }
+        fence_before_sync();
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tb, 256);
 }
 
 // ------------------------------------------------------------------------------------ apply kernel
@@ -2983,9 +3187,10 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<small>");
     {
-        FParams f{part, 2 * sp.nsplit, c->Qp0, c->WoT[0], m00.bo, c->WkvT[0], m01.bkv, kvblk, dbg ? dbg->H1 : nullptr};
+        F2Params f{part, 2 * sp.nsplit, B, c->Qp0, c->WoS[0][0], m00.bo, c->WkvS[0][0], m01.bkv, kvblk, dbg ? dbg->H1 : nullptr};
         LaunchTimer lt("finalize_isab_kernel", st, (double)B * 2.0 * (TM * TD * TD + TM * TD * 2 * TD), (double)B * 32768.0);
-        finalize_isab_kernel<<<B, 256, fsmem, st>>>(f);
+        const int npairs = (B + 1) / 2;
+        finalize_isab_tc_kernel<<<npairs < 2 * g_num_sms ? npairs : 2 * g_num_sms, 128, F2Smem::TOTAL, st>>>(f);
     }
     PCA_CHECK_LAUNCH("finalize_isab_kernel");
     {
@@ -3005,9 +3210,10 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<64>");
     {
-        FParams f{part, 2 * sp.nsplit, c->Qp1, c->WoT[1], m10.bo, c->WkvT[1], m11.bkv, kvblk, dbg ? dbg->H2 : nullptr};
+        F2Params f{part, 2 * sp.nsplit, B, c->Qp1, c->WoS[1][0], m10.bo, c->WkvS[1][0], m11.bkv, kvblk, dbg ? dbg->H2 : nullptr};
         LaunchTimer lt("finalize_isab_kernel", st, (double)B * 2.0 * (TM * TD * TD + TM * TD * 2 * TD), (double)B * 32768.0);
-        finalize_isab_kernel<<<B, 256, fsmem, st>>>(f);
+        const int npairs = (B + 1) / 2;
+        finalize_isab_tc_kernel<<<npairs < 2 * g_num_sms ? npairs : 2 * g_num_sms, 128, F2Smem::TOTAL, st>>>(f);
     }
     PCA_CHECK_LAUNCH("finalize_isab_kernel");
     {
@@ -3063,6 +3269,7 @@ static int tc_configure() {
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(pma_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PoolSmem::TOTAL));
     done = true;
     return 0;
@@ -3079,7 +3286,7 @@ int st_tc_forward_dbg(const float* X, int B, int N, const pca_st_dims* d, const 
     if (dbg && chunk < B) return fail(PCA_EWORKSPACE, "ST(bf16) debug: workspace must hold the whole batch");
     uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
     TcConsts* c = reinterpret_cast<TcConsts*>(w8 + tc_layout(chunk, N).consts);
-    prep_kernel<<<13, 256, 0, st>>>(params, d->d_in, c);
+    prep_kernel<<<17, 256, 0, st>>>(params, d->d_in, c);
     PCA_CHECK_LAUNCH("prep_kernel");
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int bc = (B - b0) < chunk ? (B - b0) : chunk;
