@@ -1306,6 +1306,365 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const R
     if (warp == 12) tmem_dealloc(tb, 512);
 }
 
+// Rare path of mab_reduce5_tc_kernel for one 64-column item of a row (ragged last tile, or a row whose scores outgrew
+// its reference exponent): everything goes through TMEM in 16-column steps so that no register state of the caller is
+// needed.  Called warp-uniformly.  Returns the row sum of the item; P (bf16) is written over columns [0, 32) of the
+// score buffer; the row's accumulator (8 columns at oaddr) and running sum are rescaled if the reference moves.
+__device__ __noinline__ float reduce5_item_slow(uint32_t sbase, uint32_t oaddr, int nv, bool first, float& m_used, float& l_run) {
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c0 = 0; c0 < nv; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(sbase + c0, v);
+        tmem_ld_wait16(v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (c0 + j < nv) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
+    if (first) {                         // the chain's first P V of the work item overwrites the accumulator
+        m_used = mx;
+        l_run = 0.f;
+    } else {
+        const bool move = mx >= m_used + 53.f;
+        if (__any_sync(0xffffffffu, move)) {
+            const float f = move ? ex2(m_used - mx) : 1.f;
+            uint32_t o[8];
+            tmem_ld8(oaddr, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+            tmem_st8(oaddr, o);
+            tmem_st_wait();
+            l_run *= f;
+            if (move) m_used = mx;
+        }
+    }
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16], pk[8];
+        if (c0 < nv) {
+            tmem_ld16(sbase + c0, v);
+            tmem_ld_wait16(v);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            const float p0 = (c0 + j < nv) ? ex2(__uint_as_float(v[j]) - m_used) : 0.f;
+            const float p1 = (c0 + j + 1 < nv) ? ex2(__uint_as_float(v[j + 1]) - m_used) : 0.f;
+            sum += p0 + p1;
+            pk[j >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st8(sbase + (c0 >> 1), pk);
+    }
+    tmem_st_wait();
+    return sum;
+}
+
+// Fifth generation of the reduce kernel: like mab_reduce2_tc_kernel (persistent, 4 chains), but the outputs ACCUMULATE IN TMEM
+// across the tiles of a work item against a per-row reference exponent m_used that is fixed by the first tile (softmax is
+// shift invariant; with fp32 sums, bf16 probabilities and fp32 accumulators any reference within 2^+-60 of the true row
+// maximum is exact to rounding).  No row maximum is taken after the first tile; a row whose running sum shows that some
+// score exceeded the reference by more than 2^54 takes a slow path that re-references the row (rescales its sum and its
+// TMEM accumulator).  The softmax warps therefore never read the outputs until the work item ends.
+// Persistent: grid = min(#work items, #SMs); CTA k walks the work items (cloud, point-split) k, k + grid, ...
+// Barriers, TMEM and the resident operands are set up once; all pipelines (producer -> MMA -> softmax) run
+// straight across work-item boundaries, so there is no per-cloud fill/drain bubble.
+template <bool DIN64>
+__global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const RParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sAq = smem + R2Smem::AQ;
+    uint8_t* sKV = smem + R2Smem::KV;
+    uint8_t* sW = smem + R2Smem::W;
+    uint8_t* sY = smem + R2Smem::Y;
+    float* sWsm = reinterpret_cast<float*>(smem + R2Smem::SMALL);
+    float* sBias = sWsm + 128 * 4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + R2Smem::BARS);
+    uint64_t* kv_full = bars;          // [2] count 4 (producer warps)
+    uint64_t* kv_empty = bars + 2;     // [2] count 4 (chains)
+    uint64_t* s_full = bars + 4;       // [4] count 1
+    uint64_t* p_ready = bars + 8;      // [4] count 4 (warps of the owning warpgroup)
+    uint64_t* o_done = bars + 12;      // [4] count 1   (chain: all P V of the work item complete)
+    uint64_t* y_full = bars + 20;      // count 4
+    uint64_t* proj_done = bars + 21;   // count 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_work = P.n_work, wstep = gridDim.x;
+    auto work_tiles = [&](int w, int& cloud, int& split, int& tile0) {
+        cloud = w / P.nsplit;
+        split = w - cloud * P.nsplit;
+        tile0 = split * P.tiles_per_split;
+        return min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+    };
+
+    copy_to_smem(sAq, P.Aq, 16384);
+    if (DIN64) copy_to_smem(sW, P.Wkv16, 16384);
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+        sBias[i] = P.bkv[i];
+        if (!DIN64) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sWsm[i * 4 + k] = (k < P.d_in) ? P.Wkv32[i * P.d_in + k] : 0.f;
+        }
+    }
+    if (warp == 12) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 4); mbar_init(&kv_empty[i], 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
+        for (int i = 0; i < 4; ++i) mbar_init(&o_done[i], 1);
+        mbar_init(y_full, 4);
+        mbar_init(proj_done, 1);
+        fence_barrier_init();
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp >= 12) {
+        reg_dec<40>();
+        if (lane == 0) {
+            // =================================================================== one MMA-issuing thread per chain
+            // chain c = warp - 12: strictly serial  Q K^T -> (warpgroup softmax) -> P V -> next Q K^T  on its own
+            // half-buffer; the four chains never wait on each other.
+            const int c = warp - 12, half = c & 1;
+            const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
+            const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
+            const uint32_t aq = smem_u32(sAq), kvb = smem_u32(sKV);
+            int gt = 0;                                    // tiles processed by this CTA so far
+            uint32_t ph_p = 0;                             // phase of this chain's p_ready barrier
+            for (int w = blockIdx.x; w < n_work; w += wstep) {
+                int cloud, split, tile0;
+                const int ntiles = work_tiles(w, cloud, split, tile0);
+                for (int it = 0; it < ntiles; ++it, ++gt) {
+                    const uint32_t kbase = kvb + (gt & 1) * 32768, vbase = kbase + 16384;
+                    mbar_wait(&kv_full[gt & 1], (gt >> 1) & 1);
+                    fence_after_sync();
+                    // a half without valid points (ragged last tile) is skipped by the chain and by its warpgroup alike
+                    const bool empty_half = P.N - (tile0 + it) * 128 <= 64 * half;
+#pragma unroll
+                    for (int pp = 0; pp < 2; ++pp) {
+                        if (empty_half) break;
+                        const int p = (c >> 1) + 2 * pp;
+                        mma_ss(tmem_addr(tb, 0, R2_S + 64 * c), smem_desc(aq + p * 4096, 2048, 128),
+                               smem_desc(kbase + 2 * p * 2048 + half * 1024, 2048, 128), idesc_s, 0);
+                        mma_commit(&s_full[c]);
+                        mbar_wait(&p_ready[c], ph_p);
+                        ph_p ^= 1;
+                        fence_after_sync();
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ts(tmem_addr(tb, 0, R2_O + 16 * (2 * p + half)), tmem_addr(tb, 0, R2_S + 64 * c + ks * 8),
+                                   smem_desc(vbase + 2 * p * 2048 + half * 1024 + ks * 256, 128, 2048), idesc_pv, (it > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    mma_commit(&kv_empty[gt & 1]);            // 4 chains x 1 arrival free the K|V stage
+                }
+                mma_commit(&o_done[c]);                       // the work item's accumulators are final
+            }
+        }
+    } else if (warp >= 8) {
+        reg_dec<88>();
+        // =================================================================== producer: K|V tiles
+        const int quad = warp & 3;
+        const int row = 32 * quad + lane;
+        int gt = 0;
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, split, tile0;
+            const int ntiles = work_tiles(w, cloud, split, tile0);
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int stage = gt & 1;
+                const int n = (tile0 + it) * 128 + row;
+                const bool valid = n < P.N;
+                uint8_t* sK = sKV + stage * 32768;
+                uint8_t* sV = sK + 16384;
+                if (!DIN64) {
+                    float x[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (valid) {
+                        const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                        for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
+                    }
+                    if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
+#pragma unroll 4
+                    for (int c = 0; c < 16; ++c) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 wv = *reinterpret_cast<const float4*>(sWsm + (c * 8 + j) * 4);
+                            o[j] = valid ? fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBias[c * 8 + j])))) : 0.f;
+                        }
+                        st_shared_8bf16((c < 8 ? sK + c * 2048 : sV + (c - 8) * 2048) + row * 16, o);
+                    }
+                } else {
+                    const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
+                    uint4 yv[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sY + c * 2048 + row * 16) = yv[c];
+                    fence_async_smem();
+                    fence_before_sync();
+                    warp_arrive(y_full);
+                    if (warp == 8 && lane == 0) {
+                        // one producer thread issues the K|V projection MMA once all 128 rows of Y are staged
+                        mbar_wait(y_full, gt & 1);
+                        fence_after_sync();
+                        const uint32_t yb = smem_u32(sY), wb = smem_u32(sW);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ss(tmem_addr(tb, 0, R2_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
+                                   idesc_bf16(128, 128, 0, 0), ks > 0);
+                        mma_commit(proj_done);
+                    }
+                    mbar_wait(proj_done, gt & 1);
+                    fence_after_sync();
+                    if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
+#pragma unroll
+                    for (int c0 = 0; c0 < 128; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_addr(tb, 32 * quad, R2_PROJ + c0), v);
+                        tmem_ld_wait32(v);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float o[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = valid ? __uint_as_float(v[8 * q + j]) + sBias[c0 + 8 * q + j] : 0.f;
+                            const int chunk = c0 / 8 + q;
+                            st_shared_8bf16((chunk < 8 ? sK + chunk * 2048 : sV + (chunk - 8) * 2048) + row * 16, o);
+                        }
+                    }
+                }
+                fence_async_smem();
+                fence_before_sync();
+                warp_arrive(&kv_full[stage]);
+            }
+        }
+    } else {
+        reg_inc<184>();
+        // =================================================================== softmax warpgroups (2 chains each)
+        const int g = warp >> 2, quad = warp & 3;
+        const int row = 32 * quad + lane;
+        const uint32_t lane_base = 32 * quad;
+        const uint32_t ocol_off = (row >= 64) ? 8u : 0u;
+        float m_used[2][2], l_run[2][2];          // reference exponent and running sum per (half, pp)
+        uint32_t ph_s[2] = {0, 0}, ph_done = 0;
+        constexpr float kOverflow = 1.152921504606847e18f;      // 2^60
+#ifdef PCA_TIMELINE
+        long long* tl = (P.timeline != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0) ? P.timeline : nullptr;
+        int tl_n = 0;
+        auto stamp = [&](int tag) {
+            if (tl != nullptr && tl_n < 4000) { tl[2 * tl_n] = tag; tl[2 * tl_n + 1] = clock64(); ++tl_n; }
+        };
+#else
+        auto stamp = [&](int) {};
+#endif
+
+        auto softmax_item = [&](const int half, const int pp, const int nv, const bool first) {
+            const int c = 2 * g + half, p = g + 2 * pp;
+            const uint32_t sbase = tmem_addr(tb, lane_base, R2_S + 64 * c);
+            const uint32_t oaddr = tmem_addr(tb, lane_base, R2_O + 16 * (2 * p + half) + ocol_off);
+            if (nv == 0) {                     // empty half of a ragged tile: skipped (the chain thread skips it as well)
+                if (first) { m_used[half][pp] = -INFINITY; l_run[half][pp] = 0.f; }
+                return;
+            }
+            stamp(20);
+            mbar_wait(&s_full[c], ph_s[half]);
+            ph_s[half] ^= 1;
+            fence_after_sync();
+            stamp(24);
+            uint32_t va[32], vb[32], pk0[16], pk1[16];
+            tmem_ld32(sbase, va);
+            tmem_ld32(sbase + 32, vb);
+            tmem_ld_wait64(va, vb);
+            stamp(25);
+            float sum;
+            if (nv == 64) {
+                if (first) { m_used[half][pp] = max64(va, vb); l_run[half][pp] = 0.f; }
+                const float2 neg2 = make_float2(-m_used[half][pp], -m_used[half][pp]);
+                float2 sum2 = make_float2(0.f, 0.f);
+                exp_chunk32(va, neg2, sum2, pk0);
+                exp_chunk32(vb, neg2, sum2, pk1);
+                sum = sum2.x + sum2.y;
+            } else {
+                // ragged tail: columns >= nv are padding
+                if (first) {
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < nv) mx = fmaxf(mx, __uint_as_float(va[j]));
+                        if (32 + j < nv) mx = fmaxf(mx, __uint_as_float(vb[j]));
+                    }
+                    m_used[half][pp] = mx;
+                    l_run[half][pp] = 0.f;
+                }
+                const float m = m_used[half][pp];
+                sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = (j < nv) ? ex2(__uint_as_float(va[j]) - m) : 0.f;
+                    const float p1 = (j + 1 < nv) ? ex2(__uint_as_float(va[j + 1]) - m) : 0.f;
+                    const float p2 = (32 + j < nv) ? ex2(__uint_as_float(vb[j]) - m) : 0.f;
+                    const float p3 = (33 + j < nv) ? ex2(__uint_as_float(vb[j + 1]) - m) : 0.f;
+                    sum += (p0 + p1) + (p2 + p3);
+                    pk0[j >> 1] = pack_bf16(p0, p1);
+                    pk1[j >> 1] = pack_bf16(p2, p3);
+                }
+            }
+            // Some score exceeded the reference by more than ~2^54 (or the sum overflowed): re-reference those rows.  All
+            // earlier P V of this chain have completed (the chain thread's commit for THIS item's scores covers them), so
+            // the slow path may rescale the accumulator in place.
+            if (__any_sync(0xffffffffu, !(sum < kOverflow))) {
+                l_run[half][pp] += reduce5_item_slow(sbase, oaddr, nv, false, m_used[half][pp], l_run[half][pp]);
+            } else {
+                l_run[half][pp] += sum;
+                tmem_st16(sbase, pk0);
+                tmem_st16(sbase + 16, pk1);
+                stamp(26);
+                tmem_st_wait();
+                stamp(27);
+            }
+            fence_before_sync();
+            warp_arrive(&p_ready[c]);
+        };
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, split, tile0;
+            const int ntiles = work_tiles(w, cloud, split, tile0);
+            for (int it = 0; it < ntiles; ++it) {
+                const int n_valid = min(128, P.N - (tile0 + it) * 128);
+                const int nv0 = min(64, n_valid), nv1 = max(0, n_valid - 64);
+                const bool first = it == 0;
+                softmax_item(0, 0, nv0, first);
+                softmax_item(1, 0, nv1, first);
+                softmax_item(0, 1, nv0, first);
+                softmax_item(1, 1, nv1, first);
+            }
+            // ---- the work item's accumulators are final once both chains have drained
+            mbar_wait(&o_done[2 * g], ph_done);
+            mbar_wait(&o_done[2 * g + 1], ph_done);
+            ph_done ^= 1;
+            fence_after_sync();
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp) {
+                    const int p = g + 2 * pp;
+                    uint32_t o[8];
+                    tmem_ld8(tmem_addr(tb, lane_base, R2_O + 16 * (2 * p + half) + ocol_off), o);
+                    tmem_ld_wait();
+                    const int h = 2 * p + (row >> 6);
+                    float* dst = P.part + (((size_t)cloud * (2 * P.nsplit) + 2 * split + half) * TH + h) * 10 * TM + (row & 63);
+                    dst[0] = m_used[half][pp];
+                    dst[TM] = l_run[half][pp];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[(2 + j) * TM] = (l_run[half][pp] > 0.f) ? __uint_as_float(o[j]) : 0.f;
+                }
+            fence_before_sync();
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tb, 512);
+}
+
 // TMEM columns (apply): 4 x 64 half-buffers | 4 x 16 pair outputs | 64 fc_o | 2 x 64 Q projection
 constexpr uint32_t A2_S = 0, A2_O = 256, A2_F = 320, A2_QP = 384;
 
@@ -3110,7 +3469,7 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 static int g_num_sms = 148;
 // softmax warpgroups per CTA (2 = 16 warps with TMEM prefetch, 4 = 24 warps): measured best is 4 for the reduce kernel
 // and 2 for the apply kernel (profiles/); PCA_TC_REDUCE_WG / PCA_TC_APPLY_WG override for experiments
-static int g_reduce_wg = 4, g_apply_wg = 3;      // apply: 3 = third-generation kernel (20 warps, epilogue warps)
+static int g_reduce_wg = 5, g_apply_wg = 3;      // apply: 3 = third-generation kernel (20 warps, epilogue warps)
 static long long* g_timeline = nullptr;      // set through pca_debug_set_timeline
 void set_timeline(long long* p) { g_timeline = p; }
 struct TcSplit { int tiles_total, tiles_per_split, nsplit; };
@@ -3180,9 +3539,10 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
 
     // ---- ISAB 0
     {
-        RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->Aq0, m00.Wkv, m00.bkv, nullptr, g_timeline, part};
+        RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->Aq0, m00.Wkv, m00.bkv, nullptr, getenv("PCA_TL_APPLY") ? nullptr : g_timeline, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * d_in * TD + 2.0 * TM * TD), pts * 4.0 * d_in);
-        if (g_reduce_wg == 4) mab_reduce4_tc_kernel<false><<<pgrid, TC_THREADS24, R2Smem::TOTAL, st>>>(r);
+        if (g_reduce_wg == 5) mab_reduce5_tc_kernel<false><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
+        else if (g_reduce_wg == 4) mab_reduce4_tc_kernel<false><<<pgrid, TC_THREADS24, R2Smem::TOTAL, st>>>(r);
         else mab_reduce2_tc_kernel<false><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<small>");
@@ -3194,7 +3554,7 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     }
     PCA_CHECK_LAUNCH("finalize_isab_kernel");
     {
-        AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, kvblk, m01.Wq, m01.bq, nullptr, c->Wo0, m01.bo, Y1, g_timeline};
+        AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, kvblk, m01.Wq, m01.bq, nullptr, c->Wo0, m01.bo, Y1, getenv("PCA_TL_APPLY") ? g_timeline : nullptr};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * d_in * TD + 2.0 * TM * TD + TD * TD), pts * (4.0 * d_in + 128.0));
         if (g_apply_wg == 3) { a.Wq16 = c->WqS0; mab_apply3_tc_kernel<false><<<pgrid, TC_THREADS20, A3Smem::TOTAL, st>>>(a); }
         else if (g_apply_wg == 4) mab_apply4_tc_kernel<false><<<pgrid, TC_THREADS24, A2Smem::TOTAL, st>>>(a);
@@ -3205,7 +3565,8 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     {
         RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->Aq1, nullptr, m10.bkv, c->Wkv1, nullptr, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TM * TD), pts * 128.0);
-        if (g_reduce_wg == 4) mab_reduce4_tc_kernel<true><<<pgrid, TC_THREADS24, R2Smem::TOTAL, st>>>(r);
+        if (g_reduce_wg == 5) mab_reduce5_tc_kernel<true><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
+        else if (g_reduce_wg == 4) mab_reduce4_tc_kernel<true><<<pgrid, TC_THREADS24, R2Smem::TOTAL, st>>>(r);
         else mab_reduce2_tc_kernel<true><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<64>");
@@ -3262,7 +3623,9 @@ static int tc_configure() {
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce4_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply4_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply4_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
-    if (const char* v = getenv("PCA_TC_REDUCE_WG")) g_reduce_wg = (v[0] == '2') ? 2 : 4;
+    if (const char* v = getenv("PCA_TC_REDUCE_WG")) g_reduce_wg = (v[0] == '2') ? 2 : (v[0] == '4') ? 4 : 5;
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce5_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce5_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
     if (const char* v = getenv("PCA_TC_APPLY_WG")) g_apply_wg = (v[0] == '4') ? 4 : (v[0] == '2') ? 2 : 3;
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));

@@ -87,3 +87,30 @@ def test_tc_unsupported_dims_fail_loudly(pca):
     st = pca.ST(dim_input=2, num_outputs=1, dim_output=10, num_inds=16, dim_hidden=32, num_heads=4).to(dev).set_precision("bf16")
     with pytest.raises(RuntimeError, match="tcgen05 path needs"):
         st(torch.zeros(2, 10, 2, device=dev))
+
+
+@pytest.mark.parametrize("N", [200, 1025, 2500])
+@pytest.mark.parametrize("gain", [50.0, 2000.0])
+def test_tc_set_invariance_with_growing_scores(pca, N, gain):
+    """The reduce kernel fixes each row's reference exponent on the first 128-point tile and re-references a row only
+    when its scores outgrow it by 2^54.  Points whose projections are `gain` times larger are placed LAST (so the
+    reference must move, exercising the rescale path) or FIRST (so it never moves); a Set Transformer is permutation
+    invariant, so both orders -- and a random shuffle -- must give the same logits, all finite."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    st = pca.ST(dim_input=3, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev).set_precision("bf16")
+    g = torch.Generator().manual_seed(N)
+    X = torch.randn(4, N, 3, generator=g) * 0.05
+    n_big = max(1, N // 7)
+    X[:, N - n_big:] *= gain                              # big points last
+    Xd = X.to(dev)
+    with torch.no_grad():
+        last = st(Xd).float().cpu()
+        first = st(torch.flip(Xd, dims=[1]).contiguous()).float().cpu()
+        perm = torch.randperm(N, generator=g)
+        shuf = st(Xd[:, perm].contiguous()).float().cpu()
+    assert torch.isfinite(last).all() and torch.isfinite(first).all() and torch.isfinite(shuf).all()
+    scale = first.abs().max().item()
+    for name, other in (("big-last", last), ("shuffled", shuf)):
+        err = (other - first).abs().max().item() / scale
+        assert err < BF16_REL_TOL, f"N={N} gain={gain}: {name} vs big-first rel err {err:.3e}"
