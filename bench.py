@@ -270,6 +270,17 @@ def run_ours(args):
             roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                         "frac": ach / peak, "traffic": traffic, "peak_source": f"{peaks['source']} copy bandwidth",
                         "avg_launch_ms": avg_s * 1e3, "share_of_step": top["ms"] / tot}
+    # The softmax kernels are bound by the MUFU (ex2) pipe, not by the tensor pipe (head dim 8: 512 exponentials per
+    # point and MAB against ~31 kFLOP): report that unit next to the contract's tensor roofline.  Peak = 16 ex2/clk/SM
+    # (tools/microbench_mufu.cu, measured) x SMs x the SM clock sampled under load.
+    if roofline is not None and roofline["kernel"] in ("mab_apply_tc_kernel", "mab_reduce_tc_kernel"):
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        ex2_per_launch = clouds_per_step * pipe.points_per_cloud * 8 * 64
+        ach = ex2_per_launch / (roofline["avg_launch_ms"] / 1e3)
+        roofline["binding_unit"] = {"unit": "MUFU ex2", "per_launch": ex2_per_launch, "achieved_per_s": ach,
+                                    "peak_per_s": 16.0 * n_sm * clk, "frac": ach / (16.0 * n_sm * clk),
+                                    "peak_source": "16 ex2/clk/SM measured (tools/microbench_mufu.cu) x SMs x sampled SM clock"}
     enc_flops = clouds_per_step * st_flops_per_cloud(pipe.points_per_cloud)
     whole = {"algorithmic_tflop_per_step": enc_flops / 1e12,
              "achieved_tflops": world * enc_flops / (ms / args.steps / 1e3) / 1e12 / world,

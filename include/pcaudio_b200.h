@@ -186,6 +186,17 @@ int pca_pipeline_run_host(const pca_pipeline_cfg* cfg, const float* host_audio, 
                           float* dev_logits, float* host_logits, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* Same, with the host->device copy overlapped with compute: the batch is cut into n_chunks (1..16) clip ranges; chunk
+ * k+1 is copied on `copy_stream` while chunk k runs on `stream` (ordering by events created inside the call; both
+ * streams are the caller's, the library keeps no state).  copy_stream == stream or n_chunks == 1 degrades to
+ * pca_pipeline_run_host.  Results are identical to the unchunked call (per-cloud arithmetic never depends on the
+ * batch).  The workspace only needs to hold the largest chunk. */
+int pca_pipeline_run_host_chunked(const pca_pipeline_cfg* cfg, const float* host_audio, int n_clips,
+                                  float* dev_audio, const float* window, const float* twiddle,
+                                  const float* farr, const float* tarr, const float* st_params,
+                                  float* dev_logits, float* host_logits, void* workspace,
+                                  size_t workspace_bytes, int n_chunks, void* copy_stream, void* stream);
+
 /* number of kernels the library has launched in this process (for bench.py gpu_launches) */
 unsigned long long pca_launch_count(void);
 

@@ -64,6 +64,7 @@ PROTOTYPES = {
     "pca_pipeline_workspace_bytes": (_SZ, [C.POINTER(PipelineCfg), _I]),
     "pca_pipeline_run": (_I, [C.POINTER(PipelineCfg), _P, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "pca_pipeline_run_host": (_I, [C.POINTER(PipelineCfg), _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "pca_pipeline_run_host_chunked": (_I, [C.POINTER(PipelineCfg), _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I, _P, _P]),
 }
 
 _lib = None

@@ -485,6 +485,50 @@ int pca_pipeline_run_host(const pca_pipeline_cfg* cfg, const float* host_audio, 
     return 0;
 }
 
+int pca_pipeline_run_host_chunked(const pca_pipeline_cfg* cfg, const float* host_audio, int n_clips, float* dev_audio,
+                                  const float* window, const float* twiddle, const float* farr, const float* tarr,
+                                  const float* st_params, float* dev_logits, float* host_logits, void* workspace,
+                                  size_t workspace_bytes, int n_chunks, void* copy_stream, void* stream) {
+    if (!host_audio || !dev_audio || !dev_logits || !host_logits) return fail(PCA_EINVAL, "pipeline: null pointer");
+    if (n_clips <= 0) return 0;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > 16) n_chunks = 16;
+    if (n_chunks > n_clips) n_chunks = n_clips;
+    PipeShape s;
+    PCA_TRY(pipe_shape(cfg, &s));
+    cudaStream_t st = (cudaStream_t)stream, cs = (cudaStream_t)copy_stream;
+    if (cs == st || n_chunks == 1)
+        return pca_pipeline_run_host(cfg, host_audio, n_clips, dev_audio, window, twiddle, farr, tarr, st_params, dev_logits,
+                                     host_logits, workspace, workspace_bytes, stream);
+    cudaEvent_t ev[17];
+    for (int k = 0; k <= n_chunks; ++k) PCA_CHECK_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+    int rc = 0;
+    // the staging buffer may still be read by earlier work on `stream`
+    cudaError_t e = cudaEventRecord(ev[n_chunks], st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ev[n_chunks], 0);
+    const size_t clip_floats = (size_t)cfg->n_samples;
+    const size_t out_floats = (size_t)s.clouds_per_clip * cfg->st.S * cfg->st.C;
+    for (int k = 0; k < n_chunks && e == cudaSuccess; ++k) {
+        const size_t c0 = (size_t)n_clips * k / n_chunks, c1 = (size_t)n_clips * (k + 1) / n_chunks;
+        e = cudaMemcpyAsync(dev_audio + c0 * clip_floats, host_audio + c0 * clip_floats, (c1 - c0) * clip_floats * sizeof(float),
+                            cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[k], cs);
+    }
+    for (int k = 0; k < n_chunks && e == cudaSuccess && rc == 0; ++k) {
+        const size_t c0 = (size_t)n_clips * k / n_chunks, c1 = (size_t)n_clips * (k + 1) / n_chunks;
+        e = cudaStreamWaitEvent(st, ev[k], 0);
+        if (e != cudaSuccess) break;
+        rc = pca_pipeline_run(cfg, dev_audio + c0 * clip_floats, (int)(c1 - c0), window, twiddle, farr, tarr, st_params,
+                              dev_logits + c0 * out_floats, workspace, workspace_bytes, stream);
+    }
+    if (e == cudaSuccess && rc == 0)
+        e = cudaMemcpyAsync(host_logits, dev_logits, (size_t)n_clips * out_floats * sizeof(float), cudaMemcpyDeviceToHost, st);
+    for (int k = 0; k <= n_chunks; ++k) cudaEventDestroy(ev[k]);     // release is deferred until the events complete
+    if (rc != 0) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "pipeline_run_host_chunked");
+    return 0;
+}
+
 int pca_debug_st_stages(const float* X, int B, int N, const pca_st_dims* dims, const float* params, float* logits,
                         float* H1, float* Y1, float* H2, float* Y2, float* pooled, void* workspace,
                         size_t workspace_bytes, void* stream) {

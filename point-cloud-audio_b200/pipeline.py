@@ -53,6 +53,7 @@ class AudioSetPipeline:
         self.tarr = None if tarr is None else rt.coord_table(tarr, self.device)
         self.window, self.twiddle = rt.stft_tables(cfg.window_size, cfg.window_size, self.device)
         self._staging = {}
+        self._copy_stream = None
 
     def _ws(self, n_clips):
         need = _lib.lib().pca_pipeline_workspace_bytes(C.byref(self.c), n_clips)
@@ -75,9 +76,11 @@ class AudioSetPipeline:
                 rt.stream_ptr(self.device)), "pipeline_run")
         return out.squeeze(1) if st.S == 1 else out
 
-    def run_host(self, host_audio: torch.Tensor, host_logits: torch.Tensor | None = None) -> torch.Tensor:
+    def run_host(self, host_audio: torch.Tensor, host_logits: torch.Tensor | None = None, chunks: int | None = None) -> torch.Tensor:
         """host_audio: (n_clips, n_samples) float32 CPU tensor (pin it for async copies).  Returns the
-        host logits tensor; the work is enqueued on the current stream -- synchronise before reading."""
+        host logits tensor; the work is enqueued on the current stream -- synchronise before reading.
+        With chunks > 1 the host->device copy of clip range k+1 overlaps the kernels of range k (a private copy
+        stream of this pipeline object); default: 4 ranges for batches of >= 128 clips."""
         if host_audio.is_cuda or host_audio.dtype != torch.float32 or not host_audio.is_contiguous():
             raise ValueError("host_audio must be a contiguous float32 CPU tensor")
         n_clips = host_audio.shape[0]
@@ -92,12 +95,23 @@ class AudioSetPipeline:
             host_logits = torch.empty((n_out, st.S, st.C), dtype=torch.float32).pin_memory()
         ws = self._ws(n_clips)
         blob = self.model._blob()
+        if chunks is None:
+            chunks = 4 if n_clips >= 128 else 1
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().pca_pipeline_run_host(
-                C.byref(self.c), _lib.ptr(host_audio), n_clips, _lib.ptr(dev_audio), _lib.ptr(self.window),
-                _lib.ptr(self.twiddle), _lib.ptr(self.farr), _lib.ptr(self.tarr), _lib.ptr(blob),
-                _lib.ptr(dev_logits), _lib.ptr(host_logits), _lib.ptr(ws), ws.numel(),
-                rt.stream_ptr(self.device)), "pipeline_run_host")
+            if chunks > 1:
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=self.device)
+                _lib.check(_lib.lib().pca_pipeline_run_host_chunked(
+                    C.byref(self.c), _lib.ptr(host_audio), n_clips, _lib.ptr(dev_audio), _lib.ptr(self.window),
+                    _lib.ptr(self.twiddle), _lib.ptr(self.farr), _lib.ptr(self.tarr), _lib.ptr(blob),
+                    _lib.ptr(dev_logits), _lib.ptr(host_logits), _lib.ptr(ws), ws.numel(), int(chunks),
+                    C.c_void_p(self._copy_stream.cuda_stream), rt.stream_ptr(self.device)), "pipeline_run_host_chunked")
+            else:
+                _lib.check(_lib.lib().pca_pipeline_run_host(
+                    C.byref(self.c), _lib.ptr(host_audio), n_clips, _lib.ptr(dev_audio), _lib.ptr(self.window),
+                    _lib.ptr(self.twiddle), _lib.ptr(self.farr), _lib.ptr(self.tarr), _lib.ptr(blob),
+                    _lib.ptr(dev_logits), _lib.ptr(host_logits), _lib.ptr(ws), ws.numel(),
+                    rt.stream_ptr(self.device)), "pipeline_run_host")
         return host_logits
 
     @property
