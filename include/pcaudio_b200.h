@@ -186,7 +186,8 @@ int pca_pipeline_run_host(const pca_pipeline_cfg* cfg, const float* host_audio, 
                           float* dev_logits, float* host_logits, void* workspace,
                           size_t workspace_bytes, void* stream);
 
-/* Same, with the host->device copy overlapped with compute: the batch is cut into n_chunks (1..16) clip ranges; chunk
+/* Same, with the host->device copy overlapped with compute: the batch is cut into n_chunks (1..16) clip ranges (a short head range of 1/8 of the clips so the kernels start
+ * early, the rest split evenly); chunk
  * k+1 is copied on `copy_stream` while chunk k runs on `stream` (ordering by events created inside the call; both
  * streams are the caller's, the library keeps no state).  copy_stream == stream or n_chunks == 1 degrades to
  * pca_pipeline_run_host.  Results are identical to the unchunked call (per-cloud arithmetic never depends on the

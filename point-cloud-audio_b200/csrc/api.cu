@@ -506,16 +506,23 @@ int pca_pipeline_run_host_chunked(const pca_pipeline_cfg* cfg, const float* host
     // the staging buffer may still be read by earlier work on `stream`
     cudaError_t e = cudaEventRecord(ev[n_chunks], st);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ev[n_chunks], 0);
+    // clip ranges: a short head range (1/8 of the batch) so the kernels start early, the rest split evenly
+    size_t bound[17];
+    bound[0] = 0;
+    bound[1] = (size_t)n_clips / 8 > 0 ? (size_t)n_clips / 8 : 1;
+    for (int k = 2; k <= n_chunks; ++k) bound[k] = bound[1] + ((size_t)n_clips - bound[1]) * (k - 1) / (n_chunks - 1);
     const size_t clip_floats = (size_t)cfg->n_samples;
     const size_t out_floats = (size_t)s.clouds_per_clip * cfg->st.S * cfg->st.C;
     for (int k = 0; k < n_chunks && e == cudaSuccess; ++k) {
-        const size_t c0 = (size_t)n_clips * k / n_chunks, c1 = (size_t)n_clips * (k + 1) / n_chunks;
+        const size_t c0 = bound[k], c1 = bound[k + 1];
+        if (c1 == c0) { e = cudaEventRecord(ev[k], cs); continue; }
         e = cudaMemcpyAsync(dev_audio + c0 * clip_floats, host_audio + c0 * clip_floats, (c1 - c0) * clip_floats * sizeof(float),
                             cudaMemcpyHostToDevice, cs);
         if (e == cudaSuccess) e = cudaEventRecord(ev[k], cs);
     }
     for (int k = 0; k < n_chunks && e == cudaSuccess && rc == 0; ++k) {
-        const size_t c0 = (size_t)n_clips * k / n_chunks, c1 = (size_t)n_clips * (k + 1) / n_chunks;
+        const size_t c0 = bound[k], c1 = bound[k + 1];
+        if (c1 == c0) continue;
         e = cudaStreamWaitEvent(st, ev[k], 0);
         if (e != cudaSuccess) break;
         rc = pca_pipeline_run(cfg, dev_audio + c0 * clip_floats, (int)(c1 - c0), window, twiddle, farr, tarr, st_params,

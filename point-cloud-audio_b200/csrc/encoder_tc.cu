@@ -3288,6 +3288,10 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
             m_run = -INFINITY; l_run = 0.f; alpha = 0.f;
 #pragma unroll
             for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+            // Within a work item this warpgroup sees either the even or the odd tiles; which of the two depends on how many
+            // tiles the CTA has processed before.  The partial is filed under the tile PARITY, so the grouping (and hence
+            // every rounding) of a cloud is independent of the batch it is part of.
+            const int group = (g ^ t) & 1;
             for (int it = 0; it < ntiles; ++it, ++t) {
                 if ((t & 1) != g) continue;
                 const int n_valid = min(128, P.N - (tile0 + it) * 128);
@@ -3358,7 +3362,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
             }
             if ((row & 15) == 0) {
                 const int h = row >> 4;
-                float* dst = P.part + ((((size_t)cloud * P.nsplit + split) * 2 + g) * TH + h) * 66;
+                float* dst = P.part + ((((size_t)cloud * P.nsplit + split) * 2 + group) * TH + h) * 66;
                 dst[0] = m_run;
                 dst[1] = l_run;
 #pragma unroll

@@ -80,7 +80,8 @@ class AudioSetPipeline:
         """host_audio: (n_clips, n_samples) float32 CPU tensor (pin it for async copies).  Returns the
         host logits tensor; the work is enqueued on the current stream -- synchronise before reading.
         With chunks > 1 the host->device copy of clip range k+1 overlaps the kernels of range k (a private copy
-        stream of this pipeline object); default: 4 ranges for batches of >= 128 clips."""
+        stream of this pipeline object); default 1: measured on B200, the extra launches
+        of a second range cost as much as the overlap saves at the bench shape (tools/e2e_chunks.py)."""
         if host_audio.is_cuda or host_audio.dtype != torch.float32 or not host_audio.is_contiguous():
             raise ValueError("host_audio must be a contiguous float32 CPU tensor")
         n_clips = host_audio.shape[0]
@@ -96,7 +97,7 @@ class AudioSetPipeline:
         ws = self._ws(n_clips)
         blob = self.model._blob()
         if chunks is None:
-            chunks = 4 if n_clips >= 128 else 1
+            chunks = 1
         with torch.cuda.device(self.device):
             if chunks > 1:
                 if self._copy_stream is None:

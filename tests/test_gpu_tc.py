@@ -114,3 +114,25 @@ def test_tc_set_invariance_with_growing_scores(pca, N, gain):
     for name, other in (("big-last", last), ("shuffled", shuf)):
         err = (other - first).abs().max().item() / scale
         assert err < BF16_REL_TOL, f"N={N} gain={gain}: {name} vs big-first rel err {err:.3e}"
+
+
+def test_tc_batch_split_is_bit_identical(pca):
+    """Per-cloud results of the bf16 path must not depend on the batch a cloud is part of (this is what lets the path
+    shard over GPUs / chunk host transfers with bit-identical logits): uneven splits of a 256-clip FST batch."""
+    dev = torch.device("cuda:0")
+    w = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, "fst_weights.npz")).items()}
+    st = pca.ST(dim_input=2, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev)
+    st.load_state_dict(w)
+    g = torch.Generator().manual_seed(21)
+    audio = (0.1 * torch.randn(256, 16000, generator=g)).to(dev)
+    pipe = pca.AudioSetPipeline(st, pca.AudioConfig(window_size=2048, n_samples=16000, mode=2, precision="bf16"), dev)
+    full = pipe(audio).clone()
+    assert full.shape == (4096, 10) and torch.isfinite(full).all()
+    for cut in (37, 128, 255):
+        parts = torch.cat([pipe(audio[:cut]).clone(), pipe(audio[cut:]).clone()])
+        assert torch.equal(full, parts), f"split at {cut} changes logits (max diff {(full - parts).abs().max().item():.3e})"
+    host = audio.cpu().pin_memory()
+    for chunks in (1, 3):
+        out = pipe.run_host(host, chunks=chunks)
+        torch.cuda.synchronize()
+        assert torch.equal(out.squeeze(1), full.cpu()), f"run_host(chunks={chunks}) differs from the device-resident call"
