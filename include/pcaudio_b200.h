@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PCA_VERSION 100 /* 0.1.0 */
+#define PCA_VERSION 101 /* 0.1.1 */
 
 enum {
     PCA_OK = 0,
@@ -81,6 +81,14 @@ int pca_build_clouds_f32(const float* logmag, int n_clouds, int nf, int nt, cons
 int pca_topk_compact_f32(const float* keys, int n_clouds, int nf, int nt, const float* farr,
                          const float* tarr, int K, int sorted_desc, float* pts, int32_t* idx,
                          void* stream);
+
+/* Threshold / capped selection with padded output (extension of the rule above): per cloud keep the
+ * points with key >= threshold (use_threshold != 0), at most K of them chosen by the top-K rule, emitted as above;
+ * rows past the number kept are zero-filled (idx -1) and counts[c] (nullable) receives the number kept.  With
+ * use_threshold == 0 this is pca_topk_compact_f32 plus counts[c] = K. */
+int pca_select_compact_f32(const float* keys, int n_clouds, int nf, int nt, const float* farr,
+                           const float* tarr, int K, int sorted_desc, int use_threshold,
+                           float threshold, float* pts, int32_t* idx, int32_t* counts, void* stream);
 
 /* ---------------------------------------------------------------- L4: set encoder
  * Weights are passed as ONE packed float32 blob per block, nn.Linear layout (out, in):
@@ -137,6 +145,13 @@ int pca_st_fwd(const float* X, int B, int N, const pca_st_dims* dims, const floa
                float* logits, void* workspace, size_t workspace_bytes, int precision,
                void* stream);
 
+/* Variable-size sets (extension; the reference batches only equal-size sets): cloud b consists of the first counts[b]
+ * (1 <= counts[b] <= N) rows of its padded (N, d_in) slot; padding rows never act as keys of mab0 / PMA, so the logits
+ * equal ST.forward on X[b:b+1, :counts[b]].  counts == NULL is pca_st_fwd. */
+int pca_st_fwd_masked(const float* X, const int32_t* counts, int B, int N, const pca_st_dims* dims,
+                      const float* params, float* logits, void* workspace, size_t workspace_bytes,
+                      int precision, void* stream);
+
 /* DeepSet.forward (set_transformer-master/models.py:25-28) / SmallDeepSet
  * (max_regression_demo.ipynb:41-48): 4 shared Linear (+ReLU) over points, pool over points
  * (0 mean, 1 max, 2 sum), 4 Linear decoder.  params := for enc then dec, 4 x (W (out,in) | b).
@@ -145,6 +160,11 @@ size_t pca_deepset_workspace_bytes(int B, int N, int d_in, int dim_hidden, int o
 int pca_deepset_fwd_f32(const float* X, int B, int N, int d_in, int dim_hidden, int out_dim,
                         int pool, const float* params, float* out, void* workspace,
                         size_t workspace_bytes, void* stream);
+
+/* Masked pooling variant (north_star: PointNet-style shared MLP + masked max-pool): pools over the first counts[b] points. */
+int pca_deepset_fwd_masked_f32(const float* X, const int32_t* counts, int B, int N, int d_in, int dim_hidden,
+                               int out_dim, int pool, const float* params, float* out, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- whole path, one call
  * audio -> STFT/log-magnitude -> [Ntemp chunking] -> [top-K] -> clouds -> ST -> logits.
@@ -162,6 +182,8 @@ typedef struct {
     int top_k;          /* 0 = all points */
     int precision;      /* PCA_PREC_* for the encoder */
     pca_st_dims st;
+    int use_threshold;  /* != 0: keep only points with log-magnitude >= threshold (capped at top_k if top_k > 0), */
+    float threshold;    /*       padded to the full width; the encoder masks the padding (variable-size sets)      */
 } pca_pipeline_cfg;
 
 /* number of clouds produced per clip and points per cloud for a config */

@@ -4,13 +4,13 @@ arithmetic runs in hand-written sm_100a CUDA kernels behind a C ABI (include/pca
 from . import _lib
 from .data_processing import load_esc, tt_split
 from .dataset import ESC_pc, ESC_pc_ss, ESC_pc_temp, ESC_pc_temp_maxKSS
-from .frontend import build_clouds, coord_tables, spectral_point_cloud, stft_logmag, topk_points
+from .frontend import build_clouds, coord_tables, select_points, spectral_point_cloud, stft_logmag, topk_points
 from .models import ST, DeepSet, SetTransformer, strip_module_prefix
 from .modules import ISAB, MAB, PMA, SAB
 from .pipeline import AudioConfig, AudioSetPipeline
 from .utils import pc_maxK
 
 __all__ = ["load_esc", "tt_split", "ESC_pc", "ESC_pc_ss", "ESC_pc_temp", "ESC_pc_temp_maxKSS", "build_clouds",
-           "coord_tables", "spectral_point_cloud", "stft_logmag", "topk_points", "ST", "DeepSet",
+           "coord_tables", "select_points", "spectral_point_cloud", "stft_logmag", "topk_points", "ST", "DeepSet",
            "SetTransformer", "strip_module_prefix", "ISAB", "MAB", "PMA", "SAB", "AudioConfig",
            "AudioSetPipeline", "pc_maxK"]

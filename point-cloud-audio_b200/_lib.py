@@ -24,7 +24,7 @@ class StDims(C.Structure):
 class PipelineCfg(C.Structure):
     _fields_ = [("n_samples", C.c_int), ("n_fft", C.c_int), ("hop", C.c_int), ("scale", C.c_float),
                 ("mode", C.c_int), ("ntemp", C.c_int), ("top_k", C.c_int), ("precision", C.c_int),
-                ("st", StDims)]
+                ("st", StDims), ("use_threshold", C.c_int), ("threshold", C.c_float)]
 
 
 _P = C.c_void_p
@@ -42,6 +42,9 @@ PROTOTYPES = {
     "pca_stft_logmag_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _I, _I, _P, _P]),
     "pca_build_clouds_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "pca_topk_compact_f32": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P]),
+    "pca_select_compact_f32": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "pca_st_fwd_masked": (_I, [_P, _P, _I, _I, C.POINTER(StDims), _P, _P, _P, _SZ, _I, _P]),
+    "pca_deepset_fwd_masked_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),
     "pca_mab_param_count": (C.c_longlong, [_I, _I, _I, _I]),
     "pca_isab_param_count": (C.c_longlong, [_I, _I, _I, _I]),
     "pca_pma_param_count": (C.c_longlong, [_I, _I, _I]),

@@ -13,18 +13,18 @@ namespace pca {
 // ---- kernels / launchers defined in the other translation units
 int launch_stft_logmag(const float*, int, int, int, int, const float*, const float*, float, int, int, float*, cudaStream_t);
 int launch_build_clouds(const float*, int, int, int, const float*, const float*, float*, cudaStream_t);
-int launch_topk(const float*, int, int, int, const float*, const float*, int, int, float*, int32_t*, cudaStream_t);
+int launch_topk(const float*, int, int, int, const float*, const float*, int, int, int, float, float*, int32_t*, int32_t*, cudaStream_t);
 int launch_linear(const float*, const float*, const float*, float*, long long, int, int, int, cudaStream_t);
-int launch_attn(const float*, long long, const float*, int, int, int, int, int, float*, float*, cudaStream_t);
+int launch_attn(const float*, long long, const float*, int, int, int, int, int, float*, float*, const int*, cudaStream_t);
 size_t attn_part_floats(int B, int nq, int nk, int D, int H);
 int launch_layernorm(float*, long long, int, const float*, const float*, cudaStream_t);
-int launch_pool(const float*, int, int, int, int, float*, cudaStream_t);
+int launch_pool(const float*, int, int, int, int, float*, const int*, cudaStream_t);
 void set_timeline(long long* p);
 int launch_umma_probe(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 // tcgen05 path (encoder_tc.cu)
 size_t st_tc_workspace_bytes(const pca_st_dims* d, int B, int N);
 int st_tc_supported(const pca_st_dims* d, int N);
-int st_tc_forward(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
+int st_tc_forward(const float* X, const int* counts, int B, int N, const pca_st_dims* d, const float* params, float* logits,
                   void* ws, size_t ws_bytes, cudaStream_t st);
 int st_tc_forward_stages(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
                          float* H1, float* Y1, float* H2, float* Y2, float* pooled, void* ws, size_t ws_bytes,
@@ -83,7 +83,7 @@ static size_t mab_ws_floats(int B, int qb, int nq, int nk, int D, int H) {
 // Q (qb, nq, dq) with qb in {1, B}; K (B, nk, dk); out (B, nq, D)
 static int mab_forward(const float* Q, int qb, const float* K, int B, int nq, int nk, int dq, int dk, int D,
                        int H, int ln, const float* params, float* out, void* ws, size_t ws_bytes,
-                       cudaStream_t st) {
+                       cudaStream_t st, const int* key_counts = nullptr) {
     if (qb != 1 && qb != B) return fail(PCA_EINVAL, "MAB: query batch must be 1 or B");
     if (nq <= 0 || nk <= 0) return fail(PCA_EINVAL, "MAB: empty query or key set (nq=%d, nk=%d)", nq, nk);
     const MabParams m = mab_slice(params, dq, dk, D, ln);
@@ -95,7 +95,7 @@ static int mab_forward(const float* Q, int qb, const float* K, int B, int nq, in
     if (!a.ok()) return fail(PCA_EWORKSPACE, "MAB: workspace too small (%zu bytes given)", ws_bytes);
     PCA_TRY(launch_linear(Q, m.Wq, m.bq, Qp, (long long)qb * nq, dq, D, 0, st));
     PCA_TRY(launch_linear(K, m.Wkv, m.bkv, KV, (long long)B * nk, dk, 2 * D, 0, st));
-    PCA_TRY(launch_attn(Qp, qb == 1 ? 0 : (long long)nq * D, KV, B, nq, nk, D, H, O, part, st));
+    PCA_TRY(launch_attn(Qp, qb == 1 ? 0 : (long long)nq * D, KV, B, nq, nk, D, H, O, part, key_counts, st));
     if (ln) PCA_TRY(launch_layernorm(O, (long long)B * nq, D, m.ln0w, m.ln0b, st));
     PCA_TRY(launch_linear(O, m.Wo, m.bo, out, (long long)B * nq, D, D, 2, st));
     if (ln) PCA_TRY(launch_layernorm(out, (long long)B * nq, D, m.ln1w, m.ln1b, st));
@@ -110,7 +110,8 @@ static size_t isab_ws_bytes(int B, int N, int d_in, int D, int H, int M) {
     return a.off + (w0 > w1 ? w0 : w1);
 }
 static int isab_forward(const float* X, int B, int N, int d_in, int D, int H, int M, int ln,
-                        const float* params, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                        const float* params, float* out, void* ws, size_t ws_bytes, cudaStream_t st,
+                        const int* counts = nullptr) {
     const float* I = params;
     const float* p0 = I + (long long)M * D;
     const float* p1 = p0 + mab_count(D, d_in, D, ln);
@@ -119,15 +120,15 @@ static int isab_forward(const float* X, int B, int N, int d_in, int D, int H, in
     if (!a.ok()) return fail(PCA_EWORKSPACE, "ISAB: workspace too small");
     void* sub = (char*)ws + a.off;
     const size_t sub_bytes = ws_bytes - a.off;
-    PCA_TRY(mab_forward(I, 1, X, B, M, N, D, d_in, D, H, ln, p0, Hb, sub, sub_bytes, st));      // mab0(I, X)
+    PCA_TRY(mab_forward(I, 1, X, B, M, N, D, d_in, D, H, ln, p0, Hb, sub, sub_bytes, st, counts));   // mab0(I, X): padded points masked
     PCA_TRY(mab_forward(X, B, Hb, B, N, M, d_in, D, D, H, ln, p1, out, sub, sub_bytes, st));    // mab1(X, H)
     return 0;
 }
 static size_t pma_ws_bytes(int B, int N, int D, int H, int S) { return mab_ws_floats(B, 1, S, N, D, H); }
 static int pma_forward(const float* X, int B, int N, int D, int H, int S, int ln, const float* params,
-                       float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                       float* out, void* ws, size_t ws_bytes, cudaStream_t st, const int* counts = nullptr) {
     const float* Sd = params;
-    return mab_forward(Sd, 1, X, B, S, N, D, D, D, H, ln, Sd + (long long)S * D, out, ws, ws_bytes, st);
+    return mab_forward(Sd, 1, X, B, S, N, D, D, D, H, ln, Sd + (long long)S * D, out, ws, ws_bytes, st, counts);
 }
 
 static long long st_count(const pca_st_dims* d) {
@@ -149,7 +150,7 @@ static size_t st_f32_ws_bytes(const pca_st_dims* d, int B, int N) {
     return a.off + w;
 }
 
-static int st_f32_forward_chunk(const float* X, int B, int N, const pca_st_dims* d, const float* params,
+static int st_f32_forward_chunk(const float* X, const int* counts, int B, int N, const pca_st_dims* d, const float* params,
                                 float* logits, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int D = d->D, H = d->H, M = d->M, S = d->S, C = d->C, ln = d->ln;
     const float* p_isab0 = params;
@@ -163,9 +164,9 @@ static int st_f32_forward_chunk(const float* X, int B, int N, const pca_st_dims*
     if (!a.ok()) return fail(PCA_EWORKSPACE, "ST: workspace too small");
     void* sub = (char*)ws + a.off;
     const size_t sub_bytes = ws_bytes - a.off;
-    PCA_TRY(isab_forward(X, B, N, d->d_in, D, H, M, ln, p_isab0, Y1, sub, sub_bytes, st));
-    PCA_TRY(isab_forward(Y1, B, N, D, D, H, M, ln, p_isab1, Y2, sub, sub_bytes, st));
-    PCA_TRY(pma_forward(Y2, B, N, D, H, S, ln, p_pma, P, sub, sub_bytes, st));
+    PCA_TRY(isab_forward(X, B, N, d->d_in, D, H, M, ln, p_isab0, Y1, sub, sub_bytes, st, counts));
+    PCA_TRY(isab_forward(Y1, B, N, D, D, H, M, ln, p_isab1, Y2, sub, sub_bytes, st, counts));
+    PCA_TRY(pma_forward(Y2, B, N, D, H, S, ln, p_pma, P, sub, sub_bytes, st, counts));
     PCA_TRY(launch_linear(P, p_lin, p_lin + (long long)C * D, logits, (long long)B * S, D, C, 0, st));
     return 0;
 }
@@ -180,7 +181,7 @@ static int check_dims(const pca_st_dims* d) {
 }
 
 static int st_forward(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
-                      void* ws, size_t ws_bytes, int precision, cudaStream_t st) {
+                      void* ws, size_t ws_bytes, int precision, cudaStream_t st, const int* counts = nullptr) {
     PCA_TRY(check_dims(d));
     if (!X || !params || !logits) return fail(PCA_EINVAL, "ST: null pointer");
     if (B < 0 || N <= 0) return fail(PCA_EINVAL, "ST: bad batch/points (B=%d, N=%d)", B, N);
@@ -189,7 +190,7 @@ static int st_forward(const float* X, int B, int N, const pca_st_dims* d, const 
         if (!st_tc_supported(d, N))
             return fail(PCA_EUNSUPPORTED, "ST: tcgen05 path needs D=64,H=8,M=64,S=1,ln=0,d_in<=3 (got D=%d,H=%d,M=%d,S=%d,ln=%d,d_in=%d)",
                         d->D, d->H, d->M, d->S, d->ln, d->d_in);
-        return st_tc_forward(X, B, N, d, params, logits, ws, ws_bytes, st);
+        return st_tc_forward(X, counts, B, N, d, params, logits, ws, ws_bytes, st);
     }
     if (precision != PCA_PREC_FP32) return fail(PCA_EINVAL, "ST: unknown precision %d", precision);
     // largest chunk of clouds whose scratch fits the caller's workspace
@@ -200,7 +201,7 @@ static int st_forward(const float* X, int B, int N, const pca_st_dims* d, const 
     if (chunk > 32768) chunk = 32768;
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int bc = (B - b0) < chunk ? (B - b0) : chunk;
-        PCA_TRY(st_f32_forward_chunk(X + (long long)b0 * N * d->d_in, bc, N, d, params,
+        PCA_TRY(st_f32_forward_chunk(X + (long long)b0 * N * d->d_in, counts ? counts + b0 : nullptr, bc, N, d, params,
                                      logits + (long long)b0 * d->S * d->C, ws, ws_bytes, st));
     }
     return 0;
@@ -216,7 +217,8 @@ static size_t deepset_ws_bytes(int B, int N, int dh) {
     return a.off;
 }
 static int deepset_forward(const float* X, int B, int N, int d_in, int dh, int out_dim, int pool,
-                           const float* p, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                           const float* p, float* out, void* ws, size_t ws_bytes, cudaStream_t st,
+                           const int* counts = nullptr) {
     Arena a(ws, ws_bytes);
     float* t0 = a.take<float>((size_t)B * N * dh);
     float* t1 = a.take<float>((size_t)B * N * dh);
@@ -237,7 +239,7 @@ static int deepset_forward(const float* X, int B, int N, int d_in, int dh, int o
     PCA_TRY(launch_linear(t0, W[1], bb[1], t1, rows, dh, dh, 1, st));
     PCA_TRY(launch_linear(t1, W[2], bb[2], t0, rows, dh, dh, 1, st));
     PCA_TRY(launch_linear(t0, W[3], bb[3], t1, rows, dh, dh, 0, st));
-    PCA_TRY(launch_pool(t1, B, N, dh, pool, u0, st));
+    PCA_TRY(launch_pool(t1, B, N, dh, pool, u0, counts, st));
     PCA_TRY(launch_linear(u0, W[4], bb[4], u1, B, dh, dh, 1, st));
     PCA_TRY(launch_linear(u1, W[5], bb[5], u0, B, dh, dh, 1, st));
     PCA_TRY(launch_linear(u0, W[6], bb[6], u1, B, dh, dh, 1, st));
@@ -283,6 +285,7 @@ static size_t pipe_ws_bytes(const pca_pipeline_cfg* c, const PipeShape& s, int n
     const size_t n_clouds = (size_t)n_clips * s.clouds_per_clip;
     a.take<float>((size_t)n_clips * s.nt_out * s.nf);        // log-magnitudes
     a.take<float>(n_clouds * s.pts * s.width);               // clouds
+    a.take<int32_t>(n_clouds);                               // kept points per cloud (threshold mode)
     if (st_off) *st_off = a.off;
     // encoder scratch: chunks of <= 256 clouds for the fp32 path (more only helps launch overhead); the
     // tcgen05 path runs one CTA per cloud, so it gets up to 4096 clouds per launch to fill many waves
@@ -307,16 +310,21 @@ static int pipeline_run(const pca_pipeline_cfg* c, const float* audio, int n_cli
     const int n_clouds = n_clips * s.clouds_per_clip;
     float* logmag = a.take<float>((size_t)n_clips * s.nt_out * s.nf);
     float* pts = a.take<float>((size_t)n_clouds * s.pts * s.width);
+    int32_t* kept = a.take<int32_t>((size_t)n_clouds);
     PCA_TRY(launch_stft_logmag(audio, n_clips, c->n_samples, c->n_fft, c->hop, window, twiddle, c->scale,
                                c->mode == 3, s.nt_out, logmag, st));
     const int nt_cloud = c->mode == 3 ? c->ntemp : 1;
     const float* tarr_use = c->mode == 3 ? tarr : nullptr;
-    if (c->top_k)
-        PCA_TRY(launch_topk(logmag, n_clouds, s.nf, nt_cloud, farr, tarr_use, c->top_k, 1, pts, nullptr, st));
+    // threshold mode: points with log-magnitude >= threshold, capped at top_k (or all points), padded; the encoder then
+    // runs on variable-size sets (kept[] points per cloud)
+    const bool thr = c->use_threshold != 0;
+    if (c->top_k || thr)
+        PCA_TRY(launch_topk(logmag, n_clouds, s.nf, nt_cloud, farr, tarr_use, s.pts, 1, thr, c->threshold, pts, nullptr,
+                            thr ? kept : nullptr, st));
     else
         PCA_TRY(launch_build_clouds(logmag, n_clouds, s.nf, nt_cloud, farr, tarr_use, pts, st));
     return st_forward(pts, n_clouds, s.pts, &c->st, st_params, logits, (char*)ws + st_off, ws_bytes - st_off,
-                      c->precision, st);
+                      c->precision, st, thr ? kept : nullptr);
 }
 
 }  // namespace pca
@@ -382,7 +390,13 @@ int pca_build_clouds_f32(const float* logmag, int n_clouds, int nf, int nt, cons
 
 int pca_topk_compact_f32(const float* keys, int n_clouds, int nf, int nt, const float* farr,
                          const float* tarr, int K, int sorted_desc, float* pts, int32_t* idx, void* stream) {
-    return launch_topk(keys, n_clouds, nf, nt, farr, tarr, K, sorted_desc, pts, idx, (cudaStream_t)stream);
+    return launch_topk(keys, n_clouds, nf, nt, farr, tarr, K, sorted_desc, 0, 0.f, pts, idx, nullptr, (cudaStream_t)stream);
+}
+int pca_select_compact_f32(const float* keys, int n_clouds, int nf, int nt, const float* farr, const float* tarr, int K,
+                           int sorted_desc, int use_threshold, float threshold, float* pts, int32_t* idx,
+                           int32_t* counts, void* stream) {
+    return launch_topk(keys, n_clouds, nf, nt, farr, tarr, K, sorted_desc, use_threshold, threshold, pts, idx, counts,
+                       (cudaStream_t)stream);
 }
 
 long long pca_mab_param_count(int dq, int dk, int D, int ln) { return mab_count(dq, dk, D, ln); }
@@ -435,6 +449,11 @@ int pca_st_fwd(const float* X, int B, int N, const pca_st_dims* dims, const floa
     return st_forward(X, B, N, dims, params, logits, workspace, workspace_bytes, precision, (cudaStream_t)stream);
 }
 
+int pca_st_fwd_masked(const float* X, const int32_t* counts, int B, int N, const pca_st_dims* dims, const float* params,
+                      float* logits, void* workspace, size_t workspace_bytes, int precision, void* stream) {
+    return st_forward(X, B, N, dims, params, logits, workspace, workspace_bytes, precision, (cudaStream_t)stream, counts);
+}
+
 size_t pca_deepset_workspace_bytes(int B, int N, int d_in, int dim_hidden, int out_dim) {
     (void)d_in; (void)out_dim;
     return deepset_ws_bytes(B, N, dim_hidden);
@@ -446,6 +465,16 @@ int pca_deepset_fwd_f32(const float* X, int B, int N, int d_in, int dim_hidden, 
     if (N <= 0) return fail(PCA_EINVAL, "DeepSet: empty set");
     return deepset_forward(X, B, N, d_in, dim_hidden, out_dim, pool, params, out, workspace, workspace_bytes,
                            (cudaStream_t)stream);
+}
+
+int pca_deepset_fwd_masked_f32(const float* X, const int32_t* counts, int B, int N, int d_in, int dim_hidden, int out_dim,
+                               int pool, const float* params, float* out, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    if (!X || !params || !out) return fail(PCA_EINVAL, "DeepSet: null pointer");
+    if (B == 0) return 0;
+    if (N <= 0) return fail(PCA_EINVAL, "DeepSet: empty set");
+    return deepset_forward(X, B, N, d_in, dim_hidden, out_dim, pool, params, out, workspace, workspace_bytes,
+                           (cudaStream_t)stream, counts);
 }
 
 int pca_pipeline_clouds_per_clip(const pca_pipeline_cfg* cfg) {

@@ -104,7 +104,8 @@ template <int DH>
 __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstride,
                                 const float* __restrict__ KV, int nq, int nk, int D, int tq_log,
                                 int tk, int nsplit, int chunk, float scale_log2e,
-                                float* __restrict__ O, float* __restrict__ part) {
+                                float* __restrict__ O, float* __restrict__ part,
+                                const int* __restrict__ key_counts) {
     extern __shared__ __align__(16) float kv_s[];     // tk rows x (2D + 4)
     const int H = blockDim.x >> 5;
     const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,8 +122,10 @@ __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstrid
     for (int j = 0; j < DH; ++j) { qv[j] = __ldg(qptr + j) * scale_log2e; acc[j] = 0.f; }
     float m = -INFINITY, l = 0.f;
 
+    // variable-size sets: only the first key_counts[b] keys of the padded set take part
+    const int nk_b = key_counts ? max(1, min(nk, __ldg(key_counts + b))) : nk;
     const int k_begin = split * chunk;
-    const int k_end = min(nk, k_begin + chunk);
+    const int k_end = min(nk_b, k_begin + chunk);
     const float* kvb = KV + (long long)b * nk * 2 * D;
 
     for (int kt = k_begin; kt < k_end; kt += tk) {
@@ -282,7 +285,7 @@ size_t attn_part_floats(int B, int nq, int nk, int D, int H) { return plan_attn(
 
 template <int DH>
 static int launch_attn_t(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk,
-                         int D, int H, float* O, float* part, cudaStream_t st) {
+                         int D, int H, float* O, float* part, const int* key_counts, cudaStream_t st) {
     const AttnPlan p = plan_attn(B, nq, nk, D, H);
     const int tq = 1 << p.tq_log;
     dim3 grid((nq + tq - 1) / tq, p.nsplit, B);
@@ -293,7 +296,7 @@ static int launch_attn_t(const float* Qp, long long q_bstride, const float* KV, 
         LaunchTimer lt("attn_f32_kernel", st, 4.0 * B * nq * (double)nk * D,
                        4.0 * ((double)B * nk * 2 * D + 2.0 * B * nq * D));
         attn_f32_kernel<DH><<<grid, 32 * H, p.smem, st>>>(Qp, q_bstride, KV, nq, nk, D, p.tq_log, p.tk,
-                                                          p.nsplit, p.chunk, scale_log2e, O, part);
+                                                          p.nsplit, p.chunk, scale_log2e, O, part, key_counts);
     }
     PCA_CHECK_LAUNCH("attn_f32_kernel");
     if (p.nsplit > 1) {
@@ -308,16 +311,16 @@ static int launch_attn_t(const float* Qp, long long q_bstride, const float* KV, 
 }
 
 int launch_attn(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D,
-                int H, float* O, float* part, cudaStream_t st) {
+                int H, float* O, float* part, const int* key_counts, cudaStream_t st) {
     if (B == 0 || nq == 0) return 0;
     if (H < 1 || H > 32 || D % H) return fail(PCA_EUNSUPPORTED, "attention: need 1 <= H <= 32 and D %% H == 0 (D=%d, H=%d)", D, H);
     if (B > 65535) return fail(PCA_EUNSUPPORTED, "attention: batch chunk %d exceeds the grid limit", B);
     switch (D / H) {
-        case 4: return launch_attn_t<4>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st);
-        case 8: return launch_attn_t<8>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st);
-        case 16: return launch_attn_t<16>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st);
-        case 32: return launch_attn_t<32>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st);
-        case 64: return launch_attn_t<64>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st);
+        case 4: return launch_attn_t<4>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st);
+        case 8: return launch_attn_t<8>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st);
+        case 16: return launch_attn_t<16>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st);
+        case 32: return launch_attn_t<32>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st);
+        case 64: return launch_attn_t<64>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st);
         default: return fail(PCA_EUNSUPPORTED, "attention: head dim %d not in {4,8,16,32,64}", D / H);
     }
 }
@@ -348,15 +351,17 @@ int launch_layernorm(float* X, long long rows, int D, const float* g, const floa
 
 // ------------------------------------------------------------------------------------ pooling
 // X (B, N, D) -> out (B, D); pool 0 mean, 1 max, 2 sum
-__global__ void pool_kernel(const float* __restrict__ X, int N, int D, int pool, float* __restrict__ out) {
+__global__ void pool_kernel(const float* __restrict__ X, int N, int D, int pool, float* __restrict__ out,
+                            const int* __restrict__ counts) {
     __shared__ float red[8][33];
     const int b = blockIdx.y;
+    const int Nb = counts ? max(1, min(N, __ldg(counts + b))) : N;      // masked pooling over the first counts[b] points
     const int d = blockIdx.x * 32 + threadIdx.x;
     const int ty = threadIdx.y;
     float v = pool == 1 ? -INFINITY : 0.f;
     if (d < D) {
         const float* x = X + (long long)b * N * D + d;
-        for (int p = ty; p < N; p += 8) {
+        for (int p = ty; p < Nb; p += 8) {
             const float t = __ldg(x + (long long)p * D);
             v = pool == 1 ? fmaxf(v, t) : v + t;
         }
@@ -365,18 +370,18 @@ __global__ void pool_kernel(const float* __restrict__ X, int N, int D, int pool,
     __syncthreads();
     if (ty == 0 && d < D) {
         for (int i = 1; i < 8; ++i) v = pool == 1 ? fmaxf(v, red[i][threadIdx.x]) : v + red[i][threadIdx.x];
-        if (pool == 0) v /= (float)N;
+        if (pool == 0) v /= (float)Nb;
         out[(long long)b * D + d] = v;
     }
 }
 
-int launch_pool(const float* X, int B, int N, int D, int pool, float* out, cudaStream_t st) {
+int launch_pool(const float* X, int B, int N, int D, int pool, float* out, const int* counts, cudaStream_t st) {
     if (B == 0) return 0;
     if (pool < 0 || pool > 2) return fail(PCA_EINVAL, "pool: mode %d not in {0 mean, 1 max, 2 sum}", pool);
     if (B > 65535) return fail(PCA_EUNSUPPORTED, "pool: batch too large");
     dim3 grid((D + 31) / 32, B), block(32, 8);
     LaunchTimer lt("pool_kernel", st, 0.0, 4.0 * (double)B * N * D);
-    pool_kernel<<<grid, block, 0, st>>>(X, N, D, pool, out);
+    pool_kernel<<<grid, block, 0, st>>>(X, N, D, pool, out, counts);
     PCA_CHECK_LAUNCH("pool_kernel");
     return 0;
 }

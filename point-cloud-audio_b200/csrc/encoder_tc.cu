@@ -2,19 +2,20 @@
 // inducing points, one PMA seed, no LayerNorm; ST of Code/models.py:13-44 with the hyper-parameters of
 // Code/settransformer.py:81-85).  bf16 operands, fp32 accumulation in TMEM, fp32 softmax statistics.
 //
-//   prep_kernel            : batch-independent work hoisted out of the per-cloud path: fc_q(I), fc_q(S)
-//                            (the I.repeat / S.repeat of modules.py:52,63 is never materialised) and the
-//                            bf16 UMMA operand images of the weights.
-//   mab_reduce_tc_kernel   : MAB(Q = inducing points | seed, K = points)  (ISAB mab0, PMA).  Rows of the
-//                            128-row MMA tile are (head-of-pair, query); two heads are stacked per MMA so the
-//                            K=16 bf16 instruction depth is fully used by 2 x head-dim 8.  Online softmax over
-//                            the points with the running statistics in registers (thread = row).
-//   finalize_isab_kernel   : merges the point splits, O = Qp + A V, H = O + relu(fc_o(O)), then the K/V
-//                            projections of H for mab1, emitted as block-diagonal bf16 operand images.
-//   mab_apply_tc_kernel    : MAB(Q = points, K = H) (ISAB mab1): per 128-point tile, Q projection,
-//                            QK^T (2 heads per MMA via the block-diagonal K image), softmax over the 64 keys in
-//                            registers, P V with P fed from TMEM, +Qp residual, fc_o + ReLU residual.
-//   finalize_pma_kernel    : merge, residuals, final Linear -> logits.
+//   prep_kernel             : batch-independent work hoisted out of the per-cloud path: fc_q(I), fc_q(S) (the I.repeat /
+//                             S.repeat of modules.py:52,63 is never materialised), the bf16 UMMA operand images of the
+//                             weights (plain, split hi/lo, and the pooled-attention query image).
+//   mab_reduce5_tc_kernel   : MAB(Q = inducing points, K = points) (ISAB mab0).  Rows of the 128-row MMA tile are
+//                             (head-of-pair, query); two heads are stacked per MMA so the K=16 bf16 instruction depth is
+//                             fully used by 2 x head-dim 8.  Softmax over the points against a fixed per-row reference
+//                             exponent, outputs accumulating in TMEM.
+//   finalize_isab_tc_kernel : merges the point splits, O = Qp + A V, H = O + relu(fc_o(O)), then the K/V projections of H
+//                             for mab1 (split-bf16 MMAs), emitted as block-diagonal bf16 operand images.
+//   mab_apply3_tc_kernel    : MAB(Q = points, K = H) (ISAB mab1): per 128-point tile, Q projection MMA, QK^T (one head per
+//                             MMA via the block-diagonal K image), softmax over the 64 keys in registers, P V accumulating
+//                             onto the Q projection, fc_o + ReLU residual by dedicated epilogue warps.
+//   pma_pool_tc_kernel      : PMA with one seed on the un-projected points; finalize_pool_kernel applies fc_v, the MAB
+//                             tail and the final Linear -> logits.
 #include "common.cuh"
 #include "tc_prims.cuh"
 #include <stdlib.h>
@@ -196,6 +197,7 @@ struct RParams {
     const __nv_bfloat16* Y16;     // (B, N, 64) bf16        [DIN64 == true]
     int N, d_in, tiles_total, tiles_per_split, nsplit;
     int n_work;                   // work items (cloud, split) for the persistent kernels
+    const int* counts;            // nullable (B): valid points per cloud (variable-size sets); rows past it are padding
     const uint8_t* Aq;            // 16 KB query operand (stacked pairs, or all-heads image in PMA mode)
     const float* Wkv32;           // (128, d_in) fp32       [DIN64 == false]
     const float* bkv;             // (128)
@@ -203,21 +205,6 @@ struct RParams {
     long long* timeline;          // debug: per-phase clock64 stamps of CTA 0 / softmax warp 0 (nullptr = off)
     float* part;                  // (B, slots, 8, 10, 64): per (head, query) row: m (log2 domain), l, acc[8];
                                   // query index fastest so that a warp's 32 rows store/load 128 contiguous bytes
-};
-
-// TMEM columns of the reduce kernel
-constexpr uint32_t RC_S = 0;        // 2 score / probability buffers of 128 columns
-constexpr uint32_t RC_O = 256;      // pair mode: 4 pair outputs of 16 columns; PMA mode: 2 outputs of 64 columns
-constexpr uint32_t RC_PROJ = 384;   // 128 columns: K|V projection accumulator (DIN64)
-
-struct RSmem {
-    static constexpr int AQ = 0;
-    static constexpr int KV = 16384;              // 2 stages x (K 16384 | V 16384)
-    static constexpr int W = KV + 65536;          // Wkv16 operand (DIN64)
-    static constexpr int Y = W + 16384;           // Y tile operand (DIN64)
-    static constexpr int SMALL = Y + 16384;       // fp32: Wkv32 padded (128 x 4) + bkv (128)
-    static constexpr int BARS = SMALL + (128 * 4 + 128) * 4;
-    static constexpr int TOTAL = BARS + 16 * 8 + 16;
 };
 
 // One 32-column chunk of the online softmax: p = 2^(s - m) as bf16 pairs, partial row sum (packed fp32x2 math).
@@ -242,514 +229,7 @@ __device__ __forceinline__ float max_chunk32(const uint32_t* v, float mx) {
     return fmaxf(m0, m1);
 }
 
-// Warp roles (16 warps): 0-7 softmax (two warpgroups), 8-11 producer, 12 MMA issuer, 13-15 idle.
 constexpr int TC_THREADS16 = 16 * 32;
-
-template <bool DIN64, bool PMA>
-__global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce_tc_kernel(const RParams P) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sAq = smem + RSmem::AQ;
-    uint8_t* sKV = smem + RSmem::KV;
-    uint8_t* sW = smem + RSmem::W;
-    uint8_t* sY = smem + RSmem::Y;
-    float* sWsm = reinterpret_cast<float*>(smem + RSmem::SMALL);
-    float* sBias = sWsm + 128 * 4;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RSmem::BARS);
-    uint64_t* kv_full = bars;          // [2] count 128
-    uint64_t* kv_empty = bars + 2;     // [2] count 1 (tcgen05.commit)
-    uint64_t* s_full = bars + 4;       // [2] count 1
-    uint64_t* p_ready = bars + 6;      // [2] count 128
-    uint64_t* o_full = bars + 8;       // [4] count 1
-    uint64_t* y_full = bars + 12;      // count 128
-    uint64_t* proj_done = bars + 13;   // count 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cloud = blockIdx.y, split = blockIdx.x;
-    const int tile0 = split * P.tiles_per_split;
-    const int ntiles = min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
-
-    // ---- one-time setup
-    copy_to_smem(sAq, P.Aq, 16384);
-    if (DIN64) copy_to_smem(sW, P.Wkv16, 16384);
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
-        sBias[i] = P.bkv[i];
-        if (!DIN64) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) sWsm[i * 4 + k] = (k < P.d_in) ? P.Wkv32[i * P.d_in + k] : 0.f;
-        }
-    }
-    if (warp == 12) tmem_alloc(tmem_slot, 512);
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 128); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); }
-        for (int i = 0; i < 4; ++i) mbar_init(&o_full[i], 1);
-        mbar_init(y_full, 128);
-        mbar_init(proj_done, 1);
-        fence_barrier_init();
-    }
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tb = *tmem_slot;
-
-    if (warp >= 12) {
-        reg_dec<40>();
-        if (warp == 12) {
-            // =================================================================== MMA issuer
-            const bool leader = lane == 0;
-            const uint32_t idesc_s = idesc_bf16(128, 128, 0, 0);
-            const uint32_t idesc_pv = idesc_bf16(128, PMA ? 64 : 16, 0, 1);
-            const uint32_t aq = smem_u32(sAq), kvb = smem_u32(sKV), wb = smem_u32(sW), yb = smem_u32(sY);
-            uint32_t ph_p[2] = {0, 0};
-            auto issue_proj = [&]() {
-                if (leader) {
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_ss(tmem_addr(tb, 0, RC_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
-                               idesc_s, ks > 0);
-                    mma_commit(proj_done);
-                }
-                __syncwarp();
-            };
-            auto issue_s = [&](int p, uint32_t kbase) {          // pair mode: 2 heads, K = 16
-                if (leader) {
-                    mma_ss(tmem_addr(tb, 0, RC_S + 128 * (p & 1)), smem_desc(aq + p * 4096, 2048, 128),
-                           smem_desc(kbase + 2 * p * 2048, 2048, 128), idesc_s, 0);
-                    mma_commit(&s_full[p & 1]);
-                }
-                __syncwarp();
-            };
-            auto issue_pv = [&](int p, uint32_t vbase) {
-                const int g = p & 1;
-                mbar_wait(&p_ready[g], ph_p[g]);
-                ph_p[g] ^= 1;
-                fence_after_sync();
-                if (leader) {
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        mma_ts(tmem_addr(tb, 0, RC_O + 16 * p), tmem_addr(tb, 0, RC_S + 128 * g + ks * 8),
-                               smem_desc(vbase + 2 * p * 2048 + ks * 256, 128, 2048), idesc_pv, ks > 0);
-                    mma_commit(&o_full[p]);
-                }
-                __syncwarp();
-            };
-            if (DIN64) {
-                mbar_wait(y_full, 0);
-                fence_after_sync();
-                issue_proj();
-            }
-            for (int it = 0; it < ntiles; ++it) {
-                const int stage = it & 1;
-                const uint32_t kbase = kvb + stage * 32768, vbase = kbase + 16384;
-                mbar_wait(&kv_full[stage], (it >> 1) & 1);
-                fence_after_sync();
-                if (!PMA) {
-                    issue_s(0, kbase);
-                    issue_s(1, kbase);
-                } else {
-                    // all 8 heads in one accumulate chain: A = all-heads query image (128 x 64), B = K tile
-                    const int g = it & 1;
-                    if (leader) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ss(tmem_addr(tb, 0, RC_S + 128 * g), smem_desc(aq + ks * 4096, 2048, 128),
-                                   smem_desc(kbase + ks * 4096, 2048, 128), idesc_s, ks > 0);
-                        mma_commit(&s_full[g]);
-                    }
-                    __syncwarp();
-                }
-                if (DIN64 && it + 1 < ntiles) {
-                    mbar_wait(y_full, (it + 1) & 1);
-                    fence_after_sync();
-                    issue_proj();
-                }
-                if (!PMA) {
-                    issue_pv(0, vbase);
-                    issue_s(2, kbase);
-                    issue_pv(1, vbase);
-                    issue_s(3, kbase);
-                    issue_pv(2, vbase);
-                    issue_pv(3, vbase);
-                } else {
-                    const int g = it & 1;
-                    mbar_wait(&p_ready[g], ph_p[g]);
-                    ph_p[g] ^= 1;
-                    fence_after_sync();
-                    if (leader) {
-#pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-                            mma_ts(tmem_addr(tb, 0, RC_O + 64 * g), tmem_addr(tb, 0, RC_S + 128 * g + ks * 8),
-                                   smem_desc(vbase + ks * 256, 128, 2048), idesc_pv, ks > 0);
-                        mma_commit(&o_full[g]);
-                    }
-                    __syncwarp();
-                }
-                if (leader) mma_commit(&kv_empty[stage]);
-                __syncwarp();
-            }
-        }
-    } else if (warp >= 8) {
-        reg_dec<88>();
-        // =================================================================== producer: K|V tiles
-        const int quad = warp & 3;
-        const int row = 32 * quad + lane;
-        for (int it = 0; it < ntiles; ++it) {
-            const int stage = it & 1;
-            const int n = (tile0 + it) * 128 + row;
-            const bool valid = n < P.N;
-            uint8_t* sK = sKV + stage * 32768;
-            uint8_t* sV = sK + 16384;
-            if (!DIN64) {
-                float x[4] = {0.f, 0.f, 0.f, 0.f};
-                if (valid) {
-                    const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
-                    for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
-                }
-                if (it >= 2) mbar_wait(&kv_empty[stage], ((it >> 1) - 1) & 1);
-#pragma unroll 4
-                for (int c = 0; c < 16; ++c) {
-                    float o[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 w = *reinterpret_cast<const float4*>(sWsm + (c * 8 + j) * 4);
-                        o[j] = valid ? fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], sBias[c * 8 + j])))) : 0.f;
-                    }
-                    st_shared_8bf16((c < 8 ? sK + c * 2048 : sV + (c - 8) * 2048) + row * 16, o);
-                }
-            } else {
-                const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
-                uint4 yv[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
-                // the previous tile's projection MMA (the only reader of sY) has completed: proj_done was waited
-#pragma unroll
-                for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sY + c * 2048 + row * 16) = yv[c];
-                fence_async_smem();
-                fence_before_sync();
-                mbar_arrive(y_full);
-                mbar_wait(proj_done, it & 1);
-                fence_after_sync();
-                if (it >= 2) mbar_wait(&kv_empty[stage], ((it >> 1) - 1) & 1);
-#pragma unroll
-                for (int c0 = 0; c0 < 128; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_addr(tb, 32 * quad, RC_PROJ + c0), v);
-                    tmem_ld_wait32(v);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float o[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] = valid ? __uint_as_float(v[8 * q + j]) + sBias[c0 + 8 * q + j] : 0.f;
-                        const int chunk = c0 / 8 + q;
-                        st_shared_8bf16((chunk < 8 ? sK + chunk * 2048 : sV + (chunk - 8) * 2048) + row * 16, o);
-                    }
-                }
-            }
-            fence_async_smem();
-            fence_before_sync();
-            mbar_arrive(&kv_full[stage]);
-        }
-    } else {
-        reg_inc<184>();
-        // =================================================================== softmax warpgroups
-        const int g = warp >> 2, quad = warp & 3;
-        const int row = 32 * quad + lane;
-        const uint32_t lane_base = 32 * quad;
-        float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
-        float acc[2][8];
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
-        float alpha[2] = {0.f, 0.f};
-        uint32_t ph_s = 0;
-        const uint32_t sbase = tmem_addr(tb, lane_base, RC_S + 128 * g);
-
-        auto softmax_item = [&](const int pp, const int n_valid) {
-            mbar_wait(&s_full[g], ph_s);
-            ph_s ^= 1;
-            fence_after_sync();
-            uint32_t va[32], vb[32];
-            if (n_valid == 128) {
-                // ---- pass 1: row max, TMEM loads software-pipelined against the max chain
-                tmem_ld32(sbase, va);
-                tmem_ld_wait32(va);
-                tmem_ld32(sbase + 32, vb);
-                float mx = max_chunk32(va, -INFINITY);
-                tmem_ld_wait32(vb);
-                tmem_ld32(sbase + 64, va);
-                mx = max_chunk32(vb, mx);
-                tmem_ld_wait32(va);
-                tmem_ld32(sbase + 96, vb);
-                mx = max_chunk32(va, mx);
-                tmem_ld_wait32(vb);
-                tmem_ld32(sbase, va);                       // first chunk of pass 2 already in flight
-                mx = max_chunk32(vb, mx);
-                const float m_new = fmaxf(m_run[pp], mx);
-                alpha[pp] = ex2(m_run[pp] - m_new);
-                const float2 neg_m2 = make_float2(-m_new, -m_new);
-                float2 sum2 = make_float2(0.f, 0.f);
-                uint32_t pk[16];
-                // ---- pass 2: probabilities; P (bf16) overwrites score columns that were already consumed
-                tmem_ld_wait32(va);
-                tmem_ld32(sbase + 32, vb);
-                exp_chunk32(va, neg_m2, sum2, pk);
-                tmem_st16(sbase, pk);
-                tmem_ld_wait32(vb);
-                tmem_ld32(sbase + 64, va);
-                exp_chunk32(vb, neg_m2, sum2, pk);
-                tmem_st16(sbase + 16, pk);
-                tmem_ld_wait32(va);
-                tmem_ld32(sbase + 96, vb);
-                exp_chunk32(va, neg_m2, sum2, pk);
-                tmem_st16(sbase + 32, pk);
-                tmem_ld_wait32(vb);
-                exp_chunk32(vb, neg_m2, sum2, pk);
-                tmem_st16(sbase + 48, pk);
-                l_run[pp] = l_run[pp] * alpha[pp] + (sum2.x + sum2.y);
-                m_run[pp] = m_new;
-            } else {
-                // ---- ragged last tile: only columns < n_valid take part; the rest of P is zero
-                float mx = -INFINITY;
-                for (int c0 = 0; c0 < n_valid; c0 += 32) {
-                    tmem_ld32(sbase + c0, va);
-                    tmem_ld_wait32(va);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + j < n_valid) mx = fmaxf(mx, __uint_as_float(va[j]));
-                }
-                const float m_new = fmaxf(m_run[pp], mx);
-                alpha[pp] = ex2(m_run[pp] - m_new);
-                float sum = 0.f;
-                for (int c0 = 0; c0 < 128; c0 += 32) {
-                    uint32_t pk[16];
-                    if (c0 < n_valid) {
-                        tmem_ld32(sbase + c0, va);
-                        tmem_ld_wait32(va);
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const float p0 = (c0 + j < n_valid) ? ex2(__uint_as_float(va[j]) - m_new) : 0.f;
-                            const float p1 = (c0 + j + 1 < n_valid) ? ex2(__uint_as_float(va[j + 1]) - m_new) : 0.f;
-                            sum += p0 + p1;
-                            pk[j >> 1] = pack_bf16(p0, p1);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[j] = 0u;
-                    }
-                    tmem_st16(sbase + (c0 >> 1), pk);
-                }
-                l_run[pp] = l_run[pp] * alpha[pp] + sum;
-                m_run[pp] = m_new;
-            }
-            tmem_st_wait();
-            fence_before_sync();
-            mbar_arrive(&p_ready[g]);
-        };
-        if (!PMA) {
-            const uint32_t ocol_off = (row >= 64) ? 8u : 0u;      // second head of the pair lives in columns 8..15
-            auto consume_item = [&](const int pp, const int it) {
-                const int p = g + 2 * pp;
-                mbar_wait(&o_full[p], it & 1);
-                fence_after_sync();
-                uint32_t o[8];
-                tmem_ld8(tmem_addr(tb, lane_base, RC_O + 16 * p + ocol_off), o);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[pp][j] = fmaf(acc[pp][j], alpha[pp], __uint_as_float(o[j]));
-            };
-            for (int it = 0; it < ntiles; ++it) {
-                const int n_valid = min(128, P.N - (tile0 + it) * 128);
-                softmax_item(0, n_valid);
-                if (it > 0) consume_item(1, it - 1);
-                softmax_item(1, n_valid);
-                consume_item(0, it);
-            }
-            consume_item(1, ntiles - 1);
-#pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-                const int h = 2 * (g + 2 * pp) + (row >> 6);
-                float* dst = P.part + (((size_t)cloud * P.nsplit + split) * TH + h) * 10 * TM + (row & 63);
-                dst[0] = m_run[pp];
-                dst[TM] = l_run[pp];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) dst[(2 + j) * TM] = acc[pp][j];
-            }
-        } else {
-            // PMA: rows are (head = row / 16, 16 redundant copies); warpgroup g owns the tiles with it % 2 == g
-            const bool hi = (lane >> 4) != 0;
-            auto consume_pma = [&](const int it) {
-                mbar_wait(&o_full[g], (it >> 1) & 1);
-                fence_after_sync();
-                uint32_t o[16];
-                tmem_ld16(tmem_addr(tb, lane_base, RC_O + 64 * g + 16 * quad), o);
-                tmem_ld_wait16(o);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    acc[0][j] = fmaf(acc[0][j], alpha[0], __uint_as_float(hi ? o[8 + j] : o[j]));
-            };
-            int last = -1;
-            for (int it = g; it < ntiles; it += 2) {
-                const int n_valid = min(128, P.N - (tile0 + it) * 128);
-                softmax_item(0, n_valid);
-                consume_pma(it);
-                last = it;
-            }
-            (void)last;
-            if ((row & 15) == 0) {
-                const int h = row >> 4;
-                float* dst = P.part + (((size_t)cloud * P.nsplit + split) * TH + h) * 10 * TM + g;
-                dst[0] = m_run[0];
-                dst[TM] = l_run[0];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) dst[(2 + j) * TM] = acc[0][j];
-            }
-        }
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 12) tmem_dealloc(tb, 512);
-}
-
-// ------------------------------------------------------------------------------------ finalize (ISAB)
-// One block per cloud.  part -> O -> H = O + relu(fc_o(O)) -> [Kp | Vp] = H [Wk;Wv]^T + b  ->  block-diagonal
-// bf16 operand images:  Kblk/Vblk [4 pairs][2 chunks][128 rows][16 B], chunk = h % 2, row = (h % 2) * 64 + m.
-struct FParams {
-    const float* part; int nsplit;
-    const float* Qp;              // (64, 64) hoisted fc_q(I)
-    const float* WoT; const float* bo;       // mab0.fc_o transposed (k, f), bias
-    const float* WkvT; const float* bkv;     // mab1 [Wk;Wv] transposed (k, 128), bias (128)
-    uint8_t* KVblk;               // per cloud 32768 B
-    float* H_debug;               // nullable (B, 64, 64)
-};
-
-constexpr int FT_LD = 68;        // padded leading dimension of the transposed O / H tiles
-constexpr size_t FT_SMEM = (size_t)(2 * 64 * FT_LD + 64 * 128) * sizeof(float);
-
-__global__ void __launch_bounds__(256) finalize_isab_kernel(const FParams P) {
-    extern __shared__ __align__(16) float fs[];
-    float* sOT = fs;                       // O^T  [k][m]
-    float* sHT = sOT + 64 * FT_LD;         // H^T  [k][m]
-    float* sWT = sHT + 64 * FT_LD;         // weights, k-major [k][128]
-    const int cloud = blockIdx.x, tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
-
-    for (int i = tid; i < 64 * 16; i += 256) {       // fc_o^T: 64 x 64 floats as float4
-        const int k = i >> 4, f4 = i & 15;
-        *reinterpret_cast<float4*>(sWT + k * 128 + f4 * 4) = __ldg(reinterpret_cast<const float4*>(P.WoT + k * 64) + f4);
-    }
-    // merge the splits: 512 (h, m) rows, 2 per thread
-    if (P.nsplit == 2) {
-        // common case (one point-split, two column halves): all 40 loads of the thread's two rows are issued up front
-        float v[2][2][10];
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int r = tid + 256 * rr, h = r / TM, m = r % TM;
-#pragma unroll
-            for (int sl = 0; sl < 2; ++sl) {
-                const float* pp = P.part + (((size_t)cloud * 2 + sl) * TH + h) * 10 * TM + m;
-#pragma unroll
-                for (int j = 0; j < 10; ++j) v[rr][sl][j] = __ldg(pp + j * TM);
-            }
-        }
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int r = tid + 256 * rr, h = r / TM, m = r % TM;
-            const float mmax = fmaxf(v[rr][0][0], v[rr][1][0]);
-            const float w0 = exp2f(v[rr][0][0] - mmax), w1 = exp2f(v[rr][1][0] - mmax);
-            const float inv = 1.f / fmaf(v[rr][0][1], w0, v[rr][1][1] * w1);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                sOT[(h * 8 + j) * FT_LD + m] = __ldg(P.Qp + m * TD + h * 8 + j) + fmaf(v[rr][0][2 + j], w0, v[rr][1][2 + j] * w1) * inv;
-        }
-    } else
-    for (int r = tid; r < TH * TM; r += 256) {
-        const int h = r / TM, m = r % TM;
-        float mmax = -INFINITY;
-        for (int s = 0; s < P.nsplit; ++s)
-            mmax = fmaxf(mmax, P.part[(((size_t)cloud * P.nsplit + s) * TH + h) * 10 * TM + m]);
-        float l = 0.f, a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int s = 0; s < P.nsplit; ++s) {
-            const float* pp = P.part + (((size_t)cloud * P.nsplit + s) * TH + h) * 10 * TM + m;
-            const float w = exp2f(pp[0] - mmax);
-            l = fmaf(pp[TM], w, l);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = fmaf(pp[(2 + j) * TM], w, a[j]);
-        }
-        const float inv = 1.f / l;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sOT[(h * 8 + j) * FT_LD + m] = P.Qp[m * TD + h * 8 + j] + a[j] * inv;
-    }
-    __syncthreads();
-    {   // H = O + relu(O Wo^T + bo): 4 x 4 register tile per thread (rows 4ty.., columns 4tx..)
-        float acc[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float b = P.bo[4 * tx + j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i][j] = b;
-        }
-#pragma unroll 8
-        for (int k = 0; k < 64; ++k) {
-            const float4 a = *reinterpret_cast<const float4*>(sOT + k * FT_LD + 4 * ty);
-            const float4 w = *reinterpret_cast<const float4*>(sWT + k * 128 + 4 * tx);
-            const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int m = 4 * ty + i, f = 4 * tx + j;
-                const float hv = sOT[f * FT_LD + m] + fmaxf(acc[i][j], 0.f);
-                sHT[f * FT_LD + m] = hv;
-                if (P.H_debug) P.H_debug[((size_t)cloud * TM + m) * TD + f] = hv;
-            }
-    }
-    __syncthreads();
-    for (int i = tid; i < 64 * 32; i += 256) {       // [Wk;Wv]^T: 64 x 128 floats as float4
-        const int k = i >> 5, j4 = i & 31;
-        *reinterpret_cast<float4*>(sWT + k * 128 + j4 * 4) = __ldg(reinterpret_cast<const float4*>(P.WkvT + k * 128) + j4);
-    }
-    __syncthreads();
-    {   // [Kp | Vp] = H Wkv^T + b: 4 x 8 register tile (rows 4ty.., columns 8tx.. = one head chunk)
-        float acc[4][8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float b = P.bkv[8 * tx + j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i][j] = b;
-        }
-#pragma unroll 4
-        for (int k = 0; k < 64; ++k) {
-            const float4 a = *reinterpret_cast<const float4*>(sHT + k * FT_LD + 4 * ty);
-            const float4 w0 = *reinterpret_cast<const float4*>(sWT + k * 128 + 8 * tx);
-            const float4 w1 = *reinterpret_cast<const float4*>(sWT + k * 128 + 8 * tx + 4);
-            const float av[4] = {a.x, a.y, a.z, a.w};
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
-        }
-        // block-diagonal operand images: chunk c = h % 2 holds head h in rows c*64 + m and zeros in the other half
-        uint8_t* img = P.KVblk + (size_t)cloud * 32768 + (tx >= 8 ? 16384 : 0);
-        const int h = tx & 7, pr = h >> 1, c = h & 1;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int m = 4 * ty + i;
-            uint4 u;
-            u.x = pack_bf16(acc[i][0], acc[i][1]); u.y = pack_bf16(acc[i][2], acc[i][3]);
-            u.z = pack_bf16(acc[i][4], acc[i][5]); u.w = pack_bf16(acc[i][6], acc[i][7]);
-            *reinterpret_cast<uint4*>(img + pr * 4096 + c * 2048 + (c * 64 + m) * 16) = u;
-            *reinterpret_cast<uint4*>(img + pr * 4096 + c * 2048 + ((1 - c) * 64 + m) * 16) = make_uint4(0, 0, 0, 0);
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------ finalize (ISAB) on tensor cores
 // Same arithmetic as finalize_isab_kernel, two clouds per CTA iteration (MMA rows = (cloud of the pair, inducing point)).
@@ -942,10 +422,11 @@ struct AParams {
     const float* X32;             // (B, N, d_in)           [DIN64 == false]
     const __nv_bfloat16* Y16in;   // (B, N, 64)             [DIN64 == true]
     int N, d_in, tiles_total, tiles_per_split, nsplit, n_work;
+    const int* counts;            // nullable (B): valid points per cloud
     const uint8_t* KVblk;         // per cloud: K image 16384 B | V image 16384 B
     const float* Wq32;            // (64, d_in)             [DIN64 == false]
     const float* bq;              // (64)
-    const uint8_t* Wq16;          // 8 KB B operand         [DIN64 == true]
+    const uint8_t* Wq16;          // fc_q B operand: 8 KB (N=64, K=64) [DIN64] or the 2 KB split-bf16 K=16 image
     const uint8_t* Wo16;          // 8 KB B operand
     const float* bo;              // (64)
     __nv_bfloat16* Yout;          // (B, N, 64)
@@ -953,11 +434,11 @@ struct AParams {
 };
 
 // ====================================================================================== chain-scheduled kernels
-// Second generation of the two hot kernels.  The 128 score columns of a head pair are produced and consumed as
-// two independent 64-column "chains" per softmax warpgroup (4 chains per CTA, each with its own TMEM half-buffer
-// and barriers).  A single MMA-issuing thread POLLS the chains instead of following a fixed order, so the
-// P V -> next Q K^T round trip of one chain is hidden behind the softmax of the warpgroup's other chain and the
-// two warpgroups never wait on each other.
+// The 128 score columns of a head pair are produced and consumed as two independent 64-column "chains" per softmax
+// warpgroup (4 chains per CTA, each with its own TMEM half-buffer, barriers and MMA-issuing thread), so the
+// P V -> next Q K^T round trip of one chain is hidden behind the softmax of the warpgroup's other chain and the two
+// warpgroups never wait on each other.  (Earlier generations of these kernels -- fixed MMA order, 24-warp variants,
+// epilogue on the softmax warps, CUDA-core finalize -- are in the git history; DESIGN.md records what each step bought.)
 
 // one mbarrier arrival per warp (barrier counts are in warps): every lane has fenced its own writes, the
 // __syncwarp orders them before the elected lane's releasing arrive
@@ -982,329 +463,6 @@ struct R2Smem {
 // 64-column softmax step on registers: returns the chunk max
 __device__ __forceinline__ float max64(const uint32_t* va, const uint32_t* vb) { return max_chunk32(vb, max_chunk32(va, -INFINITY)); }
 
-// Persistent: grid = min(#work items, #SMs); CTA k walks the work items (cloud, point-split) k, k + grid, ...
-// Barriers, TMEM and the resident operands are set up once; all pipelines (producer -> MMA -> softmax) run
-// straight across work-item boundaries, so there is no per-cloud fill/drain bubble.
-template <bool DIN64>
-__global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce2_tc_kernel(const RParams P) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sAq = smem + R2Smem::AQ;
-    uint8_t* sKV = smem + R2Smem::KV;
-    uint8_t* sW = smem + R2Smem::W;
-    uint8_t* sY = smem + R2Smem::Y;
-    float* sWsm = reinterpret_cast<float*>(smem + R2Smem::SMALL);
-    float* sBias = sWsm + 128 * 4;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + R2Smem::BARS);
-    uint64_t* kv_full = bars;          // [2] count 4 (producer warps)
-    uint64_t* kv_empty = bars + 2;     // [2] count 4 (chains)
-    uint64_t* s_full = bars + 4;       // [4] count 1
-    uint64_t* p_ready = bars + 8;      // [4] count 4 (warps of the owning warpgroup)
-    uint64_t* o_full = bars + 12;      // [8] count 1   (region = 2 * pair + half)
-    uint64_t* y_full = bars + 20;      // count 4
-    uint64_t* proj_done = bars + 21;   // count 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_work = P.n_work, wstep = gridDim.x;
-    auto work_tiles = [&](int w, int& cloud, int& split, int& tile0) {
-        cloud = w / P.nsplit;
-        split = w - cloud * P.nsplit;
-        tile0 = split * P.tiles_per_split;
-        return min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
-    };
-
-    copy_to_smem(sAq, P.Aq, 16384);
-    if (DIN64) copy_to_smem(sW, P.Wkv16, 16384);
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
-        sBias[i] = P.bkv[i];
-        if (!DIN64) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) sWsm[i * 4 + k] = (k < P.d_in) ? P.Wkv32[i * P.d_in + k] : 0.f;
-        }
-    }
-    if (warp == 12) tmem_alloc(tmem_slot, 512);
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 4); mbar_init(&kv_empty[i], 4); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
-        for (int i = 0; i < 8; ++i) mbar_init(&o_full[i], 1);
-        mbar_init(y_full, 4);
-        mbar_init(proj_done, 1);
-        fence_barrier_init();
-    }
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tb = *tmem_slot;
-
-    if (warp >= 12) {
-        reg_dec<40>();
-        if (lane == 0) {
-            // =================================================================== one MMA-issuing thread per chain
-            // chain c = warp - 12: strictly serial  Q K^T -> (warpgroup softmax) -> P V -> next Q K^T  on its own
-            // half-buffer; the four chains never wait on each other.
-            const int c = warp - 12, half = c & 1;
-            const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
-            const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
-            const uint32_t aq = smem_u32(sAq), kvb = smem_u32(sKV);
-            int gt = 0;                                    // tiles processed by this CTA so far
-            for (int w = blockIdx.x; w < n_work; w += wstep) {
-                int cloud, split, tile0;
-                const int ntiles = work_tiles(w, cloud, split, tile0);
-                for (int it = 0; it < ntiles; ++it, ++gt) {
-                    const uint32_t kbase = kvb + (gt & 1) * 32768, vbase = kbase + 16384;
-                    mbar_wait(&kv_full[gt & 1], (gt >> 1) & 1);
-                    fence_after_sync();
-#pragma unroll
-                    for (int pp = 0; pp < 2; ++pp) {
-                        const int p = (c >> 1) + 2 * pp;
-                        mma_ss(tmem_addr(tb, 0, R2_S + 64 * c), smem_desc(aq + p * 4096, 2048, 128),
-                               smem_desc(kbase + 2 * p * 2048 + half * 1024, 2048, 128), idesc_s, 0);
-                        mma_commit(&s_full[c]);
-                        mbar_wait(&p_ready[c], pp);          // two items per tile: parities 0, 1
-                        fence_after_sync();
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ts(tmem_addr(tb, 0, R2_O + 16 * (2 * p + half)), tmem_addr(tb, 0, R2_S + 64 * c + ks * 8),
-                                   smem_desc(vbase + 2 * p * 2048 + half * 1024 + ks * 256, 128, 2048), idesc_pv, ks > 0);
-                        mma_commit(&o_full[2 * p + half]);
-                    }
-                    mma_commit(&kv_empty[gt & 1]);            // 4 chains x 1 arrival free the K|V stage
-                }
-            }
-        }
-    } else if (warp >= 8) {
-        reg_dec<88>();
-        // =================================================================== producer: K|V tiles
-        const int quad = warp & 3;
-        const int row = 32 * quad + lane;
-        int gt = 0;
-        for (int w = blockIdx.x; w < n_work; w += wstep) {
-            int cloud, split, tile0;
-            const int ntiles = work_tiles(w, cloud, split, tile0);
-            for (int it = 0; it < ntiles; ++it, ++gt) {
-                const int stage = gt & 1;
-                const int n = (tile0 + it) * 128 + row;
-                const bool valid = n < P.N;
-                uint8_t* sK = sKV + stage * 32768;
-                uint8_t* sV = sK + 16384;
-                if (!DIN64) {
-                    float x[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (valid) {
-                        const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
-                        for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
-                    }
-                    if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
-#pragma unroll 4
-                    for (int c = 0; c < 16; ++c) {
-                        float o[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 wv = *reinterpret_cast<const float4*>(sWsm + (c * 8 + j) * 4);
-                            o[j] = valid ? fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBias[c * 8 + j])))) : 0.f;
-                        }
-                        st_shared_8bf16((c < 8 ? sK + c * 2048 : sV + (c - 8) * 2048) + row * 16, o);
-                    }
-                } else {
-                    const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
-                    uint4 yv[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sY + c * 2048 + row * 16) = yv[c];
-                    fence_async_smem();
-                    fence_before_sync();
-                    warp_arrive(y_full);
-                    if (warp == 8 && lane == 0) {
-                        // one producer thread issues the K|V projection MMA once all 128 rows of Y are staged
-                        mbar_wait(y_full, gt & 1);
-                        fence_after_sync();
-                        const uint32_t yb = smem_u32(sY), wb = smem_u32(sW);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ss(tmem_addr(tb, 0, R2_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
-                                   idesc_bf16(128, 128, 0, 0), ks > 0);
-                        mma_commit(proj_done);
-                    }
-                    mbar_wait(proj_done, gt & 1);
-                    fence_after_sync();
-                    if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
-#pragma unroll
-                    for (int c0 = 0; c0 < 128; c0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_addr(tb, 32 * quad, R2_PROJ + c0), v);
-                        tmem_ld_wait32(v);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float o[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = valid ? __uint_as_float(v[8 * q + j]) + sBias[c0 + 8 * q + j] : 0.f;
-                            const int chunk = c0 / 8 + q;
-                            st_shared_8bf16((chunk < 8 ? sK + chunk * 2048 : sV + (chunk - 8) * 2048) + row * 16, o);
-                        }
-                    }
-                }
-                fence_async_smem();
-                fence_before_sync();
-                warp_arrive(&kv_full[stage]);
-            }
-        }
-    } else {
-        reg_inc<184>();
-        // =================================================================== softmax warpgroups (2 chains each)
-        const int g = warp >> 2, quad = warp & 3;
-        const int row = 32 * quad + lane;
-        const uint32_t lane_base = 32 * quad;
-        const uint32_t ocol_off = (row >= 64) ? 8u : 0u;
-        // running statistics per (half, pp)
-        float m_run[2][2], l_run[2][2], alpha[2][2], acc[2][2][8];
-        uint32_t ph_s[2] = {0, 0};
-        uint32_t va[32], vb[32];        // scores of the item being processed / prefetched for the next item
-        int gt = 0;
-        long long* tl = (P.timeline != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0) ? P.timeline : nullptr;
-        int tl_n = 0;
-#ifdef PCA_TIMELINE
-        auto stamp = [&](int tag) {
-            if (tl != nullptr && tl_n < 4000) { tl[2 * tl_n] = tag; tl[2 * tl_n + 1] = clock64(); ++tl_n; }
-        };
-#else
-        auto stamp = [&](int) {};
-        (void)tl; (void)tl_n;
-#endif
-
-        auto issue_loads = [&](const int half) {
-            const int c = 2 * g + half;
-            mbar_wait(&s_full[c], ph_s[half]);
-            ph_s[half] ^= 1;
-            fence_after_sync();
-            const uint32_t sb = tmem_addr(tb, lane_base, R2_S + 64 * c);
-            tmem_ld32(sb, va);
-            tmem_ld32(sb + 32, vb);
-        };
-        // One 64-column item.  va/vb already hold (in-flight) loads of this item; while its exponentials run, the
-        // loads of the warpgroup's NEXT item (other chain) are issued so TMEM latency never sits on the MUFU path.
-        auto softmax_item = [&](const int half, const int pp, const int nv, const bool has_next) {
-            const int c = 2 * g + half, cn = 2 * g + (half ^ 1);
-            const uint32_t sbase = tmem_addr(tb, lane_base, R2_S + 64 * c);
-            const uint32_t snext = tmem_addr(tb, lane_base, R2_S + 64 * cn);
-            uint32_t pk[16];
-            stamp(0);
-            tmem_ld_wait64(va, vb);
-            stamp(1);
-            if (nv == 64) {
-                const float m_new = fmaxf(m_run[half][pp], max64(va, vb));
-                alpha[half][pp] = ex2(m_run[half][pp] - m_new);
-                const float2 neg2 = make_float2(-m_new, -m_new);
-                float2 sum2 = make_float2(0.f, 0.f);
-                exp_chunk32(va, neg2, sum2, pk);
-                tmem_st16(sbase, pk);
-                stamp(2);
-                if (has_next) {
-                    mbar_wait(&s_full[cn], ph_s[half ^ 1]);
-                    ph_s[half ^ 1] ^= 1;
-                    fence_after_sync();
-                    tmem_ld32(snext, va);
-                }
-                stamp(3);
-                exp_chunk32(vb, neg2, sum2, pk);
-                tmem_st16(sbase + 16, pk);
-                if (has_next) tmem_ld32(snext + 32, vb);
-                l_run[half][pp] = l_run[half][pp] * alpha[half][pp] + (sum2.x + sum2.y);
-                m_run[half][pp] = m_new;
-                stamp(4);
-            } else {
-                // ragged tail: columns >= nv are padding (nv may be 0: the half contributes nothing)
-                float mx = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (j < nv) mx = fmaxf(mx, __uint_as_float(va[j]));
-                    if (32 + j < nv) mx = fmaxf(mx, __uint_as_float(vb[j]));
-                }
-                const float m_new = fmaxf(m_run[half][pp], mx);
-                alpha[half][pp] = (m_new == -INFINITY) ? 1.f : ex2(m_run[half][pp] - m_new);
-                float sum = 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float p0 = (j < nv) ? ex2(__uint_as_float(va[j]) - m_new) : 0.f;
-                    const float p1 = (j + 1 < nv) ? ex2(__uint_as_float(va[j + 1]) - m_new) : 0.f;
-                    sum += p0 + p1;
-                    pk[j >> 1] = pack_bf16(p0, p1);
-                }
-                tmem_st16(sbase, pk);
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float p0 = (32 + j < nv) ? ex2(__uint_as_float(vb[j]) - m_new) : 0.f;
-                    const float p1 = (33 + j < nv) ? ex2(__uint_as_float(vb[j + 1]) - m_new) : 0.f;
-                    sum += p0 + p1;
-                    pk[j >> 1] = pack_bf16(p0, p1);
-                }
-                tmem_st16(sbase + 16, pk);
-                l_run[half][pp] = l_run[half][pp] * alpha[half][pp] + sum;
-                m_run[half][pp] = m_new;
-                if (has_next) issue_loads(half ^ 1);
-            }
-            tmem_st_wait();
-            stamp(5);
-            fence_before_sync();
-            warp_arrive(&p_ready[c]);
-            stamp(6);
-        };
-        auto consume_item = [&](const int half, const int pp, const int tile_parity) {
-            const int p = g + 2 * pp;
-            mbar_wait(&o_full[2 * p + half], tile_parity);
-            stamp(7);
-            fence_after_sync();
-            uint32_t o[8];
-            tmem_ld8(tmem_addr(tb, lane_base, R2_O + 16 * (2 * p + half) + ocol_off), o);
-            // wait::ld also drains the prefetched score loads, which is harmless (they are needed next anyway)
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[half][pp][j] = fmaf(acc[half][pp][j], alpha[half][pp], __uint_as_float(o[j]));
-            stamp(8);
-        };
-        if (blockIdx.x < n_work) issue_loads(0);
-        for (int w = blockIdx.x; w < n_work; w += wstep) {
-            int cloud, split, tile0;
-            const int ntiles = work_tiles(w, cloud, split, tile0);
-            const bool more_work = w + wstep < n_work;
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    m_run[a][b] = -INFINITY; l_run[a][b] = 0.f; alpha[a][b] = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[a][b][j] = 0.f;
-                }
-            for (int it = 0; it < ntiles; ++it, ++gt) {
-                const int n_valid = min(128, P.N - (tile0 + it) * 128);
-                const int nv0 = min(64, n_valid), nv1 = max(0, n_valid - 64);
-                softmax_item(0, 0, nv0, true);
-                if (it > 0) consume_item(1, 1, (gt - 1) & 1);
-                softmax_item(1, 0, nv1, true);
-                consume_item(0, 0, gt & 1);
-                softmax_item(0, 1, nv0, true);
-                consume_item(1, 0, gt & 1);
-                softmax_item(1, 1, nv1, it + 1 < ntiles || more_work);
-                consume_item(0, 1, gt & 1);
-            }
-            consume_item(1, 1, (gt - 1) & 1);
-#pragma unroll
-            for (int half = 0; half < 2; ++half)
-#pragma unroll
-                for (int pp = 0; pp < 2; ++pp) {
-                    const int h = 2 * (g + 2 * pp) + (row >> 6);
-                    float* dst = P.part + (((size_t)cloud * (2 * P.nsplit) + 2 * split + half) * TH + h) * 10 * TM + (row & 63);
-                    dst[0] = m_run[half][pp];
-                    dst[TM] = l_run[half][pp];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[(2 + j) * TM] = acc[half][pp][j];
-                }
-        }
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 12) tmem_dealloc(tb, 512);
-}
 
 // Rare path of mab_reduce5_tc_kernel for one 64-column item of a row (ragged last tile, or a row whose scores outgrew
 // its reference exponent): everything goes through TMEM in 16-column steps so that no register state of the caller is
@@ -1390,11 +548,13 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_work = P.n_work, wstep = gridDim.x;
-    auto work_tiles = [&](int w, int& cloud, int& split, int& tile0) {
+    // tiles of work item w; nb = valid points of its cloud (variable-size sets: rows past nb are padding)
+    auto work_tiles = [&](int w, int& cloud, int& split, int& tile0, int& nb) {
         cloud = w / P.nsplit;
         split = w - cloud * P.nsplit;
         tile0 = split * P.tiles_per_split;
-        return min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+        nb = P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N;
+        return max(0, min((nb + 127) >> 7, tile0 + P.tiles_per_split) - tile0);
     };
 
     copy_to_smem(sAq, P.Aq, 16384);
@@ -1434,14 +594,14 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
             int gt = 0;                                    // tiles processed by this CTA so far
             uint32_t ph_p = 0;                             // phase of this chain's p_ready barrier
             for (int w = blockIdx.x; w < n_work; w += wstep) {
-                int cloud, split, tile0;
-                const int ntiles = work_tiles(w, cloud, split, tile0);
+                int cloud, split, tile0, nb;
+                const int ntiles = work_tiles(w, cloud, split, tile0, nb);
                 for (int it = 0; it < ntiles; ++it, ++gt) {
                     const uint32_t kbase = kvb + (gt & 1) * 32768, vbase = kbase + 16384;
                     mbar_wait(&kv_full[gt & 1], (gt >> 1) & 1);
                     fence_after_sync();
                     // a half without valid points (ragged last tile) is skipped by the chain and by its warpgroup alike
-                    const bool empty_half = P.N - (tile0 + it) * 128 <= 64 * half;
+                    const bool empty_half = nb - (tile0 + it) * 128 <= 64 * half;
 #pragma unroll
                     for (int pp = 0; pp < 2; ++pp) {
                         if (empty_half) break;
@@ -1469,12 +629,12 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
         const int row = 32 * quad + lane;
         int gt = 0;
         for (int w = blockIdx.x; w < n_work; w += wstep) {
-            int cloud, split, tile0;
-            const int ntiles = work_tiles(w, cloud, split, tile0);
+            int cloud, split, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, split, tile0, nb);
             for (int it = 0; it < ntiles; ++it, ++gt) {
                 const int stage = gt & 1;
                 const int n = (tile0 + it) * 128 + row;
-                const bool valid = n < P.N;
+                const bool valid = n < nb;
                 uint8_t* sK = sKV + stage * 32768;
                 uint8_t* sV = sK + 16384;
                 if (!DIN64) {
@@ -1626,10 +786,14 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
             warp_arrive(&p_ready[c]);
         };
         for (int w = blockIdx.x; w < n_work; w += wstep) {
-            int cloud, split, tile0;
-            const int ntiles = work_tiles(w, cloud, split, tile0);
+            int cloud, split, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, split, tile0, nb);
+#pragma unroll
+            for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+                for (int b2 = 0; b2 < 2; ++b2) { m_used[a2][b2] = -INFINITY; l_run[a2][b2] = 0.f; }     // a split may hold no tile of a short cloud
             for (int it = 0; it < ntiles; ++it) {
-                const int n_valid = min(128, P.N - (tile0 + it) * 128);
+                const int n_valid = min(128, nb - (tile0 + it) * 128);
                 const int nv0 = min(64, n_valid), nv1 = max(0, n_valid - 64);
                 const bool first = it == 0;
                 softmax_item(0, 0, nv0, first);
@@ -1663,1052 +827,6 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
     fence_before_sync();
     __syncthreads();
     if (warp == 12) tmem_dealloc(tb, 512);
-}
-
-// TMEM columns (apply): 4 x 64 half-buffers | 4 x 16 pair outputs | 64 fc_o | 2 x 64 Q projection
-constexpr uint32_t A2_S = 0, A2_O = 256, A2_F = 320, A2_QP = 384;
-
-struct A2Smem {
-    static constexpr int IMG = 0;                 // 2 x (K image 16384 | V image 16384), one per work item in flight
-    static constexpr int WO = 65536;
-    static constexpr int WQ = WO + 8192;
-    static constexpr int AQ = WQ + 8192;          // 2 stages x 16384
-    static constexpr int YA = AQ + 32768;
-    static constexpr int O1 = YA + 16384;
-    static constexpr int SMALL = O1 + 16384;      // fp32: Wq32 padded (64 x 4) | bq (64) | bo (64)
-    static constexpr int BARS = SMALL + (64 * 4 + 128) * 4;
-    static constexpr int TOTAL = BARS + 40 * 8 + 16;
-};
-
-// Persistent like the reduce kernel: one CTA per SM walks the work items (cloud, point-split); the per-cloud
-// K / V operand images of the next work item are staged while the current one is still being processed.
-template <bool DIN64>
-__global__ void __launch_bounds__(TC_THREADS16, 1) mab_apply2_tc_kernel(const AParams P) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sImg = smem + A2Smem::IMG;
-    uint8_t* sWo = smem + A2Smem::WO;
-    uint8_t* sWq = smem + A2Smem::WQ;
-    uint8_t* sAQ = smem + A2Smem::AQ;
-    uint8_t* sYA = smem + A2Smem::YA;
-    uint8_t* sO1 = smem + A2Smem::O1;
-    float* sWq32 = reinterpret_cast<float*>(smem + A2Smem::SMALL);
-    float* sBq = sWq32 + 64 * 4;
-    float* sBo = sBq + 64;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A2Smem::BARS);
-    uint64_t* aq_full = bars;          // [2] count 4
-    uint64_t* aq_empty = bars + 2;     // [2] count 4
-    uint64_t* s_full = bars + 4;       // [4] count 1
-    uint64_t* p_ready = bars + 8;      // [4] count 4
-    uint64_t* o_full = bars + 12;      // [4] count 1
-    uint64_t* o1_ready = bars + 16;    // count 8
-    uint64_t* f_full = bars + 17;      // count 1
-    uint64_t* ya_full = bars + 18;     // count 4
-    uint64_t* qp_done = bars + 19;     // count 1
-    uint64_t* qp_free = bars + 20;     // [2] count 8
-    uint64_t* pv0_done = bars + 22;    // [4] count 1
-    uint64_t* img_full = bars + 26;    // [2] count 4 (producer warps)
-    uint64_t* img_empty = bars + 28;   // [2] count 4 (chains)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_work = P.n_work, wstep = gridDim.x;
-    auto work_tiles = [&](int w, int& cloud, int& tile0) {
-        cloud = w / P.nsplit;
-        const int split = w - cloud * P.nsplit;
-        tile0 = split * P.tiles_per_split;
-        return min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
-    };
-
-    copy_to_smem(sWo, P.Wo16, 8192);
-    if (DIN64) copy_to_smem(sWq, P.Wq16, 8192);
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
-        sBq[i] = P.bq[i];
-        sBo[i] = P.bo[i];
-        if (!DIN64) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) sWq32[i * 4 + k] = (k < P.d_in) ? P.Wq32[i * P.d_in + k] : 0.f;
-        }
-    }
-    if (warp == 12) tmem_alloc(tmem_slot, 512);
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&aq_full[i], 4); mbar_init(&aq_empty[i], 4); mbar_init(&qp_free[i], 8);
-            mbar_init(&img_full[i], 4); mbar_init(&img_empty[i], 4);
-        }
-        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); mbar_init(&pv0_done[i], 1); }
-        mbar_init(o1_ready, 8);
-        mbar_init(f_full, 1);
-        mbar_init(ya_full, 4);
-        mbar_init(qp_done, 1);
-        fence_barrier_init();
-    }
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tb = *tmem_slot;
-
-    if (warp >= 12) {
-        reg_dec<40>();
-        if (lane == 0) {
-            // =================================================================== one MMA-issuing thread per chain
-            // chain c = warp - 12 <-> head hh = c & 1 of the pairs (c >> 1) + 2 pp.  The two heads of a pair share the
-            // pair's 16 output columns: hh = 0 writes (accumulate off), hh = 1 accumulates after pv0_done.
-            const int c = warp - 12, hh = c & 1;
-            const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
-            const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
-            const uint32_t idesc_64 = idesc_bf16(128, 64, 0, 0);
-            const uint32_t img = smem_u32(sImg), wo = smem_u32(sWo);
-            const uint32_t aqb = smem_u32(sAQ), o1b = smem_u32(sO1);
-            auto issue_f = [&](int tile_parity) {          // fc_o of a tile once both warpgroups have staged O1
-                mbar_wait(o1_ready, tile_parity);
-                fence_after_sync();
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma_ss(tmem_addr(tb, 0, A2_F), smem_desc(o1b + ks * 4096, 2048, 128), smem_desc(wo + ks * 2048, 1024, 128),
-                           idesc_64, ks > 0);
-                mma_commit(f_full);
-            };
-            int gt = 0, wl = 0;
-            for (int w = blockIdx.x; w < n_work; w += wstep, ++wl) {
-                int cloud, tile0;
-                const int ntiles = work_tiles(w, cloud, tile0);
-                const uint32_t kb = img + (wl & 1) * 32768, vb = kb + 16384;
-                mbar_wait(&img_full[wl & 1], (wl >> 1) & 1);
-                fence_after_sync();
-                for (int it = 0; it < ntiles; ++it, ++gt) {
-                    mbar_wait(&aq_full[gt & 1], (gt >> 1) & 1);
-                    fence_after_sync();
-#pragma unroll
-                    for (int pp = 0; pp < 2; ++pp) {
-                        const int p = (c >> 1) + 2 * pp;
-                        mma_ss(tmem_addr(tb, 0, A2_S + 64 * c), smem_desc(aqb + (gt & 1) * 16384 + 2 * p * 2048, 2048, 128),
-                               smem_desc(kb + p * 4096 + hh * 1024, 2048, 128), idesc_s, 0);
-                        mma_commit(&s_full[c]);
-                        if (pp == 0 && gt > 0) {
-                            // the pair outputs of the previous tile are consumed once its O1 is staged; chain 0 also
-                            // launches that tile's fc_o
-                            if (c == 0) issue_f((gt - 1) & 1);
-                            else { mbar_wait(o1_ready, (gt - 1) & 1); fence_after_sync(); }
-                        }
-                        mbar_wait(&p_ready[c], pp);
-                        fence_after_sync();
-                        if (hh == 1) { mbar_wait(&pv0_done[p], gt & 1); fence_after_sync(); }
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ts(tmem_addr(tb, 0, A2_O + 16 * p), tmem_addr(tb, 0, A2_S + 64 * c + ks * 8),
-                                   smem_desc(vb + p * 4096 + hh * 1024 + ks * 256, 128, 2048), idesc_pv, (hh == 1 || ks > 0) ? 1u : 0u);
-                        mma_commit(hh == 0 ? &pv0_done[p] : &o_full[p]);
-                    }
-                    mma_commit(&aq_empty[gt & 1]);          // 4 chains x 1 arrival free the query stage
-                }
-                mma_commit(&img_empty[wl & 1]);             // ... and the K / V images of this work item
-            }
-            if (c == 0 && gt > 0) issue_f((gt - 1) & 1);
-        }
-    } else if (warp >= 8) {
-        reg_dec<88>();
-        // =================================================================== producer: images + scaled query operand
-        const int quad = warp & 3;
-        const int row = 32 * quad + lane;
-        const int ptid = threadIdx.x - 256;          // 0..127
-        int gt = 0, wl = 0;
-        for (int w = blockIdx.x; w < n_work; w += wstep, ++wl) {
-            int cloud, tile0;
-            const int ntiles = work_tiles(w, cloud, tile0);
-            {   // stage this cloud's block-diagonal K / V images (32 KB)
-                if (wl >= 2) mbar_wait(&img_empty[wl & 1], ((wl >> 1) - 1) & 1);
-                const uint4* src = reinterpret_cast<const uint4*>(P.KVblk + (size_t)cloud * 32768);
-                uint4* dst = reinterpret_cast<uint4*>(sImg + (wl & 1) * 32768);
-#pragma unroll 4
-                for (int i = ptid; i < 2048; i += 128) dst[i] = __ldg(src + i);
-                fence_async_smem();
-                fence_before_sync();
-                warp_arrive(&img_full[wl & 1]);
-            }
-            for (int it = 0; it < ntiles; ++it, ++gt) {
-                const int stage = gt & 1;
-                const int n = (tile0 + it) * 128 + row;
-                const bool valid = n < P.N;
-                uint8_t* dst = sAQ + stage * 16384;
-                if (!DIN64) {
-                    float x[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (valid) {
-                        const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
-                        for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
-                    }
-                    if (gt >= 2) mbar_wait(&aq_empty[stage], ((gt >> 1) - 1) & 1);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        float o[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 wv = *reinterpret_cast<const float4*>(sWq32 + (c * 8 + j) * 4);
-                            const float q = fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBq[c * 8 + j]))));
-                            o[j] = valid ? q * kScaleLog2e : 0.f;
-                        }
-                        st_shared_8bf16(dst + c * 2048 + row * 16, o);
-                    }
-                } else {
-                    const uint4* src = reinterpret_cast<const uint4*>(P.Y16in + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
-                    uint4 yv[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sYA + c * 2048 + row * 16) = yv[c];
-                    fence_async_smem();
-                    fence_before_sync();
-                    warp_arrive(ya_full);
-                    if (warp == 8 && lane == 0) {
-                        // one producer thread issues the Q projection MMA (its TMEM buffer must have been read by the
-                        // epilogue of two tiles ago)
-                        mbar_wait(ya_full, gt & 1);
-                        if (gt >= 2) mbar_wait(&qp_free[gt & 1], ((gt >> 1) - 1) & 1);
-                        fence_after_sync();
-                        const uint32_t yab = smem_u32(sYA), wq = smem_u32(sWq);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ss(tmem_addr(tb, 0, A2_QP + 64 * (gt & 1)), smem_desc(yab + ks * 4096, 2048, 128),
-                                   smem_desc(wq + ks * 2048, 1024, 128), idesc_bf16(128, 64, 0, 0), ks > 0);
-                        mma_commit(qp_done);
-                    }
-                    mbar_wait(qp_done, gt & 1);
-                    fence_after_sync();
-                    if (gt >= 2) mbar_wait(&aq_empty[stage], ((gt >> 1) - 1) & 1);
-#pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_addr(tb, 32 * quad, A2_QP + 64 * (gt & 1) + c0), v);
-                        tmem_ld_wait32(v);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float o[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                o[j] = valid ? (__uint_as_float(v[8 * q + j]) + sBq[c0 + 8 * q + j]) * kScaleLog2e : 0.f;
-                            st_shared_8bf16(dst + (c0 / 8 + q) * 2048 + row * 16, o);
-                        }
-                    }
-                }
-                fence_async_smem();
-                fence_before_sync();
-                warp_arrive(&aq_full[stage]);
-            }
-        }
-    } else {
-        reg_inc<184>();
-        // =================================================================== softmax + epilogue warpgroups
-        const int g = warp >> 2, quad = warp & 3;
-        const int row = 32 * quad + lane;
-        const uint32_t lane_base = 32 * quad;
-        uint32_t ph_s[2] = {0, 0};
-        float o1[2][16];                 // O1 of the tile whose fc_o is in flight (features 16p.. of the two pairs)
-        float inv_l[2][2] = {{1.f, 1.f}, {1.f, 1.f}};
-        uint32_t va[32], vb[32];
-        // the tile whose fc_o epilogue is still pending (deferred behind the next tile's first softmax item)
-        __nv_bfloat16* pend_dst = nullptr;   // output row of this thread, nullptr = padding row
-        bool pend_live = false, pend_any = false;
-        int pend_parity = 0;
-        int gt = 0;
-#ifdef PCA_TIMELINE
-        long long* tl = (P.timeline != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0) ? P.timeline : nullptr;
-        int tl_n = 0;
-        auto stamp = [&](int tag) {
-            if (tl != nullptr && tl_n < 4000) { tl[2 * tl_n] = tag; tl[2 * tl_n + 1] = clock64(); ++tl_n; }
-        };
-#else
-        auto stamp = [&](int) {};
-#endif
-
-        auto issue_loads = [&](const int hh, const bool live) {
-            const int c = 2 * g + hh;
-            mbar_wait(&s_full[c], ph_s[hh]);
-            ph_s[hh] ^= 1;
-            fence_after_sync();
-            if (live) {
-                const uint32_t sb = tmem_addr(tb, lane_base, A2_S + 64 * c);
-                tmem_ld32(sb, va);
-                tmem_ld32(sb + 32, vb);
-            }
-        };
-        // softmax over the 64 keys of one head; the next item's scores (other chain) are prefetched meanwhile
-        auto softmax_item = [&](const int hh, const int pp, const bool live, const bool has_next) {
-            const int c = 2 * g + hh, cn = 2 * g + (hh ^ 1);
-            const uint32_t sbase = tmem_addr(tb, lane_base, A2_S + 64 * c);
-            const uint32_t snext = tmem_addr(tb, lane_base, A2_S + 64 * cn);
-            if (live) {
-                uint32_t pk[16];
-                stamp(0);
-                tmem_ld_wait64(va, vb);
-                stamp(1);
-                const float mx = max64(va, vb);
-                const float2 neg2 = make_float2(-mx, -mx);
-                float2 sum2 = make_float2(0.f, 0.f);
-                exp_chunk32(va, neg2, sum2, pk);
-                tmem_st16(sbase, pk);
-                stamp(2);
-                if (has_next) {
-                    mbar_wait(&s_full[cn], ph_s[hh ^ 1]);
-                    ph_s[hh ^ 1] ^= 1;
-                    fence_after_sync();
-                    tmem_ld32(snext, va);
-                }
-                stamp(3);
-                exp_chunk32(vb, neg2, sum2, pk);
-                tmem_st16(sbase + 16, pk);
-                if (has_next) tmem_ld32(snext + 32, vb);
-                inv_l[pp][hh] = __fdividef(1.f, sum2.x + sum2.y);
-                stamp(4);
-                tmem_st_wait();
-                stamp(5);
-            } else if (has_next) {
-                mbar_wait(&s_full[cn], ph_s[hh ^ 1]);
-                ph_s[hh ^ 1] ^= 1;
-                fence_after_sync();
-            }
-            fence_before_sync();
-            warp_arrive(&p_ready[c]);
-            stamp(6);
-        };
-        // Y = O1 + relu(fc_o(O1) + bo) for the pending tile (its O1 is held in o1[][])
-        auto f_epilogue = [&]() {
-            stamp(12);
-            mbar_wait(f_full, pend_parity);
-            stamp(13);
-            fence_after_sync();
-            if (pend_live) {
-#pragma unroll
-                for (int pp = 0; pp < 2; ++pp) {
-                    const int p = g + 2 * pp;
-                    uint32_t fv[16];
-                    tmem_ld16(tmem_addr(tb, lane_base, A2_F + 16 * p), fv);
-                    tmem_ld_wait16(fv);
-                    uint4 out[2];
-                    uint32_t* ow = reinterpret_cast<uint32_t*>(out);
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        const float y0 = o1[pp][j] + fmaxf(__uint_as_float(fv[j]) + sBo[16 * p + j], 0.f);
-                        const float y1 = o1[pp][j + 1] + fmaxf(__uint_as_float(fv[j + 1]) + sBo[16 * p + j + 1], 0.f);
-                        ow[j >> 1] = pack_bf16(y0, y1);
-                    }
-                    if (pend_dst != nullptr) {
-                        uint4* dst = reinterpret_cast<uint4*>(pend_dst + 16 * p);
-                        dst[0] = out[0];
-                        dst[1] = out[1];
-                    }
-                }
-            }
-            fence_before_sync();
-            pend_any = false;
-            stamp(14);
-        };
-        for (int w = blockIdx.x; w < n_work; w += wstep) {
-            int cloud, tile0;
-            const int ntiles = work_tiles(w, cloud, tile0);
-            for (int it = 0; it < ntiles; ++it, ++gt) {
-                const int n = (tile0 + it) * 128 + row;
-                const bool valid = n < P.N;
-                const bool live = (tile0 + it) * 128 + 32 * quad < P.N;     // warps whose 32 rows are all padding idle
-                stamp(15);
-                issue_loads(0, live);
-                stamp(16);
-                softmax_item(0, 0, live, true);
-                if (pend_any) f_epilogue();              // deferred: the fc_o round trip hides behind the first softmax
-                softmax_item(1, 0, live, true);
-                softmax_item(0, 1, live, true);
-                softmax_item(1, 1, live, false);
-                // ---- O1 = Qp + (P V) / l, features 16p .. 16p+15 for this warpgroup's two pairs
-                float x[4] = {0.f, 0.f, 0.f, 0.f};
-                if (!DIN64 && valid) {
-                    const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
-                    for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
-                }
-#pragma unroll
-                for (int pp = 0; pp < 2; ++pp) {
-                    const int p = g + 2 * pp;
-                    mbar_wait(&o_full[p], gt & 1);
-                    stamp(7 + 2 * pp);
-                    fence_after_sync();
-                    if (live) {
-                        uint32_t o[16], qv[16];
-                        tmem_ld16(tmem_addr(tb, lane_base, A2_O + 16 * p), o);
-                        if (DIN64) tmem_ld16(tmem_addr(tb, lane_base, A2_QP + 64 * (gt & 1) + 16 * p), qv);
-                        tmem_ld_wait16(o);
-                        if (DIN64) tmem_ld_wait16(qv);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int f = 16 * p + j;
-                            float q;
-                            if (DIN64) {
-                                q = __uint_as_float(qv[j]) + sBq[f];
-                            } else {
-                                const float4 wv = *reinterpret_cast<const float4*>(sWq32 + f * 4);
-                                q = fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBq[f]))));
-                            }
-                            o1[pp][j] = q + __uint_as_float(o[j]) * inv_l[pp][j >> 3];
-                        }
-                        st_shared_8bf16(sO1 + (2 * p) * 2048 + row * 16, &o1[pp][0]);
-                        st_shared_8bf16(sO1 + (2 * p + 1) * 2048 + row * 16, &o1[pp][8]);
-                    }
-                    stamp(8 + 2 * pp);
-                }
-                if (DIN64) {
-                    fence_before_sync();
-                    warp_arrive(&qp_free[gt & 1]);
-                }
-                fence_async_smem();
-                fence_before_sync();
-                warp_arrive(o1_ready);
-                stamp(11);
-                pend_any = true;
-                pend_live = live;
-                pend_parity = gt & 1;
-                pend_dst = valid ? P.Yout + ((size_t)cloud * P.N + n) * 64 : nullptr;
-            }
-        }
-        if (pend_any) f_epilogue();
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 12) tmem_dealloc(tb, 512);
-}
-
-// ====================================================================================== 24-warp variants
-constexpr int TC_THREADS24 = 24 * 32;
-
-// 24-warp variant (16 softmax warps = 4 warpgroups, one chain each; 4 producer warps; 4 MMA threads): twice the
-// softmax warps per SM sub-partition hide the fixed latency of the per-item barrier / TMEM round trips.
-// Persistent: grid = min(#work items, #SMs); CTA k walks the work items (cloud, point-split) k, k + grid, ...
-// Barriers, TMEM and the resident operands are set up once; all pipelines (producer -> MMA -> softmax) run
-// straight across work-item boundaries, so there is no per-cloud fill/drain bubble.
-template <bool DIN64>
-__global__ void __launch_bounds__(TC_THREADS24, 1) mab_reduce4_tc_kernel(const RParams P) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sAq = smem + R2Smem::AQ;
-    uint8_t* sKV = smem + R2Smem::KV;
-    uint8_t* sW = smem + R2Smem::W;
-    uint8_t* sY = smem + R2Smem::Y;
-    float* sWsm = reinterpret_cast<float*>(smem + R2Smem::SMALL);
-    float* sBias = sWsm + 128 * 4;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + R2Smem::BARS);
-    uint64_t* kv_full = bars;          // [2] count 4 (producer warps)
-    uint64_t* kv_empty = bars + 2;     // [2] count 4 (chains)
-    uint64_t* s_full = bars + 4;       // [4] count 1
-    uint64_t* p_ready = bars + 8;      // [4] count 4 (warps of the owning warpgroup)
-    uint64_t* o_full = bars + 12;      // [8] count 1   (region = 2 * pair + half)
-    uint64_t* y_full = bars + 20;      // count 4
-    uint64_t* proj_done = bars + 21;   // count 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_work = P.n_work, wstep = gridDim.x;
-    auto work_tiles = [&](int w, int& cloud, int& split, int& tile0) {
-        cloud = w / P.nsplit;
-        split = w - cloud * P.nsplit;
-        tile0 = split * P.tiles_per_split;
-        return min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
-    };
-
-    copy_to_smem(sAq, P.Aq, 16384);
-    if (DIN64) copy_to_smem(sW, P.Wkv16, 16384);
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
-        sBias[i] = P.bkv[i];
-        if (!DIN64) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) sWsm[i * 4 + k] = (k < P.d_in) ? P.Wkv32[i * P.d_in + k] : 0.f;
-        }
-    }
-    if (warp == 20) tmem_alloc(tmem_slot, 512);
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 4); mbar_init(&kv_empty[i], 4); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
-        for (int i = 0; i < 8; ++i) mbar_init(&o_full[i], 1);
-        mbar_init(y_full, 4);
-        mbar_init(proj_done, 1);
-        fence_barrier_init();
-    }
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tb = *tmem_slot;
-
-    if (warp >= 20) {
-        reg_dec<24>();
-        if (lane == 0) {
-            // =================================================================== one MMA-issuing thread per chain
-            // chain c = warp - 12: strictly serial  Q K^T -> (warpgroup softmax) -> P V -> next Q K^T  on its own
-            // half-buffer; the four chains never wait on each other.
-            const int c = warp - 20, half = c & 1;
-            const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
-            const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
-            const uint32_t aq = smem_u32(sAq), kvb = smem_u32(sKV);
-            int gt = 0;                                    // tiles processed by this CTA so far
-            for (int w = blockIdx.x; w < n_work; w += wstep) {
-                int cloud, split, tile0;
-                const int ntiles = work_tiles(w, cloud, split, tile0);
-                for (int it = 0; it < ntiles; ++it, ++gt) {
-                    const uint32_t kbase = kvb + (gt & 1) * 32768, vbase = kbase + 16384;
-                    mbar_wait(&kv_full[gt & 1], (gt >> 1) & 1);
-                    fence_after_sync();
-#pragma unroll
-                    for (int pp = 0; pp < 2; ++pp) {
-                        const int p = (c >> 1) + 2 * pp;
-                        mma_ss(tmem_addr(tb, 0, R2_S + 64 * c), smem_desc(aq + p * 4096, 2048, 128),
-                               smem_desc(kbase + 2 * p * 2048 + half * 1024, 2048, 128), idesc_s, 0);
-                        mma_commit(&s_full[c]);
-                        mbar_wait(&p_ready[c], pp);          // two items per tile: parities 0, 1
-                        fence_after_sync();
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)       // P columns 32..63: keys 32..63 first, then keys 0..31
-                            mma_ts(tmem_addr(tb, 0, R2_O + 16 * (2 * p + half)), tmem_addr(tb, 0, R2_S + 64 * c + 32 + ks * 8),
-                                   smem_desc(vbase + 2 * p * 2048 + half * 1024 + ((ks + 2) & 3) * 256, 128, 2048), idesc_pv, ks > 0);
-                        mma_commit(&o_full[2 * p + half]);
-                    }
-                    mma_commit(&kv_empty[gt & 1]);            // 4 chains x 1 arrival free the K|V stage
-                }
-            }
-        }
-    } else if (warp >= 16) {
-        reg_dec<56>();
-        // =================================================================== producer: K|V tiles
-        const int quad = warp & 3;
-        const int row = 32 * quad + lane;
-        int gt = 0;
-        for (int w = blockIdx.x; w < n_work; w += wstep) {
-            int cloud, split, tile0;
-            const int ntiles = work_tiles(w, cloud, split, tile0);
-            for (int it = 0; it < ntiles; ++it, ++gt) {
-                const int stage = gt & 1;
-                const int n = (tile0 + it) * 128 + row;
-                const bool valid = n < P.N;
-                uint8_t* sK = sKV + stage * 32768;
-                uint8_t* sV = sK + 16384;
-                if (!DIN64) {
-                    float x[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (valid) {
-                        const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
-                        for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
-                    }
-                    if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
-#pragma unroll 4
-                    for (int c = 0; c < 16; ++c) {
-                        float o[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 wv = *reinterpret_cast<const float4*>(sWsm + (c * 8 + j) * 4);
-                            o[j] = valid ? fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBias[c * 8 + j])))) : 0.f;
-                        }
-                        st_shared_8bf16((c < 8 ? sK + c * 2048 : sV + (c - 8) * 2048) + row * 16, o);
-                    }
-                } else {
-                    const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
-                    uint4 yv[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sY + c * 2048 + row * 16) = yv[c];
-                    fence_async_smem();
-                    fence_before_sync();
-                    warp_arrive(y_full);
-                    if (warp == 16 && lane == 0) {
-                        // one producer thread issues the K|V projection MMA once all 128 rows of Y are staged
-                        mbar_wait(y_full, gt & 1);
-                        fence_after_sync();
-                        const uint32_t yb = smem_u32(sY), wb = smem_u32(sW);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ss(tmem_addr(tb, 0, R2_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
-                                   idesc_bf16(128, 128, 0, 0), ks > 0);
-                        mma_commit(proj_done);
-                    }
-                    mbar_wait(proj_done, gt & 1);
-                    fence_after_sync();
-                    if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
-#pragma unroll
-                    for (int c0 = 0; c0 < 128; c0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_addr(tb, 32 * quad, R2_PROJ + c0), v);
-                        tmem_ld_wait32(v);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float o[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = valid ? __uint_as_float(v[8 * q + j]) + sBias[c0 + 8 * q + j] : 0.f;
-                            const int chunk = c0 / 8 + q;
-                            st_shared_8bf16((chunk < 8 ? sK + chunk * 2048 : sV + (chunk - 8) * 2048) + row * 16, o);
-                        }
-                    }
-                }
-                fence_async_smem();
-                fence_before_sync();
-                warp_arrive(&kv_full[stage]);
-            }
-        }
-    } else {
-        reg_inc<96>();
-        // =================================================================== softmax warpgroups (one chain each)
-        const int c = warp >> 2, quad = warp & 3;          // chain c: half = c & 1 of the pairs (c >> 1) + 2 pp
-        const int half = c & 1, g = c >> 1;
-        const int row = 32 * quad + lane;
-        const uint32_t lane_base = 32 * quad;
-        const uint32_t ocol_off = (row >= 64) ? 8u : 0u;
-        const uint32_t sbase = tmem_addr(tb, lane_base, R2_S + 64 * c);
-        float m_run[2], l_run[2], alpha[2], acc[2][8];
-        uint32_t ph_s = 0;
-        int gt = 0;
-
-        // One 64-key item with 32 live score registers: pass over keys 0..31 (max), keys 32..63 (max, kept), then
-        // probabilities of keys 32..63, reload keys 0..31, their probabilities.  P occupies columns 32..63 of the
-        // half-buffer in that order (the MMA thread feeds V rows in the matching order).
-        auto softmax_item = [&](const int pp, const int nv) {
-            mbar_wait(&s_full[c], ph_s);
-            ph_s ^= 1;
-            fence_after_sync();
-            uint32_t v[32], pk[16];
-            tmem_ld32(sbase, v);
-            tmem_ld_wait32(v);
-            if (nv == 64) {
-                const float mA = max_chunk32(v, -INFINITY);
-                tmem_ld32(sbase + 32, v);
-                tmem_ld_wait32(v);
-                const float m_new = fmaxf(m_run[pp], max_chunk32(v, mA));
-                alpha[pp] = ex2(m_run[pp] - m_new);
-                const float2 neg2 = make_float2(-m_new, -m_new);
-                float2 sum2 = make_float2(0.f, 0.f);
-                exp_chunk32(v, neg2, sum2, pk);
-                tmem_st16(sbase + 32, pk);
-                tmem_ld32(sbase, v);
-                tmem_ld_wait32(v);
-                exp_chunk32(v, neg2, sum2, pk);
-                tmem_st16(sbase + 48, pk);
-                l_run[pp] = l_run[pp] * alpha[pp] + (sum2.x + sum2.y);
-                m_run[pp] = m_new;
-            } else {
-                // ragged tail: keys >= nv are padding (nv may be 0: the half contributes nothing)
-                float mx = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < nv) mx = fmaxf(mx, __uint_as_float(v[j]));
-                tmem_ld32(sbase + 32, v);
-                tmem_ld_wait32(v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (32 + j < nv) mx = fmaxf(mx, __uint_as_float(v[j]));
-                const float m_new = fmaxf(m_run[pp], mx);
-                alpha[pp] = (m_new == -INFINITY) ? 1.f : ex2(m_run[pp] - m_new);
-                float sum = 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float p0 = (32 + j < nv) ? ex2(__uint_as_float(v[j]) - m_new) : 0.f;
-                    const float p1 = (33 + j < nv) ? ex2(__uint_as_float(v[j + 1]) - m_new) : 0.f;
-                    sum += p0 + p1;
-                    pk[j >> 1] = pack_bf16(p0, p1);
-                }
-                tmem_st16(sbase + 32, pk);
-                tmem_ld32(sbase, v);
-                tmem_ld_wait32(v);
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float p0 = (j < nv) ? ex2(__uint_as_float(v[j]) - m_new) : 0.f;
-                    const float p1 = (j + 1 < nv) ? ex2(__uint_as_float(v[j + 1]) - m_new) : 0.f;
-                    sum += p0 + p1;
-                    pk[j >> 1] = pack_bf16(p0, p1);
-                }
-                tmem_st16(sbase + 48, pk);
-                l_run[pp] = l_run[pp] * alpha[pp] + sum;
-                m_run[pp] = m_new;
-            }
-            tmem_st_wait();
-            fence_before_sync();
-            warp_arrive(&p_ready[c]);
-        };
-        auto consume_item = [&](const int pp, const int tile_parity) {
-            const int p = g + 2 * pp;
-            mbar_wait(&o_full[2 * p + half], tile_parity);
-            fence_after_sync();
-            uint32_t o[8];
-            tmem_ld8(tmem_addr(tb, lane_base, R2_O + 16 * (2 * p + half) + ocol_off), o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[pp][j] = fmaf(acc[pp][j], alpha[pp], __uint_as_float(o[j]));
-        };
-        for (int w = blockIdx.x; w < n_work; w += wstep) {
-            int cloud, split, tile0;
-            const int ntiles = work_tiles(w, cloud, split, tile0);
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                m_run[a] = -INFINITY; l_run[a] = 0.f; alpha[a] = 0.f;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
-            }
-            for (int it = 0; it < ntiles; ++it, ++gt) {
-                const int n_valid = min(128, P.N - (tile0 + it) * 128);
-                const int nv = half == 0 ? min(64, n_valid) : max(0, n_valid - 64);
-                softmax_item(0, nv);
-                if (it > 0) consume_item(1, (gt - 1) & 1);
-                softmax_item(1, nv);
-                consume_item(0, gt & 1);
-            }
-            consume_item(1, (gt - 1) & 1);
-#pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-                const int h = 2 * (g + 2 * pp) + (row >> 6);
-                float* dst = P.part + (((size_t)cloud * (2 * P.nsplit) + 2 * split + half) * TH + h) * 10 * TM + (row & 63);
-                dst[0] = m_run[pp];
-                dst[TM] = l_run[pp];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) dst[(2 + j) * TM] = acc[pp][j];
-            }
-        }
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 20) tmem_dealloc(tb, 512);
-}
-
-// 24-warp variant of the apply kernel (see mab_reduce4_tc_kernel).
-// Persistent like the reduce kernel: one CTA per SM walks the work items (cloud, point-split); the per-cloud
-// K / V operand images of the next work item are staged while the current one is still being processed.
-template <bool DIN64>
-__global__ void __launch_bounds__(TC_THREADS24, 1) mab_apply4_tc_kernel(const AParams P) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sImg = smem + A2Smem::IMG;
-    uint8_t* sWo = smem + A2Smem::WO;
-    uint8_t* sWq = smem + A2Smem::WQ;
-    uint8_t* sAQ = smem + A2Smem::AQ;
-    uint8_t* sYA = smem + A2Smem::YA;
-    uint8_t* sO1 = smem + A2Smem::O1;
-    float* sWq32 = reinterpret_cast<float*>(smem + A2Smem::SMALL);
-    float* sBq = sWq32 + 64 * 4;
-    float* sBo = sBq + 64;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A2Smem::BARS);
-    uint64_t* aq_full = bars;          // [2] count 4
-    uint64_t* aq_empty = bars + 2;     // [2] count 4
-    uint64_t* s_full = bars + 4;       // [4] count 1
-    uint64_t* p_ready = bars + 8;      // [4] count 4
-    uint64_t* o_full = bars + 12;      // [4] count 1
-    uint64_t* o1_ready = bars + 16;    // count 8
-    uint64_t* f_full = bars + 17;      // count 1
-    uint64_t* ya_full = bars + 18;     // count 4
-    uint64_t* qp_done = bars + 19;     // count 1
-    uint64_t* qp_free = bars + 20;     // [2] count 8
-    uint64_t* pv0_done = bars + 22;    // [4] count 1
-    uint64_t* img_full = bars + 26;    // [2] count 4 (producer warps)
-    uint64_t* img_empty = bars + 28;   // [2] count 4 (chains)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_work = P.n_work, wstep = gridDim.x;
-    auto work_tiles = [&](int w, int& cloud, int& tile0) {
-        cloud = w / P.nsplit;
-        const int split = w - cloud * P.nsplit;
-        tile0 = split * P.tiles_per_split;
-        return min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
-    };
-
-    copy_to_smem(sWo, P.Wo16, 8192);
-    if (DIN64) copy_to_smem(sWq, P.Wq16, 8192);
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
-        sBq[i] = P.bq[i];
-        sBo[i] = P.bo[i];
-        if (!DIN64) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) sWq32[i * 4 + k] = (k < P.d_in) ? P.Wq32[i * P.d_in + k] : 0.f;
-        }
-    }
-    if (warp == 20) tmem_alloc(tmem_slot, 512);
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&aq_full[i], 4); mbar_init(&aq_empty[i], 4); mbar_init(&qp_free[i], 16);
-            mbar_init(&img_full[i], 4); mbar_init(&img_empty[i], 4);
-        }
-        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); mbar_init(&pv0_done[i], 1); }
-        mbar_init(o1_ready, 16);
-        mbar_init(f_full, 1);
-        mbar_init(ya_full, 4);
-        mbar_init(qp_done, 1);
-        fence_barrier_init();
-    }
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tb = *tmem_slot;
-
-    if (warp >= 20) {
-        reg_dec<24>();
-        if (lane == 0) {
-            // =================================================================== one MMA-issuing thread per chain
-            // chain c = warp - 12 <-> head hh = c & 1 of the pairs (c >> 1) + 2 pp.  The two heads of a pair share the
-            // pair's 16 output columns: hh = 0 writes (accumulate off), hh = 1 accumulates after pv0_done.
-            const int c = warp - 20, hh = c & 1;
-            const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
-            const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
-            const uint32_t idesc_64 = idesc_bf16(128, 64, 0, 0);
-            const uint32_t img = smem_u32(sImg), wo = smem_u32(sWo);
-            const uint32_t aqb = smem_u32(sAQ), o1b = smem_u32(sO1);
-            auto issue_f = [&](int tile_parity) {          // fc_o of a tile once both warpgroups have staged O1
-                mbar_wait(o1_ready, tile_parity);
-                fence_after_sync();
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma_ss(tmem_addr(tb, 0, A2_F), smem_desc(o1b + ks * 4096, 2048, 128), smem_desc(wo + ks * 2048, 1024, 128),
-                           idesc_64, ks > 0);
-                mma_commit(f_full);
-            };
-            int gt = 0, wl = 0;
-            for (int w = blockIdx.x; w < n_work; w += wstep, ++wl) {
-                int cloud, tile0;
-                const int ntiles = work_tiles(w, cloud, tile0);
-                const uint32_t kb = img + (wl & 1) * 32768, vb = kb + 16384;
-                mbar_wait(&img_full[wl & 1], (wl >> 1) & 1);
-                fence_after_sync();
-                for (int it = 0; it < ntiles; ++it, ++gt) {
-                    mbar_wait(&aq_full[gt & 1], (gt >> 1) & 1);
-                    fence_after_sync();
-#pragma unroll
-                    for (int pp = 0; pp < 2; ++pp) {
-                        const int p = (c >> 1) + 2 * pp;
-                        mma_ss(tmem_addr(tb, 0, A2_S + 64 * c), smem_desc(aqb + (gt & 1) * 16384 + 2 * p * 2048, 2048, 128),
-                               smem_desc(kb + p * 4096 + hh * 1024, 2048, 128), idesc_s, 0);
-                        mma_commit(&s_full[c]);
-                        if (pp == 0 && gt > 0) {
-                            // the pair outputs of the previous tile are consumed once its O1 is staged; chain 0 also
-                            // launches that tile's fc_o
-                            if (c == 0) issue_f((gt - 1) & 1);
-                            else { mbar_wait(o1_ready, (gt - 1) & 1); fence_after_sync(); }
-                        }
-                        mbar_wait(&p_ready[c], pp);
-                        fence_after_sync();
-                        if (hh == 1) { mbar_wait(&pv0_done[p], gt & 1); fence_after_sync(); }
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)       // P columns 32..63: keys 32..63 first, then keys 0..31
-                            mma_ts(tmem_addr(tb, 0, A2_O + 16 * p), tmem_addr(tb, 0, A2_S + 64 * c + 32 + ks * 8),
-                                   smem_desc(vb + p * 4096 + hh * 1024 + ((ks + 2) & 3) * 256, 128, 2048), idesc_pv,
-                                   (hh == 1 || ks > 0) ? 1u : 0u);
-                        mma_commit(hh == 0 ? &pv0_done[p] : &o_full[p]);
-                    }
-                    mma_commit(&aq_empty[gt & 1]);          // 4 chains x 1 arrival free the query stage
-                }
-                mma_commit(&img_empty[wl & 1]);             // ... and the K / V images of this work item
-            }
-            if (c == 0 && gt > 0) issue_f((gt - 1) & 1);
-        }
-    } else if (warp >= 16) {
-        reg_dec<56>();
-        // =================================================================== producer: images + scaled query operand
-        const int quad = warp & 3;
-        const int row = 32 * quad + lane;
-        const int ptid = threadIdx.x - 512;          // 0..127
-        int gt = 0, wl = 0;
-        for (int w = blockIdx.x; w < n_work; w += wstep, ++wl) {
-            int cloud, tile0;
-            const int ntiles = work_tiles(w, cloud, tile0);
-            {   // stage this cloud's block-diagonal K / V images (32 KB)
-                if (wl >= 2) mbar_wait(&img_empty[wl & 1], ((wl >> 1) - 1) & 1);
-                const uint4* src = reinterpret_cast<const uint4*>(P.KVblk + (size_t)cloud * 32768);
-                uint4* dst = reinterpret_cast<uint4*>(sImg + (wl & 1) * 32768);
-#pragma unroll 4
-                for (int i = ptid; i < 2048; i += 128) dst[i] = __ldg(src + i);
-                fence_async_smem();
-                fence_before_sync();
-                warp_arrive(&img_full[wl & 1]);
-            }
-            for (int it = 0; it < ntiles; ++it, ++gt) {
-                const int stage = gt & 1;
-                const int n = (tile0 + it) * 128 + row;
-                const bool valid = n < P.N;
-                uint8_t* dst = sAQ + stage * 16384;
-                if (!DIN64) {
-                    float x[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (valid) {
-                        const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
-                        for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
-                    }
-                    if (gt >= 2) mbar_wait(&aq_empty[stage], ((gt >> 1) - 1) & 1);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        float o[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 wv = *reinterpret_cast<const float4*>(sWq32 + (c * 8 + j) * 4);
-                            const float q = fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBq[c * 8 + j]))));
-                            o[j] = valid ? q * kScaleLog2e : 0.f;
-                        }
-                        st_shared_8bf16(dst + c * 2048 + row * 16, o);
-                    }
-                } else {
-                    const uint4* src = reinterpret_cast<const uint4*>(P.Y16in + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
-                    uint4 yv[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sYA + c * 2048 + row * 16) = yv[c];
-                    fence_async_smem();
-                    fence_before_sync();
-                    warp_arrive(ya_full);
-                    if (warp == 16 && lane == 0) {
-                        // one producer thread issues the Q projection MMA (its TMEM buffer must have been read by the
-                        // epilogue of two tiles ago)
-                        mbar_wait(ya_full, gt & 1);
-                        if (gt >= 2) mbar_wait(&qp_free[gt & 1], ((gt >> 1) - 1) & 1);
-                        fence_after_sync();
-                        const uint32_t yab = smem_u32(sYA), wq = smem_u32(sWq);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ss(tmem_addr(tb, 0, A2_QP + 64 * (gt & 1)), smem_desc(yab + ks * 4096, 2048, 128),
-                                   smem_desc(wq + ks * 2048, 1024, 128), idesc_bf16(128, 64, 0, 0), ks > 0);
-                        mma_commit(qp_done);
-                    }
-                    mbar_wait(qp_done, gt & 1);
-                    fence_after_sync();
-                    if (gt >= 2) mbar_wait(&aq_empty[stage], ((gt >> 1) - 1) & 1);
-#pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_addr(tb, 32 * quad, A2_QP + 64 * (gt & 1) + c0), v);
-                        tmem_ld_wait32(v);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float o[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                o[j] = valid ? (__uint_as_float(v[8 * q + j]) + sBq[c0 + 8 * q + j]) * kScaleLog2e : 0.f;
-                            st_shared_8bf16(dst + (c0 / 8 + q) * 2048 + row * 16, o);
-                        }
-                    }
-                }
-                fence_async_smem();
-                fence_before_sync();
-                warp_arrive(&aq_full[stage]);
-            }
-        }
-    } else {
-        reg_inc<96>();
-        // =================================================================== softmax + epilogue warpgroups (one chain each)
-        const int c = warp >> 2, quad = warp & 3;          // chain c: head hh = c & 1 of the pairs (c >> 1) + 2 pp
-        const int hh = c & 1, g = c >> 1;
-        const int row = 32 * quad + lane;
-        const uint32_t lane_base = 32 * quad;
-        const uint32_t sbase = tmem_addr(tb, lane_base, A2_S + 64 * c);
-        uint32_t ph_s = 0;
-        float o1[2][8];                  // O1 of the tile whose fc_o is in flight: the 8 features of head 2p+hh, p = g, g+2
-        float inv_l[2] = {1.f, 1.f};
-        __nv_bfloat16* pend_dst = nullptr;
-        bool pend_live = false, pend_any = false;
-        int pend_parity = 0;
-        int gt = 0;
-
-        auto softmax_item = [&](const int pp, const bool live) {
-            mbar_wait(&s_full[c], ph_s);
-            ph_s ^= 1;
-            fence_after_sync();
-            if (live) {
-                uint32_t v[32], pk[16];
-                tmem_ld32(sbase, v);
-                tmem_ld_wait32(v);
-                const float mA = max_chunk32(v, -INFINITY);
-                tmem_ld32(sbase + 32, v);
-                tmem_ld_wait32(v);
-                const float mx = max_chunk32(v, mA);
-                const float2 neg2 = make_float2(-mx, -mx);
-                float2 sum2 = make_float2(0.f, 0.f);
-                exp_chunk32(v, neg2, sum2, pk);
-                tmem_st16(sbase + 32, pk);
-                tmem_ld32(sbase, v);
-                tmem_ld_wait32(v);
-                exp_chunk32(v, neg2, sum2, pk);
-                tmem_st16(sbase + 48, pk);
-                inv_l[pp] = __fdividef(1.f, sum2.x + sum2.y);
-                tmem_st_wait();
-            }
-            fence_before_sync();
-            warp_arrive(&p_ready[c]);
-        };
-        auto f_epilogue = [&]() {
-            mbar_wait(f_full, pend_parity);
-            fence_after_sync();
-            if (pend_live) {
-#pragma unroll
-                for (int pp = 0; pp < 2; ++pp) {
-                    const int p = g + 2 * pp, f0 = 16 * p + 8 * hh;
-                    uint32_t fv[8];
-                    tmem_ld8(tmem_addr(tb, lane_base, A2_F + f0), fv);
-                    tmem_ld_wait();
-                    uint4 out;
-                    uint32_t* ow = reinterpret_cast<uint32_t*>(&out);
-#pragma unroll
-                    for (int j = 0; j < 8; j += 2) {
-                        const float y0 = o1[pp][j] + fmaxf(__uint_as_float(fv[j]) + sBo[f0 + j], 0.f);
-                        const float y1 = o1[pp][j + 1] + fmaxf(__uint_as_float(fv[j + 1]) + sBo[f0 + j + 1], 0.f);
-                        ow[j >> 1] = pack_bf16(y0, y1);
-                    }
-                    if (pend_dst != nullptr) *reinterpret_cast<uint4*>(pend_dst + f0) = out;
-                }
-            }
-            fence_before_sync();
-            pend_any = false;
-        };
-        for (int w = blockIdx.x; w < n_work; w += wstep) {
-            int cloud, tile0;
-            const int ntiles = work_tiles(w, cloud, tile0);
-            for (int it = 0; it < ntiles; ++it, ++gt) {
-                const int n = (tile0 + it) * 128 + row;
-                const bool valid = n < P.N;
-                const bool live = (tile0 + it) * 128 + 32 * quad < P.N;     // warps whose 32 rows are all padding idle
-                softmax_item(0, live);
-                if (pend_any) f_epilogue();              // deferred: the fc_o round trip hides behind the first softmax
-                softmax_item(1, live);
-                // ---- O1 = Qp + (P V) / l for the 8 features of this chain's head in each of its two pairs
-                float x[4] = {0.f, 0.f, 0.f, 0.f};
-                if (!DIN64 && valid) {
-                    const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
-                    for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
-                }
-#pragma unroll
-                for (int pp = 0; pp < 2; ++pp) {
-                    const int p = g + 2 * pp, f0 = 16 * p + 8 * hh;
-                    mbar_wait(&o_full[p], gt & 1);
-                    fence_after_sync();
-                    if (live) {
-                        uint32_t o[8], qv[8];
-                        tmem_ld8(tmem_addr(tb, lane_base, A2_O + f0), o);
-                        if (DIN64) tmem_ld8(tmem_addr(tb, lane_base, A2_QP + 64 * (gt & 1) + f0), qv);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int f = f0 + j;
-                            float q;
-                            if (DIN64) {
-                                q = __uint_as_float(qv[j]) + sBq[f];
-                            } else {
-                                const float4 wv = *reinterpret_cast<const float4*>(sWq32 + f * 4);
-                                q = fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBq[f]))));
-                            }
-                            o1[pp][j] = q + __uint_as_float(o[j]) * inv_l[pp];
-                        }
-                        st_shared_8bf16(sO1 + (2 * p + hh) * 2048 + row * 16, &o1[pp][0]);
-                    }
-                }
-                if (DIN64) {
-                    fence_before_sync();
-                    warp_arrive(&qp_free[gt & 1]);
-                }
-                fence_async_smem();
-                fence_before_sync();
-                warp_arrive(o1_ready);
-                pend_any = true;
-                pend_live = live;
-                pend_parity = gt & 1;
-                pend_dst = valid ? P.Yout + ((size_t)cloud * P.N + n) * 64 : nullptr;
-            }
-        }
-        if (pend_any) f_epilogue();
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 20) tmem_dealloc(tb, 512);
 }
 
 // ====================================================================================== apply kernel, third generation
@@ -2795,11 +913,13 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_work = P.n_work, wstep = gridDim.x;
-    auto work_tiles = [&](int w, int& cloud, int& tile0) {
+    // tiles of work item w; nb = valid points of its cloud (variable-size sets: rows past nb are padding)
+    auto work_tiles = [&](int w, int& cloud, int& tile0, int& nb) {
         cloud = w / P.nsplit;
         const int split = w - cloud * P.nsplit;
         tile0 = split * P.tiles_per_split;
-        return min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+        nb = P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N;
+        return max(0, min((nb + 127) >> 7, tile0 + P.tiles_per_split) - tile0);
     };
 
     copy_to_smem(sWo, P.Wo16, 8192);
@@ -2835,13 +955,13 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
         const uint32_t lane_base = 32 * quad;
         int gt = 0;
         for (int w = blockIdx.x; w < n_work; w += wstep) {
-            int cloud, tile0;
-            const int ntiles = work_tiles(w, cloud, tile0);
+            int cloud, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, tile0, nb);
             for (int it = 0; it < ntiles; ++it, ++gt) {
                 const int buf = gt & 1;
                 const int n = (tile0 + it) * 128 + row;
-                const bool valid = n < P.N;
-                const bool live = (tile0 + it) * 128 + 32 * quad < P.N;
+                const bool valid = n < nb;
+                const bool live = (tile0 + it) * 128 + 32 * quad < nb;
                 const uint32_t oq = tmem_addr(tb, lane_base, A3_OQ + 64 * buf);
                 // ---- O1 = OQ + bq  ->  bf16 A operand of fc_o, written back to TMEM
                 mbar_wait(&o_full[buf], (gt >> 1) & 1);
@@ -2915,8 +1035,8 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
             const uint32_t img = smem_u32(sImg), aqb = smem_u32(sAQ);
             int gt = 0, wl = 0;
             for (int w = blockIdx.x; w < n_work; w += wstep, ++wl) {
-                int cloud, tile0;
-                const int ntiles = work_tiles(w, cloud, tile0);
+                int cloud, tile0, nb;
+                const int ntiles = work_tiles(w, cloud, tile0, nb);
                 const uint32_t kb = img + (wl & 1) * 32768 + c * 4096, vb = kb + 16384;
                 mbar_wait(&img_full[wl & 1], (wl >> 1) & 1);
                 fence_after_sync();
@@ -2951,8 +1071,8 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
         const int ptid = threadIdx.x - 256;          // 0..127
         int gt = 0, wl = 0;
         for (int w = blockIdx.x; w < n_work; w += wstep, ++wl) {
-            int cloud, tile0;
-            const int ntiles = work_tiles(w, cloud, tile0);
+            int cloud, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, tile0, nb);
             {   // stage this cloud's block-diagonal K / V images (32 KB)
                 if (wl >= 2) mbar_wait(&img_empty[wl & 1], ((wl >> 1) - 1) & 1);
                 const uint4* src = reinterpret_cast<const uint4*>(P.KVblk + (size_t)cloud * 32768);
@@ -2966,7 +1086,7 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
             for (int it = 0; it < ntiles; ++it, ++gt) {
                 const int stage = gt & 1;
                 const int n = (tile0 + it) * 128 + row;
-                const bool valid = n < P.N;
+                const bool valid = n < nb;
                 uint8_t* dst = sAQ + stage * 16384;
                 // ---- stage the input tile (sYA is free: the previous tile's projection MMA was waited for below)
                 if (!DIN64) {
@@ -3092,11 +1212,11 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
             tmem_ld32(tmem_addr(tb, lane_base, A3_S + 64 * (2 * g) + 32), vb);
         }
         for (int w = blockIdx.x; w < n_work; w += wstep) {
-            int cloud, tile0;
-            const int ntiles = work_tiles(w, cloud, tile0);
+            int cloud, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, tile0, nb);
             const bool more_work = w + wstep < n_work;
             for (int it = 0; it < ntiles; ++it) {
-                const bool live = (tile0 + it) * 128 + 32 * quad < P.N;     // warps whose 32 rows are all padding idle
+                const bool live = (tile0 + it) * 128 + 32 * quad < nb;     // warps whose 32 rows are all padding idle
                 softmax_item(0, live, true);
                 softmax_item(1, live, true);
                 softmax_item(0, live, true);
@@ -3109,10 +1229,10 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
         if (g == 1) __nanosleep(PCA_A3_STAGGER);      // start the two warpgroups in anti-phase (they share the MUFU pipe)
 #endif
         for (int w = blockIdx.x; w < n_work; w += wstep) {
-            int cloud, tile0;
-            const int ntiles = work_tiles(w, cloud, tile0);
+            int cloud, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, tile0, nb);
             for (int it = 0; it < ntiles; ++it) {
-                const bool live = (tile0 + it) * 128 + 32 * quad < P.N;     // warps whose 32 rows are all padding idle
+                const bool live = (tile0 + it) * 128 + 32 * quad < nb;     // warps whose 32 rows are all padding idle
 #pragma unroll
                 for (int step = 0; step < 4; ++step) {
                     const int j = step & 1;
@@ -3167,6 +1287,7 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
 struct PoolParams {
     const __nv_bfloat16* Y16;     // (B, N, 64)
     int N, tiles_total, tiles_per_split, nsplit, n_work;
+    const int* counts;            // nullable (B): valid points per cloud
     const uint8_t* Aq;            // AqPool image
     float* part;                  // (B, 2 nsplit, 8 heads, 66): m (log2 domain), l, Z[64]
 };
@@ -3193,11 +1314,13 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_work = P.n_work, wstep = gridDim.x;
-    auto work_tiles = [&](int w, int& cloud, int& split, int& tile0) {
+    // tiles of work item w; nb = valid points of its cloud (variable-size sets: rows past nb are padding)
+    auto work_tiles = [&](int w, int& cloud, int& split, int& tile0, int& nb) {
         cloud = w / P.nsplit;
         split = w - cloud * P.nsplit;
         tile0 = split * P.tiles_per_split;
-        return min(P.tiles_total, tile0 + P.tiles_per_split) - tile0;
+        nb = P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N;
+        return max(0, min((nb + 127) >> 7, tile0 + P.tiles_per_split) - tile0);
     };
     copy_to_smem(sAq, P.Aq, 16384);
     if (warp == 12) tmem_alloc(tmem_slot, 512);
@@ -3220,7 +1343,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
             const uint32_t idesc_pv = idesc_bf16(128, 64, 0, 1);
             const uint32_t aq = smem_u32(sAq), yb = smem_u32(sY);
             int total = 0;
-            for (int w = blockIdx.x; w < n_work; w += wstep) { int a, b, c; total += work_tiles(w, a, b, c); }
+            for (int w = blockIdx.x; w < n_work; w += wstep) { int a, b, c, e; total += work_tiles(w, a, b, c, e); }
             auto issue_s = [&](int t) {
                 const int stage = t % POOL_STAGES;
                 mbar_wait(&y_full[stage], (t / POOL_STAGES) & 1);
@@ -3252,12 +1375,12 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
         const int row = 32 * (warp & 3) + lane;
         int t = 0;
         for (int w = blockIdx.x; w < n_work; w += wstep) {
-            int cloud, split, tile0;
-            const int ntiles = work_tiles(w, cloud, split, tile0);
+            int cloud, split, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, split, tile0, nb);
             for (int it = 0; it < ntiles; ++it, ++t) {
                 const int stage = t % POOL_STAGES;
                 const int n = (tile0 + it) * 128 + row;
-                const bool valid = n < P.N;
+                const bool valid = n < nb;
                 const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
                 uint4 yv[8];
 #pragma unroll
@@ -3283,8 +1406,8 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
         uint32_t ph_s = 0, ph_o = 0;
         int t = 0;
         for (int w = blockIdx.x; w < n_work; w += wstep) {
-            int cloud, split, tile0;
-            const int ntiles = work_tiles(w, cloud, split, tile0);
+            int cloud, split, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, split, tile0, nb);
             m_run = -INFINITY; l_run = 0.f; alpha = 0.f;
 #pragma unroll
             for (int j = 0; j < 64; ++j) acc[j] = 0.f;
@@ -3294,7 +1417,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
             const int group = (g ^ t) & 1;
             for (int it = 0; it < ntiles; ++it, ++t) {
                 if ((t & 1) != g) continue;
-                const int n_valid = min(128, P.N - (tile0 + it) * 128);
+                const int n_valid = min(128, nb - (tile0 + it) * 128);
                 mbar_wait(&s_full[g], ph_s);
                 ph_s ^= 1;
                 fence_after_sync();
@@ -3422,48 +1545,6 @@ __global__ void __launch_bounds__(64) finalize_pool_kernel(const PoolFinParams P
     }
 }
 
-// ------------------------------------------------------------------------------------ finalize (PMA + Linear)
-struct PParams {
-    const float* part; int nsplit;
-    const float* QpS;             // (64)
-    const float* Wo; const float* bo;        // pma.mab.fc_o
-    const float* Wl; const float* bl; int C; // final Linear (C, 64)
-    float* logits;                // (B, C)
-    float* pooled_debug;          // nullable (B, 64)
-};
-
-__global__ void __launch_bounds__(64) finalize_pma_kernel(const PParams P) {
-    __shared__ float sO[64], sO1[64];
-    const int cloud = blockIdx.x, f = threadIdx.x;
-    const int h = f >> 3, d = f & 7;
-    // partial slots: (split, warpgroup 0/1) -- each softmax warpgroup of the reduce kernel owns alternate tiles
-    float mmax = -INFINITY;
-    for (int s = 0; s < P.nsplit; ++s)
-        for (int w2 = 0; w2 < 2; ++w2)
-            mmax = fmaxf(mmax, P.part[(((size_t)cloud * P.nsplit + s) * TH + h) * 10 * TM + w2]);
-    float l = 0.f, a = 0.f;
-    for (int s = 0; s < P.nsplit; ++s)
-        for (int w2 = 0; w2 < 2; ++w2) {
-            const float* pp = P.part + (((size_t)cloud * P.nsplit + s) * TH + h) * 10 * TM + w2;
-            const float w = exp2f(pp[0] - mmax);
-            l = fmaf(pp[TM], w, l);
-            a = fmaf(pp[(2 + d) * TM], w, a);
-        }
-    sO[f] = P.QpS[f] + a / l;
-    __syncthreads();
-    float acc = P.bo[f];
-    for (int k = 0; k < 64; ++k) acc = fmaf(sO[k], P.Wo[f * 64 + k], acc);
-    const float o1 = sO[f] + fmaxf(acc, 0.f);
-    sO1[f] = o1;
-    if (P.pooled_debug) P.pooled_debug[(size_t)cloud * 64 + f] = o1;
-    __syncthreads();
-    for (int c = f; c < P.C; c += 64) {
-        float z = P.bl[c];
-        for (int k = 0; k < 64; ++k) z = fmaf(sO1[k], P.Wl[c * 64 + k], z);
-        P.logits[(size_t)cloud * P.C + c] = z;
-    }
-}
-
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __bfloat162float(in[i]);
@@ -3471,9 +1552,6 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 
 // ------------------------------------------------------------------------------------ host orchestration
 static int g_num_sms = 148;
-// softmax warpgroups per CTA (2 = 16 warps with TMEM prefetch, 4 = 24 warps): measured best is 4 for the reduce kernel
-// and 2 for the apply kernel (profiles/); PCA_TC_REDUCE_WG / PCA_TC_APPLY_WG override for experiments
-static int g_reduce_wg = 5, g_apply_wg = 3;      // apply: 3 = third-generation kernel (20 warps, epilogue warps)
 static long long* g_timeline = nullptr;      // set through pca_debug_set_timeline
 void set_timeline(long long* p) { g_timeline = p; }
 struct TcSplit { int tiles_total, tiles_per_split, nsplit; };
@@ -3513,10 +1591,8 @@ int st_tc_supported(const pca_st_dims* d, int N) {
 
 struct TcDebug { float *H1, *Y1, *H2, *Y2, *pooled; };
 
-static double st_flops_per_point(int d_in) { return 2.0 * (3.0 * d_in * TD + 8.0 * TM * TD + 7.0 * TD * TD + 2.0 * TD); }
-
-static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
-                       uint8_t* ws, const TcConsts* c, const TcDebug* dbg, cudaStream_t st) {
+static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pca_st_dims* d, const float* params,
+                       float* logits, uint8_t* ws, const TcConsts* c, const TcDebug* dbg, cudaStream_t st) {
     const TcLayout L = tc_layout(B, N);
     const TcSplit sp = plan_split(B, N);
     float* part = reinterpret_cast<float*>(ws + L.part);
@@ -3535,63 +1611,58 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
     const MabParams m11 = mab_slice(p_isab1 + TM * TD + mab_count(TD, TD, TD, 0), TD, TD, TD, 0);
     const MabParams mp = mab_slice(p_pma + TD, TD, TD, TD, 0);
 
-    const dim3 grid(sp.nsplit, B);
     const int n_work = sp.nsplit * B;                          // persistent kernels: one CTA per SM walks the work items
     const int pgrid = n_work < g_num_sms ? n_work : g_num_sms;
+    const int npairs = (B + 1) / 2;
+    const int fgrid = npairs < 2 * g_num_sms ? npairs : 2 * g_num_sms;
     const double pts = (double)B * N;
-    const size_t fsmem = FT_SMEM;
+    const bool tl_apply = getenv("PCA_TL_APPLY") != nullptr;   // which kernel a PCA_TIMELINE build records
 
     // ---- ISAB 0
     {
-        RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->Aq0, m00.Wkv, m00.bkv, nullptr, getenv("PCA_TL_APPLY") ? nullptr : g_timeline, part};
+        RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, c->Aq0, m00.Wkv, m00.bkv,
+                  nullptr, tl_apply ? nullptr : g_timeline, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * d_in * TD + 2.0 * TM * TD), pts * 4.0 * d_in);
-        if (g_reduce_wg == 5) mab_reduce5_tc_kernel<false><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
-        else if (g_reduce_wg == 4) mab_reduce4_tc_kernel<false><<<pgrid, TC_THREADS24, R2Smem::TOTAL, st>>>(r);
-        else mab_reduce2_tc_kernel<false><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
+        mab_reduce5_tc_kernel<false><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<small>");
     {
         F2Params f{part, 2 * sp.nsplit, B, c->Qp0, c->WoS[0][0], m00.bo, c->WkvS[0][0], m01.bkv, kvblk, dbg ? dbg->H1 : nullptr};
         LaunchTimer lt("finalize_isab_kernel", st, (double)B * 2.0 * (TM * TD * TD + TM * TD * 2 * TD), (double)B * 32768.0);
-        const int npairs = (B + 1) / 2;
-        finalize_isab_tc_kernel<<<npairs < 2 * g_num_sms ? npairs : 2 * g_num_sms, 128, F2Smem::TOTAL, st>>>(f);
+        finalize_isab_tc_kernel<<<fgrid, 128, F2Smem::TOTAL, st>>>(f);
     }
     PCA_CHECK_LAUNCH("finalize_isab_kernel");
     {
-        AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, kvblk, m01.Wq, m01.bq, nullptr, c->Wo0, m01.bo, Y1, getenv("PCA_TL_APPLY") ? g_timeline : nullptr};
+        AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, kvblk, m01.Wq, m01.bq, c->WqS0,
+                  c->Wo0, m01.bo, Y1, tl_apply ? g_timeline : nullptr};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * d_in * TD + 2.0 * TM * TD + TD * TD), pts * (4.0 * d_in + 128.0));
-        if (g_apply_wg == 3) { a.Wq16 = c->WqS0; mab_apply3_tc_kernel<false><<<pgrid, TC_THREADS20, A3Smem::TOTAL, st>>>(a); }
-        else if (g_apply_wg == 4) mab_apply4_tc_kernel<false><<<pgrid, TC_THREADS24, A2Smem::TOTAL, st>>>(a);
-        else mab_apply2_tc_kernel<false><<<pgrid, TC_THREADS16, A2Smem::TOTAL, st>>>(a);
+        mab_apply3_tc_kernel<false><<<pgrid, TC_THREADS20, A3Smem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<small>");
     // ---- ISAB 1
     {
-        RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->Aq1, nullptr, m10.bkv, c->Wkv1, nullptr, part};
+        RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, c->Aq1, nullptr, m10.bkv,
+                  c->Wkv1, nullptr, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TM * TD), pts * 128.0);
-        if (g_reduce_wg == 5) mab_reduce5_tc_kernel<true><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
-        else if (g_reduce_wg == 4) mab_reduce4_tc_kernel<true><<<pgrid, TC_THREADS24, R2Smem::TOTAL, st>>>(r);
-        else mab_reduce2_tc_kernel<true><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
+        mab_reduce5_tc_kernel<true><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<64>");
     {
         F2Params f{part, 2 * sp.nsplit, B, c->Qp1, c->WoS[1][0], m10.bo, c->WkvS[1][0], m11.bkv, kvblk, dbg ? dbg->H2 : nullptr};
         LaunchTimer lt("finalize_isab_kernel", st, (double)B * 2.0 * (TM * TD * TD + TM * TD * 2 * TD), (double)B * 32768.0);
-        const int npairs = (B + 1) / 2;
-        finalize_isab_tc_kernel<<<npairs < 2 * g_num_sms ? npairs : 2 * g_num_sms, 128, F2Smem::TOTAL, st>>>(f);
+        finalize_isab_tc_kernel<<<fgrid, 128, F2Smem::TOTAL, st>>>(f);
     }
     PCA_CHECK_LAUNCH("finalize_isab_kernel");
     {
-        AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, kvblk, nullptr, m11.bq, c->Wq1, c->Wo1, m11.bo, Y2, nullptr};
+        AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, kvblk, nullptr, m11.bq, c->Wq1,
+                  c->Wo1, m11.bo, Y2, nullptr};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * TD * TD + 2.0 * TM * TD + TD * TD), pts * 256.0);
-        if (g_apply_wg == 3) mab_apply3_tc_kernel<true><<<pgrid, TC_THREADS20, A3Smem::TOTAL, st>>>(a);
-        else if (g_apply_wg == 4) mab_apply4_tc_kernel<true><<<pgrid, TC_THREADS24, A2Smem::TOTAL, st>>>(a);
-        else mab_apply2_tc_kernel<true><<<pgrid, TC_THREADS16, A2Smem::TOTAL, st>>>(a);
+        mab_apply3_tc_kernel<true><<<pgrid, TC_THREADS20, A3Smem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<64>");
     // ---- PMA + Linear
     {
-        PoolParams r{Y2, N, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, c->AqPool, part};
+        PoolParams r{Y2, N, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, c->AqPool, part};
         LaunchTimer lt("pma_pool_tc_kernel", st, pts * 2.0 * (2.0 * TH * TD), pts * 128.0);
         pma_pool_tc_kernel<<<pgrid, TC_THREADS16, PoolSmem::TOTAL, st>>>(r);
     }
@@ -3608,7 +1679,6 @@ static int st_tc_chunk(const float* X, int B, int N, const pca_st_dims* d, const
         if (dbg->Y1) { bf16_to_f32_kernel<<<1024, 256, 0, st>>>(Y1, dbg->Y1, n); PCA_CHECK_LAUNCH("bf16_to_f32_kernel"); }
         if (dbg->Y2) { bf16_to_f32_kernel<<<1024, 256, 0, st>>>(Y2, dbg->Y2, n); PCA_CHECK_LAUNCH("bf16_to_f32_kernel"); }
     }
-    (void)st_flops_per_point;
     return 0;
 }
 
@@ -3620,30 +1690,18 @@ static int tc_configure() {
     PCA_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     PCA_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     if (major != 10) return fail(PCA_EDEVICE, "tcgen05 path needs an sm_100 device (found compute capability %d.x)", major);
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSmem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce4_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce4_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply4_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply4_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
-    if (const char* v = getenv("PCA_TC_REDUCE_WG")) g_reduce_wg = (v[0] == '2') ? 2 : (v[0] == '4') ? 4 : 5;
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce5_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce5_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
-    if (const char* v = getenv("PCA_TC_APPLY_WG")) g_apply_wg = (v[0] == '4') ? 4 : (v[0] == '2') ? 2 : 3;
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(pma_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PoolSmem::TOTAL));
     done = true;
     return 0;
 }
 
-int st_tc_forward_dbg(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits, void* ws,
-                      size_t ws_bytes, const TcDebug* dbg, cudaStream_t st) {
+int st_tc_forward_dbg(const float* X, const int* counts, int B, int N, const pca_st_dims* d, const float* params, float* logits,
+                      void* ws, size_t ws_bytes, const TcDebug* dbg, cudaStream_t st) {
     PCA_TRY(tc_configure());
     const size_t one = tc_layout(1, N).total;
     if (!ws || ws_bytes < one) return fail(PCA_EWORKSPACE, "ST(bf16): workspace %zu B < minimum %zu B", ws_bytes, one);
@@ -3658,21 +1716,22 @@ int st_tc_forward_dbg(const float* X, int B, int N, const pca_st_dims* d, const 
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int bc = (B - b0) < chunk ? (B - b0) : chunk;
         // the layout of a smaller last chunk fits inside the layout of `chunk` (same consts offset 0)
-        PCA_TRY(st_tc_chunk(X + (size_t)b0 * N * d->d_in, bc, N, d, params, logits + (size_t)b0 * d->C, w8, c, dbg, st));
+        PCA_TRY(st_tc_chunk(X + (size_t)b0 * N * d->d_in, counts ? counts + b0 : nullptr, bc, N, d, params,
+                            logits + (size_t)b0 * d->C, w8, c, dbg, st));
     }
     return 0;
 }
 
-int st_tc_forward(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits, void* ws,
-                  size_t ws_bytes, cudaStream_t st) {
-    return st_tc_forward_dbg(X, B, N, d, params, logits, ws, ws_bytes, nullptr, st);
+int st_tc_forward(const float* X, const int* counts, int B, int N, const pca_st_dims* d, const float* params, float* logits,
+                  void* ws, size_t ws_bytes, cudaStream_t st) {
+    return st_tc_forward_dbg(X, counts, B, N, d, params, logits, ws, ws_bytes, nullptr, st);
 }
 
 int st_tc_forward_stages(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
                          float* H1, float* Y1, float* H2, float* Y2, float* pooled, void* ws, size_t ws_bytes,
                          cudaStream_t st) {
     TcDebug dbg{H1, Y1, H2, Y2, pooled};
-    return st_tc_forward_dbg(X, B, N, d, params, logits, ws, ws_bytes, &dbg, st);
+    return st_tc_forward_dbg(X, nullptr, B, N, d, params, logits, ws, ws_bytes, &dbg, st);
 }
 
 }  // namespace pca

@@ -151,8 +151,8 @@ constexpr int TOPK_THREADS = 512;
 
 __global__ void __launch_bounds__(TOPK_THREADS)
 topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __restrict__ farr,
-            const float* __restrict__ tarr, int K, int kpad, int sorted, float* __restrict__ pts_all,
-            int32_t* __restrict__ idx_all) {
+            const float* __restrict__ tarr, int K, int kpad, int sorted, int use_tau, float tau,
+            float* __restrict__ pts_all, int32_t* __restrict__ idx_all, int32_t* __restrict__ counts) {
     extern __shared__ unsigned long long sortbuf[];      // kpad entries when sorted
     __shared__ int hist[256];
     __shared__ int warp_gt[TOPK_THREADS / 32], warp_eq[TOPK_THREADS / 32];
@@ -223,6 +223,11 @@ topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __re
         kth = s_prefix;
         n_ties_take = s_remaining;
     }
+    // Threshold mode (extension): keep key >= tau, capped at K by the rule above.  When tau lies above the
+    // K-th largest key the threshold alone decides ("greater" class = key >= tau, no tie class); otherwise the cap does.
+    const uint32_t thr = use_tau ? ordered_key(tau) : 0u;
+    const bool tau_rules = use_tau && (all || thr > kth);
+    if (tau_rules) n_ties_take = 0;
     if (tid == 0) { s_gt_base = 0; s_eq_base = 0; }
     if (sorted) {
         for (int i = tid; i < kpad; i += TOPK_THREADS) sortbuf[i] = ~0ull;
@@ -236,8 +241,8 @@ topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __re
         float kv = 0.f;
         uint32_t o = 0;
         if (act) { kv = __ldg(keys + i); o = ordered_key(kv); }
-        const bool gt = act && (all || o > kth);
-        const bool eq = act && !all && (o == kth);
+        const bool gt = act && (tau_rules ? (o >= thr) : (all || o > kth));
+        const bool eq = act && !all && !tau_rules && (o == kth);
         const uint32_t bg = __ballot_sync(0xffffffffu, gt);
         const uint32_t be = __ballot_sync(0xffffffffu, eq);
         const uint32_t lt = (1u << lane) - 1;
@@ -269,7 +274,16 @@ topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __re
         }
         __syncthreads();
     }
-    if (!sorted) return;
+    // rows past the number of kept points are padding: zeros, index -1
+    const int n_kept = s_gt_base + min(s_eq_base, n_ties_take);
+    if (counts != nullptr && tid == 0) counts[cloud] = n_kept;
+    if (!sorted) {
+        for (int r = n_kept + tid; r < K; r += TOPK_THREADS) {
+            if (pts) { for (int j = 0; j < width; ++j) pts[r * width + j] = 0.f; }
+            if (idx_out) idx_out[r] = -1;
+        }
+        return;
+    }
 
     // ---- bitonic sort of the survivors: ascending (~key, index) == descending key, stable
     for (int k2 = 2; k2 <= kpad; k2 <<= 1) {
@@ -285,6 +299,11 @@ topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __re
         }
     }
     for (int r = tid; r < K; r += TOPK_THREADS) {
+        if (r >= n_kept) {
+            if (pts) { for (int j = 0; j < width; ++j) pts[r * width + j] = 0.f; }
+            if (idx_out) idx_out[r] = -1;
+            continue;
+        }
         const int i = (int)(uint32_t)sortbuf[r];
         const float kv = __ldg(keys + i);
         const int f = i % nf, t = i / nf;
@@ -345,8 +364,9 @@ int launch_build_clouds(const float* logmag, int n_clouds, int nf, int nt, const
 }
 
 int launch_topk(const float* keys, int n_clouds, int nf, int nt, const float* farr, const float* tarr,
-                int K, int sorted_desc, float* pts, int32_t* idx, cudaStream_t st) {
-    if (!keys || (!pts && !idx)) return fail(PCA_EINVAL, "topk: null pointer");
+                int K, int sorted_desc, int use_tau, float tau, float* pts, int32_t* idx, int32_t* counts, cudaStream_t st) {
+    if (!keys || (!pts && !idx && !counts)) return fail(PCA_EINVAL, "topk: null pointer");
+    if (use_tau && tau != tau) return fail(PCA_EINVAL, "topk: threshold is NaN");
     if (pts && !farr) return fail(PCA_EINVAL, "topk: farr required when pts is requested");
     if (n_clouds < 0 || nf <= 0 || nt <= 0) return fail(PCA_EINVAL, "topk: bad shape");
     const long long N = (long long)nf * nt;
@@ -365,7 +385,7 @@ int launch_topk(const float* keys, int n_clouds, int nf, int nt, const float* fa
     {
         // algorithmic traffic: keys read once, 16 B per selected point written
         LaunchTimer lt("topk_kernel", st, 0.0, (double)n_clouds * (4.0 * N + 16.0 * K));
-        topk_kernel<<<n_clouds, TOPK_THREADS, smem, st>>>(keys, (int)N, nf, farr, tarr, K, kpad, sorted_desc, pts, idx);
+        topk_kernel<<<n_clouds, TOPK_THREADS, smem, st>>>(keys, (int)N, nf, farr, tarr, K, kpad, sorted_desc, use_tau, tau, pts, idx, counts);
     }
     PCA_CHECK_LAUNCH("topk_kernel");
     return 0;

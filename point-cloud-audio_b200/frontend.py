@@ -95,14 +95,39 @@ def topk_points(logmag: torch.Tensor, farr, tarr, k: int, sorted_desc: bool = Tr
     return pts, idx
 
 
+def select_points(logmag: torch.Tensor, farr, tarr, k: int, threshold: float | None = None, sorted_desc: bool = True):
+    """Threshold / capped selection into padded sets (extension of ``topk_points``): per cloud the points with
+    log-magnitude >= threshold, at most k of them by the top-K rule; rows past the number kept are zero (index -1).
+    Returns (pts (n,k,2|3), idx (n,k) int32, counts (n,) int32)."""
+    rt.require_cuda(logmag, "select_points")
+    logmag = rt.f32c(logmag)
+    if logmag.dim() == 2:
+        logmag = logmag.unsqueeze(1)
+    n, nt, nf = logmag.shape
+    dev = logmag.device
+    f_t = farr if isinstance(farr, torch.Tensor) else rt.coord_table(farr, dev)
+    t_t = None if tarr is None else (tarr if isinstance(tarr, torch.Tensor) else rt.coord_table(tarr, dev))
+    width = 2 if t_t is None else 3
+    pts = torch.empty((n, k, width), dtype=torch.float32, device=dev)
+    idx = torch.empty((n, k), dtype=torch.int32, device=dev)
+    counts = torch.empty((n,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pca_select_compact_f32(
+            _lib.ptr(logmag), n, nf, nt, _lib.ptr(f_t), _lib.ptr(t_t), int(k), int(sorted_desc),
+            int(threshold is not None), float(threshold if threshold is not None else 0.0), _lib.ptr(pts), _lib.ptr(idx),
+            _lib.ptr(counts), rt.stream_ptr(dev)), "select_points")
+    return pts, idx, counts
+
+
 def spectral_point_cloud(audio: torch.Tensor, *, n_fft: int, sr: float, win_length: int | None = None,
                          hop_factor: float = 0.5, drop_nyquist: bool = True, ntemp: int | None = None,
-                         top_k: int | None = None, sorted_desc: bool = True):
+                         top_k: int | None = None, sorted_desc: bool = True, threshold: float | None = None):
     """NEW batched front end: audio (B, L) -> (points (B', K, 3), counts (B',), indices).
 
     Per clip: STFT recipe -> log-magnitude -> [drop Nyquist] -> non-overlapping ``ntemp``-frame chunks
     (remainder dropped; ntemp=None keeps the whole clip as one cloud) -> (f, t, mag) clouds -> optional
-    top-K.  B' = B * chunks_per_clip, clouds of one clip are consecutive."""
+    top-K and/or magnitude threshold (padded sets, ``counts`` = points kept).  B' = B * chunks_per_clip, clouds of
+    one clip are consecutive."""
     win_length = n_fft if win_length is None else int(win_length)
     hop = int(win_length * hop_factor)
     B, L = audio.shape
@@ -114,6 +139,11 @@ def spectral_point_cloud(audio: torch.Tensor, *, n_fft: int, sr: float, win_leng
     logmag = logmag.view(B * chunks, ntemp_eff, nf)
     farr, tarr = coord_tables(sr, nf, n_fft, hop_factor, ntemp_eff)
     n_pts = ntemp_eff * nf
+    if threshold is not None:
+        # threshold mode: log-magnitude >= threshold, capped at top_k, zero-padded; counts = points kept per cloud
+        pts, idx, counts = select_points(logmag, farr, tarr, n_pts if top_k is None else min(int(top_k), n_pts),
+                                         float(threshold), sorted_desc)
+        return pts, counts, idx
     if top_k is None or top_k >= n_pts and not sorted_desc:
         pts = build_clouds(logmag, farr, tarr)
         idx = torch.arange(n_pts, dtype=torch.int32, device=audio.device).expand(B * chunks, -1)

@@ -50,11 +50,18 @@ class _SetEncoderBase(nn.Module):
     def load_state_dict(self, state_dict, *args, **kwargs):
         return super().load_state_dict(strip_module_prefix(state_dict), *args, **kwargs)
 
-    def encode(self, X: torch.Tensor) -> torch.Tensor:
-        """(B, N, d_in) CUDA -> logits (B, S, C) (before the reference's .squeeze())."""
+    def encode(self, X: torch.Tensor, counts: torch.Tensor | None = None) -> torch.Tensor:
+        """(B, N, d_in) CUDA -> logits (B, S, C) (before the reference's .squeeze()).
+        ``counts`` (B,) int32 CUDA, optional extension: cloud b consists of its first counts[b] rows, the rest is
+        padding (variable-size sets); the result equals the reference module applied to X[b:b+1, :counts[b]]."""
         rt.require_cuda(X, type(self).__name__ + ".forward")
         X = rt.f32c(X)
         B, N, d_in = X.shape
+        if counts is not None:
+            rt.require_cuda(counts, type(self).__name__ + ".forward(counts)")
+            if counts.shape != (B,):
+                raise ValueError(f"counts must have shape ({B},), got {tuple(counts.shape)}")
+            counts = counts.to(torch.int32).contiguous()
         dims = self._dims()
         if d_in != dims.d_in:
             raise ValueError(f"expected clouds of width {dims.d_in}, got {d_in}")
@@ -68,8 +75,8 @@ class _SetEncoderBase(nn.Module):
         needB = L.pca_st_workspace_bytes(C.byref(dims), B, N, self.precision)
         ws = rt.workspace(X.device, max(need1, min(needB, ST_WORKSPACE_BYTES)))
         with torch.cuda.device(X.device):
-            _lib.check(L.pca_st_fwd(_lib.ptr(X), B, N, C.byref(dims), _lib.ptr(blob), _lib.ptr(out), _lib.ptr(ws),
-                                    ws.numel(), self.precision, rt.stream_ptr(X.device)),
+            _lib.check(L.pca_st_fwd_masked(_lib.ptr(X), _lib.ptr(counts), B, N, C.byref(dims), _lib.ptr(blob), _lib.ptr(out),
+                                           _lib.ptr(ws), ws.numel(), self.precision, rt.stream_ptr(X.device)),
                        type(self).__name__ + ".forward")
         return _guard(out, self)
 
@@ -91,8 +98,8 @@ class ST(_SetEncoderBase):
     def _parts(self):
         return self.enc[0], self.enc[1], self.dec[0], self.dec[1]
 
-    def forward(self, X):
-        return self.encode(X).squeeze()       # (B,1,C)->(B,C); (C,) when B == 1 (Code/models.py:44)
+    def forward(self, X, counts=None):
+        return self.encode(X, counts).squeeze()       # (B,1,C)->(B,C); (C,) when B == 1 (Code/models.py:44)
 
 
 class SetTransformer(_SetEncoderBase):
@@ -116,10 +123,10 @@ class SetTransformer(_SetEncoderBase):
     def _parts(self):
         return self.enc[0], self.enc[1], self.dec[1], self.dec[3]
 
-    def forward(self, X):
+    def forward(self, X, counts=None):
         if self.training:
             raise NotImplementedError("SetTransformer: train-mode (Dropout) forward is not implemented; call .eval()")
-        return self.encode(X).squeeze()
+        return self.encode(X, counts).squeeze()
 
 
 class DeepSet(nn.Module):
@@ -143,10 +150,16 @@ class DeepSet(nn.Module):
             nn.Linear(dim_hidden, num_outputs * dim_output))
         self._packed = _PackedParams()
 
-    def forward(self, X):
+    def forward(self, X, counts=None):
+        """``counts`` (B,) int32 CUDA, optional: pool only over the first counts[b] points (masked mean / max / sum)."""
         rt.require_cuda(X, "DeepSet.forward")
         X = rt.f32c(X)
         B, N, d_in = X.shape
+        if counts is not None:
+            rt.require_cuda(counts, "DeepSet.forward(counts)")
+            if counts.shape != (B,):
+                raise ValueError(f"counts must have shape ({B},), got {tuple(counts.shape)}")
+            counts = counts.to(torch.int32).contiguous()
         dh = self.enc[0].out_features
         out_dim = self.num_outputs * self.dim_output
         ts = []
@@ -159,7 +172,7 @@ class DeepSet(nn.Module):
         ws = rt.workspace(X.device, L.pca_deepset_workspace_bytes(B, N, d_in, dh, out_dim))
         pool = {"mean": 0, "max": 1, "sum": 2}[self.pool]
         with torch.cuda.device(X.device):
-            _lib.check(L.pca_deepset_fwd_f32(_lib.ptr(X), B, N, d_in, dh, out_dim, pool, _lib.ptr(blob),
-                                             _lib.ptr(out), _lib.ptr(ws), ws.numel(), rt.stream_ptr(X.device)),
+            _lib.check(L.pca_deepset_fwd_masked_f32(_lib.ptr(X), _lib.ptr(counts), B, N, d_in, dh, out_dim, pool, _lib.ptr(blob),
+                                                    _lib.ptr(out), _lib.ptr(ws), ws.numel(), rt.stream_ptr(X.device)),
                        "DeepSet.forward")
         return _guard(out.reshape(-1, self.num_outputs, self.dim_output), self)

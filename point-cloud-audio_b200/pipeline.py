@@ -25,6 +25,7 @@ class AudioConfig:
     Ntemp: int = 10                  # mode 3: frames per cloud
     top_k: int = 0                   # 0 = keep all points
     precision: str = "fp32"          # encoder precision: 'fp32' | 'bf16'
+    threshold: float | None = None   # keep only points with log-magnitude >= threshold (padded, masked sets)
 
 
 class AudioSetPipeline:
@@ -40,7 +41,9 @@ class AudioSetPipeline:
         hop = int(cfg.window_size * cfg.hop_factor)
         self.c = _lib.PipelineCfg(n_samples=cfg.n_samples, n_fft=cfg.window_size, hop=hop,
                                   scale=1.0 / cfg.window_size, mode=cfg.mode, ntemp=cfg.Ntemp, top_k=cfg.top_k,
-                                  precision={"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[cfg.precision], st=dims)
+                                  precision={"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[cfg.precision], st=dims,
+                                  use_threshold=int(cfg.threshold is not None),
+                                  threshold=float(cfg.threshold if cfg.threshold is not None else 0.0))
         L = _lib.lib()
         self.clouds_per_clip = L.pca_pipeline_clouds_per_clip(C.byref(self.c))
         self.points_per_cloud = L.pca_pipeline_points_per_cloud(C.byref(self.c))
