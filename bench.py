@@ -27,6 +27,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# keep stdout to the ONE JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "clips/sec audio->point-cloud->encoder"
 UNIT = "clips/s"

@@ -90,6 +90,18 @@ int pca_select_compact_f32(const float* keys, int n_clouds, int nf, int nt, cons
                            const float* tarr, int K, int sorted_desc, int use_threshold,
                            float threshold, float* pts, int32_t* idx, int32_t* counts, void* stream);
 
+/* Whole front end in one launch (a1 -> a7 of SURVEY.md 8a; the fused call of SURVEY.md 8b): per clip, STFT ->
+ * log-magnitude -> non-overlapping ntemp-frame (f, t, mag) clouds (remainder frames dropped, as
+ * Code/settransformertemp.py:54-58) -> selection as pca_select_compact_f32, one thread block per cloud with the
+ * cloud's log-magnitudes held in shared memory (HBM traffic: the audio once + 16 B per selected point).
+ * pts (n_clips * (Nt / ntemp), K, 3), idx, counts as in pca_select_compact_f32 (any may be NULL, not all).
+ * Clouds whose keys + sort buffer exceed 227 KB of shared memory return PCA_EUNSUPPORTED: use the unfused calls. */
+int pca_frontend_fused_f32(const float* audio, int n_clips, int n_samples, int n_fft, int hop,
+                           const float* window, const float* twiddle, float scale, int drop_nyquist,
+                           int ntemp, const float* farr, const float* tarr, int K, int sorted_desc,
+                           int use_threshold, float threshold, float* pts, int32_t* idx, int32_t* counts,
+                           void* stream);
+
 /* ---------------------------------------------------------------- L4: set encoder
  * Weights are passed as ONE packed float32 blob per block, nn.Linear layout (out, in):
  *   MAB  := Wq (D,dq) | bq (D) | Wk (D,dk) | Wv (D,dk) | bk (D) | bv (D) | Wo (D,D) | bo (D)

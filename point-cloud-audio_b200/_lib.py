@@ -43,6 +43,7 @@ PROTOTYPES = {
     "pca_build_clouds_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "pca_topk_compact_f32": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P]),
     "pca_select_compact_f32": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "pca_frontend_fused_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _I, _I, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
     "pca_st_fwd_masked": (_I, [_P, _P, _I, _I, C.POINTER(StDims), _P, _P, _P, _SZ, _I, _P]),
     "pca_deepset_fwd_masked_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),
     "pca_mab_param_count": (C.c_longlong, [_I, _I, _I, _I]),

@@ -19,6 +19,8 @@ int launch_attn(const float*, long long, const float*, int, int, int, int, int, 
 size_t attn_part_floats(int B, int nq, int nk, int D, int H);
 int launch_layernorm(float*, long long, int, const float*, const float*, cudaStream_t);
 int launch_pool(const float*, int, int, int, int, float*, const int*, cudaStream_t);
+int launch_fused_frontend(const float*, int, int, int, int, const float*, const float*, float, int, int, const float*, const float*,
+                          int, int, int, float, float*, int32_t*, int32_t*, cudaStream_t);
 void set_timeline(long long* p);
 int launch_umma_probe(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 // tcgen05 path (encoder_tc.cu)
@@ -311,13 +313,26 @@ static int pipeline_run(const pca_pipeline_cfg* c, const float* audio, int n_cli
     float* logmag = a.take<float>((size_t)n_clips * s.nt_out * s.nf);
     float* pts = a.take<float>((size_t)n_clouds * s.pts * s.width);
     int32_t* kept = a.take<int32_t>((size_t)n_clouds);
+    const bool thr = c->use_threshold != 0;
+    // 3-D clouds with a selection step: one fused launch (the log-magnitudes stay in shared memory) when the cloud fits
+    // (opt-in: measured slower than the two-kernel route on B200 while the batch's log-magnitudes fit the L2)
+    if (c->mode == 3 && (c->top_k || thr) && getenv("PCA_FUSED_FRONTEND") != nullptr) {
+        int kpad = 2;
+        while (kpad < s.pts) kpad <<= 1;
+        const size_t smem = (size_t)kpad * 8 + (size_t)(c->n_fft / 2) * 8 * 9 + (size_t)c->n_fft * 4 + (size_t)s.pts_full * 4;
+        if (smem <= 227 * 1024 && s.pts <= 16384) {
+            PCA_TRY(launch_fused_frontend(audio, n_clips, c->n_samples, c->n_fft, c->hop, window, twiddle, c->scale, 1, c->ntemp,
+                                          farr, tarr, s.pts, 1, thr, c->threshold, pts, nullptr, thr ? kept : nullptr, st));
+            return st_forward(pts, n_clouds, s.pts, &c->st, st_params, logits, (char*)ws + st_off, ws_bytes - st_off,
+                              c->precision, st, thr ? kept : nullptr);
+        }
+    }
     PCA_TRY(launch_stft_logmag(audio, n_clips, c->n_samples, c->n_fft, c->hop, window, twiddle, c->scale,
                                c->mode == 3, s.nt_out, logmag, st));
     const int nt_cloud = c->mode == 3 ? c->ntemp : 1;
     const float* tarr_use = c->mode == 3 ? tarr : nullptr;
     // threshold mode: points with log-magnitude >= threshold, capped at top_k (or all points), padded; the encoder then
     // runs on variable-size sets (kept[] points per cloud)
-    const bool thr = c->use_threshold != 0;
     if (c->top_k || thr)
         PCA_TRY(launch_topk(logmag, n_clouds, s.nf, nt_cloud, farr, tarr_use, s.pts, 1, thr, c->threshold, pts, nullptr,
                             thr ? kept : nullptr, st));
@@ -397,6 +412,14 @@ int pca_select_compact_f32(const float* keys, int n_clouds, int nf, int nt, cons
                            int32_t* counts, void* stream) {
     return launch_topk(keys, n_clouds, nf, nt, farr, tarr, K, sorted_desc, use_threshold, threshold, pts, idx, counts,
                        (cudaStream_t)stream);
+}
+
+int pca_frontend_fused_f32(const float* audio, int n_clips, int n_samples, int n_fft, int hop, const float* window,
+                           const float* twiddle, float scale, int drop_nyquist, int ntemp, const float* farr,
+                           const float* tarr, int K, int sorted_desc, int use_threshold, float threshold, float* pts,
+                           int32_t* idx, int32_t* counts, void* stream) {
+    return launch_fused_frontend(audio, n_clips, n_samples, n_fft, hop, window, twiddle, scale, drop_nyquist, ntemp, farr, tarr,
+                                 K, sorted_desc, use_threshold, threshold, pts, idx, counts, (cudaStream_t)stream);
 }
 
 long long pca_mab_param_count(int dq, int dk, int D, int ln) { return mab_count(dq, dk, D, ln); }

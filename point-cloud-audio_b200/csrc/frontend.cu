@@ -21,6 +21,97 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
+// One STFT frame by `nthr` cooperating threads (all threads of the block must call: block-wide barriers inside).
+// x: the clip (L samples); frame t is centred on sample t*hop (reflect padding by index mirroring); tw / win: shared
+// twiddle and window tables; bufa / bufb: this thread group's ping-pong buffers (n_fft/2 complex each);
+// o: nf_out log-magnitudes (shared or global).  `active` == false runs the barriers only (ragged frame groups).
+__device__ __forceinline__ void stft_frame(const float* __restrict__ x, int L, int n_fft, int hop, int t,
+                                           const float2* tw, const float* win, float2* bufa, float2* bufb,
+                                           float scale, int nf_out, float* o, int tid, int nthr, bool active) {
+    const int nc = n_fft >> 1;
+    const int tw_shift_base = 31 - __clz(n_fft);   // log2(n_fft)
+    // ---- load + window, pack even/odd samples into one complex sequence
+    if (active) {
+        const int start = t * hop - nc;            // centre=True: frame t starts at t*hop - n_fft/2
+        for (int i = tid; i < nc; i += nthr) {
+            int j0 = start + 2 * i, j1 = j0 + 1;
+            j0 = j0 < 0 ? -j0 : (j0 >= L ? 2 * (L - 1) - j0 : j0);
+            j1 = j1 < 0 ? -j1 : (j1 >= L ? 2 * (L - 1) - j1 : j1);
+            bufa[i] = make_float2(win[2 * i] * __ldg(x + j0), win[2 * i + 1] * __ldg(x + j1));
+        }
+    }
+    __syncthreads();
+
+    // ---- Stockham autosort, radix 4 (+ one radix-2 stage when log2(nc) is odd)
+    float2* src = bufa;
+    float2* dst = bufb;
+    int n = nc, s_log = 0;
+    while (n >= 4) {
+        const int n1 = n >> 2;
+        const int tsh = tw_shift_base - (31 - __clz(n));     // log2(n_fft / n)
+        if (active) {
+            for (int i = tid; i < (nc >> 2); i += nthr) {
+                const int p = i >> s_log, q = i & ((1 << s_log) - 1);
+                const float2 w1 = tw[p << tsh];
+                const float2 w2 = tw[(2 * p) << tsh];
+                const float2 w3 = cmul(w1, w2);
+                const float2 a = src[q + ((p) << s_log)];
+                const float2 b = src[q + ((p + n1) << s_log)];
+                const float2 c = src[q + ((p + 2 * n1) << s_log)];
+                const float2 d = src[q + ((p + 3 * n1) << s_log)];
+                const float2 apc = make_float2(a.x + c.x, a.y + c.y);
+                const float2 amc = make_float2(a.x - c.x, a.y - c.y);
+                const float2 bpd = make_float2(b.x + d.x, b.y + d.y);
+                const float2 jbmd = make_float2(-(b.y - d.y), b.x - d.x);   // i*(b-d)
+                const int o2 = q + ((4 * p) << s_log);
+                dst[o2] = make_float2(apc.x + bpd.x, apc.y + bpd.y);
+                dst[o2 + (1 << s_log)] = cmul(w1, make_float2(amc.x - jbmd.x, amc.y - jbmd.y));
+                dst[o2 + (2 << s_log)] = cmul(w2, make_float2(apc.x - bpd.x, apc.y - bpd.y));
+                dst[o2 + (3 << s_log)] = cmul(w3, make_float2(amc.x + jbmd.x, amc.y + jbmd.y));
+            }
+        }
+        __syncthreads();
+        float2* tmp = src; src = dst; dst = tmp;
+        n >>= 2;
+        s_log += 2;
+    }
+    if (n == 2) {   // p = 0 only, twiddle = 1
+        if (active) {
+            for (int q = tid; q < (nc >> 1); q += nthr) {
+                const float2 a = src[q];
+                const float2 b = src[q + (nc >> 1)];
+                dst[q] = make_float2(a.x + b.x, a.y + b.y);
+                dst[q + (nc >> 1)] = make_float2(a.x - b.x, a.y - b.y);
+            }
+        }
+        __syncthreads();
+        float2* tmp = src; src = dst; dst = tmp;
+    }
+
+    // ---- split the packed spectrum, magnitude, log
+    if (active) {
+        for (int k = tid; k < nf_out; k += nthr) {
+            float re, im;
+            if (k == 0) {
+                re = src[0].x + src[0].y; im = 0.f;
+            } else if (k == nc) {
+                re = src[0].x - src[0].y; im = 0.f;
+            } else {
+                const float2 zk = src[k];
+                const float2 zc = src[nc - k];
+                const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+                // odd part = -i/2 * (zk - conj(zc))
+                const float2 od = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+                const float2 r = cmul(tw[k], od);
+                re = e.x + r.x; im = e.y + r.y;
+            }
+            const float mag = sqrtf(re * re + im * im) * scale;
+            o[k] = logf(1.0e-8f + mag);
+        }
+    }
+    __syncthreads();   // bufa/bufb reused by the next frame
+}
+
 __global__ void stft_logmag_kernel(const float* __restrict__ audio, int L, int n_fft, int hop,
                                    const float* __restrict__ window,
                                    const float2* __restrict__ twiddle, float scale, int nf_out,
@@ -42,83 +133,8 @@ __global__ void stft_logmag_kernel(const float* __restrict__ audio, int L, int n
 
     const int t0 = blockIdx.x * frames_per_block;
     const int t1 = min(nt_out, t0 + frames_per_block);
-    const int tw_shift_base = 31 - __clz(n_fft);   // log2(n_fft)
-
-    for (int t = t0; t < t1; ++t) {
-        // ---- load + window, pack even/odd samples into one complex sequence
-        const int start = t * hop - nc;            // centre=True: frame t starts at t*hop - n_fft/2
-        for (int i = tid; i < nc; i += nthr) {
-            int j0 = start + 2 * i, j1 = j0 + 1;
-            j0 = j0 < 0 ? -j0 : (j0 >= L ? 2 * (L - 1) - j0 : j0);
-            j1 = j1 < 0 ? -j1 : (j1 >= L ? 2 * (L - 1) - j1 : j1);
-            bufa[i] = make_float2(win[2 * i] * __ldg(x + j0), win[2 * i + 1] * __ldg(x + j1));
-        }
-        __syncthreads();
-
-        // ---- Stockham autosort, radix 4 (+ one radix-2 stage when log2(nc) is odd)
-        float2* src = bufa;
-        float2* dst = bufb;
-        int n = nc, s_log = 0;
-        while (n >= 4) {
-            const int n1 = n >> 2;
-            const int tsh = tw_shift_base - (31 - __clz(n));     // log2(n_fft / n)
-            for (int i = tid; i < (nc >> 2); i += nthr) {
-                const int p = i >> s_log, q = i & ((1 << s_log) - 1);
-                const float2 w1 = tw[p << tsh];
-                const float2 w2 = tw[(2 * p) << tsh];
-                const float2 w3 = cmul(w1, w2);
-                const float2 a = src[q + ((p) << s_log)];
-                const float2 b = src[q + ((p + n1) << s_log)];
-                const float2 c = src[q + ((p + 2 * n1) << s_log)];
-                const float2 d = src[q + ((p + 3 * n1) << s_log)];
-                const float2 apc = make_float2(a.x + c.x, a.y + c.y);
-                const float2 amc = make_float2(a.x - c.x, a.y - c.y);
-                const float2 bpd = make_float2(b.x + d.x, b.y + d.y);
-                const float2 jbmd = make_float2(-(b.y - d.y), b.x - d.x);   // i*(b-d)
-                const int o = q + ((4 * p) << s_log);
-                dst[o] = make_float2(apc.x + bpd.x, apc.y + bpd.y);
-                dst[o + (1 << s_log)] = cmul(w1, make_float2(amc.x - jbmd.x, amc.y - jbmd.y));
-                dst[o + (2 << s_log)] = cmul(w2, make_float2(apc.x - bpd.x, apc.y - bpd.y));
-                dst[o + (3 << s_log)] = cmul(w3, make_float2(amc.x + jbmd.x, amc.y + jbmd.y));
-            }
-            __syncthreads();
-            float2* tmp = src; src = dst; dst = tmp;
-            n >>= 2;
-            s_log += 2;
-        }
-        if (n == 2) {   // p = 0 only, twiddle = 1
-            for (int q = tid; q < (nc >> 1); q += nthr) {
-                const float2 a = src[q];
-                const float2 b = src[q + (nc >> 1)];
-                dst[q] = make_float2(a.x + b.x, a.y + b.y);
-                dst[q + (nc >> 1)] = make_float2(a.x - b.x, a.y - b.y);
-            }
-            __syncthreads();
-            float2* tmp = src; src = dst; dst = tmp;
-        }
-
-        // ---- split the packed spectrum, magnitude, log
-        float* o = out + ((size_t)clip * nt_out + t) * nf_out;
-        for (int k = tid; k < nf_out; k += nthr) {
-            float re, im;
-            if (k == 0) {
-                re = src[0].x + src[0].y; im = 0.f;
-            } else if (k == nc) {
-                re = src[0].x - src[0].y; im = 0.f;
-            } else {
-                const float2 zk = src[k];
-                const float2 zc = src[nc - k];
-                const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
-                // odd part = -i/2 * (zk - conj(zc))
-                const float2 od = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
-                const float2 r = cmul(tw[k], od);
-                re = e.x + r.x; im = e.y + r.y;
-            }
-            const float mag = sqrtf(re * re + im * im) * scale;
-            o[k] = logf(1.0e-8f + mag);
-        }
-        __syncthreads();   // bufa/bufb reused by the next frame
-    }
+    for (int t = t0; t < t1; ++t)
+        stft_frame(x, L, n_fft, hop, t, tw, win, bufa, bufb, scale, nf_out, out + ((size_t)clip * nt_out + t) * nf_out, tid, nthr, true);
 }
 
 // ------------------------------------------------------------------------------------ clouds
@@ -149,11 +165,13 @@ __device__ __forceinline__ uint32_t ordered_key(float x) {
 
 constexpr int TOPK_THREADS = 512;
 
-__global__ void __launch_bounds__(TOPK_THREADS)
-topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __restrict__ farr,
-            const float* __restrict__ tarr, int K, int kpad, int sorted, int use_tau, float tau,
-            float* __restrict__ pts_all, int32_t* __restrict__ idx_all, int32_t* __restrict__ counts) {
-    extern __shared__ unsigned long long sortbuf[];      // kpad entries when sorted
+// Selection of one cloud by the whole block (TOPK_THREADS threads).  keys: the cloud's N keys, in global memory
+// (SMEM_KEYS == false, read through the read-only path) or already in shared memory (fused front end).
+template <bool SMEM_KEYS>
+__device__ __forceinline__ void topk_core(const float* keys, const int cloud, int N, int nf, const float* __restrict__ farr,
+                                          const float* __restrict__ tarr, int K, int kpad, int sorted, int use_tau, float tau,
+                                          float* __restrict__ pts_all, int32_t* __restrict__ idx_all,
+                                          int32_t* __restrict__ counts, unsigned long long* sortbuf) {
     __shared__ int hist[256];
     __shared__ int warp_gt[TOPK_THREADS / 32], warp_eq[TOPK_THREADS / 32];
     __shared__ uint32_t s_prefix;
@@ -161,8 +179,7 @@ topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __re
     __shared__ int s_gt_base, s_eq_base;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int cloud = blockIdx.x;
-    const float* keys = keys_all + (size_t)cloud * N;
+    auto ldkey = [&](int i) { return SMEM_KEYS ? keys[i] : __ldg(keys + i); };
     const int width = tarr != nullptr ? 3 : 2;
     float* pts = pts_all ? pts_all + (size_t)cloud * K * width : nullptr;
     int32_t* idx_out = idx_all ? idx_all + (size_t)cloud * K : nullptr;
@@ -181,7 +198,7 @@ topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __re
             for (int base = 0; base < N; base += TOPK_THREADS) {
                 const int i = base + tid;
                 const bool act = i < N;
-                uint32_t o = act ? ordered_key(__ldg(keys + i)) : 0u;
+                uint32_t o = act ? ordered_key(ldkey(i)) : 0u;
                 const bool cand = act && ((o & mask) == prefix);
                 const uint32_t digit = (o >> shift) & 255u;
                 // warp-aggregated shared atomics: log-magnitudes share their top bytes
@@ -240,7 +257,7 @@ topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __re
         const bool act = i < N;
         float kv = 0.f;
         uint32_t o = 0;
-        if (act) { kv = __ldg(keys + i); o = ordered_key(kv); }
+        if (act) { kv = ldkey(i); o = ordered_key(kv); }
         const bool gt = act && (tau_rules ? (o >= thr) : (all || o > kth));
         const bool eq = act && !all && !tau_rules && (o == kth);
         const uint32_t bg = __ballot_sync(0xffffffffu, gt);
@@ -305,7 +322,7 @@ topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __re
             continue;
         }
         const int i = (int)(uint32_t)sortbuf[r];
-        const float kv = __ldg(keys + i);
+        const float kv = ldkey(i);
         const int f = i % nf, t = i / nf;
         if (pts) {
             if (width == 3) { pts[r * 3] = __ldg(farr + f); pts[r * 3 + 1] = __ldg(tarr + t); pts[r * 3 + 2] = kv; }
@@ -313,6 +330,53 @@ topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __re
         }
         if (idx_out) idx_out[r] = i;
     }
+}
+
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __restrict__ farr,
+            const float* __restrict__ tarr, int K, int kpad, int sorted, int use_tau, float tau,
+            float* __restrict__ pts_all, int32_t* __restrict__ idx_all, int32_t* __restrict__ counts) {
+    extern __shared__ unsigned long long sortbuf[];      // kpad entries when sorted
+    topk_core<false>(keys_all + (size_t)blockIdx.x * N, blockIdx.x, N, nf, farr, tarr, K, kpad, sorted, use_tau, tau, pts_all,
+                     idx_all, counts, sortbuf);
+}
+
+// ------------------------------------------------------------------------------------ fused front end
+// audio -> STFT -> log-magnitude -> (f, t, mag) cloud -> selection in ONE launch (a1..a7 of SURVEY.md 8a): one block per
+// cloud (= ntemp consecutive frames of a clip).  The cloud's log-magnitudes never leave shared memory, so the HBM traffic
+// is the audio read (4 L bytes per clip) plus 16 B per selected point.  Four 128-thread groups transform four frames at
+// a time; the selection then runs on the shared-memory keys.
+constexpr int FUSED_GROUPS = TOPK_THREADS / 128;
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+fused_frontend_kernel(const float* __restrict__ audio, int L, int n_fft, int hop, const float* __restrict__ window,
+                      const float2* __restrict__ twiddle, float scale, int nf, int nt_cloud, int clouds_per_clip,
+                      const float* __restrict__ farr, const float* __restrict__ tarr, int K, int kpad, int sorted,
+                      int use_tau, float tau, float* __restrict__ pts_all, int32_t* __restrict__ idx_all,
+                      int32_t* __restrict__ counts) {
+    extern __shared__ unsigned long long fused_smem[];
+    const int nc = n_fft >> 1;
+    unsigned long long* sortbuf = fused_smem;                               // kpad entries (8-byte aligned first)
+    float2* tw = reinterpret_cast<float2*>(sortbuf + kpad);                 // nc
+    float2* bufs = tw + nc;                                                 // FUSED_GROUPS x 2 x nc
+    float* win = reinterpret_cast<float*>(bufs + 2 * FUSED_GROUPS * nc);    // n_fft
+    float* keys = win + n_fft;                                              // nt_cloud * nf
+
+    const int tid = threadIdx.x;
+    const int cloud = blockIdx.x, clip = cloud / clouds_per_clip, chunk = cloud - clip * clouds_per_clip;
+    const float* x = audio + (size_t)clip * L;
+    for (int i = tid; i < nc; i += TOPK_THREADS) tw[i] = twiddle[i];
+    for (int i = tid; i < n_fft; i += TOPK_THREADS) win[i] = window[i];
+    __syncthreads();
+    const int g = tid >> 7, ltid = tid & 127;
+    for (int t0 = 0; t0 < nt_cloud; t0 += FUSED_GROUPS) {
+        const int t = t0 + g;
+        stft_frame(x, L, n_fft, hop, chunk * nt_cloud + t, tw, win, bufs + (2 * g) * nc, bufs + (2 * g + 1) * nc, scale, nf,
+                   keys + (size_t)t * nf, ltid, 128, t < nt_cloud);
+    }
+    __syncthreads();
+    topk_core<true>(keys, cloud, nt_cloud * nf, nf, farr, tarr, K, kpad, sorted, use_tau, tau, pts_all, idx_all, counts, sortbuf);
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -388,6 +452,45 @@ int launch_topk(const float* keys, int n_clouds, int nf, int nt, const float* fa
         topk_kernel<<<n_clouds, TOPK_THREADS, smem, st>>>(keys, (int)N, nf, farr, tarr, K, kpad, sorted_desc, use_tau, tau, pts, idx, counts);
     }
     PCA_CHECK_LAUNCH("topk_kernel");
+    return 0;
+}
+
+int launch_fused_frontend(const float* audio, int n_clips, int n_samples, int n_fft, int hop, const float* window,
+                          const float* twiddle, float scale, int drop_nyquist, int ntemp, const float* farr,
+                          const float* tarr, int K, int sorted_desc, int use_tau, float tau, float* pts, int32_t* idx,
+                          int32_t* counts, cudaStream_t st) {
+    if (!audio || !window || !twiddle || !farr || !tarr) return fail(PCA_EINVAL, "fused front end: null pointer");
+    if (!pts && !idx && !counts) return fail(PCA_EINVAL, "fused front end: no output requested");
+    if (n_fft < 16 || n_fft > 8192 || (n_fft & (n_fft - 1))) return fail(PCA_EUNSUPPORTED, "fused front end: n_fft=%d must be a power of two in [16, 8192]", n_fft);
+    if (hop <= 0 || n_clips < 0 || n_samples <= n_fft / 2) return fail(PCA_EINVAL, "fused front end: need hop > 0 and n_samples > n_fft/2");
+    if (use_tau && tau != tau) return fail(PCA_EINVAL, "fused front end: threshold is NaN");
+    const int nt_all = 1 + n_samples / hop;
+    if (ntemp <= 0 || ntemp > nt_all) return fail(PCA_EINVAL, "fused front end: ntemp=%d outside [1, %d]", ntemp, nt_all);
+    const int clouds_per_clip = nt_all / ntemp;
+    const int nc = n_fft / 2, nf = nc + 1 - (drop_nyquist ? 1 : 0);
+    const long long N = (long long)nf * ntemp;
+    if (K <= 0 || K > N) return fail(PCA_EINVAL, "fused front end: K=%d outside [1, %lld]", K, N);
+    if (n_clips == 0) return 0;
+    int kpad = 0;
+    if (sorted_desc) {
+        if (K > 16384) return fail(PCA_EUNSUPPORTED, "fused front end: sorted output supports K <= 16384 (got %d)", K);
+        kpad = 2;
+        while (kpad < K) kpad <<= 1;
+    }
+    const size_t smem = (size_t)kpad * 8 + (size_t)nc * 8 * (1 + 2 * FUSED_GROUPS) + (size_t)n_fft * 4 + (size_t)N * 4;
+    if (smem > 227 * 1024)
+        return fail(PCA_EUNSUPPORTED, "fused front end: cloud of %lld points with K=%d needs %zu B of shared memory (> 227 KB); use the unfused calls",
+                    N, K, smem);
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(fused_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        const double clouds = (double)n_clips * clouds_per_clip;
+        LaunchTimer lt("fused_frontend_kernel", st, clouds * ntemp * (2.5 * n_fft * log2((double)n_fft) + n_fft + 6.0 * nf),
+                       4.0 * n_clips * (double)n_samples + clouds * 16.0 * K);
+        fused_frontend_kernel<<<n_clips * clouds_per_clip, TOPK_THREADS, smem, st>>>(
+            audio, n_samples, n_fft, hop, window, reinterpret_cast<const float2*>(twiddle), scale, nf, ntemp, clouds_per_clip, farr,
+            tarr, K, kpad, sorted_desc, use_tau, tau, pts, idx, counts);
+    }
+    PCA_CHECK_LAUNCH("fused_frontend_kernel");
     return 0;
 }
 

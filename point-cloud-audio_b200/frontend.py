@@ -119,9 +119,18 @@ def select_points(logmag: torch.Tensor, farr, tarr, k: int, threshold: float | N
     return pts, idx, counts
 
 
+def fused_frontend_fits(n_fft: int, n_pts: int, k: int) -> bool:
+    """Shared-memory budget of pca_frontend_fused_f32: sort buffer + FFT tables/buffers + the cloud's keys <= 227 KB."""
+    kpad = 2
+    while kpad < k:
+        kpad <<= 1
+    return k <= 16384 and kpad * 8 + (n_fft // 2) * 8 * 9 + n_fft * 4 + n_pts * 4 <= 227 * 1024
+
+
 def spectral_point_cloud(audio: torch.Tensor, *, n_fft: int, sr: float, win_length: int | None = None,
                          hop_factor: float = 0.5, drop_nyquist: bool = True, ntemp: int | None = None,
-                         top_k: int | None = None, sorted_desc: bool = True, threshold: float | None = None):
+                         top_k: int | None = None, sorted_desc: bool = True, threshold: float | None = None,
+                         fused: bool | None = None):
     """NEW batched front end: audio (B, L) -> (points (B', K, 3), counts (B',), indices).
 
     Per clip: STFT recipe -> log-magnitude -> [drop Nyquist] -> non-overlapping ``ntemp``-frame chunks
@@ -135,10 +144,34 @@ def spectral_point_cloud(audio: torch.Tensor, *, n_fft: int, sr: float, win_leng
     ntemp_eff = nt_all if ntemp is None else int(ntemp)
     chunks = nt_all // ntemp_eff
     nf = n_fft // 2 + 1 - (1 if drop_nyquist else 0)
+    n_pts = ntemp_eff * nf
+    k_sel = n_pts if top_k is None else min(int(top_k), n_pts)
+    if fused is None:
+        # Measured on B200 (tools/frontend_sweep.py, profiles/): the two-kernel route is faster at every K of the
+        # BASELINE sweep because the log-magnitude intermediate of a batch stays in the 126 MB L2, while the fused kernel
+        # runs one 512-thread block per SM.  The fused launch is kept for callers that must not touch HBM in between.
+        fused = False
+    if fused:
+        # one launch: the log-magnitudes never leave shared memory
+        farr, tarr = coord_tables(sr, nf, n_fft, hop_factor, ntemp_eff)
+        dev = audio.device
+        rt.require_cuda(audio, "spectral_point_cloud")
+        audio = rt.f32c(audio)
+        win, tw = rt.stft_tables(n_fft, win_length, dev)
+        f_t, t_t = rt.coord_table(farr, dev), rt.coord_table(tarr, dev)
+        pts = torch.empty((B * chunks, k_sel, 3), dtype=torch.float32, device=dev)
+        idx = torch.empty((B * chunks, k_sel), dtype=torch.int32, device=dev)
+        counts = torch.empty((B * chunks,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().pca_frontend_fused_f32(
+                _lib.ptr(audio), B, L, n_fft, hop, _lib.ptr(win), _lib.ptr(tw), 1.0 / win_length, int(drop_nyquist), ntemp_eff,
+                _lib.ptr(f_t), _lib.ptr(t_t), k_sel, int(sorted_desc), int(threshold is not None),
+                float(threshold if threshold is not None else 0.0), _lib.ptr(pts), _lib.ptr(idx), _lib.ptr(counts),
+                rt.stream_ptr(dev)), "spectral_point_cloud(fused)")
+        return pts, counts, idx
     logmag = stft_logmag(audio, n_fft, win_length, hop_factor, drop_nyquist, n_frames=chunks * ntemp_eff)
     logmag = logmag.view(B * chunks, ntemp_eff, nf)
     farr, tarr = coord_tables(sr, nf, n_fft, hop_factor, ntemp_eff)
-    n_pts = ntemp_eff * nf
     if threshold is not None:
         # threshold mode: log-magnitude >= threshold, capped at top_k, zero-padded; counts = points kept per cloud
         pts, idx, counts = select_points(logmag, farr, tarr, n_pts if top_k is None else min(int(top_k), n_pts),

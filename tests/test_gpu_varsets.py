@@ -154,3 +154,26 @@ def test_pipeline_threshold_mode(pca, precision, tol):
     assert (counts >= 1).all() and (counts < K).any(), counts          # the threshold actually bites
     ref = np.stack([orc.st_forward(params, pts[b:b + 1, :counts[b]], 8).reshape(10).numpy() for b in range(9)])
     assert rel_err(logits, ref) < tol, rel_err(logits, ref)
+
+
+# ------------------------------------------------------------------------------------ fused front end
+@pytest.mark.parametrize("n_fft,L,ntemp,K,tau", [(1024, 16000, None, 1024, None), (1024, 16000, None, 8192, None),
+                                                 (1024, 16000, 10, 5120, None), (1024, 16000, 10, 300, -5.0),
+                                                 (256, 4000, 7, 64, None), (2048, 16000, 5, 1000, -7.5),
+                                                 (1024, 16000, None, 8192, -6.0)])
+def test_fused_frontend_equals_unfused(pca, n_fft, L, ntemp, K, tau):
+    """audio -> points in one launch (log-magnitudes held in shared memory) must equal STFT kernel + selection kernel
+    bit for bit: same per-frame arithmetic, same selection rule."""
+    dev = torch.device("cuda:0")
+    audio = torch.from_numpy(orc.synth_audio(5, L, 16000.0, seed=n_fft + K)).to(dev)
+    kw = dict(n_fft=n_fft, sr=16000.0, ntemp=ntemp, top_k=K, threshold=tau)
+    p1, c1, i1 = pca.spectral_point_cloud(audio, fused=True, **kw)
+    p0, c0, i0 = pca.spectral_point_cloud(audio, fused=False, **kw)
+    assert p1.shape == p0.shape and torch.equal(i1, i0) and torch.equal(p1, p0) and torch.equal(c1.cpu(), c0.cpu())
+
+
+def test_fused_frontend_rejects_oversized_clouds(pca):
+    dev = torch.device("cuda:0")
+    audio = torch.zeros(1, 64000, device=dev)
+    with pytest.raises(RuntimeError, match="shared memory"):
+        pca.spectral_point_cloud(audio, n_fft=1024, sr=16000.0, ntemp=None, top_k=8192, fused=True)     # 64512-point cloud
