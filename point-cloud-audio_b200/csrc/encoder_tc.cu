@@ -1225,9 +1225,7 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
         }
 #else
         (void)softmax_item;
-#if PCA_A3_STAGGER
-        if (g == 1) __nanosleep(PCA_A3_STAGGER);      // start the two warpgroups in anti-phase (they share the MUFU pipe)
-#endif
+        bool stagger = (PCA_A3_STAGGER != 0) && g == 1;      // experiment: start the two warpgroups in anti-phase
         for (int w = blockIdx.x; w < n_work; w += wstep) {
             int cloud, tile0, nb;
             const int ntiles = work_tiles(w, cloud, tile0, nb);
@@ -1242,6 +1240,7 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
                     mbar_wait(&s_full[c], ph_s[j]);
                     ph_s[j] ^= 1;
                     fence_after_sync();
+                    if (stagger) { __nanosleep(PCA_A3_STAGGER); stagger = false; }
                     stamp(24);
                     if (live) {
                         uint32_t pk[16];
