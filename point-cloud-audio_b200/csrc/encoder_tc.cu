@@ -37,6 +37,7 @@ struct TcConsts {
     // split-bf16 (hi | lo) B operands of the finalize GEMMs, per ISAB: mab0.fc_o (N=64, K=64) and mab1 [Wk;Wv] (N=128, K=64)
     uint8_t WoS[2][2][8192];
     uint8_t WkvS[2][2][16384];
+    float WvT_P[64 * 64], WoT_P[64 * 64];          // pma.mab fc_v / fc_o transposed (k, f): coalesced reads in finalize_pool_kernel
     uint8_t AqPool[16384];                        // PMA: row r = scale * Wk_h^T fc_q(S)_h, h = r / 16 (A operand, 128 x 64)
     uint8_t WqS0[2048];                           // isab0.mab1.fc_q (64, d_in <= 4) as a split-bf16 K=16 B operand
     // k-major fp32 copies for finalize_isab: mab0.fc_o^T (64 x 64) and mab1 [Wk;Wv]^T (64 x 128), per ISAB
@@ -175,6 +176,8 @@ __global__ void prep_kernel(const float* __restrict__ params, int d_in, TcConsts
         case 14: pack_b_operand_split(m01.Wkv, 128, c->WkvS[0][0], c->WkvS[0][1]); break;
         case 15: pack_b_operand_split(m10.Wo, 64, c->WoS[1][0], c->WoS[1][1]); break;
         case 16: pack_b_operand_split(m11.Wkv, 128, c->WkvS[1][0], c->WkvS[1][1]); break;
+        case 17: transpose_weight(mp.Wkv + TD * TD, 64, c->WvT_P); break;
+        case 18: transpose_weight(mp.Wo, 64, c->WoT_P); break;
         default: break;
     }
 }
@@ -1497,50 +1500,65 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
     if (warp == 12) tmem_dealloc(tb, 512);
 }
 
-// merge the pooled partials, apply fc_v to the 8 pooled vectors, then the MAB tail and the final Linear
+// merge the pooled partials, apply fc_v to the 8 pooled vectors, then the MAB tail and the final Linear.
+// 4 clouds per 256-thread block (64 threads = 64 features per cloud); weights are read through k-major copies so that
+// the 64 threads of a cloud read consecutive addresses.
 struct PoolFinParams {
-    const float* part; int nslots;           // (B, nslots, 8, 66)
+    const float* part; int nslots; int B;    // (B, nslots, 8, 66)
     const float* QpS;                         // (64) fc_q(S)
-    const float* Wv; const float* bv;         // pma.mab.fc_v (64, 64), (64)
-    const float* Wo; const float* bo;         // pma.mab.fc_o
+    const float* WvT; const float* bv;        // pma.mab.fc_v transposed (k, f), bias (64)
+    const float* WoT; const float* bo;        // pma.mab.fc_o transposed (k, f), bias
     const float* Wl; const float* bl; int C;  // final Linear (C, 64)
     float* logits;                            // (B, C)
     float* pooled_debug;                      // nullable (B, 64)
 };
-__global__ void __launch_bounds__(64) finalize_pool_kernel(const PoolFinParams P) {
-    __shared__ float sZ[TH][TD + 1], sO[64], sO1[64];
-    const int cloud = blockIdx.x, f = threadIdx.x;
-    // thread f merges feature f of every head
-    for (int h = 0; h < TH; ++h) {
-        float mmax = -INFINITY;
-        for (int s = 0; s < P.nslots; ++s) mmax = fmaxf(mmax, P.part[(((size_t)cloud * P.nslots + s) * TH + h) * 66]);
-        float l = 0.f, z = 0.f;
-        for (int s = 0; s < P.nslots; ++s) {
-            const float* pp = P.part + (((size_t)cloud * P.nslots + s) * TH + h) * 66;
-            const float wgt = (pp[0] == -INFINITY) ? 0.f : exp2f(pp[0] - mmax);      // a warpgroup that saw no tile
-            l = fmaf(pp[1], wgt, l);
-            z = fmaf(pp[2 + f], wgt, z);
+__global__ void __launch_bounds__(256) finalize_pool_kernel(const PoolFinParams P) {
+    __shared__ float sZ[4][TH][TD + 1], sO[4][64], sO1[4][64];
+    const int sub = threadIdx.x >> 6, f = threadIdx.x & 63;
+    const int cloud = blockIdx.x * 4 + sub;
+    const bool valid = cloud < P.B;
+    if (valid) {
+        // thread f merges feature f of every head
+#pragma unroll
+        for (int h = 0; h < TH; ++h) {
+            const float* p0 = P.part + (((size_t)cloud * P.nslots) * TH + h) * 66;
+            float mmax = -INFINITY;
+            for (int s = 0; s < P.nslots; ++s) mmax = fmaxf(mmax, __ldg(p0 + (size_t)s * TH * 66));
+            float l = 0.f, z = 0.f;
+            for (int s = 0; s < P.nslots; ++s) {
+                const float* pp = p0 + (size_t)s * TH * 66;
+                const float m = __ldg(pp);
+                const float wgt = (m == -INFINITY) ? 0.f : exp2f(m - mmax);      // a warpgroup that saw no tile
+                l = fmaf(__ldg(pp + 1), wgt, l);
+                z = fmaf(__ldg(pp + 2 + f), wgt, z);
+            }
+            sZ[sub][h][f] = z / l;
         }
-        sZ[h][f] = z / l;
     }
     __syncthreads();
-    {
+    if (valid) {
         const int h = f >> 3;
-        float a = P.bv[f];
-        for (int k = 0; k < 64; ++k) a = fmaf(sZ[h][k], P.Wv[f * 64 + k], a);
-        sO[f] = P.QpS[f] + a;
+        float a = __ldg(P.bv + f);
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k) a = fmaf(sZ[sub][h][k], __ldg(P.WvT + k * 64 + f), a);
+        sO[sub][f] = __ldg(P.QpS + f) + a;
     }
     __syncthreads();
-    float acc = P.bo[f];
-    for (int k = 0; k < 64; ++k) acc = fmaf(sO[k], P.Wo[f * 64 + k], acc);
-    const float o1 = sO[f] + fmaxf(acc, 0.f);
-    sO1[f] = o1;
-    if (P.pooled_debug) P.pooled_debug[(size_t)cloud * 64 + f] = o1;
+    if (valid) {
+        float acc = __ldg(P.bo + f);
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k) acc = fmaf(sO[sub][k], __ldg(P.WoT + k * 64 + f), acc);
+        const float o1 = sO[sub][f] + fmaxf(acc, 0.f);
+        sO1[sub][f] = o1;
+        if (P.pooled_debug) P.pooled_debug[(size_t)cloud * 64 + f] = o1;
+    }
     __syncthreads();
-    for (int c = f; c < P.C; c += 64) {
-        float z = P.bl[c];
-        for (int k = 0; k < 64; ++k) z = fmaf(sO1[k], P.Wl[c * 64 + k], z);
-        P.logits[(size_t)cloud * P.C + c] = z;
+    if (valid) {
+        for (int c = f; c < P.C; c += 64) {
+            float z = __ldg(P.bl + c);
+            for (int k = 0; k < 64; ++k) z = fmaf(sO1[sub][k], __ldg(P.Wl + c * 64 + k), z);
+            P.logits[(size_t)cloud * P.C + c] = z;
+        }
     }
 }
 
@@ -1667,10 +1685,10 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     }
     PCA_CHECK_LAUNCH("pma_pool_tc_kernel");
     {
-        PoolFinParams p{part, 2 * sp.nsplit, c->QpS, mp.Wkv + TD * TD, mp.bkv + TD, mp.Wo, mp.bo, p_lin, p_lin + (long long)d->C * TD,
+        PoolFinParams p{part, 2 * sp.nsplit, B, c->QpS, c->WvT_P, mp.bkv + TD, c->WoT_P, mp.bo, p_lin, p_lin + (long long)d->C * TD,
                         d->C, logits, dbg ? dbg->pooled : nullptr};
         LaunchTimer lt("finalize_pool_kernel", st, (double)B * 2.0 * (2.0 * TD * TD + TD * d->C), (double)B * 4.0 * d->C);
-        finalize_pool_kernel<<<B, 64, 0, st>>>(p);
+        finalize_pool_kernel<<<(B + 3) / 4, 256, 0, st>>>(p);
     }
     PCA_CHECK_LAUNCH("finalize_pool_kernel");
     if (dbg) {
@@ -1710,7 +1728,7 @@ int st_tc_forward_dbg(const float* X, const int* counts, int B, int N, const pca
     if (dbg && chunk < B) return fail(PCA_EWORKSPACE, "ST(bf16) debug: workspace must hold the whole batch");
     uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
     TcConsts* c = reinterpret_cast<TcConsts*>(w8 + tc_layout(chunk, N).consts);
-    prep_kernel<<<17, 256, 0, st>>>(params, d->d_in, c);
+    prep_kernel<<<19, 256, 0, st>>>(params, d->d_in, c);
     PCA_CHECK_LAUNCH("prep_kernel");
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int bc = (B - b0) < chunk ? (B - b0) : chunk;
