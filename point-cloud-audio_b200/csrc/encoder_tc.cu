@@ -841,12 +841,16 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
 //     register work (bias bq is added where OQ is read);
 //   * probabilities are normalised before they are written (P = e / sum), so no per-row rescale of the outputs;
 //   * the softmax warps do nothing but  wait -> tcgen05.ld -> max -> 2^x -> sum -> scale -> pack -> tcgen05.st -> arrive;
-//   * dedicated epilogue warps turn OQ into the bf16 A operand of fc_o (written back to TMEM, not shared memory), and
-//     after the fc_o MMA emit Y = O1 + relu(fc_o(O1) + bo).
+//   * dedicated epilogue warps turn OQ into the bf16 A operand of fc_o (staged in shared memory), and after the fc_o MMA
+//     emit Y = O1 + relu(fc_o(O1) + bo); three tile accumulators are in flight (Q projection -> P V -> epilogue), so
+//     the projection of tile t+2 never waits for the epilogue of tile t;
+//   * every MMA-issuing warp runs in uniform control flow with one elected lane issuing (descriptors stay in uniform
+//     registers; a lone `if (lane == 0)` thread costs ~250 cycles per tcgen05.mma in R2UR/ELECT loops and spills).
 // A chain is a head PAIR (its two heads run back to back on the chain's score buffer and accumulate into the pair's 16
 // output columns from one issuing thread, so no cross-thread accumulate hazard exists).
 constexpr int TC_THREADS20 = 20 * 32;
-constexpr uint32_t A3_S = 0, A3_OQ = 256, A3_O1B = 384, A3_F = 416;      // 4 x 64 | 2 x 64 | 32 | 64  (of 512 columns)
+constexpr int A3_NBUF = 3;                        // tile accumulators in flight (Q projection -> P V -> epilogue)
+constexpr uint32_t A3_S = 0, A3_OQ = 256, A3_F = 448;      // 4 x 64 scores | 3 x 64 tile accumulators | 64 fc_o  (= 512 columns)
 
 struct A3Smem {
     static constexpr int IMG = 0;                 // 2 x (K image 16384 | V image 16384), one per work item in flight
@@ -854,7 +858,8 @@ struct A3Smem {
     static constexpr int WQ = WO + 8192;          // fc_q B operand: (N=64, K=64) or the split-bf16 K=16 image
     static constexpr int AQ = WQ + 8192;          // 2 stages x 16384: scaled bf16 queries (A operand of Q K^T)
     static constexpr int YA = AQ + 32768;         // input tile: Y (128 x 64 bf16) or the split-bf16 X columns (128 x 16)
-    static constexpr int SMALL = YA + 16384;      // bq (64) | bo (64)
+    static constexpr int O1 = YA + 16384;         // O1 tile as the bf16 A operand of fc_o (written by the epilogue warps)
+    static constexpr int SMALL = O1 + 16384;      // bq (64) | bo (64)
     static constexpr int BARS = SMALL + 128 * 4;
     static constexpr int TOTAL = BARS + 40 * 8 + 16;
 };
@@ -874,7 +879,12 @@ constexpr uint32_t kPolyPairs3 = PCA_POLY3;
 __device__ __forceinline__ void exp_keep32(uint32_t* v, const float2 neg_m2, float2& sum2) {
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
+#ifdef PCA_A3_NOMAX
+        const float2 x = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+        (void)neg_m2;
+#else
         const float2 x = add2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), neg_m2);
+#endif
         const float2 e = ((kPolyPairs3 >> (j >> 1)) & 1u) ? ex2_poly2(x) : make_float2(ex2(x.x), ex2(x.y));
         sum2 = add2(sum2, e);
         v[j] = __float_as_uint(e.x);
@@ -897,6 +907,7 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
     uint8_t* sWq = smem + A3Smem::WQ;
     uint8_t* sAQ = smem + A3Smem::AQ;
     uint8_t* sYA = smem + A3Smem::YA;
+    uint8_t* sO1 = smem + A3Smem::O1;
     float* sBq = reinterpret_cast<float*>(smem + A3Smem::SMALL);
     float* sBo = sBq + 64;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A3Smem::BARS);
@@ -904,18 +915,33 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
     uint64_t* aq_empty = bars + 2;     // [2] count 4 (chain commits)
     uint64_t* s_full = bars + 4;       // [4] count 1
     uint64_t* p_ready = bars + 8;      // [4] count 4 (warps of the owning warpgroup)
-    uint64_t* o_full = bars + 12;      // [2] count 4 (chain commits)          -- per OQ buffer
-    uint64_t* oq_free = bars + 14;     // [2] count 4 (epilogue warps)         -- per OQ buffer
-    uint64_t* ya_full = bars + 16;     // count 4
-    uint64_t* qp_done = bars + 17;     // count 1
-    uint64_t* o1_ready = bars + 18;    // count 4 (epilogue warps)
-    uint64_t* f_full = bars + 19;      // count 1
-    uint64_t* img_full = bars + 20;    // [2] count 4 (producer warps)
-    uint64_t* img_empty = bars + 22;   // [2] count 4 (chain commits)
+    uint64_t* o_full = bars + 12;      // [3] count 4 (chain commits)          -- per OQ buffer
+    uint64_t* oq_free = bars + 15;     // [3] count 4 (epilogue warps)         -- per OQ buffer
+    uint64_t* ya_full = bars + 18;     // count 4
+    uint64_t* qp_done = bars + 19;     // count 1
+    uint64_t* o1_ready = bars + 20;    // count 4 (epilogue warps)
+    uint64_t* f_full = bars + 21;      // count 1
+    uint64_t* img_full = bars + 22;    // [2] count 4 (producer warps)
+    uint64_t* img_empty = bars + 24;   // [2] count 4 (chain commits)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_work = P.n_work, wstep = gridDim.x;
+#ifdef PCA_TIMELINE
+    // debug: role warps 16 (epilogue), 8 (producer), 12 (MMA chain 0) of CTA 0 record into their own 1000-stamp segments
+    long long* tl2 = nullptr;
+    int tl2_n = 0;
+    if (P.timeline != nullptr && blockIdx.x == 0 && lane == 0) {
+        if (warp == 16) tl2 = P.timeline + 2000;
+        else if (warp == 8) tl2 = P.timeline + 4000;
+        else if (warp == 12) tl2 = P.timeline + 6000;
+    }
+    auto stamp2 = [&](int tag) {
+        if (tl2 != nullptr && tl2_n < 1000) { tl2[2 * tl2_n] = tag; tl2[2 * tl2_n + 1] = clock64(); ++tl2_n; }
+    };
+#else
+    auto stamp2 = [&](int) {};
+#endif
     // tiles of work item w; nb = valid points of its cloud (variable-size sets: rows past nb are padding)
     auto work_tiles = [&](int w, int& cloud, int& tile0, int& nb) {
         cloud = w / P.nsplit;
@@ -934,9 +960,10 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
     if (warp == 12) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&aq_full[i], 4); mbar_init(&aq_empty[i], 4); mbar_init(&o_full[i], 4); mbar_init(&oq_free[i], 4);
+            mbar_init(&aq_full[i], 4); mbar_init(&aq_empty[i], 4);
             mbar_init(&img_full[i], 4); mbar_init(&img_empty[i], 4);
         }
+        for (int i = 0; i < A3_NBUF; ++i) { mbar_init(&o_full[i], 4); mbar_init(&oq_free[i], 4); }
         for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
         mbar_init(ya_full, 4);
         mbar_init(qp_done, 1);
@@ -951,7 +978,7 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
     const uint32_t tb = *tmem_slot;
 
     if (warp >= 16) {
-        // register budget: the CTA's pool is 20 warps x 96; softmax 8 x 152 + producer 4 x 56 + MMA 4 x 24 + epilogue 4 x 96 = 1920
+        // register budget: the CTA's pool is 20 warps x 96; softmax 8 x 144 + producer 4 x 56 + MMA 4 x 40 + epilogue 4 x 96 = 1920
         // =================================================================== epilogue warps (thread = point row)
         const int quad = warp & 3;
         const int row = 32 * quad + lane;
@@ -961,43 +988,53 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
             int cloud, tile0, nb;
             const int ntiles = work_tiles(w, cloud, tile0, nb);
             for (int it = 0; it < ntiles; ++it, ++gt) {
-                const int buf = gt & 1;
+                const int buf = gt % A3_NBUF;
                 const int n = (tile0 + it) * 128 + row;
                 const bool valid = n < nb;
                 const bool live = (tile0 + it) * 128 + 32 * quad < nb;
                 const uint32_t oq = tmem_addr(tb, lane_base, A3_OQ + 64 * buf);
                 // ---- O1 = OQ + bq  ->  bf16 A operand of fc_o, written back to TMEM
-                mbar_wait(&o_full[buf], (gt >> 1) & 1);
+                stamp2(40);
+                mbar_wait(&o_full[buf], (gt / A3_NBUF) & 1);
+                stamp2(41);
                 fence_after_sync();
                 if (live) {
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
-                        uint32_t v[32], pk[16];
+                        uint32_t v[32];
                         tmem_ld32(oq + 32 * hf, v);
                         tmem_ld_wait32(v);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2)
-                            pk[j >> 1] = pack_bf16(__uint_as_float(v[j]) + sBq[32 * hf + j], __uint_as_float(v[j + 1]) + sBq[32 * hf + j + 1]);
-                        tmem_st16(tmem_addr(tb, lane_base, A3_O1B + 16 * hf), pk);
+                        for (int q = 0; q < 4; ++q) {
+                            float o[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[8 * q + j]) + sBq[32 * hf + 8 * q + j];
+                            st_shared_8bf16(sO1 + (4 * hf + q) * 2048 + row * 16, o);
+                        }
                     }
-                    tmem_st_wait();
                 }
+                stamp2(42);
+                fence_async_smem();
                 fence_before_sync();
                 warp_arrive(o1_ready);
-                if (warp == 16 && lane == 0) {
-                    // one epilogue thread issues fc_o: F = O1 Wo^T, A operand from TMEM
+                if (warp == 16) {
+                    // one epilogue warp issues fc_o (elected lane): F = O1 Wo^T, A operand from TMEM
                     mbar_wait(o1_ready, gt & 1);
                     fence_after_sync();
-                    const uint32_t wo = smem_u32(sWo);
+                    if (elect_one()) {
+                        const uint32_t wo = smem_u32(sWo), o1b = smem_u32(sO1);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_ts(tmem_addr(tb, 0, A3_F), tmem_addr(tb, 0, A3_O1B + 8 * ks), smem_desc(wo + ks * 2048, 1024, 128),
-                               idesc_bf16(128, 64, 0, 0), ks > 0);
-                    mma_commit(f_full);
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ss(tmem_addr(tb, 0, A3_F), smem_desc(o1b + ks * 4096, 2048, 128), smem_desc(wo + ks * 2048, 1024, 128),
+                                   idesc_bf16(128, 64, 0, 0), ks > 0);
+                        mma_commit(f_full);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
                 // ---- Y = O1 + relu(F + bo)
+                stamp2(43);
                 mbar_wait(f_full, gt & 1);
+                stamp2(44);
                 fence_after_sync();
                 if (live) {
                     __nv_bfloat16* dst = P.Yout + ((size_t)cloud * P.N + (valid ? n : 0)) * 64;
@@ -1024,15 +1061,19 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
                         }
                     }
                 }
+                stamp2(45);
                 fence_before_sync();
                 warp_arrive(&oq_free[buf]);
             }
         }
     } else if (warp >= 12) {
-        reg_dec<24>();
-        if (lane == 0) {
-            // =================================================================== one MMA-issuing thread per chain (= head pair)
+        reg_dec<40>();
+        {
+            // =================================================================== one MMA-issuing warp per chain (= head pair)
+            // The whole warp runs the loop (uniform control flow keeps the descriptors in uniform registers); one
+            // elected lane issues the tcgen05 instructions.
             const int c = warp - 12;                      // pair c, score buffer c, output columns 16c..16c+15
+            const bool leader = elect_one();
             const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
             const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
             const uint32_t img = smem_u32(sImg), aqb = smem_u32(sAQ);
@@ -1044,26 +1085,41 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
                 mbar_wait(&img_full[wl & 1], (wl >> 1) & 1);
                 fence_after_sync();
                 for (int it = 0; it < ntiles; ++it, ++gt) {
+                    const int buf = gt % A3_NBUF;
                     const uint32_t a_desc_base = aqb + (gt & 1) * 16384 + 2 * c * 2048;
-                    const uint32_t d_o = tmem_addr(tb, 0, A3_OQ + 64 * (gt & 1) + 16 * c);
+                    const uint32_t d_o = tmem_addr(tb, 0, A3_OQ + 64 * buf + 16 * c);
+                    stamp2(60);
                     mbar_wait(&aq_full[gt & 1], (gt >> 1) & 1);
                     fence_after_sync();
+                    stamp2(61);
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        mma_ss(tmem_addr(tb, 0, A3_S + 64 * c), smem_desc(a_desc_base, 2048, 128),
-                               smem_desc(kb + hh * 1024, 2048, 128), idesc_s, 0);
-                        mma_commit(&s_full[c]);
+                        if (leader) {
+                            mma_ss(tmem_addr(tb, 0, A3_S + 64 * c), smem_desc(a_desc_base, 2048, 128),
+                                   smem_desc(kb + hh * 1024, 2048, 128), idesc_s, 0);
+                            mma_commit(&s_full[c]);
+                        }
+                        __syncwarp();
+                        stamp2(62);
                         mbar_wait(&p_ready[c], hh);          // two items per tile: parities 0, 1
                         fence_after_sync();
+                        stamp2(63);
+                        if (leader) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ts(d_o, tmem_addr(tb, 0, A3_S + 64 * c + ks * 8), smem_desc(vb + hh * 1024 + ks * 256, 128, 2048),
-                                   idesc_pv, 1u);
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_ts(d_o, tmem_addr(tb, 0, A3_S + 64 * c + ks * 8), smem_desc(vb + hh * 1024 + ks * 256, 128, 2048),
+                                       idesc_pv, 1u);
+                        }
+                        __syncwarp();
                     }
-                    mma_commit(&o_full[gt & 1]);            // 4 chains: the tile's O1 is complete
-                    mma_commit(&aq_empty[gt & 1]);          // ... and its query stage is free
+                    if (leader) {
+                        mma_commit(&o_full[buf]);               // 4 chains: the tile's O1 is complete
+                        mma_commit(&aq_empty[gt & 1]);          // ... and its query stage is free
+                    }
+                    __syncwarp();
                 }
-                mma_commit(&img_empty[wl & 1]);
+                if (leader) mma_commit(&img_empty[wl & 1]);
+                __syncwarp();
             }
         }
     } else if (warp >= 8) {
@@ -1091,6 +1147,7 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
                 const int n = (tile0 + it) * 128 + row;
                 const bool valid = n < nb;
                 uint8_t* dst = sAQ + stage * 16384;
+                stamp2(50);
                 // ---- stage the input tile (sYA is free: the previous tile's projection MMA was waited for below)
                 if (!DIN64) {
                     float x[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1113,26 +1170,34 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
                 fence_async_smem();
                 fence_before_sync();
                 warp_arrive(ya_full);
-                if (warp == 8 && lane == 0) {
-                    // one producer thread issues the Q projection into the tile's accumulator (free once the epilogue of
-                    // two tiles ago has read it)
+                stamp2(51);
+                const int buf = gt % A3_NBUF;
+                if (warp == 8) {
+                    // one producer warp issues the Q projection (elected lane) into the tile's accumulator, which is free
+                    // once the epilogue of A3_NBUF tiles ago has read it
                     mbar_wait(ya_full, gt & 1);
-                    if (gt >= 2) mbar_wait(&oq_free[stage], ((gt >> 1) - 1) & 1);
+                    if (gt >= A3_NBUF) mbar_wait(&oq_free[buf], ((gt / A3_NBUF) - 1) & 1);
+                    stamp2(56);
                     fence_after_sync();
-                    const uint32_t yab = smem_u32(sYA), wq = smem_u32(sWq);
+                    if (elect_one()) {
+                        const uint32_t yab = smem_u32(sYA), wq = smem_u32(sWq);
 #pragma unroll
-                    for (int ks = 0; ks < (DIN64 ? 4 : 1); ++ks)
-                        mma_ss(tmem_addr(tb, 0, A3_OQ + 64 * stage), smem_desc(yab + ks * 4096, 2048, 128),
-                               smem_desc(wq + ks * 2048, 1024, 128), idesc_bf16(128, 64, 0, 0), ks > 0);
-                    mma_commit(qp_done);
+                        for (int ks = 0; ks < (DIN64 ? 4 : 1); ++ks)
+                            mma_ss(tmem_addr(tb, 0, A3_OQ + 64 * buf), smem_desc(yab + ks * 4096, 2048, 128),
+                                   smem_desc(wq + ks * 2048, 1024, 128), idesc_bf16(128, 64, 0, 0), ks > 0);
+                        mma_commit(qp_done);
+                    }
+                    __syncwarp();
                 }
                 mbar_wait(qp_done, gt & 1);
                 fence_after_sync();
+                stamp2(52);
                 if (gt >= 2) mbar_wait(&aq_empty[stage], ((gt >> 1) - 1) & 1);
+                stamp2(53);
 #pragma unroll
                 for (int c0 = 0; c0 < 64; c0 += 32) {
                     uint32_t v[32];
-                    tmem_ld32(tmem_addr(tb, 32 * quad, A3_OQ + 64 * stage + c0), v);
+                    tmem_ld32(tmem_addr(tb, 32 * quad, A3_OQ + 64 * buf + c0), v);
                     tmem_ld_wait32(v);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -1142,13 +1207,14 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
                         st_shared_8bf16(dst + (c0 / 8 + q) * 2048 + row * 16, o);
                     }
                 }
+                stamp2(54);
                 fence_async_smem();
                 fence_before_sync();
                 warp_arrive(&aq_full[stage]);
             }
         }
     } else {
-        reg_inc<152>();
+        reg_inc<144>();
         // =================================================================== softmax warpgroups (chains 2g, 2g+1)
         const int g = warp >> 2, quad = warp & 3;
         const uint32_t lane_base = 32 * quad;
@@ -1157,7 +1223,7 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
         long long* tl = (P.timeline != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0) ? P.timeline : nullptr;
         int tl_n = 0;
         auto stamp = [&](int tag) {
-            if (tl != nullptr && tl_n < 4000) { tl[2 * tl_n] = tag; tl[2 * tl_n + 1] = clock64(); ++tl_n; }
+            if (tl != nullptr && tl_n < 1000) { tl[2 * tl_n] = tag; tl[2 * tl_n + 1] = clock64(); ++tl_n; }
         };
 #else
         auto stamp = [&](int) {};
@@ -1251,7 +1317,24 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
                         tmem_ld32(sbase + 32, vb);
                         tmem_ld_wait64(va, vb);
                         stamp(25);
+#ifdef PCA_A3_NOEXP
+                        // EXPERIMENT ONLY: no softmax arithmetic at all (what does the rest of the pipeline cost?)
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) pk[q] = pack_bf16(__uint_as_float(va[2 * q]), __uint_as_float(va[2 * q + 1]));
+                        tmem_st16(sbase, pk);
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) pk[q] = pack_bf16(__uint_as_float(vb[2 * q]), __uint_as_float(vb[2 * q + 1]));
+                        tmem_st16(sbase + 16, pk);
+                        tmem_st_wait();
+                        fence_before_sync();
+                        warp_arrive(&p_ready[c]);
+                        continue;
+#endif
+#ifdef PCA_A3_NOMAX
+                        const float mx = 0.f;      // EXPERIMENT ONLY (upper bound of folding the shift into the MMA)
+#else
                         const float mx = max64(va, vb);
+#endif
                         const float2 neg2 = make_float2(-mx, -mx);
                         float2 sum2 = make_float2(0.f, 0.f);
                         exp_keep32(va, neg2, sum2);

@@ -41,25 +41,25 @@ with torch.no_grad():
     st(X)
     torch.cuda.synchronize()
     _lib.lib().pca_debug_set_timeline(None)
-t = buf.cpu().numpy().reshape(-1, 2)
-t = t[t[:, 1] > 0]
-tags, clk = t[:, 0], t[:, 1]
-names = {0: "item: before ld wait", 1: "ld wait done", 2: "max + exp a + st", 3: "s_full(next) wait + ld issue", 4: "exp b + st",
-         5: "st wait", 6: "fence + arrive p_ready", 7: "o_full[0] wait", 8: "O1 pair 0", 9: "o_full[1] wait", 10: "O1 pair 1",
-         11: "arrive o1_ready", 12: "f_epilogue start", 13: "f_full wait", 14: "f_epilogue done", 15: "tile start",
-         16: "issue_loads(0) done", 20: "item0 start", 21: "item1 start", 22: "item2 start", 23: "item3 start", 24: "s_full wait done",
-         25: "ld wait done", 26: "max/exp/scale/pack/st issued", 27: "st wait done"}
-d = np.diff(clk)
-agg = collections.defaultdict(list)
-for i in range(1, len(tags)):
-    agg[(int(tags[i - 1]), int(tags[i]))].append(int(d[i - 1]))
-ntile = int((tags == 15).sum()) or int((tags == 20).sum())
-print("stamps", len(tags), "span cycles", int(clk[-1] - clk[0]), "tiles", ntile)
-tot = 0
-for k, v in sorted(agg.items()):
-    v = np.array(v[4:]) if len(v) > 16 else np.array(v)
-    print(f"{names[k[0]]:30s} -> {names[k[1]]:30s} n={len(v):4d} median={int(np.median(v)):6d} mean={int(v.mean()):6d} "
-          f"p90={int(np.percentile(v, 90)):6d}  per-tile {v.sum() / max(ntile, 1):8.0f}")
-    tot += v.sum()
-per_tile = np.diff(clk[tags == (15 if (tags == 15).any() else 20)])
-print("cycles per tile: median", int(np.median(per_tile)), "mean", int(per_tile.mean()))
+raw = buf.cpu().numpy()
+names = {20: "item start", 24: "s_full wait done", 25: "ld wait done", 26: "softmax math + st issued", 27: "st wait done",
+         40: "epi: tile start", 41: "epi: o_full wait done", 42: "epi: O1 -> bf16 TMEM done", 43: "epi: arrived o1_ready (+MMA issue)",
+         44: "epi: f_full wait done", 45: "epi: Y stored", 50: "prod: tile start", 51: "prod: input staged + arrived",
+         52: "prod: qp_done wait done", 53: "prod: aq_empty wait done", 54: "prod: AQ converted", 56: "prod0: oq_free wait done",
+         60: "mma: tile start", 61: "mma: aq_full wait done", 62: "mma: S issued", 63: "mma: p_ready wait done"}
+for role, off in (("softmax warp 0", 0), ("epilogue warp 16", 2000), ("producer warp 8", 4000), ("MMA chain 0", 6000)):
+    t = raw[off:off + 2000].reshape(-1, 2)
+    t = t[t[:, 1] > 0]
+    if len(t) < 10:
+        continue
+    tags, clk = t[:, 0], t[:, 1]
+    d = np.diff(clk)
+    agg = collections.defaultdict(list)
+    for i in range(1, len(tags)):
+        agg[(int(tags[i - 1]), int(tags[i]))].append(int(d[i - 1]))
+    first = int(tags[0])
+    per = np.diff(clk[tags == first])
+    print(f"== {role}: {len(tags)} stamps; cycles per period (tag {first}): median {int(np.median(per))} mean {int(per.mean())}")
+    for k, v in sorted(agg.items()):
+        v = np.array(v[2:]) if len(v) > 8 else np.array(v)
+        print(f"   {names.get(k[0], k[0]):36s} -> {names.get(k[1], k[1]):36s} n={len(v):4d} median={int(np.median(v)):6d} mean={int(v.mean()):6d} p90={int(np.percentile(v, 90)):6d}")
