@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(128) finalize_isab_tc_kernel(const F2Params P)
         tmem_st_wait();
         fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             fence_after_sync();
             const uint32_t idesc = idesc_bf16(128, 64, 0, 0);
 #pragma unroll
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(128) finalize_isab_tc_kernel(const F2Params P)
         tmem_st_wait();
         fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             fence_after_sync();
             const uint32_t idesc = idesc_bf16(128, 128, 0, 0);
 #pragma unroll
@@ -586,11 +586,13 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
 
     if (warp >= 12) {
         reg_dec<40>();
-        if (lane == 0) {
-            // =================================================================== one MMA-issuing thread per chain
+        {
+            // =================================================================== one MMA-issuing warp per chain
             // chain c = warp - 12: strictly serial  Q K^T -> (warpgroup softmax) -> P V -> next Q K^T  on its own
-            // half-buffer; the four chains never wait on each other.
+            // half-buffer; the four chains never wait on each other.  The whole warp runs the loop (uniform control flow
+            // keeps the descriptors in uniform registers); one elected lane issues the tcgen05 instructions.
             const int c = warp - 12, half = c & 1;
+            const bool leader = elect_one();
             const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
             const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
             const uint32_t aq = smem_u32(sAq), kvb = smem_u32(sKV);
@@ -609,20 +611,29 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                     for (int pp = 0; pp < 2; ++pp) {
                         if (empty_half) break;
                         const int p = (c >> 1) + 2 * pp;
-                        mma_ss(tmem_addr(tb, 0, R2_S + 64 * c), smem_desc(aq + p * 4096, 2048, 128),
-                               smem_desc(kbase + 2 * p * 2048 + half * 1024, 2048, 128), idesc_s, 0);
-                        mma_commit(&s_full[c]);
+                        if (leader) {
+                            mma_ss(tmem_addr(tb, 0, R2_S + 64 * c), smem_desc(aq + p * 4096, 2048, 128),
+                                   smem_desc(kbase + 2 * p * 2048 + half * 1024, 2048, 128), idesc_s, 0);
+                            mma_commit(&s_full[c]);
+                        }
+                        __syncwarp();
                         mbar_wait(&p_ready[c], ph_p);
                         ph_p ^= 1;
                         fence_after_sync();
+                        if (leader) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ts(tmem_addr(tb, 0, R2_O + 16 * (2 * p + half)), tmem_addr(tb, 0, R2_S + 64 * c + ks * 8),
-                                   smem_desc(vbase + 2 * p * 2048 + half * 1024 + ks * 256, 128, 2048), idesc_pv, (it > 0 || ks > 0) ? 1u : 0u);
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_ts(tmem_addr(tb, 0, R2_O + 16 * (2 * p + half)), tmem_addr(tb, 0, R2_S + 64 * c + ks * 8),
+                                       smem_desc(vbase + 2 * p * 2048 + half * 1024 + ks * 256, 128, 2048), idesc_pv,
+                                       (it > 0 || ks > 0) ? 1u : 0u);
+                        }
+                        __syncwarp();
                     }
-                    mma_commit(&kv_empty[gt & 1]);            // 4 chains x 1 arrival free the K|V stage
+                    if (leader) mma_commit(&kv_empty[gt & 1]);            // 4 chains x 1 arrival free the K|V stage
+                    __syncwarp();
                 }
-                mma_commit(&o_done[c]);                       // the work item's accumulators are final
+                if (leader) mma_commit(&o_done[c]);                       // the work item's accumulators are final
+                __syncwarp();
             }
         }
     } else if (warp >= 8) {
@@ -667,16 +678,19 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                     fence_async_smem();
                     fence_before_sync();
                     warp_arrive(y_full);
-                    if (warp == 8 && lane == 0) {
-                        // one producer thread issues the K|V projection MMA once all 128 rows of Y are staged
+                    if (warp == 8) {
+                        // one producer warp issues the K|V projection MMA (elected lane) once all 128 rows of Y are staged
                         mbar_wait(y_full, gt & 1);
                         fence_after_sync();
-                        const uint32_t yb = smem_u32(sY), wb = smem_u32(sW);
+                        if (elect_one()) {
+                            const uint32_t yb = smem_u32(sY), wb = smem_u32(sW);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ss(tmem_addr(tb, 0, R2_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
-                                   idesc_bf16(128, 128, 0, 0), ks > 0);
-                        mma_commit(proj_done);
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_ss(tmem_addr(tb, 0, R2_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
+                                       idesc_bf16(128, 128, 0, 0), ks > 0);
+                            mma_commit(proj_done);
+                        }
+                        __syncwarp();
                     }
                     mbar_wait(proj_done, gt & 1);
                     fence_after_sync();
@@ -1422,8 +1436,10 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
 
     if (warp >= 12) {
         reg_dec<40>();
-        if (warp == 12 && lane == 0) {
+        if (warp == 12) {
             // =================================================================== MMA issuer (tiles in order; S runs one tile ahead)
+            // whole warp in uniform control flow, one elected lane issues
+            const bool leader = elect_one();
             const uint32_t idesc_s = idesc_bf16(128, 128, 0, 0);
             const uint32_t idesc_pv = idesc_bf16(128, 64, 0, 1);
             const uint32_t aq = smem_u32(sAq), yb = smem_u32(sY);
@@ -1433,25 +1449,31 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
                 const int stage = t % POOL_STAGES;
                 mbar_wait(&y_full[stage], (t / POOL_STAGES) & 1);
                 fence_after_sync();
+                if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma_ss(tmem_addr(tb, 0, PC_S + 128 * (t & 1)), smem_desc(aq + ks * 4096, 2048, 128),
-                           smem_desc(yb + stage * 16384 + ks * 4096, 2048, 128), idesc_s, ks > 0);
-                mma_commit(&s_full[t & 1]);
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_ss(tmem_addr(tb, 0, PC_S + 128 * (t & 1)), smem_desc(aq + ks * 4096, 2048, 128),
+                               smem_desc(yb + stage * 16384 + ks * 4096, 2048, 128), idesc_s, ks > 0);
+                    mma_commit(&s_full[t & 1]);
+                }
+                __syncwarp();
             };
             if (total > 0) issue_s(0);
             for (int t = 0; t < total; ++t) {
-                // S(t+1) overwrites the buffer whose P was consumed by PV(t-1): issued earlier by this thread, in order
+                // S(t+1) overwrites the buffer whose P was consumed by PV(t-1): issued earlier by this warp, in order
                 if (t + 1 < total) issue_s(t + 1);
                 const int b = t & 1, stage = t % POOL_STAGES;
                 mbar_wait(&p_ready[b], (t >> 1) & 1);
                 fence_after_sync();
+                if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    mma_ts(tmem_addr(tb, 0, PC_O + 64 * b), tmem_addr(tb, 0, PC_S + 128 * b + ks * 8),
-                           smem_desc(yb + stage * 16384 + ks * 256, 128, 2048), idesc_pv, ks > 0);
-                mma_commit(&o_full[b]);
-                mma_commit(&y_empty[stage]);
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_ts(tmem_addr(tb, 0, PC_O + 64 * b), tmem_addr(tb, 0, PC_S + 128 * b + ks * 8),
+                               smem_desc(yb + stage * 16384 + ks * 256, 128, 2048), idesc_pv, ks > 0);
+                    mma_commit(&o_full[b]);
+                    mma_commit(&y_empty[stage]);
+                }
+                __syncwarp();
             }
         }
     } else if (warp >= 8) {
