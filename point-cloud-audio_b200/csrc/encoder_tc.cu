@@ -756,11 +756,18 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
             float sum;
             if (nv == 64) {
                 if (first) { m_used[half][pp] = max64(va, vb); l_run[half][pp] = 0.f; }
+#ifdef PCA_R5_NOEXP
+                // EXPERIMENT ONLY: no softmax arithmetic (what does the rest of the pipeline cost?)
+#pragma unroll
+                for (int q = 0; q < 16; ++q) { pk0[q] = pack_bf16(__uint_as_float(va[2 * q]), __uint_as_float(va[2 * q + 1])); pk1[q] = pack_bf16(__uint_as_float(vb[2 * q]), __uint_as_float(vb[2 * q + 1])); }
+                sum = 1.f;
+#else
                 const float2 neg2 = make_float2(-m_used[half][pp], -m_used[half][pp]);
                 float2 sum2 = make_float2(0.f, 0.f);
                 exp_chunk32(va, neg2, sum2, pk0);
                 exp_chunk32(vb, neg2, sum2, pk1);
                 sum = sum2.x + sum2.y;
+#endif
             } else {
                 // ragged tail: columns >= nv are padding
                 if (first) {

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib, _runtime as rt
+from . import ops as _ops  # noqa: F401  (registers torch.ops.pcaudio.*)
 
 
 def coord_tables(fs: float, nf: int, n_fft: int, hop_factor: float, ntemp: int | None = None):
@@ -40,14 +41,7 @@ def stft_logmag(audio: torch.Tensor, n_fft: int, win_length: int | None = None, 
     nt = nt_all if n_frames is None else int(n_frames)
     nf = n_fft // 2 + 1 - (1 if drop_nyquist else 0)
     win, tw = rt.stft_tables(n_fft, win_length, audio.device)
-    out = torch.empty((B, nt, nf), dtype=torch.float32, device=audio.device)
-    if out.numel() == 0:
-        return out
-    with torch.cuda.device(audio.device):
-        _lib.check(_lib.lib().pca_stft_logmag_f32(
-            _lib.ptr(audio), B, L, n_fft, hop, _lib.ptr(win), _lib.ptr(tw), 1.0 / divisor,
-            int(drop_nyquist), nt, _lib.ptr(out), rt.stream_ptr(audio.device)), "stft_logmag")
-    return out
+    return torch.ops.pcaudio.stft_logmag(audio, win, tw, n_fft, hop, 1.0 / divisor, bool(drop_nyquist), nt)
 
 
 def build_clouds(logmag: torch.Tensor, farr, tarr=None) -> torch.Tensor:
@@ -107,16 +101,8 @@ def select_points(logmag: torch.Tensor, farr, tarr, k: int, threshold: float | N
     dev = logmag.device
     f_t = farr if isinstance(farr, torch.Tensor) else rt.coord_table(farr, dev)
     t_t = None if tarr is None else (tarr if isinstance(tarr, torch.Tensor) else rt.coord_table(tarr, dev))
-    width = 2 if t_t is None else 3
-    pts = torch.empty((n, k, width), dtype=torch.float32, device=dev)
-    idx = torch.empty((n, k), dtype=torch.int32, device=dev)
-    counts = torch.empty((n,), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(_lib.lib().pca_select_compact_f32(
-            _lib.ptr(logmag), n, nf, nt, _lib.ptr(f_t), _lib.ptr(t_t), int(k), int(sorted_desc),
-            int(threshold is not None), float(threshold if threshold is not None else 0.0), _lib.ptr(pts), _lib.ptr(idx),
-            _lib.ptr(counts), rt.stream_ptr(dev)), "select_points")
-    return pts, idx, counts
+    return torch.ops.pcaudio.select_points(logmag, f_t, t_t, int(k), bool(sorted_desc), threshold is not None,
+                                           float(threshold if threshold is not None else 0.0))
 
 
 def fused_frontend_fits(n_fft: int, n_pts: int, k: int) -> bool:

@@ -11,10 +11,9 @@ import torch
 import torch.nn as nn
 
 from . import _lib, _runtime as rt
+from . import ops as _ops  # noqa: F401  (registers torch.ops.pcaudio.*)
 from .modules import ISAB, PMA, SAB, _PackedParams, _guard, _mab_tensors
 
-# scratch budget for the encoder: the batch is processed in chunks that fit (bigger = fewer launches)
-ST_WORKSPACE_BYTES = 1 << 30
 
 
 def strip_module_prefix(state_dict):
@@ -66,18 +65,9 @@ class _SetEncoderBase(nn.Module):
         if d_in != dims.d_in:
             raise ValueError(f"expected clouds of width {dims.d_in}, got {d_in}")
         blob = self._blob()
-        L = _lib.lib()
-        assert blob.numel() == L.pca_st_param_count(C.byref(dims))
-        out = torch.empty((B, dims.S, dims.C), dtype=torch.float32, device=X.device)
-        if B == 0:
-            return out
-        need1 = L.pca_st_workspace_bytes(C.byref(dims), 1, N, self.precision)
-        needB = L.pca_st_workspace_bytes(C.byref(dims), B, N, self.precision)
-        ws = rt.workspace(X.device, max(need1, min(needB, ST_WORKSPACE_BYTES)))
-        with torch.cuda.device(X.device):
-            _lib.check(L.pca_st_fwd_masked(_lib.ptr(X), _lib.ptr(counts), B, N, C.byref(dims), _lib.ptr(blob), _lib.ptr(out),
-                                           _lib.ptr(ws), ws.numel(), self.precision, rt.stream_ptr(X.device)),
-                       type(self).__name__ + ".forward")
+        assert blob.numel() == _lib.lib().pca_st_param_count(C.byref(dims))
+        # one dispatcher-visible custom op (pcaudio_b200/ops.py) -> pca_st_fwd_masked of the C ABI
+        out = torch.ops.pcaudio.st_fwd(X, counts, blob, dims.d_in, dims.D, dims.H, dims.M, dims.S, dims.C, dims.ln, self.precision)
         return _guard(out, self)
 
 

@@ -164,3 +164,26 @@ def test_two_rank_gloo_shard_gather_and_grad_allreduce():
     for r, ok, g in res:
         assert ok, f"rank {r}: gathered rows differ from the unsharded tensor"
         assert g == [1.5] * 5
+
+
+def test_torch_custom_ops_registered_with_fake_impls(built):
+    """The host mirrors reach the C ABI through torch.ops.pcaudio.* (dispatcher-visible custom ops); shape inference
+    must work without running a kernel (fake tensors), and there is no CPU kernel to fall back to."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    import pcaudio_b200  # noqa: F401
+    for name in ("st_fwd", "stft_logmag", "select_points"):
+        assert hasattr(torch.ops.pcaudio, name)
+    with FakeTensorMode():
+        X = torch.empty(5, 300, 2, device="cuda")
+        blob = torch.empty(100, device="cuda")
+        out = torch.ops.pcaudio.st_fwd(X, None, blob, 2, 64, 8, 64, 1, 10, 0, 0)
+        assert out.shape == (5, 1, 10) and out.device.type == "cuda"
+        lm = torch.ops.pcaudio.stft_logmag(torch.empty(3, 16000, device="cuda"), torch.empty(1024, device="cuda"),
+                                           torch.empty(512, 2, device="cuda"), 1024, 512, 1.0 / 1024, True, 30)
+        assert lm.shape == (3, 30, 512)
+        pts, idx, cnt = torch.ops.pcaudio.select_points(lm.view(9, 10, 512), torch.empty(512, device="cuda"),
+                                                        torch.empty(10, device="cuda"), 256, True, True, -6.0)
+        assert pts.shape == (9, 256, 3) and idx.shape == (9, 256) and cnt.shape == (9,)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.pcaudio.st_fwd(torch.zeros(1, 4, 2), None, torch.zeros(10), 2, 64, 8, 64, 1, 10, 0, 0)   # CPU: no kernel
