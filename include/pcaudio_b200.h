@@ -253,6 +253,10 @@ int pca_debug_st_stages(const float* X, int B, int N, const pca_st_dims* dims, c
  * records (phase tag, clock64) pairs of its softmax loop there.  NULL switches it off. */
 void pca_debug_set_timeline(long long* device_buffer);
 
+/* Debug / experiments: the bf16 path hands clouds with 1..tail_max (<= 4, the default) points past a multiple of 128 to exact
+ * fp32 tail paths instead of a ninth, nearly empty tensor-core tile.  0 switches the rule off. */
+void pca_debug_set_tail_max(int tail_max);
+
 /* Unit probe of the tcgen05 building blocks used by the bf16 encoder path: one CTA computes
  * D (128, N) = A (128, K) * B (K, N), bf16 operands, fp32 accumulation in TMEM.
  * a_mode: 0 A (128,K) via shared memory K-major, 1 A via TMEM, 2 A given as (K,128) via shared memory MN-major;

@@ -22,6 +22,7 @@ int launch_pool(const float*, int, int, int, int, float*, const int*, cudaStream
 int launch_fused_frontend(const float*, int, int, int, int, const float*, const float*, float, int, int, const float*, const float*,
                           int, int, int, float, float*, int32_t*, int32_t*, cudaStream_t);
 void set_timeline(long long* p);
+void set_tail_max(int t);
 int launch_umma_probe(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 // tcgen05 path (encoder_tc.cu)
 size_t st_tc_workspace_bytes(const pca_st_dims* d, int B, int N);
@@ -600,6 +601,7 @@ int pca_debug_st_stages(const float* X, int B, int N, const pca_st_dims* dims, c
 }
 
 void pca_debug_set_timeline(long long* device_buffer) { set_timeline(device_buffer); }
+void pca_debug_set_tail_max(int tail_max) { set_tail_max(tail_max); }
 
 int pca_debug_umma_probe(const float* A, const float* B, float* D, int N, int K, int a_mode, int b_mode, void* stream) {
     return launch_umma_probe(A, B, D, N, K, a_mode, b_mode, (cudaStream_t)stream);

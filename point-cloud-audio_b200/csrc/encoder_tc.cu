@@ -37,6 +37,11 @@ struct TcConsts {
     // split-bf16 (hi | lo) B operands of the finalize GEMMs, per ISAB: mab0.fc_o (N=64, K=64) and mab1 [Wk;Wv] (N=128, K=64)
     uint8_t WoS[2][2][8192];
     uint8_t WkvS[2][2][16384];
+    // k-major fp32 copies for the tail paths (leftover points of a cloud, N mod 128 <= TC_TAIL_MAX, handled on CUDA cores):
+    float Wkv0T[2][64 * 128];          // per ISAB: mab0 [Wk;Wv]^T (dk <= 64 rows used, 128 columns)
+    float Wq1T[2][64 * 64];            // per ISAB: mab1 fc_q^T (dq rows used, 64 columns)
+    float Wo1T[2][64 * 64];            // per ISAB: mab1 fc_o^T
+    float WqkPool[TH * TD];            // PMA: scale * Wk_h^T fc_q(S)_h (fp32 twin of AqPool)
     float WvT_P[64 * 64], WoT_P[64 * 64];          // pma.mab fc_v / fc_o transposed (k, f): coalesced reads in finalize_pool_kernel
     uint8_t AqPool[16384];                        // PMA: row r = scale * Wk_h^T fc_q(S)_h, h = r / 16 (A operand, 128 x 64)
     uint8_t WqS0[2048];                           // isab0.mab1.fc_q (64, d_in <= 4) as a split-bf16 K=16 B operand
@@ -49,6 +54,14 @@ __device__ void transpose_weight(const float* __restrict__ W, int n_rows, float*
     // W (n_rows, 64) -> out (64, n_rows)
     for (int i = threadIdx.x; i < n_rows * 64; i += blockDim.x) {
         const int n = i / 64, k = i % 64;
+        out[k * n_rows + n] = W[i];
+    }
+}
+
+__device__ void transpose_generic(const float* __restrict__ W, int n_rows, int n_cols, float* __restrict__ out) {
+    // W (n_rows, n_cols) -> out (n_cols, n_rows)
+    for (int i = threadIdx.x; i < n_rows * n_cols; i += blockDim.x) {
+        const int n = i / n_cols, k = i % n_cols;
         out[k * n_rows + n] = W[i];
     }
 }
@@ -104,7 +117,7 @@ __device__ void pack_b_operand_split(const float* __restrict__ W, int n_rows, ui
 __device__ void prep_queries(const float* __restrict__ Qin, int nq, const float* __restrict__ Wq,
                              const float* __restrict__ bq, float* __restrict__ Qp_out, uint8_t* __restrict__ Aq,
                              float* sq /* smem 64*64 */, const float* __restrict__ Wk = nullptr,
-                             uint8_t* __restrict__ AqPool = nullptr) {
+                             uint8_t* __restrict__ AqPool = nullptr, float* __restrict__ WqkPool = nullptr) {
     for (int i = threadIdx.x; i < nq * TD; i += blockDim.x) {
         const int m = i / TD, f = i % TD;
         float a = bq[f];
@@ -123,6 +136,7 @@ __device__ void prep_queries(const float* __restrict__ Qin, int nq, const float*
             float a = 0.f;
             for (int d = 0; d < 8; ++d) a = fmaf(sq[h * 8 + d], Wk[(h * 8 + d) * TD + f], a);
             sq[64 + i] = a * kScaleLog2e;
+            if (WqkPool != nullptr) WqkPool[i] = a * kScaleLog2e;
         }
         __syncthreads();
         for (int i = threadIdx.x; i < 8 * 128 * 8; i += blockDim.x) {
@@ -161,7 +175,7 @@ __global__ void prep_kernel(const float* __restrict__ params, int d_in, TcConsts
     switch (blockIdx.x) {
         case 0: prep_queries(p_isab0, TM, m00.Wq, m00.bq, c->Qp0, c->Aq0, sq); break;
         case 1: prep_queries(p_isab1, TM, m10.Wq, m10.bq, c->Qp1, c->Aq1, sq); break;
-        case 2: prep_queries(p_pma, 1, mp.Wq, mp.bq, c->QpS, c->AqP, sq, mp.Wkv, c->AqPool); break;
+        case 2: prep_queries(p_pma, 1, mp.Wq, mp.bq, c->QpS, c->AqP, sq, mp.Wkv, c->AqPool, c->WqkPool); break;
         case 3: pack_b_operand(m10.Wkv, 128, c->Wkv1); break;
         case 4: pack_b_operand(mp.Wkv, 128, c->WkvP); break;
         case 5: pack_b_operand(m11.Wq, 64, c->Wq1); break;
@@ -176,6 +190,12 @@ __global__ void prep_kernel(const float* __restrict__ params, int d_in, TcConsts
         case 14: pack_b_operand_split(m01.Wkv, 128, c->WkvS[0][0], c->WkvS[0][1]); break;
         case 15: pack_b_operand_split(m10.Wo, 64, c->WoS[1][0], c->WoS[1][1]); break;
         case 16: pack_b_operand_split(m11.Wkv, 128, c->WkvS[1][0], c->WkvS[1][1]); break;
+        case 19: transpose_generic(m00.Wkv, 128, d_in, c->Wkv0T[0]); break;
+        case 20: transpose_generic(m10.Wkv, 128, TD, c->Wkv0T[1]); break;
+        case 21: transpose_generic(m01.Wq, 64, d_in, c->Wq1T[0]); break;
+        case 22: transpose_generic(m11.Wq, 64, TD, c->Wq1T[1]); break;
+        case 23: transpose_generic(m01.Wo, 64, TD, c->Wo1T[0]); break;
+        case 24: transpose_generic(m11.Wo, 64, TD, c->Wo1T[1]); break;
         case 17: transpose_weight(mp.Wkv + TD * TD, 64, c->WvT_P); break;
         case 18: transpose_weight(mp.Wo, 64, c->WoT_P); break;
         default: break;
@@ -194,6 +214,18 @@ __device__ __forceinline__ void st_shared_8bf16(uint8_t* dst, const float* v) {
     *reinterpret_cast<uint4*>(dst) = u;
 }
 
+// ------------------------------------------------------------------------------------ tail rule
+// A cloud whose point count leaves 1..tail_max points past a multiple of 128 (the FST cloud: 1025 = 8 x 128 + 1) would
+// pay a whole pipeline pass of the tensor-core kernels for them (measured: the 9th tile of the FST cloud costs 77 % of a
+// full tile).  Those leftover points are handled exactly (fp32, CUDA cores) where the partial results are merged anyway:
+// as an extra softmax slot in the finalize kernels (mab0 / PMA, where points are keys) and by a one-block-per-point
+// kernel for mab1 (where points are queries).  main_points() is the prefix the tensor-core kernels process.
+constexpr int TC_TAIL_MAX = 4;
+__host__ __device__ __forceinline__ int main_points(int nb, int tail_max) {
+    const int r = nb & 127;
+    return (tail_max > 0 && nb >= 128 && r != 0 && r <= tail_max) ? (nb - r) : nb;
+}
+
 // ------------------------------------------------------------------------------------ reduce kernel
 struct RParams {
     const float* X32;             // (B, N, d_in) fp32      [DIN64 == false]
@@ -201,6 +233,7 @@ struct RParams {
     int N, d_in, tiles_total, tiles_per_split, nsplit;
     int n_work;                   // work items (cloud, split) for the persistent kernels
     const int* counts;            // nullable (B): valid points per cloud (variable-size sets); rows past it are padding
+    int tail_max;                 // leftover points (N mod 128 <= tail_max) are left to the tail paths
     const uint8_t* Aq;            // 16 KB query operand (stacked pairs, or all-heads image in PMA mode)
     const float* Wkv32;           // (128, d_in) fp32       [DIN64 == false]
     const float* bkv;             // (128)
@@ -247,6 +280,15 @@ struct F2Params {
     const float* bkv;
     uint8_t* KVblk;               // per cloud 32768 B
     float* H_debug;               // nullable (B, 64, 64)
+    // leftover points (tail rule): the mab0 keys / values of those points are formed here in fp32 and merged as one more
+    // softmax slot
+    const float* X32;             // (B, N, dk) fp32 points       [dk <= 4]
+    const __nv_bfloat16* Y16;     // (B, N, 64) bf16 points       [dk == 64]
+    int N, dk;
+    const int* counts;            // nullable (B)
+    int tail_max;
+    const float* Wkv0T;           // mab0 [Wk;Wv]^T, k-major (dk, 128)
+    const float* bkv0;            // mab0 bk | bv (128)
 };
 constexpr uint32_t F2_A = 0, F2_F = 64, F2_KV = 128;       // hi 32 | lo 32 | F 64 | KV 128  (256 columns)
 struct F2Smem {
@@ -281,6 +323,7 @@ __global__ void __launch_bounds__(128) finalize_isab_tc_kernel(const F2Params P)
     float* sBkv = sBo + 64;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + F2Smem::BARS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    __shared__ float sKt[2][TC_TAIL_MAX][TD], sVt[2][TC_TAIL_MAX][TD];      // leftover points: K / V rows
     const int tid = threadIdx.x, warp = tid >> 5;
     copy_to_smem(sWo, P.WoS, 16384);
     copy_to_smem(sWkv, P.WkvS, 32768);
@@ -301,7 +344,44 @@ __global__ void __launch_bounds__(128) finalize_isab_tc_kernel(const F2Params P)
         const int cloud = 2 * pair + cc;
         const bool valid = cloud < P.B;
         float o[64];
-        // ---- merge the point splits / column halves: O = Qp + A V
+        // ---- leftover points of this cloud (tail rule): K|V rows in fp32; thread m forms K[.][m] and V[.][m]
+        int r_tail = 0;
+        if (valid && P.tail_max > 0) {
+            const int nbt = P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N;
+            const int n0 = main_points(nbt, P.tail_max);
+            r_tail = nbt - n0;
+            for (int j = 0; j < r_tail; ++j) {
+                float kacc = __ldg(P.bkv0 + m), vacc = __ldg(P.bkv0 + 64 + m);
+                if (P.X32 != nullptr) {
+                    const float* xp = P.X32 + ((size_t)cloud * P.N + n0 + j) * P.dk;
+                    for (int k = 0; k < P.dk; ++k) {
+                        const float x = __ldg(xp + k);
+                        kacc = fmaf(x, __ldg(P.Wkv0T + k * 128 + m), kacc);
+                        vacc = fmaf(x, __ldg(P.Wkv0T + k * 128 + 64 + m), vacc);
+                    }
+                } else {
+                    const uint4* yp = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)cloud * P.N + n0 + j) * 64);
+#pragma unroll 2
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        const uint4 u = __ldg(yp + c8);
+                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 xy = __bfloat1622float2(h2[q]);
+                            const int k = c8 * 8 + 2 * q;
+                            kacc = fmaf(xy.x, __ldg(P.Wkv0T + k * 128 + m), kacc);
+                            vacc = fmaf(xy.x, __ldg(P.Wkv0T + k * 128 + 64 + m), vacc);
+                            kacc = fmaf(xy.y, __ldg(P.Wkv0T + (k + 1) * 128 + m), kacc);
+                            vacc = fmaf(xy.y, __ldg(P.Wkv0T + (k + 1) * 128 + 64 + m), vacc);
+                        }
+                    }
+                }
+                sKt[cc][j][m] = kacc;
+                sVt[cc][j][m] = vacc;
+            }
+        }
+        __syncthreads();
+        // ---- merge the point splits / column halves (+ the tail slot): O = Qp + A V
         if (valid) {
 #pragma unroll
             for (int h = 0; h < TH; ++h) {
@@ -331,10 +411,22 @@ __global__ void __launch_bounds__(128) finalize_isab_tc_kernel(const F2Params P)
                         for (int j = 0; j < 8; ++j) a[j] = fmaf(__ldg(ps + (2 + j) * TM), wgt, a[j]);
                     }
                 }
-                const float inv = 1.f / l;
                 const float4 q0 = __ldg(reinterpret_cast<const float4*>(P.Qp + m * TD + h * 8));
                 const float4 q1 = __ldg(reinterpret_cast<const float4*>(P.Qp + m * TD + h * 8) + 1);
                 const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                for (int jt = 0; jt < r_tail; ++jt) {         // leftover points: one more key each, exact fp32 scores
+                    float sc = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) sc = fmaf(qv[d], sKt[cc][jt][h * 8 + d], sc);
+                    sc *= kScaleLog2e;
+                    const float mnew = fmaxf(mmax, sc);
+                    const float w_old = exp2f(mmax - mnew), w_new = exp2f(sc - mnew);
+                    l = fmaf(l, w_old, w_new);
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) a[d] = fmaf(a[d], w_old, w_new * sVt[cc][jt][h * 8 + d]);
+                    mmax = mnew;
+                }
+                const float inv = 1.f / l;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[h * 8 + j] = fmaf(a[j], inv, qv[j]);
             }
@@ -426,6 +518,7 @@ struct AParams {
     const __nv_bfloat16* Y16in;   // (B, N, 64)             [DIN64 == true]
     int N, d_in, tiles_total, tiles_per_split, nsplit, n_work;
     const int* counts;            // nullable (B): valid points per cloud
+    int tail_max;                 // leftover points (N mod 128 <= tail_max) are left to the tail kernel
     const uint8_t* KVblk;         // per cloud: K image 16384 B | V image 16384 B
     const float* Wq32;            // (64, d_in)             [DIN64 == false]
     const float* bq;              // (64)
@@ -556,7 +649,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
         cloud = w / P.nsplit;
         split = w - cloud * P.nsplit;
         tile0 = split * P.tiles_per_split;
-        nb = P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N;
+        nb = main_points(P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N, P.tail_max);
         return max(0, min((nb + 127) >> 7, tile0 + P.tiles_per_split) - tile0);
     };
 
@@ -968,7 +1061,7 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
         cloud = w / P.nsplit;
         const int split = w - cloud * P.nsplit;
         tile0 = split * P.tiles_per_split;
-        nb = P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N;
+        nb = main_points(P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N, P.tail_max);
         return max(0, min((nb + 127) >> 7, tile0 + P.tiles_per_split) - tile0);
     };
 
@@ -1382,6 +1475,79 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
     if (warp == 12) tmem_dealloc(tb, 512);
 }
 
+// ------------------------------------------------------------------------------------ apply kernel: leftover points
+// MAB(Q = one leftover point, K = H) in fp32 on CUDA cores (tail rule): one 64-thread block per leftover point, thread f <->
+// feature f = head h * 8 + d.  Same arithmetic as mab_apply3_tc_kernel with the cloud's bf16 K / V images as keys.
+struct ATailParams {
+    const float* X32;             // (B, N, dq) fp32              [dq <= 4]
+    const __nv_bfloat16* Y16in;   // (B, N, 64) bf16              [dq == 64]
+    int N, dq;
+    const int* counts;            // nullable (B)
+    int tail_max;
+    const uint8_t* KVblk;         // per cloud: K image 16384 B | V image 16384 B
+    const float* WqT;             // fc_q^T k-major (dq, 64)
+    const float* bq;
+    const float* WoT;             // fc_o^T k-major (64, 64)
+    const float* bo;
+    __nv_bfloat16* Yout;          // (B, N, 64)
+};
+__global__ void __launch_bounds__(64) mab_apply_tail_kernel(const ATailParams P) {
+    __shared__ float sX[64], sQ[64], sP[TH][TM], sO1[64];
+    const int cloud = blockIdx.x, j = blockIdx.y, f = threadIdx.x;
+    const int nb = P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N;
+    const int n0 = main_points(nb, P.tail_max);
+    if (j >= nb - n0) return;
+    const size_t rowi = (size_t)cloud * P.N + n0 + j;
+    if (P.X32 != nullptr) { if (f < P.dq) sX[f] = __ldg(P.X32 + rowi * P.dq + f); }
+    else sX[f] = __bfloat162float(P.Y16in[rowi * 64 + f]);
+    __syncthreads();
+    float q = __ldg(P.bq + f);
+    for (int k = 0; k < P.dq; ++k) q = fmaf(sX[k], __ldg(P.WqT + k * 64 + f), q);
+    sQ[f] = q;
+    __syncthreads();
+    const int h = f >> 3, part = f & 7, pr = h >> 1, ch = h & 1;
+    const uint8_t* kimg = P.KVblk + (size_t)cloud * 32768 + pr * 4096 + ch * 2048 + (size_t)(ch * 64) * 16;
+    const uint8_t* vimg = kimg + 16384;
+    // scores of head h against keys 8*part .. 8*part+7
+    float sc[8], mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(kimg + (size_t)(8 * part + i) * 16));
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+        float d = 0.f;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            const float2 kk = __bfloat1622float2(h2[qd]);
+            d = fmaf(sQ[h * 8 + 2 * qd], kk.x, d);
+            d = fmaf(sQ[h * 8 + 2 * qd + 1], kk.y, d);
+        }
+        sc[i] = d * kScaleLog2e;
+        mx = fmaxf(mx, sc[i]);
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = exp2f(sc[i] - mx); sum += sc[i]; }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sP[h][8 * part + i] = sc[i] * inv;
+    __syncthreads();
+    float o = 0.f;
+#pragma unroll 8
+    for (int mm = 0; mm < TM; ++mm)
+        o = fmaf(sP[h][mm], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(vimg + (size_t)mm * 16 + part * 2)), o);
+    const float o1 = sQ[f] + o;
+    sO1[f] = o1;
+    __syncthreads();
+    float fo = __ldg(P.bo + f);
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) fo = fmaf(sO1[k], __ldg(P.WoT + k * 64 + f), fo);
+    P.Yout[rowi * 64 + f] = __float2bfloat16(o1 + fmaxf(fo, 0.f));
+}
+
 // ====================================================================================== pooled attention (PMA)
 // PMA with one seed, computed on the UN-projected points (see prep_queries): per 128-point tile
 //   S (128 rows = head x 16 copies, 128 points) = AqPool (128 x 64) . Ytile^T      [4 MMAs, K = 64]
@@ -1394,6 +1560,7 @@ struct PoolParams {
     const __nv_bfloat16* Y16;     // (B, N, 64)
     int N, tiles_total, tiles_per_split, nsplit, n_work;
     const int* counts;            // nullable (B): valid points per cloud
+    int tail_max;                 // leftover points (N mod 128 <= tail_max) are merged in finalize_pool_kernel
     const uint8_t* Aq;            // AqPool image
     float* part;                  // (B, 2 nsplit, 8 heads, 66): m (log2 domain), l, Z[64]
 };
@@ -1425,7 +1592,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
         cloud = w / P.nsplit;
         split = w - cloud * P.nsplit;
         tile0 = split * P.tiles_per_split;
-        nb = P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N;
+        nb = main_points(P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N, P.tail_max);
         return max(0, min((nb + 127) >> 7, tile0 + P.tiles_per_split) - tile0);
     };
     copy_to_smem(sAq, P.Aq, 16384);
@@ -1623,12 +1790,35 @@ struct PoolFinParams {
     const float* Wl; const float* bl; int C;  // final Linear (C, 64)
     float* logits;                            // (B, C)
     float* pooled_debug;                      // nullable (B, 64)
+    // leftover points (tail rule): merged here as one more softmax slot each
+    const __nv_bfloat16* Y16;                 // (B, N, 64) the pooled points
+    int N; const int* counts; int tail_max;
+    const float* Wqk;                         // (8, 64) scale * Wk_h^T fc_q(S)_h
 };
 __global__ void __launch_bounds__(256) finalize_pool_kernel(const PoolFinParams P) {
-    __shared__ float sZ[4][TH][TD + 1], sO[4][64], sO1[4][64];
+    __shared__ float sZ[4][TH][TD + 1], sO[4][64], sO1[4][64], sY[4][TC_TAIL_MAX][64], sS[4][TC_TAIL_MAX][TH];
     const int sub = threadIdx.x >> 6, f = threadIdx.x & 63;
     const int cloud = blockIdx.x * 4 + sub;
     const bool valid = cloud < P.B;
+    // ---- leftover points: rows of Y and their 8 seed scores (thread f: head f / 8, 8-feature slice f % 8)
+    int r_tail = 0;
+    if (valid && P.tail_max > 0) {
+        const int nbt = P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N;
+        const int n0 = main_points(nbt, P.tail_max);
+        r_tail = nbt - n0;
+        for (int j = 0; j < r_tail; ++j) sY[sub][j][f] = __bfloat162float(P.Y16[((size_t)cloud * P.N + n0 + j) * 64 + f]);
+    }
+    __syncthreads();
+    for (int j = 0; j < r_tail; ++j) {
+        const int h = f >> 3, part = f & 7;
+        float d = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d = fmaf(__ldg(P.Wqk + h * TD + 8 * part + k), sY[sub][j][8 * part + k], d);
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (part == 0) sS[sub][j][h] = d;
+    }
+    __syncthreads();
     if (valid) {
         // thread f merges feature f of every head
 #pragma unroll
@@ -1636,6 +1826,7 @@ __global__ void __launch_bounds__(256) finalize_pool_kernel(const PoolFinParams 
             const float* p0 = P.part + (((size_t)cloud * P.nslots) * TH + h) * 66;
             float mmax = -INFINITY;
             for (int s = 0; s < P.nslots; ++s) mmax = fmaxf(mmax, __ldg(p0 + (size_t)s * TH * 66));
+            for (int j = 0; j < r_tail; ++j) mmax = fmaxf(mmax, sS[sub][j][h]);
             float l = 0.f, z = 0.f;
             for (int s = 0; s < P.nslots; ++s) {
                 const float* pp = p0 + (size_t)s * TH * 66;
@@ -1643,6 +1834,11 @@ __global__ void __launch_bounds__(256) finalize_pool_kernel(const PoolFinParams 
                 const float wgt = (m == -INFINITY) ? 0.f : exp2f(m - mmax);      // a warpgroup that saw no tile
                 l = fmaf(__ldg(pp + 1), wgt, l);
                 z = fmaf(__ldg(pp + 2 + f), wgt, z);
+            }
+            for (int j = 0; j < r_tail; ++j) {
+                const float wgt = exp2f(sS[sub][j][h] - mmax);
+                l += wgt;
+                z = fmaf(sY[sub][j][f], wgt, z);
             }
             sZ[sub][h][f] = z / l;
         }
@@ -1681,8 +1877,10 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 
 // ------------------------------------------------------------------------------------ host orchestration
 static int g_num_sms = 148;
+static int g_tail_max = TC_TAIL_MAX;       // tail rule (PCA_TC_TAIL=0 disables it: every point goes through the tensor-core kernels)
 static long long* g_timeline = nullptr;      // set through pca_debug_set_timeline
 void set_timeline(long long* p) { g_timeline = p; }
+void set_tail_max(int t) { g_tail_max = t < 0 ? 0 : (t > TC_TAIL_MAX ? TC_TAIL_MAX : t); }
 struct TcSplit { int tiles_total, tiles_per_split, nsplit; };
 // The point range of a cloud is cut into fixed spans of 16 tiles (2048 points).  The cut depends on N only, never
 // on the batch size, so a cloud's logits are bit-identical however the batch is sharded across calls / GPUs.
@@ -1746,59 +1944,77 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     const int fgrid = npairs < 2 * g_num_sms ? npairs : 2 * g_num_sms;
     const double pts = (double)B * N;
     const bool tl_apply = getenv("PCA_TL_APPLY") != nullptr;   // which kernel a PCA_TIMELINE build records
+    const int tm = g_tail_max;
+    const dim3 tgrid(B, tm > 0 ? tm : 1);
+    // the tail kernel only has work when some cloud can leave 1..tm points past a multiple of 128
+    const bool has_tail = tm > 0 && (counts != nullptr ? N >= 129 : main_points(N, tm) != N);
 
     // ---- ISAB 0
     {
-        RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, c->Aq0, m00.Wkv, m00.bkv,
+        RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Aq0, m00.Wkv, m00.bkv,
                   nullptr, tl_apply ? nullptr : g_timeline, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * d_in * TD + 2.0 * TM * TD), pts * 4.0 * d_in);
         mab_reduce5_tc_kernel<false><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<small>");
     {
-        F2Params f{part, 2 * sp.nsplit, B, c->Qp0, c->WoS[0][0], m00.bo, c->WkvS[0][0], m01.bkv, kvblk, dbg ? dbg->H1 : nullptr};
+        F2Params f{part, 2 * sp.nsplit, B, c->Qp0, c->WoS[0][0], m00.bo, c->WkvS[0][0], m01.bkv, kvblk, dbg ? dbg->H1 : nullptr,
+                   X, nullptr, N, d_in, counts, tm, c->Wkv0T[0], m00.bkv};
         LaunchTimer lt("finalize_isab_kernel", st, (double)B * 2.0 * (TM * TD * TD + TM * TD * 2 * TD), (double)B * 32768.0);
         finalize_isab_tc_kernel<<<fgrid, 128, F2Smem::TOTAL, st>>>(f);
     }
     PCA_CHECK_LAUNCH("finalize_isab_kernel");
     {
-        AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, kvblk, m01.Wq, m01.bq, c->WqS0,
+        AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, kvblk, m01.Wq, m01.bq, c->WqS0,
                   c->Wo0, m01.bo, Y1, tl_apply ? g_timeline : nullptr};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * d_in * TD + 2.0 * TM * TD + TD * TD), pts * (4.0 * d_in + 128.0));
         mab_apply3_tc_kernel<false><<<pgrid, TC_THREADS20, A3Smem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<small>");
+    if (has_tail) {
+        ATailParams t{X, nullptr, N, d_in, counts, tm, kvblk, c->Wq1T[0], m01.bq, c->Wo1T[0], m01.bo, Y1};
+        LaunchTimer lt("mab_apply_tail_kernel", st, 0.0, 0.0);
+        mab_apply_tail_kernel<<<tgrid, 64, 0, st>>>(t);
+        PCA_CHECK_LAUNCH("mab_apply_tail_kernel");
+    }
     // ---- ISAB 1
     {
-        RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, c->Aq1, nullptr, m10.bkv,
+        RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Aq1, nullptr, m10.bkv,
                   c->Wkv1, nullptr, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TM * TD), pts * 128.0);
         mab_reduce5_tc_kernel<true><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<64>");
     {
-        F2Params f{part, 2 * sp.nsplit, B, c->Qp1, c->WoS[1][0], m10.bo, c->WkvS[1][0], m11.bkv, kvblk, dbg ? dbg->H2 : nullptr};
+        F2Params f{part, 2 * sp.nsplit, B, c->Qp1, c->WoS[1][0], m10.bo, c->WkvS[1][0], m11.bkv, kvblk, dbg ? dbg->H2 : nullptr,
+                   nullptr, Y1, N, TD, counts, tm, c->Wkv0T[1], m10.bkv};
         LaunchTimer lt("finalize_isab_kernel", st, (double)B * 2.0 * (TM * TD * TD + TM * TD * 2 * TD), (double)B * 32768.0);
         finalize_isab_tc_kernel<<<fgrid, 128, F2Smem::TOTAL, st>>>(f);
     }
     PCA_CHECK_LAUNCH("finalize_isab_kernel");
     {
-        AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, kvblk, nullptr, m11.bq, c->Wq1,
+        AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, kvblk, nullptr, m11.bq, c->Wq1,
                   c->Wo1, m11.bo, Y2, nullptr};
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * TD * TD + 2.0 * TM * TD + TD * TD), pts * 256.0);
         mab_apply3_tc_kernel<true><<<pgrid, TC_THREADS20, A3Smem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<64>");
+    if (has_tail) {
+        ATailParams t{nullptr, Y1, N, TD, counts, tm, kvblk, c->Wq1T[1], m11.bq, c->Wo1T[1], m11.bo, Y2};
+        LaunchTimer lt("mab_apply_tail_kernel", st, 0.0, 0.0);
+        mab_apply_tail_kernel<<<tgrid, 64, 0, st>>>(t);
+        PCA_CHECK_LAUNCH("mab_apply_tail_kernel");
+    }
     // ---- PMA + Linear
     {
-        PoolParams r{Y2, N, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, c->AqPool, part};
+        PoolParams r{Y2, N, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->AqPool, part};
         LaunchTimer lt("pma_pool_tc_kernel", st, pts * 2.0 * (2.0 * TH * TD), pts * 128.0);
         pma_pool_tc_kernel<<<pgrid, TC_THREADS16, PoolSmem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("pma_pool_tc_kernel");
     {
         PoolFinParams p{part, 2 * sp.nsplit, B, c->QpS, c->WvT_P, mp.bkv + TD, c->WoT_P, mp.bo, p_lin, p_lin + (long long)d->C * TD,
-                        d->C, logits, dbg ? dbg->pooled : nullptr};
+                        d->C, logits, dbg ? dbg->pooled : nullptr, Y2, N, counts, tm, c->WqkPool};
         LaunchTimer lt("finalize_pool_kernel", st, (double)B * 2.0 * (2.0 * TD * TD + TD * d->C), (double)B * 4.0 * d->C);
         finalize_pool_kernel<<<(B + 3) / 4, 256, 0, st>>>(p);
     }
@@ -1819,6 +2035,7 @@ static int tc_configure() {
     PCA_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     PCA_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     if (major != 10) return fail(PCA_EDEVICE, "tcgen05 path needs an sm_100 device (found compute capability %d.x)", major);
+    if (const char* v = getenv("PCA_TC_TAIL")) { g_tail_max = atoi(v); if (g_tail_max < 0) g_tail_max = 0; if (g_tail_max > TC_TAIL_MAX) g_tail_max = TC_TAIL_MAX; }
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce5_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce5_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
@@ -1840,7 +2057,7 @@ int st_tc_forward_dbg(const float* X, const int* counts, int B, int N, const pca
     if (dbg && chunk < B) return fail(PCA_EWORKSPACE, "ST(bf16) debug: workspace must hold the whole batch");
     uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
     TcConsts* c = reinterpret_cast<TcConsts*>(w8 + tc_layout(chunk, N).consts);
-    prep_kernel<<<19, 256, 0, st>>>(params, d->d_in, c);
+    prep_kernel<<<25, 256, 0, st>>>(params, d->d_in, c);
     PCA_CHECK_LAUNCH("prep_kernel");
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int bc = (B - b0) < chunk ? (B - b0) : chunk;

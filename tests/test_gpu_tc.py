@@ -136,3 +136,40 @@ def test_tc_batch_split_is_bit_identical(pca):
         out = pipe.run_host(host, chunks=chunks)
         torch.cuda.synchronize()
         assert torch.equal(out.squeeze(1), full.cpu()), f"run_host(chunks={chunks}) differs from the device-resident call"
+
+
+@pytest.mark.parametrize("d_in,B,N", [(2, 3, 129), (3, 2, 130), (2, 4, 1027), (3, 3, 1028), (2, 2, 2049), (3, 2, 2052), (2, 2, 133)])
+def test_tc_tail_points_vs_oracle(pca, d_in, B, N):
+    """Clouds with 1..4 points past a multiple of 128 take the exact fp32 tail paths (extra softmax slot in the finalize
+    kernels, one block per leftover query point); N = 133 (5 leftover points) stays on the tensor-core tiles."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import debug_tc_stages
+    errs = debug_tc_stages.run(d_in, B, N)
+    for k, v in errs.items():
+        assert v < BF16_REL_TOL, f"stage {k}: rel err {v:.3e} (all: {errs})"
+
+
+def test_tc_tail_rule_on_off_agree(pca):
+    """The tail rule is an execution detail: switching it off (every point through the tcgen05 tiles) must give the same
+    logits to bf16 tolerance, on the FST bench shape (1025 points) and on masked sets with mixed remainders."""
+    from pcaudio_b200 import _lib
+    dev = torch.device("cuda:0")
+    w = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, "fst_weights.npz")).items()}
+    st = pca.ST(dim_input=2, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev)
+    st.load_state_dict(w)
+    st.set_precision("bf16")
+    g = torch.Generator().manual_seed(33)
+    X = torch.rand(64, 1025, 2, generator=g).to(dev)
+    X[:, :, 1] = X[:, :, 1] * 12.0 - 14.0                      # log-magnitude-like second coordinate
+    counts = torch.tensor([1025, 1024, 1026, 129, 128, 127, 900, 515] * 8, dtype=torch.int32, device=dev)
+    try:
+        with torch.no_grad():
+            a = st(X).float().cpu(); am = st(X, counts=counts).float().cpu()
+            _lib.lib().pca_debug_set_tail_max(0)
+            b = st(X).float().cpu(); bm = st(X, counts=counts).float().cpu()
+    finally:
+        _lib.lib().pca_debug_set_tail_max(4)
+    for x, y in ((a, b), (am, bm)):
+        assert torch.isfinite(x).all() and torch.isfinite(y).all()
+        assert (x - y).abs().max().item() / y.abs().max().item() < BF16_REL_TOL
