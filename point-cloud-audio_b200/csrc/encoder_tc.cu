@@ -644,6 +644,19 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_work = P.n_work, wstep = gridDim.x;
+#ifdef PCA_TIMELINE
+    long long* tl2 = nullptr;
+    int tl2_n = 0;
+    if (P.timeline != nullptr && blockIdx.x == 0 && lane == 0) {
+        if (warp == 8) tl2 = P.timeline + 4000;
+        else if (warp == 12) tl2 = P.timeline + 6000;
+    }
+    auto stamp2 = [&](int tag) {
+        if (tl2 != nullptr && tl2_n < 1000) { tl2[2 * tl2_n] = tag; tl2[2 * tl2_n + 1] = clock64(); ++tl2_n; }
+    };
+#else
+    auto stamp2 = [&](int) {};
+#endif
     // tiles of work item w; nb = valid points of its cloud (variable-size sets: rows past nb are padding)
     auto work_tiles = [&](int w, int& cloud, int& split, int& tile0, int& nb) {
         cloud = w / P.nsplit;
@@ -696,8 +709,10 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                 const int ntiles = work_tiles(w, cloud, split, tile0, nb);
                 for (int it = 0; it < ntiles; ++it, ++gt) {
                     const uint32_t kbase = kvb + (gt & 1) * 32768, vbase = kbase + 16384;
+                    stamp2(60);
                     mbar_wait(&kv_full[gt & 1], (gt >> 1) & 1);
                     fence_after_sync();
+                    stamp2(61);
                     // a half without valid points (ragged last tile) is skipped by the chain and by its warpgroup alike
                     const bool empty_half = nb - (tile0 + it) * 128 <= 64 * half;
 #pragma unroll
@@ -710,9 +725,11 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                             mma_commit(&s_full[c]);
                         }
                         __syncwarp();
+                        stamp2(62);
                         mbar_wait(&p_ready[c], ph_p);
                         ph_p ^= 1;
                         fence_after_sync();
+                        stamp2(63);
                         if (leader) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks)
@@ -742,6 +759,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                 const int stage = gt & 1;
                 const int n = (tile0 + it) * 128 + row;
                 const bool valid = n < nb;
+                stamp2(50);
                 uint8_t* sK = sKV + stage * 32768;
                 uint8_t* sV = sK + 16384;
                 if (!DIN64) {
@@ -750,7 +768,9 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                         const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
                         for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
                     }
+                    stamp2(51);
                     if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
+                    stamp2(53);
 #pragma unroll 4
                     for (int c = 0; c < 16; ++c) {
                         float o[8];
@@ -785,9 +805,12 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                         }
                         __syncwarp();
                     }
+                    stamp2(51);
                     mbar_wait(proj_done, gt & 1);
                     fence_after_sync();
+                    stamp2(52);
                     if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
+                    stamp2(53);
 #pragma unroll
                     for (int c0 = 0; c0 < 128; c0 += 32) {
                         uint32_t v[32];
@@ -803,6 +826,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                         }
                     }
                 }
+                stamp2(54);
                 fence_async_smem();
                 fence_before_sync();
                 warp_arrive(&kv_full[stage]);
@@ -822,13 +846,18 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
         long long* tl = (P.timeline != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0) ? P.timeline : nullptr;
         int tl_n = 0;
         auto stamp = [&](int tag) {
-            if (tl != nullptr && tl_n < 4000) { tl[2 * tl_n] = tag; tl[2 * tl_n + 1] = clock64(); ++tl_n; }
+            if (tl != nullptr && tl_n < 1000) { tl[2 * tl_n] = tag; tl[2 * tl_n + 1] = clock64(); ++tl_n; }
         };
 #else
         auto stamp = [&](int) {};
 #endif
 
-        auto softmax_item = [&](const int half, const int pp, const int nv, const bool first) {
+        uint32_t va[32], vb[32];           // scores of the item being processed; refilled early with the next item's
+        bool have = false;                 // va / vb already hold (in-flight) loads of the item about to be processed
+        // `prefetch`: the next item of this warpgroup exists and lives on the OTHER chain (its scores were issued a whole
+        // item ago and never wait for this item's probabilities), so its barrier wait and TMEM loads are issued before
+        // this item's store-wait / fence / arrive instead of after them.
+        auto softmax_item = [&](const int half, const int pp, const int nv, const bool first, const bool prefetch) {
             const int c = 2 * g + half, p = g + 2 * pp;
             const uint32_t sbase = tmem_addr(tb, lane_base, R2_S + 64 * c);
             const uint32_t oaddr = tmem_addr(tb, lane_base, R2_O + 16 * (2 * p + half) + ocol_off);
@@ -837,13 +866,16 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                 return;
             }
             stamp(20);
-            mbar_wait(&s_full[c], ph_s[half]);
-            ph_s[half] ^= 1;
-            fence_after_sync();
+            uint32_t pk0[16], pk1[16];
+            if (!have) {
+                mbar_wait(&s_full[c], ph_s[half]);
+                ph_s[half] ^= 1;
+                fence_after_sync();
+                tmem_ld32(sbase, va);
+                tmem_ld32(sbase + 32, vb);
+            }
+            have = false;
             stamp(24);
-            uint32_t va[32], vb[32], pk0[16], pk1[16];
-            tmem_ld32(sbase, va);
-            tmem_ld32(sbase + 32, vb);
             tmem_ld_wait64(va, vb);
             stamp(25);
             float sum;
@@ -896,6 +928,16 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                 tmem_st16(sbase, pk0);
                 tmem_st16(sbase + 16, pk1);
                 stamp(26);
+                if (prefetch) {
+                    const int cn = 2 * g + (half ^ 1);
+                    mbar_wait(&s_full[cn], ph_s[half ^ 1]);
+                    ph_s[half ^ 1] ^= 1;
+                    fence_after_sync();
+                    const uint32_t snext = tmem_addr(tb, lane_base, R2_S + 64 * cn);
+                    tmem_ld32(snext, va);
+                    tmem_ld32(snext + 32, vb);
+                    have = true;
+                }
                 tmem_st_wait();
                 stamp(27);
             }
@@ -913,10 +955,18 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                 const int n_valid = min(128, nb - (tile0 + it) * 128);
                 const int nv0 = min(64, n_valid), nv1 = max(0, n_valid - 64);
                 const bool first = it == 0;
-                softmax_item(0, 0, nv0, first);
-                softmax_item(1, 0, nv1, first);
-                softmax_item(0, 1, nv0, first);
-                softmax_item(1, 1, nv1, first);
+                // Prefetching the next item's scores ahead of this item's store-wait / arrive is measured SLOWER on B200
+                // (1.58 -> 1.69 ms/step), as it was for the apply kernel; kept behind PCA_R5_PREFETCH for experiments.
+#ifdef PCA_R5_PREFETCH
+                const bool both = nv1 > 0;                          // the tile has points in both column halves
+#else
+                const bool both = false;
+#endif
+                const bool next_tile = it + 1 < ntiles;             // ... and is followed by another tile of this work item
+                softmax_item(0, 0, nv0, first, both);
+                softmax_item(1, 0, nv1, first, both);
+                softmax_item(0, 1, nv0, first, both);
+                softmax_item(1, 1, nv1, first, both && next_tile);  // next: half 0 of the next tile (never empty)
             }
             // ---- the work item's accumulators are final once both chains have drained
             mbar_wait(&o_done[2 * g], ph_done);
@@ -1952,7 +2002,7 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     // ---- ISAB 0
     {
         RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Aq0, m00.Wkv, m00.bkv,
-                  nullptr, tl_apply ? nullptr : g_timeline, part};
+                  nullptr, (tl_apply || getenv("PCA_TL_REDUCE64")) ? nullptr : g_timeline, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * d_in * TD + 2.0 * TM * TD), pts * 4.0 * d_in);
         mab_reduce5_tc_kernel<false><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
@@ -1980,7 +2030,7 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     // ---- ISAB 1
     {
         RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Aq1, nullptr, m10.bkv,
-                  c->Wkv1, nullptr, part};
+                  c->Wkv1, getenv("PCA_TL_REDUCE64") ? g_timeline : nullptr, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TM * TD), pts * 128.0);
         mab_reduce5_tc_kernel<true><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }

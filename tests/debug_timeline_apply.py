@@ -32,7 +32,7 @@ from pcaudio_b200 import _lib
 _lib.LIB_PATH = TL_LIB
 dev = torch.device("cuda:0")
 st = pca.ST(dim_input=2, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev).set_precision("bf16")
-X = torch.rand(4096, 1025, 2, device=dev)
+X = torch.rand(4096, 1024, 2, device=dev)
 buf = torch.zeros(8000, dtype=torch.int64, device=dev)
 with torch.no_grad():
     st(X)
@@ -44,7 +44,7 @@ with torch.no_grad():
 raw = buf.cpu().numpy()
 names = {20: "item start", 24: "s_full wait done", 25: "ld wait done", 26: "softmax math + st issued", 27: "st wait done",
          40: "epi: tile start", 41: "epi: o_full wait done", 42: "epi: O1 -> bf16 TMEM done", 43: "epi: arrived o1_ready (+MMA issue)",
-         44: "epi: f_full wait done", 45: "epi: Y stored", 50: "prod: tile start", 51: "prod: input staged + arrived",
+         44: "epi: f_full wait done", 45: "epi: Y stored", 50: "prod: tile start", 51: "prod: input staged + arrived (reduce: loaded)",
          52: "prod: qp_done wait done", 53: "prod: aq_empty wait done", 54: "prod: AQ converted", 56: "prod0: oq_free wait done",
          60: "mma: tile start", 61: "mma: aq_full wait done", 62: "mma: S issued", 63: "mma: p_ready wait done"}
 for role, off in (("softmax warp 0", 0), ("epilogue warp 16", 2000), ("producer warp 8", 4000), ("MMA chain 0", 6000)):
