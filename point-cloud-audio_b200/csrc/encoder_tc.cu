@@ -118,12 +118,30 @@ __device__ void prep_queries(const float* __restrict__ Qin, int nq, const float*
                              const float* __restrict__ bq, float* __restrict__ Qp_out, uint8_t* __restrict__ Aq,
                              float* sq /* smem 64*64 */, const float* __restrict__ Wk = nullptr,
                              uint8_t* __restrict__ AqPool = nullptr, float* __restrict__ WqkPool = nullptr) {
-    for (int i = threadIdx.x; i < nq * TD; i += blockDim.x) {
-        const int m = i / TD, f = i % TD;
-        float a = bq[f];
-        for (int k = 0; k < TD; ++k) a = fmaf(Qin[m * TD + k], Wq[f * TD + k], a);
-        sq[i] = a;
-        Qp_out[i] = a;
+    {   // Qp = Qin Wq^T + bq from shared-memory copies (Wq rows padded to 65 floats: thread <-> output feature is conflict free)
+        __shared__ float sW[TD * 65];
+        float* sI = sq;                                  // the inputs are staged in sq, then replaced by the outputs
+        for (int i = threadIdx.x; i < nq * TD; i += blockDim.x) sI[i] = Qin[i];
+        for (int i = threadIdx.x; i < TD * TD; i += blockDim.x) sW[(i / TD) * 65 + (i % TD)] = Wq[i];
+        __syncthreads();
+        float outv[(TM * TD) / 256];
+#pragma unroll
+        for (int j = 0; j < (TM * TD) / 256; ++j) {
+            const int i = threadIdx.x + j * 256;
+            if (i < nq * TD) {
+                const int m = i / TD, f = i % TD;
+                float a = bq[f];
+#pragma unroll 8
+                for (int k = 0; k < TD; ++k) a = fmaf(sI[m * TD + k], sW[f * 65 + k], a);
+                outv[j] = a;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < (TM * TD) / 256; ++j) {
+            const int i = threadIdx.x + j * 256;
+            if (i < nq * TD) { sq[i] = outv[j]; Qp_out[i] = outv[j]; }
+        }
     }
     __syncthreads();
     if (nq == 1 && AqPool != nullptr) {
