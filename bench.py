@@ -10,8 +10,9 @@ scaling, one process per GPU, no data-path collective): BASELINE config 2 -- FST
 n_fft 2048 / hop 1024 -> 16 frame clouds of 1025 (f, mag) points per clip = 4096 clouds per step.
 
 `value`  : clips/s with the audio already resident in HBM (device-timed with CUDA events, max over ranks)
-`e2e`    : clips/s through the public host-buffer entry point (pinned host audio -> H2D -> kernels ->
-           D2H logits inside the timed region)
+`e2e`    : clips/s through the public host-buffer interface (AudioSetPipeline.submit_host / wait_host: every
+           step copies its pinned host audio H2D, runs the kernels and copies its logits D2H inside the timed
+           region; the copy of step i+1 overlaps the kernels of step i, the host reads each step's logits)
 `roofline`: dominant kernel (by device time inside the timed region, measured live with CUDA events on
            the launching stream) against the measured peak in MEASURED_PEAKS.json
 `cpu_baseline`: the CPU oracle port of the reference path on the host cores, bounded sample
@@ -194,14 +195,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, tail=None):
         for i in range(warmup):
             fn(i)
+        if tail is not None:
+            tail()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+        if tail is not None:
+            tail()                        # the last batch's logits are read inside the timed region too
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -216,10 +221,23 @@ def run_ours(args):
     def step_dev(i):
         last["logits"] = pipe(pool[i % pool_n])
 
+    host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
+    pending = []
+
     def step_host(i):
-        pipe.run_host(host_pool[i % len(host_pool)], host_out)
-        torch.cuda.current_stream(dev).synchronize()      # the caller reads the logits every step
-        last["host"] = float(host_out[0, 0, 0])
+        # public pipelined host-buffer API: batch i is submitted (its H2D copy overlaps the kernels of batch i-1), then
+        # the logits of batch i-1 are read on the host.  Every step copies its 16.4 MB in and its logits out.
+        pending.append((pipe.submit_host(host_pool[i % len(host_pool)], host_outs[i & 1]), i & 1))
+        if len(pending) > 1:
+            t, slot = pending.pop(0)
+            pipe.wait_host(t)
+            last["host"] = float(host_outs[slot][0, 0, 0])
+
+    def drain_host():
+        while pending:
+            t, slot = pending.pop(0)
+            pipe.wait_host(t)
+            last["host"] = float(host_outs[slot][0, 0, 0])
 
     # ---- device-resident timing (value)
     sampler = ClockSampler(local)
@@ -233,7 +251,7 @@ def run_ours(args):
     value = world * CLIPS_PER_STEP * args.steps / (ms / 1e3)
 
     # ---- end-to-end timing through the host-buffer entry point (e2e)
-    ms_e2e = timed(step_host, args.steps, min(3, args.warmup))
+    ms_e2e = timed(step_host, args.steps, min(3, args.warmup), tail=drain_host)
     e2e_value = world * CLIPS_PER_STEP * args.steps / (ms_e2e / 1e3)
     clocks = sampler.stop()
 

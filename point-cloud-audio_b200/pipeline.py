@@ -57,6 +57,7 @@ class AudioSetPipeline:
         self.window, self.twiddle = rt.stft_tables(cfg.window_size, cfg.window_size, self.device)
         self._staging = {}
         self._copy_stream = None
+        self._pipe = None
 
     def _ws(self, n_clips):
         need = _lib.lib().pca_pipeline_workspace_bytes(C.byref(self.c), n_clips)
@@ -117,6 +118,52 @@ class AudioSetPipeline:
                     _lib.ptr(dev_logits), _lib.ptr(host_logits), _lib.ptr(ws), ws.numel(),
                     rt.stream_ptr(self.device)), "pipeline_run_host")
         return host_logits
+
+    # ---- pipelined host-buffer interface: the H2D copy of batch k+1 overlaps the kernels of batch k ----------------
+    def submit_host(self, host_audio: torch.Tensor, host_logits: torch.Tensor):
+        """Enqueue one whole-path pass over a pinned host batch and return a ticket; ``wait_host(ticket)`` blocks until
+        ``host_logits`` (pinned, (n_clips * clouds_per_clip, S, C)) holds its result.  Two staging slots: the copy of
+        batch k+1 runs on a private copy stream while batch k computes on the current stream, so a loop
+        ``t1 = submit(b1); wait(t0); t2 = submit(b2); wait(t1); ...`` streams batches at the speed of the slower of
+        {copy, compute}.  Every batch is still copied host->device and its logits device->host."""
+        if host_audio.is_cuda or host_audio.dtype != torch.float32 or not host_audio.is_contiguous():
+            raise ValueError("host_audio must be a contiguous float32 CPU tensor")
+        n_clips = host_audio.shape[0]
+        st = self.c.st
+        n_out = n_clips * self.clouds_per_clip
+        if self._pipe is None or self._pipe["n_clips"] != n_clips:
+            self._pipe = {"n_clips": n_clips, "k": 0,
+                          "audio": [torch.empty((n_clips, self.cfg.n_samples), dtype=torch.float32, device=self.device) for _ in range(2)],
+                          "logits": [torch.empty((n_out, st.S, st.C), dtype=torch.float32, device=self.device) for _ in range(2)],
+                          "copied": [torch.cuda.Event() for _ in range(2)], "done": [None, None]}
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+        P = self._pipe
+        slot = P["k"] & 1
+        P["k"] += 1
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            with torch.cuda.stream(self._copy_stream):
+                if P["done"][slot] is not None:
+                    self._copy_stream.wait_event(P["done"][slot])        # the slot's previous batch has been consumed
+                P["audio"][slot].copy_(host_audio, non_blocking=True)
+                P["copied"][slot].record(self._copy_stream)
+            cur.wait_event(P["copied"][slot])
+            ws = self._ws(n_clips)
+            blob = self.model._blob()
+            _lib.check(_lib.lib().pca_pipeline_run(
+                C.byref(self.c), _lib.ptr(P["audio"][slot]), n_clips, _lib.ptr(self.window), _lib.ptr(self.twiddle),
+                _lib.ptr(self.farr), _lib.ptr(self.tarr), _lib.ptr(blob), _lib.ptr(P["logits"][slot]), _lib.ptr(ws), ws.numel(),
+                rt.stream_ptr(self.device)), "pipeline_run")
+            host_logits.copy_(P["logits"][slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            P["done"][slot] = ev
+        return ev
+
+    @staticmethod
+    def wait_host(ticket) -> None:
+        ticket.synchronize()
 
     @property
     def h2d_bytes_per_clip(self) -> int:

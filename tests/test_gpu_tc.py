@@ -173,3 +173,25 @@ def test_tc_tail_rule_on_off_agree(pca):
     for x, y in ((a, b), (am, bm)):
         assert torch.isfinite(x).all() and torch.isfinite(y).all()
         assert (x - y).abs().max().item() / y.abs().max().item() < BF16_REL_TOL
+
+
+def test_pipelined_host_interface_matches_device_call(pca):
+    """submit_host / wait_host (H2D of batch k+1 overlapping the kernels of batch k, two staging slots) returns, for
+    every batch, exactly the logits of the device-resident call."""
+    dev = torch.device("cuda:0")
+    w = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, "fst_weights.npz")).items()}
+    st = pca.ST(dim_input=2, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev)
+    st.load_state_dict(w)
+    pipe = pca.AudioSetPipeline(st, pca.AudioConfig(window_size=2048, n_samples=16000, mode=2, precision="bf16"), dev)
+    g = torch.Generator().manual_seed(5)
+    batches = [(0.1 * torch.randn(32, 16000, generator=g)).pin_memory() for _ in range(5)]
+    outs = [torch.empty(32 * 16, 1, 10).pin_memory() for _ in range(5)]
+    tickets = []
+    for b, o in zip(batches, outs):
+        tickets.append(pipe.submit_host(b, o))
+        if len(tickets) > 1:
+            pipe.wait_host(tickets[-2])
+    pipe.wait_host(tickets[-1])
+    for b, o in zip(batches, outs):
+        ref = pipe(b.to(dev)).cpu()
+        assert torch.equal(o.squeeze(1), ref)
