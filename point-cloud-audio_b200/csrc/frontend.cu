@@ -184,11 +184,53 @@ __device__ __forceinline__ void topk_core(const float* keys, const int cloud, in
     float* pts = pts_all ? pts_all + (size_t)cloud * K * width : nullptr;
     int32_t* idx_out = idx_all ? idx_all + (size_t)cloud * K : nullptr;
 
-    // ---- K-th largest key by radix select (skipped when every point is kept)
+    // ---- K-th largest key (skipped when every point is kept)
     uint32_t kth = 0;
     int n_ties_take = 0;
     const bool all = (K >= N);
-    if (!all) {
+    if (!all && SMEM_KEYS) {
+        // Keys in shared memory: bitwise search for the largest v with #{key >= v} >= K, two bits per round (three
+        // candidate thresholds counted in one sweep over the keys; plain compares, no histogram, no atomics).
+        __shared__ int s_cnt[2][3][TOPK_THREADS / 32];
+        uint32_t prefix = 0;
+        int cnt_ge_prefix = N;                       // #{key >= prefix}
+        for (int round = 0; round < 16; ++round) {
+            const int bit = 30 - 2 * round;
+            const uint32_t c1 = prefix | (1u << bit), c2 = prefix | (2u << bit), c3 = prefix | (3u << bit);
+            int n1 = 0, n2 = 0, n3 = 0;
+            for (int i = tid; i < N; i += TOPK_THREADS) {
+                const uint32_t o = ordered_key(keys[i]);
+                n1 += o >= c1; n2 += o >= c2; n3 += o >= c3;
+            }
+            n1 = __reduce_add_sync(0xffffffffu, n1);
+            n2 = __reduce_add_sync(0xffffffffu, n2);
+            n3 = __reduce_add_sync(0xffffffffu, n3);
+            int (*sc)[TOPK_THREADS / 32] = s_cnt[round & 1];
+            if (lane == 0) { sc[0][wid] = n1; sc[1][wid] = n2; sc[2][wid] = n3; }
+            __syncthreads();
+            int t1 = 0, t2 = 0, t3 = 0;
+#pragma unroll
+            for (int w = 0; w < TOPK_THREADS / 32; ++w) { t1 += sc[0][w]; t2 += sc[1][w]; t3 += sc[2][w]; }
+            if (t3 >= K) { prefix = c3; cnt_ge_prefix = t3; }
+            else if (t2 >= K) { prefix = c2; cnt_ge_prefix = t2; }
+            else if (t1 >= K) { prefix = c1; cnt_ge_prefix = t1; }
+            // (the double-buffered counters make one barrier per round sufficient)
+        }
+        kth = prefix;
+        // ties: #{key > kth} by one more sweep
+        int ngt = 0;
+        for (int i = tid; i < N; i += TOPK_THREADS) ngt += ordered_key(keys[i]) > kth;
+        ngt = __reduce_add_sync(0xffffffffu, ngt);
+        __syncthreads();
+        if (lane == 0) s_cnt[0][0][wid] = ngt;
+        __syncthreads();
+        int tgt = 0;
+#pragma unroll
+        for (int w = 0; w < TOPK_THREADS / 32; ++w) tgt += s_cnt[0][0][w];
+        n_ties_take = K - tgt;
+        (void)cnt_ge_prefix;
+        __syncthreads();
+    } else if (!all) {
         if (tid == 0) { s_prefix = 0; s_remaining = K; }
         uint32_t mask = 0;
         for (int shift = 24; shift >= 0; shift -= 8) {
@@ -342,6 +384,205 @@ topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __re
                      idx_all, counts, sortbuf);
 }
 
+// ------------------------------------------------------------------------------------ top-K, keys in registers
+// Clouds of up to 512 * KPT points: thread t owns the KPT CONSECUTIVE flat indices [t KPT, (t+1) KPT), as order-preserving
+// uint keys in registers.  The same selection rule as topk_core, but every pass is register-only:
+//   * 4-pass 8-bit radix select with warp-private shared-memory histograms (plain shared atomics; after the first byte
+//     the digits of log-magnitudes are well spread),
+//   * selection flags as two 32-bit masks per thread, ONE block-wide exclusive scan of the per-thread counts gives every
+//     selected point its position in flat-index order (ties at the K boundary keep the lowest indices),
+//   * the K survivors are sorted in shared memory on (~key, index) for the descending emission order.
+// ~6x fewer instructions than the global-memory version (which ncu shows issue-bound at IPC 3.4).
+template <int KPT>
+__global__ void __launch_bounds__(TOPK_THREADS)
+topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __restrict__ farr,
+                const float* __restrict__ tarr, int K, int kpad, int sorted, int use_tau, float tau,
+                float* __restrict__ pts_all, int32_t* __restrict__ idx_all, int32_t* __restrict__ counts) {
+    extern __shared__ unsigned long long sortbuf[];      // kpad entries when sorted
+    constexpr int NW = TOPK_THREADS / 32;
+    __shared__ int hist[NW][256];
+    __shared__ int tot[256];
+    __shared__ int warp_sum[NW];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_remaining, s_total;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int cloud = blockIdx.x;
+    const float* keys = keys_all + (size_t)cloud * N;
+    const int width = tarr != nullptr ? 3 : 2;
+    float* pts = pts_all ? pts_all + (size_t)cloud * K * width : nullptr;
+    int32_t* idx_out = idx_all ? idx_all + (size_t)cloud * K : nullptr;
+
+    const int i0 = tid * KPT;
+    const int nval = max(0, min(KPT, N - i0));          // valid keys of this thread
+    uint32_t o[KPT];
+    if (nval == KPT && ((reinterpret_cast<size_t>(keys + i0) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < KPT; j += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(keys + i0 + j));
+            o[j] = ordered_key(v.x); o[j + 1] = ordered_key(v.y); o[j + 2] = ordered_key(v.z); o[j + 3] = ordered_key(v.w);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) o[j] = (j < nval) ? ordered_key(__ldg(keys + i0 + j)) : 0u;
+    }
+
+    // ---- K-th largest key by radix select (skipped when every point is kept)
+    uint32_t kth = 0;
+    int n_ties_take = 0;
+    const bool all = (K >= N);
+    if (!all) {
+        uint32_t prefix = 0, mask = 0;
+        int remaining = K;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) hist[wid][lane + 32 * b] = 0;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < KPT; ++j)
+                if (j < nval && (o[j] & mask) == prefix) atomicAdd(&hist[wid][(o[j] >> shift) & 255u], 1);
+            __syncthreads();
+            if (tid < 256) {
+                int t = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) t += hist[w][tid];
+                tot[tid] = t;
+            }
+            __syncthreads();
+            if (wid == 0) {
+                // lane l owns digits [8l, 8l+8); find the digit holding the `remaining`-th largest candidate
+                int c[8], tl = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c[j] = tot[lane * 8 + j]; tl += c[j]; }
+                int suf = tl;        // inclusive suffix sum over lanes >= lane
+#pragma unroll
+                for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                    const int v = __shfl_down_sync(0xffffffffu, suf, o2);
+                    if (lane + o2 < 32) suf += v;
+                }
+                const int above = suf - tl;   // candidates with a larger digit than this lane's
+                if (above < remaining && remaining <= above + tl) {
+                    int cum = above;
+#pragma unroll
+                    for (int j = 7; j >= 0; --j) {
+                        if (cum < remaining && remaining <= cum + c[j]) {
+                            s_prefix = prefix | ((uint32_t)(lane * 8 + j) << shift);
+                            s_remaining = remaining - cum;
+                        }
+                        cum += c[j];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            remaining = s_remaining;
+            mask |= 255u << shift;
+        }
+        kth = prefix;
+        n_ties_take = remaining;
+    }
+    // Threshold mode: see topk_core
+    const uint32_t thr = use_tau ? ordered_key(tau) : 0u;
+    const bool tau_rules = use_tau && (all || thr > kth);
+    if (tau_rules) n_ties_take = 0;
+
+    // ---- selection flags and ONE block-wide exclusive scan of (greater, equal) counts
+    uint32_t gtm = 0, eqm = 0;
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+        if (j < nval) {
+            const bool gt = tau_rules ? (o[j] >= thr) : (all || o[j] > kth);
+            const bool eq = !all && !tau_rules && (o[j] == kth);
+            gtm |= (uint32_t)gt << j;
+            eqm |= (uint32_t)eq << j;
+        }
+    }
+    const int mine = __popc(gtm) | (__popc(eqm) << 16);          // both counts fit 15 bits (N <= 16384)
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) warp_sum[wid] = incl;
+    if (sorted) {
+        for (int i = tid; i < kpad; i += TOPK_THREADS) sortbuf[i] = ~0ull;
+    }
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const int v = warp_sum[w];
+        if (w < wid) base += v;
+        total += v;
+    }
+    int gt_before = (base + incl - mine) & 0xffff, eq_before = (base + incl - mine) >> 16;
+    const int n_kept = (total & 0xffff) + min(total >> 16, n_ties_take);
+    if (counts != nullptr && tid == 0) counts[cloud] = n_kept;
+
+    // ---- ordered compaction of this thread's selected keys
+    const uint32_t selm = gtm | eqm;
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {                      // static indices keep o[] in registers
+        if (!((selm >> j) & 1u)) continue;
+        const bool gt = (gtm >> j) & 1u;
+        const bool take = gt || eq_before < n_ties_take;
+        if (take) {
+            const int pos = gt_before + min(eq_before, n_ties_take);
+            const int i = i0 + j;
+            if (sorted) {
+                sortbuf[pos] = ((unsigned long long)(~o[j]) << 32) | (uint32_t)i;
+            } else {
+                const int f = i % nf, t = i / nf;
+                const float kv = __ldg(keys + i);
+                if (pts) {
+                    if (width == 3) { pts[pos * 3] = __ldg(farr + f); pts[pos * 3 + 1] = __ldg(tarr + t); pts[pos * 3 + 2] = kv; }
+                    else { pts[pos * 2] = __ldg(farr + f); pts[pos * 2 + 1] = kv; }
+                }
+                if (idx_out) idx_out[pos] = i;
+            }
+        }
+        if (gt) ++gt_before; else ++eq_before;
+    }
+    if (!sorted) {
+        for (int r = n_kept + tid; r < K; r += TOPK_THREADS) {
+            if (pts) { for (int j = 0; j < width; ++j) pts[r * width + j] = 0.f; }
+            if (idx_out) idx_out[r] = -1;
+        }
+        return;
+    }
+    __syncthreads();
+
+    // ---- bitonic sort of the survivors: ascending (~key, index) == descending key, stable
+    for (int k2 = 2; k2 <= kpad; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (kpad >> 1); t += TOPK_THREADS) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int ixj = i | j;
+                const unsigned long long a = sortbuf[i], b = sortbuf[ixj];
+                const bool asc = (i & k2) == 0;
+                if ((a > b) == asc) { sortbuf[i] = b; sortbuf[ixj] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int r = tid; r < K; r += TOPK_THREADS) {
+        if (r >= n_kept) {
+            if (pts) { for (int j = 0; j < width; ++j) pts[r * width + j] = 0.f; }
+            if (idx_out) idx_out[r] = -1;
+            continue;
+        }
+        const int i = (int)(uint32_t)sortbuf[r];
+        const float kv = __ldg(keys + i);
+        const int f = i % nf, t = i / nf;
+        if (pts) {
+            if (width == 3) { pts[r * 3] = __ldg(farr + f); pts[r * 3 + 1] = __ldg(tarr + t); pts[r * 3 + 2] = kv; }
+            else { pts[r * 2] = __ldg(farr + f); pts[r * 2 + 1] = kv; }
+        }
+        if (idx_out) idx_out[r] = i;
+    }
+}
+
 // ------------------------------------------------------------------------------------ fused front end
 // audio -> STFT -> log-magnitude -> (f, t, mag) cloud -> selection in ONE launch (a1..a7 of SURVEY.md 8a): one block per
 // cloud (= ntemp consecutive frames of a clip).  The cloud's log-magnitudes never leave shared memory, so the HBM traffic
@@ -444,12 +685,22 @@ int launch_topk(const float* keys, int n_clouds, int nf, int nt, const float* fa
         kpad = 2;
         while (kpad < K) kpad <<= 1;
         smem = (size_t)kpad * sizeof(unsigned long long);
-        if (smem > 48 * 1024) PCA_CHECK_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 24 * 1024) {      // static (17.5 KB of histograms) + dynamic beyond the 48 KB default
+            PCA_CHECK_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PCA_CHECK_CUDA(cudaFuncSetAttribute(topk_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PCA_CHECK_CUDA(cudaFuncSetAttribute(topk_reg_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PCA_CHECK_CUDA(cudaFuncSetAttribute(topk_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
     }
     {
         // algorithmic traffic: keys read once, 16 B per selected point written
         LaunchTimer lt("topk_kernel", st, 0.0, (double)n_clouds * (4.0 * N + 16.0 * K));
-        topk_kernel<<<n_clouds, TOPK_THREADS, smem, st>>>(keys, (int)N, nf, farr, tarr, K, kpad, sorted_desc, use_tau, tau, pts, idx, counts);
+        // clouds of up to 16 384 points: keys in registers (one thread owns KPT consecutive points)
+        const int kpt = (int)((N + TOPK_THREADS - 1) / TOPK_THREADS);
+        if (kpt <= 8) topk_reg_kernel<8><<<n_clouds, TOPK_THREADS, smem, st>>>(keys, (int)N, nf, farr, tarr, K, kpad, sorted_desc, use_tau, tau, pts, idx, counts);
+        else if (kpt <= 16) topk_reg_kernel<16><<<n_clouds, TOPK_THREADS, smem, st>>>(keys, (int)N, nf, farr, tarr, K, kpad, sorted_desc, use_tau, tau, pts, idx, counts);
+        else if (kpt <= 32) topk_reg_kernel<32><<<n_clouds, TOPK_THREADS, smem, st>>>(keys, (int)N, nf, farr, tarr, K, kpad, sorted_desc, use_tau, tau, pts, idx, counts);
+        else topk_kernel<<<n_clouds, TOPK_THREADS, smem, st>>>(keys, (int)N, nf, farr, tarr, K, kpad, sorted_desc, use_tau, tau, pts, idx, counts);
     }
     PCA_CHECK_LAUNCH("topk_kernel");
     return 0;
