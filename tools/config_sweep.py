@@ -53,4 +53,21 @@ if not quick:
     # config 4: top-K sweep on the 16 384-point clip cloud (a7 semantics), 10k clips
     for K in (256, 512, 1024, 2048, 4096, 8192):
         run(f"4: sweep 10k clips top-K={K}", "3st", 3, 10000, 16000, 1024, 3, 32, K, "bf16", 3)
+# config 5 (forward only; training is the next scope row): main_pointcloud.SetTransformer D=256,H=4,M=16,C=40 on
+# ModelNet40-shaped clouds, fp32 CUDA-core path (no tcgen05 kernels for these dims yet)
+torch.manual_seed(0)
+mn = pca.SetTransformer(dim_input=3, num_outputs=1, dim_output=40, num_inds=16, dim_hidden=256, num_heads=4).to(dev).eval()
+Xm = torch.randn(256, 1000, 3, device=dev)
+Xm = (Xm - Xm.mean(1, keepdim=True)) / Xm.std(1, keepdim=True)
+with torch.no_grad():
+    ms = timeit(lambda: mn(Xm), 5)
+r = {"config": "5: ModelNet SetTransformer forward B=256 N=1000 (fp32 path)", "precision": "fp32", "clouds": 256, "ms": ms,
+     "clouds_per_s": 256 / ms * 1e3, "encoder_tflops": 256 * 1.006e9 / ms / 1e9}
+rows.append(r); print(json.dumps(r), flush=True)
+ds = pca.DeepSet(3, 1, 40, dim_hidden=256, pool="max").to(dev)
+with torch.no_grad():
+    ms = timeit(lambda: ds(Xm), 5)
+r = {"config": "DeepSet (shared MLP + max-pool) B=256 N=1000 dim_hidden=256 (fp32 path)", "precision": "fp32", "clouds": 256, "ms": ms,
+     "clouds_per_s": 256 / ms * 1e3}
+rows.append(r); print(json.dumps(r), flush=True)
 json.dump(rows, open(os.path.join("gpurun_out", "config_sweep.json"), "w"), indent=1)
