@@ -257,6 +257,7 @@ struct RParams {
     const float* bkv;             // (128)
     const uint8_t* Wkv16;         // 16 KB B operand        [DIN64 == true]
     long long* timeline;          // debug: per-phase clock64 stamps of CTA 0 / softmax warp 0 (nullptr = off)
+    int* redo;                    // experiment (NWG == 4): set when a row outgrew its reference exponent
     float* part;                  // (B, slots, 8, 10, 64): per (head, query) row: m (log2 domain), l, acc[8];
                                   // query index fastest so that a warp's 32 rows store/load 128 contiguous bytes
 };
@@ -641,8 +642,12 @@ __device__ __noinline__ float reduce5_item_slow(uint32_t sbase, uint32_t oaddr, 
 // Persistent: grid = min(#work items, #SMs); CTA k walks the work items (cloud, point-split) k, k + grid, ...
 // Barriers, TMEM and the resident operands are set up once; all pipelines (producer -> MMA -> softmax) run
 // straight across work-item boundaries, so there is no per-cloud fill/drain bubble.
-template <bool DIN64>
-__global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const RParams P) {
+// NWG softmax warpgroups: 2 (two chains each, 64 score registers per thread) or 4 (one chain each, scores streamed in
+// 32-column chunks at 88 registers; experiment, see the host code).
+template <bool DIN64, int NWG>
+__global__ void __launch_bounds__((4 * NWG + 8) * 32, 1) mab_reduce5_tc_kernel(const RParams P) {
+    constexpr int WP = 4 * NWG;          // first producer warp
+    constexpr int WM = WP + 4;           // first MMA warp
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sAq = smem + R2Smem::AQ;
     uint8_t* sKV = smem + R2Smem::KV;
@@ -666,8 +671,8 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
     long long* tl2 = nullptr;
     int tl2_n = 0;
     if (P.timeline != nullptr && blockIdx.x == 0 && lane == 0) {
-        if (warp == 8) tl2 = P.timeline + 4000;
-        else if (warp == 12) tl2 = P.timeline + 6000;
+        if (warp == WP) tl2 = P.timeline + 4000;
+        else if (warp == WM) tl2 = P.timeline + 6000;
     }
     auto stamp2 = [&](int tag) {
         if (tl2 != nullptr && tl2_n < 1000) { tl2[2 * tl2_n] = tag; tl2[2 * tl2_n + 1] = clock64(); ++tl2_n; }
@@ -693,7 +698,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
             for (int k = 0; k < 4; ++k) sWsm[i * 4 + k] = (k < P.d_in) ? P.Wkv32[i * P.d_in + k] : 0.f;
         }
     }
-    if (warp == 12) tmem_alloc(tmem_slot, 512);
+    if (warp == WM) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 4); mbar_init(&kv_empty[i], 4); }
         for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
@@ -708,14 +713,14 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
     fence_after_sync();
     const uint32_t tb = *tmem_slot;
 
-    if (warp >= 12) {
+    if (warp >= WM) {
         reg_dec<40>();
         {
             // =================================================================== one MMA-issuing warp per chain
             // chain c = warp - 12: strictly serial  Q K^T -> (warpgroup softmax) -> P V -> next Q K^T  on its own
             // half-buffer; the four chains never wait on each other.  The whole warp runs the loop (uniform control flow
             // keeps the descriptors in uniform registers); one elected lane issues the tcgen05 instructions.
-            const int c = warp - 12, half = c & 1;
+            const int c = warp - WM, half = c & 1;
             const bool leader = elect_one();
             const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
             const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
@@ -750,10 +755,14 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                         stamp2(63);
                         if (leader) {
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                mma_ts(tmem_addr(tb, 0, R2_O + 16 * (2 * p + half)), tmem_addr(tb, 0, R2_S + 64 * c + ks * 8),
-                                       smem_desc(vbase + 2 * p * 2048 + half * 1024 + ks * 256, 128, 2048), idesc_pv,
+                            for (int ks = 0; ks < 4; ++ks) {
+                                // NWG == 4: P occupies columns 32..63 of the buffer, keys 32..63 first, then keys 0..31
+                                const uint32_t pcol = NWG == 4 ? 32 + ks * 8 : ks * 8;
+                                const int vrow = NWG == 4 ? ((ks + 2) & 3) : ks;
+                                mma_ts(tmem_addr(tb, 0, R2_O + 16 * (2 * p + half)), tmem_addr(tb, 0, R2_S + 64 * c + pcol),
+                                       smem_desc(vbase + 2 * p * 2048 + half * 1024 + vrow * 256, 128, 2048), idesc_pv,
                                        (it > 0 || ks > 0) ? 1u : 0u);
+                            }
                         }
                         __syncwarp();
                     }
@@ -764,8 +773,8 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                 __syncwarp();
             }
         }
-    } else if (warp >= 8) {
-        reg_dec<88>();
+    } else if (warp >= WP) {
+        if constexpr (NWG == 4) reg_inc<88>(); else reg_dec<88>();      // launch allocation: 80 (24 warps) / 128 (16 warps)
         // =================================================================== producer: K|V tiles
         const int quad = warp & 3;
         const int row = 32 * quad + lane;
@@ -809,7 +818,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                     fence_async_smem();
                     fence_before_sync();
                     warp_arrive(y_full);
-                    if (warp == 8) {
+                    if (warp == WP) {
                         // one producer warp issues the K|V projection MMA (elected lane) once all 128 rows of Y are staged
                         mbar_wait(y_full, gt & 1);
                         fence_after_sync();
@@ -850,7 +859,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                 warp_arrive(&kv_full[stage]);
             }
         }
-    } else {
+    } else if constexpr (NWG == 2) {
         reg_inc<184>();
         // =================================================================== softmax warpgroups (2 chains each)
         const int g = warp >> 2, quad = warp & 3;
@@ -1008,10 +1017,115 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) mab_reduce5_tc_kernel(const R
                 }
             fence_before_sync();
         }
+        } else {
+        reg_inc<88>();
+        // =================================================================== 4 softmax warpgroups, one chain each
+        // Scores are streamed in 32-column chunks (keys 32..63 first): after the work item's first tile no row maximum
+        // is taken, so nothing but one chunk has to be live.  P goes to columns 32..63 of the chain's buffer.
+        const int c = warp >> 2, quad = warp & 3;          // chain c: half = c & 1 of the pairs (c >> 1) + 2 pp
+        const int half = c & 1, g = c >> 1;
+        const int row = 32 * quad + lane;
+        const uint32_t lane_base = 32 * quad;
+        const uint32_t ocol_off = (row >= 64) ? 8u : 0u;
+        const uint32_t sbase = tmem_addr(tb, lane_base, R2_S + 64 * c);
+        float m_used[2], l_run[2];
+        uint32_t ph_s = 0, ph_done = 0;
+        constexpr float kOverflow = 1.152921504606847e18f;      // 2^60
+        auto softmax_item = [&](const int pp, const int nv, const bool first) {
+            if (nv == 0) {
+                if (first) { m_used[pp] = -INFINITY; l_run[pp] = 0.f; }
+                return;
+            }
+            mbar_wait(&s_full[c], ph_s);
+            ph_s ^= 1;
+            fence_after_sync();
+            uint32_t v[32], pk[16];
+            float sum;
+            if (nv == 64 && !first) {
+                const float2 neg2 = make_float2(-m_used[pp], -m_used[pp]);
+                float2 sum2 = make_float2(0.f, 0.f);
+                tmem_ld32(sbase + 32, v);
+                tmem_ld_wait32(v);
+                exp_chunk32(v, neg2, sum2, pk);
+                tmem_st16(sbase + 32, pk);
+                tmem_ld32(sbase, v);
+                tmem_ld_wait32(v);
+                exp_chunk32(v, neg2, sum2, pk);
+                tmem_st16(sbase + 48, pk);
+                sum = sum2.x + sum2.y;
+            } else {
+                // first tile of the work item (reference exponent = row maximum) and ragged tails: masked two-pass
+                float mx = -INFINITY;
+                tmem_ld32(sbase + 32, v);
+                tmem_ld_wait32(v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (32 + j < nv) mx = fmaxf(mx, __uint_as_float(v[j]));
+                uint32_t v0[32];
+                tmem_ld32(sbase, v0);
+                tmem_ld_wait32(v0);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < nv) mx = fmaxf(mx, __uint_as_float(v0[j]));
+                if (first) { m_used[pp] = mx; l_run[pp] = 0.f; }
+                const float m = m_used[pp];
+                sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = (32 + j < nv) ? ex2(__uint_as_float(v[j]) - m) : 0.f;
+                    const float p1 = (33 + j < nv) ? ex2(__uint_as_float(v[j + 1]) - m) : 0.f;
+                    sum += p0 + p1;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                }
+                tmem_st16(sbase + 32, pk);
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = (j < nv) ? ex2(__uint_as_float(v0[j]) - m) : 0.f;
+                    const float p1 = (j + 1 < nv) ? ex2(__uint_as_float(v0[j + 1]) - m) : 0.f;
+                    sum += p0 + p1;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                }
+                tmem_st16(sbase + 48, pk);
+            }
+            if (!(sum < kOverflow) && P.redo != nullptr) P.redo[0] = 1;       // EXPERIMENT: a score outgrew the reference
+            l_run[pp] += sum;
+            tmem_st_wait();
+            fence_before_sync();
+            warp_arrive(&p_ready[c]);
+        };
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, split, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, split, tile0, nb);
+            m_used[0] = m_used[1] = -INFINITY;
+            l_run[0] = l_run[1] = 0.f;
+            for (int it = 0; it < ntiles; ++it) {
+                const int n_valid = min(128, nb - (tile0 + it) * 128);
+                const int nv = half == 0 ? min(64, n_valid) : max(0, n_valid - 64);
+                softmax_item(0, nv, it == 0);
+                softmax_item(1, nv, it == 0);
+            }
+            mbar_wait(&o_done[c], ph_done);
+            ph_done ^= 1;
+            fence_after_sync();
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+                const int p = g + 2 * pp;
+                uint32_t o[8];
+                tmem_ld8(tmem_addr(tb, lane_base, R2_O + 16 * (2 * p + half) + ocol_off), o);
+                tmem_ld_wait();
+                const int h = 2 * p + (row >> 6);
+                float* dst = P.part + (((size_t)cloud * (2 * P.nsplit) + 2 * split + half) * TH + h) * 10 * TM + (row & 63);
+                dst[0] = m_used[pp];
+                dst[TM] = l_run[pp];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[(2 + j) * TM] = (l_run[pp] > 0.f) ? __uint_as_float(o[j]) : 0.f;
+            }
+            fence_before_sync();
+        }
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 12) tmem_dealloc(tb, 512);
+    if (warp == WM) tmem_dealloc(tb, 512);
 }
 
 // ====================================================================================== apply kernel, third generation
@@ -1945,6 +2059,7 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 
 // ------------------------------------------------------------------------------------ host orchestration
 static int g_num_sms = 148;
+static int g_reduce_wg = 2;               // softmax warpgroups of the reduce kernel (PCA_TC_REDUCE_WG=4: streaming experiment)
 static int g_tail_max = TC_TAIL_MAX;       // tail rule (PCA_TC_TAIL=0 disables it: every point goes through the tensor-core kernels)
 static long long* g_timeline = nullptr;      // set through pca_debug_set_timeline
 void set_timeline(long long* p) { g_timeline = p; }
@@ -2020,9 +2135,10 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     // ---- ISAB 0
     {
         RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Aq0, m00.Wkv, m00.bkv,
-                  nullptr, (tl_apply || getenv("PCA_TL_REDUCE64")) ? nullptr : g_timeline, part};
+                  nullptr, (tl_apply || getenv("PCA_TL_REDUCE64")) ? nullptr : g_timeline, nullptr, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * d_in * TD + 2.0 * TM * TD), pts * 4.0 * d_in);
-        mab_reduce5_tc_kernel<false><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
+        if (g_reduce_wg == 4) mab_reduce5_tc_kernel<false, 4><<<pgrid, 24 * 32, R2Smem::TOTAL, st>>>(r);
+        else mab_reduce5_tc_kernel<false, 2><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<small>");
     {
@@ -2048,9 +2164,10 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     // ---- ISAB 1
     {
         RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Aq1, nullptr, m10.bkv,
-                  c->Wkv1, getenv("PCA_TL_REDUCE64") ? g_timeline : nullptr, part};
+                  c->Wkv1, getenv("PCA_TL_REDUCE64") ? g_timeline : nullptr, nullptr, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TM * TD), pts * 128.0);
-        mab_reduce5_tc_kernel<true><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
+        if (g_reduce_wg == 4) mab_reduce5_tc_kernel<true, 4><<<pgrid, 24 * 32, R2Smem::TOTAL, st>>>(r);
+        else mab_reduce5_tc_kernel<true, 2><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<64>");
     {
@@ -2104,8 +2221,11 @@ static int tc_configure() {
     PCA_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     if (major != 10) return fail(PCA_EDEVICE, "tcgen05 path needs an sm_100 device (found compute capability %d.x)", major);
     if (const char* v = getenv("PCA_TC_TAIL")) { g_tail_max = atoi(v); if (g_tail_max < 0) g_tail_max = 0; if (g_tail_max > TC_TAIL_MAX) g_tail_max = TC_TAIL_MAX; }
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce5_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_reduce5_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL));
+    PCA_CHECK_CUDA((cudaFuncSetAttribute(mab_reduce5_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL)));
+    PCA_CHECK_CUDA((cudaFuncSetAttribute(mab_reduce5_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL)));
+    PCA_CHECK_CUDA((cudaFuncSetAttribute(mab_reduce5_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL)));
+    PCA_CHECK_CUDA((cudaFuncSetAttribute(mab_reduce5_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL)));
+    if (const char* v = getenv("PCA_TC_REDUCE_WG")) g_reduce_wg = (v[0] == '4') ? 4 : 2;
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2Smem::TOTAL));
