@@ -257,6 +257,11 @@ void pca_debug_set_timeline(long long* device_buffer);
  * fp32 tail paths instead of a ninth, nearly empty tensor-core tile.  0 switches the rule off. */
 void pca_debug_set_tail_max(int tail_max);
 
+/* Debug / experiments: variant of the mab0 (reduce) kernel of the bf16 path: 4 = four softmax warpgroups streaming the scores
+ * in 32-column chunks, followed by the exact 2-warpgroup variant on the work items in which a row outgrew its reference
+ * exponent (normally none); 2 = the 2-warpgroup variant only. */
+void pca_debug_set_reduce_variant(int warpgroups);
+
 /* Unit probe of the tcgen05 building blocks used by the bf16 encoder path: one CTA computes
  * D (128, N) = A (128, K) * B (K, N), bf16 operands, fp32 accumulation in TMEM.
  * a_mode: 0 A (128,K) via shared memory K-major, 1 A via TMEM, 2 A given as (K,128) via shared memory MN-major;

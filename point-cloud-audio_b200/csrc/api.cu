@@ -23,6 +23,7 @@ int launch_fused_frontend(const float*, int, int, int, int, const float*, const 
                           int, int, int, float, float*, int32_t*, int32_t*, cudaStream_t);
 void set_timeline(long long* p);
 void set_tail_max(int t);
+void set_reduce_wg(int n);
 int launch_umma_probe(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 // tcgen05 path (encoder_tc.cu)
 size_t st_tc_workspace_bytes(const pca_st_dims* d, int B, int N);
@@ -602,6 +603,7 @@ int pca_debug_st_stages(const float* X, int B, int N, const pca_st_dims* dims, c
 
 void pca_debug_set_timeline(long long* device_buffer) { set_timeline(device_buffer); }
 void pca_debug_set_tail_max(int tail_max) { set_tail_max(tail_max); }
+void pca_debug_set_reduce_variant(int warpgroups) { set_reduce_wg(warpgroups); }
 
 int pca_debug_umma_probe(const float* A, const float* B, float* D, int N, int K, int a_mode, int b_mode, void* stream) {
     return launch_umma_probe(A, B, D, N, K, a_mode, b_mode, (cudaStream_t)stream);

@@ -257,7 +257,9 @@ struct RParams {
     const float* bkv;             // (128)
     const uint8_t* Wkv16;         // 16 KB B operand        [DIN64 == true]
     long long* timeline;          // debug: per-phase clock64 stamps of CTA 0 / softmax warp 0 (nullptr = off)
-    int* redo;                    // experiment (NWG == 4): set when a row outgrew its reference exponent
+    int* redo;                    // (n_work) flags: the streaming variant (NWG == 4) marks work items in which a row outgrew its
+                                  // reference exponent; they are redone by the NWG == 2 variant launched with redo_only = 1
+    int redo_only;
     float* part;                  // (B, slots, 8, 10, 64): per (head, query) row: m (log2 domain), l, acc[8];
                                   // query index fastest so that a warp's 32 rows store/load 128 contiguous bytes
 };
@@ -645,9 +647,9 @@ __device__ __noinline__ float reduce5_item_slow(uint32_t sbase, uint32_t oaddr, 
 // NWG softmax warpgroups: 2 (two chains each, 64 score registers per thread) or 4 (one chain each, scores streamed in
 // 32-column chunks at 88 registers; experiment, see the host code).
 template <bool DIN64, int NWG>
-__global__ void __launch_bounds__((4 * NWG + 8) * 32, 1) mab_reduce5_tc_kernel(const RParams P) {
-    constexpr int WP = 4 * NWG;          // first producer warp
-    constexpr int WM = WP + 4;           // first MMA warp
+__global__ void __launch_bounds__((4 * NWG + 12) * 32, 1) mab_reduce5_tc_kernel(const RParams P) {
+    constexpr int WP = 4 * NWG;          // first producer warp (8 of them: two per row quadrant, K columns / V columns)
+    constexpr int WM = WP + 8;           // first MMA warp
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sAq = smem + R2Smem::AQ;
     uint8_t* sKV = smem + R2Smem::KV;
@@ -656,12 +658,12 @@ __global__ void __launch_bounds__((4 * NWG + 8) * 32, 1) mab_reduce5_tc_kernel(c
     float* sWsm = reinterpret_cast<float*>(smem + R2Smem::SMALL);
     float* sBias = sWsm + 128 * 4;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + R2Smem::BARS);
-    uint64_t* kv_full = bars;          // [2] count 4 (producer warps)
+    uint64_t* kv_full = bars;          // [2] count 8 (producer warps)
     uint64_t* kv_empty = bars + 2;     // [2] count 4 (chains)
     uint64_t* s_full = bars + 4;       // [4] count 1
     uint64_t* p_ready = bars + 8;      // [4] count 4 (warps of the owning warpgroup)
     uint64_t* o_done = bars + 12;      // [4] count 1   (chain: all P V of the work item complete)
-    uint64_t* y_full = bars + 20;      // count 4
+    uint64_t* y_full = bars + 20;      // count 8
     uint64_t* proj_done = bars + 21;   // count 1
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
@@ -689,6 +691,13 @@ __global__ void __launch_bounds__((4 * NWG + 8) * 32, 1) mab_reduce5_tc_kernel(c
         return max(0, min((nb + 127) >> 7, tile0 + P.tiles_per_split) - tile0);
     };
 
+    // redo mode: only the work items flagged by the streaming variant are processed (normally none: leave at once)
+    auto skipped = [&](int w) { return P.redo_only != 0 && __ldg(P.redo + w) == 0; };
+    if (P.redo_only != 0) {
+        bool any = false;
+        for (int w = blockIdx.x; w < n_work; w += wstep) any = any || (__ldg(P.redo + w) != 0);
+        if (!any) return;
+    }
     copy_to_smem(sAq, P.Aq, 16384);
     if (DIN64) copy_to_smem(sW, P.Wkv16, 16384);
     for (int i = threadIdx.x; i < 128; i += blockDim.x) {
@@ -700,10 +709,10 @@ __global__ void __launch_bounds__((4 * NWG + 8) * 32, 1) mab_reduce5_tc_kernel(c
     }
     if (warp == WM) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 4); mbar_init(&kv_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 8); mbar_init(&kv_empty[i], 4); }
         for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
         for (int i = 0; i < 4; ++i) mbar_init(&o_done[i], 1);
-        mbar_init(y_full, 4);
+        mbar_init(y_full, 8);
         mbar_init(proj_done, 1);
         fence_barrier_init();
     }
@@ -728,6 +737,7 @@ __global__ void __launch_bounds__((4 * NWG + 8) * 32, 1) mab_reduce5_tc_kernel(c
             int gt = 0;                                    // tiles processed by this CTA so far
             uint32_t ph_p = 0;                             // phase of this chain's p_ready barrier
             for (int w = blockIdx.x; w < n_work; w += wstep) {
+                if (skipped(w)) continue;
                 int cloud, split, tile0, nb;
                 const int ntiles = work_tiles(w, cloud, split, tile0, nb);
                 for (int it = 0; it < ntiles; ++it, ++gt) {
@@ -774,93 +784,121 @@ __global__ void __launch_bounds__((4 * NWG + 8) * 32, 1) mab_reduce5_tc_kernel(c
             }
         }
     } else if (warp >= WP) {
-        if constexpr (NWG == 4) reg_inc<88>(); else reg_dec<88>();      // launch allocation: 80 (24 warps) / 128 (16 warps)
-        // =================================================================== producer: K|V tiles
-        const int quad = warp & 3;
+        // launch allocation: 96 registers (20 warps) / 72 (28 warps)
+        reg_dec<56>();
+        // =================================================================== producers: K|V tiles
+        // 8 warps: warp pw stages / converts row quadrant pw & 3; pw < 4 produces the K columns, pw >= 4 the V columns.
+        // The global loads of tile t+1 are issued before tile t is converted (they are the longest latency on this path).
+        const int pw = warp - WP, quad = pw & 3, colhalf = pw >> 2;
         const int row = 32 * quad + lane;
         int gt = 0;
-        for (int w = blockIdx.x; w < n_work; w += wstep) {
-            int cloud, split, tile0, nb;
-            const int ntiles = work_tiles(w, cloud, split, tile0, nb);
-            for (int it = 0; it < ntiles; ++it, ++gt) {
-                const int stage = gt & 1;
-                const int n = (tile0 + it) * 128 + row;
-                const bool valid = n < nb;
-                stamp2(50);
-                uint8_t* sK = sKV + stage * 32768;
-                uint8_t* sV = sK + 16384;
-                if (!DIN64) {
-                    float x[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (valid) {
-                        const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
-                        for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
-                    }
-                    stamp2(51);
-                    if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
-                    stamp2(53);
-#pragma unroll 4
-                    for (int c = 0; c < 16; ++c) {
-                        float o[8];
+        uint4 yv[4];                              // DIN64: this thread's half row (4 x 8 bf16) of the NEXT tile
+        float xn[4] = {0.f, 0.f, 0.f, 0.f};       // !DIN64: the next tile's point
+        bool vnext = false;
+        auto prefetch = [&](int cloud, int n, int nb) {
+            vnext = n < nb;
+            if (DIN64) {
+                const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)cloud * P.N + (vnext ? n : 0)) * 64) + 4 * colhalf;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 wv = *reinterpret_cast<const float4*>(sWsm + (c * 8 + j) * 4);
-                            o[j] = valid ? fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBias[c * 8 + j])))) : 0.f;
-                        }
-                        st_shared_8bf16((c < 8 ? sK + c * 2048 : sV + (c - 8) * 2048) + row * 16, o);
-                    }
-                } else {
-                    const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)cloud * P.N + (valid ? n : 0)) * 64);
-                    uint4 yv[8];
+                for (int c = 0; c < 4; ++c) yv[c] = vnext ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+            } else {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) yv[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sY + c * 2048 + row * 16) = yv[c];
-                    fence_async_smem();
-                    fence_before_sync();
-                    warp_arrive(y_full);
-                    if (warp == WP) {
-                        // one producer warp issues the K|V projection MMA (elected lane) once all 128 rows of Y are staged
-                        mbar_wait(y_full, gt & 1);
-                        fence_after_sync();
-                        if (elect_one()) {
-                            const uint32_t yb = smem_u32(sY), wb = smem_u32(sW);
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                mma_ss(tmem_addr(tb, 0, R2_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
-                                       idesc_bf16(128, 128, 0, 0), ks > 0);
-                            mma_commit(proj_done);
-                        }
-                        __syncwarp();
-                    }
-                    stamp2(51);
-                    mbar_wait(proj_done, gt & 1);
-                    fence_after_sync();
-                    stamp2(52);
-                    if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
-                    stamp2(53);
-#pragma unroll
-                    for (int c0 = 0; c0 < 128; c0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_addr(tb, 32 * quad, R2_PROJ + c0), v);
-                        tmem_ld_wait32(v);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float o[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = valid ? __uint_as_float(v[8 * q + j]) + sBias[c0 + 8 * q + j] : 0.f;
-                            const int chunk = c0 / 8 + q;
-                            st_shared_8bf16((chunk < 8 ? sK + chunk * 2048 : sV + (chunk - 8) * 2048) + row * 16, o);
-                        }
-                    }
+                for (int kk = 0; kk < 4; ++kk) xn[kk] = 0.f;
+                if (vnext) {
+                    const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                    for (int kk = 0; kk < P.d_in; ++kk) xn[kk] = __ldg(xp + kk);
                 }
-                stamp2(54);
+            }
+        };
+        // (cloud, tile) iterator one step ahead of the processing loop
+        int w_n = blockIdx.x, it_n = 0, cloud_n = 0, split_n = 0, tile0_n = 0, nb_n = 0, ntiles_n = 0;
+        auto advance = [&]() {           // move (w_n, it_n) to the next existing tile; returns false at the end
+            while (w_n < n_work) {
+                if (it_n == 0) ntiles_n = skipped(w_n) ? 0 : work_tiles(w_n, cloud_n, split_n, tile0_n, nb_n);
+                if (it_n < ntiles_n) return true;
+                w_n += wstep;
+                it_n = 0;
+            }
+            return false;
+        };
+        bool have_next = advance();
+        if (have_next) prefetch(cloud_n, (tile0_n + it_n) * 128 + row, nb_n);
+        while (have_next) {
+            const bool valid = vnext;
+            const int stage = gt & 1;
+            stamp2(50);
+            uint8_t* sK = sKV + stage * 32768;
+            uint8_t* sV = sK + 16384;
+            float x[4] = {xn[0], xn[1], xn[2], xn[3]};
+            if (DIN64) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(sY + (4 * colhalf + c) * 2048 + row * 16) = yv[c];
                 fence_async_smem();
                 fence_before_sync();
-                warp_arrive(&kv_full[stage]);
+                warp_arrive(y_full);
+                if (warp == WP) {
+                    // one producer warp issues the K|V projection MMA (elected lane) once all 128 rows of Y are staged
+                    mbar_wait(y_full, gt & 1);
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const uint32_t yb = smem_u32(sY), wb = smem_u32(sW);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ss(tmem_addr(tb, 0, R2_PROJ), smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wb + ks * 4096, 2048, 128),
+                                   idesc_bf16(128, 128, 0, 0), ks > 0);
+                        mma_commit(proj_done);
+                    }
+                    __syncwarp();
+                }
             }
+            // ---- next tile's loads in flight while this one is converted
+            ++it_n;
+            have_next = advance();
+            if (have_next) prefetch(cloud_n, (tile0_n + it_n) * 128 + row, nb_n);
+            stamp2(51);
+            if (DIN64) {
+                mbar_wait(proj_done, gt & 1);
+                fence_after_sync();
+            }
+            stamp2(52);
+            if (gt >= 2) mbar_wait(&kv_empty[stage], ((gt >> 1) - 1) & 1);
+            stamp2(53);
+            uint8_t* dstbase = colhalf == 0 ? sK : sV;
+            if (!DIN64) {
+#pragma unroll 4
+                for (int c = 0; c < 8; ++c) {
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int f = 64 * colhalf + c * 8 + j;
+                        const float4 wv = *reinterpret_cast<const float4*>(sWsm + f * 4);
+                        o[j] = valid ? fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBias[f])))) : 0.f;
+                    }
+                    st_shared_8bf16(dstbase + c * 2048 + row * 16, o);
+                }
+            } else {
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_addr(tb, 32 * quad, R2_PROJ + 64 * colhalf + c0), v);
+                    tmem_ld_wait32(v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = valid ? __uint_as_float(v[8 * q + j]) + sBias[64 * colhalf + c0 + 8 * q + j] : 0.f;
+                        st_shared_8bf16(dstbase + (c0 / 8 + q) * 2048 + row * 16, o);
+                    }
+                }
+            }
+            stamp2(54);
+            fence_async_smem();
+            fence_before_sync();
+            warp_arrive(&kv_full[stage]);
+            ++gt;
         }
     } else if constexpr (NWG == 2) {
-        reg_inc<184>();
+        reg_inc<160>();
         // =================================================================== softmax warpgroups (2 chains each)
         const int g = warp >> 2, quad = warp & 3;
         const int row = 32 * quad + lane;
@@ -972,6 +1010,7 @@ __global__ void __launch_bounds__((4 * NWG + 8) * 32, 1) mab_reduce5_tc_kernel(c
             warp_arrive(&p_ready[c]);
         };
         for (int w = blockIdx.x; w < n_work; w += wstep) {
+            if (skipped(w)) continue;
             int cloud, split, tile0, nb;
             const int ntiles = work_tiles(w, cloud, split, tile0, nb);
 #pragma unroll
@@ -1029,6 +1068,7 @@ __global__ void __launch_bounds__((4 * NWG + 8) * 32, 1) mab_reduce5_tc_kernel(c
         const uint32_t ocol_off = (row >= 64) ? 8u : 0u;
         const uint32_t sbase = tmem_addr(tb, lane_base, R2_S + 64 * c);
         float m_used[2], l_run[2];
+        int cur_w = 0;
         uint32_t ph_s = 0, ph_done = 0;
         constexpr float kOverflow = 1.152921504606847e18f;      // 2^60
         auto softmax_item = [&](const int pp, const int nv, const bool first) {
@@ -1087,13 +1127,17 @@ __global__ void __launch_bounds__((4 * NWG + 8) * 32, 1) mab_reduce5_tc_kernel(c
                 }
                 tmem_st16(sbase + 48, pk);
             }
-            if (!(sum < kOverflow) && P.redo != nullptr) P.redo[0] = 1;       // EXPERIMENT: a score outgrew the reference
+            // a score outgrew the row's reference exponent by more than ~2^54 (or the sum overflowed): this variant cannot
+            // re-reference a row (its scores are gone once P is written) -- the work item is redone by the exact variant
+            if (!(sum < kOverflow)) P.redo[cur_w] = 1;
             l_run[pp] += sum;
             tmem_st_wait();
             fence_before_sync();
             warp_arrive(&p_ready[c]);
         };
         for (int w = blockIdx.x; w < n_work; w += wstep) {
+            if (skipped(w)) continue;
+            cur_w = w;
             int cloud, split, tile0, nb;
             const int ntiles = work_tiles(w, cloud, split, tile0, nb);
             m_used[0] = m_used[1] = -INFINITY;
@@ -2059,11 +2103,12 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 
 // ------------------------------------------------------------------------------------ host orchestration
 static int g_num_sms = 148;
-static int g_reduce_wg = 2;               // softmax warpgroups of the reduce kernel (PCA_TC_REDUCE_WG=4: streaming experiment)
+static int g_reduce_wg = 4;               // reduce kernel variant: 4 = streaming (+ exact redo of flagged items), 2 = exact only
 static int g_tail_max = TC_TAIL_MAX;       // tail rule (PCA_TC_TAIL=0 disables it: every point goes through the tensor-core kernels)
 static long long* g_timeline = nullptr;      // set through pca_debug_set_timeline
 void set_timeline(long long* p) { g_timeline = p; }
 void set_tail_max(int t) { g_tail_max = t < 0 ? 0 : (t > TC_TAIL_MAX ? TC_TAIL_MAX : t); }
+void set_reduce_wg(int n) { g_reduce_wg = (n == 4) ? 4 : 2; }
 struct TcSplit { int tiles_total, tiles_per_split, nsplit; };
 // The point range of a cloud is cut into fixed spans of 16 tiles (2048 points).  The cut depends on N only, never
 // on the batch size, so a cloud's logits are bit-identical however the batch is sharded across calls / GPUs.
@@ -2076,7 +2121,7 @@ static TcSplit plan_split(int B, int N) {
     return s;
 }
 
-struct TcLayout { size_t consts, part, kvblk, y1, y2, total; };
+struct TcLayout { size_t consts, part, kvblk, redo, y1, y2, total; };
 static TcLayout tc_layout(int B, int N) {
     const TcSplit s = plan_split(B, N);
     Arena a(nullptr, 0);
@@ -2084,6 +2129,7 @@ static TcLayout tc_layout(int B, int N) {
     L.consts = a.off; a.take<uint8_t>(sizeof(TcConsts));
     L.part = a.off; a.take<float>((size_t)B * 2 * s.nsplit * TH * TM * 10);
     L.kvblk = a.off; a.take<uint8_t>((size_t)B * 32768);
+    L.redo = a.off; a.take<int>((size_t)B * s.nsplit);
     L.y1 = a.off; a.take<__nv_bfloat16>((size_t)B * N * 64);
     L.y2 = a.off; a.take<__nv_bfloat16>((size_t)B * N * 64);
     L.total = a.off;
@@ -2107,6 +2153,7 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     const TcSplit sp = plan_split(B, N);
     float* part = reinterpret_cast<float*>(ws + L.part);
     uint8_t* kvblk = ws + L.kvblk;
+    int* redo = reinterpret_cast<int*>(ws + L.redo);
     __nv_bfloat16* Y1 = reinterpret_cast<__nv_bfloat16*>(ws + L.y1);
     __nv_bfloat16* Y2 = reinterpret_cast<__nv_bfloat16*>(ws + L.y2);
     const int d_in = d->d_in;
@@ -2135,10 +2182,19 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     // ---- ISAB 0
     {
         RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Aq0, m00.Wkv, m00.bkv,
-                  nullptr, (tl_apply || getenv("PCA_TL_REDUCE64")) ? nullptr : g_timeline, nullptr, part};
+                  nullptr, (tl_apply || getenv("PCA_TL_REDUCE64")) ? nullptr : g_timeline, redo, 0, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * d_in * TD + 2.0 * TM * TD), pts * 4.0 * d_in);
-        if (g_reduce_wg == 4) mab_reduce5_tc_kernel<false, 4><<<pgrid, 24 * 32, R2Smem::TOTAL, st>>>(r);
-        else mab_reduce5_tc_kernel<false, 2><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
+        if (g_reduce_wg == 4) {
+            // streaming variant, then the exact variant on the (normally empty) list of flagged work items
+            PCA_CHECK_CUDA(cudaMemsetAsync(redo, 0, (size_t)n_work * sizeof(int), st));
+            mab_reduce5_tc_kernel<false, 4><<<pgrid, 28 * 32, R2Smem::TOTAL, st>>>(r);
+            r.redo_only = 1;
+            r.timeline = nullptr;
+            mab_reduce5_tc_kernel<false, 2><<<pgrid, TC_THREADS20, R2Smem::TOTAL, st>>>(r);
+            count_launch();
+        } else {
+            mab_reduce5_tc_kernel<false, 2><<<pgrid, TC_THREADS20, R2Smem::TOTAL, st>>>(r);
+        }
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<small>");
     {
@@ -2164,10 +2220,18 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     // ---- ISAB 1
     {
         RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Aq1, nullptr, m10.bkv,
-                  c->Wkv1, getenv("PCA_TL_REDUCE64") ? g_timeline : nullptr, nullptr, part};
+                  c->Wkv1, getenv("PCA_TL_REDUCE64") ? g_timeline : nullptr, redo, 0, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TM * TD), pts * 128.0);
-        if (g_reduce_wg == 4) mab_reduce5_tc_kernel<true, 4><<<pgrid, 24 * 32, R2Smem::TOTAL, st>>>(r);
-        else mab_reduce5_tc_kernel<true, 2><<<pgrid, TC_THREADS16, R2Smem::TOTAL, st>>>(r);
+        if (g_reduce_wg == 4) {
+            PCA_CHECK_CUDA(cudaMemsetAsync(redo, 0, (size_t)n_work * sizeof(int), st));
+            mab_reduce5_tc_kernel<true, 4><<<pgrid, 28 * 32, R2Smem::TOTAL, st>>>(r);
+            r.redo_only = 1;
+            r.timeline = nullptr;
+            mab_reduce5_tc_kernel<true, 2><<<pgrid, TC_THREADS20, R2Smem::TOTAL, st>>>(r);
+            count_launch();
+        } else {
+            mab_reduce5_tc_kernel<true, 2><<<pgrid, TC_THREADS20, R2Smem::TOTAL, st>>>(r);
+        }
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<64>");
     {
@@ -2225,7 +2289,7 @@ static int tc_configure() {
     PCA_CHECK_CUDA((cudaFuncSetAttribute(mab_reduce5_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL)));
     PCA_CHECK_CUDA((cudaFuncSetAttribute(mab_reduce5_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL)));
     PCA_CHECK_CUDA((cudaFuncSetAttribute(mab_reduce5_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL)));
-    if (const char* v = getenv("PCA_TC_REDUCE_WG")) g_reduce_wg = (v[0] == '4') ? 4 : 2;
+    if (const char* v = getenv("PCA_TC_REDUCE_WG")) g_reduce_wg = (v[0] == '2') ? 2 : 4;
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2Smem::TOTAL));

@@ -28,20 +28,10 @@ def stage_oracle(p, X, heads=8):
     return H1, Y1, H2, Y2, pooled.squeeze(1), logits.squeeze(1)
 
 
-def run(d_in=2, B=3, N=300, seed=0, ckpt=True):
-    dev = torch.device("cuda:0")
-    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    model = pca.ST(dim_input=d_in, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev)
-    if ckpt:
-        tag = "fst" if d_in == 2 else "3st"
-        model.load_state_dict({k: torch.from_numpy(v) for k, v in np.load(os.path.join(gdir, f"{tag}_weights.npz")).items()})
-    rs = np.random.RandomState(seed)
-    X = np.empty((B, N, d_in), dtype=np.float32)
-    X[:, :, 0] = rs.uniform(0, 0.5, (B, N))
-    if d_in == 3:
-        X[:, :, 1] = rs.uniform(0, 0.12, (B, N))
-    X[:, :, -1] = rs.uniform(-18, -1, (B, N))
-    Xd = torch.from_numpy(X).to(dev)
+def stages(model, Xd):
+    """Every stage output of the bf16 path for the device batch Xd (B, N, d_in), as fp32 device tensors."""
+    B, N, _ = Xd.shape
+    dev = Xd.device
     dims = model._dims()
     blob = model._blob()
     L = _lib.lib()
@@ -55,6 +45,23 @@ def run(d_in=2, B=3, N=300, seed=0, ckpt=True):
                                      _lib.ptr(outs["pooled"]), _lib.ptr(ws), ws.numel(),
                                      torch.cuda.current_stream().cuda_stream), "debug_st_stages")
     torch.cuda.synchronize()
+    return outs
+
+
+def run(d_in=2, B=3, N=300, seed=0, ckpt=True):
+    dev = torch.device("cuda:0")
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    model = pca.ST(dim_input=d_in, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev)
+    if ckpt:
+        tag = "fst" if d_in == 2 else "3st"
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in np.load(os.path.join(gdir, f"{tag}_weights.npz")).items()})
+    rs = np.random.RandomState(seed)
+    X = np.empty((B, N, d_in), dtype=np.float32)
+    X[:, :, 0] = rs.uniform(0, 0.5, (B, N))
+    if d_in == 3:
+        X[:, :, 1] = rs.uniform(0, 0.12, (B, N))
+    X[:, :, -1] = rs.uniform(-18, -1, (B, N))
+    outs = stages(model, torch.from_numpy(X).to(dev))
     p = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     ref = dict(zip(["H1", "Y1", "H2", "Y2", "pooled", "logits"], stage_oracle(p, torch.from_numpy(X))))
     errs = {}
