@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PCA_VERSION 101 /* 0.1.1 */
+#define PCA_VERSION 102 /* 0.1.2 */
 
 enum {
     PCA_OK = 0,
@@ -177,6 +177,35 @@ int pca_deepset_fwd_f32(const float* X, int B, int N, int d_in, int dim_hidden, 
 int pca_deepset_fwd_masked_f32(const float* X, const int32_t* counts, int B, int N, int d_in, int dim_hidden,
                                int out_dim, int pool, const float* params, float* out, void* workspace,
                                size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- training (fp32, every dim; ln = 0)
+ * The reference trains these models with loss.backward() + torch.optim.Adam under nn.DataParallel
+ * (Code/settransformer.py:89-109, Code/settransformertemp.py:110-128, set_transformer-master/main_pointcloud.py:61-79).
+ * Here the training forward keeps the activations the hand-derived backward needs in a caller-owned buffer
+ * (`saved`, pca_st_train_saved_bytes), and the backward returns the gradient of EVERY parameter as one flat blob in
+ * the layout of `params` -- the unit of the per-step gradient allreduce and of pca_adam_step_f32.
+ * dropout_p > 0 is nn.Dropout(p) before and after the PMA (main_pointcloud.py:30-33); the (seed, element index) mask
+ * is regenerated by the backward call, which must be given the same seed.  Equal-size sets only (counts == NULL).
+ * dlogits (B, S, C); dparams (pca_st_param_count) is overwritten; dX (B, N, d_in) may be NULL. */
+size_t pca_st_train_saved_bytes(const pca_st_dims* dims, int B, int N, float dropout_p);
+size_t pca_st_train_workspace_bytes(const pca_st_dims* dims, int B, int N);
+int pca_st_train_fwd_f32(const float* X, int B, int N, const pca_st_dims* dims, const float* params, float dropout_p,
+                         unsigned long long seed, float* logits, void* saved, size_t saved_bytes, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int pca_st_train_bwd_f32(const float* X, int B, int N, const pca_st_dims* dims, const float* params, float dropout_p,
+                         unsigned long long seed, const float* dlogits, const void* saved, size_t saved_bytes,
+                         float* dparams, float* dX, void* workspace, size_t workspace_bytes, void* stream);
+
+/* nn.CrossEntropyLoss(reduction='mean') on logits (B, C) with int64 labels: loss[0] += mean loss, correct[0] +=
+ * number of rows whose arg-max equals the label (both caller-zeroed, either may be NULL except loss),
+ * dlogits (B, C) = d loss / d logits (may be NULL). */
+int pca_cross_entropy_f32(const float* logits, const int64_t* labels, int B, int C, float* loss, int32_t* correct,
+                          float* dlogits, void* stream);
+
+/* torch.optim.Adam step (L2 weight_decay folded into the gradient, bias-corrected moments; `step` counts from 1) over
+ * a flat fp32 blob in one launch; grads are multiplied by grad_scale first (1/world_size after a summing allreduce). */
+int pca_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
 /* ---------------------------------------------------------------- whole path, one call
  * audio -> STFT/log-magnitude -> [Ntemp chunking] -> [top-K] -> clouds -> ST -> logits.

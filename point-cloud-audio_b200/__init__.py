@@ -8,9 +8,10 @@ from .frontend import build_clouds, coord_tables, select_points, spectral_point_
 from .models import ST, DeepSet, SetTransformer, strip_module_prefix
 from .modules import ISAB, MAB, PMA, SAB
 from .pipeline import AudioConfig, AudioSetPipeline
+from .training import SetTrainer, STTrainFunction
 from .utils import pc_maxK
 
 __all__ = ["load_esc", "tt_split", "ESC_pc", "ESC_pc_ss", "ESC_pc_temp", "ESC_pc_temp_maxKSS", "build_clouds",
            "coord_tables", "select_points", "spectral_point_cloud", "stft_logmag", "topk_points", "ST", "DeepSet",
            "SetTransformer", "strip_module_prefix", "ISAB", "MAB", "PMA", "SAB", "AudioConfig",
-           "AudioSetPipeline", "pc_maxK"]
+           "AudioSetPipeline", "pc_maxK", "SetTrainer", "STTrainFunction"]

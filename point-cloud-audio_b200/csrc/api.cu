@@ -14,13 +14,19 @@ namespace pca {
 int launch_stft_logmag(const float*, int, int, int, int, const float*, const float*, float, int, int, float*, cudaStream_t);
 int launch_build_clouds(const float*, int, int, int, const float*, const float*, float*, cudaStream_t);
 int launch_topk(const float*, int, int, int, const float*, const float*, int, int, int, float, float*, int32_t*, int32_t*, cudaStream_t);
-int launch_linear(const float*, const float*, const float*, float*, long long, int, int, int, cudaStream_t);
-int launch_attn(const float*, long long, const float*, int, int, int, int, int, float*, float*, const int*, cudaStream_t);
-size_t attn_part_floats(int B, int nq, int nk, int D, int H);
 int launch_layernorm(float*, long long, int, const float*, const float*, cudaStream_t);
 int launch_pool(const float*, int, int, int, int, float*, const int*, cudaStream_t);
 int launch_fused_frontend(const float*, int, int, int, int, const float*, const float*, float, int, int, const float*, const float*,
                           int, int, int, float, float*, int32_t*, int32_t*, cudaStream_t);
+// training path (encoder_train.cu)
+size_t st_train_saved_bytes(const pca_st_dims* d, int B, int N, float dropout_p);
+size_t st_train_ws_bytes(const pca_st_dims* d, int B, int N);
+int st_train_forward(const float*, int, int, const pca_st_dims*, const float*, float, unsigned long long, float*, void*, size_t, void*,
+                     size_t, cudaStream_t);
+int st_train_backward(const float*, int, int, const pca_st_dims*, const float*, float, unsigned long long, const float*, const void*,
+                      size_t, float*, float*, void*, size_t, cudaStream_t);
+int launch_cross_entropy(const float*, const long long*, int, int, float, float*, int*, float*, cudaStream_t);
+int launch_adam(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float, cudaStream_t);
 void set_timeline(long long* p);
 void set_tail_max(int t);
 void set_reduce_wg(int n);
@@ -599,6 +605,38 @@ int pca_debug_st_stages(const float* X, int B, int N, const pca_st_dims* dims, c
     if (!st_tc_supported(dims, N)) return fail(PCA_EUNSUPPORTED, "ST stages: dims not supported by the tcgen05 path");
     return st_tc_forward_stages(X, B, N, dims, params, logits, H1, Y1, H2, Y2, pooled, workspace, workspace_bytes,
                                 (cudaStream_t)stream);
+}
+
+size_t pca_st_train_saved_bytes(const pca_st_dims* dims, int B, int N, float dropout_p) {
+    if (!dims || B <= 0 || N <= 0) return 0;
+    return st_train_saved_bytes(dims, B, N, dropout_p);
+}
+size_t pca_st_train_workspace_bytes(const pca_st_dims* dims, int B, int N) {
+    if (!dims || B <= 0 || N <= 0) return 0;
+    return st_train_ws_bytes(dims, B, N);
+}
+int pca_st_train_fwd_f32(const float* X, int B, int N, const pca_st_dims* dims, const float* params, float dropout_p,
+                         unsigned long long seed, float* logits, void* saved, size_t saved_bytes, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    return st_train_forward(X, B, N, dims, params, dropout_p, seed, logits, saved, saved_bytes, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
+}
+int pca_st_train_bwd_f32(const float* X, int B, int N, const pca_st_dims* dims, const float* params, float dropout_p,
+                         unsigned long long seed, const float* dlogits, const void* saved, size_t saved_bytes, float* dparams,
+                         float* dX, void* workspace, size_t workspace_bytes, void* stream) {
+    return st_train_backward(X, B, N, dims, params, dropout_p, seed, dlogits, saved, saved_bytes, dparams, dX, workspace,
+                             workspace_bytes, (cudaStream_t)stream);
+}
+int pca_cross_entropy_f32(const float* logits, const int64_t* labels, int B, int C, float* loss, int32_t* correct, float* dlogits,
+                          void* stream) {
+    if (!logits || !labels || !loss) return fail(PCA_EINVAL, "cross entropy: null pointer");
+    return launch_cross_entropy(logits, (const long long*)labels, B, C, 1.0f / (float)(B > 0 ? B : 1), loss, correct, dlogits,
+                                (cudaStream_t)stream);
+}
+int pca_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq) return fail(PCA_EINVAL, "adam: null pointer");
+    return launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, (cudaStream_t)stream);
 }
 
 void pca_debug_set_timeline(long long* device_buffer) { set_timeline(device_buffer); }

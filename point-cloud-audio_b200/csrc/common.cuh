@@ -84,6 +84,13 @@ __host__ __device__ static inline MabParams mab_slice(const float* p, int dq, in
     return m;
 }
 
+// fp32 encoder launchers shared by the inference (api.cu) and training (encoder_train.cu) orchestration
+int launch_linear(const float* X, const float* W, const float* b, float* Y, long long rows, int din, int dout, int mode,
+                  cudaStream_t st, float* R = nullptr);
+int launch_attn(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D, int H, float* O, float* part,
+                const int* key_counts, cudaStream_t st, float* lse = nullptr);
+size_t attn_part_floats(int B, int nq, int nk, int D, int H);
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

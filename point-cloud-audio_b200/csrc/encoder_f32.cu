@@ -16,10 +16,10 @@ namespace pca {
 // ------------------------------------------------------------------------------------ linear
 constexpr int LBM = 128, LBN = 64, LBK = 16, LTHREADS = 256;
 
-template <int MODE>   // 0 plain, 1 relu, 2 residual: Y = X + relu(XW^T + b) (din == dout)
+template <int MODE>   // 0 plain, 1 relu, 2 residual: Y = X + relu(XW^T + b) (din == dout), 3 = 2 that also stores relu(.) in R
 __global__ void __launch_bounds__(LTHREADS)
 linear_f32_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
-                  float* __restrict__ Y, long long rows, int din, int dout) {
+                  float* __restrict__ Y, long long rows, int din, int dout, float* __restrict__ R) {
     __shared__ __align__(16) float Xs[LBK][LBM + 4];
     __shared__ __align__(16) float Ws[LBK][LBN + 4];
     const int tid = threadIdx.x;
@@ -76,21 +76,28 @@ linear_f32_kernel(const float* __restrict__ X, const float* __restrict__ W, cons
             float v = acc[i][j] + __ldg(bias + c);
             if (MODE == 1) v = fmaxf(v, 0.f);
             if (MODE == 2) v = __ldg(X + r * din + c) + fmaxf(v, 0.f);
+            if (MODE == 3) {
+                const float rl = fmaxf(v, 0.f);
+                R[r * dout + c] = rl;
+                v = __ldg(X + r * din + c) + rl;
+            }
             Y[r * dout + c] = v;
         }
     }
 }
 
 int launch_linear(const float* X, const float* W, const float* b, float* Y, long long rows, int din,
-                  int dout, int mode, cudaStream_t st) {
+                  int dout, int mode, cudaStream_t st, float* R) {
     if (rows == 0) return 0;
-    if (mode == 2 && din != dout) return fail(PCA_EINVAL, "linear: residual mode needs din == dout");
+    if (mode == 3 && !R) return fail(PCA_EINVAL, "linear: mode 3 needs the relu output buffer");
+    if (mode >= 2 && din != dout) return fail(PCA_EINVAL, "linear: residual mode needs din == dout");
     dim3 grid((unsigned)((rows + LBM - 1) / LBM), (dout + LBN - 1) / LBN);
     {
         LaunchTimer lt("linear_f32_kernel", st, 2.0 * rows * din * dout, 4.0 * rows * (din + dout));
-        if (mode == 0) linear_f32_kernel<0><<<grid, LTHREADS, 0, st>>>(X, W, b, Y, rows, din, dout);
-        else if (mode == 1) linear_f32_kernel<1><<<grid, LTHREADS, 0, st>>>(X, W, b, Y, rows, din, dout);
-        else linear_f32_kernel<2><<<grid, LTHREADS, 0, st>>>(X, W, b, Y, rows, din, dout);
+        if (mode == 0) linear_f32_kernel<0><<<grid, LTHREADS, 0, st>>>(X, W, b, Y, rows, din, dout, nullptr);
+        else if (mode == 1) linear_f32_kernel<1><<<grid, LTHREADS, 0, st>>>(X, W, b, Y, rows, din, dout, nullptr);
+        else if (mode == 2) linear_f32_kernel<2><<<grid, LTHREADS, 0, st>>>(X, W, b, Y, rows, din, dout, nullptr);
+        else linear_f32_kernel<3><<<grid, LTHREADS, 0, st>>>(X, W, b, Y, rows, din, dout, R);
     }
     PCA_CHECK_LAUNCH("linear_f32_kernel");
     return 0;
@@ -105,7 +112,7 @@ __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstrid
                                 const float* __restrict__ KV, int nq, int nk, int D, int tq_log,
                                 int tk, int nsplit, int chunk, float scale_log2e,
                                 float* __restrict__ O, float* __restrict__ part,
-                                const int* __restrict__ key_counts) {
+                                const int* __restrict__ key_counts, float* __restrict__ lse) {
     extern __shared__ __align__(16) float kv_s[];     // tk rows x (2D + 4)
     const int H = blockDim.x >> 5;
     const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -206,6 +213,7 @@ __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstrid
         float* o = O + ((long long)b * nq + q) * D + h * DH;
 #pragma unroll
         for (int j = 0; j < DH; ++j) o[j] = __ldg(qptr + j) + acc[j] * inv;
+        if (lse) lse[((long long)b * nq + q) * H + h] = m + log2f(l);      // log2 of sum_k 2^(s_k), s in the scaled log2 domain
     } else {
         float* pp = part + ((((long long)b * nsplit + split) * nq + q) * H + h) * (DH + 2);
         pp[0] = m; pp[1] = l;
@@ -217,7 +225,7 @@ __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstrid
 template <int DH>
 __global__ void attn_merge_kernel(const float* __restrict__ part, const float* __restrict__ Qp,
                                   long long q_bstride, int B, int nq, int H, int nsplit,
-                                  float* __restrict__ O) {
+                                  float* __restrict__ O, float* __restrict__ lse) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * nq * H;
     if (i >= total) return;
@@ -243,6 +251,7 @@ __global__ void attn_merge_kernel(const float* __restrict__ part, const float* _
     float* o = O + ((long long)b * nq + q) * D + h * DH;
 #pragma unroll
     for (int j = 0; j < DH; ++j) o[j] = __ldg(qptr + j) + acc[j] * inv;
+    if (lse) lse[i] = m + log2f(l);
 }
 
 struct AttnPlan { int tq_log, tk, nsplit, chunk; size_t smem; size_t part_floats; };
@@ -285,7 +294,7 @@ size_t attn_part_floats(int B, int nq, int nk, int D, int H) { return plan_attn(
 
 template <int DH>
 static int launch_attn_t(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk,
-                         int D, int H, float* O, float* part, const int* key_counts, cudaStream_t st) {
+                         int D, int H, float* O, float* part, const int* key_counts, cudaStream_t st, float* lse) {
     const AttnPlan p = plan_attn(B, nq, nk, D, H);
     const int tq = 1 << p.tq_log;
     dim3 grid((nq + tq - 1) / tq, p.nsplit, B);
@@ -296,14 +305,14 @@ static int launch_attn_t(const float* Qp, long long q_bstride, const float* KV, 
         LaunchTimer lt("attn_f32_kernel", st, 4.0 * B * nq * (double)nk * D,
                        4.0 * ((double)B * nk * 2 * D + 2.0 * B * nq * D));
         attn_f32_kernel<DH><<<grid, 32 * H, p.smem, st>>>(Qp, q_bstride, KV, nq, nk, D, p.tq_log, p.tk,
-                                                          p.nsplit, p.chunk, scale_log2e, O, part, key_counts);
+                                                          p.nsplit, p.chunk, scale_log2e, O, part, key_counts, lse);
     }
     PCA_CHECK_LAUNCH("attn_f32_kernel");
     if (p.nsplit > 1) {
         const long long total = (long long)B * nq * H;
         {
             LaunchTimer lt("attn_merge_kernel", st, 0.0, 4.0 * (double)p.part_floats);
-            attn_merge_kernel<DH><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(part, Qp, q_bstride, B, nq, H, p.nsplit, O);
+            attn_merge_kernel<DH><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(part, Qp, q_bstride, B, nq, H, p.nsplit, O, lse);
         }
         PCA_CHECK_LAUNCH("attn_merge_kernel");
     }
@@ -311,16 +320,16 @@ static int launch_attn_t(const float* Qp, long long q_bstride, const float* KV, 
 }
 
 int launch_attn(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D,
-                int H, float* O, float* part, const int* key_counts, cudaStream_t st) {
+                int H, float* O, float* part, const int* key_counts, cudaStream_t st, float* lse) {
     if (B == 0 || nq == 0) return 0;
     if (H < 1 || H > 32 || D % H) return fail(PCA_EUNSUPPORTED, "attention: need 1 <= H <= 32 and D %% H == 0 (D=%d, H=%d)", D, H);
     if (B > 65535) return fail(PCA_EUNSUPPORTED, "attention: batch chunk %d exceeds the grid limit", B);
     switch (D / H) {
-        case 4: return launch_attn_t<4>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st);
-        case 8: return launch_attn_t<8>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st);
-        case 16: return launch_attn_t<16>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st);
-        case 32: return launch_attn_t<32>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st);
-        case 64: return launch_attn_t<64>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st);
+        case 4: return launch_attn_t<4>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
+        case 8: return launch_attn_t<8>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
+        case 16: return launch_attn_t<16>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
+        case 32: return launch_attn_t<32>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
+        case 64: return launch_attn_t<64>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
         default: return fail(PCA_EUNSUPPORTED, "attention: head dim %d not in {4,8,16,32,64}", D / H);
     }
 }

@@ -1,0 +1,695 @@
+// Training path of the set encoder: fp32 forward that keeps the activations the
+// backward pass needs, the backward pass of ST / SetTransformer (modules.py:6-63 differentiated by hand), dropout,
+// cross-entropy and a fused Adam step on the flat parameter blob.  CUDA-core fp32 kernels, every MAB shape.
+//
+//   MAB forward (modules.py:18-33, ln=False)      backward (given dOut)
+//     Qp = Qin Wq^T + bq                            dZ  = dOut o [R > 0]
+//     KV = Kin [Wk;Wv]^T + [bk;bv]                  dWo += dZ^T O,  dbo += colsum dZ
+//     O  = Qp + softmax(Qp_h Kp_h^T / sqrt(D)) Vp_h  dO  = dOut + dZ Wo
+//     R  = relu(O Wo^T + bo)                        delta_h = rowsum_h(dO o (O - Qp))
+//     Out = O + R                                   dS = P o (dO_h Vp_h^T - delta_h) / sqrt(D)   (P recomputed from lse)
+//                                                   dQp = dO + dS Kp_h,  dKp_h = dS^T Qp_h,  dVp_h = P^T dO_h
+//                                                   dWq += dQp^T Qin, dQin = dQp Wq, dWkv += dKV^T Kin, dKin = dKV Wkv
+#include "common.cuh"
+#include <math.h>
+
+namespace pca {
+
+// ------------------------------------------------------------------------------------ generic fp32 GEMM
+// C (M, N) [+]= opA (M, K) opB (K, N) [+ Cadd];  opA(m,k) = TA ? A[k*lda+m] : A[m*lda+k];  opB(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n].
+// blockIdx.z splits K (partial products are added atomically: gradient accumulation over rows).
+constexpr int GBM = 128, GBN = 64, GBK = 16, GTHREADS = 256;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(GTHREADS)
+gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C, const float* __restrict__ Cadd,
+                long long M, int N, long long K, long long lda, long long ldb, long long ldc, long long kchunk, int atomic) {
+    __shared__ __align__(16) float As[GBK][GBM + 4];
+    __shared__ __align__(16) float Bs[GBK][GBN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long long m0 = (long long)blockIdx.x * GBM;
+    const int n0 = blockIdx.y * GBN;
+    const long long kbeg = (long long)blockIdx.z * kchunk;
+    const long long kend = (kbeg + kchunk < K) ? kbeg + kchunk : K;
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (long long k0 = kbeg; k0 < kend; k0 += GBK) {
+        if (TA) {
+            const int lm = tid & 127, lk = tid >> 7;
+            const long long m = m0 + lm;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const long long k = k0 + lk + 2 * j;
+                As[lk + 2 * j][lm] = (m < M && k < kend) ? __ldg(A + k * lda + m) : 0.f;
+            }
+        } else {
+            const int lk = tid & 15, lr = tid >> 4;
+            const long long k = k0 + lk;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const long long m = m0 + lr + 16 * j;
+                As[lk][lr + 16 * j] = (m < M && k < kend) ? __ldg(A + m * lda + k) : 0.f;
+            }
+        }
+        if (TB) {
+            const int lk = tid & 15, lr = tid >> 4;
+            const long long k = k0 + lk;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + lr + 16 * j;
+                Bs[lk][lr + 16 * j] = (n < N && k < kend) ? __ldg(Bm + (long long)n * ldb + k) : 0.f;
+            }
+        } else {
+            const int ln = tid & 63, lk = tid >> 6;
+            const int n = n0 + ln;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long k = k0 + lk + 4 * j;
+                Bs[lk + 4 * j][ln] = (n < N && k < kend) ? __ldg(Bm + k * ldb + n) : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GBK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long m = m0 + ty * 8 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (Cadd) v += Cadd[m * ldc + n];
+            if (atomic) atomicAdd(C + m * ldc + n, v);
+            else C[m * ldc + n] = v;
+        }
+    }
+}
+
+// dX (rows, din) = dY (rows, dout) W (dout, din) [+ add (rows, din)]; add may alias dX (accumulation)
+static int launch_grad_input(const float* dY, const float* W, float* dX, const float* add, long long rows, int din, int dout,
+                             cudaStream_t st) {
+    if (rows == 0) return 0;
+    dim3 grid((unsigned)((rows + GBM - 1) / GBM), (din + GBN - 1) / GBN, 1);
+    {
+        LaunchTimer lt("gemm_f32_kernel", st, 2.0 * rows * din * dout, 4.0 * rows * (din + dout));
+        gemm_f32_kernel<false, false><<<grid, GTHREADS, 0, st>>>(dY, W, dX, add, rows, din, dout, dout, din, din, dout, 0);
+    }
+    PCA_CHECK_LAUNCH("gemm_f32_kernel<grad_input>");
+    return 0;
+}
+
+// dW (dout, din) += dY (rows, dout)^T X (rows, din): the row range is split across blockIdx.z, partial sums added atomically
+static int launch_grad_weight(const float* dY, const float* X, float* dW, long long rows, int din, int dout, cudaStream_t st) {
+    if (rows == 0) return 0;
+    const int tiles = ((dout + GBM - 1) / GBM) * ((din + GBN - 1) / GBN);
+    long long nsplit = (148 * 4 + tiles - 1) / tiles;
+    const long long max_split = (rows + 4 * GBK - 1) / (4 * GBK);
+    if (nsplit > max_split) nsplit = max_split;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > 65535) nsplit = 65535;
+    long long kchunk = (rows + nsplit - 1) / nsplit;
+    kchunk = (kchunk + GBK - 1) / GBK * GBK;
+    nsplit = (rows + kchunk - 1) / kchunk;
+    dim3 grid((dout + GBM - 1) / GBM, (din + GBN - 1) / GBN, (unsigned)nsplit);
+    {
+        LaunchTimer lt("gemm_f32_kernel", st, 2.0 * rows * din * dout, 4.0 * rows * (din + dout));
+        gemm_f32_kernel<true, false><<<grid, GTHREADS, 0, st>>>(dY, X, dW, nullptr, dout, din, rows, dout, din, din, kchunk, 1);
+    }
+    PCA_CHECK_LAUNCH("gemm_f32_kernel<grad_weight>");
+    return 0;
+}
+
+// out (cols) += sum over rows of A (rows, cols)
+__global__ void colsum_kernel(const float* __restrict__ A, long long rows, int cols, long long rchunk, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * rchunk;
+    const long long r1 = (r0 + rchunk < rows) ? r0 + rchunk : rows;
+    float v = 0.f;
+    if (c < cols)
+        for (long long r = r0 + threadIdx.y; r < r1; r += 8) v += __ldg(A + r * cols + c);
+    red[threadIdx.y][threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        for (int i = 1; i < 8; ++i) v += red[i][threadIdx.x];
+        atomicAdd(out + c, v);
+    }
+}
+static int launch_colsum(const float* A, long long rows, int cols, float* out, cudaStream_t st) {
+    if (rows == 0 || cols == 0) return 0;
+    const int ctiles = (cols + 31) / 32;
+    long long nsplit = (148 * 8 + ctiles - 1) / ctiles;
+    const long long max_split = (rows + 63) / 64;
+    if (nsplit > max_split) nsplit = max_split;
+    if (nsplit > 65535) nsplit = 65535;
+    if (nsplit < 1) nsplit = 1;
+    const long long rchunk = (rows + nsplit - 1) / nsplit;
+    nsplit = (rows + rchunk - 1) / rchunk;
+    dim3 grid(ctiles, (unsigned)nsplit), block(32, 8);
+    {
+        LaunchTimer lt("colsum_kernel", st, 0.0, 4.0 * rows * cols);
+        colsum_kernel<<<grid, block, 0, st>>>(A, rows, cols, rchunk, out);
+    }
+    PCA_CHECK_LAUNCH("colsum_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ elementwise pieces
+__global__ void relu_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ R, float* __restrict__ dZ, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dZ[i] = R[i] > 0.f ? dOut[i] : 0.f;
+}
+
+// delta (B, nq, H) = sum over the head's dims of dO o (O - Qp)     (= sum_k P dP of the softmax backward)
+__global__ void attn_delta_kernel(const float* __restrict__ dO, const float* __restrict__ O, const float* __restrict__ Qp,
+                                  long long q_bstride, int nq, int D, int DH, long long total, float* __restrict__ delta) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over (b, q, h)
+    if (i >= total) return;
+    const int H = D / DH;
+    const int h = (int)(i % H);
+    const long long bq = i / H;
+    const int q = (int)(bq % nq);
+    const long long b = bq / nq;
+    const float* o = O + bq * D + h * DH;
+    const float* g = dO + bq * D + h * DH;
+    const float* qp = Qp + b * q_bstride + (long long)q * D + h * DH;
+    float s = 0.f;
+    for (int j = 0; j < DH; ++j) s = fmaf(g[j], o[j] - __ldg(qp + j), s);
+    delta[i] = s;
+}
+
+__device__ __forceinline__ uint32_t dropout_bits(unsigned long long seed, unsigned long long idx) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);        // splitmix64 finaliser as a counter-based generator
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 32);
+}
+// out = in * keep / (1 - p); the same (seed, index) mask is regenerated by the backward pass (in-place allowed)
+__global__ void dropout_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, unsigned long long seed,
+                               uint32_t thresh, float inv_keep) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = dropout_bits(seed, (unsigned long long)i) >= thresh ? in[i] * inv_keep : 0.f;
+}
+static int launch_dropout(const float* in, float* out, long long n, float p, unsigned long long seed, cudaStream_t st) {
+    if (n == 0) return 0;
+    const double t = (double)p * 4294967296.0;
+    const uint32_t thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+    dropout_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n, seed, thresh, 1.0f / (1.0f - p));
+    PCA_CHECK_LAUNCH("dropout_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ attention backward
+// Warp = head.  Lane = (dim slice g of G, own item, loop slice): an "own" item (MODE 0: a query -> dQp; MODE 1: a key -> dKp,
+// dVp) keeps its DH = G*DL head dims in the registers of G adjacent lanes; the "loop" items (MODE 0: keys; MODE 1: queries)
+// are staged through shared memory and read as broadcasts.  Loop ranges are cut across blockIdx.y; results are added atomically.
+template <int DL, int G, int MODE>
+__global__ void attn_bwd_kernel(const float* __restrict__ Qp, long long q_bstride, const float* __restrict__ KV,
+                                const float* __restrict__ dO, const float* __restrict__ lse, const float* __restrict__ delta,
+                                int nq, int nk, int D, int town_log, int tl, int chunk, float scale, float scale_log2e,
+                                float* __restrict__ dQp, float* __restrict__ dKV) {
+    extern __shared__ __align__(16) float rows_s[];
+    constexpr int DH = DL * G;
+    const int H = blockDim.x >> 5;
+    const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int TOWN = 1 << town_log;
+    const int LS = 32 / (G * TOWN);
+    const int g = lane & (G - 1);
+    const int own_l = (lane / G) & (TOWN - 1);
+    const int ls = lane / (G * TOWN);
+    const int b = blockIdx.z;
+    const int n_own = MODE == 0 ? nq : nk;
+    const int n_loop = MODE == 0 ? nk : nq;
+    const int own = blockIdx.x * TOWN + own_l;
+    const bool ovalid = own < n_own;
+    const int oc = ovalid ? own : 0;
+    const int H2 = (2 * H + 3) & ~3;
+    const int rs = MODE == 0 ? 2 * D + 4 : 2 * D + H2 + 4;        // smem row stride (floats)
+    const int hoff = h * DH + g * DL;
+
+    float a0[DL], a1[DL], acc0[DL], acc1[DL];
+    float lse_o = 0.f, delta_o = 0.f;
+    if (MODE == 0) {
+        const float* qp = Qp + (long long)b * q_bstride + (long long)oc * D + hoff;
+        const float* gp = dO + ((long long)b * nq + oc) * D + hoff;
+#pragma unroll
+        for (int j = 0; j < DL; ++j) { a0[j] = __ldg(qp + j) * scale_log2e; a1[j] = __ldg(gp + j); acc0[j] = 0.f; acc1[j] = 0.f; }
+        lse_o = __ldg(lse + ((long long)b * nq + oc) * H + h);
+        delta_o = __ldg(delta + ((long long)b * nq + oc) * H + h);
+    } else {
+        const float* kp = KV + ((long long)b * nk + oc) * 2 * D + hoff;
+#pragma unroll
+        for (int j = 0; j < DL; ++j) { a0[j] = __ldg(kp + j); a1[j] = __ldg(kp + D + j); acc0[j] = 0.f; acc1[j] = 0.f; }
+    }
+
+    const int l_begin = blockIdx.y * chunk;
+    const int l_end = min(n_loop, l_begin + chunk);
+    for (int lt = l_begin; lt < l_end; lt += tl) {
+        const int tn = min(tl, l_end - lt);
+        if (MODE == 0) {
+            const int vec_per_row = (2 * D) >> 2;
+            const float* kvb = KV + ((long long)b * nk + lt) * 2 * D;
+            for (int i = threadIdx.x; i < tn * vec_per_row; i += blockDim.x) {
+                const int r = i / vec_per_row, c = i - r * vec_per_row;
+                *reinterpret_cast<float4*>(rows_s + r * rs + c * 4) = __ldg(reinterpret_cast<const float4*>(kvb + (long long)r * 2 * D) + c);
+            }
+        } else {
+            const int vq = D >> 2;
+            for (int i = threadIdx.x; i < tn * vq; i += blockDim.x) {
+                const int r = i / vq, c = i - r * vq;
+                *reinterpret_cast<float4*>(rows_s + r * rs + c * 4) =
+                    __ldg(reinterpret_cast<const float4*>(Qp + (long long)b * q_bstride + (long long)(lt + r) * D) + c);
+                *reinterpret_cast<float4*>(rows_s + r * rs + D + c * 4) =
+                    __ldg(reinterpret_cast<const float4*>(dO + ((long long)b * nq + lt + r) * D) + c);
+            }
+            for (int i = threadIdx.x; i < tn * H; i += blockDim.x) {
+                const int r = i / H, c = i - r * H;
+                rows_s[r * rs + 2 * D + c] = __ldg(lse + ((long long)b * nq + lt + r) * H + c);
+                rows_s[r * rs + 2 * D + H + c] = __ldg(delta + ((long long)b * nq + lt + r) * H + c);
+            }
+        }
+        __syncthreads();
+        // warp-uniform trip count (the dim-slice reductions are full-warp shuffles); out-of-range items contribute zero
+        for (int it = 0; it < tn; it += LS) {
+            const int li = it + ls;
+            const bool lv = li < tn;
+            const float* row = rows_s + (lv ? li : 0) * rs;
+            if (MODE == 0) {
+                const float* kr = row + hoff;
+                const float* vr = row + D + hoff;
+                float s = 0.f, dp = 0.f;
+#pragma unroll
+                for (int j = 0; j < DL; ++j) { s = fmaf(a0[j], kr[j], s); dp = fmaf(a1[j], vr[j], dp); }
+#pragma unroll
+                for (int o = 1; o < G; o <<= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); dp += __shfl_xor_sync(0xffffffffu, dp, o); }
+                const float p = lv ? exp2f(s - lse_o) : 0.f;
+                const float ds = p * (dp - delta_o) * scale;
+#pragma unroll
+                for (int j = 0; j < DL; ++j) acc0[j] = fmaf(ds, kr[j], acc0[j]);
+            } else {
+                const float* qr = row + hoff;
+                const float* gr = row + D + hoff;
+                float s = 0.f, dp = 0.f;
+#pragma unroll
+                for (int j = 0; j < DL; ++j) { s = fmaf(qr[j], a0[j], s); dp = fmaf(gr[j], a1[j], dp); }
+#pragma unroll
+                for (int o = 1; o < G; o <<= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); dp += __shfl_xor_sync(0xffffffffu, dp, o); }
+                const float p = lv ? exp2f(s * scale_log2e - row[2 * D + h]) : 0.f;
+                const float ds = p * (dp - row[2 * D + H + h]) * scale;
+#pragma unroll
+                for (int j = 0; j < DL; ++j) { acc0[j] = fmaf(ds, qr[j], acc0[j]); acc1[j] = fmaf(p, gr[j], acc1[j]); }
+            }
+        }
+        __syncthreads();
+    }
+    // merge the loop slices of one own item across lanes
+    for (int off = G * TOWN; off < 32; off <<= 1) {
+#pragma unroll
+        for (int j = 0; j < DL; ++j) {
+            acc0[j] += __shfl_xor_sync(0xffffffffu, acc0[j], off);
+            if (MODE == 1) acc1[j] += __shfl_xor_sync(0xffffffffu, acc1[j], off);
+        }
+    }
+    if (!ovalid || ls != 0) return;
+    if (MODE == 0) {
+        float* o = dQp + ((long long)b * nq + own) * D + hoff;
+#pragma unroll
+        for (int j = 0; j < DL; ++j) atomicAdd(o + j, acc0[j]);
+    } else {
+        float* o = dKV + ((long long)b * nk + own) * 2 * D + hoff;
+#pragma unroll
+        for (int j = 0; j < DL; ++j) { atomicAdd(o + j, acc0[j]); atomicAdd(o + D + j, acc1[j]); }
+    }
+}
+
+template <int DL, int G, int MODE>
+static int launch_attn_bwd_t(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse,
+                             const float* delta, int B, int nq, int nk, int D, int H, float* dQp, float* dKV, cudaStream_t st) {
+    const int n_own = MODE == 0 ? nq : nk, n_loop = MODE == 0 ? nk : nq;
+    int town = 32 / G;
+    while (town > 1 && (town >> 1) >= n_own) town >>= 1;
+    int town_log = 0;
+    while ((1 << town_log) < town) ++town_log;
+    const int H2 = (2 * H + 3) & ~3;
+    const int rs = MODE == 0 ? 2 * D + 4 : 2 * D + H2 + 4;
+    int tl = (40 * 1024) / (rs * 4);
+    tl = tl > 128 ? 128 : tl;
+    if (tl < 1) tl = 1;
+    if (tl > n_loop) tl = n_loop;
+    const size_t smem = (size_t)tl * rs * 4;
+    const long long base_blocks = (long long)B * ((n_own + town - 1) / town);
+    int nsplit = 1;
+    const long long target = 148LL * 4;
+    if (base_blocks < target) {
+        nsplit = (int)((target + base_blocks - 1) / base_blocks);
+        const int max_split = (n_loop + 2 * tl - 1) / (2 * tl);
+        if (nsplit > max_split) nsplit = max_split;
+        if (nsplit < 1) nsplit = 1;
+    }
+    int chunk = (n_loop + nsplit - 1) / nsplit;
+    chunk = (chunk + tl - 1) / tl * tl;
+    nsplit = (n_loop + chunk - 1) / chunk;
+    dim3 grid((n_own + town - 1) / town, nsplit, B);
+    const float scale = 1.0f / sqrtf((float)D);
+    if (smem > 48 * 1024)
+        PCA_CHECK_CUDA((cudaFuncSetAttribute(attn_bwd_kernel<DL, G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    {
+        LaunchTimer lt(MODE == 0 ? "attn_bwd_dq_kernel" : "attn_bwd_dkv_kernel", st, (MODE == 0 ? 6.0 : 8.0) * B * nq * (double)nk * D,
+                       4.0 * ((double)B * nk * 2 * D + 3.0 * B * nq * D));
+        attn_bwd_kernel<DL, G, MODE><<<grid, 32 * H, smem, st>>>(Qp, q_bstride, KV, dO, lse, delta, nq, nk, D, town_log, tl, chunk,
+                                                                scale, scale * 1.4426950408889634f, dQp, dKV);
+    }
+    PCA_CHECK_LAUNCH("attn_bwd_kernel");
+    return 0;
+}
+
+template <int MODE>
+static int launch_attn_bwd(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse,
+                           const float* delta, int B, int nq, int nk, int D, int H, float* dQp, float* dKV, cudaStream_t st) {
+    if (B > 65535) return fail(PCA_EUNSUPPORTED, "attention backward: batch %d exceeds the grid limit", B);
+    switch (D / H) {
+        case 4: return launch_attn_bwd_t<4, 1, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st);
+        case 8: return launch_attn_bwd_t<8, 1, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st);
+        case 16: return launch_attn_bwd_t<16, 1, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st);
+        case 32: return launch_attn_bwd_t<16, 2, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st);
+        case 64: return launch_attn_bwd_t<16, 4, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st);
+        default: return fail(PCA_EUNSUPPORTED, "attention backward: head dim %d not in {4,8,16,32,64}", D / H);
+    }
+}
+
+// ------------------------------------------------------------------------------------ MAB forward (saving) / backward
+struct MabSaved { float *Qp, *KV, *O, *R, *lse, *out; };
+
+static MabSaved mab_saved_take(Arena& a, int B, int qb, int nq, int nk, int D, int H) {
+    MabSaved s;
+    s.Qp = a.take<float>((size_t)qb * nq * D);
+    s.KV = a.take<float>((size_t)B * nk * 2 * D);
+    s.O = a.take<float>((size_t)B * nq * D);
+    s.R = a.take<float>((size_t)B * nq * D);
+    s.lse = a.take<float>((size_t)B * nq * H);
+    s.out = a.take<float>((size_t)B * nq * D);
+    return s;
+}
+
+static int mab_train_forward(const MabSaved& s, const float* Qin, int qb, const float* Kin, int B, int nq, int nk, int dq, int dk,
+                             int D, int H, const float* params, float* part, cudaStream_t st) {
+    const MabParams m = mab_slice(params, dq, dk, D, 0);
+    PCA_TRY(launch_linear(Qin, m.Wq, m.bq, s.Qp, (long long)qb * nq, dq, D, 0, st));
+    PCA_TRY(launch_linear(Kin, m.Wkv, m.bkv, s.KV, (long long)B * nk, dk, 2 * D, 0, st));
+    PCA_TRY(launch_attn(s.Qp, qb == 1 ? 0 : (long long)nq * D, s.KV, B, nq, nk, D, H, s.O, part, nullptr, st, s.lse));
+    PCA_TRY(launch_linear(s.O, m.Wo, m.bo, s.out, (long long)B * nq, D, D, 3, st, s.R));
+    return 0;
+}
+
+// scratch of one MAB backward (floats)
+static size_t mab_bwd_ws_floats(int B, int qb, int nq, int nk, int D, int H) {
+    Arena a(nullptr, 0);
+    a.take<float>((size_t)B * nq * D);        // dZ, later dQp
+    a.take<float>((size_t)B * nq * D);        // dO
+    a.take<float>((size_t)B * nq * H);        // delta
+    a.take<float>((size_t)B * nk * 2 * D);    // dKV
+    if (qb == 1) a.take<float>((size_t)nq * D);
+    return a.off;
+}
+
+// dQin / dKin may be null (not needed); acc_* != 0 adds to what the buffer already holds.
+static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float* Kin, int B, int nq, int nk, int dq, int dk, int D,
+                        int H, const float* params, float* dparams, const float* dOut, float* dQin, int acc_q, float* dKin,
+                        int acc_k, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const MabParams m = mab_slice(params, dq, dk, D, 0);
+    const MabParams g = mab_slice(dparams, dq, dk, D, 0);
+    Arena a(ws, ws_bytes);
+    float* dZ = a.take<float>((size_t)B * nq * D);
+    float* dO = a.take<float>((size_t)B * nq * D);
+    float* delta = a.take<float>((size_t)B * nq * H);
+    float* dKV = a.take<float>((size_t)B * nk * 2 * D);
+    float* dQ1 = qb == 1 ? a.take<float>((size_t)nq * D) : nullptr;
+    if (!a.ok()) return fail(PCA_EWORKSPACE, "MAB backward: workspace too small");
+    const long long rq = (long long)B * nq, rk = (long long)B * nk;
+    const long long q_bstride = qb == 1 ? 0 : (long long)nq * D;
+    const long long n = rq * D;
+    relu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dOut, s.R, dZ, n);
+    PCA_CHECK_LAUNCH("relu_bwd_kernel");
+    PCA_TRY(launch_grad_weight(dZ, s.O, (float*)g.Wo, rq, D, D, st));
+    PCA_TRY(launch_colsum(dZ, rq, D, (float*)g.bo, st));
+    PCA_TRY(launch_grad_input(dZ, m.Wo, dO, dOut, rq, D, D, st));
+    {
+        const long long total = rq * H;
+        attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dO, s.O, s.Qp, q_bstride, nq, D, D / H, total, delta);
+        PCA_CHECK_LAUNCH("attn_delta_kernel");
+    }
+    PCA_CHECK_CUDA(cudaMemsetAsync(dKV, 0, (size_t)rk * 2 * D * sizeof(float), st));
+    PCA_TRY(launch_attn_bwd<1>(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, nullptr, dKV, st));
+    float* dQp = dZ;                                            // dQp = dO (residual) + attention part, added atomically
+    PCA_CHECK_CUDA(cudaMemcpyAsync(dQp, dO, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    PCA_TRY(launch_attn_bwd<0>(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, dQp, nullptr, st));
+    long long rows_q = rq;
+    if (qb == 1) {                                              // shared queries (I / S): sum the per-cloud gradients
+        PCA_CHECK_CUDA(cudaMemsetAsync(dQ1, 0, (size_t)nq * D * sizeof(float), st));
+        PCA_TRY(launch_colsum(dQp, B, nq * D, dQ1, st));
+        dQp = dQ1;
+        rows_q = nq;
+    }
+    PCA_TRY(launch_grad_weight(dQp, Qin, (float*)g.Wq, rows_q, dq, D, st));
+    PCA_TRY(launch_colsum(dQp, rows_q, D, (float*)g.bq, st));
+    if (dQin) PCA_TRY(launch_grad_input(dQp, m.Wq, dQin, acc_q ? dQin : nullptr, rows_q, dq, D, st));
+    PCA_TRY(launch_grad_weight(dKV, Kin, (float*)g.Wkv, rk, dk, 2 * D, st));
+    PCA_TRY(launch_colsum(dKV, rk, 2 * D, (float*)g.bkv, st));
+    if (dKin) PCA_TRY(launch_grad_input(dKV, m.Wkv, dKin, acc_k ? dKin : nullptr, rk, dk, 2 * D, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ ST / SetTransformer
+struct StSaved {
+    MabSaved i0m0, i0m1, i1m0, i1m1, pm;
+    float *Y2d, *Pd;       // dropout outputs (alias the un-dropped tensors when dropout_p == 0)
+};
+
+static StSaved st_saved_take(Arena& a, const pca_st_dims* d, int B, int N, float dropout_p) {
+    StSaved s;
+    const int D = d->D, H = d->H, M = d->M, S = d->S;
+    s.i0m0 = mab_saved_take(a, B, 1, M, N, D, H);
+    s.i0m1 = mab_saved_take(a, B, B, N, M, D, H);
+    s.i1m0 = mab_saved_take(a, B, 1, M, N, D, H);
+    s.i1m1 = mab_saved_take(a, B, B, N, M, D, H);
+    s.Y2d = dropout_p > 0.f ? a.take<float>((size_t)B * N * D) : s.i1m1.out;
+    s.pm = mab_saved_take(a, B, 1, S, N, D, H);
+    s.Pd = dropout_p > 0.f ? a.take<float>((size_t)B * S * D) : s.pm.out;
+    return s;
+}
+
+struct StParamOffsets { long long I0, i0m0, i0m1, I1, i1m0, i1m1, S, pm, Wl, bl, total; };
+static StParamOffsets st_offsets(const pca_st_dims* d) {
+    StParamOffsets o;
+    const int D = d->D;
+    long long p = 0;
+    o.I0 = p; p += (long long)d->M * D;
+    o.i0m0 = p; p += mab_count(D, d->d_in, D, 0);
+    o.i0m1 = p; p += mab_count(d->d_in, D, D, 0);
+    o.I1 = p; p += (long long)d->M * D;
+    o.i1m0 = p; p += mab_count(D, D, D, 0);
+    o.i1m1 = p; p += mab_count(D, D, D, 0);
+    o.S = p; p += (long long)d->S * D;
+    o.pm = p; p += mab_count(D, D, D, 0);
+    o.Wl = p; p += (long long)d->C * D;
+    o.bl = p; p += d->C;
+    o.total = p;
+    return o;
+}
+
+static int train_check(const pca_st_dims* d, int B, int N, float dropout_p) {
+    if (!d) return fail(PCA_EINVAL, "ST training: null dims");
+    if (d->d_in <= 0 || d->D <= 0 || d->H <= 0 || d->M <= 0 || d->S <= 0 || d->C <= 0) return fail(PCA_EINVAL, "ST training: non-positive dimension");
+    if (d->D % d->H || d->D % 4) return fail(PCA_EINVAL, "ST training: dim_hidden must be a multiple of 4 and of num_heads");
+    if (d->ln) return fail(PCA_EUNSUPPORTED, "ST training: ln=True is not implemented (no reference configuration trains with it)");
+    if (B <= 0 || N <= 0) return fail(PCA_EINVAL, "ST training: bad batch/points (B=%d, N=%d)", B, N);
+    if (B > 65535) return fail(PCA_EUNSUPPORTED, "ST training: batch %d exceeds the grid limit", B);
+    if (!(dropout_p >= 0.f && dropout_p < 1.f)) return fail(PCA_EINVAL, "ST training: dropout probability %f outside [0, 1)", dropout_p);
+    return 0;
+}
+
+size_t st_train_saved_bytes(const pca_st_dims* d, int B, int N, float dropout_p) {
+    Arena a(nullptr, 0);
+    st_saved_take(a, d, B, N, dropout_p);
+    return a.off;
+}
+
+size_t st_train_ws_bytes(const pca_st_dims* d, int B, int N) {
+    const int D = d->D, H = d->H, M = d->M, S = d->S;
+    Arena a(nullptr, 0);
+    a.take<float>((size_t)B * N * D);       // gradient of a (B, N, D) tensor (ping)
+    a.take<float>((size_t)B * N * D);       // (pong)
+    a.take<float>((size_t)B * M * D);       // gradient of the inducing-point summaries
+    a.take<float>((size_t)B * S * D);       // gradient of the pooled vectors
+    a.take<float>((size_t)B * S * D);
+    size_t w = mab_bwd_ws_floats(B, 1, M, N, D, H);
+    size_t w1 = mab_bwd_ws_floats(B, B, N, M, D, H);
+    size_t w2 = mab_bwd_ws_floats(B, 1, S, N, D, H);
+    w = w > w1 ? w : w1;
+    w = w > w2 ? w : w2;
+    size_t part = attn_part_floats(B, M, N, D, H), p2 = attn_part_floats(B, S, N, D, H), p3 = attn_part_floats(B, N, M, D, H);
+    part = part > p2 ? part : p2;
+    part = part > p3 ? part : p3;
+    const size_t fwd = align_up(part * sizeof(float), 256);
+    return a.off + (w > fwd ? w : fwd);
+}
+
+int st_train_forward(const float* X, int B, int N, const pca_st_dims* d, const float* params, float dropout_p,
+                     unsigned long long seed, float* logits, void* saved, size_t saved_bytes, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+    PCA_TRY(train_check(d, B, N, dropout_p));
+    if (!X || !params || !logits || !saved || !ws) return fail(PCA_EINVAL, "ST training forward: null pointer");
+    if (ws_bytes < st_train_ws_bytes(d, B, N)) return fail(PCA_EWORKSPACE, "ST training forward: workspace too small");
+    Arena sa(saved, saved_bytes);
+    const StSaved s = st_saved_take(sa, d, B, N, dropout_p);
+    if (!sa.ok()) return fail(PCA_EWORKSPACE, "ST training forward: activation buffer %zu B too small", saved_bytes);
+    const StParamOffsets o = st_offsets(d);
+    const int D = d->D, H = d->H, M = d->M, S = d->S, C = d->C, din = d->d_in;
+    float* part = (float*)ws;
+    PCA_TRY(mab_train_forward(s.i0m0, params + o.I0, 1, X, B, M, N, D, din, D, H, params + o.i0m0, part, st));
+    PCA_TRY(mab_train_forward(s.i0m1, X, B, s.i0m0.out, B, N, M, din, D, D, H, params + o.i0m1, part, st));
+    PCA_TRY(mab_train_forward(s.i1m0, params + o.I1, 1, s.i0m1.out, B, M, N, D, D, D, H, params + o.i1m0, part, st));
+    PCA_TRY(mab_train_forward(s.i1m1, s.i0m1.out, B, s.i1m0.out, B, N, M, D, D, D, H, params + o.i1m1, part, st));
+    if (dropout_p > 0.f) PCA_TRY(launch_dropout(s.i1m1.out, s.Y2d, (long long)B * N * D, dropout_p, seed, st));
+    PCA_TRY(mab_train_forward(s.pm, params + o.S, 1, s.Y2d, B, S, N, D, D, D, H, params + o.pm, part, st));
+    if (dropout_p > 0.f) PCA_TRY(launch_dropout(s.pm.out, s.Pd, (long long)B * S * D, dropout_p, seed ^ 0xD1B54A32D192ED03ull, st));
+    PCA_TRY(launch_linear(s.Pd, params + o.Wl, params + o.bl, logits, (long long)B * S, D, C, 0, st));
+    return 0;
+}
+
+int st_train_backward(const float* X, int B, int N, const pca_st_dims* d, const float* params, float dropout_p,
+                      unsigned long long seed, const float* dlogits, const void* saved, size_t saved_bytes, float* dparams,
+                      float* dX, void* ws, size_t ws_bytes, cudaStream_t st) {
+    PCA_TRY(train_check(d, B, N, dropout_p));
+    if (!X || !params || !dlogits || !saved || !dparams || !ws) return fail(PCA_EINVAL, "ST training backward: null pointer");
+    Arena sa(const_cast<void*>(saved), saved_bytes);
+    const StSaved s = st_saved_take(sa, d, B, N, dropout_p);
+    if (!sa.ok()) return fail(PCA_EWORKSPACE, "ST training backward: activation buffer too small");
+    const StParamOffsets o = st_offsets(d);
+    const int D = d->D, H = d->H, M = d->M, S = d->S, C = d->C, din = d->d_in;
+    Arena a(ws, ws_bytes);
+    float* gA = a.take<float>((size_t)B * N * D);
+    float* gB = a.take<float>((size_t)B * N * D);
+    float* gH = a.take<float>((size_t)B * M * D);
+    float* gP = a.take<float>((size_t)B * S * D);
+    float* gP2 = a.take<float>((size_t)B * S * D);
+    if (!a.ok() || ws_bytes < st_train_ws_bytes(d, B, N)) return fail(PCA_EWORKSPACE, "ST training backward: workspace too small");
+    void* sub = (char*)ws + a.off;
+    const size_t sub_bytes = ws_bytes - a.off;
+    PCA_CHECK_CUDA(cudaMemsetAsync(dparams, 0, (size_t)o.total * sizeof(float), st));
+    // final Linear
+    const long long rp = (long long)B * S;
+    PCA_TRY(launch_grad_weight(dlogits, s.Pd, dparams + o.Wl, rp, D, C, st));
+    PCA_TRY(launch_colsum(dlogits, rp, C, dparams + o.bl, st));
+    PCA_TRY(launch_grad_input(dlogits, params + o.Wl, gP, nullptr, rp, D, C, st));
+    if (dropout_p > 0.f) PCA_TRY(launch_dropout(gP, gP, rp * D, dropout_p, seed ^ 0xD1B54A32D192ED03ull, st));
+    // PMA: mab(S, Y2d)
+    PCA_TRY(mab_backward(s.pm, params + o.S, 1, s.Y2d, B, S, N, D, D, D, H, params + o.pm, dparams + o.pm, gP, dparams + o.S, 0, gA, 0,
+                         sub, sub_bytes, st));
+    if (dropout_p > 0.f) PCA_TRY(launch_dropout(gA, gA, (long long)B * N * D, dropout_p, seed, st));
+    (void)gP2;
+    // ISAB 1: Y2 = mab1(Y1, H2), H2 = mab0(I1, Y1)
+    PCA_TRY(mab_backward(s.i1m1, s.i0m1.out, B, s.i1m0.out, B, N, M, D, D, D, H, params + o.i1m1, dparams + o.i1m1, gA, gB, 0, gH, 0,
+                         sub, sub_bytes, st));
+    PCA_TRY(mab_backward(s.i1m0, params + o.I1, 1, s.i0m1.out, B, M, N, D, D, D, H, params + o.i1m0, dparams + o.i1m0, gH,
+                         dparams + o.I1, 0, gB, 1, sub, sub_bytes, st));
+    // ISAB 0: Y1 = mab1(X, H1), H1 = mab0(I0, X)
+    PCA_TRY(mab_backward(s.i0m1, X, B, s.i0m0.out, B, N, M, din, D, D, H, params + o.i0m1, dparams + o.i0m1, gB, dX, 0, gH, 0,
+                         sub, sub_bytes, st));
+    PCA_TRY(mab_backward(s.i0m0, params + o.I0, 1, X, B, M, N, D, din, D, H, params + o.i0m0, dparams + o.i0m0, gH, dparams + o.I0, 0,
+                         dX, 1, sub, sub_bytes, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ loss and optimizer
+// nn.CrossEntropyLoss (mean reduction; Code/settransformer.py:89, main_pointcloud.py:63): one warp per row.
+// loss_sum[0] += sum_b (lse_b - z_b[label_b]) * inv_batch; dlogits = (softmax - onehot) * inv_batch; correct[0] += [argmax == label]
+__global__ void cross_entropy_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int C,
+                                     float inv_batch, float* __restrict__ loss_sum, int* __restrict__ correct,
+                                     float* __restrict__ dlogits) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= B) return;
+    const int lane = threadIdx.x & 31;
+    const float* z = logits + (long long)r * C;
+    float mx = -INFINITY;
+    int arg = 0;
+    for (int j = lane; j < C; j += 32) {
+        const float v = z[j];
+        if (v > mx) { mx = v; arg = j; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+    }
+    float s = 0.f;
+    for (int j = lane; j < C; j += 32) s += expf(z[j] - mx);
+    s = warp_sum(s);
+    const int lbl = (int)labels[r];
+    const float lse = mx + logf(s);
+    if (dlogits)
+        for (int j = lane; j < C; j += 32) dlogits[(long long)r * C + j] = (expf(z[j] - lse) - (j == lbl ? 1.f : 0.f)) * inv_batch;
+    if (lane == 0) {
+        atomicAdd(loss_sum, (lse - z[lbl]) * inv_batch);
+        if (correct && arg == lbl) atomicAdd(correct, 1);
+    }
+}
+
+int launch_cross_entropy(const float* logits, const long long* labels, int B, int C, float inv_batch, float* loss_sum, int* correct,
+                         float* dlogits, cudaStream_t st) {
+    if (B <= 0 || C <= 0) return fail(PCA_EINVAL, "cross entropy: empty batch");
+    cross_entropy_kernel<<<(B + 7) / 8, 256, 0, st>>>(logits, labels, B, C, inv_batch, loss_sum, correct, dlogits);
+    PCA_CHECK_LAUNCH("cross_entropy_kernel");
+    return 0;
+}
+
+// torch.optim.Adam semantics (L2 weight decay folded into the gradient, bias-corrected moments), one launch over the flat blob.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                            float grad_scale) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i] * grad_scale;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+}
+
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
+                int step, float grad_scale, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (step < 1) return fail(PCA_EINVAL, "adam: step counts from 1");
+    const float bc1 = 1.f - powf(b1, (float)step);
+    const float bc2_sqrt = sqrtf(1.f - powf(b2, (float)step));
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale);
+    PCA_CHECK_LAUNCH("adam_kernel");
+    return 0;
+}
+
+}  // namespace pca

@@ -40,14 +40,45 @@ class _SetEncoderBase(nn.Module):
                            M=isab0.I.shape[1], S=pma.S.shape[1], C=lin.out_features, ln=isab0.mab0._ln)
 
     def _blob(self):
-        isab0, isab1, pma, lin = self._parts()
-        ts = isab0._tensors() + isab1._tensors() + pma._tensors() + [lin.weight, lin.bias]
+        ts = self._param_tensors()
+        flat = getattr(self, "_flat", None)
+        if flat is not None:
+            # parameters are views of the flat buffer (flatten_parameters): use it directly while that still holds
+            off, ok = flat.data_ptr(), True
+            for t in ts:
+                ok = ok and t.data_ptr() == off and t.dtype == torch.float32
+                off += 4 * t.numel()
+            if ok:
+                return flat
+            object.__setattr__(self, "_flat", None)
         if not hasattr(self, "_packed"):
             object.__setattr__(self, "_packed", _PackedParams())
         return self._packed.get(ts)
 
     def load_state_dict(self, state_dict, *args, **kwargs):
         return super().load_state_dict(strip_module_prefix(state_dict), *args, **kwargs)
+
+    def _param_tensors(self):
+        isab0, isab1, pma, lin = self._parts()
+        return isab0._tensors() + isab1._tensors() + pma._tensors() + [lin.weight, lin.bias]
+
+    def _dropout_p(self) -> float:
+        return 0.0
+
+    def flatten_parameters(self) -> torch.Tensor:
+        """Re-point every parameter at a view of ONE flat fp32 buffer in the blob order of include/pcaudio_b200.h, so
+        that the packed weights, the flat gradient (allreduce bucket) and the fused optimizer all address the same
+        memory and nothing is re-packed per step.  Returns the flat buffer (state-dict keys are unchanged)."""
+        ts = self._param_tensors()
+        with torch.no_grad():
+            flat = torch.cat([t.detach().reshape(-1).float() for t in ts]).contiguous()
+            off = 0
+            for t in ts:
+                n = t.numel()
+                t.data = flat[off:off + n].view(t.shape)
+                off += n
+        object.__setattr__(self, "_flat", flat)
+        return flat
 
     def encode(self, X: torch.Tensor, counts: torch.Tensor | None = None) -> torch.Tensor:
         """(B, N, d_in) CUDA -> logits (B, S, C) (before the reference's .squeeze()).
@@ -66,6 +97,17 @@ class _SetEncoderBase(nn.Module):
             raise ValueError(f"expected clouds of width {dims.d_in}, got {d_in}")
         blob = self._blob()
         assert blob.numel() == _lib.lib().pca_st_param_count(C.byref(dims))
+        ps = self._param_tensors()
+        if torch.is_grad_enabled() and (X.requires_grad or any(p.requires_grad for p in ps)):
+            # training: fp32 forward that keeps activations + hand-written backward (pcaudio_b200/training.py)
+            if counts is not None:
+                raise NotImplementedError("pcaudio_b200: training with variable-size sets (counts) is not implemented")
+            from .training import STTrainFunction
+            p = self._dropout_p()
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+            return STTrainFunction.apply(X, blob, dims, p, seed, *ps)
+        if self._dropout_p() > 0:
+            raise RuntimeError("SetTransformer: train-mode (Dropout) forward without gradients; call .eval() for inference")
         # one dispatcher-visible custom op (pcaudio_b200/ops.py) -> pca_st_fwd_masked of the C ABI
         out = torch.ops.pcaudio.st_fwd(X, counts, blob, dims.d_in, dims.D, dims.H, dims.M, dims.S, dims.C, dims.ln, self.precision)
         return _guard(out, self)
@@ -94,8 +136,8 @@ class ST(_SetEncoderBase):
 
 class SetTransformer(_SetEncoderBase):
     """ModelNet40 classifier of set_transformer-master/main_pointcloud.py:13-37: ST with Dropout
-    around the PMA.  Eval-mode forward runs the fused path; train-mode dropout belongs to the
-    training scope row and raises."""
+    around the PMA.  Eval-mode forward runs the fused inference path; with gradients enabled the
+    training path runs (dropout masks from a counter-based generator, regenerated in the backward pass)."""
 
     def __init__(self, dim_input=3, num_outputs=1, dim_output=40, num_inds=32, dim_hidden=128, num_heads=4, ln=False):
         super().__init__()
@@ -113,9 +155,10 @@ class SetTransformer(_SetEncoderBase):
     def _parts(self):
         return self.enc[0], self.enc[1], self.dec[1], self.dec[3]
 
+    def _dropout_p(self) -> float:
+        return float(self.dec[0].p) if self.training else 0.0
+
     def forward(self, X, counts=None):
-        if self.training:
-            raise NotImplementedError("SetTransformer: train-mode (Dropout) forward is not implemented; call .eval()")
         return self.encode(X, counts).squeeze()
 
 

@@ -89,3 +89,53 @@ def _(logmag, farr, tarr, k, sorted_desc, use_threshold, threshold):
     width = 2 if tarr is None else 3
     return (logmag.new_empty((n, k, width), dtype=torch.float32), logmag.new_empty((n, k), dtype=torch.int32),
             logmag.new_empty((n,), dtype=torch.int32))
+
+
+# ------------------------------------------------------------------------------------ training (fp32)
+def _train_ws(dev, dims, B, N):
+    return rt.workspace(dev, _lib.lib().pca_st_train_workspace_bytes(C.byref(dims), B, N))
+
+
+@torch.library.custom_op("pcaudio::st_train_fwd", mutates_args=(), device_types="cuda")
+def st_train_fwd(X: torch.Tensor, params: torch.Tensor, d_in: int, D: int, H: int, M: int, S: int, n_out: int, ln: int,
+                 dropout_p: float, seed: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """Training forward of ST / SetTransformer: (logits (B, S, n_out), saved activations (bytes) for st_train_bwd)."""
+    B, N, _ = X.shape
+    dims = _dims(d_in, D, H, M, S, n_out, ln)
+    L = _lib.lib()
+    logits = torch.empty((B, S, n_out), dtype=torch.float32, device=X.device)
+    saved = torch.empty(max(1, L.pca_st_train_saved_bytes(C.byref(dims), B, N, dropout_p)), dtype=torch.uint8, device=X.device)
+    ws = _train_ws(X.device, dims, B, N)
+    with torch.cuda.device(X.device):
+        _lib.check(L.pca_st_train_fwd_f32(_lib.ptr(X), B, N, C.byref(dims), _lib.ptr(params), dropout_p, seed, _lib.ptr(logits),
+                                          _lib.ptr(saved), saved.numel(), _lib.ptr(ws), ws.numel(), rt.stream_ptr(X.device)),
+                   "st_train_fwd")
+    return logits, saved
+
+
+@st_train_fwd.register_fake
+def _(X, params, d_in, D, H, M, S, n_out, ln, dropout_p, seed):
+    return X.new_empty((X.shape[0], S, n_out), dtype=torch.float32), X.new_empty((1,), dtype=torch.uint8)
+
+
+@torch.library.custom_op("pcaudio::st_train_bwd", mutates_args=(), device_types="cuda")
+def st_train_bwd(X: torch.Tensor, params: torch.Tensor, d_in: int, D: int, H: int, M: int, S: int, n_out: int, ln: int,
+                 dropout_p: float, seed: int, dlogits: torch.Tensor, saved: torch.Tensor,
+                 need_dx: bool) -> tuple[torch.Tensor, torch.Tensor]:
+    """Backward of st_train_fwd: (flat gradient of every parameter in the layout of `params`, dX or an empty tensor)."""
+    B, N, _ = X.shape
+    dims = _dims(d_in, D, H, M, S, n_out, ln)
+    L = _lib.lib()
+    dparams = torch.empty_like(params)
+    dX = torch.empty_like(X) if need_dx else X.new_empty((0,))
+    ws = _train_ws(X.device, dims, B, N)
+    with torch.cuda.device(X.device):
+        _lib.check(L.pca_st_train_bwd_f32(_lib.ptr(X), B, N, C.byref(dims), _lib.ptr(params), dropout_p, seed, _lib.ptr(dlogits),
+                                          _lib.ptr(saved), saved.numel(), _lib.ptr(dparams), _lib.ptr(dX) if need_dx else None,
+                                          _lib.ptr(ws), ws.numel(), rt.stream_ptr(X.device)), "st_train_bwd")
+    return dparams, dX
+
+
+@st_train_bwd.register_fake
+def _(X, params, d_in, D, H, M, S, n_out, ln, dropout_p, seed, dlogits, saved, need_dx):
+    return torch.empty_like(params), (torch.empty_like(X) if need_dx else X.new_empty((0,)))

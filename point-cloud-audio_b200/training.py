@@ -1,0 +1,119 @@
+"""Training of the set encoders (config 5 of BASELINE.json).
+
+Two ways in, both on the same hand-written fp32 CUDA forward/backward kernels (csrc/encoder_train.cu):
+
+* the reference's own loop works unchanged -- ``preds = model(X); loss = criterion(preds, y); loss.backward();
+  optimizer.step()`` (Code/settransformer.py:101-109, main_pointcloud.py:71-79): with gradients enabled, ``ST`` /
+  ``SetTransformer`` run through ``STTrainFunction``, which hands every parameter its gradient;
+* ``SetTrainer.step(X, labels)`` is the fused B200-first step: forward, cross-entropy, backward, ONE flat-bucket
+  gradient allreduce over NCCL (replacing nn.DataParallel's reduce_add + broadcast) and one fused Adam launch over the
+  flat parameter blob, with no autograd graph and no host synchronisation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, _runtime as rt
+from . import ops as _ops  # noqa: F401
+
+
+class STTrainFunction(torch.autograd.Function):
+    """logits = f(X, *params): forward keeps the activations, backward returns dX (if needed) and per-parameter views of
+    the flat gradient blob."""
+
+    @staticmethod
+    def forward(ctx, X, blob, dims, dropout_p, seed, *params):
+        d = dims
+        logits, saved = torch.ops.pcaudio.st_train_fwd(X, blob, d.d_in, d.D, d.H, d.M, d.S, d.C, d.ln, dropout_p, seed)
+        ctx.save_for_backward(X, blob, saved)
+        ctx.dims, ctx.dropout_p, ctx.seed = d, dropout_p, seed
+        ctx.shapes = [tuple(p.shape) for p in params]
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        X, blob, saved = ctx.saved_tensors
+        d = ctx.dims
+        need_dx = bool(ctx.needs_input_grad[0])
+        dparams, dX = torch.ops.pcaudio.st_train_bwd(X, blob, d.d_in, d.D, d.H, d.M, d.S, d.C, d.ln, ctx.dropout_p, ctx.seed,
+                                                     rt.f32c(dlogits), saved, need_dx)
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = 1
+            for s in shp:
+                n *= s
+            grads.append(dparams[off:off + n].view(shp))
+            off += n
+        assert off == dparams.numel()
+        return (dX if need_dx else None, None, None, None, None, *grads)
+
+
+class SetTrainer:
+    """Fused data-parallel training step for ``ST`` / ``SetTransformer`` (one process per GPU).
+
+    ``step(X, labels)`` enqueues forward + cross-entropy + backward + (world > 1) one NCCL allreduce of the flat fp32
+    gradient buffer + fused Adam on the caller's current stream and returns ``(loss, correct)`` as device tensors
+    (mean loss of the local batch, number of correct arg-max predictions) without synchronising.
+    Hyper-parameters follow torch.optim.Adam as the reference uses it (lr 1e-3; weight_decay 1e-3 for the audio models,
+    Code/settransformer.py:90-91)."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None, seed=0):
+        self.model = model
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.flat = model.flatten_parameters()
+        self.grads = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.t = 0
+        self.seed = int(seed)
+        self._saved = None
+        if self.world > 1:                      # replicas start from rank 0's weights, as DataParallel's broadcast does
+            dist.broadcast(self.flat, src=0, group=process_group)
+
+    def _buffers(self, dims, B, N, p, dev):
+        L = _lib.lib()
+        need = max(1, L.pca_st_train_saved_bytes(C.byref(dims), B, N, p))
+        if self._saved is None or self._saved.numel() < need:
+            self._saved = torch.empty(need, dtype=torch.uint8, device=dev)
+        ws = rt.workspace(dev, L.pca_st_train_workspace_bytes(C.byref(dims), B, N))
+        return self._saved, ws
+
+    def step(self, X, labels):
+        m = self.model
+        rt.require_cuda(X, "SetTrainer.step")
+        X = rt.f32c(X)
+        labels = labels.to(device=X.device, dtype=torch.int64).contiguous()
+        B, N, _ = X.shape
+        dev = X.device
+        dims = m._dims()
+        if dims.S != 1:
+            raise ValueError("SetTrainer: classification needs num_outputs == 1")
+        p = m._dropout_p()
+        self.t += 1
+        seed = (self.seed * 0x9E3779B1 + self.t) & 0xFFFFFFFFFFFFFFFF
+        saved, ws = self._buffers(dims, B, N, p, dev)
+        L = _lib.lib()
+        st = rt.stream_ptr(dev)
+        logits = torch.empty((B, dims.C), dtype=torch.float32, device=dev)
+        dlogits = torch.empty_like(logits)
+        stats = torch.zeros(2, dtype=torch.float32, device=dev)      # loss | correct (int32 bits)
+        with torch.cuda.device(dev):
+            _lib.check(L.pca_st_train_fwd_f32(_lib.ptr(X), B, N, C.byref(dims), _lib.ptr(self.flat), p, seed, _lib.ptr(logits),
+                                              _lib.ptr(saved), saved.numel(), _lib.ptr(ws), ws.numel(), st), "st_train_fwd")
+            _lib.check(L.pca_cross_entropy_f32(_lib.ptr(logits), _lib.ptr(labels), B, dims.C, C.c_void_p(stats.data_ptr()),
+                                               C.c_void_p(stats.data_ptr() + 4), _lib.ptr(dlogits), st), "cross_entropy")
+            _lib.check(L.pca_st_train_bwd_f32(_lib.ptr(X), B, N, C.byref(dims), _lib.ptr(self.flat), p, seed, _lib.ptr(dlogits),
+                                              _lib.ptr(saved), saved.numel(), _lib.ptr(self.grads), None, _lib.ptr(ws), ws.numel(),
+                                              st), "st_train_bwd")
+            if self.world > 1:
+                dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
+            _lib.check(L.pca_adam_step_f32(_lib.ptr(self.flat), _lib.ptr(self.grads), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                                           self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                           self.t, 1.0 / self.world, st), "adam_step")
+        self.logits = logits
+        return stats[0], stats[1:2].view(torch.int32)[0]

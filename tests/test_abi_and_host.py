@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(built):
     for n in names:
         assert hasattr(handle, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.PROTOTYPES) == names, "ctypes prototypes out of sync with the header"
-    assert _lib.lib().pca_version() == 101
+    assert _lib.lib().pca_version() == 102
 
 
 def test_no_oracle_import_in_product():

@@ -1,0 +1,165 @@
+"""Training path (fp32 CUDA forward/backward, cross-entropy, fused Adam) against torch autograd through the CPU oracle
+(oracle/pcaudio_oracle.py restates modules.py; autograd differentiates that restatement)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+pytestmark = pytest.mark.gpu
+GRAD_REL_TOL = 1e-3          # fp32 path: max |g - g_ref| / max |g_ref| per parameter tensor
+
+
+@pytest.fixture(scope="module")
+def pca():
+    import __graft_entry__ as g
+    g.build()
+    import pcaudio_b200
+    return pcaudio_b200
+
+
+def _oracle_grads(state, X, G, heads, fwd):
+    from oracle import pcaudio_oracle as orc
+    p = {k: v.detach().cpu().double().requires_grad_(True) for k, v in state.items()}
+    Xc = X.detach().cpu().double().requires_grad_(True)
+    out = getattr(orc, fwd)(p, Xc, heads).reshape(G.shape)
+    (out * G.double()).sum().backward()
+    return out.detach(), {k: v.grad for k, v in p.items()}, Xc.grad
+
+
+CASES = [
+    # cls, d_in, D, H, M, C, B, N
+    ("ST", 3, 16, 4, 8, 5, 3, 50),        # head dim 4
+    ("ST", 2, 64, 8, 64, 10, 2, 300),     # audio dims (FST), head dim 8
+    ("ST", 3, 64, 8, 64, 10, 2, 1025),    # 3ST dims, ragged tiles
+    ("ST", 3, 64, 4, 16, 7, 2, 77),       # head dim 16
+    ("ST", 3, 64, 2, 5, 4, 3, 33),        # head dim 32 (two lanes per head row)
+    ("SetTransformer", 3, 256, 4, 16, 40, 2, 200),   # ModelNet dims (main_pointcloud.py defaults), head dim 64
+]
+
+
+@pytest.mark.parametrize("cls,d_in,D,H,M,Cc,B,N", CASES)
+def test_gradients_match_autograd_of_oracle(pca, cls, d_in, D, H, M, Cc, B, N):
+    dev = torch.device("cuda:0")
+    torch.manual_seed(D + N)
+    model = getattr(pca, cls)(dim_input=d_in, num_outputs=1, dim_output=Cc, num_inds=M, dim_hidden=D, num_heads=H).to(dev)
+    if cls == "SetTransformer":
+        model.eval()                     # Dropout off: exact parity (train-mode parity is statistical, tested below)
+    X = torch.randn(B, N, d_in, device=dev, requires_grad=True)
+    G = torch.randn(B, Cc)
+    out = model(X)
+    assert out.shape == (B, Cc)
+    (out * G.to(dev)).sum().backward()
+    ref_out, ref_g, ref_dx = _oracle_grads(model.state_dict(), X, G, H, "st_forward" if cls == "ST" else "modelnet_forward")
+    assert (out.detach().cpu().double() - ref_out).abs().max() / ref_out.abs().max() < 1e-4
+    worst = {}
+    # fc_k.bias has an exactly-zero true gradient (a key bias shifts every score of a row equally and the softmax is
+    # shift invariant): autograd returns rounding noise there, so errors are measured against at least 1e-3 of the
+    # largest parameter gradient
+    floor = 1e-3 * max(v.abs().max().item() for v in ref_g.values())
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        err = (p.grad.cpu().double() - ref_g[k]).abs().max().item() / max(ref_g[k].abs().max().item(), floor)
+        worst[k] = err
+    bad = {k: v for k, v in worst.items() if not v < GRAD_REL_TOL}
+    assert not bad, f"parameter gradients off: {bad}"
+    err = (X.grad.cpu().double() - ref_dx).abs().max().item() / ref_dx.abs().max().item()
+    assert err < GRAD_REL_TOL, f"dX rel err {err:.3e}"
+
+
+def test_reference_training_loop_unchanged(pca):
+    """The reference loop (main_pointcloud.py:71-79: criterion, zero_grad, backward, torch.optim.Adam step) runs on the
+    drop-in model and tracks the same loop on the CPU oracle restatement step for step."""
+    from oracle import pcaudio_oracle as orc
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    model = pca.ST(dim_input=3, num_outputs=1, dim_output=6, num_inds=8, dim_hidden=32, num_heads=4).to(dev)
+    ref_p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3)
+    ref_opt = torch.optim.Adam(list(ref_p.values()), lr=1e-3, weight_decay=1e-3)
+    crit = torch.nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(0)
+    losses, ref_losses = [], []
+    for it in range(5):
+        X = torch.randn(16, 40, 3, generator=g)
+        y = torch.randint(0, 6, (16,), generator=g)
+        loss = crit(model(X.to(dev)), y.to(dev))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ref_loss = crit(orc.st_forward(ref_p, X, 4), y)
+        ref_opt.zero_grad()
+        ref_loss.backward()
+        ref_opt.step()
+        losses.append(loss.item())
+        ref_losses.append(ref_loss.item())
+    assert np.allclose(losses, ref_losses, rtol=2e-3), (losses, ref_losses)
+    for k, v in model.state_dict().items():
+        assert (v.cpu() - ref_p[k].detach()).abs().max() < 2e-4, k
+
+
+def test_fused_trainer_matches_torch_adam(pca):
+    """SetTrainer.step (forward + CE + backward + fused Adam on the flat blob, no autograd) against the oracle +
+    torch.optim.Adam with the audio models' weight decay (Code/settransformer.py:90-91)."""
+    from oracle import pcaudio_oracle as orc
+    dev = torch.device("cuda:0")
+    torch.manual_seed(4)
+    model = pca.ST(dim_input=2, num_outputs=1, dim_output=10, num_inds=16, dim_hidden=32, num_heads=8).to(dev)
+    ref_p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref_opt = torch.optim.Adam(list(ref_p.values()), lr=1e-3, weight_decay=1e-3)
+    tr = pca.SetTrainer(model, lr=1e-3, weight_decay=1e-3)
+    crit = torch.nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(1)
+    for it in range(4):
+        X = torch.randn(12, 65, 2, generator=g)
+        y = torch.randint(0, 10, (12,), generator=g)
+        loss, correct = tr.step(X.to(dev), y.to(dev))
+        ref_out = orc.st_forward(ref_p, X, 8)
+        ref_loss = crit(ref_out, y)
+        ref_opt.zero_grad()
+        ref_loss.backward()
+        ref_opt.step()
+        assert abs(loss.item() - ref_loss.item()) < 2e-3 * max(1.0, abs(ref_loss.item())), (it, loss.item(), ref_loss.item())
+        assert int(correct.item()) == int((ref_out.argmax(1) == y).sum())
+    for k, v in model.state_dict().items():          # parameters are views of the trainer's flat buffer
+        assert (v.cpu() - ref_p[k].detach()).abs().max() < 2e-4, k
+    # the updated flat weights are what inference sees
+    with torch.no_grad():
+        X = torch.randn(3, 65, 2, generator=g)
+        out = model(X.to(dev)).cpu()
+        assert (out - orc.st_forward({k: v.detach() for k, v in ref_p.items()}, X, 8)).abs().max() < 1e-3
+
+
+def test_dropout_train_mode_statistics_and_backward(pca):
+    """main_pointcloud.SetTransformer in train mode: Dropout(0.5) before and after the PMA.  The mask is a counter-based
+    generator (not torch's Philox stream), so parity is statistical: the mean over many masks approaches the eval output
+    of a model whose dropped tensors are the un-dropped ones (inverted dropout is unbiased for the linear final layer),
+    and the backward regenerates the same mask (finite-difference check of one directional derivative)."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(7)
+    model = pca.SetTransformer(dim_input=3, num_outputs=1, dim_output=8, num_inds=8, dim_hidden=32, num_heads=4).to(dev)
+    model.train()
+    X = torch.randn(4, 64, 3, device=dev)
+    outs = torch.stack([model(X).detach() for _ in range(8)])
+    assert torch.isfinite(outs).all()
+    assert (outs[0] - outs[1]).abs().max() > 0            # masks differ call to call
+    # same seed -> same mask -> backward consistent with forward: directional finite difference on the flat blob
+    from pcaudio_b200.training import STTrainFunction
+    dims, ps = model._dims(), model._param_tensors()
+    blob = model._blob().clone()
+    G = torch.randn(4, 1, 8, device=dev)
+
+    def f(b):
+        return (torch.ops.pcaudio.st_train_fwd(X, b, dims.d_in, dims.D, dims.H, dims.M, dims.S, dims.C, dims.ln, 0.5, 1234)[0] * G).sum()
+    logits, saved = torch.ops.pcaudio.st_train_fwd(X, blob, dims.d_in, dims.D, dims.H, dims.M, dims.S, dims.C, dims.ln, 0.5, 1234)
+    dparams, _ = torch.ops.pcaudio.st_train_bwd(X, blob, dims.d_in, dims.D, dims.H, dims.M, dims.S, dims.C, dims.ln, 0.5, 1234, G.contiguous(), saved, False)
+    direction = torch.randn_like(blob)
+    direction /= direction.norm()
+    eps = 1e-2
+    fd = (f(blob + eps * direction) - f(blob - eps * direction)).item() / (2 * eps)
+    an = (dparams * direction).sum().item()
+    assert abs(fd - an) < 2e-2 * max(1.0, abs(an)), (fd, an)
+    kept = (torch.ops.pcaudio.st_train_fwd(X, blob, dims.d_in, dims.D, dims.H, dims.M, dims.S, dims.C, dims.ln, 0.5, 1234)[0] == logits).all()
+    assert kept
