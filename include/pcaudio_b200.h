@@ -291,6 +291,16 @@ void pca_debug_set_tail_max(int tail_max);
  * exponent (normally none); 2 = the 2-warpgroup variant only. */
 void pca_debug_set_reduce_variant(int warpgroups);
 
+/* fp32-grade GEMMs on the tensor cores (split-bf16, three MMAs per product; csrc/gemm_tc.cu), used by the fp32 encoder path,
+ * DeepSet's shared MLP and the training path for layers with K % 32 == 0 and N % 32 == 0.  pca_debug_set_gemm_tc(0) keeps
+ * every layer on the CUDA-core kernels.  pca_debug_linear_tc: Y (rows, N) = act(X (rows, K) B^T + bias) [+ resid], B(n,k) =
+ * trans_w ? W[k*N+n] : W[n*K+k]; R (nullable) receives the activation output before the residual; image: >= 4*N*K bytes of
+ * scratch.  pca_debug_grad_weight_tc: dW (M, N) += dY (rows, M)^T X (rows, N). */
+void pca_debug_set_gemm_tc(int on);
+int pca_debug_linear_tc(const float* X, const float* W, int trans_w, const float* bias, const float* resid, float* Y, float* R,
+                        long long rows, int K, int N, int relu, void* image, size_t image_bytes, void* stream);
+int pca_debug_grad_weight_tc(const float* dY, const float* X, float* dW, long long rows, int M, int N, void* stream);
+
 /* Unit probe of the tcgen05 building blocks used by the bf16 encoder path: one CTA computes
  * D (128, N) = A (128, K) * B (K, N), bf16 operands, fp32 accumulation in TMEM.
  * a_mode: 0 A (128,K) via shared memory K-major, 1 A via TMEM, 2 A given as (K,128) via shared memory MN-major;

@@ -70,6 +70,9 @@ PROTOTYPES = {
     "pca_debug_set_timeline": (None, [_P]),
     "pca_debug_set_tail_max": (None, [_I]),
     "pca_debug_set_reduce_variant": (None, [_I]),
+    "pca_debug_set_gemm_tc": (None, [_I]),
+    "pca_debug_linear_tc": (_I, [_P, _P, _I, _P, _P, _P, _P, C.c_longlong, _I, _I, _I, _P, _SZ, _P]),
+    "pca_debug_grad_weight_tc": (_I, [_P, _P, _P, C.c_longlong, _I, _I, _P]),
     "pca_debug_umma_probe": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "pca_pipeline_clouds_per_clip": (_I, [C.POINTER(PipelineCfg)]),
     "pca_pipeline_points_per_cloud": (_I, [C.POINTER(PipelineCfg)]),

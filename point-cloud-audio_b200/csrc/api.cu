@@ -81,12 +81,15 @@ LaunchTimer::~LaunchTimer() {
 // ------------------------------------------------------------------------------------ params
 // ------------------------------------------------------------------------------------ MAB (fp32)
 // workspace: Qp (qb*nq*D) | KV (B*nk*2D) | O (B*nq*D) | part
+// scratch for the largest weight image of a MAB's tensor-core GEMMs (Wkv with dk <= max(D, 4) ... D x D is the largest eligible)
+static size_t mab_img_bytes(int D) { return gemm_tc_image_bytes(2 * D, D); }
 static size_t mab_ws_floats(int B, int qb, int nq, int nk, int D, int H) {
     Arena a(nullptr, 0);
     a.take<float>((size_t)qb * nq * D);
     a.take<float>((size_t)B * nk * 2 * D);
     a.take<float>((size_t)B * nq * D);
     a.take<float>(attn_part_floats(B, nq, nk, D, H));
+    a.take<uint8_t>(mab_img_bytes(D));
     return a.off;
 }
 
@@ -102,12 +105,14 @@ static int mab_forward(const float* Q, int qb, const float* K, int B, int nq, in
     float* KV = a.take<float>((size_t)B * nk * 2 * D);
     float* O = a.take<float>((size_t)B * nq * D);
     float* part = a.take<float>(attn_part_floats(B, nq, nk, D, H));
+    const size_t ib = mab_img_bytes(D);
+    void* img = a.take<uint8_t>(ib);
     if (!a.ok()) return fail(PCA_EWORKSPACE, "MAB: workspace too small (%zu bytes given)", ws_bytes);
-    PCA_TRY(launch_linear(Q, m.Wq, m.bq, Qp, (long long)qb * nq, dq, D, 0, st));
-    PCA_TRY(launch_linear(K, m.Wkv, m.bkv, KV, (long long)B * nk, dk, 2 * D, 0, st));
+    PCA_TRY(launch_linear(Q, m.Wq, m.bq, Qp, (long long)qb * nq, dq, D, 0, st, nullptr, dq <= D ? img : nullptr, ib));
+    PCA_TRY(launch_linear(K, m.Wkv, m.bkv, KV, (long long)B * nk, dk, 2 * D, 0, st, nullptr, dk <= D ? img : nullptr, ib));
     PCA_TRY(launch_attn(Qp, qb == 1 ? 0 : (long long)nq * D, KV, B, nq, nk, D, H, O, part, key_counts, st));
     if (ln) PCA_TRY(launch_layernorm(O, (long long)B * nq, D, m.ln0w, m.ln0b, st));
-    PCA_TRY(launch_linear(O, m.Wo, m.bo, out, (long long)B * nq, D, D, 2, st));
+    PCA_TRY(launch_linear(O, m.Wo, m.bo, out, (long long)B * nq, D, D, 2, st, nullptr, img, ib));
     if (ln) PCA_TRY(launch_layernorm(out, (long long)B * nq, D, m.ln1w, m.ln1b, st));
     return 0;
 }
@@ -224,6 +229,7 @@ static size_t deepset_ws_bytes(int B, int N, int dh) {
     a.take<float>((size_t)B * N * dh);
     a.take<float>((size_t)B * dh);
     a.take<float>((size_t)B * dh);
+    a.take<uint8_t>(gemm_tc_image_bytes(dh, dh));
     return a.off;
 }
 static int deepset_forward(const float* X, int B, int N, int d_in, int dh, int out_dim, int pool,
@@ -234,6 +240,8 @@ static int deepset_forward(const float* X, int B, int N, int d_in, int dh, int o
     float* t1 = a.take<float>((size_t)B * N * dh);
     float* u0 = a.take<float>((size_t)B * dh);
     float* u1 = a.take<float>((size_t)B * dh);
+    const size_t ib = gemm_tc_image_bytes(dh, dh);
+    void* img = a.take<uint8_t>(ib);
     if (!a.ok() || !ws) return fail(PCA_EWORKSPACE, "DeepSet: workspace too small");
     const long long rows = (long long)B * N;
     const float* W[8]; const float* bb[8];
@@ -246,9 +254,9 @@ static int deepset_forward(const float* X, int B, int N, int d_in, int dh, int o
         (void)din;
     }
     PCA_TRY(launch_linear(X, W[0], bb[0], t0, rows, d_in, dh, 1, st));
-    PCA_TRY(launch_linear(t0, W[1], bb[1], t1, rows, dh, dh, 1, st));
-    PCA_TRY(launch_linear(t1, W[2], bb[2], t0, rows, dh, dh, 1, st));
-    PCA_TRY(launch_linear(t0, W[3], bb[3], t1, rows, dh, dh, 0, st));
+    PCA_TRY(launch_linear(t0, W[1], bb[1], t1, rows, dh, dh, 1, st, nullptr, img, ib));      // shared MLP over points: tensor cores
+    PCA_TRY(launch_linear(t1, W[2], bb[2], t0, rows, dh, dh, 1, st, nullptr, img, ib));
+    PCA_TRY(launch_linear(t0, W[3], bb[3], t1, rows, dh, dh, 0, st, nullptr, img, ib));
     PCA_TRY(launch_pool(t1, B, N, dh, pool, u0, counts, st));
     PCA_TRY(launch_linear(u0, W[4], bb[4], u1, B, dh, dh, 1, st));
     PCA_TRY(launch_linear(u1, W[5], bb[5], u0, B, dh, dh, 1, st));
@@ -637,6 +645,15 @@ int pca_adam_step_f32(float* params, const float* grads, float* exp_avg, float* 
                       float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq) return fail(PCA_EINVAL, "adam: null pointer");
     return launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, (cudaStream_t)stream);
+}
+
+void pca_debug_set_gemm_tc(int on) { set_gemm_tc(on); }
+int pca_debug_linear_tc(const float* X, const float* W, int trans_w, const float* bias, const float* resid, float* Y, float* R,
+                        long long rows, int K, int N, int relu, void* image, size_t image_bytes, void* stream) {
+    return launch_linear_tc(X, W, trans_w, bias, resid, Y, R, rows, K, N, relu, image, image_bytes, (cudaStream_t)stream);
+}
+int pca_debug_grad_weight_tc(const float* dY, const float* X, float* dW, long long rows, int M, int N, void* stream) {
+    return launch_grad_weight_tc(dY, X, dW, rows, M, N, (cudaStream_t)stream);
 }
 
 void pca_debug_set_timeline(long long* device_buffer) { set_timeline(device_buffer); }

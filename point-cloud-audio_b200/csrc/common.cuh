@@ -85,8 +85,17 @@ __host__ __device__ static inline MabParams mab_slice(const float* p, int dq, in
 }
 
 // fp32 encoder launchers shared by the inference (api.cu) and training (encoder_train.cu) orchestration
+// img / img_bytes: optional scratch for the weight image of the tcgen05 GEMM (gemm_tc.cu); when it is given and the shape is
+// eligible the layer runs on the tensor cores (split-bf16, fp32-grade), otherwise on the CUDA-core kernel.
 int launch_linear(const float* X, const float* W, const float* b, float* Y, long long rows, int din, int dout, int mode,
-                  cudaStream_t st, float* R = nullptr);
+                  cudaStream_t st, float* R = nullptr, void* img = nullptr, size_t img_bytes = 0);
+size_t gemm_tc_image_bytes(int N, int K);
+bool linear_tc_eligible(long long rows, int K, int N);
+int launch_linear_tc(const float* X, const float* W, int trans_w, const float* bias, const float* resid, float* Y, float* R,
+                     long long rows, int K, int N, int relu, void* img, size_t img_bytes, cudaStream_t st);
+bool grad_weight_tc_eligible(long long rows, int M, int N);
+int launch_grad_weight_tc(const float* dY, const float* X, float* dW, long long rows, int M, int N, cudaStream_t st);
+void set_gemm_tc(int on);
 int launch_attn(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D, int H, float* O, float* part,
                 const int* key_counts, cudaStream_t st, float* lse = nullptr);
 size_t attn_part_floats(int B, int nq, int nk, int D, int H);

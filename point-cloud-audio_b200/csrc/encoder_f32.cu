@@ -87,10 +87,13 @@ linear_f32_kernel(const float* __restrict__ X, const float* __restrict__ W, cons
 }
 
 int launch_linear(const float* X, const float* W, const float* b, float* Y, long long rows, int din,
-                  int dout, int mode, cudaStream_t st, float* R) {
+                  int dout, int mode, cudaStream_t st, float* R, void* img, size_t img_bytes) {
     if (rows == 0) return 0;
     if (mode == 3 && !R) return fail(PCA_EINVAL, "linear: mode 3 needs the relu output buffer");
     if (mode >= 2 && din != dout) return fail(PCA_EINVAL, "linear: residual mode needs din == dout");
+    if (img && img_bytes >= gemm_tc_image_bytes(dout, din) && linear_tc_eligible(rows, din, dout))
+        return launch_linear_tc(X, W, 0, b, mode >= 2 ? X : nullptr, Y, mode == 3 ? R : nullptr, rows, din, dout, mode >= 1, img,
+                                img_bytes, st);
     dim3 grid((unsigned)((rows + LBM - 1) / LBM), (dout + LBN - 1) / LBN);
     {
         LaunchTimer lt("linear_f32_kernel", st, 2.0 * rows * din * dout, 4.0 * rows * (din + dout));

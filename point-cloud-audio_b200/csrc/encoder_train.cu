@@ -107,8 +107,10 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float
 
 // dX (rows, din) = dY (rows, dout) W (dout, din) [+ add (rows, din)]; add may alias dX (accumulation)
 static int launch_grad_input(const float* dY, const float* W, float* dX, const float* add, long long rows, int din, int dout,
-                             cudaStream_t st) {
+                             cudaStream_t st, void* img = nullptr, size_t img_bytes = 0) {
     if (rows == 0) return 0;
+    if (img && img_bytes >= gemm_tc_image_bytes(din, dout) && linear_tc_eligible(rows, dout, din))      // K = dout, N = din
+        return launch_linear_tc(dY, W, 1, nullptr, add, dX, nullptr, rows, dout, din, 0, img, img_bytes, st);
     dim3 grid((unsigned)((rows + GBM - 1) / GBM), (din + GBN - 1) / GBN, 1);
     {
         LaunchTimer lt("gemm_f32_kernel", st, 2.0 * rows * din * dout, 4.0 * rows * (din + dout));
@@ -121,6 +123,7 @@ static int launch_grad_input(const float* dY, const float* W, float* dX, const f
 // dW (dout, din) += dY (rows, dout)^T X (rows, din): the row range is split across blockIdx.z, partial sums added atomically
 static int launch_grad_weight(const float* dY, const float* X, float* dW, long long rows, int din, int dout, cudaStream_t st) {
     if (rows == 0) return 0;
+    if (grad_weight_tc_eligible(rows, dout, din)) return launch_grad_weight_tc(dY, X, dW, rows, dout, din, st);
     const int tiles = ((dout + GBM - 1) / GBM) * ((din + GBN - 1) / GBN);
     long long nsplit = (148 * 4 + tiles - 1) / tiles;
     const long long max_split = (rows + 4 * GBK - 1) / (4 * GBK);
@@ -412,13 +415,16 @@ static MabSaved mab_saved_take(Arena& a, int B, int qb, int nq, int nk, int D, i
     return s;
 }
 
+static size_t train_img_bytes(int D) { return gemm_tc_image_bytes(2 * D, D); }
+
 static int mab_train_forward(const MabSaved& s, const float* Qin, int qb, const float* Kin, int B, int nq, int nk, int dq, int dk,
-                             int D, int H, const float* params, float* part, cudaStream_t st) {
+                             int D, int H, const float* params, float* part, void* img, cudaStream_t st) {
     const MabParams m = mab_slice(params, dq, dk, D, 0);
-    PCA_TRY(launch_linear(Qin, m.Wq, m.bq, s.Qp, (long long)qb * nq, dq, D, 0, st));
-    PCA_TRY(launch_linear(Kin, m.Wkv, m.bkv, s.KV, (long long)B * nk, dk, 2 * D, 0, st));
+    const size_t ib = train_img_bytes(D);
+    PCA_TRY(launch_linear(Qin, m.Wq, m.bq, s.Qp, (long long)qb * nq, dq, D, 0, st, nullptr, dq <= D ? img : nullptr, ib));
+    PCA_TRY(launch_linear(Kin, m.Wkv, m.bkv, s.KV, (long long)B * nk, dk, 2 * D, 0, st, nullptr, dk <= D ? img : nullptr, ib));
     PCA_TRY(launch_attn(s.Qp, qb == 1 ? 0 : (long long)nq * D, s.KV, B, nq, nk, D, H, s.O, part, nullptr, st, s.lse));
-    PCA_TRY(launch_linear(s.O, m.Wo, m.bo, s.out, (long long)B * nq, D, D, 3, st, s.R));
+    PCA_TRY(launch_linear(s.O, m.Wo, m.bo, s.out, (long long)B * nq, D, D, 3, st, s.R, img, ib));
     return 0;
 }
 
@@ -430,6 +436,7 @@ static size_t mab_bwd_ws_floats(int B, int qb, int nq, int nk, int D, int H) {
     a.take<float>((size_t)B * nq * H);        // delta
     a.take<float>((size_t)B * nk * 2 * D);    // dKV
     if (qb == 1) a.take<float>((size_t)nq * D);
+    a.take<uint8_t>(train_img_bytes(D));
     return a.off;
 }
 
@@ -445,6 +452,10 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
     float* delta = a.take<float>((size_t)B * nq * H);
     float* dKV = a.take<float>((size_t)B * nk * 2 * D);
     float* dQ1 = qb == 1 ? a.take<float>((size_t)nq * D) : nullptr;
+    const size_t ib = train_img_bytes(D);
+    void* img = a.take<uint8_t>(ib);
+    void* img_q = dq <= D ? img : nullptr;
+    void* img_k = dk <= D ? img : nullptr;
     if (!a.ok()) return fail(PCA_EWORKSPACE, "MAB backward: workspace too small");
     const long long rq = (long long)B * nq, rk = (long long)B * nk;
     const long long q_bstride = qb == 1 ? 0 : (long long)nq * D;
@@ -453,7 +464,7 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
     PCA_CHECK_LAUNCH("relu_bwd_kernel");
     PCA_TRY(launch_grad_weight(dZ, s.O, (float*)g.Wo, rq, D, D, st));
     PCA_TRY(launch_colsum(dZ, rq, D, (float*)g.bo, st));
-    PCA_TRY(launch_grad_input(dZ, m.Wo, dO, dOut, rq, D, D, st));
+    PCA_TRY(launch_grad_input(dZ, m.Wo, dO, dOut, rq, D, D, st, img, ib));
     {
         const long long total = rq * H;
         attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dO, s.O, s.Qp, q_bstride, nq, D, D / H, total, delta);
@@ -473,10 +484,10 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
     }
     PCA_TRY(launch_grad_weight(dQp, Qin, (float*)g.Wq, rows_q, dq, D, st));
     PCA_TRY(launch_colsum(dQp, rows_q, D, (float*)g.bq, st));
-    if (dQin) PCA_TRY(launch_grad_input(dQp, m.Wq, dQin, acc_q ? dQin : nullptr, rows_q, dq, D, st));
+    if (dQin) PCA_TRY(launch_grad_input(dQp, m.Wq, dQin, acc_q ? dQin : nullptr, rows_q, dq, D, st, img_q, ib));
     PCA_TRY(launch_grad_weight(dKV, Kin, (float*)g.Wkv, rk, dk, 2 * D, st));
     PCA_TRY(launch_colsum(dKV, rk, 2 * D, (float*)g.bkv, st));
-    if (dKin) PCA_TRY(launch_grad_input(dKV, m.Wkv, dKin, acc_k ? dKin : nullptr, rk, dk, 2 * D, st));
+    if (dKin) PCA_TRY(launch_grad_input(dKV, m.Wkv, dKin, acc_k ? dKin : nullptr, rk, dk, 2 * D, st, img_k, ib));
     return 0;
 }
 
@@ -551,7 +562,7 @@ size_t st_train_ws_bytes(const pca_st_dims* d, int B, int N) {
     size_t part = attn_part_floats(B, M, N, D, H), p2 = attn_part_floats(B, S, N, D, H), p3 = attn_part_floats(B, N, M, D, H);
     part = part > p2 ? part : p2;
     part = part > p3 ? part : p3;
-    const size_t fwd = align_up(part * sizeof(float), 256);
+    const size_t fwd = align_up(part * sizeof(float), 256) + align_up(train_img_bytes(D), 256);
     return a.off + (w > fwd ? w : fwd);
 }
 
@@ -566,13 +577,22 @@ int st_train_forward(const float* X, int B, int N, const pca_st_dims* d, const f
     if (!sa.ok()) return fail(PCA_EWORKSPACE, "ST training forward: activation buffer %zu B too small", saved_bytes);
     const StParamOffsets o = st_offsets(d);
     const int D = d->D, H = d->H, M = d->M, S = d->S, C = d->C, din = d->d_in;
-    float* part = (float*)ws;
-    PCA_TRY(mab_train_forward(s.i0m0, params + o.I0, 1, X, B, M, N, D, din, D, H, params + o.i0m0, part, st));
-    PCA_TRY(mab_train_forward(s.i0m1, X, B, s.i0m0.out, B, N, M, din, D, D, H, params + o.i0m1, part, st));
-    PCA_TRY(mab_train_forward(s.i1m0, params + o.I1, 1, s.i0m1.out, B, M, N, D, D, D, H, params + o.i1m0, part, st));
-    PCA_TRY(mab_train_forward(s.i1m1, s.i0m1.out, B, s.i1m0.out, B, N, M, D, D, D, H, params + o.i1m1, part, st));
+    size_t part_floats = attn_part_floats(B, M, N, D, H);
+    {
+        const size_t p2 = attn_part_floats(B, S, N, D, H), p3 = attn_part_floats(B, N, M, D, H);
+        part_floats = part_floats > p2 ? part_floats : p2;
+        part_floats = part_floats > p3 ? part_floats : p3;
+    }
+    Arena wa(ws, ws_bytes);
+    float* part = wa.take<float>(part_floats);
+    void* img = wa.take<uint8_t>(train_img_bytes(D));
+    if (!wa.ok()) return fail(PCA_EWORKSPACE, "ST training forward: workspace too small");
+    PCA_TRY(mab_train_forward(s.i0m0, params + o.I0, 1, X, B, M, N, D, din, D, H, params + o.i0m0, part, img, st));
+    PCA_TRY(mab_train_forward(s.i0m1, X, B, s.i0m0.out, B, N, M, din, D, D, H, params + o.i0m1, part, img, st));
+    PCA_TRY(mab_train_forward(s.i1m0, params + o.I1, 1, s.i0m1.out, B, M, N, D, D, D, H, params + o.i1m0, part, img, st));
+    PCA_TRY(mab_train_forward(s.i1m1, s.i0m1.out, B, s.i1m0.out, B, N, M, D, D, D, H, params + o.i1m1, part, img, st));
     if (dropout_p > 0.f) PCA_TRY(launch_dropout(s.i1m1.out, s.Y2d, (long long)B * N * D, dropout_p, seed, st));
-    PCA_TRY(mab_train_forward(s.pm, params + o.S, 1, s.Y2d, B, S, N, D, D, D, H, params + o.pm, part, st));
+    PCA_TRY(mab_train_forward(s.pm, params + o.S, 1, s.Y2d, B, S, N, D, D, D, H, params + o.pm, part, img, st));
     if (dropout_p > 0.f) PCA_TRY(launch_dropout(s.pm.out, s.Pd, (long long)B * S * D, dropout_p, seed ^ 0xD1B54A32D192ED03ull, st));
     PCA_TRY(launch_linear(s.Pd, params + o.Wl, params + o.bl, logits, (long long)B * S, D, C, 0, st));
     return 0;

@@ -1,0 +1,446 @@
+// fp32-grade GEMMs on the tcgen05 tensor cores for the shared-MLP / projection layers over points
+// (Y = act(X W^T + b), dX = dY W, dW = dY^T X) of the dims the fused bf16 encoder does not cover (ModelNet D=256, DeepSet,
+// training).  Operands are split into bf16 hi + lo parts on the fly (x = hi + lo to 2^-17 relative) and every product is
+// evaluated as THREE bf16 MMAs accumulating in fp32 TMEM (a_hi b_hi + a_lo b_hi + a_hi b_lo; the dropped lo*lo term is
+// 2^-18 relative), so the results stay inside the 1e-3 fp32 parity budget while the arithmetic runs on the tensor pipe.
+//
+//   linear_tc_kernel  : persistent, warp-specialised.  4 producer warps (thread = row of the 128-row tile: fp32 global ->
+//                       hi/lo bf16 -> canonical no-swizzle smem), the weight operand arrives as a pre-built hi|lo image by
+//                       ONE bulk async copy (cp.async.bulk + mbarrier complete_tx) per K chunk, 1 MMA warp (elected lane),
+//                       4 epilogue warps (TMEM -> bias / ReLU / residual -> global).  Two TMEM accumulators of up to 256
+//                       columns: the epilogue of tile t overlaps the staging and MMAs of tile t+1.
+//   weight_image_kernel: W (fp32, optionally transposed) -> per (column pass, K chunk) [hi image | lo image].
+//   grad_weight_tc_kernel: dW (M, N) += A^T B over a range of rows (both operands MN-major from row-major activations),
+//                       split over rows across CTAs, partial results added atomically.
+#include "common.cuh"
+#include "tc_prims.cuh"
+
+namespace pca {
+using namespace tc;
+
+constexpr int GT_KC = 32;            // K elements per pipeline stage
+constexpr int GT_STAGES = 3;
+constexpr int GT_THREADS = 9 * 32;   // 4 producer + 1 MMA + 4 epilogue warps
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void gt_warp_arrive(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+// 8 fp32 -> 8 bf16 hi (one 16-byte chunk) and 8 bf16 lo
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 hb = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+        const float2 hf = __bfloat1622float2(hb);
+        h[j] = *reinterpret_cast<const uint32_t*>(&hb);
+        l[j] = pack_bf16(x[2 * j] - hf.x, x[2 * j + 1] - hf.y);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ------------------------------------------------------------------------------------ weight image
+// B(n, k) = trans ? W[k * ldw + n] : W[n * ldw + k], n < N, k < K.  Image (pass p, chunk c) at ((p * nkc + c) * 2) * nt * 64 bytes:
+// hi image (K-major canonical: byte = (kk / 8) * nt * 16 + nn * 16 + (kk % 8) * 2, nn < nt, kk < 32) then lo image.
+__global__ void weight_image_kernel(const float* __restrict__ W, int N, int K, int ldw, int trans, int nt, uint8_t* __restrict__ img) {
+    const int nkc = K / GT_KC;
+    const long long total = (long long)N * (K / 8);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i % N), k8 = (int)(i / N);
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k8 * 8 + j;
+            x[j] = trans ? __ldg(W + (long long)k * ldw + n) : __ldg(W + (long long)n * ldw + k);
+        }
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const int p = n / nt, nn = n - p * nt;
+        const int c = (k8 * 8) / GT_KC, kk8 = k8 - c * (GT_KC / 8);
+        uint8_t* base = img + ((size_t)(p * nkc + c) * 2) * nt * 64;
+        *reinterpret_cast<uint4*>(base + (size_t)kk8 * nt * 16 + nn * 16) = hi;
+        *reinterpret_cast<uint4*>(base + (size_t)nt * 64 + (size_t)kk8 * nt * 16 + nn * 16) = lo;
+    }
+}
+
+// ------------------------------------------------------------------------------------ linear (forward / grad-input)
+struct LinTcParams {
+    const float* X;          // (rows, K) row-major
+    const uint8_t* img;      // weight image
+    const float* bias;       // (N) nullable
+    const float* resid;      // (rows, N) nullable: added after the activation (may alias Y)
+    float* Y;                // (rows, N)
+    float* R;                // (rows, N) nullable: relu output
+    long long rows;
+    int K, N, nt, relu;
+};
+
+struct LinTcSmem {
+    static constexpr int A_BYTES = 128 * GT_KC * 2;                // one hi or lo image of the activation tile
+    static constexpr int STAGE = 2 * A_BYTES + 2 * 256 * GT_KC * 2;  // A hi | A lo | B hi | B lo (B sized for nt = 256)
+    static constexpr int BARS = GT_STAGES * STAGE;
+    static constexpr int TOTAL = BARS + 16 * 8 + 16;
+};
+
+__global__ void __launch_bounds__(GT_THREADS, 1) linear_tc_kernel(const LinTcParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LinTcSmem::BARS);
+    uint64_t* full = bars;                       // [3] count 5: 4 producer warps + the expect_tx arrival
+    uint64_t* empty = bars + GT_STAGES;          // [3] count 1 (MMA commit)
+    uint64_t* acc_full = bars + 2 * GT_STAGES;   // [2] count 1
+    uint64_t* acc_empty = acc_full + 2;          // [2] count 4 (epilogue warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkc = P.K / GT_KC;
+    const int npass = P.N / P.nt;
+    const long long mtiles = (P.rows + 127) / 128;
+    const long long ntiles = mtiles * npass;
+
+    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < GT_STAGES; ++i) { mbar_init(&full[i], 5); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        fence_barrier_init();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+    const uint32_t b_img_bytes = (uint32_t)P.nt * 64;           // one hi or lo weight image of a chunk
+
+    if (warp < 4) {
+        // ================================================================= producers
+        const int row = threadIdx.x;
+        uint32_t gt = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const long long mt = t / npass;
+            const int pass = (int)(t - mt * npass);
+            const long long r = mt * 128 + row;
+            const bool valid = r < P.rows;
+            const float* xp = P.X + (valid ? r : 0) * P.K;
+            for (int kc = 0; kc < nkc; ++kc, ++gt) {
+                const int stage = gt % GT_STAGES;
+                float x[GT_KC];
+#pragma unroll
+                for (int j = 0; j < GT_KC / 4; ++j) {
+                    const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(xp + kc * GT_KC) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+                }
+                if (gt >= GT_STAGES) mbar_wait(&empty[stage], ((gt / GT_STAGES) - 1) & 1);
+                uint8_t* st = smem + stage * LinTcSmem::STAGE;
+                if (threadIdx.x == 0) {
+                    mbar_arrive_expect_tx(&full[stage], 2 * b_img_bytes);
+                    bulk_copy_g2s(st + 2 * LinTcSmem::A_BYTES, P.img + ((size_t)(pass * nkc + kc) * 2) * b_img_bytes, 2 * b_img_bytes, &full[stage]);
+                }
+#pragma unroll
+                for (int c = 0; c < GT_KC / 8; ++c) {
+                    uint4 hi, lo;
+                    split8(x + 8 * c, hi, lo);
+                    *reinterpret_cast<uint4*>(st + c * 2048 + row * 16) = hi;
+                    *reinterpret_cast<uint4*>(st + LinTcSmem::A_BYTES + c * 2048 + row * 16) = lo;
+                }
+                fence_async_smem();
+                gt_warp_arrive(&full[stage]);
+            }
+        }
+    } else if (warp == 4) {
+        // ================================================================= MMA issue (warp-uniform, elected lane)
+        const uint32_t idesc = idesc_bf16(128, P.nt, 0, 0);
+        uint32_t gt = 0, tt = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tt) {
+            const uint32_t buf = tt & 1;
+            if (tt >= 2) mbar_wait(&acc_empty[buf], ((tt >> 1) - 1) & 1);
+            fence_after_sync();
+            const uint32_t acc = tmem_addr(tb, 0, 256 * buf);
+            for (int kc = 0; kc < nkc; ++kc, ++gt) {
+                const int stage = gt % GT_STAGES;
+                mbar_wait(&full[stage], (gt / GT_STAGES) & 1);
+                fence_after_sync();
+                if (elect_one()) {
+                    const uint32_t a_hi = smem_u32(smem + stage * LinTcSmem::STAGE);
+                    const uint32_t a_lo = a_hi + LinTcSmem::A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * LinTcSmem::A_BYTES;
+                    const uint32_t b_lo = b_hi + b_img_bytes;
+                    const uint32_t b_lbo = (uint32_t)P.nt * 16;
+#pragma unroll
+                    for (int ks = 0; ks < GT_KC / 16; ++ks) {
+                        const uint64_t dah = smem_desc(a_hi + ks * 4096, 2048, 128), dal = smem_desc(a_lo + ks * 4096, 2048, 128);
+                        const uint64_t dbh = smem_desc(b_hi + ks * 2 * b_lbo, b_lbo, 128), dbl = smem_desc(b_lo + ks * 2 * b_lbo, b_lbo, 128);
+                        mma_ss(acc, dah, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                        mma_ss(acc, dal, dbh, idesc, 1u);
+                        mma_ss(acc, dah, dbl, idesc, 1u);
+                    }
+                    mma_commit(&empty[stage]);
+                    if (kc == nkc - 1) mma_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================================================= epilogue
+        const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+        uint32_t tt = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tt) {
+            const uint32_t buf = tt & 1;
+            const long long mt = t / npass;
+            const int pass = (int)(t - mt * npass);
+            const long long r = mt * 128 + 32 * quad + lane;
+            const bool valid = r < P.rows;
+            mbar_wait(&acc_full[buf], (tt >> 1) & 1);
+            fence_after_sync();
+            for (int c0 = 0; c0 < P.nt; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_addr(tb, 32 * quad, 256 * buf + c0), v);
+                tmem_ld_wait32(v);
+                if (valid) {
+                    const int n0 = pass * P.nt + c0;
+                    float* yp = P.Y + r * P.N + n0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float o[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            float a = __uint_as_float(v[j + u]);
+                            if (P.bias) a += __ldg(P.bias + n0 + j + u);
+                            if (P.relu) a = fmaxf(a, 0.f);
+                            o[u] = a;
+                        }
+                        if (P.R) *reinterpret_cast<float4*>(P.R + r * P.N + n0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+                        if (P.resid) {
+                            const float4 rv = *reinterpret_cast<const float4*>(P.resid + r * P.N + n0 + j);
+                            o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+                        }
+                        *reinterpret_cast<float4*>(yp + j) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+            }
+            fence_before_sync();
+            gt_warp_arrive(&acc_empty[buf]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tb, 512);
+}
+
+static int g_gemm_tc = 1;       // 0: every GEMM stays on the CUDA-core kernels (PCA_GEMM_TC=0 / pca_debug_set_gemm_tc)
+void set_gemm_tc(int on) { g_gemm_tc = on ? 1 : 0; }
+static bool gemm_tc_on() {
+    static int env = -1;
+    if (env < 0) { const char* v = getenv("PCA_GEMM_TC"); env = (v && v[0] == '0') ? 0 : 1; }
+    return env && g_gemm_tc;
+}
+
+static int pick_nt(int N) {
+    if (N <= 256) return N;
+    for (int nt = 256; nt >= 32; nt -= 32)
+        if (N % nt == 0) return nt;
+    return 0;
+}
+
+size_t gemm_tc_image_bytes(int N, int K) { return (size_t)4 * N * K; }
+
+bool linear_tc_eligible(long long rows, int K, int N) {
+    return gemm_tc_on() && rows >= 512 && K % GT_KC == 0 && K >= GT_KC && N % 32 == 0 && N >= 32 && pick_nt(N) >= 32;
+}
+
+// Y (rows, N) = act(X (rows, K) B^T + bias) [+ resid];  B(n, k) = trans_w ? W[k * N + n] : W[n * K + k]
+int launch_linear_tc(const float* X, const float* W, int trans_w, const float* bias, const float* resid, float* Y, float* R,
+                     long long rows, int K, int N, int relu, void* img, size_t img_bytes, cudaStream_t st) {
+    if (rows == 0) return 0;
+    if (!linear_tc_eligible(rows, K, N)) return fail(PCA_EUNSUPPORTED, "linear_tc: shape (%lld, %d, %d) not eligible", rows, K, N);
+    if (!img || img_bytes < gemm_tc_image_bytes(N, K)) return fail(PCA_EWORKSPACE, "linear_tc: weight image buffer too small");
+    static bool configured = false;
+    if (!configured) {
+        PCA_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LinTcSmem::TOTAL));
+        configured = true;
+    }
+    const int nt = pick_nt(N);
+    {
+        const long long total = (long long)N * (K / 8);
+        weight_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, N, K, trans_w ? N : K, trans_w, nt, (uint8_t*)img);
+        PCA_CHECK_LAUNCH("weight_image_kernel");
+    }
+    LinTcParams p{X, (const uint8_t*)img, bias, resid, Y, R, rows, K, N, nt, relu};
+    const long long ntiles = ((rows + 127) / 128) * (N / nt);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+    {
+        LaunchTimer lt("linear_tc_kernel", st, 2.0 * rows * K * N, 4.0 * rows * (K + N));
+        linear_tc_kernel<<<grid, GT_THREADS, LinTcSmem::TOTAL, st>>>(p);
+    }
+    PCA_CHECK_LAUNCH("linear_tc_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ weight gradient
+// dW (M, N) += A (rows, M)^T B (rows, N) over the rows [r0, r1) of this CTA.  Both operands are MN-major: a 16-byte unit
+// is 8 consecutive features of one row; units of one 8-row group are contiguous (128 B), 8-feature groups 'SBO' apart:
+//   byte(mn, k) = (mn / 8) * (KC * 16) + k * 16 + (mn % 8) * 2,   k < KC = 32 rows per stage   (LBO = 128, SBO = KC * 16).
+// 4 producer warps: thread = (row k of the chunk, quarter of the features).  M = 128 per CTA (blockIdx.y), N <= 256.
+struct GwTcParams {
+    const float* A;          // (rows, lda): columns [m0, m0 + 128) of dY
+    const float* B;          // (rows, N)
+    float* dW;               // (Mtot, N)
+    long long rows, rchunk;
+    int lda, Mtot, N;
+};
+struct GwTcSmem {
+    static constexpr int A_BYTES = 128 * GT_KC * 2;
+    static constexpr int B_BYTES = 256 * GT_KC * 2;
+    static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int BARS = GT_STAGES * STAGE;
+    static constexpr int TOTAL = BARS + 16 * 8 + 16;
+};
+
+__global__ void __launch_bounds__(GT_THREADS, 1) grad_weight_tc_kernel(const GwTcParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GwTcSmem::BARS);
+    uint64_t* full = bars;                       // [3] count 4 (producer warps)
+    uint64_t* empty = bars + GT_STAGES;          // [3] count 1
+    uint64_t* acc_full = bars + 2 * GT_STAGES;   // count 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * 128;
+    const long long r0 = (long long)blockIdx.x * P.rchunk;
+    const long long r1 = (r0 + P.rchunk < P.rows) ? r0 + P.rchunk : P.rows;
+    const int nchunks = (int)((r1 - r0 + GT_KC - 1) / GT_KC);
+
+    if (warp == 4) tmem_alloc(tmem_slot, 256);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < GT_STAGES; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp < 4) {
+        const int k = lane;                      // row of the chunk
+        const int part = warp;                   // quarter of the feature groups
+        const int a_groups = 16, b_groups = P.N / 8;
+        for (int c = 0; c < nchunks; ++c) {
+            const int stage = c % GT_STAGES;
+            const long long r = r0 + (long long)c * GT_KC + k;
+            const bool valid = r < r1;
+            if (c >= GT_STAGES) mbar_wait(&empty[stage], ((c / GT_STAGES) - 1) & 1);
+            uint8_t* st = smem + stage * GwTcSmem::STAGE;
+            const float* ap = P.A + (valid ? r : 0) * P.lda + m0;
+            const float* bp = P.B + (valid ? r : 0) * P.N;
+            for (int g = part; g < a_groups; g += 4) {
+                float x[8];
+                const bool gv = valid && (m0 + 8 * g < P.Mtot);
+                const float4 v0 = gv ? __ldg(reinterpret_cast<const float4*>(ap + 8 * g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 v1 = gv ? __ldg(reinterpret_cast<const float4*>(ap + 8 * g) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+                uint4 hi, lo;
+                split8(x, hi, lo);
+                *reinterpret_cast<uint4*>(st + g * (GT_KC * 16) + k * 16) = hi;
+                *reinterpret_cast<uint4*>(st + GwTcSmem::A_BYTES + g * (GT_KC * 16) + k * 16) = lo;
+            }
+            for (int g = part; g < b_groups; g += 4) {
+                float x[8];
+                const float4 v0 = valid ? __ldg(reinterpret_cast<const float4*>(bp + 8 * g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 v1 = valid ? __ldg(reinterpret_cast<const float4*>(bp + 8 * g) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+                uint4 hi, lo;
+                split8(x, hi, lo);
+                *reinterpret_cast<uint4*>(st + 2 * GwTcSmem::A_BYTES + g * (GT_KC * 16) + k * 16) = hi;
+                *reinterpret_cast<uint4*>(st + 2 * GwTcSmem::A_BYTES + GwTcSmem::B_BYTES + g * (GT_KC * 16) + k * 16) = lo;
+            }
+            fence_async_smem();
+            gt_warp_arrive(&full[stage]);
+        }
+    } else if (warp == 4) {
+        const uint32_t idesc = idesc_bf16(128, P.N, 1, 1);
+        for (int c = 0; c < nchunks; ++c) {
+            const int stage = c % GT_STAGES;
+            mbar_wait(&full[stage], (c / GT_STAGES) & 1);
+            fence_after_sync();
+            if (elect_one()) {
+                const uint32_t a_hi = smem_u32(smem + stage * GwTcSmem::STAGE);
+                const uint32_t a_lo = a_hi + GwTcSmem::A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * GwTcSmem::A_BYTES;
+                const uint32_t b_lo = b_hi + GwTcSmem::B_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < GT_KC / 16; ++ks) {
+                    // MN-major: a K step of 16 rows = two 8-row groups = 256 bytes further
+                    const uint64_t dah = smem_desc(a_hi + ks * 256, 128, GT_KC * 16), dal = smem_desc(a_lo + ks * 256, 128, GT_KC * 16);
+                    const uint64_t dbh = smem_desc(b_hi + ks * 256, 128, GT_KC * 16), dbl = smem_desc(b_lo + ks * 256, 128, GT_KC * 16);
+                    mma_ss(tb, dah, dbh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                    mma_ss(tb, dal, dbh, idesc, 1u);
+                    mma_ss(tb, dah, dbl, idesc, 1u);
+                }
+                mma_commit(&empty[stage]);
+                if (c == nchunks - 1) mma_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else if (nchunks > 0) {
+        const int quad = warp & 3;
+        const int m = m0 + 32 * quad + lane;
+        mbar_wait(acc_full, 0);
+        fence_after_sync();
+        for (int c0 = 0; c0 < P.N; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_addr(tb, 32 * quad, c0), v);
+            tmem_ld_wait32(v);
+            if (m < P.Mtot) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(P.dW + (long long)m * P.N + c0 + j, __uint_as_float(v[j]));
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tb, 256);
+}
+
+bool grad_weight_tc_eligible(long long rows, int M, int N) {
+    return gemm_tc_on() && rows >= 2048 && M % 8 == 0 && M >= 64 && N % 32 == 0 && N >= 32 && N <= 256;
+}
+
+// dW (M, N) += dY (rows, M)^T X (rows, N)
+int launch_grad_weight_tc(const float* dY, const float* X, float* dW, long long rows, int M, int N, cudaStream_t st) {
+    if (rows == 0) return 0;
+    if (!grad_weight_tc_eligible(rows, M, N)) return fail(PCA_EUNSUPPORTED, "grad_weight_tc: shape (%lld, %d, %d) not eligible", rows, M, N);
+    static bool configured = false;
+    if (!configured) {
+        PCA_CHECK_CUDA(cudaFuncSetAttribute(grad_weight_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GwTcSmem::TOTAL));
+        configured = true;
+    }
+    const int mtiles = (M + 127) / 128;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long nsplit = (2LL * sms + mtiles - 1) / mtiles;
+    const long long max_split = (rows + 8 * GT_KC - 1) / (8 * GT_KC);
+    if (nsplit > max_split) nsplit = max_split;
+    if (nsplit < 1) nsplit = 1;
+    long long rchunk = (rows + nsplit - 1) / nsplit;
+    rchunk = (rchunk + GT_KC - 1) / GT_KC * GT_KC;
+    nsplit = (rows + rchunk - 1) / rchunk;
+    GwTcParams p{dY, X, dW, rows, rchunk, M, M, N};
+    dim3 grid((unsigned)nsplit, mtiles);
+    {
+        LaunchTimer lt("grad_weight_tc_kernel", st, 2.0 * rows * M * N, 4.0 * rows * (M + N));
+        grad_weight_tc_kernel<<<grid, GT_THREADS, GwTcSmem::TOTAL, st>>>(p);
+    }
+    PCA_CHECK_LAUNCH("grad_weight_tc_kernel");
+    return 0;
+}
+
+}  // namespace pca

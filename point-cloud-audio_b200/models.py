@@ -98,7 +98,7 @@ class _SetEncoderBase(nn.Module):
         blob = self._blob()
         assert blob.numel() == _lib.lib().pca_st_param_count(C.byref(dims))
         ps = self._param_tensors()
-        if torch.is_grad_enabled() and (X.requires_grad or any(p.requires_grad for p in ps)):
+        if B > 0 and torch.is_grad_enabled() and (X.requires_grad or any(p.requires_grad for p in ps)):
             # training: fp32 forward that keeps activations + hand-written backward (pcaudio_b200/training.py)
             if counts is not None:
                 raise NotImplementedError("pcaudio_b200: training with variable-size sets (counts) is not implemented")

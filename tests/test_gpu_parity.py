@@ -246,11 +246,16 @@ def test_deepset_pools_vs_oracle(pca, dev):
         assert rel_err(out.numpy(), ref.numpy()) < ENC_REL_TOL
 
 
-def test_backward_fails_loudly(pca, dev):
-    st = pca.ST(dim_input=2, num_outputs=1, dim_output=10, num_inds=8, dim_hidden=16, num_heads=4).to(dev)
-    out = st(torch.randn(2, 50, 2, device=dev))
+def test_backward_of_standalone_blocks_fails_loudly(pca, dev):
+    """Whole models train (tests/test_gpu_train.py); the stand-alone attention blocks and DeepSet have no backward
+    kernels yet and must say so instead of silently producing zero gradients."""
+    isab = pca.ISAB(2, 16, 4, 8).to(dev)
+    out = isab(torch.randn(2, 50, 2, device=dev))
     with pytest.raises(NotImplementedError):
         out.sum().backward()
+    ds = pca.DeepSet(3, 1, 7, dim_hidden=32).to(dev)
+    with pytest.raises(NotImplementedError):
+        ds(torch.randn(2, 20, 3, device=dev)).sum().backward()
 
 
 # ------------------------------------------------------------------------------------ whole path
