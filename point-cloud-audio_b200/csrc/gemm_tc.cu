@@ -87,7 +87,8 @@ struct LinTcParams {
 struct LinTcSmem {
     static constexpr int A_BYTES = 128 * GT_KC * 2;                // one hi or lo image of the activation tile
     static constexpr int STAGE = 2 * A_BYTES + 2 * 256 * GT_KC * 2;  // A hi | A lo | B hi | B lo (B sized for nt = 256)
-    static constexpr int BARS = GT_STAGES * STAGE;
+    static constexpr int TRANS = GT_STAGES * STAGE;                 // 4 epilogue warps x 32 x 33 floats
+    static constexpr int BARS = TRANS + 4 * 32 * 33 * 4;
     static constexpr int TOTAL = BARS + 16 * 8 + 16;
 };
 
@@ -119,38 +120,71 @@ __global__ void __launch_bounds__(GT_THREADS, 1) linear_tc_kernel(const LinTcPar
 
     if (warp < 4) {
         // ================================================================= producers
-        const int row = threadIdx.x;
+        // Warp w stages rows [32w, 32w+32) of the tile.  Lane = (row % 8, 16-byte chunk c of the 32-wide K chunk): a
+        // warp-wide load covers 8 rows x 128 contiguous bytes (coalesced), a quarter-warp store 8 consecutive rows of one
+        // chunk (128 contiguous bytes of smem, conflict free).  The loads of the next K chunk are in flight while the
+        // current one is converted.
+        const int rsub = lane & 7, c = lane >> 3;
         uint32_t gt = 0;
-        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            const long long mt = t / npass;
-            const int pass = (int)(t - mt * npass);
-            const long long r = mt * 128 + row;
-            const bool valid = r < P.rows;
-            const float* xp = P.X + (valid ? r : 0) * P.K;
-            for (int kc = 0; kc < nkc; ++kc, ++gt) {
-                const int stage = gt % GT_STAGES;
-                float x[GT_KC];
+        float4 nx[8], nx2[8];                     // the next two chunks: 4 row groups x 2 float4 (8 consecutive k of one row)
+        long long t = blockIdx.x;
+        int kc = 0;
+        auto issue = [&](float4* nx, long long tile, int kchunk) {
+            const long long mt = tile / npass;
 #pragma unroll
-                for (int j = 0; j < GT_KC / 4; ++j) {
-                    const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(xp + kc * GT_KC) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+            for (int it = 0; it < 4; ++it) {
+                const long long r = mt * 128 + 32 * warp + 8 * it + rsub;
+                if (r < P.rows) {
+                    const float4* src = reinterpret_cast<const float4*>(P.X + r * P.K + kchunk * GT_KC + 8 * c);
+                    nx[2 * it] = __ldg(src);
+                    nx[2 * it + 1] = __ldg(src + 1);
+                } else {
+                    nx[2 * it] = nx[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                if (gt >= GT_STAGES) mbar_wait(&empty[stage], ((gt / GT_STAGES) - 1) & 1);
-                uint8_t* st = smem + stage * LinTcSmem::STAGE;
-                if (threadIdx.x == 0) {
-                    mbar_arrive_expect_tx(&full[stage], 2 * b_img_bytes);
-                    bulk_copy_g2s(st + 2 * LinTcSmem::A_BYTES, P.img + ((size_t)(pass * nkc + kc) * 2) * b_img_bytes, 2 * b_img_bytes, &full[stage]);
-                }
-#pragma unroll
-                for (int c = 0; c < GT_KC / 8; ++c) {
-                    uint4 hi, lo;
-                    split8(x + 8 * c, hi, lo);
-                    *reinterpret_cast<uint4*>(st + c * 2048 + row * 16) = hi;
-                    *reinterpret_cast<uint4*>(st + LinTcSmem::A_BYTES + c * 2048 + row * 16) = lo;
-                }
-                fence_async_smem();
-                gt_warp_arrive(&full[stage]);
             }
+        };
+        auto advance = [&](long long& tile, int& kchunk) {
+            if (++kchunk == nkc) { kchunk = 0; tile += gridDim.x; }
+        };
+        long long t_n = t, t_n2;
+        int kc_n = 0, kc_n2;
+        if (t < ntiles) issue(nx, t, 0);
+        advance(t_n, kc_n);
+        if (t_n < ntiles) issue(nx2, t_n, kc_n);
+        t_n2 = t_n;
+        kc_n2 = kc_n;
+        while (t < ntiles) {
+            const int pass = (int)(t % npass);
+            const int stage = gt % GT_STAGES;
+            float4 cur[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cur[j] = nx[j]; nx[j] = nx2[j]; }
+            // two chunks ahead: put its loads in flight (the loads of the chunk after this one are still in flight)
+            advance(t_n2, kc_n2);
+            if (t_n2 < ntiles) issue(nx2, t_n2, kc_n2);
+            if (gt >= GT_STAGES) mbar_wait(&empty[stage], ((gt / GT_STAGES) - 1) & 1);
+            uint8_t* st = smem + stage * LinTcSmem::STAGE;
+            if (threadIdx.x == 0) {
+                mbar_arrive_expect_tx(&full[stage], 2 * b_img_bytes);
+                bulk_copy_g2s(st + 2 * LinTcSmem::A_BYTES, P.img + ((size_t)(pass * nkc + kc) * 2) * b_img_bytes, 2 * b_img_bytes, &full[stage]);
+            }
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const float x[8] = {cur[2 * it].x, cur[2 * it].y, cur[2 * it].z, cur[2 * it].w,
+                                    cur[2 * it + 1].x, cur[2 * it + 1].y, cur[2 * it + 1].z, cur[2 * it + 1].w};
+                uint4 hi, lo;
+                split8(x, hi, lo);
+                const int row = 32 * warp + 8 * it + rsub;
+                *reinterpret_cast<uint4*>(st + c * 2048 + row * 16) = hi;
+                *reinterpret_cast<uint4*>(st + LinTcSmem::A_BYTES + c * 2048 + row * 16) = lo;
+            }
+            fence_async_smem();
+            gt_warp_arrive(&full[stage]);
+            ++gt;
+            t = t_n;
+            kc = kc_n;
+            t_n = t_n2;
+            kc_n = kc_n2;
         }
     } else if (warp == 4) {
         // ================================================================= MMA issue (warp-uniform, elected lane)
@@ -187,41 +221,51 @@ __global__ void __launch_bounds__(GT_THREADS, 1) linear_tc_kernel(const LinTcPar
         }
     } else {
         // ================================================================= epilogue
+        // TMEM rows arrive one per thread; every 32 x 32 block is transposed through a padded per-warp smem tile so that
+        // global traffic is coalesced: lane = (row % 4, float4 of columns) -> 4 rows x 128 contiguous bytes per instruction.
         const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+        float* T = reinterpret_cast<float*>(smem + LinTcSmem::TRANS) + quad * (32 * 33);
+        const int rr = lane >> 3, cq = lane & 7;
         uint32_t tt = 0;
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tt) {
             const uint32_t buf = tt & 1;
             const long long mt = t / npass;
             const int pass = (int)(t - mt * npass);
-            const long long r = mt * 128 + 32 * quad + lane;
-            const bool valid = r < P.rows;
+            const long long r0 = mt * 128 + 32 * quad;
             mbar_wait(&acc_full[buf], (tt >> 1) & 1);
             fence_after_sync();
             for (int c0 = 0; c0 < P.nt; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_addr(tb, 32 * quad, 256 * buf + c0), v);
                 tmem_ld_wait32(v);
-                if (valid) {
-                    const int n0 = pass * P.nt + c0;
-                    float* yp = P.Y + r * P.N + n0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float o[4];
+                for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
+                __syncwarp();
+                const int n = pass * P.nt + c0 + 4 * cq;
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (P.bias) bv = __ldg(reinterpret_cast<const float4*>(P.bias + n));
+                float4 rv8[8];                    // the block's residual rows: all eight loads in flight at once
+                if (P.resid) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            float a = __uint_as_float(v[j + u]);
-                            if (P.bias) a += __ldg(P.bias + n0 + j + u);
-                            if (P.relu) a = fmaxf(a, 0.f);
-                            o[u] = a;
-                        }
-                        if (P.R) *reinterpret_cast<float4*>(P.R + r * P.N + n0 + j) = make_float4(o[0], o[1], o[2], o[3]);
-                        if (P.resid) {
-                            const float4 rv = *reinterpret_cast<const float4*>(P.resid + r * P.N + n0 + j);
-                            o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
-                        }
-                        *reinterpret_cast<float4*>(yp + j) = make_float4(o[0], o[1], o[2], o[3]);
+                    for (int i = 0; i < 8; ++i) {
+                        const long long r = r0 + 4 * i + rr;
+                        rv8[i] = r < P.rows ? *reinterpret_cast<const float4*>(P.resid + r * P.N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int lr = 4 * i + rr;
+                    const long long r = r0 + lr;
+                    float4 o = make_float4(T[lr * 33 + 4 * cq] + bv.x, T[lr * 33 + 4 * cq + 1] + bv.y, T[lr * 33 + 4 * cq + 2] + bv.z,
+                                           T[lr * 33 + 4 * cq + 3] + bv.w);
+                    if (P.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (r < P.rows) {
+                        if (P.R) *reinterpret_cast<float4*>(P.R + r * P.N + n) = o;
+                        if (P.resid) { o.x += rv8[i].x; o.y += rv8[i].y; o.z += rv8[i].z; o.w += rv8[i].w; }
+                        *reinterpret_cast<float4*>(P.Y + r * P.N + n) = o;
+                    }
+                }
+                __syncwarp();
             }
             fence_before_sync();
             gt_warp_arrive(&acc_empty[buf]);
@@ -300,7 +344,8 @@ struct GwTcSmem {
     static constexpr int A_BYTES = 128 * GT_KC * 2;
     static constexpr int B_BYTES = 256 * GT_KC * 2;
     static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int BARS = GT_STAGES * STAGE;
+    static constexpr int TRANS = GT_STAGES * STAGE;
+    static constexpr int BARS = TRANS + 4 * 32 * 33 * 4;
     static constexpr int TOTAL = BARS + 16 * 8 + 16;
 };
 
@@ -329,37 +374,61 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grad_weight_tc_kernel(const GwT
     const uint32_t tb = *tmem_slot;
 
     if (warp < 4) {
-        const int k = lane;                      // row of the chunk
-        const int part = warp;                   // quarter of the feature groups
-        const int a_groups = 16, b_groups = P.N / 8;
+        // Lane = (row % 8 of an 8-row block, feature group g % 4): a warp-wide load covers 8 rows x 128 contiguous bytes, a
+        // quarter-warp store 8 consecutive rows of one feature group (128 contiguous bytes of smem).  Warp w takes the
+        // (row block, group block) pairs w, w + 4, ...: A has 4 x 4 of them, B 4 x (N / 32); all loads of a chunk are
+        // issued before the first conversion.
+        const int ksub = lane & 7, gq = lane >> 3;
+        const int b_gblocks = P.N / 32;
         for (int c = 0; c < nchunks; ++c) {
             const int stage = c % GT_STAGES;
-            const long long r = r0 + (long long)c * GT_KC + k;
-            const bool valid = r < r1;
+            const long long rbase = r0 + (long long)c * GT_KC;
+            float4 va[8], vb[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {            // A: pair index pi = warp + 4 i -> (row block pi % 4, group block pi / 4)
+                const int pi = warp + 4 * i;
+                const int kb = pi & 3, gb = pi >> 2;
+                const long long r = rbase + 8 * kb + ksub;
+                const int g = 4 * gb + gq;
+                const bool ok = r < r1 && (m0 + 8 * g < P.Mtot);
+                const float4* src = reinterpret_cast<const float4*>(P.A + (ok ? r : 0) * P.lda + m0 + 8 * g);
+                va[2 * i] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                va[2 * i + 1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {            // B: up to 4 x 8 pairs
+                const int pi = warp + 4 * i;
+                const int kb = pi & 3, gb = pi >> 2;
+                const long long r = rbase + 8 * kb + ksub;
+                const int g = 4 * gb + gq;
+                const bool ok = r < r1 && gb < b_gblocks;
+                const float4* src = reinterpret_cast<const float4*>(P.B + (ok ? r : 0) * P.N + (ok ? 8 * g : 0));
+                vb[2 * i] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[2 * i + 1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             if (c >= GT_STAGES) mbar_wait(&empty[stage], ((c / GT_STAGES) - 1) & 1);
             uint8_t* st = smem + stage * GwTcSmem::STAGE;
-            const float* ap = P.A + (valid ? r : 0) * P.lda + m0;
-            const float* bp = P.B + (valid ? r : 0) * P.N;
-            for (int g = part; g < a_groups; g += 4) {
-                float x[8];
-                const bool gv = valid && (m0 + 8 * g < P.Mtot);
-                const float4 v0 = gv ? __ldg(reinterpret_cast<const float4*>(ap + 8 * g)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 v1 = gv ? __ldg(reinterpret_cast<const float4*>(ap + 8 * g) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int pi = warp + 4 * i;
+                const int k = 8 * (pi & 3) + ksub, g = 4 * (pi >> 2) + gq;
+                const float x[8] = {va[2 * i].x, va[2 * i].y, va[2 * i].z, va[2 * i].w, va[2 * i + 1].x, va[2 * i + 1].y, va[2 * i + 1].z, va[2 * i + 1].w};
                 uint4 hi, lo;
                 split8(x, hi, lo);
                 *reinterpret_cast<uint4*>(st + g * (GT_KC * 16) + k * 16) = hi;
                 *reinterpret_cast<uint4*>(st + GwTcSmem::A_BYTES + g * (GT_KC * 16) + k * 16) = lo;
             }
-            for (int g = part; g < b_groups; g += 4) {
-                float x[8];
-                const float4 v0 = valid ? __ldg(reinterpret_cast<const float4*>(bp + 8 * g)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 v1 = valid ? __ldg(reinterpret_cast<const float4*>(bp + 8 * g) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-                uint4 hi, lo;
-                split8(x, hi, lo);
-                *reinterpret_cast<uint4*>(st + 2 * GwTcSmem::A_BYTES + g * (GT_KC * 16) + k * 16) = hi;
-                *reinterpret_cast<uint4*>(st + 2 * GwTcSmem::A_BYTES + GwTcSmem::B_BYTES + g * (GT_KC * 16) + k * 16) = lo;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int pi = warp + 4 * i;
+                if ((pi >> 2) < b_gblocks) {
+                    const int k = 8 * (pi & 3) + ksub, g = 4 * (pi >> 2) + gq;
+                    const float x[8] = {vb[2 * i].x, vb[2 * i].y, vb[2 * i].z, vb[2 * i].w, vb[2 * i + 1].x, vb[2 * i + 1].y, vb[2 * i + 1].z, vb[2 * i + 1].w};
+                    uint4 hi, lo;
+                    split8(x, hi, lo);
+                    *reinterpret_cast<uint4*>(st + 2 * GwTcSmem::A_BYTES + g * (GT_KC * 16) + k * 16) = hi;
+                    *reinterpret_cast<uint4*>(st + 2 * GwTcSmem::A_BYTES + GwTcSmem::B_BYTES + g * (GT_KC * 16) + k * 16) = lo;
+                }
             }
             fence_async_smem();
             gt_warp_arrive(&full[stage]);
@@ -391,17 +460,23 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grad_weight_tc_kernel(const GwT
         }
     } else if (nchunks > 0) {
         const int quad = warp & 3;
-        const int m = m0 + 32 * quad + lane;
+        float* T = reinterpret_cast<float*>(smem + GwTcSmem::TRANS) + quad * (32 * 33);
         mbar_wait(acc_full, 0);
         fence_after_sync();
         for (int c0 = 0; c0 < P.N; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_addr(tb, 32 * quad, c0), v);
             tmem_ld_wait32(v);
-            if (m < P.Mtot) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(P.dW + (long long)m * P.N + c0 + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
+            __syncwarp();
+            // lane = column: one 128-byte reduction per row and instruction
+#pragma unroll 4
+            for (int lr = 0; lr < 32; ++lr) {
+                const int m = m0 + 32 * quad + lr;
+                if (m < P.Mtot) atomicAdd(P.dW + (long long)m * P.N + c0 + lane, T[lr * 33 + lane]);
             }
+            __syncwarp();
         }
     }
     fence_before_sync();
@@ -410,7 +485,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grad_weight_tc_kernel(const GwT
 }
 
 bool grad_weight_tc_eligible(long long rows, int M, int N) {
-    return gemm_tc_on() && rows >= 2048 && M % 8 == 0 && M >= 64 && N % 32 == 0 && N >= 32 && N <= 256;
+    return gemm_tc_on() && rows >= 2048 && M % 32 == 0 && M >= 64 && N % 32 == 0 && N >= 32 && N <= 256;
 }
 
 // dW (M, N) += dY (rows, M)^T X (rows, N)
