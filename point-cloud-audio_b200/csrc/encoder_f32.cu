@@ -113,7 +113,7 @@ int launch_linear(const float* X, const float* W, const float* b, float* Y, long
 template <int DH>
 __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstride,
                                 const float* __restrict__ KV, int nq, int nk, int D, int tq_log,
-                                int tk, int nsplit, int chunk, float scale_log2e,
+                                int tk, int nsplit, int chunk, int q_tiles, float scale_log2e,
                                 float* __restrict__ O, float* __restrict__ part,
                                 const int* __restrict__ key_counts, float* __restrict__ lse) {
     extern __shared__ __align__(16) float kv_s[];     // tk rows x (2D + 4)
@@ -122,14 +122,22 @@ __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstrid
     const int TQ = 1 << tq_log, KS = 32 >> tq_log;
     const int ql = lane & (TQ - 1), ks = lane >> tq_log;
     const int b = blockIdx.z, split = blockIdx.y;
-    const int q = blockIdx.x * TQ + ql;
-    const bool qvalid = q < nq;
     const int rs = 2 * D + 4;                          // padded smem row stride (floats)
+    // q_tiles > 1 only when the key set is a single smem tile: it is staged once and reused by every query tile of the block
+  for (int qt = 0; qt < q_tiles; ++qt) {
+    if ((blockIdx.x * q_tiles + qt) * TQ >= nq) break;   // block-uniform
+    const int q = (blockIdx.x * q_tiles + qt) * TQ + ql;
+    const bool qvalid = q < nq;
 
     float qv[DH], acc[DH];
     const float* qptr = Qp + (long long)b * q_bstride + (long long)(qvalid ? q : 0) * D + h * DH;
+    // per-thread rows: 16-byte accesses (a warp touches 32 different rows; scalar accesses would cost 4x the LSU wavefronts)
 #pragma unroll
-    for (int j = 0; j < DH; ++j) { qv[j] = __ldg(qptr + j) * scale_log2e; acc[j] = 0.f; }
+    for (int j = 0; j < DH; j += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(qptr + j));
+        qv[j] = t.x * scale_log2e; qv[j + 1] = t.y * scale_log2e; qv[j + 2] = t.z * scale_log2e; qv[j + 3] = t.w * scale_log2e;
+        acc[j] = acc[j + 1] = acc[j + 2] = acc[j + 3] = 0.f;
+    }
     float m = -INFINITY, l = 0.f;
 
     // variable-size sets: only the first key_counts[b] keys of the padded set take part
@@ -142,6 +150,7 @@ __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstrid
         const int tn = min(tk, k_end - kt);
         // cooperative, coalesced float4 load of tn rows x 2D floats
         const int vec_per_row = (2 * D) >> 2;
+        if (qt == 0)
         for (int i = threadIdx.x; i < tn * vec_per_row; i += blockDim.x) {
             const int r = i / vec_per_row, c = i - r * vec_per_row;
             const float4 v = __ldg(reinterpret_cast<const float4*>(kvb + (long long)(kt + r) * 2 * D) + c);
@@ -192,7 +201,7 @@ __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstrid
                 }
             }
         }
-        __syncthreads();
+        if (q_tiles == 1) __syncthreads();
     }
 
     // merge the key slices of one query across lanes (xor over the slice bits)
@@ -210,12 +219,15 @@ __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstrid
         }
         m = mn;
     }
-    if (!qvalid || ks != 0) return;
+    if (!qvalid || ks != 0) continue;
     if (nsplit == 1) {
         const float inv = 1.f / l;
         float* o = O + ((long long)b * nq + q) * D + h * DH;
 #pragma unroll
-        for (int j = 0; j < DH; ++j) o[j] = __ldg(qptr + j) + acc[j] * inv;
+        for (int j = 0; j < DH; j += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(qptr + j));
+            *reinterpret_cast<float4*>(o + j) = make_float4(t.x + acc[j] * inv, t.y + acc[j + 1] * inv, t.z + acc[j + 2] * inv, t.w + acc[j + 3] * inv);
+        }
         if (lse) lse[((long long)b * nq + q) * H + h] = m + log2f(l);      // log2 of sum_k 2^(s_k), s in the scaled log2 domain
     } else {
         float* pp = part + ((((long long)b * nsplit + split) * nq + q) * H + h) * (DH + 2);
@@ -223,6 +235,7 @@ __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstrid
 #pragma unroll
         for (int j = 0; j < DH; ++j) pp[2 + j] = acc[j];
     }
+  }
 }
 
 template <int DH>
@@ -300,7 +313,14 @@ static int launch_attn_t(const float* Qp, long long q_bstride, const float* KV, 
                          int D, int H, float* O, float* part, const int* key_counts, cudaStream_t st, float* lse) {
     const AttnPlan p = plan_attn(B, nq, nk, D, H);
     const int tq = 1 << p.tq_log;
-    dim3 grid((nq + tq - 1) / tq, p.nsplit, B);
+    // key set in one smem tile: stage it once per block and walk several query tiles (keeps >= ~8 blocks per SM)
+    const int q_blocks = (nq + tq - 1) / tq;
+    int q_tiles = 1;
+    if (p.nsplit == 1 && nk <= p.tk && key_counts == nullptr) {
+        const long long qt = ((long long)q_blocks * B) / (148LL * 8);
+        q_tiles = (int)(qt < 1 ? 1 : (qt > 16 ? 16 : qt));
+    }
+    dim3 grid((q_blocks + q_tiles - 1) / q_tiles, p.nsplit, B);
     const float scale_log2e = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
     if (p.smem > 48 * 1024)
         PCA_CHECK_CUDA(cudaFuncSetAttribute(attn_f32_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
@@ -308,7 +328,7 @@ static int launch_attn_t(const float* Qp, long long q_bstride, const float* KV, 
         LaunchTimer lt("attn_f32_kernel", st, 4.0 * B * nq * (double)nk * D,
                        4.0 * ((double)B * nk * 2 * D + 2.0 * B * nq * D));
         attn_f32_kernel<DH><<<grid, 32 * H, p.smem, st>>>(Qp, q_bstride, KV, nq, nk, D, p.tq_log, p.tk,
-                                                          p.nsplit, p.chunk, scale_log2e, O, part, key_counts, lse);
+                                                          p.nsplit, p.chunk, q_tiles, scale_log2e, O, part, key_counts, lse);
     }
     PCA_CHECK_LAUNCH("attn_f32_kernel");
     if (p.nsplit > 1) {

@@ -201,6 +201,26 @@ __global__ void attn_delta_kernel(const float* __restrict__ dO, const float* __r
     delta[i] = s;
 }
 
+// Same, one warp per (b, q) row with the lanes along D (coalesced): needs D % 32 == 0 and 32 % H == 0, so that a head is a
+// group of 32 / H adjacent lanes.
+__global__ void attn_delta_warp_kernel(const float* __restrict__ dO, const float* __restrict__ O, const float* __restrict__ Qp,
+                                       long long q_bstride, int nq, int D, int H, long long rows, float* __restrict__ delta) {
+    const long long bq = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (bq >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int per = D >> 5;                         // consecutive elements per lane
+    const int q = (int)(bq % nq);
+    const long long b = bq / nq;
+    const float* o = O + bq * D + lane * per;
+    const float* g = dO + bq * D + lane * per;
+    const float* qp = Qp + b * q_bstride + (long long)q * D + lane * per;
+    float s = 0.f;
+    for (int j = 0; j < per; ++j) s = fmaf(g[j], o[j] - __ldg(qp + j), s);
+    const int lph = 32 / H;                         // lanes per head
+    for (int off = 1; off < lph; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((lane & (lph - 1)) == 0) delta[bq * H + lane / lph] = s;
+}
+
 __device__ __forceinline__ uint32_t dropout_bits(unsigned long long seed, unsigned long long idx) {
     unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);        // splitmix64 finaliser as a counter-based generator
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -223,6 +243,11 @@ static int launch_dropout(const float* in, float* out, long long n, float p, uns
     return 0;
 }
 
+// 16-byte vector reduction (REDG.ADD.F32x4): one L2 operation for four adjacent floats
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ------------------------------------------------------------------------------------ attention backward
 // Warp = head.  Lane = (dim slice g of G, own item, loop slice): an "own" item (MODE 0: a query -> dQp; MODE 1: a key -> dKp,
 // dVp) keeps its DH = G*DL head dims in the registers of G adjacent lanes; the "loop" items (MODE 0: keys; MODE 1: queries)
@@ -230,7 +255,7 @@ static int launch_dropout(const float* in, float* out, long long n, float p, uns
 template <int DL, int G, int MODE>
 __global__ void attn_bwd_kernel(const float* __restrict__ Qp, long long q_bstride, const float* __restrict__ KV,
                                 const float* __restrict__ dO, const float* __restrict__ lse, const float* __restrict__ delta,
-                                int nq, int nk, int D, int town_log, int tl, int chunk, float scale, float scale_log2e,
+                                int nq, int nk, int D, int town_log, int tl, int chunk, int own_tiles, float scale, float scale_log2e,
                                 float* __restrict__ dQp, float* __restrict__ dKV) {
     extern __shared__ __align__(16) float rows_s[];
     constexpr int DH = DL * G;
@@ -244,12 +269,15 @@ __global__ void attn_bwd_kernel(const float* __restrict__ Qp, long long q_bstrid
     const int b = blockIdx.z;
     const int n_own = MODE == 0 ? nq : nk;
     const int n_loop = MODE == 0 ? nk : nq;
-    const int own = blockIdx.x * TOWN + own_l;
-    const bool ovalid = own < n_own;
-    const int oc = ovalid ? own : 0;
     const int H2 = (2 * H + 3) & ~3;
     const int rs = MODE == 0 ? 2 * D + 4 : 2 * D + H2 + 4;        // smem row stride (floats)
     const int hoff = h * DH + g * DL;
+    // own_tiles > 1 only when the loop set is a single smem tile (staged once, reused by every own tile of the block)
+  for (int ot = 0; ot < own_tiles; ++ot) {
+    const int own = (blockIdx.x * own_tiles + ot) * TOWN + own_l;
+    if ((blockIdx.x * own_tiles + ot) * TOWN >= n_own) break;      // block-uniform
+    const bool ovalid = own < n_own;
+    const int oc = ovalid ? own : 0;
 
     float a0[DL], a1[DL], acc0[DL], acc1[DL];
     float lse_o = 0.f, delta_o = 0.f;
@@ -257,20 +285,34 @@ __global__ void attn_bwd_kernel(const float* __restrict__ Qp, long long q_bstrid
         const float* qp = Qp + (long long)b * q_bstride + (long long)oc * D + hoff;
         const float* gp = dO + ((long long)b * nq + oc) * D + hoff;
 #pragma unroll
-        for (int j = 0; j < DL; ++j) { a0[j] = __ldg(qp + j) * scale_log2e; a1[j] = __ldg(gp + j); acc0[j] = 0.f; acc1[j] = 0.f; }
+        for (int j = 0; j < DL; j += 4) {           // per-thread rows: 16-byte accesses
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(qp + j)), t1 = __ldg(reinterpret_cast<const float4*>(gp + j));
+            a0[j] = t0.x * scale_log2e; a0[j + 1] = t0.y * scale_log2e; a0[j + 2] = t0.z * scale_log2e; a0[j + 3] = t0.w * scale_log2e;
+            a1[j] = t1.x; a1[j + 1] = t1.y; a1[j + 2] = t1.z; a1[j + 3] = t1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < DL; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
         lse_o = __ldg(lse + ((long long)b * nq + oc) * H + h);
         delta_o = __ldg(delta + ((long long)b * nq + oc) * H + h);
     } else {
         const float* kp = KV + ((long long)b * nk + oc) * 2 * D + hoff;
 #pragma unroll
-        for (int j = 0; j < DL; ++j) { a0[j] = __ldg(kp + j); a1[j] = __ldg(kp + D + j); acc0[j] = 0.f; acc1[j] = 0.f; }
+        for (int j = 0; j < DL; j += 4) {
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(kp + j)), t1 = __ldg(reinterpret_cast<const float4*>(kp + D + j));
+            a0[j] = t0.x; a0[j + 1] = t0.y; a0[j + 2] = t0.z; a0[j + 3] = t0.w;
+            a1[j] = t1.x; a1[j + 1] = t1.y; a1[j + 2] = t1.z; a1[j + 3] = t1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < DL; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
     }
 
     const int l_begin = blockIdx.y * chunk;
     const int l_end = min(n_loop, l_begin + chunk);
     for (int lt = l_begin; lt < l_end; lt += tl) {
         const int tn = min(tl, l_end - lt);
-        if (MODE == 0) {
+        if (ot > 0) {
+            // the single loop tile is already staged
+        } else if (MODE == 0) {
             const int vec_per_row = (2 * D) >> 2;
             const float* kvb = KV + ((long long)b * nk + lt) * 2 * D;
             for (int i = threadIdx.x; i < tn * vec_per_row; i += blockDim.x) {
@@ -324,7 +366,7 @@ __global__ void attn_bwd_kernel(const float* __restrict__ Qp, long long q_bstrid
                 for (int j = 0; j < DL; ++j) { acc0[j] = fmaf(ds, qr[j], acc0[j]); acc1[j] = fmaf(p, gr[j], acc1[j]); }
             }
         }
-        __syncthreads();
+        if (own_tiles == 1) __syncthreads();
     }
     // merge the loop slices of one own item across lanes
     for (int off = G * TOWN; off < 32; off <<= 1) {
@@ -334,16 +376,21 @@ __global__ void attn_bwd_kernel(const float* __restrict__ Qp, long long q_bstrid
             if (MODE == 1) acc1[j] += __shfl_xor_sync(0xffffffffu, acc1[j], off);
         }
     }
-    if (!ovalid || ls != 0) return;
-    if (MODE == 0) {
-        float* o = dQp + ((long long)b * nq + own) * D + hoff;
+    if (ovalid && ls == 0) {
+        if (MODE == 0) {
+            float* o = dQp + ((long long)b * nq + own) * D + hoff;
 #pragma unroll
-        for (int j = 0; j < DL; ++j) atomicAdd(o + j, acc0[j]);
-    } else {
-        float* o = dKV + ((long long)b * nk + own) * 2 * D + hoff;
+            for (int j = 0; j < DL; j += 4) red_add4(o + j, acc0[j], acc0[j + 1], acc0[j + 2], acc0[j + 3]);
+        } else {
+            float* o = dKV + ((long long)b * nk + own) * 2 * D + hoff;
 #pragma unroll
-        for (int j = 0; j < DL; ++j) { atomicAdd(o + j, acc0[j]); atomicAdd(o + D + j, acc1[j]); }
+            for (int j = 0; j < DL; j += 4) {
+                red_add4(o + j, acc0[j], acc0[j + 1], acc0[j + 2], acc0[j + 3]);
+                red_add4(o + D + j, acc1[j], acc1[j + 1], acc1[j + 2], acc1[j + 3]);
+            }
+        }
     }
+  }
 }
 
 template <int DL, int G, int MODE>
@@ -373,7 +420,14 @@ static int launch_attn_bwd_t(const float* Qp, long long q_bstride, const float* 
     int chunk = (n_loop + nsplit - 1) / nsplit;
     chunk = (chunk + tl - 1) / tl * tl;
     nsplit = (n_loop + chunk - 1) / chunk;
-    dim3 grid((n_own + town - 1) / town, nsplit, B);
+    // the whole loop set in one smem tile: a block stages it once and walks several own tiles (keeps >= ~8 blocks per SM)
+    const int own_blocks = (n_own + town - 1) / town;
+    int own_tiles = 1;
+    if (nsplit == 1 && n_loop <= tl) {
+        long long ot = ((long long)own_blocks * B) / (148LL * 8);
+        own_tiles = (int)(ot < 1 ? 1 : (ot > 16 ? 16 : ot));
+    }
+    dim3 grid((own_blocks + own_tiles - 1) / own_tiles, nsplit, B);
     const float scale = 1.0f / sqrtf((float)D);
     if (smem > 48 * 1024)
         PCA_CHECK_CUDA((cudaFuncSetAttribute(attn_bwd_kernel<DL, G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
@@ -381,7 +435,7 @@ static int launch_attn_bwd_t(const float* Qp, long long q_bstride, const float* 
         LaunchTimer lt(MODE == 0 ? "attn_bwd_dq_kernel" : "attn_bwd_dkv_kernel", st, (MODE == 0 ? 6.0 : 8.0) * B * nq * (double)nk * D,
                        4.0 * ((double)B * nk * 2 * D + 3.0 * B * nq * D));
         attn_bwd_kernel<DL, G, MODE><<<grid, 32 * H, smem, st>>>(Qp, q_bstride, KV, dO, lse, delta, nq, nk, D, town_log, tl, chunk,
-                                                                scale, scale * 1.4426950408889634f, dQp, dKV);
+                                                                own_tiles, scale, scale * 1.4426950408889634f, dQp, dKV);
     }
     PCA_CHECK_LAUNCH("attn_bwd_kernel");
     return 0;
@@ -467,7 +521,10 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
     PCA_TRY(launch_grad_input(dZ, m.Wo, dO, dOut, rq, D, D, st, img, ib));
     {
         const long long total = rq * H;
-        attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dO, s.O, s.Qp, q_bstride, nq, D, D / H, total, delta);
+        if (D % 32 == 0 && 32 % H == 0)
+            attn_delta_warp_kernel<<<(unsigned)((rq + 7) / 8), 256, 0, st>>>(dO, s.O, s.Qp, q_bstride, nq, D, H, rq, delta);
+        else
+            attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dO, s.O, s.Qp, q_bstride, nq, D, D / H, total, delta);
         PCA_CHECK_LAUNCH("attn_delta_kernel");
     }
     PCA_CHECK_CUDA(cudaMemsetAsync(dKV, 0, (size_t)rk * 2 * D * sizeof(float), st));
