@@ -178,6 +178,27 @@ int pca_deepset_fwd_masked_f32(const float* X, const int32_t* counts, int B, int
                                int out_dim, int pool, const float* params, float* out, void* workspace,
                                size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------- random-K / importance subsampling
+ * ESC_pc_temp_randKSS (Code/dataset.py:230-238), pc_randK (Code/utils.py:55-82): a uniformly random K-subset in random
+ * order = the K largest of i.i.d. uniform keys -> pca_random_keys_f32 (counter-based generator, keys in (0,1)) followed by
+ * pca_topk_compact_f32 (indices only) and pca_gather_points_f32.  numpy's permutation stream cannot be reproduced: parity
+ * is distributional.
+ * ESC_pc_temp_importancerandKSS (Code/dataset.py:276-290): pca_importance_map_f32 computes
+ *   heat (n_clouds, nf, nt) [t fastest = g.view(-1) of the reference] =
+ *       conv2d(|d x/d f| + |d x/d t|, kf kt^T, padding='same') + 1e-6,   x(f, t) = logmag[c, t, f], torch.gradient rule,
+ * kf (wf) / kt (wt) the two Kaiser windows (wf = 2, wt = winF in the reference); scratch: n_clouds*nf*nt floats.
+ * choice 1 = pca_topk_compact_f32 on the heat map; choice 0 = pca_multinomial_f32 (K draws with replacement from
+ * weights / sum(weights); cdf_scratch: n_clouds*n doubles).  NOTE the reference indexes the (t-major) cloud with the
+ * (f-major) heat-map index; pca_gather_points_f32 takes flat indices in CLOUD order p = t*nf + f, so passing the heat-map
+ * indices unchanged reproduces the reference's behaviour.  idx < 0 gathers a zero row. */
+int pca_random_keys_f32(float* keys, long long n, unsigned long long seed, void* stream);
+int pca_gather_points_f32(const float* logmag, int n_clouds, int nf, int nt, const float* farr, const float* tarr,
+                          const int32_t* idx, int K, float* pts, void* stream);
+int pca_importance_map_f32(const float* logmag, int n_clouds, int nf, int nt, const float* kf, int wf, const float* kt,
+                           int wt, float* heat, float* scratch, void* stream);
+int pca_multinomial_f32(const float* weights, int n_clouds, int n, int K, unsigned long long seed, double* cdf_scratch,
+                        int32_t* idx, void* stream);
+
 /* ---------------------------------------------------------------- training (fp32, every dim; ln = 0)
  * The reference trains these models with loss.backward() + torch.optim.Adam under nn.DataParallel
  * (Code/settransformer.py:89-109, Code/settransformertemp.py:110-128, set_transformer-master/main_pointcloud.py:61-79).

@@ -185,6 +185,51 @@ def cloud_3d_maxk_f64(x, farr, tarr, idx, k) -> tuple[np.ndarray, np.ndarray]:
     return pc[order, :], order
 
 
+def cloud_3d_randk_f64(x, farr, tarr, idx, k, rng=np.random):
+    """``ESC_pc_temp_randKSS.__getitem__``: full cloud, then ``np.random.permutation(P)[:K]`` rows (a uniformly random
+    K-subset in random order), float64 (K, 3).  Code/dataset.py:230-238.  ``rng`` is numpy's global generator in the
+    reference; pass a RandomState to reproduce a seeded run.  Also returns the flat indices."""
+    pc = cloud_3d_f64(x, farr, tarr, idx)
+    order = rng.permutation(pc.shape[0])[:k]
+    return pc[order, :], order
+
+
+def pc_randk(x: np.ndarray, farr: np.ndarray, kmax: int, rng=np.random):
+    """``utils.pc_randK``: per frame a random K-subset of the spectrum -> (mags (K,T), freqs (K,T)).  Code/utils.py:55-82."""
+    xs, fs_ = [], []
+    for t in range(x.shape[1]):
+        order = rng.permutation(x.shape[0])[:kmax]
+        xs.append(x[order, t])
+        fs_.append(farr[order])
+    return np.stack(xs, axis=1), np.stack(fs_, axis=1)
+
+
+def importance_heat(xt: np.ndarray, winf: int) -> np.ndarray:
+    """Heat map of ``ESC_pc_temp_importancerandKSS`` (Code/dataset.py:280-283): |d/df| + |d/dt| of the (Nf, Nt)
+    log-magnitudes by ``torch.gradient`` (unit spacing, one-sided at the edges), smoothed by the 2 x winF outer product
+    of periodic Kaiser windows (beta 5.09) with ``conv2d(padding='same')``, plus 1e-6.  float32 (Nf, Nt)."""
+    t = torch.as_tensor(np.ascontiguousarray(xt))
+    g = torch.gradient(t)
+    g = g[0].abs() + g[1].abs()
+    k = (torch.kaiser_window(window_length=2, periodic=True, beta=5.09)[:, None]
+         @ torch.kaiser_window(window_length=winf, periodic=True, beta=5.09)[None, :])
+    return (torch.nn.functional.conv2d(g[None, None, ...], k[None, None], padding="same")[0, 0] + 1.0e-6).numpy()
+
+
+def cloud_3d_importance_f64(x, farr, tarr, idx, k, winf, choice=1, generator=None):
+    """``ESC_pc_temp_importancerandKSS.__getitem__`` (Code/dataset.py:276-290): choice 1 keeps the K largest heat-map
+    entries (``(-g.view(-1)).argsort()[:K]``), choice 0 draws K of them with ``torch.multinomial(..., replacement=True)``.
+    As in the reference the heat map is flattened f-major (index f*Nt + t) while the cloud rows are t-major
+    (p = t*Nf + f), and the heat-map index is used on the cloud rows unchanged.  Returns (rows (K,3) float64, indices)."""
+    pc = cloud_3d_f64(x, farr, tarr, idx)
+    g = importance_heat(x[:, :, idx], winf)
+    if choice == 0:
+        order = torch.multinomial(torch.from_numpy(g).view(-1), k, replacement=True, generator=generator).numpy()
+    else:
+        order = topk_order(g.reshape(-1), k)
+    return pc[order, :], order
+
+
 def pc_maxk(x: np.ndarray, farr: np.ndarray, kmax: int):
     """``utils.pc_maxK``: per-frame top-K of the spectrum -> (mags (K,T), freqs (K,T)).
     Code/utils.py:25-52 (keys are the float32 spectrum column)."""

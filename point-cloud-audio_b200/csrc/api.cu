@@ -18,6 +18,11 @@ int launch_layernorm(float*, long long, int, const float*, const float*, cudaStr
 int launch_pool(const float*, int, int, int, int, float*, const int*, cudaStream_t);
 int launch_fused_frontend(const float*, int, int, int, int, const float*, const float*, float, int, int, const float*, const float*,
                           int, int, int, float, float*, int32_t*, int32_t*, cudaStream_t);
+// subsampling (sampling.cu)
+int launch_random_keys(float*, long long, unsigned long long, cudaStream_t);
+int launch_gather_points(const float*, int, int, int, const float*, const float*, const int32_t*, int, float*, cudaStream_t);
+int launch_importance_map(const float*, int, int, int, const float*, int, const float*, int, float*, float*, cudaStream_t);
+int launch_multinomial(const float*, int, int, int, unsigned long long, double*, int32_t*, cudaStream_t);
 // training path (encoder_train.cu)
 size_t st_train_saved_bytes(const pca_st_dims* d, int B, int N, float dropout_p);
 size_t st_train_ws_bytes(const pca_st_dims* d, int B, int N);
@@ -613,6 +618,28 @@ int pca_debug_st_stages(const float* X, int B, int N, const pca_st_dims* dims, c
     if (!st_tc_supported(dims, N)) return fail(PCA_EUNSUPPORTED, "ST stages: dims not supported by the tcgen05 path");
     return st_tc_forward_stages(X, B, N, dims, params, logits, H1, Y1, H2, Y2, pooled, workspace, workspace_bytes,
                                 (cudaStream_t)stream);
+}
+
+int pca_random_keys_f32(float* keys, long long n, unsigned long long seed, void* stream) {
+    if (!keys && n > 0) return fail(PCA_EINVAL, "random_keys: null pointer");
+    return launch_random_keys(keys, n, seed, (cudaStream_t)stream);
+}
+int pca_gather_points_f32(const float* logmag, int n_clouds, int nf, int nt, const float* farr, const float* tarr,
+                          const int32_t* idx, int K, float* pts, void* stream) {
+    if (!logmag || !farr || !idx || !pts) return fail(PCA_EINVAL, "gather_points: null pointer");
+    if (n_clouds < 0 || nf <= 0 || nt <= 0 || K < 0) return fail(PCA_EINVAL, "gather_points: bad shape");
+    return launch_gather_points(logmag, n_clouds, nf, nt, farr, tarr, idx, K, pts, (cudaStream_t)stream);
+}
+int pca_importance_map_f32(const float* logmag, int n_clouds, int nf, int nt, const float* kf, int wf, const float* kt, int wt,
+                           float* heat, float* scratch, void* stream) {
+    if (!logmag || !kf || !kt || !heat || !scratch) return fail(PCA_EINVAL, "importance_map: null pointer");
+    if (n_clouds < 0 || nf <= 0 || nt <= 0) return fail(PCA_EINVAL, "importance_map: bad shape");
+    return launch_importance_map(logmag, n_clouds, nf, nt, kf, wf, kt, wt, heat, scratch, (cudaStream_t)stream);
+}
+int pca_multinomial_f32(const float* weights, int n_clouds, int n, int K, unsigned long long seed, double* cdf_scratch,
+                        int32_t* idx, void* stream) {
+    if (!weights || !cdf_scratch || !idx) return fail(PCA_EINVAL, "multinomial: null pointer");
+    return launch_multinomial(weights, n_clouds, n, K, seed, cdf_scratch, idx, (cudaStream_t)stream);
 }
 
 size_t pca_st_train_saved_bytes(const pca_st_dims* dims, int B, int N, float dropout_p) {

@@ -266,7 +266,10 @@ struct RParams {
 
 // One 32-column chunk of the online softmax: p = 2^(s - m) as bf16 pairs, partial row sum (packed fp32x2 math).
 // pairs of each 32-column chunk whose exponentials run on the FMA pipe (polynomial) instead of MUFU: 6 of 16
-constexpr uint32_t kPolyPairs = 0x0u;      // measured: no gain while the kernels are latency- rather than MUFU-bound
+#ifndef PCA_POLY5
+#define PCA_POLY5 0x0u
+#endif
+constexpr uint32_t kPolyPairs = PCA_POLY5;      // measured: no gain while the kernels are latency- rather than MUFU-bound
 __device__ __forceinline__ void exp_chunk32(const uint32_t* v, const float2 neg_m2, float2& sum2, uint32_t* pk) {
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {

@@ -153,3 +153,59 @@ class ESC_pc_temp_maxKSS(ESC_pc_temp):
         pc = np.stack([np.asarray(self.farr, dtype=np.float64)[f], np.asarray(self.tarr, dtype=np.float64)[t],
                        np.asarray(self.x)[f, t, idx].astype(np.float64)], axis=1)
         return torch.tensor(pc), torch.tensor(self.labels[idx])
+
+
+class ESC_pc_temp_randKSS(ESC_pc_temp):
+    """3ST dataset with random-K subsampling (Code/dataset.py:205-238): K random points of the cloud.  The subset and its
+    order come from the CUDA path (counter-based uniform keys + radix select, ``frontend.random_points``); a fresh draw is
+    made every epoch (every ``resample()`` / first access), numpy's generator is not involved.  Items are float64
+    (K, 3) tensors gathered from the caller's arrays, as in the reference."""
+
+    def __init__(self, x, y, farr, tarr, K, device=None, seed=0):
+        super().__init__(x, y, farr, tarr, device)
+        self.K = K
+        self.seed = int(seed)
+        self._idx_host = None
+
+    def resample(self):
+        from .frontend import random_points
+        self.seed += 1
+        self._pts_sel, idx = random_points(self._logmag(), self.farr, self.tarr, self.K, seed=self.seed)
+        self._idx_host = idx.cpu().numpy().astype(np.int64)
+
+    def _ensure(self):
+        if self._idx_host is None:
+            self.resample()
+
+    def cuda_batch(self, indices):
+        self._ensure()
+        return self._pts_sel[torch.as_tensor(indices, device=self._device, dtype=torch.long)]
+
+    def indices(self, idx) -> np.ndarray:
+        self._ensure()
+        return self._idx_host[idx]
+
+    def __getitem__(self, idx):
+        order = self.indices(idx)
+        nf = np.asarray(self.farr).shape[0]
+        f, t = order % nf, order // nf
+        pc = np.stack([np.asarray(self.farr, dtype=np.float64)[f], np.asarray(self.tarr, dtype=np.float64)[t],
+                       np.asarray(self.x)[f, t, idx].astype(np.float64)], axis=1)
+        return torch.tensor(pc), torch.tensor(self.labels[idx])
+
+
+class ESC_pc_temp_importancerandKSS(ESC_pc_temp_randKSS):
+    """3ST dataset with importance subsampling (Code/dataset.py:240-290): heat map = smoothed |gradient| of the
+    spectrogram; ``choice`` 1 keeps the K hottest entries (deterministic, equals the reference on tie-free inputs),
+    ``choice`` 0 samples K with replacement (torch.multinomial in the reference; here a counter-based generator)."""
+
+    def __init__(self, x, y, farr, tarr, K, choice, winF, device=None, seed=0):
+        super().__init__(x, y, farr, tarr, K, device, seed)
+        self.choice = choice
+        self.winF = winF
+
+    def resample(self):
+        from .frontend import importance_points
+        self.seed += 1
+        self._pts_sel, idx = importance_points(self._logmag(), self.farr, self.tarr, self.K, self.winF, self.choice, seed=self.seed)
+        self._idx_host = idx.cpu().numpy().astype(np.int64)

@@ -170,3 +170,89 @@ def spectral_point_cloud(audio: torch.Tensor, *, n_fft: int, sr: float, win_leng
         pts, idx = topk_points(logmag, farr, tarr, min(int(top_k), n_pts), sorted_desc)
     counts = torch.full((B * chunks,), pts.shape[1], dtype=torch.int32, device=audio.device)
     return pts, counts, idx
+
+
+# ------------------------------------------------------------------------------------ random-K / importance subsampling
+def _tables(farr, tarr, dev):
+    f_t = farr if isinstance(farr, torch.Tensor) else rt.coord_table(farr, dev)
+    t_t = None if tarr is None else (tarr if isinstance(tarr, torch.Tensor) else rt.coord_table(tarr, dev))
+    return f_t, t_t
+
+
+def gather_points(logmag: torch.Tensor, farr, tarr, idx: torch.Tensor) -> torch.Tensor:
+    """Rows (f[, t], mag) of the flat cloud indices p = t*nf + f in idx (n, K) int32; idx < 0 gives a zero row."""
+    rt.require_cuda(logmag, "gather_points")
+    logmag = rt.f32c(logmag)
+    if logmag.dim() == 2:
+        logmag = logmag.unsqueeze(1)
+    n, nt, nf = logmag.shape
+    dev = logmag.device
+    f_t, t_t = _tables(farr, tarr, dev)
+    idx = idx.to(device=dev, dtype=torch.int32).contiguous()
+    K = idx.shape[1]
+    pts = torch.empty((n, K, 2 if t_t is None else 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pca_gather_points_f32(_lib.ptr(logmag), n, nf, nt, _lib.ptr(f_t), _lib.ptr(t_t), _lib.ptr(idx), K,
+                                                    _lib.ptr(pts), rt.stream_ptr(dev)), "gather_points")
+    return pts
+
+
+def random_points(logmag: torch.Tensor, farr, tarr, k: int, seed: int = 0):
+    """Random-K subsampling (ESC_pc_temp_randKSS, Code/dataset.py:230-238; pc_randK, Code/utils.py:55-82): per cloud a
+    uniformly random k-subset of the points in uniformly random order -- the k largest of i.i.d. uniform keys from a
+    counter-based generator (the radix-select kernel does the selection).  numpy's permutation stream is not
+    reproduced: parity with the reference is distributional.  Returns (pts (n,k,2|3), idx (n,k) int32)."""
+    rt.require_cuda(logmag, "random_points")
+    logmag = rt.f32c(logmag)
+    if logmag.dim() == 2:
+        logmag = logmag.unsqueeze(1)
+    n, nt, nf = logmag.shape
+    dev = logmag.device
+    keys = torch.empty((n, 1, nt * nf), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pca_random_keys_f32(_lib.ptr(keys), keys.numel(), int(seed) & 0xFFFFFFFFFFFFFFFF, rt.stream_ptr(dev)),
+                   "random_keys")
+    _, idx = topk_points(keys, None, None, min(int(k), nt * nf), sorted_desc=True, want_points=False)
+    return gather_points(logmag, farr, tarr, idx), idx
+
+
+def importance_heat(logmag: torch.Tensor, winF: int) -> torch.Tensor:
+    """Heat map of ESC_pc_temp_importancerandKSS (Code/dataset.py:280-283) for a batch: (n, nt, nf) log-magnitudes ->
+    (n, nf, nt) float32 = conv2d(|d/df| + |d/dt|, kaiser(2) x kaiser(winF), 'same') + 1e-6 (the reference's g, f-major)."""
+    rt.require_cuda(logmag, "importance_heat")
+    logmag = rt.f32c(logmag)
+    n, nt, nf = logmag.shape
+    dev = logmag.device
+    key = ("kaiser", int(winF), dev.index)
+    hit = rt._table_cache.get(key)
+    if hit is None:      # the reference's own window call, evaluated once on the host
+        hit = (torch.kaiser_window(window_length=2, periodic=True, beta=5.09).float().to(dev),
+               torch.kaiser_window(window_length=int(winF), periodic=True, beta=5.09).float().to(dev))
+        rt._table_cache[key] = hit
+    kf, kt = hit
+    heat = torch.empty((n, nf, nt), dtype=torch.float32, device=dev)
+    scratch = torch.empty_like(heat)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pca_importance_map_f32(_lib.ptr(logmag), n, nf, nt, _lib.ptr(kf), 2, _lib.ptr(kt), int(winF),
+                                                     _lib.ptr(heat), _lib.ptr(scratch), rt.stream_ptr(dev)), "importance_map")
+    return heat
+
+
+def importance_points(logmag: torch.Tensor, farr, tarr, k: int, winF: int, choice: int = 1, seed: int = 0):
+    """Importance subsampling (ESC_pc_temp_importancerandKSS, Code/dataset.py:276-290): choice 1 keeps the k largest
+    heat-map entries, choice 0 draws k with replacement from the heat map as a categorical distribution
+    (torch.multinomial; distributional parity).  Like the reference, the f-major heat-map index selects the row of the
+    t-major cloud unchanged.  Returns (pts (n,k,3), idx (n,k) int32 = the indices used on the cloud rows)."""
+    logmag = rt.f32c(logmag)
+    n, nt, nf = logmag.shape
+    dev = logmag.device
+    heat = importance_heat(logmag, winF)
+    if choice == 0:
+        idx = torch.empty((n, int(k)), dtype=torch.int32, device=dev)
+        cdf = torch.empty((n, nt * nf), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().pca_multinomial_f32(_lib.ptr(heat), n, nt * nf, int(k), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                      _lib.ptr(cdf), _lib.ptr(idx), rt.stream_ptr(dev)), "multinomial")
+    else:
+        _, idx = topk_points(heat.view(n, 1, nt * nf), None, None, min(int(k), nt * nf), sorted_desc=True, want_points=False)
+    return gather_points(logmag, farr, tarr, idx), idx

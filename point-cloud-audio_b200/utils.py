@@ -4,7 +4,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .frontend import topk_points
+from .frontend import random_points, topk_points
 
 
 def pc_maxK(x, farr, Kmax, device="cuda"):
@@ -22,5 +22,20 @@ def pc_maxK(x, farr, Kmax, device="cuda"):
     keys = torch.from_numpy(np.ascontiguousarray(x.T, dtype=np.float32)).to(device)     # (T, N)
     _, idx = topk_points(keys, None, None, k, sorted_desc=True, want_points=False)
     idx = idx.cpu().numpy().astype(np.int64)                                              # (T, K)
+    cols = np.arange(t)[:, None]
+    return x[idx, cols].T.copy(), farr[idx].T.copy()
+
+
+def pc_randK(x, farr, Kmax, device="cuda", seed=0):
+    """Per-frame random-K subsampling of the spectrum (Code/utils.py:55-82): (subsampled_x (K, T), subsampled_x_fs (K, T)),
+    each column a uniformly random K-subset of the bins in random order.  The draw comes from the CUDA path
+    (``frontend.random_points``); numpy's generator is not involved (distributional parity)."""
+    x = np.asarray(x)
+    farr = np.asarray(farr)
+    n, t = x.shape
+    k = min(int(Kmax), n)
+    keys = torch.from_numpy(np.ascontiguousarray(x.T, dtype=np.float32)).to(device)     # (T, N)
+    _, idx = random_points(keys, np.zeros(n), None, k, seed=seed)
+    idx = idx.cpu().numpy().astype(np.int64)
     cols = np.arange(t)[:, None]
     return x[idx, cols].T.copy(), farr[idx].T.copy()

@@ -134,3 +134,34 @@ def test_logmag_recipe_shapes_and_chunking():
     np.testing.assert_array_equal(c[:, :, 1], a[:, 10:20])
     farr, tarr = orc.coord_tables(16000, 512, 1024, 0.5, 10)
     assert farr[-1] == 0.5 and tarr.shape == (10,) and abs(tarr[-1] - 0.32) < 1e-12
+
+
+# ------------------------------------------------------------------------------------ random-K / importance subsampling
+@pytest.fixture(scope="module")
+def sampg():
+    return dict(np.load(os.path.join(G, "sampling_golden.npz")))
+
+
+@pytest.mark.parametrize("K,winF", [(16, 3), (100, 4), (480, 7)])
+def test_importance_topk_matches_reference(sampg, K, winF):
+    """ESC_pc_temp_importancerandKSS(choice=1): heat map + top-K rows, incl. the reference's f-major/t-major index quirk."""
+    x3, farr, tarr = sampg["x3"], sampg["farr"], sampg["tarr"]
+    for i in range(x3.shape[2]):
+        rows, _ = orc.cloud_3d_importance_f64(x3, farr, tarr, i, K, winF, choice=1)
+        assert np.array_equal(rows, sampg[f"imp_top_K{K}_w{winF}"][i])
+
+
+def test_importance_multinomial_and_randk_match_reference_with_seeds(sampg):
+    """The random modes with the reference's own generators re-seeded (torch.manual_seed / np.random.seed)."""
+    x3, farr, tarr = sampg["x3"], sampg["farr"], sampg["tarr"]
+    torch.manual_seed(77)
+    for i in range(x3.shape[2]):
+        rows, _ = orc.cloud_3d_importance_f64(x3, farr, tarr, i, 64, 5, choice=0)
+        assert np.array_equal(rows, sampg["imp_multinomial_K64_w5_seed77"][i])
+    np.random.seed(99)
+    for i in range(x3.shape[2]):
+        rows, _ = orc.cloud_3d_randk_f64(x3, farr, tarr, i, 50)
+        assert np.array_equal(rows, sampg["randk_K50_seed99"][i])
+    np.random.seed(98)
+    xs, fs_ = orc.pc_randk(x3[:, :, 0], farr, 10)
+    assert np.array_equal(xs, sampg["pc_randK_x_seed98"]) and np.array_equal(fs_, sampg["pc_randK_f_seed98"])
