@@ -57,3 +57,15 @@ def allreduce_mean_(flat_grad: torch.Tensor, world: int) -> torch.Tensor:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
         flat_grad.div_(world)
     return flat_grad
+
+
+def reduce_flat_gradient_(flat_grad: torch.Tensor, group=None) -> float:
+    """The per-step gradient exchange of data-parallel training (SetTrainer): ONE summing allreduce of the flat fp32
+    gradient buffer, in place.  Returns the factor the optimizer applies to the summed gradient (1 / world size; the
+    fused Adam kernel folds it in, so no separate division pass runs).  No-op (factor 1.0) without a process group."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world

@@ -18,6 +18,7 @@ import torch.distributed as dist
 
 from . import _lib, _runtime as rt
 from . import ops as _ops  # noqa: F401
+from .parallel import reduce_flat_gradient_
 
 
 class STTrainFunction(torch.autograd.Function):
@@ -110,10 +111,9 @@ class SetTrainer:
             _lib.check(L.pca_st_train_bwd_f32(_lib.ptr(X), B, N, C.byref(dims), _lib.ptr(self.flat), p, seed, _lib.ptr(dlogits),
                                               _lib.ptr(saved), saved.numel(), _lib.ptr(self.grads), None, _lib.ptr(ws), ws.numel(),
                                               st), "st_train_bwd")
-            if self.world > 1:
-                dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
+            grad_scale = reduce_flat_gradient_(self.grads, self.group)
             _lib.check(L.pca_adam_step_f32(_lib.ptr(self.flat), _lib.ptr(self.grads), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                                            self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                           self.t, 1.0 / self.world, st), "adam_step")
+                                           self.t, grad_scale, st), "adam_step")
         self.logits = logits
         return stats[0], stats[1:2].view(torch.int32)[0]

@@ -139,14 +139,17 @@ def _gloo_worker(rank, world, port, q):
     import sys
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
-    from pcaudio_b200.parallel import allreduce_mean_, gather_rows, init_distributed, shard_range
+    from pcaudio_b200.parallel import allreduce_mean_, gather_rows, init_distributed, reduce_flat_gradient_, shard_range
     r, w, _ = init_distributed("gloo")
     full = torch.arange(7 * 3, dtype=torch.float32).reshape(7, 3)
     lo, hi = shard_range(7, r, w)
     got = gather_rows(full[lo:hi].clone(), 7, r, w)
     g = torch.full((5,), float(r + 1))
     allreduce_mean_(g, w)
-    q.put((r, torch.equal(got, full), g.tolist()))
+    # the training step's exchange: one summing allreduce of the flat gradient, 1/world folded into the optimizer
+    flat = torch.arange(6, dtype=torch.float32) * (r + 1)
+    scale = reduce_flat_gradient_(flat)
+    q.put((r, torch.equal(got, full), g.tolist(), (flat * scale).tolist()))
     dist.destroy_process_group()
 
 
@@ -161,9 +164,10 @@ def test_two_rank_gloo_shard_gather_and_grad_allreduce():
     res = [q.get(timeout=120) for _ in range(2)]
     for p in procs:
         p.join(timeout=60)
-    for r, ok, g in res:
+    for r, ok, g, mean_grad in res:
         assert ok, f"rank {r}: gathered rows differ from the unsharded tensor"
         assert g == [1.5] * 5
+        assert mean_grad == [1.5 * i for i in range(6)]          # mean over ranks of i * (rank + 1)
 
 
 def test_torch_custom_ops_registered_with_fake_impls(built):
@@ -187,3 +191,28 @@ def test_torch_custom_ops_registered_with_fake_impls(built):
         assert pts.shape == (9, 256, 3) and idx.shape == (9, 256) and cnt.shape == (9,)
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.pcaudio.st_fwd(torch.zeros(1, 4, 2), None, torch.zeros(10), 2, 64, 8, 64, 1, 10, 0, 0)   # CPU: no kernel
+
+
+def test_flatten_parameters_packs_views_in_blob_order(built):
+    """SetTrainer's memory model: every parameter is a view of ONE flat fp32 buffer in the packed-weight order of the C
+    ABI, so the weights blob, the flat gradient and the fused optimizer address the same memory (host logic, no GPU)."""
+    import pcaudio_b200 as pca
+    torch.manual_seed(0)
+    m = pca.SetTransformer(dim_input=3, num_outputs=1, dim_output=5, num_inds=4, dim_hidden=8, num_heads=2)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    packed = m._blob().clone()
+    flat = m.flatten_parameters()
+    assert flat.numel() == sum(p.numel() for p in m.parameters()) == packed.numel()
+    assert torch.equal(flat, packed) and m._blob() is flat
+    assert list(m.state_dict().keys()) == list(before.keys())
+    assert all(torch.equal(v, before[k]) for k, v in m.state_dict().items())
+    off = 0
+    for t in m._param_tensors():                           # views, in order, no gaps
+        assert t.data_ptr() == flat.data_ptr() + 4 * off
+        off += t.numel()
+    flat.mul_(2.0)                                         # an in-place optimizer step on the flat buffer ...
+    assert all(torch.equal(v, 2.0 * before[k]) for k, v in m.state_dict().items())      # ... is seen by every parameter
+    m.load_state_dict(before)                              # copy_ keeps the views
+    assert m._blob() is flat and torch.equal(flat, packed)
+    m.dec[3].weight.data = m.dec[3].weight.data.clone()    # a parameter re-pointed elsewhere: fall back to re-packing
+    assert m._blob() is not flat and torch.equal(m._blob(), packed)
