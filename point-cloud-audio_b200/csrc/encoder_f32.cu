@@ -110,7 +110,7 @@ int launch_linear(const float* X, const float* W, const float* b, float* Y, long
 // Block = H warps (warp w <-> head w).  Lane <-> (query ql, key slice ks): TQ queries per block,
 // KS = 32/TQ key slices.  K|V rows ([Kp (D) | Vp (D)] per key) are staged in smem tiles; all lanes
 // of a warp with the same key slice read the same address (broadcast).
-template <int DH>
+template <int DH, int R>
 __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstride,
                                 const float* __restrict__ KV, int nq, int nk, int D, int tq_log,
                                 int tk, int nsplit, int chunk, int q_tiles, float scale_log2e,
@@ -123,22 +123,31 @@ __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstrid
     const int ql = lane & (TQ - 1), ks = lane >> tq_log;
     const int b = blockIdx.z, split = blockIdx.y;
     const int rs = 2 * D + 4;                          // padded smem row stride (floats)
+    // Register blocking: a lane owns R queries (ql, ql + TQ, ...), so every K / V element read from shared memory feeds R
+    // dot products -- these kernels are bound by the shared-memory broadcast reads (ncu: l1tex 84-96 % of peak at R = 1).
     // q_tiles > 1 only when the key set is a single smem tile: it is staged once and reused by every query tile of the block
   for (int qt = 0; qt < q_tiles; ++qt) {
-    if ((blockIdx.x * q_tiles + qt) * TQ >= nq) break;   // block-uniform
-    const int q = (blockIdx.x * q_tiles + qt) * TQ + ql;
-    const bool qvalid = q < nq;
-
-    float qv[DH], acc[DH];
-    const float* qptr = Qp + (long long)b * q_bstride + (long long)(qvalid ? q : 0) * D + h * DH;
-    // per-thread rows: 16-byte accesses (a warp touches 32 different rows; scalar accesses would cost 4x the LSU wavefronts)
+    const int q0 = (blockIdx.x * q_tiles + qt) * TQ * R;
+    if (q0 >= nq) break;                               // block-uniform
+    int q[R];
+    bool qvalid[R];
+    const float* qptr[R];
+    float qv[R][DH], acc[R][DH], m[R], l[R];
 #pragma unroll
-    for (int j = 0; j < DH; j += 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(qptr + j));
-        qv[j] = t.x * scale_log2e; qv[j + 1] = t.y * scale_log2e; qv[j + 2] = t.z * scale_log2e; qv[j + 3] = t.w * scale_log2e;
-        acc[j] = acc[j + 1] = acc[j + 2] = acc[j + 3] = 0.f;
+    for (int r = 0; r < R; ++r) {
+        q[r] = q0 + r * TQ + ql;
+        qvalid[r] = q[r] < nq;
+        qptr[r] = Qp + (long long)b * q_bstride + (long long)(qvalid[r] ? q[r] : 0) * D + h * DH;
+        // per-thread rows: 16-byte accesses (a warp touches 32 different rows; scalar accesses would cost 4x the LSU wavefronts)
+#pragma unroll
+        for (int j = 0; j < DH; j += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(qptr[r] + j));
+            qv[r][j] = t.x * scale_log2e; qv[r][j + 1] = t.y * scale_log2e; qv[r][j + 2] = t.z * scale_log2e; qv[r][j + 3] = t.w * scale_log2e;
+            acc[r][j] = acc[r][j + 1] = acc[r][j + 2] = acc[r][j + 3] = 0.f;
+        }
+        m[r] = -INFINITY;
+        l[r] = 0.f;
     }
-    float m = -INFINITY, l = 0.f;
 
     // variable-size sets: only the first key_counts[b] keys of the padded set take part
     const int nk_b = key_counts ? max(1, min(nk, __ldg(key_counts + b))) : nk;
@@ -157,45 +166,60 @@ __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstrid
             *reinterpret_cast<float4*>(kv_s + r * rs + c * 4) = v;
         }
         __syncthreads();
-        if (qvalid) {
-            for (int kk = ks; kk < tn; kk += 4 * KS) {
-                // up to 4 keys of this lane's slice per softmax update
-                float s[4];
+        for (int kk = ks; kk < tn; kk += 4 * KS) {
+            // up to 4 keys of this lane's slice per softmax update
+            float s[R][4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int key = kk + u * KS;
-                    if (key < tn) {
-                        const float* kr = kv_s + key * rs + h * DH;
-                        float d = 0.f;
+            for (int u = 0; u < 4; ++u) {
+                const int key = kk + u * KS;
+                if (key < tn) {
+                    const float* kr = kv_s + key * rs + h * DH;
+                    float d[R];
 #pragma unroll
-                        for (int j = 0; j < DH; j += 4) {
-                            const float4 kq = *reinterpret_cast<const float4*>(kr + j);
-                            d = fmaf(qv[j], kq.x, d); d = fmaf(qv[j + 1], kq.y, d);
-                            d = fmaf(qv[j + 2], kq.z, d); d = fmaf(qv[j + 3], kq.w, d);
+                    for (int r = 0; r < R; ++r) d[r] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < DH; j += 4) {
+                        const float4 kq = *reinterpret_cast<const float4*>(kr + j);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            d[r] = fmaf(qv[r][j], kq.x, d[r]); d[r] = fmaf(qv[r][j + 1], kq.y, d[r]);
+                            d[r] = fmaf(qv[r][j + 2], kq.z, d[r]); d[r] = fmaf(qv[r][j + 3], kq.w, d[r]);
                         }
-                        s[u] = d;
-                    } else {
-                        s[u] = -INFINITY;
                     }
-                }
-                const float mn = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
-                const float alpha = exp2f(m - mn);      // m = -inf on the first update -> 0
-                m = mn;
-                l *= alpha;
 #pragma unroll
-                for (int j = 0; j < DH; ++j) acc[j] *= alpha;
+                    for (int r = 0; r < R; ++r) s[r][u] = d[r];
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) s[r][u] = -INFINITY;
+                }
+            }
+            float p[R][4];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float mn = fmaxf(fmaxf(m[r], fmaxf(s[r][0], s[r][1])), fmaxf(s[r][2], s[r][3]));
+                const float alpha = exp2f(m[r] - mn);      // m = -inf on the first update -> 0
+                m[r] = mn;
+                l[r] *= alpha;
+#pragma unroll
+                for (int j = 0; j < DH; ++j) acc[r][j] *= alpha;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int key = kk + u * KS;
-                    if (key < tn) {
-                        const float p = exp2f(s[u] - mn);
-                        l += p;
-                        const float* vr = kv_s + key * rs + D + h * DH;
+                    p[r][u] = (kk + u * KS < tn) ? exp2f(s[r][u] - mn) : 0.f;
+                    l[r] += p[r][u];
+                }
+            }
 #pragma unroll
-                        for (int j = 0; j < DH; j += 4) {
-                            const float4 vv = *reinterpret_cast<const float4*>(vr + j);
-                            acc[j] = fmaf(p, vv.x, acc[j]); acc[j + 1] = fmaf(p, vv.y, acc[j + 1]);
-                            acc[j + 2] = fmaf(p, vv.z, acc[j + 2]); acc[j + 3] = fmaf(p, vv.w, acc[j + 3]);
+            for (int u = 0; u < 4; ++u) {
+                const int key = kk + u * KS;
+                if (key < tn) {
+                    const float* vr = kv_s + key * rs + D + h * DH;
+#pragma unroll
+                    for (int j = 0; j < DH; j += 4) {
+                        const float4 vv = *reinterpret_cast<const float4*>(vr + j);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            acc[r][j] = fmaf(p[r][u], vv.x, acc[r][j]); acc[r][j + 1] = fmaf(p[r][u], vv.y, acc[r][j + 1]);
+                            acc[r][j + 2] = fmaf(p[r][u], vv.z, acc[r][j + 2]); acc[r][j + 3] = fmaf(p[r][u], vv.w, acc[r][j + 3]);
                         }
                     }
                 }
@@ -205,35 +229,43 @@ __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstrid
     }
 
     // merge the key slices of one query across lanes (xor over the slice bits)
-    for (int off = TQ; off < 32; off <<= 1) {
-        const float mo = __shfl_xor_sync(0xffffffffu, m, off);
-        const float lo = __shfl_xor_sync(0xffffffffu, l, off);
-        const float mn = fmaxf(m, mo);
-        const float a0 = (m == -INFINITY) ? 0.f : exp2f(m - mn);
-        const float a1 = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
-        l = l * a0 + lo * a1;
 #pragma unroll
-        for (int j = 0; j < DH; ++j) {
-            const float ao = __shfl_xor_sync(0xffffffffu, acc[j], off);
-            acc[j] = acc[j] * a0 + ao * a1;
+    for (int r = 0; r < R; ++r) {
+        for (int off = TQ; off < 32; off <<= 1) {
+            const float mo = __shfl_xor_sync(0xffffffffu, m[r], off);
+            const float lo = __shfl_xor_sync(0xffffffffu, l[r], off);
+            const float mn = fmaxf(m[r], mo);
+            const float a0 = (m[r] == -INFINITY) ? 0.f : exp2f(m[r] - mn);
+            const float a1 = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
+            l[r] = l[r] * a0 + lo * a1;
+#pragma unroll
+            for (int j = 0; j < DH; ++j) {
+                const float ao = __shfl_xor_sync(0xffffffffu, acc[r][j], off);
+                acc[r][j] = acc[r][j] * a0 + ao * a1;
+            }
+            m[r] = mn;
         }
-        m = mn;
     }
-    if (!qvalid || ks != 0) continue;
-    if (nsplit == 1) {
-        const float inv = 1.f / l;
-        float* o = O + ((long long)b * nq + q) * D + h * DH;
+    if (ks != 0) continue;
 #pragma unroll
-        for (int j = 0; j < DH; j += 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(qptr + j));
-            *reinterpret_cast<float4*>(o + j) = make_float4(t.x + acc[j] * inv, t.y + acc[j + 1] * inv, t.z + acc[j + 2] * inv, t.w + acc[j + 3] * inv);
+    for (int r = 0; r < R; ++r) {
+        if (!qvalid[r]) continue;
+        if (nsplit == 1) {
+            const float inv = 1.f / l[r];
+            float* o = O + ((long long)b * nq + q[r]) * D + h * DH;
+#pragma unroll
+            for (int j = 0; j < DH; j += 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(qptr[r] + j));
+                *reinterpret_cast<float4*>(o + j) = make_float4(t.x + acc[r][j] * inv, t.y + acc[r][j + 1] * inv,
+                                                                t.z + acc[r][j + 2] * inv, t.w + acc[r][j + 3] * inv);
+            }
+            if (lse) lse[((long long)b * nq + q[r]) * H + h] = m[r] + log2f(l[r]);      // log2 of sum_k 2^(s_k), scaled log2 domain
+        } else {
+            float* pp = part + ((((long long)b * nsplit + split) * nq + q[r]) * H + h) * (DH + 2);
+            pp[0] = m[r]; pp[1] = l[r];
+#pragma unroll
+            for (int j = 0; j < DH; ++j) pp[2 + j] = acc[r][j];
         }
-        if (lse) lse[((long long)b * nq + q) * H + h] = m + log2f(l);      // log2 of sum_k 2^(s_k), s in the scaled log2 domain
-    } else {
-        float* pp = part + ((((long long)b * nsplit + split) * nq + q) * H + h) * (DH + 2);
-        pp[0] = m; pp[1] = l;
-#pragma unroll
-        for (int j = 0; j < DH; ++j) pp[2 + j] = acc[j];
     }
   }
 }
@@ -308,13 +340,13 @@ static AttnPlan plan_attn(int B, int nq, int nk, int D, int H) {
 
 size_t attn_part_floats(int B, int nq, int nk, int D, int H) { return plan_attn(B, nq, nk, D, H).part_floats; }
 
-template <int DH>
-static int launch_attn_t(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk,
+template <int DH, int R>
+static int launch_attn_r(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk,
                          int D, int H, float* O, float* part, const int* key_counts, cudaStream_t st, float* lse) {
     const AttnPlan p = plan_attn(B, nq, nk, D, H);
     const int tq = 1 << p.tq_log;
     // key set in one smem tile: stage it once per block and walk several query tiles (keeps >= ~8 blocks per SM)
-    const int q_blocks = (nq + tq - 1) / tq;
+    const int q_blocks = (nq + tq * R - 1) / (tq * R);
     int q_tiles = 1;
     if (p.nsplit == 1 && nk <= p.tk && key_counts == nullptr) {
         const long long qt = ((long long)q_blocks * B) / (148LL * 8);
@@ -323,12 +355,12 @@ static int launch_attn_t(const float* Qp, long long q_bstride, const float* KV, 
     dim3 grid((q_blocks + q_tiles - 1) / q_tiles, p.nsplit, B);
     const float scale_log2e = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
     if (p.smem > 48 * 1024)
-        PCA_CHECK_CUDA(cudaFuncSetAttribute(attn_f32_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        PCA_CHECK_CUDA((cudaFuncSetAttribute(attn_f32_kernel<DH, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)));
     {
         LaunchTimer lt("attn_f32_kernel", st, 4.0 * B * nq * (double)nk * D,
                        4.0 * ((double)B * nk * 2 * D + 2.0 * B * nq * D));
-        attn_f32_kernel<DH><<<grid, 32 * H, p.smem, st>>>(Qp, q_bstride, KV, nq, nk, D, p.tq_log, p.tk,
-                                                          p.nsplit, p.chunk, q_tiles, scale_log2e, O, part, key_counts, lse);
+        attn_f32_kernel<DH, R><<<grid, 32 * H, p.smem, st>>>(Qp, q_bstride, KV, nq, nk, D, p.tq_log, p.tk,
+                                                             p.nsplit, p.chunk, q_tiles, scale_log2e, O, part, key_counts, lse);
     }
     PCA_CHECK_LAUNCH("attn_f32_kernel");
     if (p.nsplit > 1) {
@@ -342,17 +374,26 @@ static int launch_attn_t(const float* Qp, long long q_bstride, const float* KV, 
     return 0;
 }
 
+// RMAX queries per lane when the query set is large enough to keep every lane busy (and the grid full), else one
+template <int DH, int RMAX>
+static int launch_attn_t(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk,
+                         int D, int H, float* O, float* part, const int* key_counts, cudaStream_t st, float* lse) {
+    if (RMAX > 1 && nq >= 32 * RMAX && (long long)B * (nq / (32 * RMAX)) >= 148LL * 4)
+        return launch_attn_r<DH, RMAX>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
+    return launch_attn_r<DH, 1>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
+}
+
 int launch_attn(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D,
                 int H, float* O, float* part, const int* key_counts, cudaStream_t st, float* lse) {
     if (B == 0 || nq == 0) return 0;
     if (H < 1 || H > 32 || D % H) return fail(PCA_EUNSUPPORTED, "attention: need 1 <= H <= 32 and D %% H == 0 (D=%d, H=%d)", D, H);
     if (B > 65535) return fail(PCA_EUNSUPPORTED, "attention: batch chunk %d exceeds the grid limit", B);
     switch (D / H) {
-        case 4: return launch_attn_t<4>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
-        case 8: return launch_attn_t<8>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
-        case 16: return launch_attn_t<16>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
-        case 32: return launch_attn_t<32>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
-        case 64: return launch_attn_t<64>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
+        case 4: return launch_attn_t<4, 2>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
+        case 8: return launch_attn_t<8, 2>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
+        case 16: return launch_attn_t<16, 1>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
+        case 32: return launch_attn_t<32, 1>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
+        case 64: return launch_attn_t<64, 1>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
         default: return fail(PCA_EUNSUPPORTED, "attention: head dim %d not in {4,8,16,32,64}", D / H);
     }
 }
