@@ -340,7 +340,8 @@ static int pipeline_run(const pca_pipeline_cfg* c, const float* audio, int n_cli
     if (c->mode == 3 && (c->top_k || thr) && getenv("PCA_FUSED_FRONTEND") != nullptr) {
         int kpad = 2;
         while (kpad < s.pts) kpad <<= 1;
-        const size_t smem = (size_t)kpad * 8 + (size_t)(c->n_fft / 2) * 8 * 9 + (size_t)c->n_fft * 4 + (size_t)s.pts_full * 4;
+        const size_t smem = (size_t)kpad * 8 + ((size_t)(c->n_fft / 2) + 8 * (size_t)(c->n_fft / 2 + c->n_fft / 32)) * 8 + (size_t)c->n_fft * 4 +
+                            (size_t)s.pts_full * 4;      // 8 padded FFT buffers: launch_fused_frontend
         if (smem <= 227 * 1024 && s.pts <= 16384) {
             PCA_TRY(launch_fused_frontend(audio, n_clips, c->n_samples, c->n_fft, c->hop, window, twiddle, c->scale, 1, c->ntemp,
                                           farr, tarr, s.pts, 1, thr, c->threshold, pts, nullptr, thr ? kept : nullptr, st));

@@ -1,8 +1,8 @@
 // Spectral front end and point selection for sm_100a.
 //
 //   stft_logmag_kernel : reflect-padded framing (index mirroring, no padded copy) -> periodic
-//                        Hann -> real FFT (packed as a half-length complex Stockham radix-4
-//                        FFT in shared memory) -> |.|*scale -> log(1e-8 + .)
+//                        Hann -> real FFT (packed as a half-length complex Stockham FFT in shared
+//                        memory: radix-8 stages in registers + one radix-4 / radix-2 stage) -> |.|*scale -> log(1e-8 + .)
 //                        replaces librosa.stft + np.log recipe (Code/settransformer.py:49-50,
 //                        Code/settransformertemp.py:51-53).
 //   build_clouds_kernel: ESC_pc / ESC_pc_temp __getitem__ (Code/dataset.py:50-54,160-166).
@@ -17,6 +17,9 @@
 namespace pca {
 
 // ------------------------------------------------------------------------------------ STFT
+// slots of one padded FFT buffer (see stft_frame)
+__host__ __device__ static inline int stft_buf_len(int nc) { return nc + (nc >> 4); }
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -30,83 +33,140 @@ __device__ __forceinline__ void stft_frame(const float* __restrict__ x, int L, i
                                            float scale, int nf_out, float* o, int tid, int nthr, bool active) {
     const int nc = n_fft >> 1;
     const int tw_shift_base = 31 - __clz(n_fft);   // log2(n_fft)
+    // buffer index padding: one extra slot per 16, so that the power-of-two strides of the Stockham stores spread over the
+    // banks (ncu on the unpadded kernel: 17 M store bank conflicts, l1tex 79 % of peak); buffers hold stft_buf_len(nc) slots
+    auto PD = [](int i) { return i + (i >> 4); };
     // ---- load + window, pack even/odd samples into one complex sequence
     if (active) {
         const int start = t * hop - nc;            // centre=True: frame t starts at t*hop - n_fft/2
-        for (int i = tid; i < nc; i += nthr) {
-            int j0 = start + 2 * i, j1 = j0 + 1;
-            j0 = j0 < 0 ? -j0 : (j0 >= L ? 2 * (L - 1) - j0 : j0);
-            j1 = j1 < 0 ? -j1 : (j1 >= L ? 2 * (L - 1) - j1 : j1);
-            bufa[i] = make_float2(win[2 * i] * __ldg(x + j0), win[2 * i + 1] * __ldg(x + j1));
+        if (start >= 0 && start + n_fft <= L && ((reinterpret_cast<size_t>(x + start) & 7) == 0)) {
+            // interior frame: no mirroring, 8-byte loads of sample pairs
+            const float2* xp = reinterpret_cast<const float2*>(x + start);
+            const float2* wp = reinterpret_cast<const float2*>(win);
+            for (int i = tid; i < nc; i += nthr) {
+                const float2 v = __ldg(xp + i), w = wp[i];
+                bufa[PD(i)] = make_float2(w.x * v.x, w.y * v.y);
+            }
+        } else {
+            for (int i = tid; i < nc; i += nthr) {
+                int j0 = start + 2 * i, j1 = j0 + 1;
+                j0 = j0 < 0 ? -j0 : (j0 >= L ? 2 * (L - 1) - j0 : j0);
+                j1 = j1 < 0 ? -j1 : (j1 >= L ? 2 * (L - 1) - j1 : j1);
+                bufa[PD(i)] = make_float2(win[2 * i] * __ldg(x + j0), win[2 * i + 1] * __ldg(x + j1));
+            }
         }
     }
     __syncthreads();
 
-    // ---- Stockham autosort, radix 4 (+ one radix-2 stage when log2(nc) is odd)
+    // ---- Stockham autosort, decimation in frequency: radix-8 stages in registers, then one radix-4 / radix-2 stage for
+    // what is left of log2(nc).  Stage of radix R on sub-length n (n1 = n / R, stride S = 2^s_log): butterfly (p, q) reads
+    // src[q + (p + r n1) S], r < R, and writes dst[q + (R p + r) S] = w_p^r Y_r, w_p = exp(-2 pi i p / n).
     float2* src = bufa;
     float2* dst = bufb;
     int n = nc, s_log = 0;
-    while (n >= 4) {
-        const int n1 = n >> 2;
+    while (n >= 8) {
+        const int n1 = n >> 3;
         const int tsh = tw_shift_base - (31 - __clz(n));     // log2(n_fft / n)
         if (active) {
-            for (int i = tid; i < (nc >> 2); i += nthr) {
+            for (int i = tid; i < (nc >> 3); i += nthr) {
                 const int p = i >> s_log, q = i & ((1 << s_log) - 1);
-                const float2 w1 = tw[p << tsh];
-                const float2 w2 = tw[(2 * p) << tsh];
-                const float2 w3 = cmul(w1, w2);
-                const float2 a = src[q + ((p) << s_log)];
-                const float2 b = src[q + ((p + n1) << s_log)];
-                const float2 c = src[q + ((p + 2 * n1) << s_log)];
-                const float2 d = src[q + ((p + 3 * n1) << s_log)];
-                const float2 apc = make_float2(a.x + c.x, a.y + c.y);
-                const float2 amc = make_float2(a.x - c.x, a.y - c.y);
-                const float2 bpd = make_float2(b.x + d.x, b.y + d.y);
-                const float2 jbmd = make_float2(-(b.y - d.y), b.x - d.x);   // i*(b-d)
-                const int o2 = q + ((4 * p) << s_log);
-                dst[o2] = make_float2(apc.x + bpd.x, apc.y + bpd.y);
-                dst[o2 + (1 << s_log)] = cmul(w1, make_float2(amc.x - jbmd.x, amc.y - jbmd.y));
-                dst[o2 + (2 << s_log)] = cmul(w2, make_float2(apc.x - bpd.x, apc.y - bpd.y));
-                dst[o2 + (3 << s_log)] = cmul(w3, make_float2(amc.x + jbmd.x, amc.y + jbmd.y));
+                const int ib = q + (p << s_log);
+                const int st = n1 << s_log;
+                const float2 a0 = src[PD(ib)], a1 = src[PD(ib + st)], a2 = src[PD(ib + 2 * st)], a3 = src[PD(ib + 3 * st)];
+                const float2 a4 = src[PD(ib + 4 * st)], a5 = src[PD(ib + 5 * st)], a6 = src[PD(ib + 6 * st)], a7 = src[PD(ib + 7 * st)];
+                // even outputs: DFT4 of (a_j + a_{j+4}); odd outputs: DFT4 of ((a_j - a_{j+4}) w8^j)
+                const float2 b0 = make_float2(a0.x + a4.x, a0.y + a4.y), b1 = make_float2(a1.x + a5.x, a1.y + a5.y);
+                const float2 b2 = make_float2(a2.x + a6.x, a2.y + a6.y), b3 = make_float2(a3.x + a7.x, a3.y + a7.y);
+                const float2 c0 = make_float2(a0.x - a4.x, a0.y - a4.y);
+                const float2 d1 = make_float2(a1.x - a5.x, a1.y - a5.y);
+                const float2 d2 = make_float2(a2.x - a6.x, a2.y - a6.y);
+                const float2 d3 = make_float2(a3.x - a7.x, a3.y - a7.y);
+                const float r2 = 0.70710678118654752f;
+                const float2 c1 = make_float2((d1.x + d1.y) * r2, (d1.y - d1.x) * r2);      // d1 (1 - i)/sqrt2
+                const float2 c2 = make_float2(d2.y, -d2.x);                                // d2 (-i)
+                const float2 c3 = make_float2((d3.y - d3.x) * r2, -(d3.x + d3.y) * r2);     // d3 (-1 - i)/sqrt2
+                // DFT4(z0..z3): y0 = (z0+z2)+(z1+z3), y2 = (z0+z2)-(z1+z3), y1 = (z0-z2) - i (z1-z3), y3 = (z0-z2) + i (z1-z3)
+                const float2 e0 = make_float2(b0.x + b2.x, b0.y + b2.y), e1 = make_float2(b1.x + b3.x, b1.y + b3.y);
+                const float2 e2 = make_float2(b0.x - b2.x, b0.y - b2.y), e3 = make_float2(b1.x - b3.x, b1.y - b3.y);
+                const float2 f0 = make_float2(c0.x + c2.x, c0.y + c2.y), f1 = make_float2(c1.x + c3.x, c1.y + c3.y);
+                const float2 f2 = make_float2(c0.x - c2.x, c0.y - c2.y), f3 = make_float2(c1.x - c3.x, c1.y - c3.y);
+                const float2 y0 = make_float2(e0.x + e1.x, e0.y + e1.y);
+                const float2 y4 = make_float2(e0.x - e1.x, e0.y - e1.y);
+                const float2 y2 = make_float2(e2.x + e3.y, e2.y - e3.x);
+                const float2 y6 = make_float2(e2.x - e3.y, e2.y + e3.x);
+                const float2 y1 = make_float2(f0.x + f1.x, f0.y + f1.y);
+                const float2 y5 = make_float2(f0.x - f1.x, f0.y - f1.y);
+                const float2 y3 = make_float2(f2.x + f3.y, f2.y - f3.x);
+                const float2 y7 = make_float2(f2.x - f3.y, f2.y + f3.x);
+                const int ob = q + ((8 * p) << s_log);
+                const int so = 1 << s_log;
+                if (n1 == 1) {            // last radix-8 stage of a power of 8: p = 0, every twiddle is 1
+                    dst[PD(ob)] = y0; dst[PD(ob + so)] = y1; dst[PD(ob + 2 * so)] = y2; dst[PD(ob + 3 * so)] = y3;
+                    dst[PD(ob + 4 * so)] = y4; dst[PD(ob + 5 * so)] = y5; dst[PD(ob + 6 * so)] = y6; dst[PD(ob + 7 * so)] = y7;
+                } else {
+                    const float2 w1 = tw[p << tsh], w2 = tw[(2 * p) << tsh], w4 = tw[(4 * p) << tsh];
+                    const float2 w3 = cmul(w1, w2), w5 = cmul(w1, w4), w6 = cmul(w2, w4);
+                    const float2 w7 = cmul(w3, w4);
+                    dst[PD(ob)] = y0;
+                    dst[PD(ob + so)] = cmul(w1, y1); dst[PD(ob + 2 * so)] = cmul(w2, y2); dst[PD(ob + 3 * so)] = cmul(w3, y3);
+                    dst[PD(ob + 4 * so)] = cmul(w4, y4); dst[PD(ob + 5 * so)] = cmul(w5, y5); dst[PD(ob + 6 * so)] = cmul(w6, y6);
+                    dst[PD(ob + 7 * so)] = cmul(w7, y7);
+                }
             }
         }
         __syncthreads();
         float2* tmp = src; src = dst; dst = tmp;
-        n >>= 2;
-        s_log += 2;
+        n >>= 3;
+        s_log += 3;
     }
-    if (n == 2) {   // p = 0 only, twiddle = 1
+    if (n == 4) {   // p = 0 only, twiddles = 1
+        if (active) {
+            const int st = 1 << s_log;               // = nc / 4
+            for (int q = tid; q < st; q += nthr) {
+                const float2 a = src[PD(q)], b = src[PD(q + st)], c = src[PD(q + 2 * st)], d = src[PD(q + 3 * st)];
+                const float2 apc = make_float2(a.x + c.x, a.y + c.y);
+                const float2 amc = make_float2(a.x - c.x, a.y - c.y);
+                const float2 bpd = make_float2(b.x + d.x, b.y + d.y);
+                const float2 bmd = make_float2(b.x - d.x, b.y - d.y);
+                dst[PD(q)] = make_float2(apc.x + bpd.x, apc.y + bpd.y);
+                dst[PD(q + st)] = make_float2(amc.x + bmd.y, amc.y - bmd.x);
+                dst[PD(q + 2 * st)] = make_float2(apc.x - bpd.x, apc.y - bpd.y);
+                dst[PD(q + 3 * st)] = make_float2(amc.x - bmd.y, amc.y + bmd.x);
+            }
+        }
+        __syncthreads();
+        float2* tmp = src; src = dst; dst = tmp;
+    } else if (n == 2) {   // p = 0 only, twiddle = 1
         if (active) {
             for (int q = tid; q < (nc >> 1); q += nthr) {
-                const float2 a = src[q];
-                const float2 b = src[q + (nc >> 1)];
-                dst[q] = make_float2(a.x + b.x, a.y + b.y);
-                dst[q + (nc >> 1)] = make_float2(a.x - b.x, a.y - b.y);
+                const float2 a = src[PD(q)];
+                const float2 b = src[PD(q + (nc >> 1))];
+                dst[PD(q)] = make_float2(a.x + b.x, a.y + b.y);
+                dst[PD(q + (nc >> 1))] = make_float2(a.x - b.x, a.y - b.y);
             }
         }
         __syncthreads();
         float2* tmp = src; src = dst; dst = tmp;
     }
 
-    // ---- split the packed spectrum, magnitude, log
+    // ---- split the packed spectrum, magnitude, log.  With Z the packed transform, Xe = (Z[k] + conj Z[nc-k]) / 2,
+    // Xo = -i (Z[k] - conj Z[nc-k]) / 2:  X[k] = Xe + tw[k] Xo  and  X[nc-k] = conj(Xe - tw[k] Xo): one pass gives both bins.
     if (active) {
-        for (int k = tid; k < nf_out; k += nthr) {
-            float re, im;
+        for (int k = tid; k <= (nc >> 1); k += nthr) {
             if (k == 0) {
-                re = src[0].x + src[0].y; im = 0.f;
-            } else if (k == nc) {
-                re = src[0].x - src[0].y; im = 0.f;
-            } else {
-                const float2 zk = src[k];
-                const float2 zc = src[nc - k];
-                const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
-                // odd part = -i/2 * (zk - conj(zc))
-                const float2 od = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
-                const float2 r = cmul(tw[k], od);
-                re = e.x + r.x; im = e.y + r.y;
+                const float2 z0 = src[0];      // PD(0) = 0
+                o[0] = __logf(1.0e-8f + fabsf(z0.x + z0.y) * scale);
+                if (nc < nf_out) o[nc] = __logf(1.0e-8f + fabsf(z0.x - z0.y) * scale);
+                continue;
             }
-            const float mag = sqrtf(re * re + im * im) * scale;
-            o[k] = logf(1.0e-8f + mag);
+            const float2 zk = src[PD(k)];
+            const float2 zc = src[PD(nc - k)];
+            const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+            const float2 od = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+            const float2 r = cmul(tw[k], od);
+            const float re0 = e.x + r.x, im0 = e.y + r.y, re1 = e.x - r.x, im1 = e.y - r.y;
+            o[k] = __logf(1.0e-8f + sqrtf(re0 * re0 + im0 * im0) * scale);
+            if (k != nc - k) o[nc - k] = __logf(1.0e-8f + sqrtf(re1 * re1 + im1 * im1) * scale);
         }
     }
     __syncthreads();   // bufa/bufb reused by the next frame
@@ -120,8 +180,8 @@ __global__ void stft_logmag_kernel(const float* __restrict__ audio, int L, int n
     const int nc = n_fft >> 1;             // complex FFT length
     float2* tw = smem_f2;                  // nc entries: exp(-2 pi i k / n_fft)
     float2* bufa = tw + nc;
-    float2* bufb = bufa + nc;
-    float* win = reinterpret_cast<float*>(bufb + nc);   // n_fft entries
+    float2* bufb = bufa + stft_buf_len(nc);
+    float* win = reinterpret_cast<float*>(bufb + stft_buf_len(nc));   // n_fft entries
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int clip = blockIdx.y;
@@ -600,8 +660,8 @@ fused_frontend_kernel(const float* __restrict__ audio, int L, int n_fft, int hop
     const int nc = n_fft >> 1;
     unsigned long long* sortbuf = fused_smem;                               // kpad entries (8-byte aligned first)
     float2* tw = reinterpret_cast<float2*>(sortbuf + kpad);                 // nc
-    float2* bufs = tw + nc;                                                 // FUSED_GROUPS x 2 x nc
-    float* win = reinterpret_cast<float*>(bufs + 2 * FUSED_GROUPS * nc);    // n_fft
+    float2* bufs = tw + nc;                                                 // FUSED_GROUPS x 2 x stft_buf_len(nc)
+    float* win = reinterpret_cast<float*>(bufs + 2 * FUSED_GROUPS * stft_buf_len(nc));    // n_fft
     float* keys = win + n_fft;                                              // nt_cloud * nf
 
     const int tid = threadIdx.x;
@@ -613,7 +673,7 @@ fused_frontend_kernel(const float* __restrict__ audio, int L, int n_fft, int hop
     const int g = tid >> 7, ltid = tid & 127;
     for (int t0 = 0; t0 < nt_cloud; t0 += FUSED_GROUPS) {
         const int t = t0 + g;
-        stft_frame(x, L, n_fft, hop, chunk * nt_cloud + t, tw, win, bufs + (2 * g) * nc, bufs + (2 * g + 1) * nc, scale, nf,
+        stft_frame(x, L, n_fft, hop, chunk * nt_cloud + t, tw, win, bufs + (2 * g) * stft_buf_len(nc), bufs + (2 * g + 1) * stft_buf_len(nc), scale, nf,
                    keys + (size_t)t * nf, ltid, 128, t < nt_cloud);
     }
     __syncthreads();
@@ -632,13 +692,13 @@ int launch_stft_logmag(const float* audio, int n_clips, int n_samples, int n_fft
     if (n_clips == 0 || nt_out == 0) return 0;
     const int nc = n_fft / 2;
     const int nf_out = nc + 1 - (drop_nyquist ? 1 : 0);
-    int threads = nc / 4;
+    int threads = nc / 8;                  // one radix-8 butterfly per thread and stage
     threads = threads < 64 ? 64 : (threads > 512 ? 512 : threads);
     // enough blocks to fill 148 SMs several times over, while amortising the table loads
     int fpb = 1;
     while ((long long)n_clips * ((nt_out + fpb - 1) / fpb) > 148LL * 32 && fpb < nt_out) fpb *= 2;
     dim3 grid((nt_out + fpb - 1) / fpb, n_clips);
-    const size_t smem = (size_t)3 * nc * sizeof(float2) + (size_t)n_fft * sizeof(float);
+    const size_t smem = ((size_t)nc + 2 * (size_t)stft_buf_len(nc)) * sizeof(float2) + (size_t)n_fft * sizeof(float);
     if (smem > 48 * 1024) PCA_CHECK_CUDA(cudaFuncSetAttribute(stft_logmag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         const double frames = (double)n_clips * nt_out;
@@ -728,7 +788,7 @@ int launch_fused_frontend(const float* audio, int n_clips, int n_samples, int n_
         kpad = 2;
         while (kpad < K) kpad <<= 1;
     }
-    const size_t smem = (size_t)kpad * 8 + (size_t)nc * 8 * (1 + 2 * FUSED_GROUPS) + (size_t)n_fft * 4 + (size_t)N * 4;
+    const size_t smem = (size_t)kpad * 8 + ((size_t)nc + 2 * FUSED_GROUPS * (size_t)stft_buf_len(nc)) * 8 + (size_t)n_fft * 4 + (size_t)N * 4;
     if (smem > 227 * 1024)
         return fail(PCA_EUNSUPPORTED, "fused front end: cloud of %lld points with K=%d needs %zu B of shared memory (> 227 KB); use the unfused calls",
                     N, K, smem);

@@ -110,7 +110,8 @@ def fused_frontend_fits(n_fft: int, n_pts: int, k: int) -> bool:
     kpad = 2
     while kpad < k:
         kpad <<= 1
-    return k <= 16384 and kpad * 8 + (n_fft // 2) * 8 * 9 + n_fft * 4 + n_pts * 4 <= 227 * 1024
+    nc = n_fft // 2
+    return k <= 16384 and kpad * 8 + (nc + 8 * (nc + nc // 16)) * 8 + n_fft * 4 + n_pts * 4 <= 227 * 1024
 
 
 def spectral_point_cloud(audio: torch.Tensor, *, n_fft: int, sr: float, win_length: int | None = None,
