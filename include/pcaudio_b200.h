@@ -164,6 +164,10 @@ int pca_st_fwd_masked(const float* X, const int32_t* counts, int B, int N, const
                       const float* params, float* logits, void* workspace, size_t workspace_bytes,
                       int precision, void* stream);
 
+/* nn.Linear on rows: Y (rows, dout) = X (rows, din) W^T + b, params := W (dout, din) | b (dout).  The final Linear of the
+ * generic SetTransformer (set_transformer-master/models.py:41) after its SAB decoder blocks. */
+int pca_linear_fwd_f32(const float* X, long long rows, int din, int dout, const float* params, float* Y, void* stream);
+
 /* DeepSet.forward (set_transformer-master/models.py:25-28) / SmallDeepSet
  * (max_regression_demo.ipynb:41-48): 4 shared Linear (+ReLU) over points, pool over points
  * (0 mean, 1 max, 2 sum), 4 Linear decoder.  params := for enc then dec, 4 x (W (out,in) | b).

@@ -7,7 +7,7 @@ from .dataset import (ESC_pc, ESC_pc_ss, ESC_pc_temp, ESC_pc_temp_importancerand
                       ESC_pc_temp_randKSS)
 from .frontend import (build_clouds, coord_tables, gather_points, importance_heat, importance_points, random_points,
                        select_points, spectral_point_cloud, stft_logmag, topk_points)
-from .models import ST, DeepSet, SetTransformer, strip_module_prefix
+from .models import ST, DeepSet, SetTransformer, SetTransformerSAB, strip_module_prefix
 from .modules import ISAB, MAB, PMA, SAB
 from .pipeline import AudioConfig, AudioSetPipeline
 from .training import SetTrainer, STTrainFunction
@@ -15,6 +15,6 @@ from .utils import pc_maxK, pc_randK
 
 __all__ = ["load_esc", "tt_split", "ESC_pc", "ESC_pc_ss", "ESC_pc_temp", "ESC_pc_temp_maxKSS", "build_clouds",
            "coord_tables", "select_points", "spectral_point_cloud", "stft_logmag", "topk_points", "ST", "DeepSet",
-           "SetTransformer", "strip_module_prefix", "ISAB", "MAB", "PMA", "SAB", "AudioConfig",
+           "SetTransformer", "SetTransformerSAB", "strip_module_prefix", "ISAB", "MAB", "PMA", "SAB", "AudioConfig",
            "AudioSetPipeline", "pc_maxK", "pc_randK", "ESC_pc_temp_randKSS", "ESC_pc_temp_importancerandKSS", "gather_points",
            "importance_heat", "importance_points", "random_points", "SetTrainer", "STTrainFunction"]

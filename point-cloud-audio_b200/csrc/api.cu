@@ -621,6 +621,12 @@ int pca_debug_st_stages(const float* X, int B, int N, const pca_st_dims* dims, c
                                 (cudaStream_t)stream);
 }
 
+int pca_linear_fwd_f32(const float* X, long long rows, int din, int dout, const float* params, float* Y, void* stream) {
+    if (!X || !params || !Y) return fail(PCA_EINVAL, "linear: null pointer");
+    if (rows < 0 || din <= 0 || dout <= 0) return fail(PCA_EINVAL, "linear: bad shape");
+    return launch_linear(X, params, params + (long long)dout * din, Y, rows, din, dout, 0, (cudaStream_t)stream);
+}
+
 int pca_random_keys_f32(float* keys, long long n, unsigned long long seed, void* stream) {
     if (!keys && n > 0) return fail(PCA_EINVAL, "random_keys: null pointer");
     return launch_random_keys(keys, n, seed, (cudaStream_t)stream);

@@ -209,3 +209,38 @@ class DeepSet(nn.Module):
                                                     _lib.ptr(out), _lib.ptr(ws), ws.numel(), rt.stream_ptr(X.device)),
                        "DeepSet.forward")
         return _guard(out.reshape(-1, self.num_outputs, self.dim_output), self)
+
+
+class SetTransformerSAB(nn.Module):
+    """The generic ``SetTransformer`` of set_transformer-master/models.py:30-44 (the clustering model): ISAB, ISAB ->
+    PMA(num_outputs seeds) -> SAB, SAB -> Linear, optional LayerNorm.  Same constructor signature, module tree and
+    state-dict keys as the reference class (which shares its name with main_pointcloud.SetTransformer, hence the suffix
+    here; ``pcaudio_b200.st_models.SetTransformer`` is the same class under the reference's name).  Forward runs the fp32
+    per-block CUDA kernels (every dim, ``ln`` included); output (B, num_outputs, dim_output), no squeeze."""
+
+    def __init__(self, dim_input, num_outputs, dim_output, num_inds=32, dim_hidden=128, num_heads=4, ln=False):
+        super().__init__()
+        self.enc = nn.Sequential(
+            ISAB(dim_input, dim_hidden, num_heads, num_inds, ln=ln),
+            ISAB(dim_hidden, dim_hidden, num_heads, num_inds, ln=ln))
+        self.dec = nn.Sequential(
+            PMA(dim_hidden, num_heads, num_outputs, ln=ln),
+            SAB(dim_hidden, dim_hidden, num_heads, ln=ln),
+            SAB(dim_hidden, dim_hidden, num_heads, ln=ln),
+            nn.Linear(dim_hidden, dim_output))
+        self._packed = _PackedParams()
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        return super().load_state_dict(strip_module_prefix(state_dict), *args, **kwargs)
+
+    def forward(self, X):
+        rt.require_cuda(X, "SetTransformerSAB.forward")
+        Y = self.dec[2](self.dec[1](self.dec[0](self.enc(rt.f32c(X)))))             # ISAB, ISAB, PMA, SAB, SAB
+        lin = self.dec[3]
+        B, S, D = Y.shape
+        out = torch.empty((B, S, lin.out_features), dtype=torch.float32, device=Y.device)
+        blob = self._packed.get([lin.weight, lin.bias])
+        with torch.cuda.device(Y.device):
+            _lib.check(_lib.lib().pca_linear_fwd_f32(_lib.ptr(Y), B * S, D, lin.out_features, _lib.ptr(blob), _lib.ptr(out),
+                                                    rt.stream_ptr(Y.device)), "SetTransformerSAB.forward(Linear)")
+        return _guard(out, self)

@@ -321,3 +321,18 @@ def test_full_size_properties(pca, dev):
         a = st3(pts)
         b = st3(pts[:, torch.randperm(8192, device=dev)])
     assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < ENC_REL_TOL
+
+
+# ------------------------------------------------------------------------------------ generic SetTransformer (SAB decoder)
+@pytest.mark.parametrize("tag", ["noln", "ln"])
+def test_generic_set_transformer_sab_decoder_matches_reference_golden(pca, dev, tag):
+    """set_transformer-master/models.py:30-44 (ISAB, ISAB -> PMA(k seeds) -> SAB, SAB -> Linear), with and without
+    LayerNorm, against outputs of the unmodified reference (tests/golden/make_golden_stmodels.py)."""
+    from pcaudio_b200 import st_models
+    g = dict(np.load(os.path.join(G, "stmodels_golden.npz")))
+    k = g[f"{tag}_Y"].shape[1]
+    m = st_models.SetTransformer(2, k, 6, num_inds=8, dim_hidden=32, num_heads=4, ln=(tag == "ln")).to(dev)
+    m.load_state_dict({key[len(tag) + 3:]: torch.from_numpy(v) for key, v in g.items() if key.startswith(f"{tag}_w_")})
+    out = m(torch.from_numpy(g[f"{tag}_X"]).to(dev)).cpu().numpy()
+    assert out.shape == g[f"{tag}_Y"].shape
+    assert rel_err(out, g[f"{tag}_Y"]) < ENC_REL_TOL
