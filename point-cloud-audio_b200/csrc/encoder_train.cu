@@ -252,7 +252,7 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
 // Warp = head.  Lane = (dim slice g of G, own item, loop slice): an "own" item (MODE 0: a query -> dQp; MODE 1: a key -> dKp,
 // dVp) keeps its DH = G*DL head dims in the registers of G adjacent lanes; the "loop" items (MODE 0: keys; MODE 1: queries)
 // are staged through shared memory and read as broadcasts.  Loop ranges are cut across blockIdx.y; results are added atomically.
-template <int DL, int G, int MODE>
+template <int DL, int G, int MODE, int R>
 __global__ void attn_bwd_kernel(const float* __restrict__ Qp, long long q_bstride, const float* __restrict__ KV,
                                 const float* __restrict__ dO, const float* __restrict__ lse, const float* __restrict__ delta,
                                 int nq, int nk, int D, int town_log, int tl, int chunk, int own_tiles, float scale, float scale_log2e,
@@ -272,38 +272,45 @@ __global__ void attn_bwd_kernel(const float* __restrict__ Qp, long long q_bstrid
     const int H2 = (2 * H + 3) & ~3;
     const int rs = MODE == 0 ? 2 * D + 4 : 2 * D + H2 + 4;        // smem row stride (floats)
     const int hoff = h * DH + g * DL;
+    // Register blocking: a thread group owns R items (own_l, own_l + TOWN, ...), so every streamed row element read from
+    // shared memory feeds R of them (ncu at R = 1: l1tex 94-96 % of peak, the broadcast reads are the binding unit).
     // own_tiles > 1 only when the loop set is a single smem tile (staged once, reused by every own tile of the block)
   for (int ot = 0; ot < own_tiles; ++ot) {
-    const int own = (blockIdx.x * own_tiles + ot) * TOWN + own_l;
-    if ((blockIdx.x * own_tiles + ot) * TOWN >= n_own) break;      // block-uniform
-    const bool ovalid = own < n_own;
-    const int oc = ovalid ? own : 0;
-
-    float a0[DL], a1[DL], acc0[DL], acc1[DL];
-    float lse_o = 0.f, delta_o = 0.f;
-    if (MODE == 0) {
-        const float* qp = Qp + (long long)b * q_bstride + (long long)oc * D + hoff;
-        const float* gp = dO + ((long long)b * nq + oc) * D + hoff;
+    const int own0 = (blockIdx.x * own_tiles + ot) * TOWN * R;
+    if (own0 >= n_own) break;                                      // block-uniform
+    int own[R];
+    bool ovalid[R];
+    float a0[R][DL], a1[R][DL], acc0[R][DL], acc1[R][DL];
+    float lse_o[R], delta_o[R];
 #pragma unroll
-        for (int j = 0; j < DL; j += 4) {           // per-thread rows: 16-byte accesses
-            const float4 t0 = __ldg(reinterpret_cast<const float4*>(qp + j)), t1 = __ldg(reinterpret_cast<const float4*>(gp + j));
-            a0[j] = t0.x * scale_log2e; a0[j + 1] = t0.y * scale_log2e; a0[j + 2] = t0.z * scale_log2e; a0[j + 3] = t0.w * scale_log2e;
-            a1[j] = t1.x; a1[j + 1] = t1.y; a1[j + 2] = t1.z; a1[j + 3] = t1.w;
+    for (int r = 0; r < R; ++r) {
+        own[r] = own0 + r * TOWN + own_l;
+        ovalid[r] = own[r] < n_own;
+        const int oc = ovalid[r] ? own[r] : 0;
+        lse_o[r] = 0.f;
+        delta_o[r] = 0.f;
+        if (MODE == 0) {
+            const float* qp = Qp + (long long)b * q_bstride + (long long)oc * D + hoff;
+            const float* gp = dO + ((long long)b * nq + oc) * D + hoff;
+#pragma unroll
+            for (int j = 0; j < DL; j += 4) {           // per-thread rows: 16-byte accesses
+                const float4 t0 = __ldg(reinterpret_cast<const float4*>(qp + j)), t1 = __ldg(reinterpret_cast<const float4*>(gp + j));
+                a0[r][j] = t0.x * scale_log2e; a0[r][j + 1] = t0.y * scale_log2e; a0[r][j + 2] = t0.z * scale_log2e; a0[r][j + 3] = t0.w * scale_log2e;
+                a1[r][j] = t1.x; a1[r][j + 1] = t1.y; a1[r][j + 2] = t1.z; a1[r][j + 3] = t1.w;
+            }
+            lse_o[r] = __ldg(lse + ((long long)b * nq + oc) * H + h);
+            delta_o[r] = __ldg(delta + ((long long)b * nq + oc) * H + h);
+        } else {
+            const float* kp = KV + ((long long)b * nk + oc) * 2 * D + hoff;
+#pragma unroll
+            for (int j = 0; j < DL; j += 4) {
+                const float4 t0 = __ldg(reinterpret_cast<const float4*>(kp + j)), t1 = __ldg(reinterpret_cast<const float4*>(kp + D + j));
+                a0[r][j] = t0.x; a0[r][j + 1] = t0.y; a0[r][j + 2] = t0.z; a0[r][j + 3] = t0.w;
+                a1[r][j] = t1.x; a1[r][j + 1] = t1.y; a1[r][j + 2] = t1.z; a1[r][j + 3] = t1.w;
+            }
         }
 #pragma unroll
-        for (int j = 0; j < DL; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
-        lse_o = __ldg(lse + ((long long)b * nq + oc) * H + h);
-        delta_o = __ldg(delta + ((long long)b * nq + oc) * H + h);
-    } else {
-        const float* kp = KV + ((long long)b * nk + oc) * 2 * D + hoff;
-#pragma unroll
-        for (int j = 0; j < DL; j += 4) {
-            const float4 t0 = __ldg(reinterpret_cast<const float4*>(kp + j)), t1 = __ldg(reinterpret_cast<const float4*>(kp + D + j));
-            a0[j] = t0.x; a0[j + 1] = t0.y; a0[j + 2] = t0.z; a0[j + 3] = t0.w;
-            a1[j] = t1.x; a1[j + 1] = t1.y; a1[j + 2] = t1.z; a1[j + 3] = t1.w;
-        }
-#pragma unroll
-        for (int j = 0; j < DL; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+        for (int j = 0; j < DL; ++j) { acc0[r][j] = 0.f; acc1[r][j] = 0.f; }
     }
 
     const int l_begin = blockIdx.y * chunk;
@@ -340,61 +347,70 @@ __global__ void attn_bwd_kernel(const float* __restrict__ Qp, long long q_bstrid
             const int li = it + ls;
             const bool lv = li < tn;
             const float* row = rows_s + (lv ? li : 0) * rs;
-            if (MODE == 0) {
-                const float* kr = row + hoff;
-                const float* vr = row + D + hoff;
+            // the streamed row's slice, read once for all R own items
+            float x0[DL], x1[DL];
+#pragma unroll
+            for (int j = 0; j < DL; j += 4) {
+                const float4 t0 = *reinterpret_cast<const float4*>(row + hoff + j), t1 = *reinterpret_cast<const float4*>(row + D + hoff + j);
+                x0[j] = t0.x; x0[j + 1] = t0.y; x0[j + 2] = t0.z; x0[j + 3] = t0.w;
+                x1[j] = t1.x; x1[j + 1] = t1.y; x1[j + 2] = t1.z; x1[j + 3] = t1.w;
+            }
+            float lse_l = 0.f, delta_l = 0.f;
+            if (MODE == 1) { lse_l = row[2 * D + h]; delta_l = row[2 * D + H + h]; }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
                 float s = 0.f, dp = 0.f;
 #pragma unroll
-                for (int j = 0; j < DL; ++j) { s = fmaf(a0[j], kr[j], s); dp = fmaf(a1[j], vr[j], dp); }
+                for (int j = 0; j < DL; ++j) { s = fmaf(a0[r][j], x0[j], s); dp = fmaf(a1[r][j], x1[j], dp); }
 #pragma unroll
                 for (int o = 1; o < G; o <<= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); dp += __shfl_xor_sync(0xffffffffu, dp, o); }
-                const float p = lv ? exp2f(s - lse_o) : 0.f;
-                const float ds = p * (dp - delta_o) * scale;
+                if (MODE == 0) {
+                    // x0 = k, x1 = v; a0 = q (scaled), a1 = dO
+                    const float p = lv ? exp2f(s - lse_o[r]) : 0.f;
+                    const float ds = p * (dp - delta_o[r]) * scale;
 #pragma unroll
-                for (int j = 0; j < DL; ++j) acc0[j] = fmaf(ds, kr[j], acc0[j]);
-            } else {
-                const float* qr = row + hoff;
-                const float* gr = row + D + hoff;
-                float s = 0.f, dp = 0.f;
+                    for (int j = 0; j < DL; ++j) acc0[r][j] = fmaf(ds, x0[j], acc0[r][j]);
+                } else {
+                    // x0 = q, x1 = dO; a0 = k, a1 = v
+                    const float p = lv ? exp2f(s * scale_log2e - lse_l) : 0.f;
+                    const float ds = p * (dp - delta_l) * scale;
 #pragma unroll
-                for (int j = 0; j < DL; ++j) { s = fmaf(qr[j], a0[j], s); dp = fmaf(gr[j], a1[j], dp); }
-#pragma unroll
-                for (int o = 1; o < G; o <<= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); dp += __shfl_xor_sync(0xffffffffu, dp, o); }
-                const float p = lv ? exp2f(s * scale_log2e - row[2 * D + h]) : 0.f;
-                const float ds = p * (dp - row[2 * D + H + h]) * scale;
-#pragma unroll
-                for (int j = 0; j < DL; ++j) { acc0[j] = fmaf(ds, qr[j], acc0[j]); acc1[j] = fmaf(p, gr[j], acc1[j]); }
+                    for (int j = 0; j < DL; ++j) { acc0[r][j] = fmaf(ds, x0[j], acc0[r][j]); acc1[r][j] = fmaf(p, x1[j], acc1[r][j]); }
+                }
             }
         }
         if (own_tiles == 1) __syncthreads();
     }
     // merge the loop slices of one own item across lanes
-    for (int off = G * TOWN; off < 32; off <<= 1) {
 #pragma unroll
-        for (int j = 0; j < DL; ++j) {
-            acc0[j] += __shfl_xor_sync(0xffffffffu, acc0[j], off);
-            if (MODE == 1) acc1[j] += __shfl_xor_sync(0xffffffffu, acc1[j], off);
+    for (int r = 0; r < R; ++r) {
+        for (int off = G * TOWN; off < 32; off <<= 1) {
+#pragma unroll
+            for (int j = 0; j < DL; ++j) {
+                acc0[r][j] += __shfl_xor_sync(0xffffffffu, acc0[r][j], off);
+                if (MODE == 1) acc1[r][j] += __shfl_xor_sync(0xffffffffu, acc1[r][j], off);
+            }
         }
-    }
-    if (ovalid && ls == 0) {
-        if (MODE == 0) {
-            float* o = dQp + ((long long)b * nq + own) * D + hoff;
+        if (ovalid[r] && ls == 0) {
+            if (MODE == 0) {
+                float* o = dQp + ((long long)b * nq + own[r]) * D + hoff;
 #pragma unroll
-            for (int j = 0; j < DL; j += 4) red_add4(o + j, acc0[j], acc0[j + 1], acc0[j + 2], acc0[j + 3]);
-        } else {
-            float* o = dKV + ((long long)b * nk + own) * 2 * D + hoff;
+                for (int j = 0; j < DL; j += 4) red_add4(o + j, acc0[r][j], acc0[r][j + 1], acc0[r][j + 2], acc0[r][j + 3]);
+            } else {
+                float* o = dKV + ((long long)b * nk + own[r]) * 2 * D + hoff;
 #pragma unroll
-            for (int j = 0; j < DL; j += 4) {
-                red_add4(o + j, acc0[j], acc0[j + 1], acc0[j + 2], acc0[j + 3]);
-                red_add4(o + D + j, acc1[j], acc1[j + 1], acc1[j + 2], acc1[j + 3]);
+                for (int j = 0; j < DL; j += 4) {
+                    red_add4(o + j, acc0[r][j], acc0[r][j + 1], acc0[r][j + 2], acc0[r][j + 3]);
+                    red_add4(o + D + j, acc1[r][j], acc1[r][j + 1], acc1[r][j + 2], acc1[r][j + 3]);
+                }
             }
         }
     }
   }
 }
 
-template <int DL, int G, int MODE>
-static int launch_attn_bwd_t(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse,
+template <int DL, int G, int MODE, int R>
+static int launch_attn_bwd_r(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse,
                              const float* delta, int B, int nq, int nk, int D, int H, float* dQp, float* dKV, cudaStream_t st) {
     const int n_own = MODE == 0 ? nq : nk, n_loop = MODE == 0 ? nk : nq;
     int town = 32 / G;
@@ -408,7 +424,7 @@ static int launch_attn_bwd_t(const float* Qp, long long q_bstride, const float* 
     if (tl < 1) tl = 1;
     if (tl > n_loop) tl = n_loop;
     const size_t smem = (size_t)tl * rs * 4;
-    const long long base_blocks = (long long)B * ((n_own + town - 1) / town);
+    const long long base_blocks = (long long)B * ((n_own + town * R - 1) / (town * R));
     int nsplit = 1;
     const long long target = 148LL * 4;
     if (base_blocks < target) {
@@ -421,7 +437,7 @@ static int launch_attn_bwd_t(const float* Qp, long long q_bstride, const float* 
     chunk = (chunk + tl - 1) / tl * tl;
     nsplit = (n_loop + chunk - 1) / chunk;
     // the whole loop set in one smem tile: a block stages it once and walks several own tiles (keeps >= ~8 blocks per SM)
-    const int own_blocks = (n_own + town - 1) / town;
+    const int own_blocks = (n_own + town * R - 1) / (town * R);
     int own_tiles = 1;
     if (nsplit == 1 && n_loop <= tl) {
         long long ot = ((long long)own_blocks * B) / (148LL * 8);
@@ -430,15 +446,26 @@ static int launch_attn_bwd_t(const float* Qp, long long q_bstride, const float* 
     dim3 grid((own_blocks + own_tiles - 1) / own_tiles, nsplit, B);
     const float scale = 1.0f / sqrtf((float)D);
     if (smem > 48 * 1024)
-        PCA_CHECK_CUDA((cudaFuncSetAttribute(attn_bwd_kernel<DL, G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        PCA_CHECK_CUDA((cudaFuncSetAttribute(attn_bwd_kernel<DL, G, MODE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     {
         LaunchTimer lt(MODE == 0 ? "attn_bwd_dq_kernel" : "attn_bwd_dkv_kernel", st, (MODE == 0 ? 6.0 : 8.0) * B * nq * (double)nk * D,
                        4.0 * ((double)B * nk * 2 * D + 3.0 * B * nq * D));
-        attn_bwd_kernel<DL, G, MODE><<<grid, 32 * H, smem, st>>>(Qp, q_bstride, KV, dO, lse, delta, nq, nk, D, town_log, tl, chunk,
+        attn_bwd_kernel<DL, G, MODE, R><<<grid, 32 * H, smem, st>>>(Qp, q_bstride, KV, dO, lse, delta, nq, nk, D, town_log, tl, chunk,
                                                                 own_tiles, scale, scale * 1.4426950408889634f, dQp, dKV);
     }
     PCA_CHECK_LAUNCH("attn_bwd_kernel");
     return 0;
+}
+
+// two own items per thread group when the own set is large enough to keep every lane busy and the grid full
+template <int DL, int G, int MODE>
+static int launch_attn_bwd_t(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse,
+                             const float* delta, int B, int nq, int nk, int D, int H, float* dQp, float* dKV, cudaStream_t st) {
+    const int n_own = MODE == 0 ? nq : nk;
+    const int per_warp = 2 * (32 / G);
+    if (n_own >= 2 * per_warp && (long long)B * (n_own / per_warp) >= 148LL * 4)
+        return launch_attn_bwd_r<DL, G, MODE, 2>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st);
+    return launch_attn_bwd_r<DL, G, MODE, 1>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st);
 }
 
 template <int MODE>
