@@ -221,6 +221,17 @@ int pca_st_train_bwd_f32(const float* X, int B, int N, const pca_st_dims* dims, 
                          unsigned long long seed, const float* dlogits, const void* saved, size_t saved_bytes,
                          float* dparams, float* dX, void* workspace, size_t workspace_bytes, void* stream);
 
+/* DeepSet training (set_transformer-master/models.py:3-28; pool 0 mean / 1 max / 2 sum): forward that keeps the activations
+ * (and the arg-max points of the max pool), backward returning the flat parameter gradient in the layout of `params`
+ * (enc then dec, 4 x (W | b)) and optionally dX.  out / dout (B, out_dim).  Equal-size sets. */
+size_t pca_deepset_train_saved_bytes(int B, int N, int dim_hidden);
+size_t pca_deepset_train_workspace_bytes(int B, int N, int dim_hidden);
+int pca_deepset_train_fwd_f32(const float* X, int B, int N, int d_in, int dim_hidden, int out_dim, int pool, const float* params,
+                              float* out, void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes, void* stream);
+int pca_deepset_train_bwd_f32(const float* X, int B, int N, int d_in, int dim_hidden, int out_dim, int pool, const float* params,
+                              const float* dout, const void* saved, size_t saved_bytes, float* dparams, float* dX,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* nn.CrossEntropyLoss(reduction='mean') on logits (B, C) with int64 labels: loss[0] += mean loss, correct[0] +=
  * number of rows whose arg-max equals the label (both caller-zeroed, either may be NULL except loss),
  * dlogits (B, C) = d loss / d logits (may be NULL). */

@@ -30,6 +30,11 @@ int st_train_forward(const float*, int, int, const pca_st_dims*, const float*, f
                      size_t, cudaStream_t);
 int st_train_backward(const float*, int, int, const pca_st_dims*, const float*, float, unsigned long long, const float*, const void*,
                       size_t, float*, float*, void*, size_t, cudaStream_t);
+size_t deepset_train_saved_bytes(int B, int N, int dh);
+size_t deepset_train_ws_bytes(int B, int N, int dh);
+int deepset_train_forward(const float*, int, int, int, int, int, int, const float*, float*, void*, size_t, void*, size_t, cudaStream_t);
+int deepset_train_backward(const float*, int, int, int, int, int, int, const float*, const float*, const void*, size_t, float*, float*,
+                           void*, size_t, cudaStream_t);
 int launch_cross_entropy(const float*, const long long*, int, int, float, float*, int*, float*, cudaStream_t);
 int launch_adam(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float, cudaStream_t);
 void set_timeline(long long* p);
@@ -668,6 +673,23 @@ int pca_st_train_bwd_f32(const float* X, int B, int N, const pca_st_dims* dims, 
                          float* dX, void* workspace, size_t workspace_bytes, void* stream) {
     return st_train_backward(X, B, N, dims, params, dropout_p, seed, dlogits, saved, saved_bytes, dparams, dX, workspace,
                              workspace_bytes, (cudaStream_t)stream);
+}
+size_t pca_deepset_train_saved_bytes(int B, int N, int dim_hidden) {
+    return (B > 0 && N > 0 && dim_hidden > 0) ? deepset_train_saved_bytes(B, N, dim_hidden) : 0;
+}
+size_t pca_deepset_train_workspace_bytes(int B, int N, int dim_hidden) {
+    return (B > 0 && N > 0 && dim_hidden > 0) ? deepset_train_ws_bytes(B, N, dim_hidden) : 0;
+}
+int pca_deepset_train_fwd_f32(const float* X, int B, int N, int d_in, int dim_hidden, int out_dim, int pool, const float* params,
+                              float* out, void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+    return deepset_train_forward(X, B, N, d_in, dim_hidden, out_dim, pool, params, out, saved, saved_bytes, workspace, workspace_bytes,
+                                 (cudaStream_t)stream);
+}
+int pca_deepset_train_bwd_f32(const float* X, int B, int N, int d_in, int dim_hidden, int out_dim, int pool, const float* params,
+                              const float* dout, const void* saved, size_t saved_bytes, float* dparams, float* dX, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    return deepset_train_backward(X, B, N, d_in, dim_hidden, out_dim, pool, params, dout, saved, saved_bytes, dparams, dX, workspace,
+                                  workspace_bytes, (cudaStream_t)stream);
 }
 int pca_cross_entropy_f32(const float* logits, const int64_t* labels, int B, int C, float* loss, int32_t* correct, float* dlogits,
                           void* stream) {

@@ -726,6 +726,175 @@ int st_train_backward(const float* X, int B, int N, const pca_st_dims* d, const 
     return 0;
 }
 
+// ------------------------------------------------------------------------------------ DeepSet training
+// set_transformer-master/models.py:3-28 (mean pool; max / sum of max_regression_demo.ipynb:41-48): enc = 4 x Linear (ReLU after
+// the first three) over points, pool over points, dec = 4 x Linear (ReLU after the first three).  Saved: the four encoder
+// activations, the pooled vectors, the three decoder activations and (max pool) the arg-max point of every (cloud, feature).
+struct DsSaved { float *t[4], *pooled, *u[3]; int* arg; };
+static DsSaved ds_saved_take(Arena& a, int B, int N, int dh) {
+    DsSaved s;
+    for (int i = 0; i < 4; ++i) s.t[i] = a.take<float>((size_t)B * N * dh);
+    s.pooled = a.take<float>((size_t)B * dh);
+    for (int i = 0; i < 3; ++i) s.u[i] = a.take<float>((size_t)B * dh);
+    s.arg = a.take<int>((size_t)B * dh);
+    return s;
+}
+size_t deepset_train_saved_bytes(int B, int N, int dh) {
+    Arena a(nullptr, 0);
+    ds_saved_take(a, B, N, dh);
+    return a.off;
+}
+size_t deepset_train_ws_bytes(int B, int N, int dh) {
+    Arena a(nullptr, 0);
+    a.take<float>((size_t)B * N * dh);
+    a.take<float>((size_t)B * N * dh);
+    a.take<float>((size_t)B * dh);
+    a.take<float>((size_t)B * dh);
+    a.take<uint8_t>(gemm_tc_image_bytes(dh, dh));
+    return a.off;
+}
+
+// pooled (B, D) over the N points of X (B, N, D): 0 mean, 1 max (arg-max kept: first maximal point), 2 sum
+__global__ void pool_train_kernel(const float* __restrict__ X, int N, int D, int pool, float* __restrict__ out, int* __restrict__ arg) {
+    const int b = blockIdx.y, d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const float* x = X + (long long)b * N * D + d;
+    float v = pool == 1 ? -INFINITY : 0.f;
+    int am = 0;
+    for (int p = 0; p < N; ++p) {
+        const float t = __ldg(x + (long long)p * D);
+        if (pool == 1) { if (t > v) { v = t; am = p; } }
+        else v += t;
+    }
+    if (pool == 0) v /= (float)N;
+    out[(long long)b * D + d] = v;
+    if (arg) arg[(long long)b * D + d] = am;
+}
+// dT (B, N, D) from dPooled (B, D), optionally masked by the ReLU... (the last encoder layer has no ReLU)
+__global__ void pool_bwd_kernel(const float* __restrict__ dP, const int* __restrict__ arg, int N, int D, int pool, long long total,
+                                float* __restrict__ dT) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int d = (int)(i % D);
+    const long long bp = i / D;
+    const int p = (int)(bp % N);
+    const long long b = bp / N;
+    const float g = __ldg(dP + b * D + d);
+    dT[i] = pool == 0 ? g / (float)N : (pool == 2 ? g : (__ldg(arg + b * D + d) == p ? g : 0.f));
+}
+
+static void ds_params(const float* p, int d_in, int dh, int out_dim, const float** W, const float** bb) {
+    for (int i = 0; i < 8; ++i) {
+        const int dout = (i == 7) ? out_dim : dh;
+        const int di = (i == 0) ? d_in : dh;
+        W[i] = p; p += (long long)dout * di;
+        bb[i] = p; p += dout;
+    }
+}
+
+int deepset_train_forward(const float* X, int B, int N, int d_in, int dh, int out_dim, int pool, const float* params, float* out,
+                          void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!X || !params || !out || !saved || !ws) return fail(PCA_EINVAL, "DeepSet training forward: null pointer");
+    if (B <= 0 || N <= 0 || d_in <= 0 || dh <= 0 || out_dim <= 0 || B > 65535) return fail(PCA_EINVAL, "DeepSet training: bad shape");
+    if (pool < 0 || pool > 2) return fail(PCA_EINVAL, "DeepSet training: pool %d not in {0 mean, 1 max, 2 sum}", pool);
+    Arena sa(saved, saved_bytes);
+    const DsSaved s = ds_saved_take(sa, B, N, dh);
+    if (!sa.ok() || ws_bytes < deepset_train_ws_bytes(B, N, dh)) return fail(PCA_EWORKSPACE, "DeepSet training forward: buffers too small");
+    Arena wa(ws, ws_bytes);
+    wa.take<float>((size_t)B * N * dh); wa.take<float>((size_t)B * N * dh); wa.take<float>((size_t)B * dh); wa.take<float>((size_t)B * dh);
+    const size_t ib = gemm_tc_image_bytes(dh, dh);
+    void* img = wa.take<uint8_t>(ib);
+    const float* W[8]; const float* bb[8];
+    ds_params(params, d_in, dh, out_dim, W, bb);
+    const long long rows = (long long)B * N;
+    PCA_TRY(launch_linear(X, W[0], bb[0], s.t[0], rows, d_in, dh, 1, st));
+    PCA_TRY(launch_linear(s.t[0], W[1], bb[1], s.t[1], rows, dh, dh, 1, st, nullptr, img, ib));
+    PCA_TRY(launch_linear(s.t[1], W[2], bb[2], s.t[2], rows, dh, dh, 1, st, nullptr, img, ib));
+    PCA_TRY(launch_linear(s.t[2], W[3], bb[3], s.t[3], rows, dh, dh, 0, st, nullptr, img, ib));
+    {
+        dim3 grid((dh + 127) / 128, B);
+        pool_train_kernel<<<grid, 128, 0, st>>>(s.t[3], N, dh, pool, s.pooled, pool == 1 ? s.arg : nullptr);
+        PCA_CHECK_LAUNCH("pool_train_kernel");
+    }
+    PCA_TRY(launch_linear(s.pooled, W[4], bb[4], s.u[0], B, dh, dh, 1, st));
+    PCA_TRY(launch_linear(s.u[0], W[5], bb[5], s.u[1], B, dh, dh, 1, st));
+    PCA_TRY(launch_linear(s.u[1], W[6], bb[6], s.u[2], B, dh, dh, 1, st));
+    PCA_TRY(launch_linear(s.u[2], W[7], bb[7], out, B, dh, out_dim, 0, st));
+    return 0;
+}
+
+int deepset_train_backward(const float* X, int B, int N, int d_in, int dh, int out_dim, int pool, const float* params,
+                           const float* dout, const void* saved, size_t saved_bytes, float* dparams, float* dX, void* ws,
+                           size_t ws_bytes, cudaStream_t st) {
+    if (!X || !params || !dout || !saved || !dparams || !ws) return fail(PCA_EINVAL, "DeepSet training backward: null pointer");
+    if (B <= 0 || N <= 0 || B > 65535) return fail(PCA_EINVAL, "DeepSet training: bad shape");
+    Arena sa(const_cast<void*>(saved), saved_bytes);
+    const DsSaved s = ds_saved_take(sa, B, N, dh);
+    if (!sa.ok() || ws_bytes < deepset_train_ws_bytes(B, N, dh)) return fail(PCA_EWORKSPACE, "DeepSet training backward: buffers too small");
+    Arena wa(ws, ws_bytes);
+    float* gA = wa.take<float>((size_t)B * N * dh);
+    float* gB = wa.take<float>((size_t)B * N * dh);
+    float* hA = wa.take<float>((size_t)B * dh);
+    float* hB = wa.take<float>((size_t)B * dh);
+    const size_t ib = gemm_tc_image_bytes(dh, dh);
+    void* img = wa.take<uint8_t>(ib);
+    const float* W[8]; const float* bb[8];
+    ds_params(params, d_in, dh, out_dim, W, bb);
+    long long total = 0;
+    for (int i = 0; i < 8; ++i) total += (long long)((i == 7) ? out_dim : dh) * ((i == 0) ? d_in : dh) + ((i == 7) ? out_dim : dh);
+    PCA_CHECK_CUDA(cudaMemsetAsync(dparams, 0, (size_t)total * sizeof(float), st));
+    float* dW[8]; float* db[8];
+    {
+        float* q = dparams;
+        for (int i = 0; i < 8; ++i) {
+            const int do_ = (i == 7) ? out_dim : dh, di = (i == 0) ? d_in : dh;
+            dW[i] = q; q += (long long)do_ * di;
+            db[i] = q; q += do_;
+        }
+    }
+    auto relu_mask = [&](const float* g, const float* act, float* o, long long n) -> int {
+        relu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, act, o, n);
+        PCA_CHECK_LAUNCH("relu_bwd_kernel");
+        return 0;
+    };
+    // ---- decoder (rows = B)
+    PCA_TRY(launch_grad_weight(dout, s.u[2], dW[7], B, dh, out_dim, st));
+    PCA_TRY(launch_colsum(dout, B, out_dim, db[7], st));
+    PCA_TRY(launch_grad_input(dout, W[7], hA, nullptr, B, dh, out_dim, st));
+    const float* acts[3] = {s.u[2], s.u[1], s.u[0]};
+    const float* ins[3] = {s.u[1], s.u[0], s.pooled};
+    float* cur = hA; float* oth = hB;
+    for (int l = 0; l < 3; ++l) {                     // layers 6, 5, 4
+        const int li = 6 - l;
+        PCA_TRY(relu_mask(cur, acts[l], cur, (long long)B * dh));
+        PCA_TRY(launch_grad_weight(cur, ins[l], dW[li], B, dh, dh, st));
+        PCA_TRY(launch_colsum(cur, B, dh, db[li], st));
+        PCA_TRY(launch_grad_input(cur, W[li], oth, nullptr, B, dh, dh, st));
+        float* t = cur; cur = oth; oth = t;
+    }
+    // ---- pool: cur = d pooled (B, dh) -> gA = d t3 (B, N, dh)
+    const long long rows = (long long)B * N, n_el = rows * dh;
+    pool_bwd_kernel<<<(unsigned)((n_el + 255) / 256), 256, 0, st>>>(cur, s.arg, N, dh, pool, n_el, gA);
+    PCA_CHECK_LAUNCH("pool_bwd_kernel");
+    // ---- encoder layer 3 (no ReLU), then 2, 1 (ReLU), then 0
+    PCA_TRY(launch_grad_weight(gA, s.t[2], dW[3], rows, dh, dh, st));
+    PCA_TRY(launch_colsum(gA, rows, dh, db[3], st));
+    PCA_TRY(launch_grad_input(gA, W[3], gB, nullptr, rows, dh, dh, st, img, ib));
+    float* g = gB; float* go = gA;
+    for (int li = 2; li >= 1; --li) {
+        PCA_TRY(relu_mask(g, s.t[li], g, n_el));
+        PCA_TRY(launch_grad_weight(g, s.t[li - 1], dW[li], rows, dh, dh, st));
+        PCA_TRY(launch_colsum(g, rows, dh, db[li], st));
+        PCA_TRY(launch_grad_input(g, W[li], go, nullptr, rows, dh, dh, st, img, ib));
+        float* t = g; g = go; go = t;
+    }
+    PCA_TRY(relu_mask(g, s.t[0], g, n_el));
+    PCA_TRY(launch_grad_weight(g, X, dW[0], rows, d_in, dh, st));
+    PCA_TRY(launch_colsum(g, rows, dh, db[0], st));
+    if (dX) PCA_TRY(launch_grad_input(g, W[0], dX, nullptr, rows, d_in, dh, st));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------ loss and optimizer
 // nn.CrossEntropyLoss (mean reduction; Code/settransformer.py:89, main_pointcloud.py:63): one warp per row.
 // loss_sum[0] += sum_b (lse_b - z_b[label_b]) * inv_batch; dlogits = (softmax - onehot) * inv_batch; correct[0] += [argmax == label]

@@ -200,10 +200,15 @@ class DeepSet(nn.Module):
             for i in (0, 2, 4, 6):
                 ts += [seq[i].weight, seq[i].bias]
         blob = self._packed.get(ts)
+        pool = {"mean": 0, "max": 1, "sum": 2}[self.pool]
+        if B > 0 and counts is None and torch.is_grad_enabled() and (X.requires_grad or any(p.requires_grad for p in ts)):
+            # training: fp32 forward that keeps activations + hand-written backward (pcaudio_b200/training.py)
+            from .training import DeepSetTrainFunction
+            out = DeepSetTrainFunction.apply(X, blob, (d_in, dh, out_dim, pool), *ts)
+            return out.reshape(-1, self.num_outputs, self.dim_output)
         out = torch.empty((B, out_dim), dtype=torch.float32, device=X.device)
         L = _lib.lib()
         ws = rt.workspace(X.device, L.pca_deepset_workspace_bytes(B, N, d_in, dh, out_dim))
-        pool = {"mean": 0, "max": 1, "sum": 2}[self.pool]
         with torch.cuda.device(X.device):
             _lib.check(L.pca_deepset_fwd_masked_f32(_lib.ptr(X), _lib.ptr(counts), B, N, d_in, dh, out_dim, pool, _lib.ptr(blob),
                                                     _lib.ptr(out), _lib.ptr(ws), ws.numel(), rt.stream_ptr(X.device)),

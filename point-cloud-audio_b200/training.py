@@ -52,6 +52,53 @@ class STTrainFunction(torch.autograd.Function):
         return (dX if need_dx else None, None, None, None, None, *grads)
 
 
+class DeepSetTrainFunction(torch.autograd.Function):
+    """out = DeepSet(X; params): training forward / backward of set_transformer-master/models.py:3-28 (pool mean / max / sum)."""
+
+    @staticmethod
+    def forward(ctx, X, blob, cfg, *params):
+        d_in, dh, out_dim, pool = cfg
+        B, N, _ = X.shape
+        L = _lib.lib()
+        dev = X.device
+        out = torch.empty((B, out_dim), dtype=torch.float32, device=dev)
+        saved = torch.empty(max(1, L.pca_deepset_train_saved_bytes(B, N, dh)), dtype=torch.uint8, device=dev)
+        ws = rt.workspace(dev, L.pca_deepset_train_workspace_bytes(B, N, dh))
+        with torch.cuda.device(dev):
+            _lib.check(L.pca_deepset_train_fwd_f32(_lib.ptr(X), B, N, d_in, dh, out_dim, pool, _lib.ptr(blob), _lib.ptr(out),
+                                                   _lib.ptr(saved), saved.numel(), _lib.ptr(ws), ws.numel(), rt.stream_ptr(dev)),
+                       "deepset_train_fwd")
+        ctx.save_for_backward(X, blob, saved)
+        ctx.cfg = cfg
+        ctx.shapes = [tuple(p.shape) for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        X, blob, saved = ctx.saved_tensors
+        d_in, dh, out_dim, pool = ctx.cfg
+        B, N, _ = X.shape
+        L = _lib.lib()
+        dev = X.device
+        need_dx = bool(ctx.needs_input_grad[0])
+        dparams = torch.empty_like(blob)
+        dX = torch.empty_like(X) if need_dx else None
+        ws = rt.workspace(dev, L.pca_deepset_train_workspace_bytes(B, N, dh))
+        dout = rt.f32c(dout)
+        with torch.cuda.device(dev):
+            _lib.check(L.pca_deepset_train_bwd_f32(_lib.ptr(X), B, N, d_in, dh, out_dim, pool, _lib.ptr(blob), _lib.ptr(dout),
+                                                   _lib.ptr(saved), saved.numel(), _lib.ptr(dparams), _lib.ptr(dX), _lib.ptr(ws),
+                                                   ws.numel(), rt.stream_ptr(dev)), "deepset_train_bwd")
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = 1
+            for s_ in shp:
+                n *= s_
+            grads.append(dparams[off:off + n].view(shp))
+            off += n
+        return (dX, None, None, *grads)
+
+
 class SetTrainer:
     """Fused data-parallel training step for ``ST`` / ``SetTransformer`` (one process per GPU).
 

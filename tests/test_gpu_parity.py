@@ -247,15 +247,15 @@ def test_deepset_pools_vs_oracle(pca, dev):
 
 
 def test_backward_of_standalone_blocks_fails_loudly(pca, dev):
-    """Whole models train (tests/test_gpu_train.py); the stand-alone attention blocks and DeepSet have no backward
-    kernels yet and must say so instead of silently producing zero gradients."""
+    """Whole models train (tests/test_gpu_train.py); the stand-alone attention blocks and the SAB-decoder model have no
+    backward kernels yet and must say so instead of silently producing zero gradients."""
     isab = pca.ISAB(2, 16, 4, 8).to(dev)
     out = isab(torch.randn(2, 50, 2, device=dev))
     with pytest.raises(NotImplementedError):
         out.sum().backward()
-    ds = pca.DeepSet(3, 1, 7, dim_hidden=32).to(dev)
+    m = pca.SetTransformerSAB(2, 3, 4, num_inds=4, dim_hidden=16, num_heads=2).to(dev)
     with pytest.raises(NotImplementedError):
-        ds(torch.randn(2, 20, 3, device=dev)).sum().backward()
+        m(torch.randn(2, 20, 2, device=dev)).sum().backward()
 
 
 # ------------------------------------------------------------------------------------ whole path
