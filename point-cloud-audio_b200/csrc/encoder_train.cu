@@ -575,6 +575,52 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
     return 0;
 }
 
+// ------------------------------------------------------------------------------------ stand-alone MAB training
+// MAB.forward / backward for user models built from the blocks (modules.py:6-33): SAB = MAB(X, X), ISAB = mab1(X, mab0(I, X)),
+// PMA = MAB(S, X) compose on the host through autograd.  Q (qb, nq, dq) with qb in {1, B}; K (B, nk, dk).
+size_t mab_train_saved_bytes(int B, int qb, int nq, int nk, int D, int H) {
+    Arena a(nullptr, 0);
+    mab_saved_take(a, B, qb, nq, nk, D, H);
+    return a.off;
+}
+size_t mab_train_ws_bytes(int B, int qb, int nq, int nk, int D, int H) {
+    const size_t fwd = align_up(attn_part_floats(B, nq, nk, D, H) * sizeof(float), 256) + align_up(train_img_bytes(D), 256);
+    const size_t bwd = mab_bwd_ws_floats(B, qb, nq, nk, D, H);
+    return fwd > bwd ? fwd : bwd;
+}
+static int mab_train_check(int qb, int B, int nq, int nk, int dq, int dk, int D, int H) {
+    if (qb != 1 && qb != B) return fail(PCA_EINVAL, "MAB training: query batch must be 1 or B");
+    if (B <= 0 || nq <= 0 || nk <= 0 || dq <= 0 || dk <= 0 || D <= 0 || H <= 0) return fail(PCA_EINVAL, "MAB training: bad shape");
+    if (D % H || D % 4) return fail(PCA_EINVAL, "MAB training: dim_V must be a multiple of 4 and of num_heads");
+    if (B > 65535) return fail(PCA_EUNSUPPORTED, "MAB training: batch %d exceeds the grid limit", B);
+    return 0;
+}
+int mab_train_forward_api(const float* Q, int qb, const float* K, int B, int nq, int nk, int dq, int dk, int D, int H,
+                          const float* params, float* out, void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, cudaStream_t st) {
+    PCA_TRY(mab_train_check(qb, B, nq, nk, dq, dk, D, H));
+    if (!Q || !K || !params || !out || !saved || !ws) return fail(PCA_EINVAL, "MAB training forward: null pointer");
+    Arena sa(saved, saved_bytes);
+    const MabSaved s = mab_saved_take(sa, B, qb, nq, nk, D, H);
+    if (!sa.ok() || ws_bytes < mab_train_ws_bytes(B, qb, nq, nk, D, H)) return fail(PCA_EWORKSPACE, "MAB training forward: buffers too small");
+    Arena wa(ws, ws_bytes);
+    float* part = wa.take<float>(attn_part_floats(B, nq, nk, D, H));
+    void* img = wa.take<uint8_t>(train_img_bytes(D));
+    PCA_TRY(mab_train_forward(s, Q, qb, K, B, nq, nk, dq, dk, D, H, params, part, img, st));
+    PCA_CHECK_CUDA(cudaMemcpyAsync(out, s.out, (size_t)B * nq * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+int mab_train_backward_api(const float* Q, int qb, const float* K, int B, int nq, int nk, int dq, int dk, int D, int H,
+                           const float* params, const float* dout, const void* saved, size_t saved_bytes, float* dparams, float* dQ,
+                           float* dK, void* ws, size_t ws_bytes, cudaStream_t st) {
+    PCA_TRY(mab_train_check(qb, B, nq, nk, dq, dk, D, H));
+    if (!Q || !K || !params || !dout || !saved || !dparams || !ws) return fail(PCA_EINVAL, "MAB training backward: null pointer");
+    Arena sa(const_cast<void*>(saved), saved_bytes);
+    const MabSaved s = mab_saved_take(sa, B, qb, nq, nk, D, H);
+    if (!sa.ok() || ws_bytes < mab_train_ws_bytes(B, qb, nq, nk, D, H)) return fail(PCA_EWORKSPACE, "MAB training backward: buffers too small");
+    PCA_CHECK_CUDA(cudaMemsetAsync(dparams, 0, (size_t)mab_count(dq, dk, D, 0) * sizeof(float), st));
+    return mab_backward(s, Q, qb, K, B, nq, nk, dq, dk, D, H, params, dparams, dout, dQ, 0, dK, 0, ws, ws_bytes, st);
+}
+
 // ------------------------------------------------------------------------------------ ST / SetTransformer
 struct StSaved {
     MabSaved i0m0, i0m1, i1m0, i1m1, pm;

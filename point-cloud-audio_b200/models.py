@@ -243,6 +243,10 @@ class SetTransformerSAB(nn.Module):
         Y = self.dec[2](self.dec[1](self.dec[0](self.enc(rt.f32c(X)))))             # ISAB, ISAB, PMA, SAB, SAB
         lin = self.dec[3]
         B, S, D = Y.shape
+        if Y.requires_grad:
+            # training (ln=False): the blocks above ran their training kernels and autograd composes them; the last layer
+            # acts on B*num_outputs rows only -- torch's own Linear keeps the graph
+            return lin(Y)
         out = torch.empty((B, S, lin.out_features), dtype=torch.float32, device=Y.device)
         blob = self._packed.get([lin.weight, lin.bias])
         with torch.cuda.device(Y.device):

@@ -12,9 +12,14 @@ import torch.nn as nn
 from . import _lib, _runtime as rt
 
 
+def _wants_grad(module, *inputs):
+    return torch.is_grad_enabled() and (any(isinstance(t, torch.Tensor) and t.requires_grad for t in inputs)
+                                        or any(p.requires_grad for p in module.parameters()))
+
+
 class _NoBackward(torch.autograd.Function):
-    """Marks the fused forward output so that a backward pass fails loudly instead of silently
-    training with zero gradients (the backward kernels are the next scope row)."""
+    """Marks a fused forward output for which no backward kernel exists (LayerNorm branches) so that a backward pass fails
+    loudly instead of silently training with zero gradients."""
 
     @staticmethod
     def forward(ctx, out, *params):
@@ -22,7 +27,7 @@ class _NoBackward(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        raise NotImplementedError("pcaudio_b200: backward of the fused set-encoder kernels is not implemented; "
+        raise NotImplementedError("pcaudio_b200: no backward kernel for this configuration (LayerNorm branches); "
                                   "run inference under torch.no_grad() or detach the output")
 
 
@@ -85,6 +90,10 @@ class MAB(nn.Module):
         qb, nq, dq = Q.shape
         D, H = self.dim_V, self.num_heads
         blob = self._packed.get(_mab_tensors(self))
+        if B > 0 and not self._ln and _wants_grad(self, Q, K):
+            # training: forward that keeps activations + hand-written backward (pcaudio_b200/training.py)
+            from .training import MABTrainFunction
+            return MABTrainFunction.apply(Q, K, blob, (D, H), *_mab_tensors(self))
         out = torch.empty((B, nq, D), dtype=torch.float32, device=K.device)
         L = _lib.lib()
         ws = rt.workspace(K.device, L.pca_mab_workspace_bytes(B, nq, nk, dq, dk, D, H))
@@ -121,6 +130,9 @@ class ISAB(nn.Module):
         X = rt.f32c(X)
         B, N, d_in = X.shape
         D, H, M = self.mab0.dim_V, self.mab0.num_heads, self.I.shape[1]
+        if B > 0 and not self.mab0._ln and _wants_grad(self, X):
+            # training: H = mab0(I, X); mab1(X, H) through the MAB training kernels (I is a shared query set: no repeat)
+            return self.mab1(X, self.mab0(self.I, X))
         blob = self._packed.get(self._tensors())
         out = torch.empty((B, N, D), dtype=torch.float32, device=X.device)
         L = _lib.lib()
@@ -148,6 +160,8 @@ class PMA(nn.Module):
         X = rt.f32c(X)
         B, N, D = X.shape
         H, S = self.mab.num_heads, self.S.shape[1]
+        if B > 0 and not self.mab._ln and _wants_grad(self, X):
+            return self.mab(self.S, X)                     # training: MAB(S, X), shared seeds
         blob = self._packed.get(self._tensors())
         out = torch.empty((B, S, D), dtype=torch.float32, device=X.device)
         L = _lib.lib()

@@ -52,6 +52,56 @@ class STTrainFunction(torch.autograd.Function):
         return (dX if need_dx else None, None, None, None, None, *grads)
 
 
+class MABTrainFunction(torch.autograd.Function):
+    """out = MAB(Q, K; params) for models composed from the blocks (modules.py:6-33, ln=False): Q (1 | B, nq, dq), K (B, nk, dk).
+    A query batch of 1 is the shared-query case (ISAB's I, PMA's S): its gradient is summed over the batch in the kernel."""
+
+    @staticmethod
+    def forward(ctx, Q, K, blob, cfg, *params):
+        D, H = cfg
+        qb, nq, dq = Q.shape
+        B, nk, dk = K.shape
+        L = _lib.lib()
+        dev = K.device
+        out = torch.empty((B, nq, D), dtype=torch.float32, device=dev)
+        saved = torch.empty(max(1, L.pca_mab_train_saved_bytes(B, qb, nq, nk, D, H)), dtype=torch.uint8, device=dev)
+        ws = rt.workspace(dev, L.pca_mab_train_workspace_bytes(B, qb, nq, nk, D, H))
+        with torch.cuda.device(dev):
+            _lib.check(L.pca_mab_train_fwd_f32(_lib.ptr(Q), qb, _lib.ptr(K), B, nq, nk, dq, dk, D, H, _lib.ptr(blob), _lib.ptr(out),
+                                               _lib.ptr(saved), saved.numel(), _lib.ptr(ws), ws.numel(), rt.stream_ptr(dev)),
+                       "mab_train_fwd")
+        ctx.save_for_backward(Q, K, blob, saved)
+        ctx.cfg = cfg
+        ctx.shapes = [tuple(p.shape) for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        Q, K, blob, saved = ctx.saved_tensors
+        D, H = ctx.cfg
+        qb, nq, dq = Q.shape
+        B, nk, dk = K.shape
+        L = _lib.lib()
+        dev = K.device
+        dparams = torch.empty_like(blob)
+        dQ = torch.empty_like(Q) if ctx.needs_input_grad[0] else None
+        dK = torch.empty_like(K) if ctx.needs_input_grad[1] else None
+        ws = rt.workspace(dev, L.pca_mab_train_workspace_bytes(B, qb, nq, nk, D, H))
+        dout = rt.f32c(dout)
+        with torch.cuda.device(dev):
+            _lib.check(L.pca_mab_train_bwd_f32(_lib.ptr(Q), qb, _lib.ptr(K), B, nq, nk, dq, dk, D, H, _lib.ptr(blob), _lib.ptr(dout),
+                                               _lib.ptr(saved), saved.numel(), _lib.ptr(dparams), _lib.ptr(dQ), _lib.ptr(dK),
+                                               _lib.ptr(ws), ws.numel(), rt.stream_ptr(dev)), "mab_train_bwd")
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = 1
+            for s_ in shp:
+                n *= s_
+            grads.append(dparams[off:off + n].view(shp))
+            off += n
+        return (dQ, dK, None, None, *grads)
+
+
 class DeepSetTrainFunction(torch.autograd.Function):
     """out = DeepSet(X; params): training forward / backward of set_transformer-master/models.py:3-28 (pool mean / max / sum)."""
 

@@ -246,16 +246,16 @@ def test_deepset_pools_vs_oracle(pca, dev):
         assert rel_err(out.numpy(), ref.numpy()) < ENC_REL_TOL
 
 
-def test_backward_of_standalone_blocks_fails_loudly(pca, dev):
-    """Whole models train (tests/test_gpu_train.py); the stand-alone attention blocks and the SAB-decoder model have no
-    backward kernels yet and must say so instead of silently producing zero gradients."""
-    isab = pca.ISAB(2, 16, 4, 8).to(dev)
+def test_backward_without_kernels_fails_loudly(pca, dev):
+    """Models and blocks train (tests/test_gpu_train.py); configurations without backward kernels (LayerNorm branches,
+    variable-size sets) must say so instead of silently producing zero gradients."""
+    isab = pca.ISAB(2, 16, 4, 8, ln=True).to(dev)
     out = isab(torch.randn(2, 50, 2, device=dev))
     with pytest.raises(NotImplementedError):
         out.sum().backward()
-    m = pca.SetTransformerSAB(2, 3, 4, num_inds=4, dim_hidden=16, num_heads=2).to(dev)
+    st = pca.ST(dim_input=2, num_outputs=1, dim_output=10, num_inds=8, dim_hidden=16, num_heads=4).to(dev)
     with pytest.raises(NotImplementedError):
-        m(torch.randn(2, 20, 2, device=dev)).sum().backward()
+        st(torch.randn(2, 50, 2, device=dev), counts=torch.tensor([50, 20], dtype=torch.int32, device=dev))
 
 
 # ------------------------------------------------------------------------------------ whole path
