@@ -210,16 +210,18 @@ int pca_multinomial_f32(const float* weights, int n_clouds, int n, int K, unsign
  * (`saved`, pca_st_train_saved_bytes), and the backward returns the gradient of EVERY parameter as one flat blob in
  * the layout of `params` -- the unit of the per-step gradient allreduce and of pca_adam_step_f32.
  * dropout_p > 0 is nn.Dropout(p) before and after the PMA (main_pointcloud.py:30-33); the (seed, element index) mask
- * is regenerated by the backward call, which must be given the same seed.  Equal-size sets only (counts == NULL).
+ * is regenerated by the backward call, which must be given the same seed.  counts (B) int32, nullable: variable-size
+ * sets as in pca_st_fwd_masked (extension) -- rows >= counts[b] never act as keys and receive zero input gradient.
  * dlogits (B, S, C); dparams (pca_st_param_count) is overwritten; dX (B, N, d_in) may be NULL. */
 size_t pca_st_train_saved_bytes(const pca_st_dims* dims, int B, int N, float dropout_p);
 size_t pca_st_train_workspace_bytes(const pca_st_dims* dims, int B, int N);
-int pca_st_train_fwd_f32(const float* X, int B, int N, const pca_st_dims* dims, const float* params, float dropout_p,
-                         unsigned long long seed, float* logits, void* saved, size_t saved_bytes, void* workspace,
-                         size_t workspace_bytes, void* stream);
-int pca_st_train_bwd_f32(const float* X, int B, int N, const pca_st_dims* dims, const float* params, float dropout_p,
-                         unsigned long long seed, const float* dlogits, const void* saved, size_t saved_bytes,
-                         float* dparams, float* dX, void* workspace, size_t workspace_bytes, void* stream);
+int pca_st_train_fwd_f32(const float* X, const int32_t* counts, int B, int N, const pca_st_dims* dims, const float* params,
+                         float dropout_p, unsigned long long seed, float* logits, void* saved, size_t saved_bytes,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int pca_st_train_bwd_f32(const float* X, const int32_t* counts, int B, int N, const pca_st_dims* dims, const float* params,
+                         float dropout_p, unsigned long long seed, const float* dlogits, const void* saved,
+                         size_t saved_bytes, float* dparams, float* dX, void* workspace, size_t workspace_bytes,
+                         void* stream);
 
 /* Stand-alone MAB training (modules.py:6-33, ln = 0) for models composed from the blocks on the host (SAB = MAB(X, X),
  * ISAB = mab1(X, mab0(I, X)), PMA = MAB(S, X)): Q (q_batch, nq, dq) with q_batch in {1, B} (1 = shared queries: dQ is summed

@@ -26,10 +26,10 @@ int launch_multinomial(const float*, int, int, int, unsigned long long, double*,
 // training path (encoder_train.cu)
 size_t st_train_saved_bytes(const pca_st_dims* d, int B, int N, float dropout_p);
 size_t st_train_ws_bytes(const pca_st_dims* d, int B, int N);
-int st_train_forward(const float*, int, int, const pca_st_dims*, const float*, float, unsigned long long, float*, void*, size_t, void*,
-                     size_t, cudaStream_t);
-int st_train_backward(const float*, int, int, const pca_st_dims*, const float*, float, unsigned long long, const float*, const void*,
-                      size_t, float*, float*, void*, size_t, cudaStream_t);
+int st_train_forward(const float*, const int*, int, int, const pca_st_dims*, const float*, float, unsigned long long, float*, void*, size_t,
+                     void*, size_t, cudaStream_t);
+int st_train_backward(const float*, const int*, int, int, const pca_st_dims*, const float*, float, unsigned long long, const float*,
+                      const void*, size_t, float*, float*, void*, size_t, cudaStream_t);
 size_t mab_train_saved_bytes(int B, int qb, int nq, int nk, int D, int H);
 size_t mab_train_ws_bytes(int B, int qb, int nq, int nk, int D, int H);
 int mab_train_forward_api(const float*, int, const float*, int, int, int, int, int, int, int, const float*, float*, void*, size_t, void*,
@@ -668,16 +668,16 @@ size_t pca_st_train_workspace_bytes(const pca_st_dims* dims, int B, int N) {
     if (!dims || B <= 0 || N <= 0) return 0;
     return st_train_ws_bytes(dims, B, N);
 }
-int pca_st_train_fwd_f32(const float* X, int B, int N, const pca_st_dims* dims, const float* params, float dropout_p,
-                         unsigned long long seed, float* logits, void* saved, size_t saved_bytes, void* workspace,
+int pca_st_train_fwd_f32(const float* X, const int32_t* counts, int B, int N, const pca_st_dims* dims, const float* params,
+                         float dropout_p, unsigned long long seed, float* logits, void* saved, size_t saved_bytes, void* workspace,
                          size_t workspace_bytes, void* stream) {
-    return st_train_forward(X, B, N, dims, params, dropout_p, seed, logits, saved, saved_bytes, workspace, workspace_bytes,
+    return st_train_forward(X, counts, B, N, dims, params, dropout_p, seed, logits, saved, saved_bytes, workspace, workspace_bytes,
                             (cudaStream_t)stream);
 }
-int pca_st_train_bwd_f32(const float* X, int B, int N, const pca_st_dims* dims, const float* params, float dropout_p,
-                         unsigned long long seed, const float* dlogits, const void* saved, size_t saved_bytes, float* dparams,
-                         float* dX, void* workspace, size_t workspace_bytes, void* stream) {
-    return st_train_backward(X, B, N, dims, params, dropout_p, seed, dlogits, saved, saved_bytes, dparams, dX, workspace,
+int pca_st_train_bwd_f32(const float* X, const int32_t* counts, int B, int N, const pca_st_dims* dims, const float* params,
+                         float dropout_p, unsigned long long seed, const float* dlogits, const void* saved, size_t saved_bytes,
+                         float* dparams, float* dX, void* workspace, size_t workspace_bytes, void* stream) {
+    return st_train_backward(X, counts, B, N, dims, params, dropout_p, seed, dlogits, saved, saved_bytes, dparams, dX, workspace,
                              workspace_bytes, (cudaStream_t)stream);
 }
 size_t pca_mab_train_saved_bytes(int B, int q_batch, int nq, int nk, int D, int H) {

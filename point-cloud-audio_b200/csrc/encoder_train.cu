@@ -256,7 +256,7 @@ template <int DL, int G, int MODE, int R>
 __global__ void attn_bwd_kernel(const float* __restrict__ Qp, long long q_bstride, const float* __restrict__ KV,
                                 const float* __restrict__ dO, const float* __restrict__ lse, const float* __restrict__ delta,
                                 int nq, int nk, int D, int town_log, int tl, int chunk, int own_tiles, float scale, float scale_log2e,
-                                float* __restrict__ dQp, float* __restrict__ dKV) {
+                                float* __restrict__ dQp, float* __restrict__ dKV, const int* __restrict__ key_counts) {
     extern __shared__ __align__(16) float rows_s[];
     constexpr int DH = DL * G;
     const int H = blockDim.x >> 5;
@@ -267,8 +267,10 @@ __global__ void attn_bwd_kernel(const float* __restrict__ Qp, long long q_bstrid
     const int own_l = (lane / G) & (TOWN - 1);
     const int ls = lane / (G * TOWN);
     const int b = blockIdx.z;
-    const int n_own = MODE == 0 ? nq : nk;
-    const int n_loop = MODE == 0 ? nk : nq;
+    // variable-size sets: only the first key_counts[b] keys of the padded set exist (their gradients stay zero otherwise)
+    const int nk_b = key_counts ? max(1, min(nk, __ldg(key_counts + b))) : nk;
+    const int n_own = MODE == 0 ? nq : nk_b;
+    const int n_loop = MODE == 0 ? nk_b : nq;
     const int H2 = (2 * H + 3) & ~3;
     const int rs = MODE == 0 ? 2 * D + 4 : 2 * D + H2 + 4;        // smem row stride (floats)
     const int hoff = h * DH + g * DL;
@@ -411,7 +413,8 @@ __global__ void attn_bwd_kernel(const float* __restrict__ Qp, long long q_bstrid
 
 template <int DL, int G, int MODE, int R>
 static int launch_attn_bwd_r(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse,
-                             const float* delta, int B, int nq, int nk, int D, int H, float* dQp, float* dKV, cudaStream_t st) {
+                             const float* delta, int B, int nq, int nk, int D, int H, float* dQp, float* dKV, cudaStream_t st,
+                             const int* key_counts) {
     const int n_own = MODE == 0 ? nq : nk, n_loop = MODE == 0 ? nk : nq;
     int town = 32 / G;
     while (town > 1 && (town >> 1) >= n_own) town >>= 1;
@@ -451,7 +454,7 @@ static int launch_attn_bwd_r(const float* Qp, long long q_bstride, const float* 
         LaunchTimer lt(MODE == 0 ? "attn_bwd_dq_kernel" : "attn_bwd_dkv_kernel", st, (MODE == 0 ? 6.0 : 8.0) * B * nq * (double)nk * D,
                        4.0 * ((double)B * nk * 2 * D + 3.0 * B * nq * D));
         attn_bwd_kernel<DL, G, MODE, R><<<grid, 32 * H, smem, st>>>(Qp, q_bstride, KV, dO, lse, delta, nq, nk, D, town_log, tl, chunk,
-                                                                own_tiles, scale, scale * 1.4426950408889634f, dQp, dKV);
+                                                                own_tiles, scale, scale * 1.4426950408889634f, dQp, dKV, key_counts);
     }
     PCA_CHECK_LAUNCH("attn_bwd_kernel");
     return 0;
@@ -460,24 +463,26 @@ static int launch_attn_bwd_r(const float* Qp, long long q_bstride, const float* 
 // two own items per thread group when the own set is large enough to keep every lane busy and the grid full
 template <int DL, int G, int MODE>
 static int launch_attn_bwd_t(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse,
-                             const float* delta, int B, int nq, int nk, int D, int H, float* dQp, float* dKV, cudaStream_t st) {
+                             const float* delta, int B, int nq, int nk, int D, int H, float* dQp, float* dKV, cudaStream_t st,
+                             const int* key_counts) {
     const int n_own = MODE == 0 ? nq : nk;
     const int per_warp = 2 * (32 / G);
     if (n_own >= 2 * per_warp && (long long)B * (n_own / per_warp) >= 148LL * 4)
-        return launch_attn_bwd_r<DL, G, MODE, 2>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st);
-    return launch_attn_bwd_r<DL, G, MODE, 1>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st);
+        return launch_attn_bwd_r<DL, G, MODE, 2>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st, key_counts);
+    return launch_attn_bwd_r<DL, G, MODE, 1>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st, key_counts);
 }
 
 template <int MODE>
 static int launch_attn_bwd(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse,
-                           const float* delta, int B, int nq, int nk, int D, int H, float* dQp, float* dKV, cudaStream_t st) {
+                           const float* delta, int B, int nq, int nk, int D, int H, float* dQp, float* dKV, cudaStream_t st,
+                           const int* key_counts) {
     if (B > 65535) return fail(PCA_EUNSUPPORTED, "attention backward: batch %d exceeds the grid limit", B);
     switch (D / H) {
-        case 4: return launch_attn_bwd_t<4, 1, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st);
-        case 8: return launch_attn_bwd_t<8, 1, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st);
-        case 16: return launch_attn_bwd_t<16, 1, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st);
-        case 32: return launch_attn_bwd_t<16, 2, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st);
-        case 64: return launch_attn_bwd_t<16, 4, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st);
+        case 4: return launch_attn_bwd_t<4, 1, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st, key_counts);
+        case 8: return launch_attn_bwd_t<8, 1, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st, key_counts);
+        case 16: return launch_attn_bwd_t<16, 1, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st, key_counts);
+        case 32: return launch_attn_bwd_t<16, 2, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st, key_counts);
+        case 64: return launch_attn_bwd_t<16, 4, MODE>(Qp, q_bstride, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, st, key_counts);
         default: return fail(PCA_EUNSUPPORTED, "attention backward: head dim %d not in {4,8,16,32,64}", D / H);
     }
 }
@@ -499,12 +504,13 @@ static MabSaved mab_saved_take(Arena& a, int B, int qb, int nq, int nk, int D, i
 static size_t train_img_bytes(int D) { return gemm_tc_image_bytes(2 * D, D); }
 
 static int mab_train_forward(const MabSaved& s, const float* Qin, int qb, const float* Kin, int B, int nq, int nk, int dq, int dk,
-                             int D, int H, const float* params, float* part, void* img, cudaStream_t st) {
+                             int D, int H, const float* params, float* part, void* img, cudaStream_t st,
+                             const int* key_counts = nullptr) {
     const MabParams m = mab_slice(params, dq, dk, D, 0);
     const size_t ib = train_img_bytes(D);
     PCA_TRY(launch_linear(Qin, m.Wq, m.bq, s.Qp, (long long)qb * nq, dq, D, 0, st, nullptr, dq <= D ? img : nullptr, ib));
     PCA_TRY(launch_linear(Kin, m.Wkv, m.bkv, s.KV, (long long)B * nk, dk, 2 * D, 0, st, nullptr, dk <= D ? img : nullptr, ib));
-    PCA_TRY(launch_attn(s.Qp, qb == 1 ? 0 : (long long)nq * D, s.KV, B, nq, nk, D, H, s.O, part, nullptr, st, s.lse));
+    PCA_TRY(launch_attn(s.Qp, qb == 1 ? 0 : (long long)nq * D, s.KV, B, nq, nk, D, H, s.O, part, key_counts, st, s.lse));
     PCA_TRY(launch_linear(s.O, m.Wo, m.bo, s.out, (long long)B * nq, D, D, 3, st, s.R, img, ib));
     return 0;
 }
@@ -524,7 +530,7 @@ static size_t mab_bwd_ws_floats(int B, int qb, int nq, int nk, int D, int H) {
 // dQin / dKin may be null (not needed); acc_* != 0 adds to what the buffer already holds.
 static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float* Kin, int B, int nq, int nk, int dq, int dk, int D,
                         int H, const float* params, float* dparams, const float* dOut, float* dQin, int acc_q, float* dKin,
-                        int acc_k, void* ws, size_t ws_bytes, cudaStream_t st) {
+                        int acc_k, void* ws, size_t ws_bytes, cudaStream_t st, const int* key_counts = nullptr) {
     const MabParams m = mab_slice(params, dq, dk, D, 0);
     const MabParams g = mab_slice(dparams, dq, dk, D, 0);
     Arena a(ws, ws_bytes);
@@ -555,10 +561,10 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
         PCA_CHECK_LAUNCH("attn_delta_kernel");
     }
     PCA_CHECK_CUDA(cudaMemsetAsync(dKV, 0, (size_t)rk * 2 * D * sizeof(float), st));
-    PCA_TRY(launch_attn_bwd<1>(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, nullptr, dKV, st));
+    PCA_TRY(launch_attn_bwd<1>(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, nullptr, dKV, st, key_counts));
     float* dQp = dZ;                                            // dQp = dO (residual) + attention part, added atomically
     PCA_CHECK_CUDA(cudaMemcpyAsync(dQp, dO, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    PCA_TRY(launch_attn_bwd<0>(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, dQp, nullptr, st));
+    PCA_TRY(launch_attn_bwd<0>(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, dQp, nullptr, st, key_counts));
     long long rows_q = rq;
     if (qb == 1) {                                              // shared queries (I / S): sum the per-cloud gradients
         PCA_CHECK_CUDA(cudaMemsetAsync(dQ1, 0, (size_t)nq * D * sizeof(float), st));
@@ -696,7 +702,7 @@ size_t st_train_ws_bytes(const pca_st_dims* d, int B, int N) {
     return a.off + (w > fwd ? w : fwd);
 }
 
-int st_train_forward(const float* X, int B, int N, const pca_st_dims* d, const float* params, float dropout_p,
+int st_train_forward(const float* X, const int* counts, int B, int N, const pca_st_dims* d, const float* params, float dropout_p,
                      unsigned long long seed, float* logits, void* saved, size_t saved_bytes, void* ws, size_t ws_bytes,
                      cudaStream_t st) {
     PCA_TRY(train_check(d, B, N, dropout_p));
@@ -717,18 +723,18 @@ int st_train_forward(const float* X, int B, int N, const pca_st_dims* d, const f
     float* part = wa.take<float>(part_floats);
     void* img = wa.take<uint8_t>(train_img_bytes(D));
     if (!wa.ok()) return fail(PCA_EWORKSPACE, "ST training forward: workspace too small");
-    PCA_TRY(mab_train_forward(s.i0m0, params + o.I0, 1, X, B, M, N, D, din, D, H, params + o.i0m0, part, img, st));
+    PCA_TRY(mab_train_forward(s.i0m0, params + o.I0, 1, X, B, M, N, D, din, D, H, params + o.i0m0, part, img, st, counts));
     PCA_TRY(mab_train_forward(s.i0m1, X, B, s.i0m0.out, B, N, M, din, D, D, H, params + o.i0m1, part, img, st));
-    PCA_TRY(mab_train_forward(s.i1m0, params + o.I1, 1, s.i0m1.out, B, M, N, D, D, D, H, params + o.i1m0, part, img, st));
+    PCA_TRY(mab_train_forward(s.i1m0, params + o.I1, 1, s.i0m1.out, B, M, N, D, D, D, H, params + o.i1m0, part, img, st, counts));
     PCA_TRY(mab_train_forward(s.i1m1, s.i0m1.out, B, s.i1m0.out, B, N, M, D, D, D, H, params + o.i1m1, part, img, st));
     if (dropout_p > 0.f) PCA_TRY(launch_dropout(s.i1m1.out, s.Y2d, (long long)B * N * D, dropout_p, seed, st));
-    PCA_TRY(mab_train_forward(s.pm, params + o.S, 1, s.Y2d, B, S, N, D, D, D, H, params + o.pm, part, img, st));
+    PCA_TRY(mab_train_forward(s.pm, params + o.S, 1, s.Y2d, B, S, N, D, D, D, H, params + o.pm, part, img, st, counts));
     if (dropout_p > 0.f) PCA_TRY(launch_dropout(s.pm.out, s.Pd, (long long)B * S * D, dropout_p, seed ^ 0xD1B54A32D192ED03ull, st));
     PCA_TRY(launch_linear(s.Pd, params + o.Wl, params + o.bl, logits, (long long)B * S, D, C, 0, st));
     return 0;
 }
 
-int st_train_backward(const float* X, int B, int N, const pca_st_dims* d, const float* params, float dropout_p,
+int st_train_backward(const float* X, const int* counts, int B, int N, const pca_st_dims* d, const float* params, float dropout_p,
                       unsigned long long seed, const float* dlogits, const void* saved, size_t saved_bytes, float* dparams,
                       float* dX, void* ws, size_t ws_bytes, cudaStream_t st) {
     PCA_TRY(train_check(d, B, N, dropout_p));
@@ -756,19 +762,19 @@ int st_train_backward(const float* X, int B, int N, const pca_st_dims* d, const 
     if (dropout_p > 0.f) PCA_TRY(launch_dropout(gP, gP, rp * D, dropout_p, seed ^ 0xD1B54A32D192ED03ull, st));
     // PMA: mab(S, Y2d)
     PCA_TRY(mab_backward(s.pm, params + o.S, 1, s.Y2d, B, S, N, D, D, D, H, params + o.pm, dparams + o.pm, gP, dparams + o.S, 0, gA, 0,
-                         sub, sub_bytes, st));
+                         sub, sub_bytes, st, counts));
     if (dropout_p > 0.f) PCA_TRY(launch_dropout(gA, gA, (long long)B * N * D, dropout_p, seed, st));
     (void)gP2;
     // ISAB 1: Y2 = mab1(Y1, H2), H2 = mab0(I1, Y1)
     PCA_TRY(mab_backward(s.i1m1, s.i0m1.out, B, s.i1m0.out, B, N, M, D, D, D, H, params + o.i1m1, dparams + o.i1m1, gA, gB, 0, gH, 0,
                          sub, sub_bytes, st));
     PCA_TRY(mab_backward(s.i1m0, params + o.I1, 1, s.i0m1.out, B, M, N, D, D, D, H, params + o.i1m0, dparams + o.i1m0, gH,
-                         dparams + o.I1, 0, gB, 1, sub, sub_bytes, st));
+                         dparams + o.I1, 0, gB, 1, sub, sub_bytes, st, counts));
     // ISAB 0: Y1 = mab1(X, H1), H1 = mab0(I0, X)
     PCA_TRY(mab_backward(s.i0m1, X, B, s.i0m0.out, B, N, M, din, D, D, H, params + o.i0m1, dparams + o.i0m1, gB, dX, 0, gH, 0,
                          sub, sub_bytes, st));
     PCA_TRY(mab_backward(s.i0m0, params + o.I0, 1, X, B, M, N, D, din, D, H, params + o.i0m0, dparams + o.i0m0, gH, dparams + o.I0, 0,
-                         dX, 1, sub, sub_bytes, st));
+                         dX, 1, sub, sub_bytes, st, counts));
     return 0;
 }
 

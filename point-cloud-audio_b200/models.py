@@ -100,12 +100,10 @@ class _SetEncoderBase(nn.Module):
         ps = self._param_tensors()
         if B > 0 and torch.is_grad_enabled() and (X.requires_grad or any(p.requires_grad for p in ps)):
             # training: fp32 forward that keeps activations + hand-written backward (pcaudio_b200/training.py)
-            if counts is not None:
-                raise NotImplementedError("pcaudio_b200: training with variable-size sets (counts) is not implemented")
             from .training import STTrainFunction
             p = self._dropout_p()
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
-            return STTrainFunction.apply(X, blob, dims, p, seed, *ps)
+            return STTrainFunction.apply(X, counts, blob, dims, p, seed, *ps)
         if self._dropout_p() > 0:
             raise RuntimeError("SetTransformer: train-mode (Dropout) forward without gradients; call .eval() for inference")
         # one dispatcher-visible custom op (pcaudio_b200/ops.py) -> pca_st_fwd_masked of the C ABI

@@ -97,8 +97,8 @@ def _train_ws(dev, dims, B, N):
 
 
 @torch.library.custom_op("pcaudio::st_train_fwd", mutates_args=(), device_types="cuda")
-def st_train_fwd(X: torch.Tensor, params: torch.Tensor, d_in: int, D: int, H: int, M: int, S: int, n_out: int, ln: int,
-                 dropout_p: float, seed: int) -> tuple[torch.Tensor, torch.Tensor]:
+def st_train_fwd(X: torch.Tensor, counts: torch.Tensor | None, params: torch.Tensor, d_in: int, D: int, H: int, M: int, S: int,
+                 n_out: int, ln: int, dropout_p: float, seed: int) -> tuple[torch.Tensor, torch.Tensor]:
     """Training forward of ST / SetTransformer: (logits (B, S, n_out), saved activations (bytes) for st_train_bwd)."""
     B, N, _ = X.shape
     dims = _dims(d_in, D, H, M, S, n_out, ln)
@@ -107,20 +107,20 @@ def st_train_fwd(X: torch.Tensor, params: torch.Tensor, d_in: int, D: int, H: in
     saved = torch.empty(max(1, L.pca_st_train_saved_bytes(C.byref(dims), B, N, dropout_p)), dtype=torch.uint8, device=X.device)
     ws = _train_ws(X.device, dims, B, N)
     with torch.cuda.device(X.device):
-        _lib.check(L.pca_st_train_fwd_f32(_lib.ptr(X), B, N, C.byref(dims), _lib.ptr(params), dropout_p, seed, _lib.ptr(logits),
+        _lib.check(L.pca_st_train_fwd_f32(_lib.ptr(X), _lib.ptr(counts), B, N, C.byref(dims), _lib.ptr(params), dropout_p, seed, _lib.ptr(logits),
                                           _lib.ptr(saved), saved.numel(), _lib.ptr(ws), ws.numel(), rt.stream_ptr(X.device)),
                    "st_train_fwd")
     return logits, saved
 
 
 @st_train_fwd.register_fake
-def _(X, params, d_in, D, H, M, S, n_out, ln, dropout_p, seed):
+def _(X, counts, params, d_in, D, H, M, S, n_out, ln, dropout_p, seed):
     return X.new_empty((X.shape[0], S, n_out), dtype=torch.float32), X.new_empty((1,), dtype=torch.uint8)
 
 
 @torch.library.custom_op("pcaudio::st_train_bwd", mutates_args=(), device_types="cuda")
-def st_train_bwd(X: torch.Tensor, params: torch.Tensor, d_in: int, D: int, H: int, M: int, S: int, n_out: int, ln: int,
-                 dropout_p: float, seed: int, dlogits: torch.Tensor, saved: torch.Tensor,
+def st_train_bwd(X: torch.Tensor, counts: torch.Tensor | None, params: torch.Tensor, d_in: int, D: int, H: int, M: int, S: int,
+                 n_out: int, ln: int, dropout_p: float, seed: int, dlogits: torch.Tensor, saved: torch.Tensor,
                  need_dx: bool) -> tuple[torch.Tensor, torch.Tensor]:
     """Backward of st_train_fwd: (flat gradient of every parameter in the layout of `params`, dX or an empty tensor)."""
     B, N, _ = X.shape
@@ -130,12 +130,12 @@ def st_train_bwd(X: torch.Tensor, params: torch.Tensor, d_in: int, D: int, H: in
     dX = torch.empty_like(X) if need_dx else X.new_empty((0,))
     ws = _train_ws(X.device, dims, B, N)
     with torch.cuda.device(X.device):
-        _lib.check(L.pca_st_train_bwd_f32(_lib.ptr(X), B, N, C.byref(dims), _lib.ptr(params), dropout_p, seed, _lib.ptr(dlogits),
+        _lib.check(L.pca_st_train_bwd_f32(_lib.ptr(X), _lib.ptr(counts), B, N, C.byref(dims), _lib.ptr(params), dropout_p, seed, _lib.ptr(dlogits),
                                           _lib.ptr(saved), saved.numel(), _lib.ptr(dparams), _lib.ptr(dX) if need_dx else None,
                                           _lib.ptr(ws), ws.numel(), rt.stream_ptr(X.device)), "st_train_bwd")
     return dparams, dX
 
 
 @st_train_bwd.register_fake
-def _(X, params, d_in, D, H, M, S, n_out, ln, dropout_p, seed, dlogits, saved, need_dx):
+def _(X, counts, params, d_in, D, H, M, S, n_out, ln, dropout_p, seed, dlogits, saved, need_dx):
     return torch.empty_like(params), (torch.empty_like(X) if need_dx else X.new_empty((0,)))

@@ -26,10 +26,11 @@ class STTrainFunction(torch.autograd.Function):
     the flat gradient blob."""
 
     @staticmethod
-    def forward(ctx, X, blob, dims, dropout_p, seed, *params):
+    def forward(ctx, X, counts, blob, dims, dropout_p, seed, *params):
         d = dims
-        logits, saved = torch.ops.pcaudio.st_train_fwd(X, blob, d.d_in, d.D, d.H, d.M, d.S, d.C, d.ln, dropout_p, seed)
+        logits, saved = torch.ops.pcaudio.st_train_fwd(X, counts, blob, d.d_in, d.D, d.H, d.M, d.S, d.C, d.ln, dropout_p, seed)
         ctx.save_for_backward(X, blob, saved)
+        ctx.counts = counts
         ctx.dims, ctx.dropout_p, ctx.seed = d, dropout_p, seed
         ctx.shapes = [tuple(p.shape) for p in params]
         return logits
@@ -39,8 +40,8 @@ class STTrainFunction(torch.autograd.Function):
         X, blob, saved = ctx.saved_tensors
         d = ctx.dims
         need_dx = bool(ctx.needs_input_grad[0])
-        dparams, dX = torch.ops.pcaudio.st_train_bwd(X, blob, d.d_in, d.D, d.H, d.M, d.S, d.C, d.ln, ctx.dropout_p, ctx.seed,
-                                                     rt.f32c(dlogits), saved, need_dx)
+        dparams, dX = torch.ops.pcaudio.st_train_bwd(X, ctx.counts, blob, d.d_in, d.D, d.H, d.M, d.S, d.C, d.ln, ctx.dropout_p,
+                                                     ctx.seed, rt.f32c(dlogits), saved, need_dx)
         grads, off = [], 0
         for shp in ctx.shapes:
             n = 1
@@ -49,7 +50,7 @@ class STTrainFunction(torch.autograd.Function):
             grads.append(dparams[off:off + n].view(shp))
             off += n
         assert off == dparams.numel()
-        return (dX if need_dx else None, None, None, None, None, *grads)
+        return (dX if need_dx else None, None, None, None, None, None, *grads)
 
 
 class MABTrainFunction(torch.autograd.Function):
@@ -181,11 +182,14 @@ class SetTrainer:
         ws = rt.workspace(dev, L.pca_st_train_workspace_bytes(C.byref(dims), B, N))
         return self._saved, ws
 
-    def step(self, X, labels):
+    def step(self, X, labels, counts=None):
+        """``counts`` (B,) int32 CUDA, optional: variable-size sets (cloud b = its first counts[b] rows)."""
         m = self.model
         rt.require_cuda(X, "SetTrainer.step")
         X = rt.f32c(X)
         labels = labels.to(device=X.device, dtype=torch.int64).contiguous()
+        if counts is not None:
+            counts = counts.to(device=X.device, dtype=torch.int32).contiguous()
         B, N, _ = X.shape
         dev = X.device
         dims = m._dims()
@@ -201,11 +205,11 @@ class SetTrainer:
         dlogits = torch.empty_like(logits)
         stats = torch.zeros(2, dtype=torch.float32, device=dev)      # loss | correct (int32 bits)
         with torch.cuda.device(dev):
-            _lib.check(L.pca_st_train_fwd_f32(_lib.ptr(X), B, N, C.byref(dims), _lib.ptr(self.flat), p, seed, _lib.ptr(logits),
+            _lib.check(L.pca_st_train_fwd_f32(_lib.ptr(X), _lib.ptr(counts), B, N, C.byref(dims), _lib.ptr(self.flat), p, seed, _lib.ptr(logits),
                                               _lib.ptr(saved), saved.numel(), _lib.ptr(ws), ws.numel(), st), "st_train_fwd")
             _lib.check(L.pca_cross_entropy_f32(_lib.ptr(logits), _lib.ptr(labels), B, dims.C, C.c_void_p(stats.data_ptr()),
                                                C.c_void_p(stats.data_ptr() + 4), _lib.ptr(dlogits), st), "cross_entropy")
-            _lib.check(L.pca_st_train_bwd_f32(_lib.ptr(X), B, N, C.byref(dims), _lib.ptr(self.flat), p, seed, _lib.ptr(dlogits),
+            _lib.check(L.pca_st_train_bwd_f32(_lib.ptr(X), _lib.ptr(counts), B, N, C.byref(dims), _lib.ptr(self.flat), p, seed, _lib.ptr(dlogits),
                                               _lib.ptr(saved), saved.numel(), _lib.ptr(self.grads), None, _lib.ptr(ws), ws.numel(),
                                               st), "st_train_bwd")
             grad_scale = reduce_flat_gradient_(self.grads, self.group)

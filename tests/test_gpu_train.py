@@ -152,16 +152,16 @@ def test_dropout_train_mode_statistics_and_backward(pca):
     G = torch.randn(4, 1, 8, device=dev)
 
     def f(b):
-        return (torch.ops.pcaudio.st_train_fwd(X, b, dims.d_in, dims.D, dims.H, dims.M, dims.S, dims.C, dims.ln, 0.5, 1234)[0] * G).sum()
-    logits, saved = torch.ops.pcaudio.st_train_fwd(X, blob, dims.d_in, dims.D, dims.H, dims.M, dims.S, dims.C, dims.ln, 0.5, 1234)
-    dparams, _ = torch.ops.pcaudio.st_train_bwd(X, blob, dims.d_in, dims.D, dims.H, dims.M, dims.S, dims.C, dims.ln, 0.5, 1234, G.contiguous(), saved, False)
+        return (torch.ops.pcaudio.st_train_fwd(X, None, b, dims.d_in, dims.D, dims.H, dims.M, dims.S, dims.C, dims.ln, 0.5, 1234)[0] * G).sum()
+    logits, saved = torch.ops.pcaudio.st_train_fwd(X, None, blob, dims.d_in, dims.D, dims.H, dims.M, dims.S, dims.C, dims.ln, 0.5, 1234)
+    dparams, _ = torch.ops.pcaudio.st_train_bwd(X, None, blob, dims.d_in, dims.D, dims.H, dims.M, dims.S, dims.C, dims.ln, 0.5, 1234, G.contiguous(), saved, False)
     direction = torch.randn_like(blob)
     direction /= direction.norm()
     eps = 1e-2
     fd = (f(blob + eps * direction) - f(blob - eps * direction)).item() / (2 * eps)
     an = (dparams * direction).sum().item()
     assert abs(fd - an) < 2e-2 * max(1.0, abs(an)), (fd, an)
-    kept = (torch.ops.pcaudio.st_train_fwd(X, blob, dims.d_in, dims.D, dims.H, dims.M, dims.S, dims.C, dims.ln, 0.5, 1234)[0] == logits).all()
+    kept = (torch.ops.pcaudio.st_train_fwd(X, None, blob, dims.d_in, dims.D, dims.H, dims.M, dims.S, dims.C, dims.ln, 0.5, 1234)[0] == logits).all()
     assert kept
 
 
@@ -224,3 +224,32 @@ def test_blocks_and_sab_decoder_model_train_through_autograd(pca):
     mln = pca.SetTransformerSAB(3, 2, 4, num_inds=4, dim_hidden=16, num_heads=2, ln=True).to(dev)
     with pytest.raises(NotImplementedError):
         mln(torch.randn(2, 20, 3, device=dev)).sum().backward()
+
+
+@pytest.mark.parametrize("d_in,D,H,M", [(3, 64, 8, 64), (2, 32, 4, 8), (3, 256, 4, 16)])
+def test_variable_size_sets_train(pca, d_in, D, H, M):
+    """Training with padded variable-size sets (counts; extension): loss and gradients equal the oracle applied
+    per cloud to its first counts[b] points; padding rows receive exactly zero input gradient."""
+    from oracle import pcaudio_oracle as orc
+    dev = torch.device("cuda:0")
+    torch.manual_seed(D + M)
+    model = pca.ST(dim_input=d_in, num_outputs=1, dim_output=7, num_inds=M, dim_hidden=D, num_heads=H).to(dev)
+    B, N = 4, 300
+    counts = torch.tensor([300, 1, 130, 257], dtype=torch.int32)
+    X = torch.randn(B, N, d_in, device=dev, requires_grad=True)
+    G = torch.randn(B, 7)
+    out = model(X, counts=counts.to(dev))
+    (out * G.to(dev)).sum().backward()
+    p = {k: v.detach().cpu().double().requires_grad_(True) for k, v in model.state_dict().items()}
+    Xc = X.detach().cpu().double().requires_grad_(True)
+    ref = torch.stack([orc.st_forward(p, Xc[b:b + 1, :int(counts[b])], H).reshape(7) for b in range(B)])
+    (ref * G.double()).sum().backward()
+    assert ((out.detach().cpu().double() - ref.detach()).abs().max() / ref.detach().abs().max()).item() < 1e-4
+    floor = 1e-3 * max(v.grad.abs().max().item() for v in p.values())
+    for k, prm in model.named_parameters():
+        err = (prm.grad.cpu().double() - p[k].grad).abs().max().item() / max(p[k].grad.abs().max().item(), floor)
+        assert err < GRAD_REL_TOL, f"{k}: rel err {err:.3e}"
+    gx = X.grad.cpu().double()
+    assert ((gx - Xc.grad).abs().max() / Xc.grad.abs().max()).item() < GRAD_REL_TOL
+    for b in range(B):
+        assert (gx[b, int(counts[b]):] == 0).all()
