@@ -223,15 +223,15 @@ int pca_st_train_bwd_f32(const float* X, const int32_t* counts, int B, int N, co
                          size_t saved_bytes, float* dparams, float* dX, void* workspace, size_t workspace_bytes,
                          void* stream);
 
-/* Stand-alone MAB training (modules.py:6-33, ln = 0) for models composed from the blocks on the host (SAB = MAB(X, X),
+/* Stand-alone MAB training (modules.py:6-33, LayerNorm branches included) for models composed from the blocks on the host (SAB = MAB(X, X),
  * ISAB = mab1(X, mab0(I, X)), PMA = MAB(S, X)): Q (q_batch, nq, dq) with q_batch in {1, B} (1 = shared queries: dQ is summed
  * over the batch), K (B, nk, dk), out / dout (B, nq, D).  dparams in the MAB blob layout; dQ / dK may be NULL. */
-size_t pca_mab_train_saved_bytes(int B, int q_batch, int nq, int nk, int D, int H);
-size_t pca_mab_train_workspace_bytes(int B, int q_batch, int nq, int nk, int D, int H);
-int pca_mab_train_fwd_f32(const float* Q, int q_batch, const float* K, int B, int nq, int nk, int dq, int dk, int D, int H,
+size_t pca_mab_train_saved_bytes(int B, int q_batch, int nq, int nk, int D, int H, int ln);
+size_t pca_mab_train_workspace_bytes(int B, int q_batch, int nq, int nk, int D, int H, int ln);
+int pca_mab_train_fwd_f32(const float* Q, int q_batch, const float* K, int B, int nq, int nk, int dq, int dk, int D, int H, int ln,
                           const float* params, float* out, void* saved, size_t saved_bytes, void* workspace,
                           size_t workspace_bytes, void* stream);
-int pca_mab_train_bwd_f32(const float* Q, int q_batch, const float* K, int B, int nq, int nk, int dq, int dk, int D, int H,
+int pca_mab_train_bwd_f32(const float* Q, int q_batch, const float* K, int B, int nq, int nk, int dq, int dk, int D, int H, int ln,
                           const float* params, const float* dout, const void* saved, size_t saved_bytes, float* dparams,
                           float* dQ, float* dK, void* workspace, size_t workspace_bytes, void* stream);
 

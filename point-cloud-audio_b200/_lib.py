@@ -69,10 +69,10 @@ PROTOTYPES = {
     "pca_st_train_workspace_bytes": (_SZ, [C.POINTER(StDims), _I, _I]),
     "pca_st_train_fwd_f32": (_I, [_P, _P, _I, _I, C.POINTER(StDims), _P, _F, C.c_ulonglong, _P, _P, _SZ, _P, _SZ, _P]),
     "pca_st_train_bwd_f32": (_I, [_P, _P, _I, _I, C.POINTER(StDims), _P, _F, C.c_ulonglong, _P, _P, _SZ, _P, _P, _P, _SZ, _P]),
-    "pca_mab_train_saved_bytes": (_SZ, [_I] * 6),
-    "pca_mab_train_workspace_bytes": (_SZ, [_I] * 6),
-    "pca_mab_train_fwd_f32": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _SZ, _P, _SZ, _P]),
-    "pca_mab_train_bwd_f32": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _SZ, _P, _P, _P, _P, _SZ, _P]),
+    "pca_mab_train_saved_bytes": (_SZ, [_I] * 7),
+    "pca_mab_train_workspace_bytes": (_SZ, [_I] * 7),
+    "pca_mab_train_fwd_f32": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _SZ, _P, _SZ, _P]),
+    "pca_mab_train_bwd_f32": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _SZ, _P, _P, _P, _P, _SZ, _P]),
     "pca_deepset_train_saved_bytes": (_SZ, [_I, _I, _I]),
     "pca_deepset_train_workspace_bytes": (_SZ, [_I, _I, _I]),
     "pca_deepset_train_fwd_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _SZ, _P, _SZ, _P]),

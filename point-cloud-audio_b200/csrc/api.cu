@@ -14,7 +14,6 @@ namespace pca {
 int launch_stft_logmag(const float*, int, int, int, int, const float*, const float*, float, int, int, float*, cudaStream_t);
 int launch_build_clouds(const float*, int, int, int, const float*, const float*, float*, cudaStream_t);
 int launch_topk(const float*, int, int, int, const float*, const float*, int, int, int, float, float*, int32_t*, int32_t*, cudaStream_t);
-int launch_layernorm(float*, long long, int, const float*, const float*, cudaStream_t);
 int launch_pool(const float*, int, int, int, int, float*, const int*, cudaStream_t);
 int launch_fused_frontend(const float*, int, int, int, int, const float*, const float*, float, int, int, const float*, const float*,
                           int, int, int, float, float*, int32_t*, int32_t*, cudaStream_t);
@@ -30,12 +29,12 @@ int st_train_forward(const float*, const int*, int, int, const pca_st_dims*, con
                      void*, size_t, cudaStream_t);
 int st_train_backward(const float*, const int*, int, int, const pca_st_dims*, const float*, float, unsigned long long, const float*,
                       const void*, size_t, float*, float*, void*, size_t, cudaStream_t);
-size_t mab_train_saved_bytes(int B, int qb, int nq, int nk, int D, int H);
-size_t mab_train_ws_bytes(int B, int qb, int nq, int nk, int D, int H);
-int mab_train_forward_api(const float*, int, const float*, int, int, int, int, int, int, int, const float*, float*, void*, size_t, void*,
-                          size_t, cudaStream_t);
-int mab_train_backward_api(const float*, int, const float*, int, int, int, int, int, int, int, const float*, const float*, const void*,
-                           size_t, float*, float*, float*, void*, size_t, cudaStream_t);
+size_t mab_train_saved_bytes(int B, int qb, int nq, int nk, int D, int H, int ln);
+size_t mab_train_ws_bytes(int B, int qb, int nq, int nk, int D, int H, int ln);
+int mab_train_forward_api(const float*, int, const float*, int, int, int, int, int, int, int, int, const float*, float*, void*, size_t,
+                          void*, size_t, cudaStream_t);
+int mab_train_backward_api(const float*, int, const float*, int, int, int, int, int, int, int, int, const float*, const float*,
+                           const void*, size_t, float*, float*, float*, void*, size_t, cudaStream_t);
 size_t deepset_train_saved_bytes(int B, int N, int dh);
 size_t deepset_train_ws_bytes(int B, int N, int dh);
 int deepset_train_forward(const float*, int, int, int, int, int, int, const float*, float*, void*, size_t, void*, size_t, cudaStream_t);
@@ -680,22 +679,22 @@ int pca_st_train_bwd_f32(const float* X, const int32_t* counts, int B, int N, co
     return st_train_backward(X, counts, B, N, dims, params, dropout_p, seed, dlogits, saved, saved_bytes, dparams, dX, workspace,
                              workspace_bytes, (cudaStream_t)stream);
 }
-size_t pca_mab_train_saved_bytes(int B, int q_batch, int nq, int nk, int D, int H) {
-    return (B > 0 && nq > 0 && nk > 0 && D > 0 && H > 0) ? mab_train_saved_bytes(B, q_batch, nq, nk, D, H) : 0;
+size_t pca_mab_train_saved_bytes(int B, int q_batch, int nq, int nk, int D, int H, int ln) {
+    return (B > 0 && nq > 0 && nk > 0 && D > 0 && H > 0) ? mab_train_saved_bytes(B, q_batch, nq, nk, D, H, ln) : 0;
 }
-size_t pca_mab_train_workspace_bytes(int B, int q_batch, int nq, int nk, int D, int H) {
-    return (B > 0 && nq > 0 && nk > 0 && D > 0 && H > 0 && D % H == 0) ? mab_train_ws_bytes(B, q_batch, nq, nk, D, H) : 0;
+size_t pca_mab_train_workspace_bytes(int B, int q_batch, int nq, int nk, int D, int H, int ln) {
+    return (B > 0 && nq > 0 && nk > 0 && D > 0 && H > 0 && D % H == 0) ? mab_train_ws_bytes(B, q_batch, nq, nk, D, H, ln) : 0;
 }
-int pca_mab_train_fwd_f32(const float* Q, int q_batch, const float* K, int B, int nq, int nk, int dq, int dk, int D, int H,
+int pca_mab_train_fwd_f32(const float* Q, int q_batch, const float* K, int B, int nq, int nk, int dq, int dk, int D, int H, int ln,
                           const float* params, float* out, void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes,
                           void* stream) {
-    return mab_train_forward_api(Q, q_batch, K, B, nq, nk, dq, dk, D, H, params, out, saved, saved_bytes, workspace, workspace_bytes,
+    return mab_train_forward_api(Q, q_batch, K, B, nq, nk, dq, dk, D, H, ln, params, out, saved, saved_bytes, workspace, workspace_bytes,
                                  (cudaStream_t)stream);
 }
-int pca_mab_train_bwd_f32(const float* Q, int q_batch, const float* K, int B, int nq, int nk, int dq, int dk, int D, int H,
+int pca_mab_train_bwd_f32(const float* Q, int q_batch, const float* K, int B, int nq, int nk, int dq, int dk, int D, int H, int ln,
                           const float* params, const float* dout, const void* saved, size_t saved_bytes, float* dparams, float* dQ,
                           float* dK, void* workspace, size_t workspace_bytes, void* stream) {
-    return mab_train_backward_api(Q, q_batch, K, B, nq, nk, dq, dk, D, H, params, dout, saved, saved_bytes, dparams, dQ, dK, workspace,
+    return mab_train_backward_api(Q, q_batch, K, B, nq, nk, dq, dk, D, H, ln, params, dout, saved, saved_bytes, dparams, dQ, dK, workspace,
                                   workspace_bytes, (cudaStream_t)stream);
 }
 size_t pca_deepset_train_saved_bytes(int B, int N, int dim_hidden) {

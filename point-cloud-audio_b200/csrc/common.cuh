@@ -99,6 +99,7 @@ void set_gemm_tc(int on);
 int launch_attn(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D, int H, float* O, float* part,
                 const int* key_counts, cudaStream_t st, float* lse = nullptr);
 size_t attn_part_floats(int B, int nq, int nk, int D, int H);
+int launch_layernorm(float* X, long long rows, int D, const float* g, const float* b, cudaStream_t st);
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

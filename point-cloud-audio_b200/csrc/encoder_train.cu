@@ -488,9 +488,61 @@ static int launch_attn_bwd(const float* Qp, long long q_bstride, const float* KV
 }
 
 // ------------------------------------------------------------------------------------ MAB forward (saving) / backward
-struct MabSaved { float *Qp, *KV, *O, *R, *lse, *out; };
+// Opre / pre1: the inputs of ln0 / ln1 (LayerNorm branches only; O and out then hold the normalised tensors)
+struct MabSaved { float *Qp, *KV, *O, *R, *lse, *out, *Opre, *pre1; };
 
-static MabSaved mab_saved_take(Arena& a, int B, int qb, int nq, int nk, int D, int H) {
+// ------------------------------------------------------------------------------------ LayerNorm backward
+// y = (x - mean) rstd gamma + beta per row.  dx = rstd (g gamma - mean(g gamma) - xhat mean(g gamma xhat)); dgamma += sum g xhat,
+// dbeta += sum g.  One warp per row, 8 rows per block; the parameter gradients are reduced in shared memory per block, then
+// added atomically.  g and dx may alias (every lane reads its elements before it writes them).
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* g, const float* __restrict__ x,
+                                                            const float* __restrict__ gamma, long long rows, int D,
+                                                            float* dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta) {
+    extern __shared__ float ln_s[];                 // 2 * D: dgamma | dbeta partials of the block
+    for (int j = threadIdx.x; j < 2 * D; j += blockDim.x) ln_s[j] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long r = (long long)blockIdx.x * 8 + w;
+    if (r < rows) {
+        const float* xr = x + r * D;
+        const float* gr = g + r * D;
+        float sum = 0.f;
+        for (int j = lane; j < D; j += 32) sum += xr[j];
+        const float mean = warp_sum(sum) / D;
+        float var = 0.f;
+        for (int j = lane; j < D; j += 32) { const float d = xr[j] - mean; var += d * d; }
+        const float rstd = rsqrtf(warp_sum(var) / D + 1e-5f);
+        float s1 = 0.f, s2 = 0.f;
+        for (int j = lane; j < D; j += 32) {
+            const float xh = (xr[j] - mean) * rstd, gg = gr[j] * __ldg(gamma + j);
+            s1 += gg;
+            s2 += gg * xh;
+        }
+        s1 = warp_sum(s1) / D;
+        s2 = warp_sum(s2) / D;
+        for (int j = lane; j < D; j += 32) {
+            const float xh = (xr[j] - mean) * rstd, gv = gr[j];
+            atomicAdd(&ln_s[j], gv * xh);
+            atomicAdd(&ln_s[D + j], gv);
+            dx[r * D + j] = rstd * (gv * __ldg(gamma + j) - s1 - xh * s2);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+        atomicAdd(dgamma + j, ln_s[j]);
+        atomicAdd(dbeta + j, ln_s[D + j]);
+    }
+}
+static int launch_layernorm_bwd(const float* g, const float* x, const float* gamma, long long rows, int D, float* dx, float* dgamma,
+                                float* dbeta, cudaStream_t st) {
+    if (rows == 0) return 0;
+    layernorm_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 2 * D * sizeof(float), st>>>(g, x, gamma, rows, D, dx, dgamma, dbeta);
+    PCA_CHECK_LAUNCH("layernorm_bwd_kernel");
+    return 0;
+}
+
+static MabSaved mab_saved_take(Arena& a, int B, int qb, int nq, int nk, int D, int H, int ln = 0) {
     MabSaved s;
     s.Qp = a.take<float>((size_t)qb * nq * D);
     s.KV = a.take<float>((size_t)B * nk * 2 * D);
@@ -498,6 +550,8 @@ static MabSaved mab_saved_take(Arena& a, int B, int qb, int nq, int nk, int D, i
     s.R = a.take<float>((size_t)B * nq * D);
     s.lse = a.take<float>((size_t)B * nq * H);
     s.out = a.take<float>((size_t)B * nq * D);
+    s.Opre = ln ? a.take<float>((size_t)B * nq * D) : nullptr;
+    s.pre1 = ln ? a.take<float>((size_t)B * nq * D) : nullptr;
     return s;
 }
 
@@ -505,19 +559,29 @@ static size_t train_img_bytes(int D) { return gemm_tc_image_bytes(2 * D, D); }
 
 static int mab_train_forward(const MabSaved& s, const float* Qin, int qb, const float* Kin, int B, int nq, int nk, int dq, int dk,
                              int D, int H, const float* params, float* part, void* img, cudaStream_t st,
-                             const int* key_counts = nullptr) {
-    const MabParams m = mab_slice(params, dq, dk, D, 0);
+                             const int* key_counts = nullptr, int ln = 0) {
+    const MabParams m = mab_slice(params, dq, dk, D, ln);
     const size_t ib = train_img_bytes(D);
     PCA_TRY(launch_linear(Qin, m.Wq, m.bq, s.Qp, (long long)qb * nq, dq, D, 0, st, nullptr, dq <= D ? img : nullptr, ib));
     PCA_TRY(launch_linear(Kin, m.Wkv, m.bkv, s.KV, (long long)B * nk, dk, 2 * D, 0, st, nullptr, dk <= D ? img : nullptr, ib));
     PCA_TRY(launch_attn(s.Qp, qb == 1 ? 0 : (long long)nq * D, s.KV, B, nq, nk, D, H, s.O, part, key_counts, st, s.lse));
+    const size_t nbytes = (size_t)B * nq * D * sizeof(float);
+    if (ln) {                                                   // O = ln0(Qp + A V); the pre-LN tensor is kept for the backward
+        PCA_CHECK_CUDA(cudaMemcpyAsync(s.Opre, s.O, nbytes, cudaMemcpyDeviceToDevice, st));
+        PCA_TRY(launch_layernorm(s.O, (long long)B * nq, D, m.ln0w, m.ln0b, st));
+    }
     PCA_TRY(launch_linear(s.O, m.Wo, m.bo, s.out, (long long)B * nq, D, D, 3, st, s.R, img, ib));
+    if (ln) {                                                   // out = ln1(O + relu(fc_o(O)))
+        PCA_CHECK_CUDA(cudaMemcpyAsync(s.pre1, s.out, nbytes, cudaMemcpyDeviceToDevice, st));
+        PCA_TRY(launch_layernorm(s.out, (long long)B * nq, D, m.ln1w, m.ln1b, st));
+    }
     return 0;
 }
 
 // scratch of one MAB backward (floats)
-static size_t mab_bwd_ws_floats(int B, int qb, int nq, int nk, int D, int H) {
+static size_t mab_bwd_ws_floats(int B, int qb, int nq, int nk, int D, int H, int ln = 0) {
     Arena a(nullptr, 0);
+    if (ln) a.take<float>((size_t)B * nq * D);   // gradient at the input of ln1
     a.take<float>((size_t)B * nq * D);        // dZ, later dQp
     a.take<float>((size_t)B * nq * D);        // dO
     a.take<float>((size_t)B * nq * H);        // delta
@@ -530,10 +594,11 @@ static size_t mab_bwd_ws_floats(int B, int qb, int nq, int nk, int D, int H) {
 // dQin / dKin may be null (not needed); acc_* != 0 adds to what the buffer already holds.
 static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float* Kin, int B, int nq, int nk, int dq, int dk, int D,
                         int H, const float* params, float* dparams, const float* dOut, float* dQin, int acc_q, float* dKin,
-                        int acc_k, void* ws, size_t ws_bytes, cudaStream_t st, const int* key_counts = nullptr) {
-    const MabParams m = mab_slice(params, dq, dk, D, 0);
-    const MabParams g = mab_slice(dparams, dq, dk, D, 0);
+                        int acc_k, void* ws, size_t ws_bytes, cudaStream_t st, const int* key_counts = nullptr, int ln = 0) {
+    const MabParams m = mab_slice(params, dq, dk, D, ln);
+    const MabParams g = mab_slice(dparams, dq, dk, D, ln);
     Arena a(ws, ws_bytes);
+    float* g1 = ln ? a.take<float>((size_t)B * nq * D) : nullptr;
     float* dZ = a.take<float>((size_t)B * nq * D);
     float* dO = a.take<float>((size_t)B * nq * D);
     float* delta = a.take<float>((size_t)B * nq * H);
@@ -547,17 +612,26 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
     const long long rq = (long long)B * nq, rk = (long long)B * nk;
     const long long q_bstride = qb == 1 ? 0 : (long long)nq * D;
     const long long n = rq * D;
+    if (ln) {                                                   // through ln1: gradient at O + relu(fc_o(O))
+        PCA_TRY(launch_layernorm_bwd(dOut, s.pre1, m.ln1w, rq, D, g1, (float*)g.ln1w, (float*)g.ln1b, st));
+        dOut = g1;
+    }
     relu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dOut, s.R, dZ, n);
     PCA_CHECK_LAUNCH("relu_bwd_kernel");
     PCA_TRY(launch_grad_weight(dZ, s.O, (float*)g.Wo, rq, D, D, st));
     PCA_TRY(launch_colsum(dZ, rq, D, (float*)g.bo, st));
     PCA_TRY(launch_grad_input(dZ, m.Wo, dO, dOut, rq, D, D, st, img, ib));
+    const float* Oatt = s.O;                                    // Qp + A V
+    if (ln) {                                                   // through ln0 (in place)
+        PCA_TRY(launch_layernorm_bwd(dO, s.Opre, m.ln0w, rq, D, dO, (float*)g.ln0w, (float*)g.ln0b, st));
+        Oatt = s.Opre;
+    }
     {
         const long long total = rq * H;
         if (D % 32 == 0 && 32 % H == 0)
-            attn_delta_warp_kernel<<<(unsigned)((rq + 7) / 8), 256, 0, st>>>(dO, s.O, s.Qp, q_bstride, nq, D, H, rq, delta);
+            attn_delta_warp_kernel<<<(unsigned)((rq + 7) / 8), 256, 0, st>>>(dO, Oatt, s.Qp, q_bstride, nq, D, H, rq, delta);
         else
-            attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dO, s.O, s.Qp, q_bstride, nq, D, D / H, total, delta);
+            attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dO, Oatt, s.Qp, q_bstride, nq, D, D / H, total, delta);
         PCA_CHECK_LAUNCH("attn_delta_kernel");
     }
     PCA_CHECK_CUDA(cudaMemsetAsync(dKV, 0, (size_t)rk * 2 * D * sizeof(float), st));
@@ -584,14 +658,14 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
 // ------------------------------------------------------------------------------------ stand-alone MAB training
 // MAB.forward / backward for user models built from the blocks (modules.py:6-33): SAB = MAB(X, X), ISAB = mab1(X, mab0(I, X)),
 // PMA = MAB(S, X) compose on the host through autograd.  Q (qb, nq, dq) with qb in {1, B}; K (B, nk, dk).
-size_t mab_train_saved_bytes(int B, int qb, int nq, int nk, int D, int H) {
+size_t mab_train_saved_bytes(int B, int qb, int nq, int nk, int D, int H, int ln) {
     Arena a(nullptr, 0);
-    mab_saved_take(a, B, qb, nq, nk, D, H);
+    mab_saved_take(a, B, qb, nq, nk, D, H, ln);
     return a.off;
 }
-size_t mab_train_ws_bytes(int B, int qb, int nq, int nk, int D, int H) {
+size_t mab_train_ws_bytes(int B, int qb, int nq, int nk, int D, int H, int ln) {
     const size_t fwd = align_up(attn_part_floats(B, nq, nk, D, H) * sizeof(float), 256) + align_up(train_img_bytes(D), 256);
-    const size_t bwd = mab_bwd_ws_floats(B, qb, nq, nk, D, H);
+    const size_t bwd = mab_bwd_ws_floats(B, qb, nq, nk, D, H, ln);
     return fwd > bwd ? fwd : bwd;
 }
 static int mab_train_check(int qb, int B, int nq, int nk, int dq, int dk, int D, int H) {
@@ -601,30 +675,30 @@ static int mab_train_check(int qb, int B, int nq, int nk, int dq, int dk, int D,
     if (B > 65535) return fail(PCA_EUNSUPPORTED, "MAB training: batch %d exceeds the grid limit", B);
     return 0;
 }
-int mab_train_forward_api(const float* Q, int qb, const float* K, int B, int nq, int nk, int dq, int dk, int D, int H,
+int mab_train_forward_api(const float* Q, int qb, const float* K, int B, int nq, int nk, int dq, int dk, int D, int H, int ln,
                           const float* params, float* out, void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, cudaStream_t st) {
     PCA_TRY(mab_train_check(qb, B, nq, nk, dq, dk, D, H));
     if (!Q || !K || !params || !out || !saved || !ws) return fail(PCA_EINVAL, "MAB training forward: null pointer");
     Arena sa(saved, saved_bytes);
-    const MabSaved s = mab_saved_take(sa, B, qb, nq, nk, D, H);
-    if (!sa.ok() || ws_bytes < mab_train_ws_bytes(B, qb, nq, nk, D, H)) return fail(PCA_EWORKSPACE, "MAB training forward: buffers too small");
+    const MabSaved s = mab_saved_take(sa, B, qb, nq, nk, D, H, ln);
+    if (!sa.ok() || ws_bytes < mab_train_ws_bytes(B, qb, nq, nk, D, H, ln)) return fail(PCA_EWORKSPACE, "MAB training forward: buffers too small");
     Arena wa(ws, ws_bytes);
     float* part = wa.take<float>(attn_part_floats(B, nq, nk, D, H));
     void* img = wa.take<uint8_t>(train_img_bytes(D));
-    PCA_TRY(mab_train_forward(s, Q, qb, K, B, nq, nk, dq, dk, D, H, params, part, img, st));
+    PCA_TRY(mab_train_forward(s, Q, qb, K, B, nq, nk, dq, dk, D, H, params, part, img, st, nullptr, ln));
     PCA_CHECK_CUDA(cudaMemcpyAsync(out, s.out, (size_t)B * nq * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
-int mab_train_backward_api(const float* Q, int qb, const float* K, int B, int nq, int nk, int dq, int dk, int D, int H,
+int mab_train_backward_api(const float* Q, int qb, const float* K, int B, int nq, int nk, int dq, int dk, int D, int H, int ln,
                            const float* params, const float* dout, const void* saved, size_t saved_bytes, float* dparams, float* dQ,
                            float* dK, void* ws, size_t ws_bytes, cudaStream_t st) {
     PCA_TRY(mab_train_check(qb, B, nq, nk, dq, dk, D, H));
     if (!Q || !K || !params || !dout || !saved || !dparams || !ws) return fail(PCA_EINVAL, "MAB training backward: null pointer");
     Arena sa(const_cast<void*>(saved), saved_bytes);
-    const MabSaved s = mab_saved_take(sa, B, qb, nq, nk, D, H);
-    if (!sa.ok() || ws_bytes < mab_train_ws_bytes(B, qb, nq, nk, D, H)) return fail(PCA_EWORKSPACE, "MAB training backward: buffers too small");
-    PCA_CHECK_CUDA(cudaMemsetAsync(dparams, 0, (size_t)mab_count(dq, dk, D, 0) * sizeof(float), st));
-    return mab_backward(s, Q, qb, K, B, nq, nk, dq, dk, D, H, params, dparams, dout, dQ, 0, dK, 0, ws, ws_bytes, st);
+    const MabSaved s = mab_saved_take(sa, B, qb, nq, nk, D, H, ln);
+    if (!sa.ok() || ws_bytes < mab_train_ws_bytes(B, qb, nq, nk, D, H, ln)) return fail(PCA_EWORKSPACE, "MAB training backward: buffers too small");
+    PCA_CHECK_CUDA(cudaMemsetAsync(dparams, 0, (size_t)mab_count(dq, dk, D, ln) * sizeof(float), st));
+    return mab_backward(s, Q, qb, K, B, nq, nk, dq, dk, D, H, params, dparams, dout, dQ, 0, dK, 0, ws, ws_bytes, st, nullptr, ln);
 }
 
 // ------------------------------------------------------------------------------------ ST / SetTransformer

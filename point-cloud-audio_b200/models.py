@@ -100,6 +100,19 @@ class _SetEncoderBase(nn.Module):
         ps = self._param_tensors()
         if B > 0 and torch.is_grad_enabled() and (X.requires_grad or any(p.requires_grad for p in ps)):
             # training: fp32 forward that keeps activations + hand-written backward (pcaudio_b200/training.py)
+            if dims.ln:
+                # LayerNorm variant: composed from the block training kernels (the fused whole-model path covers ln=False)
+                if counts is not None:
+                    raise NotImplementedError("pcaudio_b200: training with LayerNorm and variable-size sets is not implemented")
+                isab0, isab1, pma, lin = self._parts()
+                Y = isab1(isab0(X))
+                p = self._dropout_p()
+                if p > 0:
+                    Y = torch.nn.functional.dropout(Y, p)
+                Y = pma(Y)
+                if p > 0:
+                    Y = torch.nn.functional.dropout(Y, p)
+                return lin(Y)
             from .training import STTrainFunction
             p = self._dropout_p()
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0

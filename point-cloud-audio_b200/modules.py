@@ -18,8 +18,8 @@ def _wants_grad(module, *inputs):
 
 
 class _NoBackward(torch.autograd.Function):
-    """Marks a fused forward output for which no backward kernel exists (LayerNorm branches) so that a backward pass fails
-    loudly instead of silently training with zero gradients."""
+    """Marks a fused forward output for which no backward kernel exists so that a backward pass fails loudly instead of
+    silently training with zero gradients (every block and model has training kernels; this guards future gaps)."""
 
     @staticmethod
     def forward(ctx, out, *params):
@@ -27,7 +27,7 @@ class _NoBackward(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        raise NotImplementedError("pcaudio_b200: no backward kernel for this configuration (LayerNorm branches); "
+        raise NotImplementedError("pcaudio_b200: no backward kernel for this configuration; "
                                   "run inference under torch.no_grad() or detach the output")
 
 
@@ -90,10 +90,10 @@ class MAB(nn.Module):
         qb, nq, dq = Q.shape
         D, H = self.dim_V, self.num_heads
         blob = self._packed.get(_mab_tensors(self))
-        if B > 0 and not self._ln and _wants_grad(self, Q, K):
+        if B > 0 and _wants_grad(self, Q, K):
             # training: forward that keeps activations + hand-written backward (pcaudio_b200/training.py)
             from .training import MABTrainFunction
-            return MABTrainFunction.apply(Q, K, blob, (D, H), *_mab_tensors(self))
+            return MABTrainFunction.apply(Q, K, blob, (D, H, self._ln), *_mab_tensors(self))
         out = torch.empty((B, nq, D), dtype=torch.float32, device=K.device)
         L = _lib.lib()
         ws = rt.workspace(K.device, L.pca_mab_workspace_bytes(B, nq, nk, dq, dk, D, H))
@@ -130,7 +130,7 @@ class ISAB(nn.Module):
         X = rt.f32c(X)
         B, N, d_in = X.shape
         D, H, M = self.mab0.dim_V, self.mab0.num_heads, self.I.shape[1]
-        if B > 0 and not self.mab0._ln and _wants_grad(self, X):
+        if B > 0 and _wants_grad(self, X):
             # training: H = mab0(I, X); mab1(X, H) through the MAB training kernels (I is a shared query set: no repeat)
             return self.mab1(X, self.mab0(self.I, X))
         blob = self._packed.get(self._tensors())
@@ -160,7 +160,7 @@ class PMA(nn.Module):
         X = rt.f32c(X)
         B, N, D = X.shape
         H, S = self.mab.num_heads, self.S.shape[1]
-        if B > 0 and not self.mab._ln and _wants_grad(self, X):
+        if B > 0 and _wants_grad(self, X):
             return self.mab(self.S, X)                     # training: MAB(S, X), shared seeds
         blob = self._packed.get(self._tensors())
         out = torch.empty((B, S, D), dtype=torch.float32, device=X.device)

@@ -54,21 +54,21 @@ class STTrainFunction(torch.autograd.Function):
 
 
 class MABTrainFunction(torch.autograd.Function):
-    """out = MAB(Q, K; params) for models composed from the blocks (modules.py:6-33, ln=False): Q (1 | B, nq, dq), K (B, nk, dk).
+    """out = MAB(Q, K; params) for models composed from the blocks (modules.py:6-33, LayerNorm branches included): Q (1 | B, nq, dq), K (B, nk, dk).
     A query batch of 1 is the shared-query case (ISAB's I, PMA's S): its gradient is summed over the batch in the kernel."""
 
     @staticmethod
     def forward(ctx, Q, K, blob, cfg, *params):
-        D, H = cfg
+        D, H, ln = cfg
         qb, nq, dq = Q.shape
         B, nk, dk = K.shape
         L = _lib.lib()
         dev = K.device
         out = torch.empty((B, nq, D), dtype=torch.float32, device=dev)
-        saved = torch.empty(max(1, L.pca_mab_train_saved_bytes(B, qb, nq, nk, D, H)), dtype=torch.uint8, device=dev)
-        ws = rt.workspace(dev, L.pca_mab_train_workspace_bytes(B, qb, nq, nk, D, H))
+        saved = torch.empty(max(1, L.pca_mab_train_saved_bytes(B, qb, nq, nk, D, H, ln)), dtype=torch.uint8, device=dev)
+        ws = rt.workspace(dev, L.pca_mab_train_workspace_bytes(B, qb, nq, nk, D, H, ln))
         with torch.cuda.device(dev):
-            _lib.check(L.pca_mab_train_fwd_f32(_lib.ptr(Q), qb, _lib.ptr(K), B, nq, nk, dq, dk, D, H, _lib.ptr(blob), _lib.ptr(out),
+            _lib.check(L.pca_mab_train_fwd_f32(_lib.ptr(Q), qb, _lib.ptr(K), B, nq, nk, dq, dk, D, H, ln, _lib.ptr(blob), _lib.ptr(out),
                                                _lib.ptr(saved), saved.numel(), _lib.ptr(ws), ws.numel(), rt.stream_ptr(dev)),
                        "mab_train_fwd")
         ctx.save_for_backward(Q, K, blob, saved)
@@ -79,7 +79,7 @@ class MABTrainFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         Q, K, blob, saved = ctx.saved_tensors
-        D, H = ctx.cfg
+        D, H, ln = ctx.cfg
         qb, nq, dq = Q.shape
         B, nk, dk = K.shape
         L = _lib.lib()
@@ -87,10 +87,10 @@ class MABTrainFunction(torch.autograd.Function):
         dparams = torch.empty_like(blob)
         dQ = torch.empty_like(Q) if ctx.needs_input_grad[0] else None
         dK = torch.empty_like(K) if ctx.needs_input_grad[1] else None
-        ws = rt.workspace(dev, L.pca_mab_train_workspace_bytes(B, qb, nq, nk, D, H))
+        ws = rt.workspace(dev, L.pca_mab_train_workspace_bytes(B, qb, nq, nk, D, H, ln))
         dout = rt.f32c(dout)
         with torch.cuda.device(dev):
-            _lib.check(L.pca_mab_train_bwd_f32(_lib.ptr(Q), qb, _lib.ptr(K), B, nq, nk, dq, dk, D, H, _lib.ptr(blob), _lib.ptr(dout),
+            _lib.check(L.pca_mab_train_bwd_f32(_lib.ptr(Q), qb, _lib.ptr(K), B, nq, nk, dq, dk, D, H, ln, _lib.ptr(blob), _lib.ptr(dout),
                                                _lib.ptr(saved), saved.numel(), _lib.ptr(dparams), _lib.ptr(dQ), _lib.ptr(dK),
                                                _lib.ptr(ws), ws.numel(), rt.stream_ptr(dev)), "mab_train_bwd")
         grads, off = [], 0

@@ -246,15 +246,12 @@ def test_deepset_pools_vs_oracle(pca, dev):
         assert rel_err(out.numpy(), ref.numpy()) < ENC_REL_TOL
 
 
-def test_backward_without_kernels_fails_loudly(pca, dev):
-    """Models and blocks train (tests/test_gpu_train.py); configurations without backward kernels (LayerNorm branches) must say so instead of silently producing zero gradients."""
-    isab = pca.ISAB(2, 16, 4, 8, ln=True).to(dev)
-    out = isab(torch.randn(2, 50, 2, device=dev))
-    with pytest.raises(NotImplementedError):
-        out.sum().backward()
-    sab = pca.SAB(4, 16, 4, ln=True).to(dev)
-    with pytest.raises(NotImplementedError):
-        sab(torch.randn(2, 10, 4, device=dev)).sum().backward()
+def test_configurations_without_training_kernels_fail_loudly(pca, dev):
+    """Everything trains (tests/test_gpu_train.py) except LayerNorm models on variable-size sets: loud failure, no silent
+    zero gradients."""
+    st = pca.ST(dim_input=2, num_outputs=1, dim_output=10, num_inds=8, dim_hidden=16, num_heads=4, ln=True).to(dev)
+    with torch.enable_grad(), pytest.raises(NotImplementedError):
+        st(torch.randn(2, 50, 2, device=dev), counts=torch.tensor([50, 20], dtype=torch.int32, device=dev))
 
 
 # ------------------------------------------------------------------------------------ whole path

@@ -220,10 +220,43 @@ def test_blocks_and_sab_decoder_model_train_through_autograd(pca):
         err = (prm.grad.cpu().double() - p[k].grad).abs().max().item() / max(p[k].grad.abs().max().item(), floor)
         assert err < GRAD_REL_TOL, f"{k}: rel err {err:.3e}"
     assert ((X.grad.cpu().double() - Xc.grad).abs().max() / Xc.grad.abs().max()).item() < GRAD_REL_TOL
-    # LayerNorm branches have no backward kernels: loud failure
-    mln = pca.SetTransformerSAB(3, 2, 4, num_inds=4, dim_hidden=16, num_heads=2, ln=True).to(dev)
-    with pytest.raises(NotImplementedError):
-        mln(torch.randn(2, 20, 3, device=dev)).sum().backward()
+
+
+@pytest.mark.parametrize("cls", ["SetTransformerSAB", "ST"])
+def test_layernorm_branches_train(pca, cls):
+    """ln=True (modules.py:14-16,30,32): LayerNorm forward + hand-written backward inside the MAB training kernels; the
+    whole models compose the blocks.  Gradients (incl. the LayerNorm weights) against autograd of the oracle."""
+    from oracle import pcaudio_oracle as orc
+    dev = torch.device("cuda:0")
+    torch.manual_seed(21)
+    if cls == "ST":
+        m = pca.ST(dim_input=3, num_outputs=1, dim_output=6, num_inds=8, dim_hidden=64, num_heads=8, ln=True).to(dev)
+    else:
+        m = pca.SetTransformerSAB(3, 4, 6, num_inds=8, dim_hidden=32, num_heads=4, ln=True).to(dev)
+    with torch.no_grad():                                  # non-trivial LayerNorm parameters
+        for k, v in m.named_parameters():
+            if ".ln" in k:
+                v.add_(0.3 * torch.randn_like(v))
+    X = torch.randn(3, 70, 3, device=dev, requires_grad=True)
+    out = m(X)
+    G = torch.randn(*out.shape)
+    (out * G.to(dev)).sum().backward()
+    p = {k: v.detach().cpu().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    Xc = X.detach().cpu().double().requires_grad_(True)
+    if cls == "ST":
+        ref = orc.st_forward(p, Xc, 8)
+    else:
+        y = orc.isab_forward(p, "enc.1.", orc.isab_forward(p, "enc.0.", Xc, 4), 4)
+        y = orc.sab_forward(p, "dec.2.", orc.sab_forward(p, "dec.1.", orc.pma_forward(p, "dec.0.", y, 4), 4), 4)
+        ref = y @ p["dec.3.weight"].T + p["dec.3.bias"]
+    (ref.reshape(G.shape) * G.double()).sum().backward()
+    assert ((out.detach().cpu().double() - ref.detach().reshape(G.shape)).abs().max() / ref.detach().abs().max()).item() < 1e-4
+    floor = 1e-3 * max(v.grad.abs().max().item() for v in p.values())
+    for k, prm in m.named_parameters():
+        assert prm.grad is not None, k
+        err = (prm.grad.cpu().double() - p[k].grad).abs().max().item() / max(p[k].grad.abs().max().item(), floor)
+        assert err < GRAD_REL_TOL, f"{k}: rel err {err:.3e}"
+    assert ((X.grad.cpu().double() - Xc.grad).abs().max() / Xc.grad.abs().max()).item() < GRAD_REL_TOL
 
 
 @pytest.mark.parametrize("d_in,D,H,M", [(3, 64, 8, 64), (2, 32, 4, 8), (3, 256, 4, 16)])
