@@ -260,13 +260,11 @@ static int deepset_forward(const float* X, int B, int N, int d_in, int dh, int o
     if (!a.ok() || !ws) return fail(PCA_EWORKSPACE, "DeepSet: workspace too small");
     const long long rows = (long long)B * N;
     const float* W[8]; const float* bb[8];
-    int din = d_in;
     for (int i = 0; i < 8; ++i) {
         const int dout = (i == 7) ? out_dim : dh;
         const int di = (i == 0) ? d_in : dh;
         W[i] = p; p += (long long)dout * di;
         bb[i] = p; p += dout;
-        (void)din;
     }
     PCA_TRY(launch_linear(X, W[0], bb[0], t0, rows, d_in, dh, 1, st));
     PCA_TRY(launch_linear(t0, W[1], bb[1], t1, rows, dh, dh, 1, st, nullptr, img, ib));      // shared MLP over points: tensor cores

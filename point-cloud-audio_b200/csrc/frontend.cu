@@ -464,7 +464,7 @@ topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* 
     __shared__ int tot[256];
     __shared__ int warp_sum[NW];
     __shared__ uint32_t s_prefix;
-    __shared__ int s_remaining, s_total;
+    __shared__ int s_remaining;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int cloud = blockIdx.x;
