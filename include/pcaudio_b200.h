@@ -203,6 +203,16 @@ int pca_importance_map_f32(const float* logmag, int n_clouds, int nf, int nt, co
 int pca_multinomial_f32(const float* weights, int n_clouds, int n, int K, unsigned long long seed, double* cdf_scratch,
                         int32_t* idx, void* stream);
 
+/* ---------------------------------------------------------------- test-time resampling
+ * librosa.resample(x, sr_orig, sr_new, res_type='kaiser_fast', scale=True) (Code/pceval.py:75, Code/pc_temp3d_eval.py:74) =
+ * resampy 0.2.2 band-limited sinc interpolation.  x (n_clips, n_in) -> y (n_clips, n_out); win / delta: the half window of
+ * the interpolation filter and its first differences (float64, nwin entries, num_table entries per zero crossing; already
+ * multiplied by the ratio when downsampling, as resampy does); every output is multiplied by out_scale (1/sqrt(ratio) for
+ * scale=True).  Outputs past int(n_in * ratio) are the zero padding of librosa's fix_length.  resampy is not available in
+ * this image: the table comes from its published recipe and the parity of this entry point is unpinned. */
+int pca_resample_f32(const float* x, int n_clips, int n_in, int n_out, double sample_ratio, const double* win,
+                     const double* delta, int nwin, int num_table, float out_scale, float* y, void* stream);
+
 /* ---------------------------------------------------------------- training (fp32, every dim; ln = 0)
  * The reference trains these models with loss.backward() + torch.optim.Adam under nn.DataParallel
  * (Code/settransformer.py:89-109, Code/settransformertemp.py:110-128, set_transformer-master/main_pointcloud.py:61-79).

@@ -245,6 +245,82 @@ def pc_maxk(x: np.ndarray, farr: np.ndarray, kmax: int):
 
 
 # --------------------------------------------------------------------------------------
+# L1.5: test-time resampling (PARITY UNPINNED: resampy 0.2.2 / librosa 0.8.0 are not in the image)
+# --------------------------------------------------------------------------------------
+RESAMPY_FILTERS = {     # resampy 0.2.2 filters.py docstring: zero crossings, Kaiser beta, roll-off; 2**9 table entries per crossing
+    "kaiser_best": (64, 14.769656459379492, 0.9475937167399596),
+    "kaiser_fast": (16, 8.555504641634386, 0.85),
+}
+
+
+def resampy_filter(name: str = "kaiser_fast", precision: int = 9):
+    """Half window of resampy's interpolation filter, rebuilt from its published recipe ``filters.sinc_window``:
+    ``rolloff * sinc(rolloff * linspace(0, num_zeros, n+1))`` tapered by the right half of a symmetric Kaiser window of
+    2n+1 points, n = num_zeros * 2**precision.  Returns (half_window float64 (n+1,), num_table = 2**precision).
+    The shipped ``kaiser_*.npz`` tables cannot be read here, so this table -- and everything resampled with it -- is unpinned."""
+    num_zeros, beta, rolloff = RESAMPY_FILTERS[name]
+    num_table = 2 ** precision
+    n = num_table * num_zeros
+    sinc_win = rolloff * np.sinc(rolloff * np.linspace(0, num_zeros, num=n + 1, endpoint=True))
+    taper = np.kaiser(2 * n + 1, beta)[n:]
+    return taper * sinc_win, num_table
+
+
+def resample_librosa080(x: np.ndarray, orig_sr: float, target_sr: float, res_type: str = "kaiser_fast", fix: bool = True,
+                        scale: bool = False) -> np.ndarray:
+    """``librosa.resample`` 0.8.0 with a resampy 0.2.2 filter (call sites: Code/pceval.py:75, Code/pc_temp3d_eval.py:74):
+    resampy.interpn.resample_f restated per output sample (left wing over x[n-i], right wing over x[n+1+k], window linearly
+    interpolated in its table), output length int(n*ratio), then ``fix_length`` to ceil(n*ratio) and ``/= sqrt(ratio)`` for
+    scale=True.  float64 accumulation, result in x.dtype.  UNPINNED (see ``resampy_filter``)."""
+    x = np.asarray(x)
+    if orig_sr == target_sr:
+        return x
+    ratio = float(target_sr) / orig_sr
+    interp_win, num_table = resampy_filter(res_type)
+    interp_win = interp_win.copy()
+    if ratio < 1:
+        interp_win *= ratio
+    interp_delta = np.zeros_like(interp_win)
+    interp_delta[:-1] = np.diff(interp_win)
+    n_in = x.shape[-1]
+    n_res = int(n_in * ratio)
+    scale_f = min(1.0, ratio)
+    time_increment = 1.0 / ratio
+    index_step = int(scale_f * num_table)
+    nwin = interp_win.shape[0]
+    y = np.zeros(x.shape[:-1] + (n_res,), dtype=np.float64)
+    xd = x.astype(np.float64)
+    for t in range(n_res):
+        time_register = t * time_increment
+        n = int(time_register)
+        frac = scale_f * (time_register - n)
+        index_frac = frac * num_table
+        offset = int(index_frac)
+        eta = index_frac - offset
+        i_max = min(n + 1, (nwin - offset) // index_step)
+        if i_max > 0:
+            j = offset + np.arange(i_max) * index_step
+            y[..., t] += ((interp_win[j] + eta * interp_delta[j]) * xd[..., n - np.arange(i_max)]).sum(-1)
+        frac = scale_f - frac
+        index_frac = frac * num_table
+        offset = int(index_frac)
+        eta = index_frac - offset
+        k_max = min(n_in - n - 1, (nwin - offset) // index_step)
+        if k_max > 0:
+            j = offset + np.arange(k_max) * index_step
+            y[..., t] += ((interp_win[j] + eta * interp_delta[j]) * xd[..., n + 1 + np.arange(k_max)]).sum(-1)
+    if fix:
+        n_fix = int(np.ceil(n_in * ratio))
+        if n_fix > n_res:
+            y = np.concatenate([y, np.zeros(y.shape[:-1] + (n_fix - n_res,))], axis=-1)
+        else:
+            y = y[..., :n_fix]
+    if scale:
+        y = y / np.sqrt(ratio)
+    return np.ascontiguousarray(y, dtype=x.dtype)
+
+
+# --------------------------------------------------------------------------------------
 # L4: set encoder (torch CPU restatement; dtype follows the inputs/weights)
 # --------------------------------------------------------------------------------------
 def _linear(x, w, b):

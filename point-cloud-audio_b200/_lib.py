@@ -65,6 +65,7 @@ PROTOTYPES = {
     "pca_gather_points_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
     "pca_importance_map_f32": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P]),
     "pca_multinomial_f32": (_I, [_P, _I, _I, _I, C.c_ulonglong, _P, _P, _P]),
+    "pca_resample_f32": (_I, [_P, _I, _I, _I, C.c_double, _P, _P, _I, _I, _F, _P, _P]),
     "pca_st_train_saved_bytes": (_SZ, [C.POINTER(StDims), _I, _I, _F]),
     "pca_st_train_workspace_bytes": (_SZ, [C.POINTER(StDims), _I, _I]),
     "pca_st_train_fwd_f32": (_I, [_P, _P, _I, _I, C.POINTER(StDims), _P, _F, C.c_ulonglong, _P, _P, _SZ, _P, _SZ, _P]),

@@ -22,6 +22,7 @@ int launch_random_keys(float*, long long, unsigned long long, cudaStream_t);
 int launch_gather_points(const float*, int, int, int, const float*, const float*, const int32_t*, int, float*, cudaStream_t);
 int launch_importance_map(const float*, int, int, int, const float*, int, const float*, int, float*, float*, cudaStream_t);
 int launch_multinomial(const float*, int, int, int, unsigned long long, double*, int32_t*, cudaStream_t);
+int launch_resample(const float*, int, int, int, double, const double*, const double*, int, int, float, float*, cudaStream_t);
 // training path (encoder_train.cu)
 size_t st_train_saved_bytes(const pca_st_dims* d, int B, int N, float dropout_p);
 size_t st_train_ws_bytes(const pca_st_dims* d, int B, int N);
@@ -655,6 +656,12 @@ int pca_multinomial_f32(const float* weights, int n_clouds, int n, int K, unsign
                         int32_t* idx, void* stream) {
     if (!weights || !cdf_scratch || !idx) return fail(PCA_EINVAL, "multinomial: null pointer");
     return launch_multinomial(weights, n_clouds, n, K, seed, cdf_scratch, idx, (cudaStream_t)stream);
+}
+
+int pca_resample_f32(const float* x, int n_clips, int n_in, int n_out, double sample_ratio, const double* win, const double* delta,
+                     int nwin, int num_table, float out_scale, float* y, void* stream) {
+    if (!x || !win || !delta || !y) return fail(PCA_EINVAL, "resample: null pointer");
+    return launch_resample(x, n_clips, n_in, n_out, sample_ratio, win, delta, nwin, num_table, out_scale, y, (cudaStream_t)stream);
 }
 
 size_t pca_st_train_saved_bytes(const pca_st_dims* dims, int B, int N, float dropout_p) {

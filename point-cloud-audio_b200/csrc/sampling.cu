@@ -162,4 +162,62 @@ int launch_multinomial(const float* w, int n_clouds, int n, int K, unsigned long
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------ test-time resampling
+// librosa.resample(x, sr_orig, sr_new, res_type='kaiser_fast', scale=True) of the evaluation sweeps (Code/pceval.py:75,
+// Code/pc_temp3d_eval.py:74) = resampy 0.2.2's band-limited sinc interpolation (interpn.resample_f): for output sample t,
+// with time_register = t / ratio, n = floor(time_register), the left wing sums win(frac + i step) x[n - i] and the right wing
+// win(scale - frac + k step) x[n + 1 + k], the window being linearly interpolated in its table (interp_win + eta * interp_delta).
+// One thread per output sample; the (<= 64 K entry) tables stay in L2.  resampy itself is not in the image: the filter table is
+// rebuilt from resampy's published recipe on the host and the parity of this row is UNPINNED (oracle header).
+__global__ void resample_kernel(const float* __restrict__ x, int n_in, int n_out, double time_increment, double scale,
+                                const double* __restrict__ win, const double* __restrict__ delta, int nwin, int num_table,
+                                int index_step, float out_scale, float* __restrict__ y) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (t >= n_out) return;
+    const float* xb = x + (long long)b * n_in;
+    const double time_register = (double)t * time_increment;
+    const int n = (int)time_register;
+    double acc = 0.0;
+    if (n < n_in) {
+        double frac = scale * (time_register - (double)n);
+        double index_frac = frac * (double)num_table;
+        int offset = (int)index_frac;
+        double eta = index_frac - (double)offset;
+        const int i_max = min(n + 1, (nwin - offset) / index_step);
+        for (int i = 0; i < i_max; ++i) {
+            const int j = offset + i * index_step;
+            acc += (__ldg(win + j) + eta * __ldg(delta + j)) * (double)__ldg(xb + n - i);
+        }
+        frac = scale - frac;
+        index_frac = frac * (double)num_table;
+        offset = (int)index_frac;
+        eta = index_frac - (double)offset;
+        const int k_max = min(n_in - n - 1, (nwin - offset) / index_step);
+        for (int k = 0; k < k_max; ++k) {
+            const int j = offset + k * index_step;
+            acc += (__ldg(win + j) + eta * __ldg(delta + j)) * (double)__ldg(xb + n + k + 1);
+        }
+    }
+    y[(long long)b * n_out + t] = (float)acc * out_scale;
+}
+
+int launch_resample(const float* x, int n_clips, int n_in, int n_out, double sample_ratio, const double* win, const double* delta,
+                    int nwin, int num_table, float out_scale, float* y, cudaStream_t st) {
+    if (n_clips <= 0 || n_out <= 0) return 0;
+    if (n_in <= 0 || !(sample_ratio > 0.0) || nwin <= 0 || num_table <= 0) return fail(PCA_EINVAL, "resample: bad arguments");
+    if (n_clips > 65535) return fail(PCA_EUNSUPPORTED, "resample: more than 65535 clips per call");
+    const double scale = sample_ratio < 1.0 ? sample_ratio : 1.0;
+    const int index_step = (int)(scale * num_table);
+    if (index_step < 1) return fail(PCA_EUNSUPPORTED, "resample: ratio %g too small for a table of %d entries per zero crossing", sample_ratio, num_table);
+    dim3 grid((n_out + 255) / 256, n_clips);
+    {
+        LaunchTimer lt("resample_kernel", st, 4.0 * n_clips * (double)n_out * (2.0 * nwin / index_step), 4.0 * n_clips * ((double)n_in + n_out));
+        resample_kernel<<<grid, 256, 0, st>>>(x, n_in, n_out, 1.0 / sample_ratio, scale, win, delta, nwin, num_table, index_step, out_scale, y);
+    }
+    PCA_CHECK_LAUNCH("resample_kernel");
+    return 0;
+}
+
 }  // namespace pca

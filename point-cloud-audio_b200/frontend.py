@@ -257,3 +257,63 @@ def importance_points(logmag: torch.Tensor, farr, tarr, k: int, winF: int, choic
     else:
         _, idx = topk_points(heat.view(n, 1, nt * nf), None, None, min(int(k), nt * nf), sorted_desc=True, want_points=False)
     return gather_points(logmag, farr, tarr, idx), idx
+
+
+# ------------------------------------------------------------------------------------ test-time resampling
+RESAMPY_FILTERS = {     # resampy 0.2.2: zero crossings, Kaiser beta, roll-off (2**9 table entries per zero crossing)
+    "kaiser_best": (64, 14.769656459379492, 0.9475937167399596),
+    "kaiser_fast": (16, 8.555504641634386, 0.85),
+}
+
+
+def _resampy_tables(res_type: str, ratio: float, device):
+    """Half window of resampy's interpolation filter (recipe of resampy.filters.sinc_window, float64) and its first
+    differences, scaled by the ratio when downsampling; cached per (filter, ratio, device)."""
+    key = ("resampy", res_type, float(ratio), torch.device(device).index)
+    hit = rt._table_cache.get(key)
+    if hit is None:
+        num_zeros, beta, rolloff = RESAMPY_FILTERS[res_type]
+        num_table = 2 ** 9
+        n = num_table * num_zeros
+        win = np.kaiser(2 * n + 1, beta)[n:] * (rolloff * np.sinc(rolloff * np.linspace(0, num_zeros, num=n + 1, endpoint=True)))
+        if ratio < 1:
+            win = win * ratio
+        delta = np.zeros_like(win)
+        delta[:-1] = np.diff(win)
+        hit = (torch.from_numpy(win).to(device), torch.from_numpy(delta).to(device), num_table)
+        rt._table_cache[key] = hit
+    return hit
+
+
+def resample(audio: torch.Tensor, orig_sr: float, target_sr: float, res_type: str = "kaiser_fast", fix: bool = True,
+             scale: bool = False) -> torch.Tensor:
+    """Batched ``librosa.resample(x, orig_sr, target_sr, res_type='kaiser_fast', scale=True)`` of the evaluation sweeps
+    (Code/pceval.py:75, Code/pc_temp3d_eval.py:74): audio (B, L) float32 CUDA -> (B, ceil(L * ratio)) (``fix=True``; else
+    int(L * ratio)).  resampy's band-limited sinc interpolation runs one thread per output sample.  resampy / librosa are
+    not in the image: the filter table is rebuilt from resampy's published recipe and this function's parity with the
+    reference is unpinned (it is tested against the CPU restatement and cross-checked against scipy's polyphase resampler)."""
+    rt.require_cuda(audio, "resample")
+    if audio.dim() != 2:
+        raise ValueError("audio must be (n_clips, n_samples)")
+    if res_type not in RESAMPY_FILTERS:
+        raise ValueError(f"res_type must be one of {sorted(RESAMPY_FILTERS)}")
+    if orig_sr == target_sr:
+        return audio
+    audio = rt.f32c(audio)
+    B, L = audio.shape
+    ratio = float(target_sr) / float(orig_sr)
+    n_res = int(L * ratio)
+    n_out = int(np.ceil(L * ratio)) if fix else n_res
+    dev = audio.device
+    win, delta, num_table = _resampy_tables(res_type, ratio, dev)
+    out = torch.zeros((B, n_out), dtype=torch.float32, device=dev)
+    if B == 0 or n_res == 0:
+        return out
+    tmp = out if n_out == n_res else torch.empty((B, n_res), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pca_resample_f32(_lib.ptr(audio), B, L, n_res, ratio, _lib.ptr(win), _lib.ptr(delta), win.numel(),
+                                               num_table, float(1.0 / np.sqrt(ratio)) if scale else 1.0, _lib.ptr(tmp),
+                                               rt.stream_ptr(dev)), "resample")
+    if tmp is not out:
+        out[:, :min(n_res, n_out)] = tmp[:, :min(n_res, n_out)]
+    return out

@@ -137,3 +137,21 @@ def test_random_k_dataset_items(pca):
     before = ds.indices(2).copy()
     ds.resample()
     assert not np.array_equal(before, ds.indices(2))
+
+
+# ------------------------------------------------------------------------------------ test-time resampling (parity unpinned)
+@pytest.mark.parametrize("orig_sr,target_sr,L,res_type,scale", [(44100, 16000, 6000, "kaiser_fast", True),
+                                                                (44100, 32000, 5001, "kaiser_fast", True),
+                                                                (16000, 8000, 4000, "kaiser_fast", False),
+                                                                (16000, 22050, 3000, "kaiser_best", True)])
+def test_resample_matches_cpu_restatement(pca, orig_sr, target_sr, L, res_type, scale):
+    """GPU resampler against the CPU restatement of librosa.resample / resampy.resample_f (oracle; both unpinned against the
+    real resampy, which is not in the image): identical filter table, float64 accumulation on both sides."""
+    dev = torch.device("cuda:0")
+    x = orc.synth_audio(3, L, orig_sr, seed=7)
+    got = pca.resample(torch.from_numpy(x).to(dev), orig_sr, target_sr, res_type=res_type, scale=scale).cpu().numpy()
+    ref = orc.resample_librosa080(x, orig_sr, target_sr, res_type=res_type, fix=True, scale=scale)
+    assert got.shape == ref.shape == (3, int(np.ceil(L * target_sr / orig_sr)))
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    same = pca.resample(torch.from_numpy(x).to(dev), orig_sr, orig_sr)
+    assert same.shape == (3, L)

@@ -165,3 +165,21 @@ def test_importance_multinomial_and_randk_match_reference_with_seeds(sampg):
     np.random.seed(98)
     xs, fs_ = orc.pc_randk(x3[:, :, 0], farr, 10)
     assert np.array_equal(xs, sampg["pc_randK_x_seed98"]) and np.array_equal(fs_, sampg["pc_randK_f_seed98"])
+
+
+def test_resampler_restatement_sanity():
+    """The resampy / librosa.resample restatement is UNPINNED (neither library is in the image).  Sanity only: it agrees with
+    scipy's polyphase resampler (a different anti-aliasing filter) to 1e-2 away from the edges, integer up-sampling reproduces
+    the input samples, and the output length / energy scaling follow librosa 0.8.0 (ceil(n * ratio); 1/sqrt(ratio))."""
+    from scipy.signal import resample_poly
+    fs = 44100
+    t = np.arange(6000) / fs
+    x = (0.5 * np.sin(2 * np.pi * 440 * t) + 0.2 * np.sin(2 * np.pi * 3000 * t)).astype(np.float32)
+    y = orc.resample_librosa080(x, fs, 16000)
+    ref = resample_poly(x.astype(np.float64), 160, 441)
+    assert y.shape == (int(np.ceil(6000 * 16000 / fs)),) and y.dtype == np.float32
+    assert np.abs(y[200:-200] - ref[200:len(y) - 200]).max() < 1e-2
+    up = orc.resample_librosa080(x[:1500], 16000, 32000)
+    assert up.shape == (3000,) and np.abs(up[::2][50:-50] - x[:1500][50:-50]).max() < 1e-4
+    ys = orc.resample_librosa080(x, fs, 16000, scale=True)
+    assert np.allclose(ys, y / np.sqrt(16000 / fs), rtol=1e-6, atol=1e-8)
