@@ -169,7 +169,7 @@ int launch_multinomial(const float* w, int n_clouds, int n, int K, unsigned long
 // with time_register = t / ratio, n = floor(time_register), the left wing sums win(frac + i step) x[n - i] and the right wing
 // win(scale - frac + k step) x[n + 1 + k], the window being linearly interpolated in its table (interp_win + eta * interp_delta).
 // One thread per output sample; the (<= 64 K entry) tables stay in L2.  resampy itself is not in the image: the filter table is
-// rebuilt from resampy's published recipe on the host and the parity of this row is UNPINNED (oracle header).
+// rebuilt from resampy's published recipe on the host and the parity of this row is UNPINNED.
 __global__ void resample_kernel(const float* __restrict__ x, int n_in, int n_out, double time_increment, double scale,
                                 const double* __restrict__ win, const double* __restrict__ delta, int nwin, int num_table,
                                 int index_step, float out_scale, float* __restrict__ y) {
