@@ -332,3 +332,33 @@ def test_generic_set_transformer_sab_decoder_matches_reference_golden(pca, dev, 
     out = m(torch.from_numpy(g[f"{tag}_X"]).to(dev)).cpu().numpy()
     assert out.shape == g[f"{tag}_Y"].shape
     assert rel_err(out, g[f"{tag}_Y"]) < ENC_REL_TOL
+
+
+# ------------------------------------------------------------------------------------ experiment-1 chain (Code/pceval.py:61-99)
+@pytest.mark.parametrize("fs,N", [(32000, 1434), (8000, 1843)])
+def test_eval_sweep_chain_resample_window_stft_encoder(pca, dev, fs, N):
+    """The per-file body of the window-size / sampling-rate sweep (Code/pceval.py:73-82,90-99): resample to fs (kaiser_fast,
+    scale=True) -> STFT with win_length = N zero-padded to the next power of two, hop = N/2, divided by N -> log-magnitude ->
+    2-D frame clouds with farr = linspace(0, fs/2, Nf)/fs -> shipped FST checkpoint.  GPU chain against the oracle chain
+    (the resampling step is unpinned on both sides)."""
+    fsog = 16000
+    st, w = _load_ckpt(pca, dev, "fst", 2)
+    audio = orc.synth_audio(2, 12000, fsog, seed=41)
+    n_fft = int(2 ** np.ceil(np.log2(N)))
+    x_gpu = pca.resample(torch.from_numpy(audio).to(dev), fsog, fs, res_type="kaiser_fast", scale=True)
+    lm = pca.stft_logmag(x_gpu, n_fft, win_length=N, hop_factor=0.5)                  # (clips, Nt, Nf), divided by N
+    farr = np.linspace(0, fs / 2, lm.shape[2]) / fs
+    clouds = pca.build_clouds(lm.reshape(-1, 1, lm.shape[2]), farr)                   # one (Nf, 2) cloud per frame
+    with torch.no_grad():
+        got = st(clouds).cpu().numpy()
+    ref = []
+    for c in range(audio.shape[0]):
+        xr = orc.resample_librosa080(audio[c], fsog, fs, res_type="kaiser_fast", scale=True)
+        a = orc.logmag_recipe(xr, n_fft, 0.5, win_length=N)                           # (Nf, Nt)
+        pcs = np.stack([orc.cloud_2d(a, farr, t) for t in range(a.shape[1])])
+        ref.append(orc.st_forward({k: torch.from_numpy(np.asarray(v)) if not torch.is_tensor(v) else v for k, v in w.items()},
+                                  torch.from_numpy(pcs), 8).numpy())
+    ref = np.concatenate(ref)
+    assert got.shape == ref.shape
+    # fp32 STFT vs float64 FFT on near-empty bins moves the log-magnitudes slightly; logits agree to 5e-3 of their range
+    assert rel_err(got, ref) < 5e-3
