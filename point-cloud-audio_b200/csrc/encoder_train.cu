@@ -177,6 +177,71 @@ static int launch_colsum(const float* A, long long rows, int cols, float* out, c
     return 0;
 }
 
+// First layers (d_in = 2 / 3 point coordinates): bias and weight gradient of a Linear with din <= 4 in ONE pass over dY:
+// db[c] += sum_r dY[r, c];  dW[c, j] += sum_r dY[r, c] X[r, j].  (A 128 x 64 GEMM tile would be 95 % padding here.)
+template <int DIN>
+__global__ void colsum_x_kernel(const float* __restrict__ A, const float* __restrict__ X, long long rows, int cols, long long rchunk,
+                                float* __restrict__ db, float* __restrict__ dW) {
+    __shared__ float red[8][DIN + 1][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * rchunk;
+    const long long r1 = (r0 + rchunk < rows) ? r0 + rchunk : rows;
+    float acc[DIN + 1];
+#pragma unroll
+    for (int j = 0; j <= DIN; ++j) acc[j] = 0.f;
+    if (c < cols) {
+        for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+            const float a = __ldg(A + r * cols + c);
+            acc[DIN] += a;
+#pragma unroll
+            for (int j = 0; j < DIN; ++j) acc[j] = fmaf(a, __ldg(X + r * DIN + j), acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j <= DIN; ++j) red[threadIdx.y][j][threadIdx.x] = acc[j];
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+#pragma unroll
+        for (int j = 0; j <= DIN; ++j) {
+            float v = acc[j];
+            for (int i = 1; i < 8; ++i) v += red[i][j][threadIdx.x];
+            if (j == DIN) atomicAdd(db + c, v);
+            else atomicAdd(dW + (long long)c * DIN + j, v);
+        }
+    }
+}
+static int launch_colsum_x(const float* dY, const float* X, long long rows, int cols, int din, float* dW, float* db, cudaStream_t st) {
+    if (rows == 0 || cols == 0) return 0;
+    const int ctiles = (cols + 31) / 32;
+    long long nsplit = (148 * 8 + ctiles - 1) / ctiles;
+    const long long max_split = (rows + 63) / 64;
+    if (nsplit > max_split) nsplit = max_split;
+    if (nsplit > 65535) nsplit = 65535;
+    if (nsplit < 1) nsplit = 1;
+    const long long rchunk = (rows + nsplit - 1) / nsplit;
+    nsplit = (rows + rchunk - 1) / rchunk;
+    dim3 grid(ctiles, (unsigned)nsplit), block(32, 8);
+    {
+        LaunchTimer lt("colsum_x_kernel", st, 2.0 * rows * cols * din, 4.0 * rows * (cols + din));
+        switch (din) {
+            case 1: colsum_x_kernel<1><<<grid, block, 0, st>>>(dY, X, rows, cols, rchunk, db, dW); break;
+            case 2: colsum_x_kernel<2><<<grid, block, 0, st>>>(dY, X, rows, cols, rchunk, db, dW); break;
+            case 3: colsum_x_kernel<3><<<grid, block, 0, st>>>(dY, X, rows, cols, rchunk, db, dW); break;
+            case 4: colsum_x_kernel<4><<<grid, block, 0, st>>>(dY, X, rows, cols, rchunk, db, dW); break;
+            default: return fail(PCA_EINVAL, "colsum_x: din %d not in 1..4", din);
+        }
+    }
+    PCA_CHECK_LAUNCH("colsum_x_kernel");
+    return 0;
+}
+// weight + bias gradient of a Linear: one fused pass for the skinny first layers, GEMM + column sum otherwise
+static int launch_grad_weight_bias(const float* dY, const float* X, float* dW, float* db, long long rows, int din, int dout,
+                                   cudaStream_t st) {
+    if (din <= 4 && rows >= 256) return launch_colsum_x(dY, X, rows, dout, din, dW, db, st);
+    PCA_TRY(launch_grad_weight(dY, X, dW, rows, din, dout, st));
+    return launch_colsum(dY, rows, dout, db, st);
+}
+
 // ------------------------------------------------------------------------------------ elementwise pieces
 __global__ void relu_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ R, float* __restrict__ dZ, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -646,11 +711,9 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
         dQp = dQ1;
         rows_q = nq;
     }
-    PCA_TRY(launch_grad_weight(dQp, Qin, (float*)g.Wq, rows_q, dq, D, st));
-    PCA_TRY(launch_colsum(dQp, rows_q, D, (float*)g.bq, st));
+    PCA_TRY(launch_grad_weight_bias(dQp, Qin, (float*)g.Wq, (float*)g.bq, rows_q, dq, D, st));
     if (dQin) PCA_TRY(launch_grad_input(dQp, m.Wq, dQin, acc_q ? dQin : nullptr, rows_q, dq, D, st, img_q, ib));
-    PCA_TRY(launch_grad_weight(dKV, Kin, (float*)g.Wkv, rk, dk, 2 * D, st));
-    PCA_TRY(launch_colsum(dKV, rk, 2 * D, (float*)g.bkv, st));
+    PCA_TRY(launch_grad_weight_bias(dKV, Kin, (float*)g.Wkv, (float*)g.bkv, rk, dk, 2 * D, st));
     if (dKin) PCA_TRY(launch_grad_input(dKV, m.Wkv, dKin, acc_k ? dKin : nullptr, rk, dk, 2 * D, st, img_k, ib));
     return 0;
 }
@@ -1015,8 +1078,7 @@ int deepset_train_backward(const float* X, int B, int N, int d_in, int dh, int o
         float* t = g; g = go; go = t;
     }
     PCA_TRY(relu_mask(g, s.t[0], g, n_el));
-    PCA_TRY(launch_grad_weight(g, X, dW[0], rows, d_in, dh, st));
-    PCA_TRY(launch_colsum(g, rows, dh, db[0], st));
+    PCA_TRY(launch_grad_weight_bias(g, X, dW[0], db[0], rows, d_in, dh, st));
     if (dX) PCA_TRY(launch_grad_input(g, W[0], dX, nullptr, rows, d_in, dh, st));
     return 0;
 }
