@@ -2280,10 +2280,12 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
 }
 
 static int tc_configure() {
-    static bool done = false;       // attributes are per-function, idempotent; races are benign
-    if (done) return 0;
+    // function attributes belong to the current device's context: configure once per device ordinal (a single process may
+    // drive several GPUs from different threads, as nn.DataParallel does); idempotent, so races are benign
+    static std::atomic<unsigned long long> done_mask{0};
     int dev = 0, major = 0;
     PCA_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && ((done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) return 0;
     PCA_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     PCA_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     if (major != 10) return fail(PCA_EDEVICE, "tcgen05 path needs an sm_100 device (found compute capability %d.x)", major);
@@ -2297,7 +2299,7 @@ static int tc_configure() {
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(pma_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PoolSmem::TOTAL));
-    done = true;
+    if (dev < 64) done_mask.fetch_or(1ull << dev, std::memory_order_release);
     return 0;
 }
 

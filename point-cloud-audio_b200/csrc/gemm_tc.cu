@@ -276,6 +276,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) linear_tc_kernel(const LinTcPar
     if (warp == 4) tmem_dealloc(tb, 512);
 }
 
+// function attributes belong to the current device's context: configure once per device ordinal (idempotent; see tc_configure)
+static int gemm_tc_configure();
+
 static int g_gemm_tc = 1;       // 0: every GEMM stays on the CUDA-core kernels (PCA_GEMM_TC=0 / pca_debug_set_gemm_tc)
 void set_gemm_tc(int on) { g_gemm_tc = on ? 1 : 0; }
 static bool gemm_tc_on() {
@@ -303,11 +306,7 @@ int launch_linear_tc(const float* X, const float* W, int trans_w, const float* b
     if (rows == 0) return 0;
     if (!linear_tc_eligible(rows, K, N)) return fail(PCA_EUNSUPPORTED, "linear_tc: shape (%lld, %d, %d) not eligible", rows, K, N);
     if (!img || img_bytes < gemm_tc_image_bytes(N, K)) return fail(PCA_EWORKSPACE, "linear_tc: weight image buffer too small");
-    static bool configured = false;
-    if (!configured) {
-        PCA_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LinTcSmem::TOTAL));
-        configured = true;
-    }
+    PCA_TRY(gemm_tc_configure());
     const int nt = pick_nt(N);
     {
         const long long total = (long long)N * (K / 8);
@@ -484,6 +483,17 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grad_weight_tc_kernel(const GwT
     if (warp == 4) tmem_dealloc(tb, 256);
 }
 
+static int gemm_tc_configure() {
+    static std::atomic<unsigned long long> done_mask{0};
+    int dev = 0;
+    PCA_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && ((done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) return 0;
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LinTcSmem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(grad_weight_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GwTcSmem::TOTAL));
+    if (dev < 64) done_mask.fetch_or(1ull << dev, std::memory_order_release);
+    return 0;
+}
+
 bool grad_weight_tc_eligible(long long rows, int M, int N) {
     return gemm_tc_on() && rows >= 2048 && M % 32 == 0 && M >= 64 && N % 32 == 0 && N >= 32 && N <= 256;
 }
@@ -492,11 +502,7 @@ bool grad_weight_tc_eligible(long long rows, int M, int N) {
 int launch_grad_weight_tc(const float* dY, const float* X, float* dW, long long rows, int M, int N, cudaStream_t st) {
     if (rows == 0) return 0;
     if (!grad_weight_tc_eligible(rows, M, N)) return fail(PCA_EUNSUPPORTED, "grad_weight_tc: shape (%lld, %d, %d) not eligible", rows, M, N);
-    static bool configured = false;
-    if (!configured) {
-        PCA_CHECK_CUDA(cudaFuncSetAttribute(grad_weight_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GwTcSmem::TOTAL));
-        configured = true;
-    }
+    PCA_TRY(gemm_tc_configure());
     const int mtiles = (M + 127) / 128;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
