@@ -30,7 +30,8 @@ class _SetEncoderBase(nn.Module):
         raise NotImplementedError
 
     def set_precision(self, precision: str):
-        """'fp32' (CUDA-core, 1e-3 parity) or 'bf16' (tcgen05 tensor-core tiles, 2e-2 parity)."""
+        """Inference precision: 'fp32' (1e-3 parity path) or 'bf16' (tcgen05 tensor-core tiles, 2e-2 parity).  Calls made
+        with gradients enabled always take the fp32 training path, whatever is set here."""
         self.precision = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision]
         return self
 
