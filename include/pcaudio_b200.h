@@ -351,6 +351,11 @@ void pca_debug_set_tail_max(int tail_max);
  * exponent (normally none); 2 = the 2-warpgroup variant only. */
 void pca_debug_set_reduce_variant(int warpgroups);
 
+/* Debug / experiments: pooled-attention (PMA) kernel of the bf16 path: 1 = rows are (head, copy) pairs (default), 2 = transposed
+ * formulation (thread = point: 8 instead of 128 exponentials per row and tile, asynchronous-copy producer; measured at the
+ * same speed).  Also PCA_TC_POOL=2 in the environment. */
+void pca_debug_set_pool_variant(int variant);
+
 /* fp32-grade GEMMs on the tensor cores (split-bf16, three MMAs per product; csrc/gemm_tc.cu), used by the fp32 encoder path,
  * DeepSet's shared MLP and the training path for layers with K % 32 == 0 and N % 32 == 0.  pca_debug_set_gemm_tc(0) keeps
  * every layer on the CUDA-core kernels.  pca_debug_linear_tc: Y (rows, N) = act(X (rows, K) B^T + bias) [+ resid], B(n,k) =

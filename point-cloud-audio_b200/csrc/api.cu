@@ -46,6 +46,7 @@ int launch_adam(float*, const float*, float*, float*, long long, float, float, f
 void set_timeline(long long* p);
 void set_tail_max(int t);
 void set_reduce_wg(int n);
+void set_pool_variant(int v);
 int launch_umma_probe(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 // tcgen05 path (encoder_tc.cu)
 size_t st_tc_workspace_bytes(const pca_st_dims* d, int B, int N);
@@ -743,6 +744,7 @@ int pca_debug_grad_weight_tc(const float* dY, const float* X, float* dW, long lo
 void pca_debug_set_timeline(long long* device_buffer) { set_timeline(device_buffer); }
 void pca_debug_set_tail_max(int tail_max) { set_tail_max(tail_max); }
 void pca_debug_set_reduce_variant(int warpgroups) { set_reduce_wg(warpgroups); }
+void pca_debug_set_pool_variant(int variant) { set_pool_variant(variant); }
 
 int pca_debug_umma_probe(const float* A, const float* B, float* D, int N, int K, int a_mode, int b_mode, void* stream) {
     return launch_umma_probe(A, B, D, N, K, a_mode, b_mode, (cudaStream_t)stream);

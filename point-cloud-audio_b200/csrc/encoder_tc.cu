@@ -2008,6 +2008,299 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
     if (warp == 12) tmem_dealloc(tb, 512);
 }
 
+// ====================================================================================== pooled attention, transposed
+// Same arithmetic as pma_pool_tc_kernel with the roles of the MMA dimensions swapped, so that no score is computed twice:
+//   S (128 points, 16 columns = 8 heads + 8 zero) = Ytile (128 x 64, the staged tile as the A operand) . AqB^T   [4 MMAs, N = 16]
+//   thread = point: 8 exponentials per point and tile (the row-copy formulation evaluates 128 per row);
+//   the per-head tile maximum is a warp-shuffle + shared-memory reduction over the 128 points of the tile
+//   P^T (rows = heads, K = points) is written to shared memory as a K-major A operand (8 two-byte stores per thread)
+//   Z (heads, 64 features) = P^T . Ytile                                                        [8 MMAs, N = 64, MN-major B]
+//   lanes 0..7 of the first warp of a warpgroup hold the heads' running (m, Z) and rescale them per tile; the row sums l stay
+//   per-thread partials (the rescale factor is uniform over the points) and are reduced once per work item.
+constexpr int P2_NG = 2;                       // softmax warpgroups (tiles in the softmax stage)
+constexpr int P2_STAGES = 8;                   // Y tile ring (asynchronous copies keep six tiles in flight)
+constexpr int P2_WP = 4 * P2_NG;               // first producer warp
+constexpr int P2_WM = P2_WP + 4;               // MMA warp
+constexpr int P2_THREADS = (P2_WM + 4) * 32;   // 16 warps
+struct Pool2Smem {
+    static constexpr int AQB = 0;                                 // 16 x 64 K-major B image (2 KB)
+    static constexpr int Y = 2048;                                // P2_STAGES x 16384
+    static constexpr int PT = Y + P2_STAGES * 16384;              // P2_NG x 32768: P^T as a 128-row K-major A image
+    static constexpr int ACC = PT + P2_NG * 32768;                // [P2_NG][8 heads][64] running Z
+    static constexpr int RED = ACC + P2_NG * 8 * 64 * 4;          // [NG][2 parities][4 warps][8 heads] maxima, then [NG][4][8] sums
+    static constexpr int BARS = RED + (P2_NG * 2 * 4 * 8 + P2_NG * 4 * 8) * 4;
+    static constexpr int TOTAL = BARS + 32 * 8 + 16;
+};
+constexpr uint32_t P2_S = 0, P2_O = 32 * P2_NG;        // NG x 32 score columns (16 used) | NG x 64 output columns
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(P2_THREADS, 1) pma_pool2_tc_kernel(const PoolParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sAqB = smem + Pool2Smem::AQB;
+    uint8_t* sY = smem + Pool2Smem::Y;
+    uint8_t* sPT = smem + Pool2Smem::PT;
+    float* sAcc = reinterpret_cast<float*>(smem + Pool2Smem::ACC);
+    float* sRedMax = reinterpret_cast<float*>(smem + Pool2Smem::RED);
+    float* sRedSum = sRedMax + P2_NG * 2 * 4 * 8;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Pool2Smem::BARS);
+    uint64_t* y_full = bars;                        // [P2_STAGES] count 4 (producer warps)
+    uint64_t* y_empty = bars + P2_STAGES;           // [P2_STAGES] count 1 (commit)
+    uint64_t* s_full = bars + 2 * P2_STAGES;        // [NG] count 1
+    uint64_t* p_ready = s_full + P2_NG;             // [NG] count 4
+    uint64_t* o_full = p_ready + P2_NG;             // [NG] count 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_work = P.n_work, wstep = gridDim.x;
+    auto work_tiles = [&](int w, int& cloud, int& split, int& tile0, int& nb) {
+        cloud = w / P.nsplit;
+        split = w - cloud * P.nsplit;
+        tile0 = split * P.tiles_per_split;
+        nb = main_points(P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N, P.tail_max);
+        return max(0, min((nb + 127) >> 7, tile0 + P.tiles_per_split) - tile0);
+    };
+    // B image of the pooled queries: row n < 8 = head n (row 16 n of the 128-row A image built by prep_kernel), rows 8..15 zero
+    for (int i = threadIdx.x; i < 8 * 16; i += blockDim.x) {
+        const int c = i >> 4, n = i & 15;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (n < 8) v = __ldg(reinterpret_cast<const uint4*>(P.Aq + c * 2048 + (16 * n) * 16));
+        *reinterpret_cast<uint4*>(sAqB + c * 256 + n * 16) = v;
+    }
+    for (int i = threadIdx.x * 16; i < P2_NG * 32768; i += blockDim.x * 16) *reinterpret_cast<uint4*>(sPT + i) = make_uint4(0, 0, 0, 0);
+    if (warp == P2_WM) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P2_STAGES; ++i) { mbar_init(&y_full[i], 4); mbar_init(&y_empty[i], 1); }
+        for (int i = 0; i < P2_NG; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); }
+        fence_barrier_init();
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp >= P2_WM) {
+        reg_dec<40>();
+        if (warp == P2_WM) {
+            // =================================================================== MMA issuer (tiles in order; S runs NG - 1 tiles ahead)
+            const bool leader = elect_one();
+            const uint32_t idesc_s = idesc_bf16(128, 16, 0, 0);
+            const uint32_t idesc_pv = idesc_bf16(128, 64, 0, 1);
+            const uint32_t aqb = smem_u32(sAqB), yb = smem_u32(sY), ptb = smem_u32(sPT);
+            int total = 0;
+            for (int w = blockIdx.x; w < n_work; w += wstep) { int a, b, c, e; total += work_tiles(w, a, b, c, e); }
+            auto issue_s = [&](int t) {
+                // the score buffer t % NG was last read by its warpgroup before it arrived on p_ready for tile t - NG, which
+                // this warp has waited for (P V of tile t - NG is issued before S of tile t in the loop below)
+                const int stage = t % P2_STAGES;
+                mbar_spin(&y_full[stage], (t / P2_STAGES) & 1);
+                fence_after_sync();
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_ss(tmem_addr(tb, 0, P2_S + 32 * (t % P2_NG)), smem_desc(yb + stage * 16384 + ks * 4096, 2048, 128),
+                               smem_desc(aqb + ks * 512, 256, 128), idesc_s, ks > 0);
+                    mma_commit(&s_full[t % P2_NG]);
+                }
+                __syncwarp();
+            };
+            for (int t = 0; t < P2_NG - 1 && t < total; ++t) issue_s(t);
+            for (int t = 0; t < total; ++t) {
+                if (t + P2_NG - 1 < total) issue_s(t + P2_NG - 1);
+                const int b = t % P2_NG, stage = t % P2_STAGES;
+                mbar_spin(&p_ready[b], (t / P2_NG) & 1);
+                fence_after_sync();
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_ss(tmem_addr(tb, 0, P2_O + 64 * b), smem_desc(ptb + b * 32768 + ks * 4096, 2048, 128),
+                               smem_desc(yb + stage * 16384 + ks * 256, 128, 2048), idesc_pv, ks > 0);
+                    mma_commit(&o_full[b]);
+                    mma_commit(&y_empty[stage]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= P2_WP) {
+        reg_dec<88>();
+        // =================================================================== producer: Y tiles -> [chunk][row][16 B]
+        // The kernel is a stream over Y: the loads of the next tile are in flight while a tile is written to shared memory.
+        const int row = 32 * (warp & 3) + lane;
+        struct TileIt { int w, it, cloud, tile0, nb, ntiles; bool ok; };
+        auto seek = [&](TileIt& ti) {
+            ti.ok = false;
+            int split;
+            while (ti.w < n_work) {
+                if (ti.it == 0) ti.ntiles = work_tiles(ti.w, ti.cloud, split, ti.tile0, ti.nb);
+                if (ti.it < ti.ntiles) { ti.ok = true; return; }
+                ti.w += wstep;
+                ti.it = 0;
+            }
+        };
+        // asynchronous 16-byte copies straight into the operand layout: P2_DEPTH tiles in flight per thread, no register staging
+        // (one tile in flight per load latency bounded the register-staged version at 1.9 TB/s)
+        // Ordering: tile t is signalled BEFORE tile t + DEPTH is issued.  The issue may wait for the ring slot of tile
+        // t + DEPTH - STAGES to be released by its P V MMA, which the MMA warp issues only after it has seen the tiles up to
+        // NG - 1 ahead of that one -- all of them signalled by then because DEPTH <= STAGES - NG.
+        constexpr int P2_DEPTH = P2_STAGES - P2_NG;
+        auto issue = [&](const TileIt& ti, int t) {
+            if (ti.ok) {
+                const int stage = t % P2_STAGES;
+                if (t >= P2_STAGES) mbar_spin(&y_empty[stage], ((t / P2_STAGES) - 1) & 1);
+                uint8_t* dst = sY + stage * 16384 + row * 16;
+                const int n = (ti.tile0 + ti.it) * 128 + row;
+                if (n < ti.nb) {
+                    const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)ti.cloud * P.N + n) * 64);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) cp_async16(dst + c * 2048, src + c);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + c * 2048) = make_uint4(0, 0, 0, 0);
+                }
+            }
+            cp_async_commit();                    // (an empty group past the last tile keeps the group count uniform)
+        };
+        TileIt cur{(int)blockIdx.x, 0, 0, 0, 0, 0, false};
+        seek(cur);
+        TileIt ahead = cur;                       // the next tile to issue
+        int t_issue = 0;
+        for (int d = 0; d < P2_DEPTH; ++d) {
+            issue(ahead, t_issue);
+            if (ahead.ok) { ++ahead.it; seek(ahead); ++t_issue; }
+        }
+        int t = 0;
+        while (cur.ok) {
+            cp_async_wait<P2_DEPTH - 1>();        // all but the newest DEPTH - 1 groups have landed: tile t is complete
+            fence_async_smem();
+            fence_before_sync();
+            warp_arrive(&y_full[t % P2_STAGES]);
+            issue(ahead, t_issue);
+            if (ahead.ok) { ++ahead.it; seek(ahead); ++t_issue; }
+            ++cur.it;
+            seek(cur);
+            ++t;
+        }
+        cp_async_wait<0>();
+    } else {
+        reg_inc<152>();       // register pool of the CTA: 16 warps x 128 >= softmax 8 x 152 + producer 4 x 88 + MMA 4 x 40
+        // =================================================================== softmax warpgroups: g takes the tiles with t % NG == g
+        const int g = warp >> 2, quad = warp & 3;
+        const int row = 32 * quad + lane;                 // point of the tile
+        const uint32_t lane_base = 32 * quad;
+        uint8_t* pt = sPT + g * 32768;
+        float* accs = sAcc + (g * 8 + (lane & 7)) * 64;   // running Z of head `lane` (first warp of the warpgroup, lanes 0..7)
+        int t = 0, own = 0;                               // own: tiles this warpgroup has processed (phases, reduction buffer parity)
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, split, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, split, tile0, nb);
+            float m_run[8], l_part[8];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) { m_run[h] = -INFINITY; l_part[h] = 0.f; }
+            if (quad == 0 && lane < 8) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) accs[j] = 0.f;
+            }
+            // the partial is filed under (tile index within the work item) mod NG, so the grouping (and hence every rounding)
+            // of a cloud is independent of what the CTA processed before
+            const int group = (g - t) & (P2_NG - 1);
+            for (int it = 0; it < ntiles; ++it, ++t) {
+                if ((t & (P2_NG - 1)) != g) continue;
+                const int n_valid = min(128, nb - (tile0 + it) * 128);
+                const bool valid = row < n_valid;
+                mbar_spin(&s_full[g], own & 1);
+                fence_after_sync();
+                uint32_t sv[8];
+                tmem_ld8(tmem_addr(tb, lane_base, P2_S + 32 * g), sv);
+                tmem_ld_wait();
+                float s[8], mx[8];
+#pragma unroll
+                for (int h = 0; h < 8; ++h) {
+                    s[h] = __uint_as_float(sv[h]);
+                    mx[h] = valid ? s[h] : -INFINITY;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], o));
+                }
+                float* red = sRedMax + ((g * 2 + (own & 1)) * 4) * 8;
+                if (lane < 8) {
+                    float v = mx[0];
+#pragma unroll
+                    for (int h = 1; h < 8; ++h) v = lane == h ? mx[h] : v;
+                    red[quad * 8 + lane] = v;
+                }
+                named_bar_sync(1 + g, 128);
+                float a_l = 1.f;
+#pragma unroll
+                for (int h = 0; h < 8; ++h) {
+                    const float m_tile = fmaxf(fmaxf(red[h], red[8 + h]), fmaxf(red[16 + h], red[24 + h]));
+                    const float m_new = fmaxf(m_run[h], m_tile);
+                    const float alpha = (m_new == -INFINITY) ? 1.f : ex2(m_run[h] - m_new);
+                    const float p = valid ? ex2(s[h] - m_new) : 0.f;
+                    l_part[h] = fmaf(l_part[h], alpha, p);
+                    m_run[h] = m_new;
+                    a_l = lane == h ? alpha : a_l;
+                    *reinterpret_cast<__nv_bfloat16*>(pt + (row >> 3) * 2048 + h * 16 + (row & 7) * 2) = __float2bfloat16(p);
+                }
+                fence_async_smem();
+                fence_before_sync();
+                warp_arrive(&p_ready[g]);
+                // ---- Z += P^T Y: heads' running sums in shared memory (lanes 0..7 of the warpgroup's first warp)
+                mbar_spin(&o_full[g], own & 1);
+                fence_after_sync();
+                if (quad == 0) {
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        uint32_t o[32];
+                        tmem_ld32(tmem_addr(tb, 0, P2_O + 64 * g + c0), o);
+                        tmem_ld_wait32(o);
+                        if (lane < 8) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) accs[c0 + j] = fmaf(accs[c0 + j], a_l, __uint_as_float(o[j]));
+                        }
+                    }
+                }
+                fence_before_sync();
+                ++own;
+            }
+            // ---- row sums: reduce the per-point partials over the 128 threads
+            float l_tot[8];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                float v = l_part[h];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                l_tot[h] = v;
+            }
+            float* rs = sRedSum + (g * 4) * 8;
+            named_bar_sync(1 + g, 128);                    // the previous work item's sums have been read
+            if (lane < 8) {
+                float v = l_tot[0];
+#pragma unroll
+                for (int h = 1; h < 8; ++h) v = lane == h ? l_tot[h] : v;
+                rs[quad * 8 + lane] = v;
+            }
+            named_bar_sync(1 + g, 128);
+            if (quad == 0 && lane < 8) {
+                const int h = lane;
+                float m_l = m_run[0];
+#pragma unroll
+                for (int hh = 1; hh < 8; ++hh) m_l = lane == hh ? m_run[hh] : m_l;
+                float* dst = P.part + ((((size_t)cloud * P.nsplit + split) * P2_NG + group) * TH + h) * 66;
+                dst[0] = m_l;
+                dst[1] = rs[h] + rs[8 + h] + rs[16 + h] + rs[24 + h];
+#pragma unroll
+                for (int j = 0; j < 64; ++j) dst[2 + j] = accs[j];
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == P2_WM) tmem_dealloc(tb, 512);
+}
+
+
 // merge the pooled partials, apply fc_v to the 8 pooled vectors, then the MAB tail and the final Linear.
 // 4 clouds per 256-thread block (64 threads = 64 features per cloud); weights are read through k-major copies so that
 // the 64 threads of a cloud read consecutive addresses.
@@ -2106,12 +2399,14 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 
 // ------------------------------------------------------------------------------------ host orchestration
 static int g_num_sms = 148;
+static int g_pool_variant = 1;             // pooled attention: 1 = row copies, 2 = transposed (PCA_TC_POOL=2)
 static int g_reduce_wg = 4;               // reduce kernel variant: 4 = streaming (+ exact redo of flagged items), 2 = exact only
 static int g_tail_max = TC_TAIL_MAX;       // tail rule (PCA_TC_TAIL=0 disables it: every point goes through the tensor-core kernels)
 static long long* g_timeline = nullptr;      // set through pca_debug_set_timeline
 void set_timeline(long long* p) { g_timeline = p; }
 void set_tail_max(int t) { g_tail_max = t < 0 ? 0 : (t > TC_TAIL_MAX ? TC_TAIL_MAX : t); }
 void set_reduce_wg(int n) { g_reduce_wg = (n == 4) ? 4 : 2; }
+void set_pool_variant(int v) { g_pool_variant = (v == 2) ? 2 : 1; }
 struct TcSplit { int tiles_total, tiles_per_split, nsplit; };
 // The point range of a cloud is cut into fixed spans of 16 tiles (2048 points).  The cut depends on N only, never
 // on the batch size, so a cloud's logits are bit-identical however the batch is sharded across calls / GPUs.
@@ -2261,11 +2556,12 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     {
         PoolParams r{Y2, N, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->AqPool, part};
         LaunchTimer lt("pma_pool_tc_kernel", st, pts * 2.0 * (2.0 * TH * TD), pts * 128.0);
-        pma_pool_tc_kernel<<<pgrid, TC_THREADS16, PoolSmem::TOTAL, st>>>(r);
+        if (g_pool_variant == 2) pma_pool2_tc_kernel<<<pgrid, P2_THREADS, Pool2Smem::TOTAL, st>>>(r);
+        else pma_pool_tc_kernel<<<pgrid, TC_THREADS16, PoolSmem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("pma_pool_tc_kernel");
     {
-        PoolFinParams p{part, 2 * sp.nsplit, B, c->QpS, c->WvT_P, mp.bkv + TD, c->WoT_P, mp.bo, p_lin, p_lin + (long long)d->C * TD,
+        PoolFinParams p{part, (g_pool_variant == 2 ? P2_NG : 2) * sp.nsplit, B, c->QpS, c->WvT_P, mp.bkv + TD, c->WoT_P, mp.bo, p_lin, p_lin + (long long)d->C * TD,
                         d->C, logits, dbg ? dbg->pooled : nullptr, Y2, N, counts, tm, c->WqkPool};
         LaunchTimer lt("finalize_pool_kernel", st, (double)B * 2.0 * (2.0 * TD * TD + TD * d->C), (double)B * 4.0 * d->C);
         finalize_pool_kernel<<<(B + 3) / 4, 256, 0, st>>>(p);
@@ -2299,6 +2595,8 @@ static int tc_configure() {
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(pma_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PoolSmem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(pma_pool2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Pool2Smem::TOTAL));
+    if (const char* v = getenv("PCA_TC_POOL")) g_pool_variant = (v[0] == '2') ? 2 : 1;
     if (dev < 64) done_mask.fetch_or(1ull << dev, std::memory_order_release);
     return 0;
 }

@@ -60,6 +60,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     __trap();
 }
 
+// Spinning wait (no hardware suspend): lowest wake-up latency, at the price of issue slots -- for latency-bound kernels
+// whose waiting warps do not compete with a saturated pipe.  Bounded like mbar_wait.
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < (1u << 28); ++i)
+        if (mbar_test(bar, parity)) return;
+    __trap();
+}
+
+// 16-byte asynchronous global -> shared copies (LDGSTS): no register staging, many tiles in flight per thread
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ------------------------------------------------------------------------------------ fences
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

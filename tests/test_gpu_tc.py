@@ -228,3 +228,29 @@ def test_pipelined_host_interface_matches_device_call(pca):
     for b, o in zip(batches, outs):
         ref = pipe(b.to(dev)).cpu()
         assert torch.equal(o.squeeze(1), ref)
+
+
+@pytest.mark.parametrize("d_in,B,N", [(2, 5, 1025), (3, 2, 5120), (2, 3, 300), (3, 1, 1)])
+def test_tc_transposed_pooled_attention_variant(pca, d_in, B, N):
+    """The transposed pooled-attention kernel (pca_debug_set_pool_variant(2)): same stage errors against the oracle, and
+    masked sets through it."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import debug_tc_stages
+    from pcaudio_b200 import _lib
+    try:
+        _lib.lib().pca_debug_set_pool_variant(2)
+        errs = debug_tc_stages.run(d_in, B, N)
+        dev = torch.device("cuda:0")
+        torch.manual_seed(1)
+        st = pca.ST(dim_input=3, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev).set_precision("bf16")
+        X = torch.rand(6, 700, 3, device=dev)
+        counts = torch.tensor([700, 1, 129, 513, 640, 256], dtype=torch.int32, device=dev)
+        masked2 = st(X, counts=counts).clone()
+        _lib.lib().pca_debug_set_pool_variant(1)
+        masked1 = st(X, counts=counts).clone()
+    finally:
+        _lib.lib().pca_debug_set_pool_variant(1)
+    for k, v in errs.items():
+        assert v < BF16_REL_TOL, f"stage {k}: rel err {v:.3e} (all: {errs})"
+    assert ((masked2 - masked1).abs().max() / masked1.abs().max()).item() < BF16_REL_TOL
