@@ -272,10 +272,14 @@ def run_ours(args):
                           "share": v["ms"] / tot}
         name, top = max(rep.items(), key=lambda kv: kv[1]["ms"])
         # DRAM traffic per launch of that kernel from the committed ncu --set full capture (profiles/), if any
-        traffic = None
+        traffic, traffic_detail = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(name)
+            traffic_detail = json.load(open(tpath)).get(name)
+            if isinstance(traffic_detail, dict):     # contract: a number (dram read + write bytes per launch) or null
+                traffic = traffic_detail.get("dram_bytes_per_launch")
+            else:
+                traffic, traffic_detail = traffic_detail, None
         avg_s = top["ms"] / 1e3 / top["launches"]
         compute = top["flops"] > 0
         if compute:
@@ -291,6 +295,8 @@ def run_ours(args):
             roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                         "frac": ach / peak, "traffic": traffic, "peak_source": f"{peaks['source']} copy bandwidth",
                         "avg_launch_ms": avg_s * 1e3, "share_of_step": top["ms"] / tot}
+    if roofline is not None and traffic_detail is not None:
+        roofline["traffic_detail"] = traffic_detail
     # The softmax kernels are bound by the MUFU (ex2) pipe, not by the tensor pipe (head dim 8: 512 exponentials per
     # point and MAB against ~31 kFLOP): report that unit next to the contract's tensor roofline.  Peak = 16 ex2/clk/SM
     # (tools/microbench_mufu.cu, measured) x SMs x the SM clock sampled under load.

@@ -407,15 +407,29 @@ __global__ void __launch_bounds__(128) finalize_isab_tc_kernel(const F2Params P)
         __syncthreads();
         // ---- merge the point splits / column halves (+ the tail slot): O = Qp + A V
         if (valid) {
+            const size_t sstride = (size_t)TH * 10 * TM;
+            const bool two = P.nslots == 2;
 #pragma unroll
-            for (int h = 0; h < TH; ++h) {
+            for (int hb = 0; hb < TH; hb += 4) {
+            // two-slot case (the usual one): the partials of four heads are fetched together, 80 loads in flight per
+            // thread instead of 20 -- the kernel is bound by the latency of these rounds, not by bandwidth
+            float w0[4][10], w1[4][10];
+            if (two) {
+#pragma unroll
+                for (int hh = 0; hh < 4; ++hh) {
+                    const float* pq = P.part + (((size_t)cloud * 2) * TH + hb + hh) * 10 * TM + m;
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) { w0[hh][j] = __ldg(pq + j * TM); w1[hh][j] = __ldg(pq + sstride + j * TM); }
+                }
+            }
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) {
+                const int h = hb + hh;
                 const float* pp = P.part + (((size_t)cloud * P.nslots) * TH + h) * 10 * TM + m;
-                const size_t sstride = (size_t)TH * 10 * TM;
                 float a[8], l, mmax;
-                if (P.nslots == 2) {
-                    float v0[10], v1[10];
-#pragma unroll
-                    for (int j = 0; j < 10; ++j) { v0[j] = __ldg(pp + j * TM); v1[j] = __ldg(pp + sstride + j * TM); }
+                if (two) {
+                    const float* v0 = w0[hh];
+                    const float* v1 = w1[hh];
                     mmax = fmaxf(v0[0], v1[0]);
                     const float w0 = exp2f(v0[0] - mmax), w1 = exp2f(v1[0] - mmax);
                     l = fmaf(v0[1], w0, v1[1] * w1);
@@ -454,9 +468,19 @@ __global__ void __launch_bounds__(128) finalize_isab_tc_kernel(const F2Params P)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[h * 8 + j] = fmaf(a[j], inv, qv[j]);
             }
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < 64; ++j) o[j] = 0.f;
+        }
+        {   // pull the next pair's partials towards L2 while this pair's GEMMs and image stores run
+            const int ncloud = 2 * (pair + (int)gridDim.x) + cc;
+            if (ncloud < P.B) {
+                const char* nb = reinterpret_cast<const char*>(P.part + ((size_t)ncloud * P.nslots) * TH * 10 * TM);
+                const int nbytes = P.nslots * TH * 10 * TM * 4;
+                for (int off = m * 128; off < nbytes; off += 64 * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + off));
+            }
         }
         // ---- F = O Wo^T (split product), H = O + relu(F + bo)
         st_split_a(tb, lane_base, o);
