@@ -1745,12 +1745,23 @@ struct ATailParams {
     __nv_bfloat16* Yout;          // (B, N, 64)
 };
 __global__ void __launch_bounds__(64) mab_apply_tail_kernel(const ATailParams P) {
-    __shared__ float sX[64], sQ[64], sP[TH][TM], sO1[64];
+    __shared__ float sX[64], sQ[64], sO1[64];
     const int cloud = blockIdx.x, j = blockIdx.y, f = threadIdx.x;
     const int nb = P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N;
     const int n0 = main_points(nb, P.tail_max);
     if (j >= nb - n0) return;
     const size_t rowi = (size_t)cloud * P.N + n0 + j;
+    // the K and V rows of this thread's 8 keys (head h, keys 8*part .. 8*part+7) are fetched up front, in the same round as
+    // the point itself: the kernel is a chain of dependent global loads otherwise
+    const int h = f >> 3, part = f & 7, pr = h >> 1, ch = h & 1;
+    const uint8_t* kimg = P.KVblk + (size_t)cloud * 32768 + pr * 4096 + ch * 2048 + (size_t)(ch * 64) * 16;
+    const uint8_t* vimg = kimg + 16384;
+    uint4 krow[8], vrow[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        krow[i] = __ldg(reinterpret_cast<const uint4*>(kimg + (size_t)(8 * part + i) * 16));
+        vrow[i] = __ldg(reinterpret_cast<const uint4*>(vimg + (size_t)(8 * part + i) * 16));
+    }
     if (P.X32 != nullptr) { if (f < P.dq) sX[f] = __ldg(P.X32 + rowi * P.dq + f); }
     else sX[f] = __bfloat162float(P.Y16in[rowi * 64 + f]);
     __syncthreads();
@@ -1758,14 +1769,10 @@ __global__ void __launch_bounds__(64) mab_apply_tail_kernel(const ATailParams P)
     for (int k = 0; k < P.dq; ++k) q = fmaf(sX[k], __ldg(P.WqT + k * 64 + f), q);
     sQ[f] = q;
     __syncthreads();
-    const int h = f >> 3, part = f & 7, pr = h >> 1, ch = h & 1;
-    const uint8_t* kimg = P.KVblk + (size_t)cloud * 32768 + pr * 4096 + ch * 2048 + (size_t)(ch * 64) * 16;
-    const uint8_t* vimg = kimg + 16384;
-    // scores of head h against keys 8*part .. 8*part+7
     float sc[8], mx = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(kimg + (size_t)(8 * part + i) * 16));
+        const uint4 u = krow[i];
         const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
         float d = 0.f;
 #pragma unroll
@@ -1785,13 +1792,28 @@ __global__ void __launch_bounds__(64) mab_apply_tail_kernel(const ATailParams P)
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float inv = 1.f / sum;
+    // this thread's 8 keys against the 8 features of head h, then the sum over the 8 threads of the head
+    float o8[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sP[h][8 * part + i] = sc[i] * inv;
-    __syncthreads();
+    for (int d = 0; d < 8; ++d) o8[d] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float pw = sc[i] * inv;
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vrow[i]);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            const float2 vv = __bfloat1622float2(h2[qd]);
+            o8[2 * qd] = fmaf(pw, vv.x, o8[2 * qd]);
+            o8[2 * qd + 1] = fmaf(pw, vv.y, o8[2 * qd + 1]);
+        }
+    }
     float o = 0.f;
-#pragma unroll 8
-    for (int mm = 0; mm < TM; ++mm)
-        o = fmaf(sP[h][mm], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(vimg + (size_t)mm * 16 + part * 2)), o);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+#pragma unroll
+        for (int x = 1; x < 8; x <<= 1) o8[d] += __shfl_xor_sync(0xffffffffu, o8[d], x);
+        if (part == d) o = o8[d];
+    }
     const float o1 = sQ[f] + o;
     sO1[f] = o1;
     __syncthreads();
@@ -2367,6 +2389,37 @@ __global__ void __launch_bounds__(256) finalize_pool_kernel(const PoolFinParams 
     __syncthreads();
     if (valid) {
         // thread f merges feature f of every head
+        if (P.nslots == 2) {
+            // usual case: the 48 values of all heads are fetched in one round (the kernel is latency-bound); same
+            // arithmetic, in the same order, as the general loop below
+            float pm[2][TH], pl[2][TH], pz[2][TH];
+            const float* pc = P.part + ((size_t)cloud * 2) * TH * 66;
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int h = 0; h < TH; ++h) {
+                    const float* pp = pc + ((size_t)s * TH + h) * 66;
+                    pm[s][h] = __ldg(pp); pl[s][h] = __ldg(pp + 1); pz[s][h] = __ldg(pp + 2 + f);
+                }
+#pragma unroll
+            for (int h = 0; h < TH; ++h) {
+                float mmax = fmaxf(fmaxf(-INFINITY, pm[0][h]), pm[1][h]);
+                for (int j = 0; j < r_tail; ++j) mmax = fmaxf(mmax, sS[sub][j][h]);
+                float l = 0.f, z = 0.f;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const float wgt = (pm[s][h] == -INFINITY) ? 0.f : exp2f(pm[s][h] - mmax);
+                    l = fmaf(pl[s][h], wgt, l);
+                    z = fmaf(pz[s][h], wgt, z);
+                }
+                for (int j = 0; j < r_tail; ++j) {
+                    const float wgt = exp2f(sS[sub][j][h] - mmax);
+                    l += wgt;
+                    z = fmaf(sY[sub][j][f], wgt, z);
+                }
+                sZ[sub][h][f] = z / l;
+            }
+        } else
 #pragma unroll
         for (int h = 0; h < TH; ++h) {
             const float* p0 = P.part + (((size_t)cloud * P.nslots) * TH + h) * 66;
