@@ -721,9 +721,10 @@ __global__ void __launch_bounds__((4 * NWG + 12) * 32, 1) mab_reduce5_tc_kernel(
     // redo mode: only the work items flagged by the streaming variant are processed (normally none: leave at once)
     auto skipped = [&](int w) { return P.redo_only != 0 && __ldg(P.redo + w) == 0; };
     if (P.redo_only != 0) {
-        bool any = false;
-        for (int w = blockIdx.x; w < n_work; w += wstep) any = any || (__ldg(P.redo + w) != 0);
-        if (!any) return;
+        // the CTA's flags are read by all of its threads at once (one dependent load each, not a serial scan per thread)
+        int any = 0;
+        for (int w = blockIdx.x + (int)threadIdx.x * wstep; w < n_work; w += (int)blockDim.x * wstep) any |= (__ldg(P.redo + w) != 0);
+        if (!__syncthreads_or(any)) return;
     }
     copy_to_smem(sAq, P.Aq, 16384);
     if (DIN64) copy_to_smem(sW, P.Wkv16, 16384);
