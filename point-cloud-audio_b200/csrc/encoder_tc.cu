@@ -1745,7 +1745,14 @@ struct ATailParams {
     const float* bo;
     __nv_bfloat16* Yout;          // (B, N, 64)
 };
-__global__ void __launch_bounds__(64) mab_apply_tail_kernel(const ATailParams P) {
+// 16-byte read-only load that does not allocate in L1: the K / V rows are streamed once, the fc_q / fc_o weights that
+// every block of the SM re-reads stay resident
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__global__ void __launch_bounds__(64, 16) mab_apply_tail_kernel(const ATailParams P) {
     __shared__ float sX[64], sQ[64], sO1[64];
     const int cloud = blockIdx.x, j = blockIdx.y, f = threadIdx.x;
     const int nb = P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N;
@@ -1760,8 +1767,8 @@ __global__ void __launch_bounds__(64) mab_apply_tail_kernel(const ATailParams P)
     uint4 krow[8], vrow[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        krow[i] = __ldg(reinterpret_cast<const uint4*>(kimg + (size_t)(8 * part + i) * 16));
-        vrow[i] = __ldg(reinterpret_cast<const uint4*>(vimg + (size_t)(8 * part + i) * 16));
+        krow[i] = ldg_stream16(kimg + (size_t)(8 * part + i) * 16);
+        vrow[i] = ldg_stream16(vimg + (size_t)(8 * part + i) * 16);
     }
     if (P.X32 != nullptr) { if (f < P.dq) sX[f] = __ldg(P.X32 + rowi * P.dq + f); }
     else sX[f] = __bfloat162float(P.Y16in[rowi * 64 + f]);
