@@ -1753,7 +1753,7 @@ __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
     return v;
 }
 __global__ void __launch_bounds__(64, 16) mab_apply_tail_kernel(const ATailParams P) {
-    __shared__ float sX[64], sQ[64], sO1[64];
+    __shared__ __align__(16) float sX[64], sQ[64], sO1[64];
     const int cloud = blockIdx.x, j = blockIdx.y, f = threadIdx.x;
     const int nb = P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N;
     const int n0 = main_points(nb, P.tail_max);
@@ -1773,8 +1773,21 @@ __global__ void __launch_bounds__(64, 16) mab_apply_tail_kernel(const ATailParam
     if (P.X32 != nullptr) { if (f < P.dq) sX[f] = __ldg(P.X32 + rowi * P.dq + f); }
     else sX[f] = __bfloat162float(P.Y16in[rowi * 64 + f]);
     __syncthreads();
+    // the kernel is bound by l1tex instructions (weight loads + broadcast reads of the staged row): the row is read as
+    // float4, same products in the same order
     float q = __ldg(P.bq + f);
-    for (int k = 0; k < P.dq; ++k) q = fmaf(sX[k], __ldg(P.WqT + k * 64 + f), q);
+    if (P.dq == 64) {
+#pragma unroll 4
+        for (int k = 0; k < 64; k += 4) {
+            const float4 x4 = *reinterpret_cast<const float4*>(&sX[k]);
+            q = fmaf(x4.x, __ldg(P.WqT + k * 64 + f), q);
+            q = fmaf(x4.y, __ldg(P.WqT + (k + 1) * 64 + f), q);
+            q = fmaf(x4.z, __ldg(P.WqT + (k + 2) * 64 + f), q);
+            q = fmaf(x4.w, __ldg(P.WqT + (k + 3) * 64 + f), q);
+        }
+    } else {
+        for (int k = 0; k < P.dq; ++k) q = fmaf(sX[k], __ldg(P.WqT + k * 64 + f), q);
+    }
     sQ[f] = q;
     __syncthreads();
     float sc[8], mx = -INFINITY;
@@ -1826,8 +1839,14 @@ __global__ void __launch_bounds__(64, 16) mab_apply_tail_kernel(const ATailParam
     sO1[f] = o1;
     __syncthreads();
     float fo = __ldg(P.bo + f);
-#pragma unroll 8
-    for (int k = 0; k < 64; ++k) fo = fmaf(sO1[k], __ldg(P.WoT + k * 64 + f), fo);
+#pragma unroll 4
+    for (int k = 0; k < 64; k += 4) {
+        const float4 o4 = *reinterpret_cast<const float4*>(&sO1[k]);
+        fo = fmaf(o4.x, __ldg(P.WoT + k * 64 + f), fo);
+        fo = fmaf(o4.y, __ldg(P.WoT + (k + 1) * 64 + f), fo);
+        fo = fmaf(o4.z, __ldg(P.WoT + (k + 2) * 64 + f), fo);
+        fo = fmaf(o4.w, __ldg(P.WoT + (k + 3) * 64 + f), fo);
+    }
     P.Yout[rowi * 64 + f] = __float2bfloat16(o1 + fmaxf(fo, 0.f));
 }
 
