@@ -2391,7 +2391,7 @@ struct PoolFinParams {
     const float* Wqk;                         // (8, 64) scale * Wk_h^T fc_q(S)_h
 };
 __global__ void __launch_bounds__(256) finalize_pool_kernel(const PoolFinParams P) {
-    __shared__ float sZ[4][TH][TD + 1], sO[4][64], sO1[4][64], sY[4][TC_TAIL_MAX][64], sS[4][TC_TAIL_MAX][TH];
+    __shared__ __align__(16) float sZ[4][TH][TD + 4], sO[4][64], sO1[4][64], sY[4][TC_TAIL_MAX][64], sS[4][TC_TAIL_MAX][TH];
     const int sub = threadIdx.x >> 6, f = threadIdx.x & 63;
     const int cloud = blockIdx.x * 4 + sub;
     const bool valid = cloud < P.B;
@@ -2473,15 +2473,27 @@ __global__ void __launch_bounds__(256) finalize_pool_kernel(const PoolFinParams 
     if (valid) {
         const int h = f >> 3;
         float a = __ldg(P.bv + f);
-#pragma unroll 8
-        for (int k = 0; k < 64; ++k) a = fmaf(sZ[sub][h][k], __ldg(P.WvT + k * 64 + f), a);
+#pragma unroll 4
+        for (int k = 0; k < 64; k += 4) {           // staged rows as float4: same products, same order, 4x fewer LDS
+            const float4 z4 = *reinterpret_cast<const float4*>(&sZ[sub][h][k]);
+            a = fmaf(z4.x, __ldg(P.WvT + k * 64 + f), a);
+            a = fmaf(z4.y, __ldg(P.WvT + (k + 1) * 64 + f), a);
+            a = fmaf(z4.z, __ldg(P.WvT + (k + 2) * 64 + f), a);
+            a = fmaf(z4.w, __ldg(P.WvT + (k + 3) * 64 + f), a);
+        }
         sO[sub][f] = __ldg(P.QpS + f) + a;
     }
     __syncthreads();
     if (valid) {
         float acc = __ldg(P.bo + f);
-#pragma unroll 8
-        for (int k = 0; k < 64; ++k) acc = fmaf(sO[sub][k], __ldg(P.WoT + k * 64 + f), acc);
+#pragma unroll 4
+        for (int k = 0; k < 64; k += 4) {
+            const float4 o4 = *reinterpret_cast<const float4*>(&sO[sub][k]);
+            acc = fmaf(o4.x, __ldg(P.WoT + k * 64 + f), acc);
+            acc = fmaf(o4.y, __ldg(P.WoT + (k + 1) * 64 + f), acc);
+            acc = fmaf(o4.z, __ldg(P.WoT + (k + 2) * 64 + f), acc);
+            acc = fmaf(o4.w, __ldg(P.WoT + (k + 3) * 64 + f), acc);
+        }
         const float o1 = sO[sub][f] + fmaxf(acc, 0.f);
         sO1[sub][f] = o1;
         if (P.pooled_debug) P.pooled_debug[(size_t)cloud * 64 + f] = o1;
