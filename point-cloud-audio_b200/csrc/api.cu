@@ -2,6 +2,7 @@
 // orchestration of the kernels.  No torch types, no device allocation, no global mutable state
 // beyond the launch counter and the thread-local error slot.
 #include "common.cuh"
+#include "tma_host.cuh"
 #include <string.h>
 #include <map>
 #include <mutex>
@@ -72,6 +73,36 @@ int fail(int code, const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
     snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     return (int)e;
+}
+
+// ------------------------------------------------------------------------------------ TMA tensor maps (tma_host.cuh)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static std::atomic<void*> cached{nullptr};
+    void* f = cached.load(std::memory_order_acquire);
+    if (f == nullptr) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        cached.store(f, std::memory_order_release);
+    }
+    return reinterpret_cast<EncodeTiledFn>(f);
+}
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, unsigned long long inner, unsigned long long rows,
+                      unsigned long long row_stride_bytes, unsigned box_inner, unsigned box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return fail(PCA_EDEVICE, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {inner, rows};
+    const cuuint64_t strides[1] = {row_stride_bytes};
+    const cuuint32_t box[2] = {box_inner, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PCA_EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d (base %p, %llu x %llu, stride %llu)", (int)r, base, inner, rows, row_stride_bytes);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------ profiling

@@ -18,6 +18,7 @@
 //                             tail and the final Linear -> logits.
 #include "common.cuh"
 #include "tc_prims.cuh"
+#include "tma_host.cuh"
 #include <stdlib.h>
 
 namespace pca {
@@ -25,6 +26,9 @@ using namespace tc;
 
 constexpr int TD = 64, TH = 8, TM = 64;                   // dims this path is specialised for
 constexpr float kScaleLog2e = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(dim_V)
+// mab1: the scale is folded into the per-cloud K image written by finalize_isab_tc_kernel (keys are 64 per cloud, queries are
+// all points), so the query operand is the plain bf16 projection
+constexpr float kKImageScale = kScaleLog2e;
 
 struct TcConsts {
     float Qp0[TM * TD];        // isab0.mab0 fc_q(I)
@@ -45,6 +49,9 @@ struct TcConsts {
     float WvT_P[64 * 64], WoT_P[64 * 64];          // pma.mab fc_v / fc_o transposed (k, f): coalesced reads in finalize_pool_kernel
     uint8_t AqPool[16384];                        // PMA: row r = scale * Wk_h^T fc_q(S)_h, h = r / 16 (A operand, 128 x 64)
     uint8_t WqS0[2048];                           // isab0.mab1.fc_q (64, d_in <= 4) as a split-bf16 K=16 B operand
+    // apply4: the same B operands with the bias as an extra K step (rows k = 64, 65 = bias hi, lo; against the "ones" A operand)
+    uint8_t Wq1e[10240], Wo0e[10240], Wo1e[10240];
+    uint8_t WqS0e[2048];                          // WqS0 with the bias (hi, lo) in the spare columns k = 12, 13
     // k-major fp32 copies for finalize_isab: mab0.fc_o^T (64 x 64) and mab1 [Wk;Wv]^T (64 x 128), per ISAB
     float WoT[2][64 * 64];
     float WkvT[2][64 * 128];
@@ -99,6 +106,27 @@ __device__ __forceinline__ void split_x16(const float* x, float* cols) {
         cols[4 + j] = x[j] - hi;
         cols[8 + j] = hi;
         cols[12 + j] = 0.f;
+    }
+}
+
+// (N = 64, K = 80) B operand: the 64 x 64 weight followed by one K step whose rows k = 64, 65 hold the bias as bf16 hi, lo
+__device__ void pack_b_operand_bias(const float* __restrict__ W, const float* __restrict__ b, uint8_t* __restrict__ out) {
+    pack_b_operand(W, 64, out);
+    for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+        const int n = i / 16, k = i % 16;
+        const float hi = __bfloat162float(__float2bfloat16(b[n]));
+        const float v = k == 0 ? hi : (k == 1 ? b[n] - hi : 0.f);
+        *reinterpret_cast<__nv_bfloat16*>(out + 8192 + (k / 8) * 1024 + n * 16 + (k % 8) * 2) = __float2bfloat16(v);
+    }
+}
+// pack_split_b_operand plus the bias (hi, lo) in columns k = 12, 13
+__device__ void pack_split_b_operand_bias(const float* __restrict__ W, const float* __restrict__ b, int n_rows, int d, uint8_t* __restrict__ out) {
+    pack_split_b_operand(W, n_rows, d, out);
+    __syncthreads();
+    for (int n = threadIdx.x; n < n_rows; n += blockDim.x) {
+        const float hi = __bfloat162float(__float2bfloat16(b[n]));
+        *reinterpret_cast<__nv_bfloat16*>(out + (n_rows * 16) + n * 16 + 4 * 2) = __float2bfloat16(hi);          // k = 12
+        *reinterpret_cast<__nv_bfloat16*>(out + (n_rows * 16) + n * 16 + 5 * 2) = __float2bfloat16(b[n] - hi);   // k = 13
     }
 }
 
@@ -214,6 +242,10 @@ __global__ void prep_kernel(const float* __restrict__ params, int d_in, TcConsts
         case 22: transpose_generic(m11.Wq, 64, TD, c->Wq1T[1]); break;
         case 23: transpose_generic(m01.Wo, 64, TD, c->Wo1T[0]); break;
         case 24: transpose_generic(m11.Wo, 64, TD, c->Wo1T[1]); break;
+        case 25: pack_b_operand_bias(m11.Wq, m11.bq, c->Wq1e); break;
+        case 26: pack_b_operand_bias(m01.Wo, m01.bo, c->Wo0e); break;
+        case 27: pack_b_operand_bias(m11.Wo, m11.bo, c->Wo1e); break;
+        case 28: pack_split_b_operand_bias(m01.Wq, m01.bq, 64, d_in, c->WqS0e); break;
         case 17: transpose_weight(mp.Wkv + TD * TD, 64, c->WvT_P); break;
         case 18: transpose_weight(mp.Wo, 64, c->WoT_P); break;
         default: break;
@@ -544,10 +576,11 @@ __global__ void __launch_bounds__(128) finalize_isab_tc_kernel(const F2Params P)
                 for (int q = 0; q < 4; ++q) {
                     const int h = ((c0 & 63) >> 3) + q, pr = h >> 1, ch = h & 1;
                     uint4 u;
-                    u.x = pack_bf16(__uint_as_float(v[8 * q + 0]) + sBkv[c0 + 8 * q + 0], __uint_as_float(v[8 * q + 1]) + sBkv[c0 + 8 * q + 1]);
-                    u.y = pack_bf16(__uint_as_float(v[8 * q + 2]) + sBkv[c0 + 8 * q + 2], __uint_as_float(v[8 * q + 3]) + sBkv[c0 + 8 * q + 3]);
-                    u.z = pack_bf16(__uint_as_float(v[8 * q + 4]) + sBkv[c0 + 8 * q + 4], __uint_as_float(v[8 * q + 5]) + sBkv[c0 + 8 * q + 5]);
-                    u.w = pack_bf16(__uint_as_float(v[8 * q + 6]) + sBkv[c0 + 8 * q + 6], __uint_as_float(v[8 * q + 7]) + sBkv[c0 + 8 * q + 7]);
+                    const float ksc = c0 < 64 ? kKImageScale : 1.f;      // K columns carry the softmax scale
+                    u.x = pack_bf16((__uint_as_float(v[8 * q + 0]) + sBkv[c0 + 8 * q + 0]) * ksc, (__uint_as_float(v[8 * q + 1]) + sBkv[c0 + 8 * q + 1]) * ksc);
+                    u.y = pack_bf16((__uint_as_float(v[8 * q + 2]) + sBkv[c0 + 8 * q + 2]) * ksc, (__uint_as_float(v[8 * q + 3]) + sBkv[c0 + 8 * q + 3]) * ksc);
+                    u.z = pack_bf16((__uint_as_float(v[8 * q + 4]) + sBkv[c0 + 8 * q + 4]) * ksc, (__uint_as_float(v[8 * q + 5]) + sBkv[c0 + 8 * q + 5]) * ksc);
+                    u.w = pack_bf16((__uint_as_float(v[8 * q + 6]) + sBkv[c0 + 8 * q + 6]) * ksc, (__uint_as_float(v[8 * q + 7]) + sBkv[c0 + 8 * q + 7]) * ksc);
                     *reinterpret_cast<uint4*>(img + pr * 4096 + ch * 2048 + (ch * 64 + m) * 16) = u;
                     *reinterpret_cast<uint4*>(img + pr * 4096 + ch * 2048 + ((1 - ch) * 64 + m) * 16) = make_uint4(0, 0, 0, 0);
                 }
@@ -575,6 +608,8 @@ struct AParams {
     const float* bo;              // (64)
     __nv_bfloat16* Yout;          // (B, N, 64)
     long long* timeline;          // debug (PCA_TIMELINE builds): clock64 stamps of CTA 0 / softmax warp 0
+    CUtensorMap tmapY;            // [DIN64, apply4] Y16in as a (B * N, 64) bf16 tensor, box 128 rows x 8 elements (TMA)
+    CUtensorMap tmapYo;           // [apply4] Yout, same geometry (TMA stores of whole tiles)
 };
 
 // ====================================================================================== chain-scheduled kernels
@@ -583,6 +618,10 @@ struct AParams {
 // P V -> next Q K^T round trip of one chain is hidden behind the softmax of the warpgroup's other chain and the two
 // warpgroups never wait on each other.  (Earlier generations of these kernels -- fixed MMA order, 24-warp variants,
 // epilogue on the softmax warps, CUDA-core finalize -- are in the git history; DESIGN.md records what each step bought.)
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // one mbarrier arrival per warp (barrier counts are in warps): every lane has fenced its own writes, the
 // __syncwarp orders them before the elected lane's releasing arrive
@@ -685,10 +724,10 @@ __global__ void __launch_bounds__((4 * NWG + 12) * 32, 1) mab_reduce5_tc_kernel(
     float* sWsm = reinterpret_cast<float*>(smem + R2Smem::SMALL);
     float* sBias = sWsm + 128 * 4;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + R2Smem::BARS);
-    uint64_t* kv_full = bars;          // [2] count 8 (producer warps)
+    uint64_t* kv_full = bars;          // [2] count 256 (every lane of the 8 producer warps)
     uint64_t* kv_empty = bars + 2;     // [2] count 4 (chains)
     uint64_t* s_full = bars + 4;       // [4] count 1
-    uint64_t* p_ready = bars + 8;      // [4] count 4 (warps of the owning warpgroup)
+    uint64_t* p_ready = bars + 8;      // [4] count 128 (every lane of the owning warpgroup)
     uint64_t* o_done = bars + 12;      // [4] count 1   (chain: all P V of the work item complete)
     uint64_t* y_full = bars + 20;      // count 8
     uint64_t* proj_done = bars + 21;   // count 1
@@ -737,8 +776,8 @@ __global__ void __launch_bounds__((4 * NWG + 12) * 32, 1) mab_reduce5_tc_kernel(
     }
     if (warp == WM) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 8); mbar_init(&kv_empty[i], 4); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 256); mbar_init(&kv_empty[i], 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); }
         for (int i = 0; i < 4; ++i) mbar_init(&o_done[i], 1);
         mbar_init(y_full, 8);
         mbar_init(proj_done, 1);
@@ -922,7 +961,7 @@ __global__ void __launch_bounds__((4 * NWG + 12) * 32, 1) mab_reduce5_tc_kernel(
             stamp2(54);
             fence_async_smem();
             fence_before_sync();
-            warp_arrive(&kv_full[stage]);
+            mbar_arrive(&kv_full[stage]);
             ++gt;
         }
     } else if constexpr (NWG == 2) {
@@ -1035,7 +1074,7 @@ __global__ void __launch_bounds__((4 * NWG + 12) * 32, 1) mab_reduce5_tc_kernel(
                 stamp(27);
             }
             fence_before_sync();
-            warp_arrive(&p_ready[c]);
+            mbar_arrive(&p_ready[c]);        // every lane arrives (count 128): no warp sync / divergent branch
         };
         for (int w = blockIdx.x; w < n_work; w += wstep) {
             if (skipped(w)) continue;
@@ -1161,7 +1200,7 @@ __global__ void __launch_bounds__((4 * NWG + 12) * 32, 1) mab_reduce5_tc_kernel(
             l_run[pp] += sum;
             tmem_st_wait();
             fence_before_sync();
-            warp_arrive(&p_ready[c]);
+            mbar_arrive(&p_ready[c]);        // every lane arrives (count 128): no warp sync / divergent branch
         };
         for (int w = blockIdx.x; w < n_work; w += wstep) {
             if (skipped(w)) continue;
@@ -1234,7 +1273,7 @@ struct A3Smem {
 
 // pairs of each 32-column chunk whose exponentials run on the FMA pipe (degree-3 polynomial) instead of MUFU
 #ifndef PCA_POLY3
-#define PCA_POLY3 0x0u
+#define PCA_POLY3 0x1111u      // 4 of every 16 pairs: measured -2 % on the apply kernel (8 of 16: +5 %, the FMA pipe saturates)
 #endif
 #ifndef PCA_A3_PREFETCH
 #define PCA_A3_PREFETCH 0
@@ -1571,7 +1610,7 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
                     for (int q = 0; q < 4; ++q) {
                         float o[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] = (__uint_as_float(v[8 * q + j]) + sBq[c0 + 8 * q + j]) * kScaleLog2e;
+                        for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[8 * q + j]) + sBq[c0 + 8 * q + j];      // scale: K image
                         st_shared_8bf16(dst + (c0 / 8 + q) * 2048 + row * 16, o);
                     }
                 }
@@ -1729,6 +1768,568 @@ __global__ void __launch_bounds__(TC_THREADS20, 1) mab_apply3_tc_kernel(const AP
     if (warp == 12) tmem_dealloc(tb, 512);
 }
 
+// ====================================================================================== apply kernel, fourth generation
+// Same arithmetic as mab_apply3_tc_kernel; what changes is how much softmax work is in flight and who moves the data.
+// Measured with tools/mb_softmax.cu (the bare per-item instruction stream, no MMA): 8 softmax warps peak at 13.1
+// elements/clk/SM, 16 at 14.9 (MUFU limit 16); apply3's two warpgroups with one score buffer per head pair reach 9.4.
+//   * THREE softmax warpgroups (12 warps, 3 per scheduler), each with its OWN chain: a 64-column score buffer, a 32-column
+//     probability buffer and an MMA-issuing warp.  Head pairs are dealt round-robin (pair q = 4 * tile + p goes to chain
+//     q % 3) and every chain walks its own sequence at its own pace -- the schedulers favour the higher warp ids, so a
+//     common item order would run all warpgroups at the speed of the lowest one (measured: 8000 cycles per tile).
+//   * Scores and probabilities live in SEPARATE TMEM regions.  The score buffer is released the moment the warpgroup has the
+//     scores in registers, so Q K^T of the chain's next head runs under this head's arithmetic; the probabilities of head n
+//     are written after s_full(n+1) has been seen, which (same issuing thread, in-order tensor pipe) implies P V (n-1) has
+//     drained the probability buffer.  One barrier wait per head on the softmax side.
+//   * Three tile accumulators; the fc_o output F is written OVER the tile accumulator (the epilogue keeps O1 in registers
+//     from the read that builds the bf16 fc_o operand), so no F columns exist and the accumulator is read once.
+//   * Biases ride in the MMAs: fc_q / fc_o get a fifth K step against a constant "ones" operand whose weight rows hold the
+//     bias as bf16 hi + lo (d_in <= 4: the two spare columns of the split-bf16 K=16 image); the softmax scale is folded into
+//     the K image by the finalize kernel.  The producer / epilogue warps therefore do no shared-memory loads at all (they
+//     were latency-bound on them: 64 broadcast LDS per phase).
+//   * A LOADER warp brings the operands in with the copy engine: the cloud's K / V images by one 32 KB cp.async.bulk, the
+//     bf16 input tile by eight 2-D TMA boxes of 128 rows x 16 bytes (cp.async.bulk.tensor), which land directly in the
+//     canonical no-swizzle operand layout [chunk][row][16 B].
+//   * Registers live per scheduler (16 K each, five warps): 3 softmax x 104 + one producer/epilogue warp x 128 + one light
+//     warp x 40 = 480 = 5 x 96.  The producer work (projection -> bf16 query operand) and the epilogue share four warps:
+//     iteration j prepares tile j + 1 (a whole tile ahead of its first Q K^T) and then finishes tile j - 1.
+// 20 warps: 0-11 softmax (warpgroup g = warps 4g..4g+3), 12-15 producer + epilogue, 17 loader, 16 / 18 / 19 MMA chains 0 / 1 / 2.
+constexpr int A4_THREADS = 20 * 32;
+// Thread-side arrivals: EVERY lane arrives (barrier counts 128 = four warps) -- measured 3.6 % faster than the
+// __syncwarp + elected-lane arrival (no warp sync, no divergent branch on the softmax warps' critical path).
+#ifndef PCA_A4_WARPARRIVE
+#define A4_SM_ARRIVE(bar) mbar_arrive(bar)
+#define A4_SM_COUNT 128
+#else
+#define A4_SM_ARRIVE(bar) warp_arrive(bar)
+#define A4_SM_COUNT 4
+#endif
+#define A4_FENCE_BEFORE() fence_before_sync()
+#define A4_LONG_WAIT(bar, par) mbar_wait(bar, par)
+constexpr uint32_t A4_S = 0, A4_P = 192, A4_OQ = 320;   // 3 x 64 scores | 3 x 32 probabilities (+32 spare) | 3 x 64 tile accumulators
+struct A4Smem {
+    static constexpr int IMG = 0;                 // 2 x (K image 16384 | V image 16384), one per work item in flight
+    static constexpr int WO = 65536;              // fc_o B operand (N=64, K=80: weights + bias step)
+    static constexpr int WQ = WO + 10240;         // fc_q B operand: (N=64, K=80) or the split-bf16 K=16 image
+    static constexpr int AQ = WQ + 10240;         // 2 stages x 16384: bf16 queries (A operand of Q K^T)
+    static constexpr int YA = AQ + 32768;         // 2 stages x 16384: input tile, Y (128 x 64 bf16) or the split-bf16 X columns
+    static constexpr int O1 = YA + 32768;         // O1 tile as the bf16 A operand of fc_o
+    static constexpr int ONES = O1 + 16384;       // constant A operand of the bias K step: columns 0, 1 = 1, the other 14 = 0
+    static constexpr int BARS = ONES + 4096;
+    static constexpr int TOTAL = BARS + 48 * 8 + 16;
+};
+
+template <bool DIN64>
+__global__ void __launch_bounds__(A4_THREADS, 1) mab_apply4_tc_kernel(const __grid_constant__ AParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sImg = smem + A4Smem::IMG;
+    uint8_t* sWo = smem + A4Smem::WO;
+    uint8_t* sWq = smem + A4Smem::WQ;
+    uint8_t* sAQ = smem + A4Smem::AQ;
+    uint8_t* sYA = smem + A4Smem::YA;
+    uint8_t* sO1 = smem + A4Smem::O1;
+    uint8_t* sOnes = smem + A4Smem::ONES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A4Smem::BARS);
+    uint64_t* aq_full = bars;          // [2] count 4 (producer warps)
+    uint64_t* aq_empty = bars + 2;     // [2] count 4 (one commit per head pair: its scores are computed)
+    uint64_t* s_full = bars + 4;       // [3] count 1                          -- per chain
+    uint64_t* s_free = bars + 7;       // [3] count 4 (warps of the warpgroup: scores are in registers)
+    uint64_t* p_ready = bars + 10;     // [3] count 4 (warps of the warpgroup)
+    uint64_t* p_free = bars + 14;      // [3] count 1 (commit of P V; only the last head of a chain waits on it)
+    uint64_t* o_full = bars + 18;      // [3] count 4 (one commit per head pair) -- per tile accumulator
+    uint64_t* oq_free = bars + 21;     // [3] count 4 (epilogue warps)         -- per tile accumulator
+    uint64_t* ya_full = bars + 24;     // [2] count 1 (loader; + the TMA byte count)
+    uint64_t* ya_empty = bars + 26;    // [2] count 1 (commit of the projection MMA)
+    uint64_t* qp_done = bars + 28;     // count 1
+    uint64_t* o1_ready = bars + 29;    // count 4 (epilogue warps)
+    uint64_t* f_full = bars + 30;      // count 1
+    uint64_t* img_full = bars + 32;    // [2] count 1 (loader; + the bulk copy's byte count)
+    uint64_t* img_empty = bars + 34;   // [2] count 3 (the chains, as each leaves the work item)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 48);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_work = P.n_work, wstep = gridDim.x;
+#ifdef PCA_TIMELINE
+    // debug: softmax warp 0, producer/epilogue warp 12, chain warps 16 and 19 of CTA 0 record clock stamps
+    long long* tl2 = nullptr;
+    int tl2_n = 0;
+    if (P.timeline != nullptr && blockIdx.x == 0 && lane == 0) {
+        if (warp == 0) tl2 = P.timeline;
+        else if (warp == 12) tl2 = P.timeline + 2000;
+        else if (warp == 8) tl2 = P.timeline + 4000;
+        else if (warp == 16) tl2 = P.timeline + 6000;
+    }
+    auto stamp2 = [&](int tag) {
+        if (tl2 != nullptr && tl2_n < 1000) { tl2[2 * tl2_n] = tag; tl2[2 * tl2_n + 1] = clock64(); ++tl2_n; }
+    };
+#else
+    auto stamp2 = [&](int) {};
+#endif
+    // tiles of work item w; nb = valid points of its cloud (variable-size sets: rows past nb are padding)
+    auto work_tiles = [&](int w, int& cloud, int& tile0, int& nb) {
+        cloud = w / P.nsplit;
+        const int split = w - cloud * P.nsplit;
+        tile0 = split * P.tiles_per_split;
+        nb = main_points(P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N, P.tail_max);
+        return max(0, min((nb + 127) >> 7, tile0 + P.tiles_per_split) - tile0);
+    };
+
+    copy_to_smem(sWo, P.Wo16, 10240);
+    copy_to_smem(sWq, P.Wq16, DIN64 ? 10240 : 2048);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)          // [2 chunks][128 rows][16 B]: (1, 1, 0, ...) | 0
+        *reinterpret_cast<uint4*>(sOnes + i * 16) = (i < 128) ? make_uint4(0x3F803F80u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
+    if (warp == 16) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&aq_full[i], A4_SM_COUNT); mbar_init(&aq_empty[i], 4);
+            mbar_init(&img_full[i], 1); mbar_init(&img_empty[i], 3);
+            mbar_init(&ya_full[i], 1); mbar_init(&ya_empty[i], 1);
+        }
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], A4_SM_COUNT);
+            mbar_init(&p_ready[i], A4_SM_COUNT); mbar_init(&p_free[i], 1);
+            mbar_init(&o_full[i], 4); mbar_init(&oq_free[i], A4_SM_COUNT);
+        }
+        mbar_init(qp_done, 1);
+        mbar_init(o1_ready, A4_SM_COUNT);
+        mbar_init(f_full, 1);
+        fence_barrier_init();
+    }
+    if (DIN64 && threadIdx.x == 17 * 32) tma_prefetch_desc(&P.tmapY);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp == 17) {
+        reg_dec<40>();
+        // =================================================================== loader: K / V images and input tiles by TMA
+        int gt = 0, wl = 0;
+        for (int w = blockIdx.x; w < n_work; w += wstep, ++wl) {
+            int cloud, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, tile0, nb);
+            if (wl >= 2) A4_LONG_WAIT(&img_empty[wl & 1], ((wl >> 1) - 1) & 1);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&img_full[wl & 1], 32768);
+                bulk_copy_g2s(sImg + (wl & 1) * 32768, P.KVblk + (size_t)cloud * 32768, 32768, &img_full[wl & 1]);
+            }
+            __syncwarp();
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int stage = gt & 1;
+                uint8_t* dst = sYA + stage * 16384;
+                if (gt >= 2) A4_LONG_WAIT(&ya_empty[stage], ((gt >> 1) - 1) & 1);
+                if (DIN64) {
+                    // rows past the cloud's valid points (padding, or the next cloud's rows) only feed MMA rows whose
+                    // results are never stored; rows past the end of the tensor are zero-filled by the copy engine
+                    if (lane == 0) {
+                        const long long r0 = (long long)cloud * P.N + (long long)(tile0 + it) * 128;
+                        mbar_arrive_expect_tx(&ya_full[stage], 16384);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) tma_load_2d(dst + c * 2048, &P.tmapY, 8 * c, (int)r0, &ya_full[stage]);
+                    }
+                    __syncwarp();
+                } else {
+                    // d_in <= 4: the split-bf16 columns of 4 rows per lane (128 x 16 bf16 = 4 KB); columns 12, 13 = 1
+                    // meet the bias rows (hi, lo) of the weight image
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int row = 32 * rr + lane;
+                        const int n = (tile0 + it) * 128 + row;
+                        float x[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (n < nb) {
+                            const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                            for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
+                        }
+                        float cols[16];
+                        split_x16(x, cols);
+                        cols[12] = 1.f;
+                        cols[13] = 1.f;
+                        st_shared_8bf16(dst + row * 16, cols);
+                        st_shared_8bf16(dst + 2048 + row * 16, cols + 8);
+                    }
+                    fence_async_smem();
+                    fence_before_sync();
+                    warp_arrive(&ya_full[stage]);
+                }
+            }
+        }
+    } else if (warp >= 16) {
+        reg_dec<40>();
+        // =================================================================== MMA chain g (uniform control flow, one elected lane issues)
+        // Head items of the chain in order: for every tile, the pairs p with (4 * tile + p) % 3 == g, two heads each.
+        //   Q K^T (x) is issued as soon as the warpgroup has loaded the scores of the previous head (s_free), i.e. under
+        //   that head's softmax arithmetic; P V (prev) follows when its probabilities are written (p_ready).
+        const int g = warp == 16 ? 0 : warp - 17;
+        const bool leader = elect_one();
+        const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
+        const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
+        const uint32_t img = smem_u32(sImg), aqb = smem_u32(sAQ);
+        const uint32_t s_tm = tmem_addr(tb, 0, A4_S + 64 * g), p_tm = tmem_addr(tb, 0, A4_P + 32 * g);
+        uint32_t par = 0;                    // parity of the chain's barriers for the head being issued (n & 1)
+        bool have_prev = false;
+        uint32_t prev_v = 0, prev_d = 0;     // P V of the previous head: V operand address, accumulator address
+        int prev_buf = 0;
+        bool prev_last = false;              // ... it completes its pair
+        auto pv_prev = [&]() {
+            // probabilities of the previous head (barrier parity: the one before `par`)
+            stamp2(62);
+            A4_LONG_WAIT(&p_ready[g], par ^ 1);
+            fence_after_sync();
+            stamp2(63);
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) mma_ts(prev_d, p_tm + ks * 8, smem_desc(prev_v + ks * 256, 128, 2048), idesc_pv, 1u);
+                mma_commit(&p_free[g]);
+                if (prev_last) mma_commit(&o_full[prev_buf]);      // one of the tile's four pairs is complete
+            }
+            __syncwarp();
+        };
+        int gt = 0, wl = 0, q3 = 0;          // q3 = (4 * gt) % 3: pair p belongs to chain (q3 + p) % 3
+        for (int w = blockIdx.x; w < n_work; w += wstep, ++wl) {
+            int cloud, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, tile0, nb);
+            mbar_wait(&img_full[wl & 1], (wl >> 1) & 1);
+            fence_after_sync();
+            const uint32_t k_base = img + (wl & 1) * 32768, v_base = k_base + 16384;
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                stamp2(60);
+                mbar_wait(&aq_full[gt & 1], (gt >> 1) & 1);
+                fence_after_sync();
+                stamp2(61);
+                const uint32_t a_base = aqb + (gt & 1) * 16384;
+                const int buf = gt % 3;
+#pragma unroll 1
+                for (int p = 0; p < 4; ++p) {
+                    int r = q3 + p;
+                    r = r >= 3 ? r - 3 : r;
+                    r = r >= 3 ? r - 3 : r;
+                    if (r != g) continue;
+#pragma unroll 1
+                    for (int hh = 0; hh < 2; ++hh) {
+                        stamp2(64);
+                        if (have_prev) {
+                            mbar_wait(&s_free[g], par ^ 1);
+                            fence_after_sync();
+                        }
+                        stamp2(65);
+                        if (leader) {
+                            mma_ss(s_tm, smem_desc(a_base + 2 * p * 2048, 2048, 128), smem_desc(k_base + p * 4096 + hh * 1024, 2048, 128), idesc_s, 0);
+                            mma_commit(&s_full[g]);
+                            if (hh == 1) mma_commit(&aq_empty[gt & 1]);      // the pair's query operand has been consumed
+                        }
+                        __syncwarp();
+                        stamp2(66);
+                        if (have_prev) pv_prev();
+                        par ^= 1;
+                        have_prev = true;
+                        prev_v = v_base + p * 4096 + hh * 1024;
+                        prev_d = tmem_addr(tb, 0, A4_OQ + 64 * buf + 16 * p);
+                        prev_buf = buf;
+                        prev_last = hh == 1;
+                    }
+                }
+                q3 = q3 == 2 ? 0 : q3 + 1;       // (4 (gt + 1)) % 3 = (q3 + 1) % 3
+            }
+            // leaving the work item: its last P V may still be pending -- it reads the V image, so it goes first
+            if (have_prev) {
+                pv_prev();
+                have_prev = false;
+                // the next head of this chain starts a fresh hand-shake: s_free of the head just retired is consumed here
+                mbar_wait(&s_free[g], par ^ 1);
+            }
+            if (leader) mma_commit(&img_empty[wl & 1]);
+            __syncwarp();
+        }
+    } else if (warp >= 12) {
+        reg_inc<128>();
+        // =================================================================== producer + epilogue warps (thread = point row)
+        // Iteration j prepares tile k = j + 1 and finishes tile e = j - 1.  Both MMA round trips (Q projection of k, fc_o of
+        // e) are issued ahead of the register work that does not depend on them:
+        //   [0] warp 12 issues the Q projection of k                      (inputs ready since the previous iteration)
+        //   [1] O1(e): TMEM -> registers (kept) -> bf16 A operand of fc_o in shared memory
+        //   [2] warp 12 issues fc_o(e)
+        //   [3] projection(k): TMEM -> bf16 query operand               (under the fc_o MMA)
+        //   [4] Y(e) = O1 + relu(F) -> bf16 tile in shared memory -> eight TMA box stores (ragged last tiles: per-row stores)
+        const int quad = warp & 3;
+        const int row = 32 * quad + lane;
+        const uint32_t lane_base = 32 * quad;
+        int it_w = blockIdx.x, it_i = 0, it_ntiles = 0, it_cloud = 0, it_tile0 = 0, it_nb = 0;
+        if (it_w < n_work) it_ntiles = work_tiles(it_w, it_cloud, it_tile0, it_nb);
+        int e_cloud = 0, e_tile = 0, e_nb = 0, m_cloud = 0, m_tile = 0, m_nb = 0, p_cloud = 0, p_tile = 0, p_nb = 0;   // tiles j-1, j, j+1
+        bool more = true;
+        bool stored = false;                  // a TMA store of the staging tile may still be reading it
+        int n_prod = 0;                       // tiles produced so far
+        for (int j = -1;; ++j) {
+            if (more) {
+                while (it_w < n_work && it_i == it_ntiles) {
+                    it_w += wstep;
+                    it_i = 0;
+                    if (it_w < n_work) it_ntiles = work_tiles(it_w, it_cloud, it_tile0, it_nb);
+                }
+                more = it_w < n_work;
+            }
+            const bool have_k = more;
+            const bool have_e = j >= 1 && j - 1 < n_prod;
+            const int k = j + 1, kstage = k & 1, kbuf = k % 3;
+            const int e = j - 1, ebuf = (e + 3) % 3;
+            if (have_k) {
+                p_cloud = it_cloud; p_tile = it_tile0 + it_i; p_nb = it_nb;
+                ++it_i;
+                n_prod = k + 1;
+                stamp2(50);
+                if (warp == 12) {
+                    // [0] the Q projection (elected lane) into the tile's accumulator, free once the epilogue of three tiles
+                    // ago has read its fc_o output on all four warps
+                    mbar_wait(&ya_full[kstage], (k >> 1) & 1);
+                    if (k >= 3) mbar_wait(&oq_free[kbuf], ((k / 3) - 1) & 1);
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const uint32_t yab = smem_u32(sYA) + kstage * 16384, wq = smem_u32(sWq), ones = smem_u32(sOnes);
+                        const uint32_t d = tmem_addr(tb, 0, A4_OQ + 64 * kbuf);
+                        if (DIN64) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_ss(d, smem_desc(yab + ks * 4096, 2048, 128), smem_desc(wq + ks * 2048, 1024, 128), idesc_bf16(128, 64, 0, 0), ks > 0);
+                            mma_ss(d, smem_desc(ones, 2048, 128), smem_desc(wq + 8192, 1024, 128), idesc_bf16(128, 64, 0, 0), 1u);
+                        } else {
+                            mma_ss(d, smem_desc(yab, 2048, 128), smem_desc(wq, 1024, 128), idesc_bf16(128, 64, 0, 0), 0u);
+                        }
+                        mma_commit(qp_done);
+                        mma_commit(&ya_empty[kstage]);
+                    }
+                    __syncwarp();
+                }
+                stamp2(51);
+            }
+            uint32_t o1[64];                    // O1(e) (fp32 bits): kept in registers across the fc_o MMA
+            const int n = e_tile * 128 + row;
+            const bool valid = have_e && n < e_nb;
+            const bool live = have_e && e_tile * 128 + 32 * quad < e_nb;
+            const bool full_tile = e_tile * 128 + 128 <= e_nb;
+            const uint32_t oq = tmem_addr(tb, lane_base, A4_OQ + 64 * ebuf);
+            if (have_e) {
+                // [1]
+                stamp2(40);
+                A4_LONG_WAIT(&o_full[ebuf], (e / 3) & 1);
+                fence_after_sync();
+                stamp2(41);
+                if (stored) {
+                    // the staging tile is free once the previous tile's TMA store has read it (issued a whole tile ago)
+                    if (warp == 12 && lane == 0) bulk_wait_group_read0();
+                    named_bar_sync(8, 128);
+                    stored = false;
+                }
+                if (live) {
+                    tmem_ld32(oq, o1);
+                    tmem_ld32(oq + 32, o1 + 32);
+                    tmem_ld_wait64(o1, o1 + 32);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        uint4 u;
+                        u.x = pack_bf16(__uint_as_float(o1[8 * q + 0]), __uint_as_float(o1[8 * q + 1]));
+                        u.y = pack_bf16(__uint_as_float(o1[8 * q + 2]), __uint_as_float(o1[8 * q + 3]));
+                        u.z = pack_bf16(__uint_as_float(o1[8 * q + 4]), __uint_as_float(o1[8 * q + 5]));
+                        u.w = pack_bf16(__uint_as_float(o1[8 * q + 6]), __uint_as_float(o1[8 * q + 7]));
+                        *reinterpret_cast<uint4*>(sO1 + q * 2048 + row * 16) = u;
+                    }
+                }
+                stamp2(42);
+                fence_async_smem();
+                fence_before_sync();
+                A4_SM_ARRIVE(o1_ready);
+                if (warp == 12) {
+                    // [2] fc_o (elected lane): F = O1 Wo^T + bo written OVER the tile accumulator, which all four warps have
+                    // read by now (their arrivals above follow their tcgen05.wait::ld)
+                    mbar_wait(o1_ready, e & 1);
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const uint32_t wo = smem_u32(sWo), o1b = smem_u32(sO1), ones = smem_u32(sOnes);
+                        const uint32_t d = tmem_addr(tb, 0, A4_OQ + 64 * ebuf);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ss(d, smem_desc(o1b + ks * 4096, 2048, 128), smem_desc(wo + ks * 2048, 1024, 128), idesc_bf16(128, 64, 0, 0), ks > 0);
+                        mma_ss(d, smem_desc(ones, 2048, 128), smem_desc(wo + 8192, 1024, 128), idesc_bf16(128, 64, 0, 0), 1u);
+                        mma_commit(f_full);
+                    }
+                    __syncwarp();
+                }
+                stamp2(43);
+            }
+            if (have_k) {
+                // [3] projection of tile k -> bf16 query operand (two 32-column halves: O1(e) stays live)
+                uint8_t* dst = sAQ + kstage * 16384;
+                mbar_wait(qp_done, k & 1);
+                fence_after_sync();
+                stamp2(52);
+                if (k >= 2) mbar_wait(&aq_empty[kstage], ((k >> 1) - 1) & 1);
+                stamp2(53);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_addr(tb, lane_base, A4_OQ + 64 * kbuf + 32 * hf), v);
+                    tmem_ld_wait32(v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 u;
+                        u.x = pack_bf16(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+                        u.y = pack_bf16(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+                        u.z = pack_bf16(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+                        u.w = pack_bf16(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+                        *reinterpret_cast<uint4*>(dst + (4 * hf + q) * 2048 + row * 16) = u;
+                    }
+                }
+                stamp2(54);
+                fence_async_smem();
+                fence_before_sync();
+                A4_SM_ARRIVE(&aq_full[kstage]);
+            }
+            if (have_e) {
+                // [4] Y = O1 + relu(F)      (F already holds the bias)
+                mbar_wait(f_full, e & 1);
+                fence_after_sync();
+                stamp2(44);
+                if (live) {
+                    __nv_bfloat16* dstp = P.Yout + ((size_t)e_cloud * P.N + (valid ? n : 0)) * 64;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t f[32];
+                        tmem_ld32(oq + 32 * hf, f);
+                        tmem_ld_wait32(f);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 u;
+                            uint32_t* uw = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+                            for (int x = 0; x < 8; x += 2) {
+                                const int c = 32 * hf + 8 * q + x;
+                                const float y0 = __uint_as_float(o1[c]) + fmaxf(__uint_as_float(f[8 * q + x]), 0.f);
+                                const float y1 = __uint_as_float(o1[c + 1]) + fmaxf(__uint_as_float(f[8 * q + x + 1]), 0.f);
+                                uw[x >> 1] = pack_bf16(y0, y1);
+                            }
+                            if (full_tile) *reinterpret_cast<uint4*>(sO1 + (4 * hf + q) * 2048 + row * 16) = u;
+                            else if (valid) *reinterpret_cast<uint4*>(dstp + 32 * hf + 8 * q) = u;
+                        }
+                    }
+                }
+                if (full_tile) {
+                    // the tile leaves as eight 128-row x 16-byte boxes from the canonical layout (fc_o has finished reading it)
+                    fence_async_smem();
+                    named_bar_sync(8, 128);
+                    if (warp == 12 && lane == 0) {
+                        const long long r0 = (long long)e_cloud * P.N + (long long)e_tile * 128;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) tma_store_2d(&P.tmapYo, sO1 + c * 2048, 8 * c, (int)r0);
+                        bulk_commit_group();
+                    }
+                    stored = true;
+                }
+                stamp2(45);
+                fence_before_sync();
+                A4_SM_ARRIVE(&oq_free[ebuf]);
+            }
+            if (!more && (n_prod == 0 || j - 1 >= n_prod - 1)) break;
+            e_cloud = m_cloud; e_tile = m_tile; e_nb = m_nb;
+            m_cloud = p_cloud; m_tile = p_tile; m_nb = p_nb;
+        }
+        if (warp == 12 && lane == 0) bulk_wait_group0();       // the last tile's store has been performed before the CTA exits
+    } else {
+        reg_inc<104>();
+        // =================================================================== softmax warpgroup g (chain g)
+        const int g = warp >> 2, quad = warp & 3;
+        const uint32_t lane_base = 32 * quad;
+        const uint32_t sbase = tmem_addr(tb, lane_base, A4_S + 64 * g);
+        const uint32_t pbase = tmem_addr(tb, lane_base, A4_P + 32 * g);
+        uint32_t par = 0;                     // parity of the chain's barriers for the current head (n & 1)
+        bool have_scores = false;             // s_full of the current head has already been waited for (look-ahead below)
+        bool first_head = true;               // the chain's very first head finds the probability buffer free
+        int q3 = 0;
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            int cloud, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, tile0, nb);
+            // (the chain restarts its hand-shake at every work item boundary, so the look-ahead never crosses one)
+            for (int it = 0; it < ntiles; ++it) {
+                const bool live = (tile0 + it) * 128 + 32 * quad < nb;     // warps whose 32 rows are all padding idle
+#pragma unroll 1
+                for (int p = 0; p < 4; ++p) {
+                    int r = q3 + p;
+                    r = r >= 3 ? r - 3 : r;
+                    r = r >= 3 ? r - 3 : r;
+                    if (r != g) continue;
+                    // is there a later pair of this chain in this work item?  pairs of the chain are 3 apart in q = 4 * it + p
+                    const bool pair_follows = 4 * it + p + 3 < 4 * ntiles;
+#pragma unroll 1
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const bool has_next = hh == 0 || pair_follows;
+                        uint32_t va[32], vb[32], pk[16];
+                        float inv = 0.f;
+                        stamp2(20);
+                        if (!have_scores) {
+                            mbar_wait(&s_full[g], par);
+                            fence_after_sync();
+                        }
+                        stamp2(24);
+                        if (live) {
+                            tmem_ld32(sbase, va);
+                            tmem_ld32(sbase + 32, vb);
+                            tmem_ld_wait64(va, vb);
+                        }
+                        // the scores are in registers: Q K^T of the chain's next head may overwrite the buffer
+                        A4_FENCE_BEFORE();
+                        A4_SM_ARRIVE(&s_free[g]);
+                        stamp2(25);
+                        if (live) {
+                            const float mx = max64(va, vb);
+                            const float2 neg2 = make_float2(-mx, -mx);
+                            float2 sum2 = make_float2(0.f, 0.f);
+#ifndef PCA_A4_NOEXP
+                            exp_keep32(va, neg2, sum2);
+                            exp_keep32(vb, neg2, sum2);
+#else
+                            sum2 = make_float2(1.f, 1.f);      // EXPERIMENT ONLY: what does the pipeline cost without the exponentials?
+#endif
+                            inv = __fdividef(1.f, sum2.x + sum2.y);
+                        }
+                        stamp2(21);
+                        // the probability buffer still holds the previous head's P until its P V has run: the chain issues
+                        // that P V before the NEXT head's Q K^T, so s_full(next) covers it; the chain's last head of a work
+                        // item waits for the P V commit itself
+                        if (has_next) {
+                            mbar_wait(&s_full[g], par ^ 1);
+                            fence_after_sync();
+                            have_scores = true;
+                        } else {
+                            if (!first_head) {
+                                mbar_wait(&p_free[g], par ^ 1);
+                                fence_after_sync();
+                            }
+                            have_scores = false;
+                        }
+                        first_head = false;
+                        stamp2(22);
+                        if (live) {
+                            const float2 inv2 = make_float2(inv, inv);
+                            scale_pack32(va, inv2, pk);
+                            tmem_st16(pbase, pk);
+                            scale_pack32(vb, inv2, pk);
+                            tmem_st16(pbase + 16, pk);
+                            stamp2(26);
+                            tmem_st_wait();
+                            stamp2(27);
+                        }
+                        A4_FENCE_BEFORE();
+                        A4_SM_ARRIVE(&p_ready[g]);
+                        par ^= 1;
+                    }
+                }
+                q3 = q3 == 2 ? 0 : q3 + 1;
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc(tb, 512);
+}
+
 // ------------------------------------------------------------------------------------ apply kernel: leftover points
 // MAB(Q = one leftover point, K = H) in fp32 on CUDA cores (tail rule): one 64-thread block per leftover point, thread f <->
 // feature f = head h * 8 + d.  Same arithmetic as mab_apply3_tc_kernel with the cloud's bf16 K / V images as keys.
@@ -1802,7 +2403,7 @@ __global__ void __launch_bounds__(64, 16) mab_apply_tail_kernel(const ATailParam
             d = fmaf(sQ[h * 8 + 2 * qd], kk.x, d);
             d = fmaf(sQ[h * 8 + 2 * qd + 1], kk.y, d);
         }
-        sc[i] = d * kScaleLog2e;
+        sc[i] = d;                         // the K image carries the softmax scale
         mx = fmaxf(mx, sc[i]);
     }
 #pragma unroll
@@ -2106,9 +2707,6 @@ struct Pool2Smem {
 };
 constexpr uint32_t P2_S = 0, P2_O = 32 * P2_NG;        // NG x 32 score columns (16 used) | NG x 64 output columns
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 __global__ void __launch_bounds__(P2_THREADS, 1) pma_pool2_tc_kernel(const PoolParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -2517,12 +3115,14 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 static int g_num_sms = 148;
 static int g_pool_variant = 1;             // pooled attention: 1 = row copies, 2 = transposed (PCA_TC_POOL=2)
 static int g_reduce_wg = 4;               // reduce kernel variant: 4 = streaming (+ exact redo of flagged items), 2 = exact only
+static int g_apply_variant = 4;           // apply kernel: 4 = three softmax warpgroups, TMA loader; 3 = previous generation (PCA_TC_APPLY=3)
 static int g_tail_max = TC_TAIL_MAX;       // tail rule (PCA_TC_TAIL=0 disables it: every point goes through the tensor-core kernels)
 static long long* g_timeline = nullptr;      // set through pca_debug_set_timeline
 void set_timeline(long long* p) { g_timeline = p; }
 void set_tail_max(int t) { g_tail_max = t < 0 ? 0 : (t > TC_TAIL_MAX ? TC_TAIL_MAX : t); }
 void set_reduce_wg(int n) { g_reduce_wg = (n == 4) ? 4 : 2; }
 void set_pool_variant(int v) { g_pool_variant = (v == 2) ? 2 : 1; }
+void set_apply_variant(int v) { g_apply_variant = (v == 3) ? 3 : 4; }
 struct TcSplit { int tiles_total, tiles_per_split, nsplit; };
 // The point range of a cloud is cut into fixed spans of 16 tiles (2048 points).  The cut depends on N only, never
 // on the batch size, so a cloud's logits are bit-identical however the batch is sharded across calls / GPUs.
@@ -2619,10 +3219,12 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     }
     PCA_CHECK_LAUNCH("finalize_isab_kernel");
     {
-        AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, kvblk, m01.Wq, m01.bq, c->WqS0,
-                  c->Wo0, m01.bo, Y1, tl_apply ? g_timeline : nullptr};
+        AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, kvblk, m01.Wq, m01.bq,
+                  g_apply_variant == 4 ? c->WqS0e : c->WqS0, g_apply_variant == 4 ? c->Wo0e : c->Wo0, m01.bo, Y1, tl_apply ? g_timeline : nullptr};
+        if (g_apply_variant == 4) PCA_TRY(make_tmap_2d_bf16(&a.tmapYo, Y1, 64, (unsigned long long)B * N, 128, 8, 128));
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * d_in * TD + 2.0 * TM * TD + TD * TD), pts * (4.0 * d_in + 128.0));
-        mab_apply3_tc_kernel<false><<<pgrid, TC_THREADS20, A3Smem::TOTAL, st>>>(a);
+        if (g_apply_variant == 4) mab_apply4_tc_kernel<false><<<pgrid, A4_THREADS, A4Smem::TOTAL, st>>>(a);
+        else mab_apply3_tc_kernel<false><<<pgrid, TC_THREADS20, A3Smem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<small>");
     if (has_tail) {
@@ -2656,10 +3258,15 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     }
     PCA_CHECK_LAUNCH("finalize_isab_kernel");
     {
-        AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, kvblk, nullptr, m11.bq, c->Wq1,
-                  c->Wo1, m11.bo, Y2, nullptr};
+        AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, kvblk, nullptr, m11.bq,
+                  g_apply_variant == 4 ? c->Wq1e : c->Wq1, g_apply_variant == 4 ? c->Wo1e : c->Wo1, m11.bo, Y2, getenv("PCA_TL_APPLY64") ? g_timeline : nullptr};
+        if (g_apply_variant == 4) {
+            PCA_TRY(make_tmap_2d_bf16(&a.tmapY, Y1, 64, (unsigned long long)B * N, 128, 8, 128));
+            PCA_TRY(make_tmap_2d_bf16(&a.tmapYo, Y2, 64, (unsigned long long)B * N, 128, 8, 128));
+        }
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * TD * TD + 2.0 * TM * TD + TD * TD), pts * 256.0);
-        mab_apply3_tc_kernel<true><<<pgrid, TC_THREADS20, A3Smem::TOTAL, st>>>(a);
+        if (g_apply_variant == 4) mab_apply4_tc_kernel<true><<<pgrid, A4_THREADS, A4Smem::TOTAL, st>>>(a);
+        else mab_apply3_tc_kernel<true><<<pgrid, TC_THREADS20, A3Smem::TOTAL, st>>>(a);
     }
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<64>");
     if (has_tail) {
@@ -2709,6 +3316,9 @@ static int tc_configure() {
     if (const char* v = getenv("PCA_TC_REDUCE_WG")) g_reduce_wg = (v[0] == '2') ? 2 : 4;
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply4_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4Smem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply4_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4Smem::TOTAL));
+    if (const char* v = getenv("PCA_TC_APPLY")) g_apply_variant = (v[0] == '3') ? 3 : 4;
     PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(pma_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PoolSmem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(pma_pool2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Pool2Smem::TOTAL));
@@ -2728,7 +3338,7 @@ int st_tc_forward_dbg(const float* X, const int* counts, int B, int N, const pca
     if (dbg && chunk < B) return fail(PCA_EWORKSPACE, "ST(bf16) debug: workspace must hold the whole batch");
     uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
     TcConsts* c = reinterpret_cast<TcConsts*>(w8 + tc_layout(chunk, N).consts);
-    prep_kernel<<<25, 256, 0, st>>>(params, d->d_in, c);
+    prep_kernel<<<29, 256, 0, st>>>(params, d->d_in, c);
     PCA_CHECK_LAUNCH("prep_kernel");
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int bc = (B - b0) < chunk ? (B - b0) : chunk;

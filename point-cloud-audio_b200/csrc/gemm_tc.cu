@@ -22,14 +22,6 @@ constexpr int GT_KC = 32;            // K elements per pipeline stage
 constexpr int GT_STAGES = 3;
 constexpr int GT_THREADS = 9 * 32;   // 4 producer + 1 MMA + 4 epilogue warps
 
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 __device__ __forceinline__ void gt_warp_arrive(uint64_t* bar) {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(bar);

@@ -76,6 +76,40 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ------------------------------------------------------------------------------------ TMA (bulk asynchronous copies)
+// the issuing thread's arrival + the expected byte count of the copies that will complete on this barrier
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared (bytes % 16 == 0, both addresses 16-byte aligned); completes on `bar` (complete_tx)
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// 2-D tiled tensor copy global -> shared through a CUtensorMap (host-encoded, passed as a __grid_constant__ kernel
+// parameter); c0 = coordinate along the contiguous dimension, c1 = row.  Out-of-range parts of the box are zero-filled and
+// still count towards the barrier's byte count.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+// 2-D tiled tensor store shared -> global (bulk-group completion: commit, then wait_group(.read) by the same thread);
+// parts of the box outside the tensor are not written
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src_smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1),
+                 "r"(smem_u32(src_smem))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk groups have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed entirely (global writes performed)
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) { asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory"); }
+
 // ------------------------------------------------------------------------------------ fences
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -1,0 +1,15 @@
+// Host side of the TMA tensor copies: CUtensorMap encoding through the driver entry point (no link-time dependency on
+// libcuda; the runtime hands out cuTensorMapEncodeTiled).  Maps are encoded per launch (the tensors live in the caller's
+// workspace) and passed to the kernels as __grid_constant__ parameters.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace pca {
+
+// 2-D row-major bf16 tensor (rows, inner) with `row_stride_bytes` between rows; box = (box_inner, box_rows); no swizzle
+// (the kernels place 16-byte-wide boxes so that the tile lands in the canonical no-swizzle UMMA operand layout).
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, unsigned long long inner, unsigned long long rows,
+                      unsigned long long row_stride_bytes, unsigned box_inner, unsigned box_rows);
+
+}  // namespace pca
