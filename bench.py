@@ -139,9 +139,9 @@ def run_reference_arm(args):
     if rank != 0:
         return
     clips = 8          # bounded sample of the 256-clip batch: 8 clips = 128 frame clouds per step
-    r = cpu_reference_path(args.steps, min(args.warmup, 1), clips)
+    r = cpu_reference_path(args.steps, args.warmup, clips)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": r["passes"], "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * r["seconds"] / r["passes"],
+            "steps": r["passes"], "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / r["passes"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": f"{clips} of the 256 clips per step (CPU-bounded)"},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
@@ -149,6 +149,117 @@ def run_reference_arm(args):
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ other BASELINE configs
+def run_extra_configs(args, dev, rank, world, local):
+    """BASELINE.json configs 1, 3, 4, 5 and the fp32 parity path of the headline, OUTSIDE the timed headline: each record is
+    device-timed (CUDA events, >= 3 warm-up passes, max over ranks), weak scaling for the inference configs (the same
+    per-GPU work on every rank, value = aggregate), strong scaling of one optimisation step for config 5 (global batch 256,
+    one NCCL all-reduce of the flat gradient per step when N > 1).  Inputs exceed L2 or rotate through distinct batches."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import pcaudio_b200 as pca
+    from pcaudio_b200 import parallel
+
+    G = os.path.join(ROOT, "tests", "golden")
+    recs = []
+
+    def st_model(tag, d_in, precision):
+        w = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, f"{tag}_weights.npz")).items()}
+        st = pca.ST(dim_input=d_in, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev)
+        st.load_state_dict(w)
+        return st.set_precision(precision)
+
+    def timed(fn, steps, warmup=3):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    def synth(n_clips, n_samples, seed):
+        gen = torch.Generator(device=dev).manual_seed(seed + rank)
+        t = torch.arange(n_samples, device=dev, dtype=torch.float32) / FS
+        x = 0.05 * torch.randn(n_clips, n_samples, generator=gen, device=dev)
+        for _j in range(4):
+            a = torch.empty(n_clips, 1, device=dev).uniform_(0.05, 0.4, generator=gen)
+            f = torch.empty(n_clips, 1, device=dev).uniform_(50.0, FS / 2 - 50.0, generator=gen)
+            ph = torch.empty(n_clips, 1, device=dev).uniform_(0.0, 6.2831853, generator=gen)
+            x = x + a * torch.sin(6.2831853 * f * t + ph)
+        return x.clamp_(-1.0, 1.0).contiguous()
+
+    def pipeline_record(name, tag, d_in, n_clips, n_samples, n_fft, mode, ntemp, top_k, precision, steps, pool_n, seed):
+        st = st_model(tag, d_in, precision)
+        cfg = pca.AudioConfig(sampling_rate=FS, window_size=n_fft, n_samples=n_samples, mode=mode, Ntemp=ntemp, top_k=top_k,
+                              precision=precision)
+        pipe = pca.AudioSetPipeline(st, cfg, dev)
+        pool = [synth(n_clips, n_samples, seed + 17 * i) for i in range(pool_n)]
+        sampler = ClockSampler(local)
+        sampler.start()
+        ms = timed(lambda i: pipe(pool[i % pool_n]), steps)
+        clocks = sampler.stop()
+        clouds = n_clips * pipe.clouds_per_clip
+        fl = clouds * st_flops_per_cloud(pipe.points_per_cloud, d_in)
+        recs.append({"config": name, "precision": precision, "clips_per_pass_per_gpu": n_clips, "passes": steps,
+                     "clips_streamed_per_gpu": n_clips * steps, "clouds_per_clip": pipe.clouds_per_clip,
+                     "points_per_cloud": pipe.points_per_cloud, "ms_per_pass": ms, "value": world * n_clips / ms * 1e3,
+                     "unit": "clips/s", "clouds_per_s": world * clouds / ms * 1e3, "encoder_tflops_per_gpu": fl / ms / 1e9,
+                     "n_gpus": world, "scaling": "weak", "clocks": clocks})
+        del pool, pipe, st
+        torch.cuda.empty_cache()
+
+    # fp32 parity class of the headline workload (same 256-clip batches; the reference's own arithmetic is fp32)
+    pipeline_record("2 (headline workload) fp32 parity path: FST 256 clips x 16 frame clouds x 1025 points", "fst", 2,
+                    CLIPS_PER_STEP, N_SAMPLES, N_FFT, 2, 10, 0, "fp32", 3, 3, 202)
+    # config 1: 3ST (temporal model, the reference's CPU-runnable case): batch 16 x 1 s, clip-as-cloud and reference chunking
+    pipeline_record("1: 3ST batch 16 x 1 s clips, clip-as-cloud N=16384", "3st", 3, 16, 16000, 1024, 3, 32, 0, "bf16", 20, 8, 101)
+    pipeline_record("1: 3ST batch 16 x 1 s clips, 3 chunk clouds x 5120 points", "3st", 3, 16, 16000, 1024, 3, 10, 0, "bf16", 20, 8, 101)
+    # config 3: 3ST on 4 s clips, one GPU's shard of the data-parallel batch
+    pipeline_record("3: 3ST 4 s clips, 12 chunk clouds x 5120 points, 64 clips per GPU", "3st", 3, 64, 64000, 1024, 3, 10, 0, "bf16", 6, 3, 303)
+    pipeline_record("3: 3ST 4 s clips, clip-as-cloud N=64512, 32 clips per GPU", "3st", 3, 32, 64000, 1024, 3, 126, 0, "bf16", 6, 3, 303)
+    # config 4: top-K sweep on the 16 384-point clip cloud (STFT + top-K kernel + encoder), 1e5 clips streamed per GPU and K
+    for K in (256, 512, 1024, 2048, 4096, 8192):
+        pipeline_record(f"4: sweep, 1 s clips -> top-K={K} of 16384 points (front end + top-K + encoder)", "3st", 3, 10000, 16000, 1024,
+                        3, 32, K, "bf16", 10, 2, 404 + K)
+
+    # config 5: main_pointcloud.SetTransformer training step (fwd + CE + bwd + all-reduce + Adam), global batch 256
+    torch.manual_seed(505)
+    model = pca.SetTransformer(dim_hidden=256, num_heads=4, num_inds=16).to(dev).train()
+    N, d_in, Cc, Bg = 1000, 3, 40, 256
+    lo, hi = parallel.shard_range(Bg, rank, world)
+    gen = torch.Generator().manual_seed(505)
+    pool = []
+    for _i in range(4):
+        X = torch.randn(Bg, N, d_in, generator=gen)
+        X = (X - X.mean(dim=1, keepdim=True)) / X.std(dim=1, keepdim=True).clamp_min(1e-6)
+        y = torch.randint(0, Cc, (Bg,), generator=gen)
+        pool.append((X[lo:hi].to(dev), y[lo:hi].to(dev)))
+    tr = pca.SetTrainer(model, lr=1e-3)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(lambda i: tr.step(*pool[i % len(pool)]), 10)
+    clocks = sampler.stop()
+    flops_fwd = 2 * (N * (3 * 3 * 256 + 8 * 16 * 256 + 7 * 256 * 256 + 2 * 256) + 8 * 16 * 256 * 256 + 2 * 256 * 256 + 256 * 40)
+    recs.append({"config": "5: main_pointcloud.SetTransformer(256, 4 heads, 16 inducing points) training step on ModelNet40-shaped "
+                           "1000-point clouds: fwd + CE + bwd + NCCL all-reduce of the flat gradient + Adam",
+                 "precision": "fp32", "global_batch": Bg, "local_batch": hi - lo, "ms_per_step": ms, "value": Bg / ms * 1e3,
+                 "unit": "clouds/s", "achieved_tflops": 3 * flops_fwd * Bg / ms / 1e9, "n_gpus": world, "scaling": "strong",
+                 "allreduce_bytes_per_step": int(sum(p.numel() for p in model.parameters()) * 4) if world > 1 else 0, "clocks": clocks})
+    return recs
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -313,6 +424,11 @@ def run_ours(args):
              "achieved_tflops": world * enc_flops / (ms / args.steps / 1e3) / 1e12 / world,
              "frac_of_bf16_sustained": enc_flops / (ms / args.steps / 1e3) / 1e12 / peaks["tf_sustained"]}
 
+    extra = None
+    if not args.no_extra:
+        del pool, host_pool
+        torch.cuda.empty_cache()
+        extra = run_extra_configs(args, dev, rank, world, local)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -336,7 +452,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": CLIPS_PER_STEP * pipe.h2d_bytes_per_clip,
                     "d2h_bytes_per_step": CLIPS_PER_STEP * pipe.d2h_bytes_per_clip},
             "gpu_launches": int(launches),
-            "roofline": roofline, "whole_step": whole, "kernels": kernels, "cpu_baseline": cpu}
+            "roofline": roofline, "whole_step": whole, "kernels": kernels, "cpu_baseline": cpu, "extra_configs": extra}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -350,9 +466,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("PCA_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs records (BASELINE configs 1, 3, 4, 5 and the fp32 headline)")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
-        args.warmup = 3                                   # timing rule: W >= 3
+    if args.warmup < 3:
+        args.warmup = 3                                   # timing rule: W >= 3 (both arms use the same count)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -159,7 +159,8 @@ int pca_st_fwd(const float* X, int B, int N, const pca_st_dims* dims, const floa
 
 /* Variable-size sets (extension; the reference batches only equal-size sets): cloud b consists of the first counts[b]
  * (1 <= counts[b] <= N) rows of its padded (N, d_in) slot; padding rows never act as keys of mab0 / PMA, so the logits
- * equal ST.forward on X[b:b+1, :counts[b]].  counts == NULL is pca_st_fwd. */
+ * equal ST.forward on X[b:b+1, :counts[b]].  counts == NULL is pca_st_fwd.  A cloud with counts[b] <= 0 has no answer
+ * (the reference fails on an empty set): its logits are NaN; counts above N are clamped to N. */
 int pca_st_fwd_masked(const float* X, const int32_t* counts, int B, int N, const pca_st_dims* dims,
                       const float* params, float* logits, void* workspace, size_t workspace_bytes,
                       int precision, void* stream);
@@ -167,6 +168,15 @@ int pca_st_fwd_masked(const float* X, const int32_t* counts, int B, int N, const
 /* nn.Linear on rows: Y (rows, dout) = X (rows, din) W^T + b, params := W (dout, din) | b (dout).  The final Linear of the
  * generic SetTransformer (set_transformer-master/models.py:41) after its SAB decoder blocks. */
 int pca_linear_fwd_f32(const float* X, long long rows, int din, int dout, const float* params, float* Y, void* stream);
+/* Backward of that Linear (autograd of torch.nn.Linear in the reference's training loops, e.g. set_transformer-master/run.py:
+ * 97-100 through models.py:41): dparams := dW (dout, din) | db (dout) is OVERWRITTEN with dY^T X and the column sums of dY;
+ * dX (rows, din) = dY W is written when dX != NULL. */
+int pca_linear_bwd_f32(const float* dY, const float* X, long long rows, int din, int dout, const float* params, float* dX,
+                       float* dparams, void* stream);
+/* nn.Dropout (set_transformer-master/main_pointcloud.py:30,32) with a counter-based mask: out[i] = keep(seed, i) ? in[i] / (1 - p)
+ * : 0.  The mask is a pure function of (seed, i), so the backward pass is the same call on the gradient (no mask tensor);
+ * in == out is allowed.  torch's Philox stream cannot be matched: parity is statistical. */
+int pca_dropout_f32(const float* in, float* out, long long n, float p, unsigned long long seed, void* stream);
 
 /* DeepSet.forward (set_transformer-master/models.py:25-28) / SmallDeepSet
  * (max_regression_demo.ipynb:41-48): 4 shared Linear (+ReLU) over points, pool over points
@@ -258,7 +268,8 @@ int pca_deepset_train_bwd_f32(const float* X, int B, int N, int d_in, int dim_hi
 
 /* nn.CrossEntropyLoss(reduction='mean') on logits (B, C) with int64 labels: loss[0] += mean loss, correct[0] +=
  * number of rows whose arg-max equals the label (both caller-zeroed, either may be NULL except loss),
- * dlogits (B, C) = d loss / d logits (may be NULL). */
+ * dlogits (B, C) = d loss / d logits (may be NULL).  Labels must lie in [0, C): ignore_index is NOT supported; a row with
+ * an out-of-range label turns the loss and that row of dlogits into NaN (torch raises a device-side assert there). */
 int pca_cross_entropy_f32(const float* logits, const int64_t* labels, int B, int C, float* loss, int32_t* correct,
                           float* dlogits, void* stream);
 

@@ -8,7 +8,7 @@ from .dataset import (ESC_pc, ESC_pc_ss, ESC_pc_temp, ESC_pc_temp_importancerand
 from .frontend import (build_clouds, coord_tables, gather_points, importance_heat, importance_points, random_points, resample,
                        select_points, spectral_point_cloud, stft_logmag, topk_points)
 from .models import ST, DeepSet, SetTransformer, SetTransformerSAB, strip_module_prefix
-from .modules import ISAB, MAB, PMA, SAB
+from .modules import ISAB, MAB, PMA, SAB, invalidate_packed
 from .pipeline import AudioConfig, AudioSetPipeline
 from .training import SetTrainer, STTrainFunction
 from .utils import pc_maxK, pc_randK
@@ -17,4 +17,4 @@ __all__ = ["load_esc", "tt_split", "ESC_pc", "ESC_pc_ss", "ESC_pc_temp", "ESC_pc
            "coord_tables", "select_points", "spectral_point_cloud", "stft_logmag", "topk_points", "ST", "DeepSet",
            "SetTransformer", "SetTransformerSAB", "strip_module_prefix", "ISAB", "MAB", "PMA", "SAB", "AudioConfig",
            "AudioSetPipeline", "pc_maxK", "pc_randK", "ESC_pc_temp_randKSS", "ESC_pc_temp_importancerandKSS", "gather_points",
-           "importance_heat", "importance_points", "random_points", "resample", "SetTrainer", "STTrainFunction"]
+           "importance_heat", "importance_points", "random_points", "resample", "SetTrainer", "STTrainFunction", "invalidate_packed"]

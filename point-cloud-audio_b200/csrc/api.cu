@@ -43,6 +43,8 @@ int deepset_train_forward(const float*, int, int, int, int, int, int, const floa
 int deepset_train_backward(const float*, int, int, int, int, int, int, const float*, const float*, const void*, size_t, float*, float*,
                            void*, size_t, cudaStream_t);
 int launch_cross_entropy(const float*, const long long*, int, int, float, float*, int*, float*, cudaStream_t);
+int dropout_api(const float*, float*, long long, float, unsigned long long, cudaStream_t);
+int linear_bwd_api(const float*, const float*, long long, int, int, const float*, float*, float*, cudaStream_t);
 int launch_adam(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float, cudaStream_t);
 void set_timeline(long long* p);
 void set_tail_max(int t);
@@ -243,15 +245,34 @@ static int check_dims(const pca_st_dims* d) {
     return 0;
 }
 
+// Variable-size sets: every kernel clamps counts[b] to [1, N] (a set needs a key to attend to), so a cloud with NO valid point
+// would silently be encoded as the one-point cloud of its first (padding) row.  The reference has no answer for an empty
+// set either (it fails on X[:, :0]); the honest answer here is NaN logits for exactly those clouds.
+__global__ void nan_empty_sets_kernel(float* __restrict__ logits, const int* __restrict__ counts, int B, int per_cloud) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (long long)B * per_cloud && counts[i / per_cloud] <= 0) logits[i] = __int_as_float(0x7fc00000);
+}
+static int st_forward_impl(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
+                           void* ws, size_t ws_bytes, int precision, cudaStream_t st, const int* counts);
 static int st_forward(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
                       void* ws, size_t ws_bytes, int precision, cudaStream_t st, const int* counts = nullptr) {
+    PCA_TRY(st_forward_impl(X, B, N, d, params, logits, ws, ws_bytes, precision, st, counts));
+    if (counts != nullptr && B > 0) {
+        const long long n = (long long)B * d->S * d->C;
+        nan_empty_sets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(logits, counts, B, d->S * d->C);
+        PCA_CHECK_LAUNCH("nan_empty_sets_kernel");
+    }
+    return 0;
+}
+static int st_forward_impl(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
+                           void* ws, size_t ws_bytes, int precision, cudaStream_t st, const int* counts) {
     PCA_TRY(check_dims(d));
     if (!X || !params || !logits) return fail(PCA_EINVAL, "ST: null pointer");
     if (B < 0 || N <= 0) return fail(PCA_EINVAL, "ST: bad batch/points (B=%d, N=%d)", B, N);
     if (B == 0) return 0;
     if (precision == PCA_PREC_BF16) {
         if (!st_tc_supported(d, N))
-            return fail(PCA_EUNSUPPORTED, "ST: tcgen05 path needs D=64,H=8,M=64,S=1,ln=0,d_in<=3 (got D=%d,H=%d,M=%d,S=%d,ln=%d,d_in=%d)",
+            return fail(PCA_EUNSUPPORTED, "ST: tcgen05 path needs D=64,H=8,M=64,S=1,ln=0,d_in<=4 (got D=%d,H=%d,M=%d,S=%d,ln=%d,d_in=%d)",
                         d->D, d->H, d->M, d->S, d->ln, d->d_in);
         return st_tc_forward(X, counts, B, N, d, params, logits, ws, ws_bytes, st);
     }
@@ -666,6 +687,18 @@ int pca_linear_fwd_f32(const float* X, long long rows, int din, int dout, const 
     if (!X || !params || !Y) return fail(PCA_EINVAL, "linear: null pointer");
     if (rows < 0 || din <= 0 || dout <= 0) return fail(PCA_EINVAL, "linear: bad shape");
     return launch_linear(X, params, params + (long long)dout * din, Y, rows, din, dout, 0, (cudaStream_t)stream);
+}
+
+int pca_linear_bwd_f32(const float* dY, const float* X, long long rows, int din, int dout, const float* params, float* dX,
+                       float* dparams, void* stream) {
+    if (!dY || !X || !params || !dparams) return fail(PCA_EINVAL, "linear backward: null pointer");
+    if (rows < 0 || din <= 0 || dout <= 0) return fail(PCA_EINVAL, "linear backward: bad shape");
+    return linear_bwd_api(dY, X, rows, din, dout, params, dX, dparams, (cudaStream_t)stream);
+}
+int pca_dropout_f32(const float* in, float* out, long long n, float p, unsigned long long seed, void* stream) {
+    if ((!in || !out) && n > 0) return fail(PCA_EINVAL, "dropout: null pointer");
+    if (n < 0) return fail(PCA_EINVAL, "dropout: bad length");
+    return dropout_api(in, out, n, p, seed, (cudaStream_t)stream);
 }
 
 int pca_random_keys_f32(float* keys, long long n, unsigned long long seed, void* stream) {

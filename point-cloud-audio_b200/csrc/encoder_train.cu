@@ -552,6 +552,24 @@ static int launch_attn_bwd(const float* Qp, long long q_bstride, const float* KV
     }
 }
 
+// ------------------------------------------------------------------------------------ stand-alone Dropout / Linear backward
+int dropout_api(const float* in, float* out, long long n, float p, unsigned long long seed, cudaStream_t st) {
+    if (!(p >= 0.f && p < 1.f)) return fail(PCA_EINVAL, "dropout: probability %f outside [0, 1)", p);
+    if (p == 0.f) {
+        if (in != out && n > 0) PCA_CHECK_CUDA(cudaMemcpyAsync(out, in, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    return launch_dropout(in, out, n, p, seed, st);
+}
+// dparams = dW (dout, din) | db (dout), overwritten; dX optional
+int linear_bwd_api(const float* dY, const float* X, long long rows, int din, int dout, const float* W, float* dX, float* dparams,
+                   cudaStream_t st) {
+    PCA_CHECK_CUDA(cudaMemsetAsync(dparams, 0, ((size_t)dout * din + dout) * sizeof(float), st));
+    PCA_TRY(launch_grad_weight_bias(dY, X, dparams, dparams + (size_t)dout * din, rows, din, dout, st));
+    if (dX != nullptr) PCA_TRY(launch_grad_input(dY, W, dX, nullptr, rows, din, dout, st));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------ MAB forward (saving) / backward
 // Opre / pre1: the inputs of ln0 / ln1 (LayerNorm branches only; O and out then hold the normalised tensors)
 struct MabSaved { float *Qp, *KV, *O, *R, *lse, *out, *Opre, *pre1; };
@@ -1107,8 +1125,19 @@ __global__ void cross_entropy_kernel(const float* __restrict__ logits, const lon
     float s = 0.f;
     for (int j = lane; j < C; j += 32) s += expf(z[j] - mx);
     s = warp_sum(s);
-    const int lbl = (int)labels[r];
+    const long long lbl64 = labels[r];
     const float lse = mx + logf(s);
+    if (lbl64 < 0 || lbl64 >= C) {
+        // A label outside [0, C) (nn.CrossEntropyLoss's ignore_index = -100 included: it is NOT supported) must not index the
+        // logits.  torch raises a device-side assert here; this kernel poisons the loss and the row's gradient with NaN so the
+        // mistake is loud on the very first step instead of training on garbage.
+        const float qnan = __int_as_float(0x7fc00000);
+        if (dlogits)
+            for (int j = lane; j < C; j += 32) dlogits[(long long)r * C + j] = qnan;
+        if (lane == 0) atomicAdd(loss_sum, qnan);
+        return;
+    }
+    const int lbl = (int)lbl64;
     if (dlogits)
         for (int j = lane; j < C; j += 32) dlogits[(long long)r * C + j] = (expf(z[j] - lse) - (j == lbl ? 1.f : 0.f)) * inv_batch;
     if (lane == 0) {

@@ -134,8 +134,20 @@ class ESC_pc_temp_maxKSS(ESC_pc_temp):
             n_pts = np.asarray(self.x).shape[0] * np.asarray(self.x).shape[1]
             k = min(int(self.K), n_pts)
             self._pts, idx = topk_points(self._logmag(), self.farr, self.tarr, k, sorted_desc=True)
-            self._idx = idx
             self._idx_host = idx.cpu().numpy().astype(np.int64)
+            xs = np.asarray(self.x)
+            if xs.dtype == np.float64:
+                # The device keys are float32 (the reference's spectra are float32, Code/settransformertemp.py:53).  Distinct
+                # float64 magnitudes can collapse into float32 ties: re-rank the float32 candidates (everything not below the
+                # K-th float32 key) by the ORIGINAL values, lowest flat index first among equals -- the reference's
+                # (-pc[:, -1]).argsort() on float64 (Code/dataset.py:199).
+                from .utils import refine_topk_float64
+                for c in range(self._idx_host.shape[0]):
+                    self._idx_host[c] = refine_topk_float64(xs[:, :, c].T.reshape(-1), self._idx_host[c], k)
+                idx = torch.from_numpy(self._idx_host.astype(np.int32)).to(self._device)
+                from .frontend import gather_points
+                self._pts = gather_points(self._logmag(), self.farr, self.tarr, idx)
+            self._idx = idx
         return self._pts, self._idx
 
     def cuda_batch(self, indices):
@@ -157,36 +169,52 @@ class ESC_pc_temp_maxKSS(ESC_pc_temp):
 
 class ESC_pc_temp_randKSS(ESC_pc_temp):
     """3ST dataset with random-K subsampling (Code/dataset.py:205-238): K random points of the cloud.  The subset and its
-    order come from the CUDA path (counter-based uniform keys + radix select, ``frontend.random_points``); a fresh draw is
-    made every epoch (every ``resample()`` / first access), numpy's generator is not involved.  Items are float64
-    (K, 3) tensors gathered from the caller's arrays, as in the reference."""
+    order come from the CUDA path (counter-based uniform keys + radix select, ``frontend.random_points``), drawn for ALL
+    clouds at once with independent keys per cloud.
 
-    def __init__(self, x, y, farr, tarr, K, device=None, seed=0):
+    The reference draws a fresh subset on every ``__getitem__``.  Here the batched draw is renewed automatically whenever an
+    item is requested a second time since the last draw -- i.e. at the start of every new pass over the dataset, which is
+    what an unmodified reference loop (one access per item and epoch) produces -- or explicitly with ``resample()``.  The
+    default seed is taken from numpy's global generator at construction, so ``np.random.seed`` governs the sequence as it
+    does in the reference and distinct instances (the per-K datasets of the eval sweeps) get distinct, independent draws;
+    pass ``seed=`` for a fixed sequence.  Items are float64 (K, 3) tensors gathered from the caller's arrays."""
+
+    def __init__(self, x, y, farr, tarr, K, device=None, seed=None):
         super().__init__(x, y, farr, tarr, device)
         self.K = K
-        self.seed = int(seed)
+        self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
         self._idx_host = None
+        self._served = set()
+
+    def _draw(self):
+        from .frontend import random_points
+        return random_points(self._logmag(), self.farr, self.tarr, self.K, seed=self.seed)
 
     def resample(self):
-        from .frontend import random_points
         self.seed += 1
-        self._pts_sel, idx = random_points(self._logmag(), self.farr, self.tarr, self.K, seed=self.seed)
+        self._pts_sel, idx = self._draw()
         self._idx_host = idx.cpu().numpy().astype(np.int64)
+        self._served = set()
 
-    def _ensure(self):
-        if self._idx_host is None:
+    def _ensure(self, served=None):
+        """``served``: item indices about to be handed out (None: a query that does not count as an item access)."""
+        wanted = [] if served is None else [int(i) for i in np.atleast_1d(np.asarray(served)).ravel()]
+        if self._idx_host is None or any(i in self._served for i in wanted):
             self.resample()
+        self._served.update(wanted)
 
     def cuda_batch(self, indices):
-        self._ensure()
+        self._ensure(torch.as_tensor(indices).cpu().numpy())
         return self._pts_sel[torch.as_tensor(indices, device=self._device, dtype=torch.long)]
 
     def indices(self, idx) -> np.ndarray:
+        """Flat point indices of item ``idx`` in the CURRENT draw (does not count as an item access)."""
         self._ensure()
         return self._idx_host[idx]
 
     def __getitem__(self, idx):
-        order = self.indices(idx)
+        self._ensure(idx)
+        order = self._idx_host[idx]
         nf = np.asarray(self.farr).shape[0]
         f, t = order % nf, order // nf
         pc = np.stack([np.asarray(self.farr, dtype=np.float64)[f], np.asarray(self.tarr, dtype=np.float64)[t],
@@ -199,13 +227,11 @@ class ESC_pc_temp_importancerandKSS(ESC_pc_temp_randKSS):
     spectrogram; ``choice`` 1 keeps the K hottest entries (deterministic, equals the reference on tie-free inputs),
     ``choice`` 0 samples K with replacement (torch.multinomial in the reference; here a counter-based generator)."""
 
-    def __init__(self, x, y, farr, tarr, K, choice, winF, device=None, seed=0):
+    def __init__(self, x, y, farr, tarr, K, choice, winF, device=None, seed=None):
         super().__init__(x, y, farr, tarr, K, device, seed)
         self.choice = choice
         self.winF = winF
 
-    def resample(self):
+    def _draw(self):
         from .frontend import importance_points
-        self.seed += 1
-        self._pts_sel, idx = importance_points(self._logmag(), self.farr, self.tarr, self.K, self.winF, self.choice, seed=self.seed)
-        self._idx_host = idx.cpu().numpy().astype(np.int64)
+        return importance_points(self._logmag(), self.farr, self.tarr, self.K, self.winF, self.choice, seed=self.seed)

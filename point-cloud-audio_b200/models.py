@@ -84,7 +84,8 @@ class _SetEncoderBase(nn.Module):
     def encode(self, X: torch.Tensor, counts: torch.Tensor | None = None) -> torch.Tensor:
         """(B, N, d_in) CUDA -> logits (B, S, C) (before the reference's .squeeze()).
         ``counts`` (B,) int32 CUDA, optional extension: cloud b consists of its first counts[b] rows, the rest is
-        padding (variable-size sets); the result equals the reference module applied to X[b:b+1, :counts[b]]."""
+        padding (variable-size sets); the result equals the reference module applied to X[b:b+1, :counts[b]].  A cloud
+        with counts[b] <= 0 has no defined encoding (the reference fails on an empty set): its logits are NaN."""
         rt.require_cuda(X, type(self).__name__ + ".forward")
         X = rt.f32c(X)
         B, N, d_in = X.shape
@@ -105,15 +106,11 @@ class _SetEncoderBase(nn.Module):
                 # LayerNorm variant: composed from the block training kernels (the fused whole-model path covers ln=False)
                 if counts is not None:
                     raise NotImplementedError("pcaudio_b200: training with LayerNorm and variable-size sets is not implemented")
+                from .training import LinearFunction, dropout
                 isab0, isab1, pma, lin = self._parts()
-                Y = isab1(isab0(X))
                 p = self._dropout_p()
-                if p > 0:
-                    Y = torch.nn.functional.dropout(Y, p)
-                Y = pma(Y)
-                if p > 0:
-                    Y = torch.nn.functional.dropout(Y, p)
-                return lin(Y)
+                Y = pma(dropout(isab1(isab0(X)), p))
+                return LinearFunction.apply(dropout(Y, p), lin.weight, lin.bias)
             from .training import STTrainFunction
             p = self._dropout_p()
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
@@ -256,9 +253,10 @@ class SetTransformerSAB(nn.Module):
         lin = self.dec[3]
         B, S, D = Y.shape
         if Y.requires_grad:
-            # training (ln=False): the blocks above ran their training kernels and autograd composes them; the last layer
-            # acts on B*num_outputs rows only -- torch's own Linear keeps the graph
-            return lin(Y)
+            # training: the blocks above ran their training kernels and autograd composes them; the last layer runs the
+            # repo's own Linear forward / backward kernels as well
+            from .training import LinearFunction
+            return LinearFunction.apply(Y, lin.weight, lin.bias)
         out = torch.empty((B, S, lin.out_features), dtype=torch.float32, device=Y.device)
         blob = self._packed.get([lin.weight, lin.bias])
         with torch.cuda.device(Y.device):

@@ -12,9 +12,15 @@ import torch.nn as nn
 from . import _lib, _runtime as rt
 
 
-def _wants_grad(module, *inputs):
-    return torch.is_grad_enabled() and (any(isinstance(t, torch.Tensor) and t.requires_grad for t in inputs)
-                                        or any(p.requires_grad for p in module.parameters()))
+def _wants_grad(module, *inputs, tensors=None):
+    """Training path?  Decided from the parameter TENSORS the forward is about to use (``tensors``), not from
+    ``module.parameters()``: nn.DataParallel replicas hold plain attribute tensors and an empty parameter list."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(isinstance(t, torch.Tensor) and t.requires_grad for t in inputs):
+        return True
+    ps = tensors if tensors is not None else list(module.parameters())
+    return any(p.requires_grad for p in ps)
 
 
 class _NoBackward(torch.autograd.Function):
@@ -40,20 +46,39 @@ def _guard(out, module):
 
 
 class _PackedParams:
-    """Flattens a module's parameters into the canonical blob of include/pcaudio_b200.h and caches it
-    until a parameter changes (in-place update, load_state_dict, .to())."""
+    """Flattens a module's parameters into the canonical blob of include/pcaudio_b200.h and caches it per device until a
+    parameter changes (in-place update through autograd-visible ops, load_state_dict, .to()).
+
+    nn.DataParallel replicas share this object (replicate() shallow-copies ``__dict__``) and call ``get`` from one thread
+    per GPU: the cache is therefore keyed by device, every call works on local variables only, and a lost race merely
+    rebuilds a blob.  Edits that bypass the version counter (``p.data.mul_()``, ``p.data.clamp_()``) are NOT seen -- call
+    ``invalidate()`` (or ``module.invalidate_packed()``) after such an edit."""
 
     def __init__(self):
-        self._key = None
-        self._blob = None
+        self._cache = {}
+
+    def invalidate(self):
+        self._cache = {}
 
     def get(self, tensors):
-        key = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
-        if key != self._key:
-            with torch.no_grad():
-                self._blob = torch.cat([t.detach().reshape(-1).float() for t in tensors]).contiguous()
-            self._key = key
-        return self._blob
+        dev = tensors[0].device
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        hit = self._cache.get(dev)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        with torch.no_grad():
+            blob = torch.cat([t.detach().reshape(-1).float() for t in tensors]).contiguous()
+        self._cache[dev] = (key, blob)
+        return blob
+
+
+def invalidate_packed(module: nn.Module) -> None:
+    """Drop every cached parameter blob below ``module`` (needed only after edits through ``.data`` that do not bump the
+    tensors' version counters)."""
+    for m in module.modules():
+        pk = getattr(m, "_packed", None)
+        if isinstance(pk, _PackedParams):
+            pk.invalidate()
 
 
 def _mab_tensors(m: "MAB"):
@@ -90,7 +115,7 @@ class MAB(nn.Module):
         qb, nq, dq = Q.shape
         D, H = self.dim_V, self.num_heads
         blob = self._packed.get(_mab_tensors(self))
-        if B > 0 and _wants_grad(self, Q, K):
+        if B > 0 and _wants_grad(self, Q, K, tensors=_mab_tensors(self)):
             # training: forward that keeps activations + hand-written backward (pcaudio_b200/training.py)
             from .training import MABTrainFunction
             return MABTrainFunction.apply(Q, K, blob, (D, H, self._ln), *_mab_tensors(self))
@@ -130,7 +155,7 @@ class ISAB(nn.Module):
         X = rt.f32c(X)
         B, N, d_in = X.shape
         D, H, M = self.mab0.dim_V, self.mab0.num_heads, self.I.shape[1]
-        if B > 0 and _wants_grad(self, X):
+        if B > 0 and _wants_grad(self, X, tensors=self._tensors()):
             # training: H = mab0(I, X); mab1(X, H) through the MAB training kernels (I is a shared query set: no repeat)
             return self.mab1(X, self.mab0(self.I, X))
         blob = self._packed.get(self._tensors())
@@ -160,7 +185,7 @@ class PMA(nn.Module):
         X = rt.f32c(X)
         B, N, D = X.shape
         H, S = self.mab.num_heads, self.S.shape[1]
-        if B > 0 and _wants_grad(self, X):
+        if B > 0 and _wants_grad(self, X, tensors=self._tensors()):
             return self.mab(self.S, X)                     # training: MAB(S, X), shared seeds
         blob = self._packed.get(self._tensors())
         out = torch.empty((B, S, D), dtype=torch.float32, device=X.device)

@@ -3,7 +3,9 @@
 The host mirrors call the library through these ops, so the hot path is visible to the PyTorch dispatcher
 (``torch.library``: schema, fake/meta shape functions for tracing, CUDA-only implementations) while the arithmetic stays
 behind ``include/pcaudio_b200.h``.  There is no CPU implementation registered on purpose: calling an op with CPU tensors
-fails in the dispatcher.  Backward formulas are not registered either (training is the next scope row)."""
+fails in the dispatcher.  The training ops (``st_train_fwd`` / ``st_train_bwd`` ...) are plain forward ops too: gradients are
+wired by the ``torch.autograd.Function`` classes of ``training.py`` around the hand-written backward kernels, not by
+``register_autograd`` formulas."""
 from __future__ import annotations
 
 import ctypes as C

@@ -53,6 +53,70 @@ class STTrainFunction(torch.autograd.Function):
         return (dX if need_dx else None, None, None, None, None, None, *grads)
 
 
+class LinearFunction(torch.autograd.Function):
+    """Y = X W^T + b on rows through pca_linear_fwd_f32 / pca_linear_bwd_f32 (the final nn.Linear of the composed models when
+    gradients are enabled -- torch's own Linear would be a cuBLAS call on the product path)."""
+
+    @staticmethod
+    def forward(ctx, X, weight, bias):
+        X = rt.f32c(X)
+        dout, din = weight.shape
+        rows = X.numel() // din
+        with torch.no_grad():
+            blob = torch.cat([weight.detach().reshape(-1).float(), bias.detach().reshape(-1).float()]).contiguous()
+        Y = torch.empty(X.shape[:-1] + (dout,), dtype=torch.float32, device=X.device)
+        with torch.cuda.device(X.device):
+            _lib.check(_lib.lib().pca_linear_fwd_f32(_lib.ptr(X), rows, din, dout, _lib.ptr(blob), _lib.ptr(Y),
+                                                    rt.stream_ptr(X.device)), "Linear.forward")
+        ctx.save_for_backward(X, blob)
+        ctx.dims = (rows, din, dout)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        X, blob = ctx.saved_tensors
+        rows, din, dout = ctx.dims
+        dY = rt.f32c(dY)
+        need_dx = bool(ctx.needs_input_grad[0])
+        dX = torch.empty_like(X) if need_dx else None
+        dparams = torch.empty(dout * din + dout, dtype=torch.float32, device=X.device)
+        with torch.cuda.device(X.device):
+            _lib.check(_lib.lib().pca_linear_bwd_f32(_lib.ptr(dY), _lib.ptr(X), rows, din, dout, _lib.ptr(blob), _lib.ptr(dX),
+                                                    _lib.ptr(dparams), rt.stream_ptr(X.device)), "Linear.backward")
+        return dX, dparams[:dout * din].view(dout, din), dparams[dout * din:]
+
+
+class DropoutFunction(torch.autograd.Function):
+    """nn.Dropout (main_pointcloud.py:30,32) through pca_dropout_f32: the mask is a pure function of (seed, element index), so
+    backward is the same call on the gradient and no mask tensor exists."""
+
+    @staticmethod
+    def forward(ctx, X, p, seed):
+        X = rt.f32c(X)
+        out = torch.empty_like(X)
+        with torch.cuda.device(X.device):
+            _lib.check(_lib.lib().pca_dropout_f32(_lib.ptr(X), _lib.ptr(out), X.numel(), float(p), int(seed), rt.stream_ptr(X.device)),
+                       "Dropout.forward")
+        ctx.p, ctx.seed = float(p), int(seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = rt.f32c(g)
+        out = torch.empty_like(g)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().pca_dropout_f32(_lib.ptr(g), _lib.ptr(out), g.numel(), ctx.p, ctx.seed, rt.stream_ptr(g.device)),
+                       "Dropout.backward")
+        return out, None, None
+
+
+def dropout(X, p):
+    """Train-mode dropout with a fresh seed drawn from torch's global generator (so torch.manual_seed governs it)."""
+    if p <= 0:
+        return X
+    return DropoutFunction.apply(X, p, int(torch.randint(0, 2 ** 62, (1,)).item()))
+
+
 class MABTrainFunction(torch.autograd.Function):
     """out = MAB(Q, K; params) for models composed from the blocks (modules.py:6-33, LayerNorm branches included): Q (1 | B, nq, dq), K (B, nk, dk).
     A query batch of 1 is the shared-query case (ISAB's I, PMA's S): its gradient is summed over the batch in the kernel."""

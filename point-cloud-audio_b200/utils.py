@@ -22,8 +22,23 @@ def pc_maxK(x, farr, Kmax, device="cuda"):
     keys = torch.from_numpy(np.ascontiguousarray(x.T, dtype=np.float32)).to(device)     # (T, N)
     _, idx = topk_points(keys, None, None, k, sorted_desc=True, want_points=False)
     idx = idx.cpu().numpy().astype(np.int64)                                              # (T, K)
+    if x.dtype == np.float64:
+        # float32 device keys: re-rank the float32 candidates by the original float64 values (see refine_topk_float64)
+        for c in range(t):
+            idx[c] = refine_topk_float64(x[:, c], idx[c], k)
     cols = np.arange(t)[:, None]
     return x[idx, cols].T.copy(), farr[idx].T.copy()
+
+
+def refine_topk_float64(vals64, idx_f32, k):
+    """Exact ``(-vals64).argsort(kind='stable')[:k]`` from the device's float32 selection ``idx_f32`` (descending float32 keys,
+    lowest index first among equal keys): every element whose float32 key is not below the k-th selected key is a candidate
+    (float32 rounding is monotone, so the exact top-k is among them); the candidates are ordered by the float64 values."""
+    vals64 = np.asarray(vals64, dtype=np.float64)
+    k32 = vals64.astype(np.float32)
+    cand = np.nonzero(k32 >= k32[int(idx_f32[k - 1])])[0]
+    order = np.lexsort((cand, -vals64[cand]))          # primary key: descending value; secondary: ascending index
+    return cand[order][:k].astype(np.int64)
 
 
 def pc_randK(x, farr, Kmax, device="cuda", seed=0):

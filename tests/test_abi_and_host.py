@@ -216,3 +216,27 @@ def test_flatten_parameters_packs_views_in_blob_order(built):
     assert m._blob() is flat and torch.equal(flat, packed)
     m.dec[3].weight.data = m.dec[3].weight.data.clone()    # a parameter re-pointed elsewhere: fall back to re-packing
     assert m._blob() is not flat and torch.equal(m._blob(), packed)
+
+
+def test_packed_params_cache_is_per_device_and_invalidatable():
+    """nn.DataParallel replicas share the cache object: it must key by device, return local values and offer an
+    explicit invalidate for edits through .data (which do not bump the version counter)."""
+    import torch
+    from pcaudio_b200.modules import MAB, _PackedParams, _mab_tensors, invalidate_packed
+    m = MAB(4, 4, 8, 2)
+    pk = m._packed
+    assert isinstance(pk, _PackedParams)
+    b0 = pk.get(_mab_tensors(m))
+    assert pk.get(_mab_tensors(m)) is b0                      # cached
+    with torch.no_grad():
+        m.fc_q.weight.mul_(2.0)                              # version bump -> rebuilt
+    b1 = pk.get(_mab_tensors(m))
+    assert b1 is not b0 and torch.equal(b1[:32], m.fc_q.weight.reshape(-1))
+    m.fc_q.weight.data.mul_(0.5)                             # .data edit: invisible to the key ...
+    assert pk.get(_mab_tensors(m)) is b1
+    invalidate_packed(m)                                     # ... until invalidated
+    b2 = pk.get(_mab_tensors(m))
+    assert b2 is not b1 and torch.equal(b2[:32], m.fc_q.weight.reshape(-1))
+    meta = [t.to("meta") for t in _mab_tensors(m)]           # a second "device": separate slot, the first one survives
+    assert set(pk._cache) == {torch.device("cpu")}
+    del meta

@@ -133,7 +133,8 @@ def test_random_k_dataset_items(pca):
     item, label = ds[2]
     assert item.dtype == torch.float64 and item.shape == (50, 3) and int(label) == 2
     assert np.array_equal(item.numpy(), full[ds.indices(2)])                 # rows of the reference's full cloud
-    assert np.allclose(ds.cuda_batch([2]).cpu().numpy()[0], item.numpy().astype(np.float32))
+    b3 = ds.cuda_batch([3]).cpu().numpy()[0]                                  # first access of item 3: same draw
+    assert np.allclose(b3, orc.cloud_3d_f64(x3, farr, tarr, 3)[ds.indices(3)].astype(np.float32))
     before = ds.indices(2).copy()
     ds.resample()
     assert not np.array_equal(before, ds.indices(2))
@@ -155,3 +156,47 @@ def test_resample_matches_cpu_restatement(pca, orig_sr, target_sr, L, res_type, 
     assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
     same = pca.resample(torch.from_numpy(x).to(dev), orig_sr, orig_sr)
     assert same.shape == (3, L)
+
+
+def test_random_k_dataset_redraws_every_pass(pca):
+    """the reference draws a fresh subset on every __getitem__; here the batched draw is renewed whenever an item is
+    requested again (a new pass), and instances without an explicit seed follow numpy's global generator."""
+    dev = torch.device("cuda:0")
+    g = dict(np.load(os.path.join(G, "sampling_golden.npz")))
+    x3, farr, tarr = g["x3"], g["farr"], g["tarr"]
+    n = x3.shape[2]
+    np.random.seed(5)
+    ds = pca.ESC_pc_temp_randKSS(x3, np.arange(n), farr, tarr, 50, device=dev)
+    first = [ds[i][0].numpy().copy() for i in range(n)]             # pass 1: one draw serves every item
+    for i in range(n):                                              # rows of the reference's full cloud, current draw
+        assert np.array_equal(first[i], orc.cloud_3d_f64(x3, farr, tarr, i)[ds.indices(i)])
+    second = [ds[i][0].numpy().copy() for i in range(n)]            # pass 2: item 0 is requested again -> new draw
+    assert any(not np.array_equal(a, b) for a, b in zip(first, second))
+    np.random.seed(5)
+    ds2 = pca.ESC_pc_temp_randKSS(x3, np.arange(n), farr, tarr, 50, device=dev)
+    assert np.array_equal(ds2[0][0].numpy(), first[0])              # np.random.seed governs the sequence
+    ds3 = pca.ESC_pc_temp_randKSS(x3, np.arange(n), farr, tarr, 50, device=dev)
+    assert not np.array_equal(ds3[0][0].numpy(), first[0])          # a second instance gets its own draw
+
+
+def test_topk_float64_inputs_follow_the_float64_order(pca):
+    """float64 magnitudes that collapse into float32 ties must still come out in the reference's float64
+    (-x).argsort() order (lowest index first among exact ties)."""
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal((40, 3)).astype(np.float32).astype(np.float64)
+    x = np.repeat(base, 4, axis=0)                                    # 160 bins, groups of 4 equal in float32 ...
+    x += 1e-11 * rng.standard_normal(x.shape)                         # ... but distinct in float64
+    farr = np.linspace(0, 0.5, x.shape[0])
+    for K in (1, 7, 33, 160):
+        xs, fs_ = pca.pc_maxK(x, farr, K)
+        for t in range(x.shape[1]):
+            order = (-x[:, t]).argsort(kind="stable")[:K]
+            assert np.array_equal(xs[:, t], x[order, t]) and np.array_equal(fs_[:, t], farr[order])
+    # 3-D dataset class
+    x3 = np.stack([x[:, :2] for _ in range(3)], axis=2) + 1e-12 * rng.standard_normal((160, 2, 3))
+    tarr = np.array([0.0, 0.1])
+    ds = pca.ESC_pc_temp_maxKSS(x3, np.arange(3), farr, tarr, 25, device=torch.device("cuda:0"))
+    for i in range(3):
+        flat = x3[:, :, i].T.reshape(-1)
+        assert np.array_equal(ds.indices(i), (-flat).argsort(kind="stable")[:25])
+        assert np.array_equal(ds[i][0].numpy()[:, 2], flat[ds.indices(i)])

@@ -286,3 +286,66 @@ def test_variable_size_sets_train(pca, d_in, D, H, M):
     assert ((gx - Xc.grad).abs().max() / Xc.grad.abs().max()).item() < GRAD_REL_TOL
     for b in range(B):
         assert (gx[b, int(counts[b]):] == 0).all()
+
+
+def test_cross_entropy_rejects_out_of_range_labels(pca):
+    """a label outside [0, C) (ignore_index = -100 included) must not index the logits: loss and that row's
+    gradient become NaN, the other rows keep their gradient."""
+    import ctypes as C
+    from pcaudio_b200 import _lib
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    z = torch.randn(6, 10, device=dev)
+    for bad in (-100, 10, 2 ** 40):
+        y = torch.tensor([1, 2, bad, 3, 4, 5], dtype=torch.int64, device=dev)
+        loss = torch.zeros(1, device=dev)
+        correct = torch.zeros(1, dtype=torch.int32, device=dev)
+        dz = torch.empty_like(z)
+        _lib.check(_lib.lib().pca_cross_entropy_f32(_lib.ptr(z), _lib.ptr(y), 6, 10, _lib.ptr(loss), _lib.ptr(correct), _lib.ptr(dz), None),
+                   "cross_entropy")
+        torch.cuda.synchronize()
+        assert torch.isnan(loss).all() and torch.isnan(dz[2]).all()
+        assert torch.isfinite(dz[[0, 1, 3, 4, 5]]).all()
+
+
+def test_linear_and_dropout_functions_match_torch(pca):
+    """The repo's own Linear forward / backward and counter-based Dropout (used where torch's nn.Linear / F.dropout used to run
+    on the ln=True and SAB-decoder training paths)."""
+    from pcaudio_b200.training import DropoutFunction, LinearFunction
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    X = torch.randn(4, 3, 64, device=dev, requires_grad=True)
+    lin = torch.nn.Linear(64, 40).to(dev)
+    Y = LinearFunction.apply(X, lin.weight, lin.bias)
+    Yr = torch.nn.functional.linear(X.double(), lin.weight.double(), lin.bias.double())
+    assert (Y.double() - Yr).abs().max() < 1e-4
+    g = torch.randn_like(Y)
+    gx, gw, gb = torch.autograd.grad(Y, [X, lin.weight, lin.bias], g)
+    rx, rw, rb = torch.autograd.grad(Yr, [X, lin.weight, lin.bias], g.double())
+    for a, b in ((gx, rx), (gw, rw), (gb, rb)):
+        assert (a.double() - b.double()).abs().max() <= 1e-4 * max(1.0, float(b.abs().max()))
+    # dropout: keep fraction, scaling, same mask in backward, different masks for different seeds
+    A = torch.ones(200000, device=dev, requires_grad=True)
+    out = DropoutFunction.apply(A, 0.5, 1234)
+    keep = (out != 0)
+    assert abs(float(keep.float().mean()) - 0.5) < 5e-3 and torch.all(out[keep] == 2.0)
+    (ga,) = torch.autograd.grad(out, A, torch.ones_like(out))
+    assert torch.equal(ga, out)
+    out2 = DropoutFunction.apply(A, 0.5, 1235)
+    assert 0.45 < float(((out2 != 0) == keep).float().mean()) < 0.55
+
+
+def test_ln_model_trains_through_own_kernels(pca):
+    """SetTransformer(ln=True) in train mode with Dropout: forward + backward run (every parameter receives a finite,
+    non-trivial gradient) -- the path that used torch's dropout / nn.Linear before."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    m = pca.SetTransformer(dim_input=3, num_outputs=1, dim_output=7, num_inds=8, dim_hidden=32, num_heads=4, ln=True).to(dev).train()
+    X = torch.randn(6, 50, 3, device=dev)
+    y = torch.randint(0, 7, (6,), device=dev)
+    loss = torch.nn.functional.cross_entropy(m(X), y)
+    loss.backward()
+    assert torch.isfinite(loss)
+    for n, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    assert float(m.dec[2].weight.grad.abs().max() if hasattr(m, "dec") and isinstance(m.dec[2], torch.nn.Linear) else 1.0) > 0

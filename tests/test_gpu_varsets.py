@@ -177,3 +177,19 @@ def test_fused_frontend_rejects_oversized_clouds(pca):
     audio = torch.zeros(1, 64000, device=dev)
     with pytest.raises(RuntimeError, match="shared memory"):
         pca.spectral_point_cloud(audio, n_fft=1024, sr=16000.0, ntemp=None, top_k=8192, fused=True)     # 64512-point cloud
+
+
+def test_empty_sets_give_nan_logits(pca):
+    """counts[b] == 0 must not be encoded silently as a one-point cloud; the other clouds are unaffected."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    model = pca.ST(dim_input=3, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev).eval()
+    X = torch.randn(5, 300, 3, device=dev)
+    counts = torch.tensor([300, 0, 17, 0, 129], dtype=torch.int32, device=dev)
+    for prec in ("fp32", "bf16"):
+        model.set_precision(prec)
+        with torch.no_grad():
+            out = model(X, counts)
+            ref = model(X, counts.clamp(min=1))
+        assert torch.isnan(out[[1, 3]]).all()
+        assert torch.equal(out[[0, 2, 4]], ref[[0, 2, 4]]) and torch.isfinite(ref).all()
