@@ -357,9 +357,10 @@ void pca_debug_set_timeline(long long* device_buffer);
  * fp32 tail paths instead of a ninth, nearly empty tensor-core tile.  0 switches the rule off. */
 void pca_debug_set_tail_max(int tail_max);
 
-/* Debug / experiments: variant of the mab0 (reduce) kernel of the bf16 path: 4 = four softmax warpgroups streaming the scores
- * in 32-column chunks, followed by the exact 2-warpgroup variant on the work items in which a row outgrew its reference
- * exponent (normally none); 2 = the 2-warpgroup variant only. */
+/* Debug / experiments: variant of the mab0 (reduce) kernel of the bf16 path: 6 (default) = sixth generation (W_k folded into the
+ * query operand, TMA-fed tiles, one chain per head pair) and 4 = the fifth generation's four streaming softmax warpgroups, each
+ * followed by the exact 2-warpgroup variant on the work items in which a row outgrew its reference exponent (normally none);
+ * 2 = the exact 2-warpgroup variant only. */
 void pca_debug_set_reduce_variant(int warpgroups);
 
 /* Debug / experiments: pooled-attention (PMA) kernel of the bf16 path: 1 = rows are (head, copy) pairs (default), 2 = transposed

@@ -52,6 +52,10 @@ struct TcConsts {
     // apply4: the same B operands with the bias as an extra K step (rows k = 64, 65 = bias hi, lo; against the "ones" A operand)
     uint8_t Wq1e[10240], Wo0e[10240], Wo1e[10240];
     uint8_t WqS0e[2048];                          // WqS0 with the bias (hi, lo) in the spare columns k = 12, 13
+    // reduce6: mab0 query operands with W_k folded in (rows = (head of pair, query), K = input features), softmax scale included
+    uint8_t Gq1[65536];                           // isab1: [4 pairs][8 chunks][128 rows][16 B]
+    uint8_t Gq0s[16384];                          // isab0 (d_in <= 4): split-bf16 K = 16 image [4 pairs][2 chunks][128 rows][16 B]
+    uint8_t Wv1e[10240];                          // isab1.mab0 fc_v as (N = 64, K = 80) B operand with the bias step
     // k-major fp32 copies for finalize_isab: mab0.fc_o^T (64 x 64) and mab1 [Wk;Wv]^T (64 x 128), per ISAB
     float WoT[2][64 * 64];
     float WkvT[2][64 * 128];
@@ -145,7 +149,8 @@ __device__ void pack_b_operand_split(const float* __restrict__ W, int n_rows, ui
 __device__ void prep_queries(const float* __restrict__ Qin, int nq, const float* __restrict__ Wq,
                              const float* __restrict__ bq, float* __restrict__ Qp_out, uint8_t* __restrict__ Aq,
                              float* sq /* smem 64*64 */, const float* __restrict__ Wk = nullptr,
-                             uint8_t* __restrict__ AqPool = nullptr, float* __restrict__ WqkPool = nullptr) {
+                             uint8_t* __restrict__ AqPool = nullptr, float* __restrict__ WqkPool = nullptr,
+                             uint8_t* __restrict__ Gq = nullptr, uint8_t* __restrict__ GqSplit = nullptr, int dk = TD) {
     {   // Qp = Qin Wq^T + bq from shared-memory copies (Wq rows padded to 65 floats: thread <-> output feature is conflict free)
         __shared__ float sW[TD * 65];
         float* sI = sq;                                  // the inputs are staged in sq, then replaced by the outputs
@@ -199,6 +204,34 @@ __device__ void prep_queries(const float* __restrict__ Qin, int nq, const float*
         }
         return;
     }
+    // reduce6: W_k folded into the queries, G[(h, m)][f] = scale * sum_d Qp[m][8h + d] Wk[8h + d][f]   (Wk: (64, dk))
+    if (Gq != nullptr) {
+        for (int i = threadIdx.x; i < 4 * 8 * 128 * 8; i += blockDim.x) {
+            const int d = i & 7, r = (i >> 3) & 127, c = (i >> 10) & 7, p = i >> 13;
+            const int h = 2 * p + (r >> 6), m = r & 63, f = c * 8 + d;
+            float a = 0.f;
+#pragma unroll
+            for (int dd = 0; dd < 8; ++dd) a = fmaf(sq[m * TD + h * 8 + dd], Wk[(h * 8 + dd) * TD + f], a);
+            *reinterpret_cast<__nv_bfloat16*>(Gq + p * 16384 + c * 2048 + r * 16 + d * 2) = __float2bfloat16(a * kScaleLog2e);
+        }
+    }
+    if (GqSplit != nullptr) {
+        // K = 16 split image against split_x16 columns: k 0..3 G_hi (x_hi), 4..7 G_hi (x_lo), 8..11 G_lo (x_hi), 12..15 zero
+        for (int i = threadIdx.x; i < 4 * 2 * 128 * 8; i += blockDim.x) {
+            const int d = i & 7, r = (i >> 3) & 127, c = (i >> 10) & 1, p = i >> 11;
+            const int h = 2 * p + (r >> 6), m = r & 63, k = c * 8 + d, j = k & 3;
+            float v = 0.f;
+            if (k < 12 && j < dk) {
+                float a = 0.f;
+#pragma unroll
+                for (int dd = 0; dd < 8; ++dd) a = fmaf(sq[m * TD + h * 8 + dd], Wk[(h * 8 + dd) * dk + j], a);
+                a *= kScaleLog2e;
+                const float hi = __bfloat162float(__float2bfloat16(a));
+                v = (k < 8) ? hi : (a - hi);
+            }
+            *reinterpret_cast<__nv_bfloat16*>(GqSplit + p * 4096 + c * 2048 + r * 16 + d * 2) = __float2bfloat16(v);
+        }
+    }
     // Aq[p][c][r][d]: rows 0-63 carry head 2p in chunk 0, rows 64-127 carry head 2p+1 in chunk 1
     for (int i = threadIdx.x; i < 4 * 2 * 128 * 8; i += blockDim.x) {
         const int d = i & 7, r = (i >> 3) & 127, c = (i >> 10) & 1, p = i >> 11;
@@ -219,8 +252,8 @@ __global__ void prep_kernel(const float* __restrict__ params, int d_in, TcConsts
     const MabParams m11 = mab_slice(p_isab1 + TM * TD + mab_count(TD, TD, TD, 0), TD, TD, TD, 0);
     const MabParams mp = mab_slice(p_pma + TD, TD, TD, TD, 0);
     switch (blockIdx.x) {
-        case 0: prep_queries(p_isab0, TM, m00.Wq, m00.bq, c->Qp0, c->Aq0, sq); break;
-        case 1: prep_queries(p_isab1, TM, m10.Wq, m10.bq, c->Qp1, c->Aq1, sq); break;
+        case 0: prep_queries(p_isab0, TM, m00.Wq, m00.bq, c->Qp0, c->Aq0, sq, m00.Wkv, nullptr, nullptr, nullptr, c->Gq0s, d_in); break;
+        case 1: prep_queries(p_isab1, TM, m10.Wq, m10.bq, c->Qp1, c->Aq1, sq, m10.Wkv, nullptr, nullptr, c->Gq1, nullptr, TD); break;
         case 2: prep_queries(p_pma, 1, mp.Wq, mp.bq, c->QpS, c->AqP, sq, mp.Wkv, c->AqPool, c->WqkPool); break;
         case 3: pack_b_operand(m10.Wkv, 128, c->Wkv1); break;
         case 4: pack_b_operand(mp.Wkv, 128, c->WkvP); break;
@@ -246,6 +279,7 @@ __global__ void prep_kernel(const float* __restrict__ params, int d_in, TcConsts
         case 26: pack_b_operand_bias(m01.Wo, m01.bo, c->Wo0e); break;
         case 27: pack_b_operand_bias(m11.Wo, m11.bo, c->Wo1e); break;
         case 28: pack_split_b_operand_bias(m01.Wq, m01.bq, 64, d_in, c->WqS0e); break;
+        case 29: pack_b_operand_bias(m10.Wkv + TD * TD, m10.bkv + TD, c->Wv1e); break;
         case 17: transpose_weight(mp.Wkv + TD * TD, 64, c->WvT_P); break;
         case 18: transpose_weight(mp.Wo, 64, c->WoT_P); break;
         default: break;
@@ -299,9 +333,9 @@ struct RParams {
 // One 32-column chunk of the online softmax: p = 2^(s - m) as bf16 pairs, partial row sum (packed fp32x2 math).
 // pairs of each 32-column chunk whose exponentials run on the FMA pipe (polynomial) instead of MUFU: 6 of 16
 #ifndef PCA_POLY5
-#define PCA_POLY5 0x0u
+#define PCA_POLY5 0x0101u       // 2 of 16 pairs: -3 % on the reduce kernel, -5 % on the pooled kernel (4 of 16: -2 %)
 #endif
-constexpr uint32_t kPolyPairs = PCA_POLY5;      // measured: no gain while the kernels are latency- rather than MUFU-bound
+constexpr uint32_t kPolyPairs = PCA_POLY5;
 __device__ __forceinline__ void exp_chunk32(const uint32_t* v, const float2 neg_m2, float2& sum2, uint32_t* pk) {
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
@@ -1237,6 +1271,567 @@ __global__ void __launch_bounds__((4 * NWG + 12) * 32, 1) mab_reduce5_tc_kernel(
     fence_before_sync();
     __syncthreads();
     if (warp == WM) tmem_dealloc(tb, 512);
+}
+
+// ====================================================================================== reduce kernel, sixth generation
+// mab0 of an ISAB (Q = 64 inducing points, K = points) with the lessons of mab_apply4_tc_kernel (per-role clock stamps in
+// profiles/r02_timeline_*.log): what bounds these kernels is not the MUFU pipe but the serial latency of every softmax item
+// (barrier hand-offs, TMEM loads, the MMA round trip) and of the operand producers.
+//   * W_k is folded into the query operand: s[(h, m), n] = q_{h,m} . (W_k,h y_n + b_k,h) = (W_k,h^T q_{h,m}) . y_n + const(h, m), and
+//     the constant cancels in the softmax over n.  The A operand of Q K^T is therefore a MODEL constant (prep_kernel: "Gq",
+//     128 rows x 64 features per head pair, softmax scale included) and its B operand is the raw input tile exactly as the
+//     TMA engine delivers it -- no K projection, no TMEM -> register -> shared-memory round trip for the keys.  Only V is
+//     projected (one N = 64 MMA per tile + bias step) and staged as the bf16 MN-major operand of P V.
+//     (d_in <= 4: the split-bf16 point columns against a split Gq image, one K = 16 step; V on CUDA cores.)
+//   * One chain per head PAIR (4 chains = 4 softmax warpgroups = 16 warps, four per scheduler, streaming the scores in
+//     32-column chunks at 88 registers): both point halves of a tile go through the chain in turn, so a row has ONE reference
+//     exponent, ONE running sum and ONE accumulator (64 TMEM columns in all instead of 128).
+//   * Scores and probabilities live in separate TMEM regions (4 x 64 | 4 x 32): the score buffer is released as soon as the
+//     second chunk is in registers, so Q K^T of the chain's next item runs under this item's arithmetic; the packed
+//     probabilities are kept in registers (2 x 16) and written once s_full of the next item has been seen, which (same
+//     issuing thread, in-order tensor pipe) implies that P V of the previous item has drained the probability buffer.
+//   * Thread-side mbarrier arrivals by every lane (count 128); a loader warp feeds a three-deep tile ring by TMA.
+// 28 warps: 0-15 softmax (warpgroup g = pair g), 16-19 V producers, 20-23 MMA chains, 24 loader, 25-27 idle.
+// Partials: slot 2 * split holds the result, slot 2 * split + 1 is written empty (m = -inf): the finalize kernels see the
+// layout they always had.
+// EXACT = true is the redo pass over the work items the streaming pass flagged (a row outgrew its reference exponent; normally
+// none): same operands and arithmetic, but every item keeps its scores in TMEM until the row has been re-referenced if needed
+// (accumulator and running sum rescaled in place -- all earlier P V of the chain have completed by then), so no early
+// release and no look-ahead.  Both passes therefore round identically, which keeps near-tie decisions order independent.
+constexpr int R6_THREADS = 28 * 32;
+constexpr int R6_YST = 3;                                 // input tile ring
+constexpr uint32_t R6_S = 0, R6_P = 256, R6_O = 384, R6_PV = 448;      // 4 x 64 scores | 4 x 32 probabilities | 4 x 16 outputs | 64 V projection
+struct R6Smem {
+    static constexpr int GQ = 0;                          // 4 pairs x 16384 (64-wide) or 4 x 4096 (split K = 16 image)
+    static constexpr int WV = 65536;                      // V projection B operand (N = 64, K = 80)            [DIN64]
+    static constexpr int Y = WV + 10240;                  // R6_YST x 16384 input tiles (d_in <= 4: 4096 used per stage)
+    static constexpr int V = Y + R6_YST * 16384;          // 2 x 16384 bf16 V tiles (MN-major B operand of P V)
+    static constexpr int ONES = V + 32768;                // constant A operand of the bias K step
+    static constexpr int SMALL = ONES + 4096;             // d_in <= 4: Wv (64 x 4 fp32) | bv (64)
+    static constexpr int BARS = SMALL + (64 * 4 + 64) * 4;
+    static constexpr int TOTAL = BARS + 48 * 8 + 16;
+};
+struct R6Params {
+    const float* X32;             // (B, N, d_in) fp32      [DIN64 == false]
+    int N, d_in, tiles_total, tiles_per_split, nsplit, n_work;
+    const int* counts;            // nullable (B)
+    int tail_max;
+    const uint8_t* Gq;            // query operand image (see prep_kernel)
+    const uint8_t* Wv16;          // V projection B operand with bias step  [DIN64]
+    const float* Wv32;            // (64, d_in) fp32                        [DIN64 == false]
+    const float* bv;              // (64)                                   [DIN64 == false]
+    long long* timeline;
+    int* redo;                    // (n_work) flags: set by the streaming pass, consumed by the EXACT pass
+    float* part;                  // (B, 2 nsplit, 8, 10, 64)
+    CUtensorMap tmapY;            // [DIN64] the input as a (B * N, 64) bf16 tensor, box 128 rows x 8 elements
+};
+
+// One 64-column item of a row, exact variant: everything goes through TMEM in 16-column steps so that no register state of
+// the caller is needed.  Called warp-uniformly, after P V of the previous item has completed.  Returns the row sum of the item;
+// P (bf16) goes to the probability buffer; the row's accumulator (8 columns at oaddr) and running sum are rescaled if the
+// reference exponent has to move.
+__device__ __noinline__ float reduce6_item_exact(uint32_t sbase, uint32_t pbase, uint32_t oaddr, int nv, bool first, float& m_used,
+                                                 float& l_run) {
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c0 = 0; c0 < nv; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(sbase + c0, v);
+        tmem_ld_wait16(v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (c0 + j < nv) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
+    if (first) {                         // the chain's first P V of the work item overwrites the accumulator
+        m_used = mx;
+        l_run = 0.f;
+    } else {
+        const bool move = mx >= m_used + 53.f;
+        if (__any_sync(0xffffffffu, move)) {
+            const float f = move ? ex2(m_used - mx) : 1.f;
+            uint32_t o[8];
+            tmem_ld8(oaddr, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+            tmem_st8(oaddr, o);
+            tmem_st_wait();
+            l_run *= f;
+            if (move) m_used = mx;
+        }
+    }
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16], pk[8];
+        if (c0 < nv) {
+            tmem_ld16(sbase + c0, v);
+            tmem_ld_wait16(v);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            const float p0 = (c0 + j < nv) ? ex2(__uint_as_float(v[j]) - m_used) : 0.f;
+            const float p1 = (c0 + j + 1 < nv) ? ex2(__uint_as_float(v[j + 1]) - m_used) : 0.f;
+            sum += p0 + p1;
+            pk[j >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st8(pbase + (c0 >> 1), pk);
+    }
+    tmem_st_wait();
+    return sum;
+}
+
+template <bool DIN64, bool EXACT>
+__global__ void __launch_bounds__(R6_THREADS, 1) mab_reduce6_tc_kernel(const __grid_constant__ R6Params P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sGq = smem + R6Smem::GQ;
+    uint8_t* sWv = smem + R6Smem::WV;
+    uint8_t* sY = smem + R6Smem::Y;
+    uint8_t* sV = smem + R6Smem::V;
+    uint8_t* sOnes = smem + R6Smem::ONES;
+    float* sWv32 = reinterpret_cast<float*>(smem + R6Smem::SMALL);
+    float* sBv = sWv32 + 64 * 4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + R6Smem::BARS);
+    uint64_t* y_full = bars;           // [3] count 1 (loader; + TMA bytes)
+    uint64_t* y_empty = bars + 3;      // [3] count 4 chains (+ 1: the V projection commit, DIN64)
+    uint64_t* v_full = bars + 6;       // [2] count 128 (producer lanes)
+    uint64_t* v_empty = bars + 8;      // [2] count 4 (chains: their P V of the tile have run)
+    uint64_t* s_full = bars + 10;      // [4] count 1
+    uint64_t* s_free = bars + 14;      // [4] count 128 (lanes of the warpgroup: scores are in registers)
+    uint64_t* p_ready = bars + 18;     // [4] count 128
+    uint64_t* p_free = bars + 22;      // [4] count 1 (commit of P V; waited for only where no next item covers it)
+    uint64_t* o_done = bars + 26;      // [4] count 1 (chain: all P V of the work item complete)
+    uint64_t* vp_done = bars + 30;     // count 1 (V projection MMA)
+    uint64_t* vp_free = bars + 31;     // count 128 (producer lanes have read the projection)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 48);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_work = P.n_work, wstep = gridDim.x;
+#ifdef PCA_TIMELINE
+    long long* tl2 = nullptr;
+    int tl2_n = 0;
+    if (P.timeline != nullptr && blockIdx.x == 0 && lane == 0) {
+        if (warp == 0) tl2 = P.timeline;
+        else if (warp == 16) tl2 = P.timeline + 2000;
+        else if (warp == 12) tl2 = P.timeline + 4000;
+        else if (warp == 20) tl2 = P.timeline + 6000;
+    }
+    auto stamp2 = [&](int tag) {
+        if (tl2 != nullptr && tl2_n < 1000) { tl2[2 * tl2_n] = tag; tl2[2 * tl2_n + 1] = clock64(); ++tl2_n; }
+    };
+#else
+    auto stamp2 = [&](int) {};
+#endif
+    auto work_tiles = [&](int w, int& cloud, int& split, int& tile0, int& nb) {
+        cloud = w / P.nsplit;
+        split = w - cloud * P.nsplit;
+        tile0 = split * P.tiles_per_split;
+        nb = main_points(P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N, P.tail_max);
+        return max(0, min((nb + 127) >> 7, tile0 + P.tiles_per_split) - tile0);
+    };
+
+    // EXACT: only the work items flagged by the streaming pass are processed (normally none: leave at once)
+    auto skipped = [&](int w) { return EXACT && __ldg(P.redo + w) == 0; };
+    if (EXACT) {
+        int any = 0;
+        for (int w = blockIdx.x + (int)threadIdx.x * wstep; w < n_work; w += (int)blockDim.x * wstep) any |= (__ldg(P.redo + w) != 0);
+        if (!__syncthreads_or(any)) return;
+    }
+    copy_to_smem(sGq, P.Gq, DIN64 ? 65536 : 16384);
+    if (DIN64) copy_to_smem(sWv, P.Wv16, 10240);
+    else {
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+            sBv[i] = P.bv[i];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sWv32[i * 4 + k] = (k < P.d_in) ? P.Wv32[i * P.d_in + k] : 0.f;
+        }
+    }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        *reinterpret_cast<uint4*>(sOnes + i * 16) = (i < 128) ? make_uint4(0x3F803F80u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
+    if (warp == 20) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < R6_YST; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], DIN64 ? 5 : 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&v_full[i], 128); mbar_init(&v_empty[i], 4); }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128);
+            mbar_init(&p_ready[i], 128); mbar_init(&p_free[i], 1);
+            mbar_init(&o_done[i], 1);
+        }
+        mbar_init(vp_done, 1);
+        mbar_init(vp_free, 128);
+        fence_barrier_init();
+    }
+    if (DIN64 && threadIdx.x == 24 * 32) tma_prefetch_desc(&P.tmapY);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp >= 25) {
+        reg_dec<40>();
+    } else if (warp == 24) {
+        reg_dec<40>();
+        // =================================================================== loader: input tiles
+        int gt = 0;
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            if (skipped(w)) continue;
+            int cloud, split, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, split, tile0, nb);
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int stage = gt % R6_YST;
+                uint8_t* dst = sY + stage * 16384;
+                if (gt >= R6_YST) mbar_wait(&y_empty[stage], ((gt / R6_YST) - 1) & 1);
+                if (DIN64) {
+                    if (lane == 0) {
+                        const long long r0 = (long long)cloud * P.N + (long long)(tile0 + it) * 128;
+                        mbar_arrive_expect_tx(&y_full[stage], 16384);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) tma_load_2d(dst + c * 2048, &P.tmapY, 8 * c, (int)r0, &y_full[stage]);
+                    }
+                    __syncwarp();
+                } else {
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int row = 32 * rr + lane;
+                        const int n = (tile0 + it) * 128 + row;
+                        float x[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (n < nb) {
+                            const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                            for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
+                        }
+                        float cols[16];
+                        split_x16(x, cols);
+                        st_shared_8bf16(dst + row * 16, cols);
+                        st_shared_8bf16(dst + 2048 + row * 16, cols + 8);
+                    }
+                    fence_async_smem();
+                    fence_before_sync();
+                    warp_arrive(&y_full[stage]);
+                }
+            }
+        }
+    } else if (warp >= 20) {
+        reg_dec<40>();
+        // =================================================================== MMA chain g = head pair g
+        const int g = warp - 20;
+        const bool leader = elect_one();
+        const uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);
+        const uint32_t idesc_pv = idesc_bf16(128, 16, 0, 1);
+        const uint32_t gq = smem_u32(sGq) + g * (DIN64 ? 16384 : 4096), yb = smem_u32(sY), vb = smem_u32(sV);
+        const uint32_t s_tm = tmem_addr(tb, 0, R6_S + 64 * g), p_tm = tmem_addr(tb, 0, R6_P + 32 * g), o_tm = tmem_addr(tb, 0, R6_O + 16 * g);
+        uint32_t par = 0;
+        bool have_prev = false, prev_first = false, prev_tile_last = false;
+        uint32_t prev_v = 0;
+        int prev_vstage = 0;
+        auto pv_prev = [&]() {
+            stamp2(62);
+            mbar_wait(&p_ready[g], par ^ 1);
+            fence_after_sync();
+            stamp2(63);
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_ts(o_tm, p_tm + ks * 8, smem_desc(prev_v + ks * 256, 128, 2048), idesc_pv, (prev_first && ks == 0) ? 0u : 1u);
+                mma_commit(&p_free[g]);
+                if (prev_tile_last) mma_commit(&v_empty[prev_vstage]);     // this chain is done with the tile's V image
+            }
+            __syncwarp();
+        };
+        int gt = 0;
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            if (skipped(w)) continue;
+            int cloud, split, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, split, tile0, nb);
+            bool first_item = true;
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int stage = gt % R6_YST, vstage = gt & 1;
+                stamp2(60);
+                mbar_wait(&y_full[stage], (gt / R6_YST) & 1);
+                mbar_wait(&v_full[vstage], (gt >> 1) & 1);
+                fence_after_sync();
+                stamp2(61);
+                const int n_valid = min(128, nb - (tile0 + it) * 128);
+                const int n_items = n_valid > 64 ? 2 : 1;              // a half without valid points is skipped by chain and warpgroup alike
+#pragma unroll 1
+                for (int hf = 0; hf < n_items; ++hf) {
+                    if (have_prev) {
+                        mbar_wait(&s_free[g], par ^ 1);
+                        fence_after_sync();
+                    }
+                    if (leader) {
+                        if (DIN64) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_ss(s_tm, smem_desc(gq + ks * 4096, 2048, 128), smem_desc(yb + stage * 16384 + ks * 4096 + hf * 1024, 2048, 128),
+                                       idesc_s, ks > 0);
+                        } else {
+                            mma_ss(s_tm, smem_desc(gq, 2048, 128), smem_desc(yb + stage * 16384 + hf * 1024, 2048, 128), idesc_s, 0u);
+                        }
+                        mma_commit(&s_full[g]);
+                        if (hf == n_items - 1) mma_commit(&y_empty[stage]);       // this chain has consumed the input tile
+                    }
+                    __syncwarp();
+                    if (have_prev) pv_prev();
+                    par ^= 1;
+                    have_prev = true;
+                    prev_first = first_item;
+                    first_item = false;
+                    prev_tile_last = hf == n_items - 1;
+                    prev_vstage = vstage;
+                    prev_v = vb + vstage * 16384 + 2 * g * 2048 + hf * 1024;
+                }
+            }
+            // end of the work item: retire the pending P V, publish the accumulators, restart the hand-shake
+            if (have_prev) {
+                pv_prev();
+                have_prev = false;
+                mbar_wait(&s_free[g], par ^ 1);
+            }
+            if (leader) mma_commit(&o_done[g]);
+            __syncwarp();
+        }
+    } else if (warp >= 16) {
+        reg_dec<56>();
+        // =================================================================== V producers (thread = point row)
+        const int quad = warp & 3;
+        const int row = 32 * quad + lane;
+        int gt = 0;
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            if (skipped(w)) continue;
+            int cloud, split, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, split, tile0, nb);
+            for (int it = 0; it < ntiles; ++it, ++gt) {
+                const int stage = gt % R6_YST, vstage = gt & 1;
+                const int n = (tile0 + it) * 128 + row;
+                const bool valid = n < nb;
+                uint8_t* dstV = sV + vstage * 16384;
+                stamp2(50);
+                if (DIN64) {
+                    if (warp == 16) {
+                        // V = Y Wv^T + bv into the projection columns, free once all four producer warps have read the previous tile
+                        mbar_wait(&y_full[stage], (gt / R6_YST) & 1);
+                        if (gt >= 1) mbar_wait(vp_free, (gt - 1) & 1);
+                        fence_after_sync();
+                        if (elect_one()) {
+                            const uint32_t yb = smem_u32(sY) + stage * 16384, wv = smem_u32(sWv), ones = smem_u32(sOnes);
+                            const uint32_t d = tmem_addr(tb, 0, R6_PV);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_ss(d, smem_desc(yb + ks * 4096, 2048, 128), smem_desc(wv + ks * 2048, 1024, 128), idesc_bf16(128, 64, 0, 0), ks > 0);
+                            mma_ss(d, smem_desc(ones, 2048, 128), smem_desc(wv + 8192, 1024, 128), idesc_bf16(128, 64, 0, 0), 1u);
+                            mma_commit(vp_done);
+                            mma_commit(&y_empty[stage]);
+                        }
+                        __syncwarp();
+                    }
+                    mbar_wait(vp_done, gt & 1);
+                    fence_after_sync();
+                    stamp2(51);
+                    if (gt >= 2) mbar_wait(&v_empty[vstage], ((gt >> 1) - 1) & 1);
+                    stamp2(52);
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_addr(tb, 32 * quad, R6_PV + 32 * hf), v);
+                        tmem_ld_wait32(v);
+                        if (hf == 1) { fence_before_sync(); mbar_arrive(vp_free); }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 u = make_uint4(0, 0, 0, 0);
+                            if (valid) {
+                                u.x = pack_bf16(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+                                u.y = pack_bf16(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+                                u.z = pack_bf16(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+                                u.w = pack_bf16(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+                            }
+                            *reinterpret_cast<uint4*>(dstV + (4 * hf + q) * 2048 + row * 16) = u;
+                        }
+                    }
+                } else {
+                    float x[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (valid) {
+                        const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
+                        for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
+                    }
+                    if (gt >= 2) mbar_wait(&v_empty[vstage], ((gt >> 1) - 1) & 1);
+#pragma unroll 4
+                    for (int c = 0; c < 8; ++c) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int f = c * 8 + j;
+                            const float4 wv = *reinterpret_cast<const float4*>(sWv32 + f * 4);
+                            o[j] = valid ? fmaf(wv.w, x[3], fmaf(wv.z, x[2], fmaf(wv.y, x[1], fmaf(wv.x, x[0], sBv[f])))) : 0.f;
+                        }
+                        st_shared_8bf16(dstV + c * 2048 + row * 16, o);
+                    }
+                }
+                stamp2(54);
+                fence_async_smem();
+                fence_before_sync();
+                mbar_arrive(&v_full[vstage]);
+            }
+        }
+    } else {
+        reg_inc<88>();
+        // =================================================================== softmax warpgroup g = head pair g (thread = (head of pair, query) row)
+        const int g = warp >> 2, quad = warp & 3;
+        const int row = 32 * quad + lane;
+        const uint32_t lane_base = 32 * quad;
+        const uint32_t sbase = tmem_addr(tb, lane_base, R6_S + 64 * g);
+        const uint32_t pbase = tmem_addr(tb, lane_base, R6_P + 32 * g);
+        const uint32_t oaddr = tmem_addr(tb, lane_base, R6_O + 16 * g + ((row >= 64) ? 8u : 0u));
+        constexpr float kOverflow = 1.152921504606847e18f;      // 2^60
+        uint32_t par = 0, ph_done = 0;
+        bool have_scores = false, first_ever = true;
+        for (int w = blockIdx.x; w < n_work; w += wstep) {
+            if (skipped(w)) continue;
+            int cloud, split, tile0, nb;
+            const int ntiles = work_tiles(w, cloud, split, tile0, nb);
+            float m_used = -INFINITY, l_run = 0.f;
+            bool flagged = false;
+            for (int it = 0; it < ntiles; ++it) {
+                const int n_valid = min(128, nb - (tile0 + it) * 128);
+                const int n_items = n_valid > 64 ? 2 : 1;
+#pragma unroll 1
+                for (int hf = 0; hf < n_items; ++hf) {
+                    const int nv = hf == 0 ? min(64, n_valid) : n_valid - 64;
+                    const bool first = it == 0 && hf == 0;
+                    const bool has_next = hf + 1 < n_items || it + 1 < ntiles;       // a later item of this chain in this work item
+                    uint32_t v[32], pkA[16], pkB[16];
+                    float sum;
+                    stamp2(20);
+                    if (EXACT) {
+                        // scores stay in TMEM; P V of the previous item must have drained the probability buffer AND left
+                        // the accumulator quiescent before the row may be re-referenced
+                        mbar_wait(&s_full[g], par);
+                        fence_after_sync();
+                        if (!first_ever) {
+                            mbar_wait(&p_free[g], par ^ 1);
+                            fence_after_sync();
+                        }
+                        first_ever = false;
+                        l_run += reduce6_item_exact(sbase, pbase, oaddr, nv, first, m_used, l_run);
+                        fence_before_sync();
+                        mbar_arrive(&s_free[g]);
+                        mbar_arrive(&p_ready[g]);
+                        par ^= 1;
+                        continue;
+                    }
+                    if (!have_scores) {
+                        mbar_wait(&s_full[g], par);
+                        fence_after_sync();
+                    }
+                    stamp2(24);
+                    if (nv == 64 && !first) {
+                        const float2 neg2 = make_float2(-m_used, -m_used);
+                        float2 sum2 = make_float2(0.f, 0.f);
+                        tmem_ld32(sbase, v);
+                        tmem_ld_wait32(v);
+                        exp_chunk32(v, neg2, sum2, pkA);
+                        tmem_ld32(sbase + 32, v);
+                        tmem_ld_wait32(v);
+                        fence_before_sync();
+                        mbar_arrive(&s_free[g]);                 // the scores are in registers: the chain's next Q K^T may run
+                        stamp2(25);
+                        exp_chunk32(v, neg2, sum2, pkB);
+                        sum = sum2.x + sum2.y;
+                    } else {
+                        // first item of the work item (reference exponent := row maximum) and ragged tails: masked, three loads
+                        float mx = -INFINITY;
+                        tmem_ld32(sbase, v);
+                        tmem_ld_wait32(v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nv) mx = fmaxf(mx, __uint_as_float(v[j]));
+                        tmem_ld32(sbase + 32, v);
+                        tmem_ld_wait32(v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (32 + j < nv) mx = fmaxf(mx, __uint_as_float(v[j]));
+                        if (first) { m_used = mx; l_run = 0.f; }
+                        const float m = m_used;
+                        sum = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float p0 = (32 + j < nv) ? ex2(__uint_as_float(v[j]) - m) : 0.f;
+                            const float p1 = (33 + j < nv) ? ex2(__uint_as_float(v[j + 1]) - m) : 0.f;
+                            sum += p0 + p1;
+                            pkB[j >> 1] = pack_bf16(p0, p1);
+                        }
+                        tmem_ld32(sbase, v);
+                        tmem_ld_wait32(v);
+                        fence_before_sync();
+                        mbar_arrive(&s_free[g]);
+                        stamp2(25);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float p0 = (j < nv) ? ex2(__uint_as_float(v[j]) - m) : 0.f;
+                            const float p1 = (j + 1 < nv) ? ex2(__uint_as_float(v[j + 1]) - m) : 0.f;
+                            sum += p0 + p1;
+                            pkA[j >> 1] = pack_bf16(p0, p1);
+                        }
+                    }
+                    // a score outgrew the row's reference exponent by more than ~2^54 (or the sum overflowed): this streaming
+                    // kernel cannot re-reference a row -- the work item is redone by the exact variant (flag set once below)
+                    if (!(sum < kOverflow)) flagged = true;
+                    l_run += sum;
+                    stamp2(21);
+                    // the probability buffer holds the previous item's P until its P V has run: s_full of the NEXT item covers
+                    // it (the chain issues that P V before the next Q K^T); the last item of a work item waits for the commit
+                    if (has_next) {
+                        mbar_wait(&s_full[g], par ^ 1);
+                        fence_after_sync();
+                        have_scores = true;
+                    } else {
+                        if (!first_ever) {
+                            mbar_wait(&p_free[g], par ^ 1);
+                            fence_after_sync();
+                        }
+                        have_scores = false;
+                    }
+                    first_ever = false;
+                    stamp2(22);
+                    tmem_st16(pbase, pkA);
+                    tmem_st16(pbase + 16, pkB);
+                    tmem_st_wait();
+                    stamp2(27);
+                    fence_before_sync();
+                    mbar_arrive(&p_ready[g]);
+                    par ^= 1;
+                }
+            }
+            if (!EXACT && flagged) P.redo[w] = 1;
+            // ---- the work item's accumulators are final once the chain has drained
+            mbar_wait(&o_done[g], ph_done);
+            ph_done ^= 1;
+            fence_after_sync();
+            {
+                uint32_t o[8];
+                if (ntiles > 0) {
+                    tmem_ld8(oaddr, o);
+                    tmem_ld_wait();
+                }
+                const int h = 2 * g + (row >> 6);
+                float* dst = P.part + (((size_t)cloud * (2 * P.nsplit) + 2 * split) * TH + h) * 10 * TM + (row & 63);
+                float* dst1 = dst + (size_t)TH * 10 * TM;               // the second (empty) slot of the split
+                dst[0] = m_used;
+                dst[TM] = l_run;
+                dst1[0] = -INFINITY;
+                dst1[TM] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    dst[(2 + j) * TM] = (l_run > 0.f) ? __uint_as_float(o[j]) : 0.f;
+                    dst1[(2 + j) * TM] = 0.f;
+                }
+            }
+            fence_before_sync();
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 20) tmem_dealloc(tb, 512);
 }
 
 // ====================================================================================== apply kernel, third generation
@@ -3114,13 +3709,13 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 // ------------------------------------------------------------------------------------ host orchestration
 static int g_num_sms = 148;
 static int g_pool_variant = 1;             // pooled attention: 1 = row copies, 2 = transposed (PCA_TC_POOL=2)
-static int g_reduce_wg = 4;               // reduce kernel variant: 4 = streaming (+ exact redo of flagged items), 2 = exact only
+static int g_reduce_wg = 6;               // reduce kernel: 6 = sixth generation (+ exact redo of flagged items), 4 = streaming fifth generation (+ redo), 2 = exact only
 static int g_apply_variant = 4;           // apply kernel: 4 = three softmax warpgroups, TMA loader; 3 = previous generation (PCA_TC_APPLY=3)
 static int g_tail_max = TC_TAIL_MAX;       // tail rule (PCA_TC_TAIL=0 disables it: every point goes through the tensor-core kernels)
 static long long* g_timeline = nullptr;      // set through pca_debug_set_timeline
 void set_timeline(long long* p) { g_timeline = p; }
 void set_tail_max(int t) { g_tail_max = t < 0 ? 0 : (t > TC_TAIL_MAX ? TC_TAIL_MAX : t); }
-void set_reduce_wg(int n) { g_reduce_wg = (n == 4) ? 4 : 2; }
+void set_reduce_wg(int n) { g_reduce_wg = (n == 4 || n == 6) ? n : 2; }
 void set_pool_variant(int v) { g_pool_variant = (v == 2) ? 2 : 1; }
 void set_apply_variant(int v) { g_apply_variant = (v == 3) ? 3 : 4; }
 struct TcSplit { int tiles_total, tiles_per_split, nsplit; };
@@ -3198,7 +3793,15 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
         RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Aq0, m00.Wkv, m00.bkv,
                   nullptr, (tl_apply || getenv("PCA_TL_REDUCE64")) ? nullptr : g_timeline, redo, 0, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * d_in * TD + 2.0 * TM * TD), pts * 4.0 * d_in);
-        if (g_reduce_wg == 4) {
+        if (g_reduce_wg == 6) {
+            PCA_CHECK_CUDA(cudaMemsetAsync(redo, 0, (size_t)n_work * sizeof(int), st));
+            R6Params r6{X, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Gq0s, nullptr, m00.Wkv + (size_t)TD * d_in,
+                        m00.bkv + TD, r.timeline, redo, part, CUtensorMap{}};
+            mab_reduce6_tc_kernel<false, false><<<pgrid, R6_THREADS, R6Smem::TOTAL, st>>>(r6);
+            r6.timeline = nullptr;
+            mab_reduce6_tc_kernel<false, true><<<pgrid, R6_THREADS, R6Smem::TOTAL, st>>>(r6);      // exact redo of flagged work items
+            count_launch();
+        } else if (g_reduce_wg == 4) {
             // streaming variant, then the exact variant on the (normally empty) list of flagged work items
             PCA_CHECK_CUDA(cudaMemsetAsync(redo, 0, (size_t)n_work * sizeof(int), st));
             mab_reduce5_tc_kernel<false, 4><<<pgrid, 28 * 32, R2Smem::TOTAL, st>>>(r);
@@ -3238,7 +3841,16 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
         RParams r{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Aq1, nullptr, m10.bkv,
                   c->Wkv1, getenv("PCA_TL_REDUCE64") ? g_timeline : nullptr, redo, 0, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * TD * TD + 2.0 * TM * TD), pts * 128.0);
-        if (g_reduce_wg == 4) {
+        if (g_reduce_wg == 6) {
+            PCA_CHECK_CUDA(cudaMemsetAsync(redo, 0, (size_t)n_work * sizeof(int), st));
+            R6Params r6{nullptr, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Gq1, c->Wv1e, nullptr, nullptr,
+                        r.timeline, redo, part, CUtensorMap{}};
+            PCA_TRY(make_tmap_2d_bf16(&r6.tmapY, Y1, 64, (unsigned long long)B * N, 128, 8, 128));
+            mab_reduce6_tc_kernel<true, false><<<pgrid, R6_THREADS, R6Smem::TOTAL, st>>>(r6);
+            r6.timeline = nullptr;
+            mab_reduce6_tc_kernel<true, true><<<pgrid, R6_THREADS, R6Smem::TOTAL, st>>>(r6);
+            count_launch();
+        } else if (g_reduce_wg == 4) {
             PCA_CHECK_CUDA(cudaMemsetAsync(redo, 0, (size_t)n_work * sizeof(int), st));
             mab_reduce5_tc_kernel<true, 4><<<pgrid, 28 * 32, R2Smem::TOTAL, st>>>(r);
             r.redo_only = 1;
@@ -3313,7 +3925,11 @@ static int tc_configure() {
     PCA_CHECK_CUDA((cudaFuncSetAttribute(mab_reduce5_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL)));
     PCA_CHECK_CUDA((cudaFuncSetAttribute(mab_reduce5_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL)));
     PCA_CHECK_CUDA((cudaFuncSetAttribute(mab_reduce5_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, R2Smem::TOTAL)));
-    if (const char* v = getenv("PCA_TC_REDUCE_WG")) g_reduce_wg = (v[0] == '2') ? 2 : 4;
+    PCA_CHECK_CUDA((cudaFuncSetAttribute(mab_reduce6_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R6Smem::TOTAL)));
+    PCA_CHECK_CUDA((cudaFuncSetAttribute(mab_reduce6_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R6Smem::TOTAL)));
+    PCA_CHECK_CUDA((cudaFuncSetAttribute(mab_reduce6_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R6Smem::TOTAL)));
+    PCA_CHECK_CUDA((cudaFuncSetAttribute(mab_reduce6_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R6Smem::TOTAL)));
+    if (const char* v = getenv("PCA_TC_REDUCE_WG")) g_reduce_wg = (v[0] == '2') ? 2 : (v[0] == '4' ? 4 : 6);
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(mab_apply4_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4Smem::TOTAL));
@@ -3338,7 +3954,7 @@ int st_tc_forward_dbg(const float* X, const int* counts, int B, int N, const pca
     if (dbg && chunk < B) return fail(PCA_EWORKSPACE, "ST(bf16) debug: workspace must hold the whole batch");
     uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
     TcConsts* c = reinterpret_cast<TcConsts*>(w8 + tc_layout(chunk, N).consts);
-    prep_kernel<<<29, 256, 0, st>>>(params, d->d_in, c);
+    prep_kernel<<<30, 256, 0, st>>>(params, d->d_in, c);
     PCA_CHECK_LAUNCH("prep_kernel");
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int bc = (B - b0) < chunk ? (B - b0) : chunk;

@@ -267,13 +267,15 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
           "l"(*reinterpret_cast<unsigned long long*>(&c)));
     return *reinterpret_cast<float2*>(&d);
 }
-// 2^x for x <= 0 on the FMA pipe (no MUFU): round-to-nearest split x = xi + f, f in [-0.5, 0.5], degree-3 minimax
+// 2^x on the FMA pipe (no MUFU): round-to-nearest split x = xi + f, f in [-0.5, 0.5], degree-3 minimax
 // polynomial for 2^f (max relative error 7.5e-5, far below the bf16 rounding of the probabilities it feeds), exponent
 // re-inserted with one integer multiply-add.  The MUFU pipe (16 ex2/clk/SM) is the binding unit of the softmax
 // kernels; a share of the exponentials is routed here to balance it against the FMA pipe.
 __device__ __forceinline__ float2 ex2_poly2(float2 x) {
-    x.x = fmaxf(x.x, -126.f);
-    x.y = fmaxf(x.y, -126.f);
+    // clamp to [-126, 128]: below, the result underflows to ~0 as ex2 does; at 128 the exponent insertion yields +inf / NaN,
+    // which is what the reduce kernels' overflow detection (fixed reference exponent: x can be positive) must see
+    x.x = fminf(fmaxf(x.x, -126.f), 128.f);
+    x.y = fminf(fmaxf(x.y, -126.f), 128.f);
     const float2 magic = make_float2(12582912.f, 12582912.f);          // 1.5 * 2^23
     const float2 t = add2(x, magic);
     const float2 r = add2(t, make_float2(-12582912.f, -12582912.f));

@@ -10,7 +10,7 @@ import torch
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 BF16_REL_TOL = 2e-2
-DEFAULT_REDUCE_VARIANT = 4      # must match g_reduce_wg in csrc/encoder_tc.cu
+DEFAULT_REDUCE_VARIANT = 6      # must match g_reduce_wg in csrc/encoder_tc.cu
 
 
 @pytest.fixture(scope="module")
@@ -90,7 +90,7 @@ def test_tc_unsupported_dims_fail_loudly(pca):
         st(torch.zeros(2, 10, 2, device=dev))
 
 
-@pytest.fixture(params=[2, 4], ids=["reduce2wg", "reduce4wg"])
+@pytest.fixture(params=[2, 4, 6], ids=["reduce2wg", "reduce4wg", "reduce6"])
 def reduce_variant(request, pca):
     from pcaudio_b200 import _lib
     _lib.lib().pca_debug_set_reduce_variant(request.param)
