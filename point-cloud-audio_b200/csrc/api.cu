@@ -56,6 +56,9 @@ size_t st_tc_workspace_bytes(const pca_st_dims* d, int B, int N);
 int st_tc_supported(const pca_st_dims* d, int N);
 int st_tc_forward(const float* X, const int* counts, int B, int N, const pca_st_dims* d, const float* params, float* logits,
                   void* ws, size_t ws_bytes, cudaStream_t st);
+int st_tc_accepts_logmag();
+int st_tc_forward_logmag(const float* logmag, const float* farr, const float* tarr, int nf, int B, int N, const pca_st_dims* d,
+                         const float* params, float* logits, void* ws, size_t ws_bytes, cudaStream_t st);
 int st_tc_forward_stages(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,
                          float* H1, float* Y1, float* H2, float* Y2, float* pooled, void* ws, size_t ws_bytes,
                          cudaStream_t st);
@@ -420,6 +423,11 @@ static int pipeline_run(const pca_pipeline_cfg* c, const float* audio, int n_cli
     if (c->top_k || thr)
         PCA_TRY(launch_topk(logmag, n_clouds, s.nf, nt_cloud, farr, tarr_use, s.pts, 1, thr, c->threshold, pts, nullptr,
                             thr ? kept : nullptr, st));
+    else if (c->precision == PCA_PREC_BF16 && st_tc_supported(&c->st, s.pts) && st_tc_accepts_logmag() && getenv("PCA_BUILD_CLOUDS") == nullptr)
+        // front end fused into the encoder: its loader warps synthesise (f, [t,] mag) from the log-magnitudes and the coordinate
+        // tables, the ESC_pc / ESC_pc_temp rows are never written (bit-identical to the build_clouds route, tested)
+        return st_tc_forward_logmag(logmag, farr, tarr_use, s.nf, n_clouds, s.pts, &c->st, st_params, logits, (char*)ws + st_off,
+                                    ws_bytes - st_off, st);
     else
         PCA_TRY(launch_build_clouds(logmag, n_clouds, s.nf, nt_cloud, farr, tarr_use, pts, st));
     return st_forward(pts, n_clouds, s.pts, &c->st, st_params, logits, (char*)ws + st_off, ws_bytes - st_off,

@@ -298,6 +298,31 @@ __device__ __forceinline__ void st_shared_8bf16(uint8_t* dst, const float* v) {
     *reinterpret_cast<uint4*>(dst) = u;
 }
 
+// ------------------------------------------------------------------------------------ where the points come from
+// The d_in <= 4 points of a cloud are either rows of an explicit (B, N, d_in) tensor (X32) or -- on the whole-path call without
+// a selection step -- read straight from the front end's output: point n = t * nf + f of a cloud is (farr[f], [tarr[t],]
+// logmag[cloud][n]) (Code/dataset.py:50-54, 160-166), so the ESC_pc / ESC_pc_temp rows are never materialised.  The values
+// are the ones build_clouds_kernel would have written: results are bit-identical.
+struct PointSrc {
+    const float* logmag;          // (B, N) log-magnitudes, frequency fastest; nullptr = use X32
+    const float* farr;            // (nf)
+    const float* tarr;            // (N / nf) or nullptr for 2-wide clouds
+    int nf;
+};
+__device__ __forceinline__ void load_point(const float* __restrict__ X32, const PointSrc& src, int N, int d_in, size_t cloud, int n,
+                                           float* x) {
+    if (src.logmag != nullptr) {
+        const int t = n / src.nf, f = n - t * src.nf;
+        const float mag = __ldg(src.logmag + cloud * (size_t)N + n);
+        x[0] = __ldg(src.farr + f);
+        if (src.tarr != nullptr) { x[1] = __ldg(src.tarr + t); x[2] = mag; }
+        else x[1] = mag;
+    } else {
+        const float* xp = X32 + (cloud * (size_t)N + n) * d_in;
+        for (int k = 0; k < d_in; ++k) x[k] = __ldg(xp + k);
+    }
+}
+
 // ------------------------------------------------------------------------------------ tail rule
 // A cloud whose point count leaves 1..tail_max points past a multiple of 128 (the FST cloud: 1025 = 8 x 128 + 1) would
 // pay a whole pipeline pass of the tensor-core kernels for them (measured: the 9th tile of the FST cloud costs 77 % of a
@@ -379,6 +404,7 @@ struct F2Params {
     int tail_max;
     const float* Wkv0T;           // mab0 [Wk;Wv]^T, k-major (dk, 128)
     const float* bkv0;            // mab0 bk | bv (128)
+    PointSrc src;                 // [dk <= 4] alternative to X32
 };
 constexpr uint32_t F2_A = 0, F2_F = 64, F2_KV = 128;       // hi 32 | lo 32 | F 64 | KV 128  (256 columns)
 struct F2Smem {
@@ -442,10 +468,11 @@ __global__ void __launch_bounds__(128) finalize_isab_tc_kernel(const F2Params P)
             r_tail = nbt - n0;
             for (int j = 0; j < r_tail; ++j) {
                 float kacc = __ldg(P.bkv0 + m), vacc = __ldg(P.bkv0 + 64 + m);
-                if (P.X32 != nullptr) {
-                    const float* xp = P.X32 + ((size_t)cloud * P.N + n0 + j) * P.dk;
+                if (P.Y16 == nullptr) {
+                    float xr[4] = {0.f, 0.f, 0.f, 0.f};
+                    load_point(P.X32, P.src, P.N, P.dk, (size_t)cloud, n0 + j, xr);
                     for (int k = 0; k < P.dk; ++k) {
-                        const float x = __ldg(xp + k);
+                        const float x = xr[k];
                         kacc = fmaf(x, __ldg(P.Wkv0T + k * 128 + m), kacc);
                         vacc = fmaf(x, __ldg(P.Wkv0T + k * 128 + 64 + m), vacc);
                     }
@@ -644,6 +671,7 @@ struct AParams {
     long long* timeline;          // debug (PCA_TIMELINE builds): clock64 stamps of CTA 0 / softmax warp 0
     CUtensorMap tmapY;            // [DIN64, apply4] Y16in as a (B * N, 64) bf16 tensor, box 128 rows x 8 elements (TMA)
     CUtensorMap tmapYo;           // [apply4] Yout, same geometry (TMA stores of whole tiles)
+    PointSrc src;                 // [DIN64 == false, apply4] alternative to X32
 };
 
 // ====================================================================================== chain-scheduled kernels
@@ -1324,6 +1352,7 @@ struct R6Params {
     int* redo;                    // (n_work) flags: set by the streaming pass, consumed by the EXACT pass
     float* part;                  // (B, 2 nsplit, 8, 10, 64)
     CUtensorMap tmapY;            // [DIN64] the input as a (B * N, 64) bf16 tensor, box 128 rows x 8 elements
+    PointSrc src;                 // [DIN64 == false] alternative to X32
 };
 
 // One 64-column item of a row, exact variant: everything goes through TMEM in 16-column steps so that no register state of
@@ -1496,10 +1525,7 @@ __global__ void __launch_bounds__(R6_THREADS, 1) mab_reduce6_tc_kernel(const __g
                         const int row = 32 * rr + lane;
                         const int n = (tile0 + it) * 128 + row;
                         float x[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (n < nb) {
-                            const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
-                            for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
-                        }
+                        if (n < nb) load_point(P.X32, P.src, P.N, P.d_in, (size_t)cloud, n, x);
                         float cols[16];
                         split_x16(x, cols);
                         st_shared_8bf16(dst + row * 16, cols);
@@ -1650,10 +1676,7 @@ __global__ void __launch_bounds__(R6_THREADS, 1) mab_reduce6_tc_kernel(const __g
                     }
                 } else {
                     float x[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (valid) {
-                        const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
-                        for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
-                    }
+                    if (valid) load_point(P.X32, P.src, P.N, P.d_in, (size_t)cloud, n, x);
                     if (gt >= 2) mbar_wait(&v_empty[vstage], ((gt >> 1) - 1) & 1);
 #pragma unroll 4
                     for (int c = 0; c < 8; ++c) {
@@ -2531,10 +2554,7 @@ __global__ void __launch_bounds__(A4_THREADS, 1) mab_apply4_tc_kernel(const __gr
                         const int row = 32 * rr + lane;
                         const int n = (tile0 + it) * 128 + row;
                         float x[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (n < nb) {
-                            const float* xp = P.X32 + ((size_t)cloud * P.N + n) * P.d_in;
-                            for (int k = 0; k < P.d_in; ++k) x[k] = __ldg(xp + k);
-                        }
+                        if (n < nb) load_point(P.X32, P.src, P.N, P.d_in, (size_t)cloud, n, x);
                         float cols[16];
                         split_x16(x, cols);
                         cols[12] = 1.f;
@@ -2940,6 +2960,7 @@ struct ATailParams {
     const float* WoT;             // fc_o^T k-major (64, 64)
     const float* bo;
     __nv_bfloat16* Yout;          // (B, N, 64)
+    PointSrc src;                 // [dq <= 4] alternative to X32
 };
 // 16-byte read-only load that does not allocate in L1: the K / V rows are streamed once, the fc_q / fc_o weights that
 // every block of the SM re-reads stay resident
@@ -2966,8 +2987,13 @@ __global__ void __launch_bounds__(64, 16) mab_apply_tail_kernel(const ATailParam
         krow[i] = ldg_stream16(kimg + (size_t)(8 * part + i) * 16);
         vrow[i] = ldg_stream16(vimg + (size_t)(8 * part + i) * 16);
     }
-    if (P.X32 != nullptr) { if (f < P.dq) sX[f] = __ldg(P.X32 + rowi * P.dq + f); }
-    else sX[f] = __bfloat162float(P.Y16in[rowi * 64 + f]);
+    if (P.Y16in == nullptr) {
+        if (f == 0) {
+            float xr[4] = {0.f, 0.f, 0.f, 0.f};
+            load_point(P.X32, P.src, P.N, P.dq, (size_t)cloud, n0 + j, xr);
+            for (int k = 0; k < P.dq; ++k) sX[k] = xr[k];
+        }
+    } else sX[f] = __bfloat162float(P.Y16in[rowi * 64 + f]);
     __syncthreads();
     // the kernel is bound by l1tex instructions (weight loads + broadcast reads of the staged row): the row is read as
     // float4, same products in the same order
@@ -3756,7 +3782,7 @@ int st_tc_supported(const pca_st_dims* d, int N) {
 
 struct TcDebug { float *H1, *Y1, *H2, *Y2, *pooled; };
 
-static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pca_st_dims* d, const float* params,
+static int st_tc_chunk(const float* X, const PointSrc& src, const int* counts, int B, int N, const pca_st_dims* d, const float* params,
                        float* logits, uint8_t* ws, const TcConsts* c, const TcDebug* dbg, cudaStream_t st) {
     const TcLayout L = tc_layout(B, N);
     const TcSplit sp = plan_split(B, N);
@@ -3797,6 +3823,7 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
             PCA_CHECK_CUDA(cudaMemsetAsync(redo, 0, (size_t)n_work * sizeof(int), st));
             R6Params r6{X, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Gq0s, nullptr, m00.Wkv + (size_t)TD * d_in,
                         m00.bkv + TD, r.timeline, redo, part, CUtensorMap{}};
+            r6.src = src;
             mab_reduce6_tc_kernel<false, false><<<pgrid, R6_THREADS, R6Smem::TOTAL, st>>>(r6);
             r6.timeline = nullptr;
             mab_reduce6_tc_kernel<false, true><<<pgrid, R6_THREADS, R6Smem::TOTAL, st>>>(r6);      // exact redo of flagged work items
@@ -3817,6 +3844,8 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     {
         F2Params f{part, 2 * sp.nsplit, B, c->Qp0, c->WoS[0][0], m00.bo, c->WkvS[0][0], m01.bkv, kvblk, dbg ? dbg->H1 : nullptr,
                    X, nullptr, N, d_in, counts, tm, c->Wkv0T[0], m00.bkv};
+        f.src = src;
+        
         LaunchTimer lt("finalize_isab_kernel", st, (double)B * 2.0 * (TM * TD * TD + TM * TD * 2 * TD), (double)B * 32768.0);
         finalize_isab_tc_kernel<<<fgrid, 128, F2Smem::TOTAL, st>>>(f);
     }
@@ -3824,6 +3853,7 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     {
         AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, kvblk, m01.Wq, m01.bq,
                   g_apply_variant == 4 ? c->WqS0e : c->WqS0, g_apply_variant == 4 ? c->Wo0e : c->Wo0, m01.bo, Y1, tl_apply ? g_timeline : nullptr};
+        a.src = src;
         if (g_apply_variant == 4) PCA_TRY(make_tmap_2d_bf16(&a.tmapYo, Y1, 64, (unsigned long long)B * N, 128, 8, 128));
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * d_in * TD + 2.0 * TM * TD + TD * TD), pts * (4.0 * d_in + 128.0));
         if (g_apply_variant == 4) mab_apply4_tc_kernel<false><<<pgrid, A4_THREADS, A4Smem::TOTAL, st>>>(a);
@@ -3832,6 +3862,7 @@ static int st_tc_chunk(const float* X, const int* counts, int B, int N, const pc
     PCA_CHECK_LAUNCH("mab_apply_tc_kernel<small>");
     if (has_tail) {
         ATailParams t{X, nullptr, N, d_in, counts, tm, kvblk, c->Wq1T[0], m01.bq, c->Wo1T[0], m01.bo, Y1};
+        t.src = src;
         LaunchTimer lt("mab_apply_tail_kernel", st, 0.0, 0.0);
         mab_apply_tail_kernel<<<tgrid, 64, 0, st>>>(t);
         PCA_CHECK_LAUNCH("mab_apply_tail_kernel");
@@ -3943,8 +3974,11 @@ static int tc_configure() {
     return 0;
 }
 
+// the kernels that read the clouds straight from the front end's log-magnitudes are the current generations only
+int st_tc_accepts_logmag() { return g_apply_variant == 4 && g_reduce_wg == 6; }
+
 int st_tc_forward_dbg(const float* X, const int* counts, int B, int N, const pca_st_dims* d, const float* params, float* logits,
-                      void* ws, size_t ws_bytes, const TcDebug* dbg, cudaStream_t st) {
+                      void* ws, size_t ws_bytes, const TcDebug* dbg, cudaStream_t st, const PointSrc* psrc = nullptr) {
     PCA_TRY(tc_configure());
     const size_t one = tc_layout(1, N).total;
     if (!ws || ws_bytes < one) return fail(PCA_EWORKSPACE, "ST(bf16): workspace %zu B < minimum %zu B", ws_bytes, one);
@@ -3959,7 +3993,12 @@ int st_tc_forward_dbg(const float* X, const int* counts, int B, int N, const pca
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int bc = (B - b0) < chunk ? (B - b0) : chunk;
         // the layout of a smaller last chunk fits inside the layout of `chunk` (same consts offset 0)
-        PCA_TRY(st_tc_chunk(X + (size_t)b0 * N * d->d_in, counts ? counts + b0 : nullptr, bc, N, d, params,
+        PointSrc src{nullptr, nullptr, nullptr, 1};
+        if (psrc != nullptr) {
+            src = *psrc;
+            src.logmag += (size_t)b0 * N;
+        }
+        PCA_TRY(st_tc_chunk(X ? X + (size_t)b0 * N * d->d_in : nullptr, src, counts ? counts + b0 : nullptr, bc, N, d, params,
                             logits + (size_t)b0 * d->C, w8, c, dbg, st));
     }
     return 0;
@@ -3968,6 +4007,17 @@ int st_tc_forward_dbg(const float* X, const int* counts, int B, int N, const pca
 int st_tc_forward(const float* X, const int* counts, int B, int N, const pca_st_dims* d, const float* params, float* logits,
                   void* ws, size_t ws_bytes, cudaStream_t st) {
     return st_tc_forward_dbg(X, counts, B, N, d, params, logits, ws, ws_bytes, nullptr, st);
+}
+
+// ST.forward on the clouds of the whole-path call without a selection step: cloud b, point n = t * nf + f is
+// (farr[f], [tarr[t],] logmag[b][n]); no (B, N, d_in) tensor exists
+int st_tc_forward_logmag(const float* logmag, const float* farr, const float* tarr, int nf, int B, int N, const pca_st_dims* d,
+                         const float* params, float* logits, void* ws, size_t ws_bytes, cudaStream_t st) {
+    PCA_TRY(tc_configure());
+    if (!st_tc_accepts_logmag()) return fail(PCA_EUNSUPPORTED, "ST(bf16) from log-magnitudes: needs the current kernel generations");
+    if (nf <= 0 || N % nf != 0) return fail(PCA_EINVAL, "ST(bf16) from log-magnitudes: N=%d is not a multiple of nf=%d", N, nf);
+    const PointSrc src{logmag, farr, tarr, nf};
+    return st_tc_forward_dbg(nullptr, nullptr, B, N, d, params, logits, ws, ws_bytes, nullptr, st, &src);
 }
 
 int st_tc_forward_stages(const float* X, int B, int N, const pca_st_dims* d, const float* params, float* logits,

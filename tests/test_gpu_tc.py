@@ -254,3 +254,33 @@ def test_tc_transposed_pooled_attention_variant(pca, d_in, B, N):
     for k, v in errs.items():
         assert v < BF16_REL_TOL, f"stage {k}: rel err {v:.3e} (all: {errs})"
     assert ((masked2 - masked1).abs().max() / masked1.abs().max()).item() < BF16_REL_TOL
+
+
+@pytest.mark.parametrize("mode,d_in,tag,n_fft,ntemp,L", [(2, 2, "fst", 2048, 10, 16000), (3, 3, "3st", 1024, 10, 16000), (3, 3, "3st", 256, 7, 5000)])
+def test_pipeline_reads_clouds_from_logmag_bit_identically(pca, mode, d_in, tag, n_fft, ntemp, L):
+    """The whole-path call without a selection step feeds the encoder straight from the front end's log-magnitudes (the loader
+    warps of the reduce / apply kernels synthesise (f, [t,] mag); build_clouds_kernel does not run).  The logits must be
+    bit-identical to the route through materialised clouds (PCA_BUILD_CLOUDS=1), and the launch count must drop by one."""
+    from pcaudio_b200 import _lib
+    from oracle import pcaudio_oracle as orc
+    dev = torch.device("cuda:0")
+    w = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, f"{tag}_weights.npz")).items()}
+    st = pca.ST(dim_input=d_in, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev)
+    st.load_state_dict(w)
+    cfg = pca.AudioConfig(sampling_rate=16000, window_size=n_fft, n_samples=L, mode=mode, Ntemp=ntemp, precision="bf16")
+    pipe = pca.AudioSetPipeline(st, cfg, dev)
+    audio = torch.from_numpy(orc.synth_audio(5, L, 16000, seed=31)).to(dev)
+    os.environ.pop("PCA_BUILD_CLOUDS", None)
+    pipe(audio)
+    n0 = _lib.launch_count()
+    fused = pipe(audio).clone()
+    n_fused = _lib.launch_count() - n0
+    os.environ["PCA_BUILD_CLOUDS"] = "1"
+    try:
+        n0 = _lib.launch_count()
+        plain = pipe(audio).clone()
+        n_plain = _lib.launch_count() - n0
+    finally:
+        os.environ.pop("PCA_BUILD_CLOUDS", None)
+    assert torch.isfinite(fused).all() and torch.equal(fused, plain)
+    assert n_fused == n_plain - 1
