@@ -242,6 +242,15 @@ int pca_st_train_bwd_f32(const float* X, const int32_t* counts, int B, int N, co
                          float dropout_p, unsigned long long seed, const float* dlogits, const void* saved,
                          size_t saved_bytes, float* dparams, float* dX, void* workspace, size_t workspace_bytes,
                          void* stream);
+/* The same backward in two phases, for data-parallel training (replaces the reduce_add of nn.DataParallel,
+ * set_transformer-master/main_pointcloud.py:65): phase 1 differentiates the final Linear, the PMA and ISAB 1, after which
+ * dparams[*tail_offset ..) is final and its all-reduce can start; phase 2 differentiates ISAB 0 (dparams[.. *tail_offset),
+ * dX) from the workspace phase 1 left behind (same workspace, untouched in between).  phase 0 = pca_st_train_bwd_f32.
+ * tail_offset (host pointer, may be NULL) receives the float index where the tail begins. */
+int pca_st_train_bwd_phase_f32(const float* X, const int32_t* counts, int B, int N, const pca_st_dims* dims, const float* params,
+                               float dropout_p, unsigned long long seed, const float* dlogits, const void* saved,
+                               size_t saved_bytes, float* dparams, float* dX, void* workspace, size_t workspace_bytes,
+                               int phase, long long* tail_offset, void* stream);
 
 /* Stand-alone MAB training (modules.py:6-33, LayerNorm branches included) for models composed from the blocks on the host (SAB = MAB(X, X),
  * ISAB = mab1(X, mab0(I, X)), PMA = MAB(S, X)): Q (q_batch, nq, dq) with q_batch in {1, B} (1 = shared queries: dQ is summed

@@ -60,6 +60,8 @@ PROTOTYPES = {
     "pca_st_fwd": (_I, [_P, _I, _I, C.POINTER(StDims), _P, _P, _P, _SZ, _I, _P]),
     "pca_deepset_workspace_bytes": (_SZ, [_I] * 5),
     "pca_deepset_fwd_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),
+    "pca_st_train_bwd_phase_f32": (_I, [_P, _P, _I, _I, C.POINTER(StDims), _P, _F, C.c_ulonglong, _P, _P, _SZ, _P, _P, _P, _SZ, _I,
+                                        C.POINTER(C.c_longlong), _P]),
     "pca_linear_bwd_f32": (_I, [_P, _P, C.c_longlong, _I, _I, _P, _P, _P, _P]),
     "pca_dropout_f32": (_I, [_P, _P, C.c_longlong, _F, C.c_ulonglong, _P]),
     "pca_linear_fwd_f32": (_I, [_P, C.c_longlong, _I, _I, _P, _P, _P]),

@@ -30,7 +30,7 @@ size_t st_train_ws_bytes(const pca_st_dims* d, int B, int N);
 int st_train_forward(const float*, const int*, int, int, const pca_st_dims*, const float*, float, unsigned long long, float*, void*, size_t,
                      void*, size_t, cudaStream_t);
 int st_train_backward(const float*, const int*, int, int, const pca_st_dims*, const float*, float, unsigned long long, const float*,
-                      const void*, size_t, float*, float*, void*, size_t, cudaStream_t);
+                      const void*, size_t, float*, float*, void*, size_t, cudaStream_t, int phase = 0, long long* tail_offset = nullptr);
 size_t mab_train_saved_bytes(int B, int qb, int nq, int nk, int D, int H, int ln);
 size_t mab_train_ws_bytes(int B, int qb, int nq, int nk, int D, int H, int ln);
 int mab_train_forward_api(const float*, int, const float*, int, int, int, int, int, int, int, int, const float*, float*, void*, size_t,
@@ -756,6 +756,13 @@ int pca_st_train_bwd_f32(const float* X, const int32_t* counts, int B, int N, co
                          float* dparams, float* dX, void* workspace, size_t workspace_bytes, void* stream) {
     return st_train_backward(X, counts, B, N, dims, params, dropout_p, seed, dlogits, saved, saved_bytes, dparams, dX, workspace,
                              workspace_bytes, (cudaStream_t)stream);
+}
+int pca_st_train_bwd_phase_f32(const float* X, const int32_t* counts, int B, int N, const pca_st_dims* dims, const float* params,
+                               float dropout_p, unsigned long long seed, const float* dlogits, const void* saved, size_t saved_bytes,
+                               float* dparams, float* dX, void* workspace, size_t workspace_bytes, int phase, long long* tail_offset,
+                               void* stream) {
+    return st_train_backward(X, counts, B, N, dims, params, dropout_p, seed, dlogits, saved, saved_bytes, dparams, dX, workspace,
+                             workspace_bytes, (cudaStream_t)stream, phase, tail_offset);
 }
 size_t pca_mab_train_saved_bytes(int B, int q_batch, int nq, int nk, int D, int H, int ln) {
     return (B > 0 && nq > 0 && nk > 0 && D > 0 && H > 0) ? mab_train_saved_bytes(B, q_batch, nq, nk, D, H, ln) : 0;

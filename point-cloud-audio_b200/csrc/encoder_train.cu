@@ -889,9 +889,12 @@ int st_train_forward(const float* X, const int* counts, int B, int N, const pca_
     return 0;
 }
 
+// phase 0: the whole backward.  phase 1: final Linear, PMA and ISAB 1 -- everything whose parameter gradients sit in the TAIL
+// of the flat blob, dparams[*tail_offset ..); phase 2: ISAB 0 (the head of the blob), continuing from the workspace phase 1
+// left behind.  The split lets the caller start the gradient all-reduce of the tail while ISAB 0 is still differentiating.
 int st_train_backward(const float* X, const int* counts, int B, int N, const pca_st_dims* d, const float* params, float dropout_p,
                       unsigned long long seed, const float* dlogits, const void* saved, size_t saved_bytes, float* dparams,
-                      float* dX, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      float* dX, void* ws, size_t ws_bytes, cudaStream_t st, int phase = 0, long long* tail_offset = nullptr) {
     PCA_TRY(train_check(d, B, N, dropout_p));
     if (!X || !params || !dlogits || !saved || !dparams || !ws) return fail(PCA_EINVAL, "ST training backward: null pointer");
     Arena sa(const_cast<void*>(saved), saved_bytes);
@@ -908,9 +911,12 @@ int st_train_backward(const float* X, const int* counts, int B, int N, const pca
     if (!a.ok() || ws_bytes < st_train_ws_bytes(d, B, N)) return fail(PCA_EWORKSPACE, "ST training backward: workspace too small");
     void* sub = (char*)ws + a.off;
     const size_t sub_bytes = ws_bytes - a.off;
+    if (tail_offset != nullptr) *tail_offset = o.I1;
+    if (phase < 0 || phase > 2) return fail(PCA_EINVAL, "ST training backward: phase %d outside {0, 1, 2}", phase);
+    const long long rp = (long long)B * S;
+    if (phase != 2) {
     PCA_CHECK_CUDA(cudaMemsetAsync(dparams, 0, (size_t)o.total * sizeof(float), st));
     // final Linear
-    const long long rp = (long long)B * S;
     PCA_TRY(launch_grad_weight(dlogits, s.Pd, dparams + o.Wl, rp, D, C, st));
     PCA_TRY(launch_colsum(dlogits, rp, C, dparams + o.bl, st));
     PCA_TRY(launch_grad_input(dlogits, params + o.Wl, gP, nullptr, rp, D, C, st));
@@ -925,6 +931,8 @@ int st_train_backward(const float* X, const int* counts, int B, int N, const pca
                          sub, sub_bytes, st));
     PCA_TRY(mab_backward(s.i1m0, params + o.I1, 1, s.i0m1.out, B, M, N, D, D, D, H, params + o.i1m0, dparams + o.i1m0, gH,
                          dparams + o.I1, 0, gB, 1, sub, sub_bytes, st, counts));
+    }
+    if (phase == 1) return 0;
     // ISAB 0: Y1 = mab1(X, H1), H1 = mab0(I0, X)
     PCA_TRY(mab_backward(s.i0m1, X, B, s.i0m0.out, B, N, M, din, D, D, H, params + o.i0m1, dparams + o.i0m1, gB, dX, 0, gH, 0,
                          sub, sub_bytes, st));

@@ -217,14 +217,22 @@ class DeepSetTrainFunction(torch.autograd.Function):
 class SetTrainer:
     """Fused data-parallel training step for ``ST`` / ``SetTransformer`` (one process per GPU).
 
-    ``step(X, labels)`` enqueues forward + cross-entropy + backward + (world > 1) one NCCL allreduce of the flat fp32
-    gradient buffer + fused Adam on the caller's current stream and returns ``(loss, correct)`` as device tensors
+    ``step(X, labels)`` enqueues forward + cross-entropy + backward + (world > 1) the NCCL all-reduce of the flat fp32
+    gradient buffer (in two pieces: the tail of the blob -- ISAB 1, PMA, Linear -- is reduced on a side stream while ISAB 0
+    is still differentiated, the head right after) + fused Adam on the caller's current stream and returns
+    ``(loss, correct)`` as device tensors
     (mean loss of the local batch, number of correct arg-max predictions) without synchronising.
     Hyper-parameters follow torch.optim.Adam as the reference uses it (lr 1e-3; weight_decay 1e-3 for the audio models,
     Code/settransformer.py:90-91)."""
 
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None, seed=0):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None, seed=0,
+                 overlap_allreduce=None):
         self.model = model
+        if overlap_allreduce is None:                         # experiments: PCA_TRAIN_OVERLAP=0 switches the overlap off
+            import os
+            overlap_allreduce = os.environ.get("PCA_TRAIN_OVERLAP", "1") != "0"
+        self.overlap_allreduce = bool(overlap_allreduce)      # world > 1: all-reduce the blob's tail under ISAB 0's backward
+        self._comm_stream = None
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -273,10 +281,32 @@ class SetTrainer:
                                               _lib.ptr(saved), saved.numel(), _lib.ptr(ws), ws.numel(), st), "st_train_fwd")
             _lib.check(L.pca_cross_entropy_f32(_lib.ptr(logits), _lib.ptr(labels), B, dims.C, C.c_void_p(stats.data_ptr()),
                                                C.c_void_p(stats.data_ptr() + 4), _lib.ptr(dlogits), st), "cross_entropy")
-            _lib.check(L.pca_st_train_bwd_f32(_lib.ptr(X), _lib.ptr(counts), B, N, C.byref(dims), _lib.ptr(self.flat), p, seed, _lib.ptr(dlogits),
-                                              _lib.ptr(saved), saved.numel(), _lib.ptr(self.grads), None, _lib.ptr(ws), ws.numel(),
-                                              st), "st_train_bwd")
-            grad_scale = reduce_flat_gradient_(self.grads, self.group)
+            world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+            if world > 1 and self.overlap_allreduce:
+                # backward in two phases: the all-reduce of the blob's tail (ISAB 1, PMA, Linear gradients: final after phase
+                # 1) runs on a side stream while ISAB 0 is differentiated; the head follows on the main stream
+                off = C.c_longlong(0)
+                bwd = lambda phase: _lib.check(L.pca_st_train_bwd_phase_f32(
+                    _lib.ptr(X), _lib.ptr(counts), B, N, C.byref(dims), _lib.ptr(self.flat), p, seed, _lib.ptr(dlogits), _lib.ptr(saved),
+                    saved.numel(), _lib.ptr(self.grads), None, _lib.ptr(ws), ws.numel(), phase, C.byref(off), st), "st_train_bwd")
+                bwd(1)
+                main = torch.cuda.current_stream(dev)
+                if self._comm_stream is None:
+                    self._comm_stream = torch.cuda.Stream(device=dev)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(self._comm_stream):
+                    self._comm_stream.wait_event(ev)
+                    dist.all_reduce(self.grads[off.value:], op=dist.ReduceOp.SUM, group=self.group)
+                bwd(2)
+                dist.all_reduce(self.grads[:off.value], op=dist.ReduceOp.SUM, group=self.group)
+                main.wait_stream(self._comm_stream)
+                grad_scale = 1.0 / world
+            else:
+                _lib.check(L.pca_st_train_bwd_f32(_lib.ptr(X), _lib.ptr(counts), B, N, C.byref(dims), _lib.ptr(self.flat), p, seed,
+                                                  _lib.ptr(dlogits), _lib.ptr(saved), saved.numel(), _lib.ptr(self.grads), None, _lib.ptr(ws),
+                                                  ws.numel(), st), "st_train_bwd")
+                grad_scale = reduce_flat_gradient_(self.grads, self.group)
             _lib.check(L.pca_adam_step_f32(_lib.ptr(self.flat), _lib.ptr(self.grads), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                                            self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                            self.t, grad_scale, st), "adam_step")
