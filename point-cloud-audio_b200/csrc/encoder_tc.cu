@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(128) finalize_isab_tc_kernel(const F2Params P)
         // ---- merge the point splits / column halves (+ the tail slot): O = Qp + A V
         if (valid) {
             const size_t sstride = (size_t)TH * 10 * TM;
-            const bool two = P.nslots == 2;
+            const bool two = P.nslots == 2, one = P.nslots == 1;
 #pragma unroll
             for (int hb = 0; hb < TH; hb += 4) {
             // two-slot case (the usual one): the partials of four heads are fetched together, 80 loads in flight per
@@ -513,6 +513,13 @@ __global__ void __launch_bounds__(128) finalize_isab_tc_kernel(const F2Params P)
                     const float* pq = P.part + (((size_t)cloud * 2) * TH + hb + hh) * 10 * TM + m;
 #pragma unroll
                     for (int j = 0; j < 10; ++j) { w0[hh][j] = __ldg(pq + j * TM); w1[hh][j] = __ldg(pq + sstride + j * TM); }
+                }
+            } else if (one) {      // reduce6: one partial per cloud (clouds of up to 2048 points), nothing to merge but the tail slot
+#pragma unroll
+                for (int hh = 0; hh < 4; ++hh) {
+                    const float* pq = P.part + ((size_t)cloud * TH + hb + hh) * 10 * TM + m;
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) w0[hh][j] = __ldg(pq + j * TM);
                 }
             }
 #pragma unroll
@@ -528,6 +535,12 @@ __global__ void __launch_bounds__(128) finalize_isab_tc_kernel(const F2Params P)
                     l = fmaf(v0[1], w0, v1[1] * w1);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) a[j] = fmaf(v0[2 + j], w0, v1[2 + j] * w1);
+                } else if (one) {
+                    const float* v0 = w0[hh];
+                    mmax = v0[0];
+                    l = v0[1];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = v0[2 + j];
                 } else {
                     mmax = -INFINITY;
                     for (int sl = 0; sl < P.nslots; ++sl) mmax = fmaxf(mmax, __ldg(pp + sl * sstride));
@@ -1320,8 +1333,7 @@ __global__ void __launch_bounds__((4 * NWG + 12) * 32, 1) mab_reduce5_tc_kernel(
 //     issuing thread, in-order tensor pipe) implies that P V of the previous item has drained the probability buffer.
 //   * Thread-side mbarrier arrivals by every lane (count 128); a loader warp feeds a three-deep tile ring by TMA.
 // 28 warps: 0-15 softmax (warpgroup g = pair g), 16-19 V producers, 20-23 MMA chains, 24 loader, 25-27 idle.
-// Partials: slot 2 * split holds the result, slot 2 * split + 1 is written empty (m = -inf): the finalize kernels see the
-// layout they always had.
+// Partials: ONE slot per (cloud, split) -- part (B, nsplit, 8, 10, 64); the finalize kernel is told the slot count.
 // EXACT = true is the redo pass over the work items the streaming pass flagged (a row outgrew its reference exponent; normally
 // none): same operands and arithmetic, but every item keeps its scores in TMEM until the row has been re-referenced if needed
 // (accumulator and running sum rescaled in place -- all earlier P V of the chain have completed by then), so no early
@@ -1350,7 +1362,7 @@ struct R6Params {
     const float* bv;              // (64)                                   [DIN64 == false]
     long long* timeline;
     int* redo;                    // (n_work) flags: set by the streaming pass, consumed by the EXACT pass
-    float* part;                  // (B, 2 nsplit, 8, 10, 64)
+    float* part;                  // (B, nsplit, 8, 10, 64)
     CUtensorMap tmapY;            // [DIN64] the input as a (B * N, 64) bf16 tensor, box 128 rows x 8 elements
     PointSrc src;                 // [DIN64 == false] alternative to X32
 };
@@ -1837,17 +1849,11 @@ __global__ void __launch_bounds__(R6_THREADS, 1) mab_reduce6_tc_kernel(const __g
                     tmem_ld_wait();
                 }
                 const int h = 2 * g + (row >> 6);
-                float* dst = P.part + (((size_t)cloud * (2 * P.nsplit) + 2 * split) * TH + h) * 10 * TM + (row & 63);
-                float* dst1 = dst + (size_t)TH * 10 * TM;               // the second (empty) slot of the split
+                float* dst = P.part + (((size_t)cloud * P.nsplit + split) * TH + h) * 10 * TM + (row & 63);
                 dst[0] = m_used;
                 dst[TM] = l_run;
-                dst1[0] = -INFINITY;
-                dst1[TM] = 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    dst[(2 + j) * TM] = (l_run > 0.f) ? __uint_as_float(o[j]) : 0.f;
-                    dst1[(2 + j) * TM] = 0.f;
-                }
+                for (int j = 0; j < 8; ++j) dst[(2 + j) * TM] = (l_run > 0.f) ? __uint_as_float(o[j]) : 0.f;
             }
             fence_before_sync();
         }
@@ -3122,8 +3128,8 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
     copy_to_smem(sAq, P.Aq, 16384);
     if (warp == 12) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < POOL_STAGES; ++i) { mbar_init(&y_full[i], 4); mbar_init(&y_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); }
+        for (int i = 0; i < POOL_STAGES; ++i) { mbar_init(&y_full[i], 128); mbar_init(&y_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&o_full[i], 1); }
         fence_barrier_init();
     }
     fence_async_smem();
@@ -3196,7 +3202,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
                 for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + c * 2048 + row * 16) = yv[c];
                 fence_async_smem();
                 fence_before_sync();
-                warp_arrive(&y_full[stage]);
+                mbar_arrive(&y_full[stage]);
             }
         }
     } else {
@@ -3273,7 +3279,7 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
                 m_run = m_new;
                 tmem_st_wait();
                 fence_before_sync();
-                warp_arrive(&p_ready[g]);
+                mbar_arrive(&p_ready[g]);        // every lane arrives (count 128)
                 // ---- Z += P Y (rescaled running sum in registers)
                 mbar_wait(&o_full[g], ph_o);
                 ph_o ^= 1;
@@ -3842,7 +3848,7 @@ static int st_tc_chunk(const float* X, const PointSrc& src, const int* counts, i
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<small>");
     {
-        F2Params f{part, 2 * sp.nsplit, B, c->Qp0, c->WoS[0][0], m00.bo, c->WkvS[0][0], m01.bkv, kvblk, dbg ? dbg->H1 : nullptr,
+        F2Params f{part, (g_reduce_wg == 6 ? 1 : 2) * sp.nsplit, B, c->Qp0, c->WoS[0][0], m00.bo, c->WkvS[0][0], m01.bkv, kvblk, dbg ? dbg->H1 : nullptr,
                    X, nullptr, N, d_in, counts, tm, c->Wkv0T[0], m00.bkv};
         f.src = src;
         
@@ -3894,7 +3900,7 @@ static int st_tc_chunk(const float* X, const PointSrc& src, const int* counts, i
     }
     PCA_CHECK_LAUNCH("mab_reduce_tc_kernel<64>");
     {
-        F2Params f{part, 2 * sp.nsplit, B, c->Qp1, c->WoS[1][0], m10.bo, c->WkvS[1][0], m11.bkv, kvblk, dbg ? dbg->H2 : nullptr,
+        F2Params f{part, (g_reduce_wg == 6 ? 1 : 2) * sp.nsplit, B, c->Qp1, c->WoS[1][0], m10.bo, c->WkvS[1][0], m11.bkv, kvblk, dbg ? dbg->H2 : nullptr,
                    nullptr, Y1, N, TD, counts, tm, c->Wkv0T[1], m10.bkv};
         LaunchTimer lt("finalize_isab_kernel", st, (double)B * 2.0 * (TM * TD * TD + TM * TD * 2 * TD), (double)B * 32768.0);
         finalize_isab_tc_kernel<<<fgrid, 128, F2Smem::TOTAL, st>>>(f);
