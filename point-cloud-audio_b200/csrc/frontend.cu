@@ -224,6 +224,7 @@ __device__ __forceinline__ uint32_t ordered_key(float x) {
 }
 
 constexpr int TOPK_THREADS = 512;
+constexpr int TOPK_CAND = 1024;        // shared candidate list of the register-key kernel's later radix passes
 
 // Selection of one cloud by the whole block (TOPK_THREADS threads).  keys: the cloud's N keys, in global memory
 // (SMEM_KEYS == false, read through the read-only path) or already in shared memory (fused front end).
@@ -446,15 +447,95 @@ topk_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __re
 
 // ------------------------------------------------------------------------------------ top-K, keys in registers
 // Clouds of up to 512 * KPT points: thread t owns the KPT CONSECUTIVE flat indices [t KPT, (t+1) KPT), as order-preserving
-// uint keys in registers.  The same selection rule as topk_core, but every pass is register-only:
-//   * 4-pass 8-bit radix select with warp-private shared-memory histograms (plain shared atomics; after the first byte
-//     the digits of log-magnitudes are well spread),
+// uint keys in registers.  Same selection rule as topk_core (bit-identical results), organised so that the per-key work is
+// a handful of register instructions (ncu of the previous version: 95 instructions per key, issue-bound):
+//   * the select runs on u = (o - omin) << clz(omax - omin), an order- and tie-preserving map of the cloud's key range onto
+//     the full 32 bits: log-magnitudes share sign and exponent, the normalised top byte follows the value distribution;
+//   * ONE histogram pass over the registers (warp-private shared histograms) fixes the first digit D of the K-th key;
+//     keys above D are selected outright, the few keys IN D go to a shared candidate list on which the remaining three
+//     digits are resolved (register passes remain as the fallback when more than TOPK_CAND keys share D);
 //   * selection flags as two 32-bit masks per thread, ONE block-wide exclusive scan of the per-thread counts gives every
-//     selected point its position in flat-index order (ties at the K boundary keep the lowest indices),
-//   * the K survivors are sorted in shared memory on (~key, index) for the descending emission order.
-// ~6x fewer instructions than the global-memory version (which ncu shows issue-bound at IPC 3.4).
+//     selected point its position in flat-index order (ties at the K boundary keep the lowest indices);
+//   * the K survivors are sorted on (~key, index) for the descending emission order: bitonic network with the elements in
+//     registers, partner exchange by shuffles (distance < 32), shared memory (< 512) or in-thread (>= 512).
+__device__ __forceinline__ uint32_t ordered_key_fast(float x) {
+    const uint32_t u = __float_as_uint(x + 0.0f);       // -0.0 + 0.0 = +0.0 (ties with +0.0); every other value unchanged
+    return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+
+constexpr int TOPK_SORT_E = 4;         // elements per thread of the register sort: K <= 2048
+
+// Bitonic sort of kp = NE * 512 (or, for NE == 1, kp <= 512) 64-bit elements held NE per thread: element x = tid + 512 e
+// lives in v[e].  Partner exchange by warp shuffles (distance < 32), through shared memory (< 512; barrier 1 counts the kp
+// participating threads -- for kp < 512 the other warps have left) or inside the thread (>= 512).  Emits element r < K
+// through emit(r, low 32 bits).
+template <int NE, class Emit>
+__device__ __forceinline__ void sort_regs(unsigned long long* sortbuf, int kpad, int kp, int K, int tid, Emit emit) {
+    const int nthr = min(kp, TOPK_THREADS);
+    uint32_t hi[NE], lo[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const int x = tid + TOPK_THREADS * e;
+        const unsigned long long v = (x < kpad) ? sortbuf[x] : ~0ull;
+        hi[e] = (uint32_t)(v >> 32); lo[e] = (uint32_t)v;
+    }
+    // keep the smaller (keep_min) or the larger of (hi, lo)[e] and the partner's (ph, pl)
+    auto cx = [&](int e, uint32_t ph, uint32_t pl, bool keep_min) {
+        const bool p_less = (ph < hi[e]) || (ph == hi[e] && pl < lo[e]);
+        if (p_less == keep_min) { hi[e] = ph; lo[e] = pl; }
+    };
+    for (int k2 = 2; k2 <= kp; k2 <<= 1) {
+        int j = k2 >> 1;
+        if (NE > 1) {
+            for (; j >= TOPK_THREADS; j >>= 1) {                   // partner in the same thread: e ^ (j / 512)
+                const int je = j / TOPK_THREADS;
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    if (e & je) continue;
+                    const bool asc = (((tid + TOPK_THREADS * e) & k2) == 0);
+#pragma unroll
+                    for (int f = 0; f < NE; ++f) {
+                        if (f != (e | je) || f == e) continue;     // (static after unrolling: je is 1 or 2)
+                        const uint32_t ah = hi[e], al = lo[e];
+                        cx(e, hi[f], lo[f], asc);
+                        cx(f, ah, al, !asc);
+                    }
+                }
+            }
+        }
+        for (; j >= 32; j >>= 1) {                                 // partner in another warp
+            asm volatile("bar.sync 1, %0;" :: "r"(nthr) : "memory");
+#pragma unroll
+            for (int e = 0; e < NE; ++e)
+                sortbuf[tid + TOPK_THREADS * e] = ((unsigned long long)hi[e] << 32) | lo[e];
+            asm volatile("bar.sync 1, %0;" :: "r"(nthr) : "memory");
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const int x = tid + TOPK_THREADS * e;
+                const unsigned long long p = sortbuf[(tid ^ j) + TOPK_THREADS * e];
+                cx(e, (uint32_t)(p >> 32), (uint32_t)p, ((x & k2) == 0) == ((x & j) == 0));
+            }
+        }
+#pragma unroll
+        for (int jj = 16; jj > 0; jj >>= 1) {                      // partner in the same warp
+            if (jj > j) continue;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const int x = tid + TOPK_THREADS * e;
+                const uint32_t ph = __shfl_xor_sync(0xffffffffu, hi[e], jj), pl = __shfl_xor_sync(0xffffffffu, lo[e], jj);
+                cx(e, ph, pl, ((x & k2) == 0) == ((x & jj) == 0));
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const int r = tid + TOPK_THREADS * e;
+        if (r < K) emit(r, (int)lo[e]);
+    }
+}
+
 template <int KPT>
-__global__ void __launch_bounds__(TOPK_THREADS)
+__global__ void __launch_bounds__(TOPK_THREADS, 2)
 topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* __restrict__ farr,
                 const float* __restrict__ tarr, int K, int kpad, int sorted, int use_tau, float tau,
                 float* __restrict__ pts_all, int32_t* __restrict__ idx_all, int32_t* __restrict__ counts) {
@@ -463,8 +544,9 @@ topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* 
     __shared__ int hist[NW][256];
     __shared__ int tot[256];
     __shared__ int warp_sum[NW];
-    __shared__ uint32_t s_prefix;
-    __shared__ int s_remaining;
+    __shared__ uint32_t s_prefix, s_lo[NW], s_hi[NW];
+    __shared__ int s_remaining, s_bin, s_ncand;
+    __shared__ uint32_t cand[TOPK_CAND];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int cloud = blockIdx.x;
@@ -475,32 +557,78 @@ topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* 
 
     const int i0 = tid * KPT;
     const int nval = max(0, min(KPT, N - i0));          // valid keys of this thread
-    uint32_t o[KPT];
+    const uint32_t valid = nval >= 32 ? 0xffffffffu : ((1u << nval) - 1u);
+    uint32_t o[KPT];                                    // slots past the cloud repeat its last key (neutral for min / max)
     if (nval == KPT && ((reinterpret_cast<size_t>(keys + i0) & 15) == 0)) {
 #pragma unroll
         for (int j = 0; j < KPT; j += 4) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(keys + i0 + j));
-            o[j] = ordered_key(v.x); o[j + 1] = ordered_key(v.y); o[j + 2] = ordered_key(v.z); o[j + 3] = ordered_key(v.w);
+            o[j] = ordered_key_fast(v.x); o[j + 1] = ordered_key_fast(v.y);
+            o[j + 2] = ordered_key_fast(v.z); o[j + 3] = ordered_key_fast(v.w);
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < KPT; ++j) o[j] = (j < nval) ? ordered_key(__ldg(keys + i0 + j)) : 0u;
+        for (int j = 0; j < KPT; ++j) o[j] = ordered_key_fast(__ldg(keys + min(i0 + j, N - 1)));
     }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) hist[wid][lane + 32 * b] = 0;
+    if (tid == 0) s_ncand = 0;
 
-    // ---- K-th largest key by radix select (skipped when every point is kept)
-    uint32_t kth = 0;
-    int n_ties_take = 0;
+    // digit holding the `remaining`-th largest of the candidates counted in tot[] (warp 0; lane l owns digits [8l, 8l+8))
+    auto pick_digit = [&](uint32_t prefix, int remaining, int shift) {
+        int c[8], tl = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = tot[lane * 8 + j]; tl += c[j]; }
+        int suf = tl;        // inclusive suffix sum over lanes >= lane
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            const int v = __shfl_down_sync(0xffffffffu, suf, o2);
+            if (lane + o2 < 32) suf += v;
+        }
+        const int above = suf - tl;   // candidates with a larger digit than this lane's
+        if (above < remaining && remaining <= above + tl) {
+            int cum = above;
+#pragma unroll
+            for (int j = 7; j >= 0; --j) {
+                if (cum < remaining && remaining <= cum + c[j]) {
+                    s_prefix = prefix | ((uint32_t)(lane * 8 + j) << shift);
+                    s_remaining = remaining - cum;
+                    s_bin = c[j];
+                }
+                cum += c[j];
+            }
+        }
+    };
+
+    // ---- K-th largest key (skipped when every point is kept)
+    uint32_t kth = 0, kth_u = 0, omin = 0;
+    uint32_t gt1 = 0, cm = 0;          // keys above / inside the first digit of the K-th key
+    int n_ties_take = 0, lz = 32, cand_at = -1;
     const bool all = (K >= N);
     if (!all) {
-        uint32_t prefix = 0, mask = 0;
-        int remaining = K;
-        for (int shift = 24; shift >= 0; shift -= 8) {
+        uint32_t lo = o[0], hi = o[0];
 #pragma unroll
-            for (int b = 0; b < 8; ++b) hist[wid][lane + 32 * b] = 0;
-            __syncwarp();
+        for (int j = 1; j < KPT; ++j) { lo = min(lo, o[j]); hi = max(hi, o[j]); }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) { s_lo[wid] = lo; s_hi[wid] = hi; }
+        __syncthreads();
 #pragma unroll
-            for (int j = 0; j < KPT; ++j)
-                if (j < nval && (o[j] & mask) == prefix) atomicAdd(&hist[wid][(o[j] >> shift) & 255u], 1);
+        for (int w = 0; w < NW; ++w) { lo = min(lo, s_lo[w]); hi = max(hi, s_hi[w]); }
+        omin = lo;
+        lz = (hi == lo) ? 32 : __clz(hi - lo);
+        kth = omin;
+        n_ties_take = K;
+        cm = valid;                    // lz == 32: all keys equal, the K lowest indices are kept
+        if (lz < 32) {
+            // first digit: one atomic per key into the warp's histogram
+            if (nval == KPT) {
+#pragma unroll
+                for (int j = 0; j < KPT; ++j) atomicAdd(&hist[wid][((o[j] - omin) << lz) >> 24], 1);
+            } else {
+#pragma unroll
+                for (int j = 0; j < KPT; ++j) if (j < nval) atomicAdd(&hist[wid][((o[j] - omin) << lz) >> 24], 1);
+            }
             __syncthreads();
             if (tid < 256) {
                 int t = 0;
@@ -509,52 +637,102 @@ topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* 
                 tot[tid] = t;
             }
             __syncthreads();
-            if (wid == 0) {
-                // lane l owns digits [8l, 8l+8); find the digit holding the `remaining`-th largest candidate
-                int c[8], tl = 0;
+            if (wid == 0) pick_digit(0u, K, 24);
+            __syncthreads();
+            uint32_t prefix = s_prefix, mask = 0xff000000u;
+            int remaining = s_remaining;
+            const int bin = s_bin;
+            const uint32_t top = prefix | 0x00ffffffu;
+            gt1 = 0; cm = 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { c[j] = tot[lane * 8 + j]; tl += c[j]; }
-                int suf = tl;        // inclusive suffix sum over lanes >= lane
-#pragma unroll
-                for (int o2 = 1; o2 < 32; o2 <<= 1) {
-                    const int v = __shfl_down_sync(0xffffffffu, suf, o2);
-                    if (lane + o2 < 32) suf += v;
-                }
-                const int above = suf - tl;   // candidates with a larger digit than this lane's
-                if (above < remaining && remaining <= above + tl) {
-                    int cum = above;
-#pragma unroll
-                    for (int j = 7; j >= 0; --j) {
-                        if (cum < remaining && remaining <= cum + c[j]) {
-                            s_prefix = prefix | ((uint32_t)(lane * 8 + j) << shift);
-                            s_remaining = remaining - cum;
-                        }
-                        cum += c[j];
+            for (int j = 0; j < KPT; ++j) {
+                const uint32_t u = (o[j] - omin) << lz;
+                gt1 |= (uint32_t)(u > top) << j;
+                cm |= (uint32_t)(u >= prefix) << j;
+            }
+            gt1 &= valid;
+            cm &= valid & ~gt1;
+            if (lz < 24) {                     // (digits below bit lz of u are all zero)
+                const bool listed = bin <= TOPK_CAND;
+                if (listed && cm) {
+                    // this thread's candidates, in index order, at cand[cand_at ...] (keys re-read through the read-only
+                    // path: a dynamic index into o[] would spill it, a static loop costs 5 instructions per key)
+                    cand_at = atomicAdd(&s_ncand, __popc(cm));
+                    int at = cand_at;
+                    uint32_t m = cm;
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        cand[at++] = (ordered_key_fast(__ldg(keys + i0 + j)) - omin) << lz;
                     }
                 }
+                for (int shift = 16; shift >= 0 && shift + 8 > lz; shift -= 8) {
+                    if (listed) {
+                        if (tid < 256) tot[tid] = 0;
+                        __syncthreads();                 // (also publishes the list before its first use)
+                        for (int c = tid; c < bin; c += TOPK_THREADS) {
+                            const uint32_t u = cand[c];
+                            if ((u & mask) == prefix) atomicAdd(&tot[(u >> shift) & 255u], 1);
+                        }
+                        __syncthreads();
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) hist[wid][lane + 32 * b] = 0;
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < KPT; ++j) {
+                            const uint32_t u = (o[j] - omin) << lz;
+                            if (((cm >> j) & 1u) && (u & mask) == prefix) atomicAdd(&hist[wid][(u >> shift) & 255u], 1);
+                        }
+                        __syncthreads();
+                        if (tid < 256) {
+                            int t = 0;
+#pragma unroll
+                            for (int w = 0; w < NW; ++w) t += hist[w][tid];
+                            tot[tid] = t;
+                        }
+                        __syncthreads();
+                    }
+                    if (wid == 0) pick_digit(prefix, remaining, shift);
+                    __syncthreads();
+                    prefix = s_prefix;
+                    remaining = s_remaining;
+                    mask |= 255u << shift;
+                }
             }
-            __syncthreads();
-            prefix = s_prefix;
-            remaining = s_remaining;
-            mask |= 255u << shift;
+            kth_u = prefix;
+            kth = (prefix >> lz) + omin;
+            n_ties_take = remaining;
         }
-        kth = prefix;
-        n_ties_take = remaining;
     }
     // Threshold mode: see topk_core
-    const uint32_t thr = use_tau ? ordered_key(tau) : 0u;
+    const uint32_t thr = use_tau ? ordered_key_fast(tau) : 0u;
     const bool tau_rules = use_tau && (all || thr > kth);
     if (tau_rules) n_ties_take = 0;
 
     // ---- selection flags and ONE block-wide exclusive scan of (greater, equal) counts
     uint32_t gtm = 0, eqm = 0;
+    if (all || tau_rules) {
+        if (tau_rules) {
 #pragma unroll
-    for (int j = 0; j < KPT; ++j) {
-        if (j < nval) {
-            const bool gt = tau_rules ? (o[j] >= thr) : (all || o[j] > kth);
-            const bool eq = !all && !tau_rules && (o[j] == kth);
-            gtm |= (uint32_t)gt << j;
-            eqm |= (uint32_t)eq << j;
+            for (int j = 0; j < KPT; ++j) gtm |= (uint32_t)(o[j] >= thr) << j;
+            gtm &= valid;
+        } else {
+            gtm = valid;
+        }
+    } else if (lz >= 32) {
+        eqm = valid;
+    } else {
+        // keys above the K-th key's first digit are in; the candidates inside it are compared in full
+        gtm = gt1;
+        uint32_t m = cm;
+        int at = cand_at;
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t u = (at >= 0) ? cand[at++] : ((ordered_key_fast(__ldg(keys + i0 + j)) - omin) << lz);
+            if (u > kth_u) gtm |= 1u << j;
+            else if (u == kth_u) eqm |= 1u << j;
         }
     }
     const int mine = __popc(gtm) | (__popc(eqm) << 16);          // both counts fit 15 bits (N <= 16384)
@@ -580,21 +758,22 @@ topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* 
     const int n_kept = (total & 0xffff) + min(total >> 16, n_ties_take);
     if (counts != nullptr && tid == 0) counts[cloud] = n_kept;
 
-    // ---- ordered compaction of this thread's selected keys
-    const uint32_t selm = gtm | eqm;
-#pragma unroll
-    for (int j = 0; j < KPT; ++j) {                      // static indices keep o[] in registers
-        if (!((selm >> j) & 1u)) continue;
+    // ---- ordered compaction of this thread's selected keys: walk the set bits only (the key is re-read through the
+    // read-only path; a dynamic index into o[] would spill the array)
+    uint32_t selm = gtm | eqm;
+    while (selm) {
+        const int j = __ffs(selm) - 1;
+        selm &= selm - 1;
         const bool gt = (gtm >> j) & 1u;
         const bool take = gt || eq_before < n_ties_take;
         if (take) {
             const int pos = gt_before + min(eq_before, n_ties_take);
             const int i = i0 + j;
+            const float kv = __ldg(keys + i);
             if (sorted) {
-                sortbuf[pos] = ((unsigned long long)(~o[j]) << 32) | (uint32_t)i;
+                sortbuf[pos] = ((unsigned long long)(~ordered_key_fast(kv)) << 32) | (uint32_t)i;
             } else {
                 const int f = i % nf, t = i / nf;
-                const float kv = __ldg(keys + i);
                 if (pts) {
                     if (width == 3) { pts[pos * 3] = __ldg(farr + f); pts[pos * 3 + 1] = __ldg(tarr + t); pts[pos * 3 + 2] = kv; }
                     else { pts[pos * 2] = __ldg(farr + f); pts[pos * 2 + 1] = kv; }
@@ -613,7 +792,30 @@ topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* 
     }
     __syncthreads();
 
+    auto emit = [&](int r, int i) {
+        if (r >= n_kept) {
+            if (pts) { for (int j = 0; j < width; ++j) pts[r * width + j] = 0.f; }
+            if (idx_out) idx_out[r] = -1;
+            return;
+        }
+        const float kv = __ldg(keys + i);
+        const int f = i % nf, t = i / nf;
+        if (pts) {
+            if (width == 3) { pts[r * 3] = __ldg(farr + f); pts[r * 3 + 1] = __ldg(tarr + t); pts[r * 3 + 2] = kv; }
+            else { pts[r * 2] = __ldg(farr + f); pts[r * 2 + 1] = kv; }
+        }
+        if (idx_out) idx_out[r] = i;
+    };
+
     // ---- bitonic sort of the survivors: ascending (~key, index) == descending key, stable
+    if (kpad <= TOPK_THREADS * TOPK_SORT_E) {
+        const int kp = max(kpad, 32);                 // sentinels ~0 pad to a whole warp
+        if (kp < TOPK_THREADS && tid >= kp) return;   // whole warps without an element leave (the sort's barriers count kp)
+        if (kp <= TOPK_THREADS) sort_regs<1>(sortbuf, kpad, kp, K, tid, emit);
+        else if (kp == 2 * TOPK_THREADS) sort_regs<2>(sortbuf, kpad, kp, K, tid, emit);
+        else sort_regs<4>(sortbuf, kpad, kp, K, tid, emit);
+        return;
+    }
     for (int k2 = 2; k2 <= kpad; k2 <<= 1) {
         for (int j = k2 >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < (kpad >> 1); t += TOPK_THREADS) {
@@ -626,21 +828,7 @@ topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* 
             __syncthreads();
         }
     }
-    for (int r = tid; r < K; r += TOPK_THREADS) {
-        if (r >= n_kept) {
-            if (pts) { for (int j = 0; j < width; ++j) pts[r * width + j] = 0.f; }
-            if (idx_out) idx_out[r] = -1;
-            continue;
-        }
-        const int i = (int)(uint32_t)sortbuf[r];
-        const float kv = __ldg(keys + i);
-        const int f = i % nf, t = i / nf;
-        if (pts) {
-            if (width == 3) { pts[r * 3] = __ldg(farr + f); pts[r * 3 + 1] = __ldg(tarr + t); pts[r * 3 + 2] = kv; }
-            else { pts[r * 2] = __ldg(farr + f); pts[r * 2 + 1] = kv; }
-        }
-        if (idx_out) idx_out[r] = i;
-    }
+    for (int r = tid; r < K; r += TOPK_THREADS) emit(r, (int)(uint32_t)sortbuf[r]);
 }
 
 // ------------------------------------------------------------------------------------ fused front end

@@ -139,6 +139,38 @@ def test_topk_ties_keep_lowest_indices(pca, dev):
             np.testing.assert_array_equal(idx[c].cpu().numpy(), orc.topk_order(keys[c].reshape(-1), K))
 
 
+@pytest.mark.parametrize("case", ["all_equal", "narrow", "two_values", "wide", "heavy_bin", "signs"])
+def test_topk_key_range_edge_cases(pca, dev, case):
+    """The register-key kernel selects on range-normalised keys ((o - omin) << clz(omax - omin)) and moves the candidates of
+    the chosen first digit to a bounded shared list: degenerate ranges, overflow of that list and mixed signs must give the
+    oracle's order bit for bit."""
+    rs = np.random.RandomState(11)
+    nf, nt, n = 512, 32, 4
+    if case == "all_equal":
+        keys = np.full((n, nt, nf), -3.25, np.float32)
+    elif case == "narrow":                       # neighbours in float32: only the low mantissa bits differ
+        base = np.float32(-7.5).view(np.uint32)
+        keys = (base + rs.randint(0, 37, size=(n, nt, nf)).astype(np.uint32)).view(np.float32)
+    elif case == "two_values":
+        keys = np.where(rs.rand(n, nt, nf) < 0.5, np.float32(1.0), np.float32(2.0)).astype(np.float32)
+    elif case == "wide":
+        keys = (rs.randn(n, nt, nf) * 1e3).astype(np.float32)
+        keys[:, 0, :3] = [np.float32(3e38), np.float32(-3e38), np.float32(1e-30)]
+    elif case == "heavy_bin":                    # > TOPK_CAND keys share the K-th key's first digit: register fallback
+        keys = (rs.randn(n, nt, nf) * 1e-3 - 8).astype(np.float32)
+        keys[:, :, :4] = rs.randn(n, nt, 4).astype(np.float32) * 50
+    else:
+        keys = rs.randn(n, nt, nf).astype(np.float32)
+        keys[:, 1, :7] = [0.0, -0.0, 1e-45, -1e-45, 0.0, -0.0, 0.0]
+    farr, tarr = orc.coord_tables(16000, nf, 2 * nf, 0.5, nt)
+    for K in (1, 7, 256, 1500, 8192, nf * nt - 1):
+        for srt in (True, False):
+            _, idx = pca.topk_points(torch.from_numpy(keys).to(dev), farr, tarr, K, sorted_desc=srt)
+            for c in range(n):
+                want = orc.topk_order(keys[c].reshape(-1), K)
+                np.testing.assert_array_equal(idx[c].cpu().numpy(), want if srt else np.sort(want))
+
+
 def test_topk_errors(pca, dev):
     keys = torch.zeros(2, 4, 64, device=dev)
     with pytest.raises(RuntimeError, match="outside"):
