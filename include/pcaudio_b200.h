@@ -377,6 +377,10 @@ void pca_debug_set_reduce_variant(int warpgroups);
  * same speed).  Also PCA_TC_POOL=2 in the environment. */
 void pca_debug_set_pool_variant(int variant);
 
+/* Debug / tests: 1 = run the generic STFT kernel (any power-of-two n_fft, any thread count; the code the fused front end
+ * uses) also for n_fft in [512, 4096], where the size-specialised kernel is the default.  Both give bit-identical spectra. */
+void pca_debug_set_stft_generic(int on);
+
 /* fp32-grade GEMMs on the tensor cores (split-bf16, three MMAs per product; csrc/gemm_tc.cu), used by the fp32 encoder path,
  * DeepSet's shared MLP and the training path for layers with K % 32 == 0 and N % 32 == 0.  pca_debug_set_gemm_tc(0) keeps
  * every layer on the CUDA-core kernels.  pca_debug_linear_tc: Y (rows, N) = act(X (rows, K) B^T + bias) [+ resid], B(n,k) =

@@ -89,6 +89,7 @@ PROTOTYPES = {
     "pca_debug_set_tail_max": (None, [_I]),
     "pca_debug_set_reduce_variant": (None, [_I]),
     "pca_debug_set_pool_variant": (None, [_I]),
+    "pca_debug_set_stft_generic": (None, [_I]),
     "pca_debug_set_gemm_tc": (None, [_I]),
     "pca_debug_linear_tc": (_I, [_P, _P, _I, _P, _P, _P, _P, C.c_longlong, _I, _I, _I, _P, _SZ, _P]),
     "pca_debug_grad_weight_tc": (_I, [_P, _P, _P, C.c_longlong, _I, _I, _P]),

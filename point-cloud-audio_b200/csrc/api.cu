@@ -50,6 +50,7 @@ void set_timeline(long long* p);
 void set_tail_max(int t);
 void set_reduce_wg(int n);
 void set_pool_variant(int v);
+void debug_set_stft_generic(int on);
 int launch_umma_probe(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 // tcgen05 path (encoder_tc.cu)
 size_t st_tc_workspace_bytes(const pca_st_dims* d, int B, int N);
@@ -824,6 +825,7 @@ void pca_debug_set_timeline(long long* device_buffer) { set_timeline(device_buff
 void pca_debug_set_tail_max(int tail_max) { set_tail_max(tail_max); }
 void pca_debug_set_reduce_variant(int warpgroups) { set_reduce_wg(warpgroups); }
 void pca_debug_set_pool_variant(int variant) { set_pool_variant(variant); }
+void pca_debug_set_stft_generic(int on) { debug_set_stft_generic(on); }
 
 int pca_debug_umma_probe(const float* A, const float* B, float* D, int N, int K, int a_mode, int b_mode, void* stream) {
     return launch_umma_probe(A, B, D, N, K, a_mode, b_mode, (cudaStream_t)stream);

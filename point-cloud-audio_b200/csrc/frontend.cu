@@ -20,14 +20,88 @@ namespace pca {
 // slots of one padded FFT buffer (see stft_frame)
 __host__ __device__ static inline int stft_buf_len(int nc) { return nc + (nc >> 4); }
 
+// Every floating-point operation of a frame is spelled with a rounding intrinsic: the compiler then cannot contract a
+// product into a neighbouring sum differently in the generic and the size-specialised code (or from one compiler version to
+// the next), so all STFT kernels give bit-identical spectra.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    return make_float2(__fmaf_rn(a.x, b.x, -__fmul_rn(a.y, b.y)), __fmaf_rn(a.x, b.y, __fmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ float2 cwin(float2 w, float2 v) { return make_float2(__fmul_rn(w.x, v.x), __fmul_rn(w.y, v.y)); }
+
+// ---- arithmetic shared by the generic and the size-specialised frame code
+// 8-point DFT, outputs in natural order: even outputs = DFT4 of (a_j + a_{j+4}), odd = DFT4 of ((a_j - a_{j+4}) w8^j)
+__device__ __forceinline__ void dft8(const float2 (&a)[8], float2 (&y)[8]) {
+    const float2 b0 = cadd(a[0], a[4]), b1 = cadd(a[1], a[5]), b2 = cadd(a[2], a[6]), b3 = cadd(a[3], a[7]);
+    const float2 c0 = csub(a[0], a[4]), d1 = csub(a[1], a[5]), d2 = csub(a[2], a[6]), d3 = csub(a[3], a[7]);
+    const float r2 = 0.70710678118654752f;
+    const float2 s1 = make_float2(__fadd_rn(d1.x, d1.y), __fsub_rn(d1.y, d1.x));    // c1 = d1 (1 - i)/sqrt2 = s1 r2
+    const float2 c2 = make_float2(d2.y, -d2.x);                                    // d2 (-i)
+    const float2 c3 = make_float2(__fmul_rn(__fsub_rn(d3.y, d3.x), r2), -__fmul_rn(__fadd_rn(d3.x, d3.y), r2));   // d3 (-1 - i)/sqrt2
+    // DFT4(z0..z3): y0 = (z0+z2)+(z1+z3), y2 = (z0+z2)-(z1+z3), y1 = (z0-z2) - i (z1-z3), y3 = (z0-z2) + i (z1-z3)
+    const float2 e0 = cadd(b0, b2), e1 = cadd(b1, b3), e2 = csub(b0, b2), e3 = csub(b1, b3);
+    const float2 f0 = cadd(c0, c2), f2 = csub(c0, c2);
+    const float2 f1 = make_float2(__fmaf_rn(s1.x, r2, c3.x), __fmaf_rn(s1.y, r2, c3.y));       // c1 + c3
+    const float2 f3 = make_float2(__fmaf_rn(s1.x, r2, -c3.x), __fmaf_rn(s1.y, r2, -c3.y));     // c1 - c3
+    y[0] = cadd(e0, e1);
+    y[4] = csub(e0, e1);
+    y[2] = make_float2(__fadd_rn(e2.x, e3.y), __fsub_rn(e2.y, e3.x));
+    y[6] = make_float2(__fsub_rn(e2.x, e3.y), __fadd_rn(e2.y, e3.x));
+    y[1] = cadd(f0, f1);
+    y[5] = csub(f0, f1);
+    y[3] = make_float2(__fadd_rn(f2.x, f3.y), __fsub_rn(f2.y, f3.x));
+    y[7] = make_float2(__fsub_rn(f2.x, f3.y), __fadd_rn(f2.y, f3.x));
+}
+// 4-point DFT of (a, b, c, d), natural order
+__device__ __forceinline__ void dft4(float2 a, float2 b, float2 c, float2 d, float2 (&y)[4]) {
+    const float2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(b, d), bmd = csub(b, d);
+    y[0] = cadd(apc, bpd);
+    y[1] = make_float2(__fadd_rn(amc.x, bmd.y), __fsub_rn(amc.y, bmd.x));
+    y[2] = csub(apc, bpd);
+    y[3] = make_float2(__fsub_rn(amc.x, bmd.y), __fadd_rn(amc.y, bmd.x));
+}
+// exp(-2 pi i k / n_fft) for k < n_fft from the half table tw[0, nc)
+__device__ __forceinline__ float2 tw_at(const float2* tw, int k, int nc) {
+    if (k < nc) return tw[k];
+    const float2 w = tw[k - nc];
+    return make_float2(-w.x, -w.y);
+}
+// Bins k and nc - k of the real transform from the packed transform Z: Xe = (Z[k] + conj Z[nc-k]) / 2,
+// Xo = -i (Z[k] - conj Z[nc-k]) / 2, X[k] = Xe + tw[k] Xo, X[nc-k] = conj(Xe - tw[k] Xo); then log(1e-8 + |X| scale).
+// log(1e-8 + mag scale) and |z| on the special-function unit: lg2.approx / sqrt.approx (relative error ~2^-22, two orders below
+// the parity tolerance on |S|); the argument of the logarithm is >= 1e-8, so no subnormal handling is needed (.ftz)
+__device__ __forceinline__ float logmag1(float mag, float scale) {
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(__fmaf_rn(mag, scale, 1.0e-8f)));
+    return __fmul_rn(l, 0.69314718055994531f);
+}
+__device__ __forceinline__ float cabs_fast(float2 z) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(__fmaf_rn(z.x, z.x, __fmul_rn(z.y, z.y))));
+    return r;
+}
+__device__ __forceinline__ void logmag_pair(float2 zk, float2 zc, float2 w, float scale, float& lk, float& lc) {
+    const float2 e = make_float2(__fmul_rn(0.5f, __fadd_rn(zk.x, zc.x)), __fmul_rn(0.5f, __fsub_rn(zk.y, zc.y)));
+    const float2 od = make_float2(__fmul_rn(0.5f, __fadd_rn(zk.y, zc.y)), __fmul_rn(-0.5f, __fsub_rn(zk.x, zc.x)));
+    const float2 r = cmul(w, od);
+    const float2 p = cadd(e, r), m = csub(e, r);
+    lk = logmag1(cabs_fast(p), scale);
+    lc = logmag1(cabs_fast(m), scale);
+}
+// packed, windowed sample pair i of frame t (centre = True: the frame starts at t*hop - n_fft/2; reflect padding by mirroring)
+__device__ __forceinline__ float2 frame_pair(const float* __restrict__ x, int L, int start, int i, float2 w) {
+    int j0 = start + 2 * i, j1 = j0 + 1;
+    j0 = j0 < 0 ? -j0 : (j0 >= L ? 2 * (L - 1) - j0 : j0);
+    j1 = j1 < 0 ? -j1 : (j1 >= L ? 2 * (L - 1) - j1 : j1);
+    return cwin(w, make_float2(__ldg(x + j0), __ldg(x + j1)));
 }
 
 // One STFT frame by `nthr` cooperating threads (all threads of the block must call: block-wide barriers inside).
 // x: the clip (L samples); frame t is centred on sample t*hop (reflect padding by index mirroring); tw / win: shared
 // twiddle and window tables; bufa / bufb: this thread group's ping-pong buffers (n_fft/2 complex each);
 // o: nf_out log-magnitudes (shared or global).  `active` == false runs the barriers only (ragged frame groups).
+// Generic in n_fft and nthr (the fused front end and the sizes without a specialised kernel).
 __device__ __forceinline__ void stft_frame(const float* __restrict__ x, int L, int n_fft, int hop, int t,
                                            const float2* tw, const float* win, float2* bufa, float2* bufb,
                                            float scale, int nf_out, float* o, int tid, int nthr, bool active) {
@@ -39,21 +113,16 @@ __device__ __forceinline__ void stft_frame(const float* __restrict__ x, int L, i
     // ---- load + window, pack even/odd samples into one complex sequence
     if (active) {
         const int start = t * hop - nc;            // centre=True: frame t starts at t*hop - n_fft/2
+        const float2* wp = reinterpret_cast<const float2*>(win);
         if (start >= 0 && start + n_fft <= L && ((reinterpret_cast<size_t>(x + start) & 7) == 0)) {
             // interior frame: no mirroring, 8-byte loads of sample pairs
             const float2* xp = reinterpret_cast<const float2*>(x + start);
-            const float2* wp = reinterpret_cast<const float2*>(win);
             for (int i = tid; i < nc; i += nthr) {
                 const float2 v = __ldg(xp + i), w = wp[i];
-                bufa[PD(i)] = make_float2(w.x * v.x, w.y * v.y);
+                bufa[PD(i)] = cwin(w, v);
             }
         } else {
-            for (int i = tid; i < nc; i += nthr) {
-                int j0 = start + 2 * i, j1 = j0 + 1;
-                j0 = j0 < 0 ? -j0 : (j0 >= L ? 2 * (L - 1) - j0 : j0);
-                j1 = j1 < 0 ? -j1 : (j1 >= L ? 2 * (L - 1) - j1 : j1);
-                bufa[PD(i)] = make_float2(win[2 * i] * __ldg(x + j0), win[2 * i + 1] * __ldg(x + j1));
-            }
+            for (int i = tid; i < nc; i += nthr) bufa[PD(i)] = frame_pair(x, L, start, i, wp[i]);
         }
     }
     __syncthreads();
@@ -72,45 +141,19 @@ __device__ __forceinline__ void stft_frame(const float* __restrict__ x, int L, i
                 const int p = i >> s_log, q = i & ((1 << s_log) - 1);
                 const int ib = q + (p << s_log);
                 const int st = n1 << s_log;
-                const float2 a0 = src[PD(ib)], a1 = src[PD(ib + st)], a2 = src[PD(ib + 2 * st)], a3 = src[PD(ib + 3 * st)];
-                const float2 a4 = src[PD(ib + 4 * st)], a5 = src[PD(ib + 5 * st)], a6 = src[PD(ib + 6 * st)], a7 = src[PD(ib + 7 * st)];
-                // even outputs: DFT4 of (a_j + a_{j+4}); odd outputs: DFT4 of ((a_j - a_{j+4}) w8^j)
-                const float2 b0 = make_float2(a0.x + a4.x, a0.y + a4.y), b1 = make_float2(a1.x + a5.x, a1.y + a5.y);
-                const float2 b2 = make_float2(a2.x + a6.x, a2.y + a6.y), b3 = make_float2(a3.x + a7.x, a3.y + a7.y);
-                const float2 c0 = make_float2(a0.x - a4.x, a0.y - a4.y);
-                const float2 d1 = make_float2(a1.x - a5.x, a1.y - a5.y);
-                const float2 d2 = make_float2(a2.x - a6.x, a2.y - a6.y);
-                const float2 d3 = make_float2(a3.x - a7.x, a3.y - a7.y);
-                const float r2 = 0.70710678118654752f;
-                const float2 c1 = make_float2((d1.x + d1.y) * r2, (d1.y - d1.x) * r2);      // d1 (1 - i)/sqrt2
-                const float2 c2 = make_float2(d2.y, -d2.x);                                // d2 (-i)
-                const float2 c3 = make_float2((d3.y - d3.x) * r2, -(d3.x + d3.y) * r2);     // d3 (-1 - i)/sqrt2
-                // DFT4(z0..z3): y0 = (z0+z2)+(z1+z3), y2 = (z0+z2)-(z1+z3), y1 = (z0-z2) - i (z1-z3), y3 = (z0-z2) + i (z1-z3)
-                const float2 e0 = make_float2(b0.x + b2.x, b0.y + b2.y), e1 = make_float2(b1.x + b3.x, b1.y + b3.y);
-                const float2 e2 = make_float2(b0.x - b2.x, b0.y - b2.y), e3 = make_float2(b1.x - b3.x, b1.y - b3.y);
-                const float2 f0 = make_float2(c0.x + c2.x, c0.y + c2.y), f1 = make_float2(c1.x + c3.x, c1.y + c3.y);
-                const float2 f2 = make_float2(c0.x - c2.x, c0.y - c2.y), f3 = make_float2(c1.x - c3.x, c1.y - c3.y);
-                const float2 y0 = make_float2(e0.x + e1.x, e0.y + e1.y);
-                const float2 y4 = make_float2(e0.x - e1.x, e0.y - e1.y);
-                const float2 y2 = make_float2(e2.x + e3.y, e2.y - e3.x);
-                const float2 y6 = make_float2(e2.x - e3.y, e2.y + e3.x);
-                const float2 y1 = make_float2(f0.x + f1.x, f0.y + f1.y);
-                const float2 y5 = make_float2(f0.x - f1.x, f0.y - f1.y);
-                const float2 y3 = make_float2(f2.x + f3.y, f2.y - f3.x);
-                const float2 y7 = make_float2(f2.x - f3.y, f2.y + f3.x);
+                float2 a[8], y[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) a[r] = src[PD(ib + r * st)];
+                dft8(a, y);
                 const int ob = q + ((8 * p) << s_log);
                 const int so = 1 << s_log;
+                dst[PD(ob)] = y[0];
                 if (n1 == 1) {            // last radix-8 stage of a power of 8: p = 0, every twiddle is 1
-                    dst[PD(ob)] = y0; dst[PD(ob + so)] = y1; dst[PD(ob + 2 * so)] = y2; dst[PD(ob + 3 * so)] = y3;
-                    dst[PD(ob + 4 * so)] = y4; dst[PD(ob + 5 * so)] = y5; dst[PD(ob + 6 * so)] = y6; dst[PD(ob + 7 * so)] = y7;
+#pragma unroll
+                    for (int r = 1; r < 8; ++r) dst[PD(ob + r * so)] = y[r];
                 } else {
-                    const float2 w1 = tw[p << tsh], w2 = tw[(2 * p) << tsh], w4 = tw[(4 * p) << tsh];
-                    const float2 w3 = cmul(w1, w2), w5 = cmul(w1, w4), w6 = cmul(w2, w4);
-                    const float2 w7 = cmul(w3, w4);
-                    dst[PD(ob)] = y0;
-                    dst[PD(ob + so)] = cmul(w1, y1); dst[PD(ob + 2 * so)] = cmul(w2, y2); dst[PD(ob + 3 * so)] = cmul(w3, y3);
-                    dst[PD(ob + 4 * so)] = cmul(w4, y4); dst[PD(ob + 5 * so)] = cmul(w5, y5); dst[PD(ob + 6 * so)] = cmul(w6, y6);
-                    dst[PD(ob + 7 * so)] = cmul(w7, y7);
+#pragma unroll
+                    for (int r = 1; r < 8; ++r) dst[PD(ob + r * so)] = cmul(tw_at(tw, (r * p) << tsh, nc), y[r]);
                 }
             }
         }
@@ -123,15 +166,9 @@ __device__ __forceinline__ void stft_frame(const float* __restrict__ x, int L, i
         if (active) {
             const int st = 1 << s_log;               // = nc / 4
             for (int q = tid; q < st; q += nthr) {
-                const float2 a = src[PD(q)], b = src[PD(q + st)], c = src[PD(q + 2 * st)], d = src[PD(q + 3 * st)];
-                const float2 apc = make_float2(a.x + c.x, a.y + c.y);
-                const float2 amc = make_float2(a.x - c.x, a.y - c.y);
-                const float2 bpd = make_float2(b.x + d.x, b.y + d.y);
-                const float2 bmd = make_float2(b.x - d.x, b.y - d.y);
-                dst[PD(q)] = make_float2(apc.x + bpd.x, apc.y + bpd.y);
-                dst[PD(q + st)] = make_float2(amc.x + bmd.y, amc.y - bmd.x);
-                dst[PD(q + 2 * st)] = make_float2(apc.x - bpd.x, apc.y - bpd.y);
-                dst[PD(q + 3 * st)] = make_float2(amc.x - bmd.y, amc.y + bmd.x);
+                float2 y[4];
+                dft4(src[PD(q)], src[PD(q + st)], src[PD(q + 2 * st)], src[PD(q + 3 * st)], y);
+                dst[PD(q)] = y[0]; dst[PD(q + st)] = y[1]; dst[PD(q + 2 * st)] = y[2]; dst[PD(q + 3 * st)] = y[3];
             }
         }
         __syncthreads();
@@ -141,35 +178,200 @@ __device__ __forceinline__ void stft_frame(const float* __restrict__ x, int L, i
             for (int q = tid; q < (nc >> 1); q += nthr) {
                 const float2 a = src[PD(q)];
                 const float2 b = src[PD(q + (nc >> 1))];
-                dst[PD(q)] = make_float2(a.x + b.x, a.y + b.y);
-                dst[PD(q + (nc >> 1))] = make_float2(a.x - b.x, a.y - b.y);
+                dst[PD(q)] = cadd(a, b);
+                dst[PD(q + (nc >> 1))] = csub(a, b);
             }
         }
         __syncthreads();
         float2* tmp = src; src = dst; dst = tmp;
     }
 
-    // ---- split the packed spectrum, magnitude, log.  With Z the packed transform, Xe = (Z[k] + conj Z[nc-k]) / 2,
-    // Xo = -i (Z[k] - conj Z[nc-k]) / 2:  X[k] = Xe + tw[k] Xo  and  X[nc-k] = conj(Xe - tw[k] Xo): one pass gives both bins.
+    // ---- split the packed spectrum, magnitude, log: one pass gives bins k and nc - k
     if (active) {
         for (int k = tid; k <= (nc >> 1); k += nthr) {
             if (k == 0) {
                 const float2 z0 = src[0];      // PD(0) = 0
-                o[0] = __logf(1.0e-8f + fabsf(z0.x + z0.y) * scale);
-                if (nc < nf_out) o[nc] = __logf(1.0e-8f + fabsf(z0.x - z0.y) * scale);
+                o[0] = logmag1(fabsf(__fadd_rn(z0.x, z0.y)), scale);
+                if (nc < nf_out) o[nc] = logmag1(fabsf(__fsub_rn(z0.x, z0.y)), scale);
                 continue;
             }
-            const float2 zk = src[PD(k)];
-            const float2 zc = src[PD(nc - k)];
-            const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
-            const float2 od = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
-            const float2 r = cmul(tw[k], od);
-            const float re0 = e.x + r.x, im0 = e.y + r.y, re1 = e.x - r.x, im1 = e.y - r.y;
-            o[k] = __logf(1.0e-8f + sqrtf(re0 * re0 + im0 * im0) * scale);
-            if (k != nc - k) o[nc - k] = __logf(1.0e-8f + sqrtf(re1 * re1 + im1 * im1) * scale);
+            float lk, lc;
+            logmag_pair(src[PD(k)], src[PD(nc - k)], tw[k], scale, lk, lc);
+            o[k] = lk;
+            if (k != nc - k) o[nc - k] = lc;
         }
     }
     __syncthreads();   // bufa/bufb reused by the next frame
+}
+
+// ---- size-specialised frames: NC = n_fft / 2 complex points by NT = NC / 8 threads (one radix-8 butterfly per thread
+// and stage, every index a compile-time function of the thread id).  The first butterfly takes its inputs straight from
+// global memory (the windowed samples never pass through shared memory), the window pairs and first-stage twiddles of a
+// thread are the same for every frame and live in registers, and the ping-pong buffers alternate so that one named
+// barrier per stage is the only synchronisation.  Same arithmetic as stft_frame, expression for expression.
+template <int NC>
+struct StftT {
+    static constexpr int NT = NC / 8;
+    static constexpr int PST = NT + NT / 16;                  // padded distance of a butterfly's inputs
+    static constexpr int PLEN = NC + NC / 16;                 // padded buffer length
+    static constexpr int LOGNC = (NC == 256) ? 8 : (NC == 512) ? 9 : (NC == 1024) ? 10 : 11;
+    static constexpr int N8 = LOGNC / 3;                      // radix-8 stages
+    static constexpr int TAIL = 1 << (LOGNC - 3 * N8);        // 1 (none), 2 or 4
+    static constexpr int NSTAGE = N8 + (TAIL > 1 ? 1 : 0);
+
+    __device__ static __forceinline__ int PD(int i) { return i + (i >> 4); }
+    __device__ static __forceinline__ void gsync(int bar) { asm volatile("bar.sync %0, %1;" :: "r"(bar), "n"(NT) : "memory"); }
+
+    // twiddles of the radix-8 stages S >= 1 as one table per stage, [p][r - 1] = exp(-2 pi i r p / (NC >> 3 S)): 56 B per p, so the
+    // few distinct p of a warp fall into distinct banks (in the master table they are a multiple of 128 B apart)
+    __host__ __device__ static constexpr int stage_tab_off(int S) { return S <= 1 ? 0 : stage_tab_off(S - 1) + 7 * ((NC >> (3 * (S - 1))) / 8); }
+    static constexpr int STAGE_TAB = stage_tab_off(N8);          // float2 entries (stages whose N1 == 1 included: 7 entries, unused)
+
+    template <int S>
+    __device__ static __forceinline__ void r8_write(const float2 (&a)[8], const float2* stab, const float2 (&w0)[7],
+                                                    float2* dst, int ltid) {
+        constexpr int S_LOG = 3 * S, N = NC >> S_LOG, N1 = N / 8, SO = 1 << S_LOG;
+        float2 y[8];
+        dft8(a, y);
+        const int p = ltid >> S_LOG, q = ltid & (SO - 1);
+        const int ob = q + ((8 * p) << S_LOG);
+        float2* d = dst + PD(ob);
+        d[0] = y[0];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) {
+            // PD(ob + r SO) - PD(ob): SO >= 16 is a multiple of the padding period; SO = 8: ob = q + 64 p, q < 8; SO = 1: ob = 8 p
+            const int off = SO >= 16 ? r * (SO + SO / 16) : (SO == 8 ? 8 * r + (r >> 1) : r);
+            if (N1 == 1) d[off] = y[r];
+            else d[off] = cmul(S == 0 ? w0[r - 1] : stab[stage_tab_off(S) + 7 * p + r - 1], y[r]);
+        }
+    }
+
+    // wv: this thread's window pairs (ltid + r NT), w0: its first-stage twiddles exp(-2 pi i r ltid / NC); cur: buffer the first
+    // stage writes (flipped by the caller after every frame when NSTAGE is odd)
+    __device__ static __forceinline__ void frame(const float* __restrict__ x, int L, int hop, int t, const float2* tw,
+                                                 const float2* stab, const float2 (&wv)[8], const float2 (&w0)[7], float2* buf0, float2* buf1,
+                                                 float scale, int nf_out, float* __restrict__ o, int ltid, int bar) {
+        constexpr int n_fft = 2 * NC;
+        float2 a[8];
+        const int start = t * hop - NC;
+        if (start >= 0 && start + n_fft <= L && ((reinterpret_cast<size_t>(x + start) & 7) == 0)) {
+            const float2* xp = reinterpret_cast<const float2*>(x + start) + ltid;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float2 v = __ldg(xp + r * NT);
+                a[r] = cwin(wv[r], v);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) a[r] = frame_pair(x, L, start, ltid + r * NT, wv[r]);
+        }
+        float2* src = buf1;
+        float2* dst = buf0;
+        r8_write<0>(a, stab, w0, dst, ltid);
+        gsync(bar);
+#pragma unroll
+        for (int S = 1; S < 4; ++S) {
+            if (S >= N8) continue;
+            { float2* tmp = src; src = dst; dst = tmp; }
+            const float2* sp = src + PD(ltid);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) a[r] = sp[r * PST];
+            if (S == 1) r8_write<1>(a, stab, w0, dst, ltid);
+            else if (S == 2) r8_write<2>(a, stab, w0, dst, ltid);
+            else r8_write<3>(a, stab, w0, dst, ltid);
+            gsync(bar);
+        }
+        if (TAIL == 4) {
+            { float2* tmp = src; src = dst; dst = tmp; }
+            constexpr int ST = NC / 4, PSTT = ST + ST / 16;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const int pq = PD(ltid + m * NT);
+                float2 y[4];
+                dft4(src[pq], src[pq + PSTT], src[pq + 2 * PSTT], src[pq + 3 * PSTT], y);
+                dst[pq] = y[0]; dst[pq + PSTT] = y[1]; dst[pq + 2 * PSTT] = y[2]; dst[pq + 3 * PSTT] = y[3];
+            }
+            gsync(bar);
+        } else if (TAIL == 2) {
+            { float2* tmp = src; src = dst; dst = tmp; }
+            constexpr int ST = NC / 2, PSTT = ST + ST / 16;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int pq = PD(ltid + m * NT);
+                const float2 u = src[pq], v = src[pq + PSTT];
+                dst[pq] = cadd(u, v);
+                dst[pq + PSTT] = csub(u, v);
+            }
+            gsync(bar);
+        }
+        // the packed spectrum is in dst: bins k = ltid + m NT, m < 4, and nc - k; k = NC / 2 by thread 0
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int k = ltid + m * NT;
+            if (m == 0 && ltid == 0) {
+                const float2 z0 = dst[0];
+                o[0] = logmag1(fabsf(__fadd_rn(z0.x, z0.y)), scale);
+                if (NC < nf_out) o[NC] = logmag1(fabsf(__fsub_rn(z0.x, z0.y)), scale);
+                float lk, lc;
+                logmag_pair(dst[PD(NC / 2)], dst[PD(NC / 2)], tw[NC / 2], scale, lk, lc);
+                o[NC / 2] = lk;
+                continue;
+            }
+            float lk, lc;
+            logmag_pair(dst[PD(k)], dst[PD(NC - k)], tw[k], scale, lk, lc);
+            o[k] = lk;
+            o[NC - k] = lc;
+        }
+    }
+};
+
+constexpr int STFT_T_THREADS = 256;
+
+template <int NC>
+__global__ void __launch_bounds__(STFT_T_THREADS, NC <= 512 ? 4 : 3)
+stft_logmag_t_kernel(const float* __restrict__ audio, int L, int hop, const float* __restrict__ window,
+                     const float2* __restrict__ twiddle, float scale, int nf_out, int nt_out, int frames_per_group,
+                     float* __restrict__ out) {
+    using T = StftT<NC>;
+    constexpr int G = STFT_T_THREADS / T::NT;          // frames in flight per block
+    extern __shared__ float2 smem_f2[];
+    float2* tw = smem_f2;                              // NC entries: exp(-2 pi i k / n_fft)
+    float2* stab = tw + NC;                            // per-stage twiddle tables (StftT::stage_tab_off)
+    float2* bufs = stab + T::STAGE_TAB;                // G x 2 x PLEN
+    const int tid = threadIdx.x, g = tid / T::NT, ltid = tid % T::NT;
+    const int clip = blockIdx.y;
+    const float* x = audio + (size_t)clip * L;
+
+    for (int i = tid; i < NC; i += STFT_T_THREADS) tw[i] = twiddle[i];
+#pragma unroll
+    for (int S = 1; S < T::N8; ++S) {
+        const int n1 = (NC >> (3 * S)) / 8, tsh = 1 + 3 * S;
+        for (int i = tid; i < 7 * n1; i += STFT_T_THREADS) {
+            const int pp = i / 7, r = i - 7 * pp + 1, k = (r * pp) << tsh;
+            const float2 w = __ldg(twiddle + (k < NC ? k : k - NC));
+            stab[T::stage_tab_off(S) + i] = k < NC ? w : make_float2(-w.x, -w.y);
+        }
+    }
+    float2 wv[8], w0[7];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) wv[r] = __ldg(reinterpret_cast<const float2*>(window) + ltid + r * T::NT);
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+        const int k = (r * ltid) << 1;
+        const float2 w = __ldg(twiddle + (k < NC ? k : k - NC));
+        w0[r - 1] = k < NC ? w : make_float2(-w.x, -w.y);
+    }
+    __syncthreads();
+
+    float2* b0 = bufs + (size_t)(2 * g) * T::PLEN;
+    float2* b1 = b0 + T::PLEN;
+    const int t0 = blockIdx.x * G * frames_per_group;
+    for (int i = 0; i < frames_per_group; ++i) {
+        const int t = t0 + i * G + g;
+        if (t >= nt_out) break;                        // (whole groups leave together: the barriers are per group)
+        T::frame(x, L, hop, t, tw, stab, wv, w0, b0, b1, scale, nf_out, out + ((size_t)clip * nt_out + t) * nf_out, ltid, 1 + g);
+        if (T::NSTAGE & 1) { float2* tmp = b0; b0 = b1; b1 = tmp; }
+    }
 }
 
 __global__ void stft_logmag_kernel(const float* __restrict__ audio, int L, int n_fft, int hop,
@@ -869,6 +1071,9 @@ fused_frontend_kernel(const float* __restrict__ audio, int L, int n_fft, int hop
 }
 
 // ------------------------------------------------------------------------------------ host
+static bool g_stft_generic = false;     // debug: force the generic STFT kernel (pca_debug_set_stft_generic)
+void debug_set_stft_generic(int on) { g_stft_generic = on != 0; }
+
 int launch_stft_logmag(const float* audio, int n_clips, int n_samples, int n_fft, int hop,
                        const float* window, const float* twiddle, float scale, int drop_nyquist,
                        int nt_out, float* out, cudaStream_t st) {
@@ -880,6 +1085,31 @@ int launch_stft_logmag(const float* audio, int n_clips, int n_samples, int n_fft
     if (n_clips == 0 || nt_out == 0) return 0;
     const int nc = n_fft / 2;
     const int nf_out = nc + 1 - (drop_nyquist ? 1 : 0);
+    if (n_fft >= 512 && n_fft <= 4096 && (reinterpret_cast<size_t>(window) & 7) == 0 && !g_stft_generic) {
+        // size-specialised kernel: 256 threads = G frames in flight, group g of block b takes frames b G fpg + g + i G
+        const int G = STFT_T_THREADS / (nc / 8);
+        int fpg = 1;
+        while ((long long)n_clips * ((nt_out + G * fpg - 1) / (G * fpg)) > 148LL * 16 && G * fpg < nt_out) fpg *= 2;
+        dim3 grid((nt_out + G * fpg - 1) / (G * fpg), n_clips);
+        const size_t smem = ((size_t)nc + (size_t)nc / 8 + (size_t)G * 2 * (nc + nc / 16)) * sizeof(float2);   // (stage tables: < nc/8 entries)
+        const double frames = (double)n_clips * nt_out;
+        LaunchTimer lt("stft_logmag_kernel", st, frames * (2.5 * n_fft * log2((double)n_fft) + n_fft + 6.0 * nf_out),
+                       4.0 * n_clips * n_samples + 4.0 * frames * nf_out);
+        const float2* tw2 = reinterpret_cast<const float2*>(twiddle);
+#define PCA_STFT_T(NC_)                                                                                                  \
+        do {                                                                                                             \
+            if (smem > 48 * 1024) PCA_CHECK_CUDA(cudaFuncSetAttribute(stft_logmag_t_kernel<NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            PCA_CHECK_CUDA(cudaFuncSetAttribute(stft_logmag_t_kernel<NC_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+            stft_logmag_t_kernel<NC_><<<grid, STFT_T_THREADS, smem, st>>>(audio, n_samples, hop, window, tw2, scale, nf_out, nt_out, fpg, out); \
+        } while (0)
+        if (nc == 256) PCA_STFT_T(256);
+        else if (nc == 512) PCA_STFT_T(512);
+        else if (nc == 1024) PCA_STFT_T(1024);
+        else PCA_STFT_T(2048);
+#undef PCA_STFT_T
+        PCA_CHECK_LAUNCH("stft_logmag_t_kernel");
+        return 0;
+    }
     int threads = nc / 8;                  // one radix-8 butterfly per thread and stage
     threads = threads < 64 ? 64 : (threads > 512 ? 512 : threads);
     // enough blocks to fill 148 SMs several times over, while amortising the table loads

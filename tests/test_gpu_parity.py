@@ -60,6 +60,25 @@ def test_stft_logmag_matches_oracle(pca, dev, n_fft, win, L, drop):
         assert np.abs(got[c].T[strong] - ref[strong]).max() < 1e-3
 
 
+@pytest.mark.parametrize("n_fft,L,frames", [(512, 7000, None), (1024, 16000, None), (1024, 16000, 30), (2048, 9000, None),
+                                            (4096, 16000, 5), (2048, 16000, 1)])
+def test_stft_specialised_kernel_equals_generic(pca, dev, n_fft, L, frames):
+    """n_fft in [512, 4096] runs a size-specialised kernel (first butterfly fed from global memory, window and first-stage
+    twiddles in registers, G frames in flight per block); it must reproduce the generic kernel -- the code the fused front end
+    runs -- bit for bit, edge frames (reflect padding) and odd clip offsets included."""
+    from pcaudio_b200 import _lib
+    audio = torch.from_numpy(orc.synth_audio(3, L + 1, 16000, seed=n_fft)).to(dev)
+    for a in (audio[:, :L], audio[:, 1:]):               # second view: clips start at odd float offsets (no 8-byte loads)
+        a = a if a.is_contiguous() else a.contiguous()
+        fast = pca.stft_logmag(a, n_fft, drop_nyquist=False, n_frames=frames)
+        _lib.lib().pca_debug_set_stft_generic(1)
+        try:
+            slow = pca.stft_logmag(a, n_fft, drop_nyquist=False, n_frames=frames)
+        finally:
+            _lib.lib().pca_debug_set_stft_generic(0)
+        assert torch.isfinite(fast).all() and torch.equal(fast, slow)
+
+
 def test_stft_frame_limit_and_errors(pca, dev):
     audio = torch.from_numpy(orc.synth_audio(2, 16000, 16000, seed=3)).to(dev)
     full = pca.stft_logmag(audio, 1024, drop_nyquist=True)
