@@ -235,12 +235,16 @@ struct StftT {
         dft8(a, y);
         const int p = ltid >> S_LOG, q = ltid & (SO - 1);
         const int ob = q + ((8 * p) << S_LOG);
-        float2* d = dst + PD(ob);
+        // the last buffer of a frame is written without padding: its reader walks k upwards and nc - k downwards, and a run
+        // of 16 consecutive slots is conflict-free only in an unpadded buffer (the Stockham strides that need the padding
+        // are those of the earlier stages)
+        constexpr bool LAST = (S == NSTAGE - 1);
+        float2* d = dst + (LAST ? ob : PD(ob));
         d[0] = y[0];
 #pragma unroll
         for (int r = 1; r < 8; ++r) {
             // PD(ob + r SO) - PD(ob): SO >= 16 is a multiple of the padding period; SO = 8: ob = q + 64 p, q < 8; SO = 1: ob = 8 p
-            const int off = SO >= 16 ? r * (SO + SO / 16) : (SO == 8 ? 8 * r + (r >> 1) : r);
+            const int off = LAST ? r * SO : SO >= 16 ? r * (SO + SO / 16) : (SO == 8 ? 8 * r + (r >> 1) : r);
             if (N1 == 1) d[off] = y[r];
             else d[off] = cmul(S == 0 ? w0[r - 1] : stab[stage_tab_off(S) + 7 * p + r - 1], y[r]);
         }
@@ -289,7 +293,8 @@ struct StftT {
                 const int pq = PD(ltid + m * NT);
                 float2 y[4];
                 dft4(src[pq], src[pq + PSTT], src[pq + 2 * PSTT], src[pq + 3 * PSTT], y);
-                dst[pq] = y[0]; dst[pq + PSTT] = y[1]; dst[pq + 2 * PSTT] = y[2]; dst[pq + 3 * PSTT] = y[3];
+                float2* d = dst + ltid + m * NT;           // (last buffer: unpadded, see r8_write)
+                d[0] = y[0]; d[ST] = y[1]; d[2 * ST] = y[2]; d[3 * ST] = y[3];
             }
             gsync(bar);
         } else if (TAIL == 2) {
@@ -299,8 +304,8 @@ struct StftT {
             for (int m = 0; m < 4; ++m) {
                 const int pq = PD(ltid + m * NT);
                 const float2 u = src[pq], v = src[pq + PSTT];
-                dst[pq] = cadd(u, v);
-                dst[pq + PSTT] = csub(u, v);
+                dst[ltid + m * NT] = cadd(u, v);           // (last buffer: unpadded, see r8_write)
+                dst[ltid + m * NT + ST] = csub(u, v);
             }
             gsync(bar);
         }
@@ -313,12 +318,12 @@ struct StftT {
                 o[0] = logmag1(fabsf(__fadd_rn(z0.x, z0.y)), scale);
                 if (NC < nf_out) o[NC] = logmag1(fabsf(__fsub_rn(z0.x, z0.y)), scale);
                 float lk, lc;
-                logmag_pair(dst[PD(NC / 2)], dst[PD(NC / 2)], tw[NC / 2], scale, lk, lc);
+                logmag_pair(dst[NC / 2], dst[NC / 2], tw[NC / 2], scale, lk, lc);
                 o[NC / 2] = lk;
                 continue;
             }
             float lk, lc;
-            logmag_pair(dst[PD(k)], dst[PD(NC - k)], tw[k], scale, lk, lc);
+            logmag_pair(dst[k], dst[NC - k], tw[k], scale, lk, lc);
             o[k] = lk;
             o[NC - k] = lc;
         }
@@ -672,8 +677,10 @@ constexpr int TOPK_SORT_E = 4;         // elements per thread of the register so
 // participating threads -- for kp < 512 the other warps have left) or inside the thread (>= 512).  Emits element r < K
 // through emit(r, low 32 bits).
 template <int NE, class Emit>
-__device__ __forceinline__ void sort_regs(unsigned long long* sortbuf, int kpad, int kp, int K, int tid, Emit emit) {
+__device__ __forceinline__ void sort_regs(unsigned long long* sortbuf, unsigned long long* sortbuf2, int kpad, int kp, int K,
+                                          int tid, Emit emit) {
     const int nthr = min(kp, TOPK_THREADS);
+    int xsel = 0;
     uint32_t hi[NE], lo[NE];
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
@@ -684,9 +691,26 @@ __device__ __forceinline__ void sort_regs(unsigned long long* sortbuf, int kpad,
     // keep the smaller (keep_min) or the larger of (hi, lo)[e] and the partner's (ph, pl)
     auto cx = [&](int e, uint32_t ph, uint32_t pl, bool keep_min) {
         const bool p_less = (ph < hi[e]) || (ph == hi[e] && pl < lo[e]);
-        if (p_less == keep_min) { hi[e] = ph; lo[e] = pl; }
+        const bool take = (p_less == keep_min);
+        hi[e] = take ? ph : hi[e];
+        lo[e] = take ? pl : lo[e];
     };
-    for (int k2 = 2; k2 <= kp; k2 <<= 1) {
+    // compare-exchange with the lane at distance jj inside the merge of width k2 (both compile-time in the callers)
+    auto warp_stage = [&](int k2, int jj) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int x = tid + TOPK_THREADS * e;
+            const uint32_t ph = __shfl_xor_sync(0xffffffffu, hi[e], jj), pl = __shfl_xor_sync(0xffffffffu, lo[e], jj);
+            cx(e, ph, pl, ((x & k2) == 0) == ((x & jj) == 0));
+        }
+    };
+    // merges of width <= 32: all inside a warp
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+        for (int jj = k2 >> 1; jj > 0; jj >>= 1) warp_stage(k2, jj);
+    }
+    for (int k2 = 64; k2 <= kp; k2 <<= 1) {
         int j = k2 >> 1;
         if (NE > 1) {
             for (; j >= TOPK_THREADS; j >>= 1) {                   // partner in the same thread: e ^ (j / 512)
@@ -706,28 +730,23 @@ __device__ __forceinline__ void sort_regs(unsigned long long* sortbuf, int kpad,
             }
         }
         for (; j >= 32; j >>= 1) {                                 // partner in another warp
-            asm volatile("bar.sync 1, %0;" :: "r"(nthr) : "memory");
+            // two exchange buffers in turn: the barrier of the next exchange orders this one's reads before the writes of
+            // the one after it, so one barrier per exchange suffices
+            unsigned long long* xb = xsel ? sortbuf2 : sortbuf;
+            xsel ^= 1;
 #pragma unroll
             for (int e = 0; e < NE; ++e)
-                sortbuf[tid + TOPK_THREADS * e] = ((unsigned long long)hi[e] << 32) | lo[e];
+                xb[tid + TOPK_THREADS * e] = ((unsigned long long)hi[e] << 32) | lo[e];
             asm volatile("bar.sync 1, %0;" :: "r"(nthr) : "memory");
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
                 const int x = tid + TOPK_THREADS * e;
-                const unsigned long long p = sortbuf[(tid ^ j) + TOPK_THREADS * e];
+                const unsigned long long p = xb[(tid ^ j) + TOPK_THREADS * e];
                 cx(e, (uint32_t)(p >> 32), (uint32_t)p, ((x & k2) == 0) == ((x & j) == 0));
             }
         }
 #pragma unroll
-        for (int jj = 16; jj > 0; jj >>= 1) {                      // partner in the same warp
-            if (jj > j) continue;
-#pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                const int x = tid + TOPK_THREADS * e;
-                const uint32_t ph = __shfl_xor_sync(0xffffffffu, hi[e], jj), pl = __shfl_xor_sync(0xffffffffu, lo[e], jj);
-                cx(e, ph, pl, ((x & k2) == 0) == ((x & jj) == 0));
-            }
-        }
+        for (int jj = 16; jj > 0; jj >>= 1) warp_stage(k2, jj);    // partner in the same warp
     }
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
@@ -743,8 +762,9 @@ topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* 
                 float* __restrict__ pts_all, int32_t* __restrict__ idx_all, int32_t* __restrict__ counts) {
     extern __shared__ unsigned long long sortbuf[];      // kpad entries when sorted
     constexpr int NW = TOPK_THREADS / 32;
-    __shared__ int hist[NW][256];
+    __shared__ __align__(16) int hist[NW][256];          // (reused as the sort's second exchange buffer)
     __shared__ int tot[256];
+    __shared__ int ltot[3][256];                         // digit counts of the candidate list, one table per lower digit
     __shared__ int warp_sum[NW];
     __shared__ uint32_t s_prefix, s_lo[NW], s_hi[NW];
     __shared__ int s_remaining, s_bin, s_ncand;
@@ -775,31 +795,40 @@ topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* 
 #pragma unroll
     for (int b = 0; b < 8; ++b) hist[wid][lane + 32 * b] = 0;
     if (tid == 0) s_ncand = 0;
+    if (tid < 256) { ltot[0][tid] = 0; ltot[1][tid] = 0; ltot[2][tid] = 0; }
 
-    // digit holding the `remaining`-th largest of the candidates counted in tot[] (warp 0; lane l owns digits [8l, 8l+8))
-    auto pick_digit = [&](uint32_t prefix, int remaining, int shift) {
-        int c[8], tl = 0;
+    // Digit holding the `remaining`-th largest of the candidates counted in t[256], found by warp 0 (lane l owns digits
+    // [8l, 8l+8)) and published through shared memory (measured: every warp evaluating it for itself costs more issue slots
+    // than the barrier it saves).  Requires 1 <= remaining <= sum(t).  Block-wide call (one barrier inside); updates
+    // prefix / remaining, returns the population of the chosen digit.
+    auto pick_digit = [&](const int* t, uint32_t& prefix, int& remaining, int shift) {
+        if (wid == 0) {
+            int c[8], tl = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { c[j] = tot[lane * 8 + j]; tl += c[j]; }
-        int suf = tl;        // inclusive suffix sum over lanes >= lane
+            for (int j = 0; j < 8; ++j) { c[j] = t[lane * 8 + j]; tl += c[j]; }
+            int suf = tl;        // inclusive suffix sum over lanes >= lane
 #pragma unroll
-        for (int o2 = 1; o2 < 32; o2 <<= 1) {
-            const int v = __shfl_down_sync(0xffffffffu, suf, o2);
-            if (lane + o2 < 32) suf += v;
-        }
-        const int above = suf - tl;   // candidates with a larger digit than this lane's
-        if (above < remaining && remaining <= above + tl) {
-            int cum = above;
-#pragma unroll
-            for (int j = 7; j >= 0; --j) {
-                if (cum < remaining && remaining <= cum + c[j]) {
-                    s_prefix = prefix | ((uint32_t)(lane * 8 + j) << shift);
-                    s_remaining = remaining - cum;
-                    s_bin = c[j];
-                }
-                cum += c[j];
+            for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                const int v = __shfl_down_sync(0xffffffffu, suf, o2);
+                if (lane + o2 < 32) suf += v;
             }
+            const int above = suf - tl;   // candidates with a larger digit than this lane's
+            const bool mine = above < remaining && remaining <= above + tl;
+            int dj = 0, rem = 0, bin = 0;
+            if (mine) {
+                int cum = above;
+#pragma unroll
+                for (int j = 7; j >= 0; --j) {
+                    if (cum < remaining && remaining <= cum + c[j]) { dj = lane * 8 + j; rem = remaining - cum; bin = c[j]; }
+                    cum += c[j];
+                }
+            }
+    if (mine) { s_prefix = prefix | ((uint32_t)dj << shift); s_remaining = rem; s_bin = bin; }      // exactly one lane
         }
+        __syncthreads();
+        prefix = s_prefix;
+        remaining = s_remaining;
+        return s_bin;
     };
 
     // ---- K-th largest key (skipped when every point is kept)
@@ -839,11 +868,9 @@ topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* 
                 tot[tid] = t;
             }
             __syncthreads();
-            if (wid == 0) pick_digit(0u, K, 24);
-            __syncthreads();
-            uint32_t prefix = s_prefix, mask = 0xff000000u;
-            int remaining = s_remaining;
-            const int bin = s_bin;
+            uint32_t prefix = 0u, mask = 0xff000000u;
+            int remaining = K;
+            const int bin = pick_digit(tot, prefix, remaining, 24);
             const uint32_t top = prefix | 0x00ffffffu;
             gt1 = 0; cm = 0;
 #pragma unroll
@@ -869,14 +896,16 @@ topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* 
                     }
                 }
                 for (int shift = 16; shift >= 0 && shift + 8 > lz; shift -= 8) {
+                    const int* t = tot;
                     if (listed) {
-                        if (tid < 256) tot[tid] = 0;
-                        __syncthreads();                 // (also publishes the list before its first use)
+                        if (shift == 16) __syncthreads();            // publishes the list
+                        int* lt = ltot[shift >> 3];
                         for (int c = tid; c < bin; c += TOPK_THREADS) {
                             const uint32_t u = cand[c];
-                            if ((u & mask) == prefix) atomicAdd(&tot[(u >> shift) & 255u], 1);
+                            if ((u & mask) == prefix) atomicAdd(&lt[(u >> shift) & 255u], 1);
                         }
                         __syncthreads();
+                        t = lt;
                     } else {
 #pragma unroll
                         for (int b = 0; b < 8; ++b) hist[wid][lane + 32 * b] = 0;
@@ -888,17 +917,14 @@ topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* 
                         }
                         __syncthreads();
                         if (tid < 256) {
-                            int t = 0;
+                            int sum = 0;
 #pragma unroll
-                            for (int w = 0; w < NW; ++w) t += hist[w][tid];
-                            tot[tid] = t;
+                            for (int w = 0; w < NW; ++w) sum += hist[w][tid];
+                            tot[tid] = sum;
                         }
                         __syncthreads();
                     }
-                    if (wid == 0) pick_digit(prefix, remaining, shift);
-                    __syncthreads();
-                    prefix = s_prefix;
-                    remaining = s_remaining;
+                    pick_digit(t, prefix, remaining, shift);
                     mask |= 255u << shift;
                 }
             }
@@ -1013,9 +1039,10 @@ topk_reg_kernel(const float* __restrict__ keys_all, int N, int nf, const float* 
     if (kpad <= TOPK_THREADS * TOPK_SORT_E) {
         const int kp = max(kpad, 32);                 // sentinels ~0 pad to a whole warp
         if (kp < TOPK_THREADS && tid >= kp) return;   // whole warps without an element leave (the sort's barriers count kp)
-        if (kp <= TOPK_THREADS) sort_regs<1>(sortbuf, kpad, kp, K, tid, emit);
-        else if (kp == 2 * TOPK_THREADS) sort_regs<2>(sortbuf, kpad, kp, K, tid, emit);
-        else sort_regs<4>(sortbuf, kpad, kp, K, tid, emit);
+        unsigned long long* sortbuf2 = reinterpret_cast<unsigned long long*>(&hist[0][0]);   // (free after the select: 2048 entries)
+        if (kp <= TOPK_THREADS) sort_regs<1>(sortbuf, sortbuf2, kpad, kp, K, tid, emit);
+        else if (kp == 2 * TOPK_THREADS) sort_regs<2>(sortbuf, sortbuf2, kpad, kp, K, tid, emit);
+        else sort_regs<4>(sortbuf, sortbuf2, kpad, kp, K, tid, emit);
         return;
     }
     for (int k2 = 2; k2 <= kpad; k2 <<= 1) {
