@@ -86,6 +86,47 @@ linear_f32_kernel(const float* __restrict__ X, const float* __restrict__ W, cons
     }
 }
 
+// Up to 32 rows (projections of the inducing points / seeds, heads on small batches): the 128-row tile kernel would run as
+// 1 x dout/64 blocks walking din serially (measured 24 us for 16 x 256 x 256).  Here a block owns eight output columns: it
+// stages the X rows (row stride din + 1: conflict-free for lane = row) and its eight W rows in shared memory with one round
+// of coalesced loads, then lane = row, warp = column accumulates from shared memory (the W element is a broadcast).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+linear_skinny_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
+                     float* __restrict__ Y, int rows, int din, int dout, float* __restrict__ R) {
+    extern __shared__ float skinny_s[];
+    float* Xs = skinny_s;                          // rows x (din + 1)
+    float* Ws = skinny_s + rows * (din + 1);       // 8 x din
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 8, c = c0 + w;
+    for (int i = threadIdx.x; i < rows * din; i += 256) {
+        const int r = i / din, k = i - r * din;
+        Xs[r * (din + 1) + k] = __ldg(X + i);
+    }
+    for (int i = threadIdx.x; i < 8 * din; i += 256) {
+        const int cc = i / din, k = i - cc * din;
+        Ws[i] = (c0 + cc < dout) ? __ldg(W + (long long)(c0 + cc) * din + k) : 0.f;
+    }
+    __syncthreads();
+    if (c >= dout || lane >= rows) return;
+    const float* xr = Xs + lane * (din + 1);
+    const float* wc = Ws + w * din;
+    float a0 = 0.f, a1 = 0.f;
+    int k = 0;
+    for (; k + 1 < din; k += 2) { a0 = fmaf(xr[k], wc[k], a0); a1 = fmaf(xr[k + 1], wc[k + 1], a1); }
+    if (k < din) a0 = fmaf(xr[k], wc[k], a0);
+    const int r = lane;
+    float v = (a0 + a1) + __ldg(bias + c);
+    if (MODE == 1) v = fmaxf(v, 0.f);
+    if (MODE == 2) v = xr[c] + fmaxf(v, 0.f);
+    if (MODE == 3) {
+        const float rl = fmaxf(v, 0.f);
+        R[(long long)r * dout + c] = rl;
+        v = xr[c] + rl;
+    }
+    Y[(long long)r * dout + c] = v;
+}
+
 int launch_linear(const float* X, const float* W, const float* b, float* Y, long long rows, int din,
                   int dout, int mode, cudaStream_t st, float* R, void* img, size_t img_bytes) {
     if (rows == 0) return 0;
@@ -94,6 +135,17 @@ int launch_linear(const float* X, const float* W, const float* b, float* Y, long
     if (img && img_bytes >= gemm_tc_image_bytes(dout, din) && linear_tc_eligible(rows, din, dout))
         return launch_linear_tc(X, W, 0, b, mode >= 2 ? X : nullptr, Y, mode == 3 ? R : nullptr, rows, din, dout, mode >= 1, img,
                                 img_bytes, st);
+    const size_t skinny_smem = ((size_t)rows * (din + 1) + 8 * (size_t)din) * sizeof(float);
+    if (rows <= 32 && Y != X && skinny_smem <= 48 * 1024) {
+        const unsigned g = (unsigned)((dout + 7) / 8);
+        LaunchTimer lt("linear_skinny_kernel", st, 2.0 * rows * din * dout, 4.0 * ((double)rows * (din + dout) + (double)din * dout));
+        if (mode == 0) linear_skinny_kernel<0><<<g, 256, skinny_smem, st>>>(X, W, b, Y, (int)rows, din, dout, nullptr);
+        else if (mode == 1) linear_skinny_kernel<1><<<g, 256, skinny_smem, st>>>(X, W, b, Y, (int)rows, din, dout, nullptr);
+        else if (mode == 2) linear_skinny_kernel<2><<<g, 256, skinny_smem, st>>>(X, W, b, Y, (int)rows, din, dout, nullptr);
+        else linear_skinny_kernel<3><<<g, 256, skinny_smem, st>>>(X, W, b, Y, (int)rows, din, dout, R);
+        PCA_CHECK_LAUNCH("linear_skinny_kernel");
+        return 0;
+    }
     dim3 grid((unsigned)((rows + LBM - 1) / LBM), (dout + LBN - 1) / LBN);
     {
         LaunchTimer lt("linear_f32_kernel", st, 2.0 * rows * din * dout, 4.0 * rows * (din + dout));
@@ -270,36 +322,37 @@ __global__ void attn_f32_kernel(const float* __restrict__ Qp, long long q_bstrid
   }
 }
 
+// One thread per (batch, query, head, head dim): the DH threads of one (b, q, h) read its partial rows side by side
+// (coalesced), each re-deriving the row's maximum and normaliser from the nsplit (m, l) pairs (broadcast loads).  Same
+// operations in the same order as a per-row loop, so the result does not depend on the thread layout.
 template <int DH>
 __global__ void attn_merge_kernel(const float* __restrict__ part, const float* __restrict__ Qp,
                                   long long q_bstride, int B, int nq, int H, int nsplit,
                                   float* __restrict__ O, float* __restrict__ lse) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * nq * H;
+    const long long i = t / DH;
+    const int j = (int)(t - i * DH);
     if (i >= total) return;
     const int h = (int)(i % H);
     const int q = (int)((i / H) % nq);
     const int b = (int)(i / ((long long)H * nq));
+    const long long sstride = (long long)nq * H * (DH + 2);
+    const float* p0 = part + (((long long)b * nsplit * nq + q) * H + h) * (DH + 2);
     float m = -INFINITY;
-    for (int s = 0; s < nsplit; ++s)
-        m = fmaxf(m, part[((((long long)b * nsplit + s) * nq + q) * H + h) * (DH + 2)]);
-    float l = 0.f, acc[DH];
-#pragma unroll
-    for (int j = 0; j < DH; ++j) acc[j] = 0.f;
+    for (int s = 0; s < nsplit; ++s) m = fmaxf(m, __ldg(p0 + s * sstride));
+    float l = 0.f, acc = 0.f;
     for (int s = 0; s < nsplit; ++s) {
-        const float* pp = part + ((((long long)b * nsplit + s) * nq + q) * H + h) * (DH + 2);
-        const float a = (pp[0] == -INFINITY) ? 0.f : exp2f(pp[0] - m);
-        l += pp[1] * a;
-#pragma unroll
-        for (int j = 0; j < DH; ++j) acc[j] = fmaf(pp[2 + j], a, acc[j]);
+        const float* pp = p0 + s * sstride;
+        const float pm = __ldg(pp);
+        const float a = (pm == -INFINITY) ? 0.f : exp2f(pm - m);
+        l += __ldg(pp + 1) * a;
+        acc = fmaf(__ldg(pp + 2 + j), a, acc);
     }
     const float inv = 1.f / l;
     const int D = H * DH;
-    const float* qptr = Qp + (long long)b * q_bstride + (long long)q * D + h * DH;
-    float* o = O + ((long long)b * nq + q) * D + h * DH;
-#pragma unroll
-    for (int j = 0; j < DH; ++j) o[j] = __ldg(qptr + j) + acc[j] * inv;
-    if (lse) lse[i] = m + log2f(l);
+    O[((long long)b * nq + q) * D + h * DH + j] = __ldg(Qp + (long long)b * q_bstride + (long long)q * D + h * DH + j) + acc * inv;
+    if (lse && j == 0) lse[i] = m + log2f(l);
 }
 
 struct AttnPlan { int tq_log, tk, nsplit, chunk; size_t smem; size_t part_floats; };
@@ -367,7 +420,7 @@ static int launch_attn_r(const float* Qp, long long q_bstride, const float* KV, 
         const long long total = (long long)B * nq * H;
         {
             LaunchTimer lt("attn_merge_kernel", st, 0.0, 4.0 * (double)p.part_floats);
-            attn_merge_kernel<DH><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(part, Qp, q_bstride, B, nq, H, p.nsplit, O, lse);
+            attn_merge_kernel<DH><<<(unsigned)((total * DH + 255) / 256), 256, 0, st>>>(part, Qp, q_bstride, B, nq, H, p.nsplit, O, lse);
         }
         PCA_CHECK_LAUNCH("attn_merge_kernel");
     }
