@@ -372,9 +372,10 @@ void pca_debug_set_tail_max(int tail_max);
  * 2 = the exact 2-warpgroup variant only. */
 void pca_debug_set_reduce_variant(int warpgroups);
 
-/* Debug / experiments: pooled-attention (PMA) kernel of the bf16 path: 1 = rows are (head, copy) pairs (default), 2 = transposed
- * formulation (thread = point: 8 instead of 128 exponentials per row and tile, asynchronous-copy producer; measured at the
- * same speed).  Also PCA_TC_POOL=2 in the environment. */
+/* Debug / experiments: pooled-attention (PMA) kernel of the bf16 path: 2 (default) = transposed formulation (thread = point,
+ * 8 exponentials per point), streaming pass against a fixed reference exponent with the sums accumulating in TMEM + exact redo
+ * of the work items it flags; 3 = the exact (per-tile re-referencing) pass on every work item; 1 = the round-1 kernel whose rows
+ * are (head, copy) pairs.  Also PCA_TC_POOL=1|2|3 in the environment. */
 void pca_debug_set_pool_variant(int variant);
 
 /* Debug / tests: 1 = run the generic STFT kernel (any power-of-two n_fft, any thread count; the code the fused front end

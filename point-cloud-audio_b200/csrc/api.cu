@@ -111,6 +111,24 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, unsigned long long inn
     return 0;
 }
 
+// The same (rows, 64) bf16 tensor seen as (8 elements, rows, 8 chunks) with byte strides (2, row_stride, 16): ONE box of
+// (8, box_rows, 8) then lands in shared memory as [chunk][row][16 B] -- the canonical no-swizzle UMMA operand layout of a
+// 64-wide tile -- where the 2-D view needs eight 16-byte-wide boxes (measured ~90 cycles of issue per TMA instruction).
+int make_tmap_chunked_bf16(CUtensorMap* out, const void* base, unsigned long long rows, unsigned long long row_stride_bytes,
+                           unsigned box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return fail(PCA_EDEVICE, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {8, rows, 8};
+    const cuuint64_t strides[2] = {row_stride_bytes, 16};
+    const cuuint32_t box[3] = {8, box_rows, 8};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PCA_EINVAL, "cuTensorMapEncodeTiled (chunked view) failed with CUresult %d (base %p, %llu rows, stride %llu)", (int)r, base, rows, row_stride_bytes);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------ profiling
 struct ProfRec { const char* name; cudaEvent_t a, b; double flops, bytes; };
 static std::atomic<int> g_prof_on{0};

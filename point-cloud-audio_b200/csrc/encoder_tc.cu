@@ -3093,6 +3093,9 @@ struct PoolParams {
     int tail_max;                 // leftover points (N mod 128 <= tail_max) are merged in finalize_pool_kernel
     const uint8_t* Aq;            // AqPool image
     float* part;                  // (B, 2 nsplit, 8 heads, 66): m (log2 domain), l, Z[64]
+    int* redo;                    // (n_work) flags of the streaming transposed kernel (pma_pool2_tc_kernel<false>), else unused
+    long long* timeline;          // debug (PCA_TIMELINE builds, PCA_TL_POOL=1): clock64 stamps of CTA 0, one lane per role
+    CUtensorMap tmapY;            // Y16 as an (8, B N, 8 chunks) bf16 tensor, box = (8, 128, 8) (transposed kernel only)
 };
 constexpr int POOL_STAGES = 3;
 struct PoolSmem {
@@ -3314,28 +3317,43 @@ __global__ void __launch_bounds__(TC_THREADS16, 1) pma_pool_tc_kernel(const Pool
 //   S (128 points, 16 columns = 8 heads + 8 zero) = Ytile (128 x 64, the staged tile as the A operand) . AqB^T   [4 MMAs, N = 16]
 //   thread = point: 8 exponentials per point and tile (the row-copy formulation evaluates 128 per row);
 //   the per-head tile maximum is a warp-shuffle + shared-memory reduction over the 128 points of the tile
-//   P^T (rows = heads, K = points) is written to shared memory as a K-major A operand (8 two-byte stores per thread)
-//   Z (heads, 64 features) = P^T . Ytile                                                        [8 MMAs, N = 64, MN-major B]
-//   lanes 0..7 of the first warp of a warpgroup hold the heads' running (m, Z) and rescale them per tile; the row sums l stay
-//   per-thread partials (the rescale factor is uniform over the points) and are reduced once per work item.
-constexpr int P2_NG = 2;                       // softmax warpgroups (tiles in the softmax stage)
-constexpr int P2_STAGES = 8;                   // Y tile ring (asynchronous copies keep six tiles in flight)
+//   P (K = points, N = 16 columns = 8 heads + 8 zero) is written to shared memory as a K-major B operand (8 two-byte stores
+//   per thread, 4 KB per warpgroup)
+//   Z^T (128 rows = 64 features | ones row | 63 don't-care rows, 16 columns) = [Ytile | 1]^T . P    [8 MMAs, N = 16, MN-major A]
+//   -- the Y tile is the A operand of BOTH products (K-major for the scores, MN-major here), so the tensor work per tile is
+//   128 x 16 x 128 MACs instead of the 128 x 64 x 128 of the P^T-as-A form (whose 120 zero rows were multiplied as well;
+//   the timeline showed the issuing thread blocked behind them: 666 cycles per tile in the P V issue alone).
+//   Thread f < 64 of a warpgroup holds feature f of the eight heads' running sums; the row sums come out of the ones row.
+constexpr int P2_NG = 4;                       // softmax warpgroups = tiles in the softmax stage (the chain S -> softmax -> P V of a
+                                               // tile is ~2000 cycles long: with two in flight the kernel ran at 1700 cycles per tile)
+constexpr int P2_STAGES = 10;                  // Y tile ring (asynchronous copies keep six tiles in flight)
 constexpr int P2_WP = 4 * P2_NG;               // first producer warp
 constexpr int P2_WM = P2_WP + 4;               // MMA warp
 constexpr int P2_THREADS = (P2_WM + 4) * 32;   // 16 warps
+constexpr int P2_YSTAGE = 9 * 2048;            // a Y stage: 8 chunks of 8 features + one constant chunk (1, 0, ..., 0): the "ones" column
 struct Pool2Smem {
     static constexpr int AQB = 0;                                 // 16 x 64 K-major B image (2 KB)
-    static constexpr int Y = 2048;                                // P2_STAGES x 16384
-    static constexpr int PT = Y + P2_STAGES * 16384;              // P2_NG x 32768: P^T as a 128-row K-major A image
-    static constexpr int ACC = PT + P2_NG * 32768;                // [P2_NG][8 heads][64] running Z
+    static constexpr int Y = 2048;                                // P2_STAGES x P2_YSTAGE
+    static constexpr int PT = Y + P2_STAGES * P2_YSTAGE + 16384;  // (16 KB slack: the A operand of the last stage reads 16 chunks)
+                                                                  // P2_NG x 4096: P as a 16-row K-major B image
+    static constexpr int ACC = PT + P2_NG * 4096;                 // (unused)
     static constexpr int RED = ACC + P2_NG * 8 * 64 * 4;          // [NG][2 parities][4 warps][8 heads] maxima, then [NG][4][8] sums
     static constexpr int BARS = RED + (P2_NG * 2 * 4 * 8 + P2_NG * 4 * 8) * 4;
-    static constexpr int TOTAL = BARS + 32 * 8 + 16;
+    static constexpr int TOTAL = BARS + 48 * 8 + 16;
 };
-constexpr uint32_t P2_S = 0, P2_O = 32 * P2_NG;        // NG x 32 score columns (16 used) | NG x 64 output columns
+constexpr uint32_t P2_S = 0, P2_O = 32 * P2_NG, P2_OW = 32;         // NG x 32 score columns (16 used) | NG x 32 output columns (16 used)
 
-
-__global__ void __launch_bounds__(P2_THREADS, 1) pma_pool2_tc_kernel(const PoolParams P) {
+// EXACT = false (streaming, the first pass): like mab_reduce6_tc_kernel, the heads' sums ACCUMULATE IN TMEM across the tiles of
+// a work item against a FIXED reference exponent -- here simply 0: softmax is shift invariant, and with fp32 sums, bf16
+// probabilities and fp32 accumulators any reference within 2^+-60 of the true maximum is exact to rounding (log2-domain
+// scores of a trained model are O(10)).  The row sums come out of the tensor core as well: every Y stage carries a ninth,
+// constant chunk whose first column is 1, so column 64 of Z = P^T [Y | 1] is sum_n p(n).  Per tile a warpgroup then only
+// loads 8 scores, evaluates 8 exponentials and writes its P^T column: no maximum, no shuffles, no named barrier, no read-back
+// or rescale of Z -- the kernel becomes the stream over Y it should be.  A work item whose sum leaves [2^-60, 2^60] (a score
+// far from the reference, overflow, NaN) is flagged in P.redo and redone by the EXACT = true pass, which is the per-tile
+// re-referencing algorithm (running maximum, Z read back and rescaled every tile) restricted to the flagged items.
+template <bool EXACT>
+__global__ void __launch_bounds__(P2_THREADS, 1) pma_pool2_tc_kernel(const __grid_constant__ PoolParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sAqB = smem + Pool2Smem::AQB;
     uint8_t* sY = smem + Pool2Smem::Y;
@@ -3344,12 +3362,12 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pma_pool2_tc_kernel(const PoolP
     float* sRedMax = reinterpret_cast<float*>(smem + Pool2Smem::RED);
     float* sRedSum = sRedMax + P2_NG * 2 * 4 * 8;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Pool2Smem::BARS);
-    uint64_t* y_full = bars;                        // [P2_STAGES] count 4 (producer warps)
+    uint64_t* y_full = bars;                        // [P2_STAGES] count 1 + transaction bytes (TMA loads)
     uint64_t* y_empty = bars + P2_STAGES;           // [P2_STAGES] count 1 (commit)
     uint64_t* s_full = bars + 2 * P2_STAGES;        // [NG] count 1
     uint64_t* p_ready = s_full + P2_NG;             // [NG] count 4
     uint64_t* o_full = p_ready + P2_NG;             // [NG] count 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P2_STAGES + 3 * P2_NG);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_work = P.n_work, wstep = gridDim.x;
@@ -3360,6 +3378,13 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pma_pool2_tc_kernel(const PoolP
         nb = main_points(P.counts ? max(1, min(P.N, __ldg(P.counts + cloud))) : P.N, P.tail_max);
         return max(0, min((nb + 127) >> 7, tile0 + P.tiles_per_split) - tile0);
     };
+    // EXACT: only the work items flagged by the streaming pass are processed (normally none: leave at once)
+    auto skipped = [&](int w) { return EXACT && __ldg(P.redo + w) == 0; };
+    if (EXACT) {
+        int any = 0;
+        for (int w = blockIdx.x + (int)threadIdx.x * wstep; w < n_work; w += (int)blockDim.x * wstep) any |= (__ldg(P.redo + w) != 0);
+        if (!__syncthreads_or(any)) return;
+    }
     // B image of the pooled queries: row n < 8 = head n (row 16 n of the 128-row A image built by prep_kernel), rows 8..15 zero
     for (int i = threadIdx.x; i < 8 * 16; i += blockDim.x) {
         const int c = i >> 4, n = i & 15;
@@ -3367,10 +3392,12 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pma_pool2_tc_kernel(const PoolP
         if (n < 8) v = __ldg(reinterpret_cast<const uint4*>(P.Aq + c * 2048 + (16 * n) * 16));
         *reinterpret_cast<uint4*>(sAqB + c * 256 + n * 16) = v;
     }
-    for (int i = threadIdx.x * 16; i < P2_NG * 32768; i += blockDim.x * 16) *reinterpret_cast<uint4*>(sPT + i) = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x * 16; i < P2_NG * 4096; i += blockDim.x * 16) *reinterpret_cast<uint4*>(sPT + i) = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < P2_STAGES * 128; i += blockDim.x)          // the ones chunk of every stage: bf16 (1, 0, 0, 0, 0, 0, 0, 0) per row
+        *reinterpret_cast<uint4*>(sY + (i >> 7) * P2_YSTAGE + 8 * 2048 + (i & 127) * 16) = make_uint4(0x00003F80u, 0, 0, 0);
     if (warp == P2_WM) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < P2_STAGES; ++i) { mbar_init(&y_full[i], 4); mbar_init(&y_empty[i], 1); }
+        for (int i = 0; i < P2_STAGES; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
         for (int i = 0; i < P2_NG; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); }
         fence_barrier_init();
     }
@@ -3379,128 +3406,212 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pma_pool2_tc_kernel(const PoolP
     __syncthreads();
     fence_after_sync();
     const uint32_t tb = *tmem_slot;
+#ifdef PCA_TIMELINE
+    // role 0: MMA warp, 1: softmax warpgroup 0 / warp 0, 2: producer warp 0 (2000 stamps each)
+    const int tl_role = warp == P2_WM ? 0 : (warp == 0 ? 1 : (warp == P2_WP ? 2 : (warp == P2_WM + 1 ? 3 : -1)));
+    long long* tl = (!EXACT && P.timeline != nullptr && blockIdx.x == 0 && tl_role >= 0 && lane == 0) ? P.timeline + 4000 * tl_role : nullptr;
+    int tl_n = 0;
+    auto stamp = [&](int tag) {
+        if (tl != nullptr && tl_n < 2000) { tl[2 * tl_n] = tag; tl[2 * tl_n + 1] = clock64(); ++tl_n; }
+    };
+#else
+    auto stamp = [&](int) {};
+#endif
 
     if (warp >= P2_WM) {
         reg_dec<40>();
+        // Two issuing warps (the timeline of the one-warp version: ~75 cycles per tcgen05.mma issue + commits = 1000 of the 2200
+        // cycles of a tile in the issuing thread alone): warp WM issues the score products, warp WM + 1 the P V products.
+        const uint32_t aqb = smem_u32(sAqB), yb = smem_u32(sY), ptb = smem_u32(sPT);
+        int total = 0;
+        if (warp <= P2_WM + 1)
+            for (int w = blockIdx.x; w < n_work; w += wstep) { int a, b, c, e; if (!skipped(w)) total += work_tiles(w, a, b, c, e); }
         if (warp == P2_WM) {
-            // =================================================================== MMA issuer (tiles in order; S runs NG - 1 tiles ahead)
+            // =================================================================== S issuer: at most NG tiles ahead of the softmax
             const bool leader = elect_one();
             const uint32_t idesc_s = idesc_bf16(128, 16, 0, 0);
-            const uint32_t idesc_pv = idesc_bf16(128, 64, 0, 1);
-            const uint32_t aqb = smem_u32(sAqB), yb = smem_u32(sY), ptb = smem_u32(sPT);
-            int total = 0;
-            for (int w = blockIdx.x; w < n_work; w += wstep) { int a, b, c, e; total += work_tiles(w, a, b, c, e); }
-            auto issue_s = [&](int t) {
-                // the score buffer t % NG was last read by its warpgroup before it arrived on p_ready for tile t - NG, which
-                // this warp has waited for (P V of tile t - NG is issued before S of tile t in the loop below)
-                const int stage = t % P2_STAGES;
+            for (int t = 0; t < total; ++t) {
+                const int stage = t % P2_STAGES, b = t % P2_NG;
+                // the score buffer b was last read by its warpgroup before it arrived on p_ready for tile t - NG
+                if (t >= P2_NG) mbar_spin(&p_ready[b], ((t / P2_NG) - 1) & 1);
+                stamp(1);
                 mbar_spin(&y_full[stage], (t / P2_STAGES) & 1);
+                stamp(2);
                 fence_after_sync();
                 if (leader) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        mma_ss(tmem_addr(tb, 0, P2_S + 32 * (t % P2_NG)), smem_desc(yb + stage * 16384 + ks * 4096, 2048, 128),
-                               smem_desc(aqb + ks * 512, 256, 128), idesc_s, ks > 0);
-                    mma_commit(&s_full[t % P2_NG]);
+                        // (even / odd K steps into two accumulators: accumulating MMAs on ONE accumulator serialise at ~80 cycles each)
+                        mma_ss(tmem_addr(tb, 0, P2_S + 32 * b + 16 * (ks & 1)), smem_desc(yb + stage * P2_YSTAGE + ks * 4096, 2048, 128),
+                               smem_desc(aqb + ks * 512, 256, 128), idesc_s, ks > 1);
+                    mma_commit(&s_full[b]);
                 }
                 __syncwarp();
-            };
-            for (int t = 0; t < P2_NG - 1 && t < total; ++t) issue_s(t);
+                stamp(3);
+            }
+        } else if (warp == P2_WM + 1) {
+            // =================================================================== P V issuer
+            const bool leader = elect_one();
+            // A = [Y | 1]^T, MN-major: rows 0..63 features, row 64 the ones column, rows 65..127 whatever follows the stage in
+            // shared memory (they only reach output rows that are never read)
+            const uint32_t idesc_pv = idesc_bf16(128, 16, 1, 0);
+            // position of the P V stream inside its work item (streaming pass: the first tile of a warpgroup in an item starts
+            // the TMEM accumulator, the others add to it)
+            int pw = blockIdx.x - wstep, pit = 0, pnt = 0;
             for (int t = 0; t < total; ++t) {
-                if (t + P2_NG - 1 < total) issue_s(t + P2_NG - 1);
                 const int b = t % P2_NG, stage = t % P2_STAGES;
+                while (pit >= pnt) {
+                    pw += wstep;
+                    pit = 0;
+                    int a, bb, c, e;
+                    pnt = skipped(pw) ? 0 : work_tiles(pw, a, bb, c, e);
+                }
+                const uint32_t acc_in = (!EXACT && pit >= P2_NG) ? 1u : 0u;
+                ++pit;
                 mbar_spin(&p_ready[b], (t / P2_NG) & 1);
+                stamp(4);
                 fence_after_sync();
                 if (leader) {
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
-                        mma_ss(tmem_addr(tb, 0, P2_O + 64 * b), smem_desc(ptb + b * 32768 + ks * 4096, 2048, 128),
-                               smem_desc(yb + stage * 16384 + ks * 256, 128, 2048), idesc_pv, ks > 0);
+                        mma_ss(tmem_addr(tb, 0, P2_O + P2_OW * b + 16 * (ks & 1)), smem_desc(yb + stage * P2_YSTAGE + ks * 256, 128, 2048),
+                               smem_desc(ptb + b * 4096 + ks * 512, 256, 128), idesc_pv, (ks > 1) ? 1u : acc_in);
                     mma_commit(&o_full[b]);
                     mma_commit(&y_empty[stage]);
                 }
                 __syncwarp();
+                stamp(5);
             }
         }
     } else if (warp >= P2_WP) {
-        reg_dec<88>();
-        // =================================================================== producer: Y tiles -> [chunk][row][16 B]
-        // The kernel is a stream over Y: the loads of the next tile are in flight while a tile is written to shared memory.
-        const int row = 32 * (warp & 3) + lane;
-        struct TileIt { int w, it, cloud, tile0, nb, ntiles; bool ok; };
-        auto seek = [&](TileIt& ti) {
-            ti.ok = false;
-            int split;
-            while (ti.w < n_work) {
-                if (ti.it == 0) ti.ntiles = work_tiles(ti.w, ti.cloud, split, ti.tile0, ti.nb);
-                if (ti.it < ti.ntiles) { ti.ok = true; return; }
-                ti.w += wstep;
-                ti.it = 0;
-            }
-        };
-        // asynchronous 16-byte copies straight into the operand layout: P2_DEPTH tiles in flight per thread, no register staging
-        // (one tile in flight per load latency bounded the register-staged version at 1.9 TB/s)
-        // Ordering: tile t is signalled BEFORE tile t + DEPTH is issued.  The issue may wait for the ring slot of tile
-        // t + DEPTH - STAGES to be released by its P V MMA, which the MMA warp issues only after it has seen the tiles up to
-        // NG - 1 ahead of that one -- all of them signalled by then because DEPTH <= STAGES - NG.
-        constexpr int P2_DEPTH = P2_STAGES - P2_NG;
-        auto issue = [&](const TileIt& ti, int t) {
-            if (ti.ok) {
-                const int stage = t % P2_STAGES;
-                if (t >= P2_STAGES) mbar_spin(&y_empty[stage], ((t / P2_STAGES) - 1) & 1);
-                uint8_t* dst = sY + stage * 16384 + row * 16;
-                const int n = (ti.tile0 + ti.it) * 128 + row;
-                if (n < ti.nb) {
-                    const uint4* src = reinterpret_cast<const uint4*>(P.Y16 + ((size_t)ti.cloud * P.N + n) * 64);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) cp_async16(dst + c * 2048, src + c);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + c * 2048) = make_uint4(0, 0, 0, 0);
+        reg_dec<56>();
+        // =================================================================== loader: Y tiles by TMA, 8 boxes of 128 rows x 8
+        // columns land as [chunk][row][16 B].  (The four-warp cp.async producer it replaces spent ~1000 cycles per tile in its
+        // own bookkeeping, fences and arrivals: the timeline showed it as the critical path.)  Rows past the cloud's points in
+        // a ragged tile hold whatever follows in memory; the softmax warpgroup zero-fills them before the P V product.
+        if (warp == P2_WP) {
+            if (lane == 0) tma_prefetch_desc(&P.tmapY);
+            int gt = 0;
+            for (int w = blockIdx.x; w < n_work; w += wstep) {
+                if (skipped(w)) continue;
+                int cloud, split, tile0, nb;
+                const int ntiles = work_tiles(w, cloud, split, tile0, nb);
+                for (int it = 0; it < ntiles; ++it, ++gt) {
+                    const int stage = gt % P2_STAGES;
+                    stamp(20);
+                    if (gt >= P2_STAGES) mbar_wait(&y_empty[stage], ((gt / P2_STAGES) - 1) & 1);
+                    stamp(21);
+                    if (lane == 0) {
+                        uint8_t* dst = sY + stage * P2_YSTAGE;
+                        const long long r0 = (long long)cloud * P.N + (long long)(tile0 + it) * 128;
+                        mbar_arrive_expect_tx(&y_full[stage], 16384);
+                        tma_load_3d(dst, &P.tmapY, 0, (int)r0, 0, &y_full[stage]);      // one box: (8 elements, 128 rows, 8 chunks)
+                    }
+                    __syncwarp();
+                    stamp(22);
                 }
             }
-            cp_async_commit();                    // (an empty group past the last tile keeps the group count uniform)
-        };
-        TileIt cur{(int)blockIdx.x, 0, 0, 0, 0, 0, false};
-        seek(cur);
-        TileIt ahead = cur;                       // the next tile to issue
-        int t_issue = 0;
-        for (int d = 0; d < P2_DEPTH; ++d) {
-            issue(ahead, t_issue);
-            if (ahead.ok) { ++ahead.it; seek(ahead); ++t_issue; }
         }
-        int t = 0;
-        while (cur.ok) {
-            cp_async_wait<P2_DEPTH - 1>();        // all but the newest DEPTH - 1 groups have landed: tile t is complete
-            fence_async_smem();
-            fence_before_sync();
-            warp_arrive(&y_full[t % P2_STAGES]);
-            issue(ahead, t_issue);
-            if (ahead.ok) { ++ahead.it; seek(ahead); ++t_issue; }
-            ++cur.it;
-            seek(cur);
-            ++t;
-        }
-        cp_async_wait<0>();
     } else {
-        reg_inc<152>();       // register pool of the CTA: 16 warps x 128 >= softmax 8 x 152 + producer 4 x 88 + MMA 4 x 40
+        reg_inc<88>();        // per scheduler: 6 warps x 80 at launch >= softmax 4 x 88 + producer 56 + MMA 40
         // =================================================================== softmax warpgroups: g takes the tiles with t % NG == g
         const int g = warp >> 2, quad = warp & 3;
         const int row = 32 * quad + lane;                 // point of the tile
         const uint32_t lane_base = 32 * quad;
-        uint8_t* pt = sPT + g * 32768;
-        float* accs = sAcc + (g * 8 + (lane & 7)) * 64;   // running Z of head `lane` (first warp of the warpgroup, lanes 0..7)
+        uint8_t* pt = sPT + g * 4096;
         int t = 0, own = 0;                               // own: tiles this warpgroup has processed (phases, reduction buffer parity)
         for (int w = blockIdx.x; w < n_work; w += wstep) {
+            if (skipped(w)) continue;
             int cloud, split, tile0, nb;
             const int ntiles = work_tiles(w, cloud, split, tile0, nb);
+            if (!EXACT) {
+                // ---------------- streaming pass: reference exponent 0, Z and the row sums accumulate in TMEM
+                const int group = (g - t) & (P2_NG - 1);
+                int mine = 0;                              // tiles of this warpgroup in this work item
+                for (int it = 0; it < ntiles; ++it, ++t) {
+                    if ((t & (P2_NG - 1)) != g) continue;
+                    const bool valid = row < min(128, nb - (tile0 + it) * 128);
+                    stamp(10);
+                    mbar_spin(&s_full[g], own & 1);
+                    stamp(11);
+                    fence_after_sync();
+                    uint32_t sv[8], sw[8];
+                    tmem_ld8(tmem_addr(tb, lane_base, P2_S + 32 * g), sv);
+                    tmem_ld8(tmem_addr(tb, lane_base, P2_S + 32 * g + 16), sw);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) sv[h] = __float_as_uint(__uint_as_float(sv[h]) + __uint_as_float(sw[h]));
+                    stamp(12);
+                    if (own > 0) mbar_spin(&o_full[g], (own - 1) & 1);      // P V of the previous tile has read this P^T buffer
+                    stamp(13);
+                    if (!valid) {          // ragged tile: this row of the stage is not a point of the cloud (0 x NaN would poison Z)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            *reinterpret_cast<uint4*>(sY + (t % P2_STAGES) * P2_YSTAGE + c * 2048 + row * 16) = make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 8; ++h)
+#ifdef PCA_P2_NOEXP
+                        *reinterpret_cast<__nv_bfloat16*>(pt + (row >> 3) * 256 + h * 16 + (row & 7) * 2) =
+                            __float2bfloat16(valid ? __uint_as_float(sv[h]) : 0.f);
+#else
+                        *reinterpret_cast<__nv_bfloat16*>(pt + (row >> 3) * 256 + h * 16 + (row & 7) * 2) =
+                            __float2bfloat16(valid ? ex2(__uint_as_float(sv[h])) : 0.f);
+#endif
+#ifndef PCA_P2_NOFENCE
+                    fence_async_smem();
+#endif
+                    fence_before_sync();
+                    warp_arrive(&p_ready[g]);
+                    stamp(15);
+                    ++own;
+                    ++mine;
+                }
+                stamp(16);
+                {
+                    // the item's Z^T and row sums: one read of the TMEM accumulator once its last P V has completed.  Thread f < 64
+                    // holds feature f of the eight heads, thread 64 the eight row sums.  (The first P V of the next item needs
+                    // every warp's arrival, so the accumulator is not overwritten before it has been read.)
+                    float* dst = P.part + (((size_t)cloud * P.nsplit + split) * P2_NG + group) * TH * 66;
+                    uint32_t o[8];
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) o[h] = 0u;
+                    if (mine > 0 && quad < 3) {
+                        mbar_spin(&o_full[g], (own - 1) & 1);
+                        fence_after_sync();
+                        uint32_t o1[8];
+                        tmem_ld8(tmem_addr(tb, lane_base, P2_O + P2_OW * g), o);
+                        tmem_ld8(tmem_addr(tb, lane_base, P2_O + P2_OW * g + 16), o1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) o[h] = __float_as_uint(__uint_as_float(o[h]) + __uint_as_float(o1[h]));
+                        fence_before_sync();
+                    }
+                    if (row < 64) {
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) dst[h * 66 + 2 + row] = __uint_as_float(o[h]);
+                    } else if (row == 64) {
+                        bool bad = false;
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) {
+                            const float l_sum = __uint_as_float(o[h]);
+                            dst[h * 66] = mine > 0 ? 0.f : -INFINITY;
+                            dst[h * 66 + 1] = l_sum;
+                            // sum outside [2^-60, 2^60] (a score far from the reference, overflow, NaN): redo the item exactly
+                            bad |= mine > 0 && !(l_sum > 8.673617379884035e-19f && l_sum < 1.152921504606847e18f);
+                        }
+                        if (bad) P.redo[w] = 1;
+                    }
+                }
+                stamp(17);
+                continue;
+            }
             float m_run[8], l_part[8];
 #pragma unroll
             for (int h = 0; h < 8; ++h) { m_run[h] = -INFINITY; l_part[h] = 0.f; }
-            if (quad == 0 && lane < 8) {
+            float accz[8];                                 // feature `row` (< 64) of the eight heads' running sums
 #pragma unroll
-                for (int j = 0; j < 64; ++j) accs[j] = 0.f;
-            }
+            for (int h = 0; h < 8; ++h) accz[h] = 0.f;
             // the partial is filed under (tile index within the work item) mod NG, so the grouping (and hence every rounding)
             // of a cloud is independent of what the CTA processed before
             const int group = (g - t) & (P2_NG - 1);
@@ -3510,13 +3621,14 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pma_pool2_tc_kernel(const PoolP
                 const bool valid = row < n_valid;
                 mbar_spin(&s_full[g], own & 1);
                 fence_after_sync();
-                uint32_t sv[8];
+                uint32_t sv[8], sw[8];
                 tmem_ld8(tmem_addr(tb, lane_base, P2_S + 32 * g), sv);
+                tmem_ld8(tmem_addr(tb, lane_base, P2_S + 32 * g + 16), sw);
                 tmem_ld_wait();
                 float s[8], mx[8];
 #pragma unroll
                 for (int h = 0; h < 8; ++h) {
-                    s[h] = __uint_as_float(sv[h]);
+                    s[h] = __uint_as_float(sv[h]) + __uint_as_float(sw[h]);
                     mx[h] = valid ? s[h] : -INFINITY;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], o));
@@ -3529,7 +3641,12 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pma_pool2_tc_kernel(const PoolP
                     red[quad * 8 + lane] = v;
                 }
                 named_bar_sync(1 + g, 128);
-                float a_l = 1.f;
+                if (!valid) {              // ragged tile: see the streaming pass
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<uint4*>(sY + (t % P2_STAGES) * P2_YSTAGE + c * 2048 + row * 16) = make_uint4(0, 0, 0, 0);
+                }
+                float alpha_h[8];
 #pragma unroll
                 for (int h = 0; h < 8; ++h) {
                     const float m_tile = fmaxf(fmaxf(red[h], red[8 + h]), fmaxf(red[16 + h], red[24 + h]));
@@ -3538,26 +3655,22 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pma_pool2_tc_kernel(const PoolP
                     const float p = valid ? ex2(s[h] - m_new) : 0.f;
                     l_part[h] = fmaf(l_part[h], alpha, p);
                     m_run[h] = m_new;
-                    a_l = lane == h ? alpha : a_l;
-                    *reinterpret_cast<__nv_bfloat16*>(pt + (row >> 3) * 2048 + h * 16 + (row & 7) * 2) = __float2bfloat16(p);
+                    alpha_h[h] = alpha;
+                    *reinterpret_cast<__nv_bfloat16*>(pt + (row >> 3) * 256 + h * 16 + (row & 7) * 2) = __float2bfloat16(p);
                 }
                 fence_async_smem();
                 fence_before_sync();
                 warp_arrive(&p_ready[g]);
-                // ---- Z += P^T Y: heads' running sums in shared memory (lanes 0..7 of the warpgroup's first warp)
+                // ---- Z^T += [Y | 1]^T P: thread f < 64 rescales and adds feature f of the eight heads
                 mbar_spin(&o_full[g], own & 1);
                 fence_after_sync();
-                if (quad == 0) {
+                if (quad < 2) {
+                    uint32_t o[8], o1[8];
+                    tmem_ld8(tmem_addr(tb, lane_base, P2_O + P2_OW * g), o);
+                    tmem_ld8(tmem_addr(tb, lane_base, P2_O + P2_OW * g + 16), o1);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 32) {
-                        uint32_t o[32];
-                        tmem_ld32(tmem_addr(tb, 0, P2_O + 64 * g + c0), o);
-                        tmem_ld_wait32(o);
-                        if (lane < 8) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) accs[c0 + j] = fmaf(accs[c0 + j], a_l, __uint_as_float(o[j]));
-                        }
-                    }
+                    for (int h = 0; h < 8; ++h) accz[h] = fmaf(accz[h], alpha_h[h], __uint_as_float(o[h]) + __uint_as_float(o1[h]));
                 }
                 fence_before_sync();
                 ++own;
@@ -3580,16 +3693,17 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pma_pool2_tc_kernel(const PoolP
                 rs[quad * 8 + lane] = v;
             }
             named_bar_sync(1 + g, 128);
-            if (quad == 0 && lane < 8) {
-                const int h = lane;
+            float* dst = P.part + (((size_t)cloud * P.nsplit + split) * P2_NG + group) * TH * 66;
+            if (row < 64) {
+#pragma unroll
+                for (int h = 0; h < 8; ++h) dst[h * 66 + 2 + row] = accz[h];
+            } else if (row < 72) {
+                const int h = row - 64;
                 float m_l = m_run[0];
 #pragma unroll
-                for (int hh = 1; hh < 8; ++hh) m_l = lane == hh ? m_run[hh] : m_l;
-                float* dst = P.part + ((((size_t)cloud * P.nsplit + split) * P2_NG + group) * TH + h) * 66;
-                dst[0] = m_l;
-                dst[1] = rs[h] + rs[8 + h] + rs[16 + h] + rs[24 + h];
-#pragma unroll
-                for (int j = 0; j < 64; ++j) dst[2 + j] = accs[j];
+                for (int hh = 1; hh < 8; ++hh) m_l = h == hh ? m_run[hh] : m_l;
+                dst[h * 66] = m_l;
+                dst[h * 66 + 1] = rs[h] + rs[8 + h] + rs[16 + h] + rs[24 + h];
             }
         }
     }
@@ -3740,7 +3854,8 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 
 // ------------------------------------------------------------------------------------ host orchestration
 static int g_num_sms = 148;
-static int g_pool_variant = 1;             // pooled attention: 1 = row copies, 2 = transposed (PCA_TC_POOL=2)
+static int g_pool_variant = 2;             // pooled attention: 2 = transposed, streaming + exact redo (default), 3 = transposed, exact pass only,
+                                           // 1 = row copies (PCA_TC_POOL / pca_debug_set_pool_variant)
 static int g_reduce_wg = 6;               // reduce kernel: 6 = sixth generation (+ exact redo of flagged items), 4 = streaming fifth generation (+ redo), 2 = exact only
 static int g_apply_variant = 4;           // apply kernel: 4 = three softmax warpgroups, TMA loader; 3 = previous generation (PCA_TC_APPLY=3)
 static int g_tail_max = TC_TAIL_MAX;       // tail rule (PCA_TC_TAIL=0 disables it: every point goes through the tensor-core kernels)
@@ -3748,7 +3863,7 @@ static long long* g_timeline = nullptr;      // set through pca_debug_set_timeli
 void set_timeline(long long* p) { g_timeline = p; }
 void set_tail_max(int t) { g_tail_max = t < 0 ? 0 : (t > TC_TAIL_MAX ? TC_TAIL_MAX : t); }
 void set_reduce_wg(int n) { g_reduce_wg = (n == 4 || n == 6) ? n : 2; }
-void set_pool_variant(int v) { g_pool_variant = (v == 2) ? 2 : 1; }
+void set_pool_variant(int v) { g_pool_variant = (v == 1 || v == 3) ? v : 2; }
 void set_apply_variant(int v) { g_apply_variant = (v == 3) ? 3 : 4; }
 struct TcSplit { int tiles_total, tiles_per_split, nsplit; };
 // The point range of a cloud is cut into fixed spans of 16 tiles (2048 points).  The cut depends on N only, never
@@ -3823,7 +3938,7 @@ static int st_tc_chunk(const float* X, const PointSrc& src, const int* counts, i
     // ---- ISAB 0
     {
         RParams r{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Aq0, m00.Wkv, m00.bkv,
-                  nullptr, (tl_apply || getenv("PCA_TL_REDUCE64")) ? nullptr : g_timeline, redo, 0, part};
+                  nullptr, (tl_apply || getenv("PCA_TL_REDUCE64") || getenv("PCA_TL_POOL")) ? nullptr : g_timeline, redo, 0, part};
         LaunchTimer lt("mab_reduce_tc_kernel", st, pts * 2.0 * (2.0 * d_in * TD + 2.0 * TM * TD), pts * 4.0 * d_in);
         if (g_reduce_wg == 6) {
             PCA_CHECK_CUDA(cudaMemsetAsync(redo, 0, (size_t)n_work * sizeof(int), st));
@@ -3926,14 +4041,22 @@ static int st_tc_chunk(const float* X, const PointSrc& src, const int* counts, i
     }
     // ---- PMA + Linear
     {
-        PoolParams r{Y2, N, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->AqPool, part};
+        PoolParams r{Y2, N, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->AqPool, part, redo,
+                     getenv("PCA_TL_POOL") ? g_timeline : nullptr, CUtensorMap{}};
+        if (g_pool_variant >= 2) PCA_TRY(make_tmap_chunked_bf16(&r.tmapY, Y2, (unsigned long long)B * N, 128, 128));
+        if (g_pool_variant == 2) PCA_CHECK_CUDA(cudaMemsetAsync(redo, 0, (size_t)n_work * sizeof(int), st));
+        if (g_pool_variant == 3) PCA_CHECK_CUDA(cudaMemsetAsync(redo, 0xff, (size_t)n_work * sizeof(int), st));   // debug: every item exact
         LaunchTimer lt("pma_pool_tc_kernel", st, pts * 2.0 * (2.0 * TH * TD), pts * 128.0);
-        if (g_pool_variant == 2) pma_pool2_tc_kernel<<<pgrid, P2_THREADS, Pool2Smem::TOTAL, st>>>(r);
-        else pma_pool_tc_kernel<<<pgrid, TC_THREADS16, PoolSmem::TOTAL, st>>>(r);
+        if (g_pool_variant == 2) {
+            pma_pool2_tc_kernel<false><<<pgrid, P2_THREADS, Pool2Smem::TOTAL, st>>>(r);
+            pma_pool2_tc_kernel<true><<<pgrid, P2_THREADS, Pool2Smem::TOTAL, st>>>(r);       // exact redo of flagged work items
+        } else if (g_pool_variant == 3) {
+            pma_pool2_tc_kernel<true><<<pgrid, P2_THREADS, Pool2Smem::TOTAL, st>>>(r);
+        } else pma_pool_tc_kernel<<<pgrid, TC_THREADS16, PoolSmem::TOTAL, st>>>(r);
     }
     PCA_CHECK_LAUNCH("pma_pool_tc_kernel");
     {
-        PoolFinParams p{part, (g_pool_variant == 2 ? P2_NG : 2) * sp.nsplit, B, c->QpS, c->WvT_P, mp.bkv + TD, c->WoT_P, mp.bo, p_lin, p_lin + (long long)d->C * TD,
+        PoolFinParams p{part, (g_pool_variant >= 2 ? P2_NG : 2) * sp.nsplit, B, c->QpS, c->WvT_P, mp.bkv + TD, c->WoT_P, mp.bo, p_lin, p_lin + (long long)d->C * TD,
                         d->C, logits, dbg ? dbg->pooled : nullptr, Y2, N, counts, tm, c->WqkPool};
         LaunchTimer lt("finalize_pool_kernel", st, (double)B * 2.0 * (2.0 * TD * TD + TD * d->C), (double)B * 4.0 * d->C);
         finalize_pool_kernel<<<(B + 3) / 4, 256, 0, st>>>(p);
@@ -3974,8 +4097,9 @@ static int tc_configure() {
     if (const char* v = getenv("PCA_TC_APPLY")) g_apply_variant = (v[0] == '3') ? 3 : 4;
     PCA_CHECK_CUDA(cudaFuncSetAttribute(finalize_isab_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2Smem::TOTAL));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(pma_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PoolSmem::TOTAL));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(pma_pool2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Pool2Smem::TOTAL));
-    if (const char* v = getenv("PCA_TC_POOL")) g_pool_variant = (v[0] == '2') ? 2 : 1;
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(pma_pool2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pool2Smem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(pma_pool2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pool2Smem::TOTAL));
+    if (const char* v = getenv("PCA_TC_POOL")) g_pool_variant = (v[0] == '1') ? 1 : (v[0] == '3' ? 3 : 2);
     if (dev < 64) done_mask.fetch_or(1ull << dev, std::memory_order_release);
     return 0;
 }

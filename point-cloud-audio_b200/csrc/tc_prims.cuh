@@ -96,6 +96,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, in
                  "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
 // 2-D tiled tensor store shared -> global (bulk-group completion: commit, then wait_group(.read) by the same thread);
 // parts of the box outside the tensor are not written
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src_smem, int c0, int c1) {

@@ -12,4 +12,8 @@ namespace pca {
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, unsigned long long inner, unsigned long long rows,
                       unsigned long long row_stride_bytes, unsigned box_inner, unsigned box_rows);
 
+// (rows, 64) bf16 tensor viewed as (8 elements, rows, 8 chunks): one box of (8, box_rows, 8) lands as [chunk][row][16 B]
+int make_tmap_chunked_bf16(CUtensorMap* out, const void* base, unsigned long long rows, unsigned long long row_stride_bytes,
+                           unsigned box_rows);
+
 }  // namespace pca

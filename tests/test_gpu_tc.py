@@ -230,30 +230,62 @@ def test_pipelined_host_interface_matches_device_call(pca):
         assert torch.equal(o.squeeze(1), ref)
 
 
+@pytest.mark.parametrize("variant", [1, 3])
 @pytest.mark.parametrize("d_in,B,N", [(2, 5, 1025), (3, 2, 5120), (2, 3, 300), (3, 1, 1)])
-def test_tc_transposed_pooled_attention_variant(pca, d_in, B, N):
-    """The transposed pooled-attention kernel (pca_debug_set_pool_variant(2)): same stage errors against the oracle, and
-    masked sets through it."""
+def test_tc_pooled_attention_variants(pca, d_in, B, N, variant):
+    """The pooled-attention kernels that are not the default (pca_debug_set_pool_variant: 1 = rows are (head, copy) pairs,
+    3 = the transposed kernel's exact pass on every work item; the default 2 is its streaming pass + redo): same stage errors
+    against the oracle, and masked sets through them agree with the default."""
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import debug_tc_stages
     from pcaudio_b200 import _lib
     try:
-        _lib.lib().pca_debug_set_pool_variant(2)
+        _lib.lib().pca_debug_set_pool_variant(variant)
         errs = debug_tc_stages.run(d_in, B, N)
         dev = torch.device("cuda:0")
         torch.manual_seed(1)
         st = pca.ST(dim_input=3, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev).set_precision("bf16")
         X = torch.rand(6, 700, 3, device=dev)
         counts = torch.tensor([700, 1, 129, 513, 640, 256], dtype=torch.int32, device=dev)
-        masked2 = st(X, counts=counts).clone()
-        _lib.lib().pca_debug_set_pool_variant(1)
-        masked1 = st(X, counts=counts).clone()
+        other = st(X, counts=counts).clone()
+        _lib.lib().pca_debug_set_pool_variant(2)
+        default = st(X, counts=counts).clone()
     finally:
-        _lib.lib().pca_debug_set_pool_variant(1)
+        _lib.lib().pca_debug_set_pool_variant(2)
     for k, v in errs.items():
         assert v < BF16_REL_TOL, f"stage {k}: rel err {v:.3e} (all: {errs})"
-    assert ((masked2 - masked1).abs().max() / masked1.abs().max()).item() < BF16_REL_TOL
+    assert torch.isfinite(default).all()
+    assert ((other - default).abs().max() / default.abs().max()).item() < BF16_REL_TOL
+
+
+@pytest.mark.parametrize("N,gain", [(1025, 1.0), (2500, 2000.0), (2500, 1.0e5), (300, 1.0e5), (5120, 30.0)])
+def test_tc_pooled_streaming_pass_and_redo(pca, N, gain):
+    """The default pooled-attention kernel streams against reference exponent 0 (sums accumulate in TMEM, row sums through a
+    ones column) and hands work items whose sum leaves [2^-60, 2^60] to the exact pass.  Pooled vectors of both routes (2:
+    streaming + redo, 3: exact pass on everything) must agree -- moderate inputs (nothing flagged), inputs scaled until the
+    scores overflow the reference (everything flagged), ragged last tiles (N = 2500, 300: the loader's TMA box brings rows of
+    the next cloud, which the softmax warps zero)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import debug_tc_stages
+    from pcaudio_b200 import _lib
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    st = pca.ST(dim_input=3, num_outputs=1, dim_output=10, num_inds=64, dim_hidden=64, num_heads=8).to(dev)
+    gen = torch.Generator().manual_seed(N)
+    X = torch.randn(6, N, 3, generator=gen) * (0.05 if gain != 1.0 else 1.0)
+    X[:, N - max(1, N // 7):] *= gain
+    out = {}
+    try:
+        for v in (2, 3):
+            _lib.lib().pca_debug_set_pool_variant(v)
+            out[v] = debug_tc_stages.stages(st, X.to(dev))["pooled"].float().cpu()
+    finally:
+        _lib.lib().pca_debug_set_pool_variant(2)
+    assert torch.isfinite(out[2]).all() and torch.isfinite(out[3]).all()
+    err = (out[2] - out[3]).abs().max().item() / out[3].abs().max().item()
+    assert err < BF16_REL_TOL, f"N={N} gain={gain}: streaming vs exact rel err {err:.3e}"
 
 
 @pytest.mark.parametrize("mode,d_in,tag,n_fft,ntemp,L", [(2, 2, "fst", 2048, 10, 16000), (3, 3, "3st", 1024, 10, 16000), (3, 3, "3st", 256, 7, 5000)])
