@@ -682,7 +682,7 @@ struct AParams {
     const float* bo;              // (64)
     __nv_bfloat16* Yout;          // (B, N, 64)
     long long* timeline;          // debug (PCA_TIMELINE builds): clock64 stamps of CTA 0 / softmax warp 0
-    CUtensorMap tmapY;            // [DIN64, apply4] Y16in as a (B * N, 64) bf16 tensor, box 128 rows x 8 elements (TMA)
+    CUtensorMap tmapY;            // [DIN64, apply4] Y16in as an (8, B * N, 8 chunks) bf16 tensor, box (8, 128, 8): one TMA per tile
     CUtensorMap tmapYo;           // [apply4] Yout, same geometry (TMA stores of whole tiles)
     PointSrc src;                 // [DIN64 == false, apply4] alternative to X32
 };
@@ -1363,7 +1363,7 @@ struct R6Params {
     long long* timeline;
     int* redo;                    // (n_work) flags: set by the streaming pass, consumed by the EXACT pass
     float* part;                  // (B, nsplit, 8, 10, 64)
-    CUtensorMap tmapY;            // [DIN64] the input as a (B * N, 64) bf16 tensor, box 128 rows x 8 elements
+    CUtensorMap tmapY;            // [DIN64] the input as an (8, B * N, 8 chunks) bf16 tensor, box (8, 128, 8): one TMA per tile
     PointSrc src;                 // [DIN64 == false] alternative to X32
 };
 
@@ -1527,8 +1527,7 @@ __global__ void __launch_bounds__(R6_THREADS, 1) mab_reduce6_tc_kernel(const __g
                     if (lane == 0) {
                         const long long r0 = (long long)cloud * P.N + (long long)(tile0 + it) * 128;
                         mbar_arrive_expect_tx(&y_full[stage], 16384);
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) tma_load_2d(dst + c * 2048, &P.tmapY, 8 * c, (int)r0, &y_full[stage]);
+                        tma_load_3d(dst, &P.tmapY, 0, (int)r0, 0, &y_full[stage]);      // one box: (8 elements, 128 rows, 8 chunks)
                     }
                     __syncwarp();
                 } else {
@@ -2548,8 +2547,7 @@ __global__ void __launch_bounds__(A4_THREADS, 1) mab_apply4_tc_kernel(const __gr
                     if (lane == 0) {
                         const long long r0 = (long long)cloud * P.N + (long long)(tile0 + it) * 128;
                         mbar_arrive_expect_tx(&ya_full[stage], 16384);
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) tma_load_2d(dst + c * 2048, &P.tmapY, 8 * c, (int)r0, &ya_full[stage]);
+                        tma_load_3d(dst, &P.tmapY, 0, (int)r0, 0, &ya_full[stage]);     // one box: (8 elements, 128 rows, 8 chunks)
                     }
                     __syncwarp();
                 } else {
@@ -2833,13 +2831,12 @@ __global__ void __launch_bounds__(A4_THREADS, 1) mab_apply4_tc_kernel(const __gr
                     }
                 }
                 if (full_tile) {
-                    // the tile leaves as eight 128-row x 16-byte boxes from the canonical layout (fc_o has finished reading it)
+                    // the tile leaves as ONE (8 elements, 128 rows, 8 chunks) box from the canonical layout (fc_o has finished reading it)
                     fence_async_smem();
                     named_bar_sync(8, 128);
                     if (warp == 12 && lane == 0) {
                         const long long r0 = (long long)e_cloud * P.N + (long long)e_tile * 128;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) tma_store_2d(&P.tmapYo, sO1 + c * 2048, 8 * c, (int)r0);
+                        tma_store_3d(&P.tmapYo, sO1, 0, (int)r0, 0);       // one box (a TMA instruction costs its thread ~90 cycles)
                         bulk_commit_group();
                     }
                     stored = true;
@@ -3975,7 +3972,7 @@ static int st_tc_chunk(const float* X, const PointSrc& src, const int* counts, i
         AParams a{X, nullptr, N, d_in, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, kvblk, m01.Wq, m01.bq,
                   g_apply_variant == 4 ? c->WqS0e : c->WqS0, g_apply_variant == 4 ? c->Wo0e : c->Wo0, m01.bo, Y1, tl_apply ? g_timeline : nullptr};
         a.src = src;
-        if (g_apply_variant == 4) PCA_TRY(make_tmap_2d_bf16(&a.tmapYo, Y1, 64, (unsigned long long)B * N, 128, 8, 128));
+        if (g_apply_variant == 4) PCA_TRY(make_tmap_chunked_bf16(&a.tmapYo, Y1, (unsigned long long)B * N, 128, 128));
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * d_in * TD + 2.0 * TM * TD + TD * TD), pts * (4.0 * d_in + 128.0));
         if (g_apply_variant == 4) mab_apply4_tc_kernel<false><<<pgrid, A4_THREADS, A4Smem::TOTAL, st>>>(a);
         else mab_apply3_tc_kernel<false><<<pgrid, TC_THREADS20, A3Smem::TOTAL, st>>>(a);
@@ -3997,7 +3994,7 @@ static int st_tc_chunk(const float* X, const PointSrc& src, const int* counts, i
             PCA_CHECK_CUDA(cudaMemsetAsync(redo, 0, (size_t)n_work * sizeof(int), st));
             R6Params r6{nullptr, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, c->Gq1, c->Wv1e, nullptr, nullptr,
                         r.timeline, redo, part, CUtensorMap{}};
-            PCA_TRY(make_tmap_2d_bf16(&r6.tmapY, Y1, 64, (unsigned long long)B * N, 128, 8, 128));
+            PCA_TRY(make_tmap_chunked_bf16(&r6.tmapY, Y1, (unsigned long long)B * N, 128, 128));
             mab_reduce6_tc_kernel<true, false><<<pgrid, R6_THREADS, R6Smem::TOTAL, st>>>(r6);
             r6.timeline = nullptr;
             mab_reduce6_tc_kernel<true, true><<<pgrid, R6_THREADS, R6Smem::TOTAL, st>>>(r6);
@@ -4025,8 +4022,8 @@ static int st_tc_chunk(const float* X, const PointSrc& src, const int* counts, i
         AParams a{nullptr, Y1, N, TD, sp.tiles_total, sp.tiles_per_split, sp.nsplit, n_work, counts, tm, kvblk, nullptr, m11.bq,
                   g_apply_variant == 4 ? c->Wq1e : c->Wq1, g_apply_variant == 4 ? c->Wo1e : c->Wo1, m11.bo, Y2, getenv("PCA_TL_APPLY64") ? g_timeline : nullptr};
         if (g_apply_variant == 4) {
-            PCA_TRY(make_tmap_2d_bf16(&a.tmapY, Y1, 64, (unsigned long long)B * N, 128, 8, 128));
-            PCA_TRY(make_tmap_2d_bf16(&a.tmapYo, Y2, 64, (unsigned long long)B * N, 128, 8, 128));
+            PCA_TRY(make_tmap_chunked_bf16(&a.tmapY, Y1, (unsigned long long)B * N, 128, 128));
+            PCA_TRY(make_tmap_chunked_bf16(&a.tmapYo, Y2, (unsigned long long)B * N, 128, 128));
         }
         LaunchTimer lt("mab_apply_tc_kernel", st, pts * 2.0 * (1.0 * TD * TD + 2.0 * TM * TD + TD * TD), pts * 256.0);
         if (g_apply_variant == 4) mab_apply4_tc_kernel<true><<<pgrid, A4_THREADS, A4Smem::TOTAL, st>>>(a);

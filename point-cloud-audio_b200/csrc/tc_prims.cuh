@@ -109,6 +109,11 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src_s
                  "r"(smem_u32(src_smem))
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* src_smem, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(smem_u32(src_smem))
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all of this thread's bulk groups have finished READING their shared-memory source (it may be overwritten)
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
