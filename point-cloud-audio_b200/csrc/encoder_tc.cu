@@ -3333,8 +3333,7 @@ struct Pool2Smem {
     static constexpr int Y = 2048;                                // P2_STAGES x P2_YSTAGE
     static constexpr int PT = Y + P2_STAGES * P2_YSTAGE + 16384;  // (16 KB slack: the A operand of the last stage reads 16 chunks)
                                                                   // P2_NG x 4096: P as a 16-row K-major B image
-    static constexpr int ACC = PT + P2_NG * 4096;                 // (unused)
-    static constexpr int RED = ACC + P2_NG * 8 * 64 * 4;          // [NG][2 parities][4 warps][8 heads] maxima, then [NG][4][8] sums
+    static constexpr int RED = PT + P2_NG * 4096;                 // [NG][2 parities][4 warps][8 heads] maxima, then [NG][4][8] sums
     static constexpr int BARS = RED + (P2_NG * 2 * 4 * 8 + P2_NG * 4 * 8) * 4;
     static constexpr int TOTAL = BARS + 48 * 8 + 16;
 };
@@ -3355,7 +3354,6 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pma_pool2_tc_kernel(const __gri
     uint8_t* sAqB = smem + Pool2Smem::AQB;
     uint8_t* sY = smem + Pool2Smem::Y;
     uint8_t* sPT = smem + Pool2Smem::PT;
-    float* sAcc = reinterpret_cast<float*>(smem + Pool2Smem::ACC);
     float* sRedMax = reinterpret_cast<float*>(smem + Pool2Smem::RED);
     float* sRedSum = sRedMax + P2_NG * 2 * 4 * 8;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Pool2Smem::BARS);
@@ -3548,16 +3546,9 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pma_pool2_tc_kernel(const __gri
                     }
 #pragma unroll
                     for (int h = 0; h < 8; ++h)
-#ifdef PCA_P2_NOEXP
-                        *reinterpret_cast<__nv_bfloat16*>(pt + (row >> 3) * 256 + h * 16 + (row & 7) * 2) =
-                            __float2bfloat16(valid ? __uint_as_float(sv[h]) : 0.f);
-#else
                         *reinterpret_cast<__nv_bfloat16*>(pt + (row >> 3) * 256 + h * 16 + (row & 7) * 2) =
                             __float2bfloat16(valid ? ex2(__uint_as_float(sv[h])) : 0.f);
-#endif
-#ifndef PCA_P2_NOFENCE
                     fence_async_smem();
-#endif
                     fence_before_sync();
                     warp_arrive(&p_ready[g]);
                     stamp(15);
