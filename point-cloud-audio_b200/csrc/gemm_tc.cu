@@ -299,7 +299,13 @@ int launch_linear_tc(const float* X, const float* W, int trans_w, const float* b
     if (!linear_tc_eligible(rows, K, N)) return fail(PCA_EUNSUPPORTED, "linear_tc: shape (%lld, %d, %d) not eligible", rows, K, N);
     if (!img || img_bytes < gemm_tc_image_bytes(N, K)) return fail(PCA_EWORKSPACE, "linear_tc: weight image buffer too small");
     PCA_TRY(gemm_tc_configure());
-    const int nt = pick_nt(N);
+    int nt = pick_nt(N);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // few row tiles (the 16-row-per-cloud tensors of the inducing points at small batches): narrower column passes spread the
+    // work over more CTAs (every CTA re-stages its 128-row activation tile, which then comes from L2)
+    while (((rows + 127) / 128) * (N / nt) * 2 <= sms && nt >= 64 && (nt / 2) % 32 == 0 && N % (nt / 2) == 0) nt /= 2;
     {
         const long long total = (long long)N * (K / 8);
         weight_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, N, K, trans_w ? N : K, trans_w, nt, (uint8_t*)img);
@@ -307,9 +313,6 @@ int launch_linear_tc(const float* X, const float* W, int trans_w, const float* b
     }
     LinTcParams p{X, (const uint8_t*)img, bias, resid, Y, R, rows, K, N, nt, relu};
     const long long ntiles = ((rows + 127) / 128) * (N / nt);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
     {
         LaunchTimer lt("linear_tc_kernel", st, 2.0 * rows * K * N, 4.0 * rows * (K + N));
