@@ -502,9 +502,14 @@ int launch_grad_weight_tc(const float* dY, const float* X, float* dW, long long 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // one CTA per SM (227 KB of shared memory): whole waves only -- 2 x #SMs CTAs when every CTA still gets >= 256 rows, else
+    // #SMs (250 CTAs on 148 SMs run as long as 296), else whatever the row count allows
     long long nsplit = (2LL * sms + mtiles - 1) / mtiles;
     const long long max_split = (rows + 8 * GT_KC - 1) / (8 * GT_KC);
-    if (nsplit > max_split) nsplit = max_split;
+    if (nsplit > max_split) {
+        const long long one_wave = (sms + mtiles - 1) / mtiles;
+        nsplit = one_wave <= max_split ? one_wave : max_split;
+    }
     if (nsplit < 1) nsplit = 1;
     long long rchunk = (rows + nsplit - 1) / nsplit;
     rchunk = (rchunk + GT_KC - 1) / GT_KC * GT_KC;
