@@ -392,6 +392,24 @@ int pca_debug_linear_tc(const float* X, const float* W, int trans_w, const float
                         long long rows, int K, int N, int relu, void* image, size_t image_bytes, void* stream);
 int pca_debug_grad_weight_tc(const float* dY, const float* X, float* dW, long long rows, int M, int N, void* stream);
 
+/* Attention of a MAB with one small side -- at most 16 queries (ISAB mab0, PMA) or at most 16 keys (ISAB mab1) against >= 128
+ * items, dim_V <= 256 a multiple of 32, head dim a multiple of 8, num_heads * 8 or * 16 in {32, 64} (the ModelNet model of
+ * set_transformer-master/main_pointcloud.py:62) -- runs Q K^T, P V and every contraction of their gradient as split-bf16
+ * tcgen05 GEMMs (csrc/attn_tc.cu; fp32-grade, replaces set_transformer-master/modules.py:28-29 and its autograd).  It is what
+ * the fp32 encoder and the training path use for eligible shapes; pca_debug_set_attn_tc(0) keeps them on the CUDA-core kernels.
+ * pca_debug_attn_fwd: O (B, nq, D) = Qp + softmax_h(Qp K^T / sqrt(D)) V on projected operands -- Qp (B or 1, nq, D), KV
+ * (B, nk, 2D) rows [K | V] -- through the same dispatch; lse (B, nq, H) nullable receives log2 sum_k 2^(s_k log2 e).
+ * pca_debug_attn_bwd_tc: the tensor-core backward alone: dQp (B, nq, D) = dO + dS K, dKV (B, nk, 2D) = [dS^T Qp | P^T dO];
+ * delta (B, nq, H) = sum_d dO (O - Qp) per head is read when the queries are the small side.  PCA_EUNSUPPORTED for
+ * ineligible shapes.  Workspace: pca_debug_attn_ws_bytes. */
+void pca_debug_set_attn_tc(int on);
+int pca_debug_attn_tc_eligible(int B, int nq, int nk, int D, int H);
+size_t pca_debug_attn_ws_bytes(int B, int nq, int nk, int D, int H);
+int pca_debug_attn_fwd(const float* Qp, int q_shared, const float* KV, int B, int nq, int nk, int D, int H, float* O, float* lse,
+                       void* ws, size_t ws_bytes, void* stream);
+int pca_debug_attn_bwd_tc(const float* Qp, int q_shared, const float* KV, const float* dO, const float* lse, const float* delta, int B,
+                          int nq, int nk, int D, int H, float* dQp, float* dKV, void* ws, size_t ws_bytes, void* stream);
+
 /* Unit probe of the tcgen05 building blocks used by the bf16 encoder path: one CTA computes
  * D (128, N) = A (128, K) * B (K, N), bf16 operands, fp32 accumulation in TMEM.
  * a_mode: 0 A (128,K) via shared memory K-major, 1 A via TMEM, 2 A given as (K,128) via shared memory MN-major;

@@ -93,6 +93,11 @@ PROTOTYPES = {
     "pca_debug_set_gemm_tc": (None, [_I]),
     "pca_debug_linear_tc": (_I, [_P, _P, _I, _P, _P, _P, _P, C.c_longlong, _I, _I, _I, _P, _SZ, _P]),
     "pca_debug_grad_weight_tc": (_I, [_P, _P, _P, C.c_longlong, _I, _I, _P]),
+    "pca_debug_set_attn_tc": (None, [_I]),
+    "pca_debug_attn_tc_eligible": (_I, [_I, _I, _I, _I, _I]),
+    "pca_debug_attn_ws_bytes": (_SZ, [_I, _I, _I, _I, _I]),
+    "pca_debug_attn_fwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),
+    "pca_debug_attn_bwd_tc": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),
     "pca_debug_umma_probe": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "pca_pipeline_clouds_per_clip": (_I, [C.POINTER(PipelineCfg)]),
     "pca_pipeline_points_per_cloud": (_I, [C.POINTER(PipelineCfg)]),

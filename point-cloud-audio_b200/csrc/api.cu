@@ -831,6 +831,25 @@ int pca_adam_step_f32(float* params, const float* grads, float* exp_avg, float* 
 }
 
 void pca_debug_set_gemm_tc(int on) { set_gemm_tc(on); }
+void pca_debug_set_attn_tc(int on) { set_attn_tc(on); }
+size_t pca_debug_attn_ws_bytes(int B, int nq, int nk, int D, int H) {
+    const size_t f = attn_part_floats(B, nq, nk, D, H), b = attn_tc_bwd_floats(B, nq, nk, D, H);
+    return ((f > b ? f : b) + 64) * sizeof(float);
+}
+int pca_debug_attn_tc_eligible(int B, int nq, int nk, int D, int H) { return attn_tc_eligible(B, nq, nk, D, H) ? 1 : 0; }
+int pca_debug_attn_fwd(const float* Qp, int q_shared, const float* KV, int B, int nq, int nk, int D, int H, float* O, float* lse,
+                       void* ws, size_t ws_bytes, void* stream) {
+    if (!Qp || !KV || !O || !ws) return fail(PCA_EINVAL, "attn_fwd: null pointer");
+    if (ws_bytes < pca_debug_attn_ws_bytes(B, nq, nk, D, H)) return fail(PCA_EWORKSPACE, "attn_fwd: workspace too small");
+    return launch_attn(Qp, q_shared ? 0 : (long long)nq * D, KV, B, nq, nk, D, H, O, (float*)ws, nullptr, (cudaStream_t)stream, lse);
+}
+int pca_debug_attn_bwd_tc(const float* Qp, int q_shared, const float* KV, const float* dO, const float* lse, const float* delta, int B,
+                          int nq, int nk, int D, int H, float* dQp, float* dKV, void* ws, size_t ws_bytes, void* stream) {
+    if (!Qp || !KV || !dO || !dQp || !dKV || !ws) return fail(PCA_EINVAL, "attn_bwd_tc: null pointer");
+    if (ws_bytes < pca_debug_attn_ws_bytes(B, nq, nk, D, H)) return fail(PCA_EWORKSPACE, "attn_bwd_tc: workspace too small");
+    return launch_attn_bwd_tc(Qp, q_shared ? 0 : (long long)nq * D, KV, dO, lse, delta, B, nq, nk, D, H, dQp, dKV, (float*)ws,
+                              (cudaStream_t)stream);
+}
 int pca_debug_linear_tc(const float* X, const float* W, int trans_w, const float* bias, const float* resid, float* Y, float* R,
                         long long rows, int K, int N, int relu, void* image, size_t image_bytes, void* stream) {
     return launch_linear_tc(X, W, trans_w, bias, resid, Y, R, rows, K, N, relu, image, image_bytes, (cudaStream_t)stream);

@@ -1,0 +1,815 @@
+// fp32-grade multi-head attention on the tcgen05 tensor cores for MABs with ONE SMALL SIDE (set_transformer-master/modules.py:20-29
+// with 16 inducing points or 1 seed against ~1000 points: ISAB mab0 / mab1 and PMA of main_pointcloud.py:62, forward and backward).
+//
+// With ns <= 16 items on the small side and H heads, the H * ns (head, item) pairs are the COLUMNS of one matrix T (points, HS)
+// and every contraction of the attention and of its gradient is one of three GEMM shapes over the points of a cloud:
+//   G1  T  = X  Wz^T      X (points, D) activations, Wz (HS, D) a per-cloud BLOCK-STRUCTURED operand: row (h, m) carries the small
+//                          side's row m inside head h's feature slice and zeros elsewhere (scores Q K^T, dP = dO V^T)
+//   G2  Y  = T  Wz        (points, HS) x (HS, D): P V, dS K, dS^T-free forms of dK / dV when the points are the keys
+//   G3  Gz = T^T X        summed over the cloud's points, diagonal (head) blocks extracted: P^T V, dS^T Q, P^T dO
+// All three run as 3-term split-bf16 products (a_hi b_hi + a_lo b_hi + a_hi b_lo, fp32 accumulation in TMEM; gemm_tc.cu), so the
+// results stay in the 1e-3 fp32 parity class.  The softmax and its backward are fused into the epilogues of G1:
+//   points = queries (mab1):  row softmax per head over the ns keys (thread = row holds the whole row)
+//   points = keys (mab0/PMA): column softmax over the points of a cloud (col_softmax_kernel between G1 and G3)
+// The zero blocks cost 4x redundant MMA work at H = 4 -- irrelevant: these GEMMs are HBM-bound (the tensor pipe is < 25 % busy).
+#include "common.cuh"
+#include "tc_prims.cuh"
+
+namespace pca {
+using namespace tc;
+
+constexpr int AT_KC = 32;
+constexpr int AT_STAGES = 3;
+constexpr int AT_THREADS = 9 * 32;   // 4 producer + 1 MMA + 4 epilogue warps
+
+__device__ __forceinline__ void at_warp_arrive(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+__device__ __forceinline__ void at_split8(const float* x, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 hb = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+        const float2 hf = __bfloat1622float2(hb);
+        h[j] = *reinterpret_cast<const uint32_t*>(&hb);
+        l[j] = pack_bf16(x[2 * j] - hf.x, x[2 * j + 1] - hf.y);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ------------------------------------------------------------------------------------ per-cloud operand images
+// kind 0 (G1): B(n = (h, m), k)     = src[m * ld + k] when k / dh == h and m < ns, else 0     (N = HS, K = D)
+// kind 1 (G2): B(n = d, k = (h, m)) = src[m * ld + d] when d / dh == h and m < ns, else 0     (N = D,  K = HS)
+// Image of cloud b at img + b * img_bstride: per 32-wide K chunk c [hi | lo], each K-major canonical
+// (byte = (kk / 8) * N * 16 + n * 16 + (kk % 8) * 2), as weight_image_kernel of gemm_tc.cu with a single column pass.
+__global__ void cloud_image_kernel(const float* __restrict__ src, long long s_bstride, int ld, int ns, int nsp, int dh, int D, int HS,
+                                   int kind, uint8_t* __restrict__ img, long long img_bstride) {
+    const int b = blockIdx.y;
+    const int N = kind == 0 ? HS : D, K = kind == 0 ? D : HS;
+    const int total = N * (K / 8);
+    const float* s = src + (long long)b * s_bstride;
+    uint8_t* ib = img + (long long)b * img_bstride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = i % N, k8 = i / N;
+        float x[8];
+        if (kind == 0) {
+            const int h = n / nsp, m = n - h * nsp;
+            const bool on = m < ns && (k8 * 8) / dh == h;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = on ? __ldg(s + (long long)m * ld + k8 * 8 + j) : 0.f;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = k8 * 8 + j;
+                const int h = k / nsp, m = k - h * nsp;
+                x[j] = (m < ns && n / dh == h) ? __ldg(s + (long long)m * ld + n) : 0.f;
+            }
+        }
+        uint4 hi, lo;
+        at_split8(x, hi, lo);
+        const int c = (k8 * 8) / AT_KC, kk8 = k8 - c * (AT_KC / 8);
+        uint8_t* base = ib + ((size_t)c * 2) * N * 64;
+        *reinterpret_cast<uint4*>(base + (size_t)kk8 * N * 16 + n * 16) = hi;
+        *reinterpret_cast<uint4*>(base + (size_t)N * 64 + (size_t)kk8 * N * 16 + n * 16) = lo;
+    }
+}
+
+// ------------------------------------------------------------------------------------ G1 / G2: per-cloud linear maps
+enum { EPI_STORE = 0, EPI_RESID = 1, EPI_SOFTMAX = 2, EPI_DS_ROW = 3, EPI_P_COL = 4, EPI_DS_COL = 5 };
+
+struct ClinParams {
+    const float* X;        // row r of cloud b: X + b * x_bstride + r * ldx  (K columns used)
+    long long x_bstride;
+    int ldx;
+    const uint8_t* img;    // operand image of cloud b at img + b * img_bstride (0: shared by the batch)
+    long long img_bstride;
+    float* Y;              // (n_rows, N) per cloud, row stride ldy
+    long long y_bstride;
+    int ldy;
+    const float* R;        // EPI_RESID: residual rows; EPI_DS_ROW / EPI_DS_COL: probability rows
+    long long r_bstride;
+    int ldr;
+    float* lse;            // EPI_SOFTMAX: (B, n_rows, H) out, nullable
+    const float* vec;      // EPI_P_COL: log-sum-exp, EPI_DS_COL: delta; (B, ns, H)
+    int B, n_rows, K, N;
+    int H, nsp, ns;
+    float scale, scale_log2e;
+};
+
+struct AtSmem {
+    static constexpr int A_BYTES = 128 * AT_KC * 2;
+    static constexpr int STAGE = 2 * A_BYTES + 2 * 256 * AT_KC * 2;   // A hi | A lo | B hi | B lo (B sized for N = 256)
+    static constexpr int TRANS = AT_STAGES * STAGE;
+    static constexpr int BARS = TRANS + 4 * 32 * 33 * 4;
+    static constexpr int TOTAL = BARS + 16 * 8 + 16;
+};
+
+// Persistent, warp-specialised (the structure of linear_tc_kernel): 4 producer warps split the fp32 rows of a 128-row tile
+// into hi / lo bf16 in the canonical K-major layout, the cloud's operand image arrives by one bulk copy per K chunk, one warp
+// issues the MMAs, 4 epilogue warps read the accumulator (thread = row), apply the epilogue and write 128-byte coalesced rows
+// through a padded transpose tile.  Tiles never straddle clouds (tile t = (cloud t / tpc, rows 128 (t % tpc) ...)).
+template <int EPI, int NSP>
+__global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const ClinParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AtSmem::BARS);
+    uint64_t* full = bars;                       // [3] count 5: 4 producer warps + the expect_tx arrival
+    uint64_t* empty = bars + AT_STAGES;          // [3] count 1 (MMA commit)
+    uint64_t* acc_full = bars + 2 * AT_STAGES;   // [2] count 1
+    uint64_t* acc_empty = acc_full + 2;          // [2] count 4 (epilogue warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkc = P.K / AT_KC;
+    const int tpc = (P.n_rows + 127) / 128;
+    const long long ntiles = (long long)P.B * tpc;
+
+    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&full[i], 5); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        fence_barrier_init();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+    const uint32_t b_img_bytes = (uint32_t)P.N * 64;           // one hi or lo operand image of a chunk
+
+    if (warp < 4) {
+        // ================================================================= producers
+        const int rsub = lane & 7, c = lane >> 3;
+        uint32_t gt = 0;
+        float4 nx[8], nx2[8];
+        long long t = blockIdx.x;
+        int kc = 0;
+        auto issue = [&](float4* dst, long long tile, int kchunk) {
+            const int b = (int)(tile / tpc);
+            const int j = (int)(tile - (long long)b * tpc);
+            const float* xb = P.X + (long long)b * P.x_bstride;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int r = j * 128 + 32 * warp + 8 * it + rsub;
+                if (r < P.n_rows) {
+                    const float4* src = reinterpret_cast<const float4*>(xb + (long long)r * P.ldx + kchunk * AT_KC + 8 * c);
+                    dst[2 * it] = __ldg(src);
+                    dst[2 * it + 1] = __ldg(src + 1);
+                } else {
+                    dst[2 * it] = dst[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        };
+        auto advance = [&](long long& tile, int& kchunk) {
+            if (++kchunk == nkc) { kchunk = 0; tile += gridDim.x; }
+        };
+        long long t_n = t, t_n2;
+        int kc_n = 0, kc_n2;
+        if (t < ntiles) issue(nx, t, 0);
+        advance(t_n, kc_n);
+        if (t_n < ntiles) issue(nx2, t_n, kc_n);
+        t_n2 = t_n;
+        kc_n2 = kc_n;
+        while (t < ntiles) {
+            const int stage = gt % AT_STAGES;
+            float4 cur[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cur[j] = nx[j]; nx[j] = nx2[j]; }
+            advance(t_n2, kc_n2);
+            if (t_n2 < ntiles) issue(nx2, t_n2, kc_n2);
+            if (gt >= AT_STAGES) mbar_wait(&empty[stage], ((gt / AT_STAGES) - 1) & 1);
+            uint8_t* st = smem + stage * AtSmem::STAGE;
+            if (threadIdx.x == 0) {
+                const long long b = t / tpc;
+                mbar_arrive_expect_tx(&full[stage], 2 * b_img_bytes);
+                bulk_copy_g2s(st + 2 * AtSmem::A_BYTES, P.img + b * P.img_bstride + ((size_t)kc * 2) * b_img_bytes, 2 * b_img_bytes,
+                              &full[stage]);
+            }
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const float x[8] = {cur[2 * it].x, cur[2 * it].y, cur[2 * it].z, cur[2 * it].w,
+                                    cur[2 * it + 1].x, cur[2 * it + 1].y, cur[2 * it + 1].z, cur[2 * it + 1].w};
+                uint4 hi, lo;
+                at_split8(x, hi, lo);
+                const int row = 32 * warp + 8 * it + rsub;
+                *reinterpret_cast<uint4*>(st + c * 2048 + row * 16) = hi;
+                *reinterpret_cast<uint4*>(st + AtSmem::A_BYTES + c * 2048 + row * 16) = lo;
+            }
+            fence_async_smem();
+            at_warp_arrive(&full[stage]);
+            ++gt;
+            t = t_n;
+            kc = kc_n;
+            t_n = t_n2;
+            kc_n = kc_n2;
+        }
+    } else if (warp == 4) {
+        // ================================================================= MMA issue (warp-uniform, elected lane)
+        const uint32_t idesc = idesc_bf16(128, P.N, 0, 0);
+        uint32_t gt = 0, tt = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tt) {
+            const uint32_t buf = tt & 1;
+            if (tt >= 2) mbar_wait(&acc_empty[buf], ((tt >> 1) - 1) & 1);
+            fence_after_sync();
+            const uint32_t acc = tmem_addr(tb, 0, 256 * buf);
+            for (int kc = 0; kc < nkc; ++kc, ++gt) {
+                const int stage = gt % AT_STAGES;
+                mbar_wait(&full[stage], (gt / AT_STAGES) & 1);
+                fence_after_sync();
+                if (elect_one()) {
+                    const uint32_t a_hi = smem_u32(smem + stage * AtSmem::STAGE);
+                    const uint32_t a_lo = a_hi + AtSmem::A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * AtSmem::A_BYTES;
+                    const uint32_t b_lo = b_hi + b_img_bytes;
+                    const uint32_t b_lbo = (uint32_t)P.N * 16;
+#pragma unroll
+                    for (int ks = 0; ks < AT_KC / 16; ++ks) {
+                        const uint64_t dah = smem_desc(a_hi + ks * 4096, 2048, 128), dal = smem_desc(a_lo + ks * 4096, 2048, 128);
+                        const uint64_t dbh = smem_desc(b_hi + ks * 2 * b_lbo, b_lbo, 128), dbl = smem_desc(b_lo + ks * 2 * b_lbo, b_lbo, 128);
+                        mma_ss(acc, dah, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                        mma_ss(acc, dal, dbh, idesc, 1u);
+                        mma_ss(acc, dah, dbl, idesc, 1u);
+                    }
+                    mma_commit(&empty[stage]);
+                    if (kc == nkc - 1) mma_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================================================= epilogue
+        const int quad = warp & 3;
+        float* T = reinterpret_cast<float*>(smem + AtSmem::TRANS) + quad * (32 * 33);
+        const int rr = lane >> 3, cq = lane & 7;
+        uint32_t tt = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tt) {
+            const uint32_t buf = tt & 1;
+            const int b = (int)(t / tpc);
+            const int i0 = (int)(t - (long long)b * tpc) * 128 + 32 * quad;     // first row (inside the cloud) of this warp
+            float* yb = P.Y + (long long)b * P.y_bstride;
+            const float* rb = (EPI == EPI_RESID || EPI == EPI_DS_ROW || EPI == EPI_DS_COL) ? P.R + (long long)b * P.r_bstride : nullptr;
+            mbar_wait(&acc_full[buf], (tt >> 1) & 1);
+            fence_after_sync();
+            for (int c0 = 0; c0 < P.N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_addr(tb, 32 * quad, 256 * buf + c0), v);
+                tmem_ld_wait32(v);
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (EPI == EPI_DS_ROW) {
+                    // the row's probabilities: coalesced block load through the transpose tile
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int lr = 4 * i + rr, r = i0 + lr;
+                        const float4 pv = r < P.n_rows ? *reinterpret_cast<const float4*>(rb + (long long)r * P.ldr + c0 + 4 * cq)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                        T[lr * 33 + 4 * cq] = pv.x; T[lr * 33 + 4 * cq + 1] = pv.y; T[lr * 33 + 4 * cq + 2] = pv.z; T[lr * 33 + 4 * cq + 3] = pv.w;
+                    }
+                    __syncwarp();
+                    float p[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) p[j] = T[lane * 33 + j];
+                    __syncwarp();
+#pragma unroll
+                    for (int h = 0; h < 32 / NSP; ++h) {
+                        float delta = 0.f;                      // sum_m P dP of this (row, head)
+#pragma unroll
+                        for (int m = 0; m < NSP; ++m) delta = fmaf(p[h * NSP + m], f[h * NSP + m], delta);
+#pragma unroll
+                        for (int m = 0; m < NSP; ++m) f[h * NSP + m] = p[h * NSP + m] * (f[h * NSP + m] - delta) * P.scale;
+                    }
+                }
+                if (EPI == EPI_SOFTMAX) {
+#pragma unroll
+                    for (int h = 0; h < 32 / NSP; ++h) {
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int m = 0; m < NSP; ++m) {
+                            f[h * NSP + m] *= P.scale_log2e;
+                            if (m < P.ns) mx = fmaxf(mx, f[h * NSP + m]);
+                        }
+                        float l = 0.f;
+#pragma unroll
+                        for (int m = 0; m < NSP; ++m) {
+                            f[h * NSP + m] = m < P.ns ? ex2(f[h * NSP + m] - mx) : 0.f;
+                            l += f[h * NSP + m];
+                        }
+                        const float inv = 1.f / l;
+#pragma unroll
+                        for (int m = 0; m < NSP; ++m) f[h * NSP + m] *= inv;
+                        const int r = i0 + lane;
+                        if (P.lse && r < P.n_rows) P.lse[((long long)b * P.n_rows + r) * P.H + c0 / NSP + h] = mx + log2f(l);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) T[lane * 33 + j] = f[j];
+                __syncwarp();
+                const int n = c0 + 4 * cq;
+                float cv[4] = {0.f, 0.f, 0.f, 0.f};
+                bool cok[4] = {true, true, true, true};
+                if (EPI == EPI_P_COL || EPI == EPI_DS_COL) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int h = (n + u) / P.nsp, m = (n + u) - h * P.nsp;
+                        cok[u] = m < P.ns;
+                        cv[u] = cok[u] ? __ldg(P.vec + ((long long)b * P.ns + m) * P.H + h) : 0.f;
+                    }
+                }
+                float4 rv8[8];
+                if (EPI == EPI_RESID || EPI == EPI_DS_COL) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i0 + 4 * i + rr;
+                        rv8[i] = r < P.n_rows ? *reinterpret_cast<const float4*>(rb + (long long)r * P.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int lr = 4 * i + rr, r = i0 + lr;
+                    float o[4] = {T[lr * 33 + 4 * cq], T[lr * 33 + 4 * cq + 1], T[lr * 33 + 4 * cq + 2], T[lr * 33 + 4 * cq + 3]};
+                    if (EPI == EPI_RESID) { o[0] += rv8[i].x; o[1] += rv8[i].y; o[2] += rv8[i].z; o[3] += rv8[i].w; }
+                    if (EPI == EPI_P_COL) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) o[u] = cok[u] ? ex2(fmaf(o[u], P.scale_log2e, -cv[u])) : 0.f;
+                    }
+                    if (EPI == EPI_DS_COL) {
+                        const float pr[4] = {rv8[i].x, rv8[i].y, rv8[i].z, rv8[i].w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) o[u] = cok[u] ? pr[u] * (o[u] - cv[u]) * P.scale : 0.f;
+                    }
+                    if (r < P.n_rows) *reinterpret_cast<float4*>(yb + (long long)r * P.ldy + n) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                __syncwarp();
+            }
+            fence_before_sync();
+            at_warp_arrive(&acc_empty[buf]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tb, 512);
+}
+
+// ------------------------------------------------------------------------------------ G3: per-cloud T^T X, head blocks extracted
+// out[b][m][d] += sum over the rows r of the CTA's range of T[b][r][(d / dh, m)] * X[b][r][d]   (m < ns).  Both operands are
+// MN-major straight from the row-major activations (grad_weight_tc_kernel's staging); M = HS <= 128 rows, N = D <= 256 columns.
+struct ClGwParams {
+    const float* A;        // T: (n_rows, HS) per cloud
+    long long a_bstride;
+    int lda, Mtot;
+    const float* Bm;       // X: (n_rows, N) per cloud, row stride ldb
+    long long b_bstride;
+    int ldb, N;
+    float* out;            // (ns, N) per cloud, row stride ldo; added atomically
+    long long o_bstride;
+    int ldo;
+    int n_rows, rchunk, nsp, ns, dh;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AtSmem::BARS);
+    uint64_t* full = bars;                       // [3] count 4 (producer warps)
+    uint64_t* empty = bars + AT_STAGES;          // [3] count 1
+    uint64_t* acc_full = bars + 2 * AT_STAGES;   // count 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    constexpr int A_BYTES = 128 * AT_KC * 2, B_BYTES = 256 * AT_KC * 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int r0 = blockIdx.x * P.rchunk;
+    const int r1 = min(r0 + P.rchunk, P.n_rows);
+    const int nchunks = (r1 - r0 + AT_KC - 1) / AT_KC;
+    const float* Ab = P.A + (long long)b * P.a_bstride;
+    const float* Bb = P.Bm + (long long)b * P.b_bstride;
+
+    if (warp == 4) tmem_alloc(tmem_slot, 256);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp < 4) {
+        const int ksub = lane & 7, gq = lane >> 3;
+        const int b_gblocks = P.N / 32;
+        for (int c = 0; c < nchunks; ++c) {
+            const int stage = c % AT_STAGES;
+            const int rbase = r0 + c * AT_KC;
+            float4 va[8], vb[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int pi = warp + 4 * i;
+                const int kb = pi & 3, gb = pi >> 2;
+                const int r = rbase + 8 * kb + ksub;
+                const int g = 4 * gb + gq;
+                const bool ok = r < r1 && (8 * g < P.Mtot);
+                const float4* src = reinterpret_cast<const float4*>(Ab + (long long)(ok ? r : 0) * P.lda + (ok ? 8 * g : 0));
+                va[2 * i] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                va[2 * i + 1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int pi = warp + 4 * i;
+                const int kb = pi & 3, gb = pi >> 2;
+                const int r = rbase + 8 * kb + ksub;
+                const int g = 4 * gb + gq;
+                const bool ok = r < r1 && gb < b_gblocks;
+                const float4* src = reinterpret_cast<const float4*>(Bb + (long long)(ok ? r : 0) * P.ldb + (ok ? 8 * g : 0));
+                vb[2 * i] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[2 * i + 1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (c >= AT_STAGES) mbar_wait(&empty[stage], ((c / AT_STAGES) - 1) & 1);
+            uint8_t* st = smem + stage * AtSmem::STAGE;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int pi = warp + 4 * i;
+                const int k = 8 * (pi & 3) + ksub, g = 4 * (pi >> 2) + gq;
+                const float x[8] = {va[2 * i].x, va[2 * i].y, va[2 * i].z, va[2 * i].w, va[2 * i + 1].x, va[2 * i + 1].y, va[2 * i + 1].z, va[2 * i + 1].w};
+                uint4 hi, lo;
+                at_split8(x, hi, lo);
+                *reinterpret_cast<uint4*>(st + g * (AT_KC * 16) + k * 16) = hi;
+                *reinterpret_cast<uint4*>(st + A_BYTES + g * (AT_KC * 16) + k * 16) = lo;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int pi = warp + 4 * i;
+                if ((pi >> 2) < b_gblocks) {
+                    const int k = 8 * (pi & 3) + ksub, g = 4 * (pi >> 2) + gq;
+                    const float x[8] = {vb[2 * i].x, vb[2 * i].y, vb[2 * i].z, vb[2 * i].w, vb[2 * i + 1].x, vb[2 * i + 1].y, vb[2 * i + 1].z, vb[2 * i + 1].w};
+                    uint4 hi, lo;
+                    at_split8(x, hi, lo);
+                    *reinterpret_cast<uint4*>(st + 2 * A_BYTES + g * (AT_KC * 16) + k * 16) = hi;
+                    *reinterpret_cast<uint4*>(st + 2 * A_BYTES + B_BYTES + g * (AT_KC * 16) + k * 16) = lo;
+                }
+            }
+            fence_async_smem();
+            at_warp_arrive(&full[stage]);
+        }
+    } else if (warp == 4) {
+        const uint32_t idesc = idesc_bf16(128, P.N, 1, 1);
+        for (int c = 0; c < nchunks; ++c) {
+            const int stage = c % AT_STAGES;
+            mbar_wait(&full[stage], (c / AT_STAGES) & 1);
+            fence_after_sync();
+            if (elect_one()) {
+                const uint32_t a_hi = smem_u32(smem + stage * AtSmem::STAGE);
+                const uint32_t a_lo = a_hi + A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * A_BYTES;
+                const uint32_t b_lo = b_hi + B_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < AT_KC / 16; ++ks) {
+                    const uint64_t dah = smem_desc(a_hi + ks * 256, 128, AT_KC * 16), dal = smem_desc(a_lo + ks * 256, 128, AT_KC * 16);
+                    const uint64_t dbh = smem_desc(b_hi + ks * 256, 128, AT_KC * 16), dbl = smem_desc(b_lo + ks * 256, 128, AT_KC * 16);
+                    mma_ss(tb, dah, dbh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                    mma_ss(tb, dal, dbh, idesc, 1u);
+                    mma_ss(tb, dah, dbl, idesc, 1u);
+                }
+                mma_commit(&empty[stage]);
+                if (c == nchunks - 1) mma_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else if (nchunks > 0) {
+        const int quad = warp & 3;
+        float* T = reinterpret_cast<float*>(smem + AtSmem::TRANS) + quad * (32 * 33);
+        mbar_wait(acc_full, 0);
+        fence_after_sync();
+        if (32 * quad < P.Mtot) {
+            const int h_lo = (32 * quad) / P.nsp, h_hi = (32 * quad + 31) / P.nsp;      // heads of this warp's accumulator rows
+            float* ob = P.out + (long long)b * P.o_bstride;
+            for (int c0 = 0; c0 < P.N; c0 += 32) {
+                if ((c0 + 31) / P.dh < h_lo || c0 / P.dh > h_hi) continue;              // warp-uniform: no diagonal block in here
+                uint32_t v[32];
+                tmem_ld32(tmem_addr(tb, 32 * quad, c0), v);
+                tmem_ld_wait32(v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
+                __syncwarp();
+                const int col = c0 + lane;
+                const int hc = col / P.dh;
+#pragma unroll 4
+                for (int lr = 0; lr < 32; ++lr) {
+                    const int row = 32 * quad + lr;
+                    const int h = row / P.nsp, m = row - h * P.nsp;
+                    if (row < P.Mtot && m < P.ns && h == hc) atomicAdd(ob + (long long)m * P.ldo + col, T[lr * 33 + lane]);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tb, 256);
+}
+
+// ------------------------------------------------------------------------------------ column softmax (points = keys)
+// T (B, n_rows, HS) raw scores -> probabilities over the rows of a cloud, in place: P = 2^(s c - lse), lse = log2 sum_r 2^(s c).
+// Block = (32 columns, cloud); lane = column (128-byte coalesced rows), warp = row slice.
+__global__ void __launch_bounds__(256) col_softmax_kernel(float* __restrict__ T, int n_rows, int HS, int nsp, int ns, int H,
+                                                          float scale_log2e, float* __restrict__ lse_out) {
+    __shared__ float red[8][33];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    float* t = T + (long long)b * n_rows * HS + c;
+    float m = -INFINITY;
+#pragma unroll 4
+    for (int r = w; r < n_rows; r += 8) m = fmaxf(m, t[(long long)r * HS] * scale_log2e);
+    red[w][lane] = m;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m = fmaxf(m, red[i][lane]);
+    __syncthreads();
+    float l = 0.f;
+#pragma unroll 4
+    for (int r = w; r < n_rows; r += 8) l += ex2(fmaf(t[(long long)r * HS], scale_log2e, -m));
+    red[w][lane] = l;
+    __syncthreads();
+    l = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) l += red[i][lane];
+    const float lse = m + log2f(l);
+#pragma unroll 4
+    for (int r = w; r < n_rows; r += 8) t[(long long)r * HS] = ex2(fmaf(t[(long long)r * HS], scale_log2e, -lse));
+    if (w == 0 && lse_out) {
+        const int h = c / nsp, mm = c - h * nsp;
+        if (mm < ns) lse_out[((long long)b * ns + mm) * H + h] = lse;
+    }
+}
+
+// dst (B, n) = src + b * s_bstride (s_bstride = 0: one row set broadcast over the batch)
+__global__ void bcast_rows_kernel(const float* __restrict__ src, long long s_bstride, long long n, long long total, float* __restrict__ dst) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long b = i / n;
+    dst[i] = __ldg(src + b * s_bstride + (i - b * n));
+}
+
+// ------------------------------------------------------------------------------------ host side
+static int g_attn_tc = 1;        // 0: attention stays on the CUDA-core kernels (PCA_ATTN_TC=0 / pca_debug_set_attn_tc)
+void set_attn_tc(int on) { g_attn_tc = on ? 1 : 0; }
+static bool attn_tc_on() {
+    static int env = -1;
+    if (env < 0) { const char* v = getenv("PCA_ATTN_TC"); env = (v && v[0] == '0') ? 0 : 1; }
+    return env && g_attn_tc && linear_tc_eligible(512, 32, 32);      // follows the GEMM switch as well
+}
+
+struct AtcShape { int type, ns, nsp, HS, big; };     // type 1: keys are the small side (mab1), 2: queries are (mab0 / PMA)
+
+static AtcShape atc_shape(int B, int nq, int nk, int D, int H) {
+    AtcShape s{0, 0, 0, 0, 0};
+    if (!attn_tc_on() || H <= 0 || D % H) return s;
+    const int dh = D / H;
+    if (D % 32 || D < 32 || D > 256 || dh % 8) return s;
+    int type = 0, ns = 0, big = 0;
+    if (nk <= 16 && nq >= 128) { type = 1; ns = nk; big = nq; }
+    else if (nq <= 16 && nk >= 128) { type = 2; ns = nq; big = nk; }
+    else return s;
+    int nsp = 0;
+    for (int cand = 8; cand <= 16; cand *= 2)
+        if (cand >= ns && (H * cand == 32 || H * cand == 64)) { nsp = cand; break; }
+    if (!nsp || (long long)B * big < 512) return s;
+    s.type = type; s.ns = ns; s.nsp = nsp; s.HS = H * nsp; s.big = big;
+    return s;
+}
+
+bool attn_tc_eligible(int B, int nq, int nk, int D, int H) { return atc_shape(B, nq, nk, D, H).type != 0; }
+
+static size_t fl(size_t n) { return align_up(n * sizeof(float), 256) / sizeof(float); }
+
+size_t attn_tc_fwd_floats(int B, int nq, int nk, int D, int H) {
+    const AtcShape s = atc_shape(B, nq, nk, D, H);
+    if (!s.type) return 0;
+    const size_t img = (size_t)s.HS * D;             // floats per cloud image (4 N K bytes)
+    return fl((size_t)B * s.big * s.HS) + (s.type == 1 ? 2 : 1) * fl((size_t)B * img);
+}
+size_t attn_tc_bwd_floats(int B, int nq, int nk, int D, int H) {
+    const AtcShape s = atc_shape(B, nq, nk, D, H);
+    if (!s.type) return 0;
+    const size_t img = (size_t)s.HS * D;
+    return 2 * fl((size_t)B * s.big * s.HS) + (s.type == 1 ? 3 : 4) * fl((size_t)B * img);
+}
+
+static int attn_tc_configure() {
+    static std::atomic<unsigned long long> done_mask{0};
+    int dev = 0;
+    PCA_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && ((done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) return 0;
+#define ATC_ATTR(k) PCA_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, AtSmem::TOTAL))
+    ATC_ATTR((cloud_linear_tc_kernel<EPI_STORE, 16>));
+    ATC_ATTR((cloud_linear_tc_kernel<EPI_RESID, 16>));
+    ATC_ATTR((cloud_linear_tc_kernel<EPI_SOFTMAX, 8>));
+    ATC_ATTR((cloud_linear_tc_kernel<EPI_SOFTMAX, 16>));
+    ATC_ATTR((cloud_linear_tc_kernel<EPI_DS_ROW, 8>));
+    ATC_ATTR((cloud_linear_tc_kernel<EPI_DS_ROW, 16>));
+    ATC_ATTR((cloud_linear_tc_kernel<EPI_P_COL, 16>));
+    ATC_ATTR((cloud_linear_tc_kernel<EPI_DS_COL, 16>));
+    ATC_ATTR(cloud_gw_tc_kernel);
+#undef ATC_ATTR
+    if (dev < 64) done_mask.fetch_or(1ull << dev, std::memory_order_release);
+    return 0;
+}
+
+static int sm_count() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+static int launch_cloud_image(const float* src, long long s_bstride, int ld, int nb, const AtcShape& s, int D, int H, int kind, uint8_t* img,
+                              cudaStream_t st) {
+    const int total = s.HS * D / 8;
+    dim3 grid((unsigned)((total + 255) / 256), (unsigned)nb);
+    cloud_image_kernel<<<grid, 256, 0, st>>>(src, s_bstride, ld, s.ns, s.nsp, D / H, D, s.HS, kind, img, (long long)s.HS * D * 4);
+    PCA_CHECK_LAUNCH("cloud_image_kernel");
+    return 0;
+}
+
+template <int EPI>
+static int launch_cloud_linear(ClinParams p, int nsp, const char* name, cudaStream_t st) {
+    const long long ntiles = (long long)p.B * ((p.n_rows + 127) / 128);
+    const int sms = sm_count();
+    const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+    const double rows = (double)p.B * p.n_rows;
+    LaunchTimer lt(name, st, 2.0 * rows * p.K * p.N, 4.0 * rows * (p.K + p.N));
+    if (EPI == EPI_SOFTMAX || EPI == EPI_DS_ROW) {
+        if (nsp == 8) cloud_linear_tc_kernel<EPI, 8><<<grid, AT_THREADS, AtSmem::TOTAL, st>>>(p);
+        else cloud_linear_tc_kernel<EPI, 16><<<grid, AT_THREADS, AtSmem::TOTAL, st>>>(p);
+    } else {
+        cloud_linear_tc_kernel<EPI, 16><<<grid, AT_THREADS, AtSmem::TOTAL, st>>>(p);
+    }
+    return 0;
+}
+
+static int launch_cloud_gw(const float* T, const float* X, long long x_bstride, int ldx, float* out, long long o_bstride, int ldo, int B,
+                           int n_rows, const AtcShape& s, int D, int H, cudaStream_t st) {
+    const int sms = sm_count();
+    int nsplit = (2 * sms + B - 1) / B;
+    const int max_split = (n_rows + 8 * AT_KC - 1) / (8 * AT_KC);
+    if (nsplit > max_split) nsplit = max_split;
+    if (nsplit < 1) nsplit = 1;
+    int rchunk = (n_rows + nsplit - 1) / nsplit;
+    rchunk = (rchunk + AT_KC - 1) / AT_KC * AT_KC;
+    nsplit = (n_rows + rchunk - 1) / rchunk;
+    ClGwParams p{T, (long long)n_rows * s.HS, s.HS, s.HS, X, x_bstride, ldx, D, out, o_bstride, ldo, n_rows, rchunk, s.nsp, s.ns, D / H};
+    dim3 grid((unsigned)nsplit, (unsigned)B);
+    {
+        LaunchTimer lt("attn_gw_tc_kernel", st, 2.0 * B * (double)n_rows * s.HS * D, 4.0 * B * (double)n_rows * (s.HS + D));
+        cloud_gw_tc_kernel<<<grid, AT_THREADS, AtSmem::TOTAL, st>>>(p);
+    }
+    PCA_CHECK_LAUNCH("cloud_gw_tc_kernel");
+    return 0;
+}
+
+// O (B, nq, D) = Qp + softmax_h(Qp K^T / sqrt(D)) V per head; lse (B, nq, H) optional (log2 domain, as attn_f32_kernel writes it).
+// scratch: attn_tc_fwd_floats floats.
+int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D, int H, float* O, float* scratch,
+                   cudaStream_t st, float* lse) {
+    const AtcShape s = atc_shape(B, nq, nk, D, H);
+    if (!s.type) return fail(PCA_EUNSUPPORTED, "attn_tc: shape (B=%d, nq=%d, nk=%d, D=%d, H=%d) not eligible", B, nq, nk, D, H);
+    if (!scratch) return fail(PCA_EWORKSPACE, "attn_tc: no scratch");
+    PCA_TRY(attn_tc_configure());
+    const float scale = 1.0f / sqrtf((float)D), sl2e = scale * 1.4426950408889634f;
+    const size_t imgf = (size_t)s.HS * D;
+    const long long img_bytes = (long long)imgf * 4;
+    float* T = scratch;
+    uint8_t* img1 = reinterpret_cast<uint8_t*>(scratch + fl((size_t)B * s.big * s.HS));
+    if (s.type == 1) {
+        uint8_t* img2 = img1 + fl((size_t)B * imgf) * sizeof(float);
+        PCA_TRY(launch_cloud_image(KV, (long long)nk * 2 * D, 2 * D, B, s, D, H, 0, img1, st));
+        PCA_TRY(launch_cloud_image(KV + D, (long long)nk * 2 * D, 2 * D, B, s, D, H, 1, img2, st));
+        ClinParams p{};
+        p.X = Qp; p.x_bstride = q_bstride; p.ldx = D;
+        p.img = img1; p.img_bstride = img_bytes;
+        p.Y = T; p.y_bstride = (long long)nq * s.HS; p.ldy = s.HS;
+        p.lse = lse;
+        p.B = B; p.n_rows = nq; p.K = D; p.N = s.HS; p.H = H; p.nsp = s.nsp; p.ns = s.ns; p.scale = scale; p.scale_log2e = sl2e;
+        PCA_TRY(launch_cloud_linear<EPI_SOFTMAX>(p, s.nsp, "attn_scores_tc_kernel", st));
+        PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<softmax>");
+        ClinParams q{};
+        q.X = T; q.x_bstride = (long long)nq * s.HS; q.ldx = s.HS;
+        q.img = img2; q.img_bstride = img_bytes;
+        q.Y = O; q.y_bstride = (long long)nq * D; q.ldy = D;
+        q.R = Qp; q.r_bstride = q_bstride; q.ldr = D;
+        q.B = B; q.n_rows = nq; q.K = s.HS; q.N = D; q.H = H; q.nsp = s.nsp; q.ns = s.ns; q.scale = scale; q.scale_log2e = sl2e;
+        PCA_TRY(launch_cloud_linear<EPI_RESID>(q, s.nsp, "attn_pv_tc_kernel", st));
+        PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<resid>");
+        return 0;
+    }
+    const int nb = q_bstride ? B : 1;
+    PCA_TRY(launch_cloud_image(Qp, q_bstride, D, nb, s, D, H, 0, img1, st));
+    ClinParams p{};
+    p.X = KV; p.x_bstride = (long long)nk * 2 * D; p.ldx = 2 * D;
+    p.img = img1; p.img_bstride = q_bstride ? img_bytes : 0;
+    p.Y = T; p.y_bstride = (long long)nk * s.HS; p.ldy = s.HS;
+    p.B = B; p.n_rows = nk; p.K = D; p.N = s.HS; p.H = H; p.nsp = s.nsp; p.ns = s.ns; p.scale = scale; p.scale_log2e = sl2e;
+    PCA_TRY(launch_cloud_linear<EPI_STORE>(p, s.nsp, "attn_scores_tc_kernel", st));
+    PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<store>");
+    {
+        LaunchTimer lt("col_softmax_kernel", st, 0.0, 8.0 * B * (double)nk * s.HS);
+        col_softmax_kernel<<<dim3((unsigned)(s.HS / 32), (unsigned)B), 256, 0, st>>>(T, nk, s.HS, s.nsp, s.ns, H, sl2e, lse);
+    }
+    PCA_CHECK_LAUNCH("col_softmax_kernel");
+    {
+        const long long n = (long long)nq * D, total = n * B;
+        bcast_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Qp, q_bstride, n, total, O);
+        PCA_CHECK_LAUNCH("bcast_rows_kernel");
+    }
+    return launch_cloud_gw(T, KV + D, (long long)nk * 2 * D, 2 * D, O, (long long)nq * D, D, B, nk, s, D, H, st);
+}
+
+// Gradients of the attention above.  dQp (B, nq, D) is OVERWRITTEN with dO (the residual path) + the attention part; dKV
+// (B, nk, 2D) is OVERWRITTEN.  delta (B, nq, H) = sum_d dO (O - Qp) per head is needed only when the queries are the small side.
+// scratch: attn_tc_bwd_floats floats.
+int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse, const float* delta,
+                       int B, int nq, int nk, int D, int H, float* dQp, float* dKV, float* scratch, cudaStream_t st) {
+    const AtcShape s = atc_shape(B, nq, nk, D, H);
+    if (!s.type) return fail(PCA_EUNSUPPORTED, "attn_bwd_tc: shape (B=%d, nq=%d, nk=%d, D=%d, H=%d) not eligible", B, nq, nk, D, H);
+    if (!scratch) return fail(PCA_EWORKSPACE, "attn_bwd_tc: no scratch");
+    PCA_TRY(attn_tc_configure());
+    const float scale = 1.0f / sqrtf((float)D), sl2e = scale * 1.4426950408889634f;
+    const size_t imgf = (size_t)s.HS * D;
+    const long long img_bytes = (long long)imgf * 4;
+    const size_t tf = fl((size_t)B * s.big * s.HS), imf = fl((size_t)B * imgf);
+    float* Pm = scratch;
+    float* dS = scratch + tf;
+    uint8_t* imgs = reinterpret_cast<uint8_t*>(scratch + 2 * tf);
+    auto img_at = [&](int i) { return imgs + (size_t)i * imf * sizeof(float); };
+    const long long t_bstride = (long long)s.big * s.HS;
+    auto base = [&](int n_rows, int K, int N) {
+        ClinParams p{};
+        p.B = B; p.n_rows = n_rows; p.K = K; p.N = N; p.H = H; p.nsp = s.nsp; p.ns = s.ns; p.scale = scale; p.scale_log2e = sl2e;
+        return p;
+    };
+    if (s.type == 1) {
+        const long long kv_bs = (long long)nk * 2 * D;
+        PCA_TRY(launch_cloud_image(KV, kv_bs, 2 * D, B, s, D, H, 0, img_at(0), st));          // K as the G1 operand
+        PCA_TRY(launch_cloud_image(KV + D, kv_bs, 2 * D, B, s, D, H, 0, img_at(1), st));      // V as the G1 operand
+        PCA_TRY(launch_cloud_image(KV, kv_bs, 2 * D, B, s, D, H, 1, img_at(2), st));          // K as the G2 operand
+        ClinParams p = base(nq, D, s.HS);                                                     // P = softmax(Qp K^T)
+        p.X = Qp; p.x_bstride = q_bstride; p.ldx = D;
+        p.img = img_at(0); p.img_bstride = img_bytes;
+        p.Y = Pm; p.y_bstride = t_bstride; p.ldy = s.HS;
+        PCA_TRY(launch_cloud_linear<EPI_SOFTMAX>(p, s.nsp, "attn_scores_tc_kernel", st));
+        PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<softmax>");
+        ClinParams q = base(nq, D, s.HS);                                                     // dS = P o (dO V^T - delta) scale
+        q.X = dO; q.x_bstride = (long long)nq * D; q.ldx = D;
+        q.img = img_at(1); q.img_bstride = img_bytes;
+        q.Y = dS; q.y_bstride = t_bstride; q.ldy = s.HS;
+        q.R = Pm; q.r_bstride = t_bstride; q.ldr = s.HS;
+        PCA_TRY(launch_cloud_linear<EPI_DS_ROW>(q, s.nsp, "attn_ds_tc_kernel", st));
+        PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<ds_row>");
+        ClinParams g = base(nq, s.HS, D);                                                     // dQp = dO + dS K
+        g.X = dS; g.x_bstride = t_bstride; g.ldx = s.HS;
+        g.img = img_at(2); g.img_bstride = img_bytes;
+        g.Y = dQp; g.y_bstride = (long long)nq * D; g.ldy = D;
+        g.R = dO; g.r_bstride = (long long)nq * D; g.ldr = D;
+        PCA_TRY(launch_cloud_linear<EPI_RESID>(g, s.nsp, "attn_pv_tc_kernel", st));
+        PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<resid>");
+        PCA_CHECK_CUDA(cudaMemsetAsync(dKV, 0, (size_t)B * nk * 2 * D * sizeof(float), st));
+        PCA_TRY(launch_cloud_gw(dS, Qp, q_bstride, D, dKV, kv_bs, 2 * D, B, nq, s, D, H, st));         // dK = dS^T Qp
+        return launch_cloud_gw(Pm, dO, (long long)nq * D, D, dKV + D, kv_bs, 2 * D, B, nq, s, D, H, st);   // dV = P^T dO
+    }
+    if (!delta || !lse) return fail(PCA_EINVAL, "attn_bwd_tc: the small-query form needs lse and delta");
+    const int nb = q_bstride ? B : 1;
+    const long long kv_bs = (long long)nk * 2 * D, o_bs = (long long)nq * D;
+    PCA_TRY(launch_cloud_image(Qp, q_bstride, D, nb, s, D, H, 0, img_at(0), st));             // Qp as the G1 operand
+    PCA_TRY(launch_cloud_image(Qp, q_bstride, D, nb, s, D, H, 1, img_at(1), st));             // Qp as the G2 operand
+    PCA_TRY(launch_cloud_image(dO, o_bs, D, B, s, D, H, 0, img_at(2), st));                   // dO as the G1 operand
+    PCA_TRY(launch_cloud_image(dO, o_bs, D, B, s, D, H, 1, img_at(3), st));                   // dO as the G2 operand
+    ClinParams p = base(nk, D, s.HS);                                                         // P = 2^(K Qp^T c - lse)
+    p.X = KV; p.x_bstride = kv_bs; p.ldx = 2 * D;
+    p.img = img_at(0); p.img_bstride = q_bstride ? img_bytes : 0;
+    p.Y = Pm; p.y_bstride = t_bstride; p.ldy = s.HS;
+    p.vec = lse;
+    PCA_TRY(launch_cloud_linear<EPI_P_COL>(p, s.nsp, "attn_scores_tc_kernel", st));
+    PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<p_col>");
+    ClinParams q = base(nk, D, s.HS);                                                         // dS = P o (V dO^T - delta) scale
+    q.X = KV + D; q.x_bstride = kv_bs; q.ldx = 2 * D;
+    q.img = img_at(2); q.img_bstride = img_bytes;
+    q.Y = dS; q.y_bstride = t_bstride; q.ldy = s.HS;
+    q.R = Pm; q.r_bstride = t_bstride; q.ldr = s.HS;
+    q.vec = delta;
+    PCA_TRY(launch_cloud_linear<EPI_DS_COL>(q, s.nsp, "attn_ds_tc_kernel", st));
+    PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<ds_col>");
+    ClinParams gk = base(nk, s.HS, D);                                                        // dK = dS Qp
+    gk.X = dS; gk.x_bstride = t_bstride; gk.ldx = s.HS;
+    gk.img = img_at(1); gk.img_bstride = q_bstride ? img_bytes : 0;
+    gk.Y = dKV; gk.y_bstride = kv_bs; gk.ldy = 2 * D;
+    PCA_TRY(launch_cloud_linear<EPI_STORE>(gk, s.nsp, "attn_pv_tc_kernel", st));
+    PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<store>");
+    ClinParams gv = base(nk, s.HS, D);                                                        // dV = P dO
+    gv.X = Pm; gv.x_bstride = t_bstride; gv.ldx = s.HS;
+    gv.img = img_at(3); gv.img_bstride = img_bytes;
+    gv.Y = dKV + D; gv.y_bstride = kv_bs; gv.ldy = 2 * D;
+    PCA_TRY(launch_cloud_linear<EPI_STORE>(gv, s.nsp, "attn_pv_tc_kernel", st));
+    PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<store>");
+    PCA_CHECK_CUDA(cudaMemcpyAsync(dQp, dO, (size_t)B * nq * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return launch_cloud_gw(dS, KV, kv_bs, 2 * D, dQp, o_bs, D, B, nk, s, D, H, st);           // dQp = dO + dS^T K
+}
+
+}  // namespace pca

@@ -391,7 +391,11 @@ static AttnPlan plan_attn(int B, int nq, int nk, int D, int H) {
     return p;
 }
 
-size_t attn_part_floats(int B, int nq, int nk, int D, int H) { return plan_attn(B, nq, nk, D, H).part_floats; }
+// scratch of launch_attn: the split partials of the CUDA-core kernel or the score matrix + operand images of the tensor-core route
+size_t attn_part_floats(int B, int nq, int nk, int D, int H) {
+    const size_t a = plan_attn(B, nq, nk, D, H).part_floats, b = attn_tc_fwd_floats(B, nq, nk, D, H);
+    return a > b ? a : b;
+}
 
 template <int DH, int R>
 static int launch_attn_r(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk,
@@ -441,6 +445,8 @@ int launch_attn(const float* Qp, long long q_bstride, const float* KV, int B, in
     if (B == 0 || nq == 0) return 0;
     if (H < 1 || H > 32 || D % H) return fail(PCA_EUNSUPPORTED, "attention: need 1 <= H <= 32 and D %% H == 0 (D=%d, H=%d)", D, H);
     if (B > 65535) return fail(PCA_EUNSUPPORTED, "attention: batch chunk %d exceeds the grid limit", B);
+    // one small side (inducing points / seeds against a large set): Q K^T and P V as split-bf16 tensor-core GEMMs
+    if (!key_counts && attn_tc_eligible(B, nq, nk, D, H)) return launch_attn_tc(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st, lse);
     switch (D / H) {
         case 4: return launch_attn_t<4, 2>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
         case 8: return launch_attn_t<8, 2>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);

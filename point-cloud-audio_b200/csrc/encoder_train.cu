@@ -709,6 +709,7 @@ static size_t mab_bwd_ws_floats(int B, int qb, int nq, int nk, int D, int H, int
     a.take<float>((size_t)B * nk * 2 * D);    // dKV
     if (qb == 1) a.take<float>((size_t)nq * D);
     a.take<uint8_t>(train_img_bytes(D));
+    a.take<float>(attn_tc_bwd_floats(B, nq, nk, D, H));      // tensor-core attention backward (0 when the shape is not eligible)
     return a.off;
 }
 
@@ -729,6 +730,8 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
     void* img = a.take<uint8_t>(ib);
     void* img_q = dq <= D ? img : nullptr;
     void* img_k = dk <= D ? img : nullptr;
+    const bool attn_tc = !key_counts && attn_tc_eligible(B, nq, nk, D, H);
+    float* attn_scratch = a.take<float>(attn_tc_bwd_floats(B, nq, nk, D, H));
     if (!a.ok()) return fail(PCA_EWORKSPACE, "MAB backward: workspace too small");
     const long long rq = (long long)B * nq, rk = (long long)B * nk;
     const long long q_bstride = qb == 1 ? 0 : (long long)nq * D;
@@ -755,11 +758,15 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
             attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dO, Oatt, s.Qp, q_bstride, nq, D, D / H, total, delta);
         PCA_CHECK_LAUNCH("attn_delta_kernel");
     }
-    PCA_CHECK_CUDA(cudaMemsetAsync(dKV, 0, (size_t)rk * 2 * D * sizeof(float), st));
-    PCA_TRY(launch_attn_bwd<1>(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, nullptr, dKV, st, key_counts));
-    float* dQp = dZ;                                            // dQp = dO (residual) + attention part, added atomically
-    PCA_CHECK_CUDA(cudaMemcpyAsync(dQp, dO, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    PCA_TRY(launch_attn_bwd<0>(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, dQp, nullptr, st, key_counts));
+    float* dQp = dZ;                                            // dQp = dO (residual) + attention part
+    if (attn_tc) {                                              // one small side: every contraction as a split-bf16 tensor-core GEMM
+        PCA_TRY(launch_attn_bwd_tc(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, dQp, dKV, attn_scratch, st));
+    } else {
+        PCA_CHECK_CUDA(cudaMemsetAsync(dKV, 0, (size_t)rk * 2 * D * sizeof(float), st));
+        PCA_TRY(launch_attn_bwd<1>(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, nullptr, dKV, st, key_counts));
+        PCA_CHECK_CUDA(cudaMemcpyAsync(dQp, dO, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));   // added to atomically
+        PCA_TRY(launch_attn_bwd<0>(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, dQp, nullptr, st, key_counts));
+    }
     long long rows_q = rq;
     if (qb == 1) {                                              // shared queries (I / S): sum the per-cloud gradients
         PCA_CHECK_CUDA(cudaMemsetAsync(dQ1, 0, (size_t)nq * D * sizeof(float), st));
