@@ -129,6 +129,23 @@ int make_tmap_chunked_bf16(CUtensorMap* out, const void* base, unsigned long lon
     return 0;
 }
 
+int make_tmap_3d_f32(CUtensorMap* out, const void* base, unsigned long long inner, unsigned long long rows, unsigned long long batch,
+                     unsigned long long row_stride_bytes, unsigned long long batch_stride_bytes, unsigned box_inner, unsigned box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return fail(PCA_EDEVICE, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {inner, rows, batch};
+    const cuuint64_t strides[2] = {row_stride_bytes, batch_stride_bytes};
+    const cuuint32_t box[3] = {box_inner, box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(PCA_EINVAL, "cuTensorMapEncodeTiled (fp32 rows) failed with CUresult %d (base %p, %llu x %llu x %llu, strides %llu / %llu)",
+                    (int)r, base, inner, rows, batch, row_stride_bytes, batch_stride_bytes);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------ profiling
 struct ProfRec { const char* name; cudaEvent_t a, b; double flops, bytes; };
 static std::atomic<int> g_prof_on{0};

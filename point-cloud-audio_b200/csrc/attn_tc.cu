@@ -14,13 +14,20 @@
 // The zero blocks cost 4x redundant MMA work at H = 4 -- irrelevant: these GEMMs are HBM-bound (the tensor pipe is < 25 % busy).
 #include "common.cuh"
 #include "tc_prims.cuh"
+#include "tma_host.cuh"
 
 namespace pca {
 using namespace tc;
 
 constexpr int AT_KC = 32;
-constexpr int AT_STAGES = 3;
-constexpr int AT_THREADS = 9 * 32;   // 4 producer + 1 MMA + 4 epilogue warps
+constexpr int AT_STAGES = 4;
+constexpr int AT_PSETS = 2;           // producer warp sets: set s stages the K chunks s, s + 2, ... (twice the loads in flight per SM)
+constexpr int AT_MMA_WARP = 4 * AT_PSETS;
+constexpr int AT_LOAD_WARP = AT_MMA_WARP + 5;
+constexpr int AT_THREADS = (4 * AT_PSETS + 6) * 32;   // 8 producer / converter + 1 MMA + 4 epilogue + 1 TMA loader warps
+constexpr int CL_STAGES = 3;          // operand stages of the per-cloud linear kernel
+constexpr int CL_RAW_MAX = 8;         // raw fp32 tiles (128 rows x 32 floats = 16 KB) the TMA loader may have in flight
+constexpr int CL_RAW_BYTES = 128 * AT_KC * 4;
 
 __device__ __forceinline__ void at_warp_arrive(uint64_t* bar) {
     __syncwarp();
@@ -96,38 +103,83 @@ struct ClinParams {
     int B, n_rows, K, N;
     int H, nsp, ns;
     float scale, scale_log2e;
+    int raw_slots;         // raw fp32 tiles in the TMA ring (<= CL_RAW_MAX)
+    int x_shared;          // X has no batch dimension (x_bstride == 0)
 };
 
+// The activation images are written by the producers with a PADDED chunk stride (the descriptor's leading byte offset is free):
+// K-major: 16-byte chunk c of row r at c * A_LBO + r * 16 with A_LBO = 2048 + 16; MN-major (G3): 8-feature group g of row k at
+// g * G_SBO + k * 16 with G_SBO = 512 + 16 -- so that the four chunks / groups a quarter warp stores to fall into distinct banks.
 struct AtSmem {
-    static constexpr int A_BYTES = 128 * AT_KC * 2;
+    static constexpr int A_LBO = 128 * 16 + 16;
+    static constexpr int A_BYTES = 8320;                               // >= 4 * A_LBO, 128-byte multiple
     static constexpr int STAGE = 2 * A_BYTES + 2 * 256 * AT_KC * 2;   // A hi | A lo | B hi | B lo (B sized for N = 256)
-    static constexpr int TRANS = AT_STAGES * STAGE;
+    static constexpr int G_SBO = AT_KC * 16 + 16;
+    static constexpr int GA_BYTES = 16 * G_SBO;                        // 128 features
+    static constexpr int GB_BYTES = 32 * G_SBO;                        // 256 features
+    static constexpr int G_STAGE = 2 * GA_BYTES + 2 * GB_BYTES;
+    static constexpr int TRANS = AT_STAGES * G_STAGE;                  // G3 kernel: stages | transpose tiles | barriers
     static constexpr int BARS = TRANS + 4 * 32 * 33 * 4;
     static constexpr int TOTAL = BARS + 16 * 8 + 16;
+    // per-cloud linear kernel: raw fp32 ring | operand stages (B region sized for the launch's N) | transpose tiles | barriers
+    static constexpr int CL_FIXED = 4 * 32 * 33 * 4 + 256;
+    static constexpr int MAX_BYTES = 227 * 1024;
+    __host__ __device__ static int cl_stage(int N) { return 2 * A_BYTES + 2 * N * 64; }
+    __host__ static int cl_raw_slots(int N) {
+        int r = (MAX_BYTES - CL_FIXED - CL_STAGES * cl_stage(N)) / CL_RAW_BYTES;
+        return r > CL_RAW_MAX ? CL_RAW_MAX : r;
+    }
+    __host__ __device__ static int cl_total(int N, int raw_slots) { return raw_slots * CL_RAW_BYTES + CL_STAGES * cl_stage(N) + CL_FIXED; }
 };
 
-// Persistent, warp-specialised (the structure of linear_tc_kernel): 4 producer warps split the fp32 rows of a 128-row tile
-// into hi / lo bf16 in the canonical K-major layout, the cloud's operand image arrives by one bulk copy per K chunk, one warp
-// issues the MMAs, 4 epilogue warps read the accumulator (thread = row), apply the epilogue and write 128-byte coalesced rows
+// lanes 2j / 2j + 1 hold adjacent float4 pieces (a: of row A, b: of row B = A + 4); after the exchange the even lane owns the 8
+// consecutive floats of row A and the odd lane those of row B (one 16-byte bf16 chunk each)
+__device__ __forceinline__ void at_pair_exchange(const float4 a, const float4 b, bool odd, float* x) {
+    const float4 send = odd ? a : b;
+    float4 recv;
+    recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+    recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+    recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+    recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+    const float4 lo4 = odd ? recv : a, hi4 = odd ? b : recv;
+    x[0] = lo4.x; x[1] = lo4.y; x[2] = lo4.z; x[3] = lo4.w;
+    x[4] = hi4.x; x[5] = hi4.y; x[6] = hi4.z; x[7] = hi4.w;
+}
+
+// Persistent, warp-specialised.  ONE loader thread streams the fp32 rows of the 128-row tiles with TMA (a 3-D tensor map
+// (K, rows of a cloud, clouds): rows past the end of a cloud arrive as zeros) into a ring of raw 16 KB tiles -- up to eight in
+// flight per SM, independent of any warp's registers or scoreboard (with register-staged loads the kernels sat at 2.5 TB/s:
+// one chunk in flight per warp set, and the proxy fence after the operand stores waits for outstanding loads).  8 converter
+// warps (two sets on alternate K chunks) read the raw rows (quarter warp = the 128 bytes of one row), split them into hi / lo
+// bf16 and store the canonical K-major operand images; the cloud's B image arrives by one bulk copy per K chunk; one warp
+// issues the MMAs; 4 epilogue warps read the accumulator (thread = row), apply the epilogue and write 128-byte coalesced rows
 // through a padded transpose tile.  Tiles never straddle clouds (tile t = (cloud t / tpc, rows 128 (t % tpc) ...)).
 template <int EPI, int NSP>
-__global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const ClinParams P) {
+__global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const ClinParams P, const __grid_constant__ CUtensorMap tmx) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AtSmem::BARS);
-    uint64_t* full = bars;                       // [3] count 5: 4 producer warps + the expect_tx arrival
-    uint64_t* empty = bars + AT_STAGES;          // [3] count 1 (MMA commit)
-    uint64_t* acc_full = bars + 2 * AT_STAGES;   // [2] count 1
+    const int stage_bytes = AtSmem::cl_stage(P.N);
+    uint8_t* ops = smem + P.raw_slots * CL_RAW_BYTES;
+    uint8_t* trans = ops + CL_STAGES * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(trans + 4 * 32 * 33 * 4);
+    uint64_t* full = bars;                       // [3] count 5: the 4 converter warps of a set + the expect_tx arrival of the B image
+    uint64_t* empty = bars + CL_STAGES;          // [3] count 1 (MMA commit)
+    uint64_t* acc_full = bars + 2 * CL_STAGES;   // [2] count 1
     uint64_t* acc_empty = acc_full + 2;          // [2] count 4 (epilogue warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* raw_full = acc_empty + 2;          // [8] count 1 (expect_tx of the loader) + 16 KB
+    uint64_t* raw_empty = raw_full + CL_RAW_MAX; // [8] count 4 (converter warps of the set that read the slot)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + CL_RAW_MAX);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkc = P.K / AT_KC;
     const int tpc = (P.n_rows + 127) / 128;
     const long long ntiles = (long long)P.B * tpc;
+    const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const uint32_t items = (uint32_t)my_tiles * nkc;       // (tile of this CTA, K chunk) in issue order
 
-    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    if (warp == AT_MMA_WARP) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&full[i], 5); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < CL_STAGES; ++i) { mbar_init(&full[i], 5); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < CL_RAW_MAX; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 4); }
         fence_barrier_init();
     }
     fence_before_sync();
@@ -136,73 +188,67 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const Cl
     const uint32_t tb = *tmem_slot;
     const uint32_t b_img_bytes = (uint32_t)P.N * 64;           // one hi or lo operand image of a chunk
 
-    if (warp < 4) {
-        // ================================================================= producers
-        const int rsub = lane & 7, c = lane >> 3;
-        uint32_t gt = 0;
-        float4 nx[8], nx2[8];
-        long long t = blockIdx.x;
-        int kc = 0;
-        auto issue = [&](float4* dst, long long tile, int kchunk) {
-            const int b = (int)(tile / tpc);
-            const int j = (int)(tile - (long long)b * tpc);
-            const float* xb = P.X + (long long)b * P.x_bstride;
+    if (warp == AT_LOAD_WARP) {
+        // ================================================================= TMA loader (one thread)
+        if (lane == 0) {
+            tma_prefetch_desc(&tmx);
+            for (uint32_t g = 0; g < items; ++g) {
+                const int slot = g % P.raw_slots;
+                const uint32_t lt = g / nkc;
+                const int kc = (int)(g - lt * nkc);
+                const int tile = (int)(blockIdx.x + lt * gridDim.x);
+                const int b = tile / tpc, j = tile - b * tpc;
+                if (g >= (uint32_t)P.raw_slots) mbar_wait(&raw_empty[slot], ((g / P.raw_slots) - 1) & 1);
+                mbar_arrive_expect_tx(&raw_full[slot], CL_RAW_BYTES);
+                tma_load_3d(smem + slot * CL_RAW_BYTES, &tmx, kc * AT_KC, j * 128, P.x_shared ? 0 : b, &raw_full[slot]);
+            }
+        }
+    } else if (warp < AT_MMA_WARP) {
+        // ================================================================= converters
+        // Warp set g % AT_PSETS converts item g; warp pw of the set the rows [32 pw, 32 pw + 32) of the tile.  Quarter warp q
+        // reads the 128 bytes (the whole K chunk) of row 8 it + q and of row 8 it + 4 + q from the raw tile; a pair exchange
+        // gives every lane the 8 consecutive floats of one 16-byte bf16 chunk.
+        const int set = warp >> 2, pw = warp & 3;
+        const int q = lane >> 3, piece = lane & 7;
+        const bool odd = piece & 1;
+        for (uint32_t g = set; g < items; g += AT_PSETS) {
+            const int slot = g % P.raw_slots;
+            const int stage = g % CL_STAGES;
+            mbar_wait(&raw_full[slot], (g / P.raw_slots) & 1);
+            const float4* raw = reinterpret_cast<const float4*>(smem + slot * CL_RAW_BYTES) + piece;
+            float4 xv[8];
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
-                const int r = j * 128 + 32 * warp + 8 * it + rsub;
-                if (r < P.n_rows) {
-                    const float4* src = reinterpret_cast<const float4*>(xb + (long long)r * P.ldx + kchunk * AT_KC + 8 * c);
-                    dst[2 * it] = __ldg(src);
-                    dst[2 * it + 1] = __ldg(src + 1);
-                } else {
-                    dst[2 * it] = dst[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                const int rA = 32 * pw + 8 * it + q;
+                xv[2 * it] = raw[rA * 8];
+                xv[2 * it + 1] = raw[(rA + 4) * 8];
             }
-        };
-        auto advance = [&](long long& tile, int& kchunk) {
-            if (++kchunk == nkc) { kchunk = 0; tile += gridDim.x; }
-        };
-        long long t_n = t, t_n2;
-        int kc_n = 0, kc_n2;
-        if (t < ntiles) issue(nx, t, 0);
-        advance(t_n, kc_n);
-        if (t_n < ntiles) issue(nx2, t_n, kc_n);
-        t_n2 = t_n;
-        kc_n2 = kc_n;
-        while (t < ntiles) {
-            const int stage = gt % AT_STAGES;
-            float4 cur[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { cur[j] = nx[j]; nx[j] = nx2[j]; }
-            advance(t_n2, kc_n2);
-            if (t_n2 < ntiles) issue(nx2, t_n2, kc_n2);
-            if (gt >= AT_STAGES) mbar_wait(&empty[stage], ((gt / AT_STAGES) - 1) & 1);
-            uint8_t* st = smem + stage * AtSmem::STAGE;
-            if (threadIdx.x == 0) {
-                const long long b = t / tpc;
+            if (g >= CL_STAGES) mbar_wait(&empty[stage], ((g / CL_STAGES) - 1) & 1);
+            uint8_t* st = ops + stage * stage_bytes;
+            if (pw == 0 && lane == 0) {
+                const uint32_t lt = g / nkc;
+                const int kc = (int)(g - lt * nkc);
+                const long long b = (int)(blockIdx.x + lt * gridDim.x) / tpc;
                 mbar_arrive_expect_tx(&full[stage], 2 * b_img_bytes);
                 bulk_copy_g2s(st + 2 * AtSmem::A_BYTES, P.img + b * P.img_bstride + ((size_t)kc * 2) * b_img_bytes, 2 * b_img_bytes,
                               &full[stage]);
             }
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
-                const float x[8] = {cur[2 * it].x, cur[2 * it].y, cur[2 * it].z, cur[2 * it].w,
-                                    cur[2 * it + 1].x, cur[2 * it + 1].y, cur[2 * it + 1].z, cur[2 * it + 1].w};
+                float x[8];
+                at_pair_exchange(xv[2 * it], xv[2 * it + 1], odd, x);
                 uint4 hi, lo;
                 at_split8(x, hi, lo);
-                const int row = 32 * warp + 8 * it + rsub;
-                *reinterpret_cast<uint4*>(st + c * 2048 + row * 16) = hi;
-                *reinterpret_cast<uint4*>(st + AtSmem::A_BYTES + c * 2048 + row * 16) = lo;
+                const int row = 32 * pw + 8 * it + q + (odd ? 4 : 0);
+                const int off = (piece >> 1) * AtSmem::A_LBO + row * 16;
+                *reinterpret_cast<uint4*>(st + off) = hi;
+                *reinterpret_cast<uint4*>(st + AtSmem::A_BYTES + off) = lo;
             }
+            at_warp_arrive(&raw_empty[slot]);              // the raw tile is in registers / converted: the loader may refill the slot
             fence_async_smem();
             at_warp_arrive(&full[stage]);
-            ++gt;
-            t = t_n;
-            kc = kc_n;
-            t_n = t_n2;
-            kc_n = kc_n2;
         }
-    } else if (warp == 4) {
+    } else if (warp == AT_MMA_WARP) {
         // ================================================================= MMA issue (warp-uniform, elected lane)
         const uint32_t idesc = idesc_bf16(128, P.N, 0, 0);
         uint32_t gt = 0, tt = 0;
@@ -212,18 +258,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const Cl
             fence_after_sync();
             const uint32_t acc = tmem_addr(tb, 0, 256 * buf);
             for (int kc = 0; kc < nkc; ++kc, ++gt) {
-                const int stage = gt % AT_STAGES;
-                mbar_wait(&full[stage], (gt / AT_STAGES) & 1);
+                const int stage = gt % CL_STAGES;
+                mbar_wait(&full[stage], (gt / CL_STAGES) & 1);
                 fence_after_sync();
                 if (elect_one()) {
-                    const uint32_t a_hi = smem_u32(smem + stage * AtSmem::STAGE);
+                    const uint32_t a_hi = smem_u32(ops + stage * stage_bytes);
                     const uint32_t a_lo = a_hi + AtSmem::A_BYTES;
                     const uint32_t b_hi = a_hi + 2 * AtSmem::A_BYTES;
                     const uint32_t b_lo = b_hi + b_img_bytes;
                     const uint32_t b_lbo = (uint32_t)P.N * 16;
 #pragma unroll
                     for (int ks = 0; ks < AT_KC / 16; ++ks) {
-                        const uint64_t dah = smem_desc(a_hi + ks * 4096, 2048, 128), dal = smem_desc(a_lo + ks * 4096, 2048, 128);
+                        const uint64_t dah = smem_desc(a_hi + ks * 2 * AtSmem::A_LBO, AtSmem::A_LBO, 128);
+                        const uint64_t dal = smem_desc(a_lo + ks * 2 * AtSmem::A_LBO, AtSmem::A_LBO, 128);
                         const uint64_t dbh = smem_desc(b_hi + ks * 2 * b_lbo, b_lbo, 128), dbl = smem_desc(b_lo + ks * 2 * b_lbo, b_lbo, 128);
                         mma_ss(acc, dah, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
                         mma_ss(acc, dal, dbh, idesc, 1u);
@@ -235,10 +282,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const Cl
                 __syncwarp();
             }
         }
-    } else {
+    } else if (warp < AT_LOAD_WARP) {
         // ================================================================= epilogue
         const int quad = warp & 3;
-        float* T = reinterpret_cast<float*>(smem + AtSmem::TRANS) + quad * (32 * 33);
+        float* T = reinterpret_cast<float*>(trans) + quad * (32 * 33);
         const int rr = lane >> 3, cq = lane & 7;
         uint32_t tt = 0;
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tt) {
@@ -247,22 +294,39 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const Cl
             const int i0 = (int)(t - (long long)b * tpc) * 128 + 32 * quad;     // first row (inside the cloud) of this warp
             float* yb = P.Y + (long long)b * P.y_bstride;
             const float* rb = (EPI == EPI_RESID || EPI == EPI_DS_ROW || EPI == EPI_DS_COL) ? P.R + (long long)b * P.r_bstride : nullptr;
+            // the R rows (residual / probabilities) of a 32-column block are fetched one block ahead: 4 rows x 128 contiguous
+            // bytes per instruction, in flight while the previous block is processed (and, for the first, under the MMAs)
+            constexpr bool kUsesR = EPI == EPI_RESID || EPI == EPI_DS_ROW || EPI == EPI_DS_COL;
+            float4 rvn[8];
+            auto load_r = [&](int c0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i0 + 4 * i + rr;
+                    rvn[i] = r < P.n_rows ? *reinterpret_cast<const float4*>(rb + (long long)r * P.ldr + c0 + 4 * cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            if (kUsesR) load_r(0);
             mbar_wait(&acc_full[buf], (tt >> 1) & 1);
             fence_after_sync();
             for (int c0 = 0; c0 < P.N; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_addr(tb, 32 * quad, 256 * buf + c0), v);
+                float4 rv8[8];
+                if (kUsesR) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rv8[i] = rvn[i];
+                    if (c0 + 32 < P.N) load_r(c0 + 32);
+                }
                 tmem_ld_wait32(v);
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                 if (EPI == EPI_DS_ROW) {
-                    // the row's probabilities: coalesced block load through the transpose tile
+                    // the row's probabilities: coalesced block load, transposed through the tile
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int lr = 4 * i + rr, r = i0 + lr;
-                        const float4 pv = r < P.n_rows ? *reinterpret_cast<const float4*>(rb + (long long)r * P.ldr + c0 + 4 * cq)
-                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int lr = 4 * i + rr;
+                        const float4 pv = rv8[i];
                         T[lr * 33 + 4 * cq] = pv.x; T[lr * 33 + 4 * cq + 1] = pv.y; T[lr * 33 + 4 * cq + 2] = pv.z; T[lr * 33 + 4 * cq + 3] = pv.w;
                     }
                     __syncwarp();
@@ -315,14 +379,6 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const Cl
                         cv[u] = cok[u] ? __ldg(P.vec + ((long long)b * P.ns + m) * P.H + h) : 0.f;
                     }
                 }
-                float4 rv8[8];
-                if (EPI == EPI_RESID || EPI == EPI_DS_COL) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = i0 + 4 * i + rr;
-                        rv8[i] = r < P.n_rows ? *reinterpret_cast<const float4*>(rb + (long long)r * P.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int lr = 4 * i + rr, r = i0 + lr;
@@ -347,7 +403,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const Cl
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tb, 512);
+    if (warp == AT_MMA_WARP) tmem_dealloc(tb, 512);
 }
 
 // ------------------------------------------------------------------------------------ G3: per-cloud T^T X, head blocks extracted
@@ -369,11 +425,10 @@ struct ClGwParams {
 __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AtSmem::BARS);
-    uint64_t* full = bars;                       // [3] count 4 (producer warps)
-    uint64_t* empty = bars + AT_STAGES;          // [3] count 1
+    uint64_t* full = bars;                       // [stages] count 4 (the producer warps of a set)
+    uint64_t* empty = bars + AT_STAGES;          // [stages] count 1
     uint64_t* acc_full = bars + 2 * AT_STAGES;   // count 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-    constexpr int A_BYTES = 128 * AT_KC * 2, B_BYTES = 256 * AT_KC * 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AT_STAGES + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int r0 = blockIdx.x * P.rchunk;
@@ -382,7 +437,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
     const float* Ab = P.A + (long long)b * P.a_bstride;
     const float* Bb = P.Bm + (long long)b * P.b_bstride;
 
-    if (warp == 4) tmem_alloc(tmem_slot, 256);
+    if (warp == AT_MMA_WARP) tmem_alloc(tmem_slot, 256);
     if (threadIdx.x == 0) {
         for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
         mbar_init(acc_full, 1);
@@ -393,77 +448,77 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
     fence_after_sync();
     const uint32_t tb = *tmem_slot;
 
-    if (warp < 4) {
-        const int ksub = lane & 7, gq = lane >> 3;
-        const int b_gblocks = P.N / 32;
-        for (int c = 0; c < nchunks; ++c) {
+    if (warp < AT_MMA_WARP) {
+        // Warp set s stages the 32-row chunks s, s + 2, ...; warp pw of the set the rows [8 pw, 8 pw + 8) of the chunk for every
+        // 32-feature block.  Loads are row-contiguous (quarter warp q: the 128 bytes of row 8 pw + q, then of row 8 pw + 4 + q);
+        // a pair exchange gives every lane one 16-byte unit (8 consecutive features of one row).
+        const int set = warp >> 2, pw = warp & 3;
+        const int q = lane >> 3, piece = lane & 7;
+        const bool odd = piece & 1;
+        const int a_fblocks = (P.Mtot + 31) / 32, b_fblocks = P.N / 32;
+        for (int c = set; c < nchunks; c += AT_PSETS) {
             const int stage = c % AT_STAGES;
-            const int rbase = r0 + c * AT_KC;
+            const int rA = r0 + c * AT_KC + 8 * pw + q, rB = rA + 4;
+            const bool okA = rA < r1, okB = rB < r1;
             float4 va[8], vb[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int pi = warp + 4 * i;
-                const int kb = pi & 3, gb = pi >> 2;
-                const int r = rbase + 8 * kb + ksub;
-                const int g = 4 * gb + gq;
-                const bool ok = r < r1 && (8 * g < P.Mtot);
-                const float4* src = reinterpret_cast<const float4*>(Ab + (long long)(ok ? r : 0) * P.lda + (ok ? 8 * g : 0));
-                va[2 * i] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-                va[2 * i + 1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool on = i < a_fblocks;
+                const float* src = Ab + (on ? 32 * i : 0) + 4 * piece;
+                va[2 * i] = (on && okA) ? __ldg(reinterpret_cast<const float4*>(src + (long long)rA * P.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                va[2 * i + 1] = (on && okB) ? __ldg(reinterpret_cast<const float4*>(src + (long long)rB * P.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int pi = warp + 4 * i;
-                const int kb = pi & 3, gb = pi >> 2;
-                const int r = rbase + 8 * kb + ksub;
-                const int g = 4 * gb + gq;
-                const bool ok = r < r1 && gb < b_gblocks;
-                const float4* src = reinterpret_cast<const float4*>(Bb + (long long)(ok ? r : 0) * P.ldb + (ok ? 8 * g : 0));
-                vb[2 * i] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-                vb[2 * i + 1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool on = i < b_fblocks;
+                const float* src = Bb + (on ? 32 * i : 0) + 4 * piece;
+                vb[2 * i] = (on && okA) ? __ldg(reinterpret_cast<const float4*>(src + (long long)rA * P.ldb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[2 * i + 1] = (on && okB) ? __ldg(reinterpret_cast<const float4*>(src + (long long)rB * P.ldb)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (c >= AT_STAGES) mbar_wait(&empty[stage], ((c / AT_STAGES) - 1) & 1);
-            uint8_t* st = smem + stage * AtSmem::STAGE;
+            uint8_t* st = smem + stage * AtSmem::G_STAGE;
+            const int k = 8 * pw + q + (odd ? 4 : 0);                 // row of the chunk this lane stores
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int pi = warp + 4 * i;
-                const int k = 8 * (pi & 3) + ksub, g = 4 * (pi >> 2) + gq;
-                const float x[8] = {va[2 * i].x, va[2 * i].y, va[2 * i].z, va[2 * i].w, va[2 * i + 1].x, va[2 * i + 1].y, va[2 * i + 1].z, va[2 * i + 1].w};
+            for (int i = 0; i < 4; ++i) {                             // blocks past Mtot are stored as zeros (accumulator rows nobody reads)
+                float x[8];
+                at_pair_exchange(va[2 * i], va[2 * i + 1], odd, x);
                 uint4 hi, lo;
                 at_split8(x, hi, lo);
-                *reinterpret_cast<uint4*>(st + g * (AT_KC * 16) + k * 16) = hi;
-                *reinterpret_cast<uint4*>(st + A_BYTES + g * (AT_KC * 16) + k * 16) = lo;
+                const int off = (4 * i + (piece >> 1)) * AtSmem::G_SBO + k * 16;
+                *reinterpret_cast<uint4*>(st + off) = hi;
+                *reinterpret_cast<uint4*>(st + AtSmem::GA_BYTES + off) = lo;
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int pi = warp + 4 * i;
-                if ((pi >> 2) < b_gblocks) {
-                    const int k = 8 * (pi & 3) + ksub, g = 4 * (pi >> 2) + gq;
-                    const float x[8] = {vb[2 * i].x, vb[2 * i].y, vb[2 * i].z, vb[2 * i].w, vb[2 * i + 1].x, vb[2 * i + 1].y, vb[2 * i + 1].z, vb[2 * i + 1].w};
+                if (i < b_fblocks) {                                  // warp-uniform
+                    float x[8];
+                    at_pair_exchange(vb[2 * i], vb[2 * i + 1], odd, x);
                     uint4 hi, lo;
                     at_split8(x, hi, lo);
-                    *reinterpret_cast<uint4*>(st + 2 * A_BYTES + g * (AT_KC * 16) + k * 16) = hi;
-                    *reinterpret_cast<uint4*>(st + 2 * A_BYTES + B_BYTES + g * (AT_KC * 16) + k * 16) = lo;
+                    const int off = (4 * i + (piece >> 1)) * AtSmem::G_SBO + k * 16;
+                    *reinterpret_cast<uint4*>(st + 2 * AtSmem::GA_BYTES + off) = hi;
+                    *reinterpret_cast<uint4*>(st + 2 * AtSmem::GA_BYTES + AtSmem::GB_BYTES + off) = lo;
                 }
             }
             fence_async_smem();
             at_warp_arrive(&full[stage]);
         }
-    } else if (warp == 4) {
+    } else if (warp == AT_MMA_WARP) {
         const uint32_t idesc = idesc_bf16(128, P.N, 1, 1);
         for (int c = 0; c < nchunks; ++c) {
             const int stage = c % AT_STAGES;
             mbar_wait(&full[stage], (c / AT_STAGES) & 1);
             fence_after_sync();
             if (elect_one()) {
-                const uint32_t a_hi = smem_u32(smem + stage * AtSmem::STAGE);
-                const uint32_t a_lo = a_hi + A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * A_BYTES;
-                const uint32_t b_lo = b_hi + B_BYTES;
+                const uint32_t a_hi = smem_u32(smem + stage * AtSmem::G_STAGE);
+                const uint32_t a_lo = a_hi + AtSmem::GA_BYTES;
+                const uint32_t b_hi = a_hi + 2 * AtSmem::GA_BYTES;
+                const uint32_t b_lo = b_hi + AtSmem::GB_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < AT_KC / 16; ++ks) {
-                    const uint64_t dah = smem_desc(a_hi + ks * 256, 128, AT_KC * 16), dal = smem_desc(a_lo + ks * 256, 128, AT_KC * 16);
-                    const uint64_t dbh = smem_desc(b_hi + ks * 256, 128, AT_KC * 16), dbl = smem_desc(b_lo + ks * 256, 128, AT_KC * 16);
+                    // MN-major: a K step of 16 rows = two 8-row groups = 256 bytes further
+                    const uint64_t dah = smem_desc(a_hi + ks * 256, 128, AtSmem::G_SBO), dal = smem_desc(a_lo + ks * 256, 128, AtSmem::G_SBO);
+                    const uint64_t dbh = smem_desc(b_hi + ks * 256, 128, AtSmem::G_SBO), dbl = smem_desc(b_lo + ks * 256, 128, AtSmem::G_SBO);
                     mma_ss(tb, dah, dbh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
                     mma_ss(tb, dal, dbh, idesc, 1u);
                     mma_ss(tb, dah, dbl, idesc, 1u);
@@ -473,7 +528,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
             }
             __syncwarp();
         }
-    } else if (nchunks > 0) {
+    } else if (warp < AT_LOAD_WARP && nchunks > 0) {       // (the loader warp has no role in this kernel)
         const int quad = warp & 3;
         float* T = reinterpret_cast<float*>(smem + AtSmem::TRANS) + quad * (32 * 33);
         mbar_wait(acc_full, 0);
@@ -503,7 +558,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tb, 256);
+    if (warp == AT_MMA_WARP) tmem_dealloc(tb, 256);
 }
 
 // ------------------------------------------------------------------------------------ column softmax (points = keys)
@@ -598,7 +653,7 @@ static int attn_tc_configure() {
     int dev = 0;
     PCA_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && ((done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) return 0;
-#define ATC_ATTR(k) PCA_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, AtSmem::TOTAL))
+#define ATC_ATTR(k) PCA_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, AtSmem::MAX_BYTES))
     ATC_ATTR((cloud_linear_tc_kernel<EPI_STORE, 16>));
     ATC_ATTR((cloud_linear_tc_kernel<EPI_RESID, 16>));
     ATC_ATTR((cloud_linear_tc_kernel<EPI_SOFTMAX, 8>));
@@ -635,12 +690,20 @@ static int launch_cloud_linear(ClinParams p, int nsp, const char* name, cudaStre
     const int sms = sm_count();
     const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
     const double rows = (double)p.B * p.n_rows;
+    p.raw_slots = AtSmem::cl_raw_slots(p.N);
+    p.x_shared = p.x_bstride == 0 ? 1 : 0;
+    const int smem_bytes = AtSmem::cl_total(p.N, p.raw_slots);
+    // the activations as (K, rows of a cloud, clouds): a box of 32 floats x 128 rows is one raw tile
+    CUtensorMap tmx;
+    PCA_TRY(make_tmap_3d_f32(&tmx, p.X, (unsigned long long)p.K, (unsigned long long)p.n_rows, p.x_shared ? 1ull : (unsigned long long)p.B,
+                             (unsigned long long)p.ldx * 4, (unsigned long long)(p.x_shared ? (long long)p.n_rows * p.ldx : p.x_bstride) * 4,
+                             AT_KC, 128));
     LaunchTimer lt(name, st, 2.0 * rows * p.K * p.N, 4.0 * rows * (p.K + p.N));
     if (EPI == EPI_SOFTMAX || EPI == EPI_DS_ROW) {
-        if (nsp == 8) cloud_linear_tc_kernel<EPI, 8><<<grid, AT_THREADS, AtSmem::TOTAL, st>>>(p);
-        else cloud_linear_tc_kernel<EPI, 16><<<grid, AT_THREADS, AtSmem::TOTAL, st>>>(p);
+        if (nsp == 8) cloud_linear_tc_kernel<EPI, 8><<<grid, AT_THREADS, smem_bytes, st>>>(p, tmx);
+        else cloud_linear_tc_kernel<EPI, 16><<<grid, AT_THREADS, smem_bytes, st>>>(p, tmx);
     } else {
-        cloud_linear_tc_kernel<EPI, 16><<<grid, AT_THREADS, AtSmem::TOTAL, st>>>(p);
+        cloud_linear_tc_kernel<EPI, 16><<<grid, AT_THREADS, smem_bytes, st>>>(p, tmx);
     }
     return 0;
 }
@@ -658,7 +721,7 @@ static int launch_cloud_gw(const float* T, const float* X, long long x_bstride, 
     ClGwParams p{T, (long long)n_rows * s.HS, s.HS, s.HS, X, x_bstride, ldx, D, out, o_bstride, ldo, n_rows, rchunk, s.nsp, s.ns, D / H};
     dim3 grid((unsigned)nsplit, (unsigned)B);
     {
-        LaunchTimer lt("attn_gw_tc_kernel", st, 2.0 * B * (double)n_rows * s.HS * D, 4.0 * B * (double)n_rows * (s.HS + D));
+        LaunchTimer lt("attn_g3_tc_kernel", st, 2.0 * B * (double)n_rows * s.HS * D, 4.0 * B * (double)n_rows * (s.HS + D));
         cloud_gw_tc_kernel<<<grid, AT_THREADS, AtSmem::TOTAL, st>>>(p);
     }
     PCA_CHECK_LAUNCH("cloud_gw_tc_kernel");
@@ -688,7 +751,7 @@ int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B,
         p.Y = T; p.y_bstride = (long long)nq * s.HS; p.ldy = s.HS;
         p.lse = lse;
         p.B = B; p.n_rows = nq; p.K = D; p.N = s.HS; p.H = H; p.nsp = s.nsp; p.ns = s.ns; p.scale = scale; p.scale_log2e = sl2e;
-        PCA_TRY(launch_cloud_linear<EPI_SOFTMAX>(p, s.nsp, "attn_scores_tc_kernel", st));
+        PCA_TRY(launch_cloud_linear<EPI_SOFTMAX>(p, s.nsp, "attn_g1_softmax_tc_kernel", st));
         PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<softmax>");
         ClinParams q{};
         q.X = T; q.x_bstride = (long long)nq * s.HS; q.ldx = s.HS;
@@ -696,7 +759,7 @@ int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B,
         q.Y = O; q.y_bstride = (long long)nq * D; q.ldy = D;
         q.R = Qp; q.r_bstride = q_bstride; q.ldr = D;
         q.B = B; q.n_rows = nq; q.K = s.HS; q.N = D; q.H = H; q.nsp = s.nsp; q.ns = s.ns; q.scale = scale; q.scale_log2e = sl2e;
-        PCA_TRY(launch_cloud_linear<EPI_RESID>(q, s.nsp, "attn_pv_tc_kernel", st));
+        PCA_TRY(launch_cloud_linear<EPI_RESID>(q, s.nsp, "attn_g2_resid_tc_kernel", st));
         PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<resid>");
         return 0;
     }
@@ -707,7 +770,7 @@ int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B,
     p.img = img1; p.img_bstride = q_bstride ? img_bytes : 0;
     p.Y = T; p.y_bstride = (long long)nk * s.HS; p.ldy = s.HS;
     p.B = B; p.n_rows = nk; p.K = D; p.N = s.HS; p.H = H; p.nsp = s.nsp; p.ns = s.ns; p.scale = scale; p.scale_log2e = sl2e;
-    PCA_TRY(launch_cloud_linear<EPI_STORE>(p, s.nsp, "attn_scores_tc_kernel", st));
+    PCA_TRY(launch_cloud_linear<EPI_STORE>(p, s.nsp, "attn_g1_scores_tc_kernel", st));
     PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<store>");
     {
         LaunchTimer lt("col_softmax_kernel", st, 0.0, 8.0 * B * (double)nk * s.HS);
@@ -754,21 +817,21 @@ int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, co
         p.X = Qp; p.x_bstride = q_bstride; p.ldx = D;
         p.img = img_at(0); p.img_bstride = img_bytes;
         p.Y = Pm; p.y_bstride = t_bstride; p.ldy = s.HS;
-        PCA_TRY(launch_cloud_linear<EPI_SOFTMAX>(p, s.nsp, "attn_scores_tc_kernel", st));
+        PCA_TRY(launch_cloud_linear<EPI_SOFTMAX>(p, s.nsp, "attn_g1_softmax_tc_kernel", st));
         PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<softmax>");
         ClinParams q = base(nq, D, s.HS);                                                     // dS = P o (dO V^T - delta) scale
         q.X = dO; q.x_bstride = (long long)nq * D; q.ldx = D;
         q.img = img_at(1); q.img_bstride = img_bytes;
         q.Y = dS; q.y_bstride = t_bstride; q.ldy = s.HS;
         q.R = Pm; q.r_bstride = t_bstride; q.ldr = s.HS;
-        PCA_TRY(launch_cloud_linear<EPI_DS_ROW>(q, s.nsp, "attn_ds_tc_kernel", st));
+        PCA_TRY(launch_cloud_linear<EPI_DS_ROW>(q, s.nsp, "attn_g1_dsrow_tc_kernel", st));
         PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<ds_row>");
         ClinParams g = base(nq, s.HS, D);                                                     // dQp = dO + dS K
         g.X = dS; g.x_bstride = t_bstride; g.ldx = s.HS;
         g.img = img_at(2); g.img_bstride = img_bytes;
         g.Y = dQp; g.y_bstride = (long long)nq * D; g.ldy = D;
         g.R = dO; g.r_bstride = (long long)nq * D; g.ldr = D;
-        PCA_TRY(launch_cloud_linear<EPI_RESID>(g, s.nsp, "attn_pv_tc_kernel", st));
+        PCA_TRY(launch_cloud_linear<EPI_RESID>(g, s.nsp, "attn_g2_resid_tc_kernel", st));
         PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<resid>");
         PCA_CHECK_CUDA(cudaMemsetAsync(dKV, 0, (size_t)B * nk * 2 * D * sizeof(float), st));
         PCA_TRY(launch_cloud_gw(dS, Qp, q_bstride, D, dKV, kv_bs, 2 * D, B, nq, s, D, H, st));         // dK = dS^T Qp
@@ -786,7 +849,7 @@ int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, co
     p.img = img_at(0); p.img_bstride = q_bstride ? img_bytes : 0;
     p.Y = Pm; p.y_bstride = t_bstride; p.ldy = s.HS;
     p.vec = lse;
-    PCA_TRY(launch_cloud_linear<EPI_P_COL>(p, s.nsp, "attn_scores_tc_kernel", st));
+    PCA_TRY(launch_cloud_linear<EPI_P_COL>(p, s.nsp, "attn_g1_pcol_tc_kernel", st));
     PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<p_col>");
     ClinParams q = base(nk, D, s.HS);                                                         // dS = P o (V dO^T - delta) scale
     q.X = KV + D; q.x_bstride = kv_bs; q.ldx = 2 * D;
@@ -794,19 +857,19 @@ int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, co
     q.Y = dS; q.y_bstride = t_bstride; q.ldy = s.HS;
     q.R = Pm; q.r_bstride = t_bstride; q.ldr = s.HS;
     q.vec = delta;
-    PCA_TRY(launch_cloud_linear<EPI_DS_COL>(q, s.nsp, "attn_ds_tc_kernel", st));
+    PCA_TRY(launch_cloud_linear<EPI_DS_COL>(q, s.nsp, "attn_g1_dscol_tc_kernel", st));
     PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<ds_col>");
     ClinParams gk = base(nk, s.HS, D);                                                        // dK = dS Qp
     gk.X = dS; gk.x_bstride = t_bstride; gk.ldx = s.HS;
     gk.img = img_at(1); gk.img_bstride = q_bstride ? img_bytes : 0;
     gk.Y = dKV; gk.y_bstride = kv_bs; gk.ldy = 2 * D;
-    PCA_TRY(launch_cloud_linear<EPI_STORE>(gk, s.nsp, "attn_pv_tc_kernel", st));
+    PCA_TRY(launch_cloud_linear<EPI_STORE>(gk, s.nsp, "attn_g2_store_tc_kernel", st));
     PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<store>");
     ClinParams gv = base(nk, s.HS, D);                                                        // dV = P dO
     gv.X = Pm; gv.x_bstride = t_bstride; gv.ldx = s.HS;
     gv.img = img_at(3); gv.img_bstride = img_bytes;
     gv.Y = dKV + D; gv.y_bstride = kv_bs; gv.ldy = 2 * D;
-    PCA_TRY(launch_cloud_linear<EPI_STORE>(gv, s.nsp, "attn_pv_tc_kernel", st));
+    PCA_TRY(launch_cloud_linear<EPI_STORE>(gv, s.nsp, "attn_g2_store_tc_kernel", st));
     PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<store>");
     PCA_CHECK_CUDA(cudaMemcpyAsync(dQp, dO, (size_t)B * nq * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return launch_cloud_gw(dS, KV, kv_bs, 2 * D, dQp, o_bs, D, B, nk, s, D, H, st);           // dQp = dO + dS^T K

@@ -19,8 +19,10 @@ namespace pca {
 using namespace tc;
 
 constexpr int GT_KC = 32;            // K elements per pipeline stage
-constexpr int GT_STAGES = 3;
-constexpr int GT_THREADS = 9 * 32;   // 4 producer + 1 MMA + 4 epilogue warps
+constexpr int GT_STAGES = 4;
+constexpr int GT_PSETS = 2;           // producer warp sets: set s stages the work items s, s + 2, ... (twice the loads in flight per SM)
+constexpr int GT_MMA_WARP = 4 * GT_PSETS;
+constexpr int GT_THREADS = (4 * GT_PSETS + 5) * 32;   // 8 producer + 1 MMA + 4 epilogue warps
 
 __device__ __forceinline__ void gt_warp_arrive(uint64_t* bar) {
     __syncwarp();
@@ -76,8 +78,25 @@ struct LinTcParams {
     int K, N, nt, relu;
 };
 
+// lanes 2j / 2j + 1 hold adjacent float4 pieces (a: of row A, b: of row B = A + 4); after the exchange the even lane owns the 8
+// consecutive floats of row A and the odd lane those of row B (one 16-byte bf16 chunk each)
+__device__ __forceinline__ void pair_exchange(const float4 a, const float4 b, bool odd, float* x) {
+    const float4 send = odd ? a : b;
+    float4 recv;
+    recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+    recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+    recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+    recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+    const float4 lo4 = odd ? recv : a, hi4 = odd ? b : recv;
+    x[0] = lo4.x; x[1] = lo4.y; x[2] = lo4.z; x[3] = lo4.w;
+    x[4] = hi4.x; x[5] = hi4.y; x[6] = hi4.z; x[7] = hi4.w;
+}
+
+// The activation tile is staged with a PADDED chunk stride (the descriptor's leading byte offset is free): 16-byte chunk c of
+// row r at c * A_LBO + r * 16, A_LBO = 2048 + 16, so that the four chunks a quarter warp stores fall into distinct banks.
 struct LinTcSmem {
-    static constexpr int A_BYTES = 128 * GT_KC * 2;                // one hi or lo image of the activation tile
+    static constexpr int A_LBO = 128 * 16 + 16;
+    static constexpr int A_BYTES = 8320;                           // one hi or lo image of the activation tile (>= 4 * A_LBO)
     static constexpr int STAGE = 2 * A_BYTES + 2 * 256 * GT_KC * 2;  // A hi | A lo | B hi | B lo (B sized for nt = 256)
     static constexpr int TRANS = GT_STAGES * STAGE;                 // 4 epilogue warps x 32 x 33 floats
     static constexpr int BARS = TRANS + 4 * 32 * 33 * 4;
@@ -87,18 +106,18 @@ struct LinTcSmem {
 __global__ void __launch_bounds__(GT_THREADS, 1) linear_tc_kernel(const LinTcParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LinTcSmem::BARS);
-    uint64_t* full = bars;                       // [3] count 5: 4 producer warps + the expect_tx arrival
-    uint64_t* empty = bars + GT_STAGES;          // [3] count 1 (MMA commit)
+    uint64_t* full = bars;                       // [stages] count 5: the 4 producer warps of a set + the expect_tx arrival
+    uint64_t* empty = bars + GT_STAGES;          // [stages] count 1 (MMA commit)
     uint64_t* acc_full = bars + 2 * GT_STAGES;   // [2] count 1
     uint64_t* acc_empty = acc_full + 2;          // [2] count 4 (epilogue warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GT_STAGES + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkc = P.K / GT_KC;
     const int npass = P.N / P.nt;
     const long long mtiles = (P.rows + 127) / 128;
     const long long ntiles = mtiles * npass;
 
-    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    if (warp == GT_MMA_WARP) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
         for (int i = 0; i < GT_STAGES; ++i) { mbar_init(&full[i], 5); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
@@ -110,75 +129,65 @@ __global__ void __launch_bounds__(GT_THREADS, 1) linear_tc_kernel(const LinTcPar
     const uint32_t tb = *tmem_slot;
     const uint32_t b_img_bytes = (uint32_t)P.nt * 64;           // one hi or lo weight image of a chunk
 
-    if (warp < 4) {
+    if (warp < GT_MMA_WARP) {
         // ================================================================= producers
-        // Warp w stages rows [32w, 32w+32) of the tile.  Lane = (row % 8, 16-byte chunk c of the 32-wide K chunk): a
-        // warp-wide load covers 8 rows x 128 contiguous bytes (coalesced), a quarter-warp store 8 consecutive rows of one
-        // chunk (128 contiguous bytes of smem, conflict free).  The loads of the next K chunk are in flight while the
-        // current one is converted.
-        const int rsub = lane & 7, c = lane >> 3;
-        uint32_t gt = 0;
-        float4 nx[8], nx2[8];                     // the next two chunks: 4 row groups x 2 float4 (8 consecutive k of one row)
-        long long t = blockIdx.x;
-        int kc = 0;
-        auto issue = [&](float4* nx, long long tile, int kchunk) {
+        // Work items g = (tile of this CTA, K chunk) in issue order; warp set g % GT_PSETS stages item g.  Warp pw of the set
+        // stages rows [32 pw, 32 pw + 32) of the tile.  Loads are row-contiguous: quarter warp q reads the 128 bytes (the
+        // whole K chunk) of row 8 it + q and of row 8 it + 4 + q -- one L1 wavefront per row where a lane-per-(row, chunk)
+        // mapping costs one per lane (ncu: l1tex 85 % busy on global-load wavefronts); a pair exchange then gives every lane
+        // the 8 consecutive floats of one 16-byte bf16 chunk.  The loads of the set's next two items are in flight while
+        // the current one is converted.
+        const int set = warp >> 2, pw = warp & 3;
+        const int q = lane >> 3, piece = lane & 7;
+        const bool odd = piece & 1;
+        const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const uint32_t items = (uint32_t)(my_tiles * nkc);
+        float4 nx[8], nx2[8];                     // the next two items: 4 row groups x 2 float4 (8 consecutive k of one row)
+        auto issue = [&](float4* dst, uint32_t g) {
+            const long long tile = blockIdx.x + (long long)(g / nkc) * gridDim.x;
+            const int kchunk = (int)(g % nkc);
             const long long mt = tile / npass;
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
-                const long long r = mt * 128 + 32 * warp + 8 * it + rsub;
-                if (r < P.rows) {
-                    const float4* src = reinterpret_cast<const float4*>(P.X + r * P.K + kchunk * GT_KC + 8 * c);
-                    nx[2 * it] = __ldg(src);
-                    nx[2 * it + 1] = __ldg(src + 1);
-                } else {
-                    nx[2 * it] = nx[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                const long long rA = mt * 128 + 32 * pw + 8 * it + q, rB = rA + 4;
+                const float* src = P.X + kchunk * GT_KC + 4 * piece;
+                dst[2 * it] = rA < P.rows ? __ldg(reinterpret_cast<const float4*>(src + rA * P.K)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                dst[2 * it + 1] = rB < P.rows ? __ldg(reinterpret_cast<const float4*>(src + rB * P.K)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        auto advance = [&](long long& tile, int& kchunk) {
-            if (++kchunk == nkc) { kchunk = 0; tile += gridDim.x; }
-        };
-        long long t_n = t, t_n2;
-        int kc_n = 0, kc_n2;
-        if (t < ntiles) issue(nx, t, 0);
-        advance(t_n, kc_n);
-        if (t_n < ntiles) issue(nx2, t_n, kc_n);
-        t_n2 = t_n;
-        kc_n2 = kc_n;
-        while (t < ntiles) {
-            const int pass = (int)(t % npass);
-            const int stage = gt % GT_STAGES;
-            float4 cur[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { cur[j] = nx[j]; nx[j] = nx2[j]; }
-            // two chunks ahead: put its loads in flight (the loads of the chunk after this one are still in flight)
-            advance(t_n2, kc_n2);
-            if (t_n2 < ntiles) issue(nx2, t_n2, kc_n2);
-            if (gt >= GT_STAGES) mbar_wait(&empty[stage], ((gt / GT_STAGES) - 1) & 1);
+        uint32_t g = set;
+        if (g < items) issue(nx, g);
+        if (g + GT_PSETS < items) issue(nx2, g + GT_PSETS);
+        for (; g < items; g += GT_PSETS) {
+            const int stage = g % GT_STAGES;
+            if (g >= GT_STAGES) mbar_wait(&empty[stage], ((g / GT_STAGES) - 1) & 1);
             uint8_t* st = smem + stage * LinTcSmem::STAGE;
-            if (threadIdx.x == 0) {
+            if (pw == 0 && lane == 0) {
+                const int pass = (int)((blockIdx.x + (long long)(g / nkc) * gridDim.x) % npass);
+                const int kc = (int)(g % nkc);
                 mbar_arrive_expect_tx(&full[stage], 2 * b_img_bytes);
                 bulk_copy_g2s(st + 2 * LinTcSmem::A_BYTES, P.img + ((size_t)(pass * nkc + kc) * 2) * b_img_bytes, 2 * b_img_bytes, &full[stage]);
             }
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
-                const float x[8] = {cur[2 * it].x, cur[2 * it].y, cur[2 * it].z, cur[2 * it].w,
-                                    cur[2 * it + 1].x, cur[2 * it + 1].y, cur[2 * it + 1].z, cur[2 * it + 1].w};
+                float x[8];
+                pair_exchange(nx[2 * it], nx[2 * it + 1], odd, x);
                 uint4 hi, lo;
                 split8(x, hi, lo);
-                const int row = 32 * warp + 8 * it + rsub;
-                *reinterpret_cast<uint4*>(st + c * 2048 + row * 16) = hi;
-                *reinterpret_cast<uint4*>(st + LinTcSmem::A_BYTES + c * 2048 + row * 16) = lo;
+                const int row = 32 * pw + 8 * it + q + (odd ? 4 : 0);
+                const int off = (piece >> 1) * LinTcSmem::A_LBO + row * 16;
+                *reinterpret_cast<uint4*>(st + off) = hi;
+                *reinterpret_cast<uint4*>(st + LinTcSmem::A_BYTES + off) = lo;
             }
             fence_async_smem();
             gt_warp_arrive(&full[stage]);
-            ++gt;
-            t = t_n;
-            kc = kc_n;
-            t_n = t_n2;
-            kc_n = kc_n2;
+            // shift the prefetch window (13 warps share 64 K registers with four on one scheduler: 128 per thread, no room for a
+            // third buffer) and put the loads of the item after next in flight
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nx[j] = nx2[j];
+            if (g + 2 * GT_PSETS < items) issue(nx2, g + 2 * GT_PSETS);
         }
-    } else if (warp == 4) {
+    } else if (warp == GT_MMA_WARP) {
         // ================================================================= MMA issue (warp-uniform, elected lane)
         const uint32_t idesc = idesc_bf16(128, P.nt, 0, 0);
         uint32_t gt = 0, tt = 0;
@@ -199,7 +208,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) linear_tc_kernel(const LinTcPar
                     const uint32_t b_lbo = (uint32_t)P.nt * 16;
 #pragma unroll
                     for (int ks = 0; ks < GT_KC / 16; ++ks) {
-                        const uint64_t dah = smem_desc(a_hi + ks * 4096, 2048, 128), dal = smem_desc(a_lo + ks * 4096, 2048, 128);
+                        const uint64_t dah = smem_desc(a_hi + ks * 2 * LinTcSmem::A_LBO, LinTcSmem::A_LBO, 128);
+                        const uint64_t dal = smem_desc(a_lo + ks * 2 * LinTcSmem::A_LBO, LinTcSmem::A_LBO, 128);
                         const uint64_t dbh = smem_desc(b_hi + ks * 2 * b_lbo, b_lbo, 128), dbl = smem_desc(b_lo + ks * 2 * b_lbo, b_lbo, 128);
                         mma_ss(acc, dah, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
                         mma_ss(acc, dal, dbh, idesc, 1u);
@@ -265,7 +275,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) linear_tc_kernel(const LinTcPar
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tb, 512);
+    if (warp == GT_MMA_WARP) tmem_dealloc(tb, 512);
 }
 
 // function attributes belong to the current device's context: configure once per device ordinal (idempotent; see tc_configure)
@@ -334,9 +344,12 @@ struct GwTcParams {
     long long rows, rchunk;
     int lda, Mtot, N;
 };
+// 8-feature group g of chunk row k at g * G_SBO + k * 16 with G_SBO = 512 + 16 (padded: the four groups a quarter warp stores
+// fall into distinct banks)
 struct GwTcSmem {
-    static constexpr int A_BYTES = 128 * GT_KC * 2;
-    static constexpr int B_BYTES = 256 * GT_KC * 2;
+    static constexpr int G_SBO = GT_KC * 16 + 16;
+    static constexpr int A_BYTES = 16 * G_SBO;
+    static constexpr int B_BYTES = 32 * G_SBO;
     static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int TRANS = GT_STAGES * STAGE;
     static constexpr int BARS = TRANS + 4 * 32 * 33 * 4;
@@ -346,17 +359,17 @@ struct GwTcSmem {
 __global__ void __launch_bounds__(GT_THREADS, 1) grad_weight_tc_kernel(const GwTcParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GwTcSmem::BARS);
-    uint64_t* full = bars;                       // [3] count 4 (producer warps)
-    uint64_t* empty = bars + GT_STAGES;          // [3] count 1
+    uint64_t* full = bars;                       // [stages] count 4 (the producer warps of a set)
+    uint64_t* empty = bars + GT_STAGES;          // [stages] count 1
     uint64_t* acc_full = bars + 2 * GT_STAGES;   // count 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GT_STAGES + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * 128;
     const long long r0 = (long long)blockIdx.x * P.rchunk;
     const long long r1 = (r0 + P.rchunk < P.rows) ? r0 + P.rchunk : P.rows;
     const int nchunks = (int)((r1 - r0 + GT_KC - 1) / GT_KC);
 
-    if (warp == 4) tmem_alloc(tmem_slot, 256);
+    if (warp == GT_MMA_WARP) tmem_alloc(tmem_slot, 256);
     if (threadIdx.x == 0) {
         for (int i = 0; i < GT_STAGES; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
         mbar_init(acc_full, 1);
@@ -367,67 +380,63 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grad_weight_tc_kernel(const GwT
     fence_after_sync();
     const uint32_t tb = *tmem_slot;
 
-    if (warp < 4) {
-        // Lane = (row % 8 of an 8-row block, feature group g % 4): a warp-wide load covers 8 rows x 128 contiguous bytes, a
-        // quarter-warp store 8 consecutive rows of one feature group (128 contiguous bytes of smem).  Warp w takes the
-        // (row block, group block) pairs w, w + 4, ...: A has 4 x 4 of them, B 4 x (N / 32); all loads of a chunk are
-        // issued before the first conversion.
-        const int ksub = lane & 7, gq = lane >> 3;
-        const int b_gblocks = P.N / 32;
-        for (int c = 0; c < nchunks; ++c) {
+    if (warp < GT_MMA_WARP) {
+        // Warp set s stages the 32-row chunks s, s + 2, ... (two chunks of loads in flight per CTA); warp pw of the set the rows
+        // [8 pw, 8 pw + 8) of the chunk for every 32-feature block.  Loads are row-contiguous (quarter warp q: 128 bytes of row
+        // 8 pw + q, then of row 8 pw + 4 + q: one L1 wavefront per row); a pair exchange gives every lane one 16-byte unit
+        // (8 consecutive features of one row).  All loads of a chunk are issued before the first conversion.
+        const int set = warp >> 2, pw = warp & 3;
+        const int q = lane >> 3, piece = lane & 7;
+        const bool odd = piece & 1;
+        const int b_fblocks = P.N / 32;
+        for (int c = set; c < nchunks; c += GT_PSETS) {
             const int stage = c % GT_STAGES;
-            const long long rbase = r0 + (long long)c * GT_KC;
+            const long long rA = r0 + (long long)c * GT_KC + 8 * pw + q, rB = rA + 4;
+            const bool okA = rA < r1, okB = rB < r1;
             float4 va[8], vb[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {            // A: pair index pi = warp + 4 i -> (row block pi % 4, group block pi / 4)
-                const int pi = warp + 4 * i;
-                const int kb = pi & 3, gb = pi >> 2;
-                const long long r = rbase + 8 * kb + ksub;
-                const int g = 4 * gb + gq;
-                const bool ok = r < r1 && (m0 + 8 * g < P.Mtot);
-                const float4* src = reinterpret_cast<const float4*>(P.A + (ok ? r : 0) * P.lda + m0 + 8 * g);
-                va[2 * i] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-                va[2 * i + 1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {            // B: up to 4 x 8 pairs
-                const int pi = warp + 4 * i;
-                const int kb = pi & 3, gb = pi >> 2;
-                const long long r = rbase + 8 * kb + ksub;
-                const int g = 4 * gb + gq;
-                const bool ok = r < r1 && gb < b_gblocks;
-                const float4* src = reinterpret_cast<const float4*>(P.B + (ok ? r : 0) * P.N + (ok ? 8 * g : 0));
-                vb[2 * i] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-                vb[2 * i + 1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (c >= GT_STAGES) mbar_wait(&empty[stage], ((c / GT_STAGES) - 1) & 1);
-            uint8_t* st = smem + stage * GwTcSmem::STAGE;
-#pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int pi = warp + 4 * i;
-                const int k = 8 * (pi & 3) + ksub, g = 4 * (pi >> 2) + gq;
-                const float x[8] = {va[2 * i].x, va[2 * i].y, va[2 * i].z, va[2 * i].w, va[2 * i + 1].x, va[2 * i + 1].y, va[2 * i + 1].z, va[2 * i + 1].w};
-                uint4 hi, lo;
-                split8(x, hi, lo);
-                *reinterpret_cast<uint4*>(st + g * (GT_KC * 16) + k * 16) = hi;
-                *reinterpret_cast<uint4*>(st + GwTcSmem::A_BYTES + g * (GT_KC * 16) + k * 16) = lo;
+                const bool on = m0 + 32 * i < P.Mtot;
+                const float* src = P.A + m0 + (on ? 32 * i : 0) + 4 * piece;
+                va[2 * i] = (on && okA) ? __ldg(reinterpret_cast<const float4*>(src + rA * P.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                va[2 * i + 1] = (on && okB) ? __ldg(reinterpret_cast<const float4*>(src + rB * P.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int pi = warp + 4 * i;
-                if ((pi >> 2) < b_gblocks) {
-                    const int k = 8 * (pi & 3) + ksub, g = 4 * (pi >> 2) + gq;
-                    const float x[8] = {vb[2 * i].x, vb[2 * i].y, vb[2 * i].z, vb[2 * i].w, vb[2 * i + 1].x, vb[2 * i + 1].y, vb[2 * i + 1].z, vb[2 * i + 1].w};
+                const bool on = i < b_fblocks;
+                const float* src = P.B + (on ? 32 * i : 0) + 4 * piece;
+                vb[2 * i] = (on && okA) ? __ldg(reinterpret_cast<const float4*>(src + rA * P.N)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[2 * i + 1] = (on && okB) ? __ldg(reinterpret_cast<const float4*>(src + rB * P.N)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (c >= GT_STAGES) mbar_wait(&empty[stage], ((c / GT_STAGES) - 1) & 1);
+            uint8_t* st = smem + stage * GwTcSmem::STAGE;
+            const int k = 8 * pw + q + (odd ? 4 : 0);                 // row of the chunk this lane stores
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float x[8];
+                pair_exchange(va[2 * i], va[2 * i + 1], odd, x);
+                uint4 hi, lo;
+                split8(x, hi, lo);
+                const int off = (4 * i + (piece >> 1)) * GwTcSmem::G_SBO + k * 16;
+                *reinterpret_cast<uint4*>(st + off) = hi;
+                *reinterpret_cast<uint4*>(st + GwTcSmem::A_BYTES + off) = lo;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < b_fblocks) {                                  // warp-uniform
+                    float x[8];
+                    pair_exchange(vb[2 * i], vb[2 * i + 1], odd, x);
                     uint4 hi, lo;
                     split8(x, hi, lo);
-                    *reinterpret_cast<uint4*>(st + 2 * GwTcSmem::A_BYTES + g * (GT_KC * 16) + k * 16) = hi;
-                    *reinterpret_cast<uint4*>(st + 2 * GwTcSmem::A_BYTES + GwTcSmem::B_BYTES + g * (GT_KC * 16) + k * 16) = lo;
+                    const int off = (4 * i + (piece >> 1)) * GwTcSmem::G_SBO + k * 16;
+                    *reinterpret_cast<uint4*>(st + 2 * GwTcSmem::A_BYTES + off) = hi;
+                    *reinterpret_cast<uint4*>(st + 2 * GwTcSmem::A_BYTES + GwTcSmem::B_BYTES + off) = lo;
                 }
             }
             fence_async_smem();
             gt_warp_arrive(&full[stage]);
         }
-    } else if (warp == 4) {
+    } else if (warp == GT_MMA_WARP) {
         const uint32_t idesc = idesc_bf16(128, P.N, 1, 1);
         for (int c = 0; c < nchunks; ++c) {
             const int stage = c % GT_STAGES;
@@ -441,8 +450,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grad_weight_tc_kernel(const GwT
 #pragma unroll
                 for (int ks = 0; ks < GT_KC / 16; ++ks) {
                     // MN-major: a K step of 16 rows = two 8-row groups = 256 bytes further
-                    const uint64_t dah = smem_desc(a_hi + ks * 256, 128, GT_KC * 16), dal = smem_desc(a_lo + ks * 256, 128, GT_KC * 16);
-                    const uint64_t dbh = smem_desc(b_hi + ks * 256, 128, GT_KC * 16), dbl = smem_desc(b_lo + ks * 256, 128, GT_KC * 16);
+                    const uint64_t dah = smem_desc(a_hi + ks * 256, 128, GwTcSmem::G_SBO), dal = smem_desc(a_lo + ks * 256, 128, GwTcSmem::G_SBO);
+                    const uint64_t dbh = smem_desc(b_hi + ks * 256, 128, GwTcSmem::G_SBO), dbl = smem_desc(b_lo + ks * 256, 128, GwTcSmem::G_SBO);
                     mma_ss(tb, dah, dbh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
                     mma_ss(tb, dal, dbh, idesc, 1u);
                     mma_ss(tb, dah, dbl, idesc, 1u);
@@ -475,7 +484,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grad_weight_tc_kernel(const GwT
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tb, 256);
+    if (warp == GT_MMA_WARP) tmem_dealloc(tb, 256);
 }
 
 static int gemm_tc_configure() {

@@ -16,4 +16,9 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, unsigned long long inn
 int make_tmap_chunked_bf16(CUtensorMap* out, const void* base, unsigned long long rows, unsigned long long row_stride_bytes,
                            unsigned box_rows);
 
+// 3-D fp32 tensor (batch, rows, inner) with byte strides (batch_stride, row_stride, 4); box = (box_inner, box_rows, 1); no
+// swizzle: a box lands in shared memory as box_rows rows of box_inner floats.  Rows / columns outside the tensor are zero-filled.
+int make_tmap_3d_f32(CUtensorMap* out, const void* base, unsigned long long inner, unsigned long long rows, unsigned long long batch,
+                     unsigned long long row_stride_bytes, unsigned long long batch_stride_bytes, unsigned box_inner, unsigned box_rows);
+
 }  // namespace pca

@@ -140,5 +140,7 @@ def test_modelnet_model_attention_paths_agree(L):
     a, b = res[1], res[0]
     assert not torch.equal(a[0], b[0])
     assert ((a[0] - b[0]).abs().max() / b[0].abs().max()).item() < 1e-4
+    gmax = max(gb.abs().max().item() for gb in b[1])
     for ga, gb in zip(a[1], b[1]):
-        assert ((ga - gb).abs().max() / gb.abs().max().clamp_min(1e-12)).item() < 1e-3
+        # relative to the tensor's own scale, with a floor: the key-bias gradients are zero up to rounding (softmax is shift invariant)
+        assert ((ga - gb).abs().max() / gb.abs().max().clamp_min(1e-4 * gmax)).item() < 1e-3
