@@ -20,7 +20,6 @@ namespace pca {
 using namespace tc;
 
 constexpr int AT_KC = 32;
-constexpr int AT_STAGES = 4;
 constexpr int AT_PSETS = 2;           // producer warp sets: set s stages the K chunks s, s + 2, ... (twice the loads in flight per SM)
 constexpr int AT_MMA_WARP = 4 * AT_PSETS;
 constexpr int AT_LOAD_WARP = AT_MMA_WARP + 5;
@@ -118,12 +117,18 @@ struct AtSmem {
     static constexpr int GA_BYTES = 16 * G_SBO;                        // 128 features
     static constexpr int GB_BYTES = 32 * G_SBO;                        // 256 features
     static constexpr int G_STAGE = 2 * GA_BYTES + 2 * GB_BYTES;
-    static constexpr int TRANS = AT_STAGES * G_STAGE;                  // G3 kernel: stages | transpose tiles | barriers
-    static constexpr int BARS = TRANS + 4 * 32 * 33 * 4;
-    static constexpr int TOTAL = BARS + 16 * 8 + 16;
-    // per-cloud linear kernel: raw fp32 ring | operand stages (B region sized for the launch's N) | transpose tiles | barriers
-    static constexpr int CL_FIXED = 4 * 32 * 33 * 4 + 256;
+    static constexpr int CL_FIXED = 4 * 32 * 33 * 4 + 256;              // transpose tiles + barriers
     static constexpr int MAX_BYTES = 227 * 1024;
+    // G3 kernel: raw fp32 ring (32-row chunks of both operands) | 2 operand stages | transpose tiles | barriers
+    static constexpr int G_OP_STAGES = 2;
+    static constexpr int G_RAW_MAX = 4;
+    __host__ __device__ static int g_raw_bytes(int M, int N) { return AT_KC * (M + N) * 4; }
+    __host__ static int g_raw_slots(int M, int N) {
+        int r = (MAX_BYTES - CL_FIXED - G_OP_STAGES * G_STAGE) / g_raw_bytes(M, N);
+        return r > G_RAW_MAX ? G_RAW_MAX : r;
+    }
+    __host__ __device__ static int g_total(int M, int N, int raw_slots) { return raw_slots * g_raw_bytes(M, N) + G_OP_STAGES * G_STAGE + CL_FIXED; }
+    // per-cloud linear kernel: raw fp32 ring | operand stages (B region sized for the launch's N) | transpose tiles | barriers
     __host__ __device__ static int cl_stage(int N) { return 2 * A_BYTES + 2 * N * 64; }
     __host__ static int cl_raw_slots(int N) {
         int r = (MAX_BYTES - CL_FIXED - CL_STAGES * cl_stage(N)) / CL_RAW_BYTES;
@@ -420,27 +425,33 @@ struct ClGwParams {
     long long o_bstride;
     int ldo;
     int n_rows, rchunk, nsp, ns, dh;
+    int raw_slots, a_shared, b_shared;
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwParams P) {
+__global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwParams P, const __grid_constant__ CUtensorMap tma,
+                                                                    const __grid_constant__ CUtensorMap tmb) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AtSmem::BARS);
-    uint64_t* full = bars;                       // [stages] count 4 (the producer warps of a set)
-    uint64_t* empty = bars + AT_STAGES;          // [stages] count 1
-    uint64_t* acc_full = bars + 2 * AT_STAGES;   // count 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AT_STAGES + 4);
+    const int raw_bytes = AtSmem::g_raw_bytes(P.Mtot, P.N);
+    uint8_t* ops = smem + P.raw_slots * raw_bytes;
+    uint8_t* trans = ops + AtSmem::G_OP_STAGES * AtSmem::G_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(trans + 4 * 32 * 33 * 4);
+    uint64_t* full = bars;                                   // [2] count 4 (the converter warps of a set)
+    uint64_t* empty = bars + AtSmem::G_OP_STAGES;            // [2] count 1
+    uint64_t* acc_full = bars + 2 * AtSmem::G_OP_STAGES;     // count 1
+    uint64_t* raw_full = acc_full + 1;                       // [4] count 1 (expect_tx of the loader) + the chunk's bytes
+    uint64_t* raw_empty = raw_full + AtSmem::G_RAW_MAX;      // [4] count 4
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + AtSmem::G_RAW_MAX);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
-    const int r0 = blockIdx.x * P.rchunk;
+    const int r0 = blockIdx.x * P.rchunk;                    // a multiple of the chunk size: a chunk never straddles two CTAs' ranges
     const int r1 = min(r0 + P.rchunk, P.n_rows);
     const int nchunks = (r1 - r0 + AT_KC - 1) / AT_KC;
-    const float* Ab = P.A + (long long)b * P.a_bstride;
-    const float* Bb = P.Bm + (long long)b * P.b_bstride;
 
     if (warp == AT_MMA_WARP) tmem_alloc(tmem_slot, 256);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < AtSmem::G_OP_STAGES; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
         mbar_init(acc_full, 1);
+        for (int i = 0; i < AtSmem::G_RAW_MAX; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 4); }
         fence_barrier_init();
     }
     fence_before_sync();
@@ -448,36 +459,52 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
     fence_after_sync();
     const uint32_t tb = *tmem_slot;
 
-    if (warp < AT_MMA_WARP) {
-        // Warp set s stages the 32-row chunks s, s + 2, ...; warp pw of the set the rows [8 pw, 8 pw + 8) of the chunk for every
-        // 32-feature block.  Loads are row-contiguous (quarter warp q: the 128 bytes of row 8 pw + q, then of row 8 pw + 4 + q);
-        // a pair exchange gives every lane one 16-byte unit (8 consecutive features of one row).
+    if (warp == AT_LOAD_WARP) {
+        // TMA loader (one thread): chunk c = rows [r0 + 32 c, + 32) of T (Mtot columns) and of X (N columns); rows past the end
+        // of the cloud arrive as zeros
+        if (lane == 0) {
+            tma_prefetch_desc(&tma);
+            tma_prefetch_desc(&tmb);
+            for (int c = 0; c < nchunks; ++c) {
+                const int slot = c % P.raw_slots;
+                if (c >= P.raw_slots) mbar_wait(&raw_empty[slot], ((c / P.raw_slots) - 1) & 1);
+                mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)raw_bytes);
+                uint8_t* dst = smem + slot * raw_bytes;
+                tma_load_3d(dst, &tma, 0, r0 + c * AT_KC, P.a_shared ? 0 : b, &raw_full[slot]);
+                tma_load_3d(dst + AT_KC * P.Mtot * 4, &tmb, 0, r0 + c * AT_KC, P.b_shared ? 0 : b, &raw_full[slot]);
+            }
+        }
+    } else if (warp < AT_MMA_WARP) {
+        // Converters: warp set s handles the chunks s, s + 2, ...; warp pw of the set the rows [8 pw, 8 pw + 8) of the chunk for
+        // every 32-feature block.  Quarter warp q reads the 128 bytes of row 8 pw + q, then of row 8 pw + 4 + q, from the raw
+        // chunk; a pair exchange gives every lane one 16-byte unit (8 consecutive features of one row).
         const int set = warp >> 2, pw = warp & 3;
         const int q = lane >> 3, piece = lane & 7;
         const bool odd = piece & 1;
         const int a_fblocks = (P.Mtot + 31) / 32, b_fblocks = P.N / 32;
         for (int c = set; c < nchunks; c += AT_PSETS) {
-            const int stage = c % AT_STAGES;
-            const int rA = r0 + c * AT_KC + 8 * pw + q, rB = rA + 4;
-            const bool okA = rA < r1, okB = rB < r1;
+            const int slot = c % P.raw_slots;
+            const int stage = c % AtSmem::G_OP_STAGES;
+            mbar_wait(&raw_full[slot], (c / P.raw_slots) & 1);
+            const float* rawA = reinterpret_cast<const float*>(smem + slot * raw_bytes) + 4 * piece;
+            const float* rawB = rawA + AT_KC * P.Mtot;
+            const int kA = 8 * pw + q;
             float4 va[8], vb[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const bool on = i < a_fblocks;
-                const float* src = Ab + (on ? 32 * i : 0) + 4 * piece;
-                va[2 * i] = (on && okA) ? __ldg(reinterpret_cast<const float4*>(src + (long long)rA * P.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                va[2 * i + 1] = (on && okB) ? __ldg(reinterpret_cast<const float4*>(src + (long long)rB * P.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                va[2 * i] = on ? *reinterpret_cast<const float4*>(rawA + kA * P.Mtot + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                va[2 * i + 1] = on ? *reinterpret_cast<const float4*>(rawA + (kA + 4) * P.Mtot + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const bool on = i < b_fblocks;
-                const float* src = Bb + (on ? 32 * i : 0) + 4 * piece;
-                vb[2 * i] = (on && okA) ? __ldg(reinterpret_cast<const float4*>(src + (long long)rA * P.ldb)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                vb[2 * i + 1] = (on && okB) ? __ldg(reinterpret_cast<const float4*>(src + (long long)rB * P.ldb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[2 * i] = on ? *reinterpret_cast<const float4*>(rawB + kA * P.N + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[2 * i + 1] = on ? *reinterpret_cast<const float4*>(rawB + (kA + 4) * P.N + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (c >= AT_STAGES) mbar_wait(&empty[stage], ((c / AT_STAGES) - 1) & 1);
-            uint8_t* st = smem + stage * AtSmem::G_STAGE;
-            const int k = 8 * pw + q + (odd ? 4 : 0);                 // row of the chunk this lane stores
+            if (c >= AtSmem::G_OP_STAGES) mbar_wait(&empty[stage], ((c / AtSmem::G_OP_STAGES) - 1) & 1);
+            uint8_t* st = ops + stage * AtSmem::G_STAGE;
+            const int k = kA + (odd ? 4 : 0);                         // row of the chunk this lane stores
 #pragma unroll
             for (int i = 0; i < 4; ++i) {                             // blocks past Mtot are stored as zeros (accumulator rows nobody reads)
                 float x[8];
@@ -500,17 +527,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
                     *reinterpret_cast<uint4*>(st + 2 * AtSmem::GA_BYTES + AtSmem::GB_BYTES + off) = lo;
                 }
             }
+            at_warp_arrive(&raw_empty[slot]);
             fence_async_smem();
             at_warp_arrive(&full[stage]);
         }
     } else if (warp == AT_MMA_WARP) {
         const uint32_t idesc = idesc_bf16(128, P.N, 1, 1);
         for (int c = 0; c < nchunks; ++c) {
-            const int stage = c % AT_STAGES;
-            mbar_wait(&full[stage], (c / AT_STAGES) & 1);
+            const int stage = c % AtSmem::G_OP_STAGES;
+            mbar_wait(&full[stage], (c / AtSmem::G_OP_STAGES) & 1);
             fence_after_sync();
             if (elect_one()) {
-                const uint32_t a_hi = smem_u32(smem + stage * AtSmem::G_STAGE);
+                const uint32_t a_hi = smem_u32(ops + stage * AtSmem::G_STAGE);
                 const uint32_t a_lo = a_hi + AtSmem::GA_BYTES;
                 const uint32_t b_hi = a_hi + 2 * AtSmem::GA_BYTES;
                 const uint32_t b_lo = b_hi + AtSmem::GB_BYTES;
@@ -530,7 +558,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
         }
     } else if (warp < AT_LOAD_WARP && nchunks > 0) {       // (the loader warp has no role in this kernel)
         const int quad = warp & 3;
-        float* T = reinterpret_cast<float*>(smem + AtSmem::TRANS) + quad * (32 * 33);
+        float* T = reinterpret_cast<float*>(trans) + quad * (32 * 33);
         mbar_wait(acc_full, 0);
         fence_after_sync();
         if (32 * quad < P.Mtot) {
@@ -718,11 +746,19 @@ static int launch_cloud_gw(const float* T, const float* X, long long x_bstride, 
     int rchunk = (n_rows + nsplit - 1) / nsplit;
     rchunk = (rchunk + AT_KC - 1) / AT_KC * AT_KC;
     nsplit = (n_rows + rchunk - 1) / rchunk;
-    ClGwParams p{T, (long long)n_rows * s.HS, s.HS, s.HS, X, x_bstride, ldx, D, out, o_bstride, ldo, n_rows, rchunk, s.nsp, s.ns, D / H};
+    ClGwParams p{T, (long long)n_rows * s.HS, s.HS, s.HS, X, x_bstride, ldx, D, out, o_bstride, ldo, n_rows, rchunk, s.nsp, s.ns, D / H,
+                 AtSmem::g_raw_slots(s.HS, D), 0, x_bstride == 0 ? 1 : 0};
     dim3 grid((unsigned)nsplit, (unsigned)B);
+    // both operands as (columns, rows of a cloud, clouds): one box = the 32 rows of a chunk, all columns
+    CUtensorMap tma, tmb;
+    PCA_TRY(make_tmap_3d_f32(&tma, T, (unsigned long long)s.HS, (unsigned long long)n_rows, (unsigned long long)B, (unsigned long long)s.HS * 4,
+                             (unsigned long long)n_rows * s.HS * 4, (unsigned)s.HS, AT_KC));
+    PCA_TRY(make_tmap_3d_f32(&tmb, X, (unsigned long long)D, (unsigned long long)n_rows, p.b_shared ? 1ull : (unsigned long long)B,
+                             (unsigned long long)ldx * 4, (unsigned long long)(p.b_shared ? (long long)n_rows * ldx : x_bstride) * 4, (unsigned)D,
+                             AT_KC));
     {
         LaunchTimer lt("attn_g3_tc_kernel", st, 2.0 * B * (double)n_rows * s.HS * D, 4.0 * B * (double)n_rows * (s.HS + D));
-        cloud_gw_tc_kernel<<<grid, AT_THREADS, AtSmem::TOTAL, st>>>(p);
+        cloud_gw_tc_kernel<<<grid, AT_THREADS, AtSmem::g_total(s.HS, D, p.raw_slots), st>>>(p, tma, tmb);
     }
     PCA_CHECK_LAUNCH("cloud_gw_tc_kernel");
     return 0;
