@@ -14,6 +14,7 @@
 //                       split over rows across CTAs, partial results added atomically.
 #include "common.cuh"
 #include "tc_prims.cuh"
+#include "tma_host.cuh"
 
 namespace pca {
 using namespace tc;
@@ -22,7 +23,12 @@ constexpr int GT_KC = 32;            // K elements per pipeline stage
 constexpr int GT_STAGES = 4;
 constexpr int GT_PSETS = 2;           // producer warp sets: set s stages the work items s, s + 2, ... (twice the loads in flight per SM)
 constexpr int GT_MMA_WARP = 4 * GT_PSETS;
-constexpr int GT_THREADS = (4 * GT_PSETS + 5) * 32;   // 8 producer + 1 MMA + 4 epilogue warps
+constexpr int GT_THREADS = (4 * GT_PSETS + 5) * 32;   // grad-weight kernel: 8 producer + 1 MMA + 4 epilogue warps
+constexpr int GT_LOAD_WARP = GT_MMA_WARP + 5;
+constexpr int LT_THREADS = (4 * GT_PSETS + 6) * 32;   // linear kernel: 8 converter + 1 MMA + 4 epilogue + 1 TMA loader warps
+constexpr int LT_STAGES = 3;          // operand stages of the linear kernel
+constexpr int LT_RAW_MAX = 8;         // raw fp32 tiles (128 rows x 32 floats = 16 KB) the TMA loader may have in flight
+constexpr int LT_RAW_BYTES = 128 * GT_KC * 4;
 
 __device__ __forceinline__ void gt_warp_arrive(uint64_t* bar) {
     __syncwarp();
@@ -76,6 +82,7 @@ struct LinTcParams {
     float* R;                // (rows, N) nullable: relu output
     long long rows;
     int K, N, nt, relu;
+    int raw_slots;           // raw fp32 tiles in the TMA ring (<= LT_RAW_MAX)
 };
 
 // lanes 2j / 2j + 1 hold adjacent float4 pieces (a: of row A, b: of row B = A + 4); after the exchange the even lane owns the 8
@@ -97,30 +104,43 @@ __device__ __forceinline__ void pair_exchange(const float4 a, const float4 b, bo
 struct LinTcSmem {
     static constexpr int A_LBO = 128 * 16 + 16;
     static constexpr int A_BYTES = 8320;                           // one hi or lo image of the activation tile (>= 4 * A_LBO)
-    static constexpr int STAGE = 2 * A_BYTES + 2 * 256 * GT_KC * 2;  // A hi | A lo | B hi | B lo (B sized for nt = 256)
-    static constexpr int TRANS = GT_STAGES * STAGE;                 // 4 epilogue warps x 32 x 33 floats
-    static constexpr int BARS = TRANS + 4 * 32 * 33 * 4;
-    static constexpr int TOTAL = BARS + 16 * 8 + 16;
+    // raw fp32 ring | operand stages: A hi | A lo | B hi | B lo (B sized for the launch's column pass) | transpose tiles | barriers
+    static constexpr int FIXED = 4 * 32 * 33 * 4 + 256;
+    static constexpr int MAX_BYTES = 227 * 1024;
+    __host__ __device__ static int stage(int nt) { return 2 * A_BYTES + 2 * nt * 64; }
+    __host__ static int raw_slots(int nt) {
+        int r = (MAX_BYTES - FIXED - LT_STAGES * stage(nt)) / LT_RAW_BYTES;
+        return r > LT_RAW_MAX ? LT_RAW_MAX : r;
+    }
+    __host__ __device__ static int total(int nt, int raw_slots) { return raw_slots * LT_RAW_BYTES + LT_STAGES * stage(nt) + FIXED; }
 };
 
-__global__ void __launch_bounds__(GT_THREADS, 1) linear_tc_kernel(const LinTcParams P) {
+__global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcParams P, const __grid_constant__ CUtensorMap tmx) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LinTcSmem::BARS);
-    uint64_t* full = bars;                       // [stages] count 5: the 4 producer warps of a set + the expect_tx arrival
-    uint64_t* empty = bars + GT_STAGES;          // [stages] count 1 (MMA commit)
-    uint64_t* acc_full = bars + 2 * GT_STAGES;   // [2] count 1
+    const int stage_bytes = LinTcSmem::stage(P.nt);
+    uint8_t* ops = smem + P.raw_slots * LT_RAW_BYTES;
+    uint8_t* trans = ops + LT_STAGES * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(trans + 4 * 32 * 33 * 4);
+    uint64_t* full = bars;                       // [3] count 5: the 4 converter warps of a set + the expect_tx arrival of the weight image
+    uint64_t* empty = bars + LT_STAGES;          // [3] count 1 (MMA commit)
+    uint64_t* acc_full = bars + 2 * LT_STAGES;   // [2] count 1
     uint64_t* acc_empty = acc_full + 2;          // [2] count 4 (epilogue warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GT_STAGES + 4);
+    uint64_t* raw_full = acc_empty + 2;          // [8] count 1 (expect_tx of the loader) + 16 KB
+    uint64_t* raw_empty = raw_full + LT_RAW_MAX; // [8] count 4 (converter warps of the set that read the slot)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + LT_RAW_MAX);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkc = P.K / GT_KC;
     const int npass = P.N / P.nt;
     const long long mtiles = (P.rows + 127) / 128;
     const long long ntiles = mtiles * npass;
+    const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t items = (uint32_t)(my_tiles * nkc);      // (tile of this CTA, K chunk) in issue order
 
     if (warp == GT_MMA_WARP) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < GT_STAGES; ++i) { mbar_init(&full[i], 5); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < LT_STAGES; ++i) { mbar_init(&full[i], 5); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < LT_RAW_MAX; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 4); }
         fence_barrier_init();
     }
     fence_before_sync();
@@ -129,49 +149,57 @@ __global__ void __launch_bounds__(GT_THREADS, 1) linear_tc_kernel(const LinTcPar
     const uint32_t tb = *tmem_slot;
     const uint32_t b_img_bytes = (uint32_t)P.nt * 64;           // one hi or lo weight image of a chunk
 
-    if (warp < GT_MMA_WARP) {
-        // ================================================================= producers
-        // Work items g = (tile of this CTA, K chunk) in issue order; warp set g % GT_PSETS stages item g.  Warp pw of the set
-        // stages rows [32 pw, 32 pw + 32) of the tile.  Loads are row-contiguous: quarter warp q reads the 128 bytes (the
-        // whole K chunk) of row 8 it + q and of row 8 it + 4 + q -- one L1 wavefront per row where a lane-per-(row, chunk)
-        // mapping costs one per lane (ncu: l1tex 85 % busy on global-load wavefronts); a pair exchange then gives every lane
-        // the 8 consecutive floats of one 16-byte bf16 chunk.  The loads of the set's next two items are in flight while
-        // the current one is converted.
+    if (warp == GT_LOAD_WARP) {
+        // ================================================================= TMA loader (one thread)
+        // streams the fp32 rows of the tiles into a ring of raw 16 KB tiles (128 rows x 32 floats; rows past the end arrive as
+        // zeros): up to eight tiles in flight per SM whatever the converter warps are doing (register-staged loads kept one
+        // chunk per warp set in flight and the kernel at 2.5-2.9 TB/s)
+        if (lane == 0) {
+            tma_prefetch_desc(&tmx);
+            for (uint32_t g = 0; g < items; ++g) {
+                const int slot = g % P.raw_slots;
+                const uint32_t lt = g / nkc;
+                const int kc = (int)(g - lt * nkc);
+                const long long mt = (blockIdx.x + (long long)lt * gridDim.x) / npass;
+                if (g >= (uint32_t)P.raw_slots) mbar_wait(&raw_empty[slot], ((g / P.raw_slots) - 1) & 1);
+                mbar_arrive_expect_tx(&raw_full[slot], LT_RAW_BYTES);
+                tma_load_3d(smem + slot * LT_RAW_BYTES, &tmx, kc * GT_KC, (int)(mt * 128), 0, &raw_full[slot]);
+            }
+        }
+    } else if (warp < GT_MMA_WARP) {
+        // ================================================================= converters
+        // Warp set g % GT_PSETS converts item g; warp pw of the set the rows [32 pw, 32 pw + 32) of the tile.  Quarter warp q
+        // reads the 128 bytes (the whole K chunk) of row 8 it + q and of row 8 it + 4 + q from the raw tile; a pair exchange
+        // gives every lane the 8 consecutive floats of one 16-byte bf16 chunk; the chunk goes to the canonical K-major image
+        // with a padded chunk stride (conflict-free quarter-warp stores).
         const int set = warp >> 2, pw = warp & 3;
         const int q = lane >> 3, piece = lane & 7;
         const bool odd = piece & 1;
-        const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        const uint32_t items = (uint32_t)(my_tiles * nkc);
-        float4 nx[8], nx2[8];                     // the next two items: 4 row groups x 2 float4 (8 consecutive k of one row)
-        auto issue = [&](float4* dst, uint32_t g) {
-            const long long tile = blockIdx.x + (long long)(g / nkc) * gridDim.x;
-            const int kchunk = (int)(g % nkc);
-            const long long mt = tile / npass;
+        for (uint32_t g = set; g < items; g += GT_PSETS) {
+            const int slot = g % P.raw_slots;
+            const int stage = g % LT_STAGES;
+            mbar_wait(&raw_full[slot], (g / P.raw_slots) & 1);
+            const float4* raw = reinterpret_cast<const float4*>(smem + slot * LT_RAW_BYTES) + piece;
+            float4 xv[8];
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
-                const long long rA = mt * 128 + 32 * pw + 8 * it + q, rB = rA + 4;
-                const float* src = P.X + kchunk * GT_KC + 4 * piece;
-                dst[2 * it] = rA < P.rows ? __ldg(reinterpret_cast<const float4*>(src + rA * P.K)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                dst[2 * it + 1] = rB < P.rows ? __ldg(reinterpret_cast<const float4*>(src + rB * P.K)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int rA = 32 * pw + 8 * it + q;
+                xv[2 * it] = raw[rA * 8];
+                xv[2 * it + 1] = raw[(rA + 4) * 8];
             }
-        };
-        uint32_t g = set;
-        if (g < items) issue(nx, g);
-        if (g + GT_PSETS < items) issue(nx2, g + GT_PSETS);
-        for (; g < items; g += GT_PSETS) {
-            const int stage = g % GT_STAGES;
-            if (g >= GT_STAGES) mbar_wait(&empty[stage], ((g / GT_STAGES) - 1) & 1);
-            uint8_t* st = smem + stage * LinTcSmem::STAGE;
+            if (g >= LT_STAGES) mbar_wait(&empty[stage], ((g / LT_STAGES) - 1) & 1);
+            uint8_t* st = ops + stage * stage_bytes;
             if (pw == 0 && lane == 0) {
-                const int pass = (int)((blockIdx.x + (long long)(g / nkc) * gridDim.x) % npass);
-                const int kc = (int)(g % nkc);
+                const uint32_t lt = g / nkc;
+                const int kc = (int)(g - lt * nkc);
+                const int pass = (int)((blockIdx.x + (long long)lt * gridDim.x) % npass);
                 mbar_arrive_expect_tx(&full[stage], 2 * b_img_bytes);
                 bulk_copy_g2s(st + 2 * LinTcSmem::A_BYTES, P.img + ((size_t)(pass * nkc + kc) * 2) * b_img_bytes, 2 * b_img_bytes, &full[stage]);
             }
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 float x[8];
-                pair_exchange(nx[2 * it], nx[2 * it + 1], odd, x);
+                pair_exchange(xv[2 * it], xv[2 * it + 1], odd, x);
                 uint4 hi, lo;
                 split8(x, hi, lo);
                 const int row = 32 * pw + 8 * it + q + (odd ? 4 : 0);
@@ -179,13 +207,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) linear_tc_kernel(const LinTcPar
                 *reinterpret_cast<uint4*>(st + off) = hi;
                 *reinterpret_cast<uint4*>(st + LinTcSmem::A_BYTES + off) = lo;
             }
+            gt_warp_arrive(&raw_empty[slot]);              // the raw tile is converted: the loader may refill the slot
             fence_async_smem();
             gt_warp_arrive(&full[stage]);
-            // shift the prefetch window (13 warps share 64 K registers with four on one scheduler: 128 per thread, no room for a
-            // third buffer) and put the loads of the item after next in flight
-#pragma unroll
-            for (int j = 0; j < 8; ++j) nx[j] = nx2[j];
-            if (g + 2 * GT_PSETS < items) issue(nx2, g + 2 * GT_PSETS);
         }
     } else if (warp == GT_MMA_WARP) {
         // ================================================================= MMA issue (warp-uniform, elected lane)
@@ -197,11 +221,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) linear_tc_kernel(const LinTcPar
             fence_after_sync();
             const uint32_t acc = tmem_addr(tb, 0, 256 * buf);
             for (int kc = 0; kc < nkc; ++kc, ++gt) {
-                const int stage = gt % GT_STAGES;
-                mbar_wait(&full[stage], (gt / GT_STAGES) & 1);
+                const int stage = gt % LT_STAGES;
+                mbar_wait(&full[stage], (gt / LT_STAGES) & 1);
                 fence_after_sync();
                 if (elect_one()) {
-                    const uint32_t a_hi = smem_u32(smem + stage * LinTcSmem::STAGE);
+                    const uint32_t a_hi = smem_u32(ops + stage * stage_bytes);
                     const uint32_t a_lo = a_hi + LinTcSmem::A_BYTES;
                     const uint32_t b_hi = a_hi + 2 * LinTcSmem::A_BYTES;
                     const uint32_t b_lo = b_hi + b_img_bytes;
@@ -221,12 +245,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) linear_tc_kernel(const LinTcPar
                 __syncwarp();
             }
         }
-    } else {
+    } else if (warp < GT_LOAD_WARP) {
         // ================================================================= epilogue
         // TMEM rows arrive one per thread; every 32 x 32 block is transposed through a padded per-warp smem tile so that
         // global traffic is coalesced: lane = (row % 4, float4 of columns) -> 4 rows x 128 contiguous bytes per instruction.
         const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
-        float* T = reinterpret_cast<float*>(smem + LinTcSmem::TRANS) + quad * (32 * 33);
+        float* T = reinterpret_cast<float*>(trans) + quad * (32 * 33);
         const int rr = lane >> 3, cq = lane & 7;
         uint32_t tt = 0;
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tt) {
@@ -321,12 +345,15 @@ int launch_linear_tc(const float* X, const float* W, int trans_w, const float* b
         weight_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, N, K, trans_w ? N : K, trans_w, nt, (uint8_t*)img);
         PCA_CHECK_LAUNCH("weight_image_kernel");
     }
-    LinTcParams p{X, (const uint8_t*)img, bias, resid, Y, R, rows, K, N, nt, relu};
+    LinTcParams p{X, (const uint8_t*)img, bias, resid, Y, R, rows, K, N, nt, relu, LinTcSmem::raw_slots(nt)};
+    CUtensorMap tmx;                  // X as (K, rows): a box of 32 floats x 128 rows is one raw tile
+    PCA_TRY(make_tmap_3d_f32(&tmx, X, (unsigned long long)K, (unsigned long long)rows, 1ull, (unsigned long long)K * 4,
+                             (unsigned long long)rows * K * 4, GT_KC, 128));
     const long long ntiles = ((rows + 127) / 128) * (N / nt);
     const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
     {
         LaunchTimer lt("linear_tc_kernel", st, 2.0 * rows * K * N, 4.0 * rows * (K + N));
-        linear_tc_kernel<<<grid, GT_THREADS, LinTcSmem::TOTAL, st>>>(p);
+        linear_tc_kernel<<<grid, LT_THREADS, LinTcSmem::total(nt, p.raw_slots), st>>>(p, tmx);
     }
     PCA_CHECK_LAUNCH("linear_tc_kernel");
     return 0;
@@ -492,7 +519,7 @@ static int gemm_tc_configure() {
     int dev = 0;
     PCA_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && ((done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) return 0;
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LinTcSmem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LinTcSmem::MAX_BYTES));
     PCA_CHECK_CUDA(cudaFuncSetAttribute(grad_weight_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GwTcSmem::TOTAL));
     if (dev < 64) done_mask.fetch_or(1ull << dev, std::memory_order_release);
     return 0;
