@@ -125,14 +125,19 @@ struct AtSmem {
     __host__ __device__ static int g_raw_bytes(int M, int N) { return AT_KC * (M + N) * 4; }
     __host__ static int g_raw_slots(int M, int N) {
         int r = (MAX_BYTES - CL_FIXED - G_OP_STAGES * G_STAGE) / g_raw_bytes(M, N);
-        return r > G_RAW_MAX ? G_RAW_MAX : r;
+        r = r > G_RAW_MAX ? G_RAW_MAX : r;
+        return r & ~1;                                                  // even: see cl_raw_slots
     }
     __host__ __device__ static int g_total(int M, int N, int raw_slots) { return raw_slots * g_raw_bytes(M, N) + G_OP_STAGES * G_STAGE + CL_FIXED; }
     // per-cloud linear kernel: raw fp32 ring | operand stages (B region sized for the launch's N) | transpose tiles | barriers
     __host__ __device__ static int cl_stage(int N) { return 2 * A_BYTES + 2 * N * 64; }
     __host__ static int cl_raw_slots(int N) {
+        // an EVEN count: a slot is then always consumed by the same converter set, in order -- with an odd count the two sets
+        // alternate on a slot and a set could probe a slot's barrier two phases ahead (TMA boxes may land out of order), which
+        // the parity test cannot tell from "complete"
         int r = (MAX_BYTES - CL_FIXED - CL_STAGES * cl_stage(N)) / CL_RAW_BYTES;
-        return r > CL_RAW_MAX ? CL_RAW_MAX : r;
+        r = r > CL_RAW_MAX ? CL_RAW_MAX : r;
+        return r & ~1;
     }
     __host__ __device__ static int cl_total(int N, int raw_slots) { return raw_slots * CL_RAW_BYTES + CL_STAGES * cl_stage(N) + CL_FIXED; }
 };

@@ -20,10 +20,8 @@ namespace pca {
 using namespace tc;
 
 constexpr int GT_KC = 32;            // K elements per pipeline stage
-constexpr int GT_STAGES = 4;
 constexpr int GT_PSETS = 2;           // producer warp sets: set s stages the work items s, s + 2, ... (twice the loads in flight per SM)
 constexpr int GT_MMA_WARP = 4 * GT_PSETS;
-constexpr int GT_THREADS = (4 * GT_PSETS + 5) * 32;   // grad-weight kernel: 8 producer + 1 MMA + 4 epilogue warps
 constexpr int GT_LOAD_WARP = GT_MMA_WARP + 5;
 constexpr int LT_THREADS = (4 * GT_PSETS + 6) * 32;   // linear kernel: 8 converter + 1 MMA + 4 epilogue + 1 TMA loader warps
 constexpr int LT_STAGES = 3;          // operand stages of the linear kernel
@@ -109,8 +107,12 @@ struct LinTcSmem {
     static constexpr int MAX_BYTES = 227 * 1024;
     __host__ __device__ static int stage(int nt) { return 2 * A_BYTES + 2 * nt * 64; }
     __host__ static int raw_slots(int nt) {
+        // an EVEN count: a slot is then always consumed by the same converter set, in order -- with an odd count the two sets
+        // alternate on a slot and a set could probe a slot's barrier two phases ahead (TMA boxes may land out of order), which
+        // the parity test cannot tell from "complete"
         int r = (MAX_BYTES - FIXED - LT_STAGES * stage(nt)) / LT_RAW_BYTES;
-        return r > LT_RAW_MAX ? LT_RAW_MAX : r;
+        r = r > LT_RAW_MAX ? LT_RAW_MAX : r;
+        return r & ~1;
     }
     __host__ __device__ static int total(int nt, int raw_slots) { return raw_slots * LT_RAW_BYTES + LT_STAGES * stage(nt) + FIXED; }
 };
@@ -370,6 +372,7 @@ struct GwTcParams {
     float* dW;               // (Mtot, N)
     long long rows, rchunk;
     int lda, Mtot, N;
+    int mbox, raw_slots;     // columns of dY per raw chunk (min(128, Mtot)); raw chunks in the TMA ring
 };
 // 8-feature group g of chunk row k at g * G_SBO + k * 16 with G_SBO = 512 + 16 (padded: the four groups a quarter warp stores
 // fall into distinct banks)
@@ -378,28 +381,44 @@ struct GwTcSmem {
     static constexpr int A_BYTES = 16 * G_SBO;
     static constexpr int B_BYTES = 32 * G_SBO;
     static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int TRANS = GT_STAGES * STAGE;
-    static constexpr int BARS = TRANS + 4 * 32 * 33 * 4;
-    static constexpr int TOTAL = BARS + 16 * 8 + 16;
+    // raw fp32 ring (32-row chunks of both operands) | 2 operand stages | transpose tiles | barriers
+    static constexpr int OP_STAGES = 2;
+    static constexpr int RAW_MAX = 4;
+    static constexpr int FIXED = 4 * 32 * 33 * 4 + 256;
+    static constexpr int MAX_BYTES = 227 * 1024;
+    __host__ __device__ static int raw_bytes(int mbox, int N) { return GT_KC * (mbox + N) * 4; }
+    __host__ static int raw_slots(int mbox, int N) {
+        int r = (MAX_BYTES - FIXED - OP_STAGES * STAGE) / raw_bytes(mbox, N);      // even, as in the linear kernel
+        r = r > RAW_MAX ? RAW_MAX : r;
+        return r & ~1;
+    }
+    __host__ __device__ static int total(int mbox, int N, int slots) { return slots * raw_bytes(mbox, N) + OP_STAGES * STAGE + FIXED; }
 };
 
-__global__ void __launch_bounds__(GT_THREADS, 1) grad_weight_tc_kernel(const GwTcParams P) {
+__global__ void __launch_bounds__(LT_THREADS, 1) grad_weight_tc_kernel(const GwTcParams P, const __grid_constant__ CUtensorMap tma,
+                                                                       const __grid_constant__ CUtensorMap tmb) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GwTcSmem::BARS);
-    uint64_t* full = bars;                       // [stages] count 4 (the producer warps of a set)
-    uint64_t* empty = bars + GT_STAGES;          // [stages] count 1
-    uint64_t* acc_full = bars + 2 * GT_STAGES;   // count 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GT_STAGES + 4);
+    const int raw_bytes = GwTcSmem::raw_bytes(P.mbox, P.N);
+    uint8_t* ops = smem + P.raw_slots * raw_bytes;
+    uint8_t* trans = ops + GwTcSmem::OP_STAGES * GwTcSmem::STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(trans + 4 * 32 * 33 * 4);
+    uint64_t* full = bars;                                   // [2] count 4 (the converter warps of a set)
+    uint64_t* empty = bars + GwTcSmem::OP_STAGES;            // [2] count 1
+    uint64_t* acc_full = bars + 2 * GwTcSmem::OP_STAGES;     // count 1
+    uint64_t* raw_full = acc_full + 1;                       // [4] count 1 (expect_tx of the loader) + the chunk's bytes
+    uint64_t* raw_empty = raw_full + GwTcSmem::RAW_MAX;      // [4] count 4
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + GwTcSmem::RAW_MAX);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * 128;
-    const long long r0 = (long long)blockIdx.x * P.rchunk;
+    const long long r0 = (long long)blockIdx.x * P.rchunk;   // a multiple of the chunk size: a chunk never straddles two CTAs' ranges
     const long long r1 = (r0 + P.rchunk < P.rows) ? r0 + P.rchunk : P.rows;
     const int nchunks = (int)((r1 - r0 + GT_KC - 1) / GT_KC);
 
     if (warp == GT_MMA_WARP) tmem_alloc(tmem_slot, 256);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < GT_STAGES; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < GwTcSmem::OP_STAGES; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
         mbar_init(acc_full, 1);
+        for (int i = 0; i < GwTcSmem::RAW_MAX; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 4); }
         fence_barrier_init();
     }
     fence_before_sync();
@@ -407,37 +426,54 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grad_weight_tc_kernel(const GwT
     fence_after_sync();
     const uint32_t tb = *tmem_slot;
 
-    if (warp < GT_MMA_WARP) {
-        // Warp set s stages the 32-row chunks s, s + 2, ... (two chunks of loads in flight per CTA); warp pw of the set the rows
-        // [8 pw, 8 pw + 8) of the chunk for every 32-feature block.  Loads are row-contiguous (quarter warp q: 128 bytes of row
-        // 8 pw + q, then of row 8 pw + 4 + q: one L1 wavefront per row); a pair exchange gives every lane one 16-byte unit
-        // (8 consecutive features of one row).  All loads of a chunk are issued before the first conversion.
+    if (warp == GT_LOAD_WARP) {
+        // TMA loader (one thread): chunk c = rows [r0 + 32 c, + 32) of dY (columns [m0, m0 + mbox)) and of X (N columns); rows /
+        // columns outside the tensors arrive as zeros
+        if (lane == 0) {
+            tma_prefetch_desc(&tma);
+            tma_prefetch_desc(&tmb);
+            for (int c = 0; c < nchunks; ++c) {
+                const int slot = c % P.raw_slots;
+                if (c >= P.raw_slots) mbar_wait(&raw_empty[slot], ((c / P.raw_slots) - 1) & 1);
+                mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)raw_bytes);
+                uint8_t* dst = smem + slot * raw_bytes;
+                const int row = (int)(r0 + (long long)c * GT_KC);
+                tma_load_3d(dst, &tma, m0, row, 0, &raw_full[slot]);
+                tma_load_3d(dst + GT_KC * P.mbox * 4, &tmb, 0, row, 0, &raw_full[slot]);
+            }
+        }
+    } else if (warp < GT_MMA_WARP) {
+        // Converters: warp set s handles the chunks s, s + 2, ...; warp pw of the set the rows [8 pw, 8 pw + 8) of the chunk for
+        // every 32-feature block.  Quarter warp q reads the 128 bytes of row 8 pw + q, then of row 8 pw + 4 + q, from the raw
+        // chunk; a pair exchange gives every lane one 16-byte unit (8 consecutive features of one row), stored MN-major with a
+        // padded group stride (conflict-free quarter-warp stores).
         const int set = warp >> 2, pw = warp & 3;
         const int q = lane >> 3, piece = lane & 7;
         const bool odd = piece & 1;
-        const int b_fblocks = P.N / 32;
+        const int a_fblocks = P.mbox / 32, b_fblocks = P.N / 32;
         for (int c = set; c < nchunks; c += GT_PSETS) {
-            const int stage = c % GT_STAGES;
-            const long long rA = r0 + (long long)c * GT_KC + 8 * pw + q, rB = rA + 4;
-            const bool okA = rA < r1, okB = rB < r1;
+            const int slot = c % P.raw_slots;
+            const int stage = c % GwTcSmem::OP_STAGES;
+            mbar_wait(&raw_full[slot], (c / P.raw_slots) & 1);
+            const float* rawA = reinterpret_cast<const float*>(smem + slot * raw_bytes) + 4 * piece;
+            const float* rawB = rawA + GT_KC * P.mbox;
+            const int kA = 8 * pw + q;
             float4 va[8], vb[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const bool on = m0 + 32 * i < P.Mtot;
-                const float* src = P.A + m0 + (on ? 32 * i : 0) + 4 * piece;
-                va[2 * i] = (on && okA) ? __ldg(reinterpret_cast<const float4*>(src + rA * P.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                va[2 * i + 1] = (on && okB) ? __ldg(reinterpret_cast<const float4*>(src + rB * P.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool on = i < a_fblocks;
+                va[2 * i] = on ? *reinterpret_cast<const float4*>(rawA + kA * P.mbox + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                va[2 * i + 1] = on ? *reinterpret_cast<const float4*>(rawA + (kA + 4) * P.mbox + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const bool on = i < b_fblocks;
-                const float* src = P.B + (on ? 32 * i : 0) + 4 * piece;
-                vb[2 * i] = (on && okA) ? __ldg(reinterpret_cast<const float4*>(src + rA * P.N)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                vb[2 * i + 1] = (on && okB) ? __ldg(reinterpret_cast<const float4*>(src + rB * P.N)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[2 * i] = on ? *reinterpret_cast<const float4*>(rawB + kA * P.N + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[2 * i + 1] = on ? *reinterpret_cast<const float4*>(rawB + (kA + 4) * P.N + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (c >= GT_STAGES) mbar_wait(&empty[stage], ((c / GT_STAGES) - 1) & 1);
-            uint8_t* st = smem + stage * GwTcSmem::STAGE;
-            const int k = 8 * pw + q + (odd ? 4 : 0);                 // row of the chunk this lane stores
+            if (c >= GwTcSmem::OP_STAGES) mbar_wait(&empty[stage], ((c / GwTcSmem::OP_STAGES) - 1) & 1);
+            uint8_t* st = ops + stage * GwTcSmem::STAGE;
+            const int k = kA + (odd ? 4 : 0);                         // row of the chunk this lane stores
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float x[8];
@@ -460,17 +496,18 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grad_weight_tc_kernel(const GwT
                     *reinterpret_cast<uint4*>(st + 2 * GwTcSmem::A_BYTES + GwTcSmem::B_BYTES + off) = lo;
                 }
             }
+            gt_warp_arrive(&raw_empty[slot]);
             fence_async_smem();
             gt_warp_arrive(&full[stage]);
         }
     } else if (warp == GT_MMA_WARP) {
         const uint32_t idesc = idesc_bf16(128, P.N, 1, 1);
         for (int c = 0; c < nchunks; ++c) {
-            const int stage = c % GT_STAGES;
-            mbar_wait(&full[stage], (c / GT_STAGES) & 1);
+            const int stage = c % GwTcSmem::OP_STAGES;
+            mbar_wait(&full[stage], (c / GwTcSmem::OP_STAGES) & 1);
             fence_after_sync();
             if (elect_one()) {
-                const uint32_t a_hi = smem_u32(smem + stage * GwTcSmem::STAGE);
+                const uint32_t a_hi = smem_u32(ops + stage * GwTcSmem::STAGE);
                 const uint32_t a_lo = a_hi + GwTcSmem::A_BYTES;
                 const uint32_t b_hi = a_hi + 2 * GwTcSmem::A_BYTES;
                 const uint32_t b_lo = b_hi + GwTcSmem::B_BYTES;
@@ -488,9 +525,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) grad_weight_tc_kernel(const GwT
             }
             __syncwarp();
         }
-    } else if (nchunks > 0) {
+    } else if (warp < GT_LOAD_WARP && nchunks > 0) {
         const int quad = warp & 3;
-        float* T = reinterpret_cast<float*>(smem + GwTcSmem::TRANS) + quad * (32 * 33);
+        float* T = reinterpret_cast<float*>(trans) + quad * (32 * 33);
         mbar_wait(acc_full, 0);
         fence_after_sync();
         for (int c0 = 0; c0 < P.N; c0 += 32) {
@@ -520,7 +557,7 @@ static int gemm_tc_configure() {
     PCA_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && ((done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) return 0;
     PCA_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LinTcSmem::MAX_BYTES));
-    PCA_CHECK_CUDA(cudaFuncSetAttribute(grad_weight_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GwTcSmem::TOTAL));
+    PCA_CHECK_CUDA(cudaFuncSetAttribute(grad_weight_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GwTcSmem::MAX_BYTES));
     if (dev < 64) done_mask.fetch_or(1ull << dev, std::memory_order_release);
     return 0;
 }
@@ -550,11 +587,17 @@ int launch_grad_weight_tc(const float* dY, const float* X, float* dW, long long 
     long long rchunk = (rows + nsplit - 1) / nsplit;
     rchunk = (rchunk + GT_KC - 1) / GT_KC * GT_KC;
     nsplit = (rows + rchunk - 1) / rchunk;
-    GwTcParams p{dY, X, dW, rows, rchunk, M, M, N};
+    const int mbox = M < 128 ? M : 128;
+    GwTcParams p{dY, X, dW, rows, rchunk, M, M, N, mbox, GwTcSmem::raw_slots(mbox, N)};
     dim3 grid((unsigned)nsplit, mtiles);
+    CUtensorMap tma, tmb;             // dY as (M, rows), X as (N, rows): one box = the 32 rows of a chunk
+    PCA_TRY(make_tmap_3d_f32(&tma, dY, (unsigned long long)M, (unsigned long long)rows, 1ull, (unsigned long long)M * 4,
+                             (unsigned long long)rows * M * 4, (unsigned)mbox, GT_KC));
+    PCA_TRY(make_tmap_3d_f32(&tmb, X, (unsigned long long)N, (unsigned long long)rows, 1ull, (unsigned long long)N * 4,
+                             (unsigned long long)rows * N * 4, (unsigned)N, GT_KC));
     {
         LaunchTimer lt("grad_weight_tc_kernel", st, 2.0 * rows * M * N, 4.0 * rows * (M + N));
-        grad_weight_tc_kernel<<<grid, GT_THREADS, GwTcSmem::TOTAL, st>>>(p);
+        grad_weight_tc_kernel<<<grid, LT_THREADS, GwTcSmem::total(mbox, N, p.raw_slots), st>>>(p, tma, tmb);
     }
     PCA_CHECK_LAUNCH("grad_weight_tc_kernel");
     return 0;
