@@ -123,12 +123,14 @@ struct AtSmem {
     static constexpr int G_OP_STAGES = 2;
     static constexpr int G_RAW_MAX = 4;
     __host__ __device__ static int g_raw_bytes(int M, int N) { return AT_KC * (M + N) * 4; }
+    __host__ __device__ static int g_b_bytes(int N) { return (N / 8) * G_SBO; }                    // one hi or lo image of X's slice
+    __host__ __device__ static int g_stage(int N) { return 2 * GA_BYTES + 2 * g_b_bytes(N); }
     __host__ static int g_raw_slots(int M, int N) {
-        int r = (MAX_BYTES - CL_FIXED - G_OP_STAGES * G_STAGE) / g_raw_bytes(M, N);
+        int r = (MAX_BYTES - CL_FIXED - G_OP_STAGES * g_stage(N)) / g_raw_bytes(M, N);
         r = r > G_RAW_MAX ? G_RAW_MAX : r;
         return r & ~1;                                                  // even: see cl_raw_slots
     }
-    __host__ __device__ static int g_total(int M, int N, int raw_slots) { return raw_slots * g_raw_bytes(M, N) + G_OP_STAGES * G_STAGE + CL_FIXED; }
+    __host__ __device__ static int g_total(int M, int N, int raw_slots) { return raw_slots * g_raw_bytes(M, N) + G_OP_STAGES * g_stage(N) + CL_FIXED; }
     // per-cloud linear kernel: raw fp32 ring | operand stages (B region sized for the launch's N) | transpose tiles | barriers
     __host__ __device__ static int cl_stage(int N) { return 2 * A_BYTES + 2 * N * 64; }
     __host__ static int cl_raw_slots(int N) {
@@ -431,31 +433,42 @@ struct ClGwParams {
     int ldo;
     int n_rows, rchunk, nsp, ns, dh;
     int raw_slots, a_shared, b_shared;
+    int ncta;              // columns of X per CTA (= N)
+    int B, nsplit;         // work items = B clouds x nsplit row ranges
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwParams P, const __grid_constant__ CUtensorMap tma,
                                                                     const __grid_constant__ CUtensorMap tmb) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int raw_bytes = AtSmem::g_raw_bytes(P.Mtot, P.N);
+    const int raw_bytes = AtSmem::g_raw_bytes(P.Mtot, P.ncta);
+    const int col0 = 0;
     uint8_t* ops = smem + P.raw_slots * raw_bytes;
-    uint8_t* trans = ops + AtSmem::G_OP_STAGES * AtSmem::G_STAGE;
+    const int op_stage = AtSmem::g_stage(P.ncta), gb_bytes = AtSmem::g_b_bytes(P.ncta);
+    uint8_t* trans = ops + AtSmem::G_OP_STAGES * op_stage;
     uint64_t* bars = reinterpret_cast<uint64_t*>(trans + 4 * 32 * 33 * 4);
     uint64_t* full = bars;                                   // [2] count 4 (the converter warps of a set)
     uint64_t* empty = bars + AtSmem::G_OP_STAGES;            // [2] count 1
-    uint64_t* acc_full = bars + 2 * AtSmem::G_OP_STAGES;     // count 1
-    uint64_t* raw_full = acc_full + 1;                       // [4] count 1 (expect_tx of the loader) + the chunk's bytes
+    uint64_t* acc_full = bars + 2 * AtSmem::G_OP_STAGES;     // [2] count 1
+    uint64_t* acc_empty = acc_full + 2;                      // [2] count 4 (epilogue warps)
+    uint64_t* raw_full = acc_empty + 2;                      // [4] count 1 (expect_tx of the loader) + the chunk's bytes
     uint64_t* raw_empty = raw_full + AtSmem::G_RAW_MAX;      // [4] count 4
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + AtSmem::G_RAW_MAX);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y;
-    const int r0 = blockIdx.x * P.rchunk;                    // a multiple of the chunk size: a chunk never straddles two CTAs' ranges
-    const int r1 = min(r0 + P.rchunk, P.n_rows);
-    const int nchunks = (r1 - r0 + AT_KC - 1) / AT_KC;
+    // Persistent: work item = (cloud, row range of rchunk rows -- a multiple of the chunk size, so a chunk never straddles two
+    // items); this CTA walks the items blockIdx.x, + gridDim.x, ...; the raw ring / operand stages run across item boundaries
+    // (global chunk counter) and two accumulators let the epilogue of an item overlap the chunks of the next one.
+    const int n_items = P.B * P.nsplit;
+    auto item_rows = [&](int it, int& b, int& r0) -> int {   // chunks of the item
+        b = it / P.nsplit;
+        r0 = (it - b * P.nsplit) * P.rchunk;
+        const int r1 = min(r0 + P.rchunk, P.n_rows);
+        return (r1 - r0 + AT_KC - 1) / AT_KC;
+    };
 
-    if (warp == AT_MMA_WARP) tmem_alloc(tmem_slot, 256);
+    if (warp == AT_MMA_WARP) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
         for (int i = 0; i < AtSmem::G_OP_STAGES; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         for (int i = 0; i < AtSmem::G_RAW_MAX; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 4); }
         fence_barrier_init();
     }
@@ -470,13 +483,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
         if (lane == 0) {
             tma_prefetch_desc(&tma);
             tma_prefetch_desc(&tmb);
-            for (int c = 0; c < nchunks; ++c) {
-                const int slot = c % P.raw_slots;
-                if (c >= P.raw_slots) mbar_wait(&raw_empty[slot], ((c / P.raw_slots) - 1) & 1);
-                mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)raw_bytes);
-                uint8_t* dst = smem + slot * raw_bytes;
-                tma_load_3d(dst, &tma, 0, r0 + c * AT_KC, P.a_shared ? 0 : b, &raw_full[slot]);
-                tma_load_3d(dst + AT_KC * P.Mtot * 4, &tmb, 0, r0 + c * AT_KC, P.b_shared ? 0 : b, &raw_full[slot]);
+            int gc = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                int b, r0;
+                const int nchunks = item_rows(it, b, r0);
+                for (int c = 0; c < nchunks; ++c, ++gc) {
+                    const int slot = gc % P.raw_slots;
+                    if (gc >= P.raw_slots) mbar_wait(&raw_empty[slot], ((gc / P.raw_slots) - 1) & 1);
+                    mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)raw_bytes);
+                    uint8_t* dst = smem + slot * raw_bytes;
+                    tma_load_3d(dst, &tma, 0, r0 + c * AT_KC, P.a_shared ? 0 : b, &raw_full[slot]);
+                    tma_load_3d(dst + AT_KC * P.Mtot * 4, &tmb, col0, r0 + c * AT_KC, P.b_shared ? 0 : b, &raw_full[slot]);
+                }
             }
         }
     } else if (warp < AT_MMA_WARP) {
@@ -486,8 +504,13 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
         const int set = warp >> 2, pw = warp & 3;
         const int q = lane >> 3, piece = lane & 7;
         const bool odd = piece & 1;
-        const int a_fblocks = (P.Mtot + 31) / 32, b_fblocks = P.N / 32;
-        for (int c = set; c < nchunks; c += AT_PSETS) {
+        const int a_fblocks = (P.Mtot + 31) / 32, b_fblocks = P.ncta / 32;
+        int total_chunks = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            int b, r0;
+            total_chunks += item_rows(it, b, r0);
+        }
+        for (int c = set; c < total_chunks; c += AT_PSETS) {  // global chunk index: the conversion does not depend on the item
             const int slot = c % P.raw_slots;
             const int stage = c % AtSmem::G_OP_STAGES;
             mbar_wait(&raw_full[slot], (c / P.raw_slots) & 1);
@@ -504,11 +527,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const bool on = i < b_fblocks;
-                vb[2 * i] = on ? *reinterpret_cast<const float4*>(rawB + kA * P.N + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                vb[2 * i + 1] = on ? *reinterpret_cast<const float4*>(rawB + (kA + 4) * P.N + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[2 * i] = on ? *reinterpret_cast<const float4*>(rawB + kA * P.ncta + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[2 * i + 1] = on ? *reinterpret_cast<const float4*>(rawB + (kA + 4) * P.ncta + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (c >= AtSmem::G_OP_STAGES) mbar_wait(&empty[stage], ((c / AtSmem::G_OP_STAGES) - 1) & 1);
-            uint8_t* st = ops + stage * AtSmem::G_STAGE;
+            uint8_t* st = ops + stage * op_stage;
             const int k = kA + (odd ? 4 : 0);                         // row of the chunk this lane stores
 #pragma unroll
             for (int i = 0; i < 4; ++i) {                             // blocks past Mtot are stored as zeros (accumulator rows nobody reads)
@@ -529,7 +552,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
                     at_split8(x, hi, lo);
                     const int off = (4 * i + (piece >> 1)) * AtSmem::G_SBO + k * 16;
                     *reinterpret_cast<uint4*>(st + 2 * AtSmem::GA_BYTES + off) = hi;
-                    *reinterpret_cast<uint4*>(st + 2 * AtSmem::GA_BYTES + AtSmem::GB_BYTES + off) = lo;
+                    *reinterpret_cast<uint4*>(st + 2 * AtSmem::GA_BYTES + gb_bytes + off) = lo;
                 }
             }
             at_warp_arrive(&raw_empty[slot]);
@@ -537,61 +560,78 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
             at_warp_arrive(&full[stage]);
         }
     } else if (warp == AT_MMA_WARP) {
-        const uint32_t idesc = idesc_bf16(128, P.N, 1, 1);
-        for (int c = 0; c < nchunks; ++c) {
-            const int stage = c % AtSmem::G_OP_STAGES;
-            mbar_wait(&full[stage], (c / AtSmem::G_OP_STAGES) & 1);
+        const uint32_t idesc = idesc_bf16(128, P.ncta, 1, 1);
+        int gc = 0, k = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+            int b, r0;
+            const int nchunks = item_rows(it, b, r0);
+            const uint32_t buf = k & 1;
+            if (k >= 2) mbar_wait(&acc_empty[buf], ((k >> 1) - 1) & 1);
             fence_after_sync();
-            if (elect_one()) {
-                const uint32_t a_hi = smem_u32(ops + stage * AtSmem::G_STAGE);
-                const uint32_t a_lo = a_hi + AtSmem::GA_BYTES;
-                const uint32_t b_hi = a_hi + 2 * AtSmem::GA_BYTES;
-                const uint32_t b_lo = b_hi + AtSmem::GB_BYTES;
+            const uint32_t acc = tmem_addr(tb, 0, 256 * buf);
+            for (int c = 0; c < nchunks; ++c, ++gc) {
+                const int stage = gc % AtSmem::G_OP_STAGES;
+                mbar_wait(&full[stage], (gc / AtSmem::G_OP_STAGES) & 1);
+                fence_after_sync();
+                if (elect_one()) {
+                    const uint32_t a_hi = smem_u32(ops + stage * op_stage);
+                    const uint32_t a_lo = a_hi + AtSmem::GA_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * AtSmem::GA_BYTES;
+                    const uint32_t b_lo = b_hi + gb_bytes;
 #pragma unroll
-                for (int ks = 0; ks < AT_KC / 16; ++ks) {
-                    // MN-major: a K step of 16 rows = two 8-row groups = 256 bytes further
-                    const uint64_t dah = smem_desc(a_hi + ks * 256, 128, AtSmem::G_SBO), dal = smem_desc(a_lo + ks * 256, 128, AtSmem::G_SBO);
-                    const uint64_t dbh = smem_desc(b_hi + ks * 256, 128, AtSmem::G_SBO), dbl = smem_desc(b_lo + ks * 256, 128, AtSmem::G_SBO);
-                    mma_ss(tb, dah, dbh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-                    mma_ss(tb, dal, dbh, idesc, 1u);
-                    mma_ss(tb, dah, dbl, idesc, 1u);
+                    for (int ks = 0; ks < AT_KC / 16; ++ks) {
+                        // MN-major: a K step of 16 rows = two 8-row groups = 256 bytes further
+                        const uint64_t dah = smem_desc(a_hi + ks * 256, 128, AtSmem::G_SBO), dal = smem_desc(a_lo + ks * 256, 128, AtSmem::G_SBO);
+                        const uint64_t dbh = smem_desc(b_hi + ks * 256, 128, AtSmem::G_SBO), dbl = smem_desc(b_lo + ks * 256, 128, AtSmem::G_SBO);
+                        mma_ss(acc, dah, dbh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                        mma_ss(acc, dal, dbh, idesc, 1u);
+                        mma_ss(acc, dah, dbl, idesc, 1u);
+                    }
+                    mma_commit(&empty[stage]);
+                    if (c == nchunks - 1) mma_commit(&acc_full[buf]);
                 }
-                mma_commit(&empty[stage]);
-                if (c == nchunks - 1) mma_commit(acc_full);
+                __syncwarp();
             }
-            __syncwarp();
         }
-    } else if (warp < AT_LOAD_WARP && nchunks > 0) {       // (the loader warp has no role in this kernel)
+    } else if (warp < AT_LOAD_WARP) {
         const int quad = warp & 3;
         float* T = reinterpret_cast<float*>(trans) + quad * (32 * 33);
-        mbar_wait(acc_full, 0);
-        fence_after_sync();
-        if (32 * quad < P.Mtot) {
-            const int h_lo = (32 * quad) / P.nsp, h_hi = (32 * quad + 31) / P.nsp;      // heads of this warp's accumulator rows
-            float* ob = P.out + (long long)b * P.o_bstride;
-            for (int c0 = 0; c0 < P.N; c0 += 32) {
-                if ((c0 + 31) / P.dh < h_lo || c0 / P.dh > h_hi) continue;              // warp-uniform: no diagonal block in here
-                uint32_t v[32];
-                tmem_ld32(tmem_addr(tb, 32 * quad, c0), v);
-                tmem_ld_wait32(v);
+        int k = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+            int b, r0;
+            item_rows(it, b, r0);
+            const uint32_t buf = k & 1;
+            mbar_wait(&acc_full[buf], (k >> 1) & 1);
+            fence_after_sync();
+            if (32 * quad < P.Mtot) {
+                const int h_lo = (32 * quad) / P.nsp, h_hi = (32 * quad + 31) / P.nsp;      // heads of this warp's accumulator rows
+                float* ob = P.out + (long long)b * P.o_bstride;
+                for (int c0 = 0; c0 < P.ncta; c0 += 32) {
+                    if ((c0 + 31) / P.dh < h_lo || c0 / P.dh > h_hi) continue;              // warp-uniform: no diagonal block in here
+                    uint32_t v[32];
+                    tmem_ld32(tmem_addr(tb, 32 * quad, 256 * buf + c0), v);
+                    tmem_ld_wait32(v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
-                __syncwarp();
-                const int col = c0 + lane;
-                const int hc = col / P.dh;
+                    for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
+                    __syncwarp();
+                    const int col = c0 + lane;
+                    const int hc = col / P.dh;
 #pragma unroll 4
-                for (int lr = 0; lr < 32; ++lr) {
-                    const int row = 32 * quad + lr;
-                    const int h = row / P.nsp, m = row - h * P.nsp;
-                    if (row < P.Mtot && m < P.ns && h == hc) atomicAdd(ob + (long long)m * P.ldo + col, T[lr * 33 + lane]);
+                    for (int lr = 0; lr < 32; ++lr) {
+                        const int row = 32 * quad + lr;
+                        const int h = row / P.nsp, m = row - h * P.nsp;
+                        if (row < P.Mtot && m < P.ns && h == hc) atomicAdd(ob + (long long)m * P.ldo + col, T[lr * 33 + lane]);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
+            fence_before_sync();
+            at_warp_arrive(&acc_empty[buf]);
         }
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == AT_MMA_WARP) tmem_dealloc(tb, 256);
+    if (warp == AT_MMA_WARP) tmem_dealloc(tb, 512);
 }
 
 // ------------------------------------------------------------------------------------ column softmax (points = keys)
@@ -665,6 +705,8 @@ static AtcShape atc_shape(int B, int nq, int nk, int D, int H) {
 }
 
 bool attn_tc_eligible(int B, int nq, int nk, int D, int H) { return atc_shape(B, nq, nk, D, H).type != 0; }
+// 0: not eligible; 1: the keys are the small side (the backward derives delta itself); 2: the queries are (delta is an input)
+int attn_tc_kind(int B, int nq, int nk, int D, int H) { return atc_shape(B, nq, nk, D, H).type; }
 
 static size_t fl(size_t n) { return align_up(n * sizeof(float), 256) / sizeof(float); }
 
@@ -744,26 +786,33 @@ static int launch_cloud_linear(ClinParams p, int nsp, const char* name, cudaStre
 static int launch_cloud_gw(const float* T, const float* X, long long x_bstride, int ldx, float* out, long long o_bstride, int ldo, int B,
                            int n_rows, const AtcShape& s, int D, int H, cudaStream_t st) {
     const int sms = sm_count();
-    int nsplit = (2 * sms + B - 1) / B;
-    const int max_split = (n_rows + 8 * AT_KC - 1) / (8 * AT_KC);
-    if (nsplit > max_split) nsplit = max_split;
-    if (nsplit < 1) nsplit = 1;
+    // row ranges per cloud: as many as keep an item >= 128 rows and fill the last round of the persistent CTAs best
+    const int max_split = n_rows / 128 > 0 ? n_rows / 128 : 1;
+    int nsplit = 1;
+    double best = 0.0;
+    for (int c = 1; c <= max_split && c <= 8; ++c) {
+        const long long items = (long long)B * c;
+        const double fill = (double)items / (double)(((items + sms - 1) / sms) * sms);
+        if (fill > best + 0.02) { best = fill; nsplit = c; }
+    }
     int rchunk = (n_rows + nsplit - 1) / nsplit;
     rchunk = (rchunk + AT_KC - 1) / AT_KC * AT_KC;
     nsplit = (n_rows + rchunk - 1) / rchunk;
+    const int ncta = D;
     ClGwParams p{T, (long long)n_rows * s.HS, s.HS, s.HS, X, x_bstride, ldx, D, out, o_bstride, ldo, n_rows, rchunk, s.nsp, s.ns, D / H,
-                 AtSmem::g_raw_slots(s.HS, D), 0, x_bstride == 0 ? 1 : 0};
-    dim3 grid((unsigned)nsplit, (unsigned)B);
+                 AtSmem::g_raw_slots(s.HS, ncta), 0, x_bstride == 0 ? 1 : 0, ncta, B, nsplit};
+    const long long items = (long long)B * nsplit;
+    const unsigned grid = (unsigned)(items < sms ? items : sms);
     // both operands as (columns, rows of a cloud, clouds): one box = the 32 rows of a chunk, all columns
     CUtensorMap tma, tmb;
     PCA_TRY(make_tmap_3d_f32(&tma, T, (unsigned long long)s.HS, (unsigned long long)n_rows, (unsigned long long)B, (unsigned long long)s.HS * 4,
                              (unsigned long long)n_rows * s.HS * 4, (unsigned)s.HS, AT_KC));
     PCA_TRY(make_tmap_3d_f32(&tmb, X, (unsigned long long)D, (unsigned long long)n_rows, p.b_shared ? 1ull : (unsigned long long)B,
-                             (unsigned long long)ldx * 4, (unsigned long long)(p.b_shared ? (long long)n_rows * ldx : x_bstride) * 4, (unsigned)D,
+                             (unsigned long long)ldx * 4, (unsigned long long)(p.b_shared ? (long long)n_rows * ldx : x_bstride) * 4, (unsigned)ncta,
                              AT_KC));
     {
         LaunchTimer lt("attn_g3_tc_kernel", st, 2.0 * B * (double)n_rows * s.HS * D, 4.0 * B * (double)n_rows * (s.HS + D));
-        cloud_gw_tc_kernel<<<grid, AT_THREADS, AtSmem::g_total(s.HS, D, p.raw_slots), st>>>(p, tma, tmb);
+        cloud_gw_tc_kernel<<<grid, AT_THREADS, AtSmem::g_total(s.HS, ncta, p.raw_slots), st>>>(p, tma, tmb);
     }
     PCA_CHECK_LAUNCH("cloud_gw_tc_kernel");
     return 0;

@@ -101,6 +101,7 @@ int launch_attn(const float* Qp, long long q_bstride, const float* KV, int B, in
 size_t attn_part_floats(int B, int nq, int nk, int D, int H);
 // attention with one small side (<= 16 queries or keys) as split-bf16 tcgen05 GEMMs (attn_tc.cu); scratch sizes in floats
 bool attn_tc_eligible(int B, int nq, int nk, int D, int H);
+int attn_tc_kind(int B, int nq, int nk, int D, int H);
 size_t attn_tc_fwd_floats(int B, int nq, int nk, int D, int H);
 size_t attn_tc_bwd_floats(int B, int nq, int nk, int D, int H);
 int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D, int H, float* O, float* scratch,

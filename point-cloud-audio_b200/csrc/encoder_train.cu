@@ -750,7 +750,7 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
         PCA_TRY(launch_layernorm_bwd(dO, s.Opre, m.ln0w, rq, D, dO, (float*)g.ln0w, (float*)g.ln0b, st));
         Oatt = s.Opre;
     }
-    {
+    if (!(attn_tc && attn_tc_kind(B, nq, nk, D, H) == 1)) {      // (the small-key tensor-core backward computes sum_m P dP in its epilogue)
         const long long total = rq * H;
         if (D % 32 == 0 && 32 % H == 0)
             attn_delta_warp_kernel<<<(unsigned)((rq + 7) / 8), 256, 0, st>>>(dO, Oatt, s.Qp, q_bstride, nq, D, H, rq, delta);
