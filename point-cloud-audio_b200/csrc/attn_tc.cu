@@ -435,6 +435,7 @@ struct ClGwParams {
     int raw_slots, a_shared, b_shared;
     int ncta;              // columns of X per CTA (= N)
     int B, nsplit;         // work items = B clouds x nsplit row ranges
+    const int* counts;     // nullable: rows of X past counts[b] are padding (possibly NaN) and are read as zeros
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwParams P, const __grid_constant__ CUtensorMap tma,
@@ -505,12 +506,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
         const int q = lane >> 3, piece = lane & 7;
         const bool odd = piece & 1;
         const int a_fblocks = (P.Mtot + 31) / 32, b_fblocks = P.ncta / 32;
-        int total_chunks = 0;
+        int c = 0;                                            // global chunk index: ring slots and stages run across items
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-            int b, r0;
-            total_chunks += item_rows(it, b, r0);
-        }
-        for (int c = set; c < total_chunks; c += AT_PSETS) {  // global chunk index: the conversion does not depend on the item
+          int b, r0;
+          const int nchunks = item_rows(it, b, r0);
+          const int n_valid = P.counts ? max(1, min(P.n_rows, __ldg(P.counts + b))) : P.n_rows;
+          for (int ci = 0; ci < nchunks; ++ci, ++c) {
+            if ((c & (AT_PSETS - 1)) != set) continue;
+            const int rows_valid = n_valid - (r0 + ci * AT_KC);       // rows of this chunk that are real points
             const int slot = c % P.raw_slots;
             const int stage = c % AtSmem::G_OP_STAGES;
             mbar_wait(&raw_full[slot], (c / P.raw_slots) & 1);
@@ -548,6 +551,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
                 if (i < b_fblocks) {                                  // warp-uniform
                     float x[8];
                     at_pair_exchange(vb[2 * i], vb[2 * i + 1], odd, x);
+                    if (k >= rows_valid) {                            // padding row (0 x NaN would poison the sums)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) x[j] = 0.f;
+                    }
                     uint4 hi, lo;
                     at_split8(x, hi, lo);
                     const int off = (4 * i + (piece >> 1)) * AtSmem::G_SBO + k * 16;
@@ -558,6 +565,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
             at_warp_arrive(&raw_empty[slot]);
             fence_async_smem();
             at_warp_arrive(&full[stage]);
+          }
         }
     } else if (warp == AT_MMA_WARP) {
         const uint32_t idesc = idesc_bf16(128, P.ncta, 1, 1);
@@ -637,12 +645,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
 // ------------------------------------------------------------------------------------ column softmax (points = keys)
 // T (B, n_rows, HS) raw scores -> probabilities over the rows of a cloud, in place: P = 2^(s c - lse), lse = log2 sum_r 2^(s c).
 // Block = (32 columns, cloud); lane = column (128-byte coalesced rows), warp = row slice.
-__global__ void __launch_bounds__(256) col_softmax_kernel(float* __restrict__ T, int n_rows, int HS, int nsp, int ns, int H,
-                                                          float scale_log2e, float* __restrict__ lse_out) {
+// key_counts (nullable; variable-size sets): only the first key_counts[b] rows of cloud b are keys, the rest get probability 0.
+__global__ void __launch_bounds__(256) col_softmax_kernel(float* __restrict__ T, int n_all, int HS, int nsp, int ns, int H,
+                                                          float scale_log2e, float* __restrict__ lse_out,
+                                                          const int* __restrict__ key_counts) {
     __shared__ float red[8][33];
     const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
-    float* t = T + (long long)b * n_rows * HS + c;
+    float* t = T + (long long)b * n_all * HS + c;
+    const int n_rows = key_counts ? max(1, min(n_all, __ldg(key_counts + b))) : n_all;
+    for (int r = n_rows + w; r < n_all; r += 8) t[(long long)r * HS] = 0.f;
     float m = -INFINITY;
 #pragma unroll 4
     for (int r = w; r < n_rows; r += 8) m = fmaxf(m, t[(long long)r * HS] * scale_log2e);
@@ -784,10 +796,12 @@ static int launch_cloud_linear(ClinParams p, int nsp, const char* name, cudaStre
 }
 
 static int launch_cloud_gw(const float* T, const float* X, long long x_bstride, int ldx, float* out, long long o_bstride, int ldo, int B,
-                           int n_rows, const AtcShape& s, int D, int H, cudaStream_t st) {
+                           int n_rows, const AtcShape& s, int D, int H, cudaStream_t st, bool one_range, const int* counts = nullptr) {
     const int sms = sm_count();
-    // row ranges per cloud: as many as keep an item >= 128 rows and fill the last round of the persistent CTAs best
-    const int max_split = n_rows / 128 > 0 ? n_rows / 128 : 1;
+    // row ranges per cloud: as many as keep an item >= 128 rows and fill the last round of the persistent CTAs best.  one_range
+    // (the forward pass): a cloud is ONE item, so every output element receives exactly one addition and the result is bit-
+    // reproducible and independent of the batch the cloud sits in (several ranges add in whatever order the CTAs finish).
+    const int max_split = one_range ? 1 : (n_rows / 128 > 0 ? n_rows / 128 : 1);
     int nsplit = 1;
     double best = 0.0;
     for (int c = 1; c <= max_split && c <= 8; ++c) {
@@ -800,7 +814,7 @@ static int launch_cloud_gw(const float* T, const float* X, long long x_bstride, 
     nsplit = (n_rows + rchunk - 1) / rchunk;
     const int ncta = D;
     ClGwParams p{T, (long long)n_rows * s.HS, s.HS, s.HS, X, x_bstride, ldx, D, out, o_bstride, ldo, n_rows, rchunk, s.nsp, s.ns, D / H,
-                 AtSmem::g_raw_slots(s.HS, ncta), 0, x_bstride == 0 ? 1 : 0, ncta, B, nsplit};
+                 AtSmem::g_raw_slots(s.HS, ncta), 0, x_bstride == 0 ? 1 : 0, ncta, B, nsplit, counts};
     const long long items = (long long)B * nsplit;
     const unsigned grid = (unsigned)(items < sms ? items : sms);
     // both operands as (columns, rows of a cloud, clouds): one box = the 32 rows of a chunk, all columns
@@ -821,8 +835,9 @@ static int launch_cloud_gw(const float* T, const float* X, long long x_bstride, 
 // O (B, nq, D) = Qp + softmax_h(Qp K^T / sqrt(D)) V per head; lse (B, nq, H) optional (log2 domain, as attn_f32_kernel writes it).
 // scratch: attn_tc_fwd_floats floats.
 int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D, int H, float* O, float* scratch,
-                   cudaStream_t st, float* lse) {
+                   cudaStream_t st, float* lse, const int* key_counts) {
     const AtcShape s = atc_shape(B, nq, nk, D, H);
+    if (key_counts && s.type != 2) return fail(PCA_EUNSUPPORTED, "attn_tc: key counts need the small-query form");
     if (!s.type) return fail(PCA_EUNSUPPORTED, "attn_tc: shape (B=%d, nq=%d, nk=%d, D=%d, H=%d) not eligible", B, nq, nk, D, H);
     if (!scratch) return fail(PCA_EWORKSPACE, "attn_tc: no scratch");
     PCA_TRY(attn_tc_configure());
@@ -864,7 +879,7 @@ int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B,
     PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<store>");
     {
         LaunchTimer lt("col_softmax_kernel", st, 0.0, 8.0 * B * (double)nk * s.HS);
-        col_softmax_kernel<<<dim3((unsigned)(s.HS / 32), (unsigned)B), 256, 0, st>>>(T, nk, s.HS, s.nsp, s.ns, H, sl2e, lse);
+        col_softmax_kernel<<<dim3((unsigned)(s.HS / 32), (unsigned)B), 256, 0, st>>>(T, nk, s.HS, s.nsp, s.ns, H, sl2e, lse, key_counts);
     }
     PCA_CHECK_LAUNCH("col_softmax_kernel");
     {
@@ -872,7 +887,7 @@ int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B,
         bcast_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Qp, q_bstride, n, total, O);
         PCA_CHECK_LAUNCH("bcast_rows_kernel");
     }
-    return launch_cloud_gw(T, KV + D, (long long)nk * 2 * D, 2 * D, O, (long long)nq * D, D, B, nk, s, D, H, st);
+    return launch_cloud_gw(T, KV + D, (long long)nk * 2 * D, 2 * D, O, (long long)nq * D, D, B, nk, s, D, H, st, true, key_counts);
 }
 
 // Gradients of the attention above.  dQp (B, nq, D) is OVERWRITTEN with dO (the residual path) + the attention part; dKV
@@ -924,8 +939,8 @@ int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, co
         PCA_TRY(launch_cloud_linear<EPI_RESID>(g, s.nsp, "attn_g2_resid_tc_kernel", st));
         PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<resid>");
         PCA_CHECK_CUDA(cudaMemsetAsync(dKV, 0, (size_t)B * nk * 2 * D * sizeof(float), st));
-        PCA_TRY(launch_cloud_gw(dS, Qp, q_bstride, D, dKV, kv_bs, 2 * D, B, nq, s, D, H, st));         // dK = dS^T Qp
-        return launch_cloud_gw(Pm, dO, (long long)nq * D, D, dKV + D, kv_bs, 2 * D, B, nq, s, D, H, st);   // dV = P^T dO
+        PCA_TRY(launch_cloud_gw(dS, Qp, q_bstride, D, dKV, kv_bs, 2 * D, B, nq, s, D, H, st, false));         // dK = dS^T Qp
+        return launch_cloud_gw(Pm, dO, (long long)nq * D, D, dKV + D, kv_bs, 2 * D, B, nq, s, D, H, st, false);   // dV = P^T dO
     }
     if (!delta || !lse) return fail(PCA_EINVAL, "attn_bwd_tc: the small-query form needs lse and delta");
     const int nb = q_bstride ? B : 1;
@@ -962,7 +977,7 @@ int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, co
     PCA_TRY(launch_cloud_linear<EPI_STORE>(gv, s.nsp, "attn_g2_store_tc_kernel", st));
     PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<store>");
     PCA_CHECK_CUDA(cudaMemcpyAsync(dQp, dO, (size_t)B * nq * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    return launch_cloud_gw(dS, KV, kv_bs, 2 * D, dQp, o_bs, D, B, nk, s, D, H, st);           // dQp = dO + dS^T K
+    return launch_cloud_gw(dS, KV, kv_bs, 2 * D, dQp, o_bs, D, B, nk, s, D, H, st, false);    // dQp = dO + dS^T K
 }
 
 }  // namespace pca

@@ -105,7 +105,7 @@ int attn_tc_kind(int B, int nq, int nk, int D, int H);
 size_t attn_tc_fwd_floats(int B, int nq, int nk, int D, int H);
 size_t attn_tc_bwd_floats(int B, int nq, int nk, int D, int H);
 int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D, int H, float* O, float* scratch,
-                   cudaStream_t st, float* lse);
+                   cudaStream_t st, float* lse, const int* key_counts = nullptr);
 int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse, const float* delta,
                        int B, int nq, int nk, int D, int H, float* dQp, float* dKV, float* scratch, cudaStream_t st);
 void set_attn_tc(int on);

@@ -446,7 +446,9 @@ int launch_attn(const float* Qp, long long q_bstride, const float* KV, int B, in
     if (H < 1 || H > 32 || D % H) return fail(PCA_EUNSUPPORTED, "attention: need 1 <= H <= 32 and D %% H == 0 (D=%d, H=%d)", D, H);
     if (B > 65535) return fail(PCA_EUNSUPPORTED, "attention: batch chunk %d exceeds the grid limit", B);
     // one small side (inducing points / seeds against a large set): Q K^T and P V as split-bf16 tensor-core GEMMs
-    if (!key_counts && attn_tc_eligible(B, nq, nk, D, H)) return launch_attn_tc(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st, lse);
+    // (variable-size sets: the key counts only arise where the points are the keys, i.e. in the small-query form)
+    if (attn_tc_eligible(B, nq, nk, D, H) && (!key_counts || attn_tc_kind(B, nq, nk, D, H) == 2))
+        return launch_attn_tc(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st, lse, key_counts);
     switch (D / H) {
         case 4: return launch_attn_t<4, 2>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
         case 8: return launch_attn_t<8, 2>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
