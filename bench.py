@@ -259,6 +259,19 @@ def run_extra_configs(args, dev, rank, world, local):
                  "precision": "fp32", "global_batch": Bg, "local_batch": hi - lo, "ms_per_step": ms, "value": Bg / ms * 1e3,
                  "unit": "clouds/s", "achieved_tflops": 3 * flops_fwd * Bg / ms / 1e9, "n_gpus": world, "scaling": "strong",
                  "allreduce_bytes_per_step": int(sum(p.numel() for p in model.parameters()) * 4) if world > 1 else 0, "clocks": clocks})
+    # the same model, inference forward (eval mode, no dropout) on the local shard: every linear layer and every attention
+    # contraction as split-bf16 tcgen05 GEMMs (fp32 parity class)
+    model.eval()
+    Xs = [pl[0] for pl in pool]
+    sampler = ClockSampler(local)
+    sampler.start()
+    with torch.no_grad():
+        ms = timed(lambda i: model(Xs[i % len(Xs)]), 10)
+    clocks = sampler.stop()
+    recs.append({"config": "5 (inference): main_pointcloud.SetTransformer(256, 4 heads, 16 inducing points) forward on 1000-point clouds",
+                 "precision": "fp32 (split-bf16 tensor-core GEMMs + attention)", "global_batch": Bg, "local_batch": hi - lo,
+                 "ms_per_pass": ms, "value": Bg / ms * 1e3, "unit": "clouds/s", "achieved_tflops": flops_fwd * Bg / ms / 1e9,
+                 "n_gpus": world, "scaling": "strong", "clocks": clocks})
     return recs
 
 

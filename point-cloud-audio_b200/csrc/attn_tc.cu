@@ -712,6 +712,9 @@ static AtcShape atc_shape(int B, int nq, int nk, int D, int H) {
     for (int cand = 8; cand <= 16; cand *= 2)
         if (cand >= ns && (H * cand == 32 || H * cand == 64)) { nsp = cand; break; }
     if (!nsp || (long long)B * big < 512) return s;
+    // the (points, HS) score matrix travels through HBM several times: worth it only while it is much narrower than the
+    // activations (ModelNet: 64 of 256 columns; the audio models' PMA -- 8 heads x 8 padded columns against D = 64 -- is not)
+    if (2 * H * nsp > D) return s;
     s.type = type; s.ns = ns; s.nsp = nsp; s.HS = H * nsp; s.big = big;
     return s;
 }

@@ -109,6 +109,7 @@ def test_attn_tc_not_eligible_shapes(L):
     assert lib.pca_debug_attn_tc_eligible(8, 100, 16, 256, 4) == 0        # large side below one tile
     assert lib.pca_debug_attn_tc_eligible(8, 16, 16, 256, 4) == 0         # both sides small (SAB decoder)
     assert lib.pca_debug_attn_tc_eligible(8, 1000, 16, 100, 4) == 0       # dim_V not a multiple of 32
+    assert lib.pca_debug_attn_tc_eligible(64, 1, 1025, 64, 8) == 0        # audio PMA: 8 heads x 8 padded columns are as wide as D = 64
 
 
 def test_modelnet_model_attention_paths_agree(L):
@@ -144,3 +145,28 @@ def test_modelnet_model_attention_paths_agree(L):
     for ga, gb in zip(a[1], b[1]):
         # relative to the tensor's own scale, with a floor: the key-bias gradients are zero up to rounding (softmax is shift invariant)
         assert ((ga - gb).abs().max() / gb.abs().max().clamp_min(1e-4 * gmax)).item() < 1e-3
+
+
+def test_modelnet_model_variable_size_sets(L):
+    """Variable-size sets through the tensor-core attention (masked column softmax, NaN padding never read as a key): the
+    result equals the model applied to X[b:b+1, :counts[b]], and an all-valid mask reproduces the unmasked path bit for bit."""
+    import pcaudio_b200 as pca
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    model = pca.SetTransformer(dim_hidden=256, num_heads=4, num_inds=16).to(dev).eval()
+    counts = [1000, 999, 513, 128, 700, 1]
+    X = torch.randn(len(counts), 1000, 3, device=dev)
+    Xpad = X.clone()
+    for b, c in enumerate(counts):
+        Xpad[b, c:] = float("nan")
+    with torch.no_grad():
+        out = model(Xpad, counts=torch.tensor(counts, dtype=torch.int32, device=dev))
+        assert torch.isfinite(out).all()
+        try:
+            L.lib().pca_debug_set_attn_tc(0)             # per-sample reference on the CUDA-core kernels (short sets are not eligible anyway)
+            ref = torch.stack([model(X[b:b + 1, :c]).reshape(-1) for b, c in enumerate(counts)])
+        finally:
+            L.lib().pca_debug_set_attn_tc(1)
+        assert ((out.reshape(ref.shape) - ref).abs().max() / ref.abs().max()).item() < 1e-4
+        full = torch.full((len(counts),), 1000, dtype=torch.int32, device=dev)
+        assert torch.equal(model(X, counts=full), model(X))
