@@ -373,6 +373,7 @@ struct GwTcParams {
     long long rows, rchunk;
     int lda, Mtot, N;
     int mbox, raw_slots;     // columns of dY per raw chunk (min(128, Mtot)); raw chunks in the TMA ring
+    int nsplit, mtiles;      // work items = nsplit row ranges x mtiles 128-row blocks of dW
 };
 // 8-feature group g of chunk row k at g * G_SBO + k * 16 with G_SBO = 512 + 16 (padded: the four groups a quarter warp stores
 // fall into distinct banks)
@@ -404,20 +405,28 @@ __global__ void __launch_bounds__(LT_THREADS, 1) grad_weight_tc_kernel(const GwT
     uint64_t* bars = reinterpret_cast<uint64_t*>(trans + 4 * 32 * 33 * 4);
     uint64_t* full = bars;                                   // [2] count 4 (the converter warps of a set)
     uint64_t* empty = bars + GwTcSmem::OP_STAGES;            // [2] count 1
-    uint64_t* acc_full = bars + 2 * GwTcSmem::OP_STAGES;     // count 1
-    uint64_t* raw_full = acc_full + 1;                       // [4] count 1 (expect_tx of the loader) + the chunk's bytes
+    uint64_t* acc_full = bars + 2 * GwTcSmem::OP_STAGES;     // [2] count 1
+    uint64_t* acc_empty = acc_full + 2;                      // [2] count 4 (epilogue warps)
+    uint64_t* raw_full = acc_empty + 2;                      // [4] count 1 (expect_tx of the loader) + the chunk's bytes
     uint64_t* raw_empty = raw_full + GwTcSmem::RAW_MAX;      // [4] count 4
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + GwTcSmem::RAW_MAX);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * 128;
-    const long long r0 = (long long)blockIdx.x * P.rchunk;   // a multiple of the chunk size: a chunk never straddles two CTAs' ranges
-    const long long r1 = (r0 + P.rchunk < P.rows) ? r0 + P.rchunk : P.rows;
-    const int nchunks = (int)((r1 - r0 + GT_KC - 1) / GT_KC);
+    // Persistent: work item = (row range of rchunk rows -- a multiple of the chunk size --, 128-row block of dW); this CTA walks
+    // the items blockIdx.x, + gridDim.x, ...; ring slots and operand stages run across item boundaries (global chunk counter)
+    // and two accumulators let the reductions of an item overlap the chunks of the next one.
+    const int n_items = P.nsplit * P.mtiles;
+    auto item_rows = [&](int it, int& m0, long long& r0) -> int {      // chunks of the item (items of one row range are adjacent)
+        const int sp = it / P.mtiles;
+        m0 = (it - sp * P.mtiles) * 128;
+        r0 = (long long)sp * P.rchunk;
+        const long long r1 = (r0 + P.rchunk < P.rows) ? r0 + P.rchunk : P.rows;
+        return (int)((r1 - r0 + GT_KC - 1) / GT_KC);
+    };
 
-    if (warp == GT_MMA_WARP) tmem_alloc(tmem_slot, 256);
+    if (warp == GT_MMA_WARP) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
         for (int i = 0; i < GwTcSmem::OP_STAGES; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         for (int i = 0; i < GwTcSmem::RAW_MAX; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 4); }
         fence_barrier_init();
     }
@@ -432,14 +441,20 @@ __global__ void __launch_bounds__(LT_THREADS, 1) grad_weight_tc_kernel(const GwT
         if (lane == 0) {
             tma_prefetch_desc(&tma);
             tma_prefetch_desc(&tmb);
-            for (int c = 0; c < nchunks; ++c) {
-                const int slot = c % P.raw_slots;
-                if (c >= P.raw_slots) mbar_wait(&raw_empty[slot], ((c / P.raw_slots) - 1) & 1);
-                mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)raw_bytes);
-                uint8_t* dst = smem + slot * raw_bytes;
-                const int row = (int)(r0 + (long long)c * GT_KC);
-                tma_load_3d(dst, &tma, m0, row, 0, &raw_full[slot]);
-                tma_load_3d(dst + GT_KC * P.mbox * 4, &tmb, 0, row, 0, &raw_full[slot]);
+            int gc = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                int m0;
+                long long r0;
+                const int nchunks = item_rows(it, m0, r0);
+                for (int c = 0; c < nchunks; ++c, ++gc) {
+                    const int slot = gc % P.raw_slots;
+                    if (gc >= P.raw_slots) mbar_wait(&raw_empty[slot], ((gc / P.raw_slots) - 1) & 1);
+                    mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)raw_bytes);
+                    uint8_t* dst = smem + slot * raw_bytes;
+                    const int row = (int)(r0 + (long long)c * GT_KC);
+                    tma_load_3d(dst, &tma, m0, row, 0, &raw_full[slot]);
+                    tma_load_3d(dst + GT_KC * P.mbox * 4, &tmb, 0, row, 0, &raw_full[slot]);
+                }
             }
         }
     } else if (warp < GT_MMA_WARP) {
@@ -451,7 +466,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1) grad_weight_tc_kernel(const GwT
         const int q = lane >> 3, piece = lane & 7;
         const bool odd = piece & 1;
         const int a_fblocks = P.mbox / 32, b_fblocks = P.N / 32;
-        for (int c = set; c < nchunks; c += GT_PSETS) {
+        int total_chunks = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            int m0;
+            long long r0;
+            total_chunks += item_rows(it, m0, r0);
+        }
+        for (int c = set; c < total_chunks; c += GT_PSETS) {  // global chunk index: the conversion does not depend on the item
             const int slot = c % P.raw_slots;
             const int stage = c % GwTcSmem::OP_STAGES;
             mbar_wait(&raw_full[slot], (c / P.raw_slots) & 1);
@@ -502,53 +523,72 @@ __global__ void __launch_bounds__(LT_THREADS, 1) grad_weight_tc_kernel(const GwT
         }
     } else if (warp == GT_MMA_WARP) {
         const uint32_t idesc = idesc_bf16(128, P.N, 1, 1);
-        for (int c = 0; c < nchunks; ++c) {
-            const int stage = c % GwTcSmem::OP_STAGES;
-            mbar_wait(&full[stage], (c / GwTcSmem::OP_STAGES) & 1);
+        int gc = 0, k = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+            int m0;
+            long long r0;
+            const int nchunks = item_rows(it, m0, r0);
+            const uint32_t buf = k & 1;
+            if (k >= 2) mbar_wait(&acc_empty[buf], ((k >> 1) - 1) & 1);
             fence_after_sync();
-            if (elect_one()) {
-                const uint32_t a_hi = smem_u32(ops + stage * GwTcSmem::STAGE);
-                const uint32_t a_lo = a_hi + GwTcSmem::A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * GwTcSmem::A_BYTES;
-                const uint32_t b_lo = b_hi + GwTcSmem::B_BYTES;
+            const uint32_t acc = tmem_addr(tb, 0, 256 * buf);
+            for (int c = 0; c < nchunks; ++c, ++gc) {
+                const int stage = gc % GwTcSmem::OP_STAGES;
+                mbar_wait(&full[stage], (gc / GwTcSmem::OP_STAGES) & 1);
+                fence_after_sync();
+                if (elect_one()) {
+                    const uint32_t a_hi = smem_u32(ops + stage * GwTcSmem::STAGE);
+                    const uint32_t a_lo = a_hi + GwTcSmem::A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * GwTcSmem::A_BYTES;
+                    const uint32_t b_lo = b_hi + GwTcSmem::B_BYTES;
 #pragma unroll
-                for (int ks = 0; ks < GT_KC / 16; ++ks) {
-                    // MN-major: a K step of 16 rows = two 8-row groups = 256 bytes further
-                    const uint64_t dah = smem_desc(a_hi + ks * 256, 128, GwTcSmem::G_SBO), dal = smem_desc(a_lo + ks * 256, 128, GwTcSmem::G_SBO);
-                    const uint64_t dbh = smem_desc(b_hi + ks * 256, 128, GwTcSmem::G_SBO), dbl = smem_desc(b_lo + ks * 256, 128, GwTcSmem::G_SBO);
-                    mma_ss(tb, dah, dbh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-                    mma_ss(tb, dal, dbh, idesc, 1u);
-                    mma_ss(tb, dah, dbl, idesc, 1u);
+                    for (int ks = 0; ks < GT_KC / 16; ++ks) {
+                        // MN-major: a K step of 16 rows = two 8-row groups = 256 bytes further
+                        const uint64_t dah = smem_desc(a_hi + ks * 256, 128, GwTcSmem::G_SBO), dal = smem_desc(a_lo + ks * 256, 128, GwTcSmem::G_SBO);
+                        const uint64_t dbh = smem_desc(b_hi + ks * 256, 128, GwTcSmem::G_SBO), dbl = smem_desc(b_lo + ks * 256, 128, GwTcSmem::G_SBO);
+                        mma_ss(acc, dah, dbh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                        mma_ss(acc, dal, dbh, idesc, 1u);
+                        mma_ss(acc, dah, dbl, idesc, 1u);
+                    }
+                    mma_commit(&empty[stage]);
+                    if (c == nchunks - 1) mma_commit(&acc_full[buf]);
                 }
-                mma_commit(&empty[stage]);
-                if (c == nchunks - 1) mma_commit(acc_full);
+                __syncwarp();
             }
-            __syncwarp();
         }
-    } else if (warp < GT_LOAD_WARP && nchunks > 0) {
+    } else if (warp < GT_LOAD_WARP) {
         const int quad = warp & 3;
         float* T = reinterpret_cast<float*>(trans) + quad * (32 * 33);
-        mbar_wait(acc_full, 0);
-        fence_after_sync();
-        for (int c0 = 0; c0 < P.N; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_addr(tb, 32 * quad, c0), v);
-            tmem_ld_wait32(v);
+        int k = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+            int m0;
+            long long r0;
+            item_rows(it, m0, r0);
+            const uint32_t buf = k & 1;
+            mbar_wait(&acc_full[buf], (k >> 1) & 1);
+            fence_after_sync();
+            for (int c0 = 0; c0 < P.N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_addr(tb, 32 * quad, 256 * buf + c0), v);
+                tmem_ld_wait32(v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
-            __syncwarp();
-            // lane = column: one 128-byte reduction per row and instruction
+                for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
+                __syncwarp();
+                // lane = column: one 128-byte reduction per row and instruction
 #pragma unroll 4
-            for (int lr = 0; lr < 32; ++lr) {
-                const int m = m0 + 32 * quad + lr;
-                if (m < P.Mtot) atomicAdd(P.dW + (long long)m * P.N + c0 + lane, T[lr * 33 + lane]);
+                for (int lr = 0; lr < 32; ++lr) {
+                    const int m = m0 + 32 * quad + lr;
+                    if (m < P.Mtot) atomicAdd(P.dW + (long long)m * P.N + c0 + lane, T[lr * 33 + lane]);
+                }
+                __syncwarp();
             }
-            __syncwarp();
+            fence_before_sync();
+            gt_warp_arrive(&acc_empty[buf]);
         }
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == GT_MMA_WARP) tmem_dealloc(tb, 256);
+    if (warp == GT_MMA_WARP) tmem_dealloc(tb, 512);
 }
 
 static int gemm_tc_configure() {
@@ -575,21 +615,23 @@ int launch_grad_weight_tc(const float* dY, const float* X, float* dW, long long 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // one CTA per SM (227 KB of shared memory): whole waves only -- 2 x #SMs CTAs when every CTA still gets >= 256 rows, else
-    // #SMs (250 CTAs on 148 SMs run as long as 296), else whatever the row count allows
-    long long nsplit = (2LL * sms + mtiles - 1) / mtiles;
+    // persistent CTAs (one per SM) over (row range, 128-row block of dW) items: the number of row ranges that fills the last
+    // round best while an item keeps >= 256 rows (every item ends in 128 x N atomic reductions)
     const long long max_split = (rows + 8 * GT_KC - 1) / (8 * GT_KC);
-    if (nsplit > max_split) {
-        const long long one_wave = (sms + mtiles - 1) / mtiles;
-        nsplit = one_wave <= max_split ? one_wave : max_split;
+    long long nsplit = 1;
+    double best = 0.0;
+    for (long long c = 1; c <= max_split && c * mtiles <= 8LL * sms; ++c) {
+        const long long items = c * mtiles;
+        const double fill = (double)items / (double)(((items + sms - 1) / sms) * sms);
+        if (fill > best + 0.02) { best = fill; nsplit = c; }
     }
-    if (nsplit < 1) nsplit = 1;
     long long rchunk = (rows + nsplit - 1) / nsplit;
     rchunk = (rchunk + GT_KC - 1) / GT_KC * GT_KC;
     nsplit = (rows + rchunk - 1) / rchunk;
     const int mbox = M < 128 ? M : 128;
-    GwTcParams p{dY, X, dW, rows, rchunk, M, M, N, mbox, GwTcSmem::raw_slots(mbox, N)};
-    dim3 grid((unsigned)nsplit, mtiles);
+    GwTcParams p{dY, X, dW, rows, rchunk, M, M, N, mbox, GwTcSmem::raw_slots(mbox, N), (int)nsplit, mtiles};
+    const long long n_items = nsplit * mtiles;
+    const unsigned grid = (unsigned)(n_items < sms ? n_items : sms);
     CUtensorMap tma, tmb;             // dY as (M, rows), X as (N, rows): one box = the 32 rows of a chunk
     PCA_TRY(make_tmap_3d_f32(&tma, dY, (unsigned long long)M, (unsigned long long)rows, 1ull, (unsigned long long)M * 4,
                              (unsigned long long)rows * M * 4, (unsigned)mbox, GT_KC));
