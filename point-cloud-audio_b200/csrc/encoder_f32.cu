@@ -127,6 +127,42 @@ linear_skinny_kernel(const float* __restrict__ X, const float* __restrict__ W, c
     Y[(long long)r * dout + c] = v;
 }
 
+// Y (rows, dout) = X (rows, din) W^T + b for the first layers over raw points (din <= 4: (f, mag) / (f, t, mag) / xyz): the layer is
+// bound by writing Y, so a thread produces four consecutive columns of one row from registers (its W rows and bias) and the row's
+// din coordinates (a broadcast load), and a warp writes 512 contiguous bytes.  The 128x64 register-tiled GEMM spent a 16-deep K
+// loop on 3 terms (0.13 ms per 256 000 x 3 -> 256 launch; this kernel is at the write bandwidth).
+template <int DIN>
+__global__ void __launch_bounds__(256) linear_tinyk_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ b,
+                                                           float* __restrict__ Y, long long rows, int dout) {
+    const int cq = dout >> 2;                                   // float4 column groups per row
+    const int c4 = (blockIdx.y * blockDim.x + threadIdx.x) % cq;
+    const int rsub = (blockIdx.y * blockDim.x + threadIdx.x) / cq;
+    const int rstep = (gridDim.y * blockDim.x) / cq;
+    if (rstep == 0 || rsub >= rstep) return;
+    float w[4][DIN], bb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        bb[u] = __ldg(b + 4 * c4 + u);
+#pragma unroll
+        for (int k = 0; k < DIN; ++k) w[u][k] = __ldg(W + (long long)(4 * c4 + u) * DIN + k);
+    }
+    const long long r_end = min(rows, (long long)(blockIdx.x + 1) * 256);
+    for (long long r = (long long)blockIdx.x * 256 + rsub; r < r_end; r += rstep) {
+        float x[DIN];
+#pragma unroll
+        for (int k = 0; k < DIN; ++k) x[k] = __ldg(X + r * DIN + k);
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < DIN; ++k) a = fmaf(x[k], w[u][k], a);
+            o[u] = a + bb[u];
+        }
+        *reinterpret_cast<float4*>(Y + r * dout + 4 * c4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 int launch_linear(const float* X, const float* W, const float* b, float* Y, long long rows, int din,
                   int dout, int mode, cudaStream_t st, float* R, void* img, size_t img_bytes) {
     if (rows == 0) return 0;
@@ -144,6 +180,19 @@ int launch_linear(const float* X, const float* W, const float* b, float* Y, long
         else if (mode == 2) linear_skinny_kernel<2><<<g, 256, skinny_smem, st>>>(X, W, b, Y, (int)rows, din, dout, nullptr);
         else linear_skinny_kernel<3><<<g, 256, skinny_smem, st>>>(X, W, b, Y, (int)rows, din, dout, R);
         PCA_CHECK_LAUNCH("linear_skinny_kernel");
+        return 0;
+    }
+    if (mode == 0 && din >= 1 && din <= 4 && dout % 4 == 0 && rows >= 1024 && (dout / 4) <= 256 && 256 % (dout / 4) == 0) {
+        // grid.x: 256-row slabs; one block covers (256 / (dout / 4)) rows per step with all column groups
+        dim3 grid((unsigned)((rows + 255) / 256), 1);
+        LaunchTimer lt("linear_tinyk_kernel", st, 2.0 * rows * din * dout, 4.0 * rows * (din + dout));
+        switch (din) {
+            case 1: linear_tinyk_kernel<1><<<grid, 256, 0, st>>>(X, W, b, Y, rows, dout); break;
+            case 2: linear_tinyk_kernel<2><<<grid, 256, 0, st>>>(X, W, b, Y, rows, dout); break;
+            case 3: linear_tinyk_kernel<3><<<grid, 256, 0, st>>>(X, W, b, Y, rows, dout); break;
+            default: linear_tinyk_kernel<4><<<grid, 256, 0, st>>>(X, W, b, Y, rows, dout); break;
+        }
+        PCA_CHECK_LAUNCH("linear_tinyk_kernel");
         return 0;
     }
     dim3 grid((unsigned)((rows + LBM - 1) / LBM), (dout + LBN - 1) / LBN);
