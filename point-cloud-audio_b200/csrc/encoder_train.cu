@@ -281,9 +281,38 @@ static int launch_grad_weight_bias(const float* dY, const float* X, float* dW, f
 }
 
 // ------------------------------------------------------------------------------------ elementwise pieces
+__device__ __forceinline__ void red_add4_fwd(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __global__ void relu_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ R, float* __restrict__ dZ, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dZ[i] = R[i] > 0.f ? dOut[i] : 0.f;
+}
+// The same with the bias gradient folded in: dZ = [R > 0] dOut and db[c] += sum_r dZ[r, c] in ONE pass (the separate column-sum
+// kernel read dZ a second time).  Block = 256-row slab; thread = (float4 column group, row lane); D % 4 == 0, 256 % (D / 4) == 0.
+__global__ void __launch_bounds__(256) relu_bwd_colsum_kernel(const float* __restrict__ dOut, const float* __restrict__ R, float* __restrict__ dZ,
+                                                              long long rows, int D, float* __restrict__ db) {
+    __shared__ float4 red[256];
+    const int cq = D >> 2;
+    const int c4 = threadIdx.x % cq, rsub = threadIdx.x / cq, rstep = 256 / cq;
+    const long long r_end = min(rows, (long long)(blockIdx.x + 1) * 256);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long r = (long long)blockIdx.x * 256 + rsub; r < r_end; r += rstep) {
+        const float4 g = *reinterpret_cast<const float4*>(dOut + r * D + 4 * c4);
+        const float4 a = *reinterpret_cast<const float4*>(R + r * D + 4 * c4);
+        const float4 z = make_float4(a.x > 0.f ? g.x : 0.f, a.y > 0.f ? g.y : 0.f, a.z > 0.f ? g.z : 0.f, a.w > 0.f ? g.w : 0.f);
+        *reinterpret_cast<float4*>(dZ + r * D + 4 * c4) = z;
+        acc.x += z.x; acc.y += z.y; acc.z += z.z; acc.w += z.w;
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (rsub == 0) {
+        for (int j = 1; j < rstep; ++j) {
+            const float4 o = red[j * cq + c4];
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        red_add4_fwd(db + 4 * c4, acc.x, acc.y, acc.z, acc.w);
+    }
 }
 
 // delta (B, nq, H) = sum over the head's dims of dO o (O - Qp)     (= sum_k P dP of the softmax backward)
@@ -756,10 +785,16 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
         PCA_TRY(launch_layernorm_bwd(dOut, s.pre1, m.ln1w, rq, D, g1, (float*)g.ln1w, (float*)g.ln1b, st));
         dOut = g1;
     }
-    relu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dOut, s.R, dZ, n);
-    PCA_CHECK_LAUNCH("relu_bwd_kernel");
+    if (D % 4 == 0 && D / 4 <= 256 && 256 % (D / 4) == 0 && rq >= 256) {      // ReLU mask and the bias gradient in one pass over dOut / R
+        LaunchTimer lt("relu_bwd_colsum_kernel", st, 0.0, 12.0 * rq * D);
+        relu_bwd_colsum_kernel<<<(unsigned)((rq + 255) / 256), 256, 0, st>>>(dOut, s.R, dZ, rq, D, (float*)g.bo);
+        PCA_CHECK_LAUNCH("relu_bwd_colsum_kernel");
+    } else {
+        relu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dOut, s.R, dZ, n);
+        PCA_CHECK_LAUNCH("relu_bwd_kernel");
+        PCA_TRY(launch_colsum(dZ, rq, D, (float*)g.bo, st));
+    }
     PCA_TRY(launch_grad_weight(dZ, s.O, (float*)g.Wo, rq, D, D, st));
-    PCA_TRY(launch_colsum(dZ, rq, D, (float*)g.bo, st));
     PCA_TRY(launch_grad_input(dZ, m.Wo, dO, dOut, rq, D, D, st, img, ib));
     const float* Oatt = s.O;                                    // Qp + A V
     if (ln) {                                                   // through ln0 (in place)
