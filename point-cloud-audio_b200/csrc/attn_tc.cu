@@ -731,6 +731,11 @@ size_t attn_tc_fwd_floats(int B, int nq, int nk, int D, int H) {
     const size_t img = (size_t)s.HS * D;             // floats per cloud image (4 N K bytes)
     return fl((size_t)B * s.big * s.HS) + (s.type == 1 ? 2 : 1) * fl((size_t)B * img);
 }
+// floats of the probability matrix a training forward may keep for the backward (0 when the shape is not eligible)
+size_t attn_tc_p_floats(int B, int nq, int nk, int D, int H) {
+    const AtcShape s = atc_shape(B, nq, nk, D, H);
+    return s.type ? (size_t)B * s.big * s.HS : 0;
+}
 size_t attn_tc_bwd_floats(int B, int nq, int nk, int D, int H) {
     const AtcShape s = atc_shape(B, nq, nk, D, H);
     if (!s.type) return 0;
@@ -838,7 +843,7 @@ static int launch_cloud_gw(const float* T, const float* X, long long x_bstride, 
 // O (B, nq, D) = Qp + softmax_h(Qp K^T / sqrt(D)) V per head; lse (B, nq, H) optional (log2 domain, as attn_f32_kernel writes it).
 // scratch: attn_tc_fwd_floats floats.
 int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D, int H, float* O, float* scratch,
-                   cudaStream_t st, float* lse, const int* key_counts) {
+                   cudaStream_t st, float* lse, const int* key_counts, float* p_out) {
     const AtcShape s = atc_shape(B, nq, nk, D, H);
     if (key_counts && s.type != 2) return fail(PCA_EUNSUPPORTED, "attn_tc: key counts need the small-query form");
     if (!s.type) return fail(PCA_EUNSUPPORTED, "attn_tc: shape (B=%d, nq=%d, nk=%d, D=%d, H=%d) not eligible", B, nq, nk, D, H);
@@ -847,7 +852,7 @@ int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B,
     const float scale = 1.0f / sqrtf((float)D), sl2e = scale * 1.4426950408889634f;
     const size_t imgf = (size_t)s.HS * D;
     const long long img_bytes = (long long)imgf * 4;
-    float* T = scratch;
+    float* T = p_out ? p_out : scratch;          // training: the probabilities are kept (the backward does not recompute them)
     uint8_t* img1 = reinterpret_cast<uint8_t*>(scratch + fl((size_t)B * s.big * s.HS));
     if (s.type == 1) {
         uint8_t* img2 = img1 + fl((size_t)B * imgf) * sizeof(float);
@@ -897,7 +902,7 @@ int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B,
 // (B, nk, 2D) is OVERWRITTEN.  delta (B, nq, H) = sum_d dO (O - Qp) per head is needed only when the queries are the small side.
 // scratch: attn_tc_bwd_floats floats.
 int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse, const float* delta,
-                       int B, int nq, int nk, int D, int H, float* dQp, float* dKV, float* scratch, cudaStream_t st) {
+                       int B, int nq, int nk, int D, int H, float* dQp, float* dKV, float* scratch, cudaStream_t st, const float* p_saved) {
     const AtcShape s = atc_shape(B, nq, nk, D, H);
     if (!s.type) return fail(PCA_EUNSUPPORTED, "attn_bwd_tc: shape (B=%d, nq=%d, nk=%d, D=%d, H=%d) not eligible", B, nq, nk, D, H);
     if (!scratch) return fail(PCA_EWORKSPACE, "attn_bwd_tc: no scratch");
@@ -906,7 +911,8 @@ int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, co
     const size_t imgf = (size_t)s.HS * D;
     const long long img_bytes = (long long)imgf * 4;
     const size_t tf = fl((size_t)B * s.big * s.HS), imf = fl((size_t)B * imgf);
-    float* Pm = scratch;
+    const float* Pm = p_saved ? p_saved : scratch;        // the forward's probabilities when it kept them, else recomputed below
+    float* Pw = scratch;
     float* dS = scratch + tf;
     uint8_t* imgs = reinterpret_cast<uint8_t*>(scratch + 2 * tf);
     auto img_at = [&](int i) { return imgs + (size_t)i * imf * sizeof(float); };
@@ -918,15 +924,17 @@ int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, co
     };
     if (s.type == 1) {
         const long long kv_bs = (long long)nk * 2 * D;
-        PCA_TRY(launch_cloud_image(KV, kv_bs, 2 * D, B, s, D, H, 0, img_at(0), st));          // K as the G1 operand
+        if (!p_saved) PCA_TRY(launch_cloud_image(KV, kv_bs, 2 * D, B, s, D, H, 0, img_at(0), st));   // K as the G1 operand
         PCA_TRY(launch_cloud_image(KV + D, kv_bs, 2 * D, B, s, D, H, 0, img_at(1), st));      // V as the G1 operand
         PCA_TRY(launch_cloud_image(KV, kv_bs, 2 * D, B, s, D, H, 1, img_at(2), st));          // K as the G2 operand
-        ClinParams p = base(nq, D, s.HS);                                                     // P = softmax(Qp K^T)
-        p.X = Qp; p.x_bstride = q_bstride; p.ldx = D;
-        p.img = img_at(0); p.img_bstride = img_bytes;
-        p.Y = Pm; p.y_bstride = t_bstride; p.ldy = s.HS;
-        PCA_TRY(launch_cloud_linear<EPI_SOFTMAX>(p, s.nsp, "attn_g1_softmax_tc_kernel", st));
-        PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<softmax>");
+        if (!p_saved) {
+            ClinParams p = base(nq, D, s.HS);                                                 // P = softmax(Qp K^T)
+            p.X = Qp; p.x_bstride = q_bstride; p.ldx = D;
+            p.img = img_at(0); p.img_bstride = img_bytes;
+            p.Y = Pw; p.y_bstride = t_bstride; p.ldy = s.HS;
+            PCA_TRY(launch_cloud_linear<EPI_SOFTMAX>(p, s.nsp, "attn_g1_softmax_tc_kernel", st));
+            PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<softmax>");
+        }
         ClinParams q = base(nq, D, s.HS);                                                     // dS = P o (dO V^T - delta) scale
         q.X = dO; q.x_bstride = (long long)nq * D; q.ldx = D;
         q.img = img_at(1); q.img_bstride = img_bytes;
@@ -945,20 +953,22 @@ int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, co
         PCA_TRY(launch_cloud_gw(dS, Qp, q_bstride, D, dKV, kv_bs, 2 * D, B, nq, s, D, H, st, false));         // dK = dS^T Qp
         return launch_cloud_gw(Pm, dO, (long long)nq * D, D, dKV + D, kv_bs, 2 * D, B, nq, s, D, H, st, false);   // dV = P^T dO
     }
-    if (!delta || !lse) return fail(PCA_EINVAL, "attn_bwd_tc: the small-query form needs lse and delta");
+    if (!delta || (!lse && !p_saved)) return fail(PCA_EINVAL, "attn_bwd_tc: the small-query form needs delta and lse (or the saved probabilities)");
     const int nb = q_bstride ? B : 1;
     const long long kv_bs = (long long)nk * 2 * D, o_bs = (long long)nq * D;
-    PCA_TRY(launch_cloud_image(Qp, q_bstride, D, nb, s, D, H, 0, img_at(0), st));             // Qp as the G1 operand
+    if (!p_saved) PCA_TRY(launch_cloud_image(Qp, q_bstride, D, nb, s, D, H, 0, img_at(0), st));   // Qp as the G1 operand
     PCA_TRY(launch_cloud_image(Qp, q_bstride, D, nb, s, D, H, 1, img_at(1), st));             // Qp as the G2 operand
     PCA_TRY(launch_cloud_image(dO, o_bs, D, B, s, D, H, 0, img_at(2), st));                   // dO as the G1 operand
     PCA_TRY(launch_cloud_image(dO, o_bs, D, B, s, D, H, 1, img_at(3), st));                   // dO as the G2 operand
-    ClinParams p = base(nk, D, s.HS);                                                         // P = 2^(K Qp^T c - lse)
-    p.X = KV; p.x_bstride = kv_bs; p.ldx = 2 * D;
-    p.img = img_at(0); p.img_bstride = q_bstride ? img_bytes : 0;
-    p.Y = Pm; p.y_bstride = t_bstride; p.ldy = s.HS;
-    p.vec = lse;
-    PCA_TRY(launch_cloud_linear<EPI_P_COL>(p, s.nsp, "attn_g1_pcol_tc_kernel", st));
-    PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<p_col>");
+    if (!p_saved) {
+        ClinParams p = base(nk, D, s.HS);                                                     // P = 2^(K Qp^T c - lse)
+        p.X = KV; p.x_bstride = kv_bs; p.ldx = 2 * D;
+        p.img = img_at(0); p.img_bstride = q_bstride ? img_bytes : 0;
+        p.Y = Pw; p.y_bstride = t_bstride; p.ldy = s.HS;
+        p.vec = lse;
+        PCA_TRY(launch_cloud_linear<EPI_P_COL>(p, s.nsp, "attn_g1_pcol_tc_kernel", st));
+        PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<p_col>");
+    }
     ClinParams q = base(nk, D, s.HS);                                                         // dS = P o (V dO^T - delta) scale
     q.X = KV + D; q.x_bstride = kv_bs; q.ldx = 2 * D;
     q.img = img_at(2); q.img_bstride = img_bytes;

@@ -97,7 +97,7 @@ bool grad_weight_tc_eligible(long long rows, int M, int N);
 int launch_grad_weight_tc(const float* dY, const float* X, float* dW, long long rows, int M, int N, cudaStream_t st);
 void set_gemm_tc(int on);
 int launch_attn(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D, int H, float* O, float* part,
-                const int* key_counts, cudaStream_t st, float* lse = nullptr);
+                const int* key_counts, cudaStream_t st, float* lse = nullptr, float* p_out = nullptr);
 size_t attn_part_floats(int B, int nq, int nk, int D, int H);
 // attention with one small side (<= 16 queries or keys) as split-bf16 tcgen05 GEMMs (attn_tc.cu); scratch sizes in floats
 bool attn_tc_eligible(int B, int nq, int nk, int D, int H);
@@ -105,9 +105,11 @@ int attn_tc_kind(int B, int nq, int nk, int D, int H);
 size_t attn_tc_fwd_floats(int B, int nq, int nk, int D, int H);
 size_t attn_tc_bwd_floats(int B, int nq, int nk, int D, int H);
 int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D, int H, float* O, float* scratch,
-                   cudaStream_t st, float* lse, const int* key_counts = nullptr);
+                   cudaStream_t st, float* lse, const int* key_counts = nullptr, float* p_out = nullptr);
+size_t attn_tc_p_floats(int B, int nq, int nk, int D, int H);
 int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse, const float* delta,
-                       int B, int nq, int nk, int D, int H, float* dQp, float* dKV, float* scratch, cudaStream_t st);
+                       int B, int nq, int nk, int D, int H, float* dQp, float* dKV, float* scratch, cudaStream_t st,
+                       const float* p_saved = nullptr);
 void set_attn_tc(int on);
 int launch_layernorm(float* X, long long rows, int D, const float* g, const float* b, cudaStream_t st);
 

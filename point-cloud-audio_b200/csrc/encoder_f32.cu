@@ -490,14 +490,14 @@ static int launch_attn_t(const float* Qp, long long q_bstride, const float* KV, 
 }
 
 int launch_attn(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D,
-                int H, float* O, float* part, const int* key_counts, cudaStream_t st, float* lse) {
+                int H, float* O, float* part, const int* key_counts, cudaStream_t st, float* lse, float* p_out) {
     if (B == 0 || nq == 0) return 0;
     if (H < 1 || H > 32 || D % H) return fail(PCA_EUNSUPPORTED, "attention: need 1 <= H <= 32 and D %% H == 0 (D=%d, H=%d)", D, H);
     if (B > 65535) return fail(PCA_EUNSUPPORTED, "attention: batch chunk %d exceeds the grid limit", B);
     // one small side (inducing points / seeds against a large set): Q K^T and P V as split-bf16 tensor-core GEMMs
     // (variable-size sets: the key counts only arise where the points are the keys, i.e. in the small-query form)
     if (attn_tc_eligible(B, nq, nk, D, H) && (!key_counts || attn_tc_kind(B, nq, nk, D, H) == 2))
-        return launch_attn_tc(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st, lse, key_counts);
+        return launch_attn_tc(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, st, lse, key_counts, p_out);
     switch (D / H) {
         case 4: return launch_attn_t<4, 2>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);
         case 8: return launch_attn_t<8, 2>(Qp, q_bstride, KV, B, nq, nk, D, H, O, part, key_counts, st, lse);

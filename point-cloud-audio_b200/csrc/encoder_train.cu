@@ -655,7 +655,7 @@ int linear_bwd_api(const float* dY, const float* X, long long rows, int din, int
 
 // ------------------------------------------------------------------------------------ MAB forward (saving) / backward
 // Opre / pre1: the inputs of ln0 / ln1 (LayerNorm branches only; O and out then hold the normalised tensors)
-struct MabSaved { float *Qp, *KV, *O, *R, *lse, *out, *Opre, *pre1; };
+struct MabSaved { float *Qp, *KV, *O, *R, *lse, *out, *Opre, *pre1, *P; };     // P: probabilities of the tensor-core attention (attn_tc.cu)
 
 // ------------------------------------------------------------------------------------ LayerNorm backward
 // y = (x - mean) rstd gamma + beta per row.  dx = rstd (g gamma - mean(g gamma) - xhat mean(g gamma xhat)); dgamma += sum g xhat,
@@ -718,6 +718,8 @@ static MabSaved mab_saved_take(Arena& a, int B, int qb, int nq, int nk, int D, i
     s.out = a.take<float>((size_t)B * nq * D);
     s.Opre = ln ? a.take<float>((size_t)B * nq * D) : nullptr;
     s.pre1 = ln ? a.take<float>((size_t)B * nq * D) : nullptr;
+    const size_t pf = attn_tc_p_floats(B, nq, nk, D, H);       // (points, heads x small side) probabilities: the backward reuses them
+    s.P = pf ? a.take<float>(pf) : nullptr;
     return s;
 }
 
@@ -730,7 +732,7 @@ static int mab_train_forward(const MabSaved& s, const float* Qin, int qb, const 
     const size_t ib = train_img_bytes(D);
     PCA_TRY(launch_linear(Qin, m.Wq, m.bq, s.Qp, (long long)qb * nq, dq, D, 0, st, nullptr, dq <= D ? img : nullptr, ib));
     PCA_TRY(launch_linear(Kin, m.Wkv, m.bkv, s.KV, (long long)B * nk, dk, 2 * D, 0, st, nullptr, dk <= D ? img : nullptr, ib));
-    PCA_TRY(launch_attn(s.Qp, qb == 1 ? 0 : (long long)nq * D, s.KV, B, nq, nk, D, H, s.O, part, key_counts, st, s.lse));
+    PCA_TRY(launch_attn(s.Qp, qb == 1 ? 0 : (long long)nq * D, s.KV, B, nq, nk, D, H, s.O, part, key_counts, st, s.lse, s.P));
     const size_t nbytes = (size_t)B * nq * D * sizeof(float);
     if (ln) {                                                   // O = ln0(Qp + A V); the pre-LN tensor is kept for the backward
         PCA_CHECK_CUDA(cudaMemcpyAsync(s.Opre, s.O, nbytes, cudaMemcpyDeviceToDevice, st));
@@ -811,7 +813,7 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
     }
     float* dQp = dZ;                                            // dQp = dO (residual) + attention part
     if (attn_tc) {                                              // one small side: every contraction as a split-bf16 tensor-core GEMM
-        PCA_TRY(launch_attn_bwd_tc(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, dQp, dKV, attn_scratch, st));
+        PCA_TRY(launch_attn_bwd_tc(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, dQp, dKV, attn_scratch, st, s.P));
     } else {
         PCA_CHECK_CUDA(cudaMemsetAsync(dKV, 0, (size_t)rk * 2 * D * sizeof(float), st));
         PCA_TRY(launch_attn_bwd<1>(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, nullptr, dKV, st, key_counts));
