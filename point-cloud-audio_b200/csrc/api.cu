@@ -198,8 +198,13 @@ static int mab_forward(const float* Q, int qb, const float* K, int B, int nq, in
     void* img = a.take<uint8_t>(ib);
     if (!a.ok()) return fail(PCA_EWORKSPACE, "MAB: workspace too small (%zu bytes given)", ws_bytes);
     PCA_TRY(launch_linear(Q, m.Wq, m.bq, Qp, (long long)qb * nq, dq, D, 0, st, nullptr, dq <= D ? img : nullptr, ib));
-    PCA_TRY(launch_linear(K, m.Wkv, m.bkv, KV, (long long)B * nk, dk, 2 * D, 0, st, nullptr, dk <= D ? img : nullptr, ib));
-    PCA_TRY(launch_attn(Qp, qb == 1 ? 0 : (long long)nq * D, KV, B, nq, nk, D, H, O, part, key_counts, st));
+    if (qb == 1 && attn_fold_eligible(B, nq, nk, dk, D, H)) {
+        // shared inducing points / seeds against many points: the attention runs on the un-projected keys (attn_tc.cu)
+        PCA_TRY(launch_attn_folded(Qp, m.Wkv, m.bkv, K, B, nq, nk, dk, D, H, O, part, st, key_counts));
+    } else {
+        PCA_TRY(launch_linear(K, m.Wkv, m.bkv, KV, (long long)B * nk, dk, 2 * D, 0, st, nullptr, dk <= D ? img : nullptr, ib));
+        PCA_TRY(launch_attn(Qp, qb == 1 ? 0 : (long long)nq * D, KV, B, nq, nk, D, H, O, part, key_counts, st));
+    }
     if (ln) PCA_TRY(launch_layernorm(O, (long long)B * nq, D, m.ln0w, m.ln0b, st));
     PCA_TRY(launch_linear(O, m.Wo, m.bo, out, (long long)B * nq, D, D, 2, st, nullptr, img, ib));
     if (ln) PCA_TRY(launch_layernorm(out, (long long)B * nq, D, m.ln1w, m.ln1b, st));

@@ -53,14 +53,17 @@ __device__ __forceinline__ void at_split8(const float* x, uint4& hi, uint4& lo) 
 __global__ void cloud_image_kernel(const float* __restrict__ src, long long s_bstride, int ld, int ns, int nsp, int dh, int D, int HS,
                                    int kind, uint8_t* __restrict__ img, long long img_bstride) {
     const int b = blockIdx.y;
-    const int N = kind == 0 ? HS : D, K = kind == 0 ? D : HS;
+    const int N = kind == 1 ? D : HS, K = kind == 1 ? HS : D;
     const int total = N * (K / 8);
     const float* s = src + (long long)b * s_bstride;
     uint8_t* ib = img + (long long)b * img_bstride;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int n = i % N, k8 = i / N;
         float x[8];
-        if (kind == 0) {
+        if (kind == 2) {                         // dense (HS, K) matrix as it stands (the folded query image)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = __ldg(s + (long long)n * ld + k8 * 8 + j);
+        } else if (kind == 0) {
             const int h = n / nsp, m = n - h * nsp;
             const bool on = m < ns && (k8 * 8) / dh == h;
 #pragma unroll
@@ -436,6 +439,7 @@ struct ClGwParams {
     int ncta;              // columns of X per CTA (= N)
     int B, nsplit;         // work items = B clouds x nsplit row ranges
     const int* counts;     // nullable: rows of X past counts[b] are padding (possibly NaN) and are read as zeros
+    int full_rows;         // 1: out (Mtot, N) per cloud receives every accumulator row (no head-diagonal extraction)
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwParams P, const __grid_constant__ CUtensorMap tma,
@@ -615,7 +619,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
                 const int h_lo = (32 * quad) / P.nsp, h_hi = (32 * quad + 31) / P.nsp;      // heads of this warp's accumulator rows
                 float* ob = P.out + (long long)b * P.o_bstride;
                 for (int c0 = 0; c0 < P.ncta; c0 += 32) {
-                    if ((c0 + 31) / P.dh < h_lo || c0 / P.dh > h_hi) continue;              // warp-uniform: no diagonal block in here
+                    if (!P.full_rows && ((c0 + 31) / P.dh < h_lo || c0 / P.dh > h_hi)) continue;   // warp-uniform: no diagonal block in here
                     uint32_t v[32];
                     tmem_ld32(tmem_addr(tb, 32 * quad, 256 * buf + c0), v);
                     tmem_ld_wait32(v);
@@ -628,7 +632,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_gw_tc_kernel(const ClGwPa
                     for (int lr = 0; lr < 32; ++lr) {
                         const int row = 32 * quad + lr;
                         const int h = row / P.nsp, m = row - h * P.nsp;
-                        if (row < P.Mtot && m < P.ns && h == hc) atomicAdd(ob + (long long)m * P.ldo + col, T[lr * 33 + lane]);
+                        if (P.full_rows) {
+                            if (row < P.Mtot) atomicAdd(ob + (long long)row * P.ldo + col, T[lr * 33 + lane]);
+                        } else if (row < P.Mtot && m < P.ns && h == hc) {
+                            atomicAdd(ob + (long long)m * P.ldo + col, T[lr * 33 + lane]);
+                        }
                     }
                     __syncwarp();
                 }
@@ -729,7 +737,8 @@ size_t attn_tc_fwd_floats(int B, int nq, int nk, int D, int H) {
     const AtcShape s = atc_shape(B, nq, nk, D, H);
     if (!s.type) return 0;
     const size_t img = (size_t)s.HS * D;             // floats per cloud image (4 N K bytes)
-    return fl((size_t)B * s.big * s.HS) + (s.type == 1 ? 2 : 1) * fl((size_t)B * img);
+    // (small-query form: + the folded route's query matrix, its image and slack; its per-cloud sums fit the image budget)
+    return fl((size_t)B * s.big * s.HS) + (s.type == 1 ? 2 : 1) * fl((size_t)B * img) + (s.type == 2 ? 3 * fl(img) : 0);
 }
 // floats of the probability matrix a training forward may keep for the backward (0 when the shape is not eligible)
 size_t attn_tc_p_floats(int B, int nq, int nk, int D, int H) {
@@ -804,7 +813,8 @@ static int launch_cloud_linear(ClinParams p, int nsp, const char* name, cudaStre
 }
 
 static int launch_cloud_gw(const float* T, const float* X, long long x_bstride, int ldx, float* out, long long o_bstride, int ldo, int B,
-                           int n_rows, const AtcShape& s, int D, int H, cudaStream_t st, bool one_range, const int* counts = nullptr) {
+                           int n_rows, const AtcShape& s, int D, int H, cudaStream_t st, bool one_range, const int* counts = nullptr,
+                           int full_rows = 0) {
     const int sms = sm_count();
     // row ranges per cloud: as many as keep an item >= 128 rows and fill the last round of the persistent CTAs best.  one_range
     // (the forward pass): a cloud is ONE item, so every output element receives exactly one addition and the result is bit-
@@ -822,7 +832,7 @@ static int launch_cloud_gw(const float* T, const float* X, long long x_bstride, 
     nsplit = (n_rows + rchunk - 1) / rchunk;
     const int ncta = D;
     ClGwParams p{T, (long long)n_rows * s.HS, s.HS, s.HS, X, x_bstride, ldx, D, out, o_bstride, ldo, n_rows, rchunk, s.nsp, s.ns, D / H,
-                 AtSmem::g_raw_slots(s.HS, ncta), 0, x_bstride == 0 ? 1 : 0, ncta, B, nsplit, counts};
+                 AtSmem::g_raw_slots(s.HS, ncta), 0, x_bstride == 0 ? 1 : 0, ncta, B, nsplit, counts, full_rows};
     const long long items = (long long)B * nsplit;
     const unsigned grid = (unsigned)(items < sms ? items : sms);
     // both operands as (columns, rows of a cloud, clouds): one box = the 32 rows of a chunk, all columns
@@ -896,6 +906,111 @@ int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B,
         PCA_CHECK_LAUNCH("bcast_rows_kernel");
     }
     return launch_cloud_gw(T, KV + D, (long long)nk * 2 * D, 2 * D, O, (long long)nq * D, D, B, nk, s, D, H, st, true, key_counts);
+}
+
+// ------------------------------------------------------------------------------------ inference: W_k / W_v folded away
+// Small-query blocks with SHARED queries (ISAB mab0 with I, PMA with S), inference only.  With K = X Wk^T + bk, V = X Wv^T + bv:
+//   scores  q_hm . K_n = (Wk_h^T q_hm) . x_n + const(h, m)      -- the constant cancels in the softmax over the points n
+//   output  sum_n P_n V_n = Wv (sum_n P_n x_n) + bv              -- the probabilities of a (head, query) sum to one
+// so the block runs on the UN-PROJECTED points: G1 against the model-constant image Gq = (per head) Qp_h Wk_h, the column
+// softmax, G3 with full rows (Z = P^T X, (HS, dk) per cloud) and a small projection of Z's rows by their head's slice of Wv.
+// The (B n, dk) -> 2 D projection of the block -- the largest linear layer of the model -- and the K | V tensor never exist
+// (the identity the bf16 kernels of encoder_tc.cu use for mab0 and the pooled attention).
+__global__ void fold_query_kernel(const float* __restrict__ Qp, const float* __restrict__ Wk, int ns, int nsp, int dh, int D, int dk,
+                                  float* __restrict__ Gq) {
+    const int row = blockIdx.x;                      // (h, m)
+    const int h = row / nsp, m = row - h * nsp;
+    for (int k = threadIdx.x; k < dk; k += blockDim.x) {
+        float a = 0.f;
+        if (m < ns)
+            for (int d = 0; d < dh; ++d) a = fmaf(__ldg(Qp + (long long)m * D + h * dh + d), __ldg(Wk + (long long)(h * dh + d) * dk + k), a);
+        Gq[(long long)row * dk + k] = a;
+    }
+}
+// O[b][m][d] = Qp[m][d] + bv[d] + sum_k Z[b][(d / dh, m)][k] Wv[d][k];  block = (head, cloud), thread = (dim of the head, query lane)
+__global__ void __launch_bounds__(256) fold_proj_kernel(const float* __restrict__ Z, const float* __restrict__ Wv, const float* __restrict__ bv,
+                                                        const float* __restrict__ Qp, float* __restrict__ O, int ns, int nsp, int HS, int dk,
+                                                        int D, int dh) {
+    __shared__ float zs[16 * 256];
+    __shared__ float wsm[64 * 33];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int dl = threadIdx.x % dh, ml = threadIdx.x / dh, mlanes = 256 / dh;
+    const float* zb = Z + ((long long)b * HS + h * nsp) * dk;
+    for (int i = threadIdx.x; i < ns * dk; i += 256) zs[i] = zb[i];
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int k0 = 0; k0 < dk; k0 += 32) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < dh * 32; i += 256) {
+            const int dd = i >> 5, kk = i & 31;
+            wsm[dd * 33 + kk] = __ldg(Wv + (long long)(h * dh + dd) * dk + k0 + kk);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < 32; ++kk) {
+            const float w = wsm[dl * 33 + kk];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int m = ml + i * mlanes;
+                if (m < ns) acc[i] = fmaf(zs[m * dk + k0 + kk], w, acc[i]);
+            }
+        }
+    }
+    const int d = h * dh + dl;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int m = ml + i * mlanes;
+        if (m < ns) O[((long long)b * ns + m) * D + d] = __ldg(Qp + (long long)m * D + d) + __ldg(bv + d) + acc[i];
+    }
+}
+
+bool attn_fold_eligible(int B, int nq, int nk, int dk, int D, int H) {
+    const AtcShape s = atc_shape(B, nq, nk, D, H);
+    if (s.type != 2) return false;
+    const int dh = D / H;
+    return dk % 32 == 0 && dk >= 64 && dk <= 256 && dk <= D && 2 * s.HS <= dk && dh <= 64 && 256 % dh == 0 && s.ns <= 16;
+}
+
+// O (B, nq, D) = Qp + softmax_h(Qp K^T / sqrt(D)) V with K | V = X Wkv^T + bkv never formed.  Qp (nq, D) shared by the batch;
+// Wkv (2 D, dk) = Wk rows then Wv rows, bkv (2 D); X (B, nk, dk).  scratch: attn_tc_fwd_floats floats.
+int launch_attn_folded(const float* Qp, const float* Wkv, const float* bkv, const float* X, int B, int nq, int nk, int dk, int D, int H,
+                       float* O, float* scratch, cudaStream_t st, const int* key_counts) {
+    const AtcShape s = atc_shape(B, nq, nk, D, H);
+    if (!attn_fold_eligible(B, nq, nk, dk, D, H)) return fail(PCA_EUNSUPPORTED, "attn_folded: shape not eligible");
+    if (!scratch) return fail(PCA_EWORKSPACE, "attn_folded: no scratch");
+    PCA_TRY(attn_tc_configure());
+    const float scale = 1.0f / sqrtf((float)D), sl2e = scale * 1.4426950408889634f;
+    const size_t imgf = (size_t)s.HS * D;
+    float* T = scratch;
+    float* Z = scratch + fl((size_t)B * nk * s.HS);                   // (B, HS, dk) <= the per-cloud image budget (dk <= D)
+    float* Gq = Z + fl((size_t)B * imgf);
+    uint8_t* img = reinterpret_cast<uint8_t*>(Gq + fl(imgf));
+    const int dh = D / H;
+    fold_query_kernel<<<s.HS, 256, 0, st>>>(Qp, Wkv, s.ns, s.nsp, dh, D, dk, Gq);
+    PCA_CHECK_LAUNCH("fold_query_kernel");
+    {
+        const int total = s.HS * dk / 8;
+        cloud_image_kernel<<<dim3((unsigned)((total + 255) / 256), 1), 256, 0, st>>>(Gq, 0, dk, s.ns, s.nsp, dh, dk, s.HS, 2, img, 0);
+        PCA_CHECK_LAUNCH("cloud_image_kernel");
+    }
+    ClinParams p{};
+    p.X = X; p.x_bstride = (long long)nk * dk; p.ldx = dk;
+    p.img = img; p.img_bstride = 0;
+    p.Y = T; p.y_bstride = (long long)nk * s.HS; p.ldy = s.HS;
+    p.B = B; p.n_rows = nk; p.K = dk; p.N = s.HS; p.H = H; p.nsp = s.nsp; p.ns = s.ns; p.scale = scale; p.scale_log2e = sl2e;
+    PCA_TRY(launch_cloud_linear<EPI_STORE>(p, s.nsp, "attn_g1_scores_tc_kernel", st));
+    PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<store>");
+    {
+        LaunchTimer lt("col_softmax_kernel", st, 0.0, 8.0 * B * (double)nk * s.HS);
+        col_softmax_kernel<<<dim3((unsigned)(s.HS / 32), (unsigned)B), 256, 0, st>>>(T, nk, s.HS, s.nsp, s.ns, H, sl2e, nullptr, key_counts);
+    }
+    PCA_CHECK_LAUNCH("col_softmax_kernel");
+    PCA_CHECK_CUDA(cudaMemsetAsync(Z, 0, (size_t)B * s.HS * dk * sizeof(float), st));
+    PCA_TRY(launch_cloud_gw(T, X, (long long)nk * dk, dk, Z, (long long)s.HS * dk, dk, B, nk, s, dk, H, st, true, key_counts, 1));
+    fold_proj_kernel<<<dim3((unsigned)H, (unsigned)B), 256, 0, st>>>(Z, Wkv + (long long)D * dk, bkv + D, Qp, O, s.ns, s.nsp, s.HS, dk, D, dh);
+    PCA_CHECK_LAUNCH("fold_proj_kernel");
+    return 0;
 }
 
 // Gradients of the attention above.  dQp (B, nq, D) is OVERWRITTEN with dO (the residual path) + the attention part; dKV

@@ -107,6 +107,11 @@ size_t attn_tc_bwd_floats(int B, int nq, int nk, int D, int H);
 int launch_attn_tc(const float* Qp, long long q_bstride, const float* KV, int B, int nq, int nk, int D, int H, float* O, float* scratch,
                    cudaStream_t st, float* lse, const int* key_counts = nullptr, float* p_out = nullptr);
 size_t attn_tc_p_floats(int B, int nq, int nk, int D, int H);
+// inference, shared small query set: the block on the un-projected points (W_k folded into the query image, W_v applied to the
+// per-cloud sums P^T X); the K | V projection is never computed
+bool attn_fold_eligible(int B, int nq, int nk, int dk, int D, int H);
+int launch_attn_folded(const float* Qp, const float* Wkv, const float* bkv, const float* X, int B, int nq, int nk, int dk, int D, int H,
+                       float* O, float* scratch, cudaStream_t st, const int* key_counts);
 int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse, const float* delta,
                        int B, int nq, int nk, int D, int H, float* dQp, float* dKV, float* scratch, cudaStream_t st,
                        const float* p_saved = nullptr);

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib, _runtime as rt
 
-ST_WORKSPACE_BYTES = 1 << 30      # scratch budget for the encoder: the batch is processed in chunks that fit
+ST_WORKSPACE_BYTES = 8 << 30      # scratch budget for the encoder (180 GB of HBM per GPU): larger batches are processed in chunks that fit
 
 
 def _dims(d_in, D, H, M, S, Cc, ln):
