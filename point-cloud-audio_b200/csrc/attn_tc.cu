@@ -105,6 +105,8 @@ struct ClinParams {
     int B, n_rows, K, N;
     int H, nsp, ns;
     float scale, scale_log2e;
+    float* colsum;         // nullable: colsum[n] += sum over the valid rows of the stored Y[., n] (the bias gradient of the layer
+                           // that produced the operand: saves a separate pass over Y)
     int raw_slots;         // raw fp32 tiles in the TMA ring (<= CL_RAW_MAX)
     int x_shared;          // X has no batch dimension (x_bstride == 0)
 };
@@ -120,7 +122,7 @@ struct AtSmem {
     static constexpr int GA_BYTES = 16 * G_SBO;                        // 128 features
     static constexpr int GB_BYTES = 32 * G_SBO;                        // 256 features
     static constexpr int G_STAGE = 2 * GA_BYTES + 2 * GB_BYTES;
-    static constexpr int CL_FIXED = 4 * 32 * 33 * 4 + 256;              // transpose tiles + barriers
+    static constexpr int CL_FIXED = 4 * 32 * 33 * 4 + 256 + 1024;       // transpose tiles + barriers + per-CTA column sums
     static constexpr int MAX_BYTES = 227 * 1024;
     // G3 kernel: raw fp32 ring (32-row chunks of both operands) | 2 operand stages | transpose tiles | barriers
     static constexpr int G_OP_STAGES = 2;
@@ -183,9 +185,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const Cl
     uint64_t* raw_full = acc_empty + 2;          // [8] count 1 (expect_tx of the loader) + 16 KB
     uint64_t* raw_empty = raw_full + CL_RAW_MAX; // [8] count 4 (converter warps of the set that read the slot)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + CL_RAW_MAX);
+    float* cs_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);     // [256] column sums of this CTA's tiles
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkc = P.K / AT_KC;
     const int tpc = (P.n_rows + 127) / 128;
+    if (threadIdx.x < 256) cs_s[threadIdx.x] = 0.f;
     const long long ntiles = (long long)P.B * tpc;
     const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
     const uint32_t items = (uint32_t)my_tiles * nkc;       // (tile of this CTA, K chunk) in issue order
@@ -394,6 +398,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const Cl
                         cv[u] = cok[u] ? __ldg(P.vec + ((long long)b * P.ns + m) * P.H + h) : 0.f;
                     }
                 }
+                float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int lr = 4 * i + rr, r = i0 + lr;
@@ -408,7 +413,22 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const Cl
 #pragma unroll
                         for (int u = 0; u < 4; ++u) o[u] = cok[u] ? pr[u] * (o[u] - cv[u]) * P.scale : 0.f;
                     }
-                    if (r < P.n_rows) *reinterpret_cast<float4*>(yb + (long long)r * P.ldy + n) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (r < P.n_rows) {
+                        *reinterpret_cast<float4*>(yb + (long long)r * P.ldy + n) = make_float4(o[0], o[1], o[2], o[3]);
+                        cs[0] += o[0]; cs[1] += o[1]; cs[2] += o[2]; cs[3] += o[3];
+                    }
+                }
+                if (P.colsum) {                              // warp-uniform: 32 rows x 4 columns per lane group -> one 16-byte reduction
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        cs[u] += __shfl_xor_sync(0xffffffffu, cs[u], 8);
+                        cs[u] += __shfl_xor_sync(0xffffffffu, cs[u], 16);
+                    }
+                    if (rr == 0) {                           // per-CTA sums in shared memory (every tile adding to the same 256 global
+                                                             // addresses serialised in L2: +45 % on the kernel); flushed once at the end
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) atomicAdd(&cs_s[n + u], cs[u]);
+                    }
                 }
                 __syncwarp();
             }
@@ -418,6 +438,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const Cl
     }
     fence_before_sync();
     __syncthreads();
+    if (P.colsum && threadIdx.x < P.N) atomicAdd(P.colsum + threadIdx.x, cs_s[threadIdx.x]);
     if (warp == AT_MMA_WARP) tmem_dealloc(tb, 512);
 }
 
@@ -1017,7 +1038,8 @@ int launch_attn_folded(const float* Qp, const float* Wkv, const float* bkv, cons
 // (B, nk, 2D) is OVERWRITTEN.  delta (B, nq, H) = sum_d dO (O - Qp) per head is needed only when the queries are the small side.
 // scratch: attn_tc_bwd_floats floats.
 int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse, const float* delta,
-                       int B, int nq, int nk, int D, int H, float* dQp, float* dKV, float* scratch, cudaStream_t st, const float* p_saved) {
+                       int B, int nq, int nk, int D, int H, float* dQp, float* dKV, float* scratch, cudaStream_t st, const float* p_saved,
+                       float* db_q, float* db_kv) {
     const AtcShape s = atc_shape(B, nq, nk, D, H);
     if (!s.type) return fail(PCA_EUNSUPPORTED, "attn_bwd_tc: shape (B=%d, nq=%d, nk=%d, D=%d, H=%d) not eligible", B, nq, nk, D, H);
     if (!scratch) return fail(PCA_EWORKSPACE, "attn_bwd_tc: no scratch");
@@ -1062,6 +1084,7 @@ int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, co
         g.img = img_at(2); g.img_bstride = img_bytes;
         g.Y = dQp; g.y_bstride = (long long)nq * D; g.ldy = D;
         g.R = dO; g.r_bstride = (long long)nq * D; g.ldr = D;
+        g.colsum = db_q;                                                                      // (+= column sums of dQp: fc_q's bias gradient)
         PCA_TRY(launch_cloud_linear<EPI_RESID>(g, s.nsp, "attn_g2_resid_tc_kernel", st));
         PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<resid>");
         PCA_CHECK_CUDA(cudaMemsetAsync(dKV, 0, (size_t)B * nk * 2 * D * sizeof(float), st));
@@ -1096,12 +1119,14 @@ int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, co
     gk.X = dS; gk.x_bstride = t_bstride; gk.ldx = s.HS;
     gk.img = img_at(1); gk.img_bstride = q_bstride ? img_bytes : 0;
     gk.Y = dKV; gk.y_bstride = kv_bs; gk.ldy = 2 * D;
+    gk.colsum = db_kv;                                                                        // (+= fc_k | fc_v bias gradients)
     PCA_TRY(launch_cloud_linear<EPI_STORE>(gk, s.nsp, "attn_g2_store_tc_kernel", st));
     PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<store>");
     ClinParams gv = base(nk, s.HS, D);                                                        // dV = P dO
     gv.X = Pm; gv.x_bstride = t_bstride; gv.ldx = s.HS;
     gv.img = img_at(3); gv.img_bstride = img_bytes;
     gv.Y = dKV + D; gv.y_bstride = kv_bs; gv.ldy = 2 * D;
+    gv.colsum = db_kv ? db_kv + D : nullptr;
     PCA_TRY(launch_cloud_linear<EPI_STORE>(gv, s.nsp, "attn_g2_store_tc_kernel", st));
     PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<store>");
     PCA_CHECK_CUDA(cudaMemcpyAsync(dQp, dO, (size_t)B * nq * D * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -114,7 +114,7 @@ int launch_attn_folded(const float* Qp, const float* Wkv, const float* bkv, cons
                        float* O, float* scratch, cudaStream_t st, const int* key_counts);
 int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse, const float* delta,
                        int B, int nq, int nk, int D, int H, float* dQp, float* dKV, float* scratch, cudaStream_t st,
-                       const float* p_saved = nullptr);
+                       const float* p_saved = nullptr, float* db_q = nullptr, float* db_kv = nullptr);
 void set_attn_tc(int on);
 int launch_layernorm(float* X, long long rows, int D, const float* g, const float* b, cudaStream_t st);
 

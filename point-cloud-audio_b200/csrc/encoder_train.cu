@@ -811,9 +811,16 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
             attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dO, Oatt, s.Qp, q_bstride, nq, D, D / H, total, delta);
         PCA_CHECK_LAUNCH("attn_delta_kernel");
     }
+    bool fused_bq = false, fused_bkv = false;
     float* dQp = dZ;                                            // dQp = dO (residual) + attention part
     if (attn_tc) {                                              // one small side: every contraction as a split-bf16 tensor-core GEMM
-        PCA_TRY(launch_attn_bwd_tc(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, dQp, dKV, attn_scratch, st, s.P));
+        // the bias gradients of fc_q (large-query form) / fc_k | fc_v (small-query form) fall out of the epilogues that write
+        // dQp / dKV -- no separate column-sum pass (the first layers, d_in <= 4, keep their one-pass weight + bias kernel)
+        const int kind = attn_tc_kind(B, nq, nk, D, H);
+        fused_bq = kind == 1 && qb != 1 && dq > 4;
+        fused_bkv = kind == 2 && dk > 4;
+        PCA_TRY(launch_attn_bwd_tc(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, dQp, dKV, attn_scratch, st, s.P,
+                                   fused_bq ? (float*)g.bq : nullptr, fused_bkv ? (float*)g.bkv : nullptr));
     } else {
         PCA_CHECK_CUDA(cudaMemsetAsync(dKV, 0, (size_t)rk * 2 * D * sizeof(float), st));
         PCA_TRY(launch_attn_bwd<1>(s.Qp, q_bstride, s.KV, dO, s.lse, delta, B, nq, nk, D, H, nullptr, dKV, st, key_counts));
@@ -827,9 +834,11 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
         dQp = dQ1;
         rows_q = nq;
     }
-    PCA_TRY(launch_grad_weight_bias(dQp, Qin, (float*)g.Wq, (float*)g.bq, rows_q, dq, D, st));
+    if (fused_bq) PCA_TRY(launch_grad_weight(dQp, Qin, (float*)g.Wq, rows_q, dq, D, st));
+    else PCA_TRY(launch_grad_weight_bias(dQp, Qin, (float*)g.Wq, (float*)g.bq, rows_q, dq, D, st));
     if (dQin) PCA_TRY(launch_grad_input(dQp, m.Wq, dQin, acc_q ? dQin : nullptr, rows_q, dq, D, st, img_q, ib));
-    PCA_TRY(launch_grad_weight_bias(dKV, Kin, (float*)g.Wkv, (float*)g.bkv, rk, dk, 2 * D, st));
+    if (fused_bkv) PCA_TRY(launch_grad_weight(dKV, Kin, (float*)g.Wkv, rk, dk, 2 * D, st));
+    else PCA_TRY(launch_grad_weight_bias(dKV, Kin, (float*)g.Wkv, (float*)g.bkv, rk, dk, 2 * D, st));
     if (dKin) PCA_TRY(launch_grad_input(dKV, m.Wkv, dKin, acc_k ? dKin : nullptr, rk, dk, 2 * D, st, img_k, ib));
     return 0;
 }
