@@ -4,14 +4,17 @@
 // evaluated as THREE bf16 MMAs accumulating in fp32 TMEM (a_hi b_hi + a_lo b_hi + a_hi b_lo; the dropped lo*lo term is
 // 2^-18 relative), so the results stay inside the 1e-3 fp32 parity budget while the arithmetic runs on the tensor pipe.
 //
-//   linear_tc_kernel  : persistent, warp-specialised.  4 producer warps (thread = row of the 128-row tile: fp32 global ->
-//                       hi/lo bf16 -> canonical no-swizzle smem), the weight operand arrives as a pre-built hi|lo image by
-//                       ONE bulk async copy (cp.async.bulk + mbarrier complete_tx) per K chunk, 1 MMA warp (elected lane),
-//                       4 epilogue warps (TMEM -> bias / ReLU / residual -> global).  Two TMEM accumulators of up to 256
-//                       columns: the epilogue of tile t overlaps the staging and MMAs of tile t+1.
+//   linear_tc_kernel  : persistent, warp-specialised, 14 warps.  ONE loader thread streams the fp32 rows with TMA into a ring of
+//                       raw 16 KB tiles (128 rows x 32 floats; up to 8 in flight per SM), 8 converter warps (two sets on alternate
+//                       K chunks: raw rows -> hi/lo bf16 -> canonical no-swizzle smem with a padded chunk stride), the weight
+//                       operand arrives as a pre-built hi|lo image by ONE bulk async copy (cp.async.bulk + mbarrier
+//                       complete_tx) per K chunk, 1 MMA warp (elected lane), 4 epilogue warps (TMEM -> bias / ReLU / residual ->
+//                       global).  Two TMEM accumulators of up to 256 columns: the epilogue of tile t overlaps the staging and
+//                       MMAs of tile t+1.
 //   weight_image_kernel: W (fp32, optionally transposed) -> per (column pass, K chunk) [hi image | lo image].
-//   grad_weight_tc_kernel: dW (M, N) += A^T B over a range of rows (both operands MN-major from row-major activations),
-//                       split over rows across CTAs, partial results added atomically.
+//   grad_weight_tc_kernel: dW (M, N) += A^T B (both operands MN-major from row-major activations, TMA raw-chunk ring +
+//                       converter warps), persistent CTAs over (row range, 128-row block of dW) items with two accumulators,
+//                       partial results added atomically.
 #include "common.cuh"
 #include "tc_prims.cuh"
 #include "tma_host.cuh"
