@@ -240,3 +240,27 @@ def test_packed_params_cache_is_per_device_and_invalidatable():
     meta = [t.to("meta") for t in _mab_tensors(m)]           # a second "device": separate slot, the first one survives
     assert set(pk._cache) == {torch.device("cpu")}
     del meta
+
+
+def test_attention_route_dispatch_is_by_shape(built):
+    """Host logic of the tensor-core attention route (csrc/attn_tc.cu): which MAB shapes take it, and that its scratch query
+    grows with the batch (no device needed: these entry points only inspect shapes)."""
+    from pcaudio_b200 import _lib
+    L = _lib.lib()
+    # ModelNet model (main_pointcloud.py:62): 16 inducing points / 1 seed against 1000 points, dim 256, 4 heads
+    assert L.pca_debug_attn_tc_eligible(256, 1000, 16, 256, 4) == 1      # ISAB mab1: points are the queries
+    assert L.pca_debug_attn_tc_eligible(256, 16, 1000, 256, 4) == 1      # ISAB mab0: points are the keys
+    assert L.pca_debug_attn_tc_eligible(256, 1, 1000, 256, 4) == 1       # PMA
+    # audio models (Code/models.py: dim 64, 8 heads, 64 inducing points): the score matrix would be 8x the activations
+    assert L.pca_debug_attn_tc_eligible(4096, 64, 1025, 64, 8) == 0
+    assert L.pca_debug_attn_tc_eligible(4096, 1025, 64, 64, 8) == 0
+    assert L.pca_debug_attn_tc_eligible(4096, 1, 1025, 64, 8) == 0
+    assert L.pca_debug_attn_tc_eligible(2, 100, 16, 256, 4) == 0         # fewer than 128 items on the large side
+    small = L.pca_debug_attn_ws_bytes(8, 1000, 16, 256, 4)
+    large = L.pca_debug_attn_ws_bytes(64, 1000, 16, 256, 4)
+    assert 0 < small < large
+    try:
+        L.pca_debug_set_attn_tc(0)
+        assert L.pca_debug_attn_tc_eligible(256, 1000, 16, 256, 4) == 0  # the switch keeps every shape on the CUDA-core kernels
+    finally:
+        L.pca_debug_set_attn_tc(1)
