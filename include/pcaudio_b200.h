@@ -396,7 +396,9 @@ int pca_debug_grad_weight_tc(const float* dY, const float* X, float* dW, long lo
  * items, dim_V <= 256 a multiple of 32, head dim a multiple of 8, num_heads * 8 or * 16 in {32, 64} (the ModelNet model of
  * set_transformer-master/main_pointcloud.py:62) -- runs Q K^T, P V and every contraction of their gradient as split-bf16
  * tcgen05 GEMMs (csrc/attn_tc.cu; fp32-grade, replaces set_transformer-master/modules.py:28-29 and its autograd).  It is what
- * the fp32 encoder and the training path use for eligible shapes; pca_debug_set_attn_tc(0) keeps them on the CUDA-core kernels.
+ * the fp32 encoder and the training path use for eligible shapes; pca_debug_set_attn_tc(0) keeps them on the CUDA-core kernels,
+ * (2) keeps the route but makes training use the projected K | V form for the shared-query blocks (default 1: those blocks run
+ * on the un-projected points, forward and backward).
  * pca_debug_attn_fwd: O (B, nq, D) = Qp + softmax_h(Qp K^T / sqrt(D)) V on projected operands -- Qp (B or 1, nq, D), KV
  * (B, nk, 2D) rows [K | V] -- through the same dispatch; lse (B, nq, H) nullable receives log2 sum_k 2^(s_k log2 e).
  * pca_debug_attn_bwd_tc: the tensor-core backward alone: dQp (B, nq, D) = dO + dS K, dKV (B, nk, 2D) = [dS^T Qp | P^T dO];

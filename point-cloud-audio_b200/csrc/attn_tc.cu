@@ -53,7 +53,7 @@ __device__ __forceinline__ void at_split8(const float* x, uint4& hi, uint4& lo) 
 __global__ void cloud_image_kernel(const float* __restrict__ src, long long s_bstride, int ld, int ns, int nsp, int dh, int D, int HS,
                                    int kind, uint8_t* __restrict__ img, long long img_bstride) {
     const int b = blockIdx.y;
-    const int N = kind == 1 ? D : HS, K = kind == 1 ? HS : D;
+    const int N = (kind == 1 || kind == 3) ? D : HS, K = (kind == 1 || kind == 3) ? HS : D;
     const int total = N * (K / 8);
     const float* s = src + (long long)b * s_bstride;
     uint8_t* ib = img + (long long)b * img_bstride;
@@ -63,6 +63,9 @@ __global__ void cloud_image_kernel(const float* __restrict__ src, long long s_bs
         if (kind == 2) {                         // dense (HS, K) matrix as it stands (the folded query image)
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = __ldg(s + (long long)n * ld + k8 * 8 + j);
+        } else if (kind == 3) {                  // the same matrix as a G2 operand: B(n, k) = src[k][n], k < HS
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = __ldg(s + (long long)(k8 * 8 + j) * ld + n);
         } else if (kind == 0) {
             const int h = n / nsp, m = n - h * nsp;
             const bool on = m < ns && (k8 * 8) / dh == h;
@@ -719,7 +722,13 @@ __global__ void bcast_rows_kernel(const float* __restrict__ src, long long s_bst
 
 // ------------------------------------------------------------------------------------ host side
 static int g_attn_tc = 1;        // 0: attention stays on the CUDA-core kernels (PCA_ATTN_TC=0 / pca_debug_set_attn_tc)
-void set_attn_tc(int on) { g_attn_tc = on ? 1 : 0; }
+static int g_fold_train = 1;     // 0: training keeps the projected K | V form (pca_debug_set_attn_tc(2) / PCA_ATTN_FOLD_TRAIN=0)
+void set_attn_tc(int on) { g_attn_tc = on ? 1 : 0; g_fold_train = (on & 2) ? 0 : 1; }
+bool attn_fold_train_on() {
+    static int env = -1;
+    if (env < 0) { const char* v = getenv("PCA_ATTN_FOLD_TRAIN"); env = (v && v[0] == '0') ? 0 : 1; }
+    return env && g_fold_train;
+}
 static bool attn_tc_on() {
     static int env = -1;
     if (env < 0) { const char* v = getenv("PCA_ATTN_TC"); env = (v && v[0] == '0') ? 0 : 1; }
@@ -770,7 +779,9 @@ size_t attn_tc_bwd_floats(int B, int nq, int nk, int D, int H) {
     const AtcShape s = atc_shape(B, nq, nk, D, H);
     if (!s.type) return 0;
     const size_t img = (size_t)s.HS * D;
-    return 2 * fl((size_t)B * s.big * s.HS) + (s.type == 1 ? 3 : 4) * fl((size_t)B * img);
+    // (small-query form: + the folded backward's small pieces -- delta, dGq, the G2 image of Gq)
+    return 2 * fl((size_t)B * s.big * s.HS) + (s.type == 1 ? 3 : 4) * fl((size_t)B * img) +
+           (s.type == 2 ? 3 * fl(img) + fl((size_t)B * s.HS) : 0);
 }
 
 static int attn_tc_configure() {
@@ -996,17 +1007,18 @@ bool attn_fold_eligible(int B, int nq, int nk, int dk, int D, int H) {
 // O (B, nq, D) = Qp + softmax_h(Qp K^T / sqrt(D)) V with K | V = X Wkv^T + bkv never formed.  Qp (nq, D) shared by the batch;
 // Wkv (2 D, dk) = Wk rows then Wv rows, bkv (2 D); X (B, nk, dk).  scratch: attn_tc_fwd_floats floats.
 int launch_attn_folded(const float* Qp, const float* Wkv, const float* bkv, const float* X, int B, int nq, int nk, int dk, int D, int H,
-                       float* O, float* scratch, cudaStream_t st, const int* key_counts) {
+                       float* O, float* scratch, cudaStream_t st, const int* key_counts, float* p_out, float* z_out, float* gq_out) {
     const AtcShape s = atc_shape(B, nq, nk, D, H);
     if (!attn_fold_eligible(B, nq, nk, dk, D, H)) return fail(PCA_EUNSUPPORTED, "attn_folded: shape not eligible");
     if (!scratch) return fail(PCA_EWORKSPACE, "attn_folded: no scratch");
     PCA_TRY(attn_tc_configure());
     const float scale = 1.0f / sqrtf((float)D), sl2e = scale * 1.4426950408889634f;
     const size_t imgf = (size_t)s.HS * D;
-    float* T = scratch;
-    float* Z = scratch + fl((size_t)B * nk * s.HS);                   // (B, HS, dk) <= the per-cloud image budget (dk <= D)
-    float* Gq = Z + fl((size_t)B * imgf);
-    uint8_t* img = reinterpret_cast<uint8_t*>(Gq + fl(imgf));
+    // training keeps P, Z and Gq for the backward (p_out / z_out / gq_out); inference uses the scratch
+    float* T = p_out ? p_out : scratch;
+    float* Z = z_out ? z_out : scratch + fl((size_t)B * nk * s.HS);   // (B, HS, dk) <= the per-cloud image budget (dk <= D)
+    float* Gq = gq_out ? gq_out : scratch + fl((size_t)B * nk * s.HS) + fl((size_t)B * imgf);
+    uint8_t* img = reinterpret_cast<uint8_t*>(scratch + fl((size_t)B * nk * s.HS) + fl((size_t)B * imgf) + fl(imgf));
     const int dh = D / H;
     fold_query_kernel<<<s.HS, 256, 0, st>>>(Qp, Wkv, s.ns, s.nsp, dh, D, dk, Gq);
     PCA_CHECK_LAUNCH("fold_query_kernel");
@@ -1031,6 +1043,176 @@ int launch_attn_folded(const float* Qp, const float* Wkv, const float* bkv, cons
     PCA_TRY(launch_cloud_gw(T, X, (long long)nk * dk, dk, Z, (long long)s.HS * dk, dk, B, nk, s, dk, H, st, true, key_counts, 1));
     fold_proj_kernel<<<dim3((unsigned)H, (unsigned)B), 256, 0, st>>>(Z, Wkv + (long long)D * dk, bkv + D, Qp, O, s.ns, s.nsp, s.HS, dk, D, dh);
     PCA_CHECK_LAUNCH("fold_proj_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ training: the folded block's backward
+// With S = X Gq^T (Gq = per head Qp_h Wk_h), P = column softmax, Z = P^T X, O_hm = Qp_hm + bv_h + Wv_h Z_hm and dO given:
+//   dZ'_hm = Wv_h^T dO_hm                      (fold_dz_kernel; per cloud (HS, dk))
+//   a = X dZ'^T,  dS = P o (a - Z_hm . dZ'_hm) / sqrt(D)     (G1 <ds_col>: the row dots are the softmax backward's delta; dO . bv
+//                                                 is constant over the points and cancels)
+//   dX  = dS Gq + P dZ'                        (two G2 launches; the second accumulates)
+//   dGq = sum_b dS^T X                         (G3, full rows, one matrix for the batch)  ->  dWk_h += Qp_h^T dGq_h, dQp_h = dGq_h Wk_h^T
+//   dWv_h += sum_b dO_h^T Z_h, dbv += sum dO   (by the caller: a weight-gradient GEMM on the block-expanded dO, fold_dox_kernel)
+// The K | V projection, its 512-wide weight-gradient GEMM and its input-gradient GEMM do not exist in this form.
+__global__ void fold_dz_kernel(const float* __restrict__ dO, const float* __restrict__ Wv, int ns, int nsp, int dh, int D, int dk, int HS,
+                               float* __restrict__ dZ) {
+    const int row = blockIdx.x, b = blockIdx.y;      // row = (h, m)
+    const int h = row / nsp, m = row - h * nsp;
+    const float* g = dO + ((long long)b * ns + (m < ns ? m : 0)) * D + h * dh;
+    for (int k = threadIdx.x; k < dk; k += blockDim.x) {
+        float a = 0.f;
+        if (m < ns)
+            for (int d = 0; d < dh; ++d) a = fmaf(__ldg(g + d), __ldg(Wv + (long long)(h * dh + d) * dk + k), a);
+        dZ[((long long)b * HS + row) * dk + k] = a;
+    }
+}
+// delta[(b ns + m) H + h] = Z[b, (h, m), :] . dZ'[b, (h, m), :]; one warp per row
+__global__ void fold_delta_kernel(const float* __restrict__ Z, const float* __restrict__ dZ, int B, int ns, int nsp, int H, int HS, int dk,
+                                  float* __restrict__ delta) {
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= B * HS) return;
+    const int b = w / HS, row = w - b * HS;
+    const int h = row / nsp, m = row - h * nsp;
+    if (m >= ns) return;
+    float a = 0.f;
+    for (int k = lane; k < dk; k += 32) a = fmaf(Z[(long long)w * dk + k], dZ[(long long)w * dk + k], a);
+    a = warp_sum(a);
+    if (lane == 0) delta[((long long)b * ns + m) * H + h] = a;
+}
+// dWk[d, k] += sum_m Qp[m, d] dGq[(d / dh, m), k]
+__global__ void fold_dwk_kernel(const float* __restrict__ Qp, const float* __restrict__ dGq, int ns, int nsp, int dh, int D, int dk,
+                                float* __restrict__ dWk) {
+    const int d = blockIdx.x, h = d / dh;
+    for (int k = threadIdx.x; k < dk; k += blockDim.x) {
+        float a = 0.f;
+        for (int m = 0; m < ns; ++m) a = fmaf(__ldg(Qp + (long long)m * D + d), dGq[(long long)(h * nsp + m) * dk + k], a);
+        dWk[(long long)d * dk + k] += a;
+    }
+}
+// dQ[m, d] = sum_k dGq[(d / dh, m), k] Wk[d, k]; one warp per (m, d)
+__global__ void fold_dq_kernel(const float* __restrict__ dGq, const float* __restrict__ Wk, int ns, int nsp, int dh, int D, int dk,
+                               float* __restrict__ dQ) {
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= ns * D) return;
+    const int m = w / D, d = w - m * D, h = d / dh;
+    float a = 0.f;
+    for (int k = lane; k < dk; k += 32) a = fmaf(dGq[(long long)(h * nsp + m) * dk + k], __ldg(Wk + (long long)d * dk + k), a);
+    a = warp_sum(a);
+    if (lane == 0) dQ[w] = a;
+}
+// dOx[(b, h', m), d] = dO[b, m, d] when d / dh == h' and m < ns, else 0: (B HS, D), the rows of Z's layout
+__global__ void fold_dox_kernel(const float* __restrict__ dO, int ns, int nsp, int dh, int D, int HS, long long total, float* __restrict__ dOx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int d = (int)(i % D);
+    const long long r = i / D;
+    const int row = (int)(r % HS);
+    const long long b = r / HS;
+    const int h = row / nsp, m = row - h * nsp;
+    dOx[i] = (m < ns && d / dh == h) ? __ldg(dO + (b * ns + m) * D + d) : 0.f;
+}
+
+size_t attn_fold_z_floats(int B, int nq, int nk, int D, int H) {          // saved (B, HS, dk <= D) sums of a folded training block
+    const AtcShape s = atc_shape(B, nq, nk, D, H);
+    return s.type == 2 ? (size_t)B * s.HS * D : 0;
+}
+size_t attn_fold_gq_floats(int B, int nq, int nk, int D, int H) {
+    const AtcShape s = atc_shape(B, nq, nk, D, H);
+    return s.type == 2 ? (size_t)s.HS * D : 0;
+}
+int attn_fold_rows(int B, int nq, int nk, int D, int H) { return atc_shape(B, nq, nk, D, H).HS; }
+
+// dX (B, nk, dk): OVERWRITTEN (x_acc = 0) or accumulated onto (x_acc = 1), nullable; dWk (D, dk) accumulated; dQ (nq, D): the
+// attention part of the shared queries' gradient (OVERWRITTEN; the caller adds the residual part sum_b dO); *dox_out / Z: the
+// operands of the caller's Wv weight-gradient GEMM ((B HS, D) and (B HS, dk)).  scratch: attn_tc_bwd_floats floats.
+int launch_attn_folded_bwd(const float* Qp, const float* Wkv, const float* X, const float* dO, const float* P, const float* Z,
+                           const float* Gq, int B, int nq, int nk, int dk, int D, int H, float* dX, int x_acc, float* dWk, float* dQ,
+                           float** dox_out, float* scratch, cudaStream_t st) {
+    const AtcShape s = atc_shape(B, nq, nk, D, H);
+    if (!attn_fold_eligible(B, nq, nk, dk, D, H)) return fail(PCA_EUNSUPPORTED, "attn_folded_bwd: shape not eligible");
+    if (!scratch) return fail(PCA_EWORKSPACE, "attn_folded_bwd: no scratch");
+    PCA_TRY(attn_tc_configure());
+    const float scale = 1.0f / sqrtf((float)D), sl2e = scale * 1.4426950408889634f;
+    const size_t imgf = (size_t)s.HS * D;
+    const size_t tf = fl((size_t)B * nk * s.HS), imf = fl((size_t)B * imgf);
+    const int dh = D / H;
+    float* dS = scratch;                                   // (B nk, HS)   [the second score-sized region stays unused here]
+    float* big = scratch + 2 * tf;
+    float* small = big + 4 * imf;
+    float* delta = small;                                  // (B, ns, H)
+    float* dGq = delta + fl((size_t)B * s.HS);             // (HS, dk)
+    uint8_t* img_gq2 = reinterpret_cast<uint8_t*>(dGq + fl(imgf));       // Gq as the G2 operand
+    float* dZ = big;                                       // (B, HS, dk)
+    uint8_t* img_dz1 = reinterpret_cast<uint8_t*>(big + imf);            // dZ' as the G1 operand, per cloud
+    uint8_t* img_dz2 = reinterpret_cast<uint8_t*>(big + 2 * imf);        // dZ' as the G2 operand, per cloud
+    float* dOx = big + 3 * imf;                            // (B HS, D)
+    const long long img_bytes = (long long)s.HS * dk * 4;
+    const float* Wk = Wkv;
+    const float* Wv = Wkv + (long long)D * dk;
+
+    fold_dz_kernel<<<dim3((unsigned)s.HS, (unsigned)B), 256, 0, st>>>(dO, Wv, s.ns, s.nsp, dh, D, dk, s.HS, dZ);
+    PCA_CHECK_LAUNCH("fold_dz_kernel");
+    fold_delta_kernel<<<(unsigned)((B * s.HS + 7) / 8), 256, 0, st>>>(Z, dZ, B, s.ns, s.nsp, H, s.HS, dk, delta);
+    PCA_CHECK_LAUNCH("fold_delta_kernel");
+    {
+        const int total = s.HS * dk / 8;
+        const dim3 gb((unsigned)((total + 255) / 256), (unsigned)B), g1((unsigned)((total + 255) / 256), 1);
+        cloud_image_kernel<<<gb, 256, 0, st>>>(dZ, (long long)s.HS * dk, dk, s.ns, s.nsp, dh, dk, s.HS, 2, img_dz1, img_bytes);
+        PCA_CHECK_LAUNCH("cloud_image_kernel");
+        if (dX) {
+            cloud_image_kernel<<<gb, 256, 0, st>>>(dZ, (long long)s.HS * dk, dk, s.ns, s.nsp, dh, dk, s.HS, 3, img_dz2, img_bytes);
+            PCA_CHECK_LAUNCH("cloud_image_kernel");
+            cloud_image_kernel<<<g1, 256, 0, st>>>(Gq, 0, dk, s.ns, s.nsp, dh, dk, s.HS, 3, img_gq2, 0);
+            PCA_CHECK_LAUNCH("cloud_image_kernel");
+        }
+    }
+    const long long t_bs = (long long)nk * s.HS, x_bs = (long long)nk * dk;
+    auto base = [&](int K, int N) {
+        ClinParams p{};
+        p.B = B; p.n_rows = nk; p.K = K; p.N = N; p.H = H; p.nsp = s.nsp; p.ns = s.ns; p.scale = scale; p.scale_log2e = sl2e;
+        return p;
+    };
+    ClinParams q = base(dk, s.HS);                          // dS = P o (X dZ'^T - delta) / sqrt(D)
+    q.X = X; q.x_bstride = x_bs; q.ldx = dk;
+    q.img = img_dz1; q.img_bstride = img_bytes;
+    q.Y = dS; q.y_bstride = t_bs; q.ldy = s.HS;
+    q.R = P; q.r_bstride = t_bs; q.ldr = s.HS;
+    q.vec = delta;
+    PCA_TRY(launch_cloud_linear<EPI_DS_COL>(q, s.nsp, "attn_g1_dscol_tc_kernel", st));
+    PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<ds_col>");
+    if (dX) {
+        ClinParams g = base(s.HS, dk);                      // dX (+)= dS Gq
+        g.X = dS; g.x_bstride = t_bs; g.ldx = s.HS;
+        g.img = img_gq2; g.img_bstride = 0;
+        g.Y = dX; g.y_bstride = x_bs; g.ldy = dk;
+        if (x_acc) {
+            g.R = dX; g.r_bstride = x_bs; g.ldr = dk;
+            PCA_TRY(launch_cloud_linear<EPI_RESID>(g, s.nsp, "attn_g2_resid_tc_kernel", st));
+        } else {
+            PCA_TRY(launch_cloud_linear<EPI_STORE>(g, s.nsp, "attn_g2_store_tc_kernel", st));
+        }
+        PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<g2>");
+        ClinParams v = base(s.HS, dk);                      // dX += P dZ'
+        v.X = P; v.x_bstride = t_bs; v.ldx = s.HS;
+        v.img = img_dz2; v.img_bstride = img_bytes;
+        v.Y = dX; v.y_bstride = x_bs; v.ldy = dk;
+        v.R = dX; v.r_bstride = x_bs; v.ldr = dk;
+        PCA_TRY(launch_cloud_linear<EPI_RESID>(v, s.nsp, "attn_g2_resid_tc_kernel", st));
+        PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<resid>");
+    }
+    PCA_CHECK_CUDA(cudaMemsetAsync(dGq, 0, (size_t)s.HS * dk * sizeof(float), st));
+    PCA_TRY(launch_cloud_gw(dS, X, x_bs, dk, dGq, 0, dk, B, nk, s, dk, H, st, false, nullptr, 1));      // dGq = sum_b dS^T X
+    fold_dwk_kernel<<<(unsigned)D, 256, 0, st>>>(Qp, dGq, s.ns, s.nsp, dh, D, dk, dWk);
+    PCA_CHECK_LAUNCH("fold_dwk_kernel");
+    fold_dq_kernel<<<(unsigned)((s.ns * D + 7) / 8), 256, 0, st>>>(dGq, Wk, s.ns, s.nsp, dh, D, dk, dQ);
+    PCA_CHECK_LAUNCH("fold_dq_kernel");
+    {
+        const long long total = (long long)B * s.HS * D;
+        fold_dox_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dO, s.ns, s.nsp, dh, D, s.HS, total, dOx);
+        PCA_CHECK_LAUNCH("fold_dox_kernel");
+    }
+    *dox_out = dOx;
     return 0;
 }
 

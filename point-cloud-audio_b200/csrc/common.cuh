@@ -111,7 +111,16 @@ size_t attn_tc_p_floats(int B, int nq, int nk, int D, int H);
 // per-cloud sums P^T X); the K | V projection is never computed
 bool attn_fold_eligible(int B, int nq, int nk, int dk, int D, int H);
 int launch_attn_folded(const float* Qp, const float* Wkv, const float* bkv, const float* X, int B, int nq, int nk, int dk, int D, int H,
-                       float* O, float* scratch, cudaStream_t st, const int* key_counts);
+                       float* O, float* scratch, cudaStream_t st, const int* key_counts, float* p_out = nullptr, float* z_out = nullptr,
+                       float* gq_out = nullptr);
+// the same block in training: forward keeps P / Z / Gq, the backward below works on the un-projected points as well
+bool attn_fold_train_on();
+size_t attn_fold_z_floats(int B, int nq, int nk, int D, int H);
+size_t attn_fold_gq_floats(int B, int nq, int nk, int D, int H);
+int attn_fold_rows(int B, int nq, int nk, int D, int H);
+int launch_attn_folded_bwd(const float* Qp, const float* Wkv, const float* X, const float* dO, const float* P, const float* Z,
+                           const float* Gq, int B, int nq, int nk, int dk, int D, int H, float* dX, int x_acc, float* dWk, float* dQ,
+                           float** dox_out, float* scratch, cudaStream_t st);
 int launch_attn_bwd_tc(const float* Qp, long long q_bstride, const float* KV, const float* dO, const float* lse, const float* delta,
                        int B, int nq, int nk, int D, int H, float* dQp, float* dKV, float* scratch, cudaStream_t st,
                        const float* p_saved = nullptr, float* db_q = nullptr, float* db_kv = nullptr);

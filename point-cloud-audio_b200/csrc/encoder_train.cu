@@ -284,6 +284,10 @@ static int launch_grad_weight_bias(const float* dY, const float* X, float* dW, f
 __device__ __forceinline__ void red_add4_fwd(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__global__ void add_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += b[i];
+}
 __global__ void relu_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ R, float* __restrict__ dZ, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dZ[i] = R[i] > 0.f ? dOut[i] : 0.f;
@@ -655,7 +659,7 @@ int linear_bwd_api(const float* dY, const float* X, long long rows, int din, int
 
 // ------------------------------------------------------------------------------------ MAB forward (saving) / backward
 // Opre / pre1: the inputs of ln0 / ln1 (LayerNorm branches only; O and out then hold the normalised tensors)
-struct MabSaved { float *Qp, *KV, *O, *R, *lse, *out, *Opre, *pre1, *P; };     // P: probabilities of the tensor-core attention (attn_tc.cu)
+struct MabSaved { float *Qp, *KV, *O, *R, *lse, *out, *Opre, *pre1, *P, *Z, *Gq; };   // P (probabilities), Z, Gq: tensor-core attention (attn_tc.cu)
 
 // ------------------------------------------------------------------------------------ LayerNorm backward
 // y = (x - mean) rstd gamma + beta per row.  dx = rstd (g gamma - mean(g gamma) - xhat mean(g gamma xhat)); dgamma += sum g xhat,
@@ -720,10 +724,19 @@ static MabSaved mab_saved_take(Arena& a, int B, int qb, int nq, int nk, int D, i
     s.pre1 = ln ? a.take<float>((size_t)B * nq * D) : nullptr;
     const size_t pf = attn_tc_p_floats(B, nq, nk, D, H);       // (points, heads x small side) probabilities: the backward reuses them
     s.P = pf ? a.take<float>(pf) : nullptr;
+    // shared small query set (I / S against the points): room for the folded form's per-cloud sums and query matrix
+    const size_t zf = qb == 1 ? attn_fold_z_floats(B, nq, nk, D, H) : 0;
+    s.Z = zf ? a.take<float>(zf) : nullptr;
+    s.Gq = zf ? a.take<float>(attn_fold_gq_floats(B, nq, nk, D, H)) : nullptr;
     return s;
 }
 
 static size_t train_img_bytes(int D) { return gemm_tc_image_bytes(2 * D, D); }
+
+// the folded form of a block (attn_tc.cu): shared queries, no key counts, eligible dims, switch on
+static bool mab_folded(int qb, int B, int nq, int nk, int dk, int D, int H, const int* key_counts) {
+    return qb == 1 && !key_counts && attn_fold_train_on() && attn_fold_eligible(B, nq, nk, dk, D, H);
+}
 
 static int mab_train_forward(const MabSaved& s, const float* Qin, int qb, const float* Kin, int B, int nq, int nk, int dq, int dk,
                              int D, int H, const float* params, float* part, void* img, cudaStream_t st,
@@ -731,8 +744,14 @@ static int mab_train_forward(const MabSaved& s, const float* Qin, int qb, const 
     const MabParams m = mab_slice(params, dq, dk, D, ln);
     const size_t ib = train_img_bytes(D);
     PCA_TRY(launch_linear(Qin, m.Wq, m.bq, s.Qp, (long long)qb * nq, dq, D, 0, st, nullptr, dq <= D ? img : nullptr, ib));
-    PCA_TRY(launch_linear(Kin, m.Wkv, m.bkv, s.KV, (long long)B * nk, dk, 2 * D, 0, st, nullptr, dk <= D ? img : nullptr, ib));
-    PCA_TRY(launch_attn(s.Qp, qb == 1 ? 0 : (long long)nq * D, s.KV, B, nq, nk, D, H, s.O, part, key_counts, st, s.lse, s.P));
+    if (mab_folded(qb, B, nq, nk, dk, D, H, key_counts) && s.Z) {
+        // shared inducing points / seeds against many points: the block runs on the un-projected keys, forward and backward
+        // (attn_tc.cu: the K | V projection and its gradient GEMMs never run); P, Z and Gq are kept for the backward
+        PCA_TRY(launch_attn_folded(s.Qp, m.Wkv, m.bkv, Kin, B, nq, nk, dk, D, H, s.O, part, st, nullptr, s.P, s.Z, s.Gq));
+    } else {
+        PCA_TRY(launch_linear(Kin, m.Wkv, m.bkv, s.KV, (long long)B * nk, dk, 2 * D, 0, st, nullptr, dk <= D ? img : nullptr, ib));
+        PCA_TRY(launch_attn(s.Qp, qb == 1 ? 0 : (long long)nq * D, s.KV, B, nq, nk, D, H, s.O, part, key_counts, st, s.lse, s.P));
+    }
     const size_t nbytes = (size_t)B * nq * D * sizeof(float);
     if (ln) {                                                   // O = ln0(Qp + A V); the pre-LN tensor is kept for the backward
         PCA_CHECK_CUDA(cudaMemcpyAsync(s.Opre, s.O, nbytes, cudaMemcpyDeviceToDevice, st));
@@ -803,7 +822,8 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
         PCA_TRY(launch_layernorm_bwd(dO, s.Opre, m.ln0w, rq, D, dO, (float*)g.ln0w, (float*)g.ln0b, st));
         Oatt = s.Opre;
     }
-    if (!(attn_tc && attn_tc_kind(B, nq, nk, D, H) == 1)) {      // (the small-key tensor-core backward computes sum_m P dP in its epilogue)
+    const bool folded = mab_folded(qb, B, nq, nk, dk, D, H, key_counts) && s.Z;
+    if (!folded && !(attn_tc && attn_tc_kind(B, nq, nk, D, H) == 1)) {      // (the small-key tensor-core backward computes sum_m P dP in its epilogue; the folded one its own row dots)
         const long long total = rq * H;
         if (D % 32 == 0 && 32 % H == 0)
             attn_delta_warp_kernel<<<(unsigned)((rq + 7) / 8), 256, 0, st>>>(dO, Oatt, s.Qp, q_bstride, nq, D, H, rq, delta);
@@ -813,7 +833,19 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
     }
     bool fused_bq = false, fused_bkv = false;
     float* dQp = dZ;                                            // dQp = dO (residual) + attention part
-    if (attn_tc) {                                              // one small side: every contraction as a split-bf16 tensor-core GEMM
+    float* dQfold = nullptr;
+    if (folded) {
+        // the block on the un-projected keys: dKin, dWk, the attention part of the shared queries' gradient and the operands of
+        // the Wv gradient come from attn_tc.cu; the key bias has an exactly zero gradient (softmax shift invariance)
+        PCA_CHECK_CUDA(cudaMemcpyAsync(dQp, dO, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));   // residual part
+        float* dOx = nullptr;
+        dQfold = dKV;                                           // (nq, D): dKV's buffer is free in this form
+        PCA_TRY(launch_attn_folded_bwd(s.Qp, m.Wkv, Kin, dO, s.P, s.Z, s.Gq, B, nq, nk, dk, D, H, dKin, acc_k, (float*)g.Wkv, dQfold, &dOx,
+                                       attn_scratch, st));
+        const int HS = attn_fold_rows(B, nq, nk, D, H);
+        PCA_TRY(launch_grad_weight(dOx, s.Z, (float*)g.Wkv + (long long)D * dk, (long long)B * HS, dk, D, st));     // dWv
+        PCA_TRY(launch_colsum(dO, rq, D, (float*)g.bkv + D, st));                                                    // dbv
+    } else if (attn_tc) {                                       // one small side: every contraction as a split-bf16 tensor-core GEMM
         // the bias gradients of fc_q (large-query form) / fc_k | fc_v (small-query form) fall out of the epilogues that write
         // dQp / dKV -- no separate column-sum pass (the first layers, d_in <= 4, keep their one-pass weight + bias kernel)
         const int kind = attn_tc_kind(B, nq, nk, D, H);
@@ -831,12 +863,18 @@ static int mab_backward(const MabSaved& s, const float* Qin, int qb, const float
     if (qb == 1) {                                              // shared queries (I / S): sum the per-cloud gradients
         PCA_CHECK_CUDA(cudaMemsetAsync(dQ1, 0, (size_t)nq * D * sizeof(float), st));
         PCA_TRY(launch_colsum(dQp, B, nq * D, dQ1, st));
+        if (dQfold) {                                           // + the attention part of the folded form (one matrix for the batch)
+            const long long nn = (long long)nq * D;
+            add_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(dQ1, dQfold, nn);
+            PCA_CHECK_LAUNCH("add_kernel");
+        }
         dQp = dQ1;
         rows_q = nq;
     }
     if (fused_bq) PCA_TRY(launch_grad_weight(dQp, Qin, (float*)g.Wq, rows_q, dq, D, st));
     else PCA_TRY(launch_grad_weight_bias(dQp, Qin, (float*)g.Wq, (float*)g.bq, rows_q, dq, D, st));
     if (dQin) PCA_TRY(launch_grad_input(dQp, m.Wq, dQin, acc_q ? dQin : nullptr, rows_q, dq, D, st, img_q, ib));
+    if (folded) return 0;                                       // (dWkv, dbv and dKin are done)
     if (fused_bkv) PCA_TRY(launch_grad_weight(dKV, Kin, (float*)g.Wkv, rk, dk, 2 * D, st));
     else PCA_TRY(launch_grad_weight_bias(dKV, Kin, (float*)g.Wkv, (float*)g.bkv, rk, dk, 2 * D, st));
     if (dKin) PCA_TRY(launch_grad_input(dKV, m.Wkv, dKin, acc_k ? dKin : nullptr, rk, dk, 2 * D, st, img_k, ib));

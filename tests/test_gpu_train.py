@@ -37,6 +37,8 @@ CASES = [
     ("ST", 3, 64, 4, 16, 7, 2, 77),       # head dim 16
     ("ST", 3, 64, 2, 5, 4, 3, 33),        # head dim 32 (two lanes per head row)
     ("SetTransformer", 3, 256, 4, 16, 40, 2, 200),   # ModelNet dims (main_pointcloud.py defaults), head dim 64
+    ("SetTransformer", 3, 256, 4, 16, 40, 4, 300),   # the same, large enough for the tensor-core attention (csrc/attn_tc.cu: >= 512
+                                                     # rows per batch), incl. the folded form of the shared-query blocks
 ]
 
 
