@@ -112,6 +112,14 @@ struct ClinParams {
                            // that produced the operand: saves a separate pass over Y)
     int raw_slots;         // raw fp32 tiles in the TMA ring (<= CL_RAW_MAX)
     int x_shared;          // X has no batch dimension (x_bstride == 0)
+    // optional second source: the K chunks from k_split on come from X2 (its own tensor map) against the image img2 -- one
+    // launch then computes Y = X W + X2 W2 (the folded backward's dX = dS Gq + P dZ')
+    const float* X2;
+    long long x2_bstride;
+    int ldx2;
+    const uint8_t* img2;
+    long long img2_bstride;
+    int k_split;           // K chunks of the first source (= K / 32 when there is no second one)
 };
 
 // The activation images are written by the producers with a PADDED chunk stride (the descriptor's leading byte offset is free):
@@ -175,7 +183,8 @@ __device__ __forceinline__ void at_pair_exchange(const float4 a, const float4 b,
 // issues the MMAs; 4 epilogue warps read the accumulator (thread = row), apply the epilogue and write 128-byte coalesced rows
 // through a padded transpose tile.  Tiles never straddle clouds (tile t = (cloud t / tpc, rows 128 (t % tpc) ...)).
 template <int EPI, int NSP>
-__global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const ClinParams P, const __grid_constant__ CUtensorMap tmx) {
+__global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const ClinParams P, const __grid_constant__ CUtensorMap tmx,
+                                                                        const __grid_constant__ CUtensorMap tmx2) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int stage_bytes = AtSmem::cl_stage(P.N);
     uint8_t* ops = smem + P.raw_slots * CL_RAW_BYTES;
@@ -214,6 +223,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const Cl
         // ================================================================= TMA loader (one thread)
         if (lane == 0) {
             tma_prefetch_desc(&tmx);
+            tma_prefetch_desc(&tmx2);
             for (uint32_t g = 0; g < items; ++g) {
                 const int slot = g % P.raw_slots;
                 const uint32_t lt = g / nkc;
@@ -222,7 +232,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const Cl
                 const int b = tile / tpc, j = tile - b * tpc;
                 if (g >= (uint32_t)P.raw_slots) mbar_wait(&raw_empty[slot], ((g / P.raw_slots) - 1) & 1);
                 mbar_arrive_expect_tx(&raw_full[slot], CL_RAW_BYTES);
-                tma_load_3d(smem + slot * CL_RAW_BYTES, &tmx, kc * AT_KC, j * 128, P.x_shared ? 0 : b, &raw_full[slot]);
+                if (kc < P.k_split) tma_load_3d(smem + slot * CL_RAW_BYTES, &tmx, kc * AT_KC, j * 128, P.x_shared ? 0 : b, &raw_full[slot]);
+                else tma_load_3d(smem + slot * CL_RAW_BYTES, &tmx2, (kc - P.k_split) * AT_KC, j * 128, b, &raw_full[slot]);
             }
         }
     } else if (warp < AT_MMA_WARP) {
@@ -252,8 +263,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cloud_linear_tc_kernel(const Cl
                 const int kc = (int)(g - lt * nkc);
                 const long long b = (int)(blockIdx.x + lt * gridDim.x) / tpc;
                 mbar_arrive_expect_tx(&full[stage], 2 * b_img_bytes);
-                bulk_copy_g2s(st + 2 * AtSmem::A_BYTES, P.img + b * P.img_bstride + ((size_t)kc * 2) * b_img_bytes, 2 * b_img_bytes,
-                              &full[stage]);
+                const uint8_t* isrc = kc < P.k_split ? P.img + b * P.img_bstride + ((size_t)kc * 2) * b_img_bytes
+                                                     : P.img2 + b * P.img2_bstride + ((size_t)(kc - P.k_split) * 2) * b_img_bytes;
+                bulk_copy_g2s(st + 2 * AtSmem::A_BYTES, isrc, 2 * b_img_bytes, &full[stage]);
             }
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
@@ -830,16 +842,23 @@ static int launch_cloud_linear(ClinParams p, int nsp, const char* name, cudaStre
     p.x_shared = p.x_bstride == 0 ? 1 : 0;
     const int smem_bytes = AtSmem::cl_total(p.N, p.raw_slots);
     // the activations as (K, rows of a cloud, clouds): a box of 32 floats x 128 rows is one raw tile
-    CUtensorMap tmx;
-    PCA_TRY(make_tmap_3d_f32(&tmx, p.X, (unsigned long long)p.K, (unsigned long long)p.n_rows, p.x_shared ? 1ull : (unsigned long long)p.B,
+    CUtensorMap tmx, tmx2;
+    if (!p.X2) p.k_split = p.K / AT_KC;
+    const int k1 = p.k_split * AT_KC;
+    PCA_TRY(make_tmap_3d_f32(&tmx, p.X, (unsigned long long)k1, (unsigned long long)p.n_rows, p.x_shared ? 1ull : (unsigned long long)p.B,
                              (unsigned long long)p.ldx * 4, (unsigned long long)(p.x_shared ? (long long)p.n_rows * p.ldx : p.x_bstride) * 4,
                              AT_KC, 128));
+    if (p.X2)
+        PCA_TRY(make_tmap_3d_f32(&tmx2, p.X2, (unsigned long long)(p.K - k1), (unsigned long long)p.n_rows, (unsigned long long)p.B,
+                                 (unsigned long long)p.ldx2 * 4, (unsigned long long)p.x2_bstride * 4, AT_KC, 128));
+    else
+        tmx2 = tmx;
     LaunchTimer lt(name, st, 2.0 * rows * p.K * p.N, 4.0 * rows * (p.K + p.N));
     if (EPI == EPI_SOFTMAX || EPI == EPI_DS_ROW) {
-        if (nsp == 8) cloud_linear_tc_kernel<EPI, 8><<<grid, AT_THREADS, smem_bytes, st>>>(p, tmx);
-        else cloud_linear_tc_kernel<EPI, 16><<<grid, AT_THREADS, smem_bytes, st>>>(p, tmx);
+        if (nsp == 8) cloud_linear_tc_kernel<EPI, 8><<<grid, AT_THREADS, smem_bytes, st>>>(p, tmx, tmx2);
+        else cloud_linear_tc_kernel<EPI, 16><<<grid, AT_THREADS, smem_bytes, st>>>(p, tmx, tmx2);
     } else {
-        cloud_linear_tc_kernel<EPI, 16><<<grid, AT_THREADS, smem_bytes, st>>>(p, tmx);
+        cloud_linear_tc_kernel<EPI, 16><<<grid, AT_THREADS, smem_bytes, st>>>(p, tmx, tmx2);
     }
     return 0;
 }
@@ -1182,9 +1201,12 @@ int launch_attn_folded_bwd(const float* Qp, const float* Wkv, const float* X, co
     PCA_TRY(launch_cloud_linear<EPI_DS_COL>(q, s.nsp, "attn_g1_dscol_tc_kernel", st));
     PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<ds_col>");
     if (dX) {
-        ClinParams g = base(s.HS, dk);                      // dX (+)= dS Gq
+        ClinParams g = base(2 * s.HS, dk);                  // dX (+)= dS Gq + P dZ': ONE launch, the K chunks of two sources
         g.X = dS; g.x_bstride = t_bs; g.ldx = s.HS;
         g.img = img_gq2; g.img_bstride = 0;
+        g.X2 = P; g.x2_bstride = t_bs; g.ldx2 = s.HS;
+        g.img2 = img_dz2; g.img2_bstride = img_bytes;
+        g.k_split = s.HS / AT_KC;
         g.Y = dX; g.y_bstride = x_bs; g.ldy = dk;
         if (x_acc) {
             g.R = dX; g.r_bstride = x_bs; g.ldr = dk;
@@ -1193,13 +1215,6 @@ int launch_attn_folded_bwd(const float* Qp, const float* Wkv, const float* X, co
             PCA_TRY(launch_cloud_linear<EPI_STORE>(g, s.nsp, "attn_g2_store_tc_kernel", st));
         }
         PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<g2>");
-        ClinParams v = base(s.HS, dk);                      // dX += P dZ'
-        v.X = P; v.x_bstride = t_bs; v.ldx = s.HS;
-        v.img = img_dz2; v.img_bstride = img_bytes;
-        v.Y = dX; v.y_bstride = x_bs; v.ldy = dk;
-        v.R = dX; v.r_bstride = x_bs; v.ldr = dk;
-        PCA_TRY(launch_cloud_linear<EPI_RESID>(v, s.nsp, "attn_g2_resid_tc_kernel", st));
-        PCA_CHECK_LAUNCH("cloud_linear_tc_kernel<resid>");
     }
     PCA_CHECK_CUDA(cudaMemsetAsync(dGq, 0, (size_t)s.HS * dk * sizeof(float), st));
     PCA_TRY(launch_cloud_gw(dS, X, x_bs, dk, dGq, 0, dk, B, nk, s, dk, H, st, false, nullptr, 1));      // dGq = sum_b dS^T X
