@@ -12,6 +12,11 @@
 //   points = queries (mab1):  row softmax per head over the ns keys (thread = row holds the whole row)
 //   points = keys (mab0/PMA): column softmax over the points of a cloud (col_softmax_kernel between G1 and G3)
 // The zero blocks cost 4x redundant MMA work at H = 4 -- irrelevant: these GEMMs are HBM-bound (the tensor pipe is < 25 % busy).
+// Kernels: cloud_linear_tc_kernel (G1 / G2: TMA raw-tile ring, converter warps, epilogue variants, optional second K source),
+// cloud_gw_tc_kernel (G3: persistent, two accumulators), col_softmax_kernel, cloud_image_kernel (operand images), and the small
+// kernels of the FOLDED form of blocks with a shared query set (inducing points / seeds), which runs forward and backward on the
+// un-projected points: W_k is folded into the query image and W_v applied to the per-cloud sums P^T X (launch_attn_folded,
+// launch_attn_folded_bwd) -- the K | V projection of those blocks and its gradient GEMMs never run.
 #include "common.cuh"
 #include "tc_prims.cuh"
 #include "tma_host.cuh"
