@@ -983,41 +983,52 @@ __global__ void fold_query_kernel(const float* __restrict__ Qp, const float* __r
         Gq[(long long)row * dk + k] = a;
     }
 }
-// O[b][m][d] = Qp[m][d] + bv[d] + sum_k Z[b][(d / dh, m)][k] Wv[d][k];  block = (head, cloud), thread = (dim of the head, query lane)
+// O[b][m][d] = Qp[m][d] + bv[d] + sum_k Z[b][(d / dh, m)][k] Wv[d][k]: per head a (B ns, dk) x (dk, dh) product.  Block = (head,
+// FOLD_CB clouds): the head's slice of Wv is staged once per block and 32-wide k tile and reused by all the block's rows (the first
+// version, one block per (head, cloud), re-read it 1024 times and took 143 us per launch); thread = (dim of the head, row lane).
+constexpr int FOLD_CB = 8;
 __global__ void __launch_bounds__(256) fold_proj_kernel(const float* __restrict__ Z, const float* __restrict__ Wv, const float* __restrict__ bv,
-                                                        const float* __restrict__ Qp, float* __restrict__ O, int ns, int nsp, int HS, int dk,
-                                                        int D, int dh) {
-    __shared__ float zs[16 * 256];
+                                                        const float* __restrict__ Qp, float* __restrict__ O, int B, int ns, int nsp, int HS,
+                                                        int dk, int D, int dh) {
+    __shared__ float zs[FOLD_CB * 16 * 33];
     __shared__ float wsm[64 * 33];
-    const int h = blockIdx.x, b = blockIdx.y;
+    const int h = blockIdx.x, b0 = blockIdx.y * FOLD_CB;
+    const int nb = min(FOLD_CB, B - b0), rows = nb * ns;
     const int dl = threadIdx.x % dh, ml = threadIdx.x / dh, mlanes = 256 / dh;
-    const float* zb = Z + ((long long)b * HS + h * nsp) * dk;
-    for (int i = threadIdx.x; i < ns * dk; i += 256) zs[i] = zb[i];
-    float acc[16];
+    float acc[32];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
     for (int k0 = 0; k0 < dk; k0 += 32) {
         __syncthreads();
         for (int i = threadIdx.x; i < dh * 32; i += 256) {
             const int dd = i >> 5, kk = i & 31;
             wsm[dd * 33 + kk] = __ldg(Wv + (long long)(h * dh + dd) * dk + k0 + kk);
         }
+        for (int i = threadIdx.x; i < rows * 32; i += 256) {
+            const int r = i >> 5, kk = i & 31;
+            const int b = b0 + r / ns, m = r - (r / ns) * ns;
+            zs[r * 33 + kk] = Z[((long long)b * HS + h * nsp + m) * dk + k0 + kk];
+        }
         __syncthreads();
-#pragma unroll 8
+#pragma unroll 4
         for (int kk = 0; kk < 32; ++kk) {
             const float w = wsm[dl * 33 + kk];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int m = ml + i * mlanes;
-                if (m < ns) acc[i] = fmaf(zs[m * dk + k0 + kk], w, acc[i]);
+            for (int i = 0; i < 32; ++i) {
+                const int r = ml + i * mlanes;
+                if (r < rows) acc[i] = fmaf(zs[r * 33 + kk], w, acc[i]);
             }
         }
     }
     const int d = h * dh + dl;
+    const float bias = __ldg(bv + d);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int m = ml + i * mlanes;
-        if (m < ns) O[((long long)b * ns + m) * D + d] = __ldg(Qp + (long long)m * D + d) + __ldg(bv + d) + acc[i];
+    for (int i = 0; i < 32; ++i) {
+        const int r = ml + i * mlanes;
+        if (r < rows) {
+            const int b = b0 + r / ns, m = r - (r / ns) * ns;
+            O[((long long)b * ns + m) * D + d] = __ldg(Qp + (long long)m * D + d) + bias + acc[i];
+        }
     }
 }
 
@@ -1025,7 +1036,7 @@ bool attn_fold_eligible(int B, int nq, int nk, int dk, int D, int H) {
     const AtcShape s = atc_shape(B, nq, nk, D, H);
     if (s.type != 2) return false;
     const int dh = D / H;
-    return dk % 32 == 0 && dk >= 64 && dk <= 256 && dk <= D && 2 * s.HS <= dk && dh <= 64 && 256 % dh == 0 && s.ns <= 16;
+    return dk % 32 == 0 && dk >= 64 && dk <= 256 && dk <= D && 2 * s.HS <= dk && (dh == 8 || dh == 16 || dh == 32 || dh == 64) && s.ns <= 16;
 }
 
 // O (B, nq, D) = Qp + softmax_h(Qp K^T / sqrt(D)) V with K | V = X Wkv^T + bkv never formed.  Qp (nq, D) shared by the batch;
@@ -1065,7 +1076,8 @@ int launch_attn_folded(const float* Qp, const float* Wkv, const float* bkv, cons
     PCA_CHECK_LAUNCH("col_softmax_kernel");
     PCA_CHECK_CUDA(cudaMemsetAsync(Z, 0, (size_t)B * s.HS * dk * sizeof(float), st));
     PCA_TRY(launch_cloud_gw(T, X, (long long)nk * dk, dk, Z, (long long)s.HS * dk, dk, B, nk, s, dk, H, st, true, key_counts, 1));
-    fold_proj_kernel<<<dim3((unsigned)H, (unsigned)B), 256, 0, st>>>(Z, Wkv + (long long)D * dk, bkv + D, Qp, O, s.ns, s.nsp, s.HS, dk, D, dh);
+    fold_proj_kernel<<<dim3((unsigned)H, (unsigned)((B + FOLD_CB - 1) / FOLD_CB)), 256, 0, st>>>(Z, Wkv + (long long)D * dk, bkv + D, Qp, O, B,
+                                                                                                   s.ns, s.nsp, s.HS, dk, D, dh);
     PCA_CHECK_LAUNCH("fold_proj_kernel");
     return 0;
 }
@@ -1079,17 +1091,40 @@ int launch_attn_folded(const float* Qp, const float* Wkv, const float* bkv, cons
 //   dGq = sum_b dS^T X                         (G3, full rows, one matrix for the batch)  ->  dWk_h += Qp_h^T dGq_h, dQp_h = dGq_h Wk_h^T
 //   dWv_h += sum_b dO_h^T Z_h, dbv += sum dO   (by the caller: a weight-gradient GEMM on the block-expanded dO, fold_dox_kernel)
 // The K | V projection, its 512-wide weight-gradient GEMM and its input-gradient GEMM do not exist in this form.
-__global__ void fold_dz_kernel(const float* __restrict__ dO, const float* __restrict__ Wv, int ns, int nsp, int dh, int D, int dk, int HS,
-                               float* __restrict__ dZ) {
-    const int row = blockIdx.x, b = blockIdx.y;      // row = (h, m)
-    const int h = row / nsp, m = row - h * nsp;
-    const float* g = dO + ((long long)b * ns + (m < ns ? m : 0)) * D + h * dh;
-    for (int k = threadIdx.x; k < dk; k += blockDim.x) {
-        float a = 0.f;
-        if (m < ns)
-            for (int d = 0; d < dh; ++d) a = fmaf(__ldg(g + d), __ldg(Wv + (long long)(h * dh + d) * dk + k), a);
-        dZ[((long long)b * HS + row) * dk + k] = a;
+// Per head a (B ns, dh) x (dh, dk) product.  Block = (head, FOLD_CB clouds, 256 columns k): the thread keeps its column of the head's
+// Wv slice in registers, the block's dO rows sit in shared memory (broadcast reads); the padded rows (m >= ns) are written as zeros.
+template <int DH>
+__global__ void __launch_bounds__(256) fold_dz_kernel(const float* __restrict__ dO, const float* __restrict__ Wv, int B, int ns, int nsp, int D,
+                                                      int dk, int HS, float* __restrict__ dZ) {
+    __shared__ __align__(16) float gs[FOLD_CB * 16 * DH];
+    const int h = blockIdx.x, b0 = blockIdx.y * FOLD_CB;
+    const int nb = min(FOLD_CB, B - b0), rows = nb * ns;
+    const int k = blockIdx.z * 256 + threadIdx.x;
+    for (int i = threadIdx.x; i < rows * DH; i += 256) {
+        const int r = i / DH, d = i - r * DH;
+        const int b = b0 + r / ns, m = r - (r / ns) * ns;
+        gs[i] = __ldg(dO + ((long long)b * ns + m) * D + h * DH + d);
     }
+    float w[DH];
+    if (k < dk) {
+#pragma unroll
+        for (int d = 0; d < DH; ++d) w[d] = __ldg(Wv + (long long)(h * DH + d) * dk + k);
+    }
+    __syncthreads();
+    if (k >= dk) return;
+    for (int r = 0; r < rows; ++r) {
+        const float4* g4 = reinterpret_cast<const float4*>(gs + r * DH);
+        float a = 0.f;
+#pragma unroll
+        for (int d4 = 0; d4 < DH / 4; ++d4) {
+            const float4 g = g4[d4];
+            a = fmaf(g.x, w[4 * d4], a); a = fmaf(g.y, w[4 * d4 + 1], a); a = fmaf(g.z, w[4 * d4 + 2], a); a = fmaf(g.w, w[4 * d4 + 3], a);
+        }
+        const int b = b0 + r / ns, m = r - (r / ns) * ns;
+        dZ[((long long)b * HS + h * nsp + m) * dk + k] = a;
+    }
+    for (int bb = 0; bb < nb; ++bb)
+        for (int m = ns; m < nsp; ++m) dZ[((long long)(b0 + bb) * HS + h * nsp + m) * dk + k] = 0.f;
 }
 // delta[(b ns + m) H + h] = Z[b, (h, m), :] . dZ'[b, (h, m), :]; one warp per row
 __global__ void fold_delta_kernel(const float* __restrict__ Z, const float* __restrict__ dZ, int B, int ns, int nsp, int H, int HS, int dk,
@@ -1175,8 +1210,17 @@ int launch_attn_folded_bwd(const float* Qp, const float* Wkv, const float* X, co
     const float* Wk = Wkv;
     const float* Wv = Wkv + (long long)D * dk;
 
-    fold_dz_kernel<<<dim3((unsigned)s.HS, (unsigned)B), 256, 0, st>>>(dO, Wv, s.ns, s.nsp, dh, D, dk, s.HS, dZ);
-    PCA_CHECK_LAUNCH("fold_dz_kernel");
+    {
+        const dim3 gz((unsigned)H, (unsigned)((B + FOLD_CB - 1) / FOLD_CB), (unsigned)((dk + 255) / 256));
+        switch (dh) {
+            case 8: fold_dz_kernel<8><<<gz, 256, 0, st>>>(dO, Wv, B, s.ns, s.nsp, D, dk, s.HS, dZ); break;
+            case 16: fold_dz_kernel<16><<<gz, 256, 0, st>>>(dO, Wv, B, s.ns, s.nsp, D, dk, s.HS, dZ); break;
+            case 32: fold_dz_kernel<32><<<gz, 256, 0, st>>>(dO, Wv, B, s.ns, s.nsp, D, dk, s.HS, dZ); break;
+            case 64: fold_dz_kernel<64><<<gz, 256, 0, st>>>(dO, Wv, B, s.ns, s.nsp, D, dk, s.HS, dZ); break;
+            default: return fail(PCA_EUNSUPPORTED, "attn_folded_bwd: head dim %d not in {8, 16, 32, 64}", dh);
+        }
+        PCA_CHECK_LAUNCH("fold_dz_kernel");
+    }
     fold_delta_kernel<<<(unsigned)((B * s.HS + 7) / 8), 256, 0, st>>>(Z, dZ, B, s.ns, s.nsp, H, s.HS, dk, delta);
     PCA_CHECK_LAUNCH("fold_delta_kernel");
     {
